@@ -1,0 +1,73 @@
+/* oracle/ref_harness.c — TEST INFRASTRUCTURE ONLY.
+ * Linked into oracle/_ref/libopus_ref_{c,simd}.so next to the unmodified reference objects.
+ * It holds OUR small helpers that drive the reference through its own public / internal
+ * (non-static) entry points so tests and bench.py can call them in bulk through ctypes
+ * without a Python loop per frame.  Nothing here re-implements codec logic. */
+#include <stdlib.h>
+#include <string.h>
+#include "opus.h"
+
+/* Which oracle flavour is this?  (0 = pure C, 1 = RTCD/SIMD) */
+int refh_is_simd(void) {
+#ifdef OPUS_HAVE_RTCD
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+/* Encode `nframes` consecutive frames of one stream (interleaved int16 PCM) with a fresh
+ * encoder.  Packets are written back-to-back into `out` (stride `max_bytes`), sizes into
+ * `sizes`, the encoder's final range per packet into `ranges`.
+ * application: OPUS_APPLICATION_* ; returns 0 or a negative opus error. */
+int refh_encode_stream(int Fs, int channels, int application, int bitrate, int vbr, int complexity,
+                       int frame_size, int nframes, const opus_int16 *pcm, unsigned char *out,
+                       int max_bytes, int *sizes, unsigned int *ranges) {
+  int err = 0, f;
+  OpusEncoder *enc = opus_encoder_create(Fs, channels, application, &err);
+  if (!enc) return err;
+  opus_encoder_ctl(enc, OPUS_SET_BITRATE(bitrate));
+  opus_encoder_ctl(enc, OPUS_SET_VBR(vbr));
+  opus_encoder_ctl(enc, OPUS_SET_COMPLEXITY(complexity));
+  for (f = 0; f < nframes; f++) {
+    int n = opus_encode(enc, pcm + (size_t)f * frame_size * channels, frame_size,
+                        out + (size_t)f * max_bytes, max_bytes);
+    if (n < 0) { opus_encoder_destroy(enc); return n; }
+    sizes[f] = n;
+    opus_encoder_ctl(enc, OPUS_GET_FINAL_RANGE(&ranges[f]));
+  }
+  opus_encoder_destroy(enc);
+  return 0;
+}
+
+/* Decode `nframes` consecutive packets of one stream with a fresh decoder. */
+int refh_decode_stream(int Fs, int channels, int frame_size, int nframes, const unsigned char *pkts,
+                       int stride, const int *sizes, opus_int16 *pcm, unsigned int *ranges) {
+  int err = 0, f;
+  OpusDecoder *dec = opus_decoder_create(Fs, channels, &err);
+  if (!dec) return err;
+  for (f = 0; f < nframes; f++) {
+    int n = opus_decode(dec, sizes[f] ? pkts + (size_t)f * stride : NULL, sizes[f],
+                        pcm + (size_t)f * frame_size * channels, frame_size, 0);
+    if (n < 0) { opus_decoder_destroy(dec); return n; }
+    opus_decoder_ctl(dec, OPUS_GET_FINAL_RANGE(&ranges[f]));
+  }
+  opus_decoder_destroy(dec);
+  return 0;
+}
+
+/* Same, float output (no int16 rounding / soft clip applied by opus_decode_float). */
+int refh_decode_stream_float(int Fs, int channels, int frame_size, int nframes, const unsigned char *pkts,
+                             int stride, const int *sizes, float *pcm, unsigned int *ranges) {
+  int err = 0, f;
+  OpusDecoder *dec = opus_decoder_create(Fs, channels, &err);
+  if (!dec) return err;
+  for (f = 0; f < nframes; f++) {
+    int n = opus_decode_float(dec, sizes[f] ? pkts + (size_t)f * stride : NULL, sizes[f],
+                              pcm + (size_t)f * frame_size * channels, frame_size, 0);
+    if (n < 0) { opus_decoder_destroy(dec); return n; }
+    opus_decoder_ctl(dec, OPUS_GET_FINAL_RANGE(&ranges[f]));
+  }
+  opus_decoder_destroy(dec);
+  return 0;
+}
