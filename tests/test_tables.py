@@ -18,7 +18,7 @@ REF = '/root/reference'
 
 def _parse_arrays(text):
     out = {}
-    for m in re.finditer(r'(?:static const|OB_TABLE)\s+([\w ]+?)\s+(\w+)\[(\d*)\]\s*=\s*\{(.*?)\};', text, re.S):
+    for m in re.finditer(r'(?:static const|OB_TABLE)\s+([\w ]+?)\s+(\w+)((?:\[\d*\])+)\s*=\s*\{(.*?)\};', text, re.S):
         body = re.sub(r'/\*.*?\*/', '', m.group(4), flags=re.S)
         body = body.replace('{', ' ').replace('}', ' ')
         vals = [v.strip() for v in body.split(',') if v.strip()]
@@ -70,9 +70,17 @@ def test_tables_match_reference_static_mode():
     cw = open(REF + '/celt/cwrs.c').read()
     body = cw[cw.index('CELT_PVQ_U_DATA[1272]={'):]
     body = body[body.index('{') + 1:body.index('};')]
-    body = re.sub(r'#if defined\(CWRS_EXTRA_ROWS\).*?#endif', '', body, flags=re.S)
+    keep, skip = [], False
+    for l in body.split('\n'):
+        if l.startswith('#if defined(CWRS_EXTRA_ROWS)'):
+            skip = True
+        elif l.startswith('#endif'):
+            skip = False
+        elif not skip:
+            keep.append(l)
+    body = '\n'.join(keep)
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-    refu = [int(x) for x in body.replace('\n', ' ').split(',') if x.strip()]
+    refu = [int(x.strip().rstrip('uU')) for x in body.replace('\n', ' ').split(',') if x.strip()]
     assert len(refu) == 1272
     assert _ints(mine['ob_pvq_u']) == refu
     m = open(REF + '/celt/modes.c').read()
