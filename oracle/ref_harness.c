@@ -40,6 +40,33 @@ int refh_encode_stream(int Fs, int channels, int application, int bitrate, int v
   return 0;
 }
 
+/* As refh_encode_stream, plus a list of (request, value) integer "set" ctls applied after create
+ * (e.g. OPUS_SET_BANDWIDTH_REQUEST=4008, OPUS_SET_FORCE_CHANNELS_REQUEST=4022,
+ * OPUS_SET_PACKET_LOSS_PERC_REQUEST=4014 ...). */
+int refh_encode_stream_ex(int Fs, int channels, int application, int bitrate, int vbr, int complexity,
+                          int frame_size, int nframes, const opus_int16 *pcm, unsigned char *out,
+                          int max_bytes, int *sizes, unsigned int *ranges, const int *ctls, int nctl) {
+  int err = 0, f, k;
+  OpusEncoder *enc = opus_encoder_create(Fs, channels, application, &err);
+  if (!enc) return err;
+  opus_encoder_ctl(enc, OPUS_SET_BITRATE(bitrate));
+  opus_encoder_ctl(enc, OPUS_SET_VBR(vbr));
+  opus_encoder_ctl(enc, OPUS_SET_COMPLEXITY(complexity));
+  for (k = 0; k < nctl; k++) {
+    err = opus_encoder_ctl(enc, ctls[2 * k], (opus_int32)ctls[2 * k + 1]);
+    if (err != OPUS_OK) { opus_encoder_destroy(enc); return err; }
+  }
+  for (f = 0; f < nframes; f++) {
+    int n = opus_encode(enc, pcm + (size_t)f * frame_size * channels, frame_size,
+                        out + (size_t)f * max_bytes, max_bytes);
+    if (n < 0) { opus_encoder_destroy(enc); return n; }
+    sizes[f] = n;
+    opus_encoder_ctl(enc, OPUS_GET_FINAL_RANGE(&ranges[f]));
+  }
+  opus_encoder_destroy(enc);
+  return 0;
+}
+
 /* Decode `nframes` consecutive packets of one stream with a fresh decoder. */
 int refh_decode_stream(int Fs, int channels, int frame_size, int nframes, const unsigned char *pkts,
                        int stride, const int *sizes, opus_int16 *pcm, unsigned int *ranges) {
