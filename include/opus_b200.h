@@ -1,0 +1,103 @@
+/* opus_b200.h — C ABI of the B200-native batched Opus (CELT) hot path.
+ *
+ * Plain C, no CUDA/torch types in the signatures.  A "batch decoder" is N independent Opus
+ * decoders (N streams) living on one GPU; one call decodes one packet per stream.  It is the
+ * batched twin of the reference's per-stream API and keeps its conventions:
+ *
+ *   reference (xiph/opus include/opus.h)                     this library
+ *   ------------------------------------------------------  -----------------------------------
+ *   opus_decoder_create(Fs, channels, &err)        :458      opusb200_decoder_create(..., n_streams, ...)
+ *   opus_decode(st, data, len, pcm, frame_size, fec) :516    opusb200_decode(dec, packets, stride, len[], pcm, ...)
+ *   opus_decode_float(...)                         :566      opusb200_decode_float(...)
+ *   opus_decoder_ctl(st, OPUS_RESET_STATE)         :586      opusb200_decoder_reset(dec)
+ *   opus_decoder_ctl(st, OPUS_GET_FINAL_RANGE(&r)) :586      opusb200_decoder_get_final_range(dec, r[])
+ *   opus_decoder_destroy(st)                       :591      opusb200_decoder_destroy(dec)
+ *
+ * Below the API the frame path is the reference's celt_decode_with_ec() (celt/celt.h:172,
+ * celt/celt_decoder.c:1104) restated as two sm_100a kernels (opus_b200/csrc/).
+ * Return values: >= 0 success / sample counts, < 0 the reference's error codes
+ * (include/opus_defines.h:46-60): OPUS_BAD_ARG -1, OPUS_BUFFER_TOO_SMALL -2, OPUS_INTERNAL_ERROR -3,
+ * OPUS_INVALID_PACKET -4, OPUS_UNIMPLEMENTED -5, OPUS_INVALID_STATE -6, OPUS_ALLOC_FAIL -7.
+ *
+ * Scope of this round: CELT-only packets (TOC config 16..31), Fs = 48000, 1 or 2 channels, frame
+ * sizes 2.5/5/10/20 ms, all frame-packing codes.  SILK/hybrid packets, packet-loss concealment
+ * (len <= 1 / NULL data), FEC and soft clipping return OPUS_UNIMPLEMENTED per stream.
+ * There is NO CPU fallback: every entry point fails with OPUS_INTERNAL_ERROR if no CUDA device
+ * is usable. */
+#ifndef OPUS_B200_H
+#define OPUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPUSB200_OK 0
+#define OPUSB200_BAD_ARG (-1)
+#define OPUSB200_BUFFER_TOO_SMALL (-2)
+#define OPUSB200_INTERNAL_ERROR (-3)
+#define OPUSB200_INVALID_PACKET (-4)
+#define OPUSB200_UNIMPLEMENTED (-5)
+#define OPUSB200_INVALID_STATE (-6)
+#define OPUSB200_ALLOC_FAIL (-7)
+
+typedef struct OpusB200Decoder OpusB200Decoder;
+
+/* Library / device info. */
+const char *opusb200_version(void);
+int opusb200_device_count(void);
+
+/* N decoders in the state opus_decoder_create() leaves them (src/opus_decoder.c:150-188,
+ * celt/celt_decoder.c:240-268).  device: CUDA ordinal.  Fs must be 48000; channels 1 or 2. */
+int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Decoder **out);
+void opusb200_decoder_destroy(OpusB200Decoder *dec);
+int opusb200_decoder_reset(OpusB200Decoder *dec); /* OPUS_RESET_STATE on every stream */
+int opusb200_decoder_n_streams(const OpusB200Decoder *dec);
+
+/* Decode one packet per stream; HOST buffers (copies to/from the device are part of the call).
+ *   packets    : stream s's packet starts at packets + s*pkt_stride
+ *   len[s]     : packet length in bytes; 0 = no packet for this stream in this call
+ *   pcm        : stream s's output starts at pcm + s*pcm_stride (interleaved if 2 channels)
+ *   pcm_stride : elements (not bytes) between consecutive streams' outputs, >= frame_size*channels
+ *   frame_size : capacity per channel of each stream's pcm area, like opus_decode()'s argument
+ *   out_samples[s] : samples per channel decoded for stream s, or a negative error code
+ * Returns 0, or a negative error code if the call as a whole failed. */
+int opusb200_decode(OpusB200Decoder *dec, const unsigned char *packets, int pkt_stride, const int32_t *len,
+                    int16_t *pcm, int pcm_stride, int frame_size, int32_t *out_samples);
+int opusb200_decode_float(OpusB200Decoder *dec, const unsigned char *packets, int pkt_stride, const int32_t *len,
+                          float *pcm, int pcm_stride, int frame_size, int32_t *out_samples);
+
+/* Same, with every buffer already resident in device memory (no copies, no synchronisation:
+ * work is enqueued on the decoder's stream; call opusb200_decoder_sync() before reading results).
+ * max_frames_per_packet: upper bound on frames per packet the caller guarantees (1 for the
+ * usual one-frame packets, up to 48); pcm_is_int16 selects int16 or float output. */
+int opusb200_decode_device(OpusB200Decoder *dec, const unsigned char *d_packets, int pkt_stride, const int32_t *d_len,
+                           void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
+                           int32_t *d_out_samples);
+int opusb200_decoder_sync(OpusB200Decoder *dec);
+
+/* OPUS_GET_FINAL_RANGE for every stream (host array of n_streams). */
+int opusb200_decoder_get_final_range(OpusB200Decoder *dec, uint32_t *final_range);
+
+/* The CUDA stream the decoder enqueues on, as an opaque pointer (cudaStream_t). */
+void *opusb200_decoder_cuda_stream(OpusB200Decoder *dec);
+/* Number of kernels launched by this decoder since creation (for benchmarks' bookkeeping). */
+int64_t opusb200_decoder_launch_count(const OpusB200Decoder *dec);
+
+/* Profiling aid: when enabled, every kernel launch is bracketed by CUDA events on the decoder's
+ * stream and the stream is drained after each frame (so do not enable it for throughput runs).
+ * get_timing returns the accumulated device milliseconds of the band-decode and synthesis kernels
+ * and the number of (bands, synth) launch pairs they cover. */
+int opusb200_decoder_set_timing(OpusB200Decoder *dec, int enable);
+int opusb200_decoder_get_timing(OpusB200Decoder *dec, double *ms_bands, double *ms_synth, int64_t *launch_pairs);
+
+/* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
+void *opusb200_host_alloc(size_t bytes);
+void opusb200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""ctypes binding of include/opus_b200.h (the same stub a maintainer of another host language
+would write against the C ABI)."""
+import ctypes
+import os
+import subprocess
+
+OPUS_OK = 0
+OPUS_BAD_ARG = -1
+OPUS_BUFFER_TOO_SMALL = -2
+OPUS_INTERNAL_ERROR = -3
+OPUS_INVALID_PACKET = -4
+OPUS_UNIMPLEMENTED = -5
+OPUS_INVALID_STATE = -6
+OPUS_ALLOC_FAIL = -7
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-fmad=false', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-shared', '-diag-suppress', '177']
+
+# every symbol include/opus_b200.h declares
+SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create', 'opusb200_decoder_destroy',
+           'opusb200_decoder_reset', 'opusb200_decoder_n_streams', 'opusb200_decode', 'opusb200_decode_float',
+           'opusb200_decode_device', 'opusb200_decoder_sync', 'opusb200_decoder_get_final_range',
+           'opusb200_decoder_cuda_stream', 'opusb200_decoder_launch_count', 'opusb200_decoder_set_timing',
+           'opusb200_decoder_get_timing', 'opusb200_host_alloc', 'opusb200_host_free']
+
+
+class OpusB200Error(RuntimeError):
+    def __init__(self, code, what=''):
+        super().__init__('opus_b200 error %d %s' % (code, what))
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, 'libopus_b200.so')
+
+
+def build_library(force=False):
+    """Compile opus_b200/csrc/opus_b200.cu for sm_100a into opus_b200/libopus_b200.so (in tree)."""
+    out = library_path()
+    src_dir = os.path.join(_HERE, 'csrc')
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir)] + [os.path.join(ROOT, 'include', 'opus_b200.h')]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', out, os.path.join(src_dir, 'opus_b200.cu')])
+    return out
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        p = library_path()
+        if not os.path.exists(p):
+            raise OpusB200Error(OPUS_INTERNAL_ERROR, 'libopus_b200.so is not built (run __graft_entry__.build()); '
+                                'there is no CPU fallback')
+        L = ctypes.CDLL(p)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        L.opusb200_version.restype = ctypes.c_char_p
+        L.opusb200_decoder_create.argtypes = [ctypes.c_int, i32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        L.opusb200_decoder_destroy.argtypes = [vp]
+        L.opusb200_decoder_destroy.restype = None
+        L.opusb200_decoder_reset.argtypes = [vp]
+        L.opusb200_decoder_n_streams.argtypes = [vp]
+        for f in (L.opusb200_decode, L.opusb200_decode_float):
+            f.argtypes = [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        L.opusb200_decode_device.argtypes = [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, vp]
+        L.opusb200_decoder_sync.argtypes = [vp]
+        L.opusb200_decoder_get_final_range.argtypes = [vp, vp]
+        L.opusb200_decoder_cuda_stream.argtypes = [vp]
+        L.opusb200_decoder_cuda_stream.restype = vp
+        L.opusb200_decoder_launch_count.argtypes = [vp]
+        L.opusb200_decoder_launch_count.restype = i64
+        L.opusb200_decoder_set_timing.argtypes = [vp, ctypes.c_int]
+        L.opusb200_decoder_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                                  ctypes.POINTER(i64)]
+        L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
+        L.opusb200_host_alloc.restype = vp
+        L.opusb200_host_free.argtypes = [vp]
+        L.opusb200_host_free.restype = None
+        _lib = L
+    return _lib

@@ -1,0 +1,748 @@
+// celt_dec_kernels.cuh — the two kernels of the batched CELT decoder.
+//
+//   ob_celt_dec_bands   : one WARP per stream.  Opus packet -> (frame k of the packet) -> range
+//                         decode + band decode -> normalised spectrum X[C][N] (HBM) + ObFrameSide.
+//                         Latency/issue bound (serial entropy decoding).
+//   ob_celt_dec_synth   : one CTA per stream, one warp per output channel.  X * band gains ->
+//                         inverse MDCT (+TDAC overlap) -> comb post-filter -> de-emphasis -> PCM.
+//                         HBM bound (streams X in, history + PCM out).
+//
+// Written against simt.cuh so the same source also runs under the test-only host emulator.
+#pragma once
+#include "celt_dec_core.cuh"
+
+namespace ob {
+
+struct DecBandsParams {
+  const unsigned char *packets;  // [n_streams][pkt_stride], Opus packets (with TOC)
+  const int32_t *pkt_len;        // [n_streams], <=0 : nothing to decode for this stream
+  int pkt_stride;
+  int pkt_cap;      // shared-memory bytes reserved per warp for the packet (>= max len, multiple of 16)
+  int n_streams;
+  int channels;     // output channels (decoder was created with), 1 or 2
+  int frame_index;  // which frame of a multi-frame packet to decode in this launch
+  ObDecBandState *state;  // [n_streams]
+  ObFrameSide *side;      // [n_streams]
+  float *X;               // [n_streams][2][960] normalised spectrum of this frame
+  int32_t *out_samples;   // [n_streams] or null: running per-stream result (samples/channel or error)
+  int max_samples;        // per-channel capacity of each stream's pcm area
+};
+
+// src/opus.c:183-201 (parse_size)
+OB_DEV int parse_size(const unsigned char *d, int len, int &size) {
+  if (len < 1) { size = -1; return -1; }
+  if (d[0] < 252) { size = d[0]; return 1; }
+  if (len < 2) { size = -1; return -1; }
+  size = 4 * d[1] + d[0];
+  return 2;
+}
+
+// Locate frame `k` of an Opus packet (RFC 6716 section 3.2; src/opus.c:224-420).
+// Returns number of frames in the packet (<0 on a malformed packet); off/flen describe frame k.
+OB_DEV int locate_frame(const unsigned char *data, int len, int k, int &off, int &flen) {
+  int pos = 0, count, cbr = 0, last_size, sz0 = 0;
+  if (len <= 0) return -4;
+  int toc = data[0];
+  int framesize = (48000 << ((toc >> 3) & 3)) / 400;  // CELT-only TOC (checked by the caller)
+  pos = 1; len--;
+  last_size = len;
+  off = 0; flen = 0;
+  switch (toc & 3) {
+    case 0: count = 1; break;
+    case 1:
+      count = 2; cbr = 1;
+      if (len & 1) return -4;
+      last_size = len / 2;
+      sz0 = last_size;
+      break;
+    case 2: {
+      count = 2;
+      int bytes = parse_size(data + pos, len, sz0);
+      len -= bytes;
+      if (sz0 < 0 || sz0 > len) return -4;
+      pos += bytes;
+      last_size = len - sz0;
+      break;
+    }
+    default: {
+      if (len < 1) return -4;
+      int ch = data[pos++];
+      count = ch & 0x3F;
+      if (count <= 0 || framesize * count > 5760) return -4;
+      len--;
+      if (ch & 0x40) {
+        int p;
+        do {
+          if (len <= 0) return -4;
+          p = data[pos++];
+          len--;
+          int t = p == 255 ? 254 : p;
+          len -= t;
+        } while (p == 255);
+      }
+      if (len < 0) return -4;
+      cbr = !(ch & 0x80);
+      if (!cbr) {
+        // VBR: sizes of the first count-1 frames precede the frames
+        last_size = len;
+        int accum = 0, mysize = -1;
+        for (int i = 0; i < count - 1; i++) {
+          int sz;
+          int bytes = parse_size(data + pos, len, sz);
+          len -= bytes;
+          if (sz < 0 || sz > len) return -4;
+          pos += bytes;
+          last_size -= bytes + sz;
+          if (i < k) accum += sz;
+          if (i == k) mysize = sz;
+        }
+        if (last_size < 0) return -4;
+        if (last_size > 1275) return -4;
+        if (k < count) { off = pos + accum; flen = k == count - 1 ? last_size : mysize; }
+        return count;
+      } else {
+        last_size = len / count;
+        if (last_size * count != len) return -4;
+        sz0 = last_size;
+      }
+      break;
+    }
+  }
+  if (last_size > 1275) return -4;
+  if (k < count) {
+    if (cbr || count == 1) { off = pos + k * last_size; flen = last_size; }
+    else { off = pos + (k == 0 ? 0 : sz0); flen = k == 0 ? sz0 : last_size; }  // code 2
+  }
+  return count;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel A body: one warp, one stream.
+// ------------------------------------------------------------------------------------------
+OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  BandWS *ws = (BandWS *)smem_warp;
+  unsigned char *pkt = smem_warp + ((sizeof(BandWS) + 15) & ~(size_t)15);
+  ObFrameSide *side = p.side + stream;
+  ObDecBandState *st = p.state + stream;
+  const int CC = p.channels;
+  int plen = p.pkt_len[stream];
+  if (plen > p.pkt_cap) plen = -1;
+  if (plen <= 0) {
+    if (lane == 0) {
+      side->status = plen < 0 ? -1 : 0;
+      if (p.frame_index == 0) { st->last_status = side->status; if (p.out_samples) p.out_samples[stream] = side->status; }
+    }
+    return;
+  }
+  // stage the packet in shared memory (coalesced)
+  {
+    const unsigned char *g = p.packets + (size_t)stream * p.pkt_stride;
+    for (int i = lane; i < plen; i += 32) pkt[i] = g[i];
+  }
+  wsync();
+  const int toc = pkt[0];
+  int foff, flen;
+  int count = locate_frame(pkt, plen, p.frame_index, foff, flen);
+  int status = 1;
+  if (count < 0) status = count;                      // OPUS_INVALID_PACKET
+  else if (!(toc & 0x80)) status = -5;                // SILK / hybrid: OPUS_UNIMPLEMENTED here
+  else if (p.frame_index >= count) status = 0;        // no such frame in this packet
+  else if (flen <= 1) status = -5;                    // lost / DTX frame: PLC not implemented
+  const int LM = (toc >> 3) & 3;
+  const int N = OB_SHORT_N << LM, M = 1 << LM;
+  if (status > 0 && (p.frame_index + 1) * N > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // OPUS_BUFFER_TOO_SMALL
+  if (status <= 0) {
+    if (lane == 0) {
+      side->status = status;
+      if (status < 0 || p.frame_index == 0) { st->last_status = status; if (p.out_samples) p.out_samples[stream] = status; }
+    }
+    return;
+  }
+  const int C = (toc & 4) ? 2 : 1;
+  const int bw = (toc >> 5) & 3;
+  const int start = 0, end = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;
+  const int len = flen;
+  float *Xg = p.X + (size_t)stream * 2 * OB_MAXN;
+  float *Yg = Xg + N;
+
+  BandCtx ctx;
+  ctx.ws = ws;
+  ctx.lane = lane;
+  ctx.disable_inv = CC == 1;
+  ctx.seed = st->rng;
+  RangeDec &dec = ctx.ec;
+  dec.init(pkt + foff, len);
+
+  int32_t total_bits = len * 8;
+  int32_t tell = dec.tell();
+  int silence = 0;
+  if (tell >= total_bits) silence = 1;
+  else if (tell == 1) silence = dec.bit_logp(15);
+  if (silence) {
+    tell = len * 8;
+    dec.nbits_total += tell - dec.tell();
+  }
+  int pf_pitch = 0, pf_tapset = 0;
+  float pf_gain = 0.f;
+  if (start == 0 && tell + 16 <= total_bits) {
+    if (dec.bit_logp(1)) {
+      int octave = dec.uint(6);
+      pf_pitch = (16 << octave) + dec.bits(4 + octave) - 1;
+      int qg = dec.bits(3);
+      if (dec.tell() + 2 <= total_bits) pf_tapset = dec.icdf(ob_tapset_icdf, 2);
+      pf_gain = .09375f * (qg + 1);
+    }
+    tell = dec.tell();
+  }
+  int isTransient = 0;
+  if (LM > 0 && tell + 3 <= total_bits) {
+    isTransient = dec.bit_logp(3);
+    tell = dec.tell();
+  }
+  const int shortBlocks = isTransient ? M : 0;
+  const int intra = tell + 3 <= total_bits ? dec.bit_logp(3) : 0;
+
+  // ---- coarse energy (celt/quant_bands.c:431-494): reads the previous frame's energies from the
+  // stream state (HBM, read-only here), writes this frame's into shared memory ----
+  {
+    const unsigned char *prob = ob_e_prob + (LM * 2 + intra) * 42;
+    float prev0 = 0.f, prev1 = 0.f, coef, beta;
+    if (intra) { coef = 0.f; beta = 4915 / 32768.f; }
+    else {
+      beta = LM == 0 ? 30147 / 32768.f : LM == 1 ? 22282 / 32768.f : LM == 2 ? 12124 / 32768.f : 6554 / 32768.f;
+      coef = LM == 0 ? 29440 / 32768.f : LM == 1 ? 26112 / 32768.f : LM == 2 ? 21248 / 32768.f : 16384 / 32768.f;
+    }
+    const int32_t budget = dec.storage * 8;
+    const float *oldg = st->oldEBands;
+    for (int i = lane; i < 2 * OB_NBANDS; i += 32) ws->oldE[i] = oldg[i];  // bands outside [start,end) keep old values
+    wsync();
+    for (int i = start; i < end; i++) {
+      for (int c = 0; c < C; c++) {
+        int qi;
+        int32_t t = dec.tell();
+        if (budget - t >= 15) {
+          int pi = 2 * OB_IMIN(i, 20);
+          qi = dec.laplace(prob[pi] << 7, prob[pi + 1] << 6);
+        } else if (budget - t >= 2) {
+          qi = dec.icdf(ob_small_energy_icdf, 2);
+          qi = (qi >> 1) ^ -(qi & 1);
+        } else if (budget - t >= 1) {
+          qi = -dec.bit_logp(1);
+        } else qi = -1;
+        float q = (float)qi;
+        float o = oldg[i + c * OB_NBANDS];
+        if (C == 1) { float o2 = oldg[OB_NBANDS + i]; o = o > o2 ? o : o2; }  // celt_decoder.c:1306-1310
+        o = o > -9.f ? o : -9.f;
+        float prev = c ? prev1 : prev0;
+        float tmp = coef * o + prev + q;
+        prev = prev + q - beta * q;
+        if (c) prev1 = prev; else prev0 = prev;
+        if (lane == 0) ws->oldE[i + c * OB_NBANDS] = tmp;
+      }
+    }
+  }
+  // ---- tf_decode (celt/celt_decoder.c:513-547) ----
+  {
+    int curr = 0, tf_select = 0, tf_changed = 0;
+    uint32_t budget = dec.storage * 8, t = dec.tell();
+    int logp = isTransient ? 2 : 4;
+    int tf_select_rsv = LM > 0 && t + logp + 1 <= budget;
+    budget -= tf_select_rsv;
+    uint32_t raw = 0;  // per-band raw flags packed into a register
+    for (int i = start; i < end; i++) {
+      if (t + logp <= budget) {
+        curr ^= dec.bit_logp(logp);
+        t = dec.tell();
+        tf_changed |= curr;
+      }
+      raw |= (uint32_t)curr << i;
+      logp = isTransient ? 4 : 5;
+    }
+    if (tf_select_rsv && ob_tf_select[LM * 8 + 4 * isTransient + 0 + tf_changed] !=
+                             ob_tf_select[LM * 8 + 4 * isTransient + 2 + tf_changed])
+      tf_select = dec.bit_logp(1);
+    for (int i = start + lane; i < end; i += 32)
+      ws->tf_res[i] = ob_tf_select[LM * 8 + 4 * isTransient + 2 * tf_select + ((raw >> i) & 1)];
+  }
+  tell = dec.tell();
+  int spread = 2;
+  if (tell + 4 <= total_bits) spread = dec.icdf(ob_spread_icdf, 5);
+  ctx.spread = spread;
+  for (int i = lane; i < OB_NBANDS; i += 32) {  // init_caps, celt/celt.c:329-338
+    int n = (ob_ebands[i + 1] - ob_ebands[i]) << LM;
+    ws->cap[i] = (ob_cache_caps[OB_NBANDS * (2 * LM + C - 1) + i] + 64) * C * n >> 2;
+    ws->offsets[i] = 0;
+  }
+  wsync();
+  // ---- dynalloc (celt/celt_decoder.c:1412-1442) ----
+  {
+    int dynalloc_logp = 6;
+    total_bits <<= OB_BITRES;
+    int32_t tf = dec.tell_frac();
+    for (int i = start; i < end; i++) {
+      int width = C * (ob_ebands[i + 1] - ob_ebands[i]) << LM;
+      int quanta = OB_IMIN(width << OB_BITRES, OB_IMAX(6 << OB_BITRES, width));
+      int loop_logp = dynalloc_logp, boost = 0;
+      int capi = ws->cap[i];
+      while (tf + (loop_logp << OB_BITRES) < total_bits && boost < capi) {
+        int flag = dec.bit_logp(loop_logp);
+        tf = dec.tell_frac();
+        if (!flag) break;
+        boost += quanta;
+        total_bits -= quanta;
+        loop_logp = 1;
+      }
+      if (lane == 0) ws->offsets[i] = boost;
+      if (boost > 0) dynalloc_logp = OB_IMAX(2, dynalloc_logp - 1);
+    }
+    tell = tf;
+  }
+  const int alloc_trim = tell + (6 << OB_BITRES) <= total_bits ? dec.icdf(ob_trim_icdf, 7) : 5;
+  int32_t bits = (((int32_t)len * 8) << OB_BITRES) - (int32_t)dec.tell_frac() - 1;
+  const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;
+  bits -= anti_collapse_rsv;
+  int intensity = 0, dual_stereo = 0;
+  int32_t balance = 0;
+  const int codedBands = compute_allocation(ctx, start, end, alloc_trim, intensity, dual_stereo, bits, balance, C, LM);
+  ctx.intensity = intensity;
+  // ---- fine energy (celt/quant_bands.c:496-523): lane 0 owns the read-modify-write ----
+  for (int i = start; i < end; i++) {
+    int extra = ws->fine_quant[i];
+    if (extra <= 0) continue;
+    if (dec.tell() + C * extra > (int32_t)dec.storage * 8) continue;
+    for (int c = 0; c < C; c++) {
+      int q2 = dec.bits(extra);
+      float offset = (q2 + .5f) * (1 << (14 - extra)) * (1.f / 16384) - .5f;
+      if (lane == 0) ws->oldE[i + c * OB_NBANDS] += offset;
+    }
+  }
+  wsync();
+  for (int i = lane; i < 2 * OB_NBANDS; i += 32) ws->collapse[i] = 0;
+  // bands at or above `end` are never decoded: their spectrum is zero
+  for (int j = M * ob_ebands[end] + lane; j < N; j += 32) { Xg[j] = 0.f; if (C == 2) Yg[j] = 0.f; }
+  wsync();
+  decode_all_bands(ctx, start, end, Xg, C == 2 ? Yg : nullptr, shortBlocks, dual_stereo,
+                   len * (8 << OB_BITRES) - anti_collapse_rsv, balance, LM, codedBands);
+  int anti_collapse_on = 0;
+  if (anti_collapse_rsv > 0) anti_collapse_on = dec.bits(1);
+  // ---- unquant_energy_finalise (celt/quant_bands.c:525-547) ----
+  {
+    int bits_left = len * 8 - dec.tell();
+    for (int prio = 0; prio < 2; prio++) {
+      for (int i = start; i < end && bits_left >= C; i++) {
+        int fq = ws->fine_quant[i];
+        if (fq >= 8 || ws->fine_prio[i] != prio) continue;
+        for (int c = 0; c < C; c++) {
+          int q2 = dec.bits(1);
+          float offset = (q2 - .5f) * (1 << (14 - fq - 1)) * (1.f / 16384);
+          if (lane == 0) ws->oldE[i + c * OB_NBANDS] += offset;
+          bits_left--;
+        }
+      }
+    }
+  }
+  wsync();
+  if (anti_collapse_on)
+    anti_collapse(ctx, Xg, LM, C, N, start, end, ws->oldE, st->oldLogE, st->oldLogE2, ctx.seed);
+  wsync();
+  // ---- state update (celt/celt_decoder.c:1530-1600), lane-parallel over the 42 energies ----
+  for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
+    const int band = i >= OB_NBANDS ? i - OB_NBANDS : i, c = i >= OB_NBANDS;
+    float e = ws->oldE[i];
+    if (silence && i < C * OB_NBANDS) e = -28.f;
+    if (C == 1 && c == 1) { e = ws->oldE[band]; if (silence) e = -28.f; }
+    float l1 = st->oldLogE[i], l2 = st->oldLogE2[i], bg = st->backgroundLogE[i];
+    side->bandE[i] = e;  // what the synthesis uses (before the out-of-range reset below)
+    if (!isTransient) { l2 = l1; l1 = e; }
+    else l1 = l1 < e ? l1 : e;
+    float inc = OB_IMIN(160, M) * 0.001f;
+    float a = bg + inc;
+    bg = a < e ? a : e;
+    if (band < start || band >= end) { e = 0.f; l1 = l2 = -28.f; }
+    st->oldEBands[i] = e;
+    st->oldLogE[i] = l1;
+    st->oldLogE2[i] = l2;
+    st->backgroundLogE[i] = bg;
+  }
+  if (lane == 0) {
+    int ok = dec.tell() > 8 * len ? -3 : N;  // OPUS_INTERNAL_ERROR
+    side->status = ok;
+    side->LM = LM; side->transient = isTransient; side->C = C; side->silence = silence; side->end_band = end;
+    // post-filter parameter pipeline (celt_decoder.c:1540-1563)
+    int T_old = OB_IMAX(st->pf_period_old, 15), T_cur = OB_IMAX(st->pf_period, 15);
+    side->pf_T[0] = T_old; side->pf_T[1] = T_cur; side->pf_T[2] = pf_pitch;
+    side->pf_g[0] = st->pf_gain_old; side->pf_g[1] = st->pf_gain; side->pf_g[2] = pf_gain;
+    side->pf_tap[0] = st->pf_tapset_old; side->pf_tap[1] = st->pf_tapset; side->pf_tap[2] = pf_tapset;
+    float g_cur = st->pf_gain;
+    int tap_cur = st->pf_tapset;
+    st->pf_period_old = T_cur; st->pf_gain_old = g_cur; st->pf_tapset_old = tap_cur;
+    st->pf_period = pf_pitch; st->pf_gain = pf_gain; st->pf_tapset = pf_tapset;
+    if (LM != 0) { st->pf_period_old = pf_pitch; st->pf_gain_old = pf_gain; st->pf_tapset_old = pf_tapset; }
+    st->rng = dec.rng;
+    st->final_range = dec.rng;
+    if (dec.error) st->error = 1;
+    st->last_status = ok;
+    if (p.out_samples) {
+      if (ok < 0) p.out_samples[stream] = ok;
+      else if (p.frame_index == 0) p.out_samples[stream] = ok;
+      else if (p.out_samples[stream] >= 0) p.out_samples[stream] += ok;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel B: synthesis.  One CTA per stream; warp w produces output channel w.
+// ------------------------------------------------------------------------------------------
+struct DecSynthParams {
+  const ObFrameSide *side;  // [n_streams]
+  const float *X;           // [n_streams][2][960]
+  ObDecSynthState *state;   // [n_streams]
+  void *pcm;                // [n_streams][pcm_stride] interleaved, float or int16
+  int pcm_stride;           // elements per stream
+  int frame_index;          // frame k of the packet: output goes to element offset k*N*CC of the stream's area
+  int pcm_is_int16;
+  int n_streams;
+  int channels;
+};
+
+struct SynthWS {  // per warp (= per output channel)
+  float freq[OB_MAXN];            // denormalised MDCT coefficients, later the interleave staging area
+  float out[64 + OB_MAXN + 64];   // [4..64): previous tail, [64..64+N): IMDCT output (16B aligned start)
+  float gain[2 * OB_NBANDS];
+};
+#define OB_SYN_O 4 /* out[OB_SYN_O + i] <-> reference out_syn[i] ; IMDCT data starts at OB_SYN_O+60 = 64 */
+
+OB_DEV const short *bitrev_table(int shift) {
+  return shift == 0 ? ob_fft_bitrev480 : shift == 1 ? ob_fft_bitrev240 : shift == 2 ? ob_fft_bitrev120 : ob_fft_bitrev60;
+}
+
+struct cpx { float r, i; };
+OB_DEV cpx cmul(cpx a, cpx b) { cpx m; m.r = a.r * b.r - a.i * b.i; m.i = a.r * b.i + a.i * b.r; return m; }
+OB_DEV cpx ldtw(int k) { cpx t; t.r = ob_fft_tw[2 * k]; t.i = ob_fft_tw[2 * k + 1]; return t; }
+
+// All B blocks' FFTs of size nfft = 480>>shift, in place on digit-reversed data, stage order and
+// per-butterfly arithmetic of celt/kiss_fft.c:52-313,562-613.  F: B consecutive arrays of nfft cpx.
+OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
+  const short *fac = ob_fft_factors + 10 * shift;
+  const int nfft = 480 >> shift;
+  int fstride[6], L = 0, m;
+  fstride[0] = 1;
+  do {
+    int p = fac[2 * L];
+    m = fac[2 * L + 1];
+    fstride[L + 1] = fstride[L] * p;
+    L++;
+  } while (m != 1);
+  m = fac[2 * L - 1];
+  for (int st = L - 1; st >= 0; st--) {
+    const int m2 = st != 0 ? fac[2 * st - 1] : 1;
+    const int p = fac[2 * st];
+    const int Nn = fstride[st], fs = fstride[st] << shift;
+    const int per_blk = nfft / p;  // butterflies per block in this stage = Nn * m
+    wsync();
+    for (int q = lane; q < per_blk * nblk; q += 32) {
+      const int blk = q / per_blk, w = q - blk * per_blk;
+      const int i = w / m, j = w - i * m;
+      cpx *Fo = F + blk * nfft + i * m2 + j;
+      if (p == 4) {
+        if (m == 1) {
+          cpx a0 = Fo[0], a1 = Fo[1], a2 = Fo[2], a3 = Fo[3], s0, s1;
+          s0.r = a0.r - a2.r; s0.i = a0.i - a2.i;
+          a0.r += a2.r; a0.i += a2.i;
+          s1.r = a1.r + a3.r; s1.i = a1.i + a3.i;
+          a2.r = a0.r - s1.r; a2.i = a0.i - s1.i;
+          a0.r += s1.r; a0.i += s1.i;
+          s1.r = a1.r - a3.r; s1.i = a1.i - a3.i;
+          a1.r = s0.r + s1.i; a1.i = s0.i - s1.r;
+          a3.r = s0.r - s1.i; a3.i = s0.i + s1.r;
+          Fo[0] = a0; Fo[1] = a1; Fo[2] = a2; Fo[3] = a3;
+        } else {
+          cpx f0 = Fo[0];
+          cpx s0 = cmul(Fo[m], ldtw(j * fs)), s1 = cmul(Fo[2 * m], ldtw(2 * j * fs)), s2 = cmul(Fo[3 * m], ldtw(3 * j * fs));
+          cpx s5, s3, s4;
+          s5.r = f0.r - s1.r; s5.i = f0.i - s1.i;
+          f0.r += s1.r; f0.i += s1.i;
+          s3.r = s0.r + s2.r; s3.i = s0.i + s2.i;
+          s4.r = s0.r - s2.r; s4.i = s0.i - s2.i;
+          cpx o2; o2.r = f0.r - s3.r; o2.i = f0.i - s3.i;
+          f0.r += s3.r; f0.i += s3.i;
+          cpx o1, o3;
+          o1.r = s5.r + s4.i; o1.i = s5.i - s4.r;
+          o3.r = s5.r - s4.i; o3.i = s5.i + s4.r;
+          Fo[0] = f0; Fo[m] = o1; Fo[2 * m] = o2; Fo[3 * m] = o3;
+        }
+      } else if (p == 2) {  // m == 4 : Fo[0] pairs with Fo[4], fixed twiddles per j
+        const float tw = 0.7071067812f;
+        cpx *F2 = Fo + 4;
+        cpx t, a = Fo[0], b = F2[0];
+        if (j == 0) t = b;
+        else if (j == 1) { t.r = (b.r + b.i) * tw; t.i = (b.i - b.r) * tw; }
+        else if (j == 2) { t.r = b.i; t.i = -b.r; }
+        else { t.r = (b.i - b.r) * tw; t.i = (-(b.i + b.r)) * tw; }
+        F2[0].r = a.r - t.r; F2[0].i = a.i - t.i;
+        Fo[0].r = a.r + t.r; Fo[0].i = a.i + t.i;
+      } else if (p == 3) {
+        cpx epi3 = ldtw(fs * m);
+        cpx f0 = Fo[0];
+        cpx s1 = cmul(Fo[m], ldtw(j * fs)), s2 = cmul(Fo[2 * m], ldtw(2 * j * fs)), s3, s0;
+        s3.r = s1.r + s2.r; s3.i = s1.i + s2.i;
+        s0.r = s1.r - s2.r; s0.i = s1.i - s2.i;
+        cpx fm;
+        fm.r = f0.r - s3.r * .5f;
+        fm.i = f0.i - s3.i * .5f;
+        s0.r *= epi3.i; s0.i *= epi3.i;
+        f0.r += s3.r; f0.i += s3.i;
+        cpx o2, o1;
+        o2.r = fm.r + s0.i; o2.i = fm.i - s0.r;
+        o1.r = fm.r - s0.i; o1.i = fm.i + s0.r;
+        Fo[0] = f0; Fo[m] = o1; Fo[2 * m] = o2;
+      } else {  // p == 5
+        cpx ya = ldtw(fs * m), yb = ldtw(fs * 2 * m);
+        cpx s0 = Fo[0];
+        cpx s1 = cmul(Fo[m], ldtw(j * fs)), s2 = cmul(Fo[2 * m], ldtw(2 * j * fs));
+        cpx s3 = cmul(Fo[3 * m], ldtw(3 * j * fs)), s4 = cmul(Fo[4 * m], ldtw(4 * j * fs));
+        cpx s7, s10, s8, s9, s5, s6, s11, s12, o;
+        s7.r = s1.r + s4.r; s7.i = s1.i + s4.i;
+        s10.r = s1.r - s4.r; s10.i = s1.i - s4.i;
+        s8.r = s2.r + s3.r; s8.i = s2.i + s3.i;
+        s9.r = s2.r - s3.r; s9.i = s2.i - s3.i;
+        o.r = s0.r + (s7.r + s8.r); o.i = s0.i + (s7.i + s8.i);
+        Fo[0] = o;
+        s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r);
+        s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
+        s6.r = s10.i * ya.i + s9.i * yb.i;
+        s6.i = -(s10.r * ya.i + s9.r * yb.i);
+        o.r = s5.r - s6.r; o.i = s5.i - s6.i; Fo[m] = o;
+        o.r = s5.r + s6.r; o.i = s5.i + s6.i; Fo[4 * m] = o;
+        s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r);
+        s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
+        s12.r = s9.i * ya.i - s10.i * yb.i;
+        s12.i = s10.r * yb.i - s9.r * ya.i;
+        o.r = s11.r + s12.r; o.i = s11.i + s12.i; Fo[2 * m] = o;
+        o.r = s11.r - s12.r; o.i = s11.i - s12.i; Fo[3 * m] = o;
+      }
+    }
+    m = m2;
+  }
+  wsync();
+}
+
+// x[idx] with idx < 0 reaching into the stream's history ring (absolute position pos+idx)
+OB_DEV float hist_or_cur(const float *cur, const float *hist, uint32_t pos, int idx) {
+  return idx >= 0 ? cur[idx] : hist[(pos + (uint32_t)idx) & (OB_HIST - 1)];
+}
+
+// celt/celt.c:238-313 + 166-193, in place (x == y) on cur[istart .. istart+N) where cur[0] is the
+// first sample of the frame; samples before the frame come from the history ring `hist`.
+OB_DEV void comb_filter_inplace(float *cur, const float *hist, uint32_t pos, int istart, int T0, int T1, int N,
+                                float g0, float g1, int tapset0, int tapset1, int lane) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  T0 = OB_IMAX(T0, 15);
+  T1 = OB_IMAX(T1, 15);
+  const float gt[9] = {0.3066406250f, 0.2170410156f, 0.1296386719f, 0.4638671875f, 0.2680664062f, 0.f,
+                       0.7998046875f, 0.1000976562f, 0.f};
+  const float g00 = g0 * gt[tapset0 * 3 + 0], g01 = g0 * gt[tapset0 * 3 + 1], g02 = g0 * gt[tapset0 * 3 + 2];
+  const float g10 = g1 * gt[tapset1 * 3 + 0], g11 = g1 * gt[tapset1 * 3 + 1], g12 = g1 * gt[tapset1 * 3 + 2];
+  int overlap = OB_OVERLAP;
+  if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
+  // Outputs at i depend on already-filtered samples no closer than min(T)-2 behind, so blocks of
+  // that many samples are independent: process block by block, lanes across a block.
+  const int Tmin = OB_IMIN(T0, T1);
+  const int iend = istart + N, oend = istart + overlap;
+  int i0 = istart;
+  wsync();
+  while (i0 < oend) {
+    int blk = OB_IMIN(Tmin - 2, oend - i0);
+    for (int i = i0 + lane; i < i0 + blk; i += 32) {
+      float w = ob_window[i - istart];
+      float f = w * w;
+      float x0 = hist_or_cur(cur, hist, pos, i - T1 + 2), x1 = hist_or_cur(cur, hist, pos, i - T1 + 1);
+      float x2 = hist_or_cur(cur, hist, pos, i - T1), x3 = hist_or_cur(cur, hist, pos, i - T1 - 1);
+      float x4 = hist_or_cur(cur, hist, pos, i - T1 - 2);
+      float a0 = hist_or_cur(cur, hist, pos, i - T0), a1p = hist_or_cur(cur, hist, pos, i - T0 + 1);
+      float a1m = hist_or_cur(cur, hist, pos, i - T0 - 1), a2p = hist_or_cur(cur, hist, pos, i - T0 + 2);
+      float a2m = hist_or_cur(cur, hist, pos, i - T0 - 2);
+      cur[i] = cur[i] + ((1.0f - f) * g00) * a0 + ((1.0f - f) * g01) * (a1p + a1m) + ((1.0f - f) * g02) * (a2p + a2m) +
+               (f * g10) * x2 + (f * g11) * (x1 + x3) + (f * g12) * (x0 + x4);
+    }
+    i0 += blk;
+    wsync();
+  }
+  if (g1 == 0.f) return;
+  while (i0 < iend) {
+    int blk = OB_IMIN(T1 - 2, iend - i0);
+    for (int i = i0 + lane; i < i0 + blk; i += 32) {
+      float x0 = hist_or_cur(cur, hist, pos, i - T1 + 2), x1 = hist_or_cur(cur, hist, pos, i - T1 + 1);
+      float x2 = hist_or_cur(cur, hist, pos, i - T1), x3 = hist_or_cur(cur, hist, pos, i - T1 - 1);
+      float x4 = hist_or_cur(cur, hist, pos, i - T1 - 2);
+      cur[i] = cur[i] + g10 * x2 + g11 * (x1 + x3) + g12 * (x0 + x4);
+    }
+    i0 += blk;
+    wsync();
+  }
+}
+
+OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *smem) {
+  const int lane = lane_id();
+  const int ch = warp_in_block();  // output channel
+  const int CC = p.channels;
+  SynthWS *ws = (SynthWS *)smem + ch;
+  const ObFrameSide *side = p.side + stream;
+  const int status = side->status;
+  if (status <= 0) return;  // uniform over the CTA: nothing decoded for this stream in this launch
+  ObDecSynthState *st = p.state + stream;
+  const int LM = side->LM, C = side->C, transient = side->transient, silence = side->silence;
+  const int N = OB_SHORT_N << LM, M = 1 << LM;
+  const int nblk = transient ? M : 1, NB = N / nblk, shift = transient ? 3 : 3 - LM;
+  int end = side->end_band;
+  int bound = silence ? 0 : M * ob_ebands[end];
+  // ---- band gains (denormalise_bands, celt/bands.c:188-257) ----
+  for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
+    int band = i >= OB_NBANDS ? i - OB_NBANDS : i;
+    float lg = side->bandE[i] + ob_emeans[band];
+    ws->gain[i] = exp2_ref(32.f < lg ? 32.f : lg);
+  }
+  wsync();
+  // ---- load X, apply gains -> freq (coalesced) ----
+  {
+    const float *X0 = p.X + (size_t)stream * 2 * OB_MAXN;
+    const float *X1 = X0 + N;
+    const int srcc = (C == 2 && CC == 2) ? ch : 0;
+    const float *Xs = srcc ? X1 : X0;
+    const float *gs = ws->gain + srcc * OB_NBANDS;
+    int band = 0;
+    for (int j = lane; j < N; j += 32) {
+      float v = 0.f;
+      if (j < bound) {
+        int u = j >> LM;
+        while (ob_ebands[band + 1] <= u) band++;
+        v = Xs[j] * gs[band];
+        if (CC == 1 && C == 2) {  // downmix, celt_decoder.c:478-481
+          float v2 = X1[j] * ws->gain[OB_NBANDS + band];
+          v = (.5f * v) + (.5f * v2);
+        }
+      }
+      ws->freq[j] = v;
+    }
+  }
+  // previous tail -> out[0..60)
+  float *out = ws->out + OB_SYN_O;
+  for (int i = lane; i < OB_OVERLAP / 2; i += 32) out[i] = st->tail[ch][i];
+  wsync();
+  // ---- IMDCT pre-rotation into digit-reversed order (celt/mdct.c:304-331) ----
+  {
+    const int N2 = NB, N4 = NB >> 1;  // mdct size is 2*NB
+    const float *trig = ob_mdct_trig;
+    for (int i = 0; i < shift; i++) trig += (1920 >> i) >> 1;
+    const short *bitrev = bitrev_table(shift);
+    for (int q = lane; q < nblk * N4; q += 32) {
+      const int b = q / N4, i = q - b * N4;
+      const float *in = ws->freq + b;
+      float x1 = in[2 * i * nblk], x2 = in[nblk * (N2 - 1 - 2 * i)];
+      float t0 = trig[i], t1 = trig[N4 + i];
+      float yr = x2 * t0 + x1 * t1;
+      float yi = x1 * t0 - x2 * t1;
+      int rev = bitrev[i];
+      float *yp = out + OB_OVERLAP / 2 + b * NB;
+      yp[2 * rev + 1] = yr;
+      yp[2 * rev] = yi;
+    }
+    fft_stages((cpx *)(out + OB_OVERLAP / 2), shift, nblk, lane);
+    // post-rotation, both ends at once (celt/mdct.c:335-369)
+    for (int q = lane; q < nblk * (N4 >> 1); q += 32) {
+      const int b = q / (N4 >> 1), i = q - b * (N4 >> 1);
+      float *yp0 = out + OB_OVERLAP / 2 + b * NB + 2 * i;
+      float *yp1 = out + OB_OVERLAP / 2 + b * NB + N2 - 2 - 2 * i;
+      float re = yp0[1], im = yp0[0];
+      float t0 = trig[i], t1 = trig[N4 + i];
+      float yr = re * t0 + im * t1;
+      float yi = re * t1 - im * t0;
+      re = yp1[1]; im = yp1[0];
+      yp0[0] = yr;
+      yp1[1] = yi;
+      t0 = trig[N4 - i - 1]; t1 = trig[N2 - i - 1];
+      yr = re * t0 + im * t1;
+      yi = re * t1 - im * t0;
+      yp1[0] = yr;
+      yp0[1] = yi;
+    }
+    wsync();
+    // TDAC mirror (celt/mdct.c:372-388)
+    for (int q = lane; q < nblk * (OB_OVERLAP / 2); q += 32) {
+      const int b = q / (OB_OVERLAP / 2), i = q - b * (OB_OVERLAP / 2);
+      float *xp1 = out + b * NB + OB_OVERLAP - 1 - i, *yp1 = out + b * NB + i;
+      float x1 = *xp1, x2 = *yp1;
+      float w1 = ob_window[i], w2 = ob_window[OB_OVERLAP - 1 - i];
+      *yp1 = x2 * w2 - x1 * w1;
+      *xp1 = x2 * w1 + x1 * w2;
+    }
+    wsync();
+  }
+  // new tail for the next frame
+  for (int i = lane; i < OB_OVERLAP / 2; i += 32) st->tail[ch][i] = out[N + i];
+  // ---- comb post-filter (celt_decoder.c:1540-1552) ----
+  const uint32_t pos = st->pos;
+  float *hist = st->hist[ch];
+  comb_filter_inplace(out, hist, pos, 0, side->pf_T[0], side->pf_T[1], OB_SHORT_N, side->pf_g[0], side->pf_g[1],
+                      side->pf_tap[0], side->pf_tap[1], lane);
+  if (LM != 0)
+    comb_filter_inplace(out, hist, pos, OB_SHORT_N, side->pf_T[1], side->pf_T[2], N - OB_SHORT_N, side->pf_g[1],
+                        side->pf_g[2], side->pf_tap[1], side->pf_tap[2], lane);
+  wsync();
+  // history ring <- filtered samples
+  for (int i = lane; i < N; i += 32) hist[(pos + (uint32_t)i) & (OB_HIST - 1)] = out[i];
+  // ---- de-emphasis: tmp_j = x_j + 1e-30 + m ; m = coef*tmp_j  (celt_decoder.c:288-408) as a
+  // warp scan: lane l owns samples [l*seg, (l+1)*seg) ----
+  {
+    const float coef = 0.85000610f;
+    const int seg = (N + 31) >> 5;
+    const int j0 = OB_IMIN(lane * seg, N), j1 = OB_IMIN(j0 + seg, N);
+    Affine mp = {1.f, 0.f};  // maps incoming m to outgoing m over my segment
+    for (int j = j0; j < j1; j++) {
+      float x = out[j] + 1e-30f;
+      mp.b = coef * (x + mp.b);
+      mp.a = coef * mp.a;
+    }
+    Affine inc = group_scan(mp, 32, lane);
+    float pa = shfl_up(inc.a, 1), pb = shfl_up(inc.b, 1);
+    const float m0 = st->deemph_mem[ch];
+    float m = lane == 0 ? m0 : pa * m0 + pb;
+    wsync();
+    for (int j = j0; j < j1; j++) {
+      float tmp = out[j] + 1e-30f + m;
+      m = coef * tmp;
+      out[j] = tmp * (1 / 32768.f);
+    }
+    float mlast = shfl(m, (N - 1) / seg);  // lane holding the last sample
+    if (lane == 0) st->deemph_mem[ch] = mlast;
+    wsync();
+  }
+  // ---- interleave through shared memory, then fully coalesced stores ----
+  bsync();
+  if (ch == 0 && lane == 0) st->pos = pos + (uint32_t)N;
+  {
+    const size_t base = (size_t)stream * p.pcm_stride + (size_t)p.frame_index * N * CC;
+    const int total = N * CC;
+    const int tid = ch * 32 + lane, nth = CC * 32;
+    const SynthWS *w0 = (const SynthWS *)smem;
+    if (p.pcm_is_int16) {
+      int16_t *o = (int16_t *)p.pcm + base;
+      for (int e = tid; e < total; e += nth) {
+        int j = CC == 2 ? e >> 1 : e, c = CC == 2 ? e & 1 : 0;
+        float x = w0[c].out[OB_SYN_O + j] * 32768.f;
+        x = x > -32768.f ? x : -32768.f;
+        x = x < 32767.f ? x : 32767.f;
+        o[e] = (int16_t)lrintf(x);
+      }
+    } else {
+      float *o = (float *)p.pcm + base;
+      for (int e = tid; e < total; e += nth) {
+        int j = CC == 2 ? e >> 1 : e, c = CC == 2 ? e & 1 : 0;
+        o[e] = w0[c].out[OB_SYN_O + j];
+      }
+    }
+  }
+}
+
+}  // namespace ob

@@ -1,0 +1,265 @@
+// opus_b200.cu — kernels' __global__ entry points and the C ABI (include/opus_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false ... (see
+// __graft_entry__.build()).  -fmad=false: the CELT float path keeps the reference's separate
+// multiply/add roundings (the reference oracle is built with -ffp-contract=off).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/opus_b200.h"
+#include "celt_dec_kernels.cuh"
+
+using namespace ob;
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_bands(DecBandsParams p, int smem_per_warp) {
+  const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (stream >= p.n_streams) return;
+  dec_bands_warp(p, stream, dyn_smem() + (size_t)(threadIdx.x >> 5) * smem_per_warp);
+}
+
+extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParams p) {
+  dec_synth_block(p, blockIdx.x, dyn_smem());
+}
+
+// fresh decoder state (celt/celt_decoder.c:1794-1813 OPUS_RESET_STATE)
+extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState *ss, int n) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const size_t nb = (size_t)n * (sizeof(ObDecBandState) / 4), ns = (size_t)n * (sizeof(ObDecSynthState) / 4);
+  uint32_t *b = (uint32_t *)bs, *s = (uint32_t *)ss;
+  for (size_t i = tid; i < ns; i += nth) s[i] = 0u;
+  for (size_t i = tid; i < nb; i += nth) {
+    size_t w = i % (sizeof(ObDecBandState) / 4);
+    // words [42, 126) are oldLogE and oldLogE2
+    b[i] = (w >= 2 * OB_NBANDS && w < 6 * OB_NBANDS) ? __float_as_uint(-28.f) : 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct OpusB200Decoder {
+  int device, channels, n;
+  cudaStream_t stream;
+  ObDecBandState *bstate;
+  ObDecSynthState *sstate;
+  ObFrameSide *side;
+  float *X;
+  // staging for the host-buffer API
+  unsigned char *d_packets; size_t d_packets_cap;
+  int32_t *d_len, *d_out;
+  void *d_pcm; size_t d_pcm_cap;
+  int64_t launches;
+  int max_smem_optin;
+  // optional per-kernel timing (CUDA events on the decoder's stream)
+  int timing;
+  cudaEvent_t ev[3];
+  double kernel_ms[2];
+  int64_t timed_launches;
+};
+
+#define OB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "opus_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return OPUSB200_INTERNAL_ERROR; } } while (0)
+
+extern "C" {
+
+const char *opusb200_version(void) { return "opus_b200 0.1 (sm_100a; CELT decode path)"; }
+
+int opusb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int opusb200_decoder_reset(OpusB200Decoder *d) {
+  if (!d) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->device));
+  ob_celt_dec_reset<<<592, 256, 0, d->stream>>>(d->bstate, d->sstate, d->n);
+  d->launches++;
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+
+int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Decoder **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  if (Fs != 48000 || (channels != 1 && channels != 2) || n_streams <= 0) return OPUSB200_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    fprintf(stderr, "opus_b200: no usable CUDA device (there is no CPU fallback)\n");
+    return OPUSB200_INTERNAL_ERROR;
+  }
+  OB_CUDA(cudaSetDevice(device));
+  OpusB200Decoder *d = new (std::nothrow) OpusB200Decoder;
+  if (!d) return OPUSB200_ALLOC_FAIL;
+  memset(d, 0, sizeof(*d));
+  d->device = device; d->channels = channels; d->n = n_streams;
+  OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  OB_CUDA(cudaMalloc(&d->bstate, sizeof(ObDecBandState) * (size_t)n_streams));
+  OB_CUDA(cudaMalloc(&d->sstate, sizeof(ObDecSynthState) * (size_t)n_streams));
+  OB_CUDA(cudaMalloc(&d->side, sizeof(ObFrameSide) * (size_t)n_streams));
+  OB_CUDA(cudaMalloc(&d->X, sizeof(float) * 2 * OB_MAXN * (size_t)n_streams));
+  OB_CUDA(cudaMalloc(&d->d_len, sizeof(int32_t) * (size_t)n_streams));
+  OB_CUDA(cudaMalloc(&d->d_out, sizeof(int32_t) * (size_t)n_streams));
+  OB_CUDA(cudaDeviceGetAttribute(&d->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
+  // the band decoder recurses over partitions (depth <= 5)
+  size_t stk = 0;
+  cudaDeviceGetLimit(&stk, cudaLimitStackSize);
+  if (stk < 4096) OB_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+  int r = opusb200_decoder_reset(d);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaStreamSynchronize(d->stream));
+  *out = d;
+  return OPUSB200_OK;
+}
+
+void opusb200_decoder_destroy(OpusB200Decoder *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->stream);
+  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->X); cudaFree(d->d_len); cudaFree(d->d_out);
+  cudaFree(d->d_packets); cudaFree(d->d_pcm);
+  cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+int opusb200_decoder_n_streams(const OpusB200Decoder *d) { return d ? d->n : OPUSB200_BAD_ARG; }
+void *opusb200_decoder_cuda_stream(OpusB200Decoder *d) { return d ? (void *)d->stream : nullptr; }
+int64_t opusb200_decoder_launch_count(const OpusB200Decoder *d) { return d ? d->launches : 0; }
+
+int opusb200_decoder_sync(OpusB200Decoder *d) {
+  if (!d) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaStreamSynchronize(d->stream));
+  return OPUSB200_OK;
+}
+
+int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, int pkt_stride, const int32_t *d_len,
+                           void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
+                           int32_t *d_out_samples) {
+  if (!d || !d_packets || !d_len || !d_pcm || pkt_stride <= 0 || frame_size <= 0) return OPUSB200_BAD_ARG;
+  if (pcm_stride < frame_size * d->channels) return OPUSB200_BAD_ARG;
+  if (max_frames_per_packet < 1) max_frames_per_packet = 1;
+  if (max_frames_per_packet > 48) max_frames_per_packet = 48;
+  OB_CUDA(cudaSetDevice(d->device));
+  const int warps = 4;
+  const int cap = ((pkt_stride < OB_MAX_PACKET + 2 ? pkt_stride : OB_MAX_PACKET + 2) + 15) & ~15;
+  const int smem_per_warp = (int)((sizeof(BandWS) + 15) & ~(size_t)15) + cap;
+  if (warps * smem_per_warp > d->max_smem_optin) return OPUSB200_INTERNAL_ERROR;
+  for (int k = 0; k < max_frames_per_packet; k++) {
+    DecBandsParams bp;
+    bp.packets = d_packets; bp.pkt_len = d_len; bp.pkt_stride = pkt_stride; bp.pkt_cap = cap; bp.n_streams = d->n;
+    bp.channels = d->channels; bp.frame_index = k; bp.state = d->bstate; bp.side = d->side; bp.X = d->X;
+    bp.out_samples = d_out_samples ? d_out_samples : d->d_out; bp.max_samples = frame_size;
+    if (d->timing) cudaEventRecord(d->ev[0], d->stream);
+    ob_celt_dec_bands<<<(d->n + warps - 1) / warps, warps * 32, warps * smem_per_warp, d->stream>>>(bp, smem_per_warp);
+    if (d->timing) cudaEventRecord(d->ev[1], d->stream);
+    DecSynthParams sp;
+    sp.side = d->side; sp.X = d->X; sp.state = d->sstate; sp.pcm = d_pcm; sp.pcm_stride = pcm_stride; sp.frame_index = k;
+    sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = d->n; sp.channels = d->channels;
+    ob_celt_dec_synth<<<d->n, 32 * d->channels, d->channels * sizeof(SynthWS), d->stream>>>(sp);
+    d->launches += 2;
+    if (d->timing) {  // profiling mode: serialises the stream, never used for throughput numbers
+      cudaEventRecord(d->ev[2], d->stream);
+      cudaEventSynchronize(d->ev[2]);
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, d->ev[0], d->ev[1]);
+      cudaEventElapsedTime(&b, d->ev[1], d->ev[2]);
+      d->kernel_ms[0] += a; d->kernel_ms[1] += b; d->timed_launches++;
+    }
+  }
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+
+// frames in a packet as far as the TOC and the count byte tell (RFC 6716 3.2); 1 for anything odd
+static int host_frame_count(const unsigned char *p, int len) {
+  if (len < 1) return 1;
+  switch (p[0] & 3) {
+    case 0: return 1;
+    case 1: case 2: return 2;
+    default: return len >= 2 && (p[1] & 0x3F) ? (p[1] & 0x3F) : 1;
+  }
+}
+
+static int decode_host(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
+                       int pcm_stride, int is_int16, int frame_size, int32_t *out_samples) {
+  if (!d || !packets || !len || !pcm || !out_samples || pkt_stride <= 0 || frame_size <= 0) return OPUSB200_BAD_ARG;
+  if (pcm_stride < frame_size * d->channels) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->device));
+  const size_t pbytes = (size_t)d->n * pkt_stride;
+  const size_t esz = is_int16 ? 2 : 4;
+  const size_t obytes = (size_t)d->n * pcm_stride * esz;
+  if (d->d_packets_cap < pbytes) {
+    cudaFree(d->d_packets); d->d_packets = nullptr; d->d_packets_cap = 0;
+    OB_CUDA(cudaMalloc(&d->d_packets, pbytes));
+    d->d_packets_cap = pbytes;
+  }
+  if (d->d_pcm_cap < obytes) {
+    cudaFree(d->d_pcm); d->d_pcm = nullptr; d->d_pcm_cap = 0;
+    OB_CUDA(cudaMalloc(&d->d_pcm, obytes));
+    d->d_pcm_cap = obytes;
+  }
+  int maxf = 1;
+  for (int s = 0; s < d->n; s++) {
+    if (len[s] > 0 && (packets[(size_t)s * pkt_stride] & 3)) {
+      int c = host_frame_count(packets + (size_t)s * pkt_stride, len[s]);
+      if (c > maxf) maxf = c;
+    }
+  }
+  OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, pbytes, cudaMemcpyHostToDevice, d->stream));
+  OB_CUDA(cudaMemcpyAsync(d->d_len, len, sizeof(int32_t) * (size_t)d->n, cudaMemcpyHostToDevice, d->stream));
+  int r = opusb200_decode_device(d, d->d_packets, pkt_stride, d->d_len, d->d_pcm, pcm_stride, is_int16, frame_size, maxf, d->d_out);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm, obytes, cudaMemcpyDeviceToHost, d->stream));
+  OB_CUDA(cudaMemcpyAsync(out_samples, d->d_out, sizeof(int32_t) * (size_t)d->n, cudaMemcpyDeviceToHost, d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream));
+  return OPUSB200_OK;
+}
+
+int opusb200_decode(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, int16_t *pcm,
+                    int pcm_stride, int frame_size, int32_t *out_samples) {
+  return decode_host(d, packets, pkt_stride, len, pcm, pcm_stride, 1, frame_size, out_samples);
+}
+int opusb200_decode_float(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, float *pcm,
+                          int pcm_stride, int frame_size, int32_t *out_samples) {
+  return decode_host(d, packets, pkt_stride, len, pcm, pcm_stride, 0, frame_size, out_samples);
+}
+
+int opusb200_decoder_get_final_range(OpusB200Decoder *d, uint32_t *final_range) {
+  if (!d || !final_range) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->device));
+  OB_CUDA(cudaMemcpy2DAsync(final_range, sizeof(uint32_t), &d->bstate[0].final_range, sizeof(ObDecBandState),
+                            sizeof(uint32_t), d->n, cudaMemcpyDeviceToHost, d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream));
+  return OPUSB200_OK;
+}
+
+int opusb200_decoder_set_timing(OpusB200Decoder *d, int enable) {
+  if (!d) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->device));
+  if (enable && !d->ev[0]) for (int i = 0; i < 3; i++) OB_CUDA(cudaEventCreate(&d->ev[i]));
+  d->timing = enable ? 1 : 0;
+  d->kernel_ms[0] = d->kernel_ms[1] = 0.0;
+  d->timed_launches = 0;
+  return OPUSB200_OK;
+}
+int opusb200_decoder_get_timing(OpusB200Decoder *d, double *ms_bands, double *ms_synth, int64_t *launch_pairs) {
+  if (!d || !ms_bands || !ms_synth || !launch_pairs) return OPUSB200_BAD_ARG;
+  *ms_bands = d->kernel_ms[0]; *ms_synth = d->kernel_ms[1]; *launch_pairs = d->timed_launches;
+  return OPUSB200_OK;
+}
+
+void *opusb200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// simt.cuh — the small set of warp-level primitives every kernel in this library is written
+// against.  Under nvcc they are the sm_100a intrinsics.  Under a plain host compiler with
+// -DOB_HOST_EMU they map onto tests/emu/emu_runtime.h, a fiber-based 32-lane warp emulator
+// that exists ONLY so the kernel sources can be debugged and unit-tested in a container
+// without a GPU.  The emulator is never compiled into libopus_b200.so and is not a fallback:
+// the product library has no host execution path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+
+#define OB_DEV __device__ __forceinline__
+#define OB_DEVNI __device__ __noinline__
+#define OB_MDEV __device__ __forceinline__
+#define OB_HD __host__ __device__ __forceinline__
+#define OB_TABLE static __device__ const
+#define OB_RESTRICT __restrict__
+
+namespace ob {
+OB_DEV int lane_id() { return threadIdx.x & 31; }
+OB_DEV int warp_in_block() { return threadIdx.x >> 5; }
+OB_DEV int warps_per_block() { return blockDim.x >> 5; }
+OB_DEV int block_id() { return blockIdx.x; }
+OB_DEV int num_blocks() { return gridDim.x; }
+OB_DEV void wsync() { __syncwarp(); }
+OB_DEV void bsync() { __syncthreads(); }
+template <class T> OB_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class T> OB_DEV T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+template <class T> OB_DEV T shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+template <class T> OB_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+OB_DEV unsigned ballot(int p) { return __ballot_sync(0xffffffffu, p); }
+OB_DEV int clz32(uint32_t v) { return __clz((int)v); }
+OB_DEV int ffs32(uint32_t v) { return __ffs((int)v); }
+OB_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
+OB_DEV float f_add(float a, float b) { return __fadd_rn(a, b); }
+OB_DEV float f_sqrt(float a) { return __fsqrt_rn(a); }
+OB_DEV float f_div(float a, float b) { return __fdiv_rn(a, b); }
+OB_DEV unsigned char *dyn_smem() {
+  extern __shared__ __align__(16) unsigned char ob_dyn_smem[];
+  return ob_dyn_smem;
+}
+}  // namespace ob
+#define OB_KERNEL(name, ...) extern "C" __global__ void name(__VA_ARGS__)
+
+#elif defined(OB_HOST_EMU)
+
+#include "emu_runtime.h"
+
+#else
+#error "simt.cuh: compile with nvcc, or with -DOB_HOST_EMU for the test-only host emulator"
+#endif
+
+namespace ob {
+// 32 - clz, 0 for 0 (the range coder's EC_ILOG)
+OB_DEV int ilog32(uint32_t v) { return 32 - clz32(v); }
+
+template <class T> OB_DEV T warp_sum(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
+  return v;
+}
+template <class T> OB_DEV T warp_or(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v |= shfl_xor(v, m);
+  return v;
+}
+template <class T> OB_DEV T warp_max(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    T o = shfl_xor(v, m);
+    v = o > v ? o : v;
+  }
+  return v;
+}
+}  // namespace ob

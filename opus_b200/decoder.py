@@ -1,0 +1,96 @@
+"""DecoderBatch: N independent Opus decoders on one GPU (host-side mirror of the reference's
+OpusDecoder API, include/opus.h:458-591, one packet per stream per call)."""
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+MAX_FRAME = 5760  # 120 ms at 48 kHz, the largest an Opus packet can carry
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class DecoderBatch:
+    """`n_streams` decoders created like opus_decoder_create(Fs, channels) (src/opus_decoder.c:150)."""
+
+    def __init__(self, n_streams, channels=2, Fs=48000, device=0):
+        self._L = capi.lib()
+        self.n_streams, self.channels, self.Fs, self.device = int(n_streams), int(channels), int(Fs), int(device)
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_decoder_create(self.device, self.Fs, self.channels, self.n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_create')
+        self._h = h
+
+    # -- opus_decode() / opus_decode_float(), batched, host buffers ----------------------------
+    def decode(self, packets, lens, frame_size=960, dtype=np.int16, out=None):
+        """packets: uint8 [n_streams, stride]; lens: int32 [n_streams].
+        Returns (pcm [n_streams, frame_size*channels], samples_per_channel [n_streams])."""
+        packets = np.ascontiguousarray(packets, np.uint8)
+        lens = np.ascontiguousarray(lens, np.int32)
+        assert packets.shape[0] == self.n_streams and lens.shape[0] == self.n_streams
+        stride = frame_size * self.channels
+        if out is None:
+            out = np.empty((self.n_streams, stride), dtype)
+        ns = np.empty(self.n_streams, np.int32)
+        fn = self._L.opusb200_decode if np.dtype(dtype) == np.int16 else self._L.opusb200_decode_float
+        r = fn(self._h, _ptr(packets), packets.shape[1], _ptr(lens), _ptr(out), stride, frame_size, _ptr(ns))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decode')
+        return out, ns
+
+    # -- device-resident variant (torch CUDA tensors or raw pointers) --------------------------
+    def decode_device(self, d_packets, pkt_stride, d_lens, d_pcm, pcm_stride, int16=True, frame_size=960,
+                      max_frames_per_packet=1, d_out_samples=None):
+        r = self._L.opusb200_decode_device(self._h, d_packets, pkt_stride, d_lens, d_pcm, pcm_stride, 1 if int16 else 0,
+                                           frame_size, max_frames_per_packet, d_out_samples)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decode_device')
+
+    def sync(self):
+        r = self._L.opusb200_decoder_sync(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_sync')
+
+    def reset(self):  # OPUS_RESET_STATE
+        r = self._L.opusb200_decoder_reset(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_reset')
+
+    def final_range(self):  # OPUS_GET_FINAL_RANGE
+        fr = np.empty(self.n_streams, np.uint32)
+        r = self._L.opusb200_decoder_get_final_range(self._h, _ptr(fr))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_get_final_range')
+        return fr
+
+    def set_timing(self, enable):
+        self._L.opusb200_decoder_set_timing(self._h, 1 if enable else 0)
+
+    def get_timing(self):
+        """(ms in band-decode kernel, ms in synthesis kernel, launch pairs) since set_timing(True)."""
+        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+        self._L.opusb200_decoder_get_timing(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return a.value, b.value, c.value
+
+    @property
+    def cuda_stream(self):
+        return self._L.opusb200_decoder_cuda_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._L.opusb200_decoder_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,82 @@
+// tests/emu/emu_decode.cpp — TEST INFRASTRUCTURE ONLY.
+// Compiles the decoder KERNEL SOURCES (opus_b200/csrc/*.cuh) for the host SIMT emulator so that
+// their logic can be unit-tested and debugged without a GPU.  Never linked into the product.
+#define OB_HOST_EMU 1
+#include "../../opus_b200/csrc/celt_dec_kernels.cuh"
+
+#include <stdio.h>
+
+using namespace ob;
+
+struct EmuDecoder {
+  int n, channels;
+  std::vector<ObDecBandState> bstate;
+  std::vector<ObDecSynthState> sstate;
+  std::vector<ObFrameSide> side;
+  std::vector<float> X;
+};
+
+static void bands_entry(void *arg) {
+  const DecBandsParams &p = *(const DecBandsParams *)arg;
+  int stream = block_id() * warps_per_block() + warp_in_block();
+  if (stream < p.n_streams) dec_bands_warp(p, stream, dyn_smem());
+}
+static void synth_entry(void *arg) {
+  const DecSynthParams &p = *(const DecSynthParams *)arg;
+  dec_synth_block(p, block_id(), dyn_smem());
+}
+
+extern "C" {
+
+void *emu_decoder_create(int n_streams, int channels) {
+  EmuDecoder *d = new EmuDecoder;
+  d->n = n_streams;
+  d->channels = channels;
+  d->bstate.resize(n_streams);
+  d->sstate.resize(n_streams);
+  d->side.resize(n_streams);
+  d->X.assign((size_t)n_streams * 2 * OB_MAXN, 0.f);
+  memset(d->bstate.data(), 0, sizeof(ObDecBandState) * n_streams);
+  memset(d->sstate.data(), 0, sizeof(ObDecSynthState) * n_streams);
+  for (int s = 0; s < n_streams; s++)
+    for (int i = 0; i < 2 * OB_NBANDS; i++) d->bstate[s].oldLogE[i] = d->bstate[s].oldLogE2[i] = -28.f;
+  return d;
+}
+void emu_decoder_destroy(void *h) { delete (EmuDecoder *)h; }
+
+// packets: [n][stride]; pcm: [n][pcm_stride] (float or int16); out_samples[n]; final_range[n]
+int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const int *lens, void *pcm, int pcm_stride,
+                       int pcm_is_int16, int *out_samples, unsigned *final_range) {
+  EmuDecoder *d = (EmuDecoder *)h;
+  int maxlen = 0;
+  for (int s = 0; s < d->n; s++) maxlen = lens[s] > maxlen ? lens[s] : maxlen;
+  int cap = (maxlen + 15) & ~15;
+  for (int k = 0; k < 48; k++) {
+    DecBandsParams bp;
+    bp.packets = packets; bp.pkt_len = lens; bp.pkt_stride = stride; bp.pkt_cap = cap; bp.n_streams = d->n;
+    bp.channels = d->channels; bp.frame_index = k; bp.state = d->bstate.data(); bp.side = d->side.data(); bp.X = d->X.data(); bp.out_samples = out_samples; bp.max_samples = 5760;
+    size_t smemA = ((sizeof(BandWS) + 15) & ~(size_t)15) + cap;
+    emu_launch(bands_entry, &bp, d->n, 32, smemA);
+    int any = 0;
+    for (int s = 0; s < d->n; s++) {
+      int st = d->side[s].status;
+      if (st > 0) any = 1;
+    }
+    if (!any) break;
+    // synthesis needs per-stream pcm offsets (streams may have different frame sizes): launch per distinct offset
+    // (emulator only; the CUDA host side uses a per-stream offset array)
+    for (int s = 0; s < d->n; s++) {
+      if (d->side[s].status <= 0) continue;
+      DecSynthParams sp;
+      sp.side = d->side.data() + s; sp.X = d->X.data() + (size_t)s * 2 * OB_MAXN; sp.state = d->sstate.data() + s;
+      sp.pcm = pcm_is_int16 ? (void *)((int16_t *)pcm + (size_t)s * pcm_stride) : (void *)((float *)pcm + (size_t)s * pcm_stride);
+      sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels;
+      emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
+    }
+  }
+  for (int s = 0; s < d->n; s++) final_range[s] = d->bstate[s].final_range;
+  return 0;
+}
+
+long emu_yield_count(void) { return emu().yields; }
+}

@@ -1,0 +1,192 @@
+"""Parity of the CUDA decode path, called through the C ABI (opus_b200.DecoderBatch ->
+libopus_b200.so), against the oracle / the compiled reference / the golden fixtures.
+Bar: range decoder final state bit-exact on every packet; PCM within +-1 LSB at 16 bits
+(BASELINE.json north_star) — the only float differences are re-association in warp scans
+and tree reductions (measured: < 2e-5 of full scale)."""
+import numpy as np
+import pytest
+
+import util
+from test_oracle_golden import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_TOL = 2e-5
+
+
+def _check(got, ref):
+    d = np.abs(util.to_int16(got).astype(np.int32) - util.to_int16(ref).astype(np.int32))
+    assert d.max() <= 1, int(d.max())
+    assert np.abs(got - ref).max() < FLOAT_TOL, float(np.abs(got - ref).max())
+    return float((d != 0).mean())
+
+
+@pytest.mark.parametrize('case', list(golden_cases()), ids=lambda c: c[0])
+def test_golden_vectors(case):
+    import opus_b200
+    name, pkts, sizes, rng, pcm, ch, fs = case
+    dec = opus_b200.DecoderBatch(3, channels=ch)
+    for t in range(len(sizes)):
+        got, ns = dec.decode(np.repeat(pkts[t:t + 1], 3, 0), np.repeat(sizes[t:t + 1], 3), frame_size=fs, dtype=np.float32)
+        assert (ns == fs).all()
+        assert (dec.final_range() == rng[t]).all()
+        for s in range(3):
+            _check(got[s].reshape(fs, ch), pcm[t * fs:(t + 1) * fs])
+    dec.close()
+
+
+def _make_streams(n, ch, fs, nfr, seed):
+    """n different streams (signal type / bitrate / vbr vary per stream) encoded by the reference."""
+    sigs = list(util.SIGNALS)
+    rates = [24000, 48000, 64000, 96000, 128000, 192000, 16000, 320000]
+    pk = np.zeros((n, nfr, 1500), np.uint8)
+    sz = np.zeros((n, nfr), np.int32)
+    for s in range(n):
+        x = util.SIGNALS[sigs[s % 3]](seed * 1000 + s, nfr * fs, ch)
+        p, z, _ = util.ref_encode(x, ch, fs, rates[s % len(rates)], vbr=(s // 3) % 2, complexity=5 + s % 6)
+        pk[s], sz[s] = p, z
+    return pk, sz
+
+
+@pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+@pytest.mark.parametrize('ch,fs', [(2, 960), (1, 960), (2, 480), (2, 240), (1, 120)])
+def test_fresh_streams_vs_oracle_and_reference(ch, fs):
+    import opus_b200
+    n, nfr = 48, 12
+    pk, sz = _make_streams(n, ch, fs, nfr, seed=ch * 10 + fs)
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    outs = np.zeros((n, nfr * fs, ch), np.float32)
+    rngs = np.zeros((n, nfr), np.uint32)
+    for t in range(nfr):
+        got, ns = dec.decode(pk[:, t], sz[:, t], frame_size=fs, dtype=np.float32)
+        assert (ns == fs).all()
+        outs[:, t * fs:(t + 1) * fs] = got.reshape(n, fs, ch)
+        rngs[:, t] = dec.final_range()
+    dec.close()
+    frac = []
+    for s in range(n):
+        ref, ref_rng = util.ref_decode_float(pk[s], sz[s], ch, fs)
+        orc, orc_rng = util.oracle_decode_float(pk[s], sz[s], ch, fs)
+        assert (ref_rng == orc_rng).all() and np.array_equal(ref, orc)
+        assert (rngs[s] == ref_rng).all(), s
+        frac.append(_check(outs[s], ref))
+    print('fraction of int16 samples differing by 1 LSB: %.5f' % np.mean(frac))
+
+
+def test_int16_output_matches_float_path():
+    import opus_b200
+    name, pkts, sizes, rng, pcm, ch, fs = next(c for c in golden_cases() if c[0] == 'st20_64k_vbr')
+    a = opus_b200.DecoderBatch(2, channels=ch)
+    b = opus_b200.DecoderBatch(2, channels=ch)
+    for t in range(len(sizes)):
+        f, _ = a.decode(np.repeat(pkts[t:t + 1], 2, 0), np.repeat(sizes[t:t + 1], 2), frame_size=fs, dtype=np.float32)
+        i, _ = b.decode(np.repeat(pkts[t:t + 1], 2, 0), np.repeat(sizes[t:t + 1], 2), frame_size=fs, dtype=np.int16)
+        assert np.array_equal(util.to_int16(f), i)
+    a.close()
+    b.close()
+
+
+def test_fuzzed_packets_vs_oracle():
+    """Random payloads behind valid CELT TOCs (reference strategy: tests/test_opus_decode.c):
+    same per-stream status, same final range, PCM within tolerance, never a crash."""
+    import ctypes
+    import opus_b200
+    from test_oracle_vs_ref import _random_packets
+    O = util.load_oracle()
+    n, T = 64, 10
+    for ch in (1, 2):
+        dec = opus_b200.DecoderBatch(n, channels=ch)
+        packs = [_random_packets(100 * ch + s, T, max_len=300) for s in range(n)]
+        states = [ctypes.create_string_buffer(O.orc_decoder_size()) for _ in range(n)]
+        for st in states:
+            O.orc_decoder_init(st, ch)
+        buf = np.zeros((5760, ch), np.float32)
+        for t in range(T):
+            pk = np.stack([packs[s][0][t] for s in range(n)])
+            sz = np.array([packs[s][1][t] for s in range(n)], np.int32)
+            got, ns = dec.decode(pk, sz, frame_size=960, dtype=np.float32)
+            fr = dec.final_range()
+            for s in range(n):
+                want = O.orc_opus_decode_float(states[s], util._ptr(pk[s]), int(sz[s]), util._ptr(buf), 960)
+                assert ns[s] == want, (t, s, ns[s], want)
+                if want > 0:
+                    assert fr[s] == O.orc_final_range(states[s])
+                    g, r = got[s, :want * ch], buf[:want].reshape(-1)
+                    ok = np.isfinite(r)
+                    scale = max(1.0, float(np.abs(r[ok]).max())) if ok.any() else 1.0
+                    assert np.abs(g[ok] - r[ok]).max() <= 1e-4 * scale
+        dec.close()
+
+
+def test_multiframe_and_mixed_frame_sizes():
+    import opus_b200
+    g = {c[0]: c for c in golden_cases()}
+    _, p10, s10, _, pcm10, ch, fs10 = g['st10_96k']
+    _, p20, s20, _, pcm20, _, fs20 = g['st20_128k']
+    # stream 0: code-1 packet holding frames 0,1 of the 10 ms stream; stream 1: a plain 20 ms packet;
+    # stream 2: code-3 CBR packet with frames 0,1 plus padding; stream 3: nothing this call
+    f0, f1 = bytes(p10[0, 1:s10[0]]), bytes(p10[1, 1:s10[1]])
+    assert len(f0) == len(f1)
+    toc = int(p10[0, 0])
+    a = bytes([toc | 1]) + f0 + f1
+    c = bytes([toc | 3, 0x40 | 2, 3]) + f0 + f1 + b'\0\0\0'
+    pk = np.zeros((4, 1500), np.uint8)
+    sz = np.zeros(4, np.int32)
+    for i, b in enumerate((a, bytes(p20[0, :s20[0]]), c)):
+        pk[i, :len(b)] = np.frombuffer(b, np.uint8)
+        sz[i] = len(b)
+    dec = opus_b200.DecoderBatch(4, channels=ch)
+    got, ns = dec.decode(pk, sz, frame_size=960, dtype=np.float32)
+    assert list(ns) == [960, 960, 960, 0]
+    _check(got[0].reshape(960, ch), pcm10[:960])
+    _check(got[1].reshape(960, ch), pcm20[:960])
+    _check(got[2].reshape(960, ch), pcm10[:960])
+    dec.close()
+
+
+def test_error_codes():
+    import opus_b200
+    name, pkts, sizes, rng, pcm, ch, fs = next(c for c in golden_cases() if c[0] == 'st20_128k')
+    dec = opus_b200.DecoderBatch(4, channels=ch)
+    pk = np.repeat(pkts[:1], 4, 0)
+    sz = np.repeat(sizes[:1], 4).astype(np.int32)
+    pk[1, 0] = 0x08            # SILK TOC -> OPUS_UNIMPLEMENTED
+    pk[2, 0] = pk[2, 0] | 3    # code 3 with a nonsense count byte -> OPUS_INVALID_PACKET
+    pk[2, 1] = 0
+    got, ns = dec.decode(pk, sz, frame_size=480, dtype=np.int16)   # 20 ms frame into a 10 ms buffer
+    assert ns[0] == -2 and ns[1] == -5 and ns[2] == -4 and ns[3] == -2, ns
+    got, ns = dec.decode(pk, sz, frame_size=960, dtype=np.int16)
+    assert ns[0] == 960 and ns[1] == -5 and ns[2] == -4 and ns[3] == 960
+    with pytest.raises(opus_b200.OpusB200Error):
+        opus_b200.DecoderBatch(4, channels=3)
+    dec.close()
+
+
+def test_full_batch_65536_replicas_consistent():
+    """BASELINE.json config[1] size: 65 536 streams.  256 distinct streams tiled 256x; every
+    replica must equal its original bit for bit, and originals match the golden/oracle."""
+    import opus_b200
+    name, pkts, sizes, rng, pcm, ch, fs = next(c for c in golden_cases() if c[0] == 'st20_128k')
+    n = 65536
+    base = np.zeros((256, 1500), np.uint8)
+    bsz = np.zeros(256, np.int32)
+    T = len(sizes)
+    for i in range(256):
+        base[i], bsz[i] = pkts[i % T], sizes[i % T]
+    stride = int(bsz.max())
+    pk = np.tile(base[:, :stride], (n // 256, 1))
+    sz = np.tile(bsz, n // 256)
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    got, ns = dec.decode(pk, sz, frame_size=fs, dtype=np.int16)
+    assert (ns == fs).all()
+    fr = dec.final_range()
+    g = got.reshape(n // 256, 256, -1)
+    assert (g == g[0:1]).all()
+    assert (fr.reshape(-1, 256) == fr[:256][None]).all()
+    # each distinct packet decoded from a fresh state: compare with the oracle
+    for i in range(0, 256, 37):
+        want, wr = util.oracle_decode_float(base[i:i + 1], bsz[i:i + 1], ch, fs)
+        assert fr[i] == wr[0]
+        d = np.abs(got[i].astype(np.int32) - util.to_int16(want).reshape(-1).astype(np.int32))
+        assert d.max() <= 1
+    dec.close()
