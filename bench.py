@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py — batched CELT decode throughput (BASELINE.json configs[1]):
+65 536 independent 48 kHz stereo 20 ms streams @128 kb/s CBR per GPU, one packet per stream per
+step, synthetic packets from tests/golden/bench_packets.npz (256 distinct streams x 8 frames,
+produced by the reference encoder; tiled).  Weak scaling: every GPU gets its own 65 536 streams.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--impl reference]
+
+Prints ONE JSON line (see the driver contract).  `value` = frames/s with packets and PCM resident
+in HBM; `e2e` = the same through the host-buffer C-ABI call (opusb200_decode: H2D of the packets
+and D2H of the PCM inside the timed region, pinned host buffers).  `--impl reference` times the
+unmodified reference decoder (oracle/_ref, SSE/AVX2 RTCD build) on the host cores instead.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME = 960
+CH = 2
+PKT_STRIDE = 320
+# algorithmic HBM bytes per stream-frame (DESIGN.md "Roofline bookkeeping")
+BYTES_BANDS_KERNEL = 320 + 2 * 960 * 4 + 240 + 2 * 720   # packet in, X out, side info out, band state in+out
+BYTES_SYNTH_KERNEL = 2 * 960 * 4 + 240 + 2 * 960 * 4 + 2 * 960 * 2 + 2 * 2 * 60 * 4  # X in, side in, history out, PCM out, tails
+BYTES_WHOLE_FRAME = 320 + 2 * 960 * 2                    # packet in + int16 PCM out
+
+
+def load_fixture():
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_packets.npz'))
+    pk, sz = g['pkts'], g['sizes']  # [256][8][321], [256][8]
+    assert int(sz.max()) <= PKT_STRIDE
+    return np.ascontiguousarray(pk[:, :, :PKT_STRIDE]), np.ascontiguousarray(sz)
+
+
+def tile_streams(pk, sz, n):
+    reps = (n + pk.shape[0] - 1) // pk.shape[0]
+    return np.tile(pk, (reps, 1, 1))[:n], np.tile(sz, (reps, 1))[:n]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ''
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        # samples under load = upper half
+        sm_sorted = sorted(sm)
+        med = sm_sorted[len(sm_sorted) // 2] if sm_sorted else None
+        return {'sm_mhz': med, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference decoder on the host cores
+# ---------------------------------------------------------------------------------------------
+def load_cpu_decoder():
+    """(lib, kind): the compiled reference if it travelled (oracle/_ref), else the oracle port."""
+    ref = os.path.join(ROOT, 'oracle', '_ref', 'libopus_ref_simd.so')
+    if os.path.exists(ref):
+        L = ctypes.CDLL(ref)
+        L.refh_decode_bench.restype = ctypes.c_long
+        return L, 'reference'
+    L = ctypes.CDLL(os.path.join(ROOT, 'oracle', 'liboracle.so'))
+    return L, 'port'
+
+
+def cpu_decode_sample(L, kind, pk, sz, n_streams, reps, threads):
+    """Decode n_streams x 8 x reps frames spread over `threads` host threads (ctypes releases the
+    GIL; the reference has no internal threading, so one pinned-by-the-OS thread per core is its
+    best case).  Returns (frames, seconds); per-thread input slices are prepared outside the timing."""
+    T = pk.shape[1]
+    per = max(1, n_streams // threads)
+    chunks = [(i * per, min(n_streams, (i + 1) * per)) for i in range(threads) if i * per < n_streams]
+    done = [0] * len(chunks)
+    bufs = [(np.ascontiguousarray(pk[lo:hi]), np.ascontiguousarray(sz[lo:hi]), np.zeros(FRAME * CH, np.int16))
+            for lo, hi in chunks]
+    gate = threading.Barrier(len(chunks) + 1)
+
+    def work(k):
+        p, s, pcm = bufs[k]
+        gate.wait()
+        if kind == 'reference':
+            r = L.refh_decode_bench(48000, CH, FRAME, p.shape[0], T, p.ctypes.data_as(ctypes.c_void_p), p.shape[2],
+                                    s.ctypes.data_as(ctypes.c_void_p), reps, pcm.ctypes.data_as(ctypes.c_void_p))
+            done[k] = int(r)
+        else:
+            rng = np.zeros(T, np.uint32)
+            out = np.zeros((T * FRAME, CH), np.float32)
+            for _ in range(reps):
+                for i in range(p.shape[0]):
+                    L.orc_decode_stream_float(CH, FRAME, T, p[i].ctypes.data_as(ctypes.c_void_p), p.shape[2],
+                                              s[i].ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+                                              rng.ctypes.data_as(ctypes.c_void_p))
+                    done[k] += T
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(chunks))]
+    for t in th:
+        t.start()
+    gate.wait()
+    t0 = time.perf_counter()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    assert all(d > 0 for d in done), done
+    return sum(done), dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    pk, sz = load_fixture()
+    L, kind = load_cpu_decoder()
+    cores = os.cpu_count() or 1
+    # one step = a bounded sample: (64 streams per core) x 8 frames x 4 passes
+    n_streams = 64 * cores
+    reps = 4
+    pkt, szt = tile_streams(pk, sz, n_streams)
+    for _ in range(args.warmup):
+        cpu_decode_sample(L, kind, pkt, szt, n_streams, 1, cores)
+    frames = 0
+    t = 0.0
+    for _ in range(args.steps):
+        f, dt = cpu_decode_sample(L, kind, pkt, szt, n_streams, reps, cores)
+        frames += f
+        t += dt
+    val = frames / t
+    sample = '%d streams x 8 frames x %d passes per step on %d threads' % (n_streams, reps, cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'celt_decode_frames_per_s', 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * t / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'x_realtime': val / 50.0,
+        'config': {'workload': 'batched CELT decode, 48 kHz stereo 20 ms @128 kb/s CBR (BASELINE.json configs[1])',
+                   'sample': sample, 'cpu': kind},
+        'cpu_baseline': {'value': val, 'unit': 'frames/s', 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import opus_b200
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    n = args.streams
+    # the one init-time collective: rank 0 owns the workload fixture and broadcasts it
+    if rank == 0:
+        pk, sz = load_fixture()
+        t_pk = torch.from_numpy(pk).to(dev)
+        t_sz = torch.from_numpy(sz).to(dev)
+    else:
+        t_pk = torch.empty((256, 8, PKT_STRIDE), dtype=torch.uint8, device=dev)
+        t_sz = torch.empty((256, 8), dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.broadcast(t_pk, 0)
+        dist.broadcast(t_sz, 0)
+    T = t_pk.shape[1]
+    reps = (n + 255) // 256
+    # [T][n][320] resident packets (168 MB at n = 65536), [T][n] lengths
+    d_pk = t_pk.permute(1, 0, 2).repeat(1, reps, 1)[:, :n].contiguous()
+    d_len = t_sz.permute(1, 0).repeat(1, reps)[:, :n].contiguous()
+    d_pcm = torch.empty((n, FRAME * CH), dtype=torch.int16, device=dev)
+    d_ns = torch.empty((n,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    dec = opus_b200.DecoderBatch(n, channels=CH, device=local_rank)
+    ext = torch.cuda.ExternalStream(dec.cuda_stream, device=dev)
+
+    def step_device(i):
+        t = i % T
+        dec.decode_device(d_pk[t].data_ptr(), PKT_STRIDE, d_len[t].data_ptr(), d_pcm.data_ptr(), FRAME * CH, int16=True,
+                          frame_size=FRAME, max_frames_per_packet=1, d_out_samples=d_ns.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        step_device(i)
+    dec.sync()
+    assert int(d_ns.min()) == FRAME and int(d_ns.max()) == FRAME, (int(d_ns.min()), int(d_ns.max()))
+    launches0 = dec.launch_count
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    e1.record(ext)
+    dec.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = dec.launch_count - launches0
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = n * world * args.steps / (ms_max / 1000.0)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host buffers) ----
+    L = opus_b200.lib()
+    hp = L.opusb200_host_alloc(n * PKT_STRIDE * T)
+    ho = L.opusb200_host_alloc(n * FRAME * CH * 2)
+    h_pk = np.ctypeslib.as_array((ctypes.c_uint8 * (n * PKT_STRIDE * T)).from_address(hp)).reshape(T, n, PKT_STRIDE)
+    h_pcm = np.ctypeslib.as_array((ctypes.c_int16 * (n * FRAME * CH)).from_address(ho)).reshape(n, FRAME * CH)
+    h_pk[:] = d_pk.cpu().numpy()
+    h_len = d_len.cpu().numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        dec.decode(h_pk[i % T], h_len[i % T], frame_size=FRAME, dtype=np.int16, out=h_pcm)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(ext)
+    for i in range(e2e_steps):
+        _, ns = dec.decode(h_pk[i % T], h_len[i % T], frame_size=FRAME, dtype=np.int16, out=h_pcm)
+    f1.record(ext)
+    dec.sync()
+    barrier()
+    assert (ns == FRAME).all()
+    e_ms = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = n * world * e2e_steps / (float(e_ms.item()) / 1000.0)
+    h2d = n * PKT_STRIDE + n * 4
+    d2h = n * FRAME * CH * 2 + n * 4
+
+    # ---- per-kernel device time (CUDA events around each launch, on the launching stream) ----
+    dec.set_timing(True)
+    prof_steps = 5
+    for i in range(prof_steps):
+        step_device(i)
+    ms_bands, ms_synth, pairs = dec.get_timing()
+    dec.set_timing(False)
+    L.opusb200_host_free(hp)
+    L.opusb200_host_free(ho)
+
+    if rank != 0:
+        dec.close()
+        return
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    t_bands = ms_bands / pairs / 1000.0
+    t_synth = ms_synth / pairs / 1000.0
+    ach = BYTES_BANDS_KERNEL * n / t_bands / 1e9
+    roof = {'kernel': 'ob_celt_dec_bands', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': BYTES_BANDS_KERNEL * n,
+            'ms_per_launch': t_bands * 1000.0,
+            'note': 'latency/issue-bound entropy decoding; HBM fraction is reported as required, see DESIGN.md',
+            'other_kernels': {'ob_celt_dec_synth': {'ms_per_launch': t_synth * 1000.0,
+                                                   'achieved_GBs': BYTES_SYNTH_KERNEL * n / t_synth / 1e9,
+                                                   'frac': BYTES_SYNTH_KERNEL * n / t_synth / 1e9 / peak}}}
+    prof = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(prof):
+        try:
+            roof['traffic'] = json.load(open(prof)).get('ob_celt_dec_bands_dram_bytes_per_launch')
+        except Exception:
+            pass
+    # ---- CPU baseline: bounded sample on the host cores ----
+    Lc, kind = load_cpu_decoder()
+    cores = os.cpu_count() or 1
+    pkf, szf = load_fixture()
+    ns_cpu = 64 * cores
+    pkt, szt = tile_streams(pkf, szf, ns_cpu)
+    cpu_decode_sample(Lc, kind, pkt, szt, ns_cpu, 1, cores)
+    reps_cpu = 8
+    frames, dt = cpu_decode_sample(Lc, kind, pkt, szt, ns_cpu, reps_cpu, cores)
+    cpu = {'value': frames / dt, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+           'sample': '%d streams x 8 frames x %d reps on %d threads (%s)' % (ns_cpu, reps_cpu, cores,
+                                                                           'oracle/_ref SSE/AVX2 build' if kind == 'reference' else 'oracle C port')}
+    print(json.dumps({
+        'metric': 'celt_decode_frames_per_s', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'x_realtime': value / 50.0,
+        'config': {'workload': 'batched CELT decode, 48 kHz stereo 20 ms @128 kb/s CBR (BASELINE.json configs[1])',
+                   'streams_per_gpu': n, 'packets': '256 distinct streams x 8 frames from the reference encoder, tiled',
+                   'l2': 'per-step working set (spectrum 503 MB + history 503 MB at 65536 streams) exceeds the 126 MB L2',
+                   'parallelism': 'streams sharded across GPUs, no steady-state collective'},
+        'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
+        'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
+    }))
+    dec.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--streams', type=int, default=65536, help='streams per GPU')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl')
+    try:
+        run_gpu_arm(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -98,3 +98,29 @@ int refh_decode_stream_float(int Fs, int channels, int frame_size, int nframes, 
   opus_decoder_destroy(dec);
   return 0;
 }
+
+/* Throughput harness for the CPU baseline (bench.py): `n` decoders are created once, then every
+ * stream decodes its T packets `reps` times (state simply continues, as in the GPU bench).
+ * pkts: [n][T][stride].  Returns the number of frames decoded, or a negative opus error. */
+long refh_decode_bench(int Fs, int channels, int frame_size, int n, int T, const unsigned char *pkts, int stride,
+                       const int *sizes, int reps, opus_int16 *scratch_pcm) {
+  int err = 0, s, t, r;
+  long frames = 0;
+  OpusDecoder **dec = (OpusDecoder **)calloc(n, sizeof(*dec));
+  if (!dec) return OPUS_ALLOC_FAIL;
+  for (s = 0; s < n; s++) {
+    dec[s] = opus_decoder_create(Fs, channels, &err);
+    if (!dec[s]) { frames = err; goto done; }
+  }
+  for (r = 0; r < reps; r++)
+    for (t = 0; t < T; t++)
+      for (s = 0; s < n; s++) {
+        int k = opus_decode(dec[s], pkts + ((size_t)s * T + t) * stride, sizes[s * T + t], scratch_pcm, frame_size, 0);
+        if (k < 0) { frames = k; goto done; }
+        frames++;
+      }
+done:
+  for (s = 0; s < n; s++) if (dec[s]) opus_decoder_destroy(dec[s]);
+  free(dec);
+  return frames;
+}
