@@ -38,15 +38,18 @@ struct BandWS {
   int bits1[OB_NBANDS], bits2[OB_NBANDS], thresh[OB_NBANDS], trim_off[OB_NBANDS], bits_tmp[OB_NBANDS];
   unsigned char collapse[2 * OB_NBANDS];
   unsigned char pad[2];
+  // warp-uniform context of the band being decoded: written by lane 0 between bands (behind a
+  // __syncwarp), read-only while the band's partitions are processed
+  int c_band, c_intensity, c_spread, c_tf_change, c_disable_inv;
 };
 
-struct BandCtx {
+// The mutable part of the band decoder's state.  It travels BY VALUE through the (non-inlined,
+// recursive) partition functions, i.e. in registers, never through local memory.
+struct BandMut {
   RangeDec ec;
-  BandWS *ws;
-  int lane;
-  int band, intensity, spread, tf_change, disable_inv;
   int32_t remaining_bits;
   uint32_t seed;
+  unsigned cm;  // collapse mask returned by the last band/partition call
 };
 
 // ---- exact integer helpers (celt/bands.c:68-91, celt/mathops.c:45-68, celt/rate.h:48-87) ----
@@ -176,16 +179,17 @@ OB_DEV int theta_levels(int N, int b, int offset, int pulse_cap, int stereo) {
   return (qn + 1) >> 1 << 1;
 }
 
-struct SplitInfo { int inv, imid, iside, delta, itheta, qalloc; };
+struct SplitInfo { int inv, imid, iside, delta, itheta, qalloc, b, fill; };
+struct ThetaRet { RangeDec ec; SplitInfo sp; };
 
-// decode side of celt/bands.c:700-933
-OB_DEV void decode_theta(BandCtx &ctx, SplitInfo &sp, int N, int &b, int B, int B0, int LM, int stereo, int &fill) {
-  RangeDec &ec = ctx.ec;
-  int i = ctx.band, itheta = 0, inv = 0;
+// decode side of celt/bands.c:700-933.  b and fill go in by value and come back in sp.b / sp.fill.
+OB_DEVNI ThetaRet decode_theta(RangeDec ec, const BandWS *ws, int32_t remaining_bits, int N, int b, int B, int B0, int LM,
+                              int stereo, int fill) {
+  int i = ws->c_band, itheta = 0, inv = 0;
   int pulse_cap = ob_logN[i] + LM * (1 << OB_BITRES);
   int offset = (pulse_cap >> 1) - (stereo && N == 2 ? 16 : 4);
   int qn = theta_levels(N, b, offset, pulse_cap, stereo);
-  if (stereo && i >= ctx.intensity) qn = 1;
+  if (stereo && i >= ws->c_intensity) qn = 1;
   int32_t tell = ec.tell_frac();
   if (qn != 1) {
     if (stereo && N > 2) {
@@ -213,9 +217,9 @@ OB_DEV void decode_theta(BandCtx &ctx, SplitInfo &sp, int N, int &b, int B, int 
     }
     itheta = (uint32_t)((int32_t)itheta * 16384) / (uint32_t)qn;
   } else if (stereo) {
-    if (b > 2 << OB_BITRES && ctx.remaining_bits > 2 << OB_BITRES) inv = ec.bit_logp(2);
+    if (b > 2 << OB_BITRES && remaining_bits > 2 << OB_BITRES) inv = ec.bit_logp(2);
     else inv = 0;
-    if (ctx.disable_inv) inv = 0;
+    if (ws->c_disable_inv) inv = 0;
     itheta = 0;
   }
   int qalloc = ec.tell_frac() - tell;
@@ -230,117 +234,132 @@ OB_DEV void decode_theta(BandCtx &ctx, SplitInfo &sp, int N, int &b, int B, int 
     iside = bitexact_cos((int16_t)(16384 - itheta));
     delta = frac_mul16((N - 1) << 7, bitexact_log2tan(iside, imid));
   }
-  sp.inv = inv; sp.imid = imid; sp.iside = iside; sp.delta = delta; sp.itheta = itheta; sp.qalloc = qalloc;
+  ThetaRet r;
+  r.ec = ec;
+  r.sp.inv = inv; r.sp.imid = imid; r.sp.iside = iside; r.sp.delta = delta; r.sp.itheta = itheta; r.sp.qalloc = qalloc;
+  r.sp.b = b; r.sp.fill = fill;
+  return r;
 }
 
 // celt/bands.c:934-968.  X, Y: shared memory.
-OB_DEV unsigned decode_band_n1(BandCtx &ctx, float *X, float *Y, float *lowband_out) {
+OB_DEV BandMut decode_band_n1(BandMut m, float *X, float *Y, float *lowband_out, int lane) {
   int stereo = Y != nullptr;
   float *x = X;
   for (int c = 0; c < 1 + stereo; c++) {
     int sign = 0;
-    if (ctx.remaining_bits >= 1 << OB_BITRES) {
-      sign = ctx.ec.bits(1);
-      ctx.remaining_bits -= 1 << OB_BITRES;
+    if (m.remaining_bits >= 1 << OB_BITRES) {
+      sign = m.ec.bits(1);
+      m.remaining_bits -= 1 << OB_BITRES;
     }
-    if (ctx.lane == 0) x[0] = sign ? -1.f : 1.f;
+    if (lane == 0) x[0] = sign ? -1.f : 1.f;
     x = Y;
   }
   wsync();
-  if (lowband_out && ctx.lane == 0) lowband_out[0] = X[0];
+  if (lowband_out && lane == 0) lowband_out[0] = X[0];
   wsync();
-  return 1;
+  m.cm = 1;
+  return m;
 }
 
-// celt/vq.c:621-692 (alg_unquant)
-OB_DEV unsigned pvq_decode(BandCtx &ctx, float *X, int N, int K, int B, float gain) {
-  const int lane = ctx.lane;
-  int *iy = ctx.ws->iy;
-  uint32_t idx = ctx.ec.uint(pvq_u(N, K) + pvq_u(N, K + 1));
+// celt/vq.c:621-692 (alg_unquant).  Returns the collapse mask.
+OB_DEV unsigned pvq_decode(RangeDec &ec, BandWS *ws, float *X, int N, int K, int B, float gain, int lane) {
+  int *iy = ws->iy;
+  uint32_t idx = ec.uint(pvq_u(N, K) + pvq_u(N, K + 1));
   wsync();  // previous readers of iy are done
   float Ryy = pvq_index_to_pulses(N, K, idx, iy, lane);
   wsync();
   float g = rsqrt_ref(Ryy) * gain;
   unsigned mask = 0;
   const int N0 = B > 1 ? (unsigned)N / (unsigned)B : N;
+#pragma unroll 1
   for (int j = lane; j < N; j += 32) {
     int v = iy[j];
     X[j] = (float)v * g;
     if (B > 1 && v != 0) mask |= 1u << (j / N0);
   }
   mask = B > 1 ? warp_or(mask) : 1u;
-  spread_unrotate(X, ctx.ws->tmp, N, B, K, ctx.spread, lane);
+  spread_unrotate(X, ws->tmp, N, B, K, ws->c_spread, lane);
   wsync();
   return mask;
 }
 
 // decode side of celt/bands.c:973-1176 (recursive; depth <= 5)
-OB_DEVNI unsigned decode_partition(BandCtx &ctx, float *X, int N, int b, int B, float *lowband, int LM, float gain, int fill) {
-  const int lane = ctx.lane;
-  const int i = ctx.band;
+OB_DEVNI BandMut decode_partition(BandMut m, BandWS *ws, float *X, int N, int b, int B, float *lowband, int LM, float gain,
+                                 int fill) {
+  const int lane = lane_id();
+  const int i = ws->c_band;
   int B0 = B;
   unsigned cm = 0;
   const unsigned char *cache = pulse_cache_row(i, LM);
   if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
-    SplitInfo sp;
     N >>= 1;
     float *Y = X + N;
     LM -= 1;
     if (B == 1) fill = (fill & 1) | (fill << 1);
     B = (B + 1) >> 1;
-    decode_theta(ctx, sp, N, b, B, B0, LM, 0, fill);
-    int delta = sp.delta, itheta = sp.itheta;
-    float mid = (1.f / 32768) * sp.imid;
-    float side = (1.f / 32768) * sp.iside;
+    ThetaRet tr = decode_theta(m.ec, ws, m.remaining_bits, N, b, B, B0, LM, 0, fill);
+    m.ec = tr.ec;
+    b = tr.sp.b; fill = tr.sp.fill;
+    int delta = tr.sp.delta, itheta = tr.sp.itheta;
+    float mid = (1.f / 32768) * tr.sp.imid;
+    float side = (1.f / 32768) * tr.sp.iside;
     if (B0 > 1 && (itheta & 0x3fff)) {
       if (itheta > 8192) delta -= delta >> (4 - LM);
       else delta = OB_IMIN(0, delta + (N << OB_BITRES >> (5 - LM)));
     }
     int mbits = OB_IMAX(0, OB_IMIN(b, (b - delta) / 2));
     int sbits = b - mbits;
-    ctx.remaining_bits -= sp.qalloc;
+    m.remaining_bits -= tr.sp.qalloc;
     float *next_lowband2 = lowband ? lowband + N : nullptr;
-    int32_t rebalance = ctx.remaining_bits;
+    int32_t rebalance = m.remaining_bits;
     if (mbits >= sbits) {
-      cm = decode_partition(ctx, X, N, mbits, B, lowband, LM, gain * mid, fill);
-      rebalance = mbits - (rebalance - ctx.remaining_bits);
+      m = decode_partition(m, ws, X, N, mbits, B, lowband, LM, gain * mid, fill);
+      cm = m.cm;
+      rebalance = mbits - (rebalance - m.remaining_bits);
       if (rebalance > 3 << OB_BITRES && itheta != 0) sbits += rebalance - (3 << OB_BITRES);
-      cm |= decode_partition(ctx, Y, N, sbits, B, next_lowband2, LM, gain * side, fill >> B) << (B0 >> 1);
+      m = decode_partition(m, ws, Y, N, sbits, B, next_lowband2, LM, gain * side, fill >> B);
+      cm |= m.cm << (B0 >> 1);
     } else {
-      cm = decode_partition(ctx, Y, N, sbits, B, next_lowband2, LM, gain * side, fill >> B) << (B0 >> 1);
-      rebalance = sbits - (rebalance - ctx.remaining_bits);
+      m = decode_partition(m, ws, Y, N, sbits, B, next_lowband2, LM, gain * side, fill >> B);
+      cm = m.cm << (B0 >> 1);
+      rebalance = sbits - (rebalance - m.remaining_bits);
       if (rebalance > 3 << OB_BITRES && itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
-      cm |= decode_partition(ctx, X, N, mbits, B, lowband, LM, gain * mid, fill);
+      m = decode_partition(m, ws, X, N, mbits, B, lowband, LM, gain * mid, fill);
+      cm |= m.cm;
     }
   } else {
     int q = bits_to_pseudo(i, LM, b);
     int curr_bits = pseudo_to_bits(i, LM, q);
-    ctx.remaining_bits -= curr_bits;
-    while (ctx.remaining_bits < 0 && q > 0) {
-      ctx.remaining_bits += curr_bits;
+    m.remaining_bits -= curr_bits;
+#pragma unroll 1
+    while (m.remaining_bits < 0 && q > 0) {
+      m.remaining_bits += curr_bits;
       q--;
       curr_bits = pseudo_to_bits(i, LM, q);
-      ctx.remaining_bits -= curr_bits;
+      m.remaining_bits -= curr_bits;
     }
     if (q != 0) {
-      cm = pvq_decode(ctx, X, N, pseudo_to_pulses(q), B, gain);
+      cm = pvq_decode(m.ec, ws, X, N, pseudo_to_pulses(q), B, gain, lane);
     } else {
       unsigned cm_mask = (unsigned)(1UL << B) - 1;
       fill &= cm_mask;
       wsync();
       if (!fill) {
+#pragma unroll 1
         for (int j = lane; j < N; j += 32) X[j] = 0.f;
         wsync();
       } else {
         // every lane steps the LCG through all N draws and keeps its own elements
-        uint32_t seed = ctx.seed;
+        uint32_t seed = m.seed;
         if (lowband == nullptr) {
+#pragma unroll 1
           for (int j = 0; j < N; j++) {
             seed = 1664525u * seed + 1013904223u;
             if ((j & 31) == lane) X[j] = (float)((int32_t)seed >> 20);
           }
           cm = cm_mask;
         } else {
+#pragma unroll 1
           for (int j = 0; j < N; j++) {
             seed = 1664525u * seed + 1013904223u;
             if ((j & 31) == lane) {
@@ -351,32 +370,34 @@ OB_DEVNI unsigned decode_partition(BandCtx &ctx, float *X, int N, int b, int B, 
           }
           cm = fill;
         }
-        ctx.seed = seed;
+        m.seed = seed;
         renormalise(X, N, gain, lane);
       }
     }
   }
-  return cm;
+  m.cm = cm;
+  return m;
 }
 
 // decode side of celt/bands.c:1248-1379
-OB_DEVNI unsigned decode_band_mono(BandCtx &ctx, float *X, int N, int b, int B, float *lowband, int LM,
-                                  float *lowband_out, float gain, float *lowband_scratch, int fill) {
-  const int lane = ctx.lane;
-  float *tmp = ctx.ws->tmp;
+OB_DEVNI BandMut decode_band_mono(BandMut m, BandWS *ws, float *X, int N, int b, int B, float *lowband, int LM,
+                                 float *lowband_out, float gain, float *lowband_scratch, int fill) {
+  const int lane = lane_id();
+  float *tmp = ws->tmp;
   int N0 = N, N_B = N, N_B0, B0 = B, time_divide = 0, recombine = 0;
-  unsigned cm = 0;
-  int tf_change = ctx.tf_change;
+  int tf_change = ws->c_tf_change;
   const int longBlocks = B0 == 1;
   N_B = (unsigned)N_B / (unsigned)B;
-  if (N == 1) return decode_band_n1(ctx, X, nullptr, lowband_out);
+  if (N == 1) return decode_band_n1(m, X, nullptr, lowband_out, lane);
   if (tf_change > 0) recombine = tf_change;
   if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
     wsync();
+#pragma unroll 1
     for (int j = lane; j < N; j += 32) lowband_scratch[j] = lowband[j];
     wsync();
     lowband = lowband_scratch;
   }
+#pragma unroll 1
   for (int k = 0; k < recombine; k++) {
     if (lowband) haar_step(lowband, N >> k, 1 << k, lane);
     int lo = fill & 0xF, hi = fill >> 4;  // bit_interleave_table, celt/bands.c:1288
@@ -386,6 +407,7 @@ OB_DEVNI unsigned decode_band_mono(BandCtx &ctx, float *X, int N, int b, int B, 
   }
   B >>= recombine;
   N_B <<= recombine;
+#pragma unroll 1
   while ((N_B & 1) == 0 && tf_change < 0) {
     if (lowband) haar_step(lowband, N_B, B, lane);
     fill |= fill << B;
@@ -397,16 +419,19 @@ OB_DEVNI unsigned decode_band_mono(BandCtx &ctx, float *X, int N, int b, int B, 
   B0 = B;
   N_B0 = N_B;
   if (B0 > 1 && lowband) deinterleave_hadamard(lowband, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
-  cm = decode_partition(ctx, X, N, b, B, lowband, LM, gain, fill);
+  m = decode_partition(m, ws, X, N, b, B, lowband, LM, gain, fill);
+  unsigned cm = m.cm;
   if (B0 > 1) interleave_hadamard(X, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
   N_B = N_B0;
   B = B0;
+#pragma unroll 1
   for (int k = 0; k < time_divide; k++) {
     B >>= 1;
     N_B <<= 1;
     cm |= cm >> B;
     haar_step(X, N_B, B, lane);
   }
+#pragma unroll 1
   for (int k = 0; k < recombine; k++) {
     // bit_deinterleave_table, celt/bands.c:1352: each of the low 4 bits is doubled
     unsigned c4 = cm & 0xF;
@@ -417,15 +442,17 @@ OB_DEVNI unsigned decode_band_mono(BandCtx &ctx, float *X, int N, int b, int B, 
   if (lowband_out) {
     float n = f_sqrt((float)N0);
     wsync();
+#pragma unroll 1
     for (int j = lane; j < N0; j += 32) lowband_out[j] = n * X[j];
     wsync();
   }
   cm &= (1u << B) - 1;
-  return cm;
+  m.cm = cm;
+  return m;
 }
 
 // celt/bands.c:407-466 (stereo_merge)
-OB_DEV void merge_mid_side(float *X, float *Y, float mid, int N, int lane) {
+OB_DEVNI void merge_mid_side(float *X, float *Y, float mid, int N, int lane) {
   wsync();
   float xp = warp_dot(Y, X, N, lane);
   float side = warp_dot(Y, Y, N, lane);
@@ -433,11 +460,13 @@ OB_DEV void merge_mid_side(float *X, float *Y, float mid, int N, int lane) {
   float El = (mid * mid) + side - 2 * xp;
   float Er = (mid * mid) + side + 2 * xp;
   if (Er < 6e-4f || El < 6e-4f) {
+#pragma unroll 1
     for (int j = lane; j < N; j += 32) Y[j] = X[j];
     wsync();
     return;
   }
   float lgain = rsqrt_ref(El), rgain = rsqrt_ref(Er);
+#pragma unroll 1
   for (int j = lane; j < N; j += 32) {
     float l = mid * X[j], r = Y[j];
     X[j] = lgain * (l - r);
@@ -447,28 +476,30 @@ OB_DEV void merge_mid_side(float *X, float *Y, float mid, int N, int lane) {
 }
 
 // decode side of celt/bands.c:1387-1570
-OB_DEVNI unsigned decode_band_stereo(BandCtx &ctx, float *X, float *Y, int N, int b, int B, float *lowband, int LM,
-                                    float *lowband_out, float *lowband_scratch, int fill) {
-  const int lane = ctx.lane;
+OB_DEVNI BandMut decode_band_stereo(BandMut m, BandWS *ws, float *X, float *Y, int N, int b, int B, float *lowband, int LM,
+                                   float *lowband_out, float *lowband_scratch, int fill) {
+  const int lane = lane_id();
   unsigned cm = 0;
-  SplitInfo sp;
-  if (N == 1) return decode_band_n1(ctx, X, Y, lowband_out);
+  if (N == 1) return decode_band_n1(m, X, Y, lowband_out, lane);
   int orig_fill = fill;
-  decode_theta(ctx, sp, N, b, B, B, LM, 1, fill);
-  int inv = sp.inv, delta = sp.delta, itheta = sp.itheta, qalloc = sp.qalloc;
-  float mid = (1.f / 32768) * sp.imid;
-  float side = (1.f / 32768) * sp.iside;
+  ThetaRet tr = decode_theta(m.ec, ws, m.remaining_bits, N, b, B, B, LM, 1, fill);
+  m.ec = tr.ec;
+  b = tr.sp.b; fill = tr.sp.fill;
+  int inv = tr.sp.inv, delta = tr.sp.delta, itheta = tr.sp.itheta, qalloc = tr.sp.qalloc;
+  float mid = (1.f / 32768) * tr.sp.imid;
+  float side = (1.f / 32768) * tr.sp.iside;
   if (N == 2) {
     int mbits = b, sbits = 0, sign = 0;
     if (itheta != 0 && itheta != 16384) sbits = 1 << OB_BITRES;
     mbits -= sbits;
     int c = itheta > 8192;
-    ctx.remaining_bits -= qalloc + sbits;
+    m.remaining_bits -= qalloc + sbits;
     float *x2 = c ? Y : X;
     float *y2 = c ? X : Y;
-    if (sbits) sign = ctx.ec.bits(1);
+    if (sbits) sign = m.ec.bits(1);
     sign = 1 - 2 * sign;
-    cm = decode_band_mono(ctx, x2, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, orig_fill);
+    m = decode_band_mono(m, ws, x2, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, orig_fill);
+    cm = m.cm;
     wsync();
     if (lane == 0) {
       y2[0] = -sign * x2[1];
@@ -488,49 +519,60 @@ OB_DEVNI unsigned decode_band_stereo(BandCtx &ctx, float *X, float *Y, int N, in
   } else {
     int mbits = OB_IMAX(0, OB_IMIN(b, (b - delta) / 2));
     int sbits = b - mbits;
-    ctx.remaining_bits -= qalloc;
-    int32_t rebalance = ctx.remaining_bits;
-    if (mbits >= sbits) {
-      cm = decode_band_mono(ctx, X, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, fill);
-      rebalance = mbits - (rebalance - ctx.remaining_bits);
-      if (rebalance > 3 << OB_BITRES && itheta != 0) sbits += rebalance - (3 << OB_BITRES);
-      cm |= decode_band_mono(ctx, Y, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
-    } else {
-      cm = decode_band_mono(ctx, Y, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
-      rebalance = sbits - (rebalance - ctx.remaining_bits);
-      if (rebalance > 3 << OB_BITRES && itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
-      cm |= decode_band_mono(ctx, X, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, fill);
+    m.remaining_bits -= qalloc;
+    int32_t rebalance = m.remaining_bits;
+    // one call site per role (mid / side) keeps the code small: order is decided by `first`
+    const int mid_first = mbits >= sbits;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const int do_mid = (pass == 0) == (mid_first != 0);
+      if (do_mid) {
+        m = decode_band_mono(m, ws, X, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, fill);
+        if (pass == 0) {
+          cm = m.cm;
+          rebalance = mbits - (rebalance - m.remaining_bits);
+          if (rebalance > 3 << OB_BITRES && itheta != 0) sbits += rebalance - (3 << OB_BITRES);
+        } else cm |= m.cm;
+      } else {
+        m = decode_band_mono(m, ws, Y, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
+        if (pass == 0) {
+          cm = m.cm;
+          rebalance = sbits - (rebalance - m.remaining_bits);
+          if (rebalance > 3 << OB_BITRES && itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
+        } else cm |= m.cm;
+      }
     }
   }
   if (N != 2) merge_mid_side(X, Y, mid, N, lane);
   if (inv) {
     wsync();
+#pragma unroll 1
     for (int j = lane; j < N; j += 32) Y[j] = -Y[j];
     wsync();
   }
-  return cm;
+  m.cm = cm;
+  return m;
 }
 
 // decode side of celt/bands.c:1589-1923.  Xg/Yg: this frame's normalised spectrum in HBM
 // (each band is produced in shared memory and stored once it is final).
-OB_DEV void decode_all_bands(BandCtx &ctx, int start, int end, float *Xg, float *Yg, int shortBlocks, int dual_stereo,
-                             int32_t total_bits, int32_t balance, int LM, int codedBands) {
-  BandWS &ws = *ctx.ws;
-  const int lane = ctx.lane;
+OB_DEV void decode_all_bands(BandMut &m, BandWS *wsp, int start, int end, float *Xg, float *Yg, int shortBlocks,
+                             int dual_stereo, int32_t total_bits, int32_t balance, int LM, int codedBands, int lane) {
+  BandWS &ws = *wsp;
   const int M = 1 << LM, C = Yg != nullptr ? 2 : 1;
   const int B = shortBlocks ? M : 1;
   const int norm_offset = M * ob_ebands[start];
   float *norm = ws.norm, *norm2 = ws.norm + (M * ob_ebands[OB_NBANDS - 1] - norm_offset);
   int lowband_offset = 0, update_lowband = 1;
-  const int spread = ctx.spread;
+  const int spread = ws.c_spread, intensity = ws.c_intensity;
+#pragma unroll 1
   for (int i = start; i < end; i++) {
-    ctx.band = i;
     const int last = (i == end - 1);
     const int N = M * ob_ebands[i + 1] - M * ob_ebands[i];
-    int32_t tell = ctx.ec.tell_frac();
+    int32_t tell = m.ec.tell_frac();
     if (i != start) balance -= tell;
     int32_t remaining_bits = total_bits - tell - 1;
-    ctx.remaining_bits = remaining_bits;
+    m.remaining_bits = remaining_bits;
     int b;
     if (i <= codedBands - 1) {
       int32_t curr_balance = balance / OB_IMIN(3, codedBands - i);
@@ -540,7 +582,7 @@ OB_DEV void decode_all_bands(BandCtx &ctx, int start, int end, float *Xg, float 
       lowband_offset = i;
     // (special_hybrid_folding, bands.c:1572-1586, copies nothing when start == 0)
     const int tf_change = ws.tf_res[i];
-    ctx.tf_change = tf_change;
+    if (lane == 0) { ws.c_band = i; ws.c_tf_change = tf_change; }
     float *lowband_scratch = last ? nullptr : ws.scr;
     int effective_lowband = -1;
     unsigned x_cm, y_cm;
@@ -557,9 +599,10 @@ OB_DEV void decode_all_bands(BandCtx &ctx, int start, int end, float *Xg, float 
         y_cm |= ws.collapse[fold_i * C + C - 1];
       } while (++fold_i < fold_end);
     } else x_cm = y_cm = (1u << B) - 1;
-    if (dual_stereo && i == ctx.intensity) {
+    wsync();  // c_band / c_tf_change visible
+    if (dual_stereo && i == intensity) {
       dual_stereo = 0;
-      wsync();
+#pragma unroll 1
       for (int j = lane; j < M * ob_ebands[i] - norm_offset; j += 32) norm[j] = .5f * (norm[j] + norm2[j]);
       wsync();
     }
@@ -569,20 +612,24 @@ OB_DEV void decode_all_bands(BandCtx &ctx, int start, int end, float *Xg, float 
     float *lo1 = last ? nullptr : norm + M * ob_ebands[i] - norm_offset;
     float *lo2 = last ? nullptr : norm2 + M * ob_ebands[i] - norm_offset;
     if (dual_stereo) {
-      x_cm = decode_band_mono(ctx, X, N, b / 2, B, lb1, LM, lo1, 1.0f, lowband_scratch, x_cm);
-      y_cm = decode_band_mono(ctx, Y, N, b / 2, B, lb2, LM, lo2, 1.0f, lowband_scratch, y_cm);
+      m = decode_band_mono(m, wsp, X, N, b / 2, B, lb1, LM, lo1, 1.0f, lowband_scratch, x_cm);
+      x_cm = m.cm;
+      m = decode_band_mono(m, wsp, Y, N, b / 2, B, lb2, LM, lo2, 1.0f, lowband_scratch, y_cm);
+      y_cm = m.cm;
     } else {
-      if (C == 2) x_cm = decode_band_stereo(ctx, X, Y, N, b, B, lb1, LM, lo1, lowband_scratch, x_cm | y_cm);
-      else x_cm = decode_band_mono(ctx, X, N, b, B, lb1, LM, lo1, 1.0f, lowband_scratch, x_cm | y_cm);
-      y_cm = x_cm;
+      if (C == 2) m = decode_band_stereo(m, wsp, X, Y, N, b, B, lb1, LM, lo1, lowband_scratch, x_cm | y_cm);
+      else m = decode_band_mono(m, wsp, X, N, b, B, lb1, LM, lo1, 1.0f, lowband_scratch, x_cm | y_cm);
+      x_cm = y_cm = m.cm;
     }
     wsync();
     // the band is final: store it (coalesced) to the frame's spectrum in HBM
     {
       float *gx = Xg + M * ob_ebands[i];
+#pragma unroll 1
       for (int j = lane; j < N; j += 32) gx[j] = X[j];
       if (C == 2) {
         float *gy = Yg + M * ob_ebands[i];
+#pragma unroll 1
         for (int j = lane; j < N; j += 32) gy[j] = Y[j];
       }
     }
@@ -598,11 +645,9 @@ OB_DEV void decode_all_bands(BandCtx &ctx, int start, int end, float *Xg, float 
 
 // ---- bit allocation: celt/rate.c:249-646 (decode side).  Arrays in shared memory; warp-uniform,
 // lane 0 stores. -------------------------------------------------------------------------------
-OB_DEV int compute_allocation(BandCtx &ctx, int start, int end, int alloc_trim, int &intensity, int &dual_stereo,
-                              int32_t total, int32_t &balance_out, int C, int LM) {
-  BandWS &ws = *ctx.ws;
-  RangeDec &ec = ctx.ec;
-  const int lane = ctx.lane;
+OB_DEV int compute_allocation(RangeDec &ec, BandWS *wsp, int lane, int start, int end, int alloc_trim, int &intensity,
+                              int &dual_stereo, int32_t total, int32_t &balance_out, int C, int LM) {
+  BandWS &ws = *wsp;
   const int len = OB_NBANDS, nbAllocVectors = 11;
   int skip_start = start, intensity_rsv = 0, dual_stereo_rsv = 0;
   total = OB_IMAX(total, 0);
@@ -774,10 +819,9 @@ OB_DEV int compute_allocation(BandCtx &ctx, int start, int end, int alloc_trim, 
 }
 
 // celt/bands.c:259-353; X in HBM (this warp wrote it).  Rare path (transient frames that collapsed).
-OB_DEV void anti_collapse(BandCtx &ctx, float *Xg, int LM, int C, int size, int start, int end, const float *logE,
+OB_DEV void anti_collapse(BandWS *wsp, int lane, float *Xg, int LM, int C, int size, int start, int end, const float *logE,
                           const float *prev1logE, const float *prev2logE, uint32_t seed) {
-  BandWS &ws = *ctx.ws;
-  const int lane = ctx.lane;
+  BandWS &ws = *wsp;
   wsync();
   for (int i = start; i < end; i++) {
     int N0 = ob_ebands[i + 1] - ob_ebands[i];

@@ -166,12 +166,11 @@ OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *s
   float *Xg = p.X + (size_t)stream * 2 * OB_MAXN;
   float *Yg = Xg + N;
 
-  BandCtx ctx;
-  ctx.ws = ws;
-  ctx.lane = lane;
-  ctx.disable_inv = CC == 1;
-  ctx.seed = st->rng;
-  RangeDec &dec = ctx.ec;
+  BandMut bm;
+  bm.seed = st->rng;
+  bm.remaining_bits = 0;
+  bm.cm = 0;
+  RangeDec &dec = bm.ec;
   dec.init(pkt + foff, len);
 
   int32_t total_bits = len * 8;
@@ -268,7 +267,6 @@ OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *s
   tell = dec.tell();
   int spread = 2;
   if (tell + 4 <= total_bits) spread = dec.icdf(ob_spread_icdf, 5);
-  ctx.spread = spread;
   for (int i = lane; i < OB_NBANDS; i += 32) {  // init_caps, celt/celt.c:329-338
     int n = (ob_ebands[i + 1] - ob_ebands[i]) << LM;
     ws->cap[i] = (ob_cache_caps[OB_NBANDS * (2 * LM + C - 1) + i] + 64) * C * n >> 2;
@@ -304,8 +302,8 @@ OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *s
   bits -= anti_collapse_rsv;
   int intensity = 0, dual_stereo = 0;
   int32_t balance = 0;
-  const int codedBands = compute_allocation(ctx, start, end, alloc_trim, intensity, dual_stereo, bits, balance, C, LM);
-  ctx.intensity = intensity;
+  const int codedBands = compute_allocation(dec, ws, lane, start, end, alloc_trim, intensity, dual_stereo, bits, balance, C, LM);
+  if (lane == 0) { ws->c_intensity = intensity; ws->c_spread = spread; ws->c_disable_inv = CC == 1; }
   // ---- fine energy (celt/quant_bands.c:496-523): lane 0 owns the read-modify-write ----
   for (int i = start; i < end; i++) {
     int extra = ws->fine_quant[i];
@@ -322,8 +320,8 @@ OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *s
   // bands at or above `end` are never decoded: their spectrum is zero
   for (int j = M * ob_ebands[end] + lane; j < N; j += 32) { Xg[j] = 0.f; if (C == 2) Yg[j] = 0.f; }
   wsync();
-  decode_all_bands(ctx, start, end, Xg, C == 2 ? Yg : nullptr, shortBlocks, dual_stereo,
-                   len * (8 << OB_BITRES) - anti_collapse_rsv, balance, LM, codedBands);
+  decode_all_bands(bm, ws, start, end, Xg, C == 2 ? Yg : nullptr, shortBlocks, dual_stereo,
+                   len * (8 << OB_BITRES) - anti_collapse_rsv, balance, LM, codedBands, lane);
   int anti_collapse_on = 0;
   if (anti_collapse_rsv > 0) anti_collapse_on = dec.bits(1);
   // ---- unquant_energy_finalise (celt/quant_bands.c:525-547) ----
@@ -344,7 +342,7 @@ OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *s
   }
   wsync();
   if (anti_collapse_on)
-    anti_collapse(ctx, Xg, LM, C, N, start, end, ws->oldE, st->oldLogE, st->oldLogE2, ctx.seed);
+    anti_collapse(ws, lane, Xg, LM, C, N, start, end, ws->oldE, st->oldLogE, st->oldLogE2, bm.seed);
   wsync();
   // ---- state update (celt/celt_decoder.c:1530-1600), lane-parallel over the 42 energies ----
   for (int i = lane; i < 2 * OB_NBANDS; i += 32) {

@@ -16,24 +16,27 @@ OB_DEV float rsqrt_ref(float x) { return f_div(1.f, f_sqrt(x)); }  // 1.f/(float
 
 OB_DEV float warp_dot(const float *x, const float *y, int n, int lane) {
   float s = 0.f;
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) s += x[i] * y[i];
   return warp_sum(s);
 }
 
 // X *= rsqrt(eps + |X|^2) * gain   (celt/vq.c:695-722)
-OB_DEV void renormalise(float *X, int N, float gain, int lane) {
+OB_DEVNI void renormalise(float *X, int N, float gain, int lane) {
   wsync();
   float E = 1e-15f + warp_dot(X, X, N, lane);
   float g = rsqrt_ref(E) * gain;
+#pragma unroll 1
   for (int i = lane; i < N; i += 32) X[i] = g * X[i];
   wsync();
 }
 
 // One Haar butterfly level (celt/bands.c:623-636): pairs (stride*2j+i, stride*(2j+1)+i)
-OB_DEV void haar_step(float *X, int N0, int stride, int lane) {
+OB_DEVNI void haar_step(float *X, int N0, int stride, int lane) {
   wsync();
   int half = N0 >> 1;
   int npairs = half * stride;
+#pragma unroll 1
   for (int p = lane; p < npairs; p += 32) {
     int i = p % stride, j = p / stride;
     int a = stride * 2 * j + i, b = stride * (2 * j + 1) + i;
@@ -49,28 +52,32 @@ OB_TABLE unsigned char ob_hadamard_order[30] = {1, 0, 3, 0, 2, 1, 7, 0, 4, 3, 6,
                                                15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5};
 
 // celt/bands.c:574-597.  tmp: scratch of N floats.
-OB_DEV void deinterleave_hadamard(float *X, float *tmp, int N0, int stride, int hadamard, int lane) {
+OB_DEVNI void deinterleave_hadamard(float *X, float *tmp, int N0, int stride, int hadamard, int lane) {
   wsync();
   int N = N0 * stride;
+#pragma unroll 1
   for (int p = lane; p < N; p += 32) {
     int j = p / stride, i = p - j * stride;  // source index p = j*stride+i
     int row = hadamard ? ob_hadamard_order[stride - 2 + i] : i;
     tmp[row * N0 + j] = X[p];
   }
   wsync();
+#pragma unroll 1
   for (int p = lane; p < N; p += 32) X[p] = tmp[p];
   wsync();
 }
 // celt/bands.c:599-621
-OB_DEV void interleave_hadamard(float *X, float *tmp, int N0, int stride, int hadamard, int lane) {
+OB_DEVNI void interleave_hadamard(float *X, float *tmp, int N0, int stride, int hadamard, int lane) {
   wsync();
   int N = N0 * stride;
+#pragma unroll 1
   for (int p = lane; p < N; p += 32) {
     int j = p / stride, i = p - j * stride;  // destination index p = j*stride+i
     int row = hadamard ? ob_hadamard_order[stride - 2 + i] : i;
     tmp[p] = X[row * N0 + j];
   }
   wsync();
+#pragma unroll 1
   for (int p = lane; p < N; p += 32) X[p] = tmp[p];
   wsync();
 }
@@ -90,6 +97,7 @@ struct Affine { float a, b; };  // y -> a*y + b
 // inclusive scan of affine maps inside aligned groups of P lanes (P power of two)
 OB_DEV Affine group_scan(Affine m, int P, int lane) {
   int gl = lane & (P - 1);
+#pragma unroll 1
   for (int d = 1; d < P; d <<= 1) {
     float pa = shfl_up(m.a, d), pb = shfl_up(m.b, d);
     if (gl >= d) {  // compose: first the left map (pa,pb), then mine
@@ -104,26 +112,32 @@ OB_DEV Affine group_scan(Affine m, int P, int lane) {
 // back to back at X (vector v at X + v*len).  Chains = nvec*s.  T is scratch of nvec*len floats:
 // the forward sweep goes X -> T, the backward sweep T -> X (out of place: no read/write hazards
 // between lanes working on neighbouring segments).
-OB_DEV void rotate_pass(float *X, float *T, int len, int nvec, int s, float c, float sn, int lane) {
+OB_DEVNI void rotate_pass(float *X, float *T, int len, int nvec, int s, float c, float sn, int lane) {
   const int nch = nvec * s;
-  int P = 1;  // lanes per chain: largest power of two with P*nch <= 32
-  while (P * 2 * nch <= 32) P <<= 1;
-  const int G = 32 / P;  // chains in flight
-  const int gl = lane & (P - 1), g = lane / P;
+  int lgP = 0;  // lanes per chain P = 2^lgP: largest power of two with P*nch <= 32
+  while ((2 << lgP) * nch <= 32) lgP++;
+  const int P = 1 << lgP;
+  const int G = 32 >> lgP;  // chains in flight
+  const int gl = lane & (P - 1), g = lane >> lgP;
+  // x / s for 0 <= x < 5041 as a multiply-shift (s <= 13): exact, and keeps integer division
+  // (a ~30-instruction sequence each) out of the loops
+  const unsigned inv_s = 65535u / (unsigned)s + 1u;
   wsync();
   // ---------------- forward sweep X -> T : steps t = 0 .. L-2 ----------------
+#pragma unroll 1
   for (int q0 = 0; q0 < nch; q0 += G) {
     const int q = q0 + g;
     const bool live = q < nch;
-    const int v = live ? q / s : 0, r = live ? q - v * s : 0;
+    const int v = live ? (int)(((unsigned)q * inv_s) >> 16) : 0, r = live ? q - v * s : 0;
     const float *src = X + v * len + r;
     float *dst = T + v * len + r;
-    const int L = live ? (len - r + s - 1) / s : 0;
+    const int L = live ? (int)(((unsigned)(len - r + s - 1) * inv_s) >> 16) : 0;
     const int steps = L > 0 ? L - 1 : 0;
-    const int seg = (steps + P - 1) / P;
+    const int seg = (steps + P - 1) >> lgP;
     const int t0 = gl * seg < steps ? gl * seg : steps;
     const int t1 = t0 + seg < steps ? t0 + seg : steps;
     Affine m = {1.f, 0.f};
+#pragma unroll 1
     for (int t = t0; t < t1; t++) {  // a_{t+1} = sn*a_t + c*e_{t+1}
       float e1 = src[(t + 1) * s];
       m.b = sn * m.b + c * e1;
@@ -133,6 +147,7 @@ OB_DEV void rotate_pass(float *X, float *T, int len, int nvec, int s, float c, f
     float pa = shfl_up(inc.a, 1), pb = shfl_up(inc.b, 1);
     float e0 = L > 0 ? src[0] : 0.f;
     float a = gl == 0 ? e0 : pa * e0 + pb;  // a_{t0}
+#pragma unroll 1
     for (int t = t0; t < t1; t++) {
       float e1 = src[(t + 1) * s];
       dst[t * s] = c * a - sn * e1;
@@ -143,18 +158,20 @@ OB_DEV void rotate_pass(float *X, float *T, int len, int nvec, int s, float c, f
   }
   wsync();
   // ---------------- backward sweep T -> X : steps t = L-3 .. 0 ----------------
+#pragma unroll 1
   for (int q0 = 0; q0 < nch; q0 += G) {
     const int q = q0 + g;
     const bool live = q < nch;
-    const int v = live ? q / s : 0, r = live ? q - v * s : 0;
+    const int v = live ? (int)(((unsigned)q * inv_s) >> 16) : 0, r = live ? q - v * s : 0;
     const float *src = T + v * len + r;
     float *dst = X + v * len + r;
-    const int L = live ? (len - r + s - 1) / s : 0;
+    const int L = live ? (int)(((unsigned)(len - r + s - 1) * inv_s) >> 16) : 0;
     const int steps = L > 2 ? L - 2 : 0;  // step u handles t = L-3-u
-    const int seg = (steps + P - 1) / P;
+    const int seg = (steps + P - 1) >> lgP;
     const int t0 = gl * seg < steps ? gl * seg : steps;
     const int t1 = t0 + seg < steps ? t0 + seg : steps;
     Affine m = {1.f, 0.f};
+#pragma unroll 1
     for (int u = t0; u < t1; u++) {  // d <- c*f_t - sn*d
       float ft = src[(L - 3 - u) * s];
       m.b = c * ft - sn * m.b;
@@ -164,6 +181,7 @@ OB_DEV void rotate_pass(float *X, float *T, int len, int nvec, int s, float c, f
     float pa = shfl_up(inc.a, 1), pb = shfl_up(inc.b, 1);
     float d0 = L >= 2 ? src[(L - 2) * s] : 0.f;  // x2 of the first backward step
     float d = gl == 0 ? d0 : pa * d0 + pb;
+#pragma unroll 1
     for (int u = t0; u < t1; u++) {
       int t = L - 3 - u;
       float ft = src[t * s];
@@ -180,12 +198,12 @@ OB_DEV void rotate_pass(float *X, float *T, int len, int nvec, int s, float c, f
   wsync();
 }
 
-OB_DEV float cos_norm_ref(float x) {  // (float)cos((.5f*PI)*(x)) with PI a double, celt/mathops.h:229
+OB_DEVNI float cos_norm_ref(float x) {  // (float)cos((.5f*PI)*(x)) with PI a double, celt/mathops.h:229
   return (float)cos((.5f * 3.1415926535897931) * (double)x);
 }
 
 // exp_rotation(X, len, dir=-1, stride, K, spread): the decoder only ever undoes the rotation.
-OB_DEV void spread_unrotate(float *X, float *T, int len, int stride, int K, int spread, int lane) {
+OB_DEVNI void spread_unrotate(float *X, float *T, int len, int stride, int K, int spread, int lane) {
   if (2 * K >= len || spread == 0) return;
   int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
   float gain = f_div((float)len, (float)(len + factor * K));

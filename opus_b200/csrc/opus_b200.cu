@@ -16,7 +16,7 @@ using namespace ob;
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_bands(DecBandsParams p, int smem_per_warp) {
+extern "C" __global__ void __launch_bounds__(128, 5) ob_celt_dec_bands(DecBandsParams p, int smem_per_warp) {
   const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (stream >= p.n_streams) return;
   dec_bands_warp(p, stream, dyn_smem() + (size_t)(threadIdx.x >> 5) * smem_per_warp);
@@ -107,7 +107,9 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   OB_CUDA(cudaMalloc(&d->d_out, sizeof(int32_t) * (size_t)n_streams));
   OB_CUDA(cudaDeviceGetAttribute(&d->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_bands, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the band decoder recurses over partitions (depth <= 5)
   size_t stk = 0;
   cudaDeviceGetLimit(&stk, cudaLimitStackSize);
