@@ -29,8 +29,12 @@ FRAME = 960
 CH = 2
 PKT_STRIDE = 320
 # algorithmic HBM bytes per stream-frame (DESIGN.md "Roofline bookkeeping")
-BYTES_BANDS_KERNEL = 320 + 2 * 960 * 4 + 240 + 2 * 720   # packet in, X out, side info out, band state in+out
-BYTES_SYNTH_KERNEL = 2 * 960 * 4 + 240 + 2 * 960 * 4 + 2 * 960 * 2 + 2 * 2 * 60 * 4  # X in, side in, history out, PCM out, tails
+SCRIPT_BYTES = 2600  # typical script per frame at 128 kb/s: ~110 leaves x 16 B + ~220 node bytes + 21 band records x 24 B
+BYTES_KERNEL = {
+    'ob_celt_dec_entropy': 320 + 340 + SCRIPT_BYTES + 168 + 64,            # packet in, side out, script out, energies in, state
+    'ob_celt_dec_pvq': SCRIPT_BYTES + 340 + 2 * 960 * 4 + 2 * 672,         # script in, side in, X out, energy state in+out
+    'ob_celt_dec_synth': 2 * 960 * 4 + 340 + 2 * 960 * 4 + 2 * 960 * 2 + 2 * 2 * 60 * 4,  # X in, side in, history out, PCM out, tails
+}
 BYTES_WHOLE_FRAME = 320 + 2 * 960 * 2                    # packet in + int16 PCM out
 
 
@@ -279,7 +283,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     prof_steps = 5
     for i in range(prof_steps):
         step_device(i)
-    ms_bands, ms_synth, pairs = dec.get_timing()
+    kms, nfr = dec.get_timing()
     dec.set_timing(False)
     L.opusb200_host_free(hp)
     L.opusb200_host_free(ho)
@@ -292,20 +296,24 @@ def run_gpu_arm(args, rank, world, local_rank):
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    t_bands = ms_bands / pairs / 1000.0
-    t_synth = ms_synth / pairs / 1000.0
-    ach = BYTES_BANDS_KERNEL * n / t_bands / 1e9
-    roof = {'kernel': 'ob_celt_dec_bands', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-            'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': BYTES_BANDS_KERNEL * n,
-            'ms_per_launch': t_bands * 1000.0,
-            'note': 'latency/issue-bound entropy decoding; HBM fraction is reported as required, see DESIGN.md',
-            'other_kernels': {'ob_celt_dec_synth': {'ms_per_launch': t_synth * 1000.0,
-                                                   'achieved_GBs': BYTES_SYNTH_KERNEL * n / t_synth / 1e9,
-                                                   'frac': BYTES_SYNTH_KERNEL * n / t_synth / 1e9 / peak}}}
+    per = {}
+    for short, name in (('entropy', 'ob_celt_dec_entropy'), ('pvq', 'ob_celt_dec_pvq'), ('synth', 'ob_celt_dec_synth')):
+        t = kms[short] / nfr / 1000.0
+        gbs = BYTES_KERNEL[name] * n / t / 1e9
+        per[name] = {'ms_per_launch': t * 1000.0, 'achieved_GBs': gbs, 'frac': gbs / peak,
+                     'algorithmic_bytes_per_launch': BYTES_KERNEL[name] * n}
+    dom = max(per, key=lambda k: per[k]['ms_per_launch'])
+    roof = {'kernel': dom, 'bound': 'hbm', 'achieved': per[dom]['achieved_GBs'], 'peak': peak, 'unit': 'GB/s',
+            'frac': per[dom]['frac'], 'traffic': None, 'peak_source': peak_src,
+            'algorithmic_bytes_per_launch': per[dom]['algorithmic_bytes_per_launch'],
+            'ms_per_launch': per[dom]['ms_per_launch'],
+            'note': 'entropy/PVQ kernels are latency- and issue-bound (serial range decoding), not HBM-bound; '
+                    'the HBM fraction is reported as the contract requires, see DESIGN.md section 4',
+            'all_kernels': per}
     prof = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(prof):
         try:
-            roof['traffic'] = json.load(open(prof)).get('ob_celt_dec_bands_dram_bytes_per_launch')
+            roof['traffic'] = json.load(open(prof)).get(dom + '_dram_bytes_per_launch')
         except Exception:
             pass
     # ---- CPU baseline: bounded sample on the host cores ----

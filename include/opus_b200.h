@@ -88,10 +88,10 @@ int64_t opusb200_decoder_launch_count(const OpusB200Decoder *dec);
 
 /* Profiling aid: when enabled, every kernel launch is bracketed by CUDA events on the decoder's
  * stream and the stream is drained after each frame (so do not enable it for throughput runs).
- * get_timing returns the accumulated device milliseconds of the band-decode and synthesis kernels
- * and the number of (bands, synth) launch pairs they cover. */
+ * get_timing returns the accumulated device milliseconds of the three kernels (ms_kernels[3]:
+ * entropy, pvq, synthesis) and the number of frame steps they cover. */
 int opusb200_decoder_set_timing(OpusB200Decoder *dec, int enable);
-int opusb200_decoder_get_timing(OpusB200Decoder *dec, double *ms_bands, double *ms_synth, int64_t *launch_pairs);
+int opusb200_decoder_get_timing(OpusB200Decoder *dec, double *ms_kernels, int64_t *frames);
 
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);

@@ -78,8 +78,7 @@ def lib():
         L.opusb200_decoder_launch_count.argtypes = [vp]
         L.opusb200_decoder_launch_count.restype = i64
         L.opusb200_decoder_set_timing.argtypes = [vp, ctypes.c_int]
-        L.opusb200_decoder_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
-                                                  ctypes.POINTER(i64)]
+        L.opusb200_decoder_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

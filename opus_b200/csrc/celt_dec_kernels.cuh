@@ -1,393 +1,19 @@
-// celt_dec_kernels.cuh — the two kernels of the batched CELT decoder.
+// celt_dec_kernels.cuh — the kernels of the batched CELT decoder.
 //
-//   ob_celt_dec_bands   : one WARP per stream.  Opus packet -> (frame k of the packet) -> range
-//                         decode + band decode -> normalised spectrum X[C][N] (HBM) + ObFrameSide.
-//                         Latency/issue bound (serial entropy decoding).
-//   ob_celt_dec_synth   : one CTA per stream, one warp per output channel.  X * band gains ->
-//                         inverse MDCT (+TDAC overlap) -> comb post-filter -> de-emphasis -> PCM.
-//                         HBM bound (streams X in, history + PCM out).
+//   A1 ob_celt_dec_entropy : one THREAD per stream (celt_dec_entropy.cuh).  Packet framing, range
+//                            decoding, energies, allocation, band-tree control -> ObScript + ObFrameSide.
+//   A2 ob_celt_dec_pvq     : one WARP per stream (celt_dec_pvq.cuh).  Script -> normalised spectrum
+//                            X[C][N]: PVQ leaves lane-parallel, then bands in order.
+//   B  ob_celt_dec_synth   : one CTA per stream, one warp per output channel (below).  X * band
+//                            gains -> inverse MDCT (+TDAC overlap) -> comb post-filter -> de-emphasis
+//                            -> PCM.  HBM bound.
 //
 // Written against simt.cuh so the same source also runs under the test-only host emulator.
 #pragma once
-#include "celt_dec_core.cuh"
+#include "celt_dec_entropy.cuh"
+#include "celt_dec_pvq.cuh"
 
 namespace ob {
-
-struct DecBandsParams {
-  const unsigned char *packets;  // [n_streams][pkt_stride], Opus packets (with TOC)
-  const int32_t *pkt_len;        // [n_streams], <=0 : nothing to decode for this stream
-  int pkt_stride;
-  int pkt_cap;      // shared-memory bytes reserved per warp for the packet (>= max len, multiple of 16)
-  int n_streams;
-  int channels;     // output channels (decoder was created with), 1 or 2
-  int frame_index;  // which frame of a multi-frame packet to decode in this launch
-  ObDecBandState *state;  // [n_streams]
-  ObFrameSide *side;      // [n_streams]
-  float *X;               // [n_streams][2][960] normalised spectrum of this frame
-  int32_t *out_samples;   // [n_streams] or null: running per-stream result (samples/channel or error)
-  int max_samples;        // per-channel capacity of each stream's pcm area
-};
-
-// src/opus.c:183-201 (parse_size)
-OB_DEV int parse_size(const unsigned char *d, int len, int &size) {
-  if (len < 1) { size = -1; return -1; }
-  if (d[0] < 252) { size = d[0]; return 1; }
-  if (len < 2) { size = -1; return -1; }
-  size = 4 * d[1] + d[0];
-  return 2;
-}
-
-// Locate frame `k` of an Opus packet (RFC 6716 section 3.2; src/opus.c:224-420).
-// Returns number of frames in the packet (<0 on a malformed packet); off/flen describe frame k.
-OB_DEV int locate_frame(const unsigned char *data, int len, int k, int &off, int &flen) {
-  int pos = 0, count, cbr = 0, last_size, sz0 = 0;
-  if (len <= 0) return -4;
-  int toc = data[0];
-  int framesize = (48000 << ((toc >> 3) & 3)) / 400;  // CELT-only TOC (checked by the caller)
-  pos = 1; len--;
-  last_size = len;
-  off = 0; flen = 0;
-  switch (toc & 3) {
-    case 0: count = 1; break;
-    case 1:
-      count = 2; cbr = 1;
-      if (len & 1) return -4;
-      last_size = len / 2;
-      sz0 = last_size;
-      break;
-    case 2: {
-      count = 2;
-      int bytes = parse_size(data + pos, len, sz0);
-      len -= bytes;
-      if (sz0 < 0 || sz0 > len) return -4;
-      pos += bytes;
-      last_size = len - sz0;
-      break;
-    }
-    default: {
-      if (len < 1) return -4;
-      int ch = data[pos++];
-      count = ch & 0x3F;
-      if (count <= 0 || framesize * count > 5760) return -4;
-      len--;
-      if (ch & 0x40) {
-        int p;
-        do {
-          if (len <= 0) return -4;
-          p = data[pos++];
-          len--;
-          int t = p == 255 ? 254 : p;
-          len -= t;
-        } while (p == 255);
-      }
-      if (len < 0) return -4;
-      cbr = !(ch & 0x80);
-      if (!cbr) {
-        // VBR: sizes of the first count-1 frames precede the frames
-        last_size = len;
-        int accum = 0, mysize = -1;
-        for (int i = 0; i < count - 1; i++) {
-          int sz;
-          int bytes = parse_size(data + pos, len, sz);
-          len -= bytes;
-          if (sz < 0 || sz > len) return -4;
-          pos += bytes;
-          last_size -= bytes + sz;
-          if (i < k) accum += sz;
-          if (i == k) mysize = sz;
-        }
-        if (last_size < 0) return -4;
-        if (last_size > 1275) return -4;
-        if (k < count) { off = pos + accum; flen = k == count - 1 ? last_size : mysize; }
-        return count;
-      } else {
-        last_size = len / count;
-        if (last_size * count != len) return -4;
-        sz0 = last_size;
-      }
-      break;
-    }
-  }
-  if (last_size > 1275) return -4;
-  if (k < count) {
-    if (cbr || count == 1) { off = pos + k * last_size; flen = last_size; }
-    else { off = pos + (k == 0 ? 0 : sz0); flen = k == 0 ? sz0 : last_size; }  // code 2
-  }
-  return count;
-}
-
-// ------------------------------------------------------------------------------------------
-// Kernel A body: one warp, one stream.
-// ------------------------------------------------------------------------------------------
-OB_DEV void dec_bands_warp(const DecBandsParams &p, int stream, unsigned char *smem_warp) {
-  const int lane = lane_id();
-  BandWS *ws = (BandWS *)smem_warp;
-  unsigned char *pkt = smem_warp + ((sizeof(BandWS) + 15) & ~(size_t)15);
-  ObFrameSide *side = p.side + stream;
-  ObDecBandState *st = p.state + stream;
-  const int CC = p.channels;
-  int plen = p.pkt_len[stream];
-  if (plen > p.pkt_cap) plen = -1;
-  if (plen <= 0) {
-    if (lane == 0) {
-      side->status = plen < 0 ? -1 : 0;
-      if (p.frame_index == 0) { st->last_status = side->status; if (p.out_samples) p.out_samples[stream] = side->status; }
-    }
-    return;
-  }
-  // stage the packet in shared memory (coalesced)
-  {
-    const unsigned char *g = p.packets + (size_t)stream * p.pkt_stride;
-    for (int i = lane; i < plen; i += 32) pkt[i] = g[i];
-  }
-  wsync();
-  const int toc = pkt[0];
-  int foff, flen;
-  int count = locate_frame(pkt, plen, p.frame_index, foff, flen);
-  int status = 1;
-  if (count < 0) status = count;                      // OPUS_INVALID_PACKET
-  else if (!(toc & 0x80)) status = -5;                // SILK / hybrid: OPUS_UNIMPLEMENTED here
-  else if (p.frame_index >= count) status = 0;        // no such frame in this packet
-  else if (flen <= 1) status = -5;                    // lost / DTX frame: PLC not implemented
-  const int LM = (toc >> 3) & 3;
-  const int N = OB_SHORT_N << LM, M = 1 << LM;
-  if (status > 0 && (p.frame_index + 1) * N > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // OPUS_BUFFER_TOO_SMALL
-  if (status <= 0) {
-    if (lane == 0) {
-      side->status = status;
-      if (status < 0 || p.frame_index == 0) { st->last_status = status; if (p.out_samples) p.out_samples[stream] = status; }
-    }
-    return;
-  }
-  const int C = (toc & 4) ? 2 : 1;
-  const int bw = (toc >> 5) & 3;
-  const int start = 0, end = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;
-  const int len = flen;
-  float *Xg = p.X + (size_t)stream * 2 * OB_MAXN;
-  float *Yg = Xg + N;
-
-  BandMut bm;
-  bm.seed = st->rng;
-  bm.remaining_bits = 0;
-  bm.cm = 0;
-  RangeDec &dec = bm.ec;
-  dec.init(pkt + foff, len);
-
-  int32_t total_bits = len * 8;
-  int32_t tell = dec.tell();
-  int silence = 0;
-  if (tell >= total_bits) silence = 1;
-  else if (tell == 1) silence = dec.bit_logp(15);
-  if (silence) {
-    tell = len * 8;
-    dec.nbits_total += tell - dec.tell();
-  }
-  int pf_pitch = 0, pf_tapset = 0;
-  float pf_gain = 0.f;
-  if (start == 0 && tell + 16 <= total_bits) {
-    if (dec.bit_logp(1)) {
-      int octave = dec.uint(6);
-      pf_pitch = (16 << octave) + dec.bits(4 + octave) - 1;
-      int qg = dec.bits(3);
-      if (dec.tell() + 2 <= total_bits) pf_tapset = dec.icdf(ob_tapset_icdf, 2);
-      pf_gain = .09375f * (qg + 1);
-    }
-    tell = dec.tell();
-  }
-  int isTransient = 0;
-  if (LM > 0 && tell + 3 <= total_bits) {
-    isTransient = dec.bit_logp(3);
-    tell = dec.tell();
-  }
-  const int shortBlocks = isTransient ? M : 0;
-  const int intra = tell + 3 <= total_bits ? dec.bit_logp(3) : 0;
-
-  // ---- coarse energy (celt/quant_bands.c:431-494): reads the previous frame's energies from the
-  // stream state (HBM, read-only here), writes this frame's into shared memory ----
-  {
-    const unsigned char *prob = ob_e_prob + (LM * 2 + intra) * 42;
-    float prev0 = 0.f, prev1 = 0.f, coef, beta;
-    if (intra) { coef = 0.f; beta = 4915 / 32768.f; }
-    else {
-      beta = LM == 0 ? 30147 / 32768.f : LM == 1 ? 22282 / 32768.f : LM == 2 ? 12124 / 32768.f : 6554 / 32768.f;
-      coef = LM == 0 ? 29440 / 32768.f : LM == 1 ? 26112 / 32768.f : LM == 2 ? 21248 / 32768.f : 16384 / 32768.f;
-    }
-    const int32_t budget = dec.storage * 8;
-    const float *oldg = st->oldEBands;
-    for (int i = lane; i < 2 * OB_NBANDS; i += 32) ws->oldE[i] = oldg[i];  // bands outside [start,end) keep old values
-    wsync();
-    for (int i = start; i < end; i++) {
-      for (int c = 0; c < C; c++) {
-        int qi;
-        int32_t t = dec.tell();
-        if (budget - t >= 15) {
-          int pi = 2 * OB_IMIN(i, 20);
-          qi = dec.laplace(prob[pi] << 7, prob[pi + 1] << 6);
-        } else if (budget - t >= 2) {
-          qi = dec.icdf(ob_small_energy_icdf, 2);
-          qi = (qi >> 1) ^ -(qi & 1);
-        } else if (budget - t >= 1) {
-          qi = -dec.bit_logp(1);
-        } else qi = -1;
-        float q = (float)qi;
-        float o = oldg[i + c * OB_NBANDS];
-        if (C == 1) { float o2 = oldg[OB_NBANDS + i]; o = o > o2 ? o : o2; }  // celt_decoder.c:1306-1310
-        o = o > -9.f ? o : -9.f;
-        float prev = c ? prev1 : prev0;
-        float tmp = coef * o + prev + q;
-        prev = prev + q - beta * q;
-        if (c) prev1 = prev; else prev0 = prev;
-        if (lane == 0) ws->oldE[i + c * OB_NBANDS] = tmp;
-      }
-    }
-  }
-  // ---- tf_decode (celt/celt_decoder.c:513-547) ----
-  {
-    int curr = 0, tf_select = 0, tf_changed = 0;
-    uint32_t budget = dec.storage * 8, t = dec.tell();
-    int logp = isTransient ? 2 : 4;
-    int tf_select_rsv = LM > 0 && t + logp + 1 <= budget;
-    budget -= tf_select_rsv;
-    uint32_t raw = 0;  // per-band raw flags packed into a register
-    for (int i = start; i < end; i++) {
-      if (t + logp <= budget) {
-        curr ^= dec.bit_logp(logp);
-        t = dec.tell();
-        tf_changed |= curr;
-      }
-      raw |= (uint32_t)curr << i;
-      logp = isTransient ? 4 : 5;
-    }
-    if (tf_select_rsv && ob_tf_select[LM * 8 + 4 * isTransient + 0 + tf_changed] !=
-                             ob_tf_select[LM * 8 + 4 * isTransient + 2 + tf_changed])
-      tf_select = dec.bit_logp(1);
-    for (int i = start + lane; i < end; i += 32)
-      ws->tf_res[i] = ob_tf_select[LM * 8 + 4 * isTransient + 2 * tf_select + ((raw >> i) & 1)];
-  }
-  tell = dec.tell();
-  int spread = 2;
-  if (tell + 4 <= total_bits) spread = dec.icdf(ob_spread_icdf, 5);
-  for (int i = lane; i < OB_NBANDS; i += 32) {  // init_caps, celt/celt.c:329-338
-    int n = (ob_ebands[i + 1] - ob_ebands[i]) << LM;
-    ws->cap[i] = (ob_cache_caps[OB_NBANDS * (2 * LM + C - 1) + i] + 64) * C * n >> 2;
-    ws->offsets[i] = 0;
-  }
-  wsync();
-  // ---- dynalloc (celt/celt_decoder.c:1412-1442) ----
-  {
-    int dynalloc_logp = 6;
-    total_bits <<= OB_BITRES;
-    int32_t tf = dec.tell_frac();
-    for (int i = start; i < end; i++) {
-      int width = C * (ob_ebands[i + 1] - ob_ebands[i]) << LM;
-      int quanta = OB_IMIN(width << OB_BITRES, OB_IMAX(6 << OB_BITRES, width));
-      int loop_logp = dynalloc_logp, boost = 0;
-      int capi = ws->cap[i];
-      while (tf + (loop_logp << OB_BITRES) < total_bits && boost < capi) {
-        int flag = dec.bit_logp(loop_logp);
-        tf = dec.tell_frac();
-        if (!flag) break;
-        boost += quanta;
-        total_bits -= quanta;
-        loop_logp = 1;
-      }
-      if (lane == 0) ws->offsets[i] = boost;
-      if (boost > 0) dynalloc_logp = OB_IMAX(2, dynalloc_logp - 1);
-    }
-    tell = tf;
-  }
-  const int alloc_trim = tell + (6 << OB_BITRES) <= total_bits ? dec.icdf(ob_trim_icdf, 7) : 5;
-  int32_t bits = (((int32_t)len * 8) << OB_BITRES) - (int32_t)dec.tell_frac() - 1;
-  const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;
-  bits -= anti_collapse_rsv;
-  int intensity = 0, dual_stereo = 0;
-  int32_t balance = 0;
-  const int codedBands = compute_allocation(dec, ws, lane, start, end, alloc_trim, intensity, dual_stereo, bits, balance, C, LM);
-  if (lane == 0) { ws->c_intensity = intensity; ws->c_spread = spread; ws->c_disable_inv = CC == 1; }
-  // ---- fine energy (celt/quant_bands.c:496-523): lane 0 owns the read-modify-write ----
-  for (int i = start; i < end; i++) {
-    int extra = ws->fine_quant[i];
-    if (extra <= 0) continue;
-    if (dec.tell() + C * extra > (int32_t)dec.storage * 8) continue;
-    for (int c = 0; c < C; c++) {
-      int q2 = dec.bits(extra);
-      float offset = (q2 + .5f) * (1 << (14 - extra)) * (1.f / 16384) - .5f;
-      if (lane == 0) ws->oldE[i + c * OB_NBANDS] += offset;
-    }
-  }
-  wsync();
-  for (int i = lane; i < 2 * OB_NBANDS; i += 32) ws->collapse[i] = 0;
-  // bands at or above `end` are never decoded: their spectrum is zero
-  for (int j = M * ob_ebands[end] + lane; j < N; j += 32) { Xg[j] = 0.f; if (C == 2) Yg[j] = 0.f; }
-  wsync();
-  decode_all_bands(bm, ws, start, end, Xg, C == 2 ? Yg : nullptr, shortBlocks, dual_stereo,
-                   len * (8 << OB_BITRES) - anti_collapse_rsv, balance, LM, codedBands, lane);
-  int anti_collapse_on = 0;
-  if (anti_collapse_rsv > 0) anti_collapse_on = dec.bits(1);
-  // ---- unquant_energy_finalise (celt/quant_bands.c:525-547) ----
-  {
-    int bits_left = len * 8 - dec.tell();
-    for (int prio = 0; prio < 2; prio++) {
-      for (int i = start; i < end && bits_left >= C; i++) {
-        int fq = ws->fine_quant[i];
-        if (fq >= 8 || ws->fine_prio[i] != prio) continue;
-        for (int c = 0; c < C; c++) {
-          int q2 = dec.bits(1);
-          float offset = (q2 - .5f) * (1 << (14 - fq - 1)) * (1.f / 16384);
-          if (lane == 0) ws->oldE[i + c * OB_NBANDS] += offset;
-          bits_left--;
-        }
-      }
-    }
-  }
-  wsync();
-  if (anti_collapse_on)
-    anti_collapse(ws, lane, Xg, LM, C, N, start, end, ws->oldE, st->oldLogE, st->oldLogE2, bm.seed);
-  wsync();
-  // ---- state update (celt/celt_decoder.c:1530-1600), lane-parallel over the 42 energies ----
-  for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
-    const int band = i >= OB_NBANDS ? i - OB_NBANDS : i, c = i >= OB_NBANDS;
-    float e = ws->oldE[i];
-    if (silence && i < C * OB_NBANDS) e = -28.f;
-    if (C == 1 && c == 1) { e = ws->oldE[band]; if (silence) e = -28.f; }
-    float l1 = st->oldLogE[i], l2 = st->oldLogE2[i], bg = st->backgroundLogE[i];
-    side->bandE[i] = e;  // what the synthesis uses (before the out-of-range reset below)
-    if (!isTransient) { l2 = l1; l1 = e; }
-    else l1 = l1 < e ? l1 : e;
-    float inc = OB_IMIN(160, M) * 0.001f;
-    float a = bg + inc;
-    bg = a < e ? a : e;
-    if (band < start || band >= end) { e = 0.f; l1 = l2 = -28.f; }
-    st->oldEBands[i] = e;
-    st->oldLogE[i] = l1;
-    st->oldLogE2[i] = l2;
-    st->backgroundLogE[i] = bg;
-  }
-  if (lane == 0) {
-    int ok = dec.tell() > 8 * len ? -3 : N;  // OPUS_INTERNAL_ERROR
-    side->status = ok;
-    side->LM = LM; side->transient = isTransient; side->C = C; side->silence = silence; side->end_band = end;
-    // post-filter parameter pipeline (celt_decoder.c:1540-1563)
-    int T_old = OB_IMAX(st->pf_period_old, 15), T_cur = OB_IMAX(st->pf_period, 15);
-    side->pf_T[0] = T_old; side->pf_T[1] = T_cur; side->pf_T[2] = pf_pitch;
-    side->pf_g[0] = st->pf_gain_old; side->pf_g[1] = st->pf_gain; side->pf_g[2] = pf_gain;
-    side->pf_tap[0] = st->pf_tapset_old; side->pf_tap[1] = st->pf_tapset; side->pf_tap[2] = pf_tapset;
-    float g_cur = st->pf_gain;
-    int tap_cur = st->pf_tapset;
-    st->pf_period_old = T_cur; st->pf_gain_old = g_cur; st->pf_tapset_old = tap_cur;
-    st->pf_period = pf_pitch; st->pf_gain = pf_gain; st->pf_tapset = pf_tapset;
-    if (LM != 0) { st->pf_period_old = pf_pitch; st->pf_gain_old = pf_gain; st->pf_tapset_old = pf_tapset; }
-    st->rng = dec.rng;
-    st->final_range = dec.rng;
-    if (dec.error) st->error = 1;
-    st->last_status = ok;
-    if (p.out_samples) {
-      if (ok < 0) p.out_samples[stream] = ok;
-      else if (p.frame_index == 0) p.out_samples[stream] = ok;
-      else if (p.out_samples[stream] >= 0) p.out_samples[stream] += ok;
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // Kernel B: synthesis.  One CTA per stream; warp w produces output channel w.

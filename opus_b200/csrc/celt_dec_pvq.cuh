@@ -1,0 +1,600 @@
+// celt_dec_pvq.cuh — kernel A2: ONE WARP PER STREAM turns the entropy stage's script into the
+// frame's normalised spectrum X[C][N].
+//
+// Phase 1 (lane per leaf): every PVQ leaf of the frame is independent given its codeword index, so
+//   lane l handles leaves l, l+32, ...: index -> pulses (celt/cwrs.c:467-541), unit-norm scaling
+//   (celt/vq.c:150-181), inverse spreading rotation (celt/vq.c:75-147) and the collapse mask
+//   (celt/vq.c:183-203), each run SEQUENTIALLY by its lane in the reference's exact order — the
+//   serial Givens chains that cannot be split across lanes without changing the rounding become
+//   32 chains in flight, and the results are bit-identical to the scalar reference.
+// Phase 2 (band order, warp cooperative): fill / collapse-mask propagation through the partition
+//   tree, zero / noise / folded leaves (the LCG and the folding source are band-order dependent),
+//   Haar and Hadamard (de)interleaving, mid/side merge, the folding buffer, anti-collapse; one
+//   coalesced store of the whole frame at the end; the per-stream energy state update.
+//
+// Reference (resynthesis side only): celt/bands.c:259-353, 407-466, 574-636, 934-1923,
+// celt/vq.c:75-203,621-722, celt/cwrs.c:467-541, celt/celt_decoder.c:1527-1600.
+#pragma once
+#include "celt_types.h"
+#include "celt_vec.cuh"
+#include "celt_tables_data.h"
+
+namespace ob {
+
+#ifndef OB_BITRES
+#define OB_BITRES 3
+#define OB_IMIN(a, b) ((a) < (b) ? (a) : (b))
+#define OB_IMAX(a, b) ((a) > (b) ? (a) : (b))
+#endif
+
+struct DecPvqParams {
+  const ObFrameSide *side;  // [n_streams]
+  const ObScript *script;   // [n_streams]
+  ObDecBandState *state;    // [n_streams]
+  float *X;                 // [n_streams][2][960]
+  int n_streams;
+};
+
+// Shared by the warps of a CTA: the PVQ U(n,k) table (celt/cwrs.c:197-211), ~5 KB
+struct PvqShared {
+  uint32_t u[1272];
+  short rowoff[16];
+};
+// Per warp
+struct PvqWS {
+  float X[2 * OB_MAXN];  // the frame's normalised spectrum, [C][N]
+  float norm[2 * 624];   // folding source
+  float scr[176];        // lowband scratch
+  float tmp[176];        // permutation scratch
+  unsigned char leaf_cm[OB_MAX_LEAVES];
+  unsigned char collapse[2 * OB_NBANDS];
+  unsigned char pad[6];
+};
+
+OB_DEV float exp2_ref(float x) { return (float)exp(0.6931471805599453094 * (double)x); }  // celt/mathops.h:347
+
+OB_DEV uint32_t pvq_u_s(const PvqShared *t, int n, int k) {
+  int a = OB_IMIN(n, k), b = OB_IMAX(n, k);
+  return t->u[t->rowoff[a] + b];
+}
+
+// index -> pulses written as floats; returns |y|^2 (exact integer).  celt/cwrs.c:467-541
+OB_DEV int pvq_index_to_pulses_f(const PvqShared *t, int n, int k, uint32_t i, float *y) {
+  uint32_t p;
+  int s, k0, val, yy = 0;
+#pragma unroll 1
+  while (n > 2) {
+    uint32_t q;
+    if (k >= n) {
+      p = pvq_u_s(t, n, k + 1);
+      s = -(int)(i >= p);
+      i -= p & s;
+      k0 = k;
+      q = pvq_u_s(t, n, n);
+      if (q > i) {
+        k = n;
+#pragma unroll 1
+        do p = pvq_u_s(t, --k, n); while (p > i);
+      } else {
+#pragma unroll 1
+        for (p = pvq_u_s(t, n, k); p > i; p = pvq_u_s(t, n, k)) k--;
+      }
+      i -= p;
+      val = (k0 - k + s) ^ s;
+      *y++ = (float)val;
+      yy += val * val;
+    } else {
+      p = pvq_u_s(t, k, n);
+      q = pvq_u_s(t, k + 1, n);
+      if (p <= i && i < q) {
+        i -= p;
+        *y++ = 0.f;
+      } else {
+        s = -(int)(i >= q);
+        i -= q & s;
+        k0 = k;
+#pragma unroll 1
+        do p = pvq_u_s(t, --k, n); while (p > i);
+        i -= p;
+        val = (k0 - k + s) ^ s;
+        *y++ = (float)val;
+        yy += val * val;
+      }
+    }
+    n--;
+  }
+  p = 2 * k + 1;
+  s = -(int)(i >= p);
+  i -= p & s;
+  k0 = k;
+  k = (i + 1) >> 1;
+  if (k) i -= 2 * k - 1;
+  val = (k0 - k + s) ^ s;
+  *y++ = (float)val;
+  yy += val * val;
+  s = -(int)i;
+  val = (k + s) ^ s;
+  *y = (float)val;
+  yy += val * val;
+  return yy;
+}
+
+// celt/vq.c:75-102, one lane, reference order
+OB_DEV void rotate_seq(float *X, int len, int stride, float c, float s) {
+  const float ms = -s;
+  float *p = X;
+#pragma unroll 1
+  for (int i = 0; i < len - stride; i++) {
+    float x1 = p[0], x2 = p[stride];
+    p[stride] = c * x2 + s * x1;
+    *p++ = c * x1 + ms * x2;
+  }
+  p = &X[len - 2 * stride - 1];
+#pragma unroll 1
+  for (int i = len - 2 * stride - 1; i >= 0; i--) {
+    float x1 = p[0], x2 = p[stride];
+    p[stride] = c * x2 + s * x1;
+    *p-- = c * x1 + ms * x2;
+  }
+}
+// celt/vq.c:104-147 with dir = -1
+OB_DEV void unrotate_seq(float *X, int len, int stride, int K, int spread) {
+  if (2 * K >= len || spread == 0) return;
+  const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
+  float gain = f_div((float)len, (float)(len + factor * K));
+  float theta = .5f * (gain * gain);
+  float c = cos_norm_ref(theta);
+  float s = cos_norm_ref(1.0f - theta);
+  int stride2 = 0;
+  if (len >= 8 * stride) {
+    stride2 = 1;
+    while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+  }
+  len = (unsigned)len / (unsigned)stride;
+#pragma unroll 1
+  for (int i = 0; i < stride; i++) {
+    if (stride2) rotate_seq(X + i * len, len, stride2, s, c);
+    rotate_seq(X + i * len, len, 1, c, s);
+  }
+}
+
+// ---- phase 1 -------------------------------------------------------------------------------
+OB_DEV void pvq_phase1(const PvqShared *tab, PvqWS *ws, const ObScript *sc, int n_leaves, int spread, int Nframe, int lane) {
+#pragma unroll 1
+  for (int l = lane; l < n_leaves; l += 32) {
+    const ObLeaf lf = sc->leaves[l];
+    float *X = ws->X + lf.off;
+    if (lf.kind == 0) {
+      const int n = lf.n, K = lf.K, B = lf.B;
+      int yy = pvq_index_to_pulses_f(tab, n, K, lf.index, X);
+      float g = rsqrt_ref((float)yy) * lf.gain;
+      unsigned mask = 1;
+      if (B > 1) {  // extract_collapse_mask
+        mask = 0;
+        const int N0 = (unsigned)n / (unsigned)B;
+        int j = 0;
+#pragma unroll 1
+        for (int blk = 0; blk < B; blk++) {
+          int nz = 0;
+#pragma unroll 1
+          for (int e = 0; e < N0; e++, j++) nz |= X[j] != 0.f;
+          mask |= (unsigned)nz << blk;
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < n; j++) X[j] = X[j] * g;
+      unrotate_seq(X, n, B, K, spread);
+      ws->leaf_cm[l] = (unsigned char)mask;
+    } else if (lf.kind == 2) {  // N == 1 bands: a sign per channel (celt/bands.c:934-968)
+      X[0] = (lf.index & 1) ? -1.f : 1.f;
+      if (lf.K == 2) X[Nframe] = (lf.index & 2) ? -1.f : 1.f;
+      ws->leaf_cm[l] = 1;
+    }
+  }
+  wsync();
+}
+
+// ---- phase 2 -------------------------------------------------------------------------------
+struct Cursor {  // warp-uniform walk state over the script
+  const ObScript *sc;
+  int node, leaf;
+  uint32_t seed;
+};
+
+// One band part (celt/bands.c:973-1176 resynthesis side): walk the partition tree, propagate
+// `fill`, produce the zero / noise / folded leaves, combine collapse masks.  Xp: the part's vector
+// in ws->X (leaf offsets are frame-absolute; part_off is Xp's frame offset).
+OB_DEVNI unsigned walk_partition(Cursor &cur, PvqWS *ws, int part_off, int B_root, const float *lowband, int fill_root, int lane) {
+  struct WF { int fill, B, B0; unsigned cm; int stage, yfirst; };
+  WF st[6];
+  int sp = 1;
+  st[0].fill = fill_root; st[0].B = B_root; st[0].B0 = B_root; st[0].cm = 0; st[0].stage = 0; st[0].yfirst = 0;
+  unsigned result = 0;
+#pragma unroll 1
+  while (sp > 0) {
+    WF &f = st[sp - 1];
+    unsigned done_cm = 0;
+    int done = 0;
+    if (f.stage == 0) {
+      const unsigned nb = cur.sc->nodes[cur.node++];
+      if (nb & 0x80u) {
+        int fill = f.fill;
+        const int B0 = f.B;
+        if (B0 == 1) fill = (fill & 1) | (fill << 1);
+        const int B = (B0 + 1) >> 1;
+        const int cls = nb & 3;
+        if (cls == 0) fill &= (1 << B) - 1;
+        else if (cls == 1) fill &= ((1 << B) - 1) << B;
+        f.fill = fill; f.B = B; f.B0 = B0; f.yfirst = (nb & 4) != 0; f.stage = 1; f.cm = 0;
+        WF &c = st[sp++];
+        c.stage = 0; c.B = B; c.cm = 0; c.fill = f.yfirst ? fill >> B : fill;
+      } else {
+        const int l = cur.leaf++;
+        const ObLeaf lf = cur.sc->leaves[l];
+        if (lf.kind != 1) {
+          done_cm = ws->leaf_cm[l];
+        } else {
+          const int n = lf.n, B = f.B;
+          float *X = ws->X + lf.off;
+          const unsigned cm_mask = (unsigned)(1UL << B) - 1;
+          const int fill = f.fill & cm_mask;
+          wsync();
+          if (!fill) {
+#pragma unroll 1
+            for (int j = lane; j < n; j += 32) X[j] = 0.f;
+            wsync();
+          } else {
+            uint32_t seed = cur.seed;
+            if (!lf.lb || lowband == nullptr) {
+#pragma unroll 1
+              for (int j = 0; j < n; j++) {
+                seed = 1664525u * seed + 1013904223u;
+                if ((j & 31) == lane) X[j] = (float)((int32_t)seed >> 20);
+              }
+              done_cm = cm_mask;
+            } else {
+              const float *lbv = lowband + (lf.off - part_off);
+#pragma unroll 1
+              for (int j = 0; j < n; j++) {
+                seed = 1664525u * seed + 1013904223u;
+                if ((j & 31) == lane) {
+                  float t = 1.0f / 256;
+                  t = (seed & 0x8000) ? t : -t;
+                  X[j] = lbv[j] + t;
+                }
+              }
+              done_cm = fill;
+            }
+            cur.seed = seed;
+            renormalise(X, n, lf.gain, lane);
+          }
+        }
+        done = 1;
+      }
+    } else {
+      done = 0;
+    }
+    // deliver finished nodes upward
+#pragma unroll 1
+    while (done) {
+      sp--;
+      if (sp == 0) { result = done_cm; done = 0; break; }
+      WF &par = st[sp - 1];
+      if (par.stage == 1) {
+        par.cm = par.yfirst ? done_cm << (par.B0 >> 1) : done_cm;
+        par.stage = 2;
+        WF &c = st[sp++];
+        c.stage = 0; c.B = par.B; c.cm = 0; c.fill = par.yfirst ? par.fill : par.fill >> par.B;
+        done = 0;
+      } else {
+        par.cm |= par.yfirst ? done_cm : done_cm << (par.B0 >> 1);
+        done_cm = par.cm;
+      }
+    }
+  }
+  return result;
+}
+
+// resynthesis side of celt/bands.c:1248-1379
+OB_DEVNI unsigned band_mono_vec(Cursor &cur, PvqWS *ws, int part_off, int N, int B, float *lowband, int LM, float *lowband_out,
+                               float *lowband_scratch, int fill, int tf_change, int lane) {
+  float *X = ws->X + part_off;
+  float *tmp = ws->tmp;
+  int N0 = N, N_B = N, N_B0, B0 = B, time_divide = 0, recombine = 0;
+  const int longBlocks = B0 == 1;
+  (void)LM;
+  N_B = (unsigned)N_B / (unsigned)B;
+  if (N == 1) {  // sign(s) already placed by phase 1
+    cur.node++; cur.leaf++;
+    wsync();
+    if (lowband_out && lane == 0) lowband_out[0] = X[0];
+    wsync();
+    return 1;
+  }
+  if (tf_change > 0) recombine = tf_change;
+  if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
+    wsync();
+#pragma unroll 1
+    for (int j = lane; j < N; j += 32) lowband_scratch[j] = lowband[j];
+    wsync();
+    lowband = lowband_scratch;
+  }
+#pragma unroll 1
+  for (int k = 0; k < recombine; k++) {
+    if (lowband) haar_step(lowband, N >> k, 1 << k, lane);
+    int lo = fill & 0xF, hi = fill >> 4;  // bit_interleave_table, celt/bands.c:1288
+    int tl = lo == 0 ? 0 : (lo & 3 ? 1 : 0) | (lo & 12 ? 2 : 0);
+    int th = hi == 0 ? 0 : (hi & 3 ? 1 : 0) | (hi & 12 ? 2 : 0);
+    fill = tl | th << 2;
+  }
+  B >>= recombine;
+  N_B <<= recombine;
+#pragma unroll 1
+  while ((N_B & 1) == 0 && tf_change < 0) {
+    if (lowband) haar_step(lowband, N_B, B, lane);
+    fill |= fill << B;
+    B <<= 1;
+    N_B >>= 1;
+    time_divide++;
+    tf_change++;
+  }
+  B0 = B;
+  N_B0 = N_B;
+  if (B0 > 1 && lowband) deinterleave_hadamard(lowband, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
+  unsigned cm = walk_partition(cur, ws, part_off, B, lowband, fill, lane);
+  if (B0 > 1) interleave_hadamard(X, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
+  N_B = N_B0;
+  B = B0;
+#pragma unroll 1
+  for (int k = 0; k < time_divide; k++) {
+    B >>= 1;
+    N_B <<= 1;
+    cm |= cm >> B;
+    haar_step(X, N_B, B, lane);
+  }
+#pragma unroll 1
+  for (int k = 0; k < recombine; k++) {
+    unsigned c4 = cm & 0xF;  // bit_deinterleave_table, celt/bands.c:1352
+    cm = (c4 & 1 ? 0x03u : 0) | (c4 & 2 ? 0x0Cu : 0) | (c4 & 4 ? 0x30u : 0) | (c4 & 8 ? 0xC0u : 0);
+    haar_step(X, N0 >> k, 1 << k, lane);
+  }
+  B <<= recombine;
+  if (lowband_out) {
+    float n = f_sqrt((float)N0);
+    wsync();
+#pragma unroll 1
+    for (int j = lane; j < N0; j += 32) lowband_out[j] = n * X[j];
+    wsync();
+  }
+  cm &= (1u << B) - 1;
+  return cm;
+}
+
+// celt/bands.c:407-466 (stereo_merge)
+OB_DEVNI void merge_mid_side(float *X, float *Y, float mid, int N, int lane) {
+  wsync();
+  float xp = warp_dot(Y, X, N, lane);
+  float side = warp_dot(Y, Y, N, lane);
+  xp = mid * xp;
+  float El = (mid * mid) + side - 2 * xp;
+  float Er = (mid * mid) + side + 2 * xp;
+  if (Er < 6e-4f || El < 6e-4f) {
+#pragma unroll 1
+    for (int j = lane; j < N; j += 32) Y[j] = X[j];
+    wsync();
+    return;
+  }
+  float lgain = rsqrt_ref(El), rgain = rsqrt_ref(Er);
+#pragma unroll 1
+  for (int j = lane; j < N; j += 32) {
+    float l = mid * X[j], r = Y[j];
+    X[j] = lgain * (l - r);
+    Y[j] = rgain * (l + r);
+  }
+  wsync();
+}
+
+// celt/bands.c:259-353, X in shared memory
+OB_DEV void anti_collapse_vec(PvqWS *ws, const ObFrameSide *side, int lane, int LM, int C, int size, int start, int end,
+                              const float *logE, const float *prev1logE, const float *prev2logE, uint32_t seed) {
+  wsync();
+#pragma unroll 1
+  for (int i = start; i < end; i++) {
+    int N0 = ob_ebands[i + 1] - ob_ebands[i];
+    int depth = ((uint32_t)(1 + side->pulses[i]) / (uint32_t)N0) >> LM;
+    float thresh = .5f * exp2_ref(-.125f * depth);
+    float sqrt_1 = rsqrt_ref((float)(N0 << LM));
+#pragma unroll 1
+    for (int c = 0; c < C; c++) {
+      float prev1 = prev1logE[c * OB_NBANDS + i], prev2 = prev2logE[c * OB_NBANDS + i];
+      if (C == 1) {
+        float o1 = prev1logE[OB_NBANDS + i], o2 = prev2logE[OB_NBANDS + i];
+        prev1 = prev1 > o1 ? prev1 : o1;
+        prev2 = prev2 > o2 ? prev2 : o2;
+      }
+      float Ediff = logE[c * OB_NBANDS + i] - (prev1 < prev2 ? prev1 : prev2);
+      Ediff = Ediff > 0 ? Ediff : 0;
+      float r = 2.f * exp2_ref(-Ediff);
+      if (LM == 3) r *= 1.41421356f;
+      r = thresh < r ? thresh : r;
+      r = r * sqrt_1;
+      float *X = ws->X + c * size + (ob_ebands[i] << LM);
+      int renorm = 0;
+      unsigned mask = ws->collapse[i * C + c];
+#pragma unroll 1
+      for (int k = 0; k < 1 << LM; k++) {
+        if (!(mask & 1u << k)) {
+#pragma unroll 1
+          for (int j = 0; j < N0; j++) {
+            seed = 1664525u * seed + 1013904223u;
+            if (lane == 0) X[(j << LM) + k] = (seed & 0x8000 ? r : -r);
+          }
+          renorm = 1;
+        }
+      }
+      if (renorm) renormalise(X, N0 << LM, 1.0f, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel A2 body: one warp, one stream.
+// ------------------------------------------------------------------------------------------
+OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  PvqWS *ws = (PvqWS *)smem_warp;
+  const ObFrameSide *side = p.side + stream;
+  if (side->status <= 0) return;
+  const ObScript *sc = p.script + stream;
+  ObDecBandState *st = p.state + stream;
+  const int LM = side->LM, C = side->C, isTransient = side->transient, end = side->end_band, start = 0;
+  const int N = OB_SHORT_N << LM, M = 1 << LM;
+  const int spread = side->spread, intensity = side->intensity;
+  const int B = isTransient ? M : 1;
+
+  pvq_phase1(tab, ws, sc, side->n_leaves, spread, N, lane);
+
+  // ---- phase 2: bands in order (resynthesis side of celt/bands.c:1589-1923) ----
+  Cursor cur;
+  cur.sc = sc; cur.node = 0; cur.leaf = 0; cur.seed = side->seed;
+  const int norm_offset = M * ob_ebands[start];
+  float *norm = ws->norm, *norm2 = ws->norm + (M * ob_ebands[OB_NBANDS - 1] - norm_offset);
+  for (int i = lane; i < 2 * OB_NBANDS; i += 32) ws->collapse[i] = 0;
+  wsync();
+#pragma unroll 1
+  for (int i = start; i < end; i++) {
+    const ObBandRec br = sc->bands[i];
+    const int last = (i == end - 1);
+    const int Nb = M * ob_ebands[i + 1] - M * ob_ebands[i];
+    const int xoff = M * ob_ebands[i];
+    const int tf_change = side->tf_res[i];
+    const int effective_lowband = br.eff_lowband;
+    const int flags = br.flags;
+    float *lowband_scratch = last ? nullptr : ws->scr;
+    unsigned x_cm, y_cm;
+    if (effective_lowband != -1) {
+      const int lowband_offset = br.lowband_offset;
+      int fold_start = lowband_offset;
+      while (M * ob_ebands[--fold_start] > effective_lowband + norm_offset) {}
+      int fold_end = lowband_offset - 1;
+      while (++fold_end < i && M * ob_ebands[fold_end] < effective_lowband + norm_offset + Nb) {}
+      x_cm = y_cm = 0;
+      int fold_i = fold_start;
+      do {
+        x_cm |= ws->collapse[fold_i * C + 0];
+        y_cm |= ws->collapse[fold_i * C + C - 1];
+      } while (++fold_i < fold_end);
+    } else x_cm = y_cm = (1u << B) - 1;
+    if (flags & 2) {  // dual stereo switches to intensity here: norm = (norm + norm2)/2
+      wsync();
+#pragma unroll 1
+      for (int j = lane; j < M * ob_ebands[i] - norm_offset; j += 32) norm[j] = .5f * (norm[j] + norm2[j]);
+      wsync();
+    }
+    float *lb1 = effective_lowband != -1 ? norm + effective_lowband : nullptr;
+    float *lb2 = effective_lowband != -1 ? norm2 + effective_lowband : nullptr;
+    float *lo1 = last ? nullptr : norm + M * ob_ebands[i] - norm_offset;
+    float *lo2 = last ? nullptr : norm2 + M * ob_ebands[i] - norm_offset;
+    cur.node = br.node_begin;
+    cur.leaf = br.leaf_begin;
+    if (flags & 1) {
+      x_cm = band_mono_vec(cur, ws, xoff, Nb, B, lb1, LM, lo1, lowband_scratch, x_cm, tf_change, lane);
+      y_cm = band_mono_vec(cur, ws, N + xoff, Nb, B, lb2, LM, lo2, lowband_scratch, y_cm, tf_change, lane);
+    } else if (flags & 4) {
+      // resynthesis side of quant_band_stereo, celt/bands.c:1387-1570
+      float *X = ws->X + xoff, *Y = ws->X + N + xoff;
+      int fill = x_cm | y_cm;
+      unsigned cm;
+      if (Nb == 1) {
+        cur.node++; cur.leaf++;
+        wsync();
+        if (lo1 && lane == 0) lo1[0] = X[0];
+        wsync();
+        cm = 1;
+      } else {
+        const int orig_fill = fill;
+        if (br.theta_class == 0) fill &= (1 << B) - 1;
+        else if (br.theta_class == 1) fill &= ((1 << B) - 1) << B;
+        const float mid = br.mid, sidef = br.side;
+        if (flags & 16) {  // N == 2
+          const int c = (flags & 32) != 0;
+          const int sign = (flags & 64) ? -1 : 1;
+          cm = band_mono_vec(cur, ws, (c ? N : 0) + xoff, Nb, B, lb1, LM, lo1, lowband_scratch, orig_fill, tf_change, lane);
+          float *x2 = c ? Y : X, *y2 = c ? X : Y;
+          wsync();
+          if (lane == 0) {
+            y2[0] = -sign * x2[1];
+            y2[1] = sign * x2[0];
+            X[0] = mid * X[0];
+            X[1] = mid * X[1];
+            Y[0] = sidef * Y[0];
+            Y[1] = sidef * Y[1];
+            float t = X[0];
+            X[0] = t - Y[0];
+            Y[0] = t + Y[0];
+            t = X[1];
+            X[1] = t - Y[1];
+            Y[1] = t + Y[1];
+          }
+          wsync();
+        } else {
+          const int side_first = (flags & 128) != 0;
+          cm = 0;
+#pragma unroll 1
+          for (int pass = 0; pass < 2; pass++) {
+            const int do_mid = (pass == 0) != side_first;
+            if (do_mid) cm |= band_mono_vec(cur, ws, xoff, Nb, B, lb1, LM, lo1, lowband_scratch, fill, tf_change, lane);
+            else cm |= band_mono_vec(cur, ws, N + xoff, Nb, B, nullptr, LM, nullptr, nullptr, fill >> B, tf_change, lane);
+          }
+          merge_mid_side(X, Y, mid, Nb, lane);
+        }
+        if (flags & 8) {  // inv
+          wsync();
+#pragma unroll 1
+          for (int j = lane; j < Nb; j += 32) Y[j] = -Y[j];
+          wsync();
+        }
+      }
+      x_cm = y_cm = cm;
+    } else {
+      x_cm = y_cm = band_mono_vec(cur, ws, xoff, Nb, B, lb1, LM, lo1, lowband_scratch, x_cm | y_cm, tf_change, lane);
+    }
+    wsync();
+    if (lane == 0) {
+      ws->collapse[i * C + 0] = (unsigned char)x_cm;
+      ws->collapse[i * C + C - 1] = (unsigned char)y_cm;
+    }
+    wsync();
+  }
+  if (side->anti_collapse_on)
+    anti_collapse_vec(ws, side, lane, LM, C, N, start, end, side->bandE, st->oldLogE, st->oldLogE2, cur.seed);
+  wsync();
+  // ---- one coalesced store of the frame's spectrum ----
+  {
+    float *Xg = p.X + (size_t)stream * 2 * OB_MAXN;
+    const int bound = M * ob_ebands[end];
+#pragma unroll 1
+    for (int c = 0; c < C; c++)
+#pragma unroll 1
+      for (int j = lane; j < N; j += 32) Xg[c * N + j] = j < bound ? ws->X[c * N + j] : 0.f;
+  }
+  // ---- state update (celt/celt_decoder.c:1575-1600), lane-parallel over the 42 energies ----
+#pragma unroll 1
+  for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
+    const int band = i >= OB_NBANDS ? i - OB_NBANDS : i;
+    float e = side->bandE[i];
+    float l1 = st->oldLogE[i], l2 = st->oldLogE2[i], bg = st->backgroundLogE[i];
+    if (!isTransient) { l2 = l1; l1 = e; }
+    else l1 = l1 < e ? l1 : e;
+    float inc = OB_IMIN(160, M) * 0.001f;
+    float a = bg + inc;
+    bg = a < e ? a : e;
+    if (band < start || band >= end) { e = 0.f; l1 = l2 = -28.f; }
+    st->oldEBands[i] = e;
+    st->oldLogE[i] = l1;
+    st->oldLogE2[i] = l2;
+    st->backgroundLogE[i] = bg;
+  }
+}
+
+}  // namespace ob

@@ -34,6 +34,39 @@ typedef struct {
   int32_t pad[1];
 } ObDecSynthState;
 
+/* ---- entropy kernel -> PVQ kernel hand-off ("frame script"), one per stream ------------------ */
+#define OB_MAX_LEAVES 448  /* worst case 416: every band of a stereo 20 ms frame split down to LM=-1 */
+#define OB_MAX_NODES 896
+
+/* One leaf partition of the band tree (celt/bands.c quant_partition no-split case). 16 bytes. */
+typedef struct {
+  uint32_t index; /* kind 0: PVQ codeword index (ec_dec_uint result); kind 2: sign bits (bit c = channel c) */
+  float gain;     /* product of the mid/side gains down the tree (celt/bands.c:1078-1089) */
+  uint16_t off;   /* offset in the frame's X[C][N] array */
+  uint8_t n;      /* dimensions (2..176; 1 for kind 2) */
+  uint8_t K;      /* pulses (kind 0) */
+  uint8_t B;      /* blocks at this leaf */
+  uint8_t kind;   /* 0 = PVQ pulses, 1 = no pulses (zero / noise / folded, decided by `fill`), 2 = N==1 signs */
+  uint8_t lb;     /* 1 if a lowband (folding source) exists for this leaf */
+  uint8_t pad;
+} ObLeaf;
+
+/* Per band: what the vector stage cannot derive without the range decoder. 24 bytes. */
+typedef struct {
+  int16_t eff_lowband;   /* effective_lowband (offset into norm) or -1 */
+  uint8_t lowband_offset;
+  uint8_t flags;         /* bit0 dual stereo band, bit1 dual->intensity switch happens at this band,
+                            bit2 stereo split band, bit3 inv, bit4 N==2 special, bit5 n2 c, bit6 n2 sign(neg),
+                            bit7 side decoded first */
+  uint8_t theta_class;   /* stereo theta: 0 -> itheta==0, 1 -> itheta==16384, 2 -> other */
+  uint8_t pad;
+  uint16_t node_begin;   /* first tree node byte of this band */
+  uint16_t leaf_begin;   /* first leaf of this band */
+  uint16_t leaf_end;
+  float mid, side;       /* stereo mid/side gains (imid/32768, iside/32768) */
+  int32_t b;             /* bits given to the band (debug / update_lowband) */
+} ObBandRec;
+
 /* What the band decoder hands to the synthesis kernel for one stream-frame. */
 typedef struct {
   int32_t status;       /* >=0: samples per channel in this frame; <0: opus error code; 0: no frame */
@@ -41,5 +74,18 @@ typedef struct {
   int32_t pf_T[3], pf_tap[3]; /* post-filter period/tapset: [0]=old, [1]=current, [2]=new (this frame) */
   float pf_g[3];
   float bandE[2 * OB_NBANDS]; /* final log2 band energies (without the means) */
-  int32_t pad[5];
-} ObFrameSide; /* 240 bytes */
+  /* entropy -> PVQ stage */
+  int32_t spread, intensity, dual_stereo, anti_collapse_on, n_leaves, n_nodes;
+  uint32_t seed;              /* LCG seed at the start of the band loop (previous frame's final range) */
+  int8_t tf_res[OB_NBANDS];
+  uint8_t pad8[3];
+  int16_t pulses[OB_NBANDS];  /* PVQ bit allocation per band (anti-collapse depth) */
+  int16_t pad16;
+} ObFrameSide; /* 340 bytes */
+
+/* Per-stream script buffer written by the entropy kernel, read by the PVQ kernel. */
+typedef struct {
+  ObLeaf leaves[OB_MAX_LEAVES];
+  ObBandRec bands[OB_NBANDS];
+  uint8_t nodes[OB_MAX_NODES];
+} ObScript;

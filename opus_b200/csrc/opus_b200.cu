@@ -4,6 +4,7 @@
 // multiply/add roundings (the reference oracle is built with -ffp-contract=off).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -16,10 +17,21 @@ using namespace ob;
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(128, 5) ob_celt_dec_bands(DecBandsParams p, int smem_per_warp) {
+extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_entropy(DecEntropyParams p) {
+  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stream >= p.n_streams) return;
+  dec_entropy_thread(p, stream);
+}
+
+extern "C" __global__ void __launch_bounds__(512) ob_celt_dec_pvq(DecPvqParams p) {
+  PvqShared *tab = (PvqShared *)dyn_smem();
+  for (int i = threadIdx.x; i < 1272; i += blockDim.x) tab->u[i] = ob_pvq_u[i];
+  if (threadIdx.x < 15) tab->rowoff[threadIdx.x] = ob_pvq_rowoff[threadIdx.x];
+  __syncthreads();
   const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (stream >= p.n_streams) return;
-  dec_bands_warp(p, stream, dyn_smem() + (size_t)(threadIdx.x >> 5) * smem_per_warp);
+  unsigned char *ws = dyn_smem() + ((sizeof(PvqShared) + 15) & ~(size_t)15) + (size_t)(threadIdx.x >> 5) * sizeof(PvqWS);
+  dec_pvq_warp(p, stream, tab, ws);
 }
 
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParams p) {
@@ -48,7 +60,9 @@ struct OpusB200Decoder {
   ObDecBandState *bstate;
   ObDecSynthState *sstate;
   ObFrameSide *side;
+  ObScript *script;
   float *X;
+  int pvq_warps;  // warps (= streams) per CTA of the PVQ kernel
   // staging for the host-buffer API
   unsigned char *d_packets; size_t d_packets_cap;
   int32_t *d_len, *d_out;
@@ -57,8 +71,8 @@ struct OpusB200Decoder {
   int max_smem_optin;
   // optional per-kernel timing (CUDA events on the decoder's stream)
   int timing;
-  cudaEvent_t ev[3];
-  double kernel_ms[2];
+  cudaEvent_t ev[4];
+  double kernel_ms[3];
   int64_t timed_launches;
 };
 
@@ -102,12 +116,20 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   OB_CUDA(cudaMalloc(&d->bstate, sizeof(ObDecBandState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->sstate, sizeof(ObDecSynthState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->side, sizeof(ObFrameSide) * (size_t)n_streams));
+  OB_CUDA(cudaMalloc(&d->script, sizeof(ObScript) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->X, sizeof(float) * 2 * OB_MAXN * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->d_len, sizeof(int32_t) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->d_out, sizeof(int32_t) * (size_t)n_streams));
   OB_CUDA(cudaDeviceGetAttribute(&d->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
-  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_bands, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_entropy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+  {
+    const char *e = getenv("OPUSB200_PVQ_WARPS");
+    d->pvq_warps = e ? atoi(e) : 15;
+    if (d->pvq_warps < 1) d->pvq_warps = 1;
+    if (d->pvq_warps > 16) d->pvq_warps = 16;
+  }
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the band decoder recurses over partitions (depth <= 5)
@@ -125,7 +147,7 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->X); cudaFree(d->d_len); cudaFree(d->d_out);
+  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->script); cudaFree(d->X); cudaFree(d->d_len); cudaFree(d->d_out);
   cudaFree(d->d_packets); cudaFree(d->d_pcm);
   cudaStreamDestroy(d->stream);
   delete d;
@@ -149,30 +171,34 @@ int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, i
   if (max_frames_per_packet < 1) max_frames_per_packet = 1;
   if (max_frames_per_packet > 48) max_frames_per_packet = 48;
   OB_CUDA(cudaSetDevice(d->device));
-  const int warps = 4;
-  const int cap = ((pkt_stride < OB_MAX_PACKET + 2 ? pkt_stride : OB_MAX_PACKET + 2) + 15) & ~15;
-  const int smem_per_warp = (int)((sizeof(BandWS) + 15) & ~(size_t)15) + cap;
-  if (warps * smem_per_warp > d->max_smem_optin) return OPUSB200_INTERNAL_ERROR;
+  const int pw = d->pvq_warps;
+  const size_t pvq_smem = ((sizeof(PvqShared) + 15) & ~(size_t)15) + (size_t)pw * sizeof(PvqWS);
+  if ((int)pvq_smem > d->max_smem_optin) return OPUSB200_INTERNAL_ERROR;
   for (int k = 0; k < max_frames_per_packet; k++) {
-    DecBandsParams bp;
-    bp.packets = d_packets; bp.pkt_len = d_len; bp.pkt_stride = pkt_stride; bp.pkt_cap = cap; bp.n_streams = d->n;
-    bp.channels = d->channels; bp.frame_index = k; bp.state = d->bstate; bp.side = d->side; bp.X = d->X;
-    bp.out_samples = d_out_samples ? d_out_samples : d->d_out; bp.max_samples = frame_size;
+    DecEntropyParams ep;
+    ep.packets = d_packets; ep.pkt_len = d_len; ep.pkt_stride = pkt_stride; ep.n_streams = d->n; ep.channels = d->channels;
+    ep.frame_index = k; ep.state = d->bstate; ep.side = d->side; ep.script = d->script;
+    ep.out_samples = d_out_samples ? d_out_samples : d->d_out; ep.max_samples = frame_size;
+    DecPvqParams pp;
+    pp.side = d->side; pp.script = d->script; pp.state = d->bstate; pp.X = d->X; pp.n_streams = d->n;
     if (d->timing) cudaEventRecord(d->ev[0], d->stream);
-    ob_celt_dec_bands<<<(d->n + warps - 1) / warps, warps * 32, warps * smem_per_warp, d->stream>>>(bp, smem_per_warp);
+    ob_celt_dec_entropy<<<(d->n + 127) / 128, 128, 0, d->stream>>>(ep);
     if (d->timing) cudaEventRecord(d->ev[1], d->stream);
+    ob_celt_dec_pvq<<<(d->n + pw - 1) / pw, pw * 32, pvq_smem, d->stream>>>(pp);
+    if (d->timing) cudaEventRecord(d->ev[2], d->stream);
     DecSynthParams sp;
     sp.side = d->side; sp.X = d->X; sp.state = d->sstate; sp.pcm = d_pcm; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = d->n; sp.channels = d->channels;
     ob_celt_dec_synth<<<d->n, 32 * d->channels, d->channels * sizeof(SynthWS), d->stream>>>(sp);
-    d->launches += 2;
+    d->launches += 3;
     if (d->timing) {  // profiling mode: serialises the stream, never used for throughput numbers
-      cudaEventRecord(d->ev[2], d->stream);
-      cudaEventSynchronize(d->ev[2]);
-      float a = 0.f, b = 0.f;
+      cudaEventRecord(d->ev[3], d->stream);
+      cudaEventSynchronize(d->ev[3]);
+      float a = 0.f, b = 0.f, c = 0.f;
       cudaEventElapsedTime(&a, d->ev[0], d->ev[1]);
       cudaEventElapsedTime(&b, d->ev[1], d->ev[2]);
-      d->kernel_ms[0] += a; d->kernel_ms[1] += b; d->timed_launches++;
+      cudaEventElapsedTime(&c, d->ev[2], d->ev[3]);
+      d->kernel_ms[0] += a; d->kernel_ms[1] += b; d->kernel_ms[2] += c; d->timed_launches++;
     }
   }
   OB_CUDA(cudaGetLastError());
@@ -245,15 +271,16 @@ int opusb200_decoder_get_final_range(OpusB200Decoder *d, uint32_t *final_range) 
 int opusb200_decoder_set_timing(OpusB200Decoder *d, int enable) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(d->device));
-  if (enable && !d->ev[0]) for (int i = 0; i < 3; i++) OB_CUDA(cudaEventCreate(&d->ev[i]));
+  if (enable && !d->ev[0]) for (int i = 0; i < 4; i++) OB_CUDA(cudaEventCreate(&d->ev[i]));
   d->timing = enable ? 1 : 0;
-  d->kernel_ms[0] = d->kernel_ms[1] = 0.0;
+  d->kernel_ms[0] = d->kernel_ms[1] = d->kernel_ms[2] = 0.0;
   d->timed_launches = 0;
   return OPUSB200_OK;
 }
-int opusb200_decoder_get_timing(OpusB200Decoder *d, double *ms_bands, double *ms_synth, int64_t *launch_pairs) {
-  if (!d || !ms_bands || !ms_synth || !launch_pairs) return OPUSB200_BAD_ARG;
-  *ms_bands = d->kernel_ms[0]; *ms_synth = d->kernel_ms[1]; *launch_pairs = d->timed_launches;
+int opusb200_decoder_get_timing(OpusB200Decoder *d, double *ms_kernels, int64_t *frames) {
+  if (!d || !ms_kernels || !frames) return OPUSB200_BAD_ARG;
+  ms_kernels[0] = d->kernel_ms[0]; ms_kernels[1] = d->kernel_ms[1]; ms_kernels[2] = d->kernel_ms[2];
+  *frames = d->timed_launches;
   return OPUSB200_OK;
 }
 

@@ -71,10 +71,11 @@ class DecoderBatch:
         self._L.opusb200_decoder_set_timing(self._h, 1 if enable else 0)
 
     def get_timing(self):
-        """(ms in band-decode kernel, ms in synthesis kernel, launch pairs) since set_timing(True)."""
-        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
-        self._L.opusb200_decoder_get_timing(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-        return a.value, b.value, c.value
+        """({'entropy': ms, 'pvq': ms, 'synth': ms}, frame steps) accumulated since set_timing(True)."""
+        ms = (ctypes.c_double * 3)()
+        n = ctypes.c_int64(0)
+        self._L.opusb200_decoder_get_timing(self._h, ms, ctypes.byref(n))
+        return {'entropy': ms[0], 'pvq': ms[1], 'synth': ms[2]}, n.value
 
     @property
     def cuda_stream(self):

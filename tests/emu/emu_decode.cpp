@@ -13,13 +13,22 @@ struct EmuDecoder {
   std::vector<ObDecBandState> bstate;
   std::vector<ObDecSynthState> sstate;
   std::vector<ObFrameSide> side;
+  std::vector<ObScript> script;
   std::vector<float> X;
 };
 
-static void bands_entry(void *arg) {
-  const DecBandsParams &p = *(const DecBandsParams *)arg;
-  int stream = block_id() * warps_per_block() + warp_in_block();
-  if (stream < p.n_streams) dec_bands_warp(p, stream, dyn_smem());
+static void entropy_entry(void *arg) {  // one thread per stream
+  const DecEntropyParams &p = *(const DecEntropyParams *)arg;
+  int stream = block_id() * 32 + lane_id();
+  if (stream < p.n_streams) dec_entropy_thread(p, stream);
+}
+static void pvq_entry(void *arg) {  // one warp per stream (one warp per block in the emulator)
+  const DecPvqParams &p = *(const DecPvqParams *)arg;
+  PvqShared *tab = (PvqShared *)dyn_smem();
+  for (int i = lane_id(); i < 1272; i += 32) tab->u[i] = ob_pvq_u[i];
+  if (lane_id() < 15) tab->rowoff[lane_id()] = ob_pvq_rowoff[lane_id()];
+  bsync();
+  dec_pvq_warp(p, block_id(), tab, dyn_smem() + ((sizeof(PvqShared) + 15) & ~(size_t)15));
 }
 static void synth_entry(void *arg) {
   const DecSynthParams &p = *(const DecSynthParams *)arg;
@@ -35,6 +44,7 @@ void *emu_decoder_create(int n_streams, int channels) {
   d->bstate.resize(n_streams);
   d->sstate.resize(n_streams);
   d->side.resize(n_streams);
+  d->script.resize(n_streams);
   d->X.assign((size_t)n_streams * 2 * OB_MAXN, 0.f);
   memset(d->bstate.data(), 0, sizeof(ObDecBandState) * n_streams);
   memset(d->sstate.data(), 0, sizeof(ObDecSynthState) * n_streams);
@@ -48,15 +58,15 @@ void emu_decoder_destroy(void *h) { delete (EmuDecoder *)h; }
 int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const int *lens, void *pcm, int pcm_stride,
                        int pcm_is_int16, int *out_samples, unsigned *final_range) {
   EmuDecoder *d = (EmuDecoder *)h;
-  int maxlen = 0;
-  for (int s = 0; s < d->n; s++) maxlen = lens[s] > maxlen ? lens[s] : maxlen;
-  int cap = (maxlen + 15) & ~15;
   for (int k = 0; k < 48; k++) {
-    DecBandsParams bp;
-    bp.packets = packets; bp.pkt_len = lens; bp.pkt_stride = stride; bp.pkt_cap = cap; bp.n_streams = d->n;
-    bp.channels = d->channels; bp.frame_index = k; bp.state = d->bstate.data(); bp.side = d->side.data(); bp.X = d->X.data(); bp.out_samples = out_samples; bp.max_samples = 5760;
-    size_t smemA = ((sizeof(BandWS) + 15) & ~(size_t)15) + cap;
-    emu_launch(bands_entry, &bp, d->n, 32, smemA);
+    DecEntropyParams ep;
+    ep.packets = packets; ep.pkt_len = lens; ep.pkt_stride = stride; ep.n_streams = d->n; ep.channels = d->channels;
+    ep.frame_index = k; ep.state = d->bstate.data(); ep.side = d->side.data(); ep.script = d->script.data();
+    ep.out_samples = out_samples; ep.max_samples = 5760;
+    emu_launch(entropy_entry, &ep, (d->n + 31) / 32, 32, 0);
+    DecPvqParams pp;
+    pp.side = d->side.data(); pp.script = d->script.data(); pp.state = d->bstate.data(); pp.X = d->X.data(); pp.n_streams = d->n;
+    emu_launch(pvq_entry, &pp, d->n, 32, ((sizeof(PvqShared) + 15) & ~(size_t)15) + sizeof(PvqWS));
     int any = 0;
     for (int s = 0; s < d->n; s++) {
       int st = d->side[s].status;

@@ -351,7 +351,8 @@ def main(out_path):
     o.append('/* GENERATED by tools/gen_tables.py -- do not edit.  Constant tables of the Opus CELT\n'
              ' * 48 kHz mode (N=960, overlap 120, 21 bands), recomputed from their defining formulas.\n'
              ' * The includer defines OB_TABLE (e.g. `static const` or `static __device__ const`). */\n')
-    o.append('#ifndef OB_TABLE\n#error "define OB_TABLE before including celt_tables_data.h"\n#endif\n\n')
+    o.append('#ifndef OB_TABLE\n#error "define OB_TABLE before including celt_tables_data.h"\n#endif\n'
+             '#ifndef OB_CELT_TABLES_DATA_H\n#define OB_CELT_TABLES_DATA_H\n\n')
     o.append(carr('ob_ebands', 'short', EBANDS, fi, 22))
     o.append(carr('ob_band_alloc', 'unsigned char', BAND_ALLOCATION, fi, 21))
     o.append(carr('ob_logN', 'short', logN, fi, 21))
@@ -381,6 +382,7 @@ def main(out_path):
         fl += [0] * (10 - len(fl))
         facs += fl
     o.append(carr('ob_fft_factors', 'short', facs, fi, 10))
+    o.append('#endif /* OB_CELT_TABLES_DATA_H */\n')
     with open(out_path, 'w') as f:
         f.write(''.join(o))
     print('wrote', out_path, 'pvq', len(pvq_data), 'cache', len(cbits))
