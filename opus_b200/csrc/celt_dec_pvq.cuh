@@ -46,7 +46,7 @@ struct PvqWS {
   float norm[2 * 624];   // folding source
   float scr[176];        // lowband scratch
   float tmp[176];        // permutation scratch
-  unsigned char leaf_cm[OB_MAX_LEAVES];
+  unsigned short leaf_cm[OB_MAX_LEAVES];  // up to 16 blocks after a time-divide (bands.c:1303)
   unsigned char collapse[2 * OB_NBANDS];
   unsigned char pad[6];
 };
@@ -184,7 +184,7 @@ OB_DEV void pvq_phase1(const PvqShared *tab, PvqWS *ws, const ObScript *sc, int 
 #pragma unroll 1
       for (int j = 0; j < n; j++) X[j] = X[j] * g;
       unrotate_seq(X, n, B, K, spread);
-      ws->leaf_cm[l] = (unsigned char)mask;
+      ws->leaf_cm[l] = (unsigned short)mask;
     } else if (lf.kind == 2) {  // N == 1 bands: a sign per channel (celt/bands.c:934-968)
       X[0] = (lf.index & 1) ? -1.f : 1.f;
       if (lf.K == 2) X[Nframe] = (lf.index & 2) ? -1.f : 1.f;

@@ -1503,6 +1503,9 @@ static void synthesis(float *X, float *out_syn[], const float *oldBandE, int sta
   }
 }
 
+/* Debug tap for the tests: the last frame's normalised spectrum X[C][N] (after anti-collapse). */
+float orc_dbg_X[2 * MAXN];
+
 /* One CELT frame: `data` is the CELT payload (no TOC byte). Returns samples/channel or <0.
  * pcm: interleaved float, CC channels, +-1.0 full scale. */
 int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *pcm, int frame_size) {
@@ -1601,6 +1604,7 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
   decode_energy_finalise(start, end, oldBandE, fine_quant, fine_priority, len * 8 - rd_tell(&dec), &dec, C);
   if (anti_collapse_on)
     anti_collapse(X, collapse_masks, LM, C, N, start, end, oldBandE, oldLogE, oldLogE2, pulses, st->rng);
+  memcpy(orc_dbg_X, X, sizeof(float) * C * N);
   if (silence) for (i = 0; i < C * NBANDS; i++) oldBandE[i] = -28.f;
   synthesis(X, out_syn, oldBandE, start, effEnd, C, CC, isTransient, LM, silence);
   c = 0;

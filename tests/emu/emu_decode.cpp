@@ -88,5 +88,8 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
   return 0;
 }
 
+const float *emu_decoder_X(void *h, int stream) { return ((EmuDecoder *)h)->X.data() + (size_t)stream * 2 * OB_MAXN; }
+const ObFrameSide *emu_decoder_side(void *h, int stream) { return &((EmuDecoder *)h)->side[stream]; }
+
 long emu_yield_count(void) { return emu().yields; }
 }

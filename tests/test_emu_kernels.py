@@ -23,3 +23,18 @@ def test_emulated_kernels_match_golden(case):
     assert d.max() <= 1, d.max()
     # and tight in float: the only differences are float re-association (scan / tree reductions)
     assert np.abs(got - ref).max() < 2e-5
+
+
+@pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+@pytest.mark.parametrize('s', [6, 11, 18, 24])
+def test_emulated_kernels_transient_dual_stereo_streams(s):
+    """Streams whose first frames are transient with 16-block collapse masks, dual stereo and
+    anti-collapse (these exposed an 8-bit collapse-mask truncation the golden set did not)."""
+    from test_gpu_decode import _make_streams
+    ch, fs, nfr = 2, 960, 6
+    pk, sz = _make_streams(25, ch, fs, nfr, seed=ch * 10 + fs)
+    ref, rr = util.ref_decode_float(pk[s], sz[s], ch, fs)
+    got, gr = emu_util.emu_decode_stream(pk[s], sz[s], ch, fs)
+    assert (gr == rr).all()
+    assert np.abs(util.to_int16(got).astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
+    assert np.abs(got - ref).max() < 2e-6
