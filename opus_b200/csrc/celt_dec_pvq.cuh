@@ -47,6 +47,8 @@ struct PvqWS {
   float scr[176];        // lowband scratch
   float tmp[176];        // permutation scratch
   unsigned short leaf_cm[OB_MAX_LEAVES];  // up to 16 blocks after a time-divide (bands.c:1303)
+  ObBandRec bands[OB_NBANDS];             // staged copy of the script's band records
+  unsigned char nodes[OB_MAX_NODES];      // staged copy of the script's tree bytes
   unsigned char collapse[2 * OB_NBANDS];
   unsigned char pad[6];
 };
@@ -201,98 +203,74 @@ struct Cursor {  // warp-uniform walk state over the script
   uint32_t seed;
 };
 
-// One band part (celt/bands.c:973-1176 resynthesis side): walk the partition tree, propagate
-// `fill`, produce the zero / noise / folded leaves, combine collapse masks.  Xp: the part's vector
-// in ws->X (leaf offsets are frame-absolute; part_off is Xp's frame offset).
-OB_DEVNI unsigned walk_partition(Cursor &cur, PvqWS *ws, int part_off, int B_root, const float *lowband, int fill_root, int lane) {
-  struct WF { int fill, B, B0; unsigned cm; int stage, yfirst; };
-  WF st[6];
-  int sp = 1;
-  st[0].fill = fill_root; st[0].B = B_root; st[0].B0 = B_root; st[0].cm = 0; st[0].stage = 0; st[0].yfirst = 0;
-  unsigned result = 0;
+// A leaf without pulses (celt/bands.c:1131-1172): zero, LCG noise, or the folded lower band, then
+// renormalised.  Returns its collapse mask.  Rare at high rates, so kept out of line.
+OB_DEVNI unsigned fold_leaf(Cursor &cur, PvqWS *ws, int l, int part_off, int B, const float *lowband, int fill, int lane) {
+  const ObLeaf lf = cur.sc->leaves[l];
+  const int n = lf.n;
+  float *X = ws->X + lf.off;
+  const unsigned cm_mask = (unsigned)(1UL << B) - 1;
+  unsigned cm = 0;
+  fill &= cm_mask;
+  wsync();
+  if (!fill) {
 #pragma unroll 1
-  while (sp > 0) {
-    WF &f = st[sp - 1];
-    unsigned done_cm = 0;
-    int done = 0;
-    if (f.stage == 0) {
-      const unsigned nb = cur.sc->nodes[cur.node++];
-      if (nb & 0x80u) {
-        int fill = f.fill;
-        const int B0 = f.B;
-        if (B0 == 1) fill = (fill & 1) | (fill << 1);
-        const int B = (B0 + 1) >> 1;
-        const int cls = nb & 3;
-        if (cls == 0) fill &= (1 << B) - 1;
-        else if (cls == 1) fill &= ((1 << B) - 1) << B;
-        f.fill = fill; f.B = B; f.B0 = B0; f.yfirst = (nb & 4) != 0; f.stage = 1; f.cm = 0;
-        WF &c = st[sp++];
-        c.stage = 0; c.B = B; c.cm = 0; c.fill = f.yfirst ? fill >> B : fill;
-      } else {
-        const int l = cur.leaf++;
-        const ObLeaf lf = cur.sc->leaves[l];
-        if (lf.kind != 1) {
-          done_cm = ws->leaf_cm[l];
-        } else {
-          const int n = lf.n, B = f.B;
-          float *X = ws->X + lf.off;
-          const unsigned cm_mask = (unsigned)(1UL << B) - 1;
-          const int fill = f.fill & cm_mask;
-          wsync();
-          if (!fill) {
-#pragma unroll 1
-            for (int j = lane; j < n; j += 32) X[j] = 0.f;
-            wsync();
-          } else {
-            uint32_t seed = cur.seed;
-            if (!lf.lb || lowband == nullptr) {
-#pragma unroll 1
-              for (int j = 0; j < n; j++) {
-                seed = 1664525u * seed + 1013904223u;
-                if ((j & 31) == lane) X[j] = (float)((int32_t)seed >> 20);
-              }
-              done_cm = cm_mask;
-            } else {
-              const float *lbv = lowband + (lf.off - part_off);
-#pragma unroll 1
-              for (int j = 0; j < n; j++) {
-                seed = 1664525u * seed + 1013904223u;
-                if ((j & 31) == lane) {
-                  float t = 1.0f / 256;
-                  t = (seed & 0x8000) ? t : -t;
-                  X[j] = lbv[j] + t;
-                }
-              }
-              done_cm = fill;
-            }
-            cur.seed = seed;
-            renormalise(X, n, lf.gain, lane);
-          }
-        }
-        done = 1;
-      }
-    } else {
-      done = 0;
-    }
-    // deliver finished nodes upward
-#pragma unroll 1
-    while (done) {
-      sp--;
-      if (sp == 0) { result = done_cm; done = 0; break; }
-      WF &par = st[sp - 1];
-      if (par.stage == 1) {
-        par.cm = par.yfirst ? done_cm << (par.B0 >> 1) : done_cm;
-        par.stage = 2;
-        WF &c = st[sp++];
-        c.stage = 0; c.B = par.B; c.cm = 0; c.fill = par.yfirst ? par.fill : par.fill >> par.B;
-        done = 0;
-      } else {
-        par.cm |= par.yfirst ? done_cm : done_cm << (par.B0 >> 1);
-        done_cm = par.cm;
-      }
-    }
+    for (int j = lane; j < n; j += 32) X[j] = 0.f;
+    wsync();
+    return 0;
   }
-  return result;
+  uint32_t seed = cur.seed;
+  if (!lf.lb || lowband == nullptr) {
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      seed = 1664525u * seed + 1013904223u;
+      if ((j & 31) == lane) X[j] = (float)((int32_t)seed >> 20);
+    }
+    cm = cm_mask;
+  } else {
+    const float *lbv = lowband + (lf.off - part_off);
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+      seed = 1664525u * seed + 1013904223u;
+      if ((j & 31) == lane) {
+        float t = 1.0f / 256;
+        t = (seed & 0x8000) ? t : -t;
+        X[j] = lbv[j] + t;
+      }
+    }
+    cm = fill;
+  }
+  cur.seed = seed;
+  renormalise(X, n, lf.gain, lane);
+  return cm;
+}
+
+// One band part (celt/bands.c:973-1176 resynthesis side): walk the partition tree, propagate
+// `fill`, produce the zero / noise / folded leaves, combine collapse masks.  The recursion is
+// unrolled by depth at compile time (a band splits at most 4 times: LM 3 -> -1), so the walk state
+// lives in registers; node bytes come from the shared-memory copy of the script.
+template <int DEPTH>
+OB_DEV unsigned walk_node(Cursor &cur, PvqWS *ws, int part_off, int B0, const float *lowband, int fill, int lane) {
+  const unsigned nb = ws->nodes[cur.node++];
+  if (DEPTH < 4 && (nb & 0x80u)) {
+    if (B0 == 1) fill = (fill & 1) | (fill << 1);
+    const int B = (B0 + 1) >> 1;
+    const int cls = nb & 3;
+    if (cls == 0) fill &= (1 << B) - 1;
+    else if (cls == 1) fill &= ((1 << B) - 1) << B;
+    const int yfirst = (nb & 4) != 0;
+    unsigned cm = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const int is_y = (pass == 0) == (yfirst != 0);
+      unsigned c = walk_node<(DEPTH < 4 ? DEPTH + 1 : 4)>(cur, ws, part_off, B, lowband, is_y ? fill >> B : fill, lane);
+      cm |= is_y ? c << (B0 >> 1) : c;
+    }
+    return cm;
+  }
+  const int l = cur.leaf++;
+  if ((nb & 3) != 1) return ws->leaf_cm[l];
+  return fold_leaf(cur, ws, l, part_off, B0, lowband, fill, lane);
 }
 
 // resynthesis side of celt/bands.c:1248-1379
@@ -341,7 +319,7 @@ OB_DEVNI unsigned band_mono_vec(Cursor &cur, PvqWS *ws, int part_off, int N, int
   B0 = B;
   N_B0 = N_B;
   if (B0 > 1 && lowband) deinterleave_hadamard(lowband, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
-  unsigned cm = walk_partition(cur, ws, part_off, B, lowband, fill, lane);
+  unsigned cm = walk_node<0>(cur, ws, part_off, B, lowband, fill, lane);
   if (B0 > 1) interleave_hadamard(X, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
   N_B = N_B0;
   B = B0;
@@ -452,6 +430,18 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
   const int spread = side->spread, intensity = side->intensity;
   const int B = isTransient ? M : 1;
 
+  // stage the script's tree bytes and band records in shared memory (coalesced 4-byte copies)
+  {
+    const int nwords = (side->n_nodes + 3) >> 2;
+    const uint32_t *src = (const uint32_t *)sc->nodes;
+    uint32_t *dst = (uint32_t *)ws->nodes;
+#pragma unroll 1
+    for (int i = lane; i < nwords; i += 32) dst[i] = src[i];
+    const uint32_t *bs = (const uint32_t *)sc->bands;
+    uint32_t *bd = (uint32_t *)ws->bands;
+#pragma unroll 1
+    for (int i = lane; i < (int)(OB_NBANDS * sizeof(ObBandRec) / 4); i += 32) bd[i] = bs[i];
+  }
   pvq_phase1(tab, ws, sc, side->n_leaves, spread, N, lane);
 
   // ---- phase 2: bands in order (resynthesis side of celt/bands.c:1589-1923) ----
@@ -463,7 +453,7 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
   wsync();
 #pragma unroll 1
   for (int i = start; i < end; i++) {
-    const ObBandRec br = sc->bands[i];
+    const ObBandRec br = ws->bands[i];
     const int last = (i == end - 1);
     const int Nb = M * ob_ebands[i + 1] - M * ob_ebands[i];
     const int xoff = M * ob_ebands[i];

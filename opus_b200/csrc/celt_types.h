@@ -88,4 +88,5 @@ typedef struct {
   ObLeaf leaves[OB_MAX_LEAVES];
   ObBandRec bands[OB_NBANDS];
   uint8_t nodes[OB_MAX_NODES];
+  uint8_t pad[8]; /* keeps sizeof(ObScript) a multiple of 16 */
 } ObScript;

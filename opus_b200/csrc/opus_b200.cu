@@ -17,9 +17,13 @@ using namespace ob;
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_entropy(DecEntropyParams p) {
-  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
-  if (stream >= p.n_streams) return;
+// lpw = streams (active lanes) per warp.  With few streams per GPU the entropy stage is one wave of
+// long-running warps; using fewer lanes per warp trades idle lanes for more, less divergent warps.
+extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_entropy(DecEntropyParams p, int lpw) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int stream = warp * lpw + lane;
+  if (lane >= lpw || stream >= p.n_streams) return;
   dec_entropy_thread(p, stream);
 }
 
@@ -63,6 +67,7 @@ struct OpusB200Decoder {
   ObScript *script;
   float *X;
   int pvq_warps;  // warps (= streams) per CTA of the PVQ kernel
+  int ent_lpw;    // streams per warp of the entropy kernel
   // staging for the host-buffer API
   unsigned char *d_packets; size_t d_packets_cap;
   int32_t *d_len, *d_out;
@@ -129,6 +134,10 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
     d->pvq_warps = e ? atoi(e) : 15;
     if (d->pvq_warps < 1) d->pvq_warps = 1;
     if (d->pvq_warps > 16) d->pvq_warps = 16;
+    e = getenv("OPUSB200_ENT_LPW");
+    d->ent_lpw = e ? atoi(e) : 32;
+    if (d->ent_lpw < 1) d->ent_lpw = 1;
+    if (d->ent_lpw > 32) d->ent_lpw = 32;
   }
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -182,7 +191,10 @@ int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, i
     DecPvqParams pp;
     pp.side = d->side; pp.script = d->script; pp.state = d->bstate; pp.X = d->X; pp.n_streams = d->n;
     if (d->timing) cudaEventRecord(d->ev[0], d->stream);
-    ob_celt_dec_entropy<<<(d->n + 127) / 128, 128, 0, d->stream>>>(ep);
+    {
+      const int warps_needed = (d->n + d->ent_lpw - 1) / d->ent_lpw;
+      ob_celt_dec_entropy<<<(warps_needed + 3) / 4, 128, 0, d->stream>>>(ep, d->ent_lpw);
+    }
     if (d->timing) cudaEventRecord(d->ev[1], d->stream);
     ob_celt_dec_pvq<<<(d->n + pw - 1) / pw, pw * 32, pvq_smem, d->stream>>>(pp);
     if (d->timing) cudaEventRecord(d->ev[2], d->stream);
