@@ -131,7 +131,10 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_entropy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
   {
     const char *e = getenv("OPUSB200_PVQ_WARPS");
-    d->pvq_warps = e ? atoi(e) : 15;
+    // default: one CTA per SM holding as many stream-warps as its shared memory allows
+    const int fit = (int)((d->max_smem_optin - ((sizeof(PvqShared) + 15) & ~(size_t)15)) / sizeof(PvqWS));
+    d->pvq_warps = e ? atoi(e) : fit;
+    if (d->pvq_warps > fit) d->pvq_warps = fit;
     if (d->pvq_warps < 1) d->pvq_warps = 1;
     if (d->pvq_warps > 16) d->pvq_warps = 16;
     e = getenv("OPUSB200_ENT_LPW");
