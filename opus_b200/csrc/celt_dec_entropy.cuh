@@ -165,41 +165,39 @@ struct Emit {
   RangeDec ec;
   int32_t remaining_bits;
   ObLeaf *leaves;
-  unsigned char *nodes;
-  int n_leaves, n_nodes;
+  int n_leaves;
   int band, intensity, disable_inv;
 };
 
-OB_DEV void emit_node(Emit &e, unsigned v) {
-  if (e.n_nodes < OB_MAX_NODES) e.nodes[e.n_nodes] = (unsigned char)v;
-  e.n_nodes++;
-}
-OB_DEV void emit_leaf(Emit &e, uint32_t index, float gain, int off, int n, int K, int B, int kind, int lb) {
+OB_DEV void emit_leaf(Emit &e, uint32_t index, float gain, int off, int n, int K, int B, int kind, int lb, unsigned path,
+                      int depth, int cmshift) {
   if (e.n_leaves < OB_MAX_LEAVES) {
     ObLeaf l;
-    l.index = index; l.gain = gain; l.off = (uint16_t)off; l.n = (uint8_t)n; l.K = (uint8_t)K; l.B = (uint8_t)B;
-    l.kind = (uint8_t)kind; l.lb = (uint8_t)lb; l.pad = 0;
+    l.index = index; l.gain = gain; l.off = (uint16_t)off; l.n = (uint8_t)n; l.K = (uint8_t)K;
+    l.path = (uint16_t)((path & 0xFFFu) | (unsigned)depth << 12 | (lb ? 0x8000u : 0u));
+    l.B_kind = (uint8_t)(B | kind << 5);
+    l.cmshift = (uint8_t)cmshift;
     e.leaves[e.n_leaves] = l;
   }
   e.n_leaves++;
 }
 
 // The partition tree of one (mono) band call: entropy side of celt/bands.c:973-1176, as an
-// explicit-stack depth-first walk.  Node byte: bit7 split, bits0-1 theta class, bit2 second half
-// (Y) decoded first; leaves: their kind.
+// explicit-stack depth-first walk; each leaf records its split path (see ObLeaf).
 struct PFrame {
   int b, mbits, sbits, rebalance;
   float gain, mid, side;
   short off, N, itheta;
+  unsigned short path;
   signed char LM;
-  unsigned char B, B0, stage, lb, mid_first;
+  unsigned char B, B0, stage, lb, mid_first, depth, cmshift;
 };
 
 OB_DEV void ent_partition(Emit &e, int off0, int N0, int b0, int B0_, int LM0, float gain0, int lb0) {
   PFrame st[6];
   int sp = 0;
   st[0].off = (short)off0; st[0].N = (short)N0; st[0].b = b0; st[0].B = (unsigned char)B0_; st[0].LM = (signed char)LM0;
-  st[0].gain = gain0; st[0].lb = (unsigned char)lb0; st[0].stage = 0;
+  st[0].gain = gain0; st[0].lb = (unsigned char)lb0; st[0].stage = 0; st[0].path = 0; st[0].depth = 0; st[0].cmshift = 0;
   sp = 1;
   const int band = e.band;
 #pragma unroll 1
@@ -231,11 +229,17 @@ OB_DEV void ent_partition(Emit &e, int off0, int N0, int b0, int B0_, int LM0, f
         f.mid_first = mbits >= sbits;
         f.N = (short)N; f.LM = (signed char)LM; f.B = (unsigned char)B; f.B0 = (unsigned char)B0;
         f.stage = 1;
-        emit_node(e, 0x80u | theta_class(itheta) | (f.mid_first ? 0u : 4u));
         PFrame &c = st[sp++];
         c.stage = 0; c.N = (short)N; c.LM = (signed char)LM; c.B = (unsigned char)B; c.lb = f.lb;
-        if (f.mid_first) { c.off = f.off; c.b = mbits; c.gain = f.gain * f.mid; }
-        else { c.off = (short)(f.off + N); c.b = sbits; c.gain = f.gain * f.side; }
+        c.depth = (unsigned char)(f.depth + 1);
+        const unsigned cls = (unsigned)theta_class(itheta) << (3 * f.depth);
+        if (f.mid_first) {
+          c.off = f.off; c.b = mbits; c.gain = f.gain * f.mid;
+          c.path = (unsigned short)(f.path | cls); c.cmshift = f.cmshift;
+        } else {
+          c.off = (short)(f.off + N); c.b = sbits; c.gain = f.gain * f.side;
+          c.path = (unsigned short)(f.path | cls | 4u << (3 * f.depth)); c.cmshift = (unsigned char)(f.cmshift + (B0 >> 1));
+        }
       } else {
         int q = bits_to_pseudo(cache, b);
         int curr_bits = q == 0 ? 0 : cache[q] + 1;
@@ -250,11 +254,9 @@ OB_DEV void ent_partition(Emit &e, int off0, int N0, int b0, int B0_, int LM0, f
         if (q != 0) {
           const int K = pseudo_to_pulses(q);
           uint32_t idx = e.ec.uint(pvq_u(N, K) + pvq_u(N, K + 1));
-          emit_node(e, 0);
-          emit_leaf(e, idx, f.gain, f.off, N, K, B, 0, f.lb);
+          emit_leaf(e, idx, f.gain, f.off, N, K, B, 0, f.lb, f.path, f.depth, f.cmshift);
         } else {
-          emit_node(e, 1);
-          emit_leaf(e, 0, f.gain, f.off, N, 0, B, 1, f.lb);
+          emit_leaf(e, 0, f.gain, f.off, N, 0, B, 1, f.lb, f.path, f.depth, f.cmshift);
         }
         sp--;
       }
@@ -263,14 +265,18 @@ OB_DEV void ent_partition(Emit &e, int off0, int N0, int b0, int B0_, int LM0, f
       int rebalance;
       PFrame &c = st[sp];
       c.stage = 0; c.N = f.N; c.LM = f.LM; c.B = f.B; c.lb = f.lb;
+      c.depth = (unsigned char)(f.depth + 1);
+      const unsigned cls = (unsigned)theta_class(f.itheta) << (3 * f.depth);
       if (f.mid_first) {
         rebalance = f.mbits - (f.rebalance - e.remaining_bits);
         if (rebalance > 3 << OB_BITRES && f.itheta != 0) f.sbits += rebalance - (3 << OB_BITRES);
         c.off = (short)(f.off + f.N); c.b = f.sbits; c.gain = f.gain * f.side;
+        c.path = (unsigned short)(f.path | cls | 4u << (3 * f.depth)); c.cmshift = (unsigned char)(f.cmshift + (f.B0 >> 1));
       } else {
         rebalance = f.sbits - (f.rebalance - e.remaining_bits);
         if (rebalance > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rebalance - (3 << OB_BITRES);
         c.off = f.off; c.b = f.mbits; c.gain = f.gain * f.mid;
+        c.path = (unsigned short)(f.path | cls); c.cmshift = f.cmshift;
       }
       f.stage = 2;
       sp++;
@@ -289,8 +295,7 @@ OB_DEV void ent_band_mono(Emit &e, int off, int N, int b, int B, int LM, float g
       sign = e.ec.bits(1);
       e.remaining_bits -= 1 << OB_BITRES;
     }
-    emit_node(e, 2);
-    emit_leaf(e, (uint32_t)sign, gain, off, 1, 1, 1, 2, 0);
+    emit_leaf(e, (uint32_t)sign, gain, off, 1, 1, 1, 2, 0, 0, 0, 0);
     return;
   }
   int N_B = (unsigned)N / (unsigned)B;
@@ -427,7 +432,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   const int len = flen;
 
   Emit e;
-  e.leaves = sc->leaves; e.nodes = sc->nodes; e.n_leaves = 0; e.n_nodes = 0;
+  e.leaves = sc->leaves; e.n_leaves = 0;
   e.disable_inv = CC == 1;
   e.remaining_bits = 0;
   RangeDec &dec = e.ec;
@@ -784,13 +789,14 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       if (ds && i == intensity) { ds = 0; flags |= 2; }
       br.eff_lowband = (int16_t)effective_lowband;
       br.lowband_offset = (uint8_t)lowband_offset;
-      br.node_begin = (uint16_t)OB_IMIN(e.n_nodes, 65535);
       br.leaf_begin = (uint16_t)OB_IMIN(e.n_leaves, 65535);
       br.theta_class = 0; br.pad = 0; br.mid = 1.f; br.side = 0.f; br.b = b;
       const int lb = effective_lowband != -1;
+      int leaf_mid = -1;
       if (ds) {
         flags |= 1;
         ent_band_mono(e, xoff, Nb, b / 2, B, LM, 1.0f, lb, tf_change);
+        leaf_mid = e.n_leaves;
         ent_band_mono(e, N + xoff, Nb, b / 2, B, LM, 1.0f, lb, tf_change);
       } else if (C == 2) {
         // control side of quant_band_stereo, celt/bands.c:1387-1570
@@ -799,8 +805,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
           int s0 = 0, s1 = 0;
           if (e.remaining_bits >= 1 << OB_BITRES) { s0 = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; }
           if (e.remaining_bits >= 1 << OB_BITRES) { s1 = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; }
-          emit_node(e, 2);
-          emit_leaf(e, (uint32_t)(s0 | s1 << 1), 1.0f, xoff, 1, 2, 1, 2, 0);
+          emit_leaf(e, (uint32_t)(s0 | s1 << 1), 1.0f, xoff, 1, 2, 1, 2, 0, 0, 0, 0);
         } else {
           ThetaRet tr = ent_theta(dec, i, intensity, e.disable_inv, e.remaining_bits, Nb, b, B, LM, 1);
           dec = tr.ec;
@@ -827,12 +832,14 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
             int32_t rebalance = e.remaining_bits;
             if (mbits >= sbits) {
               ent_band_mono(e, xoff, Nb, mbits, B, LM, 1.0f, lb, tf_change);
+              leaf_mid = e.n_leaves;
               rebalance = mbits - (rebalance - e.remaining_bits);
               if (rebalance > 3 << OB_BITRES && itheta != 0) sbits += rebalance - (3 << OB_BITRES);
               ent_band_mono(e, N + xoff, Nb, sbits, B, LM, br.side, 0, tf_change);
             } else {
               flags |= 128;
               ent_band_mono(e, N + xoff, Nb, sbits, B, LM, br.side, 0, tf_change);
+              leaf_mid = e.n_leaves;
               rebalance = sbits - (rebalance - e.remaining_bits);
               if (rebalance > 3 << OB_BITRES && itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
               ent_band_mono(e, xoff, Nb, mbits, B, LM, 1.0f, lb, tf_change);
@@ -844,6 +851,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       }
       br.flags = (uint8_t)flags;
       br.leaf_end = (uint16_t)OB_IMIN(e.n_leaves, 65535);
+      br.leaf_mid = (uint16_t)(leaf_mid < 0 ? br.leaf_end : OB_IMIN(leaf_mid, 65535));
       sc->bands[i] = br;
       balance += pulses[i] + tl;
       update_lowband = b > (Nb << OB_BITRES);
@@ -881,11 +889,11 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   }
 #pragma unroll 1
   for (int i = 0; i < OB_NBANDS; i++) { side->tf_res[i] = tf_res[i]; side->pulses[i] = (int16_t)pulses[i]; }
-  const int overflow = e.n_leaves > OB_MAX_LEAVES || e.n_nodes > OB_MAX_NODES;
+  const int overflow = e.n_leaves > OB_MAX_LEAVES;
   const int ok = (dec.tell() > 8 * len || overflow) ? -3 : N;  // OPUS_INTERNAL_ERROR
   side->LM = LM; side->transient = isTransient; side->C = C; side->silence = silence; side->end_band = end;
   side->spread = spread; side->intensity = intensity; side->dual_stereo = dual_stereo;
-  side->anti_collapse_on = anti_collapse_on; side->n_leaves = e.n_leaves; side->n_nodes = e.n_nodes;
+  side->anti_collapse_on = anti_collapse_on; side->n_leaves = e.n_leaves; side->reserved0 = 0;
   side->seed = st->rng;
   {  // post-filter parameter pipeline (celt_decoder.c:1540-1563)
     int T_old = OB_IMAX(st->pf_period_old, 15), T_cur = OB_IMAX(st->pf_period, 15);

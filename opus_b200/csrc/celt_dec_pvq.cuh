@@ -48,7 +48,6 @@ struct PvqWS {
   float tmp[176];        // permutation scratch
   unsigned short leaf_cm[OB_MAX_LEAVES];  // up to 16 blocks after a time-divide (bands.c:1303)
   ObBandRec bands[OB_NBANDS];             // staged copy of the script's band records
-  unsigned char nodes[OB_MAX_NODES];      // staged copy of the script's tree bytes
   unsigned char collapse[2 * OB_NBANDS];
   unsigned char pad[6];
 };
@@ -166,8 +165,9 @@ OB_DEV void pvq_phase1(const PvqShared *tab, PvqWS *ws, const ObScript *sc, int 
   for (int l = lane; l < n_leaves; l += 32) {
     const ObLeaf lf = sc->leaves[l];
     float *X = ws->X + lf.off;
-    if (lf.kind == 0) {
-      const int n = lf.n, K = lf.K, B = lf.B;
+    const int kind = lf.B_kind >> 5;
+    if (kind == 0) {
+      const int n = lf.n, K = lf.K, B = lf.B_kind & 31;
       int yy = pvq_index_to_pulses_f(tab, n, K, lf.index, X);
       float g = rsqrt_ref((float)yy) * lf.gain;
       unsigned mask = 1;
@@ -187,7 +187,7 @@ OB_DEV void pvq_phase1(const PvqShared *tab, PvqWS *ws, const ObScript *sc, int 
       for (int j = 0; j < n; j++) X[j] = X[j] * g;
       unrotate_seq(X, n, B, K, spread);
       ws->leaf_cm[l] = (unsigned short)mask;
-    } else if (lf.kind == 2) {  // N == 1 bands: a sign per channel (celt/bands.c:934-968)
+    } else if (kind == 2) {  // N == 1 bands: a sign per channel (celt/bands.c:934-968)
       X[0] = (lf.index & 1) ? -1.f : 1.f;
       if (lf.K == 2) X[Nframe] = (lf.index & 2) ? -1.f : 1.f;
       ws->leaf_cm[l] = 1;
@@ -197,38 +197,32 @@ OB_DEV void pvq_phase1(const PvqShared *tab, PvqWS *ws, const ObScript *sc, int 
 }
 
 // ---- phase 2 -------------------------------------------------------------------------------
-struct Cursor {  // warp-uniform walk state over the script
-  const ObScript *sc;
-  int node, leaf;
-  uint32_t seed;
-};
+struct PartRet { unsigned cm; uint32_t seed; };
 
 // A leaf without pulses (celt/bands.c:1131-1172): zero, LCG noise, or the folded lower band, then
-// renormalised.  Returns its collapse mask.  Rare at high rates, so kept out of line.
-OB_DEVNI unsigned fold_leaf(Cursor &cur, PvqWS *ws, int l, int part_off, int B, const float *lowband, int fill, int lane) {
-  const ObLeaf lf = cur.sc->leaves[l];
-  const int n = lf.n;
-  float *X = ws->X + lf.off;
+// renormalised.  Warp cooperative; all arguments warp-uniform.  Returns collapse mask + new seed.
+OB_DEVNI PartRet fold_leaf(PvqWS *ws, int off, int n, float gain, int has_lb, const float *lbv, int B, int fill, uint32_t seed,
+                          int lane) {
+  float *X = ws->X + off;
   const unsigned cm_mask = (unsigned)(1UL << B) - 1;
-  unsigned cm = 0;
+  PartRet r;
+  r.cm = 0; r.seed = seed;
   fill &= cm_mask;
   wsync();
   if (!fill) {
 #pragma unroll 1
     for (int j = lane; j < n; j += 32) X[j] = 0.f;
     wsync();
-    return 0;
+    return r;
   }
-  uint32_t seed = cur.seed;
-  if (!lf.lb || lowband == nullptr) {
+  if (!has_lb) {
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
       seed = 1664525u * seed + 1013904223u;
       if ((j & 31) == lane) X[j] = (float)((int32_t)seed >> 20);
     }
-    cm = cm_mask;
+    r.cm = cm_mask;
   } else {
-    const float *lbv = lowband + (lf.off - part_off);
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
       seed = 1664525u * seed + 1013904223u;
@@ -238,56 +232,79 @@ OB_DEVNI unsigned fold_leaf(Cursor &cur, PvqWS *ws, int l, int part_off, int B, 
         X[j] = lbv[j] + t;
       }
     }
-    cm = fill;
+    r.cm = fill;
   }
-  cur.seed = seed;
-  renormalise(X, n, lf.gain, lane);
-  return cm;
+  r.seed = seed;
+  renormalise(X, n, gain, lane);
+  return r;
 }
 
-// One band part (celt/bands.c:973-1176 resynthesis side): walk the partition tree, propagate
-// `fill`, produce the zero / noise / folded leaves, combine collapse masks.  The recursion is
-// unrolled by depth at compile time (a band splits at most 4 times: LM 3 -> -1), so the walk state
-// lives in registers; node bytes come from the shared-memory copy of the script.
-template <int DEPTH>
-OB_DEV unsigned walk_node(Cursor &cur, PvqWS *ws, int part_off, int B0, const float *lowband, int fill, int lane) {
-  const unsigned nb = ws->nodes[cur.node++];
-  if (DEPTH < 4 && (nb & 0x80u)) {
-    if (B0 == 1) fill = (fill & 1) | (fill << 1);
-    const int B = (B0 + 1) >> 1;
-    const int cls = nb & 3;
-    if (cls == 0) fill &= (1 << B) - 1;
-    else if (cls == 1) fill &= ((1 << B) - 1) << B;
-    const int yfirst = (nb & 4) != 0;
-    unsigned cm = 0;
+// One band part (resynthesis side of celt/bands.c:973-1176) WITHOUT walking its partition tree:
+// lane l takes leaf l0+l, derives the leaf's `fill` from the part's root fill and the leaf's split
+// path (bands.c:1010-1012: B==1 duplicates the bit, theta 0 / 16384 clear one half, the second
+// child sees fill>>B), pulse-less leaves are produced one after the other in decode order (their
+// LCG draws are order dependent), and the part's collapse mask is the OR of the leaves' masks
+// shifted into place (bands.c:1121).
+OB_DEV PartRet part_leaves(PvqWS *ws, const ObScript *sc, int l0, int l1, int part_off, int B_root, const float *lowband,
+                           int fill_root, uint32_t seed, int lane) {
+  unsigned cm_part = 0;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-      const int is_y = (pass == 0) == (yfirst != 0);
-      unsigned c = walk_node<(DEPTH < 4 ? DEPTH + 1 : 4)>(cur, ws, part_off, B, lowband, is_y ? fill >> B : fill, lane);
-      cm |= is_y ? c << (B0 >> 1) : c;
+  for (int base = l0; base < l1; base += 32) {
+    const int l = base + lane;
+    const bool valid = l < l1;
+    ObLeaf lf;
+    lf.index = 0; lf.gain = 0.f; lf.off = 0; lf.n = 0; lf.K = 0; lf.path = 0; lf.B_kind = 0; lf.cmshift = 0;
+    if (valid) lf = sc->leaves[l];
+    const int kind = lf.B_kind >> 5, Bl = lf.B_kind & 31;
+    // leaf fill from the split path
+    int fill = fill_root, B0 = B_root;
+    const int depth = (lf.path >> 12) & 7;
+    unsigned path = lf.path & 0xFFFu;
+#pragma unroll 1
+    for (int d = 0; d < depth; d++, path >>= 3) {
+      if (B0 == 1) fill = (fill & 1) | (fill << 1);
+      const int B = (B0 + 1) >> 1;
+      const int cls = path & 3;
+      if (cls == 0) fill &= (1 << B) - 1;
+      else if (cls == 1) fill &= ((1 << B) - 1) << B;
+      if (path & 4) fill >>= B;
+      B0 = B;
     }
-    return cm;
+    unsigned cm = (valid && kind != 1) ? ws->leaf_cm[l] : 0u;
+    unsigned pending = ballot(valid && kind == 1);
+#pragma unroll 1
+    while (pending) {
+      const int src = ffs32(pending) - 1;
+      pending &= pending - 1;
+      const int off = shfl((int)lf.off, src), n = shfl((int)lf.n, src), Bs = shfl(Bl, src), fs = shfl(fill, src);
+      const float gain = shfl(lf.gain, src);
+      const int has_lb = shfl((int)(lf.path >> 15), src) && lowband != nullptr;
+      PartRet fr = fold_leaf(ws, off, n, gain, has_lb, has_lb ? lowband + (off - part_off) : nullptr, Bs, fs, seed, lane);
+      seed = fr.seed;
+      if (lane == src) cm = fr.cm;
+    }
+    cm_part |= warp_or(cm << lf.cmshift);
   }
-  const int l = cur.leaf++;
-  if ((nb & 3) != 1) return ws->leaf_cm[l];
-  return fold_leaf(cur, ws, l, part_off, B0, lowband, fill, lane);
+  PartRet r;
+  r.cm = cm_part; r.seed = seed;
+  return r;
 }
 
 // resynthesis side of celt/bands.c:1248-1379
-OB_DEVNI unsigned band_mono_vec(Cursor &cur, PvqWS *ws, int part_off, int N, int B, float *lowband, int LM, float *lowband_out,
-                               float *lowband_scratch, int fill, int tf_change, int lane) {
+OB_DEVNI PartRet band_mono_vec(PvqWS *ws, const ObScript *sc, int l0, int l1, uint32_t seed, int part_off, int N, int B,
+                              float *lowband, float *lowband_out, float *lowband_scratch, int fill, int tf_change, int lane) {
   float *X = ws->X + part_off;
   float *tmp = ws->tmp;
   int N0 = N, N_B = N, N_B0, B0 = B, time_divide = 0, recombine = 0;
   const int longBlocks = B0 == 1;
-  (void)LM;
+  PartRet ret;
+  ret.cm = 1; ret.seed = seed;
   N_B = (unsigned)N_B / (unsigned)B;
   if (N == 1) {  // sign(s) already placed by phase 1
-    cur.node++; cur.leaf++;
     wsync();
     if (lowband_out && lane == 0) lowband_out[0] = X[0];
     wsync();
-    return 1;
+    return ret;
   }
   if (tf_change > 0) recombine = tf_change;
   if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
@@ -319,7 +336,8 @@ OB_DEVNI unsigned band_mono_vec(Cursor &cur, PvqWS *ws, int part_off, int N, int
   B0 = B;
   N_B0 = N_B;
   if (B0 > 1 && lowband) deinterleave_hadamard(lowband, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
-  unsigned cm = walk_node<0>(cur, ws, part_off, B, lowband, fill, lane);
+  ret = part_leaves(ws, sc, l0, l1, part_off, B, lowband, fill, seed, lane);
+  unsigned cm = ret.cm;
   if (B0 > 1) interleave_hadamard(X, tmp, N_B >> recombine, B0 << recombine, longBlocks, lane);
   N_B = N_B0;
   B = B0;
@@ -345,7 +363,8 @@ OB_DEVNI unsigned band_mono_vec(Cursor &cur, PvqWS *ws, int part_off, int N, int
     wsync();
   }
   cm &= (1u << B) - 1;
-  return cm;
+  ret.cm = cm;
+  return ret;
 }
 
 // celt/bands.c:407-466 (stereo_merge)
@@ -430,13 +449,8 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
   const int spread = side->spread, intensity = side->intensity;
   const int B = isTransient ? M : 1;
 
-  // stage the script's tree bytes and band records in shared memory (coalesced 4-byte copies)
+  // stage the script's band records in shared memory (coalesced 4-byte copies)
   {
-    const int nwords = (side->n_nodes + 3) >> 2;
-    const uint32_t *src = (const uint32_t *)sc->nodes;
-    uint32_t *dst = (uint32_t *)ws->nodes;
-#pragma unroll 1
-    for (int i = lane; i < nwords; i += 32) dst[i] = src[i];
     const uint32_t *bs = (const uint32_t *)sc->bands;
     uint32_t *bd = (uint32_t *)ws->bands;
 #pragma unroll 1
@@ -445,8 +459,7 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
   pvq_phase1(tab, ws, sc, side->n_leaves, spread, N, lane);
 
   // ---- phase 2: bands in order (resynthesis side of celt/bands.c:1589-1923) ----
-  Cursor cur;
-  cur.sc = sc; cur.node = 0; cur.leaf = 0; cur.seed = side->seed;
+  uint32_t seed = side->seed;
   const int norm_offset = M * ob_ebands[start];
   float *norm = ws->norm, *norm2 = ws->norm + (M * ob_ebands[OB_NBANDS - 1] - norm_offset);
   for (int i = lane; i < 2 * OB_NBANDS; i += 32) ws->collapse[i] = 0;
@@ -485,18 +498,19 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
     float *lb2 = effective_lowband != -1 ? norm2 + effective_lowband : nullptr;
     float *lo1 = last ? nullptr : norm + M * ob_ebands[i] - norm_offset;
     float *lo2 = last ? nullptr : norm2 + M * ob_ebands[i] - norm_offset;
-    cur.node = br.node_begin;
-    cur.leaf = br.leaf_begin;
+    const int l0 = br.leaf_begin, lm = br.leaf_mid, l1 = br.leaf_end;
+    PartRet pr;
     if (flags & 1) {
-      x_cm = band_mono_vec(cur, ws, xoff, Nb, B, lb1, LM, lo1, lowband_scratch, x_cm, tf_change, lane);
-      y_cm = band_mono_vec(cur, ws, N + xoff, Nb, B, lb2, LM, lo2, lowband_scratch, y_cm, tf_change, lane);
+      pr = band_mono_vec(ws, sc, l0, lm, seed, xoff, Nb, B, lb1, lo1, lowband_scratch, x_cm, tf_change, lane);
+      x_cm = pr.cm; seed = pr.seed;
+      pr = band_mono_vec(ws, sc, lm, l1, seed, N + xoff, Nb, B, lb2, lo2, lowband_scratch, y_cm, tf_change, lane);
+      y_cm = pr.cm; seed = pr.seed;
     } else if (flags & 4) {
       // resynthesis side of quant_band_stereo, celt/bands.c:1387-1570
       float *X = ws->X + xoff, *Y = ws->X + N + xoff;
       int fill = x_cm | y_cm;
       unsigned cm;
       if (Nb == 1) {
-        cur.node++; cur.leaf++;
         wsync();
         if (lo1 && lane == 0) lo1[0] = X[0];
         wsync();
@@ -509,7 +523,8 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
         if (flags & 16) {  // N == 2
           const int c = (flags & 32) != 0;
           const int sign = (flags & 64) ? -1 : 1;
-          cm = band_mono_vec(cur, ws, (c ? N : 0) + xoff, Nb, B, lb1, LM, lo1, lowband_scratch, orig_fill, tf_change, lane);
+          pr = band_mono_vec(ws, sc, l0, l1, seed, (c ? N : 0) + xoff, Nb, B, lb1, lo1, lowband_scratch, orig_fill, tf_change, lane);
+          cm = pr.cm; seed = pr.seed;
           float *x2 = c ? Y : X, *y2 = c ? X : Y;
           wsync();
           if (lane == 0) {
@@ -533,8 +548,10 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
 #pragma unroll 1
           for (int pass = 0; pass < 2; pass++) {
             const int do_mid = (pass == 0) != side_first;
-            if (do_mid) cm |= band_mono_vec(cur, ws, xoff, Nb, B, lb1, LM, lo1, lowband_scratch, fill, tf_change, lane);
-            else cm |= band_mono_vec(cur, ws, N + xoff, Nb, B, nullptr, LM, nullptr, nullptr, fill >> B, tf_change, lane);
+            const int pl0 = pass == 0 ? l0 : lm, pl1 = pass == 0 ? lm : l1;
+            if (do_mid) pr = band_mono_vec(ws, sc, pl0, pl1, seed, xoff, Nb, B, lb1, lo1, lowband_scratch, fill, tf_change, lane);
+            else pr = band_mono_vec(ws, sc, pl0, pl1, seed, N + xoff, Nb, B, nullptr, nullptr, nullptr, fill >> B, tf_change, lane);
+            cm |= pr.cm; seed = pr.seed;
           }
           merge_mid_side(X, Y, mid, Nb, lane);
         }
@@ -547,7 +564,8 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
       }
       x_cm = y_cm = cm;
     } else {
-      x_cm = y_cm = band_mono_vec(cur, ws, xoff, Nb, B, lb1, LM, lo1, lowband_scratch, x_cm | y_cm, tf_change, lane);
+      pr = band_mono_vec(ws, sc, l0, l1, seed, xoff, Nb, B, lb1, lo1, lowband_scratch, x_cm | y_cm, tf_change, lane);
+      x_cm = y_cm = pr.cm; seed = pr.seed;
     }
     wsync();
     if (lane == 0) {
@@ -557,7 +575,7 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
     wsync();
   }
   if (side->anti_collapse_on)
-    anti_collapse_vec(ws, side, lane, LM, C, N, start, end, side->bandE, st->oldLogE, st->oldLogE2, cur.seed);
+    anti_collapse_vec(ws, side, lane, LM, C, N, start, end, side->bandE, st->oldLogE, st->oldLogE2, seed);
   wsync();
   // ---- one coalesced store of the frame's spectrum ----
   {

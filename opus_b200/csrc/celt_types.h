@@ -36,19 +36,21 @@ typedef struct {
 
 /* ---- entropy kernel -> PVQ kernel hand-off ("frame script"), one per stream ------------------ */
 #define OB_MAX_LEAVES 448  /* worst case 416: every band of a stereo 20 ms frame split down to LM=-1 */
-#define OB_MAX_NODES 896
 
-/* One leaf partition of the band tree (celt/bands.c quant_partition no-split case). 16 bytes. */
+/* One leaf partition of the band tree (celt/bands.c quant_partition no-split case). 16 bytes.
+ * `path` describes the splits between the band part's root and this leaf, root first, 3 bits per
+ * split: bits0-1 theta class (0: itheta==0, 1: itheta==16384, 2: other), bit2 set if the leaf lies in
+ * the second (Y) half.  It lets any lane derive the leaf's `fill` mask and the position of its
+ * collapse mask in the part's mask without walking the tree (celt/bands.c:1010-1012, 1121). */
 typedef struct {
-  uint32_t index; /* kind 0: PVQ codeword index (ec_dec_uint result); kind 2: sign bits (bit c = channel c) */
-  float gain;     /* product of the mid/side gains down the tree (celt/bands.c:1078-1089) */
-  uint16_t off;   /* offset in the frame's X[C][N] array */
-  uint8_t n;      /* dimensions (2..176; 1 for kind 2) */
-  uint8_t K;      /* pulses (kind 0) */
-  uint8_t B;      /* blocks at this leaf */
-  uint8_t kind;   /* 0 = PVQ pulses, 1 = no pulses (zero / noise / folded, decided by `fill`), 2 = N==1 signs */
-  uint8_t lb;     /* 1 if a lowband (folding source) exists for this leaf */
-  uint8_t pad;
+  uint32_t index;  /* kind 0: PVQ codeword index (ec_dec_uint result); kind 2: sign bits (bit c = channel c) */
+  float gain;      /* product of the mid/side gains down the tree (celt/bands.c:1078-1089) */
+  uint16_t off;    /* offset in the frame's X[C][N] array */
+  uint8_t n;       /* dimensions (2..176; 1 for kind 2) */
+  uint8_t K;       /* pulses (kind 0); channels (kind 2) */
+  uint16_t path;   /* bits0-11 split path, bits12-14 depth (number of splits), bit15 lowband present */
+  uint8_t B_kind;  /* bits0-4 blocks at this leaf, bits5-6 kind: 0 PVQ pulses, 1 no pulses, 2 N==1 signs */
+  uint8_t cmshift; /* left shift of this leaf's collapse mask inside the part's mask */
 } ObLeaf;
 
 /* Per band: what the vector stage cannot derive without the range decoder. 24 bytes. */
@@ -60,8 +62,8 @@ typedef struct {
                             bit7 side decoded first */
   uint8_t theta_class;   /* stereo theta: 0 -> itheta==0, 1 -> itheta==16384, 2 -> other */
   uint8_t pad;
-  uint16_t node_begin;   /* first tree node byte of this band */
   uint16_t leaf_begin;   /* first leaf of this band */
+  uint16_t leaf_mid;     /* end of the first decoded part's leaves (= leaf_end when the band has one part) */
   uint16_t leaf_end;
   float mid, side;       /* stereo mid/side gains (imid/32768, iside/32768) */
   int32_t b;             /* bits given to the band (debug / update_lowband) */
@@ -75,7 +77,7 @@ typedef struct {
   float pf_g[3];
   float bandE[2 * OB_NBANDS]; /* final log2 band energies (without the means) */
   /* entropy -> PVQ stage */
-  int32_t spread, intensity, dual_stereo, anti_collapse_on, n_leaves, n_nodes;
+  int32_t spread, intensity, dual_stereo, anti_collapse_on, n_leaves, reserved0;
   uint32_t seed;              /* LCG seed at the start of the band loop (previous frame's final range) */
   int8_t tf_res[OB_NBANDS];
   uint8_t pad8[3];
@@ -87,6 +89,5 @@ typedef struct {
 typedef struct {
   ObLeaf leaves[OB_MAX_LEAVES];
   ObBandRec bands[OB_NBANDS];
-  uint8_t nodes[OB_MAX_NODES];
   uint8_t pad[8]; /* keeps sizeof(ObScript) a multiple of 16 */
 } ObScript;
