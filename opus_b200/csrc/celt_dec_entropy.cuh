@@ -182,8 +182,8 @@ OB_DEV void emit_leaf(Emit &e, uint32_t index, float gain, int off, int n, int K
   e.n_leaves++;
 }
 
-// The partition tree of one (mono) band call: entropy side of celt/bands.c:973-1176, as an
-// explicit-stack depth-first walk; each leaf records its split path (see ObLeaf).
+// One frame of the explicit-stack depth-first walk over a band part's partition tree (entropy
+// side of celt/bands.c:973-1176); each leaf records its split path (see ObLeaf).
 struct PFrame {
   int b, mbits, sbits, rebalance;
   float gain, mid, side;
@@ -192,119 +192,6 @@ struct PFrame {
   signed char LM;
   unsigned char B, B0, stage, lb, mid_first, depth, cmshift;
 };
-
-OB_DEV void ent_partition(Emit &e, int off0, int N0, int b0, int B0_, int LM0, float gain0, int lb0) {
-  PFrame st[6];
-  int sp = 0;
-  st[0].off = (short)off0; st[0].N = (short)N0; st[0].b = b0; st[0].B = (unsigned char)B0_; st[0].LM = (signed char)LM0;
-  st[0].gain = gain0; st[0].lb = (unsigned char)lb0; st[0].stage = 0; st[0].path = 0; st[0].depth = 0; st[0].cmshift = 0;
-  sp = 1;
-  const int band = e.band;
-#pragma unroll 1
-  while (sp > 0) {
-    PFrame &f = st[sp - 1];
-    if (f.stage == 0) {
-      int N = f.N, LM = f.LM, b = f.b, B = f.B;
-      const unsigned char *cache = pulse_cache_row(band, LM);
-      if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
-        const int B0 = B;
-        N >>= 1;
-        LM -= 1;
-        B = (B + 1) >> 1;
-        ThetaRet tr = ent_theta(e.ec, band, e.intensity, e.disable_inv, e.remaining_bits, N, b, B0, LM, 0);
-        e.ec = tr.ec;
-        b = tr.t.b;
-        int delta = tr.t.delta;
-        const int itheta = tr.t.itheta;
-        if (B0 > 1 && (itheta & 0x3fff)) {
-          if (itheta > 8192) delta -= delta >> (4 - LM);
-          else delta = OB_IMIN(0, delta + (N << OB_BITRES >> (5 - LM)));
-        }
-        int mbits = OB_IMAX(0, OB_IMIN(b, (b - delta) / 2));
-        int sbits = b - mbits;
-        e.remaining_bits -= tr.t.qalloc;
-        f.mid = (1.f / 32768) * tr.t.imid;
-        f.side = (1.f / 32768) * tr.t.iside;
-        f.mbits = mbits; f.sbits = sbits; f.rebalance = e.remaining_bits; f.itheta = (short)itheta;
-        f.mid_first = mbits >= sbits;
-        f.N = (short)N; f.LM = (signed char)LM; f.B = (unsigned char)B; f.B0 = (unsigned char)B0;
-        f.stage = 1;
-        PFrame &c = st[sp++];
-        c.stage = 0; c.N = (short)N; c.LM = (signed char)LM; c.B = (unsigned char)B; c.lb = f.lb;
-        c.depth = (unsigned char)(f.depth + 1);
-        const unsigned cls = (unsigned)theta_class(itheta) << (3 * f.depth);
-        if (f.mid_first) {
-          c.off = f.off; c.b = mbits; c.gain = f.gain * f.mid;
-          c.path = (unsigned short)(f.path | cls); c.cmshift = f.cmshift;
-        } else {
-          c.off = (short)(f.off + N); c.b = sbits; c.gain = f.gain * f.side;
-          c.path = (unsigned short)(f.path | cls | 4u << (3 * f.depth)); c.cmshift = (unsigned char)(f.cmshift + (B0 >> 1));
-        }
-      } else {
-        int q = bits_to_pseudo(cache, b);
-        int curr_bits = q == 0 ? 0 : cache[q] + 1;
-        e.remaining_bits -= curr_bits;
-#pragma unroll 1
-        while (e.remaining_bits < 0 && q > 0) {
-          e.remaining_bits += curr_bits;
-          q--;
-          curr_bits = q == 0 ? 0 : cache[q] + 1;
-          e.remaining_bits -= curr_bits;
-        }
-        if (q != 0) {
-          const int K = pseudo_to_pulses(q);
-          uint32_t idx = e.ec.uint(pvq_u(N, K) + pvq_u(N, K + 1));
-          emit_leaf(e, idx, f.gain, f.off, N, K, B, 0, f.lb, f.path, f.depth, f.cmshift);
-        } else {
-          emit_leaf(e, 0, f.gain, f.off, N, 0, B, 1, f.lb, f.path, f.depth, f.cmshift);
-        }
-        sp--;
-      }
-    } else if (f.stage == 1) {
-      // first child done: re-balance and descend into the other half (bands.c:1104-1122)
-      int rebalance;
-      PFrame &c = st[sp];
-      c.stage = 0; c.N = f.N; c.LM = f.LM; c.B = f.B; c.lb = f.lb;
-      c.depth = (unsigned char)(f.depth + 1);
-      const unsigned cls = (unsigned)theta_class(f.itheta) << (3 * f.depth);
-      if (f.mid_first) {
-        rebalance = f.mbits - (f.rebalance - e.remaining_bits);
-        if (rebalance > 3 << OB_BITRES && f.itheta != 0) f.sbits += rebalance - (3 << OB_BITRES);
-        c.off = (short)(f.off + f.N); c.b = f.sbits; c.gain = f.gain * f.side;
-        c.path = (unsigned short)(f.path | cls | 4u << (3 * f.depth)); c.cmshift = (unsigned char)(f.cmshift + (f.B0 >> 1));
-      } else {
-        rebalance = f.sbits - (f.rebalance - e.remaining_bits);
-        if (rebalance > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rebalance - (3 << OB_BITRES);
-        c.off = f.off; c.b = f.mbits; c.gain = f.gain * f.mid;
-        c.path = (unsigned short)(f.path | cls); c.cmshift = f.cmshift;
-      }
-      f.stage = 2;
-      sp++;
-    } else {
-      sp--;
-    }
-  }
-}
-
-// entropy side of decode_band_mono (celt/bands.c:1248-1379): only the block count after the TF
-// changes matters to the parser
-OB_DEV void ent_band_mono(Emit &e, int off, int N, int b, int B, int LM, float gain, int lb, int tf_change) {
-  if (N == 1) {  // quant_band_n1, bands.c:934-968 (mono call: one sign)
-    int sign = 0;
-    if (e.remaining_bits >= 1 << OB_BITRES) {
-      sign = e.ec.bits(1);
-      e.remaining_bits -= 1 << OB_BITRES;
-    }
-    emit_leaf(e, (uint32_t)sign, gain, off, 1, 1, 1, 2, 0, 0, 0, 0);
-    return;
-  }
-  int N_B = (unsigned)N / (unsigned)B;
-  int recombine = tf_change > 0 ? tf_change : 0;
-  B >>= recombine;
-  N_B <<= recombine;
-  while ((N_B & 1) == 0 && tf_change < 0) { B <<= 1; N_B >>= 1; tf_change++; }
-  ent_partition(e, off, N, b, B, LM, gain, lb);
-}
 
 // ---- Opus packet framing (RFC 6716 section 3.2; src/opus.c:183-420) -------------------------------
 OB_DEV int parse_size(const unsigned char *d, int len, int &size) {
@@ -757,105 +644,244 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       E[i + c * OB_NBANDS] += offset;
     }
   }
-  // ---- band loop: control side of celt/bands.c:1589-1923 ----
+  // ---- band loop: control side of celt/bands.c:1589-1923, 1387-1570, 1248-1379, 973-1176 ----
+  // Written as ONE flat loop whose iteration is either "start the next band" or "process one node of
+  // the current part's partition tree".  The threads of a warp are different streams with different
+  // trees; a nested band/part/node loop would make them wait for each other at every band and part
+  // boundary, whereas here they reconverge once per iteration no matter which band they are in.
   {
-    const int B = shortBlocks ? M : 1;
+    const int B_frame = shortBlocks ? M : 1;
     const int norm_offset = M * ob_ebands[start];
-    int lowband_offset = 0, update_lowband = 1;
     const int32_t total_b = len * (8 << OB_BITRES) - anti_collapse_rsv;
+    int lowband_offset = 0, update_lowband = 1;
     int ds = dual_stereo;
+    int i = start;
+    int in_band = 0;           // 0: start band i next; 1: walking a part
+    PFrame st[6];
+    int sp = 0;
+    // per-band context
+    ObBandRec br;
+    int32_t tl = 0, rebal0 = 0;
+    int b = 0, Nb = 0, xoff = 0, lb = 0, tf_change = 0, leaf_mid = -1;
+    int nparts = 0, part = 0;  // parts of the current band and the one being walked
+    int p2_off = 0, p2_bits = 0, p1_bits = 0, p2_lb = 0, p2_itheta = 0, p2_is_mid = 0;
+    float p2_gain = 1.f;
+    unsigned flags = 0;
+    br.mid = 1.f; br.side = 0.f;
+    // start part (off, bits, gain, lb): N == 1 is a leaf by itself (quant_band_n1), otherwise the TF
+    // changes fix the block count and the tree walk begins (celt/bands.c:1262-1313)
+#define OB_START_PART(OFF, BITS, GAIN, LBF) do { \
+      if (Nb == 1) { \
+        int sign_ = 0; \
+        if (e.remaining_bits >= 1 << OB_BITRES) { sign_ = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; } \
+        emit_leaf(e, (uint32_t)sign_, (GAIN), (OFF), 1, 1, 1, 2, 0, 0, 0, 0); \
+        sp = 0; \
+      } else { \
+        int Bp_ = B_frame, tfc_ = tf_change; \
+        int N_B_ = (unsigned)Nb / (unsigned)Bp_; \
+        int rec_ = tfc_ > 0 ? tfc_ : 0; \
+        Bp_ >>= rec_; N_B_ <<= rec_; \
+        while ((N_B_ & 1) == 0 && tfc_ < 0) { Bp_ <<= 1; N_B_ >>= 1; tfc_++; } \
+        st[0].off = (short)(OFF); st[0].N = (short)Nb; st[0].b = (BITS); st[0].B = (unsigned char)Bp_; \
+        st[0].LM = (signed char)LM; st[0].gain = (GAIN); st[0].lb = (unsigned char)(LBF); st[0].stage = 0; \
+        st[0].path = 0; st[0].depth = 0; st[0].cmshift = 0; \
+        sp = 1; \
+      } } while (0)
 #pragma unroll 1
-    for (int i = start; i < end; i++) {
-      e.band = i;
-      ObBandRec br;
-      const int Nb = M * ob_ebands[i + 1] - M * ob_ebands[i];
-      const int xoff = M * ob_ebands[i];
-      int32_t tl = dec.tell_frac();
-      if (i != start) balance -= tl;
-      int32_t remaining_bits = total_b - tl - 1;
-      e.remaining_bits = remaining_bits;
-      int b;
-      if (i <= codedBands - 1) {
-        int32_t curr_balance = balance / OB_IMIN(3, codedBands - i);
-        b = OB_IMAX(0, OB_IMIN(16383, OB_IMIN(remaining_bits + 1, pulses[i] + curr_balance)));
-      } else b = 0;
-      if ((M * ob_ebands[i] - Nb >= M * ob_ebands[start] || i == start + 1) && (update_lowband || lowband_offset == 0))
-        lowband_offset = i;
-      const int tf_change = tf_res[i];
-      int effective_lowband = -1;
-      if (lowband_offset != 0 && (spread != 3 || B > 1 || tf_change < 0))
-        effective_lowband = OB_IMAX(0, M * ob_ebands[lowband_offset] - norm_offset - Nb);
-      unsigned flags = 0;
-      if (ds && i == intensity) { ds = 0; flags |= 2; }
-      br.eff_lowband = (int16_t)effective_lowband;
-      br.lowband_offset = (uint8_t)lowband_offset;
-      br.leaf_begin = (uint16_t)OB_IMIN(e.n_leaves, 65535);
-      br.theta_class = 0; br.pad = 0; br.mid = 1.f; br.side = 0.f; br.b = b;
-      const int lb = effective_lowband != -1;
-      int leaf_mid = -1;
-      if (ds) {
-        flags |= 1;
-        ent_band_mono(e, xoff, Nb, b / 2, B, LM, 1.0f, lb, tf_change);
-        leaf_mid = e.n_leaves;
-        ent_band_mono(e, N + xoff, Nb, b / 2, B, LM, 1.0f, lb, tf_change);
-      } else if (C == 2) {
-        // control side of quant_band_stereo, celt/bands.c:1387-1570
-        flags |= 4;
-        if (Nb == 1) {
-          int s0 = 0, s1 = 0;
-          if (e.remaining_bits >= 1 << OB_BITRES) { s0 = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; }
-          if (e.remaining_bits >= 1 << OB_BITRES) { s1 = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; }
-          emit_leaf(e, (uint32_t)(s0 | s1 << 1), 1.0f, xoff, 1, 2, 1, 2, 0, 0, 0, 0);
-        } else {
-          ThetaRet tr = ent_theta(dec, i, intensity, e.disable_inv, e.remaining_bits, Nb, b, B, LM, 1);
-          dec = tr.ec;
-          int bb = tr.t.b;
-          const int itheta = tr.t.itheta, delta = tr.t.delta, qalloc = tr.t.qalloc;
-          br.theta_class = (uint8_t)theta_class(itheta);
-          br.mid = (1.f / 32768) * tr.t.imid;
-          br.side = (1.f / 32768) * tr.t.iside;
-          if (tr.t.inv) flags |= 8;
-          if (Nb == 2) {
-            int mbits = bb, sbits = 0, sign = 0;
-            if (itheta != 0 && itheta != 16384) sbits = 1 << OB_BITRES;
-            mbits -= sbits;
-            const int c = itheta > 8192;
-            e.remaining_bits -= qalloc + sbits;
-            if (sbits) sign = dec.bits(1);
-            flags |= 16 | (c ? 32 : 0) | (sign ? 64 : 0);
-            // mid goes to x2 = c ? Y : X
-            ent_band_mono(e, (c ? N : 0) + xoff, Nb, mbits, B, LM, 1.0f, lb, tf_change);
+    while (i < end) {
+      if (!in_band) {
+        // ------------------------------ start band i ------------------------------
+        e.band = i;
+        Nb = M * ob_ebands[i + 1] - M * ob_ebands[i];
+        xoff = M * ob_ebands[i];
+        tl = dec.tell_frac();
+        if (i != start) balance -= tl;
+        const int32_t remaining_bits = total_b - tl - 1;
+        e.remaining_bits = remaining_bits;
+        if (i <= codedBands - 1) {
+          int32_t curr_balance = balance / OB_IMIN(3, codedBands - i);
+          b = OB_IMAX(0, OB_IMIN(16383, OB_IMIN(remaining_bits + 1, pulses[i] + curr_balance)));
+        } else b = 0;
+        if ((M * ob_ebands[i] - Nb >= M * ob_ebands[start] || i == start + 1) && (update_lowband || lowband_offset == 0))
+          lowband_offset = i;
+        tf_change = tf_res[i];
+        int effective_lowband = -1;
+        if (lowband_offset != 0 && (spread != 3 || B_frame > 1 || tf_change < 0))
+          effective_lowband = OB_IMAX(0, M * ob_ebands[lowband_offset] - norm_offset - Nb);
+        flags = 0;
+        if (ds && i == intensity) { ds = 0; flags |= 2; }
+        br.eff_lowband = (int16_t)effective_lowband;
+        br.lowband_offset = (uint8_t)lowband_offset;
+        br.leaf_begin = (uint16_t)OB_IMIN(e.n_leaves, 65535);
+        br.theta_class = 0; br.pad = 0; br.mid = 1.f; br.side = 0.f; br.b = b;
+        lb = effective_lowband != -1;
+        leaf_mid = -1;
+        part = 0;
+        in_band = 1;
+        if (ds) {
+          flags |= 1;
+          nparts = 2;
+          p1_bits = b / 2; p2_bits = b / 2; p2_off = N + xoff; p2_gain = 1.0f; p2_lb = lb; p2_itheta = -1;
+          OB_START_PART(xoff, b / 2, 1.0f, lb);
+        } else if (C == 2) {
+          // control side of quant_band_stereo, celt/bands.c:1387-1570
+          flags |= 4;
+          if (Nb == 1) {
+            int s0 = 0, s1 = 0;
+            if (e.remaining_bits >= 1 << OB_BITRES) { s0 = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; }
+            if (e.remaining_bits >= 1 << OB_BITRES) { s1 = dec.bits(1); e.remaining_bits -= 1 << OB_BITRES; }
+            emit_leaf(e, (uint32_t)(s0 | s1 << 1), 1.0f, xoff, 1, 2, 1, 2, 0, 0, 0, 0);
+            nparts = 1;
+            sp = 0;
           } else {
-            int mbits = OB_IMAX(0, OB_IMIN(bb, (bb - delta) / 2));
-            int sbits = bb - mbits;
-            e.remaining_bits -= qalloc;
-            int32_t rebalance = e.remaining_bits;
-            if (mbits >= sbits) {
-              ent_band_mono(e, xoff, Nb, mbits, B, LM, 1.0f, lb, tf_change);
-              leaf_mid = e.n_leaves;
-              rebalance = mbits - (rebalance - e.remaining_bits);
-              if (rebalance > 3 << OB_BITRES && itheta != 0) sbits += rebalance - (3 << OB_BITRES);
-              ent_band_mono(e, N + xoff, Nb, sbits, B, LM, br.side, 0, tf_change);
+            ThetaRet tr = ent_theta(dec, i, intensity, e.disable_inv, e.remaining_bits, Nb, b, B_frame, LM, 1);
+            dec = tr.ec;
+            const int bb = tr.t.b;
+            const int itheta = tr.t.itheta, delta = tr.t.delta, qalloc = tr.t.qalloc;
+            br.theta_class = (uint8_t)theta_class(itheta);
+            br.mid = (1.f / 32768) * tr.t.imid;
+            br.side = (1.f / 32768) * tr.t.iside;
+            if (tr.t.inv) flags |= 8;
+            if (Nb == 2) {
+              int mbits = bb, sbits = 0, sign = 0;
+              if (itheta != 0 && itheta != 16384) sbits = 1 << OB_BITRES;
+              mbits -= sbits;
+              const int c = itheta > 8192;
+              e.remaining_bits -= qalloc + sbits;
+              if (sbits) sign = dec.bits(1);
+              flags |= 16 | (c ? 32 : 0) | (sign ? 64 : 0);
+              nparts = 1;
+              OB_START_PART((c ? N : 0) + xoff, mbits, 1.0f, lb);  // the mid goes to x2 = c ? Y : X
             } else {
-              flags |= 128;
-              ent_band_mono(e, N + xoff, Nb, sbits, B, LM, br.side, 0, tf_change);
-              leaf_mid = e.n_leaves;
-              rebalance = sbits - (rebalance - e.remaining_bits);
-              if (rebalance > 3 << OB_BITRES && itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
-              ent_band_mono(e, xoff, Nb, mbits, B, LM, 1.0f, lb, tf_change);
+              int mbits = OB_IMAX(0, OB_IMIN(bb, (bb - delta) / 2));
+              int sbits = bb - mbits;
+              e.remaining_bits -= qalloc;
+              rebal0 = e.remaining_bits;
+              nparts = 2;
+              p2_itheta = itheta;
+              if (mbits >= sbits) {
+                p1_bits = mbits; p2_bits = sbits; p2_off = N + xoff; p2_gain = br.side; p2_lb = 0; p2_is_mid = 0;
+                OB_START_PART(xoff, mbits, 1.0f, lb);
+              } else {
+                flags |= 128;
+                p1_bits = sbits; p2_bits = mbits; p2_off = xoff; p2_gain = 1.0f; p2_lb = lb; p2_is_mid = 1;
+                OB_START_PART(N + xoff, sbits, br.side, 0);
+              }
             }
           }
+        } else {
+          nparts = 1;
+          OB_START_PART(xoff, b, 1.0f, lb);
         }
-      } else {
-        ent_band_mono(e, xoff, Nb, b, B, LM, 1.0f, lb, tf_change);
+      } else if (sp > 0) {
+        // ------------------------------ one tree node ------------------------------
+        PFrame &f = st[sp - 1];
+        if (f.stage == 0) {
+          int Np = f.N, LMp = f.LM, bp = f.b, Bp = f.B;
+          const unsigned char *cache = pulse_cache_row(i, LMp);
+          if (LMp != -1 && bp > cache[cache[0]] + 12 && Np > 2) {
+            const int B0 = Bp;
+            Np >>= 1;
+            LMp -= 1;
+            Bp = (Bp + 1) >> 1;
+            ThetaRet tr = ent_theta(dec, i, intensity, e.disable_inv, e.remaining_bits, Np, bp, B0, LMp, 0);
+            dec = tr.ec;
+            bp = tr.t.b;
+            int delta = tr.t.delta;
+            const int itheta = tr.t.itheta;
+            if (B0 > 1 && (itheta & 0x3fff)) {
+              if (itheta > 8192) delta -= delta >> (4 - LMp);
+              else delta = OB_IMIN(0, delta + (Np << OB_BITRES >> (5 - LMp)));
+            }
+            int mbits = OB_IMAX(0, OB_IMIN(bp, (bp - delta) / 2));
+            int sbits = bp - mbits;
+            e.remaining_bits -= tr.t.qalloc;
+            f.mid = (1.f / 32768) * tr.t.imid;
+            f.side = (1.f / 32768) * tr.t.iside;
+            f.mbits = mbits; f.sbits = sbits; f.rebalance = e.remaining_bits; f.itheta = (short)itheta;
+            f.mid_first = mbits >= sbits;
+            f.N = (short)Np; f.LM = (signed char)LMp; f.B = (unsigned char)Bp; f.B0 = (unsigned char)B0;
+            f.stage = 1;
+            PFrame &c = st[sp++];
+            c.stage = 0; c.N = (short)Np; c.LM = (signed char)LMp; c.B = (unsigned char)Bp; c.lb = f.lb;
+            c.depth = (unsigned char)(f.depth + 1);
+            const unsigned cls = (unsigned)theta_class(itheta) << (3 * f.depth);
+            if (f.mid_first) {
+              c.off = f.off; c.b = mbits; c.gain = f.gain * f.mid;
+              c.path = (unsigned short)(f.path | cls); c.cmshift = f.cmshift;
+            } else {
+              c.off = (short)(f.off + Np); c.b = sbits; c.gain = f.gain * f.side;
+              c.path = (unsigned short)(f.path | cls | 4u << (3 * f.depth)); c.cmshift = (unsigned char)(f.cmshift + (B0 >> 1));
+            }
+          } else {
+            int q = bits_to_pseudo(cache, bp);
+            int curr_bits = q == 0 ? 0 : cache[q] + 1;
+            e.remaining_bits -= curr_bits;
+#pragma unroll 1
+            while (e.remaining_bits < 0 && q > 0) {
+              e.remaining_bits += curr_bits;
+              q--;
+              curr_bits = q == 0 ? 0 : cache[q] + 1;
+              e.remaining_bits -= curr_bits;
+            }
+            if (q != 0) {
+              const int K = pseudo_to_pulses(q);
+              uint32_t idx = dec.uint(pvq_u(Np, K) + pvq_u(Np, K + 1));
+              emit_leaf(e, idx, f.gain, f.off, Np, K, Bp, 0, f.lb, f.path, f.depth, f.cmshift);
+            } else {
+              emit_leaf(e, 0, f.gain, f.off, Np, 0, Bp, 1, f.lb, f.path, f.depth, f.cmshift);
+            }
+            sp--;
+          }
+        } else if (f.stage == 1) {
+          // first child done: re-balance and descend into the other half (bands.c:1104-1122)
+          int rebalance;
+          PFrame &c = st[sp];
+          c.stage = 0; c.N = f.N; c.LM = f.LM; c.B = f.B; c.lb = f.lb;
+          c.depth = (unsigned char)(f.depth + 1);
+          const unsigned cls = (unsigned)theta_class(f.itheta) << (3 * f.depth);
+          if (f.mid_first) {
+            rebalance = f.mbits - (f.rebalance - e.remaining_bits);
+            if (rebalance > 3 << OB_BITRES && f.itheta != 0) f.sbits += rebalance - (3 << OB_BITRES);
+            c.off = (short)(f.off + f.N); c.b = f.sbits; c.gain = f.gain * f.side;
+            c.path = (unsigned short)(f.path | cls | 4u << (3 * f.depth)); c.cmshift = (unsigned char)(f.cmshift + (f.B0 >> 1));
+          } else {
+            rebalance = f.sbits - (f.rebalance - e.remaining_bits);
+            if (rebalance > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rebalance - (3 << OB_BITRES);
+            c.off = f.off; c.b = f.mbits; c.gain = f.gain * f.mid;
+            c.path = (unsigned short)(f.path | cls); c.cmshift = f.cmshift;
+          }
+          f.stage = 2;
+          sp++;
+        } else {
+          sp--;
+        }
       }
-      br.flags = (uint8_t)flags;
-      br.leaf_end = (uint16_t)OB_IMIN(e.n_leaves, 65535);
-      br.leaf_mid = (uint16_t)(leaf_mid < 0 ? br.leaf_end : OB_IMIN(leaf_mid, 65535));
-      sc->bands[i] = br;
-      balance += pulses[i] + tl;
-      update_lowband = b > (Nb << OB_BITRES);
+      if (in_band && sp == 0) {
+        // ------------------------------ a part is complete ------------------------------
+        part++;
+        if (part < nparts) {
+          leaf_mid = e.n_leaves;
+          int bits2 = p2_bits;
+          if (p2_itheta >= 0) {  // stereo split: give unused bits of the first part to the second (bands.c:1523-1547)
+            int32_t rebalance = p1_bits - (rebal0 - e.remaining_bits);
+            if (rebalance > 3 << OB_BITRES && p2_itheta != (p2_is_mid ? 16384 : 0)) bits2 += rebalance - (3 << OB_BITRES);
+          }
+          OB_START_PART(p2_off, bits2, p2_gain, p2_lb);
+        }
+        if (part >= nparts && sp == 0) {
+          br.flags = (uint8_t)flags;
+          br.leaf_end = (uint16_t)OB_IMIN(e.n_leaves, 65535);
+          br.leaf_mid = (uint16_t)(leaf_mid < 0 ? br.leaf_end : OB_IMIN(leaf_mid, 65535));
+          sc->bands[i] = br;
+          balance += pulses[i] + tl;
+          update_lowband = b > (Nb << OB_BITRES);
+          in_band = 0;
+          i++;
+        }
+      }
     }
+#undef OB_START_PART
   }
   int anti_collapse_on = 0;
   if (anti_collapse_rsv > 0) anti_collapse_on = dec.bits(1);

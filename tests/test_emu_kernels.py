@@ -38,3 +38,16 @@ def test_emulated_kernels_transient_dual_stereo_streams(s):
     assert (gr == rr).all()
     assert np.abs(util.to_int16(got).astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
     assert np.abs(got - ref).max() < 2e-6
+
+
+@pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+@pytest.mark.parametrize('ch,fs,br', [(2, 120, 96000), (2, 120, 24000), (2, 240, 32000), (1, 480, 20000)])
+def test_emulated_kernels_short_frames(ch, fs, br):
+    """2.5/5/10 ms frames incl. stereo N==1 bands (sign-only leaves) and low-rate folding."""
+    x = util.sig_music(77 + fs, 10 * fs, ch)
+    pk, sz, _ = util.ref_encode(x, ch, fs, br)
+    ref, rr = util.ref_decode_float(pk, sz, ch, fs)
+    got, gr = emu_util.emu_decode_stream(pk, sz, ch, fs)
+    assert (gr == rr).all()
+    assert np.abs(util.to_int16(got).astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
+    assert np.abs(got - ref).max() < 2e-6
