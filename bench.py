@@ -96,6 +96,21 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference decoder on the host cores
 # ---------------------------------------------------------------------------------------------
+def host_cores():
+    """Usable host cores: the scheduler affinity mask, further limited by a cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def load_cpu_decoder():
     """(lib, kind): the compiled reference if it travelled (oracle/_ref), else the oracle port."""
     ref = os.path.join(ROOT, 'oracle', '_ref', 'libopus_ref_simd.so')
@@ -153,7 +168,7 @@ def run_reference_arm(args, rank, world):
         return
     pk, sz = load_fixture()
     L, kind = load_cpu_decoder()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     # one step = a bounded sample: (64 streams per core) x 8 frames x 4 passes
     n_streams = 64 * cores
     reps = 4
@@ -318,7 +333,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             pass
     # ---- CPU baseline: bounded sample on the host cores ----
     Lc, kind = load_cpu_decoder()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     pkf, szf = load_fixture()
     ns_cpu = 64 * cores
     pkt, szt = tile_streams(pkf, szf, ns_cpu)
