@@ -93,6 +93,34 @@ int64_t opusb200_decoder_launch_count(const OpusB200Decoder *dec);
 int opusb200_decoder_set_timing(OpusB200Decoder *dec, int enable);
 int opusb200_decoder_get_timing(OpusB200Decoder *dec, double *ms_kernels, int64_t *frames);
 
+/* ---- Kernel-level operations, batched (the reference's per-call SIMD plug-in surface with a leading
+ * batch dimension).  Results are bit-identical to the reference's C functions.
+ * Every buffer is a HOST pointer when on_device == 0 (copied in/out, call returns when done) or a
+ * DEVICE pointer when on_device != 0 (work is enqueued on the context's stream; opusb200_ctx_sync). */
+typedef struct OpusB200Ctx OpusB200Ctx;
+int opusb200_ctx_create(int device, OpusB200Ctx **out);
+void opusb200_ctx_destroy(OpusB200Ctx *ctx);
+int opusb200_ctx_sync(OpusB200Ctx *ctx);
+void *opusb200_ctx_cuda_stream(OpusB200Ctx *ctx);
+
+/* Forward MDCT of n_items channel-frames, replaces clt_mdct_forward_c as driven by compute_mdcts
+ * (celt/mdct.c:122, celt/celt_encoder.c:511-554; NE10 plug-in slot celt/mdct.h:80-98).
+ * in: [n_items][(120<<LM)+120] time samples; out: [n_items][120<<LM] coefficients (short blocks
+ * interleaved when transient != 0). */
+int opusb200_mdct_forward(OpusB200Ctx *ctx, const float *in, float *out, int n_items, int LM, int transient, int on_device);
+
+/* celt_pitch_xcorr (celt/pitch.c:230, RTCD slot celt/x86/x86_celt_map.c:95):
+ * xcorr[i] = sum_j x[j]*y[i+j], x: [n_items][len], y: [n_items][len+max_pitch], xcorr: [n_items][max_pitch]. */
+int opusb200_pitch_xcorr(OpusB200Ctx *ctx, const float *x, const float *y, float *xcorr, int n_items, int len, int max_pitch,
+                         int on_device);
+
+/* exp_rotation (celt/vq.c:104) on n_items vectors of N floats in place; K: [n_items] pulses per vector. */
+int opusb200_exp_rotation(OpusB200Ctx *ctx, float *X, const int *K, int n_items, int N, int dir, int stride, int spread, int on_device);
+
+/* op_pvq_search (celt/vq.c:205, RTCD slot celt/x86/x86_celt_map.c:175): X [n_items][N] is replaced
+ * by |X| as in the reference, iy [n_items][N] receives the pulses, yy [n_items] the return value. */
+int opusb200_pvq_search(OpusB200Ctx *ctx, float *X, int *iy, float *yy, const int *K, int n_items, int N, int on_device);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

@@ -9,5 +9,6 @@ GPU, creating a decoder does not.
 from .capi import (OpusB200Error, lib, library_path, build_library, OPUS_OK, OPUS_BAD_ARG, OPUS_BUFFER_TOO_SMALL,
                    OPUS_INTERNAL_ERROR, OPUS_INVALID_PACKET, OPUS_UNIMPLEMENTED, OPUS_INVALID_STATE, OPUS_ALLOC_FAIL)
 from .decoder import DecoderBatch
+from .ops import Ops
 
-__all__ = ['DecoderBatch', 'OpusB200Error', 'lib', 'library_path', 'build_library']
+__all__ = ['DecoderBatch', 'Ops', 'OpusB200Error', 'lib', 'library_path', 'build_library']

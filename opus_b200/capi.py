@@ -23,7 +23,9 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_decoder_reset', 'opusb200_decoder_n_streams', 'opusb200_decode', 'opusb200_decode_float',
            'opusb200_decode_device', 'opusb200_decoder_sync', 'opusb200_decoder_get_final_range',
            'opusb200_decoder_cuda_stream', 'opusb200_decoder_launch_count', 'opusb200_decoder_set_timing',
-           'opusb200_decoder_get_timing', 'opusb200_host_alloc', 'opusb200_host_free']
+           'opusb200_decoder_get_timing', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
+           'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
+           'opusb200_pvq_search', 'opusb200_host_alloc', 'opusb200_host_free']
 
 
 class OpusB200Error(RuntimeError):
@@ -79,6 +81,17 @@ def lib():
         L.opusb200_decoder_launch_count.restype = i64
         L.opusb200_decoder_set_timing.argtypes = [vp, ctypes.c_int]
         L.opusb200_decoder_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+        L.opusb200_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+        L.opusb200_ctx_destroy.argtypes = [vp]
+        L.opusb200_ctx_destroy.restype = None
+        L.opusb200_ctx_sync.argtypes = [vp]
+        L.opusb200_ctx_cuda_stream.argtypes = [vp]
+        L.opusb200_ctx_cuda_stream.restype = vp
+        ci = ctypes.c_int
+        L.opusb200_mdct_forward.argtypes = [vp, vp, vp, ci, ci, ci, ci]
+        L.opusb200_pitch_xcorr.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci]
+        L.opusb200_exp_rotation.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci]
+        L.opusb200_pvq_search.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

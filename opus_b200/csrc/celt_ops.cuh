@@ -1,0 +1,251 @@
+// celt_ops.cuh — encoder-side CELT kernel operations as batched kernels (SURVEY §8 rows a1, a6,
+// a9), each with the reference's exact float operation order so results are bit-identical to the
+// reference's C functions (compile with -fmad=false):
+//   ob_mdct_forward  : clt_mdct_forward_c via compute_mdcts (celt/mdct.c:122-264, celt_encoder.c:511-554)
+//                      one warp per channel-frame; fold+window and pre-rotation fused, FFT in shared memory
+//   ob_pitch_xcorr   : celt_pitch_xcorr_c (celt/pitch.c:230-305); one warp per item, a lane per lag,
+//                      every lag accumulated sequentially like the reference
+//   ob_exp_rotation  : exp_rotation (celt/vq.c:75-147), both directions; one thread per vector
+//   ob_pvq_search    : op_pvq_search_c (celt/vq.c:205-374); one thread per vector, the 32 vectors of a
+//                      warp transposed in shared memory ([element][lane], conflict-free because all
+//                      lanes scan the same element index)
+// These are the building blocks of the fused encoder (next round) and the B3-level parity surface.
+#pragma once
+#include "celt_fft.cuh"
+#include "celt_vec.cuh"
+
+namespace ob {
+
+struct MdctFwdParams {
+  const float *in;   // [n_items][in_stride]: B*N + overlap samples per item
+  float *out;        // [n_items][out_stride]: B*N coefficients per item
+  int n_items, in_stride, out_stride, LM, transient;
+};
+struct MdctWS { float in[OB_MAXN + OB_OVERLAP + 8]; float f2[OB_MAXN]; };
+
+OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  MdctWS *ws = (MdctWS *)smem_warp;
+  const int LM = p.LM;
+  const int nblk = p.transient ? 1 << LM : 1, NB = p.transient ? OB_SHORT_N : OB_SHORT_N << LM;
+  const int shift = p.transient ? 3 : 3 - LM;
+  const int N2 = NB, N4 = NB >> 1, nfft = N4, overlap = OB_OVERLAP;
+  const float *g = p.in + (size_t)item * p.in_stride;
+  for (int i = lane; i < nblk * NB + overlap; i += 32) ws->in[i] = g[i];
+  wsync();
+  const float *trig = ob_mdct_trig;
+  for (int i = 0; i < shift; i++) trig += (1920 >> i) >> 1;
+  const float scale = f_div(1.f, (float)nfft);
+  const short *bitrev = bitrev_table(shift);
+  cpx *f2 = (cpx *)ws->f2;
+  const int q1 = (overlap + 3) >> 2;
+  // window + fold + pre-rotation, one (block, i) pair per lane step (celt/mdct.c:157-226)
+  for (int q = lane; q < nblk * N4; q += 32) {
+    const int b = q / N4, i = q - b * N4;
+    const float *in = ws->in + b * NB;
+    const float *xp1 = in + (overlap >> 1) + 2 * i, *xp2 = in + N2 - 1 + (overlap >> 1) - 2 * i;
+    float re, im;
+    if (i < q1) {
+      const float w1 = ob_window[(overlap >> 1) + 2 * i], w2 = ob_window[(overlap >> 1) - 1 - 2 * i];
+      re = xp1[N2] * w2 + (*xp2) * w1;
+      im = (*xp1) * w1 - xp2[-N2] * w2;
+    } else if (i < N4 - q1) {
+      re = *xp2;
+      im = *xp1;
+    } else {
+      const int k = i - (N4 - q1);
+      const float w1 = ob_window[2 * k], w2 = ob_window[overlap - 1 - 2 * k];
+      re = -(xp1[-N2] * w1) + (*xp2) * w2;
+      im = (*xp1) * w2 + xp2[N2] * w1;
+    }
+    const float t0 = trig[i], t1 = trig[N4 + i];
+    const float yr = re * t0 - im * t1;
+    const float yi = im * t0 + re * t1;
+    cpx v;
+    v.r = yr * scale;
+    v.i = yi * scale;
+    f2[b * nfft + bitrev[i]] = v;
+  }
+  fft_stages(f2, shift, nblk, lane);
+  // post-rotation straight to HBM (celt/mdct.c:236-262); out index = b + nblk*k
+  float *o = p.out + (size_t)item * p.out_stride;
+  for (int q = lane; q < nblk * N4; q += 32) {
+    const int b = q / N4, i = q - b * N4;
+    const cpx fp = f2[b * nfft + i];
+    const float t0 = trig[i], t1 = trig[N4 + i];
+    o[b + nblk * (2 * i)] = fp.i * t1 - fp.r * t0;
+    o[b + nblk * (N2 - 1 - 2 * i)] = fp.r * t1 + fp.i * t0;
+  }
+}
+
+struct XcorrParams {
+  const float *x;  // [n_items][len]
+  const float *y;  // [n_items][len + max_pitch]
+  float *xcorr;    // [n_items][max_pitch]
+  int n_items, len, max_pitch;
+};
+OB_DEV void pitch_xcorr_warp(const XcorrParams &p, int item, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  float *sx = (float *)smem_warp, *sy = sx + ((p.len + 3) & ~3);
+  const float *gx = p.x + (size_t)item * p.len, *gy = p.y + (size_t)item * (p.len + p.max_pitch);
+  for (int i = lane; i < p.len; i += 32) sx[i] = gx[i];
+  for (int i = lane; i < p.len + p.max_pitch; i += 32) sy[i] = gy[i];
+  wsync();
+  float *o = p.xcorr + (size_t)item * p.max_pitch;
+  for (int lag = lane; lag < p.max_pitch; lag += 32) {
+    float sum = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < p.len; j++) sum = sum + sx[j] * sy[lag + j];  // sequential, like xcorr_kernel_c
+    o[lag] = sum;
+  }
+}
+
+// ---- thread-per-vector operations on a transposed shared-memory tile: element j of lane l at
+// tile[j * 32 + l] ----
+struct VqParams {
+  float *X;        // [n_items][N] in/out
+  int *iy;         // [n_items][N] out (search)
+  float *yy;       // [n_items] out (search)
+  const int *K;    // [n_items]
+  int n_items, N, dir, stride, spread;
+};
+#define OB_T(tile, j) (tile)[(j) * 32 + lane]
+
+OB_DEV void rotate_seq_t(float *tile, int lane, int base, int len, int stride, float c, float s) {
+  const float ms = -s;
+  for (int i = 0; i < len - stride; i++) {
+    float x1 = OB_T(tile, base + i), x2 = OB_T(tile, base + i + stride);
+    OB_T(tile, base + i + stride) = c * x2 + s * x1;
+    OB_T(tile, base + i) = c * x1 + ms * x2;
+  }
+  for (int i = len - 2 * stride - 1; i >= 0; i--) {
+    float x1 = OB_T(tile, base + i), x2 = OB_T(tile, base + i + stride);
+    OB_T(tile, base + i + stride) = c * x2 + s * x1;
+    OB_T(tile, base + i) = c * x1 + ms * x2;
+  }
+}
+OB_DEV void exp_rotation_t(float *tile, int lane, int len, int dir, int stride, int K, int spread) {
+  if (2 * K >= len || spread == 0) return;
+  const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
+  float gain = f_div((float)len, (float)(len + factor * K));
+  float theta = .5f * (gain * gain);
+  float c = cos_norm_ref(theta), s = cos_norm_ref(1.0f - theta);
+  int stride2 = 0;
+  if (len >= 8 * stride) {
+    stride2 = 1;
+    while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+  }
+  len = (unsigned)len / (unsigned)stride;
+  for (int i = 0; i < stride; i++) {
+    if (dir < 0) {
+      if (stride2) rotate_seq_t(tile, lane, i * len, len, stride2, s, c);
+      rotate_seq_t(tile, lane, i * len, len, 1, c, s);
+    } else {
+      rotate_seq_t(tile, lane, i * len, len, 1, c, -s);
+      if (stride2) rotate_seq_t(tile, lane, i * len, len, stride2, s, -c);
+    }
+  }
+}
+
+// load / store a warp's 32 vectors between HBM ([item][N]) and the transposed tile, coalesced
+OB_DEV void tile_load(float *tile, const float *g, int first_item, int n_items, int N, int lane) {
+  for (int v = 0; v < 32; v++) {
+    const int item = first_item + v;
+    if (item >= n_items) break;
+    for (int j = lane; j < N; j += 32) tile[j * 32 + v] = g[(size_t)item * N + j];
+  }
+  wsync();
+}
+OB_DEV void tile_store(const float *tile, float *g, int first_item, int n_items, int N, int lane) {
+  wsync();
+  for (int v = 0; v < 32; v++) {
+    const int item = first_item + v;
+    if (item >= n_items) break;
+    for (int j = lane; j < N; j += 32) g[(size_t)item * N + j] = tile[j * 32 + v];
+  }
+}
+
+OB_DEV void exp_rotation_warp(const VqParams &p, int warp, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  float *tile = (float *)smem_warp;
+  const int first = warp * 32, item = first + lane;
+  tile_load(tile, p.X, first, p.n_items, p.N, lane);
+  if (item < p.n_items) exp_rotation_t(tile, lane, p.N, p.dir, p.stride, p.K[item], p.spread);
+  tile_store(tile, p.X, first, p.n_items, p.N, lane);
+}
+
+// op_pvq_search_c, one thread per vector; tiles: X (|X| on return), y (2*pulses as float), sign bytes
+OB_DEV void pvq_search_warp(const VqParams &p, int warp, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  const int N = p.N;
+  float *tx = (float *)smem_warp, *ty = tx + N * 32;
+  unsigned char *ts = (unsigned char *)(ty + N * 32);
+  const int first = warp * 32, item = first + lane;
+  tile_load(tx, p.X, first, p.n_items, N, lane);
+  if (item < p.n_items) {
+    const int K = p.K[item];
+    float sum = 0.f, xy = 0.f, yy = 0.f;
+    for (int j = 0; j < N; j++) {
+      float x = OB_T(tx, j);
+      OB_T(ts, j) = x < 0;
+      OB_T(tx, j) = fabsf(x);
+      OB_T(ty, j) = 0.f;
+    }
+    int pulsesLeft = K;
+    if (K > (N >> 1)) {
+      for (int j = 0; j < N; j++) sum += OB_T(tx, j);
+      if (!(sum > 1e-15f && sum < 64.f)) {
+        OB_T(tx, 0) = 1.f;
+        for (int j = 1; j < N; j++) OB_T(tx, j) = 0.f;
+        sum = 1.f;
+      }
+      const float rcp = (K + 0.8f) * f_div(1.f, sum);
+      for (int j = 0; j < N; j++) {
+        const float x = OB_T(tx, j);
+        const int iyj = (int)floorf(rcp * x);
+        float yj = (float)iyj;
+        yy = yy + yj * yj;
+        xy = xy + x * yj;
+        OB_T(ty, j) = yj * 2;
+        pulsesLeft -= iyj;
+      }
+    }
+    if (pulsesLeft > N + 3) {
+      float tmp = (float)pulsesLeft;
+      yy = yy + tmp * tmp;
+      yy = yy + tmp * OB_T(ty, 0);
+      OB_T(ty, 0) += 2.f * tmp;  // iy[0] += pulsesLeft (y holds 2*iy)
+      pulsesLeft = 0;
+    }
+    for (int i = 0; i < pulsesLeft; i++) {
+      int best_id = 0;
+      yy = yy + 1;
+      float Rxy = xy + OB_T(tx, 0), Ryy = yy + OB_T(ty, 0);
+      Rxy = Rxy * Rxy;
+      float best_den = Ryy, best_num = Rxy;
+      for (int j = 1; j < N; j++) {
+        Rxy = xy + OB_T(tx, j);
+        Ryy = yy + OB_T(ty, j);
+        Rxy = Rxy * Rxy;
+        if (best_den * Rxy > Ryy * best_num) { best_den = Ryy; best_num = Rxy; best_id = j; }
+      }
+      xy = xy + OB_T(tx, best_id);
+      yy = yy + OB_T(ty, best_id);
+      OB_T(ty, best_id) += 2.f;
+    }
+    p.yy[item] = yy;
+  }
+  wsync();
+  // iy out (coalesced), X out
+  for (int v = 0; v < 32; v++) {
+    const int it = first + v;
+    if (it >= p.n_items) break;
+    for (int j = lane; j < N; j += 32) {
+      int m = (int)(ty[j * 32 + v] * .5f);
+      p.iy[(size_t)it * N + j] = ts[j * 32 + v] ? -m : m;
+    }
+  }
+  tile_store(tx, p.X, first, p.n_items, N, lane);
+}
+
+}  // namespace ob

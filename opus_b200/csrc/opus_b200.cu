@@ -11,6 +11,7 @@
 
 #include "../../include/opus_b200.h"
 #include "celt_dec_kernels.cuh"
+#include "celt_ops.cuh"
 
 using namespace ob;
 
@@ -41,6 +42,20 @@ extern "C" __global__ void __launch_bounds__(512) ob_celt_dec_pvq(DecPvqParams p
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParams p) {
   dec_synth_block(p, blockIdx.x, dyn_smem());
 }
+
+// ---- encoder-side kernel operations (celt_ops.cuh) ----
+extern "C" __global__ void __launch_bounds__(128) ob_mdct_forward(MdctFwdParams p) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= p.n_items) return;
+  mdct_forward_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
+}
+extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, int smem_per_warp) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= p.n_items) return;
+  pitch_xcorr_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * smem_per_warp);
+}
+extern "C" __global__ void __launch_bounds__(32) ob_exp_rotation(VqParams p) { exp_rotation_warp(p, blockIdx.x, dyn_smem()); }
+extern "C" __global__ void __launch_bounds__(32) ob_pvq_search(VqParams p) { pvq_search_warp(p, blockIdx.x, dyn_smem()); }
 
 // fresh decoder state (celt/celt_decoder.c:1794-1813 OPUS_RESET_STATE)
 extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState *ss, int n) {
@@ -297,6 +312,147 @@ int opusb200_decoder_get_timing(OpusB200Decoder *d, double *ms_kernels, int64_t 
   ms_kernels[0] = d->kernel_ms[0]; ms_kernels[1] = d->kernel_ms[1]; ms_kernels[2] = d->kernel_ms[2];
   *frames = d->timed_launches;
   return OPUSB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel-level operations (B3-level surface, batched)
+// ------------------------------------------------------------------------------------------
+struct OpusB200Ctx { int device; cudaStream_t stream; int max_smem_optin; int64_t launches; };
+
+int opusb200_ctx_create(int device, OpusB200Ctx **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    fprintf(stderr, "opus_b200: no usable CUDA device (there is no CPU fallback)\n");
+    return OPUSB200_INTERNAL_ERROR;
+  }
+  OB_CUDA(cudaSetDevice(device));
+  OpusB200Ctx *c = new (std::nothrow) OpusB200Ctx;
+  if (!c) return OPUSB200_ALLOC_FAIL;
+  c->device = device; c->launches = 0;
+  OB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OB_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_pitch_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_exp_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_pvq_search, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+  *out = c;
+  return OPUSB200_OK;
+}
+void opusb200_ctx_destroy(OpusB200Ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+int opusb200_ctx_sync(OpusB200Ctx *c) {
+  if (!c) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+void *opusb200_ctx_cuda_stream(OpusB200Ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+// device staging helper for the host-buffer variants of the ops
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 4) == cudaSuccess ? 0 : -1; }
+};
+
+int opusb200_mdct_forward(OpusB200Ctx *c, const float *in, float *out, int n_items, int LM, int transient, int on_device) {
+  if (!c || !in || !out || n_items <= 0 || LM < 0 || LM > 3) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  const int N = OB_SHORT_N << LM, in_stride = N + OB_OVERLAP, out_stride = N;
+  DevBuf di, dout;
+  const float *pin = in;
+  float *pout = out;
+  if (!on_device) {
+    if (di.alloc(sizeof(float) * (size_t)n_items * in_stride) || dout.alloc(sizeof(float) * (size_t)n_items * out_stride)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(di.p, in, sizeof(float) * (size_t)n_items * in_stride, cudaMemcpyHostToDevice, c->stream));
+    pin = (const float *)di.p; pout = (float *)dout.p;
+  }
+  MdctFwdParams p;
+  p.in = pin; p.out = pout; p.n_items = n_items; p.in_stride = in_stride; p.out_stride = out_stride; p.LM = LM; p.transient = transient;
+  const int warps = 4;
+  ob_mdct_forward<<<(n_items + warps - 1) / warps, warps * 32, warps * sizeof(MdctWS), c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(out, pout, sizeof(float) * (size_t)n_items * out_stride, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+
+int opusb200_pitch_xcorr(OpusB200Ctx *c, const float *x, const float *y, float *xcorr, int n_items, int len, int max_pitch,
+                         int on_device) {
+  if (!c || !x || !y || !xcorr || n_items <= 0 || len <= 0 || max_pitch <= 0) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  const int smem_per_warp = (((len + 3) & ~3) + len + max_pitch + 4) * (int)sizeof(float);
+  if (4 * smem_per_warp > c->max_smem_optin) return OPUSB200_BAD_ARG;
+  DevBuf dx, dy, dc;
+  const float *px = x, *py = y;
+  float *pc = xcorr;
+  if (!on_device) {
+    if (dx.alloc(sizeof(float) * (size_t)n_items * len) || dy.alloc(sizeof(float) * (size_t)n_items * (len + max_pitch)) ||
+        dc.alloc(sizeof(float) * (size_t)n_items * max_pitch)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(float) * (size_t)n_items * len, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(dy.p, y, sizeof(float) * (size_t)n_items * (len + max_pitch), cudaMemcpyHostToDevice, c->stream));
+    px = (const float *)dx.p; py = (const float *)dy.p; pc = (float *)dc.p;
+  }
+  XcorrParams p;
+  p.x = px; p.y = py; p.xcorr = pc; p.n_items = n_items; p.len = len; p.max_pitch = max_pitch;
+  ob_pitch_xcorr<<<(n_items + 3) / 4, 128, 4 * smem_per_warp, c->stream>>>(p, smem_per_warp);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(xcorr, pc, sizeof(float) * (size_t)n_items * max_pitch, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+
+static int vq_common(OpusB200Ctx *c, int which, float *X, int *iy, float *yy, const int *K, int n_items, int N, int dir,
+                     int stride, int spread, int on_device) {
+  if (!c || !X || !K || n_items <= 0 || N < 2 || N > 176) return OPUSB200_BAD_ARG;
+  if (which == 1 && (!iy || !yy)) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf dX, dI, dY, dK;
+  float *pX = X, *pY = yy;
+  int *pI = iy;
+  const int *pK = K;
+  const size_t xb = sizeof(float) * (size_t)n_items * N;
+  if (!on_device) {
+    if (dX.alloc(xb) || dK.alloc(sizeof(int) * (size_t)n_items) || dI.alloc(xb) || dY.alloc(sizeof(float) * (size_t)n_items)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(dX.p, X, xb, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(dK.p, K, sizeof(int) * (size_t)n_items, cudaMemcpyHostToDevice, c->stream));
+    pX = (float *)dX.p; pK = (const int *)dK.p; pI = (int *)dI.p; pY = (float *)dY.p;
+  }
+  VqParams p;
+  p.X = pX; p.iy = pI; p.yy = pY; p.K = pK; p.n_items = n_items; p.N = N; p.dir = dir; p.stride = stride; p.spread = spread;
+  const int blocks = (n_items + 31) / 32;
+  if (which == 0) ob_exp_rotation<<<blocks, 32, (size_t)N * 32 * sizeof(float), c->stream>>>(p);
+  else ob_pvq_search<<<blocks, 32, (size_t)N * 32 * (2 * sizeof(float) + 1), c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(X, pX, xb, cudaMemcpyDeviceToHost, c->stream));
+    if (which == 1) {
+      OB_CUDA(cudaMemcpyAsync(iy, pI, xb, cudaMemcpyDeviceToHost, c->stream));
+      OB_CUDA(cudaMemcpyAsync(yy, pY, sizeof(float) * (size_t)n_items, cudaMemcpyDeviceToHost, c->stream));
+    }
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+int opusb200_exp_rotation(OpusB200Ctx *c, float *X, const int *K, int n_items, int N, int dir, int stride, int spread, int on_device) {
+  if (stride < 1 || (N % stride) || (dir != 1 && dir != -1) || spread < 0 || spread > 3) return OPUSB200_BAD_ARG;
+  return vq_common(c, 0, X, nullptr, nullptr, K, n_items, N, dir, stride, spread, on_device);
+}
+int opusb200_pvq_search(OpusB200Ctx *c, float *X, int *iy, float *yy, const int *K, int n_items, int N, int on_device) {
+  return vq_common(c, 1, X, iy, yy, K, n_items, N, 1, 1, 0, on_device);
 }
 
 void *opusb200_host_alloc(size_t bytes) {

@@ -1,0 +1,71 @@
+"""Batched kernel-level operations (host-side mirror of the reference's per-call SIMD plug-in
+functions, with a leading batch dimension).  numpy in / numpy out through the C ABI."""
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Ops:
+    def __init__(self, device=0):
+        self._L = capi.lib()
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_ctx_create(device, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_ctx_create')
+        self._h = h
+
+    def _chk(self, r, what):
+        if r != 0:
+            raise capi.OpusB200Error(r, what)
+
+    def mdct_forward(self, x, LM, transient):
+        """x: [n, (120<<LM)+120] float32 -> [n, 120<<LM]  (clt_mdct_forward via compute_mdcts)"""
+        x = np.ascontiguousarray(x, np.float32)
+        n, N = x.shape[0], 120 << LM
+        assert x.shape[1] == N + 120
+        out = np.empty((n, N), np.float32)
+        self._chk(self._L.opusb200_mdct_forward(self._h, _p(x), _p(out), n, LM, int(transient), 0), 'mdct_forward')
+        return out
+
+    def pitch_xcorr(self, x, y, max_pitch):
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.ascontiguousarray(y, np.float32)
+        n, length = x.shape
+        assert y.shape == (n, length + max_pitch)
+        out = np.empty((n, max_pitch), np.float32)
+        self._chk(self._L.opusb200_pitch_xcorr(self._h, _p(x), _p(y), _p(out), n, length, max_pitch, 0), 'pitch_xcorr')
+        return out
+
+    def exp_rotation(self, X, K, direction, stride, spread):
+        X = np.array(X, np.float32, order='C')
+        K = np.ascontiguousarray(K, np.int32)
+        n, N = X.shape
+        self._chk(self._L.opusb200_exp_rotation(self._h, _p(X), _p(K), n, N, direction, stride, spread, 0), 'exp_rotation')
+        return X
+
+    def pvq_search(self, X, K):
+        """Returns (|X|, iy, yy) like op_pvq_search_c (which overwrites X with |X|)."""
+        X = np.array(X, np.float32, order='C')
+        K = np.ascontiguousarray(K, np.int32)
+        n, N = X.shape
+        iy = np.empty((n, N), np.int32)
+        yy = np.empty(n, np.float32)
+        self._chk(self._L.opusb200_pvq_search(self._h, _p(X), _p(iy), _p(yy), _p(K), n, N, 0), 'pvq_search')
+        return X, iy, yy
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -124,3 +124,36 @@ done:
   free(dec);
   return frames;
 }
+
+/* ---- kernel-level entry points of the reference, for the B3-level parity tests --------------
+ * These wrappers only fetch the reference's static mode (mdct lookup, window) and call the
+ * reference's own non-static functions. */
+#include "celt/modes.h"
+#include "celt/mdct.h"
+#include "celt/pitch.h"
+#include "celt/vq.h"
+#include "celt/bands.h"
+
+static const OpusCustomMode *refh_mode(void) { return opus_custom_mode_create(48000, 960, NULL); }
+
+/* clt_mdct_forward on one block set: in has B*N+overlap samples (N = 120<<LM if !transient, else 120 with
+ * B = 1<<LM blocks), out has B*N coefficients (interleaved by B).  celt/celt_encoder.c:511-554 */
+void refh_mdct_forward(const float *in, float *out, int LM, int transient) {
+  const OpusCustomMode *m = refh_mode();
+  int B = transient ? 1 << LM : 1, N = transient ? 120 : 120 << LM, shift = transient ? 3 : 3 - LM, b;
+  float tmp[960 + 120 + 8];
+  memcpy(tmp, in, sizeof(float) * (B * N + 120));
+  for (b = 0; b < B; b++) clt_mdct_forward_c(&m->mdct, tmp + b * N, &out[b], m->window, 120, shift, B, 0);
+}
+void refh_mdct_backward(const float *in, float *out, int LM, int transient) {
+  const OpusCustomMode *m = refh_mode();
+  int B = transient ? 1 << LM : 1, N = transient ? 120 : 120 << LM, shift = transient ? 3 : 3 - LM, b;
+  float tmp[960 + 8];
+  memcpy(tmp, in, sizeof(float) * B * N);
+  for (b = 0; b < B; b++) clt_mdct_backward_c(&m->mdct, &tmp[b], out + N * b, m->window, 120, shift, B, 0);
+}
+void refh_pitch_xcorr(const float *x, const float *y, float *xcorr, int len, int max_pitch) {
+  celt_pitch_xcorr_c(x, y, xcorr, len, max_pitch, 0);
+}
+void refh_exp_rotation(float *X, int len, int dir, int stride, int K, int spread) { exp_rotation(X, len, dir, stride, K, spread); }
+float refh_pvq_search(float *X, int *iy, int K, int N) { return op_pvq_search_c(X, iy, K, N, 0); }

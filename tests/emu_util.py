@@ -12,9 +12,9 @@ EMU_DIR = os.path.join(util.ROOT, 'tests', 'emu')
 _lib = None
 
 
-def build_emu():
-    src = os.path.join(EMU_DIR, 'emu_decode.cpp')
-    out = os.path.join(EMU_DIR, 'libemu_decode.so')
+def build_emu(name='emu_decode'):
+    src = os.path.join(EMU_DIR, name + '.cpp')
+    out = os.path.join(EMU_DIR, 'lib%s.so' % name)
     deps = [src, os.path.join(EMU_DIR, 'emu_runtime.h')] + [
         os.path.join(util.ROOT, 'opus_b200', 'csrc', f) for f in os.listdir(os.path.join(util.ROOT, 'opus_b200', 'csrc'))]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
@@ -22,6 +22,16 @@ def build_emu():
     subprocess.check_call(['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-unknown-pragmas',
                            '-I' + os.path.join(util.ROOT, 'opus_b200', 'csrc'), '-I' + EMU_DIR, '-o', out, src])
     return out
+
+
+_ops_lib = None
+
+
+def load_emu_ops():
+    global _ops_lib
+    if _ops_lib is None:
+        _ops_lib = ctypes.CDLL(build_emu('emu_ops'))
+    return _ops_lib
 
 
 def load_emu():

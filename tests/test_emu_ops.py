@@ -1,0 +1,67 @@
+"""Encoder-side op kernel SOURCES on the host SIMT emulator vs the oracle restatement: bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu_util
+import util
+
+
+def _f(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize('LM,transient', [(3, 0), (3, 1), (2, 1), (1, 0), (0, 0)])
+def test_emu_mdct_forward(LM, transient):
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(5)
+    N = 120 << LM
+    x = (rng.standard_normal((3, N + 120)) * 1000).astype(np.float32)
+    got = np.zeros((3, N), np.float32)
+    E.emu_mdct_forward(_f(x), _f(got), 3, LM, transient)
+    for i in range(3):
+        want = np.zeros(N, np.float32)
+        O.orc_mdct_forward(_f(x[i]), _f(want), LM, transient)
+        assert np.array_equal(got[i], want)
+
+
+def test_emu_pitch_xcorr():
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(6)
+    n, length, mp = 3, 240, 244
+    x = rng.standard_normal((n, length)).astype(np.float32)
+    y = rng.standard_normal((n, length + mp)).astype(np.float32)
+    got = np.zeros((n, mp), np.float32)
+    E.emu_pitch_xcorr(_f(x), _f(y), _f(got), n, length, mp)
+    for i in range(n):
+        want = np.zeros(mp, np.float32)
+        O.orc_pitch_xcorr(_f(x[i]), _f(y[i]), _f(want), length, mp)
+        assert np.array_equal(got[i], want)
+
+
+@pytest.mark.parametrize('N', [2, 8, 22, 48, 176])
+def test_emu_rotation_and_search(N):
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    O.orc_pvq_search.restype = ctypes.c_float
+    rng = np.random.default_rng(N)
+    n = 40
+    X = rng.standard_normal((n, N)).astype(np.float32)
+    X /= np.sqrt((X.astype(np.float64) ** 2).sum(1))[:, None].astype(np.float32)
+    K = rng.integers(1, 129, size=n).astype(np.int32)
+    for d in (1, -1):
+        for stride in (1, 2):
+            if N % stride:
+                continue
+            got = X.copy()
+            E.emu_exp_rotation(_f(got), _f(K), n, N, d, stride, 2)
+            for i in range(n):
+                w = X[i].copy()
+                O.orc_exp_rotation(_f(w), N, d, stride, int(K[i]), 2)
+                assert np.array_equal(got[i], w)
+    gx, giy, gyy = X.copy(), np.zeros((n, N), np.int32), np.zeros(n, np.float32)
+    E.emu_pvq_search(_f(gx), _f(giy), _f(gyy), _f(K), n, N)
+    for i in range(n):
+        w, wi = X[i].copy(), np.zeros(N, np.int32)
+        wy = O.orc_pvq_search(_f(w), _f(wi), int(K[i]), N)
+        assert np.array_equal(giy[i], wi) and gyy[i] == wy and np.array_equal(gx[i], w)

@@ -1,0 +1,105 @@
+"""Encoder-side batched kernel operations on the GPU, through the C ABI, vs the oracle (and the
+compiled reference where it travelled): bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _f(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope='module')
+def ops():
+    import opus_b200
+    o = opus_b200.Ops()
+    yield o
+    o.close()
+
+
+@pytest.mark.parametrize('LM,transient', [(3, 0), (3, 1), (2, 0), (2, 1), (1, 0), (1, 1), (0, 0)])
+def test_mdct_forward(ops, LM, transient):
+    O = util.load_oracle()
+    rng = np.random.default_rng(LM + 10 * transient)
+    N = 120 << LM
+    n = 300
+    x = (rng.standard_normal((n, N + 120)) * rng.choice([1.0, 300.0, 32768.0], size=(n, 1))).astype(np.float32)
+    got = ops.mdct_forward(x, LM, transient)
+    want = np.zeros(N, np.float32)
+    for i in range(0, n, 7):
+        O.orc_mdct_forward(_f(x[i]), _f(want), LM, transient)
+        assert np.array_equal(got[i], want), i
+    if util.ref_available('c'):
+        R = util.load_ref('c')
+        R.refh_mdct_forward(_f(x[3]), _f(want), LM, transient)
+        assert np.array_equal(got[3], want)
+    # property at scale (reference unit test celt/tests/test_unit_mdct.c): SNR vs a float64 MDCT
+    if not transient:
+        k = np.arange(N)
+        nn = np.arange(2 * N)
+        # the MDCT input is N+overlap samples; the implied 2N window has (N-overlap)/2 zeros on each side
+        win = np.sin(.5 * np.pi * np.sin(.5 * np.pi * (np.arange(120) + .5) / 120) ** 2)
+        full = np.zeros(2 * N)
+        z = (N - 120) // 2
+        xin = x[0].astype(np.float64)
+        full[z:z + N + 120] = xin
+        w = np.ones(2 * N)
+        w[:z] = 0
+        w[z:z + 120] = win
+        w[z + N:z + N + 120] = win[::-1]
+        w[z + N + 120:] = 0
+        ref = np.array([(full * w * np.cos(2 * np.pi / (2 * N) * (nn + .5 + N / 2) * (kk + .5))).sum() for kk in k]) / (N // 2) / 2
+        # scale conventions differ by a constant factor; fit it
+        g = (ref * got[0]).sum() / (ref * ref).sum()
+        snr = 10 * np.log10((got[0].astype(np.float64) ** 2).sum() / ((got[0] - g * ref) ** 2).sum())
+        assert snr > 120, snr
+
+
+@pytest.mark.parametrize('length,max_pitch', [(240, 244), (480, 8), (1024, 64)])
+def test_pitch_xcorr(ops, length, max_pitch):
+    O = util.load_oracle()
+    rng = np.random.default_rng(length)
+    n = 200
+    x = rng.standard_normal((n, length)).astype(np.float32)
+    y = rng.standard_normal((n, length + max_pitch)).astype(np.float32)
+    got = ops.pitch_xcorr(x, y, max_pitch)
+    want = np.zeros(max_pitch, np.float32)
+    for i in range(0, n, 11):
+        O.orc_pitch_xcorr(_f(x[i]), _f(y[i]), _f(want), length, max_pitch)
+        assert np.array_equal(got[i], want)
+
+
+@pytest.mark.parametrize('N', [2, 4, 8, 16, 22, 32, 48, 88, 144, 176])
+def test_rotation_and_search(ops, N):
+    O = util.load_oracle()
+    O.orc_pvq_search.restype = ctypes.c_float
+    rng = np.random.default_rng(N)
+    n = 500
+    X = rng.standard_normal((n, N)).astype(np.float32)
+    X /= np.sqrt((X.astype(np.float64) ** 2).sum(1))[:, None].astype(np.float32)
+    X[0] = 0
+    X[1] = 1e-20
+    K = rng.integers(1, 129, size=n).astype(np.int32)
+    for d in (1, -1):
+        for stride in (1, 2, 8):
+            if N % stride:
+                continue
+            got = ops.exp_rotation(X, K, d, stride, 3)
+            for i in range(0, n, 13):
+                w = X[i].copy()
+                O.orc_exp_rotation(_f(w), N, d, stride, int(K[i]), 3)
+                assert np.array_equal(got[i], w)
+            # invertibility (celt/tests/test_unit_rotation.c)
+            back = ops.exp_rotation(got, K, -d, stride, 3)
+            assert np.abs(back[2:] - X[2:]).max() < 1e-5
+    gx, giy, gyy = ops.pvq_search(X, K)
+    assert (np.abs(giy).sum(1) == K).all()
+    for i in range(0, n, 3):
+        w, wi = X[i].copy(), np.zeros(N, np.int32)
+        wy = O.orc_pvq_search(_f(w), _f(wi), int(K[i]), N)
+        assert np.array_equal(giy[i], wi) and gyy[i] == wy and np.array_equal(gx[i], w), i
