@@ -121,6 +121,20 @@ int opusb200_exp_rotation(OpusB200Ctx *ctx, float *X, const int *K, int n_items,
  * by |X| as in the reference, iy [n_items][N] receives the pulses, yy [n_items] the return value. */
 int opusb200_pvq_search(OpusB200Ctx *ctx, float *X, int *iy, float *yy, const int *K, int n_items, int N, int on_device);
 
+/* silk_LPC_analysis_filter (silk/LPC_analysis_filter.c:49; called from silk/NSQ_del_dec.c:252 and the
+ * float wrappers): out/in [n_items][len] int16, B [n_items][d] Q12 coefficients, d even, 6..24. */
+int opusb200_silk_lpc_analysis_filter(OpusB200Ctx *ctx, int16_t *out, const int16_t *in, const int16_t *B, int n_items, int len,
+                                      int d, int on_device);
+
+/* silk_resampler (silk/resampler.c:77 init, :183 process), encoder-side down-sampling with persistent
+ * per-stream state; integer ratios 1:2, 1:3, 1:4, 1:6 (48->16 kHz is config 4's).  in [n][in_len],
+ * out [n][in_len*Fs_out/Fs_in]; in_len a multiple of 1 ms, at most 40 ms. */
+typedef struct OpusB200SilkResampler OpusB200SilkResampler;
+int opusb200_silk_resampler_create(OpusB200Ctx *ctx, int n_streams, int32_t Fs_in, int32_t Fs_out, OpusB200SilkResampler **out);
+void opusb200_silk_resampler_destroy(OpusB200SilkResampler *rs);
+int opusb200_silk_resampler_reset(OpusB200SilkResampler *rs);
+int opusb200_silk_resampler_process(OpusB200SilkResampler *rs, const int16_t *in, int16_t *out, int in_len, int on_device);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

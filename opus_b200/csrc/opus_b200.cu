@@ -12,6 +12,7 @@
 #include "../../include/opus_b200.h"
 #include "celt_dec_kernels.cuh"
 #include "celt_ops.cuh"
+#include "silk_ops.cuh"
 
 using namespace ob;
 
@@ -56,6 +57,16 @@ extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, 
 }
 extern "C" __global__ void __launch_bounds__(32) ob_exp_rotation(VqParams p) { exp_rotation_warp(p, blockIdx.x, dyn_smem()); }
 extern "C" __global__ void __launch_bounds__(32) ob_pvq_search(VqParams p) { pvq_search_warp(p, blockIdx.x, dyn_smem()); }
+
+// ---- SILK integer kernels (silk_ops.cuh): one thread per stream ----
+extern "C" __global__ void __launch_bounds__(128) ob_silk_lpc_analysis_filter(SilkLpcParams p) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < p.n_items) silk_lpc_analysis_filter_thread(p, item);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_silk_resampler_down(SilkResamplerParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) silk_resampler_thread(p, s);
+}
 
 // fresh decoder state (celt/celt_decoder.c:1794-1813 OPUS_RESET_STATE)
 extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState *ss, int n) {
@@ -453,6 +464,114 @@ int opusb200_exp_rotation(OpusB200Ctx *c, float *X, const int *K, int n_items, i
 }
 int opusb200_pvq_search(OpusB200Ctx *c, float *X, int *iy, float *yy, const int *K, int n_items, int N, int on_device) {
   return vq_common(c, 1, X, iy, yy, K, n_items, N, 1, 1, 0, on_device);
+}
+
+int opusb200_silk_lpc_analysis_filter(OpusB200Ctx *c, int16_t *out, const int16_t *in, const int16_t *B, int n_items, int len,
+                                      int d, int on_device) {
+  if (!c || !out || !in || !B || n_items <= 0 || d < 6 || (d & 1) || d > 24 || d > len) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf di, dob, db;
+  const int16_t *pin = in, *pB = B;
+  int16_t *pout = out;
+  const size_t nb = sizeof(int16_t) * (size_t)n_items * len, bb = sizeof(int16_t) * (size_t)n_items * d;
+  if (!on_device) {
+    if (di.alloc(nb) || dob.alloc(nb) || db.alloc(bb)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(di.p, in, nb, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(db.p, B, bb, cudaMemcpyHostToDevice, c->stream));
+    pin = (const int16_t *)di.p; pB = (const int16_t *)db.p; pout = (int16_t *)dob.p;
+  }
+  SilkLpcParams p;
+  p.out = pout; p.in = pin; p.B = pB; p.n_items = n_items; p.len = len; p.d = d;
+  ob_silk_lpc_analysis_filter<<<(n_items + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(out, pout, nb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+
+struct OpusB200SilkResampler {
+  OpusB200Ctx *ctx;
+  int n, fs_in, fs_out;
+  ObSilkResamplerState *state;
+  SilkResamplerParams proto;
+};
+
+int opusb200_silk_resampler_create(OpusB200Ctx *c, int n_streams, int32_t Fs_in, int32_t Fs_out, OpusB200SilkResampler **out) {
+  if (!c || !out || n_streams <= 0) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  static const int8_t delay_enc[5][3] = {{6, 0, 3}, {0, 7, 3}, {0, 1, 10}, {0, 2, 6}, {18, 10, 12}};  // silk/resampler.c:53-61
+  static const int16_t c12[14] = {616, -14323, -10, 39, 58, -46, -84, 120, 184, -315, -541, 1284, 5380, 9024};
+  static const int16_t c13[20] = {16102, -15162, -13, 0, 20, 26, 5, -31, -43, -4, 65, 90, 7, -157, -248, -44, 593, 1583, 2612, 3271};
+  static const int16_t c14[20] = {22500, -15099, 3, -14, -20, -15, 2, 25, 37, 25, -16, -71, -107, -79, 50, 292, 623, 982, 1288, 1464};
+  static const int16_t c16[20] = {27540, -15257, 17, 12, 8, 1, -10, -22, -30, -32, -22, 3, 44, 100, 168, 243, 317, 381, 429, 455};
+  const int ri = Fs_in == 8000 ? 0 : Fs_in == 12000 ? 1 : Fs_in == 16000 ? 2 : Fs_in == 24000 ? 3 : Fs_in == 48000 ? 4 : -1;
+  const int ro = Fs_out == 8000 ? 0 : Fs_out == 12000 ? 1 : Fs_out == 16000 ? 2 : -1;
+  if (ri < 0 || ro < 0) return OPUSB200_BAD_ARG;
+  const int16_t *cf;
+  int order;
+  if (Fs_out * 2 == Fs_in) { cf = c12; order = 24; }
+  else if (Fs_out * 3 == Fs_in) { cf = c13; order = 36; }
+  else if (Fs_out * 4 == Fs_in) { cf = c14; order = 36; }
+  else if (Fs_out * 6 == Fs_in) { cf = c16; order = 36; }
+  else return OPUSB200_UNIMPLEMENTED;  // fractional ratios (3:4, 2:3) and up-sampling: not on the hot path
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200SilkResampler *r = new (std::nothrow) OpusB200SilkResampler;
+  if (!r) return OPUSB200_ALLOC_FAIL;
+  r->ctx = c; r->n = n_streams; r->fs_in = Fs_in; r->fs_out = Fs_out;
+  OB_CUDA(cudaMalloc(&r->state, sizeof(ObSilkResamplerState) * (size_t)n_streams));
+  OB_CUDA(cudaMemsetAsync(r->state, 0, sizeof(ObSilkResamplerState) * (size_t)n_streams, c->stream));
+  SilkResamplerParams &p = r->proto;
+  memset(&p, 0, sizeof(p));
+  p.state = r->state; p.n_streams = n_streams; p.fir_order = order; p.fs_in_khz = Fs_in / 1000; p.fs_out_khz = Fs_out / 1000;
+  p.input_delay = delay_enc[ri][ro]; p.batch = p.fs_in_khz * 10;
+  p.inv_ratio_q16 = (int32_t)((((int64_t)Fs_in << 14) / Fs_out) << 2);
+  while ((int32_t)(((int64_t)p.inv_ratio_q16 * Fs_out) >> 16) < Fs_in) p.inv_ratio_q16++;
+  for (int i = 0; i < 2 + order / 2; i++) p.coefs[i] = cf[i];
+  *out = r;
+  return OPUSB200_OK;
+}
+void opusb200_silk_resampler_destroy(OpusB200SilkResampler *r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->state);
+  delete r;
+}
+int opusb200_silk_resampler_reset(OpusB200SilkResampler *r) {
+  if (!r) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(r->ctx->device));
+  OB_CUDA(cudaMemsetAsync(r->state, 0, sizeof(ObSilkResamplerState) * (size_t)r->n, r->ctx->stream));
+  return OPUSB200_OK;
+}
+int opusb200_silk_resampler_process(OpusB200SilkResampler *r, const int16_t *in, int16_t *out, int in_len, int on_device) {
+  if (!r || !in || !out) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = r->ctx;
+  const int khz = r->fs_in / 1000;
+  if (in_len < khz || in_len % khz || in_len > 480 * 4) return OPUSB200_BAD_ARG;
+  const int out_len = in_len / khz * (r->fs_out / 1000);
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf di, dob;
+  const int16_t *pin = in;
+  int16_t *pout = out;
+  const size_t ib = sizeof(int16_t) * (size_t)r->n * in_len, ob_ = sizeof(int16_t) * (size_t)r->n * out_len;
+  if (!on_device) {
+    if (di.alloc(ib) || dob.alloc(ob_)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(di.p, in, ib, cudaMemcpyHostToDevice, c->stream));
+    pin = (const int16_t *)di.p; pout = (int16_t *)dob.p;
+  }
+  SilkResamplerParams p = r->proto;
+  p.in = pin; p.out = pout; p.in_len = in_len; p.out_len = out_len;
+  ob_silk_resampler_down<<<(r->n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(out, pout, ob_, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
 }
 
 void *opusb200_host_alloc(size_t bytes) {

@@ -59,6 +59,18 @@ class Ops:
         self._chk(self._L.opusb200_pvq_search(self._h, _p(X), _p(iy), _p(yy), _p(K), n, N, 0), 'pvq_search')
         return X, iy, yy
 
+    def silk_lpc_analysis_filter(self, x, B):
+        """x [n, len] int16, B [n, d] int16 Q12 -> [n, len] int16 (silk_LPC_analysis_filter)"""
+        x = np.ascontiguousarray(x, np.int16)
+        B = np.ascontiguousarray(B, np.int16)
+        out = np.empty_like(x)
+        self._chk(self._L.opusb200_silk_lpc_analysis_filter(self._h, _p(out), _p(x), _p(B), x.shape[0], x.shape[1], B.shape[1], 0),
+                  'silk_lpc_analysis_filter')
+        return out
+
+    def silk_resampler(self, n_streams, fs_in, fs_out):
+        return SilkResampler(self, n_streams, fs_in, fs_out)
+
     def close(self):
         if getattr(self, '_h', None):
             self._L.opusb200_ctx_destroy(self._h)
@@ -69,3 +81,29 @@ class Ops:
             self.close()
         except Exception:
             pass
+
+
+class SilkResampler:
+    """n_streams encoder-side SILK resamplers (silk_resampler_init(S, fs_in, fs_out, 1) / silk_resampler)."""
+
+    def __init__(self, ops, n_streams, fs_in, fs_out):
+        self._ops, self._L, self.n, self.fs_in, self.fs_out = ops, ops._L, n_streams, fs_in, fs_out
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_silk_resampler_create(ops._h, n_streams, fs_in, fs_out, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_resampler_create')
+        self._h = h
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, np.int16)
+        assert x.shape[0] == self.n
+        out = np.empty((self.n, x.shape[1] * self.fs_out // self.fs_in), np.int16)
+        r = self._L.opusb200_silk_resampler_process(self._h, _p(x), _p(out), x.shape[1], 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_resampler_process')
+        return out
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_silk_resampler_destroy(self._h)
+            self._h = None

@@ -157,3 +157,8 @@ void refh_pitch_xcorr(const float *x, const float *y, float *xcorr, int len, int
 }
 void refh_exp_rotation(float *X, int len, int dir, int stride, int K, int spread) { exp_rotation(X, len, dir, stride, K, spread); }
 float refh_pvq_search(float *X, int *iy, int K, int N) { return op_pvq_search_c(X, iy, K, N, 0); }
+
+/* ---- SILK kernel-level entry points ---- */
+#include "silk/SigProc_FIX.h"
+#include "silk/resampler_structs.h"
+int refh_resampler_size(void) { return (int)sizeof(silk_resampler_state_struct); }

@@ -33,3 +33,36 @@ void emu_pvq_search(float *X, int *iy, float *yy, const int *K, int n, int N) {
   emu_launch(search_entry, &p, (n + 31) / 32, 32, (size_t)N * 32 * (2 * sizeof(float) + 1));
 }
 }
+
+// ---- SILK integer kernels ----
+#include "../../opus_b200/csrc/silk_ops.cuh"
+static void lpc_entry(void *a) {
+  const SilkLpcParams &p = *(const SilkLpcParams *)a;
+  int item = block_id() * 32 + lane_id();
+  if (item < p.n_items) silk_lpc_analysis_filter_thread(p, item);
+}
+static void rs_entry(void *a) {
+  const SilkResamplerParams &p = *(const SilkResamplerParams *)a;
+  int s = block_id() * 32 + lane_id();
+  if (s < p.n_streams) silk_resampler_thread(p, s);
+}
+extern "C" {
+void emu_silk_lpc(int16_t *out, const int16_t *in, const int16_t *B, int n, int len, int d) {
+  SilkLpcParams p;
+  p.out = out; p.in = in; p.B = B; p.n_items = n; p.len = len; p.d = d;
+  emu_launch(lpc_entry, &p, (n + 31) / 32, 32, 0);
+}
+int emu_silk_resampler_state_size(void) { return (int)sizeof(ObSilkResamplerState); }
+// 48 kHz -> 16 kHz only (the emulator test's configuration)
+void emu_silk_resampler_48_16(void *state, const int16_t *in, int16_t *out, int n, int in_len) {
+  static const int16_t c13[20] = {16102, -15162, -13, 0, 20, 26, 5, -31, -43, -4, 65, 90, 7, -157, -248, -44, 593, 1583, 2612, 3271};
+  SilkResamplerParams p;
+  memset(&p, 0, sizeof(p));
+  p.state = (ObSilkResamplerState *)state; p.in = in; p.out = out; p.n_streams = n; p.in_len = in_len; p.out_len = in_len / 3;
+  p.fir_order = 36; p.fs_in_khz = 48; p.fs_out_khz = 16; p.input_delay = 12; p.batch = 480;
+  p.inv_ratio_q16 = (int32_t)((((int64_t)48000 << 14) / 16000) << 2);
+  while ((int32_t)(((int64_t)p.inv_ratio_q16 * 16000) >> 16) < 48000) p.inv_ratio_q16++;
+  for (int i = 0; i < 20; i++) p.coefs[i] = c13[i];
+  emu_launch(rs_entry, &p, (n + 31) / 32, 32, 0);
+}
+}

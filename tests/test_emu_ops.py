@@ -65,3 +65,30 @@ def test_emu_rotation_and_search(N):
         w, wi = X[i].copy(), np.zeros(N, np.int32)
         wy = O.orc_pvq_search(_f(w), _f(wi), int(K[i]), N)
         assert np.array_equal(giy[i], wi) and gyy[i] == wy and np.array_equal(gx[i], w)
+
+
+def test_emu_silk_lpc_and_resampler():
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(9)
+    n, length, d = 40, 320, 16
+    x = rng.integers(-20000, 20000, size=(n, length)).astype(np.int16)
+    B = rng.integers(-4000, 4000, size=(n, d)).astype(np.int16)
+    got = np.zeros_like(x)
+    E.emu_silk_lpc(_f(got), _f(x), _f(B), n, length, d)
+    want = np.zeros(length, np.int16)
+    for i in range(n):
+        O.orc_silk_lpc_analysis_filter(_f(want), _f(x[i]), _f(B[i]), length, d)
+        assert np.array_equal(got[i], want)
+    # resampler 48 -> 16 kHz, 3 frames of 20 ms, state carried
+    st = np.zeros(n * E.emu_silk_resampler_state_size(), np.uint8)
+    os_ = [ctypes.create_string_buffer(O.orc_resampler_size()) for _ in range(n)]
+    for s in os_:
+        assert O.orc_resampler_init(s, 48000, 16000) == 0
+    for fr in range(3):
+        xin = rng.integers(-30000, 30000, size=(n, 960)).astype(np.int16)
+        got = np.zeros((n, 320), np.int16)
+        E.emu_silk_resampler_48_16(_f(st), _f(xin), _f(got), n, 960)
+        w = np.zeros(320, np.int16)
+        for i in range(n):
+            O.orc_resampler_process(os_[i], _f(w), _f(xin[i]), 960)
+            assert np.array_equal(got[i], w), (fr, i)

@@ -103,3 +103,38 @@ def test_rotation_and_search(ops, N):
         w, wi = X[i].copy(), np.zeros(N, np.int32)
         wy = O.orc_pvq_search(_f(w), _f(wi), int(K[i]), N)
         assert np.array_equal(giy[i], wi) and gyy[i] == wy and np.array_equal(gx[i], w), i
+
+
+@pytest.mark.parametrize('d,length', [(16, 320), (10, 160), (24, 200)])
+def test_silk_lpc_analysis_filter(ops, d, length):
+    O = util.load_oracle()
+    rng = np.random.default_rng(d)
+    n = 3000
+    x = rng.integers(-32768, 32768, size=(n, length)).astype(np.int16)
+    B = rng.integers(-32768, 32768, size=(n, d)).astype(np.int16)
+    got = ops.silk_lpc_analysis_filter(x, B)
+    want = np.zeros(length, np.int16)
+    for i in range(0, n, 97):
+        O.orc_silk_lpc_analysis_filter(_f(want), _f(x[i]), _f(B[i]), length, d)
+        assert np.array_equal(got[i], want)
+
+
+@pytest.mark.parametrize('fs_in,fs_out', [(48000, 16000), (48000, 8000), (48000, 12000), (24000, 12000), (16000, 8000)])
+def test_silk_resampler(ops, fs_in, fs_out):
+    O = util.load_oracle()
+    rng = np.random.default_rng(fs_in + fs_out)
+    n = 1000
+    rs = ops.silk_resampler(n, fs_in, fs_out)
+    check = list(range(0, n, 83))
+    orc = {i: ctypes.create_string_buffer(O.orc_resampler_size()) for i in check}
+    for s in orc.values():
+        assert O.orc_resampler_init(s, fs_in, fs_out) == 0
+    n_in, n_out = fs_in // 50, fs_out // 50
+    for fr in range(6):
+        x = rng.integers(-32768, 32768, size=(n, n_in)).astype(np.int16)
+        got = rs.process(x)
+        w = np.zeros(n_out, np.int16)
+        for i in check:
+            O.orc_resampler_process(orc[i], _f(w), _f(x[i]), n_in)
+            assert np.array_equal(got[i], w), (fr, i)
+    rs.close()

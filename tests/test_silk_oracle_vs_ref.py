@@ -1,0 +1,48 @@
+"""SILK integer kernels: oracle restatement vs the reference's functions, bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built (reference absent)')
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize('d,length', [(16, 320), (10, 160), (16, 496), (6, 40), (24, 100)])
+def test_lpc_analysis_filter(d, length):
+    R, O = util.load_ref('c'), util.load_oracle()
+    rng = np.random.default_rng(d * 1000 + length)
+    for amp, camp in ((3000, 2000), (32767, 32767), (100, 30000)):
+        x = rng.integers(-amp, amp + 1, size=length).astype(np.int16)
+        B = rng.integers(-camp, camp + 1, size=d).astype(np.int16)
+        a = np.zeros(length, np.int16)
+        b = np.zeros(length, np.int16)
+        R.silk_LPC_analysis_filter(_p(a), _p(x), _p(B), length, d, 0)
+        O.orc_silk_lpc_analysis_filter(_p(b), _p(x), _p(B), length, d)
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('fs_in,fs_out', [(48000, 16000), (48000, 8000), (48000, 12000), (24000, 12000), (24000, 8000), (16000, 8000)])
+def test_resampler_down(fs_in, fs_out):
+    R, O = util.load_ref('c'), util.load_oracle()
+    rs = ctypes.create_string_buffer(R.refh_resampler_size())
+    os_ = ctypes.create_string_buffer(O.orc_resampler_size())
+    assert R.silk_resampler_init(rs, fs_in, fs_out, 1) == 0
+    assert O.orc_resampler_init(os_, fs_in, fs_out) == 0
+    rng = np.random.default_rng(fs_in // 1000 + fs_out)
+    n_in, n_out = fs_in // 50, fs_out // 50
+    t = 0
+    for frame in range(12):
+        amp = [3000, 32767, 10][frame % 3]
+        x = (amp * np.sin(2 * np.pi * 440 * (np.arange(n_in) + t) / fs_in) + rng.integers(-amp // 4 - 1, amp // 4 + 1, size=n_in)).clip(-32768, 32767).astype(np.int16)
+        t += n_in
+        a = np.zeros(n_out, np.int16)
+        b = np.zeros(n_out, np.int16)
+        R.silk_resampler(rs, _p(a), _p(x), n_in)
+        O.orc_resampler_process(os_, _p(b), _p(x), n_in)
+        assert np.array_equal(a, b), frame
