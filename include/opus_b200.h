@@ -135,6 +135,13 @@ void opusb200_silk_resampler_destroy(OpusB200SilkResampler *rs);
 int opusb200_silk_resampler_reset(OpusB200SilkResampler *rs);
 int opusb200_silk_resampler_process(OpusB200SilkResampler *rs, const int16_t *in, int16_t *out, int in_len, int on_device);
 
+/* silk_burg_modified_FLP (silk/float/burg_modified_FLP.c:39; called from find_LPC_FLP.c:60,65):
+ * x [n_items][nb_subfr*subfr_length] -> A [n_items][D] prediction coefficients, nrg [n_items] residual energy. */
+int opusb200_silk_burg_modified(OpusB200Ctx *ctx, float *A, float *nrg, const float *x, float minInvGain, int n_items,
+                                int subfr_length, int nb_subfr, int D, int on_device);
+/* silk_autocorrelation_FLP (silk/float/autocorrelation_FLP.c:36): results [n_items][count] */
+int opusb200_silk_autocorrelation(OpusB200Ctx *ctx, float *results, const float *x, int n_items, int size, int count, int on_device);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

@@ -68,6 +68,15 @@ extern "C" __global__ void __launch_bounds__(128) ob_silk_resampler_down(SilkRes
   if (s < p.n_streams) silk_resampler_thread(p, s);
 }
 
+extern "C" __global__ void __launch_bounds__(128) ob_silk_burg_modified(SilkBurgParams p) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < p.n_items) silk_burg_thread(p, item);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_silk_autocorrelation(SilkAutocorrParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < p.n_items * p.count) silk_autocorr_thread(p, idx);
+}
+
 // fresh decoder state (celt/celt_decoder.c:1794-1813 OPUS_RESET_STATE)
 extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState *ss, int n) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
@@ -487,6 +496,59 @@ int opusb200_silk_lpc_analysis_filter(OpusB200Ctx *c, int16_t *out, const int16_
   OB_CUDA(cudaGetLastError());
   if (!on_device) {
     OB_CUDA(cudaMemcpyAsync(out, pout, nb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+
+int opusb200_silk_burg_modified(OpusB200Ctx *c, float *A, float *nrg, const float *x, float minInvGain, int n_items,
+                                int subfr_length, int nb_subfr, int D, int on_device) {
+  if (!c || !A || !nrg || !x || n_items <= 0 || D < 2 || D > 24 || nb_subfr < 1 || subfr_length <= D ||
+      subfr_length * nb_subfr > 384) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf dA, dn, dx;
+  float *pA = A, *pn = nrg;
+  const float *px = x;
+  const size_t xb = sizeof(float) * (size_t)n_items * subfr_length * nb_subfr, ab = sizeof(float) * (size_t)n_items * D;
+  if (!on_device) {
+    if (dA.alloc(ab) || dn.alloc(sizeof(float) * (size_t)n_items) || dx.alloc(xb)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(dx.p, x, xb, cudaMemcpyHostToDevice, c->stream));
+    pA = (float *)dA.p; pn = (float *)dn.p; px = (const float *)dx.p;
+  }
+  SilkBurgParams p;
+  p.A = pA; p.nrg = pn; p.x = px; p.minInvGain = minInvGain; p.n_items = n_items; p.subfr_length = subfr_length;
+  p.nb_subfr = nb_subfr; p.D = D;
+  ob_silk_burg_modified<<<(n_items + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(A, pA, ab, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaMemcpyAsync(nrg, pn, sizeof(float) * (size_t)n_items, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+
+int opusb200_silk_autocorrelation(OpusB200Ctx *c, float *results, const float *x, int n_items, int size, int count, int on_device) {
+  if (!c || !results || !x || n_items <= 0 || size <= 0 || count <= 0) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf dr, dx;
+  float *pr = results;
+  const float *px = x;
+  const size_t xb = sizeof(float) * (size_t)n_items * size, rb = sizeof(float) * (size_t)n_items * count;
+  if (!on_device) {
+    if (dr.alloc(rb) || dx.alloc(xb)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(dx.p, x, xb, cudaMemcpyHostToDevice, c->stream));
+    pr = (float *)dr.p; px = (const float *)dx.p;
+  }
+  SilkAutocorrParams p;
+  p.results = pr; p.x = px; p.n_items = n_items; p.size = size; p.count = count;
+  const long total = (long)n_items * count;
+  ob_silk_autocorrelation<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(results, pr, rb, cudaMemcpyDeviceToHost, c->stream));
     OB_CUDA(cudaStreamSynchronize(c->stream));
   }
   return OPUSB200_OK;

@@ -121,4 +121,140 @@ OB_DEV void silk_resampler_thread(const SilkResamplerParams &p, int stream) {
   S->sIIR[0] = sIIR[0]; S->sIIR[1] = sIIR[1];
 }
 
+// ---- float analysis kernels (row a17): double accumulators, one thread per item -----------------
+// silk/float/inner_product_FLP.c:35-59 (and energy_FLP.c): the products float*double are exact in
+// double; sums keep the reference's grouping of four.
+OB_DEV double silk_inner_product_flp(const float *a, const float *b, int n) {
+  int i;
+  double r = 0.0;
+#pragma unroll 1
+  for (i = 0; i < n - 3; i += 4)
+    r += a[i + 0] * (double)b[i + 0] + a[i + 1] * (double)b[i + 1] + a[i + 2] * (double)b[i + 2] + a[i + 3] * (double)b[i + 3];
+#pragma unroll 1
+  for (; i < n; i++) r += a[i] * (double)b[i];
+  return r;
+}
+struct SilkBurgParams {
+  float *A;         // [n_items][D] out
+  float *nrg;       // [n_items] out: residual energy
+  const float *x;   // [n_items][nb_subfr*subfr_length]
+  float minInvGain;
+  int n_items, subfr_length, nb_subfr, D;
+};
+// silk/float/burg_modified_FLP.c:39-187
+OB_DEV void silk_burg_thread(const SilkBurgParams &p, int item) {
+  const int subfr_length = p.subfr_length, nb_subfr = p.nb_subfr, D = p.D;
+  const float *x = p.x + (size_t)item * nb_subfr * subfr_length;
+  float *A = p.A + (size_t)item * D;
+  const double minInvGain = p.minInvGain;
+  int reached_max_gain = 0;
+  double Cf[24], Cl[24], CAf[25], CAb[25], Af[24];
+  double C0 = silk_inner_product_flp(x, x, nb_subfr * subfr_length);
+#pragma unroll 1
+  for (int k = 0; k < 24; k++) Cf[k] = 0.0;
+#pragma unroll 1
+  for (int s = 0; s < nb_subfr; s++) {
+    const float *xp = x + s * subfr_length;
+#pragma unroll 1
+    for (int n = 1; n < D + 1; n++) Cf[n - 1] += silk_inner_product_flp(xp, xp + n, subfr_length - n);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 24; k++) Cl[k] = Cf[k];
+  CAb[0] = CAf[0] = C0 + 1e-5f * C0 + 1e-9f;
+  double invGain = 1.0;
+  int n;
+#pragma unroll 1
+  for (n = 0; n < D; n++) {
+#pragma unroll 1
+    for (int s = 0; s < nb_subfr; s++) {
+      const float *xp = x + s * subfr_length;
+      double tmp1 = xp[n], tmp2 = xp[subfr_length - n - 1];
+#pragma unroll 1
+      for (int k = 0; k < n; k++) {
+        Cf[k] -= (double)(xp[n] * xp[n - k - 1]);                                // float product, as in the reference
+        Cl[k] -= (double)(xp[subfr_length - n - 1] * xp[subfr_length - n + k]);  // float product
+        const double Atmp = Af[k];
+        tmp1 += xp[n - k - 1] * Atmp;
+        tmp2 += xp[subfr_length - n + k] * Atmp;
+      }
+#pragma unroll 1
+      for (int k = 0; k <= n; k++) {
+        CAf[k] -= tmp1 * xp[n - k];
+        CAb[k] -= tmp2 * xp[subfr_length - n + k - 1];
+      }
+    }
+    double tmp1 = Cf[n], tmp2 = Cl[n];
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+      const double Atmp = Af[k];
+      tmp1 += Cl[n - k - 1] * Atmp;
+      tmp2 += Cf[n - k - 1] * Atmp;
+    }
+    CAf[n + 1] = tmp1;
+    CAb[n + 1] = tmp2;
+    double num = CAb[n + 1], nrg_b = CAb[0], nrg_f = CAf[0];
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+      const double Atmp = Af[k];
+      num += CAb[n - k] * Atmp;
+      nrg_b += CAb[k + 1] * Atmp;
+      nrg_f += CAf[k + 1] * Atmp;
+    }
+    double rc = -2.0 * num / (nrg_f + nrg_b);
+    tmp1 = invGain * (1.0 - rc * rc);
+    if (tmp1 <= minInvGain) {
+      rc = sqrt(1.0 - minInvGain / invGain);
+      if (num > 0) rc = -rc;
+      invGain = minInvGain;
+      reached_max_gain = 1;
+    } else invGain = tmp1;
+#pragma unroll 1
+    for (int k = 0; k < (n + 1) >> 1; k++) {
+      const double t1 = Af[k], t2 = Af[n - k - 1];
+      Af[k] = t1 + rc * t2;
+      Af[n - k - 1] = t2 + rc * t1;
+    }
+    Af[n] = rc;
+    if (reached_max_gain) {
+#pragma unroll 1
+      for (int k = n + 1; k < D; k++) Af[k] = 0.0;
+      break;
+    }
+#pragma unroll 1
+    for (int k = 0; k <= n + 1; k++) {
+      const double t1 = CAf[k];
+      CAf[k] += rc * CAb[n - k + 1];
+      CAb[n - k + 1] += rc * t1;
+    }
+  }
+  double nrg_f;
+  if (reached_max_gain) {
+#pragma unroll 1
+    for (int k = 0; k < D; k++) A[k] = (float)(-Af[k]);
+#pragma unroll 1
+    for (int s = 0; s < nb_subfr; s++) C0 -= silk_inner_product_flp(x + s * subfr_length, x + s * subfr_length, D);
+    nrg_f = C0 * invGain;
+  } else {
+    nrg_f = CAf[0];
+    double t1 = 1.0;
+#pragma unroll 1
+    for (int k = 0; k < D; k++) {
+      const double Atmp = Af[k];
+      nrg_f += CAf[k + 1] * Atmp;
+      t1 += Atmp * Atmp;
+      A[k] = (float)(-Atmp);
+    }
+    nrg_f -= 1e-5f * C0 * t1;
+  }
+  p.nrg[item] = (float)nrg_f;
+}
+
+struct SilkAutocorrParams { float *results; const float *x; int n_items, size, count; };
+// silk/float/autocorrelation_FLP.c:36-55; one thread per (item, lag)
+OB_DEV void silk_autocorr_thread(const SilkAutocorrParams &p, int idx) {
+  const int item = idx / p.count, lag = idx - item * p.count;
+  const float *x = p.x + (size_t)item * p.size;
+  p.results[idx] = lag < p.size ? (float)silk_inner_product_flp(x, x + lag, p.size - lag) : 0.f;
+}
+
 }  // namespace ob

@@ -68,6 +68,22 @@ class Ops:
                   'silk_lpc_analysis_filter')
         return out
 
+    def silk_burg_modified(self, x, min_inv_gain, subfr_length, nb_subfr, D):
+        """x [n, nb_subfr*subfr_length] float32 -> (A [n, D], residual energy [n])"""
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0]
+        A = np.empty((n, D), np.float32)
+        nrg = np.empty(n, np.float32)
+        self._chk(self._L.opusb200_silk_burg_modified(self._h, _p(A), _p(nrg), _p(x), float(min_inv_gain), n, subfr_length,
+                                                     nb_subfr, D, 0), 'silk_burg_modified')
+        return A, nrg
+
+    def silk_autocorrelation(self, x, count):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty((x.shape[0], count), np.float32)
+        self._chk(self._L.opusb200_silk_autocorrelation(self._h, _p(out), _p(x), x.shape[0], x.shape[1], count, 0), 'silk_autocorrelation')
+        return out
+
     def silk_resampler(self, n_streams, fs_in, fs_out):
         return SilkResampler(self, n_streams, fs_in, fs_out)
 

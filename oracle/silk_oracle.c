@@ -2,6 +2,7 @@
  * Plain-C restatements of the SILK integer kernels on the hot path (a15
  * and a17 follow), bit-exact by construction (32-bit wrap-around arithmetic as in the reference).
  * Pinned against the reference's functions in oracle/_ref by tests/test_silk_oracle_vs_ref.py. */
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -99,4 +100,114 @@ void orc_resampler_process(OrcResampler *S, int16_t *out, const int16_t *in, int
   down_fir(S, out, S->delayBuf, S->fs_in_khz);
   down_fir(S, &out[S->fs_out_khz], &in[nSamples], inLen - S->fs_in_khz);
   memcpy(S->delayBuf, &in[inLen - S->input_delay], S->input_delay * sizeof(int16_t));
+}
+
+/* ---- float analysis kernels -------------------------------------------- */
+/* silk/float/inner_product_FLP.c:35-59, energy_FLP.c:35-62: double accumulation, 4-way grouped */
+static double inner_product_flp(const float *a, const float *b, int n) {
+  int i;
+  double r = 0.0;
+  for (i = 0; i < n - 3; i += 4)
+    r += a[i + 0] * (double)b[i + 0] + a[i + 1] * (double)b[i + 1] + a[i + 2] * (double)b[i + 2] + a[i + 3] * (double)b[i + 3];
+  for (; i < n; i++) r += a[i] * (double)b[i];
+  return r;
+}
+/* silk/float/autocorrelation_FLP.c:36-55 */
+void orc_silk_autocorrelation(float *results, const float *x, int size, int count) {
+  int i;
+  if (count > size) count = size;
+  for (i = 0; i < count; i++) results[i] = (float)inner_product_flp(x, x + i, size - i);
+}
+/* silk/float/burg_modified_FLP.c:39-187 */
+float orc_silk_burg_modified(float *A, const float *x, float minInvGain, int subfr_length, int nb_subfr, int D) {
+  int k, n, s, reached_max_gain;
+  double C0, invGain, num, nrg_f, nrg_b, rc, Atmp, tmp1, tmp2;
+  const float *xp;
+  double Cf[24], Cl[24], CAf[25], CAb[25], Af[24];
+  C0 = inner_product_flp(x, x, nb_subfr * subfr_length);
+  memset(Cf, 0, sizeof(Cf));
+  for (s = 0; s < nb_subfr; s++) {
+    xp = x + s * subfr_length;
+    for (n = 1; n < D + 1; n++) Cf[n - 1] += inner_product_flp(xp, xp + n, subfr_length - n);
+  }
+  memcpy(Cl, Cf, sizeof(Cf));
+  CAb[0] = CAf[0] = C0 + 1e-5f * C0 + 1e-9f;
+  invGain = 1.0f;
+  reached_max_gain = 0;
+  for (n = 0; n < D; n++) {
+    for (s = 0; s < nb_subfr; s++) {
+      xp = x + s * subfr_length;
+      tmp1 = xp[n];
+      tmp2 = xp[subfr_length - n - 1];
+      for (k = 0; k < n; k++) {
+        Cf[k] -= xp[n] * xp[n - k - 1];                                  /* float product */
+        Cl[k] -= xp[subfr_length - n - 1] * xp[subfr_length - n + k];    /* float product */
+        Atmp = Af[k];
+        tmp1 += xp[n - k - 1] * Atmp;
+        tmp2 += xp[subfr_length - n + k] * Atmp;
+      }
+      for (k = 0; k <= n; k++) {
+        CAf[k] -= tmp1 * xp[n - k];
+        CAb[k] -= tmp2 * xp[subfr_length - n + k - 1];
+      }
+    }
+    tmp1 = Cf[n];
+    tmp2 = Cl[n];
+    for (k = 0; k < n; k++) {
+      Atmp = Af[k];
+      tmp1 += Cl[n - k - 1] * Atmp;
+      tmp2 += Cf[n - k - 1] * Atmp;
+    }
+    CAf[n + 1] = tmp1;
+    CAb[n + 1] = tmp2;
+    num = CAb[n + 1];
+    nrg_b = CAb[0];
+    nrg_f = CAf[0];
+    for (k = 0; k < n; k++) {
+      Atmp = Af[k];
+      num += CAb[n - k] * Atmp;
+      nrg_b += CAb[k + 1] * Atmp;
+      nrg_f += CAf[k + 1] * Atmp;
+    }
+    rc = -2.0 * num / (nrg_f + nrg_b);
+    tmp1 = invGain * (1.0 - rc * rc);
+    if (tmp1 <= minInvGain) {
+      rc = sqrt(1.0 - minInvGain / invGain);
+      if (num > 0) rc = -rc;
+      invGain = minInvGain;
+      reached_max_gain = 1;
+    } else invGain = tmp1;
+    for (k = 0; k < (n + 1) >> 1; k++) {
+      tmp1 = Af[k];
+      tmp2 = Af[n - k - 1];
+      Af[k] = tmp1 + rc * tmp2;
+      Af[n - k - 1] = tmp2 + rc * tmp1;
+    }
+    Af[n] = rc;
+    if (reached_max_gain) {
+      for (k = n + 1; k < D; k++) Af[k] = 0.0;
+      break;
+    }
+    for (k = 0; k <= n + 1; k++) {
+      tmp1 = CAf[k];
+      CAf[k] += rc * CAb[n - k + 1];
+      CAb[n - k + 1] += rc * tmp1;
+    }
+  }
+  if (reached_max_gain) {
+    for (k = 0; k < D; k++) A[k] = (float)(-Af[k]);
+    for (s = 0; s < nb_subfr; s++) C0 -= inner_product_flp(x + s * subfr_length, x + s * subfr_length, D);
+    nrg_f = C0 * invGain;
+  } else {
+    nrg_f = CAf[0];
+    tmp1 = 1.0;
+    for (k = 0; k < D; k++) {
+      Atmp = Af[k];
+      nrg_f += CAf[k + 1] * Atmp;
+      tmp1 += Atmp * Atmp;
+      A[k] = (float)(-Atmp);
+    }
+    nrg_f -= 1e-5f * C0 * tmp1;
+  }
+  return (float)nrg_f;
 }

@@ -66,3 +66,14 @@ void emu_silk_resampler_48_16(void *state, const int16_t *in, int16_t *out, int 
   emu_launch(rs_entry, &p, (n + 31) / 32, 32, 0);
 }
 }
+
+static void burg_entry(void *a) {
+  const SilkBurgParams &p = *(const SilkBurgParams *)a;
+  int item = block_id() * 32 + lane_id();
+  if (item < p.n_items) silk_burg_thread(p, item);
+}
+extern "C" void emu_silk_burg(float *A, float *nrg, const float *x, float mig, int n, int subfr, int nb, int D) {
+  SilkBurgParams p;
+  p.A = A; p.nrg = nrg; p.x = x; p.minInvGain = mig; p.n_items = n; p.subfr_length = subfr; p.nb_subfr = nb; p.D = D;
+  emu_launch(burg_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -92,3 +92,22 @@ def test_emu_silk_lpc_and_resampler():
         for i in range(n):
             O.orc_resampler_process(os_[i], _f(w), _f(xin[i]), 960)
             assert np.array_equal(got[i], w), (fr, i)
+
+
+def test_emu_silk_burg():
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    O.orc_silk_burg_modified.restype = ctypes.c_float
+    O.orc_silk_burg_modified.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    E.emu_silk_burg.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(3)
+    n, subfr, nb, D = 40, 96, 4, 16
+    t = np.arange(subfr * nb)
+    x = np.stack([(3000 * np.sin(0.03 * (i + 1) * t) + (3 if i % 2 else 500) * rng.standard_normal(t.size)) for i in range(n)]).astype(np.float32)
+    for mig in (1e-4, 0.5):
+        A = np.zeros((n, D), np.float32)
+        nrg = np.zeros(n, np.float32)
+        E.emu_silk_burg(_f(A), _f(nrg), _f(x), mig, n, subfr, nb, D)
+        w = np.zeros(D, np.float32)
+        for i in range(n):
+            r = O.orc_silk_burg_modified(_f(w), _f(x[i]), mig, subfr, nb, D)
+            assert r == nrg[i] and np.array_equal(A[i], w)

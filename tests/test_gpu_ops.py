@@ -138,3 +138,25 @@ def test_silk_resampler(ops, fs_in, fs_out):
             O.orc_resampler_process(orc[i], _f(w), _f(x[i]), n_in)
             assert np.array_equal(got[i], w), (fr, i)
     rs.close()
+
+
+def test_silk_burg_and_autocorr(ops):
+    O = util.load_oracle()
+    O.orc_silk_burg_modified.restype = ctypes.c_float
+    O.orc_silk_burg_modified.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(17)
+    n, subfr, nb, D = 2000, 96, 4, 16
+    t = np.arange(subfr * nb)
+    f = rng.uniform(0.01, 0.5, size=(n, 1))
+    x = (3000 * np.sin(f * t[None, :]) + rng.choice([3.0, 300.0, 3000.0], size=(n, 1)) * rng.standard_normal((n, t.size))).astype(np.float32)
+    for mig in (1e-4, 0.3):
+        A, nrg = ops.silk_burg_modified(x, mig, subfr, nb, D)
+        w = np.zeros(D, np.float32)
+        for i in range(0, n, 53):
+            r = O.orc_silk_burg_modified(_f(w), _f(x[i]), mig, subfr, nb, D)
+            assert r == nrg[i] and np.array_equal(A[i], w), i
+    ac = ops.silk_autocorrelation(x, D + 1)
+    w = np.zeros(D + 1, np.float32)
+    for i in range(0, n, 101):
+        O.orc_silk_autocorrelation(_f(w), _f(x[i]), x.shape[1], D + 1)
+        assert np.array_equal(ac[i], w)

@@ -46,3 +46,28 @@ def test_resampler_down(fs_in, fs_out):
         R.silk_resampler(rs, _p(a), _p(x), n_in)
         O.orc_resampler_process(os_, _p(b), _p(x), n_in)
         assert np.array_equal(a, b), frame
+
+
+@pytest.mark.parametrize('subfr,nb,D', [(96, 4, 16), (96, 2, 16), (50, 4, 10), (56, 4, 16)])
+def test_burg_and_autocorr(subfr, nb, D):
+    R, O = util.load_ref('c'), util.load_oracle()
+    R.silk_burg_modified_FLP.restype = ctypes.c_float
+    R.silk_burg_modified_FLP.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    O.orc_silk_burg_modified.restype = ctypes.c_float
+    O.orc_silk_burg_modified.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(subfr + D)
+    for trial in range(6):
+        L = subfr * nb
+        t = np.arange(L)
+        x = (3000 * np.sin(0.05 * (trial + 1) * t) + 1000 * np.sin(0.31 * t + trial) + [300, 3, 3000][trial % 3] * rng.standard_normal(L)).astype(np.float32)
+        for mig in (1e-4, 0.5, 1.0 / 1e4 * 100):
+            a = np.zeros(D, np.float32)
+            b = np.zeros(D, np.float32)
+            ra = R.silk_burg_modified_FLP(_p(a), _p(x), mig, subfr, nb, D, 0)
+            rb = O.orc_silk_burg_modified(_p(b), _p(x), mig, subfr, nb, D)
+            assert ra == rb and np.array_equal(a, b)
+        ca = np.zeros(D + 1, np.float32)
+        cb = np.zeros(D + 1, np.float32)
+        R.silk_autocorrelation_FLP(_p(ca), _p(x), L, D + 1, 0)
+        O.orc_silk_autocorrelation(_p(cb), _p(x), L, D + 1)
+        assert np.array_equal(ca, cb)
