@@ -162,3 +162,55 @@ float refh_pvq_search(float *X, int *iy, int K, int N) { return op_pvq_search_c(
 #include "silk/SigProc_FIX.h"
 #include "silk/resampler_structs.h"
 int refh_resampler_size(void) { return (int)sizeof(silk_resampler_state_struct); }
+
+/* ---- SILK noise-shaping quantizer (silk_NSQ / silk_NSQ_del_dec through the reference's own dispatch) ---- */
+#include "silk/main.h"
+#include "celt/cpu_support.h"
+typedef struct { opus_int32 fs_khz, nb_subfr, predictLPCOrder, shapingLPCOrder, warping_Q16, nStates; } RefhNsqCfg;
+typedef struct {
+  opus_int32 signalType, quantOffsetType, NLSFInterpCoef_Q2, Seed;
+  opus_int32 HarmShapeGain_Q14[4], Tilt_Q14[4], LF_shp_Q14[4], Gains_Q16[4], pitchL[4];
+  opus_int32 Lambda_Q10, LTP_scale_Q14;
+  opus_int16 PredCoef_Q12[32], LTPCoef_Q14[20], AR_Q13[96];
+} RefhNsqFrame;
+int refh_nsq_state_size(void) { return (int)sizeof(silk_nsq_state); }
+void refh_nsq_state_init(silk_nsq_state *S) {
+  memset(S, 0, sizeof(*S));
+  S->prev_gain_Q16 = 65536;
+  S->lagPrev = 100;
+}
+void refh_silk_nsq(const RefhNsqCfg *c, silk_nsq_state *S, RefhNsqFrame *f, const opus_int16 *x16, opus_int8 *pulses) {
+  static silk_encoder_state enc; /* only the fields the quantizers read are set */
+  SideInfoIndices idx;
+  memset(&enc, 0, sizeof(enc));
+  memset(&idx, 0, sizeof(idx));
+  enc.fs_kHz = c->fs_khz;
+  enc.nb_subfr = c->nb_subfr;
+  enc.subfr_length = 5 * c->fs_khz;
+  enc.frame_length = enc.subfr_length * c->nb_subfr;
+  enc.ltp_mem_length = 20 * c->fs_khz;
+  enc.predictLPCOrder = c->predictLPCOrder;
+  enc.shapingLPCOrder = c->shapingLPCOrder;
+  enc.warping_Q16 = c->warping_Q16;
+  enc.nStatesDelayedDecision = c->nStates;
+  enc.arch = opus_select_arch();
+  idx.signalType = (opus_int8)f->signalType;
+  idx.quantOffsetType = (opus_int8)f->quantOffsetType;
+  idx.NLSFInterpCoef_Q2 = (opus_int8)f->NLSFInterpCoef_Q2;
+  idx.Seed = (opus_int8)f->Seed;
+  if (c->nStates > 1 || c->warping_Q16 > 0)
+    silk_NSQ_del_dec(&enc, S, &idx, x16, pulses, f->PredCoef_Q12, f->LTPCoef_Q14, f->AR_Q13, f->HarmShapeGain_Q14, f->Tilt_Q14,
+                     f->LF_shp_Q14, f->Gains_Q16, f->pitchL, f->Lambda_Q10, f->LTP_scale_Q14, enc.arch);
+  else
+    silk_NSQ(&enc, S, &idx, x16, pulses, f->PredCoef_Q12, f->LTPCoef_Q14, f->AR_Q13, f->HarmShapeGain_Q14, f->Tilt_Q14, f->LF_shp_Q14,
+             f->Gains_Q16, f->pitchL, f->Lambda_Q10, f->LTP_scale_Q14, enc.arch);
+  f->Seed = idx.Seed;
+}
+void refh_nsq_state_export(const silk_nsq_state *S, opus_int32 *o) {
+  int i;
+  for (i = 0; i < 640; i++) *o++ = S->xq[i];
+  for (i = 0; i < 640; i++) *o++ = S->sLTP_shp_Q14[i];
+  for (i = 0; i < 16; i++) *o++ = S->sLPC_Q14[i];
+  for (i = 0; i < 24; i++) *o++ = S->sAR2_Q14[i];
+  *o++ = S->sLF_AR_shp_Q14; *o++ = S->sDiff_shp_Q14; *o++ = S->lagPrev; *o++ = S->rand_seed; *o++ = S->prev_gain_Q16;
+}

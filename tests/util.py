@@ -141,3 +141,81 @@ def oracle_decode_float(pkts, sizes, channels, frame_size):
 def to_int16(pcm_float):
     x = np.clip(pcm_float.astype(np.float32) * np.float32(32768.0), -32768, 32767)
     return np.rint(x).astype(np.int16)
+
+
+# ---- SILK NSQ test-case generator (shared by the oracle-vs-reference, emulator and GPU tests) --------------------------------
+NSQ_FRAME_DTYPE = np.dtype([('signalType', '<i4'), ('quantOffsetType', '<i4'), ('NLSFInterpCoef_Q2', '<i4'), ('Seed', '<i4'),
+                            ('HarmShapeGain_Q14', '<i4', 4), ('Tilt_Q14', '<i4', 4), ('LF_shp_Q14', '<i4', 4), ('Gains_Q16', '<i4', 4),
+                            ('pitchL', '<i4', 4), ('Lambda_Q10', '<i4'), ('LTP_scale_Q14', '<i4'),
+                            ('PredCoef_Q12', '<i2', 32), ('LTPCoef_Q14', '<i2', 20), ('AR_Q13', '<i2', 96)])
+NSQ_STATE_EXPORT_WORDS = 640 + 640 + 16 + 24 + 5
+
+
+def nsq_cfg(fs_khz, nb_subfr, predict_order, shaping_order, warping_Q16, n_states):
+    return np.array([fs_khz, nb_subfr, predict_order, shaping_order, warping_Q16, n_states], np.int32)
+
+
+def _lpc_levinson(x, order):
+    r = np.array([np.dot(x[:len(x) - k], x[k:]) for k in range(order + 1)], np.float64)
+    r[0] = r[0] * 1.0001 + 1.0
+    a = np.zeros(order + 1)
+    a[0] = 1.0
+    e = r[0]
+    for i in range(1, order + 1):
+        k = -(r[i] + np.dot(a[1:i], r[i - 1:0:-1])) / e
+        a[1:i] = a[1:i] + k * a[i - 1:0:-1]
+        a[i] = k
+        e *= (1 - k * k)
+    return -a[1:]          # prediction coefficients: x[n] ~ sum a[k] x[n-1-k]
+
+
+def make_nsq_frames(seed, cfg, n_frames):
+    """Plausible (stable, in-range) NSQ inputs for n_frames consecutive frames of one stream.
+    Returns (x16 [n_frames, frame_length] int16, frames structured array [n_frames])."""
+    rng = np.random.default_rng(seed)
+    fs, nb, po, so = int(cfg[0]), int(cfg[1]), int(cfg[2]), int(cfg[3])
+    sub = 5 * fs
+    fl = sub * nb
+    n = fl * n_frames
+    t = np.arange(n)
+    pitch = rng.integers(2 * fs + 4, 18 * fs - 4)
+    sig = np.zeros(n)
+    for h in range(1, 9):
+        sig += rng.uniform(0.2, 1.0) / h * np.sin(2 * np.pi * h * t / pitch + rng.uniform(0, 6.28))
+    sig = sig * rng.uniform(500, 6000) + rng.standard_normal(n) * rng.uniform(20, 1500)
+    env = 0.3 + 0.7 * np.abs(np.sin(2 * np.pi * t / (fl * 2.7) + rng.uniform(0, 3)))
+    x = np.clip(np.round(sig * env), -32768, 32767).astype(np.int16).reshape(n_frames, fl)
+    frames = np.zeros(n_frames, NSQ_FRAME_DTYPE)
+    for f in range(n_frames):
+        fr = frames[f]
+        st = int(rng.choice([0, 1, 2, 2]))
+        fr['signalType'] = st
+        fr['quantOffsetType'] = rng.integers(0, 2)
+        fr['NLSFInterpCoef_Q2'] = rng.choice([4, 4, 0, 1, 2, 3])
+        fr['Seed'] = rng.integers(0, 4)
+        xf = x[f].astype(np.float64)
+        for half in range(2):
+            seg = xf[half * (fl // 2):(half + 1) * (fl // 2)] if nb == 4 else xf
+            a = _lpc_levinson(seg, po) * 0.98 ** np.arange(1, po + 1)
+            fr['PredCoef_Q12'][half * 16:half * 16 + po] = np.clip(np.round(a * 4096), -32768, 32767)
+        for k in range(nb):
+            seg = xf[k * sub:(k + 1) * sub]
+            a = _lpc_levinson(seg, so)
+            ar = a * 0.94 ** np.arange(1, so + 1) * rng.uniform(0.5, 1.0)
+            fr['AR_Q13'][k * 24:k * 24 + so] = np.clip(np.round(ar * 8192), -32768, 32767)
+            g = 2.0 ** rng.uniform(5, 12.5)
+            fr['Gains_Q16'][k] = int(g * 65536) if rng.random() > 0.25 or k == 0 else fr['Gains_Q16'][k - 1]
+            fr['Tilt_Q14'][k] = int(-rng.uniform(0.05, 0.45) * 16384)
+            b = 0.2 / fs + 3.0 / max(pitch, 1)
+            ma = int(round((-1.0 + b) * 16384))
+            arq = int(round((1.0 - b - b * rng.uniform(0, 0.6)) * 16384))
+            fr['LF_shp_Q14'][k] = np.array((arq << 16) | (ma & 0xFFFF), np.int64).astype(np.uint32).view(np.int32) if False else \
+                np.int32(np.uint32(((arq & 0xFFFF) << 16) | (ma & 0xFFFF)))
+            if st == 2:
+                fr['pitchL'][k] = int(np.clip(pitch + rng.integers(-3, 4), 2 * fs, 18 * fs))
+                taps = np.array([0.05, 0.2, 0.45, 0.2, 0.05]) * rng.uniform(0.2, 1.6) + rng.uniform(-0.05, 0.05, 5)
+                fr['LTPCoef_Q14'][k * 5:k * 5 + 5] = np.round(taps * 16384)
+                fr['HarmShapeGain_Q14'][k] = int(rng.uniform(0, 0.45) * 16384)
+        fr['Lambda_Q10'] = rng.integers(900, 2900)
+        fr['LTP_scale_Q14'] = rng.choice([15565, 12288, 8192])
+    return x, frames
