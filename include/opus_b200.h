@@ -142,6 +142,38 @@ int opusb200_silk_burg_modified(OpusB200Ctx *ctx, float *A, float *nrg, const fl
 /* silk_autocorrelation_FLP (silk/float/autocorrelation_FLP.c:36): results [n_items][count] */
 int opusb200_silk_autocorrelation(OpusB200Ctx *ctx, float *results, const float *x, int n_items, int size, int count, int on_device);
 
+/* ---- SILK noise-shaping quantizer, batched: silk_NSQ / silk_NSQ_del_dec (silk/main.h:250-300; silk/NSQ.c:76,
+ * silk/NSQ_del_dec.c:113), called once per frame from silk_NSQ_wrapper_FLP (silk/float/wrappers_FLP.c:106-170).
+ * One object holds the silk_nsq_state (silk/structs.h:56-69) of n_streams encoders in device memory. ---- */
+typedef struct OpusB200SilkNsq OpusB200SilkNsq;
+/* the fields of silk_encoder_state (silk/structs.h) the quantizers read; identical for every stream of the batch */
+typedef struct {
+  int32_t fs_khz;                 /* 8, 12, 16: subfr_length = 5*fs_khz, ltp_mem_length = 20*fs_khz */
+  int32_t nb_subfr;               /* 2 or 4 */
+  int32_t predictLPCOrder;        /* 10 or 16 */
+  int32_t shapingLPCOrder;        /* even, <= 24 */
+  int32_t warping_Q16;
+  int32_t nStatesDelayedDecision; /* 1..4; >1 or warping_Q16>0 selects silk_NSQ_del_dec (wrappers_FLP.c:163) */
+} OpusB200NsqConfig;
+/* per stream and frame: SideInfoIndices fields + the arguments of silk_NSQ (silk/main.h:250-266) */
+typedef struct {
+  int32_t signalType, quantOffsetType, NLSFInterpCoef_Q2;
+  int32_t Seed;                   /* in/out: silk_NSQ_del_dec rewrites psIndices->Seed */
+  int32_t HarmShapeGain_Q14[4], Tilt_Q14[4], LF_shp_Q14[4], Gains_Q16[4], pitchL[4];
+  int32_t Lambda_Q10, LTP_scale_Q14;
+  int16_t PredCoef_Q12[2 * 16];   /* [2][MAX_LPC_ORDER] */
+  int16_t LTPCoef_Q14[4 * 5];     /* [MAX_NB_SUBFR][LTP_ORDER] */
+  int16_t AR_Q13[4 * 24];         /* [MAX_NB_SUBFR][MAX_SHAPE_LPC_ORDER] */
+} OpusB200NsqFrame;
+int opusb200_silk_nsq_create(OpusB200Ctx *ctx, int n_streams, const OpusB200NsqConfig *cfg, OpusB200SilkNsq **out);
+void opusb200_silk_nsq_destroy(OpusB200SilkNsq *q);
+int opusb200_silk_nsq_reset(OpusB200SilkNsq *q);
+/* frames [n_streams], x16 [n_streams][frame_length], pulses [n_streams][frame_length] (out) */
+int opusb200_silk_nsq_process(OpusB200SilkNsq *q, OpusB200NsqFrame *frames, const int16_t *x16, int8_t *pulses, int on_device);
+/* debug / parity: the carried state as [n_streams][1325] int32 words (host):
+ * xq[640] sLTP_shp_Q14[640] sLPC_Q14[16] sAR2_Q14[24] sLF_AR_shp_Q14 sDiff_shp_Q14 lagPrev rand_seed prev_gain_Q16 */
+int opusb200_silk_nsq_get_state(OpusB200SilkNsq *q, int32_t *out);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

@@ -27,7 +27,9 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
            'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create',
            'opusb200_silk_resampler_destroy', 'opusb200_silk_resampler_reset', 'opusb200_silk_resampler_process',
-           'opusb200_silk_burg_modified', 'opusb200_silk_autocorrelation', 'opusb200_host_alloc', 'opusb200_host_free']
+           'opusb200_silk_burg_modified', 'opusb200_silk_autocorrelation',
+           'opusb200_silk_nsq_create', 'opusb200_silk_nsq_destroy', 'opusb200_silk_nsq_reset', 'opusb200_silk_nsq_process',
+           'opusb200_silk_nsq_get_state', 'opusb200_host_alloc', 'opusb200_host_free']
 
 
 class OpusB200Error(RuntimeError):
@@ -102,6 +104,12 @@ def lib():
         L.opusb200_silk_resampler_process.argtypes = [vp, vp, vp, ci, ci]
         L.opusb200_silk_burg_modified.argtypes = [vp, vp, vp, vp, ctypes.c_float, ci, ci, ci, ci, ci]
         L.opusb200_silk_autocorrelation.argtypes = [vp, vp, vp, ci, ci, ci, ci]
+        L.opusb200_silk_nsq_create.argtypes = [vp, ci, vp, ctypes.POINTER(vp)]
+        L.opusb200_silk_nsq_destroy.argtypes = [vp]
+        L.opusb200_silk_nsq_destroy.restype = None
+        L.opusb200_silk_nsq_reset.argtypes = [vp]
+        L.opusb200_silk_nsq_process.argtypes = [vp, vp, vp, vp, ci]
+        L.opusb200_silk_nsq_get_state.argtypes = [vp, vp]
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

@@ -13,6 +13,7 @@
 #include "celt_dec_kernels.cuh"
 #include "celt_ops.cuh"
 #include "silk_ops.cuh"
+#include "silk_nsq.cuh"
 
 using namespace ob;
 
@@ -75,6 +76,32 @@ extern "C" __global__ void __launch_bounds__(128) ob_silk_burg_modified(SilkBurg
 extern "C" __global__ void __launch_bounds__(128) ob_silk_autocorrelation(SilkAutocorrParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < p.n_items * p.count) silk_autocorr_thread(p, idx);
+}
+
+// SILK noise-shaping quantizers.  Delayed decision: one warp per block, 8 streams x 4 states per warp; the decision rings
+// take 29.4 KB of shared memory per warp, so 7 blocks are resident per SM.
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec(SilkNsqParams p) {
+  nsq_del_dec_warp(p, blockIdx.x * 8, (int32_t *)dyn_smem());
+}
+extern "C" __global__ void __launch_bounds__(64) ob_silk_nsq(SilkNsqParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) nsq_plain_thread(p, s);
+}
+extern "C" __global__ void ob_silk_nsq_reset(ObNsqState *st, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) {  // silk/init_encoder.c + control_codec.c: prev_gain 1.0, lagPrev 100 (the arrays were memset to 0)
+    st[s].prev_gain_Q16 = 65536;
+    st[s].lagPrev = 100;
+  }
+}
+extern "C" __global__ void ob_silk_nsq_export(const ObNsqState *st, int32_t *out, int n) {
+  const int s = blockIdx.x, t = threadIdx.x;
+  const ObNsqState &S = st[s];
+  int32_t *o = out + (size_t)s * 1325;
+  for (int i = t; i < 640; i += blockDim.x) { o[i] = S.xq[i]; o[640 + i] = S.sLTP_shp_Q14[i]; }
+  if (t < 16) o[1280 + t] = S.sLPC_Q14[t];
+  if (t < 24) o[1296 + t] = S.sAR2_Q14[t];
+  if (t == 0) { o[1320] = S.sLF_AR_shp_Q14; o[1321] = S.sDiff_shp_Q14; o[1322] = S.lagPrev; o[1323] = S.rand_seed; o[1324] = S.prev_gain_Q16; }
 }
 
 // fresh decoder state (celt/celt_decoder.c:1794-1813 OPUS_RESET_STATE)
@@ -551,6 +578,94 @@ int opusb200_silk_autocorrelation(OpusB200Ctx *c, float *results, const float *x
     OB_CUDA(cudaMemcpyAsync(results, pr, rb, cudaMemcpyDeviceToHost, c->stream));
     OB_CUDA(cudaStreamSynchronize(c->stream));
   }
+  return OPUSB200_OK;
+}
+
+struct OpusB200SilkNsq {
+  OpusB200Ctx *ctx;
+  int n, frame_length;
+  ObNsqCfg cfg;
+  ObNsqState *state;
+};
+static_assert(sizeof(OpusB200NsqFrame) == sizeof(ObNsqFrame), "OpusB200NsqFrame layout");
+static_assert(sizeof(OpusB200NsqConfig) == sizeof(ObNsqCfg), "OpusB200NsqConfig layout");
+
+int opusb200_silk_nsq_reset(OpusB200SilkNsq *q) {
+  if (!q) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(q->ctx->device));
+  OB_CUDA(cudaMemsetAsync(q->state, 0, sizeof(ObNsqState) * (size_t)q->n, q->ctx->stream));
+  ob_silk_nsq_reset<<<(q->n + 127) / 128, 128, 0, q->ctx->stream>>>(q->state, q->n);
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+int opusb200_silk_nsq_create(OpusB200Ctx *c, int n_streams, const OpusB200NsqConfig *cfg, OpusB200SilkNsq **out) {
+  if (!c || !out || !cfg || n_streams <= 0) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  // the ranges silk/control_codec.c can set
+  if ((cfg->fs_khz != 8 && cfg->fs_khz != 12 && cfg->fs_khz != 16) || (cfg->nb_subfr != 2 && cfg->nb_subfr != 4) ||
+      (cfg->predictLPCOrder != 10 && cfg->predictLPCOrder != 16) || cfg->shapingLPCOrder < 2 || cfg->shapingLPCOrder > 24 ||
+      (cfg->shapingLPCOrder & 1) || cfg->nStatesDelayedDecision < 1 || cfg->nStatesDelayedDecision > 4 || cfg->warping_Q16 < 0 ||
+      cfg->warping_Q16 > 32767)
+    return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200SilkNsq *q = new (std::nothrow) OpusB200SilkNsq;
+  if (!q) return OPUSB200_ALLOC_FAIL;
+  q->ctx = c; q->n = n_streams; q->frame_length = 5 * cfg->fs_khz * cfg->nb_subfr;
+  memcpy(&q->cfg, cfg, sizeof(q->cfg));
+  q->state = nullptr;
+  if (cudaMalloc(&q->state, sizeof(ObNsqState) * (size_t)n_streams) != cudaSuccess) { delete q; return OPUSB200_ALLOC_FAIL; }
+  cudaFuncSetAttribute(ob_silk_nsq_del_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, kNsqWarpSmemWords * 4);
+  const int rc = opusb200_silk_nsq_reset(q);
+  if (rc != OPUSB200_OK) { cudaFree(q->state); delete q; return rc; }
+  *out = q;
+  return OPUSB200_OK;
+}
+void opusb200_silk_nsq_destroy(OpusB200SilkNsq *q) {
+  if (!q) return;
+  cudaSetDevice(q->ctx->device);
+  cudaStreamSynchronize(q->ctx->stream);
+  cudaFree(q->state);
+  delete q;
+}
+int opusb200_silk_nsq_process(OpusB200SilkNsq *q, OpusB200NsqFrame *frames, const int16_t *x16, int8_t *pulses, int on_device) {
+  if (!q || !frames || !x16 || !pulses) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = q->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf df, dx, dp;
+  const size_t fb = sizeof(ObNsqFrame) * (size_t)q->n, xb = sizeof(int16_t) * (size_t)q->n * q->frame_length, pb = (size_t)q->n * q->frame_length;
+  SilkNsqParams p;
+  p.state = q->state; p.n_streams = q->n; p.cfg = q->cfg;
+  p.frames = (ObNsqFrame *)frames; p.x16 = x16; p.pulses = pulses;
+  if (!on_device) {
+    if (df.alloc(fb) || dx.alloc(xb) || dp.alloc(pb)) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(df.p, frames, fb, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(dx.p, x16, xb, cudaMemcpyHostToDevice, c->stream));
+    p.frames = (ObNsqFrame *)df.p; p.x16 = (const int16_t *)dx.p; p.pulses = (int8_t *)dp.p;
+  }
+  if (q->cfg.nStates > 1 || q->cfg.warping_Q16 > 0)  // silk/float/wrappers_FLP.c:163
+    ob_silk_nsq_del_dec<<<(q->n + 7) / 8, 32, kNsqWarpSmemWords * 4, c->stream>>>(p);
+  else
+    ob_silk_nsq<<<(q->n + 63) / 64, 64, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(pulses, dp.p, pb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaMemcpyAsync(frames, df.p, fb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+int opusb200_silk_nsq_get_state(OpusB200SilkNsq *q, int32_t *out) {
+  if (!q || !out) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = q->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  DevBuf d;
+  const size_t b = sizeof(int32_t) * 1325 * (size_t)q->n;
+  if (d.alloc(b)) return OPUSB200_ALLOC_FAIL;
+  ob_silk_nsq_export<<<q->n, 128, 0, c->stream>>>(q->state, (int32_t *)d.p, q->n);
+  OB_CUDA(cudaGetLastError());
+  OB_CUDA(cudaMemcpyAsync(out, d.p, b, cudaMemcpyDeviceToHost, c->stream));
+  OB_CUDA(cudaStreamSynchronize(c->stream));
   return OPUSB200_OK;
 }
 

@@ -51,6 +51,14 @@ OB_DEV unsigned char *dyn_smem() {
 #endif
 
 namespace ob {
+// high word of the signed 32x32 product (one IMAD.HI on the device)
+OB_DEV int32_t mulhi32(int32_t a, int32_t b) {
+#if defined(__CUDACC__)
+  return __mulhi(a, b);
+#else
+  return (int32_t)(((int64_t)a * b) >> 32);
+#endif
+}
 // 32 - clz, 0 for 0 (the range coder's EC_ILOG)
 OB_DEV int ilog32(uint32_t v) { return 32 - clz32(v); }
 

@@ -87,6 +87,9 @@ class Ops:
     def silk_resampler(self, n_streams, fs_in, fs_out):
         return SilkResampler(self, n_streams, fs_in, fs_out)
 
+    def silk_nsq(self, n_streams, fs_khz, nb_subfr, predict_order, shaping_order, warping_Q16, n_states):
+        return SilkNsq(self, n_streams, (fs_khz, nb_subfr, predict_order, shaping_order, warping_Q16, n_states))
+
     def close(self):
         if getattr(self, '_h', None):
             self._L.opusb200_ctx_destroy(self._h)
@@ -123,3 +126,59 @@ class SilkResampler:
         if getattr(self, '_h', None):
             self._L.opusb200_silk_resampler_destroy(self._h)
             self._h = None
+
+
+NSQ_FRAME_DTYPE = np.dtype([('signalType', '<i4'), ('quantOffsetType', '<i4'), ('NLSFInterpCoef_Q2', '<i4'), ('Seed', '<i4'),
+                            ('HarmShapeGain_Q14', '<i4', 4), ('Tilt_Q14', '<i4', 4), ('LF_shp_Q14', '<i4', 4), ('Gains_Q16', '<i4', 4),
+                            ('pitchL', '<i4', 4), ('Lambda_Q10', '<i4'), ('LTP_scale_Q14', '<i4'),
+                            ('PredCoef_Q12', '<i2', 32), ('LTPCoef_Q14', '<i2', 20), ('AR_Q13', '<i2', 96)])  # OpusB200NsqFrame
+
+
+class SilkNsq:
+    """n_streams SILK noise-shaping quantizers (silk_NSQ / silk_NSQ_del_dec, chosen as silk_NSQ_wrapper_FLP does)."""
+    STATE_WORDS = 1325
+
+    def __init__(self, ops, n_streams, cfg):
+        self._ops, self._L, self.n = ops, ops._L, n_streams
+        self.cfg = np.array(cfg, np.int32)
+        self.frame_length = 5 * int(cfg[0]) * int(cfg[1])
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_silk_nsq_create(ops._h, n_streams, _p(self.cfg), ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_nsq_create')
+        self._h = h
+
+    def process(self, frames, x16):
+        """frames: structured array [n] of NSQ_FRAME_DTYPE (Seed updated in the returned copy); x16 [n, frame_length].
+        Returns (pulses int8 [n, frame_length], frames_out)."""
+        fr = np.ascontiguousarray(frames, NSQ_FRAME_DTYPE).copy()
+        x = np.ascontiguousarray(x16, np.int16)
+        assert fr.shape == (self.n,) and x.shape == (self.n, self.frame_length)
+        pulses = np.empty(x.shape, np.int8)
+        r = self._L.opusb200_silk_nsq_process(self._h, _p(fr), _p(x), _p(pulses), 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_nsq_process')
+        return pulses, fr
+
+    def state(self):
+        out = np.empty((self.n, self.STATE_WORDS), np.int32)
+        r = self._L.opusb200_silk_nsq_get_state(self._h, _p(out))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_nsq_get_state')
+        return out
+
+    def reset(self):
+        r = self._L.opusb200_silk_nsq_reset(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_nsq_reset')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_silk_nsq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

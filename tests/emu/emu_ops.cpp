@@ -77,3 +77,33 @@ extern "C" void emu_silk_burg(float *A, float *nrg, const float *x, float mig, i
   p.A = A; p.nrg = nrg; p.x = x; p.minInvGain = mig; p.n_items = n; p.subfr_length = subfr; p.nb_subfr = nb; p.D = D;
   emu_launch(burg_entry, &p, (n + 31) / 32, 32, 0);
 }
+
+#include "../../opus_b200/csrc/silk_nsq.cuh"
+static void nsq_dd_entry(void *a) {
+  const SilkNsqParams &p = *(const SilkNsqParams *)a;
+  nsq_del_dec_warp(p, block_id() * 8, (int32_t *)dyn_smem());
+}
+static void nsq_plain_entry(void *a) {
+  const SilkNsqParams &p = *(const SilkNsqParams *)a;
+  int s = block_id() * 32 + lane_id();
+  if (s < p.n_streams) nsq_plain_thread(p, s);
+}
+extern "C" int emu_nsq_state_size(void) { return (int)sizeof(ObNsqState); }
+extern "C" void emu_nsq_state_init(ObNsqState *S, int n) {
+  memset(S, 0, sizeof(ObNsqState) * (size_t)n);
+  for (int i = 0; i < n; i++) { S[i].prev_gain_Q16 = 65536; S[i].lagPrev = 100; }
+}
+extern "C" void emu_silk_nsq(const int32_t *cfg, ObNsqState *state, ObNsqFrame *frames, const int16_t *x16, int8_t *pulses, int n) {
+  SilkNsqParams p;
+  p.state = state; p.frames = frames; p.x16 = x16; p.pulses = pulses; p.n_streams = n;
+  memcpy(&p.cfg, cfg, sizeof(p.cfg));
+  if (p.cfg.nStates > 1 || p.cfg.warping_Q16 > 0) emu_launch(nsq_dd_entry, &p, (n + 7) / 8, 32, kNsqWarpSmemWords * 4);
+  else emu_launch(nsq_plain_entry, &p, (n + 31) / 32, 32, 0);
+}
+extern "C" void emu_nsq_state_export(const ObNsqState *S, int32_t *o) {
+  for (int i = 0; i < 640; i++) *o++ = S->xq[i];
+  for (int i = 0; i < 640; i++) *o++ = S->sLTP_shp_Q14[i];
+  for (int i = 0; i < 16; i++) *o++ = S->sLPC_Q14[i];
+  for (int i = 0; i < 24; i++) *o++ = S->sAR2_Q14[i];
+  *o++ = S->sLF_AR_shp_Q14; *o++ = S->sDiff_shp_Q14; *o++ = S->lagPrev; *o++ = S->rand_seed; *o++ = S->prev_gain_Q16;
+}

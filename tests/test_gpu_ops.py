@@ -160,3 +160,24 @@ def test_silk_burg_and_autocorr(ops):
     for i in range(0, n, 101):
         O.orc_silk_autocorrelation(_f(w), _f(x[i]), x.shape[1], D + 1)
         assert np.array_equal(ac[i], w)
+
+
+@pytest.mark.parametrize('c', [(16, 4, 16, 24, 15729, 4), (16, 4, 16, 16, 0, 2), (16, 4, 16, 20, 15729, 3), (12, 4, 10, 14, 11796, 2),
+                               (8, 2, 10, 16, 0, 4), (16, 4, 16, 16, 15729, 1), (16, 4, 16, 16, 0, 1), (8, 4, 10, 12, 0, 1)])
+def test_silk_nsq(ops, c):
+    """silk_NSQ / silk_NSQ_del_dec: pulses, seed and carried state bit-exact against the pinned oracle over 3 frames"""
+    from test_emu_nsq import make_batch, oracle_run
+    O = util.load_oracle()
+    for nm in ['orc_nsq_state_init', 'orc_silk_nsq', 'orc_nsq_state_export']:
+        getattr(O, nm).restype = None
+    cfg = util.nsq_cfg(*c)
+    n, nf = 203, 3
+    x, frames = make_batch(100 + c[0] + c[3] + c[5], cfg, n, nf)
+    po, so, eo = oracle_run(O, cfg, x, frames)
+    q = ops.silk_nsq(n, *c)
+    for f in range(nf):
+        pulses, fr = q.process(frames[:, f], x[:, f])
+        assert np.array_equal(pulses, po[:, f]), (c, f)
+        assert np.array_equal(fr['Seed'], so[:, f])
+    assert np.array_equal(q.state(), eo)
+    q.close()

@@ -1,0 +1,229 @@
+#!/usr/bin/env python
+"""Device-resident timing of the batched kernel-level ops (the §8 rows outside the decoder), with the reference's own
+function timed beside each on one host core (oracle/_ref, when present).  One JSON line per op -> stdout.
+
+    python tools/bench_ops.py [--n 65536] [--reps 5]
+
+Inputs are resident in HBM; times are CUDA events on the library's own stream (torch.cuda.ExternalStream)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import opus_b200  # noqa: E402
+from opus_b200 import capi  # noqa: E402
+import util  # noqa: E402
+
+
+def dptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def time_gpu(stream, fn, reps, warmup=3):
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            fn()
+        stream.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def time_cpu(fn, min_s=1.0):
+    fn()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        fn()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > min_s:
+            return dt / n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=65536)
+    ap.add_argument('--reps', type=int, default=5)
+    a = ap.parse_args()
+    n = a.n
+    ops = opus_b200.Ops(0)
+    L = ops._L
+    stream = torch.cuda.ExternalStream(L.opusb200_ctx_cuda_stream(ops._h))
+    R = util.load_ref('simd') if util.ref_available('simd') else (util.load_ref('c') if util.ref_available('c') else None)
+    dev = torch.device('cuda:0')
+    rng = np.random.default_rng(0)
+    out = []
+
+    def emit(op, unit_name, units, ms, bytes_per_unit, cpu_s_per_unit=None, note=''):
+        rec = {'op': op, 'n': units, 'unit': unit_name, 'ms': round(ms, 4), 'units_per_s': units / (ms * 1e-3),
+               'algorithmic_GBps': units * bytes_per_unit / (ms * 1e-3) / 1e9,
+               'cpu_ref_units_per_s_1core': (1.0 / cpu_s_per_unit) if cpu_s_per_unit else None, 'note': note}
+        if cpu_s_per_unit:
+            rec['speedup_vs_1core'] = rec['units_per_s'] * cpu_s_per_unit
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+
+    # ---- SILK NSQ (delayed decision, 4 states, 16 kHz, 20 ms) and plain ----
+    for name, c in (('silk_nsq_del_dec_4st_wb', (16, 4, 16, 24, 15729, 4)), ('silk_nsq_del_dec_2st_wb', (16, 4, 16, 16, 0, 2)),
+                    ('silk_nsq_plain_wb', (16, 4, 16, 16, 0, 1))):
+        cfg = util.nsq_cfg(*c)
+        base = 256
+        xs, fs = [], []
+        for s in range(base):
+            x, fr = util.make_nsq_frames(s, cfg, 1)
+            xs.append(x[0])
+            fs.append(fr[0])
+        x = np.stack(xs)
+        fr = np.stack(fs)
+        reps_n = (n + base - 1) // base
+        xd = torch.from_numpy(np.tile(x, (reps_n, 1))[:n].copy()).to(dev)
+        frd = torch.from_numpy(np.tile(fr, reps_n)[:n].copy().view(np.uint8)).to(dev)
+        pd = torch.empty((n, x.shape[1]), dtype=torch.int8, device=dev)
+        q = ops.silk_nsq(n, *c)
+        fn = lambda: L.opusb200_silk_nsq_process(q._h, dptr(frd), dptr(xd), dptr(pd), 1)
+        ms = time_gpu(stream, fn, a.reps)
+        cpu = None
+        if R is not None:
+            st = np.zeros(R.refh_nsq_state_size(), np.uint8)
+            R.refh_nsq_state_init.restype = None
+            R.refh_silk_nsq.restype = None
+            R.refh_nsq_state_init(st.ctypes.data_as(ctypes.c_void_p))
+            pul = np.zeros(x.shape[1], np.int8)
+            state = {'i': 0}
+
+            def one():
+                i = state['i'] % base
+                state['i'] += 1
+                f1 = fr[i:i + 1].copy()
+                R.refh_silk_nsq(cfg.ctypes.data_as(ctypes.c_void_p), st.ctypes.data_as(ctypes.c_void_p),
+                                f1.ctypes.data_as(ctypes.c_void_p), x[i].ctypes.data_as(ctypes.c_void_p),
+                                pul.ctypes.data_as(ctypes.c_void_p))
+            cpu = time_cpu(one)
+        # algorithmic bytes / frame: x16 in + pulses out + frame params + state read/write (xq, sLTP_shp carried: 2*(1280+2560))
+        emit(name, 'frames(20ms)', n, ms, 320 * 2 + 320 + 400 + 2 * (1280 + 2560), cpu, 'cfg=%s' % (c,))
+        q.close()
+
+    # ---- SILK Burg (16 kHz: 4 x (80+16) samples, order 16) ----
+    subfr, nb, D = 96, 4, 16
+    t = np.arange(subfr * nb)
+    base = 512
+    xb = (3000 * np.sin(rng.uniform(0.01, 0.5, (base, 1)) * t) + 300 * rng.standard_normal((base, t.size))).astype(np.float32)
+    xd = torch.from_numpy(np.tile(xb, ((n + base - 1) // base, 1))[:n].copy()).to(dev)
+    Ad = torch.empty((n, D), dtype=torch.float32, device=dev)
+    nd = torch.empty(n, dtype=torch.float32, device=dev)
+    fn = lambda: L.opusb200_silk_burg_modified(ops._h, dptr(Ad), dptr(nd), dptr(xd), ctypes.c_float(1e-4), n, subfr, nb, D, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        R.silk_burg_modified_FLP.restype = ctypes.c_float
+        R.silk_burg_modified_FLP.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int]
+        Aw = np.zeros(D, np.float32)
+        arch = R.opus_select_arch() if hasattr(R, 'opus_select_arch') else 0
+        cpu = time_cpu(lambda: R.silk_burg_modified_FLP(Aw.ctypes.data_as(ctypes.c_void_p), xb[0].ctypes.data_as(ctypes.c_void_p),
+                                                        1e-4, subfr, nb, D, arch))
+    emit('silk_burg_modified', 'calls(384 smp, order 16)', n, ms, 384 * 4 + D * 4 + 4, cpu)
+
+    # ---- SILK LPC analysis filter (320 samples, order 16) ----
+    ln, d = 320, 16
+    xi = rng.integers(-8000, 8000, size=(n, ln)).astype(np.int16)
+    Bq = rng.integers(-3000, 3000, size=(n, d)).astype(np.int16)
+    xd = torch.from_numpy(xi).to(dev)
+    Bd = torch.from_numpy(Bq).to(dev)
+    od = torch.empty((n, ln), dtype=torch.int16, device=dev)
+    fn = lambda: L.opusb200_silk_lpc_analysis_filter(ops._h, dptr(od), dptr(xd), dptr(Bd), n, ln, d, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        o1 = np.zeros(ln, np.int16)
+        R.silk_LPC_analysis_filter.restype = None
+        cpu = time_cpu(lambda: R.silk_LPC_analysis_filter(o1.ctypes.data_as(ctypes.c_void_p), xi[0].ctypes.data_as(ctypes.c_void_p),
+                                                          Bq[0].ctypes.data_as(ctypes.c_void_p), ln, d, 0), 0.5)
+    emit('silk_lpc_analysis_filter', 'calls(320 smp, order 16)', n, ms, ln * 4 + d * 2, cpu)
+
+    # ---- SILK resampler 48 -> 16 kHz, 20 ms ----
+    xi = rng.integers(-8000, 8000, size=(n, 960)).astype(np.int16)
+    xd = torch.from_numpy(xi).to(dev)
+    od = torch.empty((n, 320), dtype=torch.int16, device=dev)
+    rs = ops.silk_resampler(n, 48000, 16000)
+    fn = lambda: L.opusb200_silk_resampler_process(rs._h, dptr(xd), dptr(od), 960, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        S = np.zeros(R.refh_resampler_size(), np.uint8)
+        R.silk_resampler_init(S.ctypes.data_as(ctypes.c_void_p), 48000, 16000, 1)
+        o1 = np.zeros(320, np.int16)
+        cpu = time_cpu(lambda: R.silk_resampler(S.ctypes.data_as(ctypes.c_void_p), o1.ctypes.data_as(ctypes.c_void_p),
+                                                xi[0].ctypes.data_as(ctypes.c_void_p), 960), 0.5)
+    emit('silk_resampler_48_16', 'frames(20ms)', n, ms, 960 * 2 + 320 * 2, cpu)
+
+    # ---- CELT forward MDCT, LM=3 long block ----
+    xi = rng.standard_normal((n, 1080)).astype(np.float32)
+    xd = torch.from_numpy(xi).to(dev)
+    od = torch.empty((n, 960), dtype=torch.float32, device=dev)
+    fn = lambda: L.opusb200_mdct_forward(ops._h, dptr(xd), dptr(od), n, 3, 0, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        o1 = np.zeros(960, np.float32)
+        R.refh_mdct_forward.restype = None
+        cpu = time_cpu(lambda: R.refh_mdct_forward(xi[0].ctypes.data_as(ctypes.c_void_p), o1.ctypes.data_as(ctypes.c_void_p), 3, 0), 0.5)
+    emit('celt_mdct_forward_960', 'transforms', n, ms, 1080 * 4 + 960 * 4, cpu)
+
+    # ---- CELT pitch xcorr (len 840, max_pitch 332: the 48 kHz/20 ms encoder pitch search after /2 decimation uses 240/~334) ----
+    ln, mp = 240, 332
+    xi = rng.standard_normal((n, ln)).astype(np.float32)
+    yi = rng.standard_normal((n, ln + mp)).astype(np.float32)
+    xd, yd = torch.from_numpy(xi).to(dev), torch.from_numpy(yi).to(dev)
+    od = torch.empty((n, mp), dtype=torch.float32, device=dev)
+    fn = lambda: L.opusb200_pitch_xcorr(ops._h, dptr(xd), dptr(yd), dptr(od), n, ln, mp, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        o1 = np.zeros(mp, np.float32)
+        R.refh_pitch_xcorr.restype = None
+        cpu = time_cpu(lambda: R.refh_pitch_xcorr(xi[0].ctypes.data_as(ctypes.c_void_p), yi[0].ctypes.data_as(ctypes.c_void_p),
+                                                  o1.ctypes.data_as(ctypes.c_void_p), ln, mp), 0.5)
+    emit('celt_pitch_xcorr_240x332', 'calls', n, ms, (ln + ln + mp + mp) * 4, cpu)
+
+    # ---- CELT PVQ search N=16 K=8 ----
+    N, K = 16, 8
+    xi = rng.standard_normal((n * 8, N)).astype(np.float32)
+    xd = torch.from_numpy(xi).to(dev)
+    iy = torch.empty((n * 8, N), dtype=torch.int32, device=dev)
+    yy = torch.empty(n * 8, dtype=torch.float32, device=dev)
+    Kd = torch.full((n * 8,), K, dtype=torch.int32, device=dev)
+    fn = lambda: L.opusb200_pvq_search(ops._h, dptr(xd), dptr(iy), dptr(yy), dptr(Kd), n * 8, N, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        x1 = xi[0].copy()
+        i1 = np.zeros(N, np.int32)
+        R.refh_pvq_search.restype = ctypes.c_float
+        def one():
+            x1[:] = xi[0]
+            R.refh_pvq_search(x1.ctypes.data_as(ctypes.c_void_p), i1.ctypes.data_as(ctypes.c_void_p), K, N)
+        cpu = time_cpu(one, 0.5)
+    emit('celt_pvq_search_N16_K8', 'vectors', n * 8, ms, N * 8 + 8, cpu)
+
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'bench_ops.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
