@@ -79,9 +79,27 @@ extern "C" __global__ void __launch_bounds__(128) ob_silk_autocorrelation(SilkAu
 }
 
 // SILK noise-shaping quantizers.  Delayed decision: one warp per block, 8 streams x 4 states per warp; the decision rings
-// take 29.4 KB of shared memory per warp, so 7 blocks are resident per SM.
-extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec(SilkNsqParams p) {
-  nsq_del_dec_warp(p, blockIdx.x * 8, (int32_t *)dyn_smem());
+// take 26.9 KB of shared memory per warp, so 8 blocks are resident per SM.
+template <int ORDER> __device__ __forceinline__ void nsq_del_dec_entry(const SilkNsqParams &p) {
+  nsq_del_dec_warp<ORDER>(p, blockIdx.x * 8, (int32_t *)dyn_smem());
+}
+// one instance per shapingLPCOrder the reference configures (silk/control_codec.c:316-386) + a generic one
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec(SilkNsqParams p) { nsq_del_dec_entry<0>(p); }
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec_o12(SilkNsqParams p) { nsq_del_dec_entry<12>(p); }
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec_o14(SilkNsqParams p) { nsq_del_dec_entry<14>(p); }
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec_o16(SilkNsqParams p) { nsq_del_dec_entry<16>(p); }
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec_o20(SilkNsqParams p) { nsq_del_dec_entry<20>(p); }
+extern "C" __global__ void __launch_bounds__(32) ob_silk_nsq_del_dec_o24(SilkNsqParams p) { nsq_del_dec_entry<24>(p); }
+typedef void (*NsqDdKernel)(SilkNsqParams);
+static NsqDdKernel nsq_dd_kernel(int order) {
+  switch (order) {
+    case 12: return ob_silk_nsq_del_dec_o12;
+    case 14: return ob_silk_nsq_del_dec_o14;
+    case 16: return ob_silk_nsq_del_dec_o16;
+    case 20: return ob_silk_nsq_del_dec_o20;
+    case 24: return ob_silk_nsq_del_dec_o24;
+    default: return ob_silk_nsq_del_dec;
+  }
 }
 extern "C" __global__ void __launch_bounds__(64) ob_silk_nsq(SilkNsqParams p) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -614,7 +632,7 @@ int opusb200_silk_nsq_create(OpusB200Ctx *c, int n_streams, const OpusB200NsqCon
   memcpy(&q->cfg, cfg, sizeof(q->cfg));
   q->state = nullptr;
   if (cudaMalloc(&q->state, sizeof(ObNsqState) * (size_t)n_streams) != cudaSuccess) { delete q; return OPUSB200_ALLOC_FAIL; }
-  cudaFuncSetAttribute(ob_silk_nsq_del_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, kNsqWarpSmemWords * 4);
+  cudaFuncSetAttribute(nsq_dd_kernel(cfg->shapingLPCOrder), cudaFuncAttributeMaxDynamicSharedMemorySize, kNsqWarpSmemWords * 4);
   const int rc = opusb200_silk_nsq_reset(q);
   if (rc != OPUSB200_OK) { cudaFree(q->state); delete q; return rc; }
   *out = q;
@@ -643,7 +661,7 @@ int opusb200_silk_nsq_process(OpusB200SilkNsq *q, OpusB200NsqFrame *frames, cons
     p.frames = (ObNsqFrame *)df.p; p.x16 = (const int16_t *)dx.p; p.pulses = (int8_t *)dp.p;
   }
   if (q->cfg.nStates > 1 || q->cfg.warping_Q16 > 0)  // silk/float/wrappers_FLP.c:163
-    ob_silk_nsq_del_dec<<<(q->n + 7) / 8, 32, kNsqWarpSmemWords * 4, c->stream>>>(p);
+    nsq_dd_kernel(q->cfg.shapingLPCOrder)<<<(q->n + 7) / 8, 32, kNsqWarpSmemWords * 4, c->stream>>>(p);
   else
     ob_silk_nsq<<<(q->n + 63) / 64, 64, 0, c->stream>>>(p);
   c->launches++;

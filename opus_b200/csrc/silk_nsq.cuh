@@ -45,7 +45,7 @@ struct SilkNsqParams {
 
 constexpr int kNsqDelay = 40;
 constexpr int kNsqRingWords = 5 * kNsqDelay * 32;            // per warp
-constexpr int kNsqWarpSmemWords = kNsqRingWords + 80 * 8 + kNsqDelay * 8;
+constexpr int kNsqWarpSmemWords = kNsqRingWords + kNsqDelay * 8;  // 26.9 KB: 8 warps per SM
 enum { RING_RAND = 0, RING_Q = 1, RING_XQ = 2, RING_PRED = 3, RING_SHAPE = 4 };
 
 OB_DEV int32_t nsq_addw(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -165,6 +165,9 @@ OB_DEV void nsq_grp_argmax(int32_t &v, int &idx) {
   }
 }
 
+// ORDER = shapingLPCOrder when it is one of the reference's settings (12, 14, 16, 20, 24: silk/control_codec.c:316-386),
+// 0 = read it from the configuration (sections past the order are then skipped with warp-uniform selects).
+template <int ORDER>
 OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem) {
   const int lane = lane_id(), g = lane >> 2, k = lane & 3, gbase = lane & ~3;
   const bool live = stream0 + g < p.n_streams;
@@ -177,8 +180,7 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
   const int16_t *x16 = p.x16 + (size_t)stream * frame_length;
   int8_t *pulses = p.pulses + (size_t)stream * frame_length;
   int32_t *ring = smem;                         // [5][40][32]
-  int32_t *xsc = smem + kNsqRingWords;          // [80][8]
-  int32_t *dgain = xsc + 80 * 8;                // [40][8]
+  int32_t *dgain = smem + kNsqRingWords;        // [40][8]
 #define RING(a, t, col) ring[((a) * kNsqDelay + (t)) * 32 + (col)]
 
   // ---- per-state registers ----
@@ -249,30 +251,41 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
     // ---- scale states (NSQ_del_dec.c:655-730), the 4 lanes of a group share the per-stream loops ----
     int32_t inv_gain_Q31 = nsq_inverse32_varq(Gain_Q16 > 1 ? Gain_Q16 : 1, 47);
     const int32_t inv_gain_Q26 = silk_rshift_round(inv_gain_Q31, 5);
-#pragma unroll 1
-    for (int i = k; i < subfr_length; i += 4) xsc[i * 8 + g] = nsq_smulww(x16[sf * subfr_length + i], inv_gain_Q26);
     if (rewhite) {
       // re-whitening (silk_LPC_analysis_filter over xq, NSQ_del_dec.c:243-248) fused with its rescale into sLTP_Q15
       if (sf == 0) inv_gain_Q31 = nsq_shl(silk_smulwb(inv_gain_Q31, F.LTP_scale_Q14), 2);
-      const int d = c.predictLPCOrder;
+      // Each lane filters one contiguous quarter of the lag+2 samples with the 16 previous inputs in a register window.
       const int16_t *xin = &S.xq[sf * subfr_length];  // index n here = xq[n + sf*subfr_length]
-#pragma unroll 1
-      for (int n = ltp_mem - lag - 2 + k; n < ltp_mem; n += 4) {
+      int32_t A[16], w[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) A[j] = j < c.predictLPCOrder ? (int32_t)A_Q12[j] : 0;
+      const int chunk = (lag + 2 + 3) >> 2;
+      const int nb = ltp_mem - lag - 2 + k * chunk, ne = nsq_min(nb + chunk, ltp_mem);
+#pragma unroll
+      for (int j = 0; j < 16; j++) w[j] = xin[nb - 1 - j];
+      int32_t cur = xin[nb];
+#pragma unroll 2
+      for (int n = nb; n < ne; n++) {
+        const int32_t nxt = xin[n + 1];
         uint32_t acc = 0;
-#pragma unroll 1
-        for (int j = 0; j < d; j++) acc += (uint32_t)((int32_t)xin[n - 1 - j] * A_Q12[j]);
-        acc = ((uint32_t)((int32_t)xin[n]) << 12) - acc;
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc += (uint32_t)(w[j] * A[j]);
+        acc = ((uint32_t)cur << 12) - acc;
         const int32_t res = silk_sat16(silk_rshift_round((int32_t)acc, 12));
         if (live) S.sLTP_Q15[n] = silk_smulwb(inv_gain_Q31, res);
+#pragma unroll
+        for (int j = 15; j > 0; j--) w[j] = w[j - 1];
+        w[0] = cur;
+        cur = nxt;
       }
     }
     if (Gain_Q16 != prev_gain_Q16) {
       const int32_t adj = nsq_div32_varq(prev_gain_Q16, Gain_Q16, 16);
       if (live) {
-#pragma unroll 1
+#pragma unroll 8
         for (int i = shp_idx - ltp_mem + k; i < shp_idx; i += 4) S.sLTP_shp_Q14[i] = nsq_smulww(adj, S.sLTP_shp_Q14[i]);
         if (voiced && !rewhite) {
-#pragma unroll 1
+#pragma unroll 4
           for (int i = ltp_idx - lag - 2 + k; i < ltp_idx - decisionDelay; i += 4) S.sLTP_Q15[i] = nsq_smulww(adj, S.sLTP_Q15[i]);
         }
       }
@@ -307,27 +320,38 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
     const int32_t lf_lo = nsq_hi16(LF), lf_hi = (int32_t)((uint32_t)LF & 0xffff0000u);
     const int32_t warp_sh = nsq_hi16(c.warping_Q16);
     const int32_t Gain_Q10 = Gain_Q16 >> 6;
-    const int order = c.shapingLPCOrder;
+    const int order = ORDER ? ORDER : c.shapingLPCOrder;
     const int32_t *shp_ptr = &S.sLTP_shp_Q14[shp_idx - lag + 1];
     const int32_t *pred_ptr = &S.sLTP_Q15[ltp_idx - lag + 2];
     const int out0 = sf * subfr_length - decisionDelay;  // frame-relative index of the sample decided at i == 0
+    // Register windows over the LTP and harmonic-shaping taps.  The element entering at sample i+1 was written (by this
+    // group's winner) at sample i+1-lag+2+delay <= i at the latest, so it is fetched right after sample i's closing wsync.
+    int32_t pw[5] = {0, 0, 0, 0, 0}, sw[3] = {0, 0, 0};
+    if (voiced) {
+#pragma unroll
+      for (int j = 0; j < 5; j++) pw[j] = pred_ptr[-j];
+    }
+    if (lag > 0) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) sw[j] = shp_ptr[-j];
+    }
 
 #pragma unroll 1
     for (int i = 0; i < subfr_length; i++) {
-      // ---- common to all states of the stream ----
+      // ---- common to all states of the stream (tap windows pw/sw were loaded one sample ahead) ----
       int32_t LTP_pred_Q14 = 0, n_LTP_Q14 = 0;
       if (voiced) {
         int32_t acc = 2;
 #pragma unroll
-        for (int j = 0; j < 5; j++) acc = nsq_addw(acc, mulhi32(pred_ptr[i - j], b_sh[j]));
+        for (int j = 0; j < 5; j++) acc = nsq_addw(acc, mulhi32(pw[j], b_sh[j]));
         LTP_pred_Q14 = nsq_shl(acc, 1);
       }
       if (lag > 0) {
-        int32_t n = mulhi32(nsq_add_sat(shp_ptr[i], shp_ptr[i - 2]), harm_lo);
-        n = nsq_addw(n, mulhi32(shp_ptr[i - 1], harm_hi));
+        int32_t n = mulhi32(nsq_add_sat(sw[0], sw[2]), harm_lo);
+        n = nsq_addw(n, mulhi32(sw[1], harm_hi));
         n_LTP_Q14 = LTP_pred_Q14 - nsq_shl(n, 2);
       }
-      const int32_t x_Q10 = xsc[i * 8 + g];
+      const int32_t x_Q10 = nsq_smulww(x16[sf * subfr_length + i], inv_gain_Q26);
 
       // ---- this lane's state ----
       Seed = nsq_lcg(Seed);
@@ -340,22 +364,27 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
       int32_t t1 = nsq_addw(sAR2[0], mulhi32(nsq_subw(sAR2[1], t2), warp_sh));
       sAR2[0] = t2;
       int32_t n_AR_Q14 = nsq_addw(order >> 1, mulhi32(t2, ar_sh[0]));
-      // Sections beyond the configured order are computed and discarded with warp-uniform selects, which keeps the
+      // With a run-time order, sections beyond it are computed and discarded with warp-uniform selects, which keeps the
       // whole delay line in registers.  ar_sh[] is zero from `order` on, so the first skipped section contributes
       // exactly the reference's closing tap t1*AR[order-1] and the later ones nothing.
 #pragma unroll
-      for (int j = 2; j < 24; j += 2) {
-        const bool on = j < order;
+      for (int j = 2; j < (ORDER ? ORDER : 24); j += 2) {
+        const bool on = ORDER ? true : j < order;
         const int32_t u2 = nsq_addw(sAR2[j - 1], mulhi32(nsq_subw(sAR2[j], t1), warp_sh));
         const int32_t u1 = nsq_addw(sAR2[j], mulhi32(nsq_subw(sAR2[j + 1], u2), warp_sh));
         n_AR_Q14 = nsq_addw(n_AR_Q14, mulhi32(t1, ar_sh[j - 1]));
         n_AR_Q14 = nsq_addw(n_AR_Q14, mulhi32(u2, on ? ar_sh[j] : 0));
-        sAR2[j - 1] = j <= order ? t1 : sAR2[j - 1];
+        sAR2[j - 1] = (ORDER || j <= order) ? t1 : sAR2[j - 1];
         sAR2[j] = on ? u2 : sAR2[j];
         t1 = on ? u1 : t1;
       }
-      n_AR_Q14 = nsq_addw(n_AR_Q14, mulhi32(t1, ar_sh[23]));
-      sAR2[23] = order == 24 ? t1 : sAR2[23];
+      if (ORDER) {
+        n_AR_Q14 = nsq_addw(n_AR_Q14, mulhi32(t1, ar_sh[ORDER ? ORDER - 1 : 23]));
+        sAR2[ORDER ? ORDER - 1 : 23] = t1;
+      } else {
+        n_AR_Q14 = nsq_addw(n_AR_Q14, mulhi32(t1, ar_sh[23]));
+        sAR2[23] = order == 24 ? t1 : sAR2[23];
+      }
       n_AR_Q14 = nsq_shl(n_AR_Q14, 1);
       n_AR_Q14 = nsq_addw(n_AR_Q14, mulhi32(LF_AR, tilt_sh));
       n_AR_Q14 = nsq_shl(n_AR_Q14, 2);
@@ -409,8 +438,9 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
       const int src = take ? gbase + imin : lane;
 #pragma unroll
       for (int j = 0; j < 16; j++) sLPC[j] = shfl(sLPC[j], src);
+      // taps past a compile-time order never diverge between the states (same start, same rescaling): nothing to copy
 #pragma unroll
-      for (int j = 0; j < 24; j++) sAR2[j] = shfl(sAR2[j], src);
+      for (int j = 0; j < (ORDER ? ORDER : 24); j++) sAR2[j] = shfl(sAR2[j], src);
       Seed = shfl(Seed, src);
       SeedInit = shfl(SeedInit, src);
       map.w0 = shfl(map.w0, src); map.w1 = shfl(map.w1, src); map.w2 = shfl(map.w2, src);
@@ -444,6 +474,15 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
       map.set(smpl, k);
       if (k == 0) dgain[smpl * 8 + g] = Gain_Q10;
       wsync();  // publishes the rings and the sLTP / shaping samples to the group's other lanes
+      if (voiced) {
+#pragma unroll
+        for (int j = 4; j > 0; j--) pw[j] = pw[j - 1];
+        pw[0] = pred_ptr[i + 1];
+      }
+      if (lag > 0) {
+        sw[2] = sw[1]; sw[1] = sw[0];
+        sw[0] = shp_ptr[i + 1];
+      }
     }
     shp_idx += subfr_length;
     ltp_idx += subfr_length;
@@ -482,15 +521,17 @@ OB_DEV void nsq_del_dec_warp(const SilkNsqParams &p, int stream0, int32_t *smem)
     }
   }
   wsync();
-  // ---- slide the output / shaping histories by one frame (memmove, NSQ_del_dec.c:325-326) ----
+  // ---- slide the output / shaping histories by one frame (memmove, NSQ_del_dec.c:325-326): blocks of frame_length
+  //      elements never overlap their own source, so only block boundaries need ordering ----
 #pragma unroll 1
-  for (int i = k; i < ltp_mem; i += 4) {
-    const int16_t a = S.xq[i + frame_length];
-    const int32_t b = S.sLTP_shp_Q14[i + frame_length];
-    wsync();
+  for (int base = 0; base < ltp_mem; base += frame_length) {
+    const int end = nsq_min(base + frame_length, ltp_mem);
     if (live) {
-      S.xq[i] = a;
-      S.sLTP_shp_Q14[i] = b;
+#pragma unroll 4
+      for (int i = base + k; i < end; i += 4) {
+        S.xq[i] = S.xq[i + frame_length];
+        S.sLTP_shp_Q14[i] = S.sLTP_shp_Q14[i + frame_length];
+      }
     }
     wsync();
   }

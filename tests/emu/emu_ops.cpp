@@ -81,7 +81,11 @@ extern "C" void emu_silk_burg(float *A, float *nrg, const float *x, float mig, i
 #include "../../opus_b200/csrc/silk_nsq.cuh"
 static void nsq_dd_entry(void *a) {
   const SilkNsqParams &p = *(const SilkNsqParams *)a;
-  nsq_del_dec_warp(p, block_id() * 8, (int32_t *)dyn_smem());
+  if (p.cfg.shapingLPCOrder == 24) nsq_del_dec_warp<24>(p, block_id() * 8, (int32_t *)dyn_smem());
+  else if (p.cfg.shapingLPCOrder == 16) nsq_del_dec_warp<16>(p, block_id() * 8, (int32_t *)dyn_smem());
+  else if (p.cfg.shapingLPCOrder == 20) nsq_del_dec_warp<20>(p, block_id() * 8, (int32_t *)dyn_smem());
+  else if (p.cfg.shapingLPCOrder == 12) nsq_del_dec_warp<12>(p, block_id() * 8, (int32_t *)dyn_smem());
+  else nsq_del_dec_warp<0>(p, block_id() * 8, (int32_t *)dyn_smem());
 }
 static void nsq_plain_entry(void *a) {
   const SilkNsqParams &p = *(const SilkNsqParams *)a;

@@ -14,6 +14,8 @@ CONFIGS = [
     (12, 4, 10, 14, 11796, 2),
     (8, 2, 10, 16, 0, 4),
     (16, 4, 16, 16, 15729, 1),
+    (16, 4, 16, 12, 0, 2),
+    (16, 2, 16, 18, 15729, 4),
     (16, 4, 16, 16, 0, 1),
     (8, 4, 10, 12, 0, 1),
 ]
