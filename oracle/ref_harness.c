@@ -214,3 +214,25 @@ void refh_nsq_state_export(const silk_nsq_state *S, opus_int32 *o) {
   for (i = 0; i < 24; i++) *o++ = S->sAR2_Q14[i];
   *o++ = S->sLF_AR_shp_Q14; *o++ = S->sDiff_shp_Q14; *o++ = S->lagPrev; *o++ = S->rand_seed; *o++ = S->prev_gain_Q16;
 }
+
+/* ---- dnn primitives (pure-C library only: the RTCD build would need the dnn/x86 dispatch tables) ---- */
+#ifndef OPUS_HAVE_RTCD
+#include "dnn/nnet.h"
+void compute_linear_c(const LinearLayer *linear, float *out, const float *in);
+void compute_activation_c(float *output, const float *input, int N, int activation);
+void compute_conv2d_c(const Conv2dLayer *conv, float *out, float *mem, const float *in, int height, int hstride, int activation);
+void refh_nnet_linear(float *out, const float *in, const float *bias, const float *subias, const opus_int8 *weights, const float *float_weights,
+                      const int *idx, const float *diag, const float *scale, int nb_inputs, int nb_outputs) {
+  LinearLayer l;
+  l.bias = bias; l.subias = subias; l.weights = weights; l.float_weights = float_weights; l.weights_idx = idx; l.diag = diag;
+  l.scale = scale; l.nb_inputs = nb_inputs; l.nb_outputs = nb_outputs;
+  compute_linear_c(&l, out, in);
+}
+void refh_nnet_activation(float *out, const float *in, int N, int act) { compute_activation_c(out, in, N, act); }
+void refh_nnet_conv2d(float *out, float *mem, const float *in, const float *bias, const float *w, int in_ch, int out_ch, int ktime,
+                      int kheight, int height, int hstride, int act) {
+  Conv2dLayer c;
+  c.bias = bias; c.float_weights = w; c.in_channels = in_ch; c.out_channels = out_ch; c.ktime = ktime; c.kheight = kheight;
+  compute_conv2d_c(&c, out, mem, in, height, hstride, act);
+}
+#endif

@@ -219,3 +219,66 @@ def make_nsq_frames(seed, cfg, n_frames):
         fr['Lambda_Q10'] = rng.integers(900, 2900)
         fr['LTP_scale_Q14'] = rng.choice([15565, 12288, 8192])
     return x, frames
+
+
+# ---- dnn layer generators (shared by oracle-vs-reference, emulator and GPU tests) ---------------------------------------------
+class CLinear(ctypes.Structure):  # dnn/nnet.h:66-76 LinearLayer == OrcLinear == OpusB200LinearLayer
+    _fields_ = [('bias', ctypes.c_void_p), ('subias', ctypes.c_void_p), ('weights', ctypes.c_void_p), ('float_weights', ctypes.c_void_p),
+                ('weights_idx', ctypes.c_void_p), ('diag', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('nb_inputs', ctypes.c_int),
+                ('nb_outputs', ctypes.c_int)]
+
+
+class CConv2d(ctypes.Structure):  # dnn/nnet.h:79-86
+    _fields_ = [('bias', ctypes.c_void_p), ('float_weights', ctypes.c_void_p), ('in_channels', ctypes.c_int), ('out_channels', ctypes.c_int),
+                ('ktime', ctypes.c_int), ('kheight', ctypes.c_int)]
+
+
+class Layer:
+    """A random LinearLayer with its arrays kept alive; .c is the C struct."""
+
+    def __init__(self, seed, nb_in, nb_out, kind, bias=True, diag=False, density=0.3):
+        rng = np.random.default_rng(seed)
+        self.nb_in, self.nb_out, self.kind = nb_in, nb_out, kind
+        self.bias = (rng.standard_normal(nb_out) * 0.1).astype(np.float32) if bias else None
+        self.diag = (rng.standard_normal(nb_out) * 0.3).astype(np.float32) if diag else None
+        self.weights = self.float_weights = self.idx = self.scale = None
+        sparse = kind in ('f32_sparse', 'i8_sparse')
+        if sparse:
+            idx, nblk = [], 0
+            for rb in range(nb_out // 8):
+                cols = [4 * c for c in range(nb_in // 4) if rng.random() < density]
+                idx.append(len(cols))
+                idx.extend(cols)
+                nblk += len(cols)
+            self.idx = np.array(idx, np.int32)
+        else:
+            nblk = (nb_out // 8) * (nb_in // 4)
+        if kind == 'f32':
+            self.float_weights = (rng.standard_normal((nb_in, nb_out)) / np.sqrt(nb_in)).astype(np.float32)  # [j*N + i]
+        elif kind == 'f32_sparse':
+            self.float_weights = (rng.standard_normal(nblk * 32) / np.sqrt(nb_in * density)).astype(np.float32)
+        else:
+            self.weights = rng.integers(-127, 128, size=max(nblk, 1) * 32).astype(np.int8)
+            self.scale = (rng.uniform(0.5, 1.5, nb_out) / (127.0 * 127.0 * np.sqrt(nb_in) * 0.6)).astype(np.float32)
+        self.subias = None
+        if self.weights is not None and self.bias is not None:
+            # what the reference's weight exporter stores next to an int8 matrix: the bias compensated for the +127 offset
+            if sparse:
+                wsum, pos, blk = np.zeros(nb_out, np.float64), 0, 0
+                for rb in range(nb_out // 8):
+                    cnt = int(self.idx[pos]); pos += 1 + cnt
+                    for _ in range(cnt):
+                        wsum[rb * 8:rb * 8 + 8] += self.weights[blk * 32:blk * 32 + 32].reshape(8, 4).sum(axis=1)
+                        blk += 1
+            else:
+                wsum = self.weights.reshape(nb_out // 8, nb_in // 4, 8, 4).astype(np.float64).sum(axis=(1, 3)).reshape(-1)
+            self.subias = (self.bias - 127.0 * self.scale * wsum).astype(np.float32)
+        c = CLinear()
+        for name, arr in (('bias', self.bias), ('subias', self.subias), ('weights', self.weights), ('float_weights', self.float_weights), ('weights_idx', self.idx),
+                          ('diag', self.diag), ('scale', self.scale)):
+            setattr(c, name, arr.ctypes.data if arr is not None else None)
+        c.nb_inputs, c.nb_outputs = nb_in, nb_out
+        self.c = c
+
+    def ptr(self, arr):
+        return arr.ctypes.data_as(ctypes.c_void_p) if arr is not None else None
