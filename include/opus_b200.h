@@ -174,6 +174,61 @@ int opusb200_silk_nsq_process(OpusB200SilkNsq *q, OpusB200NsqFrame *frames, cons
  * xq[640] sLTP_shp_Q14[640] sLPC_Q14[16] sAR2_Q14[24] sLF_AR_shp_Q14 sDiff_shp_Q14 lagPrev rand_seed prev_gain_Q16 */
 int opusb200_silk_nsq_get_state(OpusB200SilkNsq *q, int32_t *out);
 
+/* ---- dnn/ inference primitives, batched over n streams that share one set of weights (dnn/nnet.h:88-93, dnn/nnet_arch.h:69-243).
+ * Activations are row-major [n][dim] float.  int8 layers run on the tensor cores (exact integer dot products). ---- */
+#define OPUSB200_ACTIVATION_LINEAR 0   /* dnn/nnet.h:34-40 */
+#define OPUSB200_ACTIVATION_SIGMOID 1
+#define OPUSB200_ACTIVATION_TANH 2
+#define OPUSB200_ACTIVATION_RELU 3
+#define OPUSB200_ACTIVATION_SOFTMAX 4
+#define OPUSB200_ACTIVATION_SWISH 5
+#define OPUSB200_ACTIVATION_EXP 6
+/* = LinearLayer (dnn/nnet.h:66-76), host pointers */
+typedef struct {
+  const float *bias;
+  const float *subias;
+  const int8_t *weights;        /* 8x4-blocked int8 (cgemv8x4), with per-row `scale` */
+  const float *float_weights;   /* [j*nb_outputs + i], or 8x4 blocks when weights_idx != NULL */
+  const int *weights_idx;       /* block-sparse: per 8 rows a count followed by that many column positions */
+  const float *diag;            /* GRU recurrent layers only (nb_outputs == 3*nb_inputs) */
+  const float *scale;
+  int nb_inputs;
+  int nb_outputs;
+} OpusB200LinearLayer;
+/* = Conv2dLayer (dnn/nnet.h:79-86) */
+typedef struct {
+  const float *bias;
+  const float *float_weights;   /* [out][in][ktime][kheight] */
+  int in_channels, out_channels, ktime, kheight;
+} OpusB200Conv2dLayer;
+typedef struct OpusB200Linear OpusB200Linear;
+typedef struct OpusB200Conv2d OpusB200Conv2d;
+/* Uploads a layer.  su_bias != 0 selects the x86 reference convention for int8 layers (dnn/vec_avx.h:41 USE_SU_BIAS:
+ * activations quantised to unsigned 127+q and `subias` as the bias, dnn/nnet_arch.h:136-139); 0 = the generic C convention. */
+int opusb200_nnet_linear_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *layer, int su_bias, OpusB200Linear **out);
+void opusb200_nnet_linear_destroy(OpusB200Linear *l);
+/* compute_linear (dnn/nnet_arch.h:122): out [n][nb_outputs], in [n][nb_inputs] */
+int opusb200_nnet_compute_linear(OpusB200Ctx *ctx, const OpusB200Linear *l, float *out, const float *in, int n, int on_device);
+/* compute_activation (dnn/nnet_arch.h:69): [n][N]; softmax normalises each row */
+int opusb200_nnet_compute_activation(OpusB200Ctx *ctx, float *out, const float *in, int n, int N, int activation, int on_device);
+/* compute_generic_dense (dnn/nnet.c:60) */
+int opusb200_nnet_compute_dense(OpusB200Ctx *ctx, const OpusB200Linear *l, float *out, const float *in, int n, int activation, int on_device);
+/* compute_generic_gru (dnn/nnet.c:76): state [n][N] in/out, in [n][input_weights.nb_inputs] */
+int opusb200_nnet_compute_gru(OpusB200Ctx *ctx, const OpusB200Linear *input_weights, const OpusB200Linear *recurrent_weights, float *state,
+                              const float *in, int n, int on_device);
+/* compute_glu (dnn/nnet.c:107): out = in * sigmoid(W in + b); out may alias in */
+int opusb200_nnet_compute_glu(OpusB200Ctx *ctx, const OpusB200Linear *l, float *out, const float *in, int n, int on_device);
+/* compute_generic_conv1d (dilation 1; mem [n][nb_inputs-input_size]) / compute_generic_conv1d_dilation
+ * (mem [n][input_size*dilation*(ksize-1)]) (dnn/nnet.c:124-153) */
+int opusb200_nnet_compute_conv1d(OpusB200Ctx *ctx, const OpusB200Linear *l, float *out, float *mem, const float *in, int n, int input_size,
+                                 int dilation, int activation, int on_device);
+int opusb200_nnet_conv2d_create(OpusB200Ctx *ctx, const OpusB200Conv2dLayer *layer, OpusB200Conv2d **out);
+void opusb200_nnet_conv2d_destroy(OpusB200Conv2d *q);
+/* compute_conv2d (dnn/nnet_arch.h:217): in [n][in_ch*(height+kheight-1)], mem [n][(ktime-1)*in_ch*(height+kheight-1)],
+ * out [n][out_ch*hstride] */
+int opusb200_nnet_compute_conv2d(OpusB200Ctx *ctx, const OpusB200Conv2d *q, float *out, float *mem, const float *in, int n, int height,
+                                 int hstride, int activation, int on_device);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

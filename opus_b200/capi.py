@@ -29,7 +29,10 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_silk_resampler_destroy', 'opusb200_silk_resampler_reset', 'opusb200_silk_resampler_process',
            'opusb200_silk_burg_modified', 'opusb200_silk_autocorrelation',
            'opusb200_silk_nsq_create', 'opusb200_silk_nsq_destroy', 'opusb200_silk_nsq_reset', 'opusb200_silk_nsq_process',
-           'opusb200_silk_nsq_get_state', 'opusb200_host_alloc', 'opusb200_host_free']
+           'opusb200_silk_nsq_get_state', 'opusb200_nnet_linear_create', 'opusb200_nnet_linear_destroy',
+           'opusb200_nnet_compute_linear', 'opusb200_nnet_compute_activation', 'opusb200_nnet_compute_dense',
+           'opusb200_nnet_compute_gru', 'opusb200_nnet_compute_glu', 'opusb200_nnet_compute_conv1d',
+           'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d', 'opusb200_host_alloc', 'opusb200_host_free']
 
 
 class OpusB200Error(RuntimeError):
@@ -110,6 +113,19 @@ def lib():
         L.opusb200_silk_nsq_reset.argtypes = [vp]
         L.opusb200_silk_nsq_process.argtypes = [vp, vp, vp, vp, ci]
         L.opusb200_silk_nsq_get_state.argtypes = [vp, vp]
+        L.opusb200_nnet_linear_create.argtypes = [vp, vp, ci, ctypes.POINTER(vp)]
+        L.opusb200_nnet_linear_destroy.argtypes = [vp]
+        L.opusb200_nnet_linear_destroy.restype = None
+        L.opusb200_nnet_compute_linear.argtypes = [vp, vp, vp, vp, ci, ci]
+        L.opusb200_nnet_compute_activation.argtypes = [vp, vp, vp, ci, ci, ci, ci]
+        L.opusb200_nnet_compute_dense.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+        L.opusb200_nnet_compute_gru.argtypes = [vp, vp, vp, vp, vp, ci, ci]
+        L.opusb200_nnet_compute_glu.argtypes = [vp, vp, vp, vp, ci, ci]
+        L.opusb200_nnet_compute_conv1d.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci]
+        L.opusb200_nnet_conv2d_create.argtypes = [vp, vp, ctypes.POINTER(vp)]
+        L.opusb200_nnet_conv2d_destroy.argtypes = [vp]
+        L.opusb200_nnet_conv2d_destroy.restype = None
+        L.opusb200_nnet_compute_conv2d.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci]
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

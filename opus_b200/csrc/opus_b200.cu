@@ -382,7 +382,10 @@ int opusb200_decoder_get_timing(OpusB200Decoder *d, double *ms_kernels, int64_t 
 // ------------------------------------------------------------------------------------------
 // kernel-level operations (B3-level surface, batched)
 // ------------------------------------------------------------------------------------------
-struct OpusB200Ctx { int device; cudaStream_t stream; int max_smem_optin; int64_t launches; };
+struct OpusB200Ctx {
+  int device; cudaStream_t stream; int max_smem_optin; int64_t launches;
+  void *scratch[2]; size_t scratch_bytes[2];   // dnn temporaries (nnet_host.cuh)
+};
 
 int opusb200_ctx_create(int device, OpusB200Ctx **out) {
   if (!out) return OPUSB200_BAD_ARG;
@@ -396,6 +399,7 @@ int opusb200_ctx_create(int device, OpusB200Ctx **out) {
   OpusB200Ctx *c = new (std::nothrow) OpusB200Ctx;
   if (!c) return OPUSB200_ALLOC_FAIL;
   c->device = device; c->launches = 0;
+  c->scratch[0] = c->scratch[1] = nullptr; c->scratch_bytes[0] = c->scratch_bytes[1] = 0;
   OB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -409,6 +413,7 @@ void opusb200_ctx_destroy(OpusB200Ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  cudaFree(c->scratch[0]); cudaFree(c->scratch[1]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -777,3 +782,5 @@ void *opusb200_host_alloc(size_t bytes) {
 void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"
+
+#include "nnet_host.cuh"

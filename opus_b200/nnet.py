@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's dnn/nnet.h layer API (LinearLayer, Conv2dLayer, compute_generic_*) with a leading
+batch dimension: n streams share one set of weights.  numpy in / numpy out through the C ABI."""
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+ACTIVATION_LINEAR, ACTIVATION_SIGMOID, ACTIVATION_TANH, ACTIVATION_RELU, ACTIVATION_SOFTMAX, ACTIVATION_SWISH, ACTIVATION_EXP = range(7)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class _CLinear(ctypes.Structure):  # OpusB200LinearLayer
+    _fields_ = [('bias', ctypes.c_void_p), ('subias', ctypes.c_void_p), ('weights', ctypes.c_void_p), ('float_weights', ctypes.c_void_p),
+                ('weights_idx', ctypes.c_void_p), ('diag', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('nb_inputs', ctypes.c_int),
+                ('nb_outputs', ctypes.c_int)]
+
+
+class _CConv2d(ctypes.Structure):  # OpusB200Conv2dLayer
+    _fields_ = [('bias', ctypes.c_void_p), ('float_weights', ctypes.c_void_p), ('in_channels', ctypes.c_int), ('out_channels', ctypes.c_int),
+                ('ktime', ctypes.c_int), ('kheight', ctypes.c_int)]
+
+
+class LinearLayer:
+    """Device copy of a LinearLayer (dnn/nnet.h:66-76).  Arrays as in the reference's weight blobs."""
+
+    def __init__(self, ops, nb_inputs, nb_outputs, bias=None, subias=None, weights=None, float_weights=None, weights_idx=None, diag=None,
+                 scale=None, su_bias=True):
+        self._ops, self._L = ops, ops._L
+        self.nb_inputs, self.nb_outputs = nb_inputs, nb_outputs
+        keep = []
+
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+            return a.ctypes.data
+
+        c = _CLinear(arr(bias, np.float32), arr(subias, np.float32), arr(weights, np.int8), arr(float_weights, np.float32),
+                     arr(weights_idx, np.int32), arr(diag, np.float32), arr(scale, np.float32), nb_inputs, nb_outputs)
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_nnet_linear_create(ops._h, ctypes.byref(c), 1 if su_bias else 0, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_nnet_linear_create')
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_nnet_linear_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Conv2dLayer:
+    def __init__(self, ops, float_weights, bias, in_channels, out_channels, ktime, kheight):
+        self._ops, self._L = ops, ops._L
+        self.in_channels, self.out_channels, self.ktime, self.kheight = in_channels, out_channels, ktime, kheight
+        w = np.ascontiguousarray(float_weights, np.float32)
+        b = np.ascontiguousarray(bias, np.float32) if bias is not None else None
+        c = _CConv2d(b.ctypes.data if b is not None else None, w.ctypes.data, in_channels, out_channels, ktime, kheight)
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_nnet_conv2d_create(ops._h, ctypes.byref(c), ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_nnet_conv2d_create')
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_nnet_conv2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Nnet:
+    """compute_* entry points of dnn/nnet.h:88-93 over a batch."""
+
+    def __init__(self, ops):
+        self._ops, self._L, self._c = ops, ops._L, ops._h
+
+    def _chk(self, r, what):
+        if r != 0:
+            raise capi.OpusB200Error(r, what)
+
+    def linear(self, layer, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty((x.shape[0], layer.nb_outputs), np.float32)
+        self._chk(self._L.opusb200_nnet_compute_linear(self._c, layer._h, _p(out), _p(x), x.shape[0], 0), 'nnet_compute_linear')
+        return out
+
+    def activation(self, x, act):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(x)
+        self._chk(self._L.opusb200_nnet_compute_activation(self._c, _p(out), _p(x), x.shape[0], x.shape[1], act, 0), 'nnet_compute_activation')
+        return out
+
+    def dense(self, layer, x, act):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty((x.shape[0], layer.nb_outputs), np.float32)
+        self._chk(self._L.opusb200_nnet_compute_dense(self._c, layer._h, _p(out), _p(x), x.shape[0], act, 0), 'nnet_compute_dense')
+        return out
+
+    def gru(self, input_weights, recurrent_weights, state, x):
+        """returns the new state [n][N]"""
+        x = np.ascontiguousarray(x, np.float32)
+        st = np.ascontiguousarray(state, np.float32).copy()
+        self._chk(self._L.opusb200_nnet_compute_gru(self._c, input_weights._h, recurrent_weights._h, _p(st), _p(x), x.shape[0], 0), 'nnet_compute_gru')
+        return st
+
+    def glu(self, layer, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(x)
+        self._chk(self._L.opusb200_nnet_compute_glu(self._c, layer._h, _p(out), _p(x), x.shape[0], 0), 'nnet_compute_glu')
+        return out
+
+    def conv1d(self, layer, mem, x, act, dilation=1):
+        """returns (out, new mem)"""
+        x = np.ascontiguousarray(x, np.float32)
+        m = np.ascontiguousarray(mem, np.float32).copy()
+        out = np.empty((x.shape[0], layer.nb_outputs), np.float32)
+        self._chk(self._L.opusb200_nnet_compute_conv1d(self._c, layer._h, _p(out), _p(m) if m.size else None, _p(x), x.shape[0], x.shape[1],
+                                                      dilation, act, 0), 'nnet_compute_conv1d')
+        return out, m
+
+    def conv2d(self, layer, mem, x, height, hstride, act):
+        x = np.ascontiguousarray(x, np.float32)
+        m = np.ascontiguousarray(mem, np.float32).copy()
+        out = np.zeros((x.shape[0], layer.out_channels * hstride), np.float32)
+        self._chk(self._L.opusb200_nnet_compute_conv2d(self._c, layer._h, _p(out), _p(m) if m.size else None, _p(x), x.shape[0], height, hstride,
+                                                      act, 0), 'nnet_compute_conv2d')
+        return out, m

@@ -1,6 +1,8 @@
 // tests/emu/emu_ops.cpp — TEST INFRASTRUCTURE ONLY: the encoder-side op KERNEL SOURCES
 // (opus_b200/csrc/celt_ops.cuh) on the host SIMT emulator.
 #define OB_HOST_EMU 1
+#include <vector>
+#include <string.h>
 #include "../../opus_b200/csrc/celt_types.h"
 #include "../../opus_b200/csrc/celt_ops.cuh"
 
@@ -110,4 +112,71 @@ extern "C" void emu_nsq_state_export(const ObNsqState *S, int32_t *o) {
   for (int i = 0; i < 16; i++) *o++ = S->sLPC_Q14[i];
   for (int i = 0; i < 24; i++) *o++ = S->sAR2_Q14[i];
   *o++ = S->sLF_AR_shp_Q14; *o++ = S->sDiff_shp_Q14; *o++ = S->lagPrev; *o++ = S->rand_seed; *o++ = S->prev_gain_Q16;
+}
+
+// ---- dnn primitives -------------------------------------------------------------------------------------------------
+#include "../../opus_b200/csrc/nnet.cuh"
+struct EmuNnetArgs { NnetLinearParams p; int nsb; };
+static void nnet_quant_entry(void *a) { nnet_quant_thread(*(const NnetQuantParams *)a, (long)block_id() * 32 + lane_id()); }
+static void nnet_mma_entry(void *a) {
+  const EmuNnetArgs &g = *(const EmuNnetArgs *)a;
+  const int sb = block_id() % g.nsb, ob_ = block_id() / g.nsb;
+  if (g.p.L.su) nnet_linear_i8_mma_warp<true>(g.p, sb * 32, ob_ * 64);
+  else nnet_linear_i8_mma_warp<false>(g.p, sb * 32, ob_ * 64);
+}
+static void nnet_i8s_entry(void *a) { nnet_linear_i8_sparse_thread(((const EmuNnetArgs *)a)->p, (long)block_id() * 32 + lane_id()); }
+static void nnet_f32s_entry(void *a) { nnet_linear_f32_sparse_thread(((const EmuNnetArgs *)a)->p, (long)block_id() * 32 + lane_id()); }
+static void nnet_f32_entry(void *a) {
+  const EmuNnetArgs &g = *(const EmuNnetArgs *)a;
+  const int sb = block_id() % g.nsb, ob_ = block_id() / g.nsb;
+  nnet_linear_f32_block(g.p, sb * kNnF32Tile, ob_ * kNnF32Tile, *(NnetF32Smem *)dyn_smem(), warp_in_block() * 32 + lane_id());
+}
+static void nnet_gru_entry(void *a) { nnet_gru_thread(*(const NnetGruParams *)a, (long)block_id() * 32 + lane_id()); }
+static void nnet_act_entry(void *a) { nnet_activation_thread(*(const NnetActParams *)a, (long)block_id() * 32 + lane_id()); }
+
+// host-side LinearLayer as the tests pass it (same fields as dnn/nnet.h:66-76)
+struct EmuLinearLayer { const float *bias, *subias; const int8_t *weights; const float *float_weights; const int *weights_idx; const float *diag, *scale; int nb_inputs, nb_outputs; };
+extern "C" void emu_nnet_linear(const EmuLinearLayer *h, int su, float *out, const float *in, int n) {
+  const int M = h->nb_inputs, N = h->nb_outputs;
+  std::vector<int> rb_off, pos;
+  EmuNnetArgs g;
+  NnetLinear &L = g.p.L;
+  memset(&L, 0, sizeof(L));
+  L.M = M; L.N = N;
+  const bool i8 = !h->float_weights && h->weights;
+  L.su = (i8 && su) ? 1 : 0;
+  L.bias = (i8 && su) ? h->subias : h->bias;
+  L.diag = h->diag; L.scale = h->scale; L.w8 = i8 ? h->weights : nullptr; L.wf = h->float_weights;
+  if (h->weights_idx) {
+    const int *idx = h->weights_idx;
+    int nb = 0;
+    for (int rb = 0; rb < N / 8; rb++) { rb_off.push_back(nb); int cnt = *idx++; for (int j = 0; j < cnt; j++) pos.push_back(*idx++); nb += cnt; }
+    rb_off.push_back(nb);
+    pos.push_back(0);
+    L.rb_off = rb_off.data(); L.pos = pos.data();
+  }
+  g.p.out = out; g.p.in = in; g.p.n = n; g.p.Mp = (M + 31) & ~31; g.p.xq = nullptr;
+  std::vector<int8_t> xq;
+  if (i8) {
+    xq.resize((size_t)n * g.p.Mp);
+    NnetQuantParams q;
+    q.xq = xq.data(); q.in = in; q.n = n; q.M = M; q.Mp = g.p.Mp; q.su = L.su;
+    emu_launch(nnet_quant_entry, &q, (n * (g.p.Mp / 4) + 31) / 32, 32, 0);
+    g.p.xq = xq.data();
+    if (L.rb_off) emu_launch(nnet_i8s_entry, &g, (n * (N / 8) + 31) / 32, 32, 0);
+    else { g.nsb = (n + 31) / 32; emu_launch(nnet_mma_entry, &g, g.nsb * ((N + 63) / 64), 32, 0); }
+  } else if (L.wf) {
+    if (L.rb_off) emu_launch(nnet_f32s_entry, &g, (n * (N / 8) + 31) / 32, 32, 0);
+    else { g.nsb = (n + kNnF32Tile - 1) / kNnF32Tile; emu_launch(nnet_f32_entry, &g, g.nsb * ((N + kNnF32Tile - 1) / kNnF32Tile), 256, sizeof(NnetF32Smem)); }
+  }
+}
+extern "C" void emu_nnet_gru_gates(float *state, const float *zrh, const float *recur, int n, int N) {
+  NnetGruParams p;
+  p.state = state; p.zrh = zrh; p.recur = recur; p.n = n; p.N = N;
+  emu_launch(nnet_gru_entry, &p, (n * N + 31) / 32, 32, 0);
+}
+extern "C" void emu_nnet_activation(float *out, const float *in, int n, int N, int act) {
+  NnetActParams p;
+  p.out = out; p.in = in; p.n = n; p.N = N; p.act = act;
+  emu_launch(nnet_act_entry, &p, ((act == NN_SOFTMAX ? n : n * N) + 31) / 32, 32, 0);
 }

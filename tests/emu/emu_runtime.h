@@ -30,11 +30,11 @@
 namespace ob {
 struct EmuState {
   ucontext_t sched;
-  ucontext_t lanes[64];
-  bool done[64];
+  ucontext_t lanes[256];
+  bool done[256];
   int cur, nthreads;
   int block, nblocks;
-  uint64_t xchg[64];
+  uint64_t xchg[256];
   unsigned char *smem;
   size_t smem_bytes;
   long yields;
@@ -112,7 +112,7 @@ inline void emu_trampoline(unsigned lo, unsigned hi) {
   e.done[e.cur] = true;
   swapcontext(&e.lanes[e.cur], &e.sched);
 }
-// Run `fn(arg)` as a grid of `nblocks` blocks of `nthreads` (32 or 64) threads with `smem_bytes` of
+// Run `fn(arg)` as a grid of `nblocks` blocks of `nthreads` (a multiple of 32, at most 256) threads with `smem_bytes` of
 // dynamic shared memory.  With two warps per block every scheduling point synchronises the whole
 // block, which is only valid for kernels whose warps execute identical sync sequences.
 inline void emu_launch(void (*fn)(void *), void *arg, int nblocks, int nthreads, size_t smem_bytes) {

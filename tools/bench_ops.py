@@ -64,6 +64,7 @@ def main():
     L = ops._L
     stream = torch.cuda.ExternalStream(L.opusb200_ctx_cuda_stream(ops._h))
     R = util.load_ref('simd') if util.ref_available('simd') else (util.load_ref('c') if util.ref_available('c') else None)
+    RC = util.load_ref('c') if util.ref_available('c') else None
     dev = torch.device('cuda:0')
     rng = np.random.default_rng(0)
     out = []
@@ -116,6 +117,34 @@ def main():
         # algorithmic bytes / frame: x16 in + pulses out + frame params + state read/write (xq, sLTP_shp carried: 2*(1280+2560))
         emit(name, 'frames(20ms)', n, ms, 320 * 2 + 320 + 400 + 2 * (1280 + 2560), cpu, 'cfg=%s' % (c,))
         q.close()
+
+    # ---- dnn: FARGAN-sized int8 GRU step (272 -> 160; dnn/fargan.c sig_net gru1) on the tensor cores, and its pieces ----
+    from opus_b200 import nnet as nnet_mod
+    M, N = 272, 160
+    Wi, Wr = util.Layer(1, M, 3 * N, 'i8'), util.Layer(2, N, 3 * N, 'i8', diag=True)
+
+    def upl(Lh):
+        return nnet_mod.LinearLayer(ops, Lh.nb_in, Lh.nb_out, bias=Lh.bias, subias=Lh.subias, weights=Lh.weights, float_weights=Lh.float_weights,
+                                    weights_idx=Lh.idx, diag=Lh.diag, scale=Lh.scale, su_bias=True)
+    dWi, dWr = upl(Wi), upl(Wr)
+    xs = torch.from_numpy(np.clip(rng.standard_normal((n, M)) * 0.4, -1, 1).astype(np.float32)).to(dev)
+    sts = torch.zeros((n, N), dtype=torch.float32, device=dev)
+    outl = torch.empty((n, 3 * N), dtype=torch.float32, device=dev)
+    fn = lambda: L.opusb200_nnet_compute_linear(ops._h, dWi._h, dptr(outl), dptr(xs), n, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if RC is not None and hasattr(RC, 'refh_nnet_linear'):
+        RC.refh_nnet_linear.restype = None
+        x1 = np.clip(rng.standard_normal(M) * 0.4, -1, 1).astype(np.float32)
+        o1 = np.zeros(3 * N, np.float32)
+        vp = lambda arr: arr.ctypes.data_as(ctypes.c_void_p) if arr is not None else None
+        cpu = time_cpu(lambda: RC.refh_nnet_linear(vp(o1), vp(x1), vp(Wi.bias), vp(Wi.subias), vp(Wi.weights), None, None, None, vp(Wi.scale), M, 3 * N), 0.5)
+    rec_l = {'int8_TOPS': 2.0 * n * M * 3 * N / (ms * 1e-3) / 1e12}
+    emit('nnet_linear_i8_272x480', 'stream-layers', n, ms, M * 4 + 3 * N * 4, cpu, 'tensor-core mma.sync int8; %.2f TOPS' % rec_l['int8_TOPS'])
+    fn = lambda: L.opusb200_nnet_compute_gru(ops._h, dWi._h, dWr._h, dptr(sts), dptr(xs), n, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    emit('nnet_gru_272_160', 'stream-steps', n, ms, M * 4 + 2 * N * 4, None, 'two int8 linears + gate kernel; %.2f TOPS' % (2.0 * n * (M + N) * 3 * N / (ms * 1e-3) / 1e12))
+    dWi.close(); dWr.close()
 
     # ---- SILK Burg (16 kHz: 4 x (80+16) samples, order 16) ----
     subfr, nb, D = 96, 4, 16
