@@ -154,6 +154,9 @@ struct OpusB200Decoder {
   void *d_pcm; size_t d_pcm_cap;
   int64_t launches;
   int max_smem_optin;
+  cudaEvent_t ev_join;
+  cudaStream_t stream2;   // host-buffer API: chunks alternate between two streams so one chunk's D2H overlaps the next one's kernels
+  int e2e_chunks;
   // optional per-kernel timing (CUDA events on the decoder's stream)
   int timing;
   cudaEvent_t ev[4];
@@ -198,6 +201,10 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   memset(d, 0, sizeof(*d));
   d->device = device; d->channels = channels; d->n = n_streams;
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  OB_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+  OB_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+  d->e2e_chunks = 4;
+  if (const char *ec = getenv("OPUSB200_E2E_CHUNKS")) { const int v = atoi(ec); if (v >= 1 && v <= 64) d->e2e_chunks = v; }
   OB_CUDA(cudaMalloc(&d->bstate, sizeof(ObDecBandState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->sstate, sizeof(ObDecSynthState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->side, sizeof(ObFrameSide) * (size_t)n_streams));
@@ -242,6 +249,8 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->script); cudaFree(d->X); cudaFree(d->d_len); cudaFree(d->d_out);
   cudaFree(d->d_packets); cudaFree(d->d_pcm);
   cudaStreamDestroy(d->stream);
+  cudaStreamDestroy(d->stream2);
+  cudaEventDestroy(d->ev_join);
   delete d;
 }
 
@@ -255,39 +264,39 @@ int opusb200_decoder_sync(OpusB200Decoder *d) {
   return OPUSB200_OK;
 }
 
-int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, int pkt_stride, const int32_t *d_len,
-                           void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
-                           int32_t *d_out_samples) {
-  if (!d || !d_packets || !d_len || !d_pcm || pkt_stride <= 0 || frame_size <= 0) return OPUSB200_BAD_ARG;
-  if (pcm_stride < frame_size * d->channels) return OPUSB200_BAD_ARG;
-  if (max_frames_per_packet < 1) max_frames_per_packet = 1;
-  if (max_frames_per_packet > 48) max_frames_per_packet = 48;
-  OB_CUDA(cudaSetDevice(d->device));
+// Launch the three decode kernels for streams [s0, s0+cn) on stream `st`.  Every per-stream array is indexed by stream id,
+// so a sub-range is just an offset of the base pointers.
+static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, const unsigned char *d_packets, int pkt_stride,
+                         const int32_t *d_len, void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
+                         int32_t *d_out_samples) {
   const int pw = d->pvq_warps;
   const size_t pvq_smem = ((sizeof(PvqShared) + 15) & ~(size_t)15) + (size_t)pw * sizeof(PvqWS);
   if ((int)pvq_smem > d->max_smem_optin) return OPUSB200_INTERNAL_ERROR;
+  const size_t esz = pcm_is_int16 ? 2 : 4;
   for (int k = 0; k < max_frames_per_packet; k++) {
     DecEntropyParams ep;
-    ep.packets = d_packets; ep.pkt_len = d_len; ep.pkt_stride = pkt_stride; ep.n_streams = d->n; ep.channels = d->channels;
-    ep.frame_index = k; ep.state = d->bstate; ep.side = d->side; ep.script = d->script;
-    ep.out_samples = d_out_samples ? d_out_samples : d->d_out; ep.max_samples = frame_size;
+    ep.packets = d_packets + (size_t)s0 * pkt_stride; ep.pkt_len = d_len + s0; ep.pkt_stride = pkt_stride; ep.n_streams = cn;
+    ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side + s0; ep.script = d->script + s0;
+    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out) + s0; ep.max_samples = frame_size;
     DecPvqParams pp;
-    pp.side = d->side; pp.script = d->script; pp.state = d->bstate; pp.X = d->X; pp.n_streams = d->n;
-    if (d->timing) cudaEventRecord(d->ev[0], d->stream);
+    pp.side = d->side + s0; pp.script = d->script + s0; pp.state = d->bstate + s0; pp.X = d->X + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
+    const bool timing = d->timing && st == d->stream;
+    if (timing) cudaEventRecord(d->ev[0], st);
     {
-      const int warps_needed = (d->n + d->ent_lpw - 1) / d->ent_lpw;
-      ob_celt_dec_entropy<<<(warps_needed + 3) / 4, 128, 0, d->stream>>>(ep, d->ent_lpw);
+      const int warps_needed = (cn + d->ent_lpw - 1) / d->ent_lpw;
+      ob_celt_dec_entropy<<<(warps_needed + 3) / 4, 128, 0, st>>>(ep, d->ent_lpw);
     }
-    if (d->timing) cudaEventRecord(d->ev[1], d->stream);
-    ob_celt_dec_pvq<<<(d->n + pw - 1) / pw, pw * 32, pvq_smem, d->stream>>>(pp);
-    if (d->timing) cudaEventRecord(d->ev[2], d->stream);
+    if (timing) cudaEventRecord(d->ev[1], st);
+    ob_celt_dec_pvq<<<(cn + pw - 1) / pw, pw * 32, pvq_smem, st>>>(pp);
+    if (timing) cudaEventRecord(d->ev[2], st);
     DecSynthParams sp;
-    sp.side = d->side; sp.X = d->X; sp.state = d->sstate; sp.pcm = d_pcm; sp.pcm_stride = pcm_stride; sp.frame_index = k;
-    sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = d->n; sp.channels = d->channels;
-    ob_celt_dec_synth<<<d->n, 32 * d->channels, d->channels * sizeof(SynthWS), d->stream>>>(sp);
+    sp.side = d->side + s0; sp.X = d->X + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
+    sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
+    sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels;
+    ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), st>>>(sp);
     d->launches += 3;
-    if (d->timing) {  // profiling mode: serialises the stream, never used for throughput numbers
-      cudaEventRecord(d->ev[3], d->stream);
+    if (timing) {  // profiling mode: serialises the stream, never used for throughput numbers
+      cudaEventRecord(d->ev[3], st);
       cudaEventSynchronize(d->ev[3]);
       float a = 0.f, b = 0.f, c = 0.f;
       cudaEventElapsedTime(&a, d->ev[0], d->ev[1]);
@@ -298,6 +307,18 @@ int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, i
   }
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;
+}
+
+int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, int pkt_stride, const int32_t *d_len,
+                           void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
+                           int32_t *d_out_samples) {
+  if (!d || !d_packets || !d_len || !d_pcm || pkt_stride <= 0 || frame_size <= 0) return OPUSB200_BAD_ARG;
+  if (pcm_stride < frame_size * d->channels) return OPUSB200_BAD_ARG;
+  if (max_frames_per_packet < 1) max_frames_per_packet = 1;
+  if (max_frames_per_packet > 48) max_frames_per_packet = 48;
+  OB_CUDA(cudaSetDevice(d->device));
+  return decode_launch(d, d->stream, 0, d->n, d_packets, pkt_stride, d_len, d_pcm, pcm_stride, pcm_is_int16, frame_size,
+                       max_frames_per_packet, d_out_samples);
 }
 
 // frames in a packet as far as the TOC and the count byte tell (RFC 6716 3.2); 1 for anything odd
@@ -335,13 +356,31 @@ static int decode_host(OpusB200Decoder *d, const unsigned char *packets, int pkt
       if (c > maxf) maxf = c;
     }
   }
-  OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, pbytes, cudaMemcpyHostToDevice, d->stream));
-  OB_CUDA(cudaMemcpyAsync(d->d_len, len, sizeof(int32_t) * (size_t)d->n, cudaMemcpyHostToDevice, d->stream));
-  int r = opusb200_decode_device(d, d->d_packets, pkt_stride, d->d_len, d->d_pcm, pcm_stride, is_int16, frame_size, maxf, d->d_out);
-  if (r != OPUSB200_OK) return r;
-  OB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm, obytes, cudaMemcpyDeviceToHost, d->stream));
-  OB_CUDA(cudaMemcpyAsync(out_samples, d->d_out, sizeof(int32_t) * (size_t)d->n, cudaMemcpyDeviceToHost, d->stream));
+  // Chunked two-stream pipeline: each chunk does H2D -> 3 kernels -> D2H in its own stream; consecutive chunks alternate
+  // streams, so the PCM read-back of one chunk (the largest transfer by far) runs under the kernels of the next.
+  if (maxf > 48) maxf = 48;
+  int chunks = d->e2e_chunks;
+  if (d->timing || d->n < 4096 * chunks) chunks = 1;
+  const int per = (d->n + chunks - 1) / chunks;
+  if (chunks > 1) {  // whatever is pending on the main stream (reset, a device-side decode) comes first
+    OB_CUDA(cudaEventRecord(d->ev_join, d->stream));
+    OB_CUDA(cudaStreamWaitEvent(d->stream2, d->ev_join, 0));
+  }
+  for (int ci = 0; ci < chunks; ci++) {
+    const int s0 = ci * per, cn = s0 + per <= d->n ? per : d->n - s0;
+    if (cn <= 0) break;
+    cudaStream_t st = (ci & 1) ? d->stream2 : d->stream;
+    OB_CUDA(cudaMemcpyAsync(d->d_packets + (size_t)s0 * pkt_stride, packets + (size_t)s0 * pkt_stride, (size_t)cn * pkt_stride,
+                            cudaMemcpyHostToDevice, st));
+    OB_CUDA(cudaMemcpyAsync(d->d_len + s0, len + s0, sizeof(int32_t) * (size_t)cn, cudaMemcpyHostToDevice, st));
+    const int r = decode_launch(d, st, s0, cn, d->d_packets, pkt_stride, d->d_len, d->d_pcm, pcm_stride, is_int16, frame_size, maxf, d->d_out);
+    if (r != OPUSB200_OK) return r;
+    OB_CUDA(cudaMemcpyAsync((char *)pcm + (size_t)s0 * pcm_stride * esz, (char *)d->d_pcm + (size_t)s0 * pcm_stride * esz,
+                            (size_t)cn * pcm_stride * esz, cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaMemcpyAsync(out_samples + s0, d->d_out + s0, sizeof(int32_t) * (size_t)cn, cudaMemcpyDeviceToHost, st));
+  }
   OB_CUDA(cudaStreamSynchronize(d->stream));
+  if (chunks > 1) OB_CUDA(cudaStreamSynchronize(d->stream2));
   return OPUSB200_OK;
 }
 
