@@ -68,6 +68,12 @@ int opusb200_decode(OpusB200Decoder *dec, const unsigned char *packets, int pkt_
                     int16_t *pcm, int pcm_stride, int frame_size, int32_t *out_samples);
 int opusb200_decode_float(OpusB200Decoder *dec, const unsigned char *packets, int pkt_stride, const int32_t *len,
                           float *pcm, int pcm_stride, int frame_size, int32_t *out_samples);
+/* Asynchronous form of the two calls above for batch servers: enqueue call k+1 before waiting for call k and the PCM
+ * read-back of k overlaps the kernels of k+1 (device staging is double-buffered; results are identical).  The host buffers
+ * of a submitted call must stay valid and untouched until opusb200_decode_wait returns; at most two calls may be in flight. */
+int opusb200_decode_submit(OpusB200Decoder *dec, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
+                           int pcm_stride, int pcm_is_int16, int frame_size, int32_t *out_samples);
+int opusb200_decode_wait(OpusB200Decoder *dec);
 
 /* Same, with every buffer already resident in device memory (no copies, no synchronisation:
  * work is enqueued on the decoder's stream; call opusb200_decoder_sync() before reading results).

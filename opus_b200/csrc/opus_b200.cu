@@ -149,14 +149,15 @@ struct OpusB200Decoder {
   int pvq_warps;  // warps (= streams) per CTA of the PVQ kernel
   int ent_lpw;    // streams per warp of the entropy kernel
   // staging for the host-buffer API
-  unsigned char *d_packets; size_t d_packets_cap;
-  int32_t *d_len, *d_out;
-  void *d_pcm; size_t d_pcm_cap;
+  // (two slots: opusb200_decode_submit double-buffers, so one call's PCM read-back runs under the next call's kernels)
+  unsigned char *d_packets[2]; size_t d_packets_cap[2];
+  int32_t *d_len[2], *d_out[2];
+  void *d_pcm[2]; size_t d_pcm_cap[2];
+  int slot;
+  cudaEvent_t ev_ready[2], ev_done[2];
   int64_t launches;
   int max_smem_optin;
-  cudaEvent_t ev_join;
-  cudaStream_t stream2;   // host-buffer API: chunks alternate between two streams so one chunk's D2H overlaps the next one's kernels
-  int e2e_chunks;
+  cudaStream_t stream2;   // read-back stream of the host-buffer API
   // optional per-kernel timing (CUDA events on the decoder's stream)
   int timing;
   cudaEvent_t ev[4];
@@ -202,16 +203,19 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   d->device = device; d->channels = channels; d->n = n_streams;
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
-  OB_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
-  d->e2e_chunks = 4;
-  if (const char *ec = getenv("OPUSB200_E2E_CHUNKS")) { const int v = atoi(ec); if (v >= 1 && v <= 64) d->e2e_chunks = v; }
+  for (int b = 0; b < 2; b++) {
+    OB_CUDA(cudaEventCreateWithFlags(&d->ev_ready[b], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&d->ev_done[b], cudaEventDisableTiming));
+  }
   OB_CUDA(cudaMalloc(&d->bstate, sizeof(ObDecBandState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->sstate, sizeof(ObDecSynthState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->side, sizeof(ObFrameSide) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->script, sizeof(ObScript) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->X, sizeof(float) * 2 * OB_MAXN * (size_t)n_streams));
-  OB_CUDA(cudaMalloc(&d->d_len, sizeof(int32_t) * (size_t)n_streams));
-  OB_CUDA(cudaMalloc(&d->d_out, sizeof(int32_t) * (size_t)n_streams));
+  for (int b = 0; b < 2; b++) {
+    OB_CUDA(cudaMalloc(&d->d_len[b], sizeof(int32_t) * (size_t)n_streams));
+    OB_CUDA(cudaMalloc(&d->d_out[b], sizeof(int32_t) * (size_t)n_streams));
+  }
   OB_CUDA(cudaDeviceGetAttribute(&d->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -246,11 +250,11 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->script); cudaFree(d->X); cudaFree(d->d_len); cudaFree(d->d_out);
-  cudaFree(d->d_packets); cudaFree(d->d_pcm);
+  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->script); cudaFree(d->X);
+  for (int b = 0; b < 2; b++) { cudaFree(d->d_len[b]); cudaFree(d->d_out[b]); cudaFree(d->d_packets[b]); cudaFree(d->d_pcm[b]); }
   cudaStreamDestroy(d->stream);
   cudaStreamDestroy(d->stream2);
-  cudaEventDestroy(d->ev_join);
+  for (int b = 0; b < 2; b++) { cudaEventDestroy(d->ev_ready[b]); cudaEventDestroy(d->ev_done[b]); }
   delete d;
 }
 
@@ -277,7 +281,7 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     DecEntropyParams ep;
     ep.packets = d_packets + (size_t)s0 * pkt_stride; ep.pkt_len = d_len + s0; ep.pkt_stride = pkt_stride; ep.n_streams = cn;
     ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side + s0; ep.script = d->script + s0;
-    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out) + s0; ep.max_samples = frame_size;
+    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size;
     DecPvqParams pp;
     pp.side = d->side + s0; pp.script = d->script + s0; pp.state = d->bstate + s0; pp.X = d->X + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
     const bool timing = d->timing && st == d->stream;
@@ -331,23 +335,31 @@ static int host_frame_count(const unsigned char *p, int len) {
   }
 }
 
-static int decode_host(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
-                       int pcm_stride, int is_int16, int frame_size, int32_t *out_samples) {
+// Enqueue one batched decode with HOST buffers: H2D + kernels on the main stream, PCM read-back on the second stream.
+// Staging is double-buffered, so a caller that submits call k+1 before waiting for call k gets k's read-back (the largest
+// transfer by far) for free under k+1's kernels.  The host buffers must stay valid until opusb200_decode_wait returns.
+static int decode_submit(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
+                         int pcm_stride, int is_int16, int frame_size, int32_t *out_samples) {
   if (!d || !packets || !len || !pcm || !out_samples || pkt_stride <= 0 || frame_size <= 0) return OPUSB200_BAD_ARG;
   if (pcm_stride < frame_size * d->channels) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(d->device));
+  const int b = d->slot;
   const size_t pbytes = (size_t)d->n * pkt_stride;
   const size_t esz = is_int16 ? 2 : 4;
   const size_t obytes = (size_t)d->n * pcm_stride * esz;
-  if (d->d_packets_cap < pbytes) {
-    cudaFree(d->d_packets); d->d_packets = nullptr; d->d_packets_cap = 0;
-    OB_CUDA(cudaMalloc(&d->d_packets, pbytes));
-    d->d_packets_cap = pbytes;
-  }
-  if (d->d_pcm_cap < obytes) {
-    cudaFree(d->d_pcm); d->d_pcm = nullptr; d->d_pcm_cap = 0;
-    OB_CUDA(cudaMalloc(&d->d_pcm, obytes));
-    d->d_pcm_cap = obytes;
+  if (d->d_packets_cap[b] < pbytes || d->d_pcm_cap[b] < obytes) {
+    OB_CUDA(cudaStreamSynchronize(d->stream));
+    OB_CUDA(cudaStreamSynchronize(d->stream2));
+    if (d->d_packets_cap[b] < pbytes) {
+      cudaFree(d->d_packets[b]); d->d_packets[b] = nullptr; d->d_packets_cap[b] = 0;
+      OB_CUDA(cudaMalloc(&d->d_packets[b], pbytes));
+      d->d_packets_cap[b] = pbytes;
+    }
+    if (d->d_pcm_cap[b] < obytes) {
+      cudaFree(d->d_pcm[b]); d->d_pcm[b] = nullptr; d->d_pcm_cap[b] = 0;
+      OB_CUDA(cudaMalloc(&d->d_pcm[b], obytes));
+      d->d_pcm_cap[b] = obytes;
+    }
   }
   int maxf = 1;
   for (int s = 0; s < d->n; s++) {
@@ -356,32 +368,37 @@ static int decode_host(OpusB200Decoder *d, const unsigned char *packets, int pkt
       if (c > maxf) maxf = c;
     }
   }
-  // Chunked two-stream pipeline: each chunk does H2D -> 3 kernels -> D2H in its own stream; consecutive chunks alternate
-  // streams, so the PCM read-back of one chunk (the largest transfer by far) runs under the kernels of the next.
   if (maxf > 48) maxf = 48;
-  int chunks = d->e2e_chunks;
-  if (d->timing || d->n < 4096 * chunks) chunks = 1;
-  const int per = (d->n + chunks - 1) / chunks;
-  if (chunks > 1) {  // whatever is pending on the main stream (reset, a device-side decode) comes first
-    OB_CUDA(cudaEventRecord(d->ev_join, d->stream));
-    OB_CUDA(cudaStreamWaitEvent(d->stream2, d->ev_join, 0));
-  }
-  for (int ci = 0; ci < chunks; ci++) {
-    const int s0 = ci * per, cn = s0 + per <= d->n ? per : d->n - s0;
-    if (cn <= 0) break;
-    cudaStream_t st = (ci & 1) ? d->stream2 : d->stream;
-    OB_CUDA(cudaMemcpyAsync(d->d_packets + (size_t)s0 * pkt_stride, packets + (size_t)s0 * pkt_stride, (size_t)cn * pkt_stride,
-                            cudaMemcpyHostToDevice, st));
-    OB_CUDA(cudaMemcpyAsync(d->d_len + s0, len + s0, sizeof(int32_t) * (size_t)cn, cudaMemcpyHostToDevice, st));
-    const int r = decode_launch(d, st, s0, cn, d->d_packets, pkt_stride, d->d_len, d->d_pcm, pcm_stride, is_int16, frame_size, maxf, d->d_out);
-    if (r != OPUSB200_OK) return r;
-    OB_CUDA(cudaMemcpyAsync((char *)pcm + (size_t)s0 * pcm_stride * esz, (char *)d->d_pcm + (size_t)s0 * pcm_stride * esz,
-                            (size_t)cn * pcm_stride * esz, cudaMemcpyDeviceToHost, st));
-    OB_CUDA(cudaMemcpyAsync(out_samples + s0, d->d_out + s0, sizeof(int32_t) * (size_t)cn, cudaMemcpyDeviceToHost, st));
-  }
-  OB_CUDA(cudaStreamSynchronize(d->stream));
-  if (chunks > 1) OB_CUDA(cudaStreamSynchronize(d->stream2));
+  OB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_done[b], 0));  // the read-back that last used this slot (no-op if none)
+  OB_CUDA(cudaMemcpyAsync(d->d_packets[b], packets, pbytes, cudaMemcpyHostToDevice, d->stream));
+  OB_CUDA(cudaMemcpyAsync(d->d_len[b], len, sizeof(int32_t) * (size_t)d->n, cudaMemcpyHostToDevice, d->stream));
+  const int r = decode_launch(d, d->stream, 0, d->n, d->d_packets[b], pkt_stride, d->d_len[b], d->d_pcm[b], pcm_stride, is_int16,
+                              frame_size, maxf, d->d_out[b]);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaEventRecord(d->ev_ready[b], d->stream));
+  OB_CUDA(cudaStreamWaitEvent(d->stream2, d->ev_ready[b], 0));
+  OB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm[b], obytes, cudaMemcpyDeviceToHost, d->stream2));
+  OB_CUDA(cudaMemcpyAsync(out_samples, d->d_out[b], sizeof(int32_t) * (size_t)d->n, cudaMemcpyDeviceToHost, d->stream2));
+  OB_CUDA(cudaEventRecord(d->ev_done[b], d->stream2));
+  d->slot ^= 1;
   return OPUSB200_OK;
+}
+int opusb200_decode_wait(OpusB200Decoder *d) {
+  if (!d) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->device));
+  OB_CUDA(cudaStreamSynchronize(d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream2));
+  return OPUSB200_OK;
+}
+int opusb200_decode_submit(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
+                           int pcm_stride, int pcm_is_int16, int frame_size, int32_t *out_samples) {
+  return decode_submit(d, packets, pkt_stride, len, pcm, pcm_stride, pcm_is_int16 ? 1 : 0, frame_size, out_samples);
+}
+static int decode_host(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
+                       int pcm_stride, int is_int16, int frame_size, int32_t *out_samples) {
+  const int r = decode_submit(d, packets, pkt_stride, len, pcm, pcm_stride, is_int16, frame_size, out_samples);
+  if (r != OPUSB200_OK) return r;
+  return opusb200_decode_wait(d);
 }
 
 int opusb200_decode(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, int16_t *pcm,

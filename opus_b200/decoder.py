@@ -42,6 +42,21 @@ class DecoderBatch:
             raise capi.OpusB200Error(r, 'opusb200_decode')
         return out, ns
 
+    # -- asynchronous host-buffer variant: submit k+1 before wait()ing for k to overlap read-back with compute ---------
+    def submit(self, packets, lens, out, ns, frame_size=960):
+        """packets uint8 [n, stride], lens int32 [n], out int16|float32 [n, frame_size*channels], ns int32 [n]: all C-contiguous
+        and kept alive (ideally pinned) until wait() returns."""
+        assert packets.flags.c_contiguous and out.flags.c_contiguous and packets.dtype == np.uint8 and lens.dtype == np.int32
+        r = self._L.opusb200_decode_submit(self._h, _ptr(packets), packets.shape[1], _ptr(lens), _ptr(out), out.shape[1],
+                                           1 if out.dtype == np.int16 else 0, frame_size, _ptr(ns))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decode_submit')
+
+    def wait(self):
+        r = self._L.opusb200_decode_wait(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decode_wait')
+
     # -- device-resident variant (torch CUDA tensors or raw pointers) --------------------------
     def decode_device(self, d_packets, pkt_stride, d_lens, d_pcm, pcm_stride, int16=True, frame_size=960,
                       max_frames_per_packet=1, d_out_samples=None):

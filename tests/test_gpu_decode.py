@@ -190,3 +190,29 @@ def test_full_batch_65536_replicas_consistent():
         d = np.abs(got[i].astype(np.int32) - util.to_int16(want).reshape(-1).astype(np.int32))
         assert d.max() <= 1
     dec.close()
+
+
+def test_submit_wait_matches_synchronous_calls():
+    """opusb200_decode_submit/_wait (double-buffered staging, read-back on a second stream) == opusb200_decode, frame by frame"""
+    import opus_b200
+    case = [c for c in golden_cases() if c[5] == 2 and c[6] == 960][0]
+    name, pkts, sizes, rng, pcm, ch, fs = case
+    n, nfr = 5000, min(6, len(sizes))
+    a, b = opus_b200.DecoderBatch(n, channels=ch), opus_b200.DecoderBatch(n, channels=ch)
+    want = []
+    for t in range(nfr):
+        got, ns = a.decode(np.repeat(pkts[t:t + 1], n, 0), np.repeat(sizes[t:t + 1], n), frame_size=fs, dtype=np.int16)
+        want.append(got.copy())
+    pk = [np.ascontiguousarray(np.repeat(pkts[t:t + 1], n, 0)) for t in range(nfr)]
+    ln = [np.ascontiguousarray(np.repeat(sizes[t:t + 1], n).astype(np.int32)) for t in range(nfr)]
+    outs = [np.zeros((n, fs * ch), np.int16) for _ in range(nfr)]
+    nss = [np.zeros(n, np.int32) for _ in range(nfr)]
+    for t in range(0, nfr, 2):          # two calls in flight, then wait
+        for u in range(t, min(t + 2, nfr)):
+            b.submit(pk[u], ln[u], outs[u], nss[u], frame_size=fs)
+        b.wait()
+    for t in range(nfr):
+        assert (nss[t] == fs).all()
+        assert np.array_equal(outs[t], want[t]), t
+    assert (a.final_range() == b.final_range()).all()
+    a.close(); b.close()
