@@ -155,6 +155,9 @@ struct OpusB200Decoder {
   void *d_pcm[2]; size_t d_pcm_cap[2];
   int slot;
   cudaEvent_t ev_ready[2], ev_done[2];
+  int32_t *h_len[2], *h_out[2];   // pinned staging of the two small per-stream arrays (callers rarely pin those)
+  int32_t *user_out[2];
+  int pending[2];
   int64_t launches;
   int max_smem_optin;
   cudaStream_t stream2;   // read-back stream of the host-buffer API
@@ -215,6 +218,8 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   for (int b = 0; b < 2; b++) {
     OB_CUDA(cudaMalloc(&d->d_len[b], sizeof(int32_t) * (size_t)n_streams));
     OB_CUDA(cudaMalloc(&d->d_out[b], sizeof(int32_t) * (size_t)n_streams));
+    OB_CUDA(cudaMallocHost(&d->h_len[b], sizeof(int32_t) * (size_t)n_streams));
+    OB_CUDA(cudaMallocHost(&d->h_out[b], sizeof(int32_t) * (size_t)n_streams));
   }
   OB_CUDA(cudaDeviceGetAttribute(&d->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
@@ -251,7 +256,7 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
   cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->script); cudaFree(d->X);
-  for (int b = 0; b < 2; b++) { cudaFree(d->d_len[b]); cudaFree(d->d_out[b]); cudaFree(d->d_packets[b]); cudaFree(d->d_pcm[b]); }
+  for (int b = 0; b < 2; b++) { cudaFree(d->d_len[b]); cudaFree(d->d_out[b]); cudaFree(d->d_packets[b]); cudaFree(d->d_pcm[b]); cudaFreeHost(d->h_len[b]); cudaFreeHost(d->h_out[b]); }
   cudaStreamDestroy(d->stream);
   cudaStreamDestroy(d->stream2);
   for (int b = 0; b < 2; b++) { cudaEventDestroy(d->ev_ready[b]); cudaEventDestroy(d->ev_done[b]); }
@@ -369,17 +374,25 @@ static int decode_submit(OpusB200Decoder *d, const unsigned char *packets, int p
     }
   }
   if (maxf > 48) maxf = 48;
+  if (d->pending[b]) {  // a third call in flight: finish the one that owns this slot first
+    OB_CUDA(cudaEventSynchronize(d->ev_done[b]));
+    memcpy(d->user_out[b], d->h_out[b], sizeof(int32_t) * (size_t)d->n);
+    d->pending[b] = 0;
+  }
+  memcpy(d->h_len[b], len, sizeof(int32_t) * (size_t)d->n);
   OB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_done[b], 0));  // the read-back that last used this slot (no-op if none)
   OB_CUDA(cudaMemcpyAsync(d->d_packets[b], packets, pbytes, cudaMemcpyHostToDevice, d->stream));
-  OB_CUDA(cudaMemcpyAsync(d->d_len[b], len, sizeof(int32_t) * (size_t)d->n, cudaMemcpyHostToDevice, d->stream));
+  OB_CUDA(cudaMemcpyAsync(d->d_len[b], d->h_len[b], sizeof(int32_t) * (size_t)d->n, cudaMemcpyHostToDevice, d->stream));
   const int r = decode_launch(d, d->stream, 0, d->n, d->d_packets[b], pkt_stride, d->d_len[b], d->d_pcm[b], pcm_stride, is_int16,
                               frame_size, maxf, d->d_out[b]);
   if (r != OPUSB200_OK) return r;
   OB_CUDA(cudaEventRecord(d->ev_ready[b], d->stream));
   OB_CUDA(cudaStreamWaitEvent(d->stream2, d->ev_ready[b], 0));
   OB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm[b], obytes, cudaMemcpyDeviceToHost, d->stream2));
-  OB_CUDA(cudaMemcpyAsync(out_samples, d->d_out[b], sizeof(int32_t) * (size_t)d->n, cudaMemcpyDeviceToHost, d->stream2));
+  OB_CUDA(cudaMemcpyAsync(d->h_out[b], d->d_out[b], sizeof(int32_t) * (size_t)d->n, cudaMemcpyDeviceToHost, d->stream2));
   OB_CUDA(cudaEventRecord(d->ev_done[b], d->stream2));
+  d->user_out[b] = out_samples;
+  d->pending[b] = 1;
   d->slot ^= 1;
   return OPUSB200_OK;
 }
@@ -388,6 +401,11 @@ int opusb200_decode_wait(OpusB200Decoder *d) {
   OB_CUDA(cudaSetDevice(d->device));
   OB_CUDA(cudaStreamSynchronize(d->stream));
   OB_CUDA(cudaStreamSynchronize(d->stream2));
+  for (int b = 0; b < 2; b++)
+    if (d->pending[b]) {
+      memcpy(d->user_out[b], d->h_out[b], sizeof(int32_t) * (size_t)d->n);
+      d->pending[b] = 0;
+    }
   return OPUSB200_OK;
 }
 int opusb200_decode_submit(OpusB200Decoder *d, const unsigned char *packets, int pkt_stride, const int32_t *len, void *pcm,
