@@ -148,6 +148,19 @@ int opusb200_silk_burg_modified(OpusB200Ctx *ctx, float *A, float *nrg, const fl
 /* silk_autocorrelation_FLP (silk/float/autocorrelation_FLP.c:36): results [n_items][count] */
 int opusb200_silk_autocorrelation(OpusB200Ctx *ctx, float *results, const float *x, int n_items, int size, int count, int on_device);
 
+/* ---- CELT encoder front end, fused: celt_preemphasis (celt/celt_encoder.c:557) -> compute_mdcts (:511) -> compute_band_energies
+ * (celt/bands.c:151) -> amp2Log2 (celt/quant_bands.c:553) -> normalise_bands (celt/bands.c:169), i.e. lines 2007-2265 of
+ * celt_encode_with_ec with the pitch pre-filter off.  The object keeps, per stream and channel, the pre-emphasis memory and
+ * the `overlap` tail of the previous frame (CELTEncoder preemph_memE / prefilter_mem tail).
+ * pcm [n][frame_size*channels] interleaved floats (+-1.0), short_blocks [n] (the transient decision per stream, NULL = none),
+ * X [n][channels*frame_size] normalised MDCT, bandE / bandLogE [n][channels*21]. ---- */
+typedef struct OpusB200CeltAnalysis OpusB200CeltAnalysis;
+int opusb200_celt_analysis_create(OpusB200Ctx *ctx, int n_streams, int channels, OpusB200CeltAnalysis **out);
+void opusb200_celt_analysis_destroy(OpusB200CeltAnalysis *a);
+int opusb200_celt_analysis_reset(OpusB200CeltAnalysis *a);
+int opusb200_celt_analysis_process(OpusB200CeltAnalysis *a, const float *pcm, const int32_t *short_blocks, float *X, float *bandE,
+                                   float *bandLogE, int frame_size, int on_device);
+
 /* ---- SILK noise-shaping quantizer, batched: silk_NSQ / silk_NSQ_del_dec (silk/main.h:250-300; silk/NSQ.c:76,
  * silk/NSQ_del_dec.c:113), called once per frame from silk_NSQ_wrapper_FLP (silk/float/wrappers_FLP.c:106-170).
  * One object holds the silk_nsq_state (silk/structs.h:56-69) of n_streams encoders in device memory. ---- */

@@ -23,7 +23,8 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_decoder_reset', 'opusb200_decoder_n_streams', 'opusb200_decode', 'opusb200_decode_float',
            'opusb200_decode_device', 'opusb200_decoder_sync', 'opusb200_decoder_get_final_range',
            'opusb200_decoder_cuda_stream', 'opusb200_decoder_launch_count', 'opusb200_decoder_set_timing',
-           'opusb200_decoder_get_timing', 'opusb200_decode_submit', 'opusb200_decode_wait', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
+           'opusb200_decoder_get_timing', 'opusb200_decode_submit', 'opusb200_decode_wait', 'opusb200_celt_analysis_create',
+           'opusb200_celt_analysis_destroy', 'opusb200_celt_analysis_reset', 'opusb200_celt_analysis_process', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
            'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
            'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create',
            'opusb200_silk_resampler_destroy', 'opusb200_silk_resampler_reset', 'opusb200_silk_resampler_process',
@@ -128,6 +129,11 @@ def lib():
         L.opusb200_nnet_compute_conv2d.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci]
         L.opusb200_decode_submit.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, vp]
         L.opusb200_decode_wait.argtypes = [vp]
+        L.opusb200_celt_analysis_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_celt_analysis_destroy.argtypes = [vp]
+        L.opusb200_celt_analysis_destroy.restype = None
+        L.opusb200_celt_analysis_reset.argtypes = [vp]
+        L.opusb200_celt_analysis_process.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci]
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

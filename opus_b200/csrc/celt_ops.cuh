@@ -23,16 +23,12 @@ struct MdctFwdParams {
 };
 struct MdctWS { float in[OB_MAXN + OB_OVERLAP + 8]; float f2[OB_MAXN]; };
 
-OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *smem_warp) {
-  const int lane = lane_id();
-  MdctWS *ws = (MdctWS *)smem_warp;
-  const int LM = p.LM;
-  const int nblk = p.transient ? 1 << LM : 1, NB = p.transient ? OB_SHORT_N : OB_SHORT_N << LM;
-  const int shift = p.transient ? 3 : 3 - LM;
+// forward MDCT of the B*N+overlap samples already in ws->in; coefficients go to `o` (HBM, or ws->in itself: the time
+// samples are dead once the pre-rotation has run)
+OB_DEV void mdct_forward_from_ws(MdctWS *ws, int LM, int transient, float *o, int lane) {
+  const int nblk = transient ? 1 << LM : 1, NB = transient ? OB_SHORT_N : OB_SHORT_N << LM;
+  const int shift = transient ? 3 : 3 - LM;
   const int N2 = NB, N4 = NB >> 1, nfft = N4, overlap = OB_OVERLAP;
-  const float *g = p.in + (size_t)item * p.in_stride;
-  for (int i = lane; i < nblk * NB + overlap; i += 32) ws->in[i] = g[i];
-  wsync();
   const float *trig = ob_mdct_trig;
   for (int i = 0; i < shift; i++) trig += (1920 >> i) >> 1;
   const float scale = f_div(1.f, (float)nfft);
@@ -67,14 +63,79 @@ OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *s
     f2[b * nfft + bitrev[i]] = v;
   }
   fft_stages(f2, shift, nblk, lane);
-  // post-rotation straight to HBM (celt/mdct.c:236-262); out index = b + nblk*k
-  float *o = p.out + (size_t)item * p.out_stride;
+  // post-rotation (celt/mdct.c:236-262); out index = b + nblk*k
   for (int q = lane; q < nblk * N4; q += 32) {
     const int b = q / N4, i = q - b * N4;
     const cpx fp = f2[b * nfft + i];
     const float t0 = trig[i], t1 = trig[N4 + i];
     o[b + nblk * (2 * i)] = fp.i * t1 - fp.r * t0;
     o[b + nblk * (N2 - 1 - 2 * i)] = fp.r * t1 + fp.i * t0;
+  }
+}
+OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  MdctWS *ws = (MdctWS *)smem_warp;
+  const int n_in = (OB_SHORT_N << p.LM) + OB_OVERLAP;
+  const float *g = p.in + (size_t)item * p.in_stride;
+  for (int i = lane; i < n_in; i += 32) ws->in[i] = g[i];
+  wsync();
+  mdct_forward_from_ws(ws, p.LM, p.transient, p.out + (size_t)item * p.out_stride, lane);
+}
+
+// ---- encoder front end, one warp per (stream, channel): pre-emphasis -> MDCT -> band energies -> log2 -> normalised bands
+//      (celt_preemphasis celt/celt_encoder.c:557, compute_mdcts :511, compute_band_energies celt/bands.c:151,
+//       amp2Log2 celt/quant_bands.c:553, normalise_bands celt/bands.c:169), the path of celt_encode_with_ec when the pitch
+//      pre-filter is off.  The spectrum never leaves shared memory; HBM sees the PCM once and the normalised bands once. ----
+struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; };
+struct EncAnalysisParams {
+  ObEncAnalysisState *state;   // [n_streams]
+  const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
+  const int32_t *short_blocks; // [n_streams] transient decision per stream, or null (= long blocks)
+  float *X;                    // [n_streams][C*N]
+  float *bandE, *bandLogE;     // [n_streams][C*21]
+  int n_streams, C, LM;
+};
+OB_DEV void enc_analysis_warp(const EncAnalysisParams &p, int stream, int c, unsigned char *smem_warp) {
+  const int lane = lane_id();
+  MdctWS *ws = (MdctWS *)smem_warp;
+  const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C;
+  const int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
+  ObEncAnalysisState &st = p.state[stream];
+  const float *pcm = p.pcm + (size_t)stream * N * C + c;
+  // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
+  const float coef0 = 0.85000610f;
+  for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = st.overlap_mem[c][i];
+  for (int i = lane; i < N; i += 32) {
+    const float x = f_mul(32768.f, pcm[(size_t)C * i]);
+    const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (i - 1)]));
+    ws->in[OB_OVERLAP + i] = f_add(x, -m);
+  }
+  wsync();
+  if (lane == 0) st.preemph_mem[c] = f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)]));
+  for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
+  wsync();
+  float *freq = ws->in;
+  mdct_forward_from_ws(ws, LM, transient, freq, lane);
+  wsync();
+  // band energies: one lane per band, summed in index order like celt_inner_prod_c
+  float E = 0.f, g = 0.f;
+  if (lane < OB_NBANDS) {
+    float sum = 0.f;
+    const int j0 = M * ob_ebands[lane], j1 = M * ob_ebands[lane + 1];
+#pragma unroll 4
+    for (int j = j0; j < j1; j++) sum = f_add(sum, f_mul(freq[j], freq[j]));
+    E = f_sqrt(f_add(1e-27f, sum));
+    g = f_div(1.f, f_add(1e-27f, E));
+    const size_t o = (size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane;
+    p.bandE[o] = E;
+    p.bandLogE[o] = f_add((float)(1.442695040888963387 * log((double)E)), -ob_emeans[lane]);
+  }
+  float *X = p.X + (size_t)stream * C * N + (size_t)c * N;
+#pragma unroll 1
+  for (int b = 0; b < OB_NBANDS; b++) {
+    const float gb = shfl(g, b);
+    const int j1 = M * ob_ebands[b + 1];
+    for (int j = M * ob_ebands[b] + lane; j < j1; j += 32) X[j] = f_mul(freq[j], gb);
   }
 }
 

@@ -51,6 +51,11 @@ extern "C" __global__ void __launch_bounds__(128) ob_mdct_forward(MdctFwdParams 
   if (item >= p.n_items) return;
   mdct_forward_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
 }
+extern "C" __global__ void __launch_bounds__(128) ob_celt_enc_analysis(EncAnalysisParams p) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= p.n_streams * p.C) return;
+  enc_analysis_warp(p, item / p.C, item % p.C, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
+}
 extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, int smem_per_warp) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= p.n_items) return;
@@ -477,6 +482,7 @@ int opusb200_ctx_create(int device, OpusB200Ctx **out) {
   OB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_pitch_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_exp_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_pvq_search, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -525,6 +531,71 @@ int opusb200_mdct_forward(OpusB200Ctx *c, const float *in, float *out, int n_ite
   OB_CUDA(cudaGetLastError());
   if (!on_device) {
     OB_CUDA(cudaMemcpyAsync(out, pout, sizeof(float) * (size_t)n_items * out_stride, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}
+
+struct OpusB200CeltAnalysis {
+  OpusB200Ctx *ctx;
+  int n, channels;
+  ObEncAnalysisState *state;
+};
+int opusb200_celt_analysis_reset(OpusB200CeltAnalysis *a) {
+  if (!a) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(a->ctx->device));
+  OB_CUDA(cudaMemsetAsync(a->state, 0, sizeof(ObEncAnalysisState) * (size_t)a->n, a->ctx->stream));
+  return OPUSB200_OK;
+}
+int opusb200_celt_analysis_create(OpusB200Ctx *c, int n_streams, int channels, OpusB200CeltAnalysis **out) {
+  if (!c || !out || n_streams <= 0 || (channels != 1 && channels != 2)) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200CeltAnalysis *a = new (std::nothrow) OpusB200CeltAnalysis;
+  if (!a) return OPUSB200_ALLOC_FAIL;
+  a->ctx = c; a->n = n_streams; a->channels = channels; a->state = nullptr;
+  if (cudaMalloc(&a->state, sizeof(ObEncAnalysisState) * (size_t)n_streams) != cudaSuccess) { delete a; return OPUSB200_ALLOC_FAIL; }
+  const int r = opusb200_celt_analysis_reset(a);
+  if (r != OPUSB200_OK) { cudaFree(a->state); delete a; return r; }
+  *out = a;
+  return OPUSB200_OK;
+}
+void opusb200_celt_analysis_destroy(OpusB200CeltAnalysis *a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  cudaStreamSynchronize(a->ctx->stream);
+  cudaFree(a->state);
+  delete a;
+}
+int opusb200_celt_analysis_process(OpusB200CeltAnalysis *a, const float *pcm, const int32_t *short_blocks, float *X, float *bandE,
+                                   float *bandLogE, int frame_size, int on_device) {
+  if (!a || !pcm || !X || !bandE || !bandLogE) return OPUSB200_BAD_ARG;
+  int LM = -1;
+  for (int l = 0; l <= 3; l++) if (frame_size == OB_SHORT_N << l) LM = l;
+  if (LM < 0) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = a->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  const int C = a->channels;
+  const size_t pb = sizeof(float) * (size_t)a->n * frame_size * C, eb = sizeof(float) * (size_t)a->n * C * OB_NBANDS, sb = sizeof(int32_t) * (size_t)a->n;
+  DevBuf dp, ds, dX, dE, dL;
+  EncAnalysisParams p;
+  p.state = a->state; p.pcm = pcm; p.short_blocks = short_blocks; p.X = X; p.bandE = bandE; p.bandLogE = bandLogE;
+  p.n_streams = a->n; p.C = C; p.LM = LM;
+  if (!on_device) {
+    if (dp.alloc(pb) || dX.alloc(pb) || dE.alloc(eb) || dL.alloc(eb) || (short_blocks && ds.alloc(sb))) return OPUSB200_ALLOC_FAIL;
+    OB_CUDA(cudaMemcpyAsync(dp.p, pcm, pb, cudaMemcpyHostToDevice, c->stream));
+    if (short_blocks) OB_CUDA(cudaMemcpyAsync(ds.p, short_blocks, sb, cudaMemcpyHostToDevice, c->stream));
+    p.pcm = (const float *)dp.p; p.short_blocks = short_blocks ? (const int32_t *)ds.p : nullptr;
+    p.X = (float *)dX.p; p.bandE = (float *)dE.p; p.bandLogE = (float *)dL.p;
+  }
+  const int warps = 4, items = a->n * C;
+  ob_celt_enc_analysis<<<(items + warps - 1) / warps, warps * 32, warps * sizeof(MdctWS), c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(X, p.X, pb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaMemcpyAsync(bandE, p.bandE, eb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaMemcpyAsync(bandLogE, p.bandLogE, eb, cudaMemcpyDeviceToHost, c->stream));
     OB_CUDA(cudaStreamSynchronize(c->stream));
   }
   return OPUSB200_OK;

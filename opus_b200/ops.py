@@ -87,6 +87,9 @@ class Ops:
     def silk_resampler(self, n_streams, fs_in, fs_out):
         return SilkResampler(self, n_streams, fs_in, fs_out)
 
+    def celt_analysis(self, n_streams, channels):
+        return CeltAnalysis(self, n_streams, channels)
+
     def silk_nsq(self, n_streams, fs_khz, nb_subfr, predict_order, shaping_order, warping_Q16, n_states):
         return SilkNsq(self, n_streams, (fs_khz, nb_subfr, predict_order, shaping_order, warping_Q16, n_states))
 
@@ -175,6 +178,42 @@ class SilkNsq:
     def close(self):
         if getattr(self, '_h', None):
             self._L.opusb200_silk_nsq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CeltAnalysis:
+    """n_streams CELT encoder front ends (pre-emphasis -> MDCT -> band energies -> normalised bands), state carried."""
+
+    def __init__(self, ops, n_streams, channels):
+        self._ops, self._L, self.n, self.channels = ops, ops._L, n_streams, channels
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_celt_analysis_create(ops._h, n_streams, channels, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_celt_analysis_create')
+        self._h = h
+
+    def process(self, pcm, short_blocks=None):
+        """pcm float32 [n, frame_size*channels] interleaved -> (X [n, channels*frame_size], bandE [n, channels*21], bandLogE)"""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        fs = pcm.shape[1] // self.channels
+        X = np.empty_like(pcm)
+        E = np.empty((self.n, self.channels * 21), np.float32)
+        Lg = np.empty_like(E)
+        sb = np.ascontiguousarray(short_blocks, np.int32) if short_blocks is not None else None
+        r = self._L.opusb200_celt_analysis_process(self._h, _p(pcm), _p(sb) if sb is not None else None, _p(X), _p(E), _p(Lg), fs, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_celt_analysis_process')
+        return X, E, Lg
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_celt_analysis_destroy(self._h)
             self._h = None
 
     def __del__(self):

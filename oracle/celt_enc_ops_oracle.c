@@ -198,3 +198,40 @@ float orc_pvq_search(float *X, int *iy, int K, int N) {
   do iy[j] = (iy[j] ^ -signx[j]) + signx[j]; while (++j < N);
   return yy;
 }
+
+/* ---- encoder front end of celt_encode_with_ec without the pitch pre-filter (complexity < 5 or pf disabled):
+ *   celt_preemphasis (celt/celt_encoder.c:557-646, 48 kHz fast path) -> [overlap history | frame]
+ *   compute_mdcts (:511-554) -> compute_band_energies (celt/bands.c:151-165) -> amp2Log2 (celt/quant_bands.c:553-572)
+ *   -> normalise_bands (celt/bands.c:169-183)
+ * state per channel: the pre-emphasis memory and the last `overlap` pre-emphasised samples (what the reference keeps at
+ * the tail of prefilter_mem, celt_encoder.c:2014).  pcm is interleaved, +-1.0 full scale. */
+typedef struct { float preemph_mem[2]; float overlap_mem[2][120]; } OrcEncAnalysisState;
+int orc_enc_analysis_state_size(void) { return (int)sizeof(OrcEncAnalysisState); }
+void orc_celt_enc_analysis(OrcEncAnalysisState *st, const float *pcm, int CC, int LM, int shortBlocks, float *X, float *bandE, float *bandLogE) {
+  const int N = 120 << LM, overlap = 120, M = 1 << LM;
+  float in[960 + 120], freq[960];
+  int c, i, j;
+  for (c = 0; c < CC; c++) {
+    float m = st->preemph_mem[c];
+    memcpy(in, st->overlap_mem[c], overlap * sizeof(float));
+    for (i = 0; i < N; i++) {
+      float x = 32768.f * pcm[CC * i + c];
+      in[overlap + i] = x - m;
+      m = 0.85000610f * x;   /* mode->preemph[0] (celt/static_modes_float.h) */
+    }
+    st->preemph_mem[c] = m;
+    memcpy(st->overlap_mem[c], in + N, overlap * sizeof(float));
+    orc_mdct_forward(in, freq, LM, shortBlocks);
+    for (i = 0; i < 21; i++) {
+      float sum = 0;
+      for (j = M * ob_ebands[i]; j < M * ob_ebands[i + 1]; j++) sum = sum + freq[j] * freq[j];   /* celt_inner_prod_c */
+      sum = 1e-27f + sum;
+      bandE[c * 21 + i] = (float)sqrt(sum);
+      bandLogE[c * 21 + i] = (float)(1.442695040888963387 * log(bandE[c * 21 + i])) - ob_emeans[i];
+      {
+        float g = 1.f / (1e-27f + bandE[c * 21 + i]);
+        for (j = M * ob_ebands[i]; j < M * ob_ebands[i + 1]; j++) X[c * N + j] = freq[j] * g;
+      }
+    }
+  }
+}

@@ -236,3 +236,24 @@ void refh_nnet_conv2d(float *out, float *mem, const float *in, const float *bias
   compute_conv2d_c(&c, out, mem, in, height, hstride, act);
 }
 #endif
+
+/* ---- encoder front end: the reference's celt_preemphasis / clt_mdct_forward (as compute_mdcts drives it) /
+ * compute_band_energies / amp2Log2 / normalise_bands on one frame.  mem: [CC] pre-emphasis memories,
+ * hist: [CC][120] previous frame tails (both in/out). ---- */
+#include "celt/celt.h"
+#include "celt/quant_bands.h"
+void refh_celt_enc_analysis(float *mem, float *hist, const float *pcm, int CC, int LM, int shortBlocks, float *X, float *bandE, float *bandLogE) {
+  const OpusCustomMode *m = refh_mode();
+  const int N = 120 << LM, overlap = 120;
+  float in[2 * (960 + 120)], freq[2 * 960];
+  int c;
+  for (c = 0; c < CC; c++) {
+    memcpy(in + c * (N + overlap), hist + c * overlap, overlap * sizeof(float));
+    celt_preemphasis(pcm + c, in + c * (N + overlap) + overlap, N, CC, 1, m->preemph, mem + c, 0);
+    memcpy(hist + c * overlap, in + c * (N + overlap) + N, overlap * sizeof(float));
+    refh_mdct_forward(in + c * (N + overlap), freq + c * N, LM, shortBlocks);
+  }
+  compute_band_energies(m, freq, bandE, 21, CC, LM, 0);
+  amp2Log2(m, 21, 21, bandE, bandLogE, CC);
+  normalise_bands(m, freq, X, bandE, 21, CC, 1 << LM);
+}

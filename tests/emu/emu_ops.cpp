@@ -180,3 +180,16 @@ extern "C" void emu_nnet_activation(float *out, const float *in, int n, int N, i
   p.out = out; p.in = in; p.n = n; p.N = N; p.act = act;
   emu_launch(nnet_act_entry, &p, ((act == NN_SOFTMAX ? n : n * N) + 31) / 32, 32, 0);
 }
+
+// ---- encoder front end ----
+static void enc_analysis_entry(void *a) {
+  const EncAnalysisParams &p = *(const EncAnalysisParams *)a;
+  const int item = block_id();
+  enc_analysis_warp(p, item / p.C, item % p.C, dyn_smem());
+}
+extern "C" int emu_enc_analysis_state_size(void) { return (int)sizeof(ObEncAnalysisState); }
+extern "C" void emu_celt_enc_analysis(void *state, const float *pcm, const int32_t *sb, float *X, float *E, float *Lg, int n, int C, int LM) {
+  EncAnalysisParams p;
+  p.state = (ObEncAnalysisState *)state; p.pcm = pcm; p.short_blocks = sb; p.X = X; p.bandE = E; p.bandLogE = Lg; p.n_streams = n; p.C = C; p.LM = LM;
+  emu_launch(enc_analysis_entry, &p, n * C, 32, sizeof(MdctWS));
+}

@@ -111,3 +111,24 @@ def test_emu_silk_burg():
         for i in range(n):
             r = O.orc_silk_burg_modified(_f(w), _f(x[i]), mig, subfr, nb, D)
             assert r == nrg[i] and np.array_equal(A[i], w)
+
+
+@pytest.mark.parametrize('cc,lm', [(2, 3), (1, 3), (2, 2), (2, 0)])
+def test_emu_enc_analysis(cc, lm):
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    N = 120 << lm
+    n, nf = 5, 3
+    x = np.stack([util.sig_music(50 + s, N * nf, cc).astype(np.float32).reshape(nf, N * cc) / 32768.0 for s in range(n)])
+    sb = np.array([0, 1, 0, 1, 1], np.int32) if lm else np.zeros(n, np.int32)
+    st_e = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
+    st_o = [np.zeros(O.orc_enc_analysis_state_size(), np.uint8) for _ in range(n)]
+    for f in range(nf):
+        pcm = np.ascontiguousarray(x[:, f])
+        X, En, Lg = np.zeros((n, cc * N), np.float32), np.zeros((n, cc * 21), np.float32), np.zeros((n, cc * 21), np.float32)
+        E.emu_celt_enc_analysis(_f(st_e), _f(pcm), _f(sb), _f(X), _f(En), _f(Lg), n, cc, lm)
+        for s in range(n):
+            Xo, Eo, Lo = np.zeros(cc * N, np.float32), np.zeros(cc * 21, np.float32), np.zeros(cc * 21, np.float32)
+            O.orc_celt_enc_analysis(_f(st_o[s]), _f(pcm[s]), cc, lm, int(sb[s]), _f(Xo), _f(Eo), _f(Lo))
+            assert np.array_equal(En[s].view(np.uint32), Eo.view(np.uint32)), (f, s)
+            assert np.array_equal(Lg[s].view(np.uint32), Lo.view(np.uint32))
+            assert np.array_equal(X[s].view(np.uint32), Xo.view(np.uint32))

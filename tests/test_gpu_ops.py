@@ -181,3 +181,28 @@ def test_silk_nsq(ops, c):
         assert np.array_equal(fr['Seed'], so[:, f])
     assert np.array_equal(q.state(), eo)
     q.close()
+
+
+@pytest.mark.parametrize('cc,lm', [(2, 3), (1, 3), (2, 2), (2, 1), (1, 0)])
+def test_celt_enc_analysis(ops, cc, lm):
+    """fused encoder front end vs the pinned oracle over 4 consecutive frames: energies and normalised bands bit-exact
+    (log energies go through the device's fp64 log: allowed to differ by one float ulp)"""
+    O = util.load_oracle()
+    N = 120 << lm
+    n, nf = 300, 4
+    x = np.stack([util.sig_music(900 + s, N * nf, cc).astype(np.float32).reshape(nf, N * cc) / 32768.0 for s in range(24)])
+    x = np.tile(x, (n // 24 + 1, 1, 1))[:n]
+    sb = (np.arange(n) % 3 == 1).astype(np.int32) if lm else np.zeros(n, np.int32)
+    an = ops.celt_analysis(n, cc)
+    st_o = [np.zeros(O.orc_enc_analysis_state_size(), np.uint8) for _ in range(n)]
+    for f in range(nf):
+        pcm = np.ascontiguousarray(x[:, f])
+        X, En, Lg = an.process(pcm, sb)
+        for s in range(0, n, 7):
+            Xo, Eo, Lo = np.zeros(cc * N, np.float32), np.zeros(cc * 21, np.float32), np.zeros(cc * 21, np.float32)
+            # the oracle must follow every frame of the streams it checks
+            O.orc_celt_enc_analysis(_f(st_o[s]), _f(pcm[s]), cc, lm, int(sb[s]), _f(Xo), _f(Eo), _f(Lo))
+            assert np.array_equal(En[s].view(np.uint32), Eo.view(np.uint32)), (f, s)
+            assert np.array_equal(X[s].view(np.uint32), Xo.view(np.uint32))
+            assert np.abs(Lg[s].view(np.int32).astype(np.int64) - Lo.view(np.int32).astype(np.int64)).max() <= 1
+    an.close()

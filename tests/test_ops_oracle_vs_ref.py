@@ -71,3 +71,25 @@ def test_exp_rotation_and_pvq_search(N):
             yb = O.orc_pvq_search(_f(b), _f(ib), K, N)
             assert ya == yb and np.array_equal(ia, ib) and np.array_equal(a, b), K
             assert np.abs(ia).sum() == K
+
+
+@pytest.mark.parametrize('cc', [1, 2])
+@pytest.mark.parametrize('lm,short', [(3, 0), (3, 1), (2, 0), (2, 1), (1, 1), (0, 0)])
+def test_enc_analysis_front_end(cc, lm, short):
+    """pre-emphasis -> MDCT -> band energies -> log energies -> normalised bands, over consecutive frames (state carried)"""
+    R, O = util.load_ref('c'), util.load_oracle()
+    N = 120 << lm
+    x = util.sig_music(7 + cc + lm, N * 6, cc).astype(np.float32) / 32768.0 if hasattr(util, 'sig_music') else None
+    x = np.ascontiguousarray(x.reshape(6, N * cc))
+    mem = np.zeros(2, np.float32)
+    hist = np.zeros(2 * 120, np.float32)
+    st = np.zeros(O.orc_enc_analysis_state_size(), np.uint8)
+    for f in range(6):
+        Xa, Ea, La = np.zeros(cc * N, np.float32), np.zeros(cc * 21, np.float32), np.zeros(cc * 21, np.float32)
+        Xb, Eb, Lb = np.zeros_like(Xa), np.zeros_like(Ea), np.zeros_like(La)
+        R.refh_celt_enc_analysis(_f(mem), _f(hist), _f(x[f]), cc, lm, short, _f(Xa), _f(Ea), _f(La))
+        O.orc_celt_enc_analysis(_f(st), _f(x[f]), cc, lm, short, _f(Xb), _f(Eb), _f(Lb))
+        assert np.array_equal(Ea.view(np.uint32), Eb.view(np.uint32)), f
+        assert np.array_equal(La.view(np.uint32), Lb.view(np.uint32))
+        assert np.array_equal(Xa.view(np.uint32), Xb.view(np.uint32))
+        assert Ea.max() > 1

@@ -200,6 +200,26 @@ def main():
                                                 xi[0].ctypes.data_as(ctypes.c_void_p), 960), 0.5)
     emit('silk_resampler_48_16', 'frames(20ms)', n, ms, 960 * 2 + 320 * 2, cpu)
 
+    # ---- CELT encoder front end, 48 kHz stereo 20 ms: pre-emphasis -> MDCT -> band energies -> normalised bands (fused) ----
+    base = 64
+    xb = np.stack([util.sig_music(s, 960, 2).astype(np.float32).reshape(-1) / 32768.0 for s in range(base)])
+    pcm = torch.from_numpy(np.tile(xb, ((n + base - 1) // base, 1))[:n].copy()).to(dev)
+    Xd = torch.empty((n, 1920), dtype=torch.float32, device=dev)
+    Ed = torch.empty((n, 42), dtype=torch.float32, device=dev)
+    Ld = torch.empty((n, 42), dtype=torch.float32, device=dev)
+    an = ops.celt_analysis(n, 2)
+    fn = lambda: L.opusb200_celt_analysis_process(an._h, dptr(pcm), None, dptr(Xd), dptr(Ed), dptr(Ld), 960, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if R is not None:
+        mem, hist = np.zeros(2, np.float32), np.zeros(240, np.float32)
+        X1, E1, L1 = np.zeros(1920, np.float32), np.zeros(42, np.float32), np.zeros(42, np.float32)
+        R.refh_celt_enc_analysis.restype = None
+        vp = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+        cpu = time_cpu(lambda: R.refh_celt_enc_analysis(vp(mem), vp(hist), vp(xb[0]), 2, 3, 0, vp(X1), vp(E1), vp(L1)), 0.5)
+    emit('celt_enc_analysis_stereo_20ms', 'frames', n, ms, 1920 * 4 + 1920 * 4 + 84 * 4 + 2 * 488, cpu, 'algorithmic bytes: pcm in + X out + energies + state r/w')
+    an.close()
+
     # ---- CELT forward MDCT, LM=3 long block ----
     xi = rng.standard_normal((n, 1080)).astype(np.float32)
     xd = torch.from_numpy(xi).to(dev)
