@@ -187,27 +187,41 @@ OB_DEV void nnet_linear_i8_mma_warp(const NnetLinearParams &p, int stream0, int 
       const int s = stream0 + mt * 16 + h * 8 + gid;
       rowA[mt][h] = (s < p.n ? s : p.n - 1) * wpr;
     }
-#pragma unroll 1
-  for (int k0 = 0; k0 < p.Mp; k0 += 32) {
+  // software pipeline: the fragments of k-step s+1 are in flight while the 16 MMAs of step s issue
+  uint32_t a[2][2][4], b[2][8][2];
+  auto load_frags = [&](int k0, uint32_t (&af)[2][4], uint32_t (&bf)[8][2]) {
     const int cb = (k0 >> 2) + tig;
-    uint32_t a[2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; mt++) {
-      a[mt][0] = X[rowA[mt][0] + cb];
-      a[mt][1] = X[rowA[mt][1] + cb];
-      a[mt][2] = X[rowA[mt][0] + cb + 4];
-      a[mt][3] = X[rowA[mt][1] + cb + 4];
+      af[mt][0] = X[rowA[mt][0] + cb];
+      af[mt][1] = X[rowA[mt][1] + cb];
+      af[mt][2] = X[rowA[mt][0] + cb + 4];
+      af[mt][3] = X[rowA[mt][1] + cb + 4];
     }
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
       const int rb = rb0 + nt;
-      uint32_t b[2] = {0u, 0u};
+      bf[nt][0] = bf[nt][1] = 0u;
       if (rb < NB) {
-        if (cb < CB) b[0] = W[((size_t)rb * CB + cb) * 8 + gid];
-        if (cb + 4 < CB) b[1] = W[((size_t)rb * CB + cb + 4) * 8 + gid];
+        if (cb < CB) bf[nt][0] = W[((size_t)rb * CB + cb) * 8 + gid];
+        if (cb + 4 < CB) bf[nt][1] = W[((size_t)rb * CB + cb + 4) * 8 + gid];
       }
-      mma_m16n8k32_i8<UNSIGNED_A>(acc[0][nt], a[0], b);
-      mma_m16n8k32_i8<UNSIGNED_A>(acc[1][nt], a[1], b);
+    }
+  };
+  load_frags(0, a[0], b[0]);
+#pragma unroll 1
+  for (int k0 = 0; k0 < p.Mp; k0 += 64) {
+#pragma unroll
+    for (int st = 0; st < 2; st++) {
+      const int k = k0 + st * 32;
+      if (k < p.Mp) {
+        if (k + 32 < p.Mp) load_frags(k + 32, a[st ^ 1], b[st ^ 1]);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          mma_m16n8k32_i8<UNSIGNED_A>(acc[0][nt], a[st][0], b[st][nt]);
+          mma_m16n8k32_i8<UNSIGNED_A>(acc[1][nt], a[st][1], b[st][nt]);
+        }
+      }
     }
   }
   // epilogue: (float)acc * scale (+bias) (+diag.in), vec.h:312 / nnet_arch.h:141-153
