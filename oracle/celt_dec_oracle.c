@@ -37,6 +37,7 @@
 #define ALLOC_STEPS 6
 #define LOG_MAX_PSEUDO 6
 #define SPREAD_NONE 0
+#define SPREAD_NORMAL 2
 #define SPREAD_AGGRESSIVE 3
 #define COMB_MINPERIOD 15
 #define PI_D 3.1415926535897931
@@ -201,6 +202,8 @@ static int rd_laplace(RangeDec *d, unsigned fs, int decay) {
   rd_update(d, fl, IMIN(fl + fs, 32768), 32768);
   return val;
 }
+
+#include "celt_rangeenc.inc"
 
 /* ------------------------------------------------------------------------------------------
  * Small exact integer helpers (celt/bands.c:68-91, celt/mathops.c:45-68, celt/rate.h:48-87)
@@ -886,7 +889,7 @@ static void decode_all_bands(int start, int end, float *X_, float *Y_, unsigned 
 static int interp_alloc(int start, int end, int skip_start, const int *bits1, const int *bits2, const int *thresh,
                         const int *cap, int32_t total, int32_t *balance_out, int skip_rsv, int *intensity,
                         int intensity_rsv, int *dual_stereo, int dual_stereo_rsv, int *bits, int *ebits,
-                        int *fine_priority, int C, int LM, RangeDec *ec) {
+                        int *fine_priority, int C, int LM, RangeDec *ec, AllocEnc *ae) {
   int32_t psum, left, percoeff, balance;
   int lo = 0, hi = 1 << ALLOC_STEPS, i, j, logM = LM << BITRES, stereo = C > 1, codedBands, alloc_floor = C << BITRES, done;
   for (i = 0; i < ALLOC_STEPS; i++) {
@@ -919,7 +922,14 @@ static int interp_alloc(int start, int end, int skip_start, const int *bits1, co
     band_width = ob_ebands[codedBands] - ob_ebands[j];
     band_bits = (int)(bits[j] + percoeff * band_width + rem);
     if (band_bits >= IMAX(thresh[j], alloc_floor + (1 << BITRES))) {
-      if (rd_bit_logp(ec, 1)) break;
+      if (ae) { /* encoder: the only free decision of the allocator (celt/rate.c:346-369) */
+        int depth_threshold = codedBands > 17 ? (j < ae->prev ? 7 : 9) : 0;
+        if (codedBands <= start + 2 || (band_bits > (depth_threshold * band_width << LM << BITRES) >> 4 && j <= ae->signalBandwidth)) {
+          re_bit_logp(ae->enc, 1, 1);
+          break;
+        }
+        re_bit_logp(ae->enc, 0, 1);
+      } else if (rd_bit_logp(ec, 1)) break;
       psum += 1 << BITRES;
       band_bits -= 1 << BITRES;
     }
@@ -929,11 +939,17 @@ static int interp_alloc(int start, int end, int skip_start, const int *bits1, co
     if (band_bits >= alloc_floor) { psum += alloc_floor; bits[j] = alloc_floor; }
     else bits[j] = 0;
   }
-  if (intensity_rsv > 0) *intensity = start + rd_uint(ec, codedBands + 1 - start);
-  else *intensity = 0;
+  if (intensity_rsv > 0) {
+    if (ae) {
+      *intensity = IMIN(*intensity, codedBands);
+      re_uint(ae->enc, *intensity - start, codedBands + 1 - start);
+    } else *intensity = start + rd_uint(ec, codedBands + 1 - start);
+  } else *intensity = 0;
   if (*intensity <= start) { total += dual_stereo_rsv; dual_stereo_rsv = 0; }
-  if (dual_stereo_rsv > 0) *dual_stereo = rd_bit_logp(ec, 1);
-  else *dual_stereo = 0;
+  if (dual_stereo_rsv > 0) {
+    if (ae) re_bit_logp(ae->enc, *dual_stereo, 1);
+    else *dual_stereo = rd_bit_logp(ec, 1);
+  } else *dual_stereo = 0;
   left = total - psum;
   percoeff = (uint32_t)left / (uint32_t)(ob_ebands[codedBands] - ob_ebands[start]);
   left -= (ob_ebands[codedBands] - ob_ebands[start]) * percoeff;
@@ -989,7 +1005,7 @@ static int interp_alloc(int start, int end, int skip_start, const int *bits1, co
 
 static int compute_allocation(int start, int end, const int *offsets, const int *cap, int alloc_trim, int *intensity,
                               int *dual_stereo, int32_t total, int32_t *balance, int *pulses, int *ebits,
-                              int *fine_priority, int C, int LM, RangeDec *ec) {
+                              int *fine_priority, int C, int LM, RangeDec *ec, AllocEnc *ae) {
   int lo, hi, len = NBANDS, j, skip_start = start, skip_rsv, intensity_rsv = 0, dual_stereo_rsv = 0;
   int bits1[NBANDS], bits2[NBANDS], thresh[NBANDS], trim_offset[NBANDS];
   const int nbAllocVectors = 11;
@@ -1040,7 +1056,7 @@ static int compute_allocation(int start, int end, const int *offsets, const int 
     bits2[j] = bits2j;
   }
   return interp_alloc(start, end, skip_start, bits1, bits2, thresh, cap, total, balance, skip_rsv, intensity,
-                      intensity_rsv, dual_stereo, dual_stereo_rsv, pulses, ebits, fine_priority, C, LM, ec);
+                      intensity_rsv, dual_stereo, dual_stereo_rsv, pulses, ebits, fine_priority, C, LM, ec, ae);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1505,6 +1521,8 @@ static void synthesis(float *X, float *out_syn[], const float *oldBandE, int sta
 
 /* Debug tap for the tests: the last frame's normalised spectrum X[C][N] (after anti-collapse). */
 float orc_dbg_X[2 * MAXN];
+/* [0..15] scalars, [16] tf_res, [40] dynalloc offsets, [64] pulses, [88] fine_quant, [112] coarse energies*1024 */
+int orc_dbg_side[160];
 
 /* One CELT frame: `data` is the CELT payload (no TOC byte). Returns samples/channel or <0.
  * pcm: interleaved float, CC channels, +-1.0 full scale. */
@@ -1593,7 +1611,14 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
   anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << BITRES) ? (1 << BITRES) : 0;
   bits -= anti_collapse_rsv;
   codedBands = compute_allocation(start, end, offsets, cap, alloc_trim, &intensity, &dual_stereo, bits, &balance,
-                                  pulses, fine_quant, fine_priority, C, LM, &dec);
+                                  pulses, fine_quant, fine_priority, C, LM, &dec, NULL);
+  {  /* debug tap: the side information of this frame (tests diff it between two packets) */
+    int *t = orc_dbg_side;
+    t[0] = silence; t[1] = isTransient; t[2] = intra_ener; t[3] = spread; t[4] = alloc_trim; t[5] = intensity; t[6] = dual_stereo;
+    t[7] = codedBands; t[8] = postfilter_pitch; t[9] = (int)(postfilter_gain * 1000); t[10] = postfilter_tapset; t[11] = bits;
+    for (i = 0; i < NBANDS; i++) { t[16 + i] = tf_res[i]; t[40 + i] = offsets[i]; t[64 + i] = pulses[i]; t[88 + i] = fine_quant[i]; }
+    for (i = 0; i < 2 * NBANDS; i++) t[112 + i] = (int)floor(oldBandE[i] * 1024 + .5);
+  }
   decode_fine_energy(start, end, oldBandE, fine_quant, &dec, C);
   c = 0;
   do memmove(decode_mem[c], decode_mem[c] + N, (DEC_BUF - N + OVERLAP) * sizeof(float)); while (++c < CC);
@@ -1807,3 +1832,5 @@ int orc_decode_stream_float(int channels, int frame_size, int nframes, const uin
   free(st);
   return 0;
 }
+
+#include "celt_enc.inc"

@@ -257,3 +257,23 @@ void refh_celt_enc_analysis(float *mem, float *hist, const float *pcm, int CC, i
   amp2Log2(m, 21, 21, bandE, bandLogE, CC);
   normalise_bands(m, freq, X, bandE, 21, CC, 1 << LM);
 }
+
+/* ---- the reference CELT encoder driven directly (celt_encoder_init + celt_encode_with_ec), bypassing the Opus-layer glue ---- */
+#include "celt/celt.h"
+int refh_celt_encoder_size(int channels) { return celt_encoder_get_size(channels); }
+int refh_celt_encoder_init(CELTEncoder *st, int channels, int complexity, int bitrate, int vbr, int lsb_depth) {
+  int ret = celt_encoder_init(st, 48000, channels, opus_select_arch());
+  if (ret != OPUS_OK) return ret;
+  celt_encoder_ctl(st, CELT_SET_SIGNALLING(0));
+  celt_encoder_ctl(st, OPUS_SET_COMPLEXITY(complexity));
+  celt_encoder_ctl(st, OPUS_SET_BITRATE(bitrate));
+  celt_encoder_ctl(st, OPUS_SET_VBR(vbr));
+  celt_encoder_ctl(st, OPUS_SET_LSB_DEPTH(lsb_depth));
+  return OPUS_OK;
+}
+/* pcm: interleaved floats +-1.0; returns bytes written (or < 0); *rng = final range */
+int refh_celt_encode(CELTEncoder *st, const float *pcm, int frame_size, unsigned char *out, int max_bytes, unsigned int *rng) {
+  int n = celt_encode_with_ec(st, pcm, frame_size, out, max_bytes, NULL);
+  celt_encoder_ctl(st, OPUS_GET_FINAL_RANGE(rng));
+  return n;
+}
