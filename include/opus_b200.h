@@ -148,6 +148,31 @@ int opusb200_silk_burg_modified(OpusB200Ctx *ctx, float *A, float *nrg, const fl
 /* silk_autocorrelation_FLP (silk/float/autocorrelation_FLP.c:36): results [n_items][count] */
 int opusb200_silk_autocorrelation(OpusB200Ctx *ctx, float *results, const float *x, int n_items, int size, int count, int on_device);
 
+/* ---- Batched CELT encoder: n independent streams, one frame each per call.
+ * Replaces celt_encoder_init / celt_encoder_ctl / celt_encode_with_ec (celt/celt.h:157-160, celt/celt_encoder.c:240,1726,2953):
+ * the output is the CELT payload exactly as celt_encode_with_ec(st, pcm, frame_size, compressed, nbCompressedBytes, NULL) writes it
+ * (the Opus layer's TOC byte, dc_reject and mode decisions stay in src/opus_encoder.c:1830-2200 on the host).
+ * Round 1 implements what the reference does at OPUS_SET_COMPLEXITY(0) in CBR (every decision that complexity level takes:
+ * dynalloc_analysis, alloc_trim_analysis, stereo_analysis, intensity hysteresis, intra-energy switching); other settings
+ * return OPUSB200_UNIMPLEMENTED from the ctl.  nbytes[s] == OPUS_UNIMPLEMENTED (-5) flags a frame that needed the tone-driven
+ * pre-filter (a pure sinusoid, celt/celt_encoder.c:1441-1461), which is not on the device yet. ---- */
+typedef struct OpusB200Encoder OpusB200Encoder;
+int opusb200_encoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Encoder **out);
+void opusb200_encoder_destroy(OpusB200Encoder *enc);
+int opusb200_encoder_reset(OpusB200Encoder *enc);                                   /* OPUS_RESET_STATE */
+/* request = the OPUS_SET_*_REQUEST number of include/opus_defines.h: 4002 bitrate, 4006 vbr, 4010 complexity, 4036 lsb depth,
+ * 4046 phase inversion disabled */
+int opusb200_encoder_ctl_set(OpusB200Encoder *enc, int request, int32_t value);
+/* pcm [n][frame_size*channels] interleaved float (+-1.0); packets [n][pkt_stride]; nbytes [n] */
+int opusb200_encode_float(OpusB200Encoder *enc, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride,
+                          int max_data_bytes, int32_t *nbytes);
+int opusb200_encode_device(OpusB200Encoder *enc, const float *d_pcm, int frame_size, unsigned char *d_packets, int pkt_stride,
+                           int max_data_bytes, int32_t *d_nbytes);
+int opusb200_encoder_get_final_range(OpusB200Encoder *enc, uint32_t *final_range);   /* OPUS_GET_FINAL_RANGE */
+int opusb200_encoder_sync(OpusB200Encoder *enc);
+void *opusb200_encoder_cuda_stream(OpusB200Encoder *enc);
+int64_t opusb200_encoder_launch_count(OpusB200Encoder *enc);
+
 /* ---- CELT encoder front end, fused: celt_preemphasis (celt/celt_encoder.c:557) -> compute_mdcts (:511) -> compute_band_energies
  * (celt/bands.c:151) -> amp2Log2 (celt/quant_bands.c:553) -> normalise_bands (celt/bands.c:169), i.e. lines 2007-2265 of
  * celt_encode_with_ec with the pitch pre-filter off.  The object keeps, per stream and channel, the pre-emphasis memory and

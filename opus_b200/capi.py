@@ -23,7 +23,9 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_decoder_reset', 'opusb200_decoder_n_streams', 'opusb200_decode', 'opusb200_decode_float',
            'opusb200_decode_device', 'opusb200_decoder_sync', 'opusb200_decoder_get_final_range',
            'opusb200_decoder_cuda_stream', 'opusb200_decoder_launch_count', 'opusb200_decoder_set_timing',
-           'opusb200_decoder_get_timing', 'opusb200_decode_submit', 'opusb200_decode_wait', 'opusb200_celt_analysis_create',
+           'opusb200_decoder_get_timing', 'opusb200_decode_submit', 'opusb200_decode_wait', 'opusb200_celt_analysis_create', 'opusb200_encoder_create', 'opusb200_encoder_destroy',
+           'opusb200_encoder_reset', 'opusb200_encoder_ctl_set', 'opusb200_encode_float', 'opusb200_encode_device',
+           'opusb200_encoder_get_final_range', 'opusb200_encoder_sync', 'opusb200_encoder_cuda_stream', 'opusb200_encoder_launch_count',
            'opusb200_celt_analysis_destroy', 'opusb200_celt_analysis_reset', 'opusb200_celt_analysis_process', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
            'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
            'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create',
@@ -134,6 +136,19 @@ def lib():
         L.opusb200_celt_analysis_destroy.restype = None
         L.opusb200_celt_analysis_reset.argtypes = [vp]
         L.opusb200_celt_analysis_process.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci]
+        L.opusb200_encoder_create.argtypes = [ci, i32, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_encoder_destroy.argtypes = [vp]
+        L.opusb200_encoder_destroy.restype = None
+        L.opusb200_encoder_reset.argtypes = [vp]
+        L.opusb200_encoder_ctl_set.argtypes = [vp, ci, i32]
+        L.opusb200_encode_float.argtypes = [vp, vp, ci, vp, ci, ci, vp]
+        L.opusb200_encode_device.argtypes = [vp, vp, ci, vp, ci, ci, vp]
+        L.opusb200_encoder_get_final_range.argtypes = [vp, vp]
+        L.opusb200_encoder_sync.argtypes = [vp]
+        L.opusb200_encoder_cuda_stream.argtypes = [vp]
+        L.opusb200_encoder_cuda_stream.restype = vp
+        L.opusb200_encoder_launch_count.argtypes = [vp]
+        L.opusb200_encoder_launch_count.restype = ctypes.c_int64
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

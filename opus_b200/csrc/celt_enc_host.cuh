@@ -1,0 +1,154 @@
+// celt_enc_host.cuh — kernel entry points and C ABI of the batched CELT encoder (included at the end of opus_b200.cu).
+#pragma once
+#include "celt_enc_frame.cuh"
+
+extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame(EncFrameParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) enc_frame_thread(p, s);
+}
+extern "C" __global__ void ob_celt_enc_reset(ObEncState *st, ObEncAnalysisState *an, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  // OPUS_RESET_STATE (celt/celt_encoder.c:3076-3094); everything else was memset to 0
+  for (int i = 0; i < 2 * OB_NBANDS; i++) st[s].oldLogE[i] = st[s].oldLogE2[i] = -28.f;
+  st[s].delayedIntra = 1.f;
+  st[s].spread_decision = 2;
+  st[s].tonal_average = 256;
+  (void)an;
+}
+extern "C" __global__ void ob_celt_enc_get_range(const ObEncState *st, uint32_t *out, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) out[s] = st[s].rng;
+}
+
+struct OpusB200Encoder {
+  int device, channels, n;
+  cudaStream_t stream;
+  ObEncState *state;
+  ObEncAnalysisState *an_state;
+  ObEncFrameInfo *info;
+  float *X, *bandE, *bandLogE;
+  int32_t *d_nbytes;
+  // settings (celt_encoder_ctl)
+  int complexity, bitrate, vbr, lsb_depth, force_intra, disable_inv, disable_pf;
+  // staging for the host-buffer call
+  float *d_pcm; size_t d_pcm_cap;
+  unsigned char *d_pkt; size_t d_pkt_cap;
+  int64_t launches;
+};
+
+extern "C" int opusb200_encoder_reset(OpusB200Encoder *e) {
+  if (!e) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  OB_CUDA(cudaMemsetAsync(e->state, 0, sizeof(ObEncState) * (size_t)e->n, e->stream));
+  OB_CUDA(cudaMemsetAsync(e->an_state, 0, sizeof(ObEncAnalysisState) * (size_t)e->n, e->stream));
+  ob_celt_enc_reset<<<(e->n + 127) / 128, 128, 0, e->stream>>>(e->state, e->an_state, e->n);
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Encoder **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  if (Fs != 48000 || (channels != 1 && channels != 2) || n_streams <= 0) return OPUSB200_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    fprintf(stderr, "opus_b200: no usable CUDA device (there is no CPU fallback)\n");
+    return OPUSB200_INTERNAL_ERROR;
+  }
+  OB_CUDA(cudaSetDevice(device));
+  OpusB200Encoder *e = new (std::nothrow) OpusB200Encoder;
+  if (!e) return OPUSB200_ALLOC_FAIL;
+  memset(e, 0, sizeof(*e));
+  e->device = device; e->channels = channels; e->n = n_streams;
+  e->complexity = 0; e->bitrate = -1; e->vbr = 0; e->lsb_depth = 24;   // celt_encoder_init defaults except complexity (see ctl)
+  OB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)n_streams;
+  OB_CUDA(cudaMalloc(&e->state, sizeof(ObEncState) * n));
+  OB_CUDA(cudaMalloc(&e->an_state, sizeof(ObEncAnalysisState) * n));
+  OB_CUDA(cudaMalloc(&e->info, sizeof(ObEncFrameInfo) * n));
+  OB_CUDA(cudaMalloc(&e->X, sizeof(float) * n * channels * OB_MAXN));
+  OB_CUDA(cudaMalloc(&e->bandE, sizeof(float) * n * channels * OB_NBANDS));
+  OB_CUDA(cudaMalloc(&e->bandLogE, sizeof(float) * n * channels * OB_NBANDS));
+  OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 16));
+  const int r = opusb200_encoder_reset(e);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaStreamSynchronize(e->stream));
+  *out = e;
+  return OPUSB200_OK;
+}
+extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE);
+  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+// the subset of opus_encoder_ctl / celt_encoder_ctl requests the device path implements (include/opus_defines.h request numbers)
+extern "C" int opusb200_encoder_ctl_set(OpusB200Encoder *e, int request, int32_t value) {
+  if (!e) return OPUSB200_BAD_ARG;
+  switch (request) {
+    case 4002: if (value != -1 && (value < 500 || value > 750000 * e->channels)) return OPUSB200_BAD_ARG; e->bitrate = value; return OPUSB200_OK;  // OPUS_SET_BITRATE (-1 = OPUS_BITRATE_MAX)
+    case 4006: if (value != 0) return OPUSB200_UNIMPLEMENTED; e->vbr = 0; return OPUSB200_OK;              // OPUS_SET_VBR: CBR only this round
+    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; if (value != 0) return OPUSB200_UNIMPLEMENTED; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY
+    case 4036: if (value < 8 || value > 24) return OPUSB200_BAD_ARG; e->lsb_depth = value; return OPUSB200_OK;  // OPUS_SET_LSB_DEPTH
+    case 4046: e->disable_inv = value != 0; return OPUSB200_OK;                                                // OPUS_SET_PHASE_INVERSION_DISABLED
+    default: return OPUSB200_UNIMPLEMENTED;
+  }
+}
+extern "C" void *opusb200_encoder_cuda_stream(OpusB200Encoder *e) { return e ? (void *)e->stream : nullptr; }
+extern "C" int opusb200_encoder_sync(OpusB200Encoder *e) {
+  if (!e) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaStreamSynchronize(e->stream));
+  return OPUSB200_OK;
+}
+// device pointers: pcm [n][frame_size*channels] float (+-1.0), packets [n][pkt_stride], nbytes [n]
+extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, int frame_size, unsigned char *d_packets, int pkt_stride,
+                                      int max_data_bytes, int32_t *d_nbytes) {
+  if (!e || !d_pcm || !d_packets || !d_nbytes || pkt_stride < max_data_bytes || max_data_bytes < 2) return OPUSB200_BAD_ARG;
+  int LM = -1;
+  for (int l = 0; l <= 3; l++) if (frame_size == OB_SHORT_N << l) LM = l;
+  if (LM < 0) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  EncAnalysisParams a;
+  a.state = e->an_state; a.pcm = d_pcm; a.short_blocks = nullptr; a.X = e->X; a.bandE = e->bandE; a.bandLogE = e->bandLogE; a.info = e->info;
+  a.n_streams = e->n; a.C = e->channels; a.LM = LM;
+  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 16, e->stream>>>(a);
+  EncFrameParams p;
+  p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.packets = d_packets; p.nbytes = d_nbytes;
+  p.n_streams = e->n; p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
+  p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf;
+  ob_celt_enc_frame<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
+  e->launches += 2;
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+// host buffers; returns when the packets are on the host.  nbytes[s] = payload size (CBR: the same for all) or a negative code.
+extern "C" int opusb200_encode_float(OpusB200Encoder *e, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                                     int32_t *nbytes) {
+  if (!e || !pcm || !packets || !nbytes || frame_size <= 0) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  const size_t pb = sizeof(float) * (size_t)e->n * frame_size * e->channels, kb = (size_t)e->n * pkt_stride;
+  if (e->d_pcm_cap < pb) { cudaFree(e->d_pcm); e->d_pcm = nullptr; e->d_pcm_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm, pb)); e->d_pcm_cap = pb; }
+  if (e->d_pkt_cap < kb) { cudaFree(e->d_pkt); e->d_pkt = nullptr; e->d_pkt_cap = 0; OB_CUDA(cudaMalloc(&e->d_pkt, kb)); e->d_pkt_cap = kb; }
+  OB_CUDA(cudaMemcpyAsync(e->d_pcm, pcm, pb, cudaMemcpyHostToDevice, e->stream));
+  const int r = opusb200_encode_device(e, e->d_pcm, frame_size, e->d_pkt, pkt_stride, max_data_bytes, e->d_nbytes);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaMemcpyAsync(packets, e->d_pkt, kb, cudaMemcpyDeviceToHost, e->stream));
+  OB_CUDA(cudaMemcpyAsync(nbytes, e->d_nbytes, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+  OB_CUDA(cudaStreamSynchronize(e->stream));
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_encoder_get_final_range(OpusB200Encoder *e, uint32_t *final_range) {
+  if (!e || !final_range) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  DevBuf d;
+  if (d.alloc(sizeof(uint32_t) * (size_t)e->n)) return OPUSB200_ALLOC_FAIL;
+  ob_celt_enc_get_range<<<(e->n + 127) / 128, 128, 0, e->stream>>>(e->state, (uint32_t *)d.p, e->n);
+  OB_CUDA(cudaMemcpyAsync(final_range, d.p, sizeof(uint32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+  OB_CUDA(cudaStreamSynchronize(e->stream));
+  return OPUSB200_OK;
+}
+extern "C" int64_t opusb200_encoder_launch_count(OpusB200Encoder *e) { return e ? e->launches : 0; }

@@ -86,34 +86,118 @@ OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *s
 //      (celt_preemphasis celt/celt_encoder.c:557, compute_mdcts :511, compute_band_energies celt/bands.c:151,
 //       amp2Log2 celt/quant_bands.c:553, normalise_bands celt/bands.c:169), the path of celt_encode_with_ec when the pitch
 //      pre-filter is off.  The spectrum never leaves shared memory; HBM sees the PCM once and the normalised bands once. ----
-struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; };
+struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; float overlap_max; float pad; };
+// what the frame encoder needs from the time domain (celt_encode_with_ec :1963-1970, :2017)
+struct ObEncFrameInfo { float tone_freq, toneishness, sample_max; int32_t short_blocks; };
 struct EncAnalysisParams {
   ObEncAnalysisState *state;   // [n_streams]
   const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
   const int32_t *short_blocks; // [n_streams] transient decision per stream, or null (= long blocks)
   float *X;                    // [n_streams][C*N]
   float *bandE, *bandLogE;     // [n_streams][C*21]
+  ObEncFrameInfo *info;        // [n_streams] or null
   int n_streams, C, LM;
 };
-OB_DEV void enc_analysis_warp(const EncAnalysisParams &p, int stream, int c, unsigned char *smem_warp) {
-  const int lane = lane_id();
-  MdctWS *ws = (MdctWS *)smem_warp;
+// tone_lpc (celt/celt_encoder.c:1305-1360) on x = in0 (+ in1): the six running sums are independent sequential chains,
+// one lane each (lanes 0-2: r00 r01 r02, lanes 3-5: the three edge corrections); lane 0 solves the 2x2 system.
+OB_DEV int tone_lpc_warp(const float *in0, const float *in1, int len, int delay, float *lpc, int lane) {
+  float acc = 0.f;
+  if (lane < 3) {
+    const int d = lane * delay;
+#pragma unroll 1
+    for (int i = 0; i < len - 2 * delay; i++) {
+      const float a = in1 ? in0[i] + in1[i] : in0[i], b = in1 ? in0[i + d] + in1[i + d] : in0[i + d];
+      acc += a * b;
+    }
+  } else if (lane < 6) {
+    const int o1 = lane == 4 ? len - delay : len - 2 * delay, o2 = lane == 5 ? len - delay : o1;
+    const int p1 = lane == 4 ? delay : 0, p2 = lane == 5 ? delay : p1;
+#pragma unroll 1
+    for (int i = 0; i < delay; i++) {
+      const float a = in1 ? in0[o1 + i] + in1[o1 + i] : in0[o1 + i], b = in1 ? in0[o2 + i] + in1[o2 + i] : in0[o2 + i];
+      const float c = in1 ? in0[p1 + i] + in1[p1 + i] : in0[p1 + i], d = in1 ? in0[p2 + i] + in1[p2 + i] : in0[p2 + i];
+      acc += a * b - c * d;
+    }
+  }
+  float r00 = shfl(acc, 0), r01 = shfl(acc, 1), r02 = shfl(acc, 2);
+  const float e11 = shfl(acc, 3), e22 = shfl(acc, 4), e12 = shfl(acc, 5);
+  float r11 = r00 + e11;
+  float r22 = r11 + e22;
+  float r12 = r01 + e12;
+  {
+    const float R00 = r00 + r22, R01 = r01 + r12, R11 = 2 * r11, R02 = 2 * r02, R12 = r12 + r01;
+    r00 = R00; r01 = R01; r11 = R11; r02 = R02; r12 = R12;
+  }
+  const float den = r00 * r11 - r01 * r01;
+  if (den < .001f * (r00 * r11)) return 1;
+  const float num1 = r02 * r11 - r01 * r12;
+  if (num1 >= den) lpc[1] = 1.f;
+  else if (num1 <= -den) lpc[1] = -1.f;
+  else lpc[1] = f_div(num1, den);
+  const float num0 = r00 * r12 - r02 * r01;
+  if (.5f * num0 >= den) lpc[0] = 1.999999f;
+  else if (.5f * num0 <= -den) lpc[0] = -1.999999f;
+  else lpc[0] = f_div(num0, den);
+  return 0;
+}
+// one CTA per stream, one warp per channel
+OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned char *smem) {
+  const int lane = lane_id(), c = warp_in_block();
+  MdctWS *ws = (MdctWS *)smem + c;
   const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C;
   const int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
   ObEncAnalysisState &st = p.state[stream];
   const float *pcm = p.pcm + (size_t)stream * N * C + c;
   // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
   const float coef0 = 0.85000610f;
+  float mx_new = 0.f, mx_tail = 0.f;   // celt_maxabs over the fresh part and over the part overlapping the next frame
   for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = st.overlap_mem[c][i];
   for (int i = lane; i < N; i += 32) {
-    const float x = f_mul(32768.f, pcm[(size_t)C * i]);
+    const float s = pcm[(size_t)C * i];
+    const float x = f_mul(32768.f, s);
     const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (i - 1)]));
     ws->in[OB_OVERLAP + i] = f_add(x, -m);
+    if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
+    else mx_tail = fmaxf(mx_tail, fabsf(s));
   }
+  mx_new = warp_max(mx_new);
+  mx_tail = warp_max(mx_tail);
   wsync();
   if (lane == 0) st.preemph_mem[c] = f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)]));
   for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
-  wsync();
+  // cross-channel part: maxima and the tone detector need both channels' time signals
+  float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange
+  if (lane == 0) { xch[c * 2] = mx_new; xch[c * 2 + 1] = mx_tail; }
+  bsync();
+  if (c == 0 && p.info) {
+    float a = xch[0], t = xch[1];
+    if (C == 2) { a = fmaxf(a, xch[2]); t = fmaxf(t, xch[3]); }
+    const float sample_max = fmaxf(fmaxf(st.overlap_max, a), t);
+    const float *in0 = ((MdctWS *)smem)->in, *in1 = C == 2 ? ((MdctWS *)smem + 1)->in : nullptr;
+    // tone_detect (celt/celt_encoder.c:1362-1402)
+    float lpc[2] = {0.f, 0.f};
+    int delay = 1;
+    int fail = tone_lpc_warp(in0, in1, N + OB_OVERLAP, delay, lpc, lane);
+    while (delay <= 48000 / 3000 && (fail || (lpc[0] > 1.f && lpc[1] < 0))) {
+      delay *= 2;
+      fail = tone_lpc_warp(in0, in1, N + OB_OVERLAP, delay, lpc, lane);
+    }
+    if (lane == 0) {
+      ObEncFrameInfo fi;
+      if (!fail && lpc[0] * lpc[0] + 3.999999f * lpc[1] < 0) {
+        fi.toneishness = -lpc[1];
+        fi.tone_freq = (float)(acos((double)(.5f * lpc[0])) / delay);
+      } else {
+        fi.tone_freq = -1.f;
+        fi.toneishness = 0.f;
+      }
+      fi.sample_max = sample_max;
+      fi.short_blocks = transient;
+      p.info[stream] = fi;
+      st.overlap_max = t;
+    }
+  }
+  bsync();   // the tone detector reads ws->in of both channels; the MDCT below overwrites it
   float *freq = ws->in;
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
   wsync();

@@ -51,10 +51,8 @@ extern "C" __global__ void __launch_bounds__(128) ob_mdct_forward(MdctFwdParams 
   if (item >= p.n_items) return;
   mdct_forward_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
 }
-extern "C" __global__ void __launch_bounds__(128) ob_celt_enc_analysis(EncAnalysisParams p) {
-  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (item >= p.n_streams * p.C) return;
-  enc_analysis_warp(p, item / p.C, item % p.C, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
+extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_analysis(EncAnalysisParams p) {
+  enc_analysis_block(p, blockIdx.x, dyn_smem());
 }
 extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, int smem_per_warp) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -588,8 +586,8 @@ int opusb200_celt_analysis_process(OpusB200CeltAnalysis *a, const float *pcm, co
     p.pcm = (const float *)dp.p; p.short_blocks = short_blocks ? (const int32_t *)ds.p : nullptr;
     p.X = (float *)dX.p; p.bandE = (float *)dE.p; p.bandLogE = (float *)dL.p;
   }
-  const int warps = 4, items = a->n * C;
-  ob_celt_enc_analysis<<<(items + warps - 1) / warps, warps * 32, warps * sizeof(MdctWS), c->stream>>>(p);
+  p.info = nullptr;
+  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 16, c->stream>>>(p);
   c->launches++;
   OB_CUDA(cudaGetLastError());
   if (!on_device) {
@@ -929,3 +927,4 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 #include "nnet_host.cuh"
+#include "celt_enc_host.cuh"

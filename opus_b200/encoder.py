@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference CELT encoder API (celt_encoder_init / celt_encoder_ctl / celt_encode_with_ec) for a batch
+of independent streams.  numpy in / numpy out through the C ABI."""
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+OPUS_SET_BITRATE_REQUEST, OPUS_SET_VBR_REQUEST, OPUS_SET_COMPLEXITY_REQUEST, OPUS_SET_LSB_DEPTH_REQUEST = 4002, 4006, 4010, 4036
+OPUS_SET_PHASE_INVERSION_DISABLED_REQUEST = 4046
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class EncoderBatch:
+    def __init__(self, n_streams, channels=2, fs=48000, device=0, bitrate=None, complexity=0, lsb_depth=24):
+        self._L = capi.lib()
+        self.n_streams, self.channels = n_streams, channels
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_encoder_create(device, fs, channels, n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_encoder_create')
+        self._h = h
+        self.ctl(OPUS_SET_COMPLEXITY_REQUEST, complexity)
+        self.ctl(OPUS_SET_LSB_DEPTH_REQUEST, lsb_depth)
+        if bitrate is not None:
+            self.ctl(OPUS_SET_BITRATE_REQUEST, bitrate)
+
+    def ctl(self, request, value):
+        r = self._L.opusb200_encoder_ctl_set(self._h, request, int(value))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_encoder_ctl_set(%d, %d)' % (request, value))
+
+    def encode(self, pcm, max_data_bytes, frame_size=None):
+        """pcm float32 [n, frame_size*channels] interleaved (+-1.0).  Returns (packets uint8 [n, max_data_bytes], nbytes int32 [n])."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        assert pcm.shape[0] == self.n_streams
+        fs = frame_size or pcm.shape[1] // self.channels
+        pk = np.zeros((self.n_streams, max_data_bytes), np.uint8)
+        nb = np.zeros(self.n_streams, np.int32)
+        r = self._L.opusb200_encode_float(self._h, _p(pcm), fs, _p(pk), max_data_bytes, max_data_bytes, _p(nb))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_encode_float')
+        return pk, nb
+
+    def final_range(self):
+        fr = np.empty(self.n_streams, np.uint32)
+        r = self._L.opusb200_encoder_get_final_range(self._h, _p(fr))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_encoder_get_final_range')
+        return fr
+
+    def reset(self):
+        r = self._L.opusb200_encoder_reset(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_encoder_reset')
+
+    def sync(self):
+        self._L.opusb200_encoder_sync(self._h)
+
+    @property
+    def cuda_stream(self):
+        return self._L.opusb200_encoder_cuda_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return self._L.opusb200_encoder_launch_count(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -182,14 +182,48 @@ extern "C" void emu_nnet_activation(float *out, const float *in, int n, int N, i
 }
 
 // ---- encoder front end ----
+static ObEncFrameInfo *g_enc_info = nullptr;
+extern "C" void emu_set_enc_info(void *p) { g_enc_info = (ObEncFrameInfo *)p; }
 static void enc_analysis_entry(void *a) {
   const EncAnalysisParams &p = *(const EncAnalysisParams *)a;
-  const int item = block_id();
-  enc_analysis_warp(p, item / p.C, item % p.C, dyn_smem());
+  enc_analysis_block(p, block_id(), dyn_smem());
 }
 extern "C" int emu_enc_analysis_state_size(void) { return (int)sizeof(ObEncAnalysisState); }
 extern "C" void emu_celt_enc_analysis(void *state, const float *pcm, const int32_t *sb, float *X, float *E, float *Lg, int n, int C, int LM) {
   EncAnalysisParams p;
-  p.state = (ObEncAnalysisState *)state; p.pcm = pcm; p.short_blocks = sb; p.X = X; p.bandE = E; p.bandLogE = Lg; p.n_streams = n; p.C = C; p.LM = LM;
-  emu_launch(enc_analysis_entry, &p, n * C, 32, sizeof(MdctWS));
+  p.state = (ObEncAnalysisState *)state; p.pcm = pcm; p.short_blocks = sb; p.X = X; p.bandE = E; p.bandLogE = Lg; p.n_streams = n; p.C = C; p.LM = LM; p.info = g_enc_info;
+  emu_launch(enc_analysis_entry, &p, n, 32 * C, C * sizeof(MdctWS) + 16);
+}
+
+// ---- frame encoder (analysis block + thread-per-stream coder) ----
+#include "../../opus_b200/csrc/celt_enc_frame.cuh"
+static void enc_frame_entry(void *a) {
+  const EncFrameParams &p = *(const EncFrameParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n_streams) enc_frame_thread(p, s);
+}
+extern "C" int emu_enc_state_size(void) { return (int)sizeof(ObEncState); }
+extern "C" void emu_enc_state_init(ObEncState *st, int n) {
+  memset(st, 0, sizeof(ObEncState) * (size_t)n);
+  for (int s = 0; s < n; s++) {
+    for (int i = 0; i < 2 * OB_NBANDS; i++) st[s].oldLogE[i] = st[s].oldLogE2[i] = -28.f;
+    st[s].delayedIntra = 1.f; st[s].spread_decision = 2; st[s].tonal_average = 256;
+  }
+}
+// one frame for n streams: an_state/enc_state carried by the caller
+extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const float *pcm, int n, int C, int LM, int max_bytes, int bitrate, int lsb_depth,
+                                unsigned char *packets, int32_t *nbytes, uint32_t *rng) {
+  const int N = OB_SHORT_N << LM;
+  std::vector<float> X((size_t)n * C * N), E((size_t)n * C * OB_NBANDS), Lg((size_t)n * C * OB_NBANDS);
+  std::vector<ObEncFrameInfo> info(n);
+  EncAnalysisParams a;
+  a.state = (ObEncAnalysisState *)an_state; a.pcm = pcm; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
+  a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM;
+  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 16);
+  EncFrameParams p;
+  p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.packets = packets; p.nbytes = nbytes;
+  p.n_streams = n; p.C = C; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = 0; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
+  p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0;
+  emu_launch(enc_frame_entry, &p, (n + 31) / 32, 32, 0);
+  for (int s = 0; s < n; s++) rng[s] = enc_state[s].rng;
 }

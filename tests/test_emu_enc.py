@@ -1,0 +1,54 @@
+"""The CELT encoder kernels (analysis block + thread-per-stream frame coder) on the host SIMT emulator against the pinned
+encoder oracle: packet bytes and final range identical, frame after frame."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu_util
+import util
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24):
+    """x [nframes, fs*ch] float -> list of (packet bytes, range)"""
+    O.orc_encoder_init.restype = None
+    O.orc_encoder_ctl.restype = None
+    O.orc_encoder_final_range.restype = ctypes.c_uint32
+    st = np.zeros(O.orc_encoder_size(), np.uint8)
+    O.orc_encoder_init(_p(st), ch)
+    O.orc_encoder_ctl(_p(st), 0, bitrate, 0, lsb)
+    out = []
+    for f in range(len(x)):
+        b = np.zeros(1275, np.uint8)
+        nb = O.orc_celt_encode_frame(_p(st), _p(x[f]), fs, _p(b), nbytes)
+        out.append((nb, b[:max(nb, 0)].copy(), O.orc_encoder_final_range(_p(st))))
+    return out
+
+
+@pytest.mark.parametrize('ch,fs,nbytes', [(2, 960, 160), (1, 960, 80), (2, 480, 60), (2, 240, 40), (1, 120, 20), (2, 960, 40)])
+def test_emu_encoder_matches_oracle(ch, fs, nbytes):
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    n, nf = 5, 4
+    LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs]
+    sigs = [util.sig_music, util.sig_white, util.sig_tonal_noise]
+    x = np.stack([sigs[s % 3](77 + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    x[4, 2] = 0          # one silent frame in the middle of a stream
+    want = [oracle_encode(O, x[s], ch, fs, nbytes) for s in range(n)]
+    an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
+    es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
+    E.emu_enc_state_init(_p(es), n)
+    for f in range(nf):
+        pcm = np.ascontiguousarray(x[:, f])
+        pk = np.zeros((n, nbytes), np.uint8)
+        nb = np.zeros(n, np.int32)
+        rng = np.zeros(n, np.uint32)
+        E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, -1, 24, _p(pk), _p(nb), _p(rng))
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            assert np.array_equal(pk[s, :wn], wb), (f, s, int(np.argmax(pk[s, :wn] != wb)))
+            assert rng[s] == wr

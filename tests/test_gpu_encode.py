@@ -1,0 +1,76 @@
+"""Parity of the CUDA CELT encoder (through the C ABI) with the pinned encoder oracle, and encoder -> decoder round trips.
+Bar: packet bytes and final range identical to the oracle (hence to the reference's celt_encode_with_ec at complexity 0, CBR)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import util
+from test_emu_enc import oracle_encode
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('ch,fs,nbytes', [(2, 960, 160), (2, 960, 320), (1, 960, 80), (2, 480, 80), (2, 240, 40), (1, 120, 20), (2, 960, 30)])
+def test_encoder_matches_oracle(ch, fs, nbytes):
+    import opus_b200
+    O = util.load_oracle()
+    n, nf, base = 257, 6, 12
+    sigs = [util.sig_music, util.sig_white, util.sig_tonal_noise]
+    xb = np.stack([sigs[s % 3](500 + s + fs + nbytes, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(base)])
+    xb[3, 2] = 0
+    x = np.tile(xb, (n // base + 1, 1, 1))[:n]
+    want = [oracle_encode(O, xb[s], ch, fs, nbytes) for s in range(base)]
+    enc = opus_b200.EncoderBatch(n, channels=ch)
+    for f in range(nf):
+        pk, nb = enc.encode(x[:, f], nbytes)
+        rng = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s % base][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            if wn > 0:
+                assert np.array_equal(pk[s, :wn], wb), (f, s)
+                assert rng[s] == wr
+    enc.close()
+
+
+def test_encode_decode_round_trip():
+    """packets from the device encoder decode on the device decoder: same final range on both sides, sane SNR"""
+    import opus_b200
+    ch, fs, nbytes, n, nf = 2, 960, 200, 300, 8
+    x = np.stack([util.sig_music(40 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(16)])
+    x = np.tile(x, (n // 16 + 1, 1, 1))[:n]
+    enc = opus_b200.EncoderBatch(n, channels=ch)
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    toc = 0xFC | 0x04   # CELT-only fullband 20 ms, stereo, one frame (RFC 6716 section 3.1: config 31, s=1, c=0)
+    outs = []
+    for f in range(nf):
+        pk, nb = enc.encode(x[:, f], nbytes)
+        assert (nb == nbytes).all()
+        full = np.zeros((n, nbytes + 1), np.uint8)
+        full[:, 0] = toc
+        full[:, 1:] = pk
+        pcm, ns = dec.decode(full, np.full(n, nbytes + 1, np.int32), frame_size=fs, dtype=np.float32)
+        assert (ns == fs).all()
+        assert (dec.final_range() == enc.final_range()).all()
+        outs.append(pcm)
+    # the codec delay is one overlap (120 samples): compare energy of the error on an aligned middle segment
+    y = np.concatenate(outs, axis=1).reshape(n, nf * fs, ch)
+    xr = x.reshape(n, nf * fs, ch)
+    err = y[:, 960 + 120:5 * 960] - xr[:, 960:5 * 960 - 120]
+    snr = 10 * np.log10((xr[:, 960:5 * 960 - 120] ** 2).sum() / (err ** 2).sum())
+    assert snr > 8, snr
+    enc.close(); dec.close()
+
+
+def test_ctl_errors():
+    import opus_b200
+    from opus_b200 import encoder as E
+    enc = opus_b200.EncoderBatch(4, channels=2)
+    with pytest.raises(opus_b200.OpusB200Error):
+        enc.ctl(E.OPUS_SET_COMPLEXITY_REQUEST, 5)     # not on the device yet -> OPUS_UNIMPLEMENTED
+    with pytest.raises(opus_b200.OpusB200Error):
+        enc.ctl(E.OPUS_SET_VBR_REQUEST, 1)
+    with pytest.raises(opus_b200.OpusB200Error):
+        enc.ctl(E.OPUS_SET_BITRATE_REQUEST, 10)
+    enc.close()
