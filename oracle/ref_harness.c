@@ -277,3 +277,4 @@ int refh_celt_encode(CELTEncoder *st, const float *pcm, int frame_size, unsigned
   celt_encoder_ctl(st, OPUS_GET_FINAL_RANGE(rng));
   return n;
 }
+void refh_celt_encoder_set_cvbr(CELTEncoder *st, int v) { celt_encoder_ctl(st, OPUS_SET_VBR_CONSTRAINT(v)); }

@@ -14,17 +14,20 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12):
+def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1):
     R, O = util.load_ref(kind), util.load_oracle()
     x = (sig.astype(np.float32) / 32768.0).reshape(-1, fs * ch)[:nframes]
     rs = np.zeros(R.refh_celt_encoder_size(ch) + 64, np.uint8)
     assert R.refh_celt_encoder_init(_p(rs), ch, complexity, bitrate, vbr, lsb) == 0
+    R.refh_celt_encoder_set_cvbr(_p(rs), cvbr)
     os_ = np.zeros(O.orc_encoder_size(), np.uint8)
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
     O.orc_encoder_final_range.restype = ctypes.c_uint32
     O.orc_encoder_init(_p(os_), ch)
     O.orc_encoder_ctl(_p(os_), complexity, -1 if bitrate == -1000 else bitrate, vbr, lsb)
+    O.orc_encoder_set_cvbr.restype = None
+    O.orc_encoder_set_cvbr(_p(os_), cvbr)
     out = []
     for f in range(len(x)):
         a, b = np.zeros(1275, np.uint8), np.zeros(1275, np.uint8)
@@ -48,3 +51,46 @@ def test_complexity0_cbr(ch, fs, nbytes, sname):
         assert na == nbo, (f, na, nbo)
         assert np.array_equal(a, b), (f, int(np.argmax(a != b)))
         assert ra == rb
+
+
+def _transient_signal(seed, n, ch):
+    """music with castanet-like clicks so that transient_analysis fires on some frames"""
+    rng = np.random.default_rng(seed)
+    x = util.sig_music(seed, n, ch).astype(np.float64).reshape(n, ch)
+    for pos in rng.integers(200, n - 400, size=max(2, n // 2500)):
+        env = np.exp(-np.arange(300) / 40.0)[:, None]
+        x[pos:pos + 300] += 12000 * env * rng.standard_normal((300, ch))
+    return np.clip(x, -32768, 32767).reshape(-1)
+
+
+@pytest.mark.parametrize('complexity', [1, 2, 3, 4])
+@pytest.mark.parametrize('ch,fs,nbytes', [(2, 960, 160), (1, 960, 80), (2, 480, 100), (2, 240, 60), (1, 120, 30), (2, 960, 40), (2, 960, 320)])
+def test_complexity_1_to_4_cbr(complexity, ch, fs, nbytes):
+    for sname in ('music', 'clicks', 'noise'):
+        n = fs * 12
+        sig = util.sig_music(complexity + ch + fs, n, ch) if sname == 'music' else util.sig_white(complexity + fs, n, ch) if sname == 'noise' \
+            else _transient_signal(complexity * 7 + fs + nbytes, n, ch)
+        for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity):
+            assert nbo != -5, 'frame needed a decision that is not restated'
+            assert na == nbo, (sname, f, na, nbo)
+            assert np.array_equal(a, b), (sname, f, int(np.argmax(a != b)))
+            assert ra == rb
+
+
+@pytest.mark.parametrize('complexity', [0, 2, 4])
+@pytest.mark.parametrize('cvbr', [1, 0])
+@pytest.mark.parametrize('ch,fs,bitrate', [(2, 960, 64000), (1, 960, 32000), (2, 480, 96000), (2, 240, 128000), (1, 120, 64000), (2, 960, 24000)])
+def test_vbr(complexity, cvbr, ch, fs, bitrate):
+    for sname in ('music', 'clicks'):
+        n = fs * 16
+        sig = util.sig_music(3 + ch + fs, n, ch) if sname == 'music' else _transient_signal(fs + bitrate // 1000, n, ch)
+        sig = np.asarray(sig, np.float64)
+        sig[fs * ch * 5:fs * ch * 7] = 0      # two silent frames: the VBR silence path
+        sizes = []
+        for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, 1275, complexity, bitrate=bitrate, vbr=1, cvbr=cvbr, nframes=16):
+            assert nbo != -5
+            assert na == nbo, (sname, f, na, nbo)
+            assert np.array_equal(a, b), (sname, f, int(np.argmax(a != b)))
+            assert ra == rb
+            sizes.append(na)
+        assert len(set(sizes)) > 2     # really variable
