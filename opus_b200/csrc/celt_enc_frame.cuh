@@ -21,6 +21,7 @@ struct ObEncState {   // CELTEncoder fields that survive a frame (celt/celt_enco
   int32_t spread_decision, tonal_average, lastCodedBands, hf_average, tapset_decision, prefilter_period, prefilter_tapset,
       consec_transient, intensity;
   float delayedIntra, prefilter_gain, stereo_saving, spec_avg;
+  int32_t vbr_reservoir, vbr_drift, vbr_offset, vbr_count;
   float oldBandE[2 * OB_NBANDS], oldLogE[2 * OB_NBANDS], oldLogE2[2 * OB_NBANDS], energyError[2 * OB_NBANDS];
 };
 struct EncFrameParams {
@@ -31,7 +32,8 @@ struct EncFrameParams {
   const float *bandLogE;        // [n][C*21]
   unsigned char *packets;       // [n][pkt_stride]
   int32_t *nbytes;              // [n] bytes produced, or a negative error
-  int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf;
+  int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf, vbr, constrained_vbr,
+      loss_rate;
 };
 
 // ---- range encoder (celt/entenc.c:60-305), state in registers, bytes straight to the packet in HBM ----
@@ -219,8 +221,10 @@ OB_DEV float enc_median3(const float *x) {
 }
 
 // ---- dynalloc_analysis (celt/celt_encoder.c:1049-1274; no lfe / surround, analysis invalid, CBR) ----
-OB_DEVNI void enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, int *offsets, int lsb_depth, int isTransient, int LM,
-                           int effectiveBytes, float tone_freq, float toneishness) {
+struct EncDyn { float maxDepth; int32_t tot_boost; };
+OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, int *offsets, int lsb_depth, int isTransient, int LM,
+                             int effectiveBytes, float tone_freq, float toneishness, int vbr, int constrained_vbr, int *importance,
+                             int *spread_weight) {
   const int end = OB_NBANDS;
   float follower[2 * OB_NBANDS], noise_floor[OB_NBANDS], bandLogE3[OB_NBANDS];
   int32_t tot_boost = 0;
@@ -229,8 +233,38 @@ OB_DEVNI void enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, 
     offsets[i] = 0;
     noise_floor[i] = 0.0625f * ob_logN[i] + .5f + (9 - lsb_depth) - ob_emeans[i] + .0062f * (i + 5) * (i + 5);
   }
-  // (maxDepth, the masking model / spread_weight and `importance` only feed VBR, spreading_decision and tf_analysis)
-  if (effectiveBytes < 30 + 5 * LM) return;
+  EncDyn ret;
+  float maxDepth = -31.9f;
+#pragma unroll 1
+  for (int c = 0; c < C; c++)
+#pragma unroll 1
+    for (int i = 0; i < end; i++) maxDepth = enc_fmax(maxDepth, bandLogE[c * OB_NBANDS + i] - noise_floor[i]);
+  ret.maxDepth = maxDepth;
+  {  // simple masking model -> spread_weight (celt/celt_encoder.c:1082-1112); follower[] doubles as mask[] / sig[] scratch
+    float *mask = follower, *sig = follower + OB_NBANDS;
+#pragma unroll 1
+    for (int i = 0; i < end; i++) {
+      mask[i] = bandLogE[i] - noise_floor[i];
+      if (C == 2) mask[i] = enc_fmax(mask[i], bandLogE[OB_NBANDS + i] - noise_floor[i]);
+      sig[i] = mask[i];
+    }
+#pragma unroll 1
+    for (int i = 1; i < end; i++) mask[i] = enc_fmax(mask[i], mask[i - 1] - 2.f);
+#pragma unroll 1
+    for (int i = end - 2; i >= 0; i--) mask[i] = enc_fmax(mask[i], mask[i + 1] - 3.f);
+#pragma unroll 1
+    for (int i = 0; i < end; i++) {
+      const float smr = sig[i] - enc_fmax(enc_fmax(0.f, maxDepth - 12.f), mask[i]);
+      const int shift = OB_IMIN(5, OB_IMAX(0, -(int)floor((double)(.5f + smr))));
+      spread_weight[i] = 32 >> shift;
+    }
+  }
+  ret.tot_boost = 0;
+  if (effectiveBytes < 30 + 5 * LM) {
+#pragma unroll 1
+    for (int i = 0; i < end; i++) importance[i] = 13;
+    return ret;
+  }
   int last = 0;
 #pragma unroll 1
   for (int c = 0; c < C; c++) {
@@ -269,7 +303,9 @@ OB_DEVNI void enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, 
 #pragma unroll 1
     for (int i = 0; i < end; i++) follower[i] = enc_fmax(0.f, bandLogE[i] - follower[i]);
   }
-  if (!isTransient)   // (!vbr || constrained_vbr) && !isTransient, CBR
+#pragma unroll 1
+  for (int i = 0; i < end; i++) importance[i] = (int)floor((double)(.5f + 13 * enc_exp2(enc_fmin(follower[i], 4.f))));
+  if ((!vbr || constrained_vbr) && !isTransient)
 #pragma unroll 1
     for (int i = 0; i < end; i++) follower[i] = .5f * follower[i];
 #pragma unroll 1
@@ -307,7 +343,7 @@ OB_DEVNI void enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, 
       boost = (int)(follower[i] * width / 6);
       boost_bits = boost * 6 << OB_BITRES;
     }
-    if ((tot_boost + boost_bits) >> OB_BITRES >> 3 > 2 * effectiveBytes / 3) {
+    if ((!vbr || (constrained_vbr && !isTransient)) && (tot_boost + boost_bits) >> OB_BITRES >> 3 > 2 * effectiveBytes / 3) {
       const int32_t cap = ((2 * effectiveBytes / 3) << OB_BITRES << 3);
       offsets[i] = cap - tot_boost;
       tot_boost = cap;
@@ -317,6 +353,205 @@ OB_DEVNI void enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, 
       tot_boost += boost_bits;
     }
   }
+  ret.tot_boost = tot_boost;
+  return ret;
+}
+
+// ---- quant_coarse_energy_impl (celt/quant_bands.c:156-254) ----
+OB_DEVNI int enc_coarse_impl(RangeEnc &enc, const float *eBands, float *oldEBands, int32_t budget, int32_t tell, const unsigned char *prob_model,
+                             float *error, int C, int LM, int intra, float max_decay) {
+  const int start = 0, end = OB_NBANDS;
+  int badness = 0;
+  float prev[2] = {0.f, 0.f}, coef, beta;
+  if (tell + 3 <= budget) re_bit_logp(enc, intra, 3);
+  if (intra) { coef = 0.f; beta = 4915 / 32768.f; }
+  else {
+    coef = LM == 0 ? 29440 / 32768.f : LM == 1 ? 26112 / 32768.f : LM == 2 ? 21248 / 32768.f : 16384 / 32768.f;
+    beta = LM == 0 ? 30147 / 32768.f : LM == 1 ? 22282 / 32768.f : LM == 2 ? 12124 / 32768.f : 6554 / 32768.f;
+  }
+#pragma unroll 1
+  for (int i = start; i < end; i++)
+#pragma unroll 1
+    for (int c = 0; c < C; c++) {
+      const float x = eBands[i + c * OB_NBANDS];
+      const float oldE = enc_fmax(-9.f, oldEBands[i + c * OB_NBANDS]);
+      const float f = x - coef * oldE - prev[c];
+      int qi = (int)floor((double)(.5f + f));
+      const float decay_bound = enc_fmax(-28.f, oldEBands[i + c * OB_NBANDS]) - max_decay;
+      if (qi < 0 && x < decay_bound) {
+        qi += (int)(decay_bound - x);
+        if (qi > 0) qi = 0;
+      }
+      const int qi0 = qi;
+      tell = re_tell(enc);
+      const int bits_left = budget - tell - 3 * C * (end - i);
+      if (i != start && bits_left < 30) {
+        if (bits_left < 24) qi = OB_IMIN(1, qi);
+        if (bits_left < 16) qi = OB_IMAX(-1, qi);
+      }
+      if (budget - tell >= 15) {
+        const int pi = 2 * OB_IMIN(i, 20);
+        re_laplace(enc, qi, prob_model[pi] << 7, prob_model[pi + 1] << 6);
+      } else if (budget - tell >= 2) {
+        qi = OB_IMAX(-1, OB_IMIN(qi, 1));
+        re_icdf(enc, 2 * qi ^ -(qi < 0), ob_small_energy_icdf, 2);
+      } else if (budget - tell >= 1) {
+        qi = OB_IMIN(0, qi);
+        re_bit_logp(enc, -qi, 1);
+      } else qi = -1;
+      error[i + c * OB_NBANDS] = f - qi;
+      badness += qi0 > qi ? qi0 - qi : qi - qi0;
+      const float q = (float)qi;
+      oldEBands[i + c * OB_NBANDS] = coef * oldE + prev[c] + q;
+      prev[c] = prev[c] + q - beta * q;
+    }
+  return badness;
+}
+
+OB_DEV void enc_haar(float *X, int N0, int stride);
+// ---- tf_analysis (celt/celt_encoder.c:648-822) ----
+OB_DEV float enc_l1(const float *tmp, int N, int LM, float bias) {
+  float L1 = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < N; i++) L1 += fabsf(tmp[i]);
+  return L1 + (LM * bias) * L1;
+}
+OB_DEVNI int enc_tf_analysis(int isTransient, int *tf_res, int lambda, const float *X, int N0, int LM, float tf_estimate, int tf_chan,
+                             const int *importance, float *tmp, float *tmp_1) {
+  const int len = OB_NBANDS;
+  int metric[OB_NBANDS];
+  unsigned path0 = 0, path1 = 0;   // one bit per band
+  const float bias = .04f * enc_fmax(-.25f, .5f - tf_estimate);
+#pragma unroll 1
+  for (int i = 0; i < len; i++) {
+    const int N = (ob_ebands[i + 1] - ob_ebands[i]) << LM, narrow = (ob_ebands[i + 1] - ob_ebands[i]) == 1;
+    int best_level = 0;
+#pragma unroll 1
+    for (int j = 0; j < N; j++) tmp[j] = X[tf_chan * N0 + (ob_ebands[i] << LM) + j];
+    float L1 = enc_l1(tmp, N, isTransient ? LM : 0, bias), best_L1 = L1;
+    if (isTransient && !narrow) {
+#pragma unroll 1
+      for (int j = 0; j < N; j++) tmp_1[j] = tmp[j];
+      enc_haar(tmp_1, N >> LM, 1 << LM);
+      L1 = enc_l1(tmp_1, N, LM + 1, bias);
+      if (L1 < best_L1) { best_L1 = L1; best_level = -1; }
+    }
+#pragma unroll 1
+    for (int k = 0; k < LM + !(isTransient || narrow); k++) {
+      const int B = isTransient ? (LM - k - 1) : k + 1;
+      enc_haar(tmp, N >> k, 1 << k);
+      L1 = enc_l1(tmp, N, B, bias);
+      if (L1 < best_L1) { best_L1 = L1; best_level = k + 1; }
+    }
+    metric[i] = isTransient ? 2 * best_level : -2 * best_level;
+    if (narrow && (metric[i] == 0 || metric[i] == -2 * LM)) metric[i] -= 1;
+  }
+  int selcost[2], tf_select = 0, cost0, cost1;
+#define OB_TFSEL(sel, w) (2 * ob_tf_select[LM * 8 + 4 * isTransient + 2 * (sel) + (w)])
+#define OB_ABSD(a, b) ((a) > (b) ? (a) - (b) : (b) - (a))
+#pragma unroll 1
+  for (int sel = 0; sel < 2; sel++) {
+    cost0 = importance[0] * OB_ABSD(metric[0], OB_TFSEL(sel, 0));
+    cost1 = importance[0] * OB_ABSD(metric[0], OB_TFSEL(sel, 1)) + (isTransient ? 0 : lambda);
+#pragma unroll 1
+    for (int i = 1; i < len; i++) {
+      const int curr0 = OB_IMIN(cost0, cost1 + lambda), curr1 = OB_IMIN(cost0 + lambda, cost1);
+      cost0 = curr0 + importance[i] * OB_ABSD(metric[i], OB_TFSEL(sel, 0));
+      cost1 = curr1 + importance[i] * OB_ABSD(metric[i], OB_TFSEL(sel, 1));
+    }
+    selcost[sel] = OB_IMIN(cost0, cost1);
+  }
+  if (selcost[1] < selcost[0] && isTransient) tf_select = 1;
+  cost0 = importance[0] * OB_ABSD(metric[0], OB_TFSEL(tf_select, 0));
+  cost1 = importance[0] * OB_ABSD(metric[0], OB_TFSEL(tf_select, 1)) + (isTransient ? 0 : lambda);
+#pragma unroll 1
+  for (int i = 1; i < len; i++) {
+    int curr0, curr1, from0 = cost0, from1 = cost1 + lambda;
+    if (from0 < from1) curr0 = from0; else { curr0 = from1; path0 |= 1u << i; }
+    from0 = cost0 + lambda;
+    from1 = cost1;
+    if (from0 < from1) curr1 = from0; else { curr1 = from1; path1 |= 1u << i; }
+    cost0 = curr0 + importance[i] * OB_ABSD(metric[i], OB_TFSEL(tf_select, 0));
+    cost1 = curr1 + importance[i] * OB_ABSD(metric[i], OB_TFSEL(tf_select, 1));
+  }
+#undef OB_TFSEL
+#undef OB_ABSD
+  tf_res[len - 1] = cost0 < cost1 ? 0 : 1;
+#pragma unroll 1
+  for (int i = len - 2; i >= 0; i--) tf_res[i] = (int)(((tf_res[i + 1] == 1 ? path1 : path0) >> (i + 1)) & 1u);
+  return tf_select;
+}
+
+// ---- spreading_decision (celt/bands.c:470-562) ----
+OB_DEVNI int enc_spreading_decision(const float *X, ObEncState &st, int update_hf, int C, int M, const int *spread_weight) {
+  const int end = OB_NBANDS, N0 = M * OB_SHORT_N;
+  int sum = 0, nbBands = 0, hf_sum = 0;
+  if (M * (ob_ebands[end] - ob_ebands[end - 1]) <= 8) return 0;
+#pragma unroll 1
+  for (int c = 0; c < C; c++)
+#pragma unroll 1
+    for (int i = 0; i < end; i++) {
+      const int N = M * (ob_ebands[i + 1] - ob_ebands[i]);
+      if (N <= 8) continue;
+      const float *x = X + M * ob_ebands[i] + c * N0;
+      int t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll 1
+      for (int j = 0; j < N; j++) {
+        const float x2N = (x[j] * x[j]) * N;
+        if (x2N < 0.25f) t0++;
+        if (x2N < 0.0625f) t1++;
+        if (x2N < 0.015625f) t2++;
+      }
+      if (i > OB_NBANDS - 4) hf_sum += (uint32_t)(32 * (t1 + t0)) / (uint32_t)N;
+      const int tmp = (2 * t2 >= N) + (2 * t1 >= N) + (2 * t0 >= N);
+      sum += tmp * spread_weight[i];
+      nbBands += spread_weight[i];
+    }
+  if (update_hf) {
+    if (hf_sum) hf_sum = (uint32_t)hf_sum / (uint32_t)(C * (4 - OB_NBANDS + end));
+    st.hf_average = (st.hf_average + hf_sum) >> 1;
+    hf_sum = st.hf_average;
+    if (st.tapset_decision == 2) hf_sum += 4;
+    else if (st.tapset_decision == 0) hf_sum -= 4;
+    if (hf_sum > 22) st.tapset_decision = 2;
+    else if (hf_sum > 18) st.tapset_decision = 1;
+    else st.tapset_decision = 0;
+  }
+  sum = (uint32_t)((int32_t)sum << 8) / (uint32_t)nbBands;
+  sum = (sum + st.tonal_average) >> 1;
+  st.tonal_average = sum;
+  sum = (3 * sum + (((3 - st.spread_decision) << 7) + 64) + 2) >> 2;
+  return sum < 80 ? 3 : sum < 256 ? 2 : sum < 384 ? 1 : 0;
+}
+
+// ---- compute_vbr (celt/celt_encoder.c:1604-1717; analysis invalid, no lfe / surround mask) ----
+OB_DEVNI int32_t enc_compute_vbr(int32_t base_target, int LM, int32_t bitrate, int lastCodedBands, int C, int intensity, int constrained_vbr,
+                                 float stereo_saving, int tot_boost, float tf_estimate, float maxDepth, float temporal_vbr) {
+  const int coded_bands = lastCodedBands ? lastCodedBands : OB_NBANDS;
+  int coded_bins = ob_ebands[coded_bands] << LM;
+  if (C == 2) coded_bins += ob_ebands[OB_IMIN(intensity, coded_bands)] << LM;
+  int32_t target = base_target;
+  if (C == 2) {
+    const int coded_stereo_bands = OB_IMIN(intensity, coded_bands);
+    const int coded_stereo_dof = (ob_ebands[coded_stereo_bands] << LM) - coded_stereo_bands;
+    const float max_frac = (0.8f * coded_stereo_dof) / coded_bins;
+    stereo_saving = enc_fmin(stereo_saving, 1.f);
+    const float a = max_frac * target, b = (stereo_saving - 0.1f) * (coded_stereo_dof << OB_BITRES);
+    target -= (int32_t)enc_fmin(a, b);
+  }
+  target += tot_boost - (19 << LM);
+  target += (int32_t)((tf_estimate - 0.044f) * target);
+  const int bins = ob_ebands[OB_NBANDS - 2] << LM;
+  int32_t floor_depth = (int32_t)((C * bins << OB_BITRES) * maxDepth);
+  floor_depth = OB_IMAX(floor_depth, target >> 2);
+  target = OB_IMIN(target, floor_depth);
+  if (constrained_vbr) target = base_target + (int32_t)(0.67f * (target - base_target));
+  if (tf_estimate < .2f) {
+    const float amount = .0000031f * OB_IMAX(0, OB_IMIN(32000, 96000 - bitrate));
+    const float tvbr_factor = temporal_vbr * amount;
+    target += (int32_t)(tvbr_factor * target);
+  }
+  return OB_IMIN(2 * base_target, target);
 }
 
 // ---- clt_compute_allocation, encode side (celt/rate.c:248-637) ----
@@ -887,32 +1122,66 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
 #pragma unroll 1
   for (int i = 0; i < C * OB_NBANDS; i++) bandLogE[i] = p.bandLogE[(size_t)stream * C * OB_NBANDS + i];
 
-  int nbCompressedBytes = OB_IMIN(p.max_bytes, 1275);
-  if (p.bitrate != -1) nbCompressedBytes = OB_IMAX(2, OB_IMIN(nbCompressedBytes, (p.bitrate * (N) + 4 * 48000) / (8 * 48000)));
-  const int effectiveBytes = nbCompressedBytes, nbAvailableBytes = nbCompressedBytes;
+  int fine_dummy = 0;
+  (void)fine_dummy;
+  int importance[OB_NBANDS], spread_weight[OB_NBANDS];
+  int nbCompressedBytes = OB_IMIN(p.max_bytes, 1275), nbAvailableBytes, effectiveBytes;
+  int32_t vbr_rate = 0;
+  if (p.vbr && p.bitrate != -1) {
+    vbr_rate = (p.bitrate * 6 / (6 * 48000 / N)) << OB_BITRES;   // bitrate_to_bits (celt/celt.h:151)
+    effectiveBytes = vbr_rate >> (3 + OB_BITRES);
+  } else {
+    if (p.bitrate != -1) nbCompressedBytes = OB_IMAX(2, OB_IMIN(nbCompressedBytes, (p.bitrate * N + 4 * 48000) / (8 * 48000)));
+    effectiveBytes = nbCompressedBytes;
+  }
+  nbAvailableBytes = nbCompressedBytes;
   int32_t equiv_rate = ((int32_t)nbCompressedBytes * 8 * 50 << (3 - LM)) - (40 * C + 20) * ((400 >> LM) - 50);
   if (p.bitrate != -1) equiv_rate = OB_IMIN(equiv_rate, p.bitrate - (40 * C + 20) * ((400 >> LM) - 50));
   RangeEnc enc;
   re_init(enc, p.packets + (size_t)stream * p.pkt_stride, nbCompressedBytes);
-  int32_t total_bits = nbCompressedBytes * 8;
   int32_t tell = 1;
+  if (vbr_rate > 0 && p.constrained_vbr) {   // :1939-1959 (nothing has been written at the end of the buffer yet: shrinking = a new size)
+    const int32_t max_allowed = OB_IMIN(OB_IMAX(2, (vbr_rate + vbr_rate - st.vbr_reservoir) >> (OB_BITRES + 3)), nbAvailableBytes);
+    if (max_allowed < nbAvailableBytes) {
+      nbCompressedBytes = max_allowed;
+      nbAvailableBytes = max_allowed;
+      enc.storage = nbCompressedBytes;
+    }
+  }
+  int32_t total_bits = nbCompressedBytes * 8;
   const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
   re_bit_logp(enc, silence, 15);
   if (silence) {
+    if (vbr_rate > 0) {
+      effectiveBytes = nbCompressedBytes = OB_IMIN(nbCompressedBytes, 2);
+      total_bits = nbCompressedBytes * 8;
+      nbAvailableBytes = 2;
+      enc.storage = nbCompressedBytes;
+    }
     tell = nbCompressedBytes * 8;
     enc.nbits_total += tell - re_tell(enc);
   }
-  // the transient decision comes from the caller (transient_analysis is not on the device yet; complexity 0 never sets it)
-  const int isTransient = fi.short_blocks != 0, shortBlocks = isTransient ? M : 0;
-  float toneishness = fi.toneishness;   // tf_estimate == 0 at this complexity
+  int isTransient = fi.is_transient;
+  const float tf_estimate = fi.tf_estimate;
+  const int tf_chan = fi.tf_chan;
+  const float toneishness = enc_fmin(fi.toneishness, 1.f - tf_estimate);
   // run_prefilter with the pitch search off: no post-filter (the tone-driven path is reported as unsupported)
   int status = 0;
+  const int pf_on = 0;
   {
     const int enabled = nbAvailableBytes > 12 * C && !silence && tell + 16 <= total_bits && !p.disable_pf;
     if (enabled && toneishness > .99f) status = -5;
     if (tell + 16 <= total_bits) re_bit_logp(enc, 0, 1);
   }
-  const int transient_got_disabled = !(LM > 0 && re_tell(enc) + 3 <= total_bits);
+  int shortBlocks = 0, transient_got_disabled = 0;
+  if (LM > 0 && re_tell(enc) + 3 <= total_bits) {
+    if (isTransient) shortBlocks = M;
+  } else {
+    isTransient = 0;
+    transient_got_disabled = 1;
+  }
+  if ((shortBlocks != 0) != (fi.short_blocks != 0)) status = -3;   // the analysis kernel transformed with the other block size
+  float temporal_vbr;
   { // temporal VBR statistics (:2213-2228) keep spec_avg current even in CBR
     float follow = -10.0f, frame_avg = 0.f;
     const float offset = shortBlocks ? .5f * LM : 0.f;
@@ -923,21 +1192,30 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
       frame_avg += follow;
     }
     frame_avg /= (end - start);
-    float temporal_vbr = frame_avg - st.spec_avg;
+    temporal_vbr = frame_avg - st.spec_avg;
     temporal_vbr = enc_fmin(3.f, enc_fmax(-1.5f, temporal_vbr));
     st.spec_avg += .02f * temporal_vbr;
   }
-  if (!transient_got_disabled) re_bit_logp(enc, isTransient, 3);
-  enc_dynalloc(bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness);
+  if (LM > 0 && re_tell(enc) + 3 <= total_bits) re_bit_logp(enc, isTransient, 3);
+  const EncDyn dyn = enc_dynalloc(bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
+                                  p.constrained_vbr, importance, spread_weight);
+  int tf_select = 0;
+  if (effectiveBytes >= 15 * C && p.complexity >= 2 && toneishness < .98f) {   // enable_tf_analysis
+    const int lambda = OB_IMAX(80, 20480 / effectiveBytes + 2);
+    tf_select = enc_tf_analysis(isTransient, tf_res, lambda, Xg, N, LM, tf_estimate, tf_chan, importance, bx, by);
+  } else {
 #pragma unroll 1
-  for (int i = 0; i < end; i++) tf_res[i] = isTransient;
+    for (int i = 0; i < end; i++) tf_res[i] = isTransient;
+  }
 #pragma unroll 1
   for (int c = 0; c < C; c++)
 #pragma unroll 1
     for (int i = start; i < end; i++)
       if (fabsf(bandLogE[i + c * OB_NBANDS] - st.oldBandE[i + c * OB_NBANDS]) < 2.f) bandLogE[i + c * OB_NBANDS] -= 0.25f * st.energyError[i + c * OB_NBANDS];
-  { // quant_coarse_energy (celt/quant_bands.c:256-365), single pass (two_pass needs complexity >= 4)
-    int intra = p.force_intra || (st.delayedIntra > 2 * C * (end - start) && nbAvailableBytes > (end - start) * C);
+  { // quant_coarse_energy (celt/quant_bands.c:256-365)
+    int two_pass = p.complexity >= 4;
+    int intra = p.force_intra || (!two_pass && st.delayedIntra > 2 * C * (end - start) && nbAvailableBytes > (end - start) * C);
+    const int32_t intra_bias = (int32_t)((total_bits * st.delayedIntra * p.loss_rate) / (C * 512));
     float new_distortion = 0.f;
 #pragma unroll 1
     for (int c = 0; c < C; c++)
@@ -947,56 +1225,46 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
         new_distortion = new_distortion + d * d;
       }
     new_distortion = enc_fmin(200.f, new_distortion);
-    int32_t t = re_tell(enc);
-    if (t + 3 > total_bits) intra = 0;
-    float max_decay = 16.f;
-    max_decay = enc_fmin(max_decay, .125f * nbAvailableBytes);   // end - start > 10
-    const unsigned char *prob_model = ob_e_prob + (LM * 2 + intra) * 42;
-    float prev[2] = {0.f, 0.f}, coef, beta;
-    if (t + 3 <= total_bits) re_bit_logp(enc, intra, 3);
-    if (intra) { coef = 0.f; beta = 4915 / 32768.f; }
-    else {
-      coef = LM == 0 ? 29440 / 32768.f : LM == 1 ? 26112 / 32768.f : LM == 2 ? 21248 / 32768.f : 16384 / 32768.f;
-      beta = LM == 0 ? 30147 / 32768.f : LM == 1 ? 22282 / 32768.f : LM == 2 ? 12124 / 32768.f : 6554 / 32768.f;
-    }
+    const int32_t t0 = re_tell(enc);
+    if (t0 + 3 > total_bits) two_pass = intra = 0;
+    const float max_decay = enc_fmin(16.f, .125f * nbAvailableBytes);   // end - start > 10
+    const float pc = LM == 0 ? 29440 / 32768.f : LM == 1 ? 26112 / 32768.f : LM == 2 ? 21248 / 32768.f : 16384 / 32768.f;
+    if (two_pass || intra) {
+      // by/bx double as oldEBands_intra / error_intra (42 floats each); a handful of packet bytes is set aside for the retry
+      float *old_intra = by, *err_intra = by + 2 * OB_NBANDS;
+      const RangeEnc start_state = enc;
 #pragma unroll 1
-    for (int i = start; i < end; i++)
+      for (int i = 0; i < C * OB_NBANDS; i++) old_intra[i] = st.oldBandE[i];
+      const int badness1 = enc_coarse_impl(enc, bandLogE, old_intra, total_bits, t0, ob_e_prob + (LM * 2 + 1) * 42, err_intra, C, LM, 1, max_decay);
+      if (!intra) {
+        unsigned char saved[160];
+        const int32_t tell_intra = re_tell_frac(enc);
+        const RangeEnc intra_state = enc;
+        const uint32_t nb0 = start_state.offs, nb1 = intra_state.offs;
+        if (nb1 - nb0 > 160) status = -3;
 #pragma unroll 1
-      for (int c = 0; c < C; c++) {
-        const float x = bandLogE[i + c * OB_NBANDS];
-        const float oldE = enc_fmax(-9.f, st.oldBandE[i + c * OB_NBANDS]);
-        const float f = x - coef * oldE - prev[c];
-        int qi = (int)floor((double)(.5f + f));
-        const float decay_bound = enc_fmax(-28.f, st.oldBandE[i + c * OB_NBANDS]) - max_decay;
-        if (qi < 0 && x < decay_bound) {
-          qi += (int)(decay_bound - x);
-          if (qi > 0) qi = 0;
+        for (uint32_t i = 0; i < nb1 - nb0 && i < 160; i++) saved[i] = enc.buf[nb0 + i];
+        enc = start_state;
+        const int badness2 = enc_coarse_impl(enc, bandLogE, st.oldBandE, total_bits, t0, ob_e_prob + (LM * 2 + 0) * 42, error, C, LM, 0, max_decay);
+        if (two_pass && (badness1 < badness2 || (badness1 == badness2 && ((int32_t)re_tell_frac(enc)) + intra_bias > tell_intra))) {
+          enc = intra_state;
+#pragma unroll 1
+          for (uint32_t i = 0; i < nb1 - nb0 && i < 160; i++) enc.buf[nb0 + i] = saved[i];
+#pragma unroll 1
+          for (int i = 0; i < C * OB_NBANDS; i++) { st.oldBandE[i] = old_intra[i]; error[i] = err_intra[i]; }
+          intra = 1;
         }
-        t = re_tell(enc);
-        const int bits_left = total_bits - t - 3 * C * (end - i);
-        if (i != start && bits_left < 30) {
-          if (bits_left < 24) qi = OB_IMIN(1, qi);
-          if (bits_left < 16) qi = OB_IMAX(-1, qi);
-        }
-        if (total_bits - t >= 15) {
-          const int pi = 2 * OB_IMIN(i, 20);
-          re_laplace(enc, qi, prob_model[pi] << 7, prob_model[pi + 1] << 6);
-        } else if (total_bits - t >= 2) {
-          qi = OB_IMAX(-1, OB_IMIN(qi, 1));
-          re_icdf(enc, 2 * qi ^ -(qi < 0), ob_small_energy_icdf, 2);
-        } else if (total_bits - t >= 1) {
-          qi = OB_IMIN(0, qi);
-          re_bit_logp(enc, -qi, 1);
-        } else qi = -1;
-        error[i + c * OB_NBANDS] = f - qi;
-        const float q = (float)qi;
-        st.oldBandE[i + c * OB_NBANDS] = coef * oldE + prev[c] + q;
-        prev[c] = prev[c] + q - beta * q;
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < C * OB_NBANDS; i++) { st.oldBandE[i] = old_intra[i]; error[i] = err_intra[i]; }
       }
+    } else {
+      enc_coarse_impl(enc, bandLogE, st.oldBandE, total_bits, t0, ob_e_prob + (LM * 2 + 0) * 42, error, C, LM, 0, max_decay);
+    }
     if (intra) st.delayedIntra = new_distortion;
-    else st.delayedIntra = (coef * coef) * st.delayedIntra + new_distortion;
+    else st.delayedIntra = (pc * pc) * st.delayedIntra + new_distortion;
   }
-  { // tf_encode (celt/celt_encoder.c:824-862); tf_select = 0 without tf_analysis
+  { // tf_encode (celt/celt_encoder.c:824-862)
     int curr = 0, tf_changed = 0, logp = isTransient ? 2 : 4;
     uint32_t budget = enc.storage * 8, t = re_tell(enc);
     const int tf_select_rsv = LM > 0 && t + logp + 1 <= budget;
@@ -1012,12 +1280,14 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
       logp = isTransient ? 4 : 5;
     }
     if (tf_select_rsv && ob_tf_select[LM * 8 + 4 * isTransient + 0 + tf_changed] != ob_tf_select[LM * 8 + 4 * isTransient + 2 + tf_changed])
-      re_bit_logp(enc, 0, 1);
+      re_bit_logp(enc, tf_select, 1);
+    else tf_select = 0;
 #pragma unroll 1
-    for (int i = start; i < end; i++) tf_res[i] = ob_tf_select[LM * 8 + 4 * isTransient + tf_res[i]];
+    for (int i = start; i < end; i++) tf_res[i] = ob_tf_select[LM * 8 + 4 * isTransient + 2 * tf_select + tf_res[i]];
   }
   if (re_tell(enc) + 4 <= total_bits) {
-    st.spread_decision = p.complexity == 0 ? 0 : 2;   // SPREAD_NONE : SPREAD_NORMAL (spreading_decision needs complexity >= 3)
+    if (shortBlocks || p.complexity < 3 || nbAvailableBytes < 10 * C) st.spread_decision = p.complexity == 0 ? 0 : 2;   // SPREAD_NONE : SPREAD_NORMAL
+    else st.spread_decision = enc_spreading_decision(Xg, st, pf_on && !shortBlocks, C, M, spread_weight);
     re_icdf(enc, st.spread_decision, ob_spread_icdf, 5);
   } else st.spread_decision = 2;
 #pragma unroll 1
@@ -1097,9 +1367,47 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
       for (int i = 0; i < end - 1; i++) diff += bandLogE[i + c * OB_NBANDS] * (int32_t)(2 + 2 * i - end);
     diff /= C * (end - 1);
     trim -= enc_fmax(-2.f, enc_fmin(2.f, (diff + 1.f) / 6));
+    trim -= 2 * tf_estimate;
     alloc_trim = OB_IMAX(0, OB_IMIN(10, (int)floor((double)(.5f + trim))));
     re_icdf(enc, alloc_trim, ob_trim_icdf, 7);
     tell = re_tell_frac(enc);
+  }
+  if (vbr_rate > 0) {   // :2432-2522
+    const int32_t min_allowed = ((tell + total_boost + (1 << (OB_BITRES + 3)) - 1) >> (OB_BITRES + 3)) + 2;
+    const int lm_diff = 3 - LM;
+    nbCompressedBytes = OB_IMIN(nbCompressedBytes, 1275 >> (3 - LM));
+    int32_t base_target = vbr_rate - ((40 * C + 20) << OB_BITRES);
+    if (p.constrained_vbr) base_target += (st.vbr_offset >> lm_diff);
+    int32_t target = enc_compute_vbr(base_target, LM, equiv_rate, st.lastCodedBands, C, st.intensity, p.constrained_vbr, st.stereo_saving, dyn.tot_boost,
+                                     tf_estimate, dyn.maxDepth, temporal_vbr);
+    target = target + tell;
+    nbAvailableBytes = (target + (1 << (OB_BITRES + 2))) >> (OB_BITRES + 3);
+    nbAvailableBytes = OB_IMAX(min_allowed, nbAvailableBytes);
+    nbAvailableBytes = OB_IMIN(nbCompressedBytes, nbAvailableBytes);
+    int32_t delta = target - vbr_rate;
+    target = nbAvailableBytes << (OB_BITRES + 3);
+    if (silence) {
+      nbAvailableBytes = 2;
+      target = 2 * 8 << OB_BITRES;
+      delta = 0;
+    }
+    float alpha;
+    if (st.vbr_count < 970) {
+      st.vbr_count++;
+      alpha = 1.0f / (st.vbr_count + 20);
+    } else alpha = .001f;
+    if (p.constrained_vbr) {
+      st.vbr_reservoir += target - vbr_rate;
+      st.vbr_drift += (int32_t)(alpha * ((delta * (1 << lm_diff)) - st.vbr_offset - st.vbr_drift));
+      st.vbr_offset = -st.vbr_drift;
+      if (st.vbr_reservoir < 0) {
+        const int adjust = (-st.vbr_reservoir) / (8 << OB_BITRES);
+        nbAvailableBytes += silence ? 0 : adjust;
+        st.vbr_reservoir = 0;
+      }
+    }
+    nbCompressedBytes = OB_IMIN(nbCompressedBytes, nbAvailableBytes);
+    enc.storage = nbCompressedBytes;   // ec_enc_shrink: no raw bits have been written yet
   }
   int32_t bits = (((int32_t)nbCompressedBytes * 8) << OB_BITRES) - (int32_t)re_tell_frac(enc) - 1;
   const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;

@@ -30,7 +30,7 @@ struct OpusB200Encoder {
   float *X, *bandE, *bandLogE;
   int32_t *d_nbytes;
   // settings (celt_encoder_ctl)
-  int complexity, bitrate, vbr, lsb_depth, force_intra, disable_inv, disable_pf;
+  int complexity, bitrate, vbr, constrained_vbr, lsb_depth, force_intra, disable_inv, disable_pf, loss_rate;
   // staging for the host-buffer call
   float *d_pcm; size_t d_pcm_cap;
   unsigned char *d_pkt; size_t d_pkt_cap;
@@ -60,7 +60,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   if (!e) return OPUSB200_ALLOC_FAIL;
   memset(e, 0, sizeof(*e));
   e->device = device; e->channels = channels; e->n = n_streams;
-  e->complexity = 0; e->bitrate = -1; e->vbr = 0; e->lsb_depth = 24;   // celt_encoder_init defaults except complexity (see ctl)
+  e->complexity = 4; e->bitrate = -1; e->vbr = 0; e->constrained_vbr = 1; e->lsb_depth = 24;   // celt_encoder_init defaults; complexity capped (see ctl)
   OB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   const size_t n = (size_t)n_streams;
   OB_CUDA(cudaMalloc(&e->state, sizeof(ObEncState) * n));
@@ -70,7 +70,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->bandE, sizeof(float) * n * channels * OB_NBANDS));
   OB_CUDA(cudaMalloc(&e->bandLogE, sizeof(float) * n * channels * OB_NBANDS));
   OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
-  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 16));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32));
   const int r = opusb200_encoder_reset(e);
   if (r != OPUSB200_OK) return r;
   OB_CUDA(cudaStreamSynchronize(e->stream));
@@ -91,8 +91,10 @@ extern "C" int opusb200_encoder_ctl_set(OpusB200Encoder *e, int request, int32_t
   if (!e) return OPUSB200_BAD_ARG;
   switch (request) {
     case 4002: if (value != -1 && (value < 500 || value > 750000 * e->channels)) return OPUSB200_BAD_ARG; e->bitrate = value; return OPUSB200_OK;  // OPUS_SET_BITRATE (-1 = OPUS_BITRATE_MAX)
-    case 4006: if (value != 0) return OPUSB200_UNIMPLEMENTED; e->vbr = 0; return OPUSB200_OK;              // OPUS_SET_VBR: CBR only this round
-    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; if (value != 0) return OPUSB200_UNIMPLEMENTED; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY
+    case 4006: e->vbr = value != 0; return OPUSB200_OK;                                                       // OPUS_SET_VBR
+    case 4020: e->constrained_vbr = value != 0; return OPUSB200_OK;                                            // OPUS_SET_VBR_CONSTRAINT
+    case 4014: if (value < 0 || value > 100) return OPUSB200_BAD_ARG; e->loss_rate = value; return OPUSB200_OK;   // OPUS_SET_PACKET_LOSS_PERC
+    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; if (value > 4) return OPUSB200_UNIMPLEMENTED; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY (0..4 on the device)
     case 4036: if (value < 8 || value > 24) return OPUSB200_BAD_ARG; e->lsb_depth = value; return OPUSB200_OK;  // OPUS_SET_LSB_DEPTH
     case 4046: e->disable_inv = value != 0; return OPUSB200_OK;                                                // OPUS_SET_PHASE_INVERSION_DISABLED
     default: return OPUSB200_UNIMPLEMENTED;
@@ -114,12 +116,13 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   OB_CUDA(cudaSetDevice(e->device));
   EncAnalysisParams a;
   a.state = e->an_state; a.pcm = d_pcm; a.short_blocks = nullptr; a.X = e->X; a.bandE = e->bandE; a.bandLogE = e->bandLogE; a.info = e->info;
-  a.n_streams = e->n; a.C = e->channels; a.LM = LM;
-  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 16, e->stream>>>(a);
+  a.n_streams = e->n; a.C = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
+  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 32, e->stream>>>(a);
   EncFrameParams p;
   p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.packets = d_packets; p.nbytes = d_nbytes;
   p.n_streams = e->n; p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf;
+  p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
   ob_celt_enc_frame<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
   e->launches += 2;
   OB_CUDA(cudaGetLastError());

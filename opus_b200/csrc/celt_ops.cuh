@@ -88,7 +88,7 @@ OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *s
 //      pre-filter is off.  The spectrum never leaves shared memory; HBM sees the PCM once and the normalised bands once. ----
 struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; float overlap_max; float pad; };
 // what the frame encoder needs from the time domain (celt_encode_with_ec :1963-1970, :2017)
-struct ObEncFrameInfo { float tone_freq, toneishness, sample_max; int32_t short_blocks; };
+struct ObEncFrameInfo { float tone_freq, toneishness, sample_max, tf_estimate; int32_t short_blocks, is_transient, tf_chan, pad; };
 struct EncAnalysisParams {
   ObEncAnalysisState *state;   // [n_streams]
   const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
@@ -97,6 +97,7 @@ struct EncAnalysisParams {
   float *bandE, *bandLogE;     // [n_streams][C*21]
   ObEncFrameInfo *info;        // [n_streams] or null
   int n_streams, C, LM;
+  int complexity, lsb_depth;   // transient_analysis runs from complexity 1 (celt/celt_encoder.c:2020); lsb_depth defines silence
 };
 // tone_lpc (celt/celt_encoder.c:1305-1360) on x = in0 (+ in1): the six running sums are independent sequential chains,
 // one lane each (lanes 0-2: r00 r01 r02, lanes 3-5: the three edge corrections); lane 0 solves the 2x2 system.
@@ -140,12 +141,59 @@ OB_DEV int tone_lpc_warp(const float *in0, const float *in1, int len, int delay,
   else lpc[0] = f_div(num0, den);
   return 0;
 }
+// transient_analysis for one channel (celt/celt_encoder.c:267-466): three first-order recurrences over the frame, serial by
+// nature (and by the float order the reference fixes) -> one lane; returns the channel's `unmask` metric.  tmp: len/2 floats.
+OB_TABLE unsigned char ob_transient_inv_table[128] = {
+    255, 255, 156, 110, 86, 70, 59, 51, 45, 40, 37, 33, 31, 28, 26, 25, 23, 22, 21, 20, 19, 18, 17, 16, 16, 15, 15, 14, 13, 13, 12, 12,
+    12,  12,  11,  11,  11, 10, 10, 10, 9,  9,  9,  9,  9,  9,  8,  8,  8,  8,  8,  7,  7,  7,  7,  7,  7,  6,  6,  6,  6,  6,  6,  6,
+    6,   6,   6,   6,   6,  6,  6,  6,  6,  5,  5,  5,  5,  5,  5,  5,  5,  5,  5,  5,  5,  4,  4,  4,  4,  4,  4,  4,  4,  4,  4,  4,
+    4,   4,   4,   4,   4,  4,  4,  4,  4,  4,  4,  4,  4,  4,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  2,
+};
+OB_DEVNI int transient_unmask_lane(const float *in, float *tmp, int len) {
+  const int len2 = len / 2;
+  const float forward_decay = .0625f;
+  // the high-pass filter (two samples per step) feeds the forward smoother directly: only len/2 values are stored
+  float hp0 = 0.f, hp1 = 0.f, mean = 0.f, mem0 = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < len2; i++) {
+    float y[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float x = in[2 * i + k], mem00 = hp0;
+      y[k] = 2 * i + k < 12 ? 0.f : hp0 + x;
+      hp0 = hp0 - x + .5f * hp1;
+      hp1 = x - mem00;
+    }
+    const float x2 = y[0] * y[0] + y[1] * y[1];
+    mean += x2;
+    mem0 = x2 + (1.f - forward_decay) * mem0;
+    tmp[i] = forward_decay * mem0;
+  }
+  mem0 = 0.f;
+  float maxE = 0.f;
+#pragma unroll 1
+  for (int i = len2 - 1; i >= 0; i--) {
+    mem0 = tmp[i] + 0.875f * mem0;
+    tmp[i] = 0.125f * mem0;
+    maxE = fmaxf(maxE, 0.125f * mem0);
+  }
+  mean = (float)sqrt((double)(mean * maxE) * .5 * len2);
+  const float norm = len2 / (1e-15f + mean);
+  int unmask = 0;
+#pragma unroll 1
+  for (int i = 12; i < len2 - 5; i += 4) {
+    const double v = floor((double)(64 * norm * (tmp[i] + 1e-15f)));
+    const int id = (int)(v < 127 ? (v > 0 ? v : 0) : 127);
+    unmask += ob_transient_inv_table[id];
+  }
+  return 64 * unmask * 4 / (6 * (len2 - 17));
+}
 // one CTA per stream, one warp per channel
 OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned char *smem) {
   const int lane = lane_id(), c = warp_in_block();
   MdctWS *ws = (MdctWS *)smem + c;
   const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C;
-  const int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
+  int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
   ObEncAnalysisState &st = p.state[stream];
   const float *pcm = p.pcm + (size_t)stream * N * C + c;
   // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
@@ -166,8 +214,13 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   if (lane == 0) st.preemph_mem[c] = f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)]));
   for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
   // cross-channel part: maxima and the tone detector need both channels' time signals
-  float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange
+  float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
   if (lane == 0) { xch[c * 2] = mx_new; xch[c * 2 + 1] = mx_tail; }
+  if (p.complexity >= 1 && p.info) {   // transient_analysis: lane 0 of each channel's warp walks its channel (f2 is free until the MDCT)
+    int um = 0;
+    if (lane == 0) um = transient_unmask_lane(ws->in, ws->f2, N + OB_OVERLAP);
+    if (lane == 0) ((int *)xch)[4 + c] = um;
+  }
   bsync();
   if (c == 0 && p.info) {
     float a = xch[0], t = xch[1];
@@ -192,12 +245,28 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
         fi.toneishness = 0.f;
       }
       fi.sample_max = sample_max;
-      fi.short_blocks = transient;
+      fi.tf_estimate = 0.f; fi.tf_chan = 0; fi.is_transient = transient; fi.pad = 0;
+      if (p.complexity >= 1) {   // the cross-channel tail of transient_analysis (celt/celt_encoder.c:437-461)
+        int mask_metric = ((int *)xch)[4];
+        if (C == 2 && ((int *)xch)[5] > mask_metric) { mask_metric = ((int *)xch)[5]; fi.tf_chan = 1; }
+        int is_tr = mask_metric > 200;
+        if (fi.toneishness > .98f && fi.tone_freq < 0.026f) { is_tr = 0; mask_metric = 0; }
+        const float tf_max = fmaxf(0.f, (float)sqrt((double)(27 * mask_metric)) - 42.f);
+        const double a = (double)((float)0.0069 * fminf(163.f, tf_max)) - 0.139;
+        fi.tf_estimate = (float)sqrt(a > 0 ? a : 0.0);
+        fi.is_transient = is_tr;
+      }
+      // short blocks need LM > 0 and 3 bits of room after the two header flags: always there unless the frame is silent
+      // (celt/celt_encoder.c:2060-2067; the frame coder re-checks with the real range-coder position)
+      const int silence = sample_max <= 1.f / (float)(1 << p.lsb_depth);
+      fi.short_blocks = fi.is_transient && LM > 0 && !silence;
       p.info[stream] = fi;
       st.overlap_max = t;
+      ((int *)xch)[6] = fi.short_blocks;
     }
   }
   bsync();   // the tone detector reads ws->in of both channels; the MDCT below overwrites it
+  if (p.info) transient = ((int *)xch)[6];
   float *freq = ws->in;
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
   wsync();

@@ -586,8 +586,8 @@ int opusb200_celt_analysis_process(OpusB200CeltAnalysis *a, const float *pcm, co
     p.pcm = (const float *)dp.p; p.short_blocks = short_blocks ? (const int32_t *)ds.p : nullptr;
     p.X = (float *)dX.p; p.bandE = (float *)dE.p; p.bandLogE = (float *)dL.p;
   }
-  p.info = nullptr;
-  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 16, c->stream>>>(p);
+  p.info = nullptr; p.complexity = 0; p.lsb_depth = 24;
+  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 32, c->stream>>>(p);
   c->launches++;
   OB_CUDA(cudaGetLastError());
   if (!on_device) {

@@ -8,6 +8,7 @@ from . import capi
 
 OPUS_SET_BITRATE_REQUEST, OPUS_SET_VBR_REQUEST, OPUS_SET_COMPLEXITY_REQUEST, OPUS_SET_LSB_DEPTH_REQUEST = 4002, 4006, 4010, 4036
 OPUS_SET_PHASE_INVERSION_DISABLED_REQUEST = 4046
+OPUS_SET_VBR_CONSTRAINT_REQUEST, OPUS_SET_PACKET_LOSS_PERC_REQUEST = 4020, 4014
 
 
 def _p(a):
@@ -15,7 +16,7 @@ def _p(a):
 
 
 class EncoderBatch:
-    def __init__(self, n_streams, channels=2, fs=48000, device=0, bitrate=None, complexity=0, lsb_depth=24):
+    def __init__(self, n_streams, channels=2, fs=48000, device=0, bitrate=None, complexity=4, lsb_depth=24, vbr=False, constrained_vbr=True):
         self._L = capi.lib()
         self.n_streams, self.channels = n_streams, channels
         h = ctypes.c_void_p()
@@ -27,6 +28,8 @@ class EncoderBatch:
         self.ctl(OPUS_SET_LSB_DEPTH_REQUEST, lsb_depth)
         if bitrate is not None:
             self.ctl(OPUS_SET_BITRATE_REQUEST, bitrate)
+        self.ctl(OPUS_SET_VBR_REQUEST, 1 if vbr else 0)
+        self.ctl(OPUS_SET_VBR_CONSTRAINT_REQUEST, 1 if constrained_vbr else 0)
 
     def ctl(self, request, value):
         r = self._L.opusb200_encoder_ctl_set(self._h, request, int(value))

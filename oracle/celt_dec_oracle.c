@@ -17,6 +17,8 @@
  * sample rates other than 48 kHz, QEXT/DRED extensions, soft clipping.
  */
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>

@@ -1,6 +1,8 @@
 // tests/emu/emu_ops.cpp — TEST INFRASTRUCTURE ONLY: the encoder-side op KERNEL SOURCES
 // (opus_b200/csrc/celt_ops.cuh) on the host SIMT emulator.
 #define OB_HOST_EMU 1
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <string.h>
 #include "../../opus_b200/csrc/celt_types.h"
@@ -191,8 +193,8 @@ static void enc_analysis_entry(void *a) {
 extern "C" int emu_enc_analysis_state_size(void) { return (int)sizeof(ObEncAnalysisState); }
 extern "C" void emu_celt_enc_analysis(void *state, const float *pcm, const int32_t *sb, float *X, float *E, float *Lg, int n, int C, int LM) {
   EncAnalysisParams p;
-  p.state = (ObEncAnalysisState *)state; p.pcm = pcm; p.short_blocks = sb; p.X = X; p.bandE = E; p.bandLogE = Lg; p.n_streams = n; p.C = C; p.LM = LM; p.info = g_enc_info;
-  emu_launch(enc_analysis_entry, &p, n, 32 * C, C * sizeof(MdctWS) + 16);
+  p.state = (ObEncAnalysisState *)state; p.pcm = pcm; p.short_blocks = sb; p.X = X; p.bandE = E; p.bandLogE = Lg; p.n_streams = n; p.C = C; p.LM = LM; p.info = g_enc_info; p.complexity = 0; p.lsb_depth = 24;
+  emu_launch(enc_analysis_entry, &p, n, 32 * C, C * sizeof(MdctWS) + 32);
 }
 
 // ---- frame encoder (analysis block + thread-per-stream coder) ----
@@ -212,18 +214,18 @@ extern "C" void emu_enc_state_init(ObEncState *st, int n) {
 }
 // one frame for n streams: an_state/enc_state carried by the caller
 extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const float *pcm, int n, int C, int LM, int max_bytes, int bitrate, int lsb_depth,
-                                unsigned char *packets, int32_t *nbytes, uint32_t *rng) {
+                                unsigned char *packets, int32_t *nbytes, uint32_t *rng, int complexity, int vbr, int cvbr) {
   const int N = OB_SHORT_N << LM;
   std::vector<float> X((size_t)n * C * N), E((size_t)n * C * OB_NBANDS), Lg((size_t)n * C * OB_NBANDS);
   std::vector<ObEncFrameInfo> info(n);
   EncAnalysisParams a;
   a.state = (ObEncAnalysisState *)an_state; a.pcm = pcm; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
-  a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM;
-  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 16);
+  a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
+  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32);
   EncFrameParams p;
   p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.packets = packets; p.nbytes = nbytes;
-  p.n_streams = n; p.C = C; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = 0; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
-  p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0;
+  p.n_streams = n; p.C = C; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = complexity; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
+  p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0; p.vbr = vbr; p.constrained_vbr = cvbr; p.loss_rate = 0;
   emu_launch(enc_frame_entry, &p, (n + 31) / 32, 32, 0);
   for (int s = 0; s < n; s++) rng[s] = enc_state[s].rng;
 }

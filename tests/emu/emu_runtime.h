@@ -34,6 +34,8 @@ struct EmuState {
   bool done[256];
   int cur, nthreads;
   int block, nblocks;
+  int bar_arrived;
+  unsigned bar_gen;
   uint64_t xchg[256];
   unsigned char *smem;
   size_t smem_bytes;
@@ -59,7 +61,18 @@ OB_DEV void emu_yield() {
   swapcontext(&e.lanes[me], &e.sched);
 }
 OB_DEV void wsync() { emu_yield(); }
-OB_DEV void bsync() { emu_yield(); }
+// block barrier: a real arrival counter (warps may run a different number of yields between two barriers)
+OB_DEV void bsync() {
+  EmuState &e = emu();
+  const unsigned gen = e.bar_gen;
+  if (++e.bar_arrived == e.nthreads) {
+    e.bar_arrived = 0;
+    e.bar_gen++;
+  } else {
+    while (e.bar_gen == gen) emu_yield();
+  }
+  emu_yield();
+}
 
 template <class T> OB_DEV T shfl(T v, int src) {
   EmuState &e = emu();
@@ -120,6 +133,8 @@ inline void emu_launch(void (*fn)(void *), void *arg, int nblocks, int nthreads,
   const size_t STK = 1 << 20;
   std::vector<unsigned char> stacks((size_t)nthreads * STK);
   e.nthreads = nthreads;
+  e.bar_arrived = 0;
+  e.bar_gen = 0;
   std::vector<unsigned char> smem(smem_bytes + 64);
   EmuLaunch l = {fn, arg};
   e.nblocks = nblocks;

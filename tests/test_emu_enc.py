@@ -13,14 +13,16 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24):
+def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1):
     """x [nframes, fs*ch] float -> list of (packet bytes, range)"""
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
     O.orc_encoder_final_range.restype = ctypes.c_uint32
     st = np.zeros(O.orc_encoder_size(), np.uint8)
     O.orc_encoder_init(_p(st), ch)
-    O.orc_encoder_ctl(_p(st), 0, bitrate, 0, lsb)
+    O.orc_encoder_ctl(_p(st), complexity, bitrate, vbr, lsb)
+    O.orc_encoder_set_cvbr.restype = None
+    O.orc_encoder_set_cvbr(_p(st), cvbr)
     out = []
     for f in range(len(x)):
         b = np.zeros(1275, np.uint8)
@@ -29,15 +31,28 @@ def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24):
     return out
 
 
-@pytest.mark.parametrize('ch,fs,nbytes', [(2, 960, 160), (1, 960, 80), (2, 480, 60), (2, 240, 40), (1, 120, 20), (2, 960, 40)])
-def test_emu_encoder_matches_oracle(ch, fs, nbytes):
+def clicks(seed, n, ch):
+    rng = np.random.default_rng(seed)
+    x = util.sig_music(seed, n, ch).astype(np.float64).reshape(n, ch)
+    w = min(300, n // 4)
+    for pos in rng.integers(w, n - 2 * w, size=max(2, n // 2500)):
+        x[pos:pos + w] += 12000 * np.exp(-np.arange(w) / 40.0)[:, None] * rng.standard_normal((w, ch))
+    return np.clip(x, -32768, 32767).reshape(-1)
+
+
+@pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr,cvbr', [
+    (2, 960, 160, 0, 0, 1), (1, 960, 80, 0, 0, 1), (2, 480, 60, 0, 0, 1), (2, 240, 40, 0, 0, 1), (1, 120, 20, 0, 0, 1), (2, 960, 40, 0, 0, 1),
+    (2, 960, 160, 1, 0, 1), (2, 960, 160, 2, 0, 1), (2, 960, 200, 3, 0, 1), (2, 960, 160, 4, 0, 1), (1, 480, 80, 4, 0, 1), (2, 240, 50, 3, 0, 1),
+    (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1)])
+def test_emu_encoder_matches_oracle(ch, fs, nbytes, complexity, vbr, cvbr):
     E, O = emu_util.load_emu_ops(), util.load_oracle()
     n, nf = 5, 4
     LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs]
-    sigs = [util.sig_music, util.sig_white, util.sig_tonal_noise]
+    sigs = [util.sig_music, util.sig_white, clicks]
+    bitrate = 64000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
     x = np.stack([sigs[s % 3](77 + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
     x[4, 2] = 0          # one silent frame in the middle of a stream
-    want = [oracle_encode(O, x[s], ch, fs, nbytes) for s in range(n)]
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, cvbr=cvbr) for s in range(n)]
     an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
     es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
     E.emu_enc_state_init(_p(es), n)
@@ -46,7 +61,7 @@ def test_emu_encoder_matches_oracle(ch, fs, nbytes):
         pk = np.zeros((n, nbytes), np.uint8)
         nb = np.zeros(n, np.int32)
         rng = np.zeros(n, np.uint32)
-        E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, -1, 24, _p(pk), _p(nb), _p(rng))
+        E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rng), complexity, vbr, cvbr)
         for s in range(n):
             wn, wb, wr = want[s][f]
             assert nb[s] == wn, (f, s, nb[s], wn)

@@ -206,20 +206,21 @@ def main():
     pcm = torch.from_numpy(np.tile(xb, ((n + base - 1) // base, 1))[:n].copy()).to(dev)
     pk = torch.empty((n, 160), dtype=torch.uint8, device=dev)
     nbd = torch.empty(n, dtype=torch.int32, device=dev)
-    enc = opus_b200.EncoderBatch(n, channels=2)
-    estream = torch.cuda.ExternalStream(enc.cuda_stream)
-    fn = lambda: L.opusb200_encode_device(enc._h, dptr(pcm), 960, dptr(pk), 160, 160, dptr(nbd))
-    ms = time_gpu(estream, fn, a.reps)
-    cpu = None
-    if R is not None:
-        rs = np.zeros(R.refh_celt_encoder_size(2) + 64, np.uint8)
-        vp = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
-        R.refh_celt_encoder_init(vp(rs), 2, 0, -1000, 0, 24)
-        o1 = np.zeros(1275, np.uint8)
-        rr = ctypes.c_uint32(0)
-        cpu = time_cpu(lambda: R.refh_celt_encode(vp(rs), vp(xb[0]), 960, vp(o1), 160, ctypes.byref(rr)), 1.0)
-    emit('celt_encode_c0_cbr64k_stereo_20ms', 'frames', n, ms, 1920 * 4 + 160, cpu, 'whole encoder: ob_celt_enc_analysis + ob_celt_enc_frame')
-    enc.close()
+    for cx in (0, 4):
+        enc = opus_b200.EncoderBatch(n, channels=2, complexity=cx)
+        estream = torch.cuda.ExternalStream(enc.cuda_stream)
+        fn = lambda: L.opusb200_encode_device(enc._h, dptr(pcm), 960, dptr(pk), 160, 160, dptr(nbd))
+        ms = time_gpu(estream, fn, a.reps)
+        cpu = None
+        if R is not None:
+            rs = np.zeros(R.refh_celt_encoder_size(2) + 64, np.uint8)
+            vp = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+            R.refh_celt_encoder_init(vp(rs), 2, cx, -1000, 0, 24)
+            o1 = np.zeros(1275, np.uint8)
+            rr = ctypes.c_uint32(0)
+            cpu = time_cpu(lambda: R.refh_celt_encode(vp(rs), vp(xb[0]), 960, vp(o1), 160, ctypes.byref(rr)), 1.0)
+        emit('celt_encode_c%d_cbr64k_stereo_20ms' % cx, 'frames', n, ms, 1920 * 4 + 160, cpu, 'whole encoder: ob_celt_enc_analysis + ob_celt_enc_frame')
+        enc.close()
 
     # ---- CELT encoder front end, 48 kHz stereo 20 ms: pre-emphasis -> MDCT -> band energies -> normalised bands (fused) ----
     base = 64
