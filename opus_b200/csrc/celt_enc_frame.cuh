@@ -1122,8 +1122,6 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
 #pragma unroll 1
   for (int i = 0; i < C * OB_NBANDS; i++) bandLogE[i] = p.bandLogE[(size_t)stream * C * OB_NBANDS + i];
 
-  int fine_dummy = 0;
-  (void)fine_dummy;
   int importance[OB_NBANDS], spread_weight[OB_NBANDS];
   int nbCompressedBytes = OB_IMIN(p.max_bytes, 1275), nbAvailableBytes, effectiveBytes;
   int32_t vbr_rate = 0;
