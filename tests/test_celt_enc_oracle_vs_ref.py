@@ -94,3 +94,38 @@ def test_vbr(complexity, cvbr, ch, fs, bitrate):
             assert ra == rb
             sizes.append(na)
         assert len(set(sizes)) > 2     # really variable
+
+
+def _harmonic_signal(seed, n, ch):
+    """voiced-speech-like: a drifting pitch with many harmonics plus a little noise, so that the pitch pre-filter switches on"""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    f0 = 110 + 60 * np.sin(2 * np.pi * t / 48000 * 0.7 + rng.uniform(0, 6))
+    ph = 2 * np.pi * np.cumsum(f0) / 48000
+    x = np.zeros(n)
+    for h in range(1, 25):
+        x += np.sin(h * ph + rng.uniform(0, 6)) / h
+    x = 6000 * x + 150 * rng.standard_normal(n)
+    if ch == 2:
+        x = np.stack([x, 0.7 * np.roll(x, 13) + 100 * rng.standard_normal(n)], axis=1)
+    return np.clip(x, -32768, 32767).reshape(-1)
+
+
+@pytest.mark.parametrize('complexity', [5, 6, 7])
+@pytest.mark.parametrize('ch,fs,nbytes,vbr', [(2, 960, 160, 0), (1, 960, 80, 0), (2, 480, 100, 0), (2, 240, 60, 0), (1, 120, 30, 0), (2, 960, 60, 0),
+                                              (2, 960, 1275, 1), (1, 480, 1275, 1)])
+def test_complexity_5_to_7(complexity, ch, fs, nbytes, vbr):
+    pf_frames = 0
+    for sname in ('harmonic', 'music', 'clicks'):
+        n = fs * 16
+        sig = _harmonic_signal(complexity + fs, n, ch) if sname == 'harmonic' else util.sig_music(complexity + ch + fs, n, ch) if sname == 'music' \
+            else _transient_signal(complexity * 7 + fs + nbytes, n, ch)
+        for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity, bitrate=(48000 * ch if vbr else -1000), vbr=vbr, nframes=16):
+            assert nbo != -5, 'frame needed a decision that is not restated'
+            assert na == nbo, (sname, f, na, nbo)
+            assert np.array_equal(a, b), (sname, f, int(np.argmax(a != b)))
+            assert ra == rb
+            if sname == 'harmonic' and len(a) > 1 and (a[0] & 0x40):
+                pf_frames += 1      # second header bit set: post-filter on (after a 0 silence flag)
+    if fs >= 480 and nbytes >= 80:
+        assert pf_frames > 0
