@@ -16,20 +16,13 @@
 
 namespace ob {
 
-struct ObEncState {   // CELTEncoder fields that survive a frame (celt/celt_encoder.c:92-140)
-  uint32_t rng;
-  int32_t spread_decision, tonal_average, lastCodedBands, hf_average, tapset_decision, prefilter_period, prefilter_tapset,
-      consec_transient, intensity;
-  float delayedIntra, prefilter_gain, stereo_saving, spec_avg;
-  int32_t vbr_reservoir, vbr_drift, vbr_offset, vbr_count;
-  float oldBandE[2 * OB_NBANDS], oldLogE[2 * OB_NBANDS], oldLogE2[2 * OB_NBANDS], energyError[2 * OB_NBANDS];
-};
 struct EncFrameParams {
   ObEncState *state;            // [n]
   const ObEncFrameInfo *info;   // [n]
   float *X;                     // [n][C*N] normalised MDCT (scratch: the band transforms work in place)
   const float *bandE;           // [n][C*21]
   const float *bandLogE;        // [n][C*21]
+  const float *bandLogE2;       // [n][C*21] valid where info.patched (else the same as bandLogE)
   unsigned char *packets;       // [n][pkt_stride]
   int32_t *nbytes;              // [n] bytes produced, or a negative error
   int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf, vbr, constrained_vbr,
@@ -222,7 +215,7 @@ OB_DEV float enc_median3(const float *x) {
 
 // ---- dynalloc_analysis (celt/celt_encoder.c:1049-1274; no lfe / surround, analysis invalid, CBR) ----
 struct EncDyn { float maxDepth; int32_t tot_boost; };
-OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *oldBandE, int C, int *offsets, int lsb_depth, int isTransient, int LM,
+OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *bandLogE2, const float *oldBandE, int C, int *offsets, int lsb_depth, int isTransient, int LM,
                              int effectiveBytes, float tone_freq, float toneishness, int vbr, int constrained_vbr, int *importance,
                              int *spread_weight) {
   const int end = OB_NBANDS;
@@ -270,9 +263,9 @@ OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *oldBandE, int C
   for (int c = 0; c < C; c++) {
     float *f = &follower[c * OB_NBANDS];
 #pragma unroll 1
-    for (int i = 0; i < end; i++) bandLogE3[i] = bandLogE[c * OB_NBANDS + i];
+    for (int i = 0; i < end; i++) bandLogE3[i] = bandLogE2[c * OB_NBANDS + i];
     if (LM == 0)
-      for (int i = 0; i < 8; i++) bandLogE3[i] = enc_fmax(bandLogE[c * OB_NBANDS + i], oldBandE[c * OB_NBANDS + i]);
+      for (int i = 0; i < 8; i++) bandLogE3[i] = enc_fmax(bandLogE2[c * OB_NBANDS + i], oldBandE[c * OB_NBANDS + i]);
     f[0] = bandLogE3[0];
 #pragma unroll 1
     for (int i = 1; i < end; i++) {
@@ -1121,31 +1114,22 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   float bx[176], by[176], tmp[176];
 #pragma unroll 1
   for (int i = 0; i < C * OB_NBANDS; i++) bandLogE[i] = p.bandLogE[(size_t)stream * C * OB_NBANDS + i];
+  float bl2[2 * OB_NBANDS];
+  if (fi.patched && p.bandLogE2)
+#pragma unroll 1
+    for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] = p.bandLogE2[(size_t)stream * C * OB_NBANDS + i];
 
   int importance[OB_NBANDS], spread_weight[OB_NBANDS];
-  int nbCompressedBytes = OB_IMIN(p.max_bytes, 1275), nbAvailableBytes, effectiveBytes;
-  int32_t vbr_rate = 0;
-  if (p.vbr && p.bitrate != -1) {
-    vbr_rate = (p.bitrate * 6 / (6 * 48000 / N)) << OB_BITRES;   // bitrate_to_bits (celt/celt.h:151)
-    effectiveBytes = vbr_rate >> (3 + OB_BITRES);
-  } else {
-    if (p.bitrate != -1) nbCompressedBytes = OB_IMAX(2, OB_IMIN(nbCompressedBytes, (p.bitrate * N + 4 * 48000) / (8 * 48000)));
-    effectiveBytes = nbCompressedBytes;
-  }
-  nbAvailableBytes = nbCompressedBytes;
-  int32_t equiv_rate = ((int32_t)nbCompressedBytes * 8 * 50 << (3 - LM)) - (40 * C + 20) * ((400 >> LM) - 50);
+  const EncBudget bud = enc_budget(p.max_bytes, p.bitrate, p.vbr, p.constrained_vbr, N, st.vbr_reservoir);
+  int nbCompressedBytes = bud.nbCompressedBytes, nbAvailableBytes = bud.nbAvailableBytes, effectiveBytes = bud.effectiveBytes;
+  const int32_t vbr_rate = bud.vbr_rate;
+  int32_t equiv_rate = ((int32_t)OB_IMIN(p.max_bytes, 1275) * 8 * 50 << (3 - LM)) - (40 * C + 20) * ((400 >> LM) - 50);
+  if (!(p.vbr && p.bitrate != -1) && p.bitrate != -1)
+    equiv_rate = ((int32_t)OB_IMAX(2, OB_IMIN(OB_IMIN(p.max_bytes, 1275), (p.bitrate * N + 4 * 48000) / (8 * 48000))) * 8 * 50 << (3 - LM)) - (40 * C + 20) * ((400 >> LM) - 50);
   if (p.bitrate != -1) equiv_rate = OB_IMIN(equiv_rate, p.bitrate - (40 * C + 20) * ((400 >> LM) - 50));
   RangeEnc enc;
   re_init(enc, p.packets + (size_t)stream * p.pkt_stride, nbCompressedBytes);
   int32_t tell = 1;
-  if (vbr_rate > 0 && p.constrained_vbr) {   // :1939-1959 (nothing has been written at the end of the buffer yet: shrinking = a new size)
-    const int32_t max_allowed = OB_IMIN(OB_IMAX(2, (vbr_rate + vbr_rate - st.vbr_reservoir) >> (OB_BITRES + 3)), nbAvailableBytes);
-    if (max_allowed < nbAvailableBytes) {
-      nbCompressedBytes = max_allowed;
-      nbAvailableBytes = max_allowed;
-      enc.storage = nbCompressedBytes;
-    }
-  }
   int32_t total_bits = nbCompressedBytes * 8;
   const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
   re_bit_logp(enc, silence, 15);
@@ -1159,17 +1143,25 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     tell = nbCompressedBytes * 8;
     enc.nbits_total += tell - re_tell(enc);
   }
-  int isTransient = fi.is_transient;
+  int isTransient = fi.is_transient && !fi.patched;   // the time-domain decision; a patched frame turns transient after the energies
   const float tf_estimate = fi.tf_estimate;
   const int tf_chan = fi.tf_chan;
-  const float toneishness = enc_fmin(fi.toneishness, 1.f - tf_estimate);
-  // run_prefilter with the pitch search off: no post-filter (the tone-driven path is reported as unsupported)
+  const float toneishness = fi.toneishness;   // already limited to 1 - tf_estimate by the analysis kernel
+  // the post-filter parameters chosen by run_prefilter in the analysis kernel (celt/celt_encoder.c:2040-2057)
   int status = 0;
-  const int pf_on = 0;
-  {
-    const int enabled = nbAvailableBytes > 12 * C && !silence && tell + 16 <= total_bits && !p.disable_pf;
-    if (enabled && toneishness > .99f) status = -5;
+  const int pf_on = fi.pf_on;
+  int pitch_index = fi.pitch_index;
+  if (pf_on == 0) {
     if (tell + 16 <= total_bits) re_bit_logp(enc, 0, 1);
+  } else {
+    re_bit_logp(enc, 1, 1);
+    pitch_index += 1;
+    const int octave = ilog32(pitch_index) - 5;
+    re_uint(enc, octave, 6);
+    re_bits(enc, pitch_index - (16 << octave), 4 + octave);
+    pitch_index -= 1;
+    re_bits(enc, fi.qg, 3);
+    re_icdf(enc, fi.pf_tapset, ob_tapset_icdf, 2);
   }
   int shortBlocks = 0, transient_got_disabled = 0;
   if (LM > 0 && re_tell(enc) + 3 <= total_bits) {
@@ -1178,15 +1170,21 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     isTransient = 0;
     transient_got_disabled = 1;
   }
+  if (fi.patched) {   // patch_transient_decision fired in the analysis kernel (needs the room for the transient flag, like the reference)
+    if (!transient_got_disabled && !isTransient) { isTransient = 1; shortBlocks = M; }
+    else status = -3;
+  }
   if ((shortBlocks != 0) != (fi.short_blocks != 0)) status = -3;   // the analysis kernel transformed with the other block size
   float temporal_vbr;
   { // temporal VBR statistics (:2213-2228) keep spec_avg current even in CBR
     float follow = -10.0f, frame_avg = 0.f;
-    const float offset = shortBlocks ? .5f * LM : 0.f;
+    // (computed on the energies of the first transform: for a patched frame those are the long-block ones, offset 0)
+    const float offset = (shortBlocks && !fi.patched) ? .5f * LM : 0.f;
+    const float *le = fi.patched ? bl2 : bandLogE;
 #pragma unroll 1
     for (int i = start; i < end; i++) {
-      follow = enc_fmax(follow - 1.0f, bandLogE[i] - offset);
-      if (C == 2) follow = enc_fmax(follow, bandLogE[i + OB_NBANDS] - offset);
+      follow = enc_fmax(follow - 1.0f, le[i] - offset);
+      if (C == 2) follow = enc_fmax(follow, le[i + OB_NBANDS] - offset);
       frame_avg += follow;
     }
     frame_avg /= (end - start);
@@ -1194,8 +1192,11 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     temporal_vbr = enc_fmin(3.f, enc_fmax(-1.5f, temporal_vbr));
     st.spec_avg += .02f * temporal_vbr;
   }
+  if (fi.patched)   // celt/celt_encoder.c:2243-2245: compensate the long-block energies for the block-size change
+#pragma unroll 1
+    for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] += .5f * LM;
   if (LM > 0 && re_tell(enc) + 3 <= total_bits) re_bit_logp(enc, isTransient, 3);
-  const EncDyn dyn = enc_dynalloc(bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
+  const EncDyn dyn = enc_dynalloc(bandLogE, fi.patched ? bl2 : bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
                                   p.constrained_vbr, importance, spread_weight);
   int tf_select = 0;
   if (effectiveBytes >= 15 * C && p.complexity >= 2 && toneishness < .98f) {   // enable_tf_analysis
@@ -1500,9 +1501,9 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   if (silence)
 #pragma unroll 1
     for (int i = 0; i < C * OB_NBANDS; i++) st.oldBandE[i] = -28.f;
-  st.prefilter_period = 15;
-  st.prefilter_gain = 0.f;
-  st.prefilter_tapset = st.tapset_decision;
+  st.prefilter_period = pitch_index;
+  st.prefilter_gain = fi.gain1;
+  st.prefilter_tapset = fi.pf_tapset;
   if (!isTransient) {
 #pragma unroll 1
     for (int i = 0; i < C * OB_NBANDS; i++) { st.oldLogE2[i] = st.oldLogE[i]; st.oldLogE[i] = st.oldBandE[i]; }

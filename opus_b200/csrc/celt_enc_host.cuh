@@ -27,7 +27,8 @@ struct OpusB200Encoder {
   ObEncState *state;
   ObEncAnalysisState *an_state;
   ObEncFrameInfo *info;
-  float *X, *bandE, *bandLogE;
+  float *X, *bandE, *bandLogE, *bandLogE2;
+  float *prefilter_mem;   // [n][C][1024]: the unfiltered history run_prefilter searches (CELTEncoder::prefilter_mem)
   int32_t *d_nbytes;
   // settings (celt_encoder_ctl)
   int complexity, bitrate, vbr, constrained_vbr, lsb_depth, force_intra, disable_inv, disable_pf, loss_rate;
@@ -42,6 +43,7 @@ extern "C" int opusb200_encoder_reset(OpusB200Encoder *e) {
   OB_CUDA(cudaSetDevice(e->device));
   OB_CUDA(cudaMemsetAsync(e->state, 0, sizeof(ObEncState) * (size_t)e->n, e->stream));
   OB_CUDA(cudaMemsetAsync(e->an_state, 0, sizeof(ObEncAnalysisState) * (size_t)e->n, e->stream));
+  OB_CUDA(cudaMemsetAsync(e->prefilter_mem, 0, sizeof(float) * (size_t)e->n * e->channels * kPfMaxPeriod, e->stream));
   ob_celt_enc_reset<<<(e->n + 127) / 128, 128, 0, e->stream>>>(e->state, e->an_state, e->n);
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;
@@ -60,7 +62,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   if (!e) return OPUSB200_ALLOC_FAIL;
   memset(e, 0, sizeof(*e));
   e->device = device; e->channels = channels; e->n = n_streams;
-  e->complexity = 4; e->bitrate = -1; e->vbr = 0; e->constrained_vbr = 1; e->lsb_depth = 24;   // celt_encoder_init defaults; complexity capped (see ctl)
+  e->complexity = 5; e->bitrate = -1; e->vbr = 0; e->constrained_vbr = 1; e->lsb_depth = 24;   // celt_encoder_init defaults
   OB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   const size_t n = (size_t)n_streams;
   OB_CUDA(cudaMalloc(&e->state, sizeof(ObEncState) * n));
@@ -69,8 +71,10 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->X, sizeof(float) * n * channels * OB_MAXN));
   OB_CUDA(cudaMalloc(&e->bandE, sizeof(float) * n * channels * OB_NBANDS));
   OB_CUDA(cudaMalloc(&e->bandLogE, sizeof(float) * n * channels * OB_NBANDS));
+  OB_CUDA(cudaMalloc(&e->bandLogE2, sizeof(float) * n * channels * OB_NBANDS));
+  OB_CUDA(cudaMalloc(&e->prefilter_mem, sizeof(float) * n * channels * kPfMaxPeriod));
   OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
-  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32 + (int)sizeof(PfWS)));
   const int r = opusb200_encoder_reset(e);
   if (r != OPUSB200_OK) return r;
   OB_CUDA(cudaStreamSynchronize(e->stream));
@@ -81,7 +85,7 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE);
+  cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
   cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -94,7 +98,7 @@ extern "C" int opusb200_encoder_ctl_set(OpusB200Encoder *e, int request, int32_t
     case 4006: e->vbr = value != 0; return OPUSB200_OK;                                                       // OPUS_SET_VBR
     case 4020: e->constrained_vbr = value != 0; return OPUSB200_OK;                                            // OPUS_SET_VBR_CONSTRAINT
     case 4014: if (value < 0 || value > 100) return OPUSB200_BAD_ARG; e->loss_rate = value; return OPUSB200_OK;   // OPUS_SET_PACKET_LOSS_PERC
-    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; if (value > 4) return OPUSB200_UNIMPLEMENTED; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY (0..4 on the device)
+    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; if (value > 7) return OPUSB200_UNIMPLEMENTED; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY (0..7 on the device)
     case 4036: if (value < 8 || value > 24) return OPUSB200_BAD_ARG; e->lsb_depth = value; return OPUSB200_OK;  // OPUS_SET_LSB_DEPTH
     case 4046: e->disable_inv = value != 0; return OPUSB200_OK;                                                // OPUS_SET_PHASE_INVERSION_DISABLED
     default: return OPUSB200_UNIMPLEMENTED;
@@ -117,9 +121,11 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   EncAnalysisParams a;
   a.state = e->an_state; a.pcm = d_pcm; a.short_blocks = nullptr; a.X = e->X; a.bandE = e->bandE; a.bandLogE = e->bandLogE; a.info = e->info;
   a.n_streams = e->n; a.C = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
-  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 32, e->stream>>>(a);
+  a.enc_state = e->state; a.prefilter_mem = e->prefilter_mem; a.bandLogE2 = e->bandLogE2; a.max_bytes = max_data_bytes; a.bitrate = e->bitrate;
+  a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate;
+  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + sizeof(PfWS), e->stream>>>(a);
   EncFrameParams p;
-  p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.packets = d_packets; p.nbytes = d_nbytes;
+  p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.bandLogE2 = e->bandLogE2; p.packets = d_packets; p.nbytes = d_nbytes;
   p.n_streams = e->n; p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf;
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;

@@ -13,6 +13,7 @@
 #pragma once
 #include "celt_fft.cuh"
 #include "celt_vec.cuh"
+#include "celt_enc_pre.cuh"
 
 namespace ob {
 
@@ -88,7 +89,13 @@ OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *s
 //      pre-filter is off.  The spectrum never leaves shared memory; HBM sees the PCM once and the normalised bands once. ----
 struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; float overlap_max; float pad; };
 // what the frame encoder needs from the time domain (celt_encode_with_ec :1963-1970, :2017)
-struct ObEncFrameInfo { float tone_freq, toneishness, sample_max, tf_estimate; int32_t short_blocks, is_transient, tf_chan, pad; };
+struct ObEncFrameInfo {
+  float tone_freq, toneishness, sample_max, tf_estimate;
+  int32_t short_blocks, is_transient, tf_chan, patched;   // patched: patch_transient_decision switched to short blocks (bandLogE2 differs)
+  int32_t pf_on, pitch_index, qg, pf_tapset;             // run_prefilter's decision
+  float gain1;
+  int32_t pad[3];
+};
 struct EncAnalysisParams {
   ObEncAnalysisState *state;   // [n_streams]
   const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
@@ -98,6 +105,11 @@ struct EncAnalysisParams {
   ObEncFrameInfo *info;        // [n_streams] or null
   int n_streams, C, LM;
   int complexity, lsb_depth;   // transient_analysis runs from complexity 1 (celt/celt_encoder.c:2020); lsb_depth defines silence
+  // pitch pre-filter / patch_transient_decision (complexity >= 5): they read the frame coder's state and the byte budget
+  const ObEncState *enc_state = nullptr; // [n_streams] or null (transform only)
+  float *prefilter_mem = nullptr;        // [n_streams][C][1024] unfiltered pre-emphasised history
+  float *bandLogE2 = nullptr;            // [n_streams][C*21]: the long-block log energies when the frame was patched to short blocks
+  int max_bytes = 0, bitrate = -1, vbr = 0, constrained_vbr = 0, disable_pf = 0, loss_rate = 0;
 };
 // tone_lpc (celt/celt_encoder.c:1305-1360) on x = in0 (+ in1): the six running sums are independent sequential chains,
 // one lane each (lanes 0-2: r00 r01 r02, lanes 3-5: the three edge corrections); lane 0 solves the 2x2 system.
@@ -199,7 +211,11 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
   const float coef0 = 0.85000610f;
   float mx_new = 0.f, mx_tail = 0.f;   // celt_maxabs over the fresh part and over the part overlapping the next frame
-  for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = st.overlap_mem[c][i];
+  const bool pf_path = p.enc_state != nullptr && p.info != nullptr;   // the frame-encoder configuration (celt_enc_host.cuh)
+  float *pmem = pf_path ? p.prefilter_mem + ((size_t)stream * C + c) * kPfMaxPeriod : nullptr;
+  // the analysis window starts with the UNFILTERED tail of the previous frame (celt/celt_encoder.c:2014); without a pre-filter
+  // history that is the same as the MDCT overlap memory
+  for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[kPfMaxPeriod - OB_OVERLAP + i] : st.overlap_mem[c][i];
   for (int i = lane; i < N; i += 32) {
     const float s = pcm[(size_t)C * i];
     const float x = f_mul(32768.f, s);
@@ -212,7 +228,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   mx_tail = warp_max(mx_tail);
   wsync();
   if (lane == 0) st.preemph_mem[c] = f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)]));
-  for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
+  if (!pf_path) for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
   // cross-channel part: maxima and the tone detector need both channels' time signals
   float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
   if (lane == 0) { xch[c * 2] = mx_new; xch[c * 2 + 1] = mx_tail; }
@@ -245,7 +261,8 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
         fi.toneishness = 0.f;
       }
       fi.sample_max = sample_max;
-      fi.tf_estimate = 0.f; fi.tf_chan = 0; fi.is_transient = transient; fi.pad = 0;
+      fi.tf_estimate = 0.f; fi.tf_chan = 0; fi.is_transient = transient; fi.patched = 0; fi.pf_on = 0; fi.pitch_index = 15; fi.qg = 0; fi.pf_tapset = 0; fi.gain1 = 0.f;
+      fi.pad[0] = fi.pad[1] = fi.pad[2] = 0;
       if (p.complexity >= 1) {   // the cross-channel tail of transient_analysis (celt/celt_encoder.c:437-461)
         int mask_metric = ((int *)xch)[4];
         if (C == 2 && ((int *)xch)[5] > mask_metric) { mask_metric = ((int *)xch)[5]; fi.tf_chan = 1; }
@@ -256,6 +273,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
         fi.tf_estimate = (float)sqrt(a > 0 ? a : 0.0);
         fi.is_transient = is_tr;
       }
+      fi.toneishness = fminf(fi.toneishness, 1.f - fi.tf_estimate);   // celt/celt_encoder.c:2026, before a patched frame resets tf_estimate
       // short blocks need LM > 0 and 3 bits of room after the two header flags: always there unless the frame is silent
       // (celt/celt_encoder.c:2060-2067; the frame coder re-checks with the real range-coder position)
       const int silence = sample_max <= 1.f / (float)(1 << p.lsb_depth);
@@ -268,8 +286,64 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   bsync();   // the tone detector reads ws->in of both channels; the MDCT below overwrites it
   if (p.info) transient = ((int *)xch)[6];
   float *freq = ws->in;
+  PfWS *pw = (PfWS *)((unsigned char *)smem + (size_t)C * sizeof(MdctWS) + 32);
+  if (pf_path) {   // run_prefilter (celt/celt_encoder.c:2029-2057): every thread of the CTA takes part
+    const ObEncState &es = p.enc_state[stream];
+    ObEncFrameInfo fi = p.info[stream];
+    const EncBudget bud = enc_budget(p.max_bytes, p.bitrate, p.vbr, p.constrained_vbr, N, es.vbr_reservoir);
+    const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
+    PfArgs a;
+    for (int cc = 0; cc < C; cc++) {
+      a.in[cc] = ((MdctWS *)smem + cc)->in;
+      a.prefilter_mem[cc] = p.prefilter_mem + ((size_t)stream * C + cc) * kPfMaxPeriod;
+      a.in_mem[cc] = st.overlap_mem[cc];
+    }
+    a.C = C; a.N = N; a.complexity = p.complexity; a.nbAvailableBytes = bud.nbAvailableBytes; a.prefilter_tapset = es.tapset_decision;
+    a.prev_period = es.prefilter_period; a.prev_tapset = es.prefilter_tapset; a.prev_gain = es.prefilter_gain; a.loss_rate = p.loss_rate;
+    a.tf_estimate = fi.tf_estimate; a.tone_freq = fi.tone_freq; a.toneishness = fminf(fi.toneishness, 1.f - fi.tf_estimate);
+    a.enabled = bud.nbAvailableBytes > 12 * C && !silence && bud.nbCompressedBytes * 8 >= 17 && !p.disable_pf;
+    const PfDecision d = enc_prefilter_stage(pw, a);
+    if (c == 0 && lane == 0) {
+      fi.pf_on = d.pf_on; fi.pitch_index = d.pitch_index; fi.qg = d.qg; fi.pf_tapset = d.tapset; fi.gain1 = d.gain1; fi.patched = 0;
+      p.info[stream] = fi;
+    }
+    freq = pw->pre[c];   // keep the time signal: patch_transient_decision may ask for a second transform
+    bsync();
+  }
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
   wsync();
+  if (pf_path && p.complexity >= 5 && LM > 0 && !transient) {
+    // patch_transient_decision (celt/celt_encoder.c:2238-2257) needs both channels' log energies: first pass of the band sums
+    float E0 = 0.f;
+    if (lane < OB_NBANDS) {
+      float sum = 0.f;
+      const int j0 = M * ob_ebands[lane], j1 = M * ob_ebands[lane + 1];
+#pragma unroll 4
+      for (int j = j0; j < j1; j++) sum = f_add(sum, f_mul(freq[j], freq[j]));
+      E0 = f_sqrt(f_add(1e-27f, sum));
+      pw->xlp[c * OB_NBANDS + lane] = f_add((float)(1.442695040888963387 * log((double)E0)), -ob_emeans[lane]);
+    }
+    bsync();
+    if (c == 0 && lane == 0) {
+      const ObEncFrameInfo fi = p.info[stream];
+      const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
+      int patch = 0;
+      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->xlp, p.enc_state[stream].oldBandE, C);
+      ((int *)xch)[6] = patch;
+    }
+    bsync();
+    if (((int *)xch)[6]) {
+      if (lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = pw->xlp[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
+      if (c == 0 && lane == 0) {
+        ObEncFrameInfo fi = p.info[stream];
+        fi.is_transient = 1; fi.short_blocks = 1; fi.patched = 1; fi.tf_estimate = .2f;
+        p.info[stream] = fi;
+      }
+      transient = 1;
+      mdct_forward_from_ws(ws, LM, 1, freq, lane);
+      wsync();
+    }
+  }
   // band energies: one lane per band, summed in index order like celt_inner_prod_c
   float E = 0.f, g = 0.f;
   if (lane < OB_NBANDS) {

@@ -16,7 +16,7 @@ def _p(a):
 
 
 class EncoderBatch:
-    def __init__(self, n_streams, channels=2, fs=48000, device=0, bitrate=None, complexity=4, lsb_depth=24, vbr=False, constrained_vbr=True):
+    def __init__(self, n_streams, channels=2, fs=48000, device=0, bitrate=None, complexity=5, lsb_depth=24, vbr=False, constrained_vbr=True):
         self._L = capi.lib()
         self.n_streams, self.channels = n_streams, channels
         h = ctypes.c_void_p()

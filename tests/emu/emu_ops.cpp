@@ -212,20 +212,25 @@ extern "C" void emu_enc_state_init(ObEncState *st, int n) {
     st[s].delayedIntra = 1.f; st[s].spread_decision = 2; st[s].tonal_average = 256;
   }
 }
+static int32_t g_enc_cov[3];   // frames that took the post-filter / patched-transient / transient paths (test coverage counters)
 // one frame for n streams: an_state/enc_state carried by the caller
 extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const float *pcm, int n, int C, int LM, int max_bytes, int bitrate, int lsb_depth,
-                                unsigned char *packets, int32_t *nbytes, uint32_t *rng, int complexity, int vbr, int cvbr) {
+                                unsigned char *packets, int32_t *nbytes, uint32_t *rng, int complexity, int vbr, int cvbr, float *prefilter_mem) {
   const int N = OB_SHORT_N << LM;
-  std::vector<float> X((size_t)n * C * N), E((size_t)n * C * OB_NBANDS), Lg((size_t)n * C * OB_NBANDS);
+  std::vector<float> X((size_t)n * C * N), E((size_t)n * C * OB_NBANDS), Lg((size_t)n * C * OB_NBANDS), Lg2((size_t)n * C * OB_NBANDS);
   std::vector<ObEncFrameInfo> info(n);
   EncAnalysisParams a;
   a.state = (ObEncAnalysisState *)an_state; a.pcm = pcm; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
   a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
-  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32);
+  a.enc_state = enc_state; a.prefilter_mem = prefilter_mem; a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = bitrate; a.vbr = vbr;
+  a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0;
+  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32 + sizeof(PfWS));
   EncFrameParams p;
-  p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.packets = packets; p.nbytes = nbytes;
+  p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.bandLogE2 = Lg2.data(); p.packets = packets; p.nbytes = nbytes;
   p.n_streams = n; p.C = C; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = complexity; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
   p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0; p.vbr = vbr; p.constrained_vbr = cvbr; p.loss_rate = 0;
   emu_launch(enc_frame_entry, &p, (n + 31) / 32, 32, 0);
   for (int s = 0; s < n; s++) rng[s] = enc_state[s].rng;
+  for (int s = 0; s < n; s++) { g_enc_cov[0] += info[s].pf_on; g_enc_cov[1] += info[s].patched; g_enc_cov[2] += info[s].is_transient; }
 }
+extern "C" void emu_enc_coverage(int32_t *out, int reset) { for (int i = 0; i < 3; i++) { out[i] = g_enc_cov[i]; if (reset) g_enc_cov[i] = 0; } }

@@ -43,27 +43,36 @@ def clicks(seed, n, ch):
 @pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr,cvbr', [
     (2, 960, 160, 0, 0, 1), (1, 960, 80, 0, 0, 1), (2, 480, 60, 0, 0, 1), (2, 240, 40, 0, 0, 1), (1, 120, 20, 0, 0, 1), (2, 960, 40, 0, 0, 1),
     (2, 960, 160, 1, 0, 1), (2, 960, 160, 2, 0, 1), (2, 960, 200, 3, 0, 1), (2, 960, 160, 4, 0, 1), (1, 480, 80, 4, 0, 1), (2, 240, 50, 3, 0, 1),
-    (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1)])
+    (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1),
+    (2, 960, 160, 5, 0, 1), (1, 960, 80, 5, 0, 1), (2, 480, 100, 6, 0, 1), (2, 240, 60, 7, 0, 1), (1, 120, 30, 5, 0, 1), (2, 960, 1275, 5, 1, 1),
+    (1, 480, 1275, 7, 1, 0)])
 def test_emu_encoder_matches_oracle(ch, fs, nbytes, complexity, vbr, cvbr):
     E, O = emu_util.load_emu_ops(), util.load_oracle()
-    n, nf = 5, 4
+    n, nf = (5, 4) if complexity < 5 else (6, 5)
     LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs]
-    sigs = [util.sig_music, util.sig_white, clicks]
+    sigs = [util.sig_music, util.sig_white, clicks] if complexity < 5 else [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
     bitrate = 64000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
-    x = np.stack([sigs[s % 3](77 + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    x = np.stack([sigs[s % len(sigs)](77 + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
     x[4, 2] = 0          # one silent frame in the middle of a stream
     want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, cvbr=cvbr) for s in range(n)]
     an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
     es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
     E.emu_enc_state_init(_p(es), n)
+    pmem = np.zeros((n, ch, 1024), np.float32)
+    cov = np.zeros(3, np.int32)
+    E.emu_enc_coverage(_p(cov), 1)
     for f in range(nf):
         pcm = np.ascontiguousarray(x[:, f])
         pk = np.zeros((n, nbytes), np.uint8)
         nb = np.zeros(n, np.int32)
         rng = np.zeros(n, np.uint32)
-        E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rng), complexity, vbr, cvbr)
+        E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rng), complexity, vbr, cvbr, _p(pmem))
         for s in range(n):
             wn, wb, wr = want[s][f]
             assert nb[s] == wn, (f, s, nb[s], wn)
             assert np.array_equal(pk[s, :wn], wb), (f, s, int(np.argmax(pk[s, :wn] != wb)))
             assert rng[s] == wr
+    E.emu_enc_coverage(_p(cov), 1)
+    print('coverage pf_on/patched/transient', cov)
+    if complexity >= 5 and fs >= 480:
+        assert cov[0] > 0      # the pitch pre-filter switched on somewhere

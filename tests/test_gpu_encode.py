@@ -1,5 +1,5 @@
 """Parity of the CUDA CELT encoder (through the C ABI) with the pinned encoder oracle, and encoder -> decoder round trips.
-Bar: packet bytes and final range identical to the oracle (hence to the reference's celt_encode_with_ec at complexity 0, CBR)."""
+Bar: packet bytes and final range identical to the oracle (hence to the reference's celt_encode_with_ec at complexity 0-7, CBR / VBR / CVBR)."""
 import ctypes
 
 import numpy as np
@@ -14,14 +14,16 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr,cvbr', [
     (2, 960, 160, 0, 0, 1), (2, 960, 320, 0, 0, 1), (1, 960, 80, 0, 0, 1), (2, 480, 80, 0, 0, 1), (2, 240, 40, 0, 0, 1), (1, 120, 20, 0, 0, 1),
     (2, 960, 30, 0, 0, 1), (2, 960, 160, 1, 0, 1), (2, 960, 160, 2, 0, 1), (2, 960, 200, 3, 0, 1), (2, 960, 160, 4, 0, 1), (1, 480, 80, 4, 0, 1),
-    (2, 240, 50, 3, 0, 1), (2, 120, 30, 4, 0, 1), (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1)])
+    (2, 240, 50, 3, 0, 1), (2, 120, 30, 4, 0, 1), (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1),
+    (2, 960, 160, 5, 0, 1), (1, 960, 80, 5, 0, 1), (2, 480, 100, 6, 0, 1), (2, 240, 60, 7, 0, 1), (1, 120, 30, 5, 0, 1), (2, 960, 60, 7, 0, 1),
+    (2, 960, 1275, 5, 1, 1), (1, 480, 1275, 7, 1, 0), (2, 960, 1275, 6, 1, 0)])
 def test_encoder_matches_oracle(ch, fs, nbytes, complexity, vbr, cvbr):
     import opus_b200
     O = util.load_oracle()
     n, nf, base = 257, 6, 12
-    sigs = [util.sig_music, util.sig_white, clicks]
+    sigs = [util.sig_music, util.sig_white, clicks] if complexity < 5 else [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
     bitrate = 64000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
-    xb = np.stack([sigs[s % 3](500 + s + fs + nbytes, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(base)])
+    xb = np.stack([sigs[s % len(sigs)](500 + s + fs + nbytes, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(base)])
     xb[3, 2] = 0
     x = np.tile(xb, (n // base + 1, 1, 1))[:n]
     want = [oracle_encode(O, xb[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, cvbr=cvbr) for s in range(base)]
@@ -42,9 +44,9 @@ def test_encode_decode_round_trip():
     """packets from the device encoder decode on the device decoder: same final range on both sides, sane SNR"""
     import opus_b200
     ch, fs, nbytes, n, nf = 2, 960, 200, 300, 8
-    x = np.stack([util.sig_music(40 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(16)])
+    x = np.stack([(util.sig_harmonic if s & 1 else util.sig_music)(40 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(16)])
     x = np.tile(x, (n // 16 + 1, 1, 1))[:n]
-    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=4)
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=5)
     dec = opus_b200.DecoderBatch(n, channels=ch)
     toc = 0xFC | 0x04   # CELT-only fullband 20 ms, stereo, one frame (RFC 6716 section 3.1: config 31, s=1, c=0)
     outs = []
@@ -72,7 +74,7 @@ def test_ctl_errors():
     from opus_b200 import encoder as E
     enc = opus_b200.EncoderBatch(4, channels=2)
     with pytest.raises(opus_b200.OpusB200Error):
-        enc.ctl(E.OPUS_SET_COMPLEXITY_REQUEST, 5)     # pitch pre-filter not on the device yet -> OPUS_UNIMPLEMENTED
+        enc.ctl(E.OPUS_SET_COMPLEXITY_REQUEST, 8)     # second MDCT / theta RDO are not on the device -> OPUS_UNIMPLEMENTED
     with pytest.raises(opus_b200.OpusB200Error):
         enc.ctl(E.OPUS_SET_BITRATE_REQUEST, 10)
     enc.close()

@@ -282,3 +282,27 @@ class Layer:
 
     def ptr(self, arr):
         return arr.ctypes.data_as(ctypes.c_void_p) if arr is not None else None
+
+
+def sig_harmonic(seed, n, ch):
+    """voiced-speech-like: a drifting pitch with many harmonics plus a little noise, so that the pitch pre-filter switches on"""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    f0 = 110 + 60 * np.sin(2 * np.pi * t / 48000 * 0.7 + rng.uniform(0, 6))
+    ph = 2 * np.pi * np.cumsum(f0) / 48000
+    x = np.zeros(n)
+    for h in range(1, 25):
+        x += np.sin(h * ph + rng.uniform(0, 6)) / h
+    x = 6000 * x + 150 * rng.standard_normal(n)
+    if ch == 2:
+        x = np.stack([x, 0.7 * np.roll(x, 13) + 100 * rng.standard_normal(n)], axis=1)
+    return np.clip(x, -32768, 32767).reshape(-1)
+
+
+def sig_swell(seed, n, ch, period=2900, rise=700):
+    """noise bursts with a soft attack: too slow for transient_analysis, fast enough for patch_transient_decision now and then"""
+    rng = np.random.default_rng(seed)
+    ph = (np.arange(n) + rng.integers(0, period)) % period
+    g = np.where(ph < rise, 0.02 + 0.98 * (ph / rise) ** 2, np.maximum(0.02, 1 - (ph - rise) / (period - rise) * 1.2))
+    x = 5000 * g[:, None] * rng.standard_normal((n, ch))
+    return np.clip(x, -32768, 32767).reshape(-1)
