@@ -123,7 +123,9 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   a.n_streams = e->n; a.C = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
   a.enc_state = e->state; a.prefilter_mem = e->prefilter_mem; a.bandLogE2 = e->bandLogE2; a.max_bytes = max_data_bytes; a.bitrate = e->bitrate;
   a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate;
-  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + sizeof(PfWS), e->stream>>>(a);
+  // the pitch-search buffers exist from complexity 5 only (PfWS: sc always, buf/xlp2 for the search)
+  const size_t pf_smem = e->complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64;
+  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
   EncFrameParams p;
   p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.bandLogE2 = e->bandLogE2; p.packets = d_packets; p.nbytes = d_nbytes;
   p.n_streams = e->n; p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;

@@ -46,85 +46,130 @@ OB_DEV EncBudget enc_budget(int max_bytes, int bitrate, int vbr, int constrained
 }
 
 constexpr int kPfMaxPeriod = 1024, kPfMinPeriod = 15;
+// Shared-memory scratch of the pre-filter stage.  Only `sc` exists below complexity 5 (the host sizes the allocation);
+// the search buffers double as the spectra once the stage is over (buf + xlp2 are contiguous: 2000 floats >= 2 x 960).
 struct PfWS {
-  float pre[2][kPfMaxPeriod + OB_MAXN];   // [history | frame] per channel; reused for the spectra afterwards
-  float xlp[(kPfMaxPeriod + OB_MAXN) / 2];
-  float xlp2[(kPfMaxPeriod + OB_MAXN) / 2];
-  float xcorr[kPfMaxPeriod / 2];
-  float yy[kPfMaxPeriod / 2 + 4];
-  float sc[64];                           // scalars handed between phases
+  float sc[64];       // scalars handed between phases
+  float buf[1008];    // xlp (992) -> after the whitening filter: xcorr [0,512) + Syy track [512,1001) -> yy_lookup [0,513)
+  float xlp2[992];    // the whitened, 2:1 decimated search signal
 };
+// The unfiltered history is a ring of 1024 samples per channel in HBM (CELTEncoder::prefilter_mem without the memmove):
+// sample j of the reference's pre[] = [history | frame] buffer is ring[(head + j) & 1023] for j < 1024, else frame[j - 1024].
+struct PfSig { const float *ring; const float *frame; int head; };
+OB_DEV float pf_at(const PfSig &p, int j) { return j < kPfMaxPeriod ? p.ring[(p.head + j) & (kPfMaxPeriod - 1)] : p.frame[j - kPfMaxPeriod]; }
 struct PfDecision { int pf_on, pitch_index, qg, tapset; float gain1; };
 
-OB_DEV float pf_dot(const float *x, const float *y, int n) {
+OB_DEV float pf_dot(const float *x, const float *y, int n) {   // index order; unrolled so the loads run ahead of the serial sum
   float s = 0.f;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < n; i++) s = s + x[i] * y[i];
   return s;
 }
-// find_best_pitch (celt/pitch.c:45-103), one thread
-OB_DEVNI void pf_find_best_pitch(const float *xcorr, const float *y, int ystride, int len, int max_pitch, int *best_pitch) {
-  float Syy = 1.f, bn0 = -1.f, bn1 = -1.f, bd0 = 0.f, bd1 = 0.f;
-  int bp0 = 0, bp1 = 1;
-#pragma unroll 1
-  for (int j = 0; j < len; j++) Syy = Syy + y[j * ystride] * y[j * ystride];
-#pragma unroll 1
-  for (int i = 0; i < max_pitch; i++) {
-    if (xcorr[i] > 0) {
-      float x16 = xcorr[i];
-      x16 *= 1e-12f;
-      const float num = x16 * x16;
-      if (num * bd1 > bn1 * Syy) {
-        if (num * bd0 > bn0 * Syy) { bn1 = bn0; bd1 = bd0; bp1 = bp0; bn0 = num; bd0 = Syy; bp0 = i; }
-        else { bn1 = num; bd1 = Syy; bp1 = i; }
+// find_best_pitch (celt/pitch.c:45-103).  The energy track Syy(i) is a serial chain, but its increments are not: all threads
+// square the samples (phase 1), one thread runs the chain and the best-two selection over pipelined loads (phase 2).
+// scratch: max_pitch floats.  Every thread of the CTA calls it; the result lands in best_pitch[0..1] (shared memory).
+OB_DEVNI void pf_find_best_pitch(const float *__restrict__ xcorr, const float *__restrict__ y, int ystride, int len, int max_pitch,
+                                 float *__restrict__ scratch, int *__restrict__ best_pitch, int tid, int nth) {
+  for (int i = tid; i < max_pitch; i += nth) {
+    const float a = y[(i + len) * ystride], b = y[i * ystride];
+    scratch[i] = a * a - b * b;
+  }
+  bsync();
+  if (tid == 0) {
+    float Syy = 1.f, bn0 = -1.f, bn1 = -1.f, bd0 = 0.f, bd1 = 0.f;
+    int bp0 = 0, bp1 = 1;
+#pragma unroll 8
+    for (int j = 0; j < len; j++) Syy = Syy + y[j * ystride] * y[j * ystride];
+#pragma unroll 4
+    for (int i = 0; i < max_pitch; i++) {   // scratch[i] <- Syy as iteration i sees it
+      const float d = scratch[i];
+      scratch[i] = Syy;
+      Syy += d;
+      Syy = Syy > 1.f ? Syy : 1.f;
+    }
+#pragma unroll 4
+    for (int i = 0; i < max_pitch; i++) {
+      const float xc = xcorr[i], Si = scratch[i];
+      if (xc > 0) {
+        float x16 = xc;
+        x16 *= 1e-12f;
+        const float num = x16 * x16;
+        if (num * bd1 > bn1 * Si) {
+          if (num * bd0 > bn0 * Si) { bn1 = bn0; bd1 = bd0; bp1 = bp0; bn0 = num; bd0 = Si; bp0 = i; }
+          else { bn1 = num; bd1 = Si; bp1 = i; }
+        }
       }
     }
-    Syy += y[(i + len) * ystride] * y[(i + len) * ystride] - y[i * ystride] * y[i * ystride];
-    Syy = Syy > 1.f ? Syy : 1.f;
+    best_pitch[0] = bp0;
+    best_pitch[1] = bp1;
   }
-  best_pitch[0] = bp0;
-  best_pitch[1] = bp1;
+  bsync();
 }
 OB_DEV float pf_pitch_gain(float xy, float xx, float yy) { return xy / (float)sqrt((double)(1 + xx * yy)); }
 
-// comb_filter with distinct input/output (celt/celt.c:238-313), elementwise over `tid`
-OB_DEV void pf_comb(float *y, const float *x, int T0, int T1, int N, float g0, float g1, int tapset0, int tapset1, int overlap, int tid, int nth) {
+// comb_filter with distinct input/output (celt/celt.c:238-313), elementwise over `tid`; x[k] = pre[base + k]
+OB_DEV void pf_comb(float *y, const PfSig &x, int base, int T0, int T1, int N, float g0, float g1, int tapset0, int tapset1, int overlap, int tid,
+                    int nth) {
   if (g0 == 0 && g1 == 0) {
-    for (int i = tid; i < N; i += nth) y[i] = x[i];
+    for (int i = tid; i < N; i += nth) y[i] = pf_at(x, base + i);
     return;
   }
   T0 = T0 > kPfMinPeriod ? T0 : kPfMinPeriod;
   T1 = T1 > kPfMinPeriod ? T1 : kPfMinPeriod;
-  const float ga[3][3] = {{0.3066406250f, 0.2170410156f, 0.1296386719f}, {0.4638671875f, 0.2680664062f, 0.f}, {0.7998046875f, 0.1000976562f, 0.f}};
-  const float g00 = g0 * ga[tapset0][0], g01 = g0 * ga[tapset0][1], g02 = g0 * ga[tapset0][2];
-  const float g10 = g1 * ga[tapset1][0], g11 = g1 * ga[tapset1][1], g12 = g1 * ga[tapset1][2];
+  const float gt0[3] = {0.3066406250f, 0.4638671875f, 0.7998046875f}, gt1[3] = {0.2170410156f, 0.2680664062f, 0.1000976562f};
+  const float g00 = g0 * (tapset0 == 0 ? gt0[0] : tapset0 == 1 ? gt0[1] : gt0[2]), g01 = g0 * (tapset0 == 0 ? gt1[0] : tapset0 == 1 ? gt1[1] : gt1[2]),
+              g02 = g0 * (tapset0 == 0 ? 0.1296386719f : 0.f);
+  const float g10 = g1 * (tapset1 == 0 ? gt0[0] : tapset1 == 1 ? gt0[1] : gt0[2]), g11 = g1 * (tapset1 == 0 ? gt1[0] : tapset1 == 1 ? gt1[1] : gt1[2]),
+              g12 = g1 * (tapset1 == 0 ? 0.1296386719f : 0.f);
   if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
   for (int i = tid; i < N; i += nth) {
+    const int j = base + i;
+    const float xi = pf_at(x, j);
     if (i < overlap) {
       const float f = ob_window[i] * ob_window[i];
-      y[i] = x[i] + ((1.f - f) * g00) * x[i - T0] + ((1.f - f) * g01) * (x[i - T0 + 1] + x[i - T0 - 1]) + ((1.f - f) * g02) * (x[i - T0 + 2] + x[i - T0 - 2]) +
-             (f * g10) * x[i - T1] + (f * g11) * (x[i - T1 + 1] + x[i - T1 - 1]) + (f * g12) * (x[i - T1 + 2] + x[i - T1 - 2]);
-    } else if (g1 == 0) y[i] = x[i];
-    else y[i] = x[i] + g10 * x[i - T1] + g11 * (x[i - T1 + 1] + x[i - T1 - 1]) + g12 * (x[i - T1 + 2] + x[i - T1 - 2]);
+      y[i] = xi + ((1.f - f) * g00) * pf_at(x, j - T0) + ((1.f - f) * g01) * (pf_at(x, j - T0 + 1) + pf_at(x, j - T0 - 1)) +
+             ((1.f - f) * g02) * (pf_at(x, j - T0 + 2) + pf_at(x, j - T0 - 2)) + (f * g10) * pf_at(x, j - T1) +
+             (f * g11) * (pf_at(x, j - T1 + 1) + pf_at(x, j - T1 - 1)) + (f * g12) * (pf_at(x, j - T1 + 2) + pf_at(x, j - T1 - 2));
+    } else if (g1 == 0) y[i] = xi;
+    else y[i] = xi + g10 * pf_at(x, j - T1) + g11 * (pf_at(x, j - T1 + 1) + pf_at(x, j - T1 - 1)) + g12 * (pf_at(x, j - T1 + 2) + pf_at(x, j - T1 - 2));
   }
 }
 
-// The whole pre-filter stage.  in[c]: the channel's [overlap | frame] buffer (ws->in), overwritten with the filtered signal and
-// the filtered overlap; prefilter_mem / in_mem: HBM state.  All threads of the CTA call it (C warps).
+// The whole pre-filter stage.  in[c]: the channel's [overlap | frame] buffer (ws->in): on return it holds the filtered
+// overlap + frame.  fr[c]: N floats of shared scratch (ws->f2) for the unfiltered frame.  ring / in_mem: HBM state.
+// All threads of the CTA call it (C warps).
 struct PfArgs {
   float *in[2];
-  float *prefilter_mem[2];   // [1024]
+  float *fr[2];
+  float *ring[2];            // [1024]
   float *in_mem[2];          // [120]
+  int head;                  // ring position of the oldest history sample
   int C, N, enabled, complexity, nbAvailableBytes, prefilter_tapset, prev_period, prev_tapset, loss_rate;
   float prev_gain, tf_estimate, tone_freq, toneishness;
 };
 OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
-  const int tid = warp_in_block() * 32 + lane_id(), nth = warps_per_block() * 32, lane = lane_id(), wid = warp_in_block();
+  const int tid = warp_in_block() * 32 + lane_id(), nth = warps_per_block() * 32;
   const int N = a.N, C = a.C, overlap = OB_OVERLAP, max_period = kPfMaxPeriod, min_period = kPfMinPeriod;
-  // pre[c] = [prefilter_mem | new frame]
+  if (a.prev_gain == 0.f && !(a.enabled && (a.toneishness > .99f || a.complexity >= 5))) {
+    // No search, no tone, nothing to fade out: both comb filters are copies, gain1 = 0 fails every threshold, and the
+    // cancel_pitch rule cannot change a copy.  Only the memories move: in = [in_mem | frame], in_mem = frame tail,
+    // the ring takes the new frame (celt/celt_encoder.c:1539-1599 with g0 = g1 = 0).
+    for (int c = 0; c < C; c++) {
+      for (int i = tid; i < overlap; i += nth) a.in[c][i] = a.in_mem[c][i];
+      for (int i = tid; i < N; i += nth) a.ring[c][(a.head + i) & (max_period - 1)] = a.in[c][overlap + i];
+    }
+    bsync();
+    for (int c = 0; c < C; c++)
+      for (int i = tid; i < overlap; i += nth) a.in_mem[c][i] = a.in[c][N + i];
+    bsync();
+    PfDecision r;
+    r.pf_on = 0; r.pitch_index = min_period; r.qg = 0; r.tapset = a.prefilter_tapset; r.gain1 = 0.f;
+    return r;
+  }
+  PfSig pre[2];
   for (int c = 0; c < C; c++) {
-    for (int i = tid; i < max_period; i += nth) w->pre[c][i] = a.prefilter_mem[c][i];
-    for (int i = tid; i < N; i += nth) w->pre[c][max_period + i] = a.in[c][overlap + i];
+    pre[c].ring = a.ring[c]; pre[c].frame = a.fr[c]; pre[c].head = a.head;
+    for (int i = tid; i < N; i += nth) a.fr[c][i] = a.in[c][overlap + i];
   }
   bsync();
   int pitch_index = min_period;
@@ -141,19 +186,23 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
     gain1 = .75f;
   } else if (a.enabled && a.complexity >= 5) {
     const int len = (max_period + N) >> 1;
+    float *xlp = w->buf, *xcorr = w->buf, *track = w->buf + 512, *yyl = w->buf;
     // pitch_downsample (celt/pitch.c:140-228): 2:1 decimation of the channel sum ...
     for (int i = tid; i < len; i += nth) {
-      float v = i == 0 ? .25f * w->pre[0][1] + .5f * w->pre[0][0] : .25f * w->pre[0][2 * i - 1] + .25f * w->pre[0][2 * i + 1] + .5f * w->pre[0][2 * i];
-      if (C == 2) v += i == 0 ? .25f * w->pre[1][1] + .5f * w->pre[1][0] : .25f * w->pre[1][2 * i - 1] + .25f * w->pre[1][2 * i + 1] + .5f * w->pre[1][2 * i];
-      w->xlp[i] = v;
+      float v = i == 0 ? .25f * pf_at(pre[0], 1) + .5f * pf_at(pre[0], 0)
+                       : .25f * pf_at(pre[0], 2 * i - 1) + .25f * pf_at(pre[0], 2 * i + 1) + .5f * pf_at(pre[0], 2 * i);
+      if (C == 2)
+        v += i == 0 ? .25f * pf_at(pre[1], 1) + .5f * pf_at(pre[1], 0)
+                    : .25f * pf_at(pre[1], 2 * i - 1) + .25f * pf_at(pre[1], 2 * i + 1) + .5f * pf_at(pre[1], 2 * i);
+      xlp[i] = v;
     }
     bsync();
     // ... _celt_autocorr over 5 lags (celt/celt_lpc.c:284-370): xcorr over fastN then the tail, one lane per lag ...
     if (tid < 5) {
       const int k = tid, fastN = len - 4;
-      float ac = pf_dot(w->xlp, w->xlp + k, fastN), d = 0.f;
+      float ac = pf_dot(xlp, xlp + k, fastN), d = 0.f;
 #pragma unroll 1
-      for (int i = k + fastN; i < len; i++) d = d + w->xlp[i] * w->xlp[i - k];
+      for (int i = k + fastN; i < len; i++) d = d + xlp[i] * xlp[i - k];
       w->sc[k] = ac + d;
     }
     bsync();
@@ -196,12 +245,12 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
     {
       const float l0 = w->sc[8], l1 = w->sc[9], l2 = w->sc[10], l3 = w->sc[11], l4 = w->sc[12];
       for (int i = tid; i < len; i += nth) {
-        float sum = w->xlp[i];
-        sum = sum + l0 * (i >= 1 ? w->xlp[i - 1] : 0.f);
-        sum = sum + l1 * (i >= 2 ? w->xlp[i - 2] : 0.f);
-        sum = sum + l2 * (i >= 3 ? w->xlp[i - 3] : 0.f);
-        sum = sum + l3 * (i >= 4 ? w->xlp[i - 4] : 0.f);
-        sum = sum + l4 * (i >= 5 ? w->xlp[i - 5] : 0.f);
+        float sum = xlp[i];
+        sum = sum + l0 * (i >= 1 ? xlp[i - 1] : 0.f);
+        sum = sum + l1 * (i >= 2 ? xlp[i - 2] : 0.f);
+        sum = sum + l2 * (i >= 3 ? xlp[i - 3] : 0.f);
+        sum = sum + l3 * (i >= 4 ? xlp[i - 4] : 0.f);
+        sum = sum + l4 * (i >= 5 ? xlp[i - 5] : 0.f);
         w->xlp2[i] = sum;
       }
     }
@@ -211,18 +260,12 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
     const int mp = max_period - 3 * min_period, len4 = N >> 2, mp4 = mp >> 2, len2 = N >> 1, mp2 = mp >> 1;
     for (int i = tid; i < mp4; i += nth) {   // coarse: both signals decimated by 2 again; one lane per lag, j in order
       float s = 0.f;
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < len4; j++) s = s + xl[2 * j] * pb[2 * (i + j)];
-      w->xcorr[i] = s;
+      xcorr[i] = s;
     }
     bsync();
-    if (tid == 0) {
-      int bp[2];
-      pf_find_best_pitch(w->xcorr, pb, 2, len4, mp4, bp);
-      ((int *)w->sc)[16] = bp[0];
-      ((int *)w->sc)[17] = bp[1];
-    }
-    bsync();
+    pf_find_best_pitch(xcorr, pb, 2, len4, mp4, track, (int *)w->sc + 16, tid, nth);
     {
       const int b0 = ((int *)w->sc)[16], b1 = ((int *)w->sc)[17];
       for (int i = tid; i < mp2; i += nth) {
@@ -232,15 +275,15 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
           const float s = pf_dot(xl, pb + i, len2);
           v = s > -1.f ? s : -1.f;
         }
-        w->xcorr[i] = v;
+        xcorr[i] = v;
       }
     }
     bsync();
+    pf_find_best_pitch(xcorr, pb, 1, len2, mp2, track, (int *)w->sc + 16, tid, nth);
     if (tid == 0) {
-      int bp[2], offset = 0;
-      pf_find_best_pitch(w->xcorr, pb, 1, len2, mp2, bp);
+      int bp[2] = {((int *)w->sc)[16], ((int *)w->sc)[17]}, offset = 0;
       if (bp[0] > 0 && bp[0] < mp2 - 1) {
-        const float aa = w->xcorr[bp[0] - 1], bb = w->xcorr[bp[0]], cc = w->xcorr[bp[0] + 1];
+        const float aa = xcorr[bp[0] - 1], bb = xcorr[bp[0]], cc = xcorr[bp[0] + 1];
         if ((cc - aa) > .7f * (bb - aa)) offset = 1;
         else if ((aa - cc) > .7f * (bb - cc)) offset = -1;
       }
@@ -254,7 +297,9 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
       int T0 = ((int *)w->sc)[18] / 2;
       if (T0 >= maxp) T0 = maxp - 1;
       const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
-      // the independent running sums: lanes 0,1: xx, xy;  lanes 2..29: (k, first/second) for k = 2..15;  thread 32: yy_lookup
+      // the independent running sums: lanes 0,1: xx, xy;  lanes 2..29: (k, first/second) for k = 2..15;  one more thread
+      // (of the second warp when there is one): xx again and the yy_lookup energy track that starts from it
+      const int ytid = nth > 32 ? 32 : 30;
       if (tid < 2) w->sc[20 + tid] = pf_dot(x, tid == 0 ? x : x - T0, Nh);
       else if (tid < 30) {
         const int k = 2 + ((tid - 2) >> 1), which = (tid - 2) & 1;
@@ -263,21 +308,21 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
         if (k == 2) T1b = T1 + T0 > maxp ? T0 : T0 + T1;
         else T1b = (unsigned)(2 * second_check[k] * T0 + k) / (unsigned)(2 * k);
         w->sc[24 + (tid - 2)] = T1 >= minp ? pf_dot(x, x - (which ? T1b : T1), Nh) : 0.f;
-      }
-      bsync();
-      if (tid == (nth > 32 ? 32 : 0)) {
-        float yy = w->sc[20];
-        w->yy[0] = yy;
-#pragma unroll 1
+      } else if (tid == ytid) {
+        float yy = pf_dot(x, x, Nh);
+        float *__restrict__ yl = yyl;
+        const float *__restrict__ xr = x;
+        yl[0] = yy;
+#pragma unroll 4
         for (int i = 1; i <= maxp; i++) {
-          yy = yy + x[-i] * x[-i] - x[Nh - i] * x[Nh - i];
-          w->yy[i] = yy > 0.f ? yy : 0.f;
+          yy = yy + xr[-i] * xr[-i] - xr[Nh - i] * xr[Nh - i];
+          yl[i] = yy > 0.f ? yy : 0.f;
         }
       }
       bsync();
       if (tid == 0) {
         const float xx = w->sc[20];
-        float xy = w->sc[21], yy = w->yy[T0];
+        float xy = w->sc[21], yy = yyl[T0];
         float best_xy = xy, best_yy = yy;
         float g, g0;
         int T = T0;
@@ -289,7 +334,7 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
           if (k == 2) T1b = T1 + T0 > maxp ? T0 : T0 + T1;
           else T1b = (unsigned)(2 * second_check[k] * T0 + k) / (unsigned)(2 * k);
           xy = .5f * (w->sc[24 + 2 * (k - 2)] + w->sc[24 + 2 * (k - 2) + 1]);
-          yy = .5f * (w->yy[T1] + w->yy[T1b]);
+          yy = .5f * (yyl[T1] + yyl[T1b]);
           const float g1 = pf_pitch_gain(xy, xx, yy);
           float cont;
           const int dT = T1 > prevp ? T1 - prevp : prevp - T1;
@@ -319,7 +364,7 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
         const float best_yy = w->sc[52];
         if (T < minp * 2) {
           const int T1 = T * 5 / 8, T2 = T * 6 / 8;
-          const float g1 = pf_pitch_gain(w->sc[53], xx, w->yy[T1]), g2 = pf_pitch_gain(w->sc[54], xx, w->yy[T2]);
+          const float g1 = pf_pitch_gain(w->sc[53], xx, yyl[T1]), g2 = pf_pitch_gain(w->sc[54], xx, yyl[T2]);
           if (g1 >= g || g2 >= g) g = 0.f;
         }
         best_xy = best_xy > 0.f ? best_xy : 0.f;
@@ -371,17 +416,17 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
   const int prev_period = a.prev_period > min_period ? a.prev_period : min_period, offset = OB_SHORT_N - overlap;
   for (int c = 0; c < C; c++) {
     for (int i = tid; i < overlap; i += nth) a.in[c][i] = a.in_mem[c][i];
-    if (offset) pf_comb(a.in[c] + overlap, w->pre[c] + max_period, prev_period, prev_period, offset, -a.prev_gain, -a.prev_gain, a.prev_tapset, a.prev_tapset, 0, tid, nth);
-    pf_comb(a.in[c] + overlap + offset, w->pre[c] + max_period + offset, prev_period, pitch_index, N - offset, -a.prev_gain, -gain1, a.prev_tapset,
+    if (offset) pf_comb(a.in[c] + overlap, pre[c], max_period, prev_period, prev_period, offset, -a.prev_gain, -a.prev_gain, a.prev_tapset, a.prev_tapset, 0, tid, nth);
+    pf_comb(a.in[c] + overlap + offset, pre[c], max_period + offset, prev_period, pitch_index, N - offset, -a.prev_gain, -gain1, a.prev_tapset,
             a.prefilter_tapset, overlap, tid, nth);
   }
   bsync();
   // |.| sums before / after, in index order: 2C lanes
   if (tid < 2 * C) {
     const int c = tid >> 1, after = tid & 1;
-    const float *src = after ? a.in[c] + overlap : w->pre[c] + max_period;
+    const float *src = after ? a.in[c] + overlap : a.fr[c];
     float s = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < N; i++) s += fabsf(src[i]);
     w->sc[40 + tid] = s;
   }
@@ -397,25 +442,24 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
     } else if (a0 > b0) cancel_pitch = 1;
   }
   if (cancel_pitch) {
-    for (int c = 0; c < C; c++) {
-      for (int i = tid; i < N; i += nth) a.in[c][overlap + i] = w->pre[c][max_period + i];
-    }
+    for (int c = 0; c < C; c++)
+      for (int i = tid; i < N; i += nth) a.in[c][overlap + i] = a.fr[c][i];
     bsync();
     for (int c = 0; c < C; c++)
-      pf_comb(a.in[c] + overlap + offset, w->pre[c] + max_period + offset, prev_period, pitch_index, overlap, -a.prev_gain, -0.f, a.prev_tapset,
+      pf_comb(a.in[c] + overlap + offset, pre[c], max_period + offset, prev_period, pitch_index, overlap, -a.prev_gain, -0.f, a.prev_tapset,
               a.prefilter_tapset, overlap, tid, nth);
     gain1 = 0.f;
     pf_on = 0;
     qg = 0;
   }
   bsync();
-  // memories (celt/celt_encoder.c:1588-1599): the filtered tail for the next MDCT overlap, the unfiltered history for the next search
+  // memories (celt/celt_encoder.c:1588-1599): the filtered tail for the next MDCT overlap; the unfiltered frame replaces the
+  // oldest N samples of the ring (every read of the history is behind the barrier above)
   for (int c = 0; c < C; c++) {
     for (int i = tid; i < overlap; i += nth) a.in_mem[c][i] = a.in[c][N + i];
-    for (int i = tid; i < max_period; i += nth) a.prefilter_mem[c][i] = w->pre[c][N + i];   // N <= max_period: shift by one frame
+    for (int i = tid; i < N; i += nth) a.ring[c][(a.head + i) & (max_period - 1)] = a.fr[c][i];
   }
   bsync();
-  (void)lane; (void)wid;
   PfDecision r;
   r.pf_on = pf_on; r.pitch_index = pitch_index; r.qg = qg; r.tapset = a.prefilter_tapset; r.gain1 = gain1;
   return r;

@@ -87,7 +87,7 @@ OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *s
 //      (celt_preemphasis celt/celt_encoder.c:557, compute_mdcts :511, compute_band_energies celt/bands.c:151,
 //       amp2Log2 celt/quant_bands.c:553, normalise_bands celt/bands.c:169), the path of celt_encode_with_ec when the pitch
 //      pre-filter is off.  The spectrum never leaves shared memory; HBM sees the PCM once and the normalised bands once. ----
-struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; float overlap_max; float pad; };
+struct ObEncAnalysisState { float preemph_mem[2]; float overlap_mem[2][OB_OVERLAP]; float overlap_max; int32_t pf_head; };   // pf_head: ring position of prefilter_mem
 // what the frame encoder needs from the time domain (celt_encode_with_ec :1963-1970, :2017)
 struct ObEncFrameInfo {
   float tone_freq, toneishness, sample_max, tf_estimate;
@@ -117,8 +117,8 @@ OB_DEV int tone_lpc_warp(const float *in0, const float *in1, int len, int delay,
   float acc = 0.f;
   if (lane < 3) {
     const int d = lane * delay;
-#pragma unroll 1
-    for (int i = 0; i < len - 2 * delay; i++) {
+#pragma unroll 8
+    for (int i = 0; i < len - 2 * delay; i++) {   // unrolled so that the shared-memory loads run ahead of the serial sum
       const float a = in1 ? in0[i] + in1[i] : in0[i], b = in1 ? in0[i + d] + in1[i + d] : in0[i + d];
       acc += a * b;
     }
@@ -161,43 +161,49 @@ OB_TABLE unsigned char ob_transient_inv_table[128] = {
     6,   6,   6,   6,   6,  6,  6,  6,  6,  5,  5,  5,  5,  5,  5,  5,  5,  5,  5,  5,  5,  4,  4,  4,  4,  4,  4,  4,  4,  4,  4,  4,
     4,   4,   4,   4,   4,  4,  4,  4,  4,  4,  4,  4,  4,  4,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  3,  2,
 };
-OB_DEVNI int transient_unmask_lane(const float *in, float *tmp, int len) {
+OB_DEVNI int transient_unmask_warp(const float *__restrict__ in, float *__restrict__ tmp, int len, int lane) {
   const int len2 = len / 2;
   const float forward_decay = .0625f;
-  // the high-pass filter (two samples per step) feeds the forward smoother directly: only len/2 values are stored
-  float hp0 = 0.f, hp1 = 0.f, mean = 0.f, mem0 = 0.f;
-#pragma unroll 1
-  for (int i = 0; i < len2; i++) {
-    float y[2];
+  float norm = 0.f;
+  if (lane == 0) {
+    // the high-pass filter (two samples per step) feeds the forward smoother directly: only len/2 values are stored
+    float hp0 = 0.f, hp1 = 0.f, mean = 0.f, mem0 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < len2; i++) {
+      float y[2];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const float x = in[2 * i + k], mem00 = hp0;
-      y[k] = 2 * i + k < 12 ? 0.f : hp0 + x;
-      hp0 = hp0 - x + .5f * hp1;
-      hp1 = x - mem00;
+      for (int k = 0; k < 2; k++) {
+        const float x = in[2 * i + k], mem00 = hp0;
+        y[k] = 2 * i + k < 12 ? 0.f : hp0 + x;
+        hp0 = hp0 - x + .5f * hp1;
+        hp1 = x - mem00;
+      }
+      const float x2 = y[0] * y[0] + y[1] * y[1];
+      mean += x2;
+      mem0 = x2 + (1.f - forward_decay) * mem0;
+      tmp[i] = forward_decay * mem0;
     }
-    const float x2 = y[0] * y[0] + y[1] * y[1];
-    mean += x2;
-    mem0 = x2 + (1.f - forward_decay) * mem0;
-    tmp[i] = forward_decay * mem0;
+    mem0 = 0.f;
+    float maxE = 0.f;
+#pragma unroll 4
+    for (int i = len2 - 1; i >= 0; i--) {
+      mem0 = tmp[i] + 0.875f * mem0;
+      tmp[i] = 0.125f * mem0;
+      maxE = fmaxf(maxE, 0.125f * mem0);
+    }
+    mean = (float)sqrt((double)(mean * maxE) * .5 * len2);
+    norm = len2 / (1e-15f + mean);
   }
-  mem0 = 0.f;
-  float maxE = 0.f;
-#pragma unroll 1
-  for (int i = len2 - 1; i >= 0; i--) {
-    mem0 = tmp[i] + 0.875f * mem0;
-    tmp[i] = 0.125f * mem0;
-    maxE = fmaxf(maxE, 0.125f * mem0);
-  }
-  mean = (float)sqrt((double)(mean * maxE) * .5 * len2);
-  const float norm = len2 / (1e-15f + mean);
+  norm = shfl(norm, 0);
+  wsync();
+  // the table pass is an integer sum: any order gives the reference's value, so the warp shares it
   int unmask = 0;
-#pragma unroll 1
-  for (int i = 12; i < len2 - 5; i += 4) {
+  for (int i = 12 + 4 * lane; i < len2 - 5; i += 4 * 32) {
     const double v = floor((double)(64 * norm * (tmp[i] + 1e-15f)));
     const int id = (int)(v < 127 ? (v > 0 ? v : 0) : 127);
     unmask += ob_transient_inv_table[id];
   }
+  for (int o = 16; o; o >>= 1) unmask += shfl_xor(unmask, o);
   return 64 * unmask * 4 / (6 * (len2 - 17));
 }
 // one CTA per stream, one warp per channel
@@ -215,7 +221,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   float *pmem = pf_path ? p.prefilter_mem + ((size_t)stream * C + c) * kPfMaxPeriod : nullptr;
   // the analysis window starts with the UNFILTERED tail of the previous frame (celt/celt_encoder.c:2014); without a pre-filter
   // history that is the same as the MDCT overlap memory
-  for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[kPfMaxPeriod - OB_OVERLAP + i] : st.overlap_mem[c][i];
+  for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[(st.pf_head + kPfMaxPeriod - OB_OVERLAP + i) & (kPfMaxPeriod - 1)] : st.overlap_mem[c][i];
   for (int i = lane; i < N; i += 32) {
     const float s = pcm[(size_t)C * i];
     const float x = f_mul(32768.f, s);
@@ -233,8 +239,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
   if (lane == 0) { xch[c * 2] = mx_new; xch[c * 2 + 1] = mx_tail; }
   if (p.complexity >= 1 && p.info) {   // transient_analysis: lane 0 of each channel's warp walks its channel (f2 is free until the MDCT)
-    int um = 0;
-    if (lane == 0) um = transient_unmask_lane(ws->in, ws->f2, N + OB_OVERLAP);
+    const int um = transient_unmask_warp(ws->in, ws->f2, N + OB_OVERLAP, lane);
     if (lane == 0) ((int *)xch)[4 + c] = um;
   }
   bsync();
@@ -295,9 +300,11 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     PfArgs a;
     for (int cc = 0; cc < C; cc++) {
       a.in[cc] = ((MdctWS *)smem + cc)->in;
-      a.prefilter_mem[cc] = p.prefilter_mem + ((size_t)stream * C + cc) * kPfMaxPeriod;
+      a.fr[cc] = ((MdctWS *)smem + cc)->f2;
+      a.ring[cc] = p.prefilter_mem + ((size_t)stream * C + cc) * kPfMaxPeriod;
       a.in_mem[cc] = st.overlap_mem[cc];
     }
+    a.head = st.pf_head;
     a.C = C; a.N = N; a.complexity = p.complexity; a.nbAvailableBytes = bud.nbAvailableBytes; a.prefilter_tapset = es.tapset_decision;
     a.prev_period = es.prefilter_period; a.prev_tapset = es.prefilter_tapset; a.prev_gain = es.prefilter_gain; a.loss_rate = p.loss_rate;
     a.tf_estimate = fi.tf_estimate; a.tone_freq = fi.tone_freq; a.toneishness = fminf(fi.toneishness, 1.f - fi.tf_estimate);
@@ -306,8 +313,11 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     if (c == 0 && lane == 0) {
       fi.pf_on = d.pf_on; fi.pitch_index = d.pitch_index; fi.qg = d.qg; fi.pf_tapset = d.tapset; fi.gain1 = d.gain1; fi.patched = 0;
       p.info[stream] = fi;
+      st.pf_head = (a.head + N) & (kPfMaxPeriod - 1);
     }
-    freq = pw->pre[c];   // keep the time signal: patch_transient_decision may ask for a second transform
+    // from complexity 5 the spectrum goes to the (now dead) search buffers and the time signal stays:
+    // patch_transient_decision may ask for a second transform
+    if (p.complexity >= 5) freq = pw->buf + c * OB_MAXN;
     bsync();
   }
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
@@ -321,19 +331,19 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
 #pragma unroll 4
       for (int j = j0; j < j1; j++) sum = f_add(sum, f_mul(freq[j], freq[j]));
       E0 = f_sqrt(f_add(1e-27f, sum));
-      pw->xlp[c * OB_NBANDS + lane] = f_add((float)(1.442695040888963387 * log((double)E0)), -ob_emeans[lane]);
+      pw->sc[c * OB_NBANDS + lane] = f_add((float)(1.442695040888963387 * log((double)E0)), -ob_emeans[lane]);
     }
     bsync();
     if (c == 0 && lane == 0) {
       const ObEncFrameInfo fi = p.info[stream];
       const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
       int patch = 0;
-      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->xlp, p.enc_state[stream].oldBandE, C);
+      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->sc, p.enc_state[stream].oldBandE, C);
       ((int *)xch)[6] = patch;
     }
     bsync();
     if (((int *)xch)[6]) {
-      if (lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = pw->xlp[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
+      if (lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = pw->sc[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
       if (c == 0 && lane == 0) {
         ObEncFrameInfo fi = p.info[stream];
         fi.is_transient = 1; fi.short_blocks = 1; fi.patched = 1; fi.tf_estimate = .2f;

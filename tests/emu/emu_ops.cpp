@@ -224,7 +224,7 @@ extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const flo
   a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
   a.enc_state = enc_state; a.prefilter_mem = prefilter_mem; a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = bitrate; a.vbr = vbr;
   a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0;
-  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32 + sizeof(PfWS));
+  emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32 + (complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams p;
   p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.bandLogE2 = Lg2.data(); p.packets = packets; p.nbytes = nbytes;
   p.n_streams = n; p.C = C; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = complexity; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
