@@ -129,3 +129,19 @@ def test_complexity_5_to_7(complexity, ch, fs, nbytes, vbr):
                 pf_frames += 1      # second header bit set: post-filter on (after a 0 silence flag)
     if fs >= 480 and nbytes >= 80:
         assert pf_frames > 0
+
+
+@pytest.mark.parametrize('complexity', [8, 10])
+@pytest.mark.parametrize('ch,fs,nbytes,vbr', [(2, 960, 160, 0), (1, 960, 80, 0), (2, 480, 100, 0), (2, 240, 60, 0), (2, 120, 30, 0), (2, 960, 60, 0),
+                                              (2, 960, 320, 0), (2, 960, 1275, 1), (2, 480, 1275, 1), (1, 480, 1275, 1)])
+def test_complexity_8_to_10(complexity, ch, fs, nbytes, vbr):
+    """second MDCT (transient frames) + theta RDO with resynthesis (stereo); CELT has no gate above 8"""
+    for sname in ('harmonic', 'music', 'clicks', 'white'):
+        n = fs * 12
+        sig = {'harmonic': lambda: _harmonic_signal(complexity + fs, n, ch), 'music': lambda: util.sig_music(complexity + ch + fs, n, ch),
+               'clicks': lambda: _transient_signal(complexity * 7 + fs + nbytes, n, ch), 'white': lambda: util.sig_white(3 + fs, n, ch)}[sname]()
+        for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity, bitrate=(64000 * ch if vbr else -1000), vbr=vbr, nframes=12):
+            assert nbo != -5, 'frame needed a decision that is not restated'
+            assert na == nbo, (sname, f, na, nbo)
+            assert np.array_equal(a, b), (sname, f, int(np.argmax(a != b)))
+            assert ra == rb
