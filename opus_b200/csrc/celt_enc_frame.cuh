@@ -787,9 +787,11 @@ OB_DEVNI void enc_exp_rotation(float *X, int len, int stride, int K, int spread)
 }
 // op_pvq_search_c (celt/vq.c:205-374) followed by icwrs (celt/cwrs.c:444-460): returns the codeword index.
 // X: the (rotated) partition, overwritten with |X|; y2: scratch holding 2*pulses
-OB_DEVNI uint32_t enc_pvq_index(float *X, float *y2, int N, int K) {
-  uint32_t signs[6] = {0, 0, 0, 0, 0, 0};
+// (the search returns yy for the resynthesis-enabled encoder; signs: bit set of the negative inputs)
+OB_DEVNI float enc_pvq_search(float *X, float *y2, int N, int K, uint32_t *signs) {
   float sum = 0.f, xy = 0.f, yy = 0.f;   // sign bits live in a small bit set (N <= 176)
+#pragma unroll
+  for (int j = 0; j < 6; j++) signs[j] = 0;
 #pragma unroll 1
   for (int j = 0; j < N; j++) {
     const float x = X[j];
@@ -844,7 +846,10 @@ OB_DEVNI uint32_t enc_pvq_index(float *X, float *y2, int N, int K) {
     yy = yy + y2[best_id];
     y2[best_id] += 2.f;
   }
-  // icwrs over the signed pulse vector
+  return yy;
+}
+// icwrs over the signed pulse vector
+OB_DEVNI uint32_t enc_icwrs(const float *y2, const uint32_t *signs, int N) {
   int j = N - 1;
   int yj = (int)(y2[j] * .5f);
   uint32_t idx = ((signs[j >> 5] >> (j & 31)) & 1u) && yj ? 1u : 0u;
@@ -857,6 +862,11 @@ OB_DEVNI uint32_t enc_pvq_index(float *X, float *y2, int N, int K) {
     if (((signs[j >> 5] >> (j & 31)) & 1u) && yj) idx += pvq_u(N - j, k + 1);
   } while (j > 0);
   return idx;
+}
+OB_DEV uint32_t enc_pvq_index(float *X, float *y2, int N, int K) {
+  uint32_t signs[6];
+  enc_pvq_search(X, y2, N, K, signs);
+  return enc_icwrs(y2, signs, N);
 }
 
 // ---- stereo_itheta (celt/vq.c:724-757) and the float arctangent (celt/mathops.h:142-186) ----
@@ -897,8 +907,10 @@ struct EncBand {
   const float *bandE;   // this stream's [C][21]
   int band, intensity, spread, tf_change, disable_inv, avoid_split_noise;
   int32_t remaining_bits;
+  int theta_round;   // -1 / +1: the two candidates of the theta RDO (complexity >= 8); 0: plain rounding
+  uint32_t seed;     // noise-fill LCG of the resynthesis path
 };
-struct EncTheta { int itheta, delta, qalloc; };
+struct EncTheta { int itheta, delta, qalloc, imid, iside, inv; };
 // encode side of compute_theta (celt/bands.c:700-933); X/Y are transformed for the stereo case
 OB_DEVNI EncTheta enc_theta(EncBand &ctx, float *X, float *Y, int N, int &b, int B, int B0, int LM, int stereo) {
   RangeEnc &ec = *ctx.ec;
@@ -907,17 +919,23 @@ OB_DEVNI EncTheta enc_theta(EncBand &ctx, float *X, float *Y, int N, int &b, int
   const int offset = (pulse_cap >> 1) - (stereo && N == 2 ? 16 : 4);   // QTHETA_OFFSET_TWOPHASE : QTHETA_OFFSET
   int qn = theta_levels(N, b, offset, pulse_cap, stereo);
   if (stereo && i >= ctx.intensity) qn = 1;
-  int itheta = enc_itheta(X, Y, stereo, N);
+  int itheta = enc_itheta(X, Y, stereo, N), inv = 0;
   const int32_t tell = re_tell_frac(ec);
   (void)B;
   if (qn != 1) {
-    itheta = (itheta * (int32_t)qn + 8192) >> 14;
-    if (!stereo && ctx.avoid_split_noise && itheta > 0 && itheta < qn) {
-      const int unquantized = (uint32_t)((int32_t)itheta * 16384) / (uint32_t)qn;
-      const int imid = bitexact_cos((int16_t)unquantized), iside = bitexact_cos((int16_t)(16384 - unquantized));
-      const int delta = frac_mul16((N - 1) << 7, bitexact_log2tan(iside, imid));
-      if (delta > b) itheta = qn;
-      else if (delta < -b) itheta = 0;
+    if (!stereo || ctx.theta_round == 0) {
+      itheta = (itheta * (int32_t)qn + 8192) >> 14;
+      if (!stereo && ctx.avoid_split_noise && itheta > 0 && itheta < qn) {
+        const int unquantized = (uint32_t)((int32_t)itheta * 16384) / (uint32_t)qn;
+        const int imid = bitexact_cos((int16_t)unquantized), iside = bitexact_cos((int16_t)(16384 - unquantized));
+        const int delta = frac_mul16((N - 1) << 7, bitexact_log2tan(iside, imid));
+        if (delta > b) itheta = qn;
+        else if (delta < -b) itheta = 0;
+      }
+    } else {   // celt/bands.c:769-778: the RDO candidates, biased towards 0 and 16384
+      const int bias = itheta > 8192 ? 32767 / qn : -32767 / qn;
+      const int down = OB_IMIN(qn - 1, OB_IMAX(0, (itheta * (int32_t)qn + bias) >> 14));
+      itheta = ctx.theta_round < 0 ? down : down + 1;
     }
     if (stereo && N > 2) {
       const int p0 = 3, x = itheta, x0 = qn / 2, ft = p0 * (x0 + 1) + x0;
@@ -948,7 +966,7 @@ OB_DEVNI EncTheta enc_theta(EncBand &ctx, float *X, float *Y, int N, int &b, int
       }
     }
   } else if (stereo) {
-    int inv = itheta > 8192 && !ctx.disable_inv;
+    inv = itheta > 8192 && !ctx.disable_inv;
     if (inv)
 #pragma unroll 1
       for (int j = 0; j < N; j++) Y[j] = -Y[j];
@@ -960,17 +978,21 @@ OB_DEVNI EncTheta enc_theta(EncBand &ctx, float *X, float *Y, int N, int &b, int
       for (int j = 0; j < N; j++) X[j] = a1 * X[j] + a2 * Y[j];
     }
     if (b > 2 << OB_BITRES && ctx.remaining_bits > 2 << OB_BITRES) re_bit_logp(ec, inv, 2);
+    else inv = 0;
+    if (ctx.disable_inv) inv = 0;
     itheta = 0;
   }
   EncTheta r;
   r.qalloc = (int)(re_tell_frac(ec) - tell);
   b -= r.qalloc;
   r.itheta = itheta;
-  if (itheta == 0) r.delta = -16384;
-  else if (itheta == 16384) r.delta = 16384;
+  r.inv = inv;
+  if (itheta == 0) { r.delta = -16384; r.imid = 32767; r.iside = 0; }
+  else if (itheta == 16384) { r.delta = 16384; r.imid = 0; r.iside = 32767; }
   else {
-    const int imid = bitexact_cos((int16_t)itheta), iside = bitexact_cos((int16_t)(16384 - itheta));
-    r.delta = frac_mul16((N - 1) << 7, bitexact_log2tan(iside, imid));
+    r.imid = bitexact_cos((int16_t)itheta);
+    r.iside = bitexact_cos((int16_t)(16384 - itheta));
+    r.delta = frac_mul16((N - 1) << 7, bitexact_log2tan(r.iside, r.imid));
   }
   return r;
 }
@@ -1102,7 +1124,13 @@ OB_DEVNI void enc_band_stereo(EncBand &ctx, float *X, float *Y, float *tmp, int 
   }
 }
 
-// ---- frame driver ----
+}  // namespace ob
+#include "celt_enc_rdo.cuh"
+namespace ob {
+
+// ---- frame driver ----  RDO: compiled with the theta-RDO band coder (complexity >= 8; a second kernel, because its
+// folding / save buffers triple the thread's local memory)
+template <bool RDO>
 OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   const int C = p.C, LM = p.LM, M = 1 << LM, N = M * OB_SHORT_N, end = OB_NBANDS, start = 0;
   ObEncState &st = p.state[stream];
@@ -1115,7 +1143,9 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
 #pragma unroll 1
   for (int i = 0; i < C * OB_NBANDS; i++) bandLogE[i] = p.bandLogE[(size_t)stream * C * OB_NBANDS + i];
   float bl2[2 * OB_NBANDS];
-  if (fi.patched && p.bandLogE2)
+  // bandLogE2 differs from bandLogE for a patched frame and, from complexity 8, for every transient frame (second MDCT)
+  const bool have_bl2 = p.bandLogE2 && (fi.patched || (p.complexity >= 8 && fi.short_blocks));
+  if (have_bl2)
 #pragma unroll 1
     for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] = p.bandLogE2[(size_t)stream * C * OB_NBANDS + i];
 
@@ -1192,11 +1222,11 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     temporal_vbr = enc_fmin(3.f, enc_fmax(-1.5f, temporal_vbr));
     st.spec_avg += .02f * temporal_vbr;
   }
-  if (fi.patched)   // celt/celt_encoder.c:2243-2245: compensate the long-block energies for the block-size change
+  if (have_bl2)   // celt/celt_encoder.c:2087, :2243-2245: compensate the long-block energies for the block-size change
 #pragma unroll 1
     for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] += .5f * LM;
   if (LM > 0 && re_tell(enc) + 3 <= total_bits) re_bit_logp(enc, isTransient, 3);
-  const EncDyn dyn = enc_dynalloc(bandLogE, fi.patched ? bl2 : bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
+  const EncDyn dyn = enc_dynalloc(bandLogE, have_bl2 ? bl2 : bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
                                   p.constrained_vbr, importance, spread_weight);
   int tf_select = 0;
   if (effectiveBytes >= 15 * C && p.complexity >= 2 && toneishness < .98f) {   // enable_tf_analysis
@@ -1437,9 +1467,17 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     }
   }
   // quant_all_bands, encode side (celt/bands.c:1589-1923): no resynthesis, so no folding state is carried
-  {
+  if (RDO && C == 2 && !dual_stereo && p.complexity >= 8) {   // theta_rdo (celt/bands.c:1618)
+    if constexpr (RDO) {
+      RdoScratch w;
+      const int r = rdo_all_bands(enc, Xg, bandE, pulses, tf_res, shortBlocks, st.spread_decision, st.intensity,
+                                  nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, al.balance, LM, codedBands, st.rng, p.disable_inv, bx, by, tmp, w);
+      if (r) status = r;
+    }
+  } else {
     EncBand ctx;
     ctx.ec = &enc; ctx.bandE = bandE; ctx.intensity = st.intensity; ctx.spread = st.spread_decision; ctx.disable_inv = p.disable_inv;
+    ctx.theta_round = 0; ctx.seed = 0;
     const int B = shortBlocks ? M : 1;
     ctx.avoid_split_noise = B > 1;
     int32_t balance = al.balance;

@@ -4,7 +4,11 @@
 
 extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame(EncFrameParams p) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < p.n_streams) enc_frame_thread(p, s);
+  if (s < p.n_streams) enc_frame_thread<false>(p, s);
+}
+extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame_rdo(EncFrameParams p) {   // complexity >= 8, stereo
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) enc_frame_thread<true>(p, s);
 }
 extern "C" __global__ void ob_celt_enc_reset(ObEncState *st, ObEncAnalysisState *an, int n) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,7 +102,7 @@ extern "C" int opusb200_encoder_ctl_set(OpusB200Encoder *e, int request, int32_t
     case 4006: e->vbr = value != 0; return OPUSB200_OK;                                                       // OPUS_SET_VBR
     case 4020: e->constrained_vbr = value != 0; return OPUSB200_OK;                                            // OPUS_SET_VBR_CONSTRAINT
     case 4014: if (value < 0 || value > 100) return OPUSB200_BAD_ARG; e->loss_rate = value; return OPUSB200_OK;   // OPUS_SET_PACKET_LOSS_PERC
-    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; if (value > 7) return OPUSB200_UNIMPLEMENTED; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY (0..7 on the device)
+    case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY
     case 4036: if (value < 8 || value > 24) return OPUSB200_BAD_ARG; e->lsb_depth = value; return OPUSB200_OK;  // OPUS_SET_LSB_DEPTH
     case 4046: e->disable_inv = value != 0; return OPUSB200_OK;                                                // OPUS_SET_PHASE_INVERSION_DISABLED
     default: return OPUSB200_UNIMPLEMENTED;
@@ -131,7 +135,8 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   p.n_streams = e->n; p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf;
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
-  ob_celt_enc_frame<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
+  if (e->complexity >= 8 && e->channels == 2) ob_celt_enc_frame_rdo<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
+  else ob_celt_enc_frame<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
   e->launches += 2;
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;

@@ -320,6 +320,21 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     if (p.complexity >= 5) freq = pw->buf + c * OB_MAXN;
     bsync();
   }
+  if (pf_path && p.complexity >= 8 && transient) {
+    // secondMdct (celt/celt_encoder.c:2077-2090): the long-block log energies of a transient frame, for dynalloc_analysis
+    mdct_forward_from_ws(ws, LM, 0, freq, lane);
+    wsync();
+    if (lane < OB_NBANDS) {
+      float sum = 0.f;
+      const int j0 = M * ob_ebands[lane], j1 = M * ob_ebands[lane + 1];
+#pragma unroll 4
+      for (int j = j0; j < j1; j++) sum = f_add(sum, f_mul(freq[j], freq[j]));
+      const float E0 = f_sqrt(f_add(1e-27f, sum));
+      // (the frame kernel adds the LM/2 compensation, as for a patched frame)
+      p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = f_add((float)(1.442695040888963387 * log((double)E0)), -ob_emeans[lane]);
+    }
+    wsync();
+  }
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
   wsync();
   if (pf_path && p.complexity >= 5 && LM > 0 && !transient) {

@@ -202,7 +202,9 @@ extern "C" void emu_celt_enc_analysis(void *state, const float *pcm, const int32
 static void enc_frame_entry(void *a) {
   const EncFrameParams &p = *(const EncFrameParams *)a;
   const int s = block_id() * 32 + lane_id();
-  if (s < p.n_streams) enc_frame_thread(p, s);
+  if (s >= p.n_streams) return;
+  if (p.complexity >= 8 && p.C == 2) enc_frame_thread<true>(p, s);
+  else enc_frame_thread<false>(p, s);
 }
 extern "C" int emu_enc_state_size(void) { return (int)sizeof(ObEncState); }
 extern "C" void emu_enc_state_init(ObEncState *st, int n) {

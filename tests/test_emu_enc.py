@@ -45,7 +45,9 @@ def clicks(seed, n, ch):
     (2, 960, 160, 1, 0, 1), (2, 960, 160, 2, 0, 1), (2, 960, 200, 3, 0, 1), (2, 960, 160, 4, 0, 1), (1, 480, 80, 4, 0, 1), (2, 240, 50, 3, 0, 1),
     (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1),
     (2, 960, 160, 5, 0, 1), (1, 960, 80, 5, 0, 1), (2, 480, 100, 6, 0, 1), (2, 240, 60, 7, 0, 1), (1, 120, 30, 5, 0, 1), (2, 960, 1275, 5, 1, 1),
-    (1, 480, 1275, 7, 1, 0)])
+    (1, 480, 1275, 7, 1, 0),
+    (2, 960, 160, 8, 0, 1), (2, 480, 100, 10, 0, 1), (2, 240, 60, 9, 0, 1), (2, 120, 40, 8, 0, 1), (1, 960, 80, 10, 0, 1), (2, 960, 1275, 10, 1, 1),
+    (2, 960, 50, 8, 0, 1), (2, 480, 1275, 8, 1, 0)])
 def test_emu_encoder_matches_oracle(ch, fs, nbytes, complexity, vbr, cvbr):
     E, O = emu_util.load_emu_ops(), util.load_oracle()
     n, nf = (5, 4) if complexity < 5 else (6, 5)

@@ -1,5 +1,5 @@
 """Parity of the CUDA CELT encoder (through the C ABI) with the pinned encoder oracle, and encoder -> decoder round trips.
-Bar: packet bytes and final range identical to the oracle (hence to the reference's celt_encode_with_ec at complexity 0-7, CBR / VBR / CVBR)."""
+Bar: packet bytes and final range identical to the oracle (hence to the reference's celt_encode_with_ec at every complexity 0-10, CBR / VBR / CVBR)."""
 import ctypes
 
 import numpy as np
@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
     (2, 960, 30, 0, 0, 1), (2, 960, 160, 1, 0, 1), (2, 960, 160, 2, 0, 1), (2, 960, 200, 3, 0, 1), (2, 960, 160, 4, 0, 1), (1, 480, 80, 4, 0, 1),
     (2, 240, 50, 3, 0, 1), (2, 120, 30, 4, 0, 1), (2, 960, 1275, 4, 1, 1), (2, 960, 1275, 2, 1, 0), (1, 480, 1275, 4, 1, 1), (2, 120, 1275, 0, 1, 1),
     (2, 960, 160, 5, 0, 1), (1, 960, 80, 5, 0, 1), (2, 480, 100, 6, 0, 1), (2, 240, 60, 7, 0, 1), (1, 120, 30, 5, 0, 1), (2, 960, 60, 7, 0, 1),
-    (2, 960, 1275, 5, 1, 1), (1, 480, 1275, 7, 1, 0), (2, 960, 1275, 6, 1, 0)])
+    (2, 960, 1275, 5, 1, 1), (1, 480, 1275, 7, 1, 0), (2, 960, 1275, 6, 1, 0),
+    (2, 960, 160, 8, 0, 1), (2, 960, 320, 10, 0, 1), (2, 480, 100, 10, 0, 1), (2, 240, 60, 9, 0, 1), (2, 120, 40, 8, 0, 1), (1, 960, 80, 10, 0, 1),
+    (2, 960, 50, 8, 0, 1), (2, 960, 1275, 10, 1, 1), (2, 480, 1275, 8, 1, 0)])
 def test_encoder_matches_oracle(ch, fs, nbytes, complexity, vbr, cvbr):
     import opus_b200
     O = util.load_oracle()
@@ -46,7 +48,7 @@ def test_encode_decode_round_trip():
     ch, fs, nbytes, n, nf = 2, 960, 200, 300, 8
     x = np.stack([(util.sig_harmonic if s & 1 else util.sig_music)(40 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(16)])
     x = np.tile(x, (n // 16 + 1, 1, 1))[:n]
-    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=5)
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=10)
     dec = opus_b200.DecoderBatch(n, channels=ch)
     toc = 0xFC | 0x04   # CELT-only fullband 20 ms, stereo, one frame (RFC 6716 section 3.1: config 31, s=1, c=0)
     outs = []
@@ -74,7 +76,7 @@ def test_ctl_errors():
     from opus_b200 import encoder as E
     enc = opus_b200.EncoderBatch(4, channels=2)
     with pytest.raises(opus_b200.OpusB200Error):
-        enc.ctl(E.OPUS_SET_COMPLEXITY_REQUEST, 8)     # second MDCT / theta RDO are not on the device -> OPUS_UNIMPLEMENTED
+        enc.ctl(E.OPUS_SET_COMPLEXITY_REQUEST, 11)    # OPUS_BAD_ARG like the reference (0..10)
     with pytest.raises(opus_b200.OpusB200Error):
         enc.ctl(E.OPUS_SET_BITRATE_REQUEST, 10)
     enc.close()

@@ -206,7 +206,7 @@ def main():
     pcm = torch.from_numpy(np.tile(xb, ((n + base - 1) // base, 1))[:n].copy()).to(dev)
     pk = torch.empty((n, 160), dtype=torch.uint8, device=dev)
     nbd = torch.empty(n, dtype=torch.int32, device=dev)
-    for cx in (0, 4, 5):
+    for cx in (0, 4, 5, 10):
         enc = opus_b200.EncoderBatch(n, channels=2, complexity=cx)
         estream = torch.cuda.ExternalStream(enc.cuda_stream)
         fn = lambda: L.opusb200_encode_device(enc._h, dptr(pcm), 960, dptr(pk), 160, 160, dptr(nbd))

@@ -11,7 +11,7 @@ from opus_b200 import capi
 ap = argparse.ArgumentParser()
 ap.add_argument('--n', type=int, default=65536)
 ap.add_argument('--reps', type=int, default=5)
-ap.add_argument('--cx', type=int, nargs='+', default=[0, 4, 5])
+ap.add_argument('--cx', type=int, nargs='+', default=[0, 4, 5, 10])
 ap.add_argument('--sig', default='harmonic')
 a = ap.parse_args()
 L = capi.lib()
