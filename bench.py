@@ -241,6 +241,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
+    # pipelined calls: frame t's synthesis (own stream) overlaps frame t+1's range decoding; join() puts the last synthesis
+    # back in front of the closing event, so the timed region holds every kernel of the K steps
+    dec.set_pipelined(True)
     for i in range(args.warmup):
         step_device(i)
     dec.sync()
@@ -254,10 +257,12 @@ def run_gpu_arm(args, rank, world, local_rank):
     e0.record(ext)
     for i in range(args.steps):
         step_device(args.warmup + i)
+    dec.join()
     e1.record(ext)
     dec.sync()
     barrier()
     ms = e0.elapsed_time(e1)
+    dec.set_pipelined(False)
     clk = clocks.stop() if rank == 0 else None
     launches = dec.launch_count - launches0
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -363,6 +368,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'x_realtime': value / 50.0,
         'config': {'workload': 'batched CELT decode, 48 kHz stereo 20 ms @128 kb/s CBR (BASELINE.json configs[1])',
                    'streams_per_gpu': n, 'packets': '256 distinct streams x 8 frames from the reference encoder, tiled',
+                   'pipelining': 'consecutive steps are consecutive frames of the same streams; the synthesis kernel of step t runs on its own CUDA stream under the range decoding of step t+1 (joined before the closing event)',
                    'l2': 'per-step working set (spectrum 503 MB + history 503 MB at 65536 streams) exceeds the 126 MB L2',
                    'parallelism': 'streams sharded across GPUs, no steady-state collective'},
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,

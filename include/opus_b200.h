@@ -83,6 +83,13 @@ int opusb200_decode_device(OpusB200Decoder *dec, const unsigned char *d_packets,
                            void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
                            int32_t *d_out_samples);
 int opusb200_decoder_sync(OpusB200Decoder *dec);
+/* The synthesis kernel of a frame runs on an internal stream so that it can overlap the next frame's bitstream parsing.
+ * By default every opusb200_decode_device call ends by making the library stream wait for it (stream-ordered results).
+ * set_pipelined(dec, 1) leaves that wait out: consecutive calls then overlap (frame t's synthesis under frame t+1's range
+ * decoding); call opusb200_decoder_join (enqueue the wait) or opusb200_decoder_sync before consuming the PCM.
+ * No reference counterpart: the reference decodes one stream synchronously (src/opus_decoder.c:opus_decode_native). */
+int opusb200_decoder_set_pipelined(OpusB200Decoder *dec, int enable);
+int opusb200_decoder_join(OpusB200Decoder *dec);
 
 /* OPUS_GET_FINAL_RANGE for every stream (host array of n_streams). */
 int opusb200_decoder_get_final_range(OpusB200Decoder *dec, uint32_t *final_range);

@@ -146,9 +146,15 @@ struct OpusB200Decoder {
   cudaStream_t stream;
   ObDecBandState *bstate;
   ObDecSynthState *sstate;
-  ObFrameSide *side;
+  // side info and spectra are double-buffered: the synthesis of frame t (own stream) overlaps the bitstream parsing of t+1
+  ObFrameSide *side[2];
   ObScript *script;
-  float *X;
+  float *X[2];
+  int par;                  // buffer parity of the next frame
+  cudaStream_t stream_b;    // synthesis stream
+  cudaEvent_t ev_a2[2], ev_b[2];
+  int last_b;               // parity whose ev_b marks the most recent synthesis (-1: none)
+  int pipelined;            // device API: leave the synthesis un-joined at the end of a call (opusb200_decoder_join)
   int pvq_warps;  // warps (= streams) per CTA of the PVQ kernel
   int ent_lpw;    // streams per warp of the entropy kernel
   // staging for the host-buffer API
@@ -187,9 +193,11 @@ int opusb200_device_count(void) {
 int opusb200_decoder_reset(OpusB200Decoder *d) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(d->device));
+  OB_CUDA(cudaStreamSynchronize(d->stream_b));   // the reset rewrites the synthesis state too
   ob_celt_dec_reset<<<592, 256, 0, d->stream>>>(d->bstate, d->sstate, d->n);
   d->launches++;
   OB_CUDA(cudaGetLastError());
+  OB_CUDA(cudaStreamSynchronize(d->stream));
   return OPUSB200_OK;
 }
 
@@ -209,15 +217,21 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   d->device = device; d->channels = channels; d->n = n_streams;
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+  OB_CUDA(cudaStreamCreateWithFlags(&d->stream_b, cudaStreamNonBlocking));
+  d->last_b = -1;
   for (int b = 0; b < 2; b++) {
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_ready[b], cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_done[b], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&d->ev_a2[b], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&d->ev_b[b], cudaEventDisableTiming));
   }
   OB_CUDA(cudaMalloc(&d->bstate, sizeof(ObDecBandState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->sstate, sizeof(ObDecSynthState) * (size_t)n_streams));
-  OB_CUDA(cudaMalloc(&d->side, sizeof(ObFrameSide) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->script, sizeof(ObScript) * (size_t)n_streams));
-  OB_CUDA(cudaMalloc(&d->X, sizeof(float) * 2 * OB_MAXN * (size_t)n_streams));
+  for (int b = 0; b < 2; b++) {
+    OB_CUDA(cudaMalloc(&d->side[b], sizeof(ObFrameSide) * (size_t)n_streams));
+    OB_CUDA(cudaMalloc(&d->X[b], sizeof(float) * 2 * OB_MAXN * (size_t)n_streams));
+  }
   for (int b = 0; b < 2; b++) {
     OB_CUDA(cudaMalloc(&d->d_len[b], sizeof(int32_t) * (size_t)n_streams));
     OB_CUDA(cudaMalloc(&d->d_out[b], sizeof(int32_t) * (size_t)n_streams));
@@ -258,7 +272,11 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->side); cudaFree(d->script); cudaFree(d->X);
+  cudaStreamSynchronize(d->stream_b);
+  cudaStreamSynchronize(d->stream2);
+  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->script);
+  for (int b = 0; b < 2; b++) { cudaFree(d->side[b]); cudaFree(d->X[b]); cudaEventDestroy(d->ev_a2[b]); cudaEventDestroy(d->ev_b[b]); }
+  cudaStreamDestroy(d->stream_b);
   for (int b = 0; b < 2; b++) { cudaFree(d->d_len[b]); cudaFree(d->d_out[b]); cudaFree(d->d_packets[b]); cudaFree(d->d_pcm[b]); cudaFreeHost(d->h_len[b]); cudaFreeHost(d->h_out[b]); }
   cudaStreamDestroy(d->stream);
   cudaStreamDestroy(d->stream2);
@@ -270,9 +288,21 @@ int opusb200_decoder_n_streams(const OpusB200Decoder *d) { return d ? d->n : OPU
 void *opusb200_decoder_cuda_stream(OpusB200Decoder *d) { return d ? (void *)d->stream : nullptr; }
 int64_t opusb200_decoder_launch_count(const OpusB200Decoder *d) { return d ? d->launches : 0; }
 
+// Make the library stream wait for the most recent synthesis: work enqueued on it afterwards sees the PCM.
+int opusb200_decoder_join(OpusB200Decoder *d) {
+  if (!d) return OPUSB200_BAD_ARG;
+  if (d->last_b >= 0) OB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_b[d->last_b], 0));
+  return OPUSB200_OK;
+}
+int opusb200_decoder_set_pipelined(OpusB200Decoder *d, int enable) {
+  if (!d) return OPUSB200_BAD_ARG;
+  d->pipelined = enable != 0;
+  return opusb200_decoder_join(d);
+}
 int opusb200_decoder_sync(OpusB200Decoder *d) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaStreamSynchronize(d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream_b));
   return OPUSB200_OK;
 }
 
@@ -286,13 +316,18 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
   if ((int)pvq_smem > d->max_smem_optin) return OPUSB200_INTERNAL_ERROR;
   const size_t esz = pcm_is_int16 ? 2 : 4;
   for (int k = 0; k < max_frames_per_packet; k++) {
+    const int par = d->par;
+    d->par ^= 1;
+    const bool timing = d->timing && st == d->stream;
+    cudaStream_t sb = timing ? st : d->stream_b;   // profiling mode keeps everything on one stream
+    // this parity's side/X buffers were last read by the synthesis two frames ago
+    if (!timing) OB_CUDA(cudaStreamWaitEvent(st, d->ev_b[par], 0));
     DecEntropyParams ep;
     ep.packets = d_packets + (size_t)s0 * pkt_stride; ep.pkt_len = d_len + s0; ep.pkt_stride = pkt_stride; ep.n_streams = cn;
-    ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side + s0; ep.script = d->script + s0;
+    ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side[par] + s0; ep.script = d->script + s0;
     ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size;
     DecPvqParams pp;
-    pp.side = d->side + s0; pp.script = d->script + s0; pp.state = d->bstate + s0; pp.X = d->X + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
-    const bool timing = d->timing && st == d->stream;
+    pp.side = d->side[par] + s0; pp.script = d->script + s0; pp.state = d->bstate + s0; pp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
     if (timing) cudaEventRecord(d->ev[0], st);
     {
       const int warps_needed = (cn + d->ent_lpw - 1) / d->ent_lpw;
@@ -301,12 +336,20 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     if (timing) cudaEventRecord(d->ev[1], st);
     ob_celt_dec_pvq<<<(cn + pw - 1) / pw, pw * 32, pvq_smem, st>>>(pp);
     if (timing) cudaEventRecord(d->ev[2], st);
+    else {
+      OB_CUDA(cudaEventRecord(d->ev_a2[par], st));
+      OB_CUDA(cudaStreamWaitEvent(sb, d->ev_a2[par], 0));
+    }
     DecSynthParams sp;
-    sp.side = d->side + s0; sp.X = d->X + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
+    sp.side = d->side[par] + s0; sp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels;
-    ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), st>>>(sp);
+    ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), sb>>>(sp);
     d->launches += 3;
+    if (!timing) {
+      OB_CUDA(cudaEventRecord(d->ev_b[par], sb));
+      d->last_b = par;
+    }
     if (timing) {  // profiling mode: serialises the stream, never used for throughput numbers
       cudaEventRecord(d->ev[3], st);
       cudaEventSynchronize(d->ev[3]);
@@ -329,8 +372,12 @@ int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, i
   if (max_frames_per_packet < 1) max_frames_per_packet = 1;
   if (max_frames_per_packet > 48) max_frames_per_packet = 48;
   OB_CUDA(cudaSetDevice(d->device));
-  return decode_launch(d, d->stream, 0, d->n, d_packets, pkt_stride, d_len, d_pcm, pcm_stride, pcm_is_int16, frame_size,
-                       max_frames_per_packet, d_out_samples);
+  const int r = decode_launch(d, d->stream, 0, d->n, d_packets, pkt_stride, d_len, d_pcm, pcm_stride, pcm_is_int16, frame_size,
+                              max_frames_per_packet, d_out_samples);
+  if (r != OPUSB200_OK) return r;
+  // stream-ordered by default: the PCM is complete for whatever is enqueued on the library stream next.  In pipelined mode
+  // the synthesis stays on its own stream so that the next call's parsing overlaps it (opusb200_decoder_join / _sync).
+  return d->pipelined ? OPUSB200_OK : opusb200_decoder_join(d);
 }
 
 // frames in a packet as far as the TOC and the count byte tell (RFC 6716 3.2); 1 for anything odd
@@ -389,8 +436,9 @@ static int decode_submit(OpusB200Decoder *d, const unsigned char *packets, int p
   const int r = decode_launch(d, d->stream, 0, d->n, d->d_packets[b], pkt_stride, d->d_len[b], d->d_pcm[b], pcm_stride, is_int16,
                               frame_size, maxf, d->d_out[b]);
   if (r != OPUSB200_OK) return r;
-  OB_CUDA(cudaEventRecord(d->ev_ready[b], d->stream));
+  OB_CUDA(cudaEventRecord(d->ev_ready[b], d->stream));   // out_samples (entropy kernel)
   OB_CUDA(cudaStreamWaitEvent(d->stream2, d->ev_ready[b], 0));
+  if (d->last_b >= 0) OB_CUDA(cudaStreamWaitEvent(d->stream2, d->ev_b[d->last_b], 0));   // the PCM (synthesis stream)
   OB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm[b], obytes, cudaMemcpyDeviceToHost, d->stream2));
   OB_CUDA(cudaMemcpyAsync(d->h_out[b], d->d_out[b], sizeof(int32_t) * (size_t)d->n, cudaMemcpyDeviceToHost, d->stream2));
   OB_CUDA(cudaEventRecord(d->ev_done[b], d->stream2));
@@ -403,6 +451,7 @@ int opusb200_decode_wait(OpusB200Decoder *d) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(d->device));
   OB_CUDA(cudaStreamSynchronize(d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream_b));
   OB_CUDA(cudaStreamSynchronize(d->stream2));
   for (int b = 0; b < 2; b++)
     if (d->pending[b]) {

@@ -70,6 +70,17 @@ class DecoderBatch:
         if r != 0:
             raise capi.OpusB200Error(r, 'opusb200_decoder_sync')
 
+    def set_pipelined(self, enable):
+        """device API: let a call's synthesis overlap the next call's parsing; join()/sync() before reading the PCM"""
+        r = self._L.opusb200_decoder_set_pipelined(self._h, 1 if enable else 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_set_pipelined')
+
+    def join(self):
+        r = self._L.opusb200_decoder_join(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_join')
+
     def reset(self):  # OPUS_RESET_STATE
         r = self._L.opusb200_decoder_reset(self._h)
         if r != 0:
