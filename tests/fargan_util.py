@@ -1,0 +1,68 @@
+"""Shared by the FARGAN tests: the reference's dnn/fargan.c built with seeded random weights (oracle/_ref/libfargan_ref.so, see
+oracle/gen_fargan_weights.py) is both the pin and the weight source: its 20 LinearLayers are read back through the harness."""
+import ctypes
+import os
+
+import numpy as np
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NL = 20
+
+
+def load_ref():
+    p = os.path.join(ROOT, 'oracle', '_ref', 'libfargan_ref.so')
+    if not os.path.exists(p):
+        return None
+    L = ctypes.CDLL(p)
+    L.refh_fargan_state_size.restype = ctypes.c_int
+    return L
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class RefFargan:
+    def __init__(self, L):
+        self.L = L
+        self.st = np.zeros(L.refh_fargan_state_size() + 64, np.uint8)
+        L.refh_fargan_init(vp(self.st))
+
+    def cont(self, pcm0, feat0):
+        self.L.refh_fargan_cont(vp(self.st), vp(pcm0), vp(feat0))
+
+    def synth(self, feat):
+        out = np.zeros(160, np.float32)
+        self.L.refh_fargan_synthesize(vp(self.st), vp(out), vp(feat))
+        return out
+
+    def layers(self):
+        """(ctypes array of 20 CLinear pointing into the reference library's own weight arrays, list of (nb_in, nb_out))"""
+        arr = (util.CLinear * NL)()
+        ptrs, dims = (ctypes.c_void_p * 7)(), (ctypes.c_int * 2)()
+        shapes = []
+        for i in range(NL):
+            self.L.refh_fargan_layer(vp(self.st), i, ptrs, dims)
+            for k, name in enumerate(('bias', 'subias', 'weights', 'float_weights', 'weights_idx', 'diag', 'scale')):
+                setattr(arr[i], name, ptrs[k])
+            arr[i].nb_inputs, arr[i].nb_outputs = dims[0], dims[1]
+            shapes.append((dims[0], dims[1]))
+        return arr, shapes
+
+    def state(self):
+        bufs = [np.zeros(k, np.float32) for k in (256, 128, 328, 160, 128, 128, 2)]
+        self.L.refh_fargan_get_state(vp(self.st), *[vp(b) for b in bufs])
+        return bufs
+
+
+def make_inputs(seed, nframes):
+    """continuation PCM (320), 5 priming feature vectors, then nframes feature vectors; feature[18] steers the pitch period"""
+    rng = np.random.default_rng(seed)
+    pcm0 = (0.1 * rng.standard_normal(320)).astype(np.float32)
+    feat0 = (0.5 * rng.standard_normal((5, 20))).astype(np.float32)
+    feats = (0.5 * rng.standard_normal((nframes, 20))).astype(np.float32)
+    feat0[:, 18] = rng.uniform(-1.4, 1.4, 5)
+    feats[:, 18] = rng.uniform(-1.4, 1.4, nframes)     # periods from ~34 to ~240 samples
+    return pcm0, feat0.reshape(-1), feats
