@@ -280,6 +280,19 @@ void opusb200_nnet_conv2d_destroy(OpusB200Conv2d *q);
 int opusb200_nnet_compute_conv2d(OpusB200Ctx *ctx, const OpusB200Conv2d *q, float *out, float *mem, const float *in, int n, int height,
                                  int hstride, int activation, int on_device);
 
+/* ---- FARGAN vocoder (dnn/fargan.h:59-65, dnn/fargan.c): one synthesis state per stream, the model shared ----------------
+ * layers: the 20 LinearLayers of the generated `FARGAN` model struct (fargan_data.h) in declaration order, i.e. what
+ * init_fargan() fills from the weight blob (cond_net_pembed ... sig_net_gain_dense_out); sizes are checked like linear_init.
+ * su_bias as for opusb200_nnet_linear_create.  All buffers are [n_streams][width] row-major floats.
+ *   opusb200_fargan_create      = fargan_init + init_fargan / fargan_load_model   dnn/fargan.c:173-189
+ *   opusb200_fargan_cont        = fargan_cont(st, pcm0[320], features0[5*20])     dnn/fargan.c:143
+ *   opusb200_fargan_synthesize  = fargan_synthesize(st, pcm[160], features[20])   dnn/fargan.c:215  (BAD_ARG before _cont) */
+typedef struct OpusB200Fargan OpusB200Fargan;
+int opusb200_fargan_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int n_streams, OpusB200Fargan **out);
+void opusb200_fargan_destroy(OpusB200Fargan *f);
+int opusb200_fargan_cont(OpusB200Fargan *f, const float *pcm0, const float *features0, int on_device);
+int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const float *features, int on_device);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

@@ -35,7 +35,8 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_silk_nsq_get_state', 'opusb200_nnet_linear_create', 'opusb200_nnet_linear_destroy',
            'opusb200_nnet_compute_linear', 'opusb200_nnet_compute_activation', 'opusb200_nnet_compute_dense',
            'opusb200_nnet_compute_gru', 'opusb200_nnet_compute_glu', 'opusb200_nnet_compute_conv1d',
-           'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d', 'opusb200_host_alloc', 'opusb200_host_free']
+           'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d',
+           'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize', 'opusb200_host_alloc', 'opusb200_host_free']
 
 
 class OpusB200Error(RuntimeError):
@@ -129,6 +130,13 @@ def lib():
         L.opusb200_nnet_conv2d_destroy.argtypes = [vp]
         L.opusb200_nnet_conv2d_destroy.restype = None
         L.opusb200_nnet_compute_conv2d.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci]
+        L.opusb200_fargan_create.argtypes = [vp, vp, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_fargan_destroy.argtypes = [vp]
+        L.opusb200_fargan_destroy.restype = None
+        L.opusb200_fargan_cont.argtypes = [vp, vp, vp, ci]
+        L.opusb200_fargan_synthesize.argtypes = [vp, vp, vp, ci]
+        L.opusb200_decoder_set_pipelined.argtypes = [vp, ci]
+        L.opusb200_decoder_join.argtypes = [vp]
         L.opusb200_decode_submit.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, vp]
         L.opusb200_decode_wait.argtypes = [vp]
         L.opusb200_celt_analysis_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]

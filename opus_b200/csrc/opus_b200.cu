@@ -976,4 +976,5 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 #include "nnet_host.cuh"
+#include "fargan_host.cuh"
 #include "celt_enc_host.cuh"

@@ -142,3 +142,45 @@ class Nnet:
         self._chk(self._L.opusb200_nnet_compute_conv2d(self._c, layer._h, _p(out), _p(m) if m.size else None, _p(x), x.shape[0], height, hstride,
                                                       act, 0), 'nnet_compute_conv2d')
         return out, m
+
+
+class Fargan:
+    """Batched FARGAN vocoder (dnn/fargan.h:59-65): n streams share the model; `layers` is a ctypes array of 20 OpusB200LinearLayer
+    (= the reference's generated FARGAN struct, in declaration order) or a pointer to one."""
+    NB_FEATURES, FRAME_SIZE, CONT_SAMPLES = 20, 160, 320
+
+    def __init__(self, ops, layers, n_streams, su_bias=False):
+        self._ops, self._L, self.n = ops, ops._L, n_streams
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_fargan_create(ops._h, layers, 20, 1 if su_bias else 0, n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_fargan_create')
+        self._h = h
+
+    def cont(self, pcm0, features0):
+        """fargan_cont: pcm0 [n][320], features0 [n][5*20]"""
+        pcm0 = np.ascontiguousarray(pcm0, np.float32).reshape(self.n, self.CONT_SAMPLES)
+        features0 = np.ascontiguousarray(features0, np.float32).reshape(self.n, 5 * self.NB_FEATURES)
+        r = self._L.opusb200_fargan_cont(self._h, _p(pcm0), _p(features0), 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_fargan_cont')
+
+    def synthesize(self, features):
+        """fargan_synthesize: features [n][20] -> pcm [n][160] float"""
+        features = np.ascontiguousarray(features, np.float32).reshape(self.n, self.NB_FEATURES)
+        out = np.empty((self.n, self.FRAME_SIZE), np.float32)
+        r = self._L.opusb200_fargan_synthesize(self._h, _p(out), _p(features), 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_fargan_synthesize')
+        return out
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_fargan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
