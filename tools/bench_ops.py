@@ -146,6 +146,30 @@ def main():
     emit('nnet_gru_272_160', 'stream-steps', n, ms, M * 4 + 2 * N * 4, None, 'two int8 linears + gate kernel; %.2f TOPS' % (2.0 * n * (M + N) * 3 * N / (ms * 1e-3) / 1e12))
     dWi.close(); dWr.close()
 
+    # ---- FARGAN vocoder (BASELINE config 5: 32768 streams, 10 ms frames): one fargan_synthesize step for the whole batch ----
+    import fargan_util as FG
+    FR = FG.load_ref()
+    if FR is not None:
+        from opus_b200 import nnet as nn_mod
+        nf = min(n, 32768)
+        ref = FG.RefFargan(FR)
+        layers, _ = ref.layers()
+        fg = nn_mod.Fargan(ops, layers, nf)
+        pcm0, feat0, feats = FG.make_inputs(5, 4)
+        fg.cont(np.tile(pcm0, (nf, 1)), np.tile(feat0, (nf, 1)))
+        d_feat = torch.from_numpy(np.tile(feats[0], (nf, 1)).astype(np.float32)).to(dev)
+        d_out = torch.empty((nf, 160), dtype=torch.float32, device=dev)
+        l0 = int(L.opusb200_ctx_launch_count(ops._h)) if hasattr(L, 'opusb200_ctx_launch_count') else 0
+        fn = lambda: L.opusb200_fargan_synthesize(fg._h, dptr(d_out), dptr(d_feat), 1)
+        ms = time_gpu(stream, fn, a.reps)
+        ref.cont(pcm0, feat0)
+        cpu = time_cpu(lambda: ref.synth(feats[0]), 1.0)
+        macs = 4 * (328 * 192 + 192 * 192 + 192 * 4 + 272 * 480 + 160 * 480 + 160 * 160 + 240 * 384 + 128 * 384 + 128 * 128 + 208 * 384 + 128 * 384 + 128 * 128
+                    + 688 * 128 + 128 * 128 + 128 * 40 + 80) + 32 * 64 + 192 * 128 + 128 * 320
+        emit('fargan_synthesize_10ms', 'frames(10ms)', nf, ms, 20 * 4 + 160 * 4, cpu,
+             'layer-by-layer graph, int8 layers on mma.sync; %.1f TOPS; CPU column = reference fargan.c, generic C branch, 1 core' % (2.0 * nf * macs / (ms * 1e-3) / 1e12))
+        fg.close()
+
     # ---- SILK Burg (16 kHz: 4 x (80+16) samples, order 16) ----
     subfr, nb, D = 96, 4, 16
     t = np.arange(subfr * nb)
