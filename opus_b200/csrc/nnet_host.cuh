@@ -1,5 +1,6 @@
 // nnet_host.cuh — kernels' entry points and the C ABI of the dnn/ primitives (included at the end of opus_b200.cu).
 #pragma once
+#include "nnet_umma.cuh"
 #include "nnet.cuh"
 
 extern "C" __global__ void __launch_bounds__(256) ob_nnet_activation(NnetActParams p) {
@@ -43,6 +44,10 @@ struct OpusB200Linear {
   OpusB200Ctx *ctx;
   NnetLinear L;            // device pointers
   void *blob;              // one allocation behind all of them
+  // dense int8 layers also keep the weights in the tcgen05 operand layout (nnet_umma.cuh); null when the layer does not qualify
+  int8_t *wt_umma;
+  int Kp, Npad, n_tiles_n, tileN, a_stages, tmem_cols;
+  size_t umma_smem;
 };
 struct OpusB200Conv2d {
   OpusB200Ctx *ctx;
@@ -110,9 +115,31 @@ extern "C" int opusb200_nnet_linear_create(OpusB200Ctx *c, const OpusB200LinearL
     up(o_rb, rb_off, (size_t)(N / 8 + 1) * 4); L.rb_off = (const int *)(b + o_rb);
     up(o_pos, pos, (size_t)nb * 4); L.pos = (const int *)(b + o_pos);
   }
+  l->wt_umma = nullptr;
+  int8_t *wt_host = nullptr;
+  if (i8 && !sparse && N <= 512 && getenv("OPUSB200_NNET_NO_UMMA") == nullptr) {
+    // tcgen05 tiling: one or two N tiles (multiples of 16, <= 256) per 128-stream tile; K padded to the MMA's 32
+    const int nt = N <= 256 ? 1 : 2, tileN = (((N + nt - 1) / nt) + 15) & ~15, Npad = nt * tileN, Kp = (M + 31) & ~31;
+    int cols = 32;
+    while (cols < ((Npad + 31) & ~31)) cols <<= 1;
+    const size_t wb = (size_t)Npad * Kp, ab = (size_t)128 * Kp, extra = 9 * 8 + 16 + 128;
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    const int stages = wb + 2 * ab + extra <= (size_t)max_optin ? 2 : (wb + ab + extra <= (size_t)max_optin ? 1 : 0);
+    if (stages && cudaMalloc(&l->wt_umma, wb) == cudaSuccess) {
+      wt_host = (int8_t *)calloc(wb, 1);
+      const int CB = M / 4;
+      for (int i = 0; i < N; i++)
+        for (int k = 0; k < M; k++)   // reference blocking: 8 rows x 4 columns per 32-byte block (dnn/vec.h:249)
+          wt_host[((size_t)(k >> 4) * Npad + i) * 16 + (k & 15)] = h->weights[((size_t)(i >> 3) * CB + (k >> 2)) * 32 + (i & 7) * 4 + (k & 3)];
+      if (e == cudaSuccess) e = cudaMemcpyAsync(l->wt_umma, wt_host, wb, cudaMemcpyHostToDevice, c->stream);
+      l->Kp = Kp; l->Npad = Npad; l->n_tiles_n = nt; l->tileN = tileN; l->a_stages = stages; l->tmem_cols = cols;
+      l->umma_smem = wb + stages * ab + extra;
+    }
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  free(rb_off); free(pos);
-  if (e != cudaSuccess) { cudaFree(l->blob); delete l; return OPUSB200_INTERNAL_ERROR; }
+  free(rb_off); free(pos); free(wt_host);
+  if (e != cudaSuccess) { cudaFree(l->blob); cudaFree(l->wt_umma); delete l; return OPUSB200_INTERNAL_ERROR; }
   *out = l;
   return OPUSB200_OK;
 }
@@ -121,6 +148,7 @@ extern "C" void opusb200_nnet_linear_destroy(OpusB200Linear *l) {
   cudaSetDevice(l->ctx->device);
   cudaStreamSynchronize(l->ctx->stream);
   cudaFree(l->blob);
+  cudaFree(l->wt_umma);
   delete l;
 }
 
@@ -129,6 +157,28 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
   NnetLinearParams p;
   p.L = l->L; p.out = out; p.in = in; p.n = n; p.xq = nullptr; p.Mp = (l->L.M + 31) & ~31;
   const NnetLinear &L = l->L;
+  if (L.w8 && l->wt_umma) {   // dense int8 layer: tcgen05 / TMEM path (nnet_umma.cuh)
+    const int mt = (n + 127) / 128;
+    void *xq;
+    if (nnet_scratch(c, 0, (size_t)mt * 128 * l->Kp, &xq)) return OPUSB200_ALLOC_FAIL;
+    UmmaQuantParams q;
+    q.xq = (int8_t *)xq; q.in = in; q.n = n; q.M = L.M; q.Kp = l->Kp; q.su = L.su;
+    ob_nnet_quant_umma<<<nblk((long)mt * 128 * (l->Kp / 16), 256), 256, 0, c->stream>>>(q);
+    UmmaLinearParams u;
+    u.wt = l->wt_umma; u.xq = (const int8_t *)xq; u.scale = L.scale; u.bias = L.bias; u.diag = L.diag; u.in = in; u.out = out; u.n = n; u.M = L.M; u.N = L.N;
+    u.Kp = l->Kp; u.Npad = l->Npad; u.n_tiles_n = l->n_tiles_n; u.tileN = l->tileN; u.a_stages = l->a_stages; u.su = L.su; u.tmem_cols = l->tmem_cols;
+    static size_t smem_set = 0;
+    if (l->umma_smem > smem_set) {
+      OB_CUDA(cudaFuncSetAttribute(ob_nnet_linear_i8_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l->umma_smem));
+      smem_set = l->umma_smem;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    ob_nnet_linear_i8_umma<<<mt < sms ? mt : sms, 192, l->umma_smem, c->stream>>>(u);
+    c->launches += 2;
+    OB_CUDA(cudaGetLastError());
+    return OPUSB200_OK;
+  }
   if (L.w8) {
     void *xq;
     if (nnet_scratch(c, 0, (size_t)n * p.Mp, &xq)) return OPUSB200_ALLOC_FAIL;
