@@ -122,7 +122,7 @@ extern "C" int opusb200_nnet_linear_create(OpusB200Ctx *c, const OpusB200LinearL
     const int nt = N <= 256 ? 1 : 2, tileN = (((N + nt - 1) / nt) + 15) & ~15, Npad = nt * tileN, Kp = (M + 31) & ~31;
     int cols = 32;
     while (cols < ((Npad + 31) & ~31)) cols <<= 1;
-    const size_t wb = (size_t)Npad * Kp, ab = (size_t)128 * Kp, extra = 9 * 8 + 16 + 128;
+    const size_t wb = (size_t)Npad * Kp, ab = (size_t)128 * Kp, extra = 12 * 8 + 8 * 32 * 33 * 4 + 128;   // barriers + TMEM slot, the epilogue's transpose tiles
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
     const int stages = wb + 2 * ab + extra <= (size_t)max_optin ? 2 : (wb + ab + extra <= (size_t)max_optin ? 1 : 0);
@@ -174,7 +174,7 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    ob_nnet_linear_i8_umma<<<mt < sms ? mt : sms, 192, l->umma_smem, c->stream>>>(u);
+    ob_nnet_linear_i8_umma<<<mt < sms ? mt : sms, 320, l->umma_smem, c->stream>>>(u);
     c->launches += 2;
     OB_CUDA(cudaGetLastError());
     return OPUSB200_OK;

@@ -3,13 +3,14 @@
 //
 //   out[s][i] = (float)( sum_k x8[s][k] * w8[i][k] ) * scale[i] (+ bias[i]) (+ diag)         s < n streams, i < N outputs
 //
-// One persistent CTA per SM (192 threads, warp-specialised):
+// One persistent CTA per SM (320 threads, warp-specialised):
 //   warp 0    producer: 1-D bulk copies (cp.async.bulk, completion on an mbarrier) — the whole weight matrix once, then one
 //             128-stream activation tile per step.  Both operands are stored in HBM already in the tensor core's canonical
 //             K-major no-swizzle layout ([k/16][row][16 bytes]: 8x16-byte core matrices), so a linear copy lands them right.
 //   warp 1    allocates TMEM, then one elected lane issues tcgen05.mma (M=128, N=tile, K=32 per instruction) and commits to
 //             mbarriers; the two N-halves of a layer use two accumulators, so the epilogue of one overlaps the MMAs of the other.
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> scale/bias in the reference's float order -> HBM.
+//   warps 2-9 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> transpose in shared memory -> scale/bias in the
+//             reference's float order -> coalesced stores.
 // Integer accumulation is exact, so the result is bit-identical to the mma.sync kernel and to the oracle.
 #pragma once
 #include <cuda_runtime.h>
@@ -74,21 +75,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }  // namespace umma
 
 // float -> (u8|s8) activations (dnn/vec.h:253 / vec_avx.h:383) straight into the tensor core's operand layout;
-// one thread per (stream, 16-byte k chunk)
+// one thread per (16-byte k chunk, stream), streams fastest: a warp writes 512 contiguous bytes and every lane reads the 64
+// contiguous bytes (two full sectors) of its own row with four 128-bit loads
 extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma(UmmaQuantParams p) {
   const int KC = p.Kp >> 4;
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long rows = (long)((p.n + 127) / 128) * 128;
   if (t >= rows * KC) return;
-  const int s = (int)(t / KC), kc = (int)(t - (long)s * KC);
+  const int kc = (int)(t / rows), s = (int)(t - (long)kc * rows);
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (s < p.n) {
+    const float *src = p.in + (size_t)s * p.M + kc * 16;
+    float x[16];
+    if (kc * 16 + 16 <= p.M && (p.M & 3) == 0) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const float4 f = *(const float4 *)(src + 4 * b);
+        x[4 * b] = f.x; x[4 * b + 1] = f.y; x[4 * b + 2] = f.z; x[4 * b + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < 16; b++) x[b] = kc * 16 + b < p.M ? src[b] : 0.f;
+    }
 #pragma unroll
     for (int b = 0; b < 16; b++) {
-      const int j = kc * 16 + b;
       int q = 0;
-      if (j < p.M) {
-        q = (int)floor(0.5 + (double)__fmul_rn(127.f, p.in[(size_t)s * p.M + j]));
+      if (kc * 16 + b < p.M) {
+        q = (int)floor(0.5 + (double)__fmul_rn(127.f, x[b]));
         if (p.su) q += 127;
       }
       w[b >> 2] |= ((uint32_t)q & 0xffu) << (8 * (b & 3));
@@ -98,7 +111,7 @@ extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma(UmmaQuantPa
   *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-extern "C" __global__ void __launch_bounds__(192, 1) ob_nnet_linear_i8_umma(UmmaLinearParams p) {
+extern "C" __global__ void __launch_bounds__(320, 1) ob_nnet_linear_i8_umma(UmmaLinearParams p) {
   using namespace umma;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,6 +119,7 @@ extern "C" __global__ void __launch_bounds__(192, 1) ob_nnet_linear_i8_umma(Umma
   unsigned char *sW = smem_raw, *sA = smem_raw + w_bytes;
   uint64_t *bars = (uint64_t *)(sA + (size_t)p.a_stages * a_bytes);   // [0] w_full, [1..2] a_full, [3..4] a_empty, [5..6] acc_full, [7..8] acc_empty
   uint32_t *tmem_slot = (uint32_t *)(bars + 9);
+  float *stage = (float *)(bars + 12) + (warp >= 2 ? (warp - 2) * 32 * 33 : 0);   // per epilogue warp: 32 x 33 floats
   const uint32_t b_w = saddr(&bars[0]);
   auto b_afull = [&](int s) { return saddr(&bars[1 + s]); };
   auto b_aempty = [&](int s) { return saddr(&bars[3 + s]); };
@@ -113,7 +127,7 @@ extern "C" __global__ void __launch_bounds__(192, 1) ob_nnet_linear_i8_umma(Umma
   auto b_accempty = [&](int s) { return saddr(&bars[7 + s]); };
   if (threadIdx.x == 0) {
     mbar_init(b_w, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(b_afull(s), 1); mbar_init(b_aempty(s), 1); mbar_init(b_accfull(s), 1); mbar_init(b_accempty(s), 4); }
+    for (int s = 0; s < 2; s++) { mbar_init(b_afull(s), 1); mbar_init(b_aempty(s), 1); mbar_init(b_accfull(s), 1); mbar_init(b_accempty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -170,33 +184,45 @@ extern "C" __global__ void __launch_bounds__(192, 1) ob_nnet_linear_i8_umma(Umma
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;   // the TMEM lane quadrant this warp may read
+    // 8 epilogue warps: warp & 3 = the TMEM lane quadrant it may read; the two warps of a quadrant split the 32-column chunks
+    const int q = warp & 3, g = (warp - 2) >> 2;
     int it = 0;
     for (int t = blockIdx.x; t < n_mtiles; t += gridDim.x, it++) {
-      const int row = t * 128 + q * 32 + lane;
+      const int row0 = t * 128 + q * 32;
       for (int nt = 0; nt < p.n_tiles_n; nt++) {
         mbar_wait(b_accfull(nt), (uint32_t)it & 1u);
         fence_after();
-        for (int c0 = 0; c0 < p.tileN; c0 += 32) {
+        for (int c0 = g * 32; c0 < p.tileN; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(nt * p.tileN + c0), v);
-          if (row < p.n) {
-            float *orow = p.out + (size_t)row * p.N;
-            const float *irow = p.in + (size_t)row * p.M;
+          // lane = row here; transpose through shared memory so that a store instruction covers 32 consecutive outputs of a row
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const int i = nt * p.tileN + c0 + j;
-              if (c0 + j < p.tileN && i < p.N) {
-                float y = __fmul_rn((float)(int32_t)v[j], p.scale[i]);
-                if (p.bias) y = __fadd_rn(y, p.bias[i]);
-                if (p.diag) {
-                  const int m = i >= 2 * p.M ? i - 2 * p.M : (i >= p.M ? i - p.M : i);
-                  y = __fadd_rn(y, __fmul_rn(p.diag[i], irow[m]));
-                }
-                orow[i] = y;
-              }
-            }
+          for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __int_as_float((int)v[j]);
+          __syncwarp();
+          const int i = nt * p.tileN + c0 + lane;
+          const bool col_ok = c0 + lane < p.tileN && i < p.N;
+          const float sc = col_ok ? p.scale[i] : 0.f, bi = (col_ok && p.bias) ? p.bias[i] : 0.f;
+          float y[32];
+#pragma unroll
+          for (int r = 0; r < 32; r++) {
+            y[r] = __fmul_rn((float)__float_as_int(stage[r * 33 + lane]), sc);
+            if (p.bias) y[r] = __fadd_rn(y[r], bi);
           }
+          if (p.diag && col_ok) {   // GRU recurrent matrices: + diag[i] * in[i mod M] (dnn/nnet_arch.h:145-152); loads issued together
+            const int m = i >= 2 * p.M ? i - 2 * p.M : (i >= p.M ? i - p.M : i);
+            const float dg = p.diag[i];
+            float xin[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) xin[r] = row0 + r < p.n ? p.in[(size_t)(row0 + r) * p.M + m] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; r++) y[r] = __fadd_rn(y[r], __fmul_rn(dg, xin[r]));
+          }
+          if (col_ok) {
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+              if (row0 + r < p.n) p.out[(size_t)(row0 + r) * p.N + i] = y[r];
+          }
+          __syncwarp();
         }
         fence_before();
         __syncwarp();
