@@ -140,7 +140,7 @@ def main():
         vp = lambda arr: arr.ctypes.data_as(ctypes.c_void_p) if arr is not None else None
         cpu = time_cpu(lambda: RC.refh_nnet_linear(vp(o1), vp(x1), vp(Wi.bias), vp(Wi.subias), vp(Wi.weights), None, None, None, vp(Wi.scale), M, 3 * N), 0.5)
     rec_l = {'int8_TOPS': 2.0 * n * M * 3 * N / (ms * 1e-3) / 1e12}
-    emit('nnet_linear_i8_272x480', 'stream-layers', n, ms, M * 4 + 3 * N * 4, cpu, 'tensor-core mma.sync int8; %.2f TOPS' % rec_l['int8_TOPS'])
+    emit('nnet_linear_i8_272x480', 'stream-layers', n, ms, M * 4 + 3 * N * 4, cpu, 'tcgen05.mma kind::i8, TMEM accumulators (quantiser + GEMM kernels); %.2f TOPS' % rec_l['int8_TOPS'])
     fn = lambda: L.opusb200_nnet_compute_gru(ops._h, dWi._h, dWr._h, dptr(sts), dptr(xs), n, 1)
     ms = time_gpu(stream, fn, a.reps)
     emit('nnet_gru_272_160', 'stream-steps', n, ms, M * 4 + 2 * N * 4, None, 'two int8 linears + gate kernel; %.2f TOPS' % (2.0 * n * (M + N) * 3 * N / (ms * 1e-3) / 1e12))
@@ -167,7 +167,7 @@ def main():
         macs = 4 * (328 * 192 + 192 * 192 + 192 * 4 + 272 * 480 + 160 * 480 + 160 * 160 + 240 * 384 + 128 * 384 + 128 * 128 + 208 * 384 + 128 * 384 + 128 * 128
                     + 688 * 128 + 128 * 128 + 128 * 40 + 80) + 32 * 64 + 192 * 128 + 128 * 320
         emit('fargan_synthesize_10ms', 'frames(10ms)', nf, ms, 20 * 4 + 160 * 4, cpu,
-             'layer-by-layer graph, int8 layers on mma.sync; %.1f TOPS; CPU column = reference fargan.c, generic C branch, 1 core' % (2.0 * nf * macs / (ms * 1e-3) / 1e12))
+             'layer-by-layer graph, int8 layers on tcgen05; %.1f TOPS; CPU column = reference fargan.c, generic C branch, 1 core' % (2.0 * nf * macs / (ms * 1e-3) / 1e12))
         fg.close()
 
     # ---- SILK Burg (16 kHz: 4 x (80+16) samples, order 16) ----
