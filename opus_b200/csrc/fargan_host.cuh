@@ -103,37 +103,48 @@ extern "C" __global__ void ob_fargan_cat(FgParams p) {
   else v = p.prev[(size_t)s * kFgSub + (j - head - kFgSub)];
   p.cat[(size_t)s * width + j] = v;
 }
-// scale by the gain, push into the pitch buffer, de-emphasis (dnn/fargan.c:136-140, :61-67); one thread per stream
-// (the de-emphasis is a 40-step recurrence).  use_last: fargan_cont's loop overwrites the newest 40 samples afterwards (:165).
-extern "C" __global__ void ob_fargan_sub_out(FgParams p) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n) return;
-  FgStreamState &st = p.st[s];
-  const float gain = p.gain[s];
-  float x[kFgSub];
+// scale by the gain, push into the pitch buffer, de-emphasis (dnn/fargan.c:136-140, :61-67).  64 threads per stream move the
+// pitch buffer (values read, barrier, values written); one of them runs the 40-step de-emphasis recurrence.
+// pcm0 != null: fargan_cont's loop, where the known signal replaces the synthesised subframe afterwards (:165).
+extern "C" __global__ void __launch_bounds__(256) ob_fargan_sub_out(FgParams p) {
+  const int s = blockIdx.x * 4 + (threadIdx.x >> 6), j = threadIdx.x & 63;
+  const bool ok = s < p.n;
+  FgStreamState *st = ok ? p.st + s : p.st;
+  const float gain = ok ? p.gain[s] : 0.f;
+  float nv[4];
 #pragma unroll
-  for (int i = 0; i < kFgSub; i++) x[i] = p.sig[(size_t)s * kFgSub + i] * gain;
-#pragma unroll 1
-  for (int i = 0; i < kFgPitchMax - kFgSub; i++) st.pitch_buf[i] = st.pitch_buf[i + kFgSub];
-  if (p.pcm0) {   // continuation: the known signal replaces the synthesised subframe
-    const float *pc = p.pcm0 + (size_t)s * kFgCont;
-#pragma unroll 1
-    for (int i = 0; i < kFgSub; i++) {
-      const int k = kFgFrame + p.sub * kFgSub + i;
-      st.pitch_buf[kFgPitchMax - kFgSub + i] = pc[k] - 0.85f * pc[k - 1];
+  for (int k = 0; k < 4; k++) {
+    const int idx = j + 64 * k;
+    if (!ok) nv[k] = 0.f;
+    else if (idx < kFgPitchMax - kFgSub) nv[k] = st->pitch_buf[idx + kFgSub];
+    else {
+      const int i = idx - (kFgPitchMax - kFgSub);
+      if (p.pcm0) {
+        const float *pc = p.pcm0 + (size_t)s * kFgCont;
+        const int kk = kFgFrame + p.sub * kFgSub + i;
+        nv[k] = pc[kk] - 0.85f * pc[kk - 1];
+      } else nv[k] = p.sig[(size_t)s * kFgSub + i] * gain;
     }
-    if (p.sub == kFgNbSub - 1) st.deemph_mem = pc[kFgCont - 1];
-    return;
   }
-  float mem = st.deemph_mem;
+  __syncthreads();
+  if (!ok) return;
 #pragma unroll
-  for (int i = 0; i < kFgSub; i++) {
-    st.pitch_buf[kFgPitchMax - kFgSub + i] = x[i];
-    x[i] += 0.85f * mem;
-    mem = x[i];
-    p.pcm[(size_t)s * kFgFrame + p.sub * kFgSub + i] = x[i];
+  for (int k = 0; k < 4; k++) st->pitch_buf[j + 64 * k] = nv[k];
+  if (j == 0) {
+    if (p.pcm0) {
+      if (p.sub == kFgNbSub - 1) st->deemph_mem = p.pcm0[(size_t)s * kFgCont + kFgCont - 1];
+    } else {
+      float mem = st->deemph_mem;
+#pragma unroll 8
+      for (int i = 0; i < kFgSub; i++) {
+        float x = p.sig[(size_t)s * kFgSub + i] * gain;
+        x += 0.85f * mem;
+        mem = x;
+        p.pcm[(size_t)s * kFgFrame + p.sub * kFgSub + i] = x;
+      }
+      st->deemph_mem = mem;
+    }
   }
-  st.deemph_mem = mem;
 }
 // fargan_cont's prologue (:157-161): x0 = pre-emphasised pcm0, first frame into the pitch buffer
 extern "C" __global__ void ob_fargan_cont_in(FgParams p) {
@@ -261,7 +272,7 @@ static int fg_subframe(OpusB200Fargan *f, int sub, float *d_pcm, const float *d_
   FG_TRY(opusb200_nnet_compute_dense(c, f->l[FG_SKIP_DENSE], f->skip, f->cat, n, NN_TANH, 1));
   FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_SKIP_GLU], f->skip, f->skip, n, 1));
   FG_TRY(opusb200_nnet_compute_dense(c, f->l[FG_SIG_OUT], f->sig, f->skip, n, NN_TANH, 1));
-  ob_fargan_sub_out<<<fg_blk(n), 256, 0, c->stream>>>(p);
+  ob_fargan_sub_out<<<(unsigned)((n + 3) / 4), 256, 0, c->stream>>>(p);
   c->launches += 5;
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;

@@ -1,7 +1,7 @@
 // nnet_host.cuh — kernels' entry points and the C ABI of the dnn/ primitives (included at the end of opus_b200.cu).
 #pragma once
-#include "nnet_umma.cuh"
 #include "nnet.cuh"
+#include "nnet_umma.cuh"
 
 extern "C" __global__ void __launch_bounds__(256) ob_nnet_activation(NnetActParams p) {
   nnet_activation_thread(p, (long)blockIdx.x * blockDim.x + threadIdx.x);
@@ -153,7 +153,10 @@ extern "C" void opusb200_nnet_linear_destroy(OpusB200Linear *l) {
 }
 
 // device-pointer core of compute_linear: out [n][N], in [n][M]
-static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, const float *in, int n) {
+// act / glu_in: fused into the tcgen05 kernel's epilogue when the layer takes that path (*fused says so); other paths ignore them
+static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, const float *in, int n, int act = NN_LINEAR,
+                           const float *glu_in = nullptr, bool *fused = nullptr) {
+  if (fused) *fused = false;
   NnetLinearParams p;
   p.L = l->L; p.out = out; p.in = in; p.n = n; p.xq = nullptr; p.Mp = (l->L.M + 31) & ~31;
   const NnetLinear &L = l->L;
@@ -167,6 +170,8 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
     UmmaLinearParams u;
     u.wt = l->wt_umma; u.xq = (const int8_t *)xq; u.scale = L.scale; u.bias = L.bias; u.diag = L.diag; u.in = in; u.out = out; u.n = n; u.M = L.M; u.N = L.N;
     u.Kp = l->Kp; u.Npad = l->Npad; u.n_tiles_n = l->n_tiles_n; u.tileN = l->tileN; u.a_stages = l->a_stages; u.su = L.su; u.tmem_cols = l->tmem_cols;
+    u.act = (act != NN_SOFTMAX) ? act : NN_LINEAR; u.glu_in = glu_in;
+    if (fused) *fused = act != NN_SOFTMAX;
     static size_t smem_set = 0;
     if (l->umma_smem > smem_set) {
       OB_CUDA(cudaFuncSetAttribute(ob_nnet_linear_i8_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l->umma_smem));
@@ -273,8 +278,9 @@ extern "C" int opusb200_nnet_compute_dense(OpusB200Ctx *c, const OpusB200Linear 
   const float *din = (const float *)st.in(in, ib, on_device, true, &err);
   float *dout = (float *)st.in(out, ob_, on_device, false, &err);
   if (err) return err;
-  if ((err = nnet_linear_dev(c, l, dout, din, n))) return err;
-  if ((err = nnet_act_dev(c, dout, dout, n, l->L.N, activation))) return err;
+  bool fused = false;
+  if ((err = nnet_linear_dev(c, l, dout, din, n, activation, nullptr, &fused))) return err;
+  if (!fused && (err = nnet_act_dev(c, dout, dout, n, l->L.N, activation))) return err;
   if ((err = st.out(out, dout, ob_, on_device))) return err;
   return st.finish(on_device);
 }
@@ -312,6 +318,12 @@ extern "C" int opusb200_nnet_compute_glu(OpusB200Ctx *c, const OpusB200Linear *l
   const float *din = (const float *)st.in(in, b, on_device, true, &err);
   float *dout = (on_device || in != out) ? (float *)st.in(out, b, on_device, false, &err) : (float *)din;
   if (err) return err;
+  if (l->wt_umma) {   // gate fused into the tensor-core kernel's epilogue
+    bool fused = false;
+    if ((err = nnet_linear_dev(c, l, dout, din, n, NN_LINEAR, din, &fused))) return err;
+    if ((err = st.out(out, dout, b, on_device))) return err;
+    return st.finish(on_device);
+  }
   void *tmp;
   if (nnet_scratch(c, 1, b, &tmp)) return OPUSB200_ALLOC_FAIL;
   if ((err = nnet_linear_dev(c, l, (float *)tmp, din, n))) return err;
@@ -346,8 +358,9 @@ extern "C" int opusb200_nnet_compute_conv1d(OpusB200Ctx *c, const OpusB200Linear
   p.tmp = (float *)tmp; p.mem = dmem; p.in = din; p.n = n; p.nb_inputs = M; p.input_size = input_size; p.dilation = dilation; p.phase = 0;
   ob_nnet_conv1d<<<nblk((long)n * M, 256), 256, 0, c->stream>>>(p);
   c->launches++;
-  if ((err = nnet_linear_dev(c, l, dout, (const float *)tmp, n))) return err;
-  if ((err = nnet_act_dev(c, dout, dout, n, l->L.N, activation))) return err;
+  bool fused = false;
+  if ((err = nnet_linear_dev(c, l, dout, (const float *)tmp, n, activation, nullptr, &fused))) return err;
+  if (!fused && (err = nnet_act_dev(c, dout, dout, n, l->L.N, activation))) return err;
   if (mem_len) {
     p.phase = 1;
     ob_nnet_conv1d<<<nblk(dilation == 1 ? (long)n * hist : (long)n * input_size, 256), 256, 0, c->stream>>>(p);

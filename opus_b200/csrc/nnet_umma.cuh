@@ -25,6 +25,8 @@ struct UmmaLinearParams {
   const float *in;      // [n][M] float input (only the diag term reads it)
   float *out;           // [n][N]
   int n, M, N, Kp, Npad, n_tiles_n, tileN, a_stages, su, tmem_cols;
+  int act;              // elementwise activation fused into the epilogue (compute_generic_dense / conv1d), 0 = none
+  const float *glu_in;  // non-null: out = glu_in * sigmoid(y)  (compute_glu, dnn/nnet.c:107-120; may alias out)
 };
 struct UmmaQuantParams { int8_t *xq; const float *in; int n, M, Kp, su; };
 
@@ -216,6 +218,16 @@ extern "C" __global__ void __launch_bounds__(320, 1) ob_nnet_linear_i8_umma(Umma
             for (int r = 0; r < 32; r++) xin[r] = row0 + r < p.n ? p.in[(size_t)(row0 + r) * p.M + m] : 0.f;
 #pragma unroll
             for (int r = 0; r < 32; r++) y[r] = __fadd_rn(y[r], __fmul_rn(dg, xin[r]));
+          }
+          if (p.glu_in && col_ok) {
+            float gin[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) gin[r] = row0 + r < p.n ? p.glu_in[(size_t)(row0 + r) * p.N + i] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; r++) y[r] = __fmul_rn(gin[r], nn_sigmoid(y[r]));
+          } else if (p.act) {
+#pragma unroll
+            for (int r = 0; r < 32; r++) y[r] = nn_act(y[r], p.act);
           }
           if (col_ok) {
 #pragma unroll
