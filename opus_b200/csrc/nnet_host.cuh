@@ -170,8 +170,11 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
     UmmaLinearParams u;
     u.wt = l->wt_umma; u.xq = (const int8_t *)xq; u.scale = L.scale; u.bias = L.bias; u.diag = L.diag; u.in = in; u.out = out; u.n = n; u.M = L.M; u.N = L.N;
     u.Kp = l->Kp; u.Npad = l->Npad; u.n_tiles_n = l->n_tiles_n; u.tileN = l->tileN; u.a_stages = l->a_stages; u.su = L.su; u.tmem_cols = l->tmem_cols;
-    u.act = (act != NN_SOFTMAX) ? act : NN_LINEAR; u.glu_in = glu_in;
-    if (fused) *fused = act != NN_SOFTMAX;
+    // Fusing tanh/sigmoid (an IEEE division each) into the 8-warp epilogue lengthens the kernel's critical path more than the
+    // separate full-occupancy activation kernel costs (measured: FARGAN 4.66 vs 4.36 ms), so it is off unless asked for.
+    static const bool fuse = getenv("OPUSB200_NNET_FUSE") != nullptr;
+    u.act = (fuse && act != NN_SOFTMAX) ? act : NN_LINEAR; u.glu_in = fuse ? glu_in : nullptr;
+    if (fused) *fused = fuse && act != NN_SOFTMAX;
     static size_t smem_set = 0;
     if (l->umma_smem > smem_set) {
       OB_CUDA(cudaFuncSetAttribute(ob_nnet_linear_i8_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l->umma_smem));
@@ -318,7 +321,7 @@ extern "C" int opusb200_nnet_compute_glu(OpusB200Ctx *c, const OpusB200Linear *l
   const float *din = (const float *)st.in(in, b, on_device, true, &err);
   float *dout = (on_device || in != out) ? (float *)st.in(out, b, on_device, false, &err) : (float *)din;
   if (err) return err;
-  if (l->wt_umma) {   // gate fused into the tensor-core kernel's epilogue
+  if (l->wt_umma && getenv("OPUSB200_NNET_FUSE") != nullptr) {   // gate fused into the tensor-core kernel's epilogue (see nnet_linear_dev)
     bool fused = false;
     if ((err = nnet_linear_dev(c, l, dout, din, n, NN_LINEAR, din, &fused))) return err;
     if ((err = st.out(out, dout, b, on_device))) return err;
