@@ -207,21 +207,14 @@ def run_gpu_arm(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     n = args.streams
     # the one init-time collective: rank 0 owns the workload fixture and broadcasts it
-    if rank == 0:
-        pk, sz = load_fixture()
-        t_pk = torch.from_numpy(pk).to(dev)
-        t_sz = torch.from_numpy(sz).to(dev)
-    else:
-        t_pk = torch.empty((256, 8, PKT_STRIDE), dtype=torch.uint8, device=dev)
-        t_sz = torch.empty((256, 8), dtype=torch.int32, device=dev)
-    if world > 1:
-        dist.broadcast(t_pk, 0)
-        dist.broadcast(t_sz, 0)
+    from opus_b200 import parallel
+    pk, sz = load_fixture() if rank == 0 else (None, None)
+    t_pk, t_sz = parallel.broadcast_fixture(pk, sz, (256, 8, PKT_STRIDE), (256, 8), dev, rank, world)
     T = t_pk.shape[1]
-    reps = (n + 255) // 256
-    # [T][n][320] resident packets (168 MB at n = 65536), [T][n] lengths
-    d_pk = t_pk.permute(1, 0, 2).repeat(1, reps, 1)[:, :n].contiguous()
-    d_len = t_sz.permute(1, 0).repeat(1, reps)[:, :n].contiguous()
+    # [T][n][320] resident packets (168 MB at n = 65536), [T][n] lengths: this rank's streams replay fixture row (global id mod 256)
+    rows = parallel.fixture_rows(rank, world, n, t_pk.shape[0]).to(dev)
+    d_pk = t_pk.permute(1, 0, 2)[:, rows].contiguous()
+    d_len = t_sz.permute(1, 0)[:, rows].contiguous()
     d_pcm = torch.empty((n, FRAME * CH), dtype=torch.int16, device=dev)
     d_ns = torch.empty((n,), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
@@ -265,11 +258,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     dec.set_pipelined(False)
     clk = clocks.stop() if rank == 0 else None
     launches = dec.launch_count - launches0
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = n * world * args.steps / (ms_max / 1000.0)
+    ms_max = parallel.max_over_ranks(ms, dev, world)
+    value = parallel.aggregate_throughput(n, world, args.steps, ms_max)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host buffers) ----
     L = opus_b200.lib()
@@ -304,10 +294,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     g1.record(ext)
     dec.sync()
     e2e_sync_val = n * e2e_steps / (g0.elapsed_time(g1) / 1000.0)
-    e_ms = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = n * world * e2e_steps / (float(e_ms.item()) / 1000.0)
+    e2e_val = parallel.aggregate_throughput(n, world, e2e_steps, parallel.max_over_ranks(f0.elapsed_time(f1), dev, world))
     h2d = n * PKT_STRIDE + n * 4
     d2h = n * FRAME * CH * 2 + n * 4
 
