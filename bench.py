@@ -382,6 +382,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'   # the version banner goes to stdout, which must hold exactly one JSON line
         dist.init_process_group('nccl')
     try:
         run_gpu_arm(args, rank, world, local_rank)
