@@ -23,14 +23,13 @@ struct FgParams {
   const float *pembed;     // [224][12]
   float *dense_in;         // [n][32]
   const float *cond;       // [n][320]
-  const float *gainlog;    // [n]
+  const float *gain_w, *gain_b;   // sig_net_cond_gain_dense: [80] float weights, [1] bias
   float *gain;             // [n]
   float *pred, *prev;      // [n][44], [n][40]
   float *fwc0_in;          // [n][164]
   const float *x192;       // [n][192]  fwc0 conv + GLU output
   const float *pgate;      // [n][4]
   const float *g1, *g2, *g3;   // GLU outputs of the three GRUs
-  float *cat;              // concatenation being built: [n][width]
   const float *sig;        // [n][40]
   float *pcm;              // [n][160]
   const float *pcm0;       // [n][320] (continuation)
@@ -61,10 +60,16 @@ extern "C" __global__ void ob_fargan_sub_in(FgParams p) {
   const int s = (int)(t / 64), j = (int)(t % 64);
   if (s >= p.n) return;
   const FgStreamState &st = p.st[s];
-  const float g = (float)exp((double)p.gainlog[s]);
+  const float *cond = p.cond + (size_t)s * 4 * kFgCond + p.sub * kFgCond;
+  // sig_net_cond_gain_dense (80 -> 1, float weights): sgemv's column order (dnn/vec.h:104-121), then the bias; every thread of the
+  // stream repeats the 80-term sum (broadcast loads) instead of exchanging it
+  float gl = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kFgCond; k++) gl = __fadd_rn(gl, __fmul_rn(p.gain_w[k], cond[k]));
+  if (p.gain_b) gl = __fadd_rn(gl, p.gain_b[0]);
+  const float g = (float)exp((double)gl);
   const float gain_1 = 1.f / (1e-5f + g);
   const int period = st.last_period;
-  const float *cond = p.cond + (size_t)s * 4 * kFgCond + p.sub * kFgCond;
   float *fin = p.fwc0_in + (size_t)s * kFgSigIn;
   if (j == 0) p.gain[s] = g;
   if (j < kFgSub + 4) {
@@ -82,26 +87,6 @@ extern "C" __global__ void ob_fargan_sub_in(FgParams p) {
     fin[kFgCond + kFgSub + 4 + j] = pv;
   }
   for (int k = j; k < kFgCond; k += 64) fin[k] = cond[k];
-}
-// [head | pitch_gate[which] * pred[2..42) | prev]  (dnn/fargan.c:112-113, :117-118, :122-123) and skip_cat (:127-132)
-extern "C" __global__ void ob_fargan_cat(FgParams p) {
-  const int head = p.which == 0 ? kFgFwc0 : p.which == 1 ? kFgGru1 : p.which == 2 ? kFgGru2 : kFgGru1 + kFgGru2 + kFgGru3 + kFgFwc0;
-  const int width = head + 2 * kFgSub;
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = (int)(t / width), j = (int)(t % width);
-  if (s >= p.n) return;
-  float v;
-  if (j < head) {
-    if (p.which == 0) v = p.x192[(size_t)s * kFgFwc0 + j];
-    else if (p.which == 1) v = p.g1[(size_t)s * kFgGru1 + j];
-    else if (p.which == 2) v = p.g2[(size_t)s * kFgGru2 + j];
-    else if (j < kFgGru1) v = p.g1[(size_t)s * kFgGru1 + j];
-    else if (j < kFgGru1 + kFgGru2) v = p.g2[(size_t)s * kFgGru2 + (j - kFgGru1)];
-    else if (j < kFgGru1 + kFgGru2 + kFgGru3) v = p.g3[(size_t)s * kFgGru3 + (j - kFgGru1 - kFgGru2)];
-    else v = p.x192[(size_t)s * kFgFwc0 + (j - kFgGru1 - kFgGru2 - kFgGru3)];
-  } else if (j < head + kFgSub) v = p.pgate[(size_t)s * 4 + p.which] * p.pred[(size_t)s * (kFgSub + 4) + (j - head) + 2];
-  else v = p.prev[(size_t)s * kFgSub + (j - head - kFgSub)];
-  p.cat[(size_t)s * width + j] = v;
 }
 // scale by the gain, push into the pitch buffer, de-emphasis (dnn/fargan.c:136-140, :61-67).  64 threads per stream move the
 // pitch buffer (values read, barrier, values written); one of them runs the 40-step de-emphasis recurrence.
@@ -164,15 +149,16 @@ struct OpusB200Fargan {
   int n, cont_initialized;
   OpusB200Linear *l[FG_COUNT];
   FgStreamState *st;
-  float *cond_conv1_state, *fwc0_mem, *gru1, *gru2, *gru3;          // layer memories [n][..]
-  float *dense_in, *conv1_in, *fdense2_in, *cond, *gainlog, *gain, *pred, *prev, *fwc0_in, *x192, *pgate, *cat, *g1, *g2, *g3, *skip, *sig;
+  float *cond_conv1_state, *fwc0_buf[2], *gru1, *gru2, *gru3;       // layer memories [n][..]; fwc0_buf: this / the previous subframe's conv input
+  int fwc0_cur;
+  float *dense_in, *conv1_in, *fdense2_in, *cond, *gain, *pred, *prev, *x192, *pgate, *g1, *g2, *g3, *skip, *sig;
   float *d_feat, *d_pcm, *d_pcm0;   // staging for host callers
 };
 static void fg_free(OpusB200Fargan *f) {
   if (!f) return;
   for (int i = 0; i < FG_COUNT; i++) opusb200_nnet_linear_destroy(f->l[i]);
-  float **bufs[] = {&f->cond_conv1_state, &f->fwc0_mem, &f->gru1, &f->gru2, &f->gru3, &f->dense_in, &f->conv1_in, &f->fdense2_in, &f->cond, &f->gainlog,
-                    &f->gain, &f->pred, &f->prev, &f->fwc0_in, &f->x192, &f->pgate, &f->cat, &f->g1, &f->g2, &f->g3, &f->skip, &f->sig, &f->d_feat, &f->d_pcm,
+  float **bufs[] = {&f->cond_conv1_state, &f->fwc0_buf[0], &f->fwc0_buf[1], &f->gru1, &f->gru2, &f->gru3, &f->dense_in, &f->conv1_in, &f->fdense2_in, &f->cond,
+                    &f->gain, &f->pred, &f->prev, &f->x192, &f->pgate, &f->g1, &f->g2, &f->g3, &f->skip, &f->sig, &f->d_feat, &f->d_pcm,
                     &f->d_pcm0};
   for (auto b : bufs) cudaFree(*b);
   cudaFree(f->st);
@@ -197,17 +183,18 @@ extern "C" int opusb200_fargan_create(OpusB200Ctx *c, const OpusB200LinearLayer 
     if (r != OPUSB200_OK) { fg_free(f); return r; }
   }
   const size_t n = (size_t)n_streams;
-  struct { float **p; size_t w; } al[] = {{&f->cond_conv1_state, 128}, {&f->fwc0_mem, kFgSigIn}, {&f->gru1, kFgGru1}, {&f->gru2, kFgGru2}, {&f->gru3, kFgGru3},
-                                          {&f->dense_in, 32}, {&f->conv1_in, 64}, {&f->fdense2_in, 128}, {&f->cond, 320}, {&f->gainlog, 1}, {&f->gain, 1},
-                                          {&f->pred, kFgSub + 4}, {&f->prev, kFgSub}, {&f->fwc0_in, kFgSigIn}, {&f->x192, kFgFwc0}, {&f->pgate, 4},
-                                          {&f->cat, kFgSkipCat}, {&f->g1, kFgGru1}, {&f->g2, kFgGru2}, {&f->g3, kFgGru3}, {&f->skip, kFgSkip}, {&f->sig, kFgSub},
+  struct { float **p; size_t w; } al[] = {{&f->cond_conv1_state, 128}, {&f->fwc0_buf[0], kFgSigIn}, {&f->fwc0_buf[1], kFgSigIn}, {&f->gru1, kFgGru1}, {&f->gru2, kFgGru2}, {&f->gru3, kFgGru3},
+                                          {&f->dense_in, 32}, {&f->conv1_in, 64}, {&f->fdense2_in, 128}, {&f->cond, 320}, {&f->gain, 1},
+                                          {&f->pred, kFgSub + 4}, {&f->prev, kFgSub}, {&f->x192, kFgFwc0}, {&f->pgate, 4},
+                                          {&f->g1, kFgGru1}, {&f->g2, kFgGru2}, {&f->g3, kFgGru3}, {&f->skip, kFgSkip}, {&f->sig, kFgSub},
                                           {&f->d_feat, 5 * kFgFeatures}, {&f->d_pcm, kFgFrame}, {&f->d_pcm0, kFgCont}};
   for (auto &a : al)
     if (cudaMalloc(a.p, sizeof(float) * n * a.w) != cudaSuccess) { fg_free(f); return OPUSB200_ALLOC_FAIL; }
   if (cudaMalloc(&f->st, sizeof(FgStreamState) * n) != cudaSuccess) { fg_free(f); return OPUSB200_ALLOC_FAIL; }
   cudaMemsetAsync(f->st, 0, sizeof(FgStreamState) * n, c->stream);
   cudaMemsetAsync(f->cond_conv1_state, 0, sizeof(float) * n * 128, c->stream);
-  cudaMemsetAsync(f->fwc0_mem, 0, sizeof(float) * n * kFgSigIn, c->stream);
+  cudaMemsetAsync(f->fwc0_buf[0], 0, sizeof(float) * n * kFgSigIn, c->stream);
+  cudaMemsetAsync(f->fwc0_buf[1], 0, sizeof(float) * n * kFgSigIn, c->stream);
   cudaMemsetAsync(f->gru1, 0, sizeof(float) * n * kFgGru1, c->stream);
   cudaMemsetAsync(f->gru2, 0, sizeof(float) * n * kFgGru2, c->stream);
   cudaMemsetAsync(f->gru3, 0, sizeof(float) * n * kFgGru3, c->stream);
@@ -241,39 +228,72 @@ static int fg_subframe(OpusB200Fargan *f, int sub, float *d_pcm, const float *d_
   OpusB200Ctx *c = f->ctx;
   const int n = f->n;
   FgParams p = {};
-  p.st = f->st; p.cond = f->cond; p.gainlog = f->gainlog; p.gain = f->gain; p.pred = f->pred; p.prev = f->prev; p.fwc0_in = f->fwc0_in; p.x192 = f->x192;
-  p.pgate = f->pgate; p.g1 = f->g1; p.g2 = f->g2; p.g3 = f->g3; p.cat = f->cat; p.sig = f->sig; p.pcm = d_pcm; p.pcm0 = d_pcm0; p.n = n; p.sub = sub;
-  // the gain layer reads this subframe's 80 conditioning values: a strided view is not what the batched layer takes, so they
-  // are staged through fwc0_in's head (the copy the conv needs anyway) -- sub_in fills it, hence the two-step order below
-  {  // cond slice -> contiguous [n][80] in `cat` (free at this point)
-    cudaMemcpy2DAsync(f->cat, sizeof(float) * kFgCond, f->cond + sub * kFgCond, sizeof(float) * 4 * kFgCond, sizeof(float) * kFgCond, n,
-                      cudaMemcpyDeviceToDevice, c->stream);
-  }
-  FG_TRY(opusb200_nnet_compute_dense(c, f->l[FG_COND_GAIN], f->gainlog, f->cat, n, NN_LINEAR, 1));
+  p.st = f->st; p.cond = f->cond; p.gain = f->gain; p.pred = f->pred; p.prev = f->prev; p.x192 = f->x192;
+  p.pgate = f->pgate; p.g1 = f->g1; p.g2 = f->g2; p.g3 = f->g3; p.sig = f->sig; p.pcm = d_pcm; p.pcm0 = d_pcm0; p.n = n; p.sub = sub;
+  // No float concatenation is ever built: every wide int8 layer gets its operand from a segmented quantiser that reads the pieces
+  // where they are ([head | pitch_gate[k] * pred[2..42) | prev], dnn/fargan.c:112-132); the first conv's window is
+  // [previous subframe's input | this one's] (kernel size 2), i.e. two buffers that swap roles.
+  float *fin_prev = f->fwc0_buf[f->fwc0_cur ^ 1], *fin = f->fwc0_buf[f->fwc0_cur];
+  f->fwc0_cur ^= 1;
+  p.fwc0_in = fin;
+  p.gain_w = f->l[FG_COND_GAIN]->L.wf; p.gain_b = f->l[FG_COND_GAIN]->L.bias;
   ob_fargan_sub_in<<<fg_blk((long)n * 64), 256, 0, c->stream>>>(p);
   c->launches++;
-  FG_TRY(opusb200_nnet_compute_conv1d(c, f->l[FG_FWC0_CONV], f->x192, f->fwc0_mem, f->fwc0_in, n, kFgSigIn, 1, NN_TANH, 1));
+  const int8_t *xq;
+  auto seg = [](const float *ptr, int width, int stride, const float *gate = nullptr, int gate_stride = 0) {
+    UmmaSeg sg; sg.ptr = ptr; sg.gate = gate; sg.width = width; sg.stride = stride; sg.gate_stride = gate_stride; return sg;
+  };
+  auto gated = [&](int k) { return seg(f->pred + 2, kFgSub, kFgSub + 4, f->pgate + k, 4); };
+  const UmmaSeg s_prev = seg(f->prev, kFgSub, kFgSub);
+  {  // compute_generic_conv1d(sig_net_fwc0_conv) + tanh
+    const UmmaSeg sg[2] = {seg(fin_prev, kFgSigIn, kFgSigIn), seg(fin, kFgSigIn, kFgSigIn)};
+    FG_TRY(nnet_umma_quant_seg(c, f->l[FG_FWC0_CONV], sg, 2, n, &xq));
+    FG_TRY(nnet_umma_gemm(c, f->l[FG_FWC0_CONV], f->x192, xq, nullptr, n));
+    FG_TRY(nnet_act_dev(c, f->x192, f->x192, n, kFgFwc0, NN_TANH));
+  }
   FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_FWC0_GLU], f->x192, f->x192, n, 1));
   FG_TRY(opusb200_nnet_compute_dense(c, f->l[FG_GAIN_OUT], f->pgate, f->x192, n, NN_SIGMOID, 1));
-  p.which = 0;
-  ob_fargan_cat<<<fg_blk((long)n * (kFgFwc0 + 2 * kFgSub)), 256, 0, c->stream>>>(p);
-  FG_TRY(opusb200_nnet_compute_gru(c, f->l[FG_GRU1_IN], f->l[FG_GRU1_REC], f->gru1, f->cat, n, 1));
-  FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_GRU1_GLU], f->g1, f->gru1, n, 1));
-  p.which = 1;
-  ob_fargan_cat<<<fg_blk((long)n * (kFgGru1 + 2 * kFgSub)), 256, 0, c->stream>>>(p);
-  FG_TRY(opusb200_nnet_compute_gru(c, f->l[FG_GRU2_IN], f->l[FG_GRU2_REC], f->gru2, f->cat, n, 1));
-  FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_GRU2_GLU], f->g2, f->gru2, n, 1));
-  p.which = 2;
-  ob_fargan_cat<<<fg_blk((long)n * (kFgGru2 + 2 * kFgSub)), 256, 0, c->stream>>>(p);
-  FG_TRY(opusb200_nnet_compute_gru(c, f->l[FG_GRU3_IN], f->l[FG_GRU3_REC], f->gru3, f->cat, n, 1));
-  FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_GRU3_GLU], f->g3, f->gru3, n, 1));
-  p.which = 3;
-  ob_fargan_cat<<<fg_blk((long)n * kFgSkipCat), 256, 0, c->stream>>>(p);
-  FG_TRY(opusb200_nnet_compute_dense(c, f->l[FG_SKIP_DENSE], f->skip, f->cat, n, NN_TANH, 1));
+  // the three GRUs: input matrix on the segmented operand, recurrent matrix on the state, then the gate kernel (dnn/nnet.c:76-105)
+  auto gru = [&](int li, int lr, float *state, const UmmaSeg *sg, int N) -> int {
+    float *zrh;
+    if (nnet_scratch(c, 1, sizeof(float) * (size_t)n * 6 * N, (void **)&zrh)) return OPUSB200_ALLOC_FAIL;
+    float *recur = zrh + (size_t)n * 3 * N;
+    const int8_t *q;
+    FG_TRY(nnet_umma_quant_seg(c, f->l[li], sg, 3, n, &q));
+    FG_TRY(nnet_umma_gemm(c, f->l[li], zrh, q, nullptr, n));
+    FG_TRY(nnet_linear_dev(c, f->l[lr], recur, state, n));
+    NnetGruParams g;
+    g.state = state; g.zrh = zrh; g.recur = recur; g.n = n; g.N = N;
+    ob_nnet_gru<<<nblk((long)n * N, 256), 256, 0, c->stream>>>(g);
+    c->launches++;
+    return OPUSB200_OK;
+  };
+  {
+    const UmmaSeg sg[3] = {seg(f->x192, kFgFwc0, kFgFwc0), gated(0), s_prev};
+    FG_TRY(gru(FG_GRU1_IN, FG_GRU1_REC, f->gru1, sg, kFgGru1));
+    FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_GRU1_GLU], f->g1, f->gru1, n, 1));
+  }
+  {
+    const UmmaSeg sg[3] = {seg(f->g1, kFgGru1, kFgGru1), gated(1), s_prev};
+    FG_TRY(gru(FG_GRU2_IN, FG_GRU2_REC, f->gru2, sg, kFgGru2));
+    FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_GRU2_GLU], f->g2, f->gru2, n, 1));
+  }
+  {
+    const UmmaSeg sg[3] = {seg(f->g2, kFgGru2, kFgGru2), gated(2), s_prev};
+    FG_TRY(gru(FG_GRU3_IN, FG_GRU3_REC, f->gru3, sg, kFgGru3));
+    FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_GRU3_GLU], f->g3, f->gru3, n, 1));
+  }
+  {  // skip_cat = [g1 | g2 | g3 | fwc0 | gated pred | prev] -> sig_net_skip_dense + tanh
+    const UmmaSeg sg[6] = {seg(f->g1, kFgGru1, kFgGru1), seg(f->g2, kFgGru2, kFgGru2), seg(f->g3, kFgGru3, kFgGru3), seg(f->x192, kFgFwc0, kFgFwc0), gated(3),
+                           s_prev};
+    FG_TRY(nnet_umma_quant_seg(c, f->l[FG_SKIP_DENSE], sg, 6, n, &xq));
+    FG_TRY(nnet_umma_gemm(c, f->l[FG_SKIP_DENSE], f->skip, xq, nullptr, n));
+    FG_TRY(nnet_act_dev(c, f->skip, f->skip, n, kFgSkip, NN_TANH));
+  }
   FG_TRY(opusb200_nnet_compute_glu(c, f->l[FG_SKIP_GLU], f->skip, f->skip, n, 1));
   FG_TRY(opusb200_nnet_compute_dense(c, f->l[FG_SIG_OUT], f->sig, f->skip, n, NN_TANH, 1));
   ob_fargan_sub_out<<<(unsigned)((n + 3) / 4), 256, 0, c->stream>>>(p);
-  c->launches += 5;
+  c->launches++;
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;
 }

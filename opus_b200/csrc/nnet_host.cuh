@@ -153,6 +153,48 @@ extern "C" void opusb200_nnet_linear_destroy(OpusB200Linear *l) {
 }
 
 // device-pointer core of compute_linear: out [n][N], in [n][M]
+// the tcgen05 GEMM on an operand that is already quantised in the tensor core's layout (xq: [ceil(n/128)][Kp/16][128][16])
+static int nnet_umma_gemm(OpusB200Ctx *c, const OpusB200Linear *l, float *out, const int8_t *xq, const float *in_for_diag, int n, int act = NN_LINEAR,
+                          const float *glu_in = nullptr, bool *fused = nullptr) {
+  const NnetLinear &L = l->L;
+  const int mt = (n + 127) / 128;
+  UmmaLinearParams u;
+  u.wt = l->wt_umma; u.xq = xq; u.scale = L.scale; u.bias = L.bias; u.diag = L.diag; u.in = in_for_diag; u.out = out; u.n = n; u.M = L.M; u.N = L.N;
+  u.Kp = l->Kp; u.Npad = l->Npad; u.n_tiles_n = l->n_tiles_n; u.tileN = l->tileN; u.a_stages = l->a_stages; u.su = L.su; u.tmem_cols = l->tmem_cols;
+  // Fusing tanh/sigmoid (an IEEE division each) into the 8-warp epilogue lengthens the kernel's critical path more than the
+  // separate full-occupancy activation kernel costs (measured: FARGAN 4.61 vs 4.49 ms), so it is off unless asked for.
+  static const bool fuse = getenv("OPUSB200_NNET_FUSE") != nullptr;
+  u.act = (fuse && act != NN_SOFTMAX) ? act : NN_LINEAR; u.glu_in = fuse ? glu_in : nullptr;
+  if (fused) *fused = fuse && act != NN_SOFTMAX;
+  static size_t smem_set = 0;
+  if (l->umma_smem > smem_set) {
+    OB_CUDA(cudaFuncSetAttribute(ob_nnet_linear_i8_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l->umma_smem));
+    smem_set = l->umma_smem;
+  }
+  static int sms = 0;
+  if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  ob_nnet_linear_i8_umma<<<mt < sms ? mt : sms, 320, l->umma_smem, c->stream>>>(u);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+// quantise a concatenation of up to 6 pieces straight into the operand of layer l (which must take the tcgen05 path)
+static int nnet_umma_quant_seg(OpusB200Ctx *c, const OpusB200Linear *l, const UmmaSeg *segs, int nseg, int n, const int8_t **xq_out) {
+  if (!l->wt_umma || nseg < 1 || nseg > 6) return OPUSB200_BAD_ARG;
+  int tot = 0;
+  for (int i = 0; i < nseg; i++) tot += segs[i].width;
+  if (tot != l->L.M) return OPUSB200_BAD_ARG;
+  const int mt = (n + 127) / 128;
+  void *xq;
+  if (nnet_scratch(c, 0, (size_t)mt * 128 * l->Kp, &xq)) return OPUSB200_ALLOC_FAIL;
+  UmmaQuantSegParams q;
+  q.xq = (int8_t *)xq; q.nseg = nseg; q.n = n; q.M = l->L.M; q.Kp = l->Kp; q.su = l->L.su;
+  for (int i = 0; i < nseg; i++) q.seg[i] = segs[i];
+  ob_nnet_quant_umma_seg<<<nblk((long)mt * 128 * (l->Kp / 16), 256), 256, 0, c->stream>>>(q);
+  c->launches++;
+  *xq_out = (const int8_t *)xq;
+  return OPUSB200_OK;
+}
 // act / glu_in: fused into the tcgen05 kernel's epilogue when the layer takes that path (*fused says so); other paths ignore them
 static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, const float *in, int n, int act = NN_LINEAR,
                            const float *glu_in = nullptr, bool *fused = nullptr) {
@@ -167,25 +209,8 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
     UmmaQuantParams q;
     q.xq = (int8_t *)xq; q.in = in; q.n = n; q.M = L.M; q.Kp = l->Kp; q.su = L.su;
     ob_nnet_quant_umma<<<nblk((long)mt * 128 * (l->Kp / 16), 256), 256, 0, c->stream>>>(q);
-    UmmaLinearParams u;
-    u.wt = l->wt_umma; u.xq = (const int8_t *)xq; u.scale = L.scale; u.bias = L.bias; u.diag = L.diag; u.in = in; u.out = out; u.n = n; u.M = L.M; u.N = L.N;
-    u.Kp = l->Kp; u.Npad = l->Npad; u.n_tiles_n = l->n_tiles_n; u.tileN = l->tileN; u.a_stages = l->a_stages; u.su = L.su; u.tmem_cols = l->tmem_cols;
-    // Fusing tanh/sigmoid (an IEEE division each) into the 8-warp epilogue lengthens the kernel's critical path more than the
-    // separate full-occupancy activation kernel costs (measured: FARGAN 4.66 vs 4.36 ms), so it is off unless asked for.
-    static const bool fuse = getenv("OPUSB200_NNET_FUSE") != nullptr;
-    u.act = (fuse && act != NN_SOFTMAX) ? act : NN_LINEAR; u.glu_in = fuse ? glu_in : nullptr;
-    if (fused) *fused = fuse && act != NN_SOFTMAX;
-    static size_t smem_set = 0;
-    if (l->umma_smem > smem_set) {
-      OB_CUDA(cudaFuncSetAttribute(ob_nnet_linear_i8_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l->umma_smem));
-      smem_set = l->umma_smem;
-    }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    ob_nnet_linear_i8_umma<<<mt < sms ? mt : sms, 320, l->umma_smem, c->stream>>>(u);
-    c->launches += 2;
-    OB_CUDA(cudaGetLastError());
-    return OPUSB200_OK;
+    c->launches++;
+    return nnet_umma_gemm(c, l, out, (const int8_t *)xq, in, n, act, glu_in, fused);
   }
   if (L.w8) {
     void *xq;

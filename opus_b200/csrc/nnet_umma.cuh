@@ -29,6 +29,10 @@ struct UmmaLinearParams {
   const float *glu_in;  // non-null: out = glu_in * sigmoid(y)  (compute_glu, dnn/nnet.c:107-120; may alias out)
 };
 struct UmmaQuantParams { int8_t *xq; const float *in; int n, M, Kp, su; };
+// The operand of a layer whose input is a concatenation: up to 6 pieces, each [n][width] with its own row stride and an
+// optional per-row multiplier (FARGAN's pitch-gated prediction); quantised in place of materialising the float concatenation.
+struct UmmaSeg { const float *ptr; const float *gate; int width, stride, gate_stride; };
+struct UmmaQuantSegParams { int8_t *xq; UmmaSeg seg[6]; int nseg, n, M, Kp, su; };
 
 #if defined(__CUDACC__)
 namespace umma {
@@ -104,6 +108,35 @@ extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma(UmmaQuantPa
       int q = 0;
       if (kc * 16 + b < p.M) {
         q = (int)floor(0.5 + (double)__fmul_rn(127.f, x[b]));
+        if (p.su) q += 127;
+      }
+      w[b >> 2] |= ((uint32_t)q & 0xffu) << (8 * (b & 3));
+    }
+  }
+  uint4 *dst = (uint4 *)(p.xq + (((size_t)(s >> 7) * KC + kc) * 128 + (s & 127)) * 16);
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma_seg(UmmaQuantSegParams p) {
+  const int KC = p.Kp >> 4;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long rows = (long)((p.n + 127) / 128) * 128;
+  if (t >= rows * KC) return;
+  const int kc = (int)(t / rows), s = (int)(t - (long)kc * rows);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (s < p.n) {
+    int g = 0, base = 0;   // segment holding column kc*16
+    while (g < p.nseg - 1 && kc * 16 >= base + p.seg[g].width) { base += p.seg[g].width; g++; }
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const int j = kc * 16 + b;
+      int q = 0;
+      if (j < p.M) {
+        while (g < p.nseg - 1 && j >= base + p.seg[g].width) { base += p.seg[g].width; g++; }
+        const UmmaSeg &sg = p.seg[g];
+        float v = sg.ptr[(size_t)s * sg.stride + (j - base)];
+        if (sg.gate) v = __fmul_rn(sg.gate[(size_t)s * sg.gate_stride], v);
+        q = (int)floor(0.5 + (double)__fmul_rn(127.f, v));
         if (p.su) q += 127;
       }
       w[b >> 2] |= ((uint32_t)q & 0xffu) << (8 * (b & 3));
