@@ -61,12 +61,14 @@ extern "C" __global__ void ob_fargan_sub_in(FgParams p) {
   if (s >= p.n) return;
   const FgStreamState &st = p.st[s];
   const float *cond = p.cond + (size_t)s * 4 * kFgCond + p.sub * kFgCond;
-  // sig_net_cond_gain_dense (80 -> 1, float weights): sgemv's column order (dnn/vec.h:104-121), then the bias; every thread of the
-  // stream repeats the 80-term sum (broadcast loads) instead of exchanging it
+  // sig_net_cond_gain_dense (80 -> 1, float weights): sgemv's column order (dnn/vec.h:104-121), then the bias; one lane per warp
   float gl = 0.f;
+  if ((threadIdx.x & 31) == 0) {   // a warp serves one stream (64 threads = 2 warps): one lane sums, the others receive
 #pragma unroll 8
-  for (int k = 0; k < kFgCond; k++) gl = __fadd_rn(gl, __fmul_rn(p.gain_w[k], cond[k]));
-  if (p.gain_b) gl = __fadd_rn(gl, p.gain_b[0]);
+    for (int k = 0; k < kFgCond; k++) gl = __fadd_rn(gl, __fmul_rn(p.gain_w[k], cond[k]));
+    if (p.gain_b) gl = __fadd_rn(gl, p.gain_b[0]);
+  }
+  gl = __shfl_sync(0xffffffffu, gl, 0);
   const float g = (float)exp((double)gl);
   const float gain_1 = 1.f / (1e-5f + g);
   const int period = st.last_period;

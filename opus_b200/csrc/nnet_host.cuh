@@ -182,7 +182,10 @@ static int nnet_umma_gemm(OpusB200Ctx *c, const OpusB200Linear *l, float *out, c
 static int nnet_umma_quant_seg(OpusB200Ctx *c, const OpusB200Linear *l, const UmmaSeg *segs, int nseg, int n, const int8_t **xq_out) {
   if (!l->wt_umma || nseg < 1 || nseg > 6) return OPUSB200_BAD_ARG;
   int tot = 0;
-  for (int i = 0; i < nseg; i++) tot += segs[i].width;
+  for (int i = 0; i < nseg; i++) {
+    if ((segs[i].width & 3) || (segs[i].stride & 3)) return OPUSB200_BAD_ARG;   // groups of 4 columns stay inside one piece
+    tot += segs[i].width;
+  }
   if (tot != l->L.M) return OPUSB200_BAD_ARG;
   const int mt = (n + 127) / 128;
   void *xq;

@@ -117,6 +117,8 @@ extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma(UmmaQuantPa
   *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// (every piece's width and row stride must be a multiple of 4 floats: a group of 4 columns then lies in one piece, is read with
+// one 128-bit load when aligned, and the segment walk runs per group; lanes of a warp share kc, so the walk is warp-uniform)
 extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma_seg(UmmaQuantSegParams p) {
   const int KC = p.Kp >> 4;
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,21 +127,34 @@ extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma_seg(UmmaQua
   const int kc = (int)(t / rows), s = (int)(t - (long)kc * rows);
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (s < p.n) {
-    int g = 0, base = 0;   // segment holding column kc*16
-    while (g < p.nseg - 1 && kc * 16 >= base + p.seg[g].width) { base += p.seg[g].width; g++; }
+    int g = 0, base = 0;
 #pragma unroll
-    for (int b = 0; b < 16; b++) {
-      const int j = kc * 16 + b;
-      int q = 0;
-      if (j < p.M) {
-        while (g < p.nseg - 1 && j >= base + p.seg[g].width) { base += p.seg[g].width; g++; }
-        const UmmaSeg &sg = p.seg[g];
-        float v = sg.ptr[(size_t)s * sg.stride + (j - base)];
-        if (sg.gate) v = __fmul_rn(sg.gate[(size_t)s * sg.gate_stride], v);
-        q = (int)floor(0.5 + (double)__fmul_rn(127.f, v));
-        if (p.su) q += 127;
+    for (int gq = 0; gq < 4; gq++) {
+      const int j = kc * 16 + gq * 4;
+      if (j >= p.M) break;
+      while (g < p.nseg - 1 && j >= base + p.seg[g].width) { base += p.seg[g].width; g++; }
+      const UmmaSeg sg = p.seg[g];
+      const float *src = sg.ptr + (size_t)s * sg.stride + (j - base);
+      float x[4];
+      if ((((size_t)src) & 15) == 0) {
+        const float4 f = *(const float4 *)src;
+        x[0] = f.x; x[1] = f.y; x[2] = f.z; x[3] = f.w;
+      } else {
+        x[0] = src[0]; x[1] = src[1]; x[2] = src[2]; x[3] = src[3];
       }
-      w[b >> 2] |= ((uint32_t)q & 0xffu) << (8 * (b & 3));
+      if (sg.gate) {
+        const float gt = sg.gate[(size_t)s * sg.gate_stride];
+#pragma unroll
+        for (int b = 0; b < 4; b++) x[b] = __fmul_rn(gt, x[b]);
+      }
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        int q = (int)floor(0.5 + (double)__fmul_rn(127.f, x[b]));
+        if (p.su) q += 127;
+        word |= ((uint32_t)q & 0xffu) << (8 * b);
+      }
+      w[gq] = word;
     }
   }
   uint4 *dst = (uint4 *)(p.xq + (((size_t)(s >> 7) * KC + kc) * 128 + (s & 127)) * 16);
