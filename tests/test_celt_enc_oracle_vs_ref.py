@@ -145,3 +145,12 @@ def test_complexity_8_to_10(complexity, ch, fs, nbytes, vbr):
             assert na == nbo, (sname, f, na, nbo)
             assert np.array_equal(a, b), (sname, f, int(np.argmax(a != b)))
             assert ra == rb
+
+
+@pytest.mark.parametrize('ch,fs,nbytes,complexity', [(2, 960, 160, 10), (1, 480, 9, 5), (2, 960, 1275, 10), (2, 120, 8, 8), (2, 960, 2, 5), (1, 240, 1275, 7),
+                                                    (2, 960, 3, 10), (1, 120, 2, 0), (2, 480, 1275, 8), (2, 960, 10, 10)])
+def test_edge_packet_sizes(ch, fs, nbytes, complexity):
+    """the smallest (2 bytes) and the largest (1275 bytes) CBR packets"""
+    sig = util.sig_harmonic(900 + nbytes, fs * 6, ch)
+    for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, nframes=6):
+        assert na == nbo and np.array_equal(a, b) and ra == rb, (f, na, nbo)

@@ -80,3 +80,25 @@ def test_ctl_errors():
     with pytest.raises(opus_b200.OpusB200Error):
         enc.ctl(E.OPUS_SET_BITRATE_REQUEST, 10)
     enc.close()
+
+
+@pytest.mark.parametrize('n,ch,fs,nbytes,complexity', [(1, 2, 960, 160, 10), (33, 1, 480, 9, 5), (5, 2, 960, 1275, 10), (3, 2, 120, 8, 8), (2, 2, 960, 2, 5),
+                                                     (7, 1, 240, 1275, 7)])
+def test_encoder_edge_sizes(n, ch, fs, nbytes, complexity):
+    """single-stream batches, the smallest and the largest CBR packets"""
+    import opus_b200
+    O = util.load_oracle()
+    nf = 5
+    x = np.stack([util.sig_harmonic(900 + s + nbytes, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=-1, complexity=complexity, vbr=0, cvbr=1) for s in range(n)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=complexity)
+    for f in range(nf):
+        pk, nb = enc.encode(x[:, f], nbytes)
+        rng = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            if wn > 0:
+                assert np.array_equal(pk[s, :wn], wb), (f, s)
+                assert rng[s] == wr
+    enc.close()
