@@ -25,6 +25,7 @@ struct EncFrameParams {
   const float *bandLogE2;       // [n][C*21] valid where info.patched (else the same as bandLogE)
   unsigned char *packets;       // [n][pkt_stride]
   int32_t *nbytes;              // [n] bytes produced, or a negative error
+  int first_stream = 0;   // this launch covers streams [first_stream, n_streams)
   int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf, vbr, constrained_vbr,
       loss_rate;
 };

@@ -3,11 +3,11 @@
 #include "celt_enc_frame.cuh"
 
 extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame(EncFrameParams p) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
   if (s < p.n_streams) enc_frame_thread<false>(p, s);
 }
 extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame_rdo(EncFrameParams p) {   // complexity >= 8, stereo
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
   if (s < p.n_streams) enc_frame_thread<true>(p, s);
 }
 extern "C" __global__ void ob_celt_enc_reset(ObEncState *st, ObEncAnalysisState *an, int n) {
@@ -40,6 +40,9 @@ struct OpusB200Encoder {
   float *d_pcm; size_t d_pcm_cap;
   unsigned char *d_pkt; size_t d_pkt_cap;
   int64_t launches;
+  // the frame coder runs on a second stream, chunk by chunk behind the analysis kernel (see opusb200_encode_device)
+  cudaStream_t stream_f;
+  cudaEvent_t ev_an[8], ev_fr;
 };
 
 extern "C" int opusb200_encoder_reset(OpusB200Encoder *e) {
@@ -68,6 +71,13 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   e->device = device; e->channels = channels; e->n = n_streams;
   e->complexity = 5; e->bitrate = -1; e->vbr = 0; e->constrained_vbr = 1; e->lsb_depth = 24;   // celt_encoder_init defaults
   OB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // the frame coder's few, long-running CTAs go ahead of the analysis kernel's many short ones
+    OB_CUDA(cudaStreamCreateWithPriority(&e->stream_f, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 8; i++) OB_CUDA(cudaEventCreateWithFlags(&e->ev_an[i], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_fr, cudaEventDisableTiming));
+  }
   const size_t n = (size_t)n_streams;
   OB_CUDA(cudaMalloc(&e->state, sizeof(ObEncState) * n));
   OB_CUDA(cudaMalloc(&e->an_state, sizeof(ObEncAnalysisState) * n));
@@ -91,6 +101,10 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
   cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt);
+  cudaStreamSynchronize(e->stream_f);
+  cudaStreamDestroy(e->stream_f);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(e->ev_an[i]);
+  cudaEventDestroy(e->ev_fr);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -129,15 +143,36 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate;
   // the pitch-search buffers exist from complexity 5 only (PfWS: sc always, buf/xlp2 for the search)
   const size_t pf_smem = e->complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64;
-  ob_celt_enc_analysis<<<e->n, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
   EncFrameParams p;
   p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.bandLogE2 = e->bandLogE2; p.packets = d_packets; p.nbytes = d_nbytes;
-  p.n_streams = e->n; p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
+  p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf;
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
-  if (e->complexity >= 8 && e->channels == 2) ob_celt_enc_frame_rdo<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
-  else ob_celt_enc_frame<<<(e->n + 63) / 64, 64, 0, e->stream>>>(p);
-  e->launches += 2;
+  // The analysis kernel is issue-bound (many short CTAs), the frame coder latency-bound (one thread per stream, no shared memory):
+  // they share SMs well.  The batch goes through in chunks: analysis(chunk k+1) on the library stream runs under
+  // frame-coder(chunk k) on a second, higher-priority stream; the library stream is joined again at the end, so the call stays
+  // stream-ordered for the caller.
+  const int chunks = e->n >= 8192 ? 4 : 1;
+  const int per = ((e->n + chunks - 1) / chunks + 63) & ~63;
+  for (int k = 0; k < chunks; k++) {
+    const int s0 = k * per, s1 = OB_IMIN(e->n, s0 + per);
+    if (s0 >= s1) break;
+    a.first_stream = s0; a.n_streams = s1;
+    ob_celt_enc_analysis<<<s1 - s0, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
+    cudaStream_t sf = chunks > 1 ? e->stream_f : e->stream;
+    if (chunks > 1) {
+      OB_CUDA(cudaEventRecord(e->ev_an[k], e->stream));
+      OB_CUDA(cudaStreamWaitEvent(sf, e->ev_an[k], 0));
+    }
+    p.first_stream = s0; p.n_streams = s1;
+    if (e->complexity >= 8 && e->channels == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    else ob_celt_enc_frame<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    e->launches += 2;
+  }
+  if (chunks > 1) {
+    OB_CUDA(cudaEventRecord(e->ev_fr, e->stream_f));
+    OB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_fr, 0));
+  }
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;
 }

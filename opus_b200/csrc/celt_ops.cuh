@@ -110,6 +110,7 @@ struct EncAnalysisParams {
   float *prefilter_mem = nullptr;        // [n_streams][C][1024] unfiltered pre-emphasised history
   float *bandLogE2 = nullptr;            // [n_streams][C*21]: the long-block log energies when the frame was patched to short blocks
   int max_bytes = 0, bitrate = -1, vbr = 0, constrained_vbr = 0, disable_pf = 0, loss_rate = 0;
+  int first_stream = 0;                  // this launch covers streams [first_stream, first_stream + gridDim.x)
 };
 // tone_lpc (celt/celt_encoder.c:1305-1360) on x = in0 (+ in1): the six running sums are independent sequential chains,
 // one lane each (lanes 0-2: r00 r01 r02, lanes 3-5: the three edge corrections); lane 0 solves the 2x2 system.

@@ -52,7 +52,7 @@ extern "C" __global__ void __launch_bounds__(128) ob_mdct_forward(MdctFwdParams 
   mdct_forward_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
 }
 extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_analysis(EncAnalysisParams p) {
-  enc_analysis_block(p, blockIdx.x, dyn_smem());
+  enc_analysis_block(p, p.first_stream + blockIdx.x, dyn_smem());
 }
 extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, int smem_per_warp) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

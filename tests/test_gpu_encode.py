@@ -102,3 +102,26 @@ def test_encoder_edge_sizes(n, ch, fs, nbytes, complexity):
                 assert np.array_equal(pk[s, :wn], wb), (f, s)
                 assert rng[s] == wr
     enc.close()
+
+
+@pytest.mark.parametrize('complexity', [5, 10])
+def test_encoder_chunked_two_stream_pipeline(complexity):
+    """from 8192 streams the batch goes through in chunks, the frame coder on a second CUDA stream: same packets"""
+    import opus_b200
+    O = util.load_oracle()
+    ch, fs, nbytes, n, nf, base = 2, 960, 160, 9001, 4, 9
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music]
+    xb = np.stack([sigs[s % 3](70 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(base)])
+    x = np.tile(xb, (n // base + 1, 1, 1))[:n]
+    want = [oracle_encode(O, xb[s], ch, fs, nbytes, bitrate=-1, complexity=complexity, vbr=0, cvbr=1) for s in range(base)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=complexity)
+    for f in range(nf):
+        pk, nb = enc.encode(x[:, f], nbytes)
+        rng = enc.final_range()
+        assert (nb == nbytes).all()
+        for s in range(base):
+            wn, wb, wr = want[s][f]
+            rows = np.arange(s, n, base)
+            assert (pk[rows, :wn] == wb[None, :]).all(), (f, s)
+            assert (rng[rows] == wr).all()
+    enc.close()
