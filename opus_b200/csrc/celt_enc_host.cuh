@@ -41,8 +41,8 @@ struct OpusB200Encoder {
   unsigned char *d_pkt; size_t d_pkt_cap;
   int64_t launches;
   // the frame coder runs on a second stream, chunk by chunk behind the analysis kernel (see opusb200_encode_device)
-  cudaStream_t stream_f;
-  cudaEvent_t ev_an[8], ev_fr;
+  cudaStream_t stream_f[4];   // one per chunk: the frame coder is latency-bound per warp, so the chunks' coders must overlap each other too
+  cudaEvent_t ev_an[4], ev_fr[4];
 };
 
 extern "C" int opusb200_encoder_reset(OpusB200Encoder *e) {
@@ -74,9 +74,11 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // the frame coder's few, long-running CTAs go ahead of the analysis kernel's many short ones
-    OB_CUDA(cudaStreamCreateWithPriority(&e->stream_f, cudaStreamNonBlocking, hi));
-    for (int i = 0; i < 8; i++) OB_CUDA(cudaEventCreateWithFlags(&e->ev_an[i], cudaEventDisableTiming));
-    OB_CUDA(cudaEventCreateWithFlags(&e->ev_fr, cudaEventDisableTiming));
+    for (int i = 0; i < 4; i++) {
+      OB_CUDA(cudaStreamCreateWithPriority(&e->stream_f[i], cudaStreamNonBlocking, hi));
+      OB_CUDA(cudaEventCreateWithFlags(&e->ev_an[i], cudaEventDisableTiming));
+      OB_CUDA(cudaEventCreateWithFlags(&e->ev_fr[i], cudaEventDisableTiming));
+    }
   }
   const size_t n = (size_t)n_streams;
   OB_CUDA(cudaMalloc(&e->state, sizeof(ObEncState) * n));
@@ -101,10 +103,12 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
   cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt);
-  cudaStreamSynchronize(e->stream_f);
-  cudaStreamDestroy(e->stream_f);
-  for (int i = 0; i < 8; i++) cudaEventDestroy(e->ev_an[i]);
-  cudaEventDestroy(e->ev_fr);
+  for (int i = 0; i < 4; i++) {
+    cudaStreamSynchronize(e->stream_f[i]);
+    cudaStreamDestroy(e->stream_f[i]);
+    cudaEventDestroy(e->ev_an[i]);
+    cudaEventDestroy(e->ev_fr[i]);
+  }
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -150,7 +154,7 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
   // The analysis kernel is issue-bound (many short CTAs), the frame coder latency-bound (one thread per stream, no shared memory):
   // they share SMs well.  The batch goes through in chunks: analysis(chunk k+1) on the library stream runs under
-  // frame-coder(chunk k) on a second, higher-priority stream; the library stream is joined again at the end, so the call stays
+  // frame-coder(chunk k) on that chunk's own higher-priority stream; the library stream is joined again at the end, so the call stays
   // stream-ordered for the caller.
   const int chunks = e->n >= 8192 ? 4 : 1;
   const int per = ((e->n + chunks - 1) / chunks + 63) & ~63;
@@ -159,7 +163,7 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
     if (s0 >= s1) break;
     a.first_stream = s0; a.n_streams = s1;
     ob_celt_enc_analysis<<<s1 - s0, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
-    cudaStream_t sf = chunks > 1 ? e->stream_f : e->stream;
+    cudaStream_t sf = chunks > 1 ? e->stream_f[k] : e->stream;
     if (chunks > 1) {
       OB_CUDA(cudaEventRecord(e->ev_an[k], e->stream));
       OB_CUDA(cudaStreamWaitEvent(sf, e->ev_an[k], 0));
@@ -168,11 +172,10 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
     if (e->complexity >= 8 && e->channels == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     else ob_celt_enc_frame<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     e->launches += 2;
+    if (chunks > 1) OB_CUDA(cudaEventRecord(e->ev_fr[k], sf));
   }
-  if (chunks > 1) {
-    OB_CUDA(cudaEventRecord(e->ev_fr, e->stream_f));
-    OB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_fr, 0));
-  }
+  if (chunks > 1)
+    for (int k = 0; k < chunks; k++) OB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_fr[k], 0));
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;
 }
