@@ -159,16 +159,18 @@ int opusb200_silk_autocorrelation(OpusB200Ctx *ctx, float *results, const float 
  * Replaces celt_encoder_init / celt_encoder_ctl / celt_encode_with_ec (celt/celt.h:157-160, celt/celt_encoder.c:240,1726,2953):
  * the output is the CELT payload exactly as celt_encode_with_ec(st, pcm, frame_size, compressed, nbCompressedBytes, NULL) writes it
  * (the Opus layer's TOC byte, dc_reject and mode decisions stay in src/opus_encoder.c:1830-2200 on the host).
- * Round 1 implements what the reference does at OPUS_SET_COMPLEXITY(0) in CBR (every decision that complexity level takes:
- * dynalloc_analysis, alloc_trim_analysis, stereo_analysis, intensity hysteresis, intra-energy switching); other settings
- * return OPUSB200_UNIMPLEMENTED from the ctl.  nbytes[s] == OPUS_UNIMPLEMENTED (-5) flags a frame that needed the tone-driven
- * pre-filter (a pure sinusoid, celt/celt_encoder.c:1441-1461), which is not on the device yet. ---- */
+ * Every complexity 0..10 (transient_analysis, tf_analysis, spreading_decision, two-pass coarse energy, the pitch pre-filter and
+ * patch_transient_decision, the second MDCT and the theta RDO), CBR, VBR and constrained VBR: packet bytes and OPUS_GET_FINAL_RANGE
+ * are bit-identical to the reference's C build at the same settings.  Inputs the Opus layer would add (st->analysis from
+ * run_analysis, silk_info, a shared range coder for hybrid frames) are absent, as in CELT-only custom-mode use.
+ * nbytes[s] < 0 flags a per-stream failure (OPUS_INTERNAL_ERROR -3). ---- */
 typedef struct OpusB200Encoder OpusB200Encoder;
 int opusb200_encoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Encoder **out);
 void opusb200_encoder_destroy(OpusB200Encoder *enc);
 int opusb200_encoder_reset(OpusB200Encoder *enc);                                   /* OPUS_RESET_STATE */
-/* request = the OPUS_SET_*_REQUEST number of include/opus_defines.h: 4002 bitrate, 4006 vbr, 4010 complexity, 4036 lsb depth,
- * 4046 phase inversion disabled */
+/* request = the OPUS_SET_*_REQUEST number of include/opus_defines.h: 4002 bitrate, 4006 vbr, 4020 vbr constraint, 4010 complexity
+ * (0..10, default 5 like celt_encoder_init), 4014 packet loss %, 4036 lsb depth, 4046 phase inversion disabled; other requests
+ * return OPUSB200_UNIMPLEMENTED */
 int opusb200_encoder_ctl_set(OpusB200Encoder *enc, int request, int32_t value);
 /* pcm [n][frame_size*channels] interleaved float (+-1.0); packets [n][pkt_stride]; nbytes [n] */
 int opusb200_encode_float(OpusB200Encoder *enc, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride,
