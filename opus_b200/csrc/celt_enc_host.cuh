@@ -152,11 +152,12 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf;
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
-  // The analysis kernel is issue-bound (many short CTAs), the frame coder latency-bound (one thread per stream, no shared memory):
-  // they share SMs well.  The batch goes through in chunks: analysis(chunk k+1) on the library stream runs under
-  // frame-coder(chunk k) on that chunk's own higher-priority stream; the library stream is joined again at the end, so the call stays
-  // stream-ordered for the caller.
-  const int chunks = e->n >= 8192 ? 4 : 1;
+  // Chunking the batch (analysis of chunk k+1 on the library stream under the frame coder of chunk k on its own higher-priority
+  // stream) was measured and is OFF: 9.6 vs 5.9 ms at complexity 0, 56 vs 29 ms at complexity 10 for 65 536 streams.  Both
+  // kernels are limited by how many of their warps are resident at once, and splitting the batch only lowers that.  The plumbing
+  // (first_stream, per-chunk streams) stays for experiments: OPUSB200_ENC_CHUNKS=4.
+  static const int want_chunks = getenv("OPUSB200_ENC_CHUNKS") ? atoi(getenv("OPUSB200_ENC_CHUNKS")) : 1;
+  const int chunks = (e->n >= 8192 && want_chunks > 1) ? OB_IMIN(want_chunks, 4) : 1;
   const int per = ((e->n + chunks - 1) / chunks + 63) & ~63;
   for (int k = 0; k < chunks; k++) {
     const int s0 = k * per, s1 = OB_IMIN(e->n, s0 + per);

@@ -105,8 +105,8 @@ def test_encoder_edge_sizes(n, ch, fs, nbytes, complexity):
 
 
 @pytest.mark.parametrize('complexity', [5, 10])
-def test_encoder_chunked_two_stream_pipeline(complexity):
-    """from 8192 streams the batch goes through in chunks, the frame coder on a second CUDA stream: same packets"""
+def test_encoder_large_batch(complexity):
+    """a batch that spans many CTAs of both kernels (and the optional chunked two-stream mode, OPUSB200_ENC_CHUNKS): same packets"""
     import opus_b200
     O = util.load_oracle()
     ch, fs, nbytes, n, nf, base = 2, 960, 160, 9001, 4, 9
