@@ -38,3 +38,30 @@ int refh_fargan_const(int which) {
     default: return -1;
   }
 }
+
+/* ---- DRED decoder (dnn/dred_rdovae_dec.c, compiled unmodified with the generated random-weight dred_rdovae_dec_data.c) ---- */
+#include "dred_rdovae_dec.h"
+#include "dred_rdovae_constants.h"
+extern const WeightArray rdovaedec_arrays[];
+static RDOVAEDec g_dred_model;
+static int g_dred_ready = 0;
+static void dred_ready(void) {
+  if (!g_dred_ready) { init_rdovaedec(&g_dred_model, rdovaedec_arrays); g_dred_ready = 1; }
+}
+int refh_dred_nlayers(void) { return (int)(sizeof(RDOVAEDec) / sizeof(LinearLayer)); }
+void refh_dred_layer(int i, const void **ptrs, int *dims) {
+  const LinearLayer *l;
+  dred_ready();
+  l = (const LinearLayer *)&g_dred_model + i;
+  ptrs[0] = l->bias; ptrs[1] = l->subias; ptrs[2] = l->weights; ptrs[3] = l->float_weights; ptrs[4] = l->weights_idx; ptrs[5] = l->diag;
+  ptrs[6] = l->scale;
+  dims[0] = l->nb_inputs; dims[1] = l->nb_outputs;
+}
+int refh_dred_const(int which) { return which == 0 ? DRED_NUM_FEATURES : which == 1 ? DRED_LATENT_DIM : which == 2 ? DRED_STATE_DIM : -1; }
+int refh_dred_state_size(void) { return (int)sizeof(RDOVAEDecState); }
+void refh_dred_init_states(RDOVAEDecState *h, const float *initial_state) { dred_ready(); dred_rdovae_dec_init_states(h, &g_dred_model, initial_state, 0); }
+void refh_dred_decode_qframe(RDOVAEDecState *h, float *qframe, const float *z) { dred_ready(); dred_rdovae_decode_qframe(h, &g_dred_model, qframe, z, 0); }
+void refh_dred_decode_all(float *features, const float *state, const float *latents, int nb_latents) {
+  dred_ready();
+  DRED_rdovae_decode_all(&g_dred_model, features, state, latents, nb_latents, 0);
+}

@@ -1,0 +1,75 @@
+"""oracle/gen_dred_weights.py — TEST INFRASTRUCTURE ONLY.
+Like gen_fargan_weights.py, for the DRED decoder (dnn/dred_rdovae_dec.c): the reference's own torch model (dnn/torch/rdovae/rdovae)
+with seeded RANDOM weights, block-sparsified the way its training does it, exported with the reference's own exporter using the
+layer list and flags of dnn/torch/rdovae/export_rdovae_weights.py (decoder half) into oracle/_ref/gen/dred_rdovae_dec_data.[ch]
+plus the constants header that script writes.  Pins the arithmetic of the decoder graph, not its quality."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get('OPUS_REF', '/root/reference')
+OUT = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'gen')
+sys.path.insert(0, os.path.join(REF, 'dnn', 'torch', 'rdovae'))
+sys.path.insert(0, os.path.join(REF, 'dnn', 'torch', 'weight-exchange'))
+from rdovae import RDOVAE                               # noqa: E402
+from wexchange.torch import dump_torch_weights          # noqa: E402
+from wexchange.c_export import CWriter                  # noqa: E402
+
+torch.manual_seed(0xD2ED)
+rng = np.random.default_rng(11)
+LATENT_DIM, STATE_DIM, FEATURE_DIM = 25, 50, 20          # the released model's sizes (DRED_LATENT_DIM 25, DRED_STATE_DIM 50)
+with contextlib.redirect_stdout(io.StringIO()):
+    model = RDOVAE(FEATURE_DIM, LATENT_DIM, 16, 256, 256, state_dim=STATE_DIM)
+dec = model.get_submodule('core_decoder.module')
+
+
+def block_sparsify(w, density):
+    """zero whole 8 (outputs) x 4 (inputs) blocks, the granularity of the reference's sparse layers"""
+    with torch.no_grad():
+        o, i = w.shape
+        keep = torch.from_numpy(rng.random((o // 8, i // 4)) < density)
+        mask = keep.repeat_interleave(8, 0).repeat_interleave(4, 1).to(w.dtype)
+        w.mul_(mask)
+
+
+with torch.no_grad():
+    for name, p in dec.named_parameters():
+        if p.dim() >= 2:
+            p.mul_(1.5)
+for g in (dec.gru1, dec.gru2, dec.gru3, dec.gru4, dec.gru5):
+    block_sparsify(g.weight_ih_l0, 0.5)
+for c in (dec.conv1, dec.conv2, dec.conv3, dec.conv4, dec.conv5):
+    block_sparsify(c.conv_dense.weight, 0.5)
+block_sparsify(dec.output.weight, 0.5)
+block_sparsify(dec.gru_init.weight, 0.5)
+
+os.makedirs(OUT, exist_ok=True)
+w = CWriter(os.path.join(OUT, 'dred_rdovae_dec_data'), message='seeded random model (oracle/gen_dred_weights.py)', model_struct_name='RDOVAEDec')
+w.header.write('\n#include "dred_rdovae.h"\n#include "dred_rdovae_constants.h"\n\n')
+with contextlib.redirect_stdout(io.StringIO()):
+    for name, export_name, quantize in [('dense_1', 'dec_dense1', False), ('glu1.gate', 'dec_glu1', True), ('glu2.gate', 'dec_glu2', True),
+                                        ('glu3.gate', 'dec_glu3', True), ('glu4.gate', 'dec_glu4', True), ('glu5.gate', 'dec_glu5', True),
+                                        ('hidden_init', 'dec_hidden_init', False)]:
+        dump_torch_weights(w, dec.get_submodule(name), name=export_name, verbose=True, quantize=quantize, scale=None)
+    for name, export_name in [('output', 'dec_output'), ('conv1.conv_dense', 'dec_conv_dense1'), ('conv2.conv_dense', 'dec_conv_dense2'),
+                              ('conv3.conv_dense', 'dec_conv_dense3'), ('conv4.conv_dense', 'dec_conv_dense4'), ('conv5.conv_dense', 'dec_conv_dense5'),
+                              ('gru_init', 'dec_gru_init')]:
+        dump_torch_weights(w, dec.get_submodule(name), name=export_name, verbose=True, sparse=True, quantize=True, scale=None)
+    rnn = max(dump_torch_weights(w, dec.get_submodule(n), e, verbose=True, input_sparse=True, quantize=True, scale=None, recurrent_scale=None)
+              for n, e in [('gru1', 'dec_gru1'), ('gru2', 'dec_gru2'), ('gru3', 'dec_gru3'), ('gru4', 'dec_gru4'), ('gru5', 'dec_gru5')])
+    conv = max(dump_torch_weights(w, dec.get_submodule(n), e, verbose=True, quantize=True, scale=None)
+               for n, e in [('conv1.conv', 'dec_conv1'), ('conv2.conv', 'dec_conv2'), ('conv3.conv', 'dec_conv3'), ('conv4.conv', 'dec_conv4'),
+                            ('conv5.conv', 'dec_conv5')])
+del w
+with open(os.path.join(OUT, 'dred_rdovae_constants.h'), 'w') as f:
+    f.write('#ifndef DRED_RDOVAE_CONSTANTS_H\n#define DRED_RDOVAE_CONSTANTS_H\n')
+    for k, v in [('DRED_NUM_FEATURES', FEATURE_DIM), ('DRED_LATENT_DIM', LATENT_DIM), ('DRED_STATE_DIM', STATE_DIM), ('DRED_PADDED_LATENT_DIM', (LATENT_DIM + 7) // 8 * 8),
+                 ('DRED_PADDED_STATE_DIM', (STATE_DIM + 7) // 8 * 8), ('DRED_NUM_QUANTIZATION_LEVELS', 16), ('DRED_MAX_RNN_NEURONS', rnn),
+                 ('DRED_MAX_CONV_INPUTS', conv), ('DRED_DEC_MAX_RNN_NEURONS', rnn)]:
+        f.write('#define %s %d\n' % (k, v))
+    f.write('#endif\n')
+print('wrote', os.path.join(OUT, 'dred_rdovae_dec_data.c'), 'max rnn', rnn, 'max conv inputs', conv)

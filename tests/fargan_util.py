@@ -66,3 +66,38 @@ def make_inputs(seed, nframes):
     feat0[:, 18] = rng.uniform(-1.4, 1.4, 5)
     feats[:, 18] = rng.uniform(-1.4, 1.4, nframes)     # periods from ~34 to ~240 samples
     return pcm0, feat0.reshape(-1), feats
+
+
+class RefDred:
+    """the reference's DRED decoder network (dnn/dred_rdovae_dec.c) with the seeded random model of oracle/gen_dred_weights.py"""
+    NL = 29
+
+    def __init__(self, L):
+        self.L = L
+        self.nf, self.latent, self.state = (L.refh_dred_const(i) for i in range(3))
+
+    def layers(self):
+        arr = (util.CLinear * self.NL)()
+        ptrs, dims = (ctypes.c_void_p * 7)(), (ctypes.c_int * 2)()
+        shapes = []
+        for i in range(self.NL):
+            self.L.refh_dred_layer(i, ptrs, dims)
+            for k, name in enumerate(('bias', 'subias', 'weights', 'float_weights', 'weights_idx', 'diag', 'scale')):
+                setattr(arr[i], name, ptrs[k])
+            arr[i].nb_inputs, arr[i].nb_outputs = dims[0], dims[1]
+            shapes.append((dims[0], dims[1], bool(ptrs[4])))
+        return arr, shapes
+
+    def decode_all(self, state, latents):
+        nb = latents.shape[0]
+        out = np.zeros(nb * 4 * self.nf, np.float32)
+        self.L.refh_dred_decode_all(vp(out), vp(np.ascontiguousarray(state, np.float32)), vp(np.ascontiguousarray(latents, np.float32)), nb)
+        return out.reshape(nb, 4 * self.nf)
+
+
+def make_dred_inputs(seed, nb_latents, latent_dim, state_dim):
+    rng = np.random.default_rng(seed)
+    state = (0.5 * rng.standard_normal(state_dim)).astype(np.float32)
+    latents = (0.5 * rng.standard_normal((nb_latents, latent_dim + 1))).astype(np.float32)
+    latents[:, -1] = rng.uniform(0, 1, nb_latents)     # the quantiser-level input the encoder appends
+    return state, latents
