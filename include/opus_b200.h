@@ -295,6 +295,15 @@ void opusb200_fargan_destroy(OpusB200Fargan *f);
 int opusb200_fargan_cont(OpusB200Fargan *f, const float *pcm0, const float *features0, int on_device);
 int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const float *features, int on_device);
 
+/* ---- DRED decoder network (dnn/dred_rdovae_dec.h:50-52, dnn/dred_rdovae_dec.c:44-145) -------------------------------------------
+ * layers: the 29 LinearLayers of the generated `RDOVAEDec` struct (dred_rdovae_dec_data.h) in declaration order (init_rdovaedec).
+ * opusb200_dred_decode_all = DRED_rdovae_decode_all(model, features, state, latents, nb_latents, arch) for n streams at once:
+ * state [n][DRED_STATE_DIM], latents [n][nb_latents][DRED_LATENT_DIM+1] -> features [n][nb_latents][4*DRED_NUM_FEATURES]. */
+typedef struct OpusB200DredDec OpusB200DredDec;
+int opusb200_dred_decoder_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int n_streams, OpusB200DredDec **out);
+void opusb200_dred_decoder_destroy(OpusB200DredDec *d);
+int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, const float *state, const float *latents, int nb_latents, int on_device);
+
 /* Pinned host memory helpers (so host-buffer calls can overlap and run at PCIe speed). */
 void *opusb200_host_alloc(size_t bytes);
 void opusb200_host_free(void *p);

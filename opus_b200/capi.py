@@ -36,7 +36,8 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_nnet_compute_linear', 'opusb200_nnet_compute_activation', 'opusb200_nnet_compute_dense',
            'opusb200_nnet_compute_gru', 'opusb200_nnet_compute_glu', 'opusb200_nnet_compute_conv1d',
            'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d',
-           'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize', 'opusb200_host_alloc', 'opusb200_host_free']
+           'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize',
+           'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free']
 
 
 class OpusB200Error(RuntimeError):
@@ -131,6 +132,10 @@ def lib():
         L.opusb200_nnet_conv2d_destroy.restype = None
         L.opusb200_nnet_compute_conv2d.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci]
         L.opusb200_fargan_create.argtypes = [vp, vp, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_dred_decoder_create.argtypes = [vp, vp, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_dred_decoder_destroy.argtypes = [vp]
+        L.opusb200_dred_decoder_destroy.restype = None
+        L.opusb200_dred_decode_all.argtypes = [vp, vp, vp, vp, ci, ci]
         L.opusb200_fargan_destroy.argtypes = [vp]
         L.opusb200_fargan_destroy.restype = None
         L.opusb200_fargan_cont.argtypes = [vp, vp, vp, ci]

@@ -1,0 +1,134 @@
+// dred_host.cuh — the DRED decoder network (dnn/dred_rdovae_dec.c:32-145) for a batch of streams: DRED_rdovae_decode_all turns one
+// initial state + nb_latents latent vectors per stream into 4*nb_latents feature frames.  The network is DenseNet-shaped: every
+// layer reads the leading columns of one growing activation row (576 floats per stream) — kept as one [n][576] matrix in HBM; the
+// int8 layers' quantiser reads it with the row stride, outputs land in their column ranges.  Layers run through the batched dnn
+// primitives (block-sparse int8 layers: dp4a kernel; the small dense ones: tcgen05).  Included at the end of opus_b200.cu.
+#pragma once
+
+namespace ob {
+constexpr int kDrFeat = 20, kDrGru = 64, kDrConv = 32, kDrDense1 = 96, kDrBuf = kDrDense1 + 5 * (kDrGru + kDrConv), kDrOut = 80;
+enum { DR_DENSE1 = 0, DR_GLU1 = 1, DR_HIDDEN_INIT = 6, DR_OUTPUT = 7, DR_CONV_DENSE1 = 8, DR_GRU_INIT = 13, DR_GRU1_IN = 14, DR_CONV1 = 24, DR_COUNT = 29 };
+}
+using namespace ob;
+
+struct OpusB200DredDec {
+  OpusB200Ctx *ctx;
+  int n, latent_dim, state_dim;
+  OpusB200Linear *l[DR_COUNT];
+  float *buf;                 // [n][576] activation rows
+  float *gru[5], *conv[5];    // [n][64], [n][32] layer memories
+  float *tmp, *tmp2;          // [n][320] scratch
+  float *d_state, *d_lat, *d_feat;   // staging for host callers
+  size_t lat_cap, feat_cap;
+};
+static void dr_free(OpusB200DredDec *d) {
+  if (!d) return;
+  for (int i = 0; i < DR_COUNT; i++) opusb200_nnet_linear_destroy(d->l[i]);
+  cudaFree(d->buf); cudaFree(d->tmp); cudaFree(d->tmp2); cudaFree(d->d_state); cudaFree(d->d_lat); cudaFree(d->d_feat);
+  for (int k = 0; k < 5; k++) { cudaFree(d->gru[k]); cudaFree(d->conv[k]); }
+  delete d;
+}
+// init_rdovaedec: the 29 LinearLayers of the generated RDOVAEDec struct (dred_rdovae_dec_data.h) in declaration order
+extern "C" int opusb200_dred_decoder_create(OpusB200Ctx *c, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int n_streams, OpusB200DredDec **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  if (!c || !layers || n_layers != DR_COUNT || n_streams <= 0) return OPUSB200_BAD_ARG;
+  // sizes as linear_init checks them; the latent / state widths come from the model
+  static const int outs[DR_COUNT] = {96, 64, 64, 64, 64, 64, 128, 80, 32, 32, 32, 32, 32, 320, 192, 192, 192, 192, 192, 192, 192, 192, 192, 192, 32, 32, 32, 32, 32};
+  static const int ins[DR_COUNT] = {0, 64, 64, 64, 64, 64, 0, 576, 160, 256, 352, 448, 544, 128, 96, 64, 192, 64, 288, 64, 384, 64, 480, 64, 64, 64, 64, 64, 64};
+  for (int i = 0; i < DR_COUNT; i++)
+    if (layers[i].nb_outputs != outs[i] || (ins[i] && layers[i].nb_inputs != ins[i])) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200DredDec *d = new (std::nothrow) OpusB200DredDec;
+  if (!d) return OPUSB200_ALLOC_FAIL;
+  memset(d, 0, sizeof(*d));
+  d->ctx = c; d->n = n_streams; d->latent_dim = layers[DR_DENSE1].nb_inputs - 1; d->state_dim = layers[DR_HIDDEN_INIT].nb_inputs;
+  for (int i = 0; i < DR_COUNT; i++) {
+    const int r = opusb200_nnet_linear_create(c, &layers[i], su_bias, &d->l[i]);
+    if (r != OPUSB200_OK) { dr_free(d); return r; }
+  }
+  const size_t n = (size_t)n_streams;
+  bool ok = cudaMalloc(&d->buf, sizeof(float) * n * kDrBuf) == cudaSuccess && cudaMalloc(&d->tmp, sizeof(float) * n * 320) == cudaSuccess &&
+            cudaMalloc(&d->tmp2, sizeof(float) * n * 320) == cudaSuccess && cudaMalloc(&d->d_state, sizeof(float) * n * d->state_dim) == cudaSuccess;
+  for (int k = 0; k < 5 && ok; k++)
+    ok = cudaMalloc(&d->gru[k], sizeof(float) * n * kDrGru) == cudaSuccess && cudaMalloc(&d->conv[k], sizeof(float) * n * kDrConv) == cudaSuccess;
+  if (!ok) { dr_free(d); return OPUSB200_ALLOC_FAIL; }
+  *out = d;
+  return OPUSB200_OK;
+}
+extern "C" void opusb200_dred_decoder_destroy(OpusB200DredDec *d) {
+  if (!d) return;
+  cudaSetDevice(d->ctx->device);
+  cudaStreamSynchronize(d->ctx->stream);
+  dr_free(d);
+}
+#define DR_TRY(x) do { const int r_ = (x); if (r_ != OPUSB200_OK) return r_; } while (0)
+// a [n][w] contiguous matrix into columns [col, col+w) of the activation rows
+static int dr_put(OpusB200DredDec *d, int col, const float *src, int w) {
+  OB_CUDA(cudaMemcpy2DAsync(d->buf + col, sizeof(float) * kDrBuf, src, sizeof(float) * w, sizeof(float) * w, d->n, cudaMemcpyDeviceToDevice, d->ctx->stream));
+  return OPUSB200_OK;
+}
+// DRED_rdovae_decode_all (dnn/dred_rdovae_dec.c:44-61): state [n][state_dim], latents [n][nb_latents][latent_dim+1]
+// -> features [n][nb_latents][4*20] (each quadruple frame in the reference's order)
+extern "C" int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, const float *state, const float *latents, int nb_latents, int on_device) {
+  if (!d || !features || !state || !latents || nb_latents <= 0) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = d->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  const int n = d->n, LW = d->latent_dim + 1;
+  const size_t lb = sizeof(float) * (size_t)n * nb_latents * LW, fb = sizeof(float) * (size_t)n * nb_latents * kDrOut;
+  const float *dst = state, *dl = latents;
+  float *df = features;
+  if (!on_device) {
+    if (d->lat_cap < lb) { cudaFree(d->d_lat); d->d_lat = nullptr; d->lat_cap = 0; OB_CUDA(cudaMalloc(&d->d_lat, lb)); d->lat_cap = lb; }
+    if (d->feat_cap < fb) { cudaFree(d->d_feat); d->d_feat = nullptr; d->feat_cap = 0; OB_CUDA(cudaMalloc(&d->d_feat, fb)); d->feat_cap = fb; }
+    OB_CUDA(cudaMemcpyAsync(d->d_state, state, sizeof(float) * (size_t)n * d->state_dim, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(d->d_lat, latents, lb, cudaMemcpyHostToDevice, c->stream));
+    dst = d->d_state; dl = d->d_lat; df = d->d_feat;
+  }
+  // dred_rdovae_dec_init_states (:63-87)
+  DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_HIDDEN_INIT], d->tmp, dst, n, NN_TANH, 1));
+  DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_GRU_INIT], d->tmp2, d->tmp, n, NN_TANH, 1));
+  for (int k = 0; k < 5; k++)
+    OB_CUDA(cudaMemcpy2DAsync(d->gru[k], sizeof(float) * kDrGru, d->tmp2 + k * kDrGru, sizeof(float) * 5 * kDrGru, sizeof(float) * kDrGru, n,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  for (int k = 0; k < 5; k++) OB_CUDA(cudaMemsetAsync(d->conv[k], 0, sizeof(float) * (size_t)n * kDrConv, c->stream));   // conv1_cond_init on the first frame
+  for (int q = 0; q < nb_latents; q++) {   // dred_rdovae_decode_qframe (:90-145)
+    // this step's latent vectors, contiguous
+    OB_CUDA(cudaMemcpy2DAsync(d->tmp, sizeof(float) * LW, dl + (size_t)q * LW, sizeof(float) * nb_latents * LW, sizeof(float) * LW, n,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_DENSE1], d->tmp2, d->tmp, n, NN_TANH, 1));
+    DR_TRY(dr_put(d, 0, d->tmp2, kDrDense1));
+    int col = kDrDense1;
+    for (int k = 0; k < 5; k++) {
+      // compute_generic_gru on the leading `col` columns of the activation rows (dnn/nnet.c:76-105)
+      const OpusB200Linear *wi = d->l[DR_GRU1_IN + 2 * k], *wr = d->l[DR_GRU1_IN + 2 * k + 1];
+      float *zrh;
+      if (nnet_scratch(c, 1, sizeof(float) * (size_t)n * 6 * kDrGru, (void **)&zrh)) return OPUSB200_ALLOC_FAIL;
+      float *recur = zrh + (size_t)n * 3 * kDrGru;
+      DR_TRY(nnet_linear_dev(c, wi, zrh, d->buf, n, NN_LINEAR, nullptr, nullptr, kDrBuf));
+      DR_TRY(nnet_linear_dev(c, wr, recur, d->gru[k], n));
+      NnetGruParams g;
+      g.state = d->gru[k]; g.zrh = zrh; g.recur = recur; g.n = n; g.N = kDrGru;
+      ob_nnet_gru<<<nblk((long)n * kDrGru, 256), 256, 0, c->stream>>>(g);
+      c->launches++;
+      DR_TRY(opusb200_nnet_compute_glu(c, d->l[DR_GLU1 + k], d->tmp, d->gru[k], n, 1));
+      DR_TRY(dr_put(d, col, d->tmp, kDrGru));
+      col += kDrGru;
+      // conv_dense on the leading columns + tanh, then the 2-tap conv1d + tanh
+      DR_TRY(nnet_linear_dev(c, d->l[DR_CONV_DENSE1 + k], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDrBuf));
+      DR_TRY(nnet_act_dev(c, d->tmp, d->tmp, n, kDrConv, NN_TANH));
+      DR_TRY(opusb200_nnet_compute_conv1d(c, d->l[DR_CONV1 + k], d->tmp2, d->conv[k], d->tmp, n, kDrConv, 1, NN_TANH, 1));
+      DR_TRY(dr_put(d, col, d->tmp2, kDrConv));
+      col += kDrConv;
+    }
+    DR_TRY(nnet_linear_dev(c, d->l[DR_OUTPUT], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDrBuf));
+    OB_CUDA(cudaMemcpy2DAsync(df + (size_t)q * kDrOut, sizeof(float) * nb_latents * kDrOut, d->tmp, sizeof(float) * kDrOut, sizeof(float) * kDrOut, n,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  }
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(features, df, fb, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}

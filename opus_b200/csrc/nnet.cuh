@@ -95,7 +95,7 @@ OB_DEV float nnet_epilogue(const NnetLinear &L, float y, const float *in_row, in
 }
 
 // ---- activation quantisation (vec.h:253/288 and vec_avx.h:383) -------------------------------------------------------
-struct NnetQuantParams { int8_t *xq; const float *in; int n, M, Mp, su; };
+struct NnetQuantParams { int8_t *xq; const float *in; int n, M, Mp, su; int in_stride; };   // in_stride: floats between rows (>= M)
 OB_DEV void nnet_quant_thread(const NnetQuantParams &p, long t) {  // one thread per 4 outputs (one word)
   const int wpr = p.Mp >> 2;
   if (t >= (long)p.n * wpr) return;
@@ -106,7 +106,7 @@ OB_DEV void nnet_quant_thread(const NnetQuantParams &p, long t) {  // one thread
     const int j = j0 + b;
     int q = 0;
     if (j < p.M) {
-      q = (int)floor(0.5 + (double)f_mul(127.f, p.in[(size_t)s * p.M + j]));
+      q = (int)floor(0.5 + (double)f_mul(127.f, p.in[(size_t)s * p.in_stride + j]));
       if (p.su) q += 127;
     }
     word |= ((uint32_t)q & 0xffu) << (8 * b);

@@ -199,9 +199,13 @@ static int nnet_umma_quant_seg(OpusB200Ctx *c, const OpusB200Linear *l, const Um
   return OPUSB200_OK;
 }
 // act / glu_in: fused into the tcgen05 kernel's epilogue when the layer takes that path (*fused says so); other paths ignore them
+// in_stride: the rows of `in` are in_stride floats apart (a layer reading the leading columns of a wider activation matrix, as
+// the DRED decoder's layers do); int8 layers only -- their quantiser absorbs the stride.  0 = contiguous.
 static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, const float *in, int n, int act = NN_LINEAR,
-                           const float *glu_in = nullptr, bool *fused = nullptr) {
+                           const float *glu_in = nullptr, bool *fused = nullptr, int in_stride = 0) {
   if (fused) *fused = false;
+  if (in_stride && in_stride != l->L.M && (!l->L.w8 || l->L.diag)) return OPUSB200_BAD_ARG;
+  if (!in_stride) in_stride = l->L.M;
   NnetLinearParams p;
   p.L = l->L; p.out = out; p.in = in; p.n = n; p.xq = nullptr; p.Mp = (l->L.M + 31) & ~31;
   const NnetLinear &L = l->L;
@@ -210,7 +214,7 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
     void *xq;
     if (nnet_scratch(c, 0, (size_t)mt * 128 * l->Kp, &xq)) return OPUSB200_ALLOC_FAIL;
     UmmaQuantParams q;
-    q.xq = (int8_t *)xq; q.in = in; q.n = n; q.M = L.M; q.Kp = l->Kp; q.su = L.su;
+    q.xq = (int8_t *)xq; q.in = in; q.n = n; q.M = L.M; q.Kp = l->Kp; q.su = L.su; q.in_stride = in_stride;
     ob_nnet_quant_umma<<<nblk((long)mt * 128 * (l->Kp / 16), 256), 256, 0, c->stream>>>(q);
     c->launches++;
     return nnet_umma_gemm(c, l, out, (const int8_t *)xq, in, n, act, glu_in, fused);
@@ -219,7 +223,7 @@ static int nnet_linear_dev(OpusB200Ctx *c, const OpusB200Linear *l, float *out, 
     void *xq;
     if (nnet_scratch(c, 0, (size_t)n * p.Mp, &xq)) return OPUSB200_ALLOC_FAIL;
     NnetQuantParams q;
-    q.xq = (int8_t *)xq; q.in = in; q.n = n; q.M = L.M; q.Mp = p.Mp; q.su = L.su;
+    q.xq = (int8_t *)xq; q.in = in; q.n = n; q.M = L.M; q.Mp = p.Mp; q.su = L.su; q.in_stride = in_stride;
     ob_nnet_quant<<<nblk((long)n * (p.Mp / 4), 256), 256, 0, c->stream>>>(q);
     p.xq = (const int8_t *)xq;
     c->launches++;

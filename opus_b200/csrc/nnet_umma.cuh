@@ -28,7 +28,7 @@ struct UmmaLinearParams {
   int act;              // elementwise activation fused into the epilogue (compute_generic_dense / conv1d), 0 = none
   const float *glu_in;  // non-null: out = glu_in * sigmoid(y)  (compute_glu, dnn/nnet.c:107-120; may alias out)
 };
-struct UmmaQuantParams { int8_t *xq; const float *in; int n, M, Kp, su; };
+struct UmmaQuantParams { int8_t *xq; const float *in; int n, M, Kp, su; int in_stride; };   // in_stride: floats between rows (>= M)
 // The operand of a layer whose input is a concatenation: up to 6 pieces, each [n][width] with its own row stride and an
 // optional per-row multiplier (FARGAN's pitch-gated prediction); quantised in place of materialising the float concatenation.
 struct UmmaSeg { const float *ptr; const float *gate; int width, stride, gate_stride; };
@@ -91,9 +91,9 @@ extern "C" __global__ void __launch_bounds__(256) ob_nnet_quant_umma(UmmaQuantPa
   const int kc = (int)(t / rows), s = (int)(t - (long)kc * rows);
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (s < p.n) {
-    const float *src = p.in + (size_t)s * p.M + kc * 16;
+    const float *src = p.in + (size_t)s * p.in_stride + kc * 16;
     float x[16];
-    if (kc * 16 + 16 <= p.M && (p.M & 3) == 0) {
+    if (kc * 16 + 16 <= p.M && (p.in_stride & 3) == 0 && ((size_t)p.in & 15) == 0) {
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         const float4 f = *(const float4 *)(src + 4 * b);

@@ -977,4 +977,5 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 #include "nnet_host.cuh"
 #include "fargan_host.cuh"
+#include "dred_host.cuh"
 #include "celt_enc_host.cuh"

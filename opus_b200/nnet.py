@@ -184,3 +184,37 @@ class Fargan:
             self.close()
         except Exception:
             pass
+
+
+class DredDecoder:
+    """Batched DRED decoder network (dnn/dred_rdovae_dec.h): `layers` = ctypes array of the 29 LinearLayers of RDOVAEDec."""
+
+    def __init__(self, ops, layers, n_streams, su_bias=False):
+        self._L, self.n = ops._L, n_streams
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_dred_decoder_create(ops._h, layers, 29, 1 if su_bias else 0, n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_decoder_create')
+        self._h = h
+
+    def decode_all(self, state, latents):
+        """state [n][state_dim], latents [n][nb_latents][latent_dim+1] -> features [n][nb_latents][80]"""
+        state = np.ascontiguousarray(state, np.float32)
+        latents = np.ascontiguousarray(latents, np.float32)
+        nb = latents.shape[1]
+        out = np.empty((self.n, nb, 80), np.float32)
+        r = self._L.opusb200_dred_decode_all(self._h, _p(out), _p(state), _p(latents), nb, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_decode_all')
+        return out
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_dred_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

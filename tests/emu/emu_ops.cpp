@@ -162,7 +162,7 @@ extern "C" void emu_nnet_linear(const EmuLinearLayer *h, int su, float *out, con
   if (i8) {
     xq.resize((size_t)n * g.p.Mp);
     NnetQuantParams q;
-    q.xq = xq.data(); q.in = in; q.n = n; q.M = M; q.Mp = g.p.Mp; q.su = L.su;
+    q.xq = xq.data(); q.in = in; q.n = n; q.M = M; q.Mp = g.p.Mp; q.su = L.su; q.in_stride = M;
     emu_launch(nnet_quant_entry, &q, (n * (g.p.Mp / 4) + 31) / 32, 32, 0);
     g.p.xq = xq.data();
     if (L.rb_off) emu_launch(nnet_i8s_entry, &g, (n * (N / 8) + 31) / 32, 32, 0);

@@ -1,0 +1,34 @@
+"""Parity of the batched CUDA DRED decoder network (opusb200_dred_decode_all) with the oracle restatement of dnn/dred_rdovae_dec.c,
+itself bit-identical to the reference's own file (tests/test_dred_oracle_vs_ref.py).  Weights: the seeded random block-sparse
+model inside oracle/_ref/libfargan_ref.so.  Bar: bit-identical feature frames."""
+import numpy as np
+import pytest
+
+import fargan_util as F
+import util
+
+pytestmark = pytest.mark.gpu
+R = F.load_ref()
+
+
+@pytest.mark.skipif(R is None or not hasattr(R, 'refh_dred_decode_all'), reason='reference DRED build missing')
+@pytest.mark.parametrize('n,nb', [(2, 3), (131, 12)])
+def test_dred_decode_all_matches_oracle(n, nb):
+    import opus_b200
+    from opus_b200 import nnet
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    ref = F.RefDred(R)
+    layers, shapes = ref.layers()
+    ins = [F.make_dred_inputs(40 + s, nb, ref.latent, ref.state) for s in range(min(n, 5))]
+    ops = opus_b200.Ops()
+    dd = nnet.DredDecoder(ops, layers, n)
+    state = np.stack([ins[s % len(ins)][0] for s in range(n)])
+    lat = np.stack([ins[s % len(ins)][1] for s in range(n)])
+    got = dd.decode_all(state, lat)
+    for s in range(len(ins)):
+        want = np.zeros((nb, 80), np.float32)
+        O.orc_dred_decode_all(layers, F.vp(want), F.vp(ins[s][0]), F.vp(ins[s][1]), nb, ref.latent)
+        for r in range(s, n, len(ins)):
+            assert np.array_equal(got[r], want), (r, float(np.abs(got[r] - want).max()))
+    dd.close()
