@@ -170,6 +170,23 @@ def main():
              'layer-by-layer graph, int8 layers on tcgen05; %.1f TOPS; CPU column = reference fargan.c, generic C branch, 1 core' % (2.0 * nf * macs / (ms * 1e-3) / 1e12))
         fg.close()
 
+    # ---- DRED decoder network: DRED_rdovae_decode_all, 25 latents (= 1 s of redundancy: 100 feature frames) per stream ----
+    if FR is not None and hasattr(FR, 'refh_dred_decode_all'):
+        nd, nbl = min(n, 32768), 25
+        rd = FG.RefDred(FR)
+        dl, _ = rd.layers()
+        dd = nn_mod.DredDecoder(ops, dl, nd)
+        st0, lat0 = FG.make_dred_inputs(3, nbl, rd.latent, rd.state)
+        d_st = torch.from_numpy(np.tile(st0, (nd, 1))).to(dev)
+        d_lat = torch.from_numpy(np.tile(lat0[None], (nd, 1, 1))).to(dev)
+        d_ft = torch.empty((nd, nbl, 80), dtype=torch.float32, device=dev)
+        fn = lambda: L.opusb200_dred_decode_all(dd._h, dptr(d_ft), dptr(d_st), dptr(d_lat), nbl, 1)
+        ms = time_gpu(stream, fn, max(2, a.reps // 2))
+        cpu = time_cpu(lambda: rd.decode_all(st0, lat0), 1.0)
+        emit('dred_decode_all_25_latents', 'streams x 1 s of DRED', nd, ms, 4 * (rd.state + nbl * (rd.latent + 1) + nbl * 80), cpu,
+             'layer-by-layer graph over block-sparse int8 layers (dp4a) + small dense ones (tcgen05); CPU column = reference dred_rdovae_dec.c, generic C branch, 1 core')
+        dd.close()
+
     # ---- SILK Burg (16 kHz: 4 x (80+16) samples, order 16) ----
     subfr, nb, D = 96, 4, 16
     t = np.arange(subfr * nb)
