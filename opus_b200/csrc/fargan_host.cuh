@@ -155,9 +155,11 @@ struct OpusB200Fargan {
   int fwc0_cur;
   float *dense_in, *conv1_in, *fdense2_in, *cond, *gain, *pred, *prev, *x192, *pgate, *g1, *g2, *g3, *skip, *sig;
   float *d_feat, *d_pcm, *d_pcm0;   // staging for host callers
+  ObGraphCache graph;               // one synthesised frame as a CUDA graph
 };
 static void fg_free(OpusB200Fargan *f) {
   if (!f) return;
+  if (f->graph.exec) cudaGraphExecDestroy(f->graph.exec);
   for (int i = 0; i < FG_COUNT; i++) opusb200_nnet_linear_destroy(f->l[i]);
   float **bufs[] = {&f->cond_conv1_state, &f->fwc0_buf[0], &f->fwc0_buf[1], &f->gru1, &f->gru2, &f->gru3, &f->dense_in, &f->conv1_in, &f->fdense2_in, &f->cond,
                     &f->gain, &f->pred, &f->prev, &f->x192, &f->pgate, &f->g1, &f->g2, &f->g3, &f->skip, &f->sig, &f->d_feat, &f->d_pcm,
@@ -342,13 +344,17 @@ extern "C" int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const f
     OB_CUDA(cudaMemcpyAsync(f->d_feat, features, sizeof(float) * n * kFgFeatures, cudaMemcpyHostToDevice, c->stream));
     df = f->d_feat; dp = f->d_pcm;
   }
-  FG_TRY(fg_cond(f, df, 0));
-  for (int i = 0; i < kFgNbSub; i++) FG_TRY(fg_subframe(f, i, dp, nullptr));
-  FgParams p = {};
-  p.st = f->st; p.n = f->n;
-  ob_fargan_end_frame<<<fg_blk(n), 256, 0, c->stream>>>(p);
-  c->launches++;
-  OB_CUDA(cudaGetLastError());
+  // a frame is ~200 launches whose arguments only depend on (features, pcm) pointers: replayed as a CUDA graph from the third call
+  FG_TRY(ob_graph_run(c, f->graph, df, dp, f->n, [&]() -> int {
+    FG_TRY(fg_cond(f, df, 0));
+    for (int i = 0; i < kFgNbSub; i++) FG_TRY(fg_subframe(f, i, dp, nullptr));
+    FgParams p = {};
+    p.st = f->st; p.n = f->n;
+    ob_fargan_end_frame<<<fg_blk(n), 256, 0, c->stream>>>(p);
+    c->launches++;
+    OB_CUDA(cudaGetLastError());
+    return OPUSB200_OK;
+  }));
   if (!on_device) {
     OB_CUDA(cudaMemcpyAsync(pcm, dp, sizeof(float) * n * kFgFrame, cudaMemcpyDeviceToHost, c->stream));
     OB_CUDA(cudaStreamSynchronize(c->stream));

@@ -153,6 +153,38 @@ extern "C" void opusb200_nnet_linear_destroy(OpusB200Linear *l) {
 }
 
 // device-pointer core of compute_linear: out [n][N], in [n][M]
+// ---- CUDA-graph cache for the launch-bound model graphs (FARGAN frame: ~200 launches, DRED decode: ~60 per latent) -----------------
+// The first call with a given key (pointers + shape) runs eagerly (it sizes the scratch buffers and sets kernel attributes), the
+// second one is captured from the very same enqueue code and every later one replays the instantiated graph.  A failed capture
+// (e.g. a scratch buffer that had to grow) falls back to eager enqueueing.  OPUSB200_NO_GRAPHS=1 disables it.
+struct ObGraphCache { cudaGraphExec_t exec; const void *a, *b; long k; int state; };   // state: 0 new, 1 warmed, 2 captured, -1 disabled
+template <class F> static int ob_graph_run(OpusB200Ctx *c, ObGraphCache &g, const void *a, const void *b, long k, F &&enqueue) {
+  static const bool off = getenv("OPUSB200_NO_GRAPHS") != nullptr;
+  if (off || g.state < 0) return enqueue();
+  if (g.a != a || g.b != b || g.k != k) {
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    g.a = a; g.b = b; g.k = k; g.state = 0;
+  }
+  if (g.state == 2) { OB_CUDA(cudaGraphLaunch(g.exec, c->stream)); return OPUSB200_OK; }
+  if (g.state == 0) { g.state = 1; return enqueue(); }
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.state = -1; return enqueue(); }
+  const int r = enqueue();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  if (r != OPUSB200_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g.state = -1;
+    return r != OPUSB200_OK ? r : enqueue();
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.state = -1; return enqueue(); }
+  g.state = 2;
+  OB_CUDA(cudaGraphLaunch(g.exec, c->stream));
+  return OPUSB200_OK;
+}
+
 // the tcgen05 GEMM on an operand that is already quantised in the tensor core's layout (xq: [ceil(n/128)][Kp/16][128][16])
 static int nnet_umma_gemm(OpusB200Ctx *c, const OpusB200Linear *l, float *out, const int8_t *xq, const float *in_for_diag, int n, int act = NN_LINEAR,
                           const float *glu_in = nullptr, bool *fused = nullptr) {
