@@ -935,6 +935,29 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   st->rng = dec.rng;
   st->final_range = dec.rng;
   if (dec.error) st->error = 1;
+  if (ok > 0) {
+    // energy-state update (celt/celt_decoder.c:1575-1600).  It only needs the decoded energies, so it lives here and not behind the
+    // vector stage: frame t+1 can be parsed while frame t's PVQ / synthesis kernels still run.  Anti-collapse (vector stage) wants
+    // the log energies of the two previous frames as they were before the update: handed over in the side info.
+    const int M = 1 << LM;
+#pragma unroll 1
+    for (int i = 0; i < 2 * OB_NBANDS; i++) {
+      const int band = i >= OB_NBANDS ? i - OB_NBANDS : i;
+      float eb = side->bandE[i];
+      float l1 = st->oldLogE[i], l2 = st->oldLogE2[i], bg = st->backgroundLogE[i];
+      if (anti_collapse_on) { side->prevLogE[0][i] = l1; side->prevLogE[1][i] = l2; }
+      if (!isTransient) { l2 = l1; l1 = eb; }
+      else l1 = l1 < eb ? l1 : eb;
+      const float inc = OB_IMIN(160, M) * 0.001f;
+      const float a = bg + inc;
+      bg = a < eb ? a : eb;
+      if (band >= end) { eb = 0.f; l1 = l2 = -28.f; }
+      st->oldEBands[i] = eb;
+      st->oldLogE[i] = l1;
+      st->oldLogE2[i] = l2;
+      st->backgroundLogE[i] = bg;
+    }
+  }
   ent_finish(p, stream, side, st, ok);
 }
 

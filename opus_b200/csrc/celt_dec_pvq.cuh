@@ -443,7 +443,6 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
   const ObFrameSide *side = p.side + stream;
   if (side->status <= 0) return;
   const ObScript *sc = p.script + stream;
-  ObDecBandState *st = p.state + stream;
   const int LM = side->LM, C = side->C, isTransient = side->transient, end = side->end_band, start = 0;
   const int N = OB_SHORT_N << LM, M = 1 << LM;
   const int spread = side->spread, intensity = side->intensity;
@@ -575,7 +574,7 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
     wsync();
   }
   if (side->anti_collapse_on)
-    anti_collapse_vec(ws, side, lane, LM, C, N, start, end, side->bandE, st->oldLogE, st->oldLogE2, seed);
+    anti_collapse_vec(ws, side, lane, LM, C, N, start, end, side->bandE, side->prevLogE[0], side->prevLogE[1], seed);
   wsync();
   // ---- one coalesced store of the frame's spectrum ----
   {
@@ -586,23 +585,7 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
 #pragma unroll 1
       for (int j = lane; j < N; j += 32) Xg[c * N + j] = j < bound ? ws->X[c * N + j] : 0.f;
   }
-  // ---- state update (celt/celt_decoder.c:1575-1600), lane-parallel over the 42 energies ----
-#pragma unroll 1
-  for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
-    const int band = i >= OB_NBANDS ? i - OB_NBANDS : i;
-    float e = side->bandE[i];
-    float l1 = st->oldLogE[i], l2 = st->oldLogE2[i], bg = st->backgroundLogE[i];
-    if (!isTransient) { l2 = l1; l1 = e; }
-    else l1 = l1 < e ? l1 : e;
-    float inc = OB_IMIN(160, M) * 0.001f;
-    float a = bg + inc;
-    bg = a < e ? a : e;
-    if (band < start || band >= end) { e = 0.f; l1 = l2 = -28.f; }
-    st->oldEBands[i] = e;
-    st->oldLogE[i] = l1;
-    st->oldLogE2[i] = l2;
-    st->backgroundLogE[i] = bg;
-  }
+  // (the energy-state update of celt/celt_decoder.c:1575-1600 is done by the entropy kernel)
 }
 
 }  // namespace ob

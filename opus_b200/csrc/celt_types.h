@@ -83,7 +83,10 @@ typedef struct {
   uint8_t pad8[3];
   int16_t pulses[OB_NBANDS];  /* PVQ bit allocation per band (anti-collapse depth) */
   int16_t pad16;
-} ObFrameSide; /* 340 bytes */
+  /* oldLogE / oldLogE2 as they were BEFORE this frame's state update (written only when anti_collapse_on): the entropy kernel
+     owns the energy state, so that the next frame's parsing does not wait for this frame's vector stage */
+  float prevLogE[2][2 * OB_NBANDS];
+} ObFrameSide; /* 676 bytes */
 
 /* Per-stream script buffer written by the entropy kernel, read by the PVQ kernel. */
 typedef struct {

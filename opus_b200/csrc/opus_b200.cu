@@ -148,11 +148,13 @@ struct OpusB200Decoder {
   ObDecSynthState *sstate;
   // side info and spectra are double-buffered: the synthesis of frame t (own stream) overlaps the bitstream parsing of t+1
   ObFrameSide *side[2];
-  ObScript *script;
+  ObScript *script[2];
   float *X[2];
   int par;                  // buffer parity of the next frame
-  cudaStream_t stream_b;    // synthesis stream
-  cudaEvent_t ev_a2[2], ev_b[2];
+  // three stages, three streams: entropy (library stream) -> vector stage (stream_v) -> synthesis (stream_b).  The entropy kernel
+  // owns the energy state, so in pipelined mode frame t+1 is parsed while frame t's vector and synthesis kernels run.
+  cudaStream_t stream_v, stream_b;
+  cudaEvent_t ev_a1[2], ev_a2[2], ev_b[2];
   int last_b;               // parity whose ev_b marks the most recent synthesis (-1: none)
   int pipelined;            // device API: leave the synthesis un-joined at the end of a call (opusb200_decoder_join)
   int pvq_warps;  // warps (= streams) per CTA of the PVQ kernel
@@ -193,6 +195,7 @@ int opusb200_device_count(void) {
 int opusb200_decoder_reset(OpusB200Decoder *d) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(d->device));
+  OB_CUDA(cudaStreamSynchronize(d->stream_v));
   OB_CUDA(cudaStreamSynchronize(d->stream_b));   // the reset rewrites the synthesis state too
   ob_celt_dec_reset<<<592, 256, 0, d->stream>>>(d->bstate, d->sstate, d->n);
   d->launches++;
@@ -218,17 +221,19 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream_b, cudaStreamNonBlocking));
+  OB_CUDA(cudaStreamCreateWithFlags(&d->stream_v, cudaStreamNonBlocking));
   d->last_b = -1;
   for (int b = 0; b < 2; b++) {
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_ready[b], cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_done[b], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&d->ev_a1[b], cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_a2[b], cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_b[b], cudaEventDisableTiming));
   }
   OB_CUDA(cudaMalloc(&d->bstate, sizeof(ObDecBandState) * (size_t)n_streams));
   OB_CUDA(cudaMalloc(&d->sstate, sizeof(ObDecSynthState) * (size_t)n_streams));
-  OB_CUDA(cudaMalloc(&d->script, sizeof(ObScript) * (size_t)n_streams));
   for (int b = 0; b < 2; b++) {
+    OB_CUDA(cudaMalloc(&d->script[b], sizeof(ObScript) * (size_t)n_streams));
     OB_CUDA(cudaMalloc(&d->side[b], sizeof(ObFrameSide) * (size_t)n_streams));
     OB_CUDA(cudaMalloc(&d->X[b], sizeof(float) * 2 * OB_MAXN * (size_t)n_streams));
   }
@@ -272,10 +277,12 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
+  cudaStreamSynchronize(d->stream_v);
   cudaStreamSynchronize(d->stream_b);
   cudaStreamSynchronize(d->stream2);
-  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->script);
-  for (int b = 0; b < 2; b++) { cudaFree(d->side[b]); cudaFree(d->X[b]); cudaEventDestroy(d->ev_a2[b]); cudaEventDestroy(d->ev_b[b]); }
+  cudaFree(d->bstate); cudaFree(d->sstate);
+  for (int b = 0; b < 2; b++) { cudaFree(d->script[b]); cudaFree(d->side[b]); cudaFree(d->X[b]); cudaEventDestroy(d->ev_a1[b]); cudaEventDestroy(d->ev_a2[b]); cudaEventDestroy(d->ev_b[b]); }
+  cudaStreamDestroy(d->stream_v);
   cudaStreamDestroy(d->stream_b);
   for (int b = 0; b < 2; b++) { cudaFree(d->d_len[b]); cudaFree(d->d_out[b]); cudaFree(d->d_packets[b]); cudaFree(d->d_pcm[b]); cudaFreeHost(d->h_len[b]); cudaFreeHost(d->h_out[b]); }
   cudaStreamDestroy(d->stream);
@@ -302,6 +309,7 @@ int opusb200_decoder_set_pipelined(OpusB200Decoder *d, int enable) {
 int opusb200_decoder_sync(OpusB200Decoder *d) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaStreamSynchronize(d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream_v));
   OB_CUDA(cudaStreamSynchronize(d->stream_b));
   return OPUSB200_OK;
 }
@@ -319,25 +327,33 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     const int par = d->par;
     d->par ^= 1;
     const bool timing = d->timing && st == d->stream;
-    cudaStream_t sb = timing ? st : d->stream_b;   // profiling mode keeps everything on one stream
-    // this parity's side/X buffers were last read by the synthesis two frames ago
-    if (!timing) OB_CUDA(cudaStreamWaitEvent(st, d->ev_b[par], 0));
+    cudaStream_t sv = timing ? st : d->stream_v, sb = timing ? st : d->stream_b;   // profiling mode keeps everything on one stream
+    // this parity's script / side / X buffers were last used two frames ago
+    if (!timing) {
+      OB_CUDA(cudaStreamWaitEvent(st, d->ev_a2[par], 0));
+      OB_CUDA(cudaStreamWaitEvent(st, d->ev_b[par], 0));
+    }
     DecEntropyParams ep;
     ep.packets = d_packets + (size_t)s0 * pkt_stride; ep.pkt_len = d_len + s0; ep.pkt_stride = pkt_stride; ep.n_streams = cn;
-    ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side[par] + s0; ep.script = d->script + s0;
+    ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side[par] + s0; ep.script = d->script[par] + s0;
     ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size;
     DecPvqParams pp;
-    pp.side = d->side[par] + s0; pp.script = d->script + s0; pp.state = d->bstate + s0; pp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
+    pp.side = d->side[par] + s0; pp.script = d->script[par] + s0; pp.state = d->bstate + s0; pp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
     if (timing) cudaEventRecord(d->ev[0], st);
     {
       const int warps_needed = (cn + d->ent_lpw - 1) / d->ent_lpw;
       ob_celt_dec_entropy<<<(warps_needed + 3) / 4, 128, 0, st>>>(ep, d->ent_lpw);
     }
     if (timing) cudaEventRecord(d->ev[1], st);
-    ob_celt_dec_pvq<<<(cn + pw - 1) / pw, pw * 32, pvq_smem, st>>>(pp);
+    else {
+      OB_CUDA(cudaEventRecord(d->ev_a1[par], st));
+      OB_CUDA(cudaStreamWaitEvent(sv, d->ev_a1[par], 0));
+      OB_CUDA(cudaStreamWaitEvent(sv, d->ev_b[par], 0));   // X[par] is free once the synthesis of two frames ago has read it
+    }
+    ob_celt_dec_pvq<<<(cn + pw - 1) / pw, pw * 32, pvq_smem, sv>>>(pp);
     if (timing) cudaEventRecord(d->ev[2], st);
     else {
-      OB_CUDA(cudaEventRecord(d->ev_a2[par], st));
+      OB_CUDA(cudaEventRecord(d->ev_a2[par], sv));
       OB_CUDA(cudaStreamWaitEvent(sb, d->ev_a2[par], 0));
     }
     DecSynthParams sp;
@@ -451,6 +467,7 @@ int opusb200_decode_wait(OpusB200Decoder *d) {
   if (!d) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(d->device));
   OB_CUDA(cudaStreamSynchronize(d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream_v));
   OB_CUDA(cudaStreamSynchronize(d->stream_b));
   OB_CUDA(cudaStreamSynchronize(d->stream2));
   for (int b = 0; b < 2; b++)
