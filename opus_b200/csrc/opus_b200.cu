@@ -218,10 +218,20 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   if (!d) return OPUSB200_ALLOC_FAIL;
   memset(d, 0, sizeof(*d));
   d->device = device; d->channels = channels; d->n = n_streams;
-  OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;   // (numerically: lo = 0 is the default and the LOWEST priority, hi < 0 the highest)
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    OB_CUDA(cudaStreamCreateWithPriority(&d->stream, cudaStreamNonBlocking, hi));
+  }
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
-  OB_CUDA(cudaStreamCreateWithFlags(&d->stream_b, cudaStreamNonBlocking));
-  OB_CUDA(cudaStreamCreateWithFlags(&d->stream_v, cudaStreamNonBlocking));
+  {
+    // the entropy kernel (few long-running CTAs, on the library stream) should win free SM resources over the vector and synthesis
+    // kernels' many short CTAs: those two streams get the lowest priority
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    OB_CUDA(cudaStreamCreateWithPriority(&d->stream_b, cudaStreamNonBlocking, lo));
+    OB_CUDA(cudaStreamCreateWithPriority(&d->stream_v, cudaStreamNonBlocking, lo));
+  }
   d->last_b = -1;
   for (int b = 0; b < 2; b++) {
     OB_CUDA(cudaEventCreateWithFlags(&d->ev_ready[b], cudaEventDisableTiming));
