@@ -11,6 +11,21 @@ enum { DR_DENSE1 = 0, DR_GLU1 = 1, DR_HIDDEN_INIT = 6, DR_OUTPUT = 7, DR_CONV_DE
 }
 using namespace ob;
 
+// dst[s*dst_stride + j] = src[s*src_stride + j], j < w (column placement in / extraction from the activation rows; the copy
+// engine's 2-D copies are slow for rows this short)
+extern "C" __global__ void __launch_bounds__(256) ob_dred_copy2d(float *dst, int dst_stride, const float *src, int src_stride, int w, int n) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)n * w) return;
+  const int s = (int)(t / w), j = (int)(t - (long)s * w);
+  dst[(size_t)s * dst_stride + j] = src[(size_t)s * src_stride + j];
+}
+static int dr_copy2d(OpusB200Ctx *c, float *dst, int dst_stride, const float *src, int src_stride, int w, int n) {
+  ob_dred_copy2d<<<(unsigned)(((long)n * w + 255) / 256), 256, 0, c->stream>>>(dst, dst_stride, src, src_stride, w, n);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+
 struct OpusB200DredDec {
   OpusB200Ctx *ctx;
   int n, latent_dim, state_dim;
@@ -67,8 +82,7 @@ extern "C" void opusb200_dred_decoder_destroy(OpusB200DredDec *d) {
 #define DR_TRY(x) do { const int r_ = (x); if (r_ != OPUSB200_OK) return r_; } while (0)
 // a [n][w] contiguous matrix into columns [col, col+w) of the activation rows
 static int dr_put(OpusB200DredDec *d, int col, const float *src, int w) {
-  OB_CUDA(cudaMemcpy2DAsync(d->buf + col, sizeof(float) * kDrBuf, src, sizeof(float) * w, sizeof(float) * w, d->n, cudaMemcpyDeviceToDevice, d->ctx->stream));
-  return OPUSB200_OK;
+  return dr_copy2d(d->ctx, d->buf + col, kDrBuf, src, w, w, d->n);
 }
 // DRED_rdovae_decode_all (dnn/dred_rdovae_dec.c:44-61): state [n][state_dim], latents [n][nb_latents][latent_dim+1]
 // -> features [n][nb_latents][4*20] (each quadruple frame in the reference's order)
@@ -93,13 +107,11 @@ extern "C" int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, con
     DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_HIDDEN_INIT], d->tmp, dst, n, NN_TANH, 1));
     DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_GRU_INIT], d->tmp2, d->tmp, n, NN_TANH, 1));
     for (int k = 0; k < 5; k++)
-      OB_CUDA(cudaMemcpy2DAsync(d->gru[k], sizeof(float) * kDrGru, d->tmp2 + k * kDrGru, sizeof(float) * 5 * kDrGru, sizeof(float) * kDrGru, n,
-                                cudaMemcpyDeviceToDevice, c->stream));
+      DR_TRY(dr_copy2d(c, d->gru[k], kDrGru, d->tmp2 + k * kDrGru, 5 * kDrGru, kDrGru, n));
     for (int k = 0; k < 5; k++) OB_CUDA(cudaMemsetAsync(d->conv[k], 0, sizeof(float) * (size_t)n * kDrConv, c->stream));   // conv1_cond_init on the first frame
     for (int q = 0; q < nb_latents; q++) {   // dred_rdovae_decode_qframe (:90-145)
       // this step's latent vectors, contiguous
-      OB_CUDA(cudaMemcpy2DAsync(d->tmp, sizeof(float) * LW, dl + (size_t)q * LW, sizeof(float) * nb_latents * LW, sizeof(float) * LW, n,
-                                cudaMemcpyDeviceToDevice, c->stream));
+      DR_TRY(dr_copy2d(c, d->tmp, LW, dl + (size_t)q * LW, nb_latents * LW, LW, n));
       DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_DENSE1], d->tmp2, d->tmp, n, NN_TANH, 1));
       DR_TRY(dr_put(d, 0, d->tmp2, kDrDense1));
       int col = kDrDense1;
@@ -126,8 +138,7 @@ extern "C" int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, con
         col += kDrConv;
       }
       DR_TRY(nnet_linear_dev(c, d->l[DR_OUTPUT], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDrBuf));
-      OB_CUDA(cudaMemcpy2DAsync(df + (size_t)q * kDrOut, sizeof(float) * nb_latents * kDrOut, d->tmp, sizeof(float) * kDrOut, sizeof(float) * kDrOut, n,
-                                cudaMemcpyDeviceToDevice, c->stream));
+      DR_TRY(dr_copy2d(c, df + (size_t)q * kDrOut, nb_latents * kDrOut, d->tmp, kDrOut, kDrOut, n));
     }
     return OPUSB200_OK;
   }));
