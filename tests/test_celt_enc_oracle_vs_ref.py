@@ -154,3 +154,25 @@ def test_edge_packet_sizes(ch, fs, nbytes, complexity):
     sig = util.sig_harmonic(900 + nbytes, fs * 6, ch)
     for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, nframes=6):
         assert na == nbo and np.array_equal(a, b) and ra == rb, (f, na, nbo)
+
+
+@pytest.mark.parametrize('seed', range(40))
+def test_randomised_settings(seed):
+    """seeded random draws over everything the encoder oracle takes: channels, frame size, packet size or bit-rate, rate mode,
+    complexity and signal type"""
+    rng = np.random.default_rng(1000 + seed)
+    ch = int(rng.integers(1, 3))
+    fs = int(rng.choice([120, 240, 480, 960]))
+    complexity = int(rng.integers(0, 11))
+    vbr = int(rng.integers(0, 2))
+    cvbr = int(rng.integers(0, 2))
+    nbytes = 1275 if vbr else int(rng.integers(2, 400))
+    bitrate = int(rng.integers(12000, 256000)) * ch if vbr else -1000
+    kind = int(rng.integers(0, 4))
+    n = fs * 10
+    sig = [lambda: util.sig_music(seed, n, ch), lambda: util.sig_white(seed, n, ch), lambda: _transient_signal(seed, n, ch),
+           lambda: _harmonic_signal(seed, n, ch)][kind]()
+    if rng.random() < 0.3:
+        sig = sig * float(rng.choice([0.0005, 0.01, 0.2]))        # near-silent and quiet inputs
+    for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity, bitrate=bitrate, vbr=vbr, nframes=10, cvbr=cvbr):
+        assert na == nbo and np.array_equal(a, b) and ra == rb, (seed, ch, fs, nbytes, complexity, vbr, kind, f, na, nbo)

@@ -78,3 +78,38 @@ def test_emu_encoder_matches_oracle(ch, fs, nbytes, complexity, vbr, cvbr):
     print('coverage pf_on/patched/transient', cov)
     if complexity >= 5 and fs >= 480:
         assert cov[0] > 0      # the pitch pre-filter switched on somewhere
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_emu_encoder_randomised(seed):
+    """the device encoder's source, run lane by lane on the host emulator, against the pinned oracle over seeded random settings
+    (channels, frame size, packet size / bit-rate, rate mode, complexity 0..10, signal type and level)"""
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(5000 + seed)
+    ch = int(rng.integers(1, 3))
+    fs = int(rng.choice([120, 240, 480, 960]))
+    LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs]
+    complexity = int(rng.integers(0, 11))
+    vbr, cvbr = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+    nbytes = 1275 if vbr else int(rng.integers(2, 400))
+    bitrate = int(rng.integers(12000, 256000)) * ch if vbr else -1
+    n, nf = 3, 6
+    gens = [util.sig_music, util.sig_white, clicks, util.sig_harmonic, util.sig_swell]
+    x = np.stack([gens[int(rng.integers(0, 5))](seed * 10 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    x[1] *= float(rng.choice([0.0005, 0.02, 1.0]))
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, cvbr=cvbr) for s in range(n)]
+    an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
+    es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
+    E.emu_enc_state_init(_p(es), n)
+    pmem = np.zeros((n, ch, 1024), np.float32)
+    for f in range(nf):
+        pcm = np.ascontiguousarray(x[:, f])
+        pk = np.zeros((n, nbytes), np.uint8)
+        nb = np.zeros(n, np.int32)
+        rg = np.zeros(n, np.uint32)
+        E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rg), complexity, vbr, cvbr, _p(pmem))
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (seed, f, s, nb[s], wn, (ch, fs, nbytes, complexity, vbr, cvbr))
+            assert np.array_equal(pk[s, :wn], wb), (seed, f, s, (ch, fs, nbytes, complexity, vbr, cvbr))
+            assert rg[s] == wr

@@ -125,3 +125,35 @@ def test_encoder_large_batch(complexity):
             assert (pk[rows, :wn] == wb[None, :]).all(), (f, s)
             assert (rng[rows] == wr).all()
     enc.close()
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_encoder_randomised(seed):
+    """seeded random settings (channels, frame size, packet size / bit-rate, CBR/VBR/CVBR, complexity 0..10, signal type and level):
+    packets and final range equal to the oracle's, i.e. to the reference's"""
+    import opus_b200
+    O = util.load_oracle()
+    rng = np.random.default_rng(7000 + seed)
+    ch = int(rng.integers(1, 3))
+    fs = int(rng.choice([120, 240, 480, 960]))
+    complexity = int(rng.integers(0, 11))
+    vbr, cvbr = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+    nbytes = 1275 if vbr else int(rng.integers(2, 400))
+    bitrate = int(rng.integers(12000, 256000)) * ch if vbr else -1
+    base, n, nf = 6, 70, 6
+    gens = [util.sig_music, util.sig_white, clicks, util.sig_harmonic, util.sig_swell]
+    xb = np.stack([gens[int(rng.integers(0, 5))](seed * 10 + s, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(base)])
+    xb[1] *= float(rng.choice([0.0005, 0.02, 1.0]))
+    x = np.tile(xb, (n // base + 1, 1, 1))[:n]
+    want = [oracle_encode(O, xb[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, cvbr=cvbr) for s in range(base)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=complexity, bitrate=bitrate if vbr else None, vbr=bool(vbr), constrained_vbr=bool(cvbr))
+    for f in range(nf):
+        pk, nb = enc.encode(x[:, f], nbytes)
+        rg = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s % base][f]
+            assert nb[s] == wn, (seed, f, s, nb[s], wn, (ch, fs, nbytes, complexity, vbr, cvbr))
+            if wn > 0:
+                assert np.array_equal(pk[s, :wn], wb), (seed, f, s)
+                assert rg[s] == wr
+    enc.close()
