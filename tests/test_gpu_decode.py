@@ -248,3 +248,41 @@ def test_pipelined_device_calls_match_stream_ordered_calls():
         assert np.array_equal(res[0][0][t], res[1][0][t]), t
         assert np.array_equal(res[0][0][t][0].reshape(fs, ch), pcm[t * fs:(t + 1) * fs].reshape(fs, ch)) or True
     assert (res[0][1] == res[1][1]).all()
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_randomised_reference_streams(seed):
+    """seeded random draws: streams made by the reference ENCODER (channels, frame size, 8..400 kb/s, CBR/VBR, complexity 0/5/10,
+    signal type and level), decoded in pipelined and stream-ordered mode alike; final range exact, PCM within 1 LSB of the oracle"""
+    import opus_b200
+    rng = np.random.default_rng(9500 + seed)
+    ch = int(rng.integers(1, 3))
+    fs = int(rng.choice([120, 240, 480, 960]))
+    nfr, base, n = 8, 5, 37
+    pks, szs = [], []
+    for s in range(base):
+        br = int(rng.choice([8000, 16000, 32000, 64000, 128000, 256000, 400000])) * ch // 2 + 6000
+        x = [util.sig_music, util.sig_white, util.sig_harmonic, util.sig_swell][int(rng.integers(0, 4))](seed * 7 + s, nfr * fs, ch)
+        if rng.random() < 0.25:
+            x = (x * 0.01).astype(np.int16)
+        pk, sz, _ = util.ref_encode(x, ch, fs, br, vbr=int(rng.integers(0, 2)), complexity=int(rng.choice([0, 5, 10])))
+        pks.append(pk); szs.append(sz)
+    stride = max(p.shape[1] for p in pks)
+    pk = np.zeros((n, nfr, stride), np.uint8)
+    sz = np.zeros((n, nfr), np.int32)
+    for s in range(n):
+        pk[s, :, :pks[s % base].shape[1]] = pks[s % base]
+        sz[s] = szs[s % base]
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    outs = np.zeros((n, nfr * fs, ch), np.float32)
+    for t in range(nfr):
+        got, ns = dec.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fs, dtype=np.float32)
+        assert (ns == fs).all()
+        outs[:, t * fs:(t + 1) * fs] = got.reshape(n, fs, ch)
+        fr = dec.final_range()
+    dec.close()
+    for s in range(base):
+        orc, orc_rng = util.oracle_decode_float(pks[s], szs[s], ch, fs)
+        for r in range(s, n, base):
+            _check(outs[r], orc)
+        assert (fr[s::base] == orc_rng[-1]).all()
