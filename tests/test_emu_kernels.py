@@ -70,6 +70,7 @@ def test_emulated_kernels_randomised(seed):
     x = gens[int(rng.integers(0, 4))](seed, nfr * fs, ch)
     if rng.random() < 0.25:
         x = (x * 0.01).astype(np.int16)
+    x = np.asarray(x).reshape(-1, ch)[:nfr * fs]       # (some generators return interleaved 1-D data)
     pk, sz, _ = util.ref_encode(x, ch, fs, br, vbr=vbr, complexity=cx)
     ref, rr = util.ref_decode_float(pk, sz, ch, fs)
     got, gr = emu_util.emu_decode_stream(pk, sz, ch, fs)

@@ -265,6 +265,7 @@ def test_randomised_reference_streams(seed):
         x = [util.sig_music, util.sig_white, util.sig_harmonic, util.sig_swell][int(rng.integers(0, 4))](seed * 7 + s, nfr * fs, ch)
         if rng.random() < 0.25:
             x = (x * 0.01).astype(np.int16)
+        x = np.asarray(x).reshape(-1, ch)[:nfr * fs]       # (some generators return interleaved 1-D data)
         pk, sz, _ = util.ref_encode(x, ch, fs, br, vbr=int(rng.integers(0, 2)), complexity=int(rng.choice([0, 5, 10])))
         pks.append(pk); szs.append(sz)
     stride = max(p.shape[1] for p in pks)
