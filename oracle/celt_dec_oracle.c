@@ -1195,8 +1195,9 @@ static void anti_collapse(float *X_, const unsigned char *collapse_masks, int LM
   }
 }
 
+static int g_denorm_downsample = 1; /* set per frame by the decoder (celt/bands.c:199-200) */
 static void denormalise(const float *X, float *freq, const float *bandLogE, int start, int end, int M, int silence) {
-  int i, N = M * SHORT_N, bound = M * ob_ebands[end];
+  int i, N = M * SHORT_N, bound = IMIN(M * ob_ebands[end], N / g_denorm_downsample);
   float *f = freq;
   const float *x;
   if (silence) { bound = 0; start = end = 0; }
@@ -1479,6 +1480,7 @@ typedef struct {
   /* Opus layer (src/opus_decoder.c) */
   int prev_mode_celt;
   uint32_t final_range;
+  int downsample; /* 48000 / Fs of the output (celt/celt_decoder.c:222-240 resampling_factor), 1 after init */
 } OrcDecoder;
 
 int orc_decoder_size(void) { return (int)sizeof(OrcDecoder); }
@@ -1491,6 +1493,13 @@ void orc_decoder_init(OrcDecoder *st, int channels) {
   st->start = 0;
   st->end = NBANDS;
   for (i = 0; i < 2 * NBANDS; i++) st->oldLogE[i] = st->oldLogE2[i] = -28.f;
+  st->downsample = 1;
+}
+/* opus_decoder_create(Fs): Fs in {48000, 24000, 16000, 12000, 8000} (celt/celt_decoder.c:222-240, resampling_factor celt/celt.c) */
+int orc_decoder_set_fs(OrcDecoder *st, int Fs) {
+  if (Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) return -1;
+  st->downsample = 48000 / Fs;
+  return 0;
 }
 
 /* celt_decoder.c:413-511 */
@@ -1547,6 +1556,7 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
   if (len < 0 || len > 1275 || pcm == NULL) return -1;
   if (data == NULL || len <= 1) return -5; /* packet loss concealment: not restated */
   N = M * SHORT_N;
+  g_denorm_downsample = st->downsample > 1 ? st->downsample : 1;
   c = 0;
   do { decode_mem[c] = st->decode_mem[c]; out_syn[c] = decode_mem[c] + DEC_BUF - N; } while (++c < CC);
   effEnd = IMIN(end, NBANDS);
@@ -1675,9 +1685,10 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
     for (i = end; i < NBANDS; i++) { oldBandE[c * NBANDS + i] = 0; oldLogE[c * NBANDS + i] = oldLogE2[c * NBANDS + i] = -28.f; }
   } while (++c < 2);
   st->rng = dec.rng;
-  /* de-emphasis, celt_decoder.c:288-408 (coef0 = 0.85000610f, 48 kHz, no downsampling) */
+  /* de-emphasis, celt_decoder.c:288-408 (coef0 = 0.85000610f at 48 kHz; the output rate is 48000/downsample) */
   {
     const float coef0 = 0.85000610f;
+    const int ds = st->downsample > 1 ? st->downsample : 1;
     c = 0;
     do {
       float m = st->preemph_mem[c];
@@ -1686,14 +1697,15 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
       for (j = 0; j < N; j++) {
         float tmp = x[j] + 1e-30f + m;
         m = coef0 * tmp;
-        pcm[j * CC + c] = (1 / 32768.f) * tmp;
+        if (ds == 1) pcm[j * CC + c] = (1 / 32768.f) * tmp;
+        else if (j % ds == 0) pcm[(j / ds) * CC + c] = (1 / 32768.f) * tmp;   /* :387-401: keep every downsample-th sample */
       }
       st->preemph_mem[c] = m;
     } while (++c < CC);
   }
   if (rd_tell(&dec) > 8 * len) return -3;
   if (dec.error) st->error = 1;
-  return frame_size;
+  return frame_size / (st->downsample > 1 ? st->downsample : 1);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1791,8 +1803,8 @@ int orc_opus_decode_float(OrcDecoder *st, const uint8_t *data, int len, float *p
   count = orc_packet_parse(data, len, &toc, offsets, sizes);
   if (count < 0) return count;
   if (!(toc & 0x80)) return -5; /* SILK / hybrid: not restated */
-  framesize = (48000 << ((toc >> 3) & 3)) / 400;
-  if (count * framesize > max_frame_size) return -2;
+  framesize = (48000 << ((toc >> 3) & 3)) / 400;   /* at 48 kHz; max_frame_size and the return value are in output-rate samples */
+  if (count * framesize / (st->downsample > 1 ? st->downsample : 1) > max_frame_size) return -2;
   bw = (toc >> 5) & 3; /* CELT-only: 0 NB, 1 WB, 2 SWB, 3 FB  (src/opus.c opus_packet_get_bandwidth) */
   endband = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;
   st->end = endband;
@@ -1826,6 +1838,21 @@ int orc_decode_stream_float(int channels, int frame_size, int nframes, const uin
   OrcDecoder *st = (OrcDecoder *)malloc(sizeof(OrcDecoder));
   int f;
   orc_decoder_init(st, channels);
+  for (f = 0; f < nframes; f++) {
+    int n = orc_opus_decode_float(st, pkts + (size_t)f * stride, sizes[f], pcm + (size_t)f * frame_size * channels, frame_size);
+    if (n < 0) { free(st); return n; }
+    ranges[f] = st->final_range;
+  }
+  free(st);
+  return 0;
+}
+/* the same with an output rate Fs <= 48000: frame_size and the PCM are in Fs samples */
+int orc_decode_stream_float_fs(int Fs, int channels, int frame_size, int nframes, const uint8_t *pkts, int stride, const int *sizes, float *pcm,
+                               uint32_t *ranges) {
+  OrcDecoder *st = (OrcDecoder *)malloc(sizeof(OrcDecoder));
+  int f;
+  orc_decoder_init(st, channels);
+  if (orc_decoder_set_fs(st, Fs)) { free(st); return -1; }
   for (f = 0; f < nframes; f++) {
     int n = orc_opus_decode_float(st, pkts + (size_t)f * stride, sizes[f], pcm + (size_t)f * frame_size * channels, frame_size);
     if (n < 0) { free(st); return n; }
