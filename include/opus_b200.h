@@ -50,7 +50,9 @@ const char *opusb200_version(void);
 int opusb200_device_count(void);
 
 /* N decoders in the state opus_decoder_create() leaves them (src/opus_decoder.c:150-188,
- * celt/celt_decoder.c:240-268).  device: CUDA ordinal.  Fs must be 48000; channels 1 or 2. */
+ * celt/celt_decoder.c:240-268).  device: CUDA ordinal.  Fs: 48000, 24000, 16000, 12000 or 8000 (the output rate: below
+ * 48 kHz the decoder keeps only the spectrum under Fs/2 and decimates after the de-emphasis, celt/celt_decoder.c:219-231,
+ * 300-405; frame_size / pcm_stride / out_samples of the decode calls are then in samples at Fs); channels 1 or 2. */
 int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Decoder **out);
 void opusb200_decoder_destroy(OpusB200Decoder *dec);
 int opusb200_decoder_reset(OpusB200Decoder *dec); /* OPUS_RESET_STATE on every stream */

@@ -36,7 +36,8 @@ struct DecEntropyParams {
   ObFrameSide *side;      // [n_streams]
   ObScript *script;       // [n_streams]
   int32_t *out_samples;   // [n_streams] or null: running per-stream result (samples/channel or error)
-  int max_samples;        // per-channel capacity of each stream's pcm area
+  int max_samples;        // per-channel capacity of each stream's pcm area, in OUTPUT-rate samples
+  int downsample;         // 48000 / output rate (1, 2, 3, 4 or 6): celt_decoder.c:219-231
 };
 
 // ---- exact integer helpers (celt/bands.c:68-91, celt/mathops.c:45-68, celt/rate.h:48-87) ----
@@ -280,12 +281,13 @@ OB_DEVNI int locate_frame(const unsigned char *data, int len, int k, int *off_ou
 }
 
 OB_DEV void ent_finish(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st, int status) {
-  side->status = status;
+  side->status = status;  // the later kernels see the 48 kHz frame length
+  const int rep = status > 0 ? status / p.downsample : status;  // the caller sees output-rate samples (opus_decoder.c:735)
   if (status < 0 || p.frame_index == 0) {
-    st->last_status = status;
-    if (p.out_samples) p.out_samples[stream] = status;
+    st->last_status = rep;
+    if (p.out_samples) p.out_samples[stream] = rep;
   } else if (status > 0 && p.out_samples && p.out_samples[stream] >= 0) {
-    p.out_samples[stream] += status;
+    p.out_samples[stream] += rep;
   }
 }
 
@@ -310,7 +312,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   else if (!(toc & 0x80)) status = -5;                // SILK / hybrid: OPUS_UNIMPLEMENTED here
   else if (p.frame_index >= count) status = 0;        // no such frame in this packet
   else if (flen <= 1) status = -5;                    // lost / DTX frame: PLC not implemented
-  if (status > 0 && (p.frame_index + 1) * N > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // BUFFER_TOO_SMALL
+  if (status > 0 && (p.frame_index + 1) * (N / p.downsample) > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // BUFFER_TOO_SMALL
   if (status <= 0) { ent_finish(p, stream, side, st, status); return; }
 
   const int C = (toc & 4) ? 2 : 1;

@@ -29,6 +29,7 @@ struct DecSynthParams {
   int pcm_is_int16;
   int n_streams;
   int channels;
+  int downsample;           // 48000 / output rate: every downsample-th de-emphasised sample is written (celt_decoder.c:300-405)
 };
 
 struct SynthWS {  // per warp (= per output channel)
@@ -107,6 +108,8 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   const int nblk = transient ? M : 1, NB = N / nblk, shift = transient ? 3 : 3 - LM;
   int end = side->end_band;
   int bound = silence ? 0 : M * ob_ebands[end];
+  const int ds = p.downsample, Nd = N / ds;
+  if (ds != 1) bound = OB_IMIN(bound, Nd);  // celt_decoder.c:451-452
   // ---- band gains (denormalise_bands, celt/bands.c:188-257) ----
   for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
     int band = i >= OB_NBANDS ? i - OB_NBANDS : i;
@@ -232,15 +235,15 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   bsync();
   if (ch == 0 && lane == 0) st->pos = pos + (uint32_t)N;
   {
-    const size_t base = (size_t)stream * p.pcm_stride + (size_t)p.frame_index * N * CC;
-    const int total = N * CC;
+    const size_t base = (size_t)stream * p.pcm_stride + (size_t)p.frame_index * Nd * CC;
+    const int total = Nd * CC;
     const int tid = ch * 32 + lane, nth = CC * 32;
     const SynthWS *w0 = (const SynthWS *)smem;
     if (p.pcm_is_int16) {
       int16_t *o = (int16_t *)p.pcm + base;
       for (int e = tid; e < total; e += nth) {
         int j = CC == 2 ? e >> 1 : e, c = CC == 2 ? e & 1 : 0;
-        float x = w0[c].out[OB_SYN_O + j] * 32768.f;
+        float x = w0[c].out[OB_SYN_O + j * ds] * 32768.f;
         x = x > -32768.f ? x : -32768.f;
         x = x < 32767.f ? x : 32767.f;
         o[e] = (int16_t)lrintf(x);
@@ -249,7 +252,7 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
       float *o = (float *)p.pcm + base;
       for (int e = tid; e < total; e += nth) {
         int j = CC == 2 ? e >> 1 : e, c = CC == 2 ? e & 1 : 0;
-        o[e] = w0[c].out[OB_SYN_O + j];
+        o[e] = w0[c].out[OB_SYN_O + j * ds];
       }
     }
   }

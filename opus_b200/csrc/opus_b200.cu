@@ -143,6 +143,7 @@ extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState
 // ------------------------------------------------------------------------------------------
 struct OpusB200Decoder {
   int device, channels, n;
+  int downsample;   // 48000 / Fs of opusb200_decoder_create
   cudaStream_t stream;
   ObDecBandState *bstate;
   ObDecSynthState *sstate;
@@ -209,7 +210,8 @@ int opusb200_decoder_reset(OpusB200Decoder *d) {
 int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Decoder **out) {
   if (!out) return OPUSB200_BAD_ARG;
   *out = nullptr;
-  if (Fs != 48000 || (channels != 1 && channels != 2) || n_streams <= 0) return OPUSB200_BAD_ARG;
+  if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2) || n_streams <= 0)
+    return OPUSB200_BAD_ARG;  // opus_decoder_init, src/opus_decoder.c:139-141
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     fprintf(stderr, "opus_b200: no usable CUDA device (there is no CPU fallback)\n");
@@ -220,6 +222,7 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   if (!d) return OPUSB200_ALLOC_FAIL;
   memset(d, 0, sizeof(*d));
   d->device = device; d->channels = channels; d->n = n_streams;
+  d->downsample = 48000 / Fs;  // resampling_factor(), celt/celt.c:66-97
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   {
     // pipelined device calls parse on a high-priority stream: the entropy kernel's few long-running CTAs then win free SM resources
@@ -364,7 +367,7 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     DecEntropyParams ep;
     ep.packets = d_packets + (size_t)s0 * pkt_stride; ep.pkt_len = d_len + s0; ep.pkt_stride = pkt_stride; ep.n_streams = cn;
     ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side[par] + s0; ep.script = d->script[par] + s0;
-    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size;
+    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size; ep.downsample = d->downsample;
     DecPvqParams pp;
     pp.side = d->side[par] + s0; pp.script = d->script[par] + s0; pp.state = d->bstate + s0; pp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
     if (timing) cudaEventRecord(d->ev[0], st);
@@ -387,7 +390,7 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     DecSynthParams sp;
     sp.side = d->side[par] + s0; sp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
-    sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels;
+    sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels; sp.downsample = d->downsample;
     ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), sb>>>(sp);
     d->launches += 3;
     if (!timing) {

@@ -9,7 +9,7 @@
 using namespace ob;
 
 struct EmuDecoder {
-  int n, channels;
+  int n, channels, downsample;
   std::vector<ObDecBandState> bstate;
   std::vector<ObDecSynthState> sstate;
   std::vector<ObFrameSide> side;
@@ -41,6 +41,7 @@ void *emu_decoder_create(int n_streams, int channels) {
   EmuDecoder *d = new EmuDecoder;
   d->n = n_streams;
   d->channels = channels;
+  d->downsample = 1;
   d->bstate.resize(n_streams);
   d->sstate.resize(n_streams);
   d->side.resize(n_streams);
@@ -52,6 +53,7 @@ void *emu_decoder_create(int n_streams, int channels) {
     for (int i = 0; i < 2 * OB_NBANDS; i++) d->bstate[s].oldLogE[i] = d->bstate[s].oldLogE2[i] = -28.f;
   return d;
 }
+void emu_decoder_set_fs(void *h, int Fs) { ((EmuDecoder *)h)->downsample = 48000 / Fs; }
 void emu_decoder_destroy(void *h) { delete (EmuDecoder *)h; }
 
 // packets: [n][stride]; pcm: [n][pcm_stride] (float or int16); out_samples[n]; final_range[n]
@@ -62,7 +64,7 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
     DecEntropyParams ep;
     ep.packets = packets; ep.pkt_len = lens; ep.pkt_stride = stride; ep.n_streams = d->n; ep.channels = d->channels;
     ep.frame_index = k; ep.state = d->bstate.data(); ep.side = d->side.data(); ep.script = d->script.data();
-    ep.out_samples = out_samples; ep.max_samples = 5760;
+    ep.out_samples = out_samples; ep.max_samples = 5760; ep.downsample = d->downsample;
     emu_launch(entropy_entry, &ep, (d->n + 31) / 32, 32, 0);
     DecPvqParams pp;
     pp.side = d->side.data(); pp.script = d->script.data(); pp.state = d->bstate.data(); pp.X = d->X.data(); pp.n_streams = d->n;
@@ -80,7 +82,7 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
       DecSynthParams sp;
       sp.side = d->side.data() + s; sp.X = d->X.data() + (size_t)s * 2 * OB_MAXN; sp.state = d->sstate.data() + s;
       sp.pcm = pcm_is_int16 ? (void *)((int16_t *)pcm + (size_t)s * pcm_stride) : (void *)((float *)pcm + (size_t)s * pcm_stride);
-      sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels;
+      sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels; sp.downsample = d->downsample;
       emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
     }
   }

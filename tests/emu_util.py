@@ -43,10 +43,11 @@ def load_emu():
 
 
 class EmuDecoder:
-    def __init__(self, n_streams, channels):
+    def __init__(self, n_streams, channels, Fs=48000):
         self.L = load_emu()
         self.n, self.ch = n_streams, channels
         self.h = ctypes.c_void_p(self.L.emu_decoder_create(n_streams, channels))
+        self.L.emu_decoder_set_fs(self.h, Fs)
 
     def decode(self, packets, lens, int16=False):
         """packets [n][stride] uint8, lens [n] -> (pcm [n][5760*ch], samples[n], final_range[n])"""
@@ -65,9 +66,9 @@ class EmuDecoder:
         self.L.emu_decoder_destroy(self.h)
 
 
-def emu_decode_stream(pkts, sizes, channels, frame_size):
-    """One stream, many packets (like util.oracle_decode_float)."""
-    d = EmuDecoder(1, channels)
+def emu_decode_stream(pkts, sizes, channels, frame_size, Fs=48000):
+    """One stream, many packets (like util.oracle_decode_float); frame_size is in samples at the output rate Fs."""
+    d = EmuDecoder(1, channels, Fs)
     T = len(sizes)
     out = np.zeros((T * frame_size, channels), np.float32)
     rng = np.zeros(T, np.uint32)

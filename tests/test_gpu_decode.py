@@ -287,3 +287,40 @@ def test_randomised_reference_streams(seed):
         for r in range(s, n, base):
             _check(outs[r], orc)
         assert (fr[s::base] == orc_rng[-1]).all()
+
+
+@pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+@pytest.mark.parametrize('Fs', [24000, 16000, 12000, 8000])
+@pytest.mark.parametrize('ch,fs48', [(2, 960), (1, 480), (2, 120)])
+def test_output_rates_below_48k(Fs, ch, fs48):
+    """opus_decoder_create(Fs < 48000): decimating de-emphasis + spectrum bound (celt/celt_decoder.c:300-405, celt/bands.c:199-200)
+    against the reference decoder opened at the same rate; both float and int16 output."""
+    import opus_b200
+    n, nfr = 12, 8
+    L = util.load_ref('c')
+    pk, sz = _make_streams(n, ch, fs48, nfr, seed=Fs // 1000 + ch + fs48)
+    fsd = fs48 * Fs // 48000
+    dec = opus_b200.DecoderBatch(n, channels=ch, Fs=Fs)
+    dec16 = opus_b200.DecoderBatch(n, channels=ch, Fs=Fs)
+    outs = np.zeros((n, nfr * fsd, ch), np.float32)
+    out16 = np.zeros((n, nfr * fsd, ch), np.int16)
+    rngs = np.zeros((n, nfr), np.uint32)
+    for t in range(nfr):
+        got, ns = dec.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fsd, dtype=np.float32)
+        assert (ns == fsd).all(), ns
+        outs[:, t * fsd:(t + 1) * fsd] = got.reshape(n, fsd, ch)
+        rngs[:, t] = dec.final_range()
+        g16, ns = dec16.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fsd, dtype=np.int16)
+        assert (ns == fsd).all(), ns
+        out16[:, t * fsd:(t + 1) * fsd] = g16.reshape(n, fsd, ch)
+    # a buffer one sample short of the frame: OPUS_BUFFER_TOO_SMALL, like opus_decode (src/opus_decoder.c:735)
+    _, ns = dec.decode(np.ascontiguousarray(pk[:, 0]), np.ascontiguousarray(sz[:, 0]), frame_size=fsd - 1, dtype=np.float32)
+    assert (ns == -2).all(), ns
+    dec.close(); dec16.close()
+    for s in range(n):
+        p, z = np.ascontiguousarray(pk[s]), np.ascontiguousarray(sz[s], np.int32)
+        ref, rr = np.zeros((nfr * fsd, ch), np.float32), np.zeros(nfr, np.uint32)
+        assert L.refh_decode_stream_float(Fs, ch, fsd, nfr, util._ptr(p), p.shape[1], util._ptr(z), util._ptr(ref), util._ptr(rr)) == 0
+        assert (rngs[s] == rr).all(), s
+        _check(outs[s], ref)
+        assert np.abs(out16[s].astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
