@@ -1481,7 +1481,14 @@ typedef struct {
   int prev_mode_celt;
   uint32_t final_range;
   int downsample; /* 48000 / Fs of the output (celt/celt_decoder.c:222-240 resampling_factor), 1 after init */
+  /* packet-loss concealment (celt/celt_decoder.c:110-124) */
+  int loss_duration, plc_duration, skip_plc, last_frame_type, prefilter_and_fold, last_pitch_index;
+  float lpc[2][24];
+  int last_frame_size48; /* Opus layer st->frame_size (48 kHz samples) of the last packet, for len <= 1 frames */
 } OrcDecoder;
+static void decode_lost(OrcDecoder *st, int N, int LM);        /* celt_plc.inc */
+static void prefilter_and_fold(OrcDecoder *st, int N);
+static void deemphasis_out(OrcDecoder *st, float *out_syn[], float *pcm, int N);
 
 int orc_decoder_size(void) { return (int)sizeof(OrcDecoder); }
 
@@ -1554,11 +1561,16 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
   if (LM > 3) return -1;
   M = 1 << LM;
   if (len < 0 || len > 1275 || pcm == NULL) return -1;
-  if (data == NULL || len <= 1) return -5; /* packet loss concealment: not restated */
   N = M * SHORT_N;
   g_denorm_downsample = st->downsample > 1 ? st->downsample : 1;
   c = 0;
   do { decode_mem[c] = st->decode_mem[c]; out_syn[c] = decode_mem[c] + DEC_BUF - N; } while (++c < CC);
+  if (data == NULL || len <= 1) { /* celt_decoder.c:1281-1291 */
+    decode_lost(st, N, LM);
+    deemphasis_out(st, out_syn, pcm, N);
+    return frame_size / (st->downsample > 1 ? st->downsample : 1);
+  }
+  if (st->loss_duration == 0) st->skip_plc = 0; /* :1299-1301 */
   effEnd = IMIN(end, NBANDS);
   rd_init(&dec, data, len);
   memset(X, 0, sizeof(X));
@@ -1590,6 +1602,30 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
   } else isTransient = 0;
   shortBlocks = isTransient ? M : 0;
   intra_ener = tell + 3 <= total_bits ? rd_bit_logp(&dec, 3) : 0;
+  if (!intra_ener && st->loss_duration != 0) { /* safe energy prediction after a loss, celt_decoder.c:1362-1393 */
+    c = 0;
+    do {
+      float safety = 0;
+      const int missing = IMIN(10, st->loss_duration >> LM);
+      if (LM == 0) safety = 1.5f;
+      else if (LM == 1) safety = .5f;
+      for (i = start; i < end; i++) {
+        float *E = &oldBandE[c * NBANDS + i];
+        const float l1 = oldLogE[c * NBANDS + i], l2 = oldLogE2[c * NBANDS + i];
+        if (*E < (l1 > l2 ? l1 : l2)) {
+          float E0 = *E, slope, a = l1 - E0, b = .5f * (l2 - E0);
+          slope = a > b ? a : b;
+          slope = slope < 2.f ? slope : 2.f;
+          { float d = (1 + missing) * slope; E0 -= 0 > d ? 0 : d; }
+          *E = -20.f > E0 ? -20.f : E0;
+        } else {
+          float m = *E < l1 ? *E : l1;
+          *E = m < l2 ? m : l2;
+        }
+        *E -= safety;
+      }
+    } while (++c < 2);
+  }
   decode_coarse_energy(start, end, oldBandE, intra_ener, &dec, C, LM);
   decode_tf(start, end, isTransient, tf_res, LM, &dec);
   tell = rd_tell(&dec);
@@ -1643,6 +1679,7 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
     anti_collapse(X, collapse_masks, LM, C, N, start, end, oldBandE, oldLogE, oldLogE2, pulses, st->rng);
   memcpy(orc_dbg_X, X, sizeof(float) * C * N);
   if (silence) for (i = 0; i < C * NBANDS; i++) oldBandE[i] = -28.f;
+  if (st->prefilter_and_fold) prefilter_and_fold(st, N);
   synthesis(X, out_syn, oldBandE, start, effEnd, C, CC, isTransient, LM, silence);
   c = 0;
   do {
@@ -1673,7 +1710,7 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
     for (i = 0; i < 2 * NBANDS; i++) oldLogE[i] = oldLogE[i] < oldBandE[i] ? oldLogE[i] : oldBandE[i];
   }
   {
-    float inc = IMIN(160, 0 + M) * 0.001f;
+    float inc = IMIN(160, st->loss_duration + M) * 0.001f;
     for (i = 0; i < 2 * NBANDS; i++) {
       float a = backgroundLogE[i] + inc;
       backgroundLogE[i] = a < oldBandE[i] ? a : oldBandE[i];
@@ -1685,27 +1722,33 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
     for (i = end; i < NBANDS; i++) { oldBandE[c * NBANDS + i] = 0; oldLogE[c * NBANDS + i] = oldLogE2[c * NBANDS + i] = -28.f; }
   } while (++c < 2);
   st->rng = dec.rng;
-  /* de-emphasis, celt_decoder.c:288-408 (coef0 = 0.85000610f at 48 kHz; the output rate is 48000/downsample) */
-  {
-    const float coef0 = 0.85000610f;
-    const int ds = st->downsample > 1 ? st->downsample : 1;
-    c = 0;
-    do {
-      float m = st->preemph_mem[c];
-      const float *x = out_syn[c];
-      int j;
-      for (j = 0; j < N; j++) {
-        float tmp = x[j] + 1e-30f + m;
-        m = coef0 * tmp;
-        if (ds == 1) pcm[j * CC + c] = (1 / 32768.f) * tmp;
-        else if (j % ds == 0) pcm[(j / ds) * CC + c] = (1 / 32768.f) * tmp;   /* :387-401: keep every downsample-th sample */
-      }
-      st->preemph_mem[c] = m;
-    } while (++c < CC);
-  }
+  deemphasis_out(st, out_syn, pcm, N);
+  st->loss_duration = 0;
+  st->plc_duration = 0;
+  st->last_frame_type = 1; /* FRAME_NORMAL */
+  st->prefilter_and_fold = 0;
   if (rd_tell(&dec) > 8 * len) return -3;
   if (dec.error) st->error = 1;
   return frame_size / (st->downsample > 1 ? st->downsample : 1);
+}
+
+/* de-emphasis, celt_decoder.c:288-408 (coef0 = 0.85000610f at 48 kHz; the output rate is 48000/downsample) */
+static void deemphasis_out(OrcDecoder *st, float *out_syn[], float *pcm, int N) {
+  const float coef0 = 0.85000610f;
+  const int ds = st->downsample > 1 ? st->downsample : 1, CC = st->channels;
+  int c = 0;
+  do {
+    float m = st->preemph_mem[c];
+    const float *x = out_syn[c];
+    int j;
+    for (j = 0; j < N; j++) {
+      float tmp = x[j] + 1e-30f + m;
+      m = coef0 * tmp;
+      if (ds == 1) pcm[j * CC + c] = (1 / 32768.f) * tmp;
+      else if (j % ds == 0) pcm[(j / ds) * CC + c] = (1 / 32768.f) * tmp;   /* :387-401: keep every downsample-th sample */
+    }
+    st->preemph_mem[c] = m;
+  } while (++c < CC);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1795,25 +1838,71 @@ int orc_packet_parse(const uint8_t *data, int len, int *toc_out, int offsets[48]
   return count;
 }
 
+/* opus_decode_frame() with data == NULL (src/opus_decoder.c:316-365, 598-613, 701-712): conceal `frame_size` output-rate samples */
+static int decode_frame_lost(OrcDecoder *st, float *pcm, int frame_size) {
+  const int ds = st->downsample > 1 ? st->downsample : 1, F20 = 960 / ds, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
+  int audiosize, i, ret;
+  if (frame_size < F2_5) return -2;
+  frame_size = IMIN(frame_size, 48000 / ds / 25 * 3);
+  audiosize = frame_size;
+  if (!st->prev_mode_celt) { /* no packet yet: zeros */
+    for (i = 0; i < audiosize * st->channels; i++) pcm[i] = 0;
+    return audiosize;
+  }
+  if (audiosize > F20) {
+    do {
+      ret = decode_frame_lost(st, pcm, IMIN(audiosize, F20));
+      if (ret < 0) return ret;
+      pcm += ret * st->channels;
+      audiosize -= ret;
+    } while (audiosize > 0);
+    return frame_size;
+  } else if (audiosize < F20) {
+    if (audiosize > F10) audiosize = F10;
+    else if (audiosize > F5 && audiosize < F10) audiosize = F5;
+  }
+  ret = orc_celt_decode_frame(st, NULL, 0, pcm, audiosize * ds);
+  st->final_range = 0;
+  return ret < 0 ? ret : audiosize;
+}
+
 /* Decode one Opus packet (CELT-only TOC configurations 16..31). pcm: interleaved float.
+ * data == NULL or len == 0: the packet is lost, conceal max_frame_size samples (src/opus_decoder.c:757-778).
  * Returns samples per channel or a negative opus error code. */
 int orc_opus_decode_float(OrcDecoder *st, const uint8_t *data, int len, float *pcm, int max_frame_size) {
   int toc, count, offsets[48], sizes[48], i, framesize, nb = 0, bw, endband;
-  if (data == NULL || len <= 0) return -5;
+  const int ds = st->downsample > 1 ? st->downsample : 1;
+  if (len < 0) return -1;
+  if (data == NULL || len == 0) {
+    int pcm_count = 0;
+    if (max_frame_size % (120 / ds) != 0) return -1;
+    do {
+      int ret = decode_frame_lost(st, pcm + pcm_count * st->channels, max_frame_size - pcm_count);
+      if (ret < 0) return ret;
+      pcm_count += ret;
+    } while (pcm_count < max_frame_size);
+    return pcm_count;
+  }
   count = orc_packet_parse(data, len, &toc, offsets, sizes);
   if (count < 0) return count;
   if (!(toc & 0x80)) return -5; /* SILK / hybrid: not restated */
   framesize = (48000 << ((toc >> 3) & 3)) / 400;   /* at 48 kHz; max_frame_size and the return value are in output-rate samples */
-  if (count * framesize / (st->downsample > 1 ? st->downsample : 1) > max_frame_size) return -2;
+  if (count * framesize / ds > max_frame_size) return -2;
   bw = (toc >> 5) & 3; /* CELT-only: 0 NB, 1 WB, 2 SWB, 3 FB  (src/opus.c opus_packet_get_bandwidth) */
   endband = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;
-  st->end = endband;
   st->stream_channels = (toc & 0x4) ? 2 : 1;
   st->start = 0;
   for (i = 0; i < count; i++) {
-    int ret = orc_celt_decode_frame(st, data + offsets[i], sizes[i], pcm + nb * st->channels, framesize);
+    int ret;
+    if (sizes[i] <= 1) { /* DTX / lost frame inside the packet: concealed at the packet's frame size; the end band stays */
+      ret = decode_frame_lost(st, pcm + nb * st->channels, framesize / ds);
+    } else {
+      st->end = endband;
+      ret = orc_celt_decode_frame(st, data + offsets[i], sizes[i], pcm + nb * st->channels, framesize);
+      st->final_range = st->rng;
+      st->prev_mode_celt = 1;
+    }
     if (ret < 0) return ret;
-    st->final_range = sizes[i] <= 1 ? 0 : st->rng;
     nb += ret;
   }
   return nb;
@@ -1863,3 +1952,4 @@ int orc_decode_stream_float_fs(int Fs, int channels, int frame_size, int nframes
 }
 
 #include "celt_enc.inc"
+#include "celt_plc.inc"
