@@ -19,9 +19,10 @@
  * (include/opus_defines.h:46-60): OPUS_BAD_ARG -1, OPUS_BUFFER_TOO_SMALL -2, OPUS_INTERNAL_ERROR -3,
  * OPUS_INVALID_PACKET -4, OPUS_UNIMPLEMENTED -5, OPUS_INVALID_STATE -6, OPUS_ALLOC_FAIL -7.
  *
- * Scope of this round: CELT-only packets (TOC config 16..31), Fs = 48000, 1 or 2 channels, frame
- * sizes 2.5/5/10/20 ms, all frame-packing codes.  SILK/hybrid packets, packet-loss concealment
- * (len <= 1 / NULL data), FEC and soft clipping return OPUS_UNIMPLEMENTED per stream.
+ * Scope of this round: CELT-only packets (TOC config 16..31), output rates 48/24/16/12/8 kHz, 1 or 2 channels, frame
+ * sizes 2.5/5/10/20 ms, all frame-packing codes, packet-loss concealment (a lost packet is len[s] == 0, like
+ * opus_decode(data = NULL); DTX frames inside a packet are concealed too: celt_decode_lost, celt/celt_decoder.c:679-1090,
+ * pitch-based and noise PLC; no DEEP_PLC).  SILK/hybrid packets and FEC return OPUS_UNIMPLEMENTED per stream.
  * There is NO CPU fallback: every entry point fails with OPUS_INTERNAL_ERROR if no CUDA device
  * is usable. */
 #ifndef OPUS_B200_H
@@ -60,7 +61,9 @@ int opusb200_decoder_n_streams(const OpusB200Decoder *dec);
 
 /* Decode one packet per stream; HOST buffers (copies to/from the device are part of the call).
  *   packets    : stream s's packet starts at packets + s*pkt_stride
- *   len[s]     : packet length in bytes; 0 = no packet for this stream in this call
+ *   len[s]     : packet length in bytes.  0 = the packet is LOST: frame_size samples are concealed (frame_size must then be a
+ *                multiple of 2.5 ms, src/opus_decoder.c:757-778), zeros if the stream has not decoded anything yet.
+ *                < 0 (this library's extension) = the stream sits this call out: 0 samples, state untouched.
  *   pcm        : stream s's output starts at pcm + s*pcm_stride (interleaved if 2 channels)
  *   pcm_stride : elements (not bytes) between consecutive streams' outputs, >= frame_size*channels
  *   frame_size : capacity per channel of each stream's pcm area, like opus_decode()'s argument
@@ -80,7 +83,8 @@ int opusb200_decode_wait(OpusB200Decoder *dec);
 /* Same, with every buffer already resident in device memory (no copies, no synchronisation:
  * work is enqueued on the decoder's stream; call opusb200_decoder_sync() before reading results).
  * max_frames_per_packet: upper bound on frames per packet the caller guarantees (1 for the
- * usual one-frame packets, up to 48); pcm_is_int16 selects int16 or float output. */
+ * usual one-frame packets, up to 48); a lost packet (d_len[s] == 0) needs frame_size / (the stream's packet frame size) of them,
+ * i.e. 1 when frame_size is the stream's frame size; pcm_is_int16 selects int16 or float output. */
 int opusb200_decode_device(OpusB200Decoder *dec, const unsigned char *d_packets, int pkt_stride, const int32_t *d_len,
                            void *d_pcm, int pcm_stride, int pcm_is_int16, int frame_size, int max_frames_per_packet,
                            int32_t *d_out_samples);

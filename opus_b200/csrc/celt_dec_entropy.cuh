@@ -195,7 +195,7 @@ struct PFrame {
 };
 
 // ---- Opus packet framing (RFC 6716 section 3.2; src/opus.c:183-420) -------------------------------
-OB_DEV int parse_size(const unsigned char *d, int len, int &size) {
+OB_HD int parse_size(const unsigned char *d, int len, int &size) {
   if (len < 1) { size = -1; return -1; }
   if (d[0] < 252) { size = d[0]; return 1; }
   if (len < 2) { size = -1; return -1; }
@@ -203,7 +203,8 @@ OB_DEV int parse_size(const unsigned char *d, int len, int &size) {
   return 2;
 }
 // Returns number of frames in the packet (<0 on a malformed packet); off/flen describe frame k.
-OB_DEVNI int locate_frame(const unsigned char *data, int len, int k, int *off_out, int *flen_out) {
+// (also compiled for the host: the host-buffer API uses it to know how many frame launches a call needs)
+OB_HDNI int locate_frame(const unsigned char *data, int len, int k, int *off_out, int *flen_out) {
   int pos = 0, count, cbr = 0, last_size, sz0 = 0, off = 0, flen = 0;
   *off_out = 0; *flen_out = 0;
   if (len <= 0) return -4;
@@ -292,6 +293,97 @@ OB_DEV void ent_finish(const DecEntropyParams &p, int stream, ObFrameSide *side,
 }
 
 // ------------------------------------------------------------------------------------------
+// A lost frame (celt_decode_lost, celt/celt_decoder.c:679-1090): everything that is a DECISION or band-energy / range-coder state
+// happens here, in stream order with the parsing of the neighbouring frames; the signal work is done by the later kernels:
+//   noise PLC  -> the vector kernel draws the noise spectrum, the synthesis kernel runs unchanged on the decayed energies;
+//   pitch PLC  -> ob_celt_dec_plc (celt_dec_plc.cuh) extrapolates the history ring.
+// ------------------------------------------------------------------------------------------
+OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st, int LM, int pcm_off) {
+  const int CC = p.channels, N = OB_SHORT_N << LM, M = 1 << LM;
+  side->pcm_off = pcm_off;
+  side->LM = LM;
+  st->final_range = 0;  // src/opus_decoder.c:701-704
+  if (!st->has_packet) {  // nothing decoded yet: zeros, the CELT state is not touched (src/opus_decoder.c:333-341)
+    side->plc = OB_PLC_ZEROS;
+    ent_finish(p, stream, side, st, N);
+    return;
+  }
+  const int noise = st->plc_duration >= 40 || st->skip_plc;  // start == 0 always here
+  if (noise) {
+    const int end = st->end_band;  // effEnd == end: the mode has 21 bands
+    const float decay = st->loss_duration == 0 ? 1.5f : .5f;
+#pragma unroll 1
+    for (int c = 0; c < CC; c++) {
+#pragma unroll 1
+      for (int i = 0; i < end; i++) {
+        const float a = st->backgroundLogE[c * OB_NBANDS + i], b = st->oldEBands[c * OB_NBANDS + i] - decay;
+        st->oldEBands[c * OB_NBANDS + i] = a > b ? a : b;
+      }
+    }
+#pragma unroll 1
+    for (int i = 0; i < 2 * OB_NBANDS; i++) side->bandE[i] = st->oldEBands[i];
+    // the LCG runs once per coefficient of every band below `end`, channel after channel (celt_decoder.c:773-790)
+    uint32_t seed = st->rng;
+    side->seed = seed;
+    const int draws = CC * M * ob_ebands[end];
+#pragma unroll 4
+    for (int j = 0; j < draws; j++) seed = 1664525u * seed + 1013904223u;
+    st->rng = seed;
+    side->transient = 0; side->C = CC; side->silence = 0; side->end_band = end;
+    side->anti_collapse_on = 0; side->n_leaves = 0;
+    {  // post-filter with the last parameters (celt_decoder.c:794-808)
+      const int T_old = OB_IMAX(st->pf_period_old, 15), T_cur = OB_IMAX(st->pf_period, 15);
+      side->pf_T[0] = T_old; side->pf_T[1] = T_cur; side->pf_T[2] = T_cur;
+      side->pf_g[0] = st->pf_gain_old; side->pf_g[1] = st->pf_gain; side->pf_g[2] = st->pf_gain;
+      side->pf_tap[0] = st->pf_tapset_old; side->pf_tap[1] = st->pf_tapset; side->pf_tap[2] = st->pf_tapset;
+      st->pf_period = T_cur;
+      st->pf_period_old = T_cur; st->pf_gain_old = st->pf_gain; st->pf_tapset_old = st->pf_tapset;
+    }
+    side->plc = OB_PLC_NOISE | (st->fold ? OB_PLC_FOLD : 0);
+    st->fold = 0;
+    st->skip_plc = 1;
+  } else {
+    side->plc = OB_PLC_PITCH | (st->last_frame_type != OB_FRAME_PLC_PERIODIC ? OB_PLC_FIRST : 0);
+    st->fold = 1;
+  }
+  st->loss_duration = OB_IMIN(10000, st->loss_duration + M);
+  st->plc_duration = OB_IMIN(10000, st->plc_duration + M);
+  st->last_frame_type = noise ? OB_FRAME_PLC_NOISE : OB_FRAME_PLC_PERIODIC;
+  ent_finish(p, stream, side, st, N);
+}
+
+// A lost PACKET (len == 0): opus_decode(NULL) conceals frame_size samples as a run of 20 / 10 / 5 / 2.5 ms frames
+// (src/opus_decoder.c:757-778 and 316-365); launch k of the call produces the k-th of them.
+OB_DEVNI void ent_lost_packet(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st) {
+  const int ds = p.downsample, F20 = 960 / ds, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1, fsz = p.max_samples;
+  const int k = p.frame_index;
+  if (fsz % F2_5 != 0) { ent_finish(p, stream, side, st, k == 0 ? -1 : 0); return; }  // OPUS_BAD_ARG
+  if (!st->has_packet) {
+    if (k != 0) { ent_finish(p, stream, side, st, 0); return; }
+    side->pcm_off = 0; side->LM = 0; side->plc = OB_PLC_ZEROS;
+    st->final_range = 0;
+    ent_finish(p, stream, side, st, fsz * ds);
+    return;
+  }
+  int rem = fsz, a = 0;
+#pragma unroll 1
+  for (int idx = 0;; idx++) {
+    if (rem <= 0) { ent_finish(p, stream, side, st, 0); return; }  // no k-th frame
+    a = OB_IMIN(rem, OB_IMAX(F2_5, st->last_N / ds));  // "don't conceal more than what the ToC says" (src/opus_decoder.c:316-321)
+    if (a > F20) a = F20;
+    else if (a < F20) {
+      if (a > F10) a = F10;
+      else if (a > F5 && a < F10) a = F5;
+    }
+    if (idx == k) break;
+    rem -= a;
+  }
+  const int N48 = a * ds;
+  const int LM = N48 == 120 ? 0 : N48 == 240 ? 1 : N48 == 480 ? 2 : 3;
+  ent_lost_frame(p, stream, side, st, LM, fsz - rem);
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel A1 body: one thread, one stream.
 // ------------------------------------------------------------------------------------------
 OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
@@ -300,7 +392,8 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   ObScript *sc = p.script + stream;
   const int CC = p.channels;
   const int plen = p.pkt_len[stream];
-  if (plen <= 0) { ent_finish(p, stream, side, st, 0); return; }
+  if (plen < 0) { ent_finish(p, stream, side, st, 0); return; }   // this library's extension: the stream sits this call out
+  if (plen == 0) { ent_lost_packet(p, stream, side, st); return; }  // opus_decode(data = NULL / len = 0): conceal frame_size samples
   const unsigned char *pkt = p.packets + (size_t)stream * p.pkt_stride;
   const int toc = pkt[0];
   int foff, flen;
@@ -311,9 +404,12 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   if (count < 0) status = count;                      // OPUS_INVALID_PACKET
   else if (!(toc & 0x80)) status = -5;                // SILK / hybrid: OPUS_UNIMPLEMENTED here
   else if (p.frame_index >= count) status = 0;        // no such frame in this packet
-  else if (flen <= 1) status = -5;                    // lost / DTX frame: PLC not implemented
-  if (status > 0 && (p.frame_index + 1) * (N / p.downsample) > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // BUFFER_TOO_SMALL
+  if (status > 0 && count * (N / p.downsample) > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // BUFFER_TOO_SMALL: the whole packet (src/opus_decoder.c:806-807)
   if (status <= 0) { ent_finish(p, stream, side, st, status); return; }
+  st->last_N = N;  // Opus layer st->frame_size: set per accepted packet (src/opus_decoder.c:842)
+  if (flen <= 1) { ent_lost_frame(p, stream, side, st, LM, p.frame_index * (N / p.downsample)); return; }  // DTX / lost frame inside the packet
+  side->pcm_off = p.frame_index * (N / p.downsample);
+  if (st->loss_duration == 0) st->skip_plc = 0;  // celt_decoder.c:1299-1301
 
   const int C = (toc & 4) ? 2 : 1;
   const int bw = (toc >> 5) & 3;
@@ -377,6 +473,32 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
     const float *oldg = st->oldEBands;
 #pragma unroll 1
     for (int i = 0; i < 2 * OB_NBANDS; i++) E[i] = oldg[i];
+    if (C == 1)  // celt_decoder.c:1306-1310
+#pragma unroll 1
+      for (int i = 0; i < OB_NBANDS; i++) E[i] = E[i] > E[OB_NBANDS + i] ? E[i] : E[OB_NBANDS + i];
+    if (!intra && st->loss_duration != 0) {  // safe energy prediction after a loss (celt_decoder.c:1362-1393), rare
+      const int missing = OB_IMIN(10, st->loss_duration >> LM);
+      const float safety = LM == 0 ? 1.5f : LM == 1 ? .5f : 0.f;
+#pragma unroll 1
+      for (int ci = 0; ci < 2 * OB_NBANDS; ci++) {
+        const int band = ci >= OB_NBANDS ? ci - OB_NBANDS : ci;
+        if (band < start || band >= end) continue;
+        const float l1 = st->oldLogE[ci], l2 = st->oldLogE2[ci];
+        float E0 = E[ci];
+        if (E0 < (l1 > l2 ? l1 : l2)) {  // going down already: continue the trend
+          const float sa = l1 - E0, sb = .5f * (l2 - E0);
+          float slope = sa > sb ? sa : sb;
+          slope = slope < 2.f ? slope : 2.f;
+          const float d = (1 + missing) * slope;
+          E0 -= 0.f > d ? 0.f : d;
+          E0 = -20.f > E0 ? -20.f : E0;
+        } else {
+          E0 = E0 < l1 ? E0 : l1;
+          E0 = E0 < l2 ? E0 : l2;
+        }
+        E[ci] = E0 - safety;
+      }
+    }
 #pragma unroll 1
     for (int i = start; i < end; i++) {
 #pragma unroll 1
@@ -393,8 +515,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
           qi = -dec.bit_logp(1);
         } else qi = -1;
         float q = (float)qi;
-        float o = oldg[i + c * OB_NBANDS];
-        if (C == 1) { float o2 = oldg[OB_NBANDS + i]; o = o > o2 ? o : o2; }  // celt_decoder.c:1306-1310
+        float o = E[i + c * OB_NBANDS];
         o = o > -9.f ? o : -9.f;
         float prev = c ? prev1 : prev0;
         float tmp = coef * o + prev + q;
@@ -921,7 +1042,8 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   const int ok = (dec.tell() > 8 * len || overflow) ? -3 : N;  // OPUS_INTERNAL_ERROR
   side->LM = LM; side->transient = isTransient; side->C = C; side->silence = silence; side->end_band = end;
   side->spread = spread; side->intensity = intensity; side->dual_stereo = dual_stereo;
-  side->anti_collapse_on = anti_collapse_on; side->n_leaves = e.n_leaves; side->reserved0 = 0;
+  side->anti_collapse_on = anti_collapse_on; side->n_leaves = e.n_leaves;
+  side->plc = st->fold ? OB_PLC_FOLD : 0;
   side->seed = st->rng;
   {  // post-filter parameter pipeline (celt_decoder.c:1540-1563)
     int T_old = OB_IMAX(st->pf_period_old, 15), T_cur = OB_IMAX(st->pf_period, 15);
@@ -950,7 +1072,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       if (anti_collapse_on) { side->prevLogE[0][i] = l1; side->prevLogE[1][i] = l2; }
       if (!isTransient) { l2 = l1; l1 = eb; }
       else l1 = l1 < eb ? l1 : eb;
-      const float inc = OB_IMIN(160, M) * 0.001f;
+      const float inc = OB_IMIN(160, st->loss_duration + M) * 0.001f;
       const float a = bg + inc;
       bg = a < eb ? a : eb;
       if (band >= end) { eb = 0.f; l1 = l2 = -28.f; }
@@ -960,6 +1082,8 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       st->backgroundLogE[i] = bg;
     }
   }
+  st->loss_duration = 0; st->plc_duration = 0; st->last_frame_type = OB_FRAME_NORMAL; st->fold = 0;  // celt_decoder.c:1604-1607
+  st->end_band = end; st->has_packet = 1;
   ent_finish(p, stream, side, st, ok);
 }
 

@@ -102,6 +102,8 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   const ObFrameSide *side = p.side + stream;
   const int status = side->status;
   if (status <= 0) return;  // uniform over the CTA: nothing decoded for this stream in this launch
+  const int plc = side->plc;
+  if (OB_PLC_TYPE(plc) >= OB_PLC_PITCH) return;  // pitch-based concealment / zeros: ob_celt_dec_plc produces this frame
   ObDecSynthState *st = p.state + stream;
   const int LM = side->LM, C = side->C, transient = side->transient, silence = side->silence;
   const int N = OB_SHORT_N << LM, M = 1 << LM;
@@ -141,7 +143,35 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   }
   // previous tail -> out[0..60)
   float *out = ws->out + OB_SYN_O;
-  for (int i = lane; i < OB_OVERLAP / 2; i += 32) out[i] = st->tail[ch][i];
+  if (plc & OB_PLC_FOLD) {
+    // prefilter_and_fold (celt_decoder.c:576-625): the previous frame was extrapolated in the time domain, 120 samples past its end.
+    // Undo the post-filter on that overhang (comb filter with the gains negated, constant part only: overlap = 0) and fold it
+    // with the window, so that it looks like the tail an MDCT frame would have left.
+    const float *hist = st->hist[ch];
+    const uint32_t pos = st->pos;
+    for (int i = lane; i < OB_OVERLAP; i += 32) out[i] = st->tail[ch][i];
+    wsync();
+    const float g1 = -side->pf_g[1];
+    const int T1 = OB_IMAX(side->pf_T[1], 15), tap = side->pf_tap[1];
+    const float gt[9] = {0.3066406250f, 0.2170410156f, 0.1296386719f, 0.4638671875f, 0.2680664062f, 0.f,
+                         0.7998046875f, 0.1000976562f, 0.f};
+    const float g10 = g1 * gt[tap * 3 + 0], g11 = g1 * gt[tap * 3 + 1], g12 = g1 * gt[tap * 3 + 2];
+    for (int i = lane; i < OB_OVERLAP; i += 32) {
+      float v = out[i];
+      if (g1 != 0.f) {
+        const float x0 = hist_or_cur(out, hist, pos, i - T1 + 2), x1 = hist_or_cur(out, hist, pos, i - T1 + 1);
+        const float x2 = hist_or_cur(out, hist, pos, i - T1), x3 = hist_or_cur(out, hist, pos, i - T1 - 1);
+        const float x4 = hist_or_cur(out, hist, pos, i - T1 - 2);
+        v = v + g10 * x2 + g11 * (x1 + x3) + g12 * (x0 + x4);
+      }
+      out[OB_OVERLAP + i] = v;  // etmp, in the still unused IMDCT area
+    }
+    wsync();
+    for (int i = lane; i < OB_OVERLAP / 2; i += 32)
+      out[i] = ob_window[i] * out[OB_OVERLAP + OB_OVERLAP - 1 - i] + ob_window[OB_OVERLAP - i - 1] * out[OB_OVERLAP + i];
+  } else {
+    for (int i = lane; i < OB_OVERLAP / 2; i += 32) out[i] = st->tail[ch][i];
+  }
   wsync();
   // ---- IMDCT pre-rotation into digit-reversed order (celt/mdct.c:304-331) ----
   {
@@ -235,7 +265,7 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   bsync();
   if (ch == 0 && lane == 0) st->pos = pos + (uint32_t)N;
   {
-    const size_t base = (size_t)stream * p.pcm_stride + (size_t)p.frame_index * Nd * CC;
+    const size_t base = (size_t)stream * p.pcm_stride + (size_t)side->pcm_off * CC;
     const int total = Nd * CC;
     const int tid = ch * 32 + lane, nth = CC * 32;
     const SynthWS *w0 = (const SynthWS *)smem;

@@ -442,6 +442,29 @@ OB_DEV void dec_pvq_warp(const DecPvqParams &p, int stream, const PvqShared *tab
   PvqWS *ws = (PvqWS *)smem_warp;
   const ObFrameSide *side = p.side + stream;
   if (side->status <= 0) return;
+  if (OB_PLC_TYPE(side->plc) != 0) {  // a lost frame
+    // Noise PLC (celt_decoder.c:773-790): every band below `end` is LCG noise of unit norm, channel after channel; the synthesis
+    // kernel then runs as for a decoded frame.  (Pitch PLC and the all-zero case have no spectrum: ob_celt_dec_plc.)
+    if (OB_PLC_TYPE(side->plc) != OB_PLC_NOISE) return;
+    const int LM = side->LM, N = OB_SHORT_N << LM, end = side->end_band;
+    float *Xg = p.X + (size_t)stream * 2 * OB_MAXN;
+    uint32_t seed = side->seed;
+#pragma unroll 1
+    for (int c = 0; c < side->C; c++) {
+#pragma unroll 1
+      for (int i = 0; i < end; i++) {
+        float *X = Xg + c * N + (ob_ebands[i] << LM);
+        const int n = (ob_ebands[i + 1] - ob_ebands[i]) << LM;
+#pragma unroll 1
+        for (int j = 0; j < n; j++) {  // every lane runs the generator, lane j mod 32 keeps the sample
+          seed = 1664525u * seed + 1013904223u;
+          if ((j & 31) == lane) X[j] = (float)((int32_t)seed >> 20);
+        }
+        renormalise(X, n, 1.0f, lane);
+      }
+    }
+    return;
+  }
   const ObScript *sc = p.script + stream;
   const int LM = side->LM, C = side->C, isTransient = side->transient, end = side->end_band, start = 0;
   const int N = OB_SHORT_N << LM, M = 1 << LM;

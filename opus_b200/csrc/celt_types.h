@@ -22,16 +22,38 @@ typedef struct {
   int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
   float pf_gain, pf_gain_old;
   int32_t last_status;
-  int32_t pad[2];
-} ObDecBandState; /* 720 bytes */
+  /* packet-loss concealment bookkeeping (celt/celt_decoder.c:110-124); all of it is decided in the entropy kernel */
+  int32_t loss_duration, plc_duration; /* in 2.5 ms units, saturating at 10000 */
+  int32_t skip_plc;                    /* noise PLC only, until two consecutive packets arrive */
+  int32_t last_frame_type;             /* OB_FRAME_* */
+  int32_t fold;                        /* prefilter_and_fold pending (the last frame was a pitch-based PLC frame) */
+  int32_t end_band;                    /* end band of the last decoded packet (a lost frame keeps it) */
+  int32_t has_packet;                  /* a packet has been decoded (Opus layer prev_mode != 0) */
+  int32_t last_N;                      /* frame size of the last packet, 48 kHz samples (Opus layer st->frame_size) */
+} ObDecBandState;
+#define OB_FRAME_NONE 0
+#define OB_FRAME_NORMAL 1
+#define OB_FRAME_PLC_NOISE 2
+#define OB_FRAME_PLC_PERIODIC 3
+/* ObFrameSide.plc: bits0-1 what the frame is (0 decoded, 1 noise PLC, 2 pitch PLC, 3 zeros: nothing decoded yet),
+   bit2 prefilter_and_fold before the synthesis, bit3 pitch PLC analyses (first lost frame of a burst) */
+#define OB_PLC_TYPE(x) ((x) & 3)
+#define OB_PLC_NOISE 1
+#define OB_PLC_PITCH 2
+#define OB_PLC_ZEROS 3
+#define OB_PLC_FOLD 4
+#define OB_PLC_FIRST 8
+#define OB_PLC_LPC_ORDER 24
 
 /* Per-stream synthesis state (one record per stream). */
 typedef struct {
   float hist[2][OB_HIST];           /* post-filtered output ring, indexed by absolute sample position */
-  float tail[2][OB_OVERLAP / 2];    /* last overlap/2 raw IMDCT outputs of the previous frame */
+  float tail[2][OB_OVERLAP];        /* [0,60): last overlap/2 raw IMDCT outputs of the previous frame; after a pitch-based PLC frame
+                                       all 120 samples that it extrapolated past the frame (celt_decoder.c:948-952) */
   float deemph_mem[2];
   uint32_t pos;                     /* absolute position of the next output sample (mod 2^32) */
-  int32_t pad[1];
+  int32_t last_pitch_index;         /* pitch-based PLC: period found at the first lost frame of the burst */
+  float lpc[2][OB_PLC_LPC_ORDER];   /* pitch-based PLC: LPC of the last good signal */
 } ObDecSynthState;
 
 /* ---- entropy kernel -> PVQ kernel hand-off ("frame script"), one per stream ------------------ */
@@ -77,16 +99,17 @@ typedef struct {
   float pf_g[3];
   float bandE[2 * OB_NBANDS]; /* final log2 band energies (without the means) */
   /* entropy -> PVQ stage */
-  int32_t spread, intensity, dual_stereo, anti_collapse_on, n_leaves, reserved0;
+  int32_t spread, intensity, dual_stereo, anti_collapse_on, n_leaves, plc; /* plc: OB_PLC_* */
   uint32_t seed;              /* LCG seed at the start of the band loop (previous frame's final range) */
   int8_t tf_res[OB_NBANDS];
   uint8_t pad8[3];
   int16_t pulses[OB_NBANDS];  /* PVQ bit allocation per band (anti-collapse depth) */
   int16_t pad16;
+  int32_t pcm_off;            /* per-channel offset of this frame in the stream's pcm area, output-rate samples */
   /* oldLogE / oldLogE2 as they were BEFORE this frame's state update (written only when anti_collapse_on): the entropy kernel
      owns the energy state, so that the next frame's parsing does not wait for this frame's vector stage */
   float prevLogE[2][2 * OB_NBANDS];
-} ObFrameSide; /* 676 bytes */
+} ObFrameSide; /* 680 bytes */
 
 /* Per-stream script buffer written by the entropy kernel, read by the PVQ kernel. */
 typedef struct {

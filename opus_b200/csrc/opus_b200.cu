@@ -11,6 +11,7 @@
 
 #include "../../include/opus_b200.h"
 #include "celt_dec_kernels.cuh"
+#include "celt_dec_plc.cuh"
 #include "celt_ops.cuh"
 #include "silk_ops.cuh"
 #include "silk_nsq.cuh"
@@ -43,6 +44,14 @@ extern "C" __global__ void __launch_bounds__(512) ob_celt_dec_pvq(DecPvqParams p
 
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParams p) {
   dec_synth_block(p, blockIdx.x, dyn_smem());
+}
+
+// Pitch-based packet-loss concealment: a persistent grid strides over the batch; a CTA only works on streams whose frame is lost.
+extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_plc(DecPlcParams p) {
+  for (int stream = blockIdx.x; stream < p.n_streams; stream += gridDim.x) {
+    dec_plc_block(p, stream, dyn_smem());
+    __syncthreads();
+  }
 }
 
 // ---- encoder-side kernel operations (celt_ops.cuh) ----
@@ -144,6 +153,8 @@ extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState
 struct OpusB200Decoder {
   int device, channels, n;
   int downsample;   // 48000 / Fs of opusb200_decoder_create
+  int plc_grid;     // CTAs of the concealment kernel's persistent grid
+  int16_t *h_last_N; // host mirror of ObDecBandState.last_N (host-buffer API: sizes the frame-launch loop of a lost packet)
   cudaStream_t stream;
   ObDecBandState *bstate;
   ObDecSynthState *sstate;
@@ -201,6 +212,7 @@ int opusb200_decoder_reset(OpusB200Decoder *d) {
   OB_CUDA(cudaStreamSynchronize(d->stream_v));
   OB_CUDA(cudaStreamSynchronize(d->stream_b));   // the reset rewrites the synthesis state too
   ob_celt_dec_reset<<<592, 256, 0, d->stream>>>(d->bstate, d->sstate, d->n);
+  for (int s = 0; s < d->n; s++) d->h_last_N[s] = OB_SHORT_N;
   d->launches++;
   OB_CUDA(cudaGetLastError());
   OB_CUDA(cudaStreamSynchronize(d->stream));
@@ -223,6 +235,8 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   memset(d, 0, sizeof(*d));
   d->device = device; d->channels = channels; d->n = n_streams;
   d->downsample = 48000 / Fs;  // resampling_factor(), celt/celt.c:66-97
+  d->h_last_N = (int16_t *)calloc((size_t)n_streams, sizeof(int16_t));
+  if (!d->h_last_N) { delete d; return OPUSB200_ALLOC_FAIL; }
   OB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   {
     // pipelined device calls parse on a high-priority stream: the entropy kernel's few long-running CTAs then win free SM resources
@@ -282,6 +296,12 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
     if (d->ent_lpw > 32) d->ent_lpw = 32;
   }
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_plc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlcWS)));
+  {
+    int sms = 0;
+    OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    d->plc_grid = sms * 4;
+  }
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the band decoder recurses over partitions (depth <= 5)
   size_t stk = 0;
@@ -305,6 +325,7 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   cudaStreamDestroy(d->stream_e);
   cudaEventDestroy(d->ev_in);
   cudaFree(d->bstate); cudaFree(d->sstate);
+  free(d->h_last_N);
   for (int b = 0; b < 2; b++) { cudaFree(d->script[b]); cudaFree(d->side[b]); cudaFree(d->X[b]); cudaEventDestroy(d->ev_a1[b]); cudaEventDestroy(d->ev_a2[b]); cudaEventDestroy(d->ev_b[b]); }
   cudaStreamDestroy(d->stream_v);
   cudaStreamDestroy(d->stream_b);
@@ -392,7 +413,13 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels; sp.downsample = d->downsample;
     ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), sb>>>(sp);
-    d->launches += 3;
+    {  // lost frames (len == 0, or a DTX frame inside a packet): concealed from the history ring; a no-op scan otherwise
+      DecPlcParams lp;
+      lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = pcm_stride; lp.pcm_is_int16 = pcm_is_int16;
+      lp.n_streams = cn; lp.channels = d->channels; lp.downsample = d->downsample;
+      ob_celt_dec_plc<<<cn < d->plc_grid ? cn : d->plc_grid, 64, sizeof(PlcWS), sb>>>(lp);
+    }
+    d->launches += 4;
     if (!timing) {
       OB_CUDA(cudaEventRecord(d->ev_b[par], sb));
       d->last_b = par;
@@ -427,14 +454,22 @@ int opusb200_decode_device(OpusB200Decoder *d, const unsigned char *d_packets, i
   return d->pipelined ? OPUSB200_OK : opusb200_decoder_join(d);
 }
 
-// frames in a packet as far as the TOC and the count byte tell (RFC 6716 3.2); 1 for anything odd
-static int host_frame_count(const unsigned char *p, int len) {
-  if (len < 1) return 1;
-  switch (p[0] & 3) {
-    case 0: return 1;
-    case 1: case 2: return 2;
-    default: return len >= 2 && (p[1] & 0x3F) ? (p[1] & 0x3F) : 1;
+// frames that conceal a lost packet of frame_size output-rate samples (src/opus_decoder.c:316-365), for a stream whose last accepted
+// packet had frames of last_N 48 kHz samples; the same walk as ent_lost_packet
+static int host_plc_frames(int frame_size, int ds, int last_N) {
+  const int F20 = 960 / ds, F10 = F20 >> 1, F5 = F10 >> 1, cap = last_N / ds;
+  int n = 0;
+  while (frame_size > 0 && n < 48) {
+    int a = frame_size < cap ? frame_size : cap;
+    if (a > F20) a = F20;
+    else if (a < F20) {
+      if (a > F10) a = F10;
+      else if (a > F5 && a < F10) a = F5;
+    }
+    frame_size -= a;
+    n++;
   }
+  return n;
 }
 
 // Enqueue one batched decode with HOST buffers: H2D + kernels on the main stream, PCM read-back on the second stream.
@@ -463,10 +498,21 @@ static int decode_submit(OpusB200Decoder *d, const unsigned char *packets, int p
       d->d_pcm_cap[b] = obytes;
     }
   }
+  // How many frame launches does the call need?  The host walks the packet framing exactly as the entropy kernel will (the same
+  // function), so it also knows each stream's frame size when a later packet is lost.
   int maxf = 1;
   for (int s = 0; s < d->n; s++) {
-    if (len[s] > 0 && (packets[(size_t)s * pkt_stride] & 3)) {
-      int c = host_frame_count(packets + (size_t)s * pkt_stride, len[s]);
+    const unsigned char *pk = packets + (size_t)s * pkt_stride;
+    if (len[s] > 0) {
+      int off = 0, fl = 0;
+      const int c = ob::locate_frame(pk, len[s], 0, &off, &fl);
+      const int N = OB_SHORT_N << ((pk[0] >> 3) & 3);
+      if (c > 0 && (pk[0] & 0x80) && c * (N / d->downsample) <= frame_size) {   // what the entropy kernel accepts
+        d->h_last_N[s] = (int16_t)N;
+        if (c > maxf) maxf = c;
+      }
+    } else if (len[s] == 0) {  // lost: concealed over the whole frame_size, possibly in several frames
+      const int c = host_plc_frames(frame_size, d->downsample, d->h_last_N[s]);
       if (c > maxf) maxf = c;
     }
   }

@@ -11,6 +11,7 @@
 
 #define OB_DEV __device__ __forceinline__
 #define OB_DEVNI __device__ __noinline__
+#define OB_HDNI __host__ __device__ __noinline__
 #define OB_MDEV __device__ __forceinline__
 #define OB_HD __host__ __device__ __forceinline__
 #define OB_TABLE static __device__ const

@@ -1501,6 +1501,7 @@ void orc_decoder_init(OrcDecoder *st, int channels) {
   st->end = NBANDS;
   for (i = 0; i < 2 * NBANDS; i++) st->oldLogE[i] = st->oldLogE2[i] = -28.f;
   st->downsample = 1;
+  st->last_frame_size48 = 120; /* src/opus_decoder.c:178 */
 }
 /* opus_decoder_create(Fs): Fs in {48000, 24000, 16000, 12000, 8000} (celt/celt_decoder.c:222-240, resampling_factor celt/celt.c) */
 int orc_decoder_set_fs(OrcDecoder *st, int Fs) {
@@ -1844,6 +1845,7 @@ static int decode_frame_lost(OrcDecoder *st, float *pcm, int frame_size) {
   int audiosize, i, ret;
   if (frame_size < F2_5) return -2;
   frame_size = IMIN(frame_size, 48000 / ds / 25 * 3);
+  frame_size = IMIN(frame_size, st->last_frame_size48 / ds); /* "don't conceal more than what the ToC says" (:316-321) */
   audiosize = frame_size;
   if (!st->prev_mode_celt) { /* no packet yet: zeros */
     for (i = 0; i < audiosize * st->channels; i++) pcm[i] = 0;
@@ -1892,6 +1894,7 @@ int orc_opus_decode_float(OrcDecoder *st, const uint8_t *data, int len, float *p
   endband = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;
   st->stream_channels = (toc & 0x4) ? 2 : 1;
   st->start = 0;
+  st->last_frame_size48 = framesize; /* st->frame_size, src/opus_decoder.c:842 */
   for (i = 0; i < count; i++) {
     int ret;
     if (sizes[i] <= 1) { /* DTX / lost frame inside the packet: concealed at the packet's frame size; the end band stays */
@@ -1909,6 +1912,9 @@ int orc_opus_decode_float(OrcDecoder *st, const uint8_t *data, int len, float *p
 }
 
 uint32_t orc_final_range(const OrcDecoder *st) { return st->final_range; }
+/* debug taps for the tests: the synthesis history (decode_mem[c][0 .. DEC_BUF + OVERLAP)) and the de-emphasis memory */
+const float *orc_dbg_decode_mem(const OrcDecoder *st, int c) { return st->decode_mem[c]; }
+float orc_dbg_preemph_mem(const OrcDecoder *st, int c) { return st->preemph_mem[c]; }
 
 /* float -> int16 as the reference's int16 API does when nothing clips (celt/float_cast.h:150-158) */
 void orc_float_to_int16(const float *in, int16_t *out, int n) {

@@ -3,13 +3,14 @@
 // their logic can be unit-tested and debugged without a GPU.  Never linked into the product.
 #define OB_HOST_EMU 1
 #include "../../opus_b200/csrc/celt_dec_kernels.cuh"
+#include "../../opus_b200/csrc/celt_dec_plc.cuh"
 
 #include <stdio.h>
 
 using namespace ob;
 
 struct EmuDecoder {
-  int n, channels, downsample;
+  int n, channels, downsample, frame_size;
   std::vector<ObDecBandState> bstate;
   std::vector<ObDecSynthState> sstate;
   std::vector<ObFrameSide> side;
@@ -35,6 +36,11 @@ static void synth_entry(void *arg) {
   dec_synth_block(p, block_id(), dyn_smem());
 }
 
+static void plc_entry(void *arg) {
+  const DecPlcParams &p = *(const DecPlcParams *)arg;
+  dec_plc_block(p, block_id(), dyn_smem());
+}
+
 extern "C" {
 
 void *emu_decoder_create(int n_streams, int channels) {
@@ -42,6 +48,7 @@ void *emu_decoder_create(int n_streams, int channels) {
   d->n = n_streams;
   d->channels = channels;
   d->downsample = 1;
+  d->frame_size = 5760;
   d->bstate.resize(n_streams);
   d->sstate.resize(n_streams);
   d->side.resize(n_streams);
@@ -54,6 +61,15 @@ void *emu_decoder_create(int n_streams, int channels) {
   return d;
 }
 void emu_decoder_set_fs(void *h, int Fs) { ((EmuDecoder *)h)->downsample = 48000 / Fs; }
+void emu_decoder_set_frame_size(void *h, int fs) { ((EmuDecoder *)h)->frame_size = fs; }  // opus_decode's frame_size (output-rate samples)
+// test hook: overwrite a stream's synthesis history with the oracle's (decode_mem[0 .. 2048+120), de-emphasis memory), so that a
+// concealed frame can be compared without the last-bit differences of the frames before it
+void emu_decoder_sync_history(void *h, int stream, int c, const float *mem, float preemph) {
+  ObDecSynthState &st = ((EmuDecoder *)h)->sstate[stream];
+  for (int k = 0; k < OB_HIST; k++) st.hist[c][(st.pos + (uint32_t)k) & (OB_HIST - 1)] = mem[k];
+  for (int i = 0; i < OB_OVERLAP; i++) st.tail[c][i] = mem[OB_HIST + i];
+  st.deemph_mem[c] = preemph;
+}
 void emu_decoder_destroy(void *h) { delete (EmuDecoder *)h; }
 
 // packets: [n][stride]; pcm: [n][pcm_stride] (float or int16); out_samples[n]; final_range[n]
@@ -64,7 +80,7 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
     DecEntropyParams ep;
     ep.packets = packets; ep.pkt_len = lens; ep.pkt_stride = stride; ep.n_streams = d->n; ep.channels = d->channels;
     ep.frame_index = k; ep.state = d->bstate.data(); ep.side = d->side.data(); ep.script = d->script.data();
-    ep.out_samples = out_samples; ep.max_samples = 5760; ep.downsample = d->downsample;
+    ep.out_samples = out_samples; ep.max_samples = d->frame_size; ep.downsample = d->downsample;
     emu_launch(entropy_entry, &ep, (d->n + 31) / 32, 32, 0);
     DecPvqParams pp;
     pp.side = d->side.data(); pp.script = d->script.data(); pp.state = d->bstate.data(); pp.X = d->X.data(); pp.n_streams = d->n;
@@ -84,6 +100,10 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
       sp.pcm = pcm_is_int16 ? (void *)((int16_t *)pcm + (size_t)s * pcm_stride) : (void *)((float *)pcm + (size_t)s * pcm_stride);
       sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels; sp.downsample = d->downsample;
       emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
+      DecPlcParams lp;
+      lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = 0; lp.pcm_is_int16 = pcm_is_int16; lp.n_streams = 1;
+      lp.channels = d->channels; lp.downsample = d->downsample;
+      emu_launch(plc_entry, &lp, 1, 64, sizeof(PlcWS));
     }
   }
   for (int s = 0; s < d->n; s++) final_range[s] = d->bstate[s].final_range;

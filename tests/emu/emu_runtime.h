@@ -21,6 +21,7 @@
 
 #define OB_DEV static inline
 #define OB_DEVNI static
+#define OB_HDNI static
 #define OB_MDEV inline
 #define OB_HD static inline
 #define OB_TABLE static const

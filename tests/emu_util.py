@@ -49,8 +49,9 @@ class EmuDecoder:
         self.h = ctypes.c_void_p(self.L.emu_decoder_create(n_streams, channels))
         self.L.emu_decoder_set_fs(self.h, Fs)
 
-    def decode(self, packets, lens, int16=False):
-        """packets [n][stride] uint8, lens [n] -> (pcm [n][5760*ch], samples[n], final_range[n])"""
+    def decode(self, packets, lens, int16=False, frame_size=5760):
+        """packets [n][stride] uint8, lens [n] (0 = lost: frame_size samples are concealed) -> (pcm [n][5760*ch], samples[n], final_range[n])"""
+        self.L.emu_decoder_set_frame_size(self.h, frame_size)
         packets = np.ascontiguousarray(packets, np.uint8)
         lens = np.ascontiguousarray(lens, np.int32)
         stride = 5760 * self.ch
@@ -73,7 +74,7 @@ def emu_decode_stream(pkts, sizes, channels, frame_size, Fs=48000):
     out = np.zeros((T * frame_size, channels), np.float32)
     rng = np.zeros(T, np.uint32)
     for t in range(T):
-        pcm, ns, fr = d.decode(pkts[t:t + 1], sizes[t:t + 1])
+        pcm, ns, fr = d.decode(pkts[t:t + 1], sizes[t:t + 1], frame_size=frame_size)
         assert ns[0] == frame_size, (t, ns[0])
         out[t * frame_size:(t + 1) * frame_size] = pcm[0, :frame_size * channels].reshape(frame_size, channels)
         rng[t] = fr[0]

@@ -1,0 +1,128 @@
+"""Packet-loss concealment of the CUDA decode path through the C ABI (len == 0 = lost packet, as opus_decode(data = NULL)), against the
+reference decoder fed the same loss pattern.  Final range bit-exact (0 on a lost frame), sample counts equal.
+
+PCM bound on streams with losses: 1e-3 of full scale.  The concealment re-estimates a 24th-order LPC from the decoded history, which
+amplifies the last-bit differences of the frames before the loss; the reference's own C and SSE/AVX2 builds differ by up to 3.5e-4 on
+the same concealed streams while agreeing to 1e-7 without loss (see tests/test_emu_plc.py, which also checks the concealment
+arithmetic exactly by giving the emulated device code the oracle's history).  Streams without loss in the same batch keep the
++-1 LSB bar."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')]
+
+PLC_TOL = 1e-3
+
+
+def _streams(n, ch, fs, nfr, seed):
+    sigs = [util.sig_music, util.sig_tonal_noise, util.sig_white, util.sig_harmonic, util.sig_swell]
+    rates = [24000, 48000, 64000, 96000, 128000, 32000]
+    pk = np.zeros((n, nfr, 1500), np.uint8)
+    sz = np.zeros((n, nfr), np.int32)
+    for s in range(n):
+        x = sigs[s % 5](seed * 1000 + s, nfr * fs, ch).reshape(-1, ch)[:nfr * fs]
+        p, z, _ = util.ref_encode(x, ch, fs, rates[s % len(rates)], vbr=(s // 3) % 2, complexity=5 + s % 6)
+        pk[s], sz[s] = p, z
+    return pk, sz
+
+
+def _ref_decode(Fs, ch, fsd, pk, sz):
+    L = util.load_ref('c')
+    T = len(sz)
+    p, z = np.ascontiguousarray(pk), np.ascontiguousarray(sz, np.int32)
+    ref, rr = np.zeros((T * fsd, ch), np.float32), np.zeros(T, np.uint32)
+    assert L.refh_decode_stream_float(Fs, ch, fsd, T, util._ptr(p), p.shape[1], util._ptr(z), util._ptr(ref), util._ptr(rr)) == 0
+    return ref, rr
+
+
+@pytest.mark.parametrize('ch,fs48,Fs', [(2, 960, 48000), (1, 960, 48000), (2, 480, 48000), (2, 240, 48000), (1, 120, 48000), (2, 960, 16000)])
+def test_random_loss_patterns_vs_reference(ch, fs48, Fs):
+    import opus_b200
+    n, nfr = 40, 30
+    rng = np.random.default_rng(ch * 100 + fs48 + Fs // 1000)
+    pk, sz = _streams(n, ch, fs48, nfr, seed=fs48 + ch)
+    lost = rng.random((n, nfr)) < 0.18
+    lost[:4] = False                    # clean streams in the same batch
+    lost[4, 6:16] = True                # a long burst: pitch PLC fades into noise PLC
+    lost[5, 0:2] = True                 # nothing decoded yet: zeros
+    lost[6, 3::2] = True                # every other packet: skip_plc
+    sz = np.where(lost, 0, sz).astype(np.int32)
+    fsd = fs48 * Fs // 48000
+    dec = opus_b200.DecoderBatch(n, channels=ch, Fs=Fs)
+    outs = np.zeros((n, nfr * fsd, ch), np.float32)
+    rngs = np.zeros((n, nfr), np.uint32)
+    for t in range(nfr):
+        got, ns = dec.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fsd, dtype=np.float32)
+        assert (ns == fsd).all(), (t, ns)
+        outs[:, t * fsd:(t + 1) * fsd] = got.reshape(n, fsd, ch)
+        rngs[:, t] = dec.final_range()
+    dec.close()
+    worst = 0.0
+    for s in range(n):
+        ref, rr = _ref_decode(Fs, ch, fsd, pk[s], sz[s])
+        assert (rngs[s] == rr).all(), s
+        err = float(np.abs(outs[s] - ref).max())
+        if not lost[s].any():
+            assert err < 2e-5, (s, err)
+            assert np.abs(util.to_int16(outs[s]).astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
+        else:
+            assert err < PLC_TOL, (s, err)
+            worst = max(worst, err)
+            # frames before the first loss are ordinary decoded frames
+            t0 = int(np.argmax(lost[s]))
+            assert np.abs(outs[s][:t0 * fsd] - ref[:t0 * fsd]).max() < 2e-5 if t0 else True
+    print('worst concealed-stream error', worst)
+
+
+def test_int16_and_long_frame_sizes():
+    """int16 output of concealed frames; opus_decode(NULL, 60 ms) = three 20 ms frames written one after the other"""
+    import opus_b200
+    ch, fs48, n, nfr, fs_arg = 2, 960, 8, 12, 2880
+    pk, sz = _streams(n, ch, fs48, nfr, seed=77)
+    lost = np.zeros((n, nfr), bool)
+    lost[:, 5] = True
+    lost[1::2, 6] = True
+    lost[2, 0] = True
+    sz = np.where(lost, 0, sz).astype(np.int32)
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    L = util.load_ref('c')
+    refs = []
+    for s in range(n):
+        p, z = np.ascontiguousarray(pk[s]), np.ascontiguousarray(sz[s])
+        ref, rr = np.zeros((nfr * fs_arg, ch), np.float32), np.zeros(nfr, np.uint32)
+        assert L.refh_decode_stream_float(48000, ch, fs_arg, nfr, util._ptr(p), p.shape[1], util._ptr(z), util._ptr(ref), util._ptr(rr)) == 0
+        refs.append((ref, rr))
+    for t in range(nfr):
+        got, ns = dec.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fs_arg, dtype=np.int16)
+        fr = dec.final_range()
+        for s in range(n):
+            want = fs_arg if lost[s, t] else fs48
+            assert ns[s] == want, (s, t, ns[s])
+            assert fr[s] == refs[s][1][t]
+            r16 = util.to_int16(refs[s][0][t * fs_arg:t * fs_arg + want])
+            assert np.abs(got[s, :want * ch].reshape(want, ch).astype(np.int32) - r16.astype(np.int32)).max() <= 33   # 1e-3 of full scale
+    dec.close()
+
+
+def test_negative_length_skips_the_stream():
+    """this library's extension: len < 0 leaves the stream untouched in this call (0 samples), neither decoded nor concealed"""
+    import opus_b200
+    ch, fs, n, nfr = 2, 960, 4, 6
+    pk, sz = _streams(n, ch, fs, nfr, seed=5)
+    a, b = opus_b200.DecoderBatch(n, channels=ch), opus_b200.DecoderBatch(n, channels=ch)
+    for t in range(nfr):
+        ga, _ = a.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fs, dtype=np.float32)
+        if t == 2:   # stream 1 sits this call out in decoder b, then catches up with the same packet
+            z = sz[:, t].copy(); z[1] = -1
+            gb, ns = b.decode(np.ascontiguousarray(pk[:, t]), z, frame_size=fs, dtype=np.float32)
+            assert ns[1] == 0 and (ns[[0, 2, 3]] == fs).all()
+            z2 = np.full(n, -1, np.int32); z2[1] = sz[1, t]
+            gb2, ns2 = b.decode(np.ascontiguousarray(pk[:, t]), z2, frame_size=fs, dtype=np.float32)
+            assert ns2[1] == fs and (ns2[[0, 2, 3]] == 0).all()
+            gb[1] = gb2[1]
+        else:
+            gb, _ = b.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fs, dtype=np.float32)
+        assert np.array_equal(ga, gb)
+    a.close(); b.close()

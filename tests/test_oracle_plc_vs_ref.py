@@ -75,3 +75,23 @@ def test_plc_randomised(seed):
     nfr = 30
     lost = sorted(set(int(v) for v in rng.integers(1, nfr, size=int(rng.integers(2, 12)))))
     _run(48000, ch, fs48, br, lost, list(util.SIGNALS)[seed % 3], nfr=nfr, cx=int(rng.integers(0, 11)))
+
+
+@pytest.mark.parametrize('fs_arg', [2880, 720, 360, 1920])
+def test_plc_long_and_odd_frame_sizes(fs_arg):
+    """opus_decode(NULL, frame_size): 60 ms = 3 x 20, 15 ms = 10 + 5, 7.5 ms = 5 + 2.5, 40 ms = 2 x 20 (src/opus_decoder.c:343-365);
+    packets are 20 ms (fs_arg >= 960) or 2.5 ms frames otherwise, every slot of the output holds fs_arg samples"""
+    O, L = util.load_oracle(), util.load_ref('c')
+    ch, fs48 = 2, 960 if fs_arg >= 960 else 120
+    nfr = 14
+    x = util.sig_music(fs_arg, nfr * fs48, ch).reshape(-1, ch)[:nfr * fs48]
+    pk, sz, _ = util.ref_encode(x, ch, fs48, 96000)
+    sz = np.ascontiguousarray(sz, np.int32)
+    for t in (0, 4, 5, 9):
+        sz[t] = 0
+    T = len(sz)
+    ref, rr = np.zeros((T * fs_arg, ch), np.float32), np.zeros(T, np.uint32)
+    assert L.refh_decode_stream_float(48000, ch, fs_arg, T, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(ref), util._ptr(rr)) == 0
+    got, gr = np.zeros((T * fs_arg, ch), np.float32), np.zeros(T, np.uint32)
+    assert O.orc_decode_stream_float(ch, fs_arg, T, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(got), util._ptr(gr)) == 0
+    assert (gr == rr).all() and np.array_equal(got, ref)
