@@ -27,7 +27,8 @@ class DecoderBatch:
 
     # -- opus_decode() / opus_decode_float(), batched, host buffers ----------------------------
     def decode(self, packets, lens, frame_size=960, dtype=np.int16, out=None):
-        """packets: uint8 [n_streams, stride]; lens: int32 [n_streams].
+        """packets: uint8 [n_streams, stride]; lens: int32 [n_streams] (0 = packet lost: frame_size samples are concealed, like
+        opus_decode(data=NULL); < 0 = the stream sits this call out).
         Returns (pcm [n_streams, frame_size*channels], samples_per_channel [n_streams])."""
         packets = np.ascontiguousarray(packets, np.uint8)
         lens = np.ascontiguousarray(lens, np.int32)
