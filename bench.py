@@ -215,6 +215,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     rows = parallel.fixture_rows(rank, world, n, t_pk.shape[0]).to(dev)
     d_pk = t_pk.permute(1, 0, 2)[:, rows].contiguous()
     d_len = t_sz.permute(1, 0)[:, rows].contiguous()
+    if args.loss > 0:   # non-default: a fraction of the packets is lost (len = 0) and concealed; never used for the headline number
+        g = torch.Generator(device='cpu').manual_seed(1234 + rank)
+        drop = (torch.rand(d_len.shape, generator=g) < args.loss).to(dev)
+        drop[0] = False   # every stream decodes one packet first
+        d_len = torch.where(drop, torch.zeros_like(d_len), d_len).contiguous()
     d_pcm = torch.empty((n, FRAME * CH), dtype=torch.int16, device=dev)
     d_ns = torch.empty((n,), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
@@ -357,7 +362,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                    'streams_per_gpu': n, 'packets': '256 distinct streams x 8 frames from the reference encoder, tiled',
                    'pipelining': 'consecutive steps are consecutive frames of the same streams; the synthesis kernel of step t runs on its own CUDA stream under the range decoding of step t+1 (joined before the closing event)',
                    'l2': 'per-step working set (spectrum 503 MB + history 503 MB at 65536 streams) exceeds the 126 MB L2',
-                   'parallelism': 'streams sharded across GPUs, no steady-state collective'},
+                   'parallelism': 'streams sharded across GPUs, no steady-state collective',
+                   **({'packet_loss': args.loss} if args.loss > 0 else {})},
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
                 'call': 'opusb200_decode_submit/_wait (double-buffered)', 'sync_call_value_rank0': e2e_sync_val},
         'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
@@ -372,6 +378,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--streams', type=int, default=65536, help='streams per GPU')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--loss', type=float, default=0.0, help='fraction of packets lost and concealed (diagnostic runs only)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -298,20 +298,23 @@ OB_DEV void ent_finish(const DecEntropyParams &p, int stream, ObFrameSide *side,
 //   noise PLC  -> the vector kernel draws the noise spectrum, the synthesis kernel runs unchanged on the decayed energies;
 //   pitch PLC  -> ob_celt_dec_plc (celt_dec_plc.cuh) extrapolates the history ring.
 // ------------------------------------------------------------------------------------------
-OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st, int LM, int pcm_off) {
+OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st, int LM, int pcm_off, uint32_t fl) {
   const int CC = p.channels, N = OB_SHORT_N << LM, M = 1 << LM;
   side->pcm_off = pcm_off;
   side->LM = LM;
   st->final_range = 0;  // src/opus_decoder.c:701-704
-  if (!st->has_packet) {  // nothing decoded yet: zeros, the CELT state is not touched (src/opus_decoder.c:333-341)
+  if (!(fl & OB_PF_HAS_PACKET)) {  // nothing decoded yet: zeros, the CELT state is not touched (src/opus_decoder.c:333-341)
     side->plc = OB_PLC_ZEROS;
+    st->plc_flags = fl;
     ent_finish(p, stream, side, st, N);
     return;
   }
-  const int noise = st->plc_duration >= 40 || st->skip_plc;  // start == 0 always here
+  const uint32_t dur = st->plc_dur;
+  const int loss_duration = dur & 0xffff, plc_duration = dur >> 16;
+  const int noise = plc_duration >= 40 || (fl & OB_PF_SKIP_PLC);  // start == 0 always here
   if (noise) {
-    const int end = st->end_band;  // effEnd == end: the mode has 21 bands
-    const float decay = st->loss_duration == 0 ? 1.5f : .5f;
+    const int end = (fl >> OB_PF_END_SHIFT) & 31;  // effEnd == end: the mode has 21 bands
+    const float decay = loss_duration == 0 ? 1.5f : .5f;
 #pragma unroll 1
     for (int c = 0; c < CC; c++) {
 #pragma unroll 1
@@ -339,16 +342,16 @@ OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide 
       st->pf_period = T_cur;
       st->pf_period_old = T_cur; st->pf_gain_old = st->pf_gain; st->pf_tapset_old = st->pf_tapset;
     }
-    side->plc = OB_PLC_NOISE | (st->fold ? OB_PLC_FOLD : 0);
-    st->fold = 0;
-    st->skip_plc = 1;
+    side->plc = OB_PLC_NOISE | ((fl & OB_PF_FOLD) ? OB_PLC_FOLD : 0);
+    fl = (fl & ~OB_PF_FOLD) | OB_PF_SKIP_PLC;
   } else {
-    side->plc = OB_PLC_PITCH | (st->last_frame_type != OB_FRAME_PLC_PERIODIC ? OB_PLC_FIRST : 0);
-    st->fold = 1;
+    const int last_type = (fl >> OB_PF_TYPE_SHIFT) & 3;
+    side->plc = OB_PLC_PITCH | (last_type != OB_FRAME_PLC_PERIODIC ? OB_PLC_FIRST : 0);
+    fl |= OB_PF_FOLD;
   }
-  st->loss_duration = OB_IMIN(10000, st->loss_duration + M);
-  st->plc_duration = OB_IMIN(10000, st->plc_duration + M);
-  st->last_frame_type = noise ? OB_FRAME_PLC_NOISE : OB_FRAME_PLC_PERIODIC;
+  fl = (fl & ~(3u << OB_PF_TYPE_SHIFT)) | ((uint32_t)(noise ? OB_FRAME_PLC_NOISE : OB_FRAME_PLC_PERIODIC) << OB_PF_TYPE_SHIFT);
+  st->plc_flags = fl;
+  st->plc_dur = (uint32_t)OB_IMIN(10000, loss_duration + M) | ((uint32_t)OB_IMIN(10000, plc_duration + M) << 16);
   ent_finish(p, stream, side, st, N);
 }
 
@@ -358,7 +361,8 @@ OB_DEVNI void ent_lost_packet(const DecEntropyParams &p, int stream, ObFrameSide
   const int ds = p.downsample, F20 = 960 / ds, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1, fsz = p.max_samples;
   const int k = p.frame_index;
   if (fsz % F2_5 != 0) { ent_finish(p, stream, side, st, k == 0 ? -1 : 0); return; }  // OPUS_BAD_ARG
-  if (!st->has_packet) {
+  const uint32_t fl = st->plc_flags;
+  if (!(fl & OB_PF_HAS_PACKET)) {
     if (k != 0) { ent_finish(p, stream, side, st, 0); return; }
     side->pcm_off = 0; side->LM = 0; side->plc = OB_PLC_ZEROS;
     st->final_range = 0;
@@ -369,7 +373,7 @@ OB_DEVNI void ent_lost_packet(const DecEntropyParams &p, int stream, ObFrameSide
 #pragma unroll 1
   for (int idx = 0;; idx++) {
     if (rem <= 0) { ent_finish(p, stream, side, st, 0); return; }  // no k-th frame
-    a = OB_IMIN(rem, OB_IMAX(F2_5, st->last_N / ds));  // "don't conceal more than what the ToC says" (src/opus_decoder.c:316-321)
+    a = OB_IMIN(rem, (OB_SHORT_N << ((fl >> OB_PF_LM_SHIFT) & 3)) / ds);  // "don't conceal more than what the ToC says" (src/opus_decoder.c:316-321)
     if (a > F20) a = F20;
     else if (a < F20) {
       if (a > F10) a = F10;
@@ -380,7 +384,7 @@ OB_DEVNI void ent_lost_packet(const DecEntropyParams &p, int stream, ObFrameSide
   }
   const int N48 = a * ds;
   const int LM = N48 == 120 ? 0 : N48 == 240 ? 1 : N48 == 480 ? 2 : 3;
-  ent_lost_frame(p, stream, side, st, LM, fsz - rem);
+  ent_lost_frame(p, stream, side, st, LM, fsz - rem, fl);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -406,10 +410,12 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   else if (p.frame_index >= count) status = 0;        // no such frame in this packet
   if (status > 0 && count * (N / p.downsample) > p.max_samples) status = p.frame_index == 0 ? -2 : 0;  // BUFFER_TOO_SMALL: the whole packet (src/opus_decoder.c:806-807)
   if (status <= 0) { ent_finish(p, stream, side, st, status); return; }
-  st->last_N = N;  // Opus layer st->frame_size: set per accepted packet (src/opus_decoder.c:842)
-  if (flen <= 1) { ent_lost_frame(p, stream, side, st, LM, p.frame_index * (N / p.downsample)); return; }  // DTX / lost frame inside the packet
+  const uint32_t fl0 = st->plc_flags, dur0 = st->plc_dur;   // two loads; a loss-free stream stores neither back
+  uint32_t fl = (fl0 & ~(3u << OB_PF_LM_SHIFT)) | ((uint32_t)LM << OB_PF_LM_SHIFT);  // Opus layer st->frame_size, per accepted packet (src/opus_decoder.c:842)
+  if (flen <= 1) { ent_lost_frame(p, stream, side, st, LM, p.frame_index * (N / p.downsample), fl); return; }  // DTX / lost frame inside the packet
   side->pcm_off = p.frame_index * (N / p.downsample);
-  if (st->loss_duration == 0) st->skip_plc = 0;  // celt_decoder.c:1299-1301
+  const int loss_dur = dur0 & 0xffff;
+  if (loss_dur == 0) fl &= ~OB_PF_SKIP_PLC;  // celt_decoder.c:1299-1301
 
   const int C = (toc & 4) ? 2 : 1;
   const int bw = (toc >> 5) & 3;
@@ -476,8 +482,8 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
     if (C == 1)  // celt_decoder.c:1306-1310
 #pragma unroll 1
       for (int i = 0; i < OB_NBANDS; i++) E[i] = E[i] > E[OB_NBANDS + i] ? E[i] : E[OB_NBANDS + i];
-    if (!intra && st->loss_duration != 0) {  // safe energy prediction after a loss (celt_decoder.c:1362-1393), rare
-      const int missing = OB_IMIN(10, st->loss_duration >> LM);
+    if (!intra && loss_dur != 0) {  // safe energy prediction after a loss (celt_decoder.c:1362-1393), rare
+      const int missing = OB_IMIN(10, loss_dur >> LM);
       const float safety = LM == 0 ? 1.5f : LM == 1 ? .5f : 0.f;
 #pragma unroll 1
       for (int ci = 0; ci < 2 * OB_NBANDS; ci++) {
@@ -1043,7 +1049,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   side->LM = LM; side->transient = isTransient; side->C = C; side->silence = silence; side->end_band = end;
   side->spread = spread; side->intensity = intensity; side->dual_stereo = dual_stereo;
   side->anti_collapse_on = anti_collapse_on; side->n_leaves = e.n_leaves;
-  side->plc = st->fold ? OB_PLC_FOLD : 0;
+  side->plc = (fl & OB_PF_FOLD) ? OB_PLC_FOLD : 0;
   side->seed = st->rng;
   {  // post-filter parameter pipeline (celt_decoder.c:1540-1563)
     int T_old = OB_IMAX(st->pf_period_old, 15), T_cur = OB_IMAX(st->pf_period, 15);
@@ -1072,7 +1078,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       if (anti_collapse_on) { side->prevLogE[0][i] = l1; side->prevLogE[1][i] = l2; }
       if (!isTransient) { l2 = l1; l1 = eb; }
       else l1 = l1 < eb ? l1 : eb;
-      const float inc = OB_IMIN(160, st->loss_duration + M) * 0.001f;
+      const float inc = OB_IMIN(160, loss_dur + M) * 0.001f;
       const float a = bg + inc;
       bg = a < eb ? a : eb;
       if (band >= end) { eb = 0.f; l1 = l2 = -28.f; }
@@ -1082,8 +1088,11 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
       st->backgroundLogE[i] = bg;
     }
   }
-  st->loss_duration = 0; st->plc_duration = 0; st->last_frame_type = OB_FRAME_NORMAL; st->fold = 0;  // celt_decoder.c:1604-1607
-  st->end_band = end; st->has_packet = 1;
+  // celt_decoder.c:1604-1607: loss counters cleared, FRAME_NORMAL, no fold pending; plus the Opus layer's prev_mode / end band
+  fl = (fl & ~(OB_PF_FOLD | (3u << OB_PF_TYPE_SHIFT) | (31u << OB_PF_END_SHIFT))) | OB_PF_HAS_PACKET |
+       ((uint32_t)OB_FRAME_NORMAL << OB_PF_TYPE_SHIFT) | ((uint32_t)end << OB_PF_END_SHIFT);
+  if (fl != fl0) st->plc_flags = fl;
+  if (dur0 != 0) st->plc_dur = 0;
   ent_finish(p, stream, side, st, ok);
 }
 

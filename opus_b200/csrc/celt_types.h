@@ -22,15 +22,17 @@ typedef struct {
   int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
   float pf_gain, pf_gain_old;
   int32_t last_status;
-  /* packet-loss concealment bookkeeping (celt/celt_decoder.c:110-124); all of it is decided in the entropy kernel */
-  int32_t loss_duration, plc_duration; /* in 2.5 ms units, saturating at 10000 */
-  int32_t skip_plc;                    /* noise PLC only, until two consecutive packets arrive */
-  int32_t last_frame_type;             /* OB_FRAME_* */
-  int32_t fold;                        /* prefilter_and_fold pending (the last frame was a pitch-based PLC frame) */
-  int32_t end_band;                    /* end band of the last decoded packet (a lost frame keeps it) */
-  int32_t has_packet;                  /* a packet has been decoded (Opus layer prev_mode != 0) */
-  int32_t last_N;                      /* frame size of the last packet, 48 kHz samples (Opus layer st->frame_size) */
+  /* packet-loss concealment bookkeeping (celt/celt_decoder.c:110-124), decided in the entropy kernel; packed in two words so that a
+     loss-free stream costs the hot path two loads and no store per frame */
+  uint32_t plc_dur;   /* bits0-15 loss_duration, bits16-31 plc_duration (2.5 ms units, saturating at 10000) */
+  uint32_t plc_flags; /* OB_PF_* */
 } ObDecBandState;
+#define OB_PF_SKIP_PLC 1u        /* noise PLC only, until two consecutive packets arrive */
+#define OB_PF_FOLD 2u            /* prefilter_and_fold pending (the last frame was a pitch-based PLC frame) */
+#define OB_PF_HAS_PACKET 4u      /* a packet has been decoded (Opus layer prev_mode != 0) */
+#define OB_PF_TYPE_SHIFT 3       /* bits3-4: last_frame_type (OB_FRAME_*) */
+#define OB_PF_END_SHIFT 5        /* bits5-9: end band of the last decoded packet (a lost frame keeps it) */
+#define OB_PF_LM_SHIFT 10        /* bits10-11: LM of the last accepted packet (Opus layer st->frame_size) */
 #define OB_FRAME_NONE 0
 #define OB_FRAME_NORMAL 1
 #define OB_FRAME_PLC_NOISE 2

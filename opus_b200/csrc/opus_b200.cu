@@ -46,10 +46,26 @@ extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParam
   dec_synth_block(p, blockIdx.x, dyn_smem());
 }
 
-// Pitch-based packet-loss concealment: a persistent grid strides over the batch; a CTA only works on streams whose frame is lost.
+// Pitch-based packet-loss concealment.  CTA b looks at streams [32b, 32b+32): warp 0 reads their side records (one lane each) and
+// ballots; the CTA then conceals the lost ones one after the other.  With nothing lost the kernel is 2 loads per stream.
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_plc(DecPlcParams p) {
-  for (int stream = blockIdx.x; stream < p.n_streams; stream += gridDim.x) {
-    dec_plc_block(p, stream, dyn_smem());
+  __shared__ unsigned lost_mask;
+  if (threadIdx.x < 32) {
+    const int s = blockIdx.x * 32 + threadIdx.x;
+    int lost = 0;
+    if (s < p.n_streams) {
+      const ObFrameSide *sd = p.side + s;
+      lost = sd->status > 0 && OB_PLC_TYPE(sd->plc) >= OB_PLC_PITCH;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, lost);
+    if (threadIdx.x == 0) lost_mask = m;
+  }
+  __syncthreads();
+  unsigned m = lost_mask;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    dec_plc_block(p, blockIdx.x * 32 + j, dyn_smem());
     __syncthreads();
   }
 }
@@ -153,7 +169,6 @@ extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState
 struct OpusB200Decoder {
   int device, channels, n;
   int downsample;   // 48000 / Fs of opusb200_decoder_create
-  int plc_grid;     // CTAs of the concealment kernel's persistent grid
   int16_t *h_last_N; // host mirror of ObDecBandState.last_N (host-buffer API: sizes the frame-launch loop of a lost packet)
   cudaStream_t stream;
   ObDecBandState *bstate;
@@ -297,11 +312,7 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   }
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_plc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlcWS)));
-  {
-    int sms = 0;
-    OB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    d->plc_grid = sms * 4;
-  }
+
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the band decoder recurses over partitions (depth <= 5)
   size_t stk = 0;
@@ -417,7 +428,7 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
       DecPlcParams lp;
       lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = pcm_stride; lp.pcm_is_int16 = pcm_is_int16;
       lp.n_streams = cn; lp.channels = d->channels; lp.downsample = d->downsample;
-      ob_celt_dec_plc<<<cn < d->plc_grid ? cn : d->plc_grid, 64, sizeof(PlcWS), sb>>>(lp);
+      ob_celt_dec_plc<<<(cn + 31) / 32, 64, sizeof(PlcWS), sb>>>(lp);
     }
     d->launches += 4;
     if (!timing) {

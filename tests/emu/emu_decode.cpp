@@ -99,11 +99,12 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
       sp.side = d->side.data() + s; sp.X = d->X.data() + (size_t)s * 2 * OB_MAXN; sp.state = d->sstate.data() + s;
       sp.pcm = pcm_is_int16 ? (void *)((int16_t *)pcm + (size_t)s * pcm_stride) : (void *)((float *)pcm + (size_t)s * pcm_stride);
       sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels; sp.downsample = d->downsample;
-      emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
+      const int lost_here = OB_PLC_TYPE(d->side[s].plc) >= OB_PLC_PITCH;   // (emulator only: skip the launch that would return at once)
+      if (!lost_here) emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
       DecPlcParams lp;
       lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = 0; lp.pcm_is_int16 = pcm_is_int16; lp.n_streams = 1;
       lp.channels = d->channels; lp.downsample = d->downsample;
-      emu_launch(plc_entry, &lp, 1, 64, sizeof(PlcWS));
+      if (lost_here) emu_launch(plc_entry, &lp, 1, 64, sizeof(PlcWS));
     }
   }
   for (int s = 0; s < d->n; s++) final_range[s] = d->bstate[s].final_range;
