@@ -4,7 +4,7 @@
 // (celt_decode_lost, celt/celt_decoder.c:813-1079; celt_plc_pitch_search :552-574).  The entropy kernel has already decided
 // the kind of concealment and advanced the loss counters (ent_lost_frame); noise PLC goes through the ordinary synthesis path.
 //
-//   one CTA of 2 warps per 32 streams; it conceals the lost ones among them, one after the other (nothing lost: a 2-load scan):
+//   one CTA of 2 warps per 8 streams; it conceals the lost ones among them, one after the other (nothing lost: a 2-load scan):
 //     both warps : pitch_downsample + pitch_search over the 2048-sample history ring (first lost frame of a burst only)
 //     warp c     : channel c: windowed autocorrelation -> LPC(24) -> excitation (FIR) -> decay estimate -> periodic extrapolation
 //                  of N+120 samples -> synthesis IIR -> energy check -> history ring / overhang / de-emphasis -> PCM

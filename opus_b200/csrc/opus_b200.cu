@@ -46,14 +46,17 @@ extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParam
   dec_synth_block(p, blockIdx.x, dyn_smem());
 }
 
-// Pitch-based packet-loss concealment.  CTA b looks at streams [32b, 32b+32): warp 0 reads their side records (one lane each) and
-// ballots; the CTA then conceals the lost ones one after the other.  With nothing lost the kernel is 2 loads per stream.
+// Pitch-based packet-loss concealment.  CTA b looks at streams [8b, 8b+8): eight lanes read their side records and ballot; the CTA
+// then conceals the lost ones one after the other.  With nothing lost the kernel is 2 loads per stream (measured: 8 us per launch at
+// 65 536 streams).  Small chunks on purpose: a concealed frame takes ~0.2 ms of mostly serial work (the 24-tap synthesis recursion),
+// so the lost streams of a batch should spread over as many CTAs as are resident (8 per SM) instead of queueing inside a few.
+#define OB_PLC_CHUNK 8
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_plc(DecPlcParams p) {
   __shared__ unsigned lost_mask;
   if (threadIdx.x < 32) {
-    const int s = blockIdx.x * 32 + threadIdx.x;
+    const int s = blockIdx.x * OB_PLC_CHUNK + threadIdx.x;
     int lost = 0;
-    if (s < p.n_streams) {
+    if (threadIdx.x < OB_PLC_CHUNK && s < p.n_streams) {
       const ObFrameSide *sd = p.side + s;
       lost = sd->status > 0 && OB_PLC_TYPE(sd->plc) >= OB_PLC_PITCH;
     }
@@ -65,7 +68,7 @@ extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_plc(DecPlcParams p)
   while (m) {
     const int j = __ffs(m) - 1;
     m &= m - 1;
-    dec_plc_block(p, blockIdx.x * 32 + j, dyn_smem());
+    dec_plc_block(p, blockIdx.x * OB_PLC_CHUNK + j, dyn_smem());
     __syncthreads();
   }
 }
@@ -428,7 +431,7 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
       DecPlcParams lp;
       lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = pcm_stride; lp.pcm_is_int16 = pcm_is_int16;
       lp.n_streams = cn; lp.channels = d->channels; lp.downsample = d->downsample;
-      ob_celt_dec_plc<<<(cn + 31) / 32, 64, sizeof(PlcWS), sb>>>(lp);
+      ob_celt_dec_plc<<<(cn + OB_PLC_CHUNK - 1) / OB_PLC_CHUNK, 64, sizeof(PlcWS), sb>>>(lp);
     }
     d->launches += 4;
     if (!timing) {

@@ -124,7 +124,7 @@ def test_multiframe_and_mixed_frame_sizes():
     _, p10, s10, _, pcm10, ch, fs10 = g['st10_96k']
     _, p20, s20, _, pcm20, _, fs20 = g['st20_128k']
     # stream 0: code-1 packet holding frames 0,1 of the 10 ms stream; stream 1: a plain 20 ms packet;
-    # stream 2: code-3 CBR packet with frames 0,1 plus padding; stream 3: nothing this call
+    # stream 2: code-3 CBR packet with frames 0,1 plus padding; stream 3: sits this call out (len < 0)
     f0, f1 = bytes(p10[0, 1:s10[0]]), bytes(p10[1, 1:s10[1]])
     assert len(f0) == len(f1)
     toc = int(p10[0, 0])
@@ -135,6 +135,7 @@ def test_multiframe_and_mixed_frame_sizes():
     for i, b in enumerate((a, bytes(p20[0, :s20[0]]), c)):
         pk[i, :len(b)] = np.frombuffer(b, np.uint8)
         sz[i] = len(b)
+    sz[3] = -1
     dec = opus_b200.DecoderBatch(4, channels=ch)
     got, ns = dec.decode(pk, sz, frame_size=960, dtype=np.float32)
     assert list(ns) == [960, 960, 960, 0]
