@@ -1927,6 +1927,73 @@ void orc_float_to_int16(const float *in, int16_t *out, int n) {
   }
 }
 
+/* opus_pcm_soft_clip (src/opus.c:39-166): what opus_decode() applies to a packet's float PCM before the int16 conversion
+ * (src/opus_decoder.c:875-878).  x: interleaved, N samples per channel; declip_mem[C] carries the non-linearity into the next call. */
+void orc_pcm_soft_clip(float *x_, int N, int C, float *declip_mem) {
+  int c, i;
+  if (C < 1 || N < 1 || !x_ || !declip_mem) return;
+  for (i = 0; i < N * C; i++) x_[i] = x_[i] > 2.f ? 2.f : x_[i] < -2.f ? -2.f : x_[i]; /* opus_limit2_checkwithin1_c */
+  for (c = 0; c < C; c++) {
+    float *x = x_ + c, a = declip_mem[c], x0;
+    int curr = 0;
+    for (i = 0; i < N; i++) { /* continue the previous frame's curve up to the first zero crossing */
+      if (x[i * C] * a >= 0) break;
+      x[i * C] = x[i * C] + a * x[i * C] * x[i * C];
+    }
+    x0 = x[0];
+    while (1) {
+      int start, end, special, peak_pos;
+      float maxval;
+      for (i = curr; i < N; i++)
+        if (x[i * C] > 1 || x[i * C] < -1) break;
+      if (i == N) { a = 0; break; }
+      peak_pos = i;
+      start = end = i;
+      maxval = (float)fabs(x[i * C]);
+      while (start > 0 && x[i * C] * x[(start - 1) * C] >= 0) start--;   /* zero crossing before the clipping */
+      while (end < N && x[i * C] * x[end * C] >= 0) {                    /* ... and after, tracking the peak */
+        if ((float)fabs(x[end * C]) > maxval) { maxval = (float)fabs(x[end * C]); peak_pos = end; }
+        end++;
+      }
+      special = (start == 0 && x[i * C] * x[0] >= 0);   /* clipping before the first zero crossing */
+      a = (maxval - 1) / (maxval * maxval);             /* maxval + a*maxval^2 = 1 */
+      a += a * 2.4e-7f;
+      if (x[i * C] > 0) a = -a;
+      for (i = start; i < end; i++) x[i * C] = x[i * C] + a * x[i * C] * x[i * C];
+      if (special && peak_pos >= 2) {   /* linear ramp from the first sample to the peak: no step at the frame start */
+        float offset = x0 - x[0], delta = offset / peak_pos;
+        for (i = curr; i < peak_pos; i++) {
+          offset -= delta;
+          x[i * C] += offset;
+          x[i * C] = x[i * C] > 1.f ? 1.f : x[i * C] < -1.f ? -1.f : x[i * C];
+        }
+      }
+      curr = end;
+      if (curr == N) break;
+    }
+    declip_mem[c] = a;
+  }
+}
+
+/* opus_decode() (int16): float decode, soft clip over the packet, FLOAT2INT16.  One stream, fresh decoder, like orc_decode_stream_float. */
+int orc_decode_stream_int16(int Fs, int channels, int frame_size, int nframes, const uint8_t *pkts, int stride, const int *sizes, int16_t *pcm,
+                            uint32_t *ranges) {
+  OrcDecoder *st = (OrcDecoder *)malloc(sizeof(OrcDecoder));
+  float *tmp = (float *)malloc(sizeof(float) * 5760 * 2), declip[2] = {0, 0};
+  int f;
+  orc_decoder_init(st, channels);
+  if (orc_decoder_set_fs(st, Fs)) { free(st); free(tmp); return -1; }
+  for (f = 0; f < nframes; f++) {
+    int n = orc_opus_decode_float(st, sizes[f] ? pkts + (size_t)f * stride : NULL, sizes[f], tmp, frame_size);
+    if (n < 0) { free(st); free(tmp); return n; }
+    orc_pcm_soft_clip(tmp, n, channels, declip);
+    orc_float_to_int16(tmp, pcm + (size_t)f * frame_size * channels, n * channels);
+    ranges[f] = st->final_range;
+  }
+  free(st); free(tmp);
+  return 0;
+}
+
 /* Convenience for the tests: decode `nframes` packets of one stream with a fresh decoder. */
 int orc_decode_stream_float(int channels, int frame_size, int nframes, const uint8_t *pkts, int stride,
                             const int *sizes, float *pcm, uint32_t *ranges) {
