@@ -298,13 +298,14 @@ OB_DEV void ent_finish(const DecEntropyParams &p, int stream, ObFrameSide *side,
 //   noise PLC  -> the vector kernel draws the noise spectrum, the synthesis kernel runs unchanged on the decayed energies;
 //   pitch PLC  -> ob_celt_dec_plc (celt_dec_plc.cuh) extrapolates the history ring.
 // ------------------------------------------------------------------------------------------
-OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st, int LM, int pcm_off, uint32_t fl) {
+OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide *side, ObDecBandState *st, int LM, int pcm_off, uint32_t fl,
+                             int packet_lost) {
   const int CC = p.channels, N = OB_SHORT_N << LM, M = 1 << LM;
   side->pcm_off = pcm_off;
   side->LM = LM;
   st->final_range = 0;  // src/opus_decoder.c:701-704
   if (!(fl & OB_PF_HAS_PACKET)) {  // nothing decoded yet: zeros, the CELT state is not touched (src/opus_decoder.c:333-341)
-    side->plc = OB_PLC_ZEROS;
+    side->plc = OB_PLC_ZEROS | (packet_lost ? OB_PLC_PACKET : 0);
     st->plc_flags = fl;
     ent_finish(p, stream, side, st, N);
     return;
@@ -342,11 +343,11 @@ OB_DEVNI void ent_lost_frame(const DecEntropyParams &p, int stream, ObFrameSide 
       st->pf_period = T_cur;
       st->pf_period_old = T_cur; st->pf_gain_old = st->pf_gain; st->pf_tapset_old = st->pf_tapset;
     }
-    side->plc = OB_PLC_NOISE | ((fl & OB_PF_FOLD) ? OB_PLC_FOLD : 0);
+    side->plc = OB_PLC_NOISE | ((fl & OB_PF_FOLD) ? OB_PLC_FOLD : 0) | (packet_lost ? OB_PLC_PACKET : 0);
     fl = (fl & ~OB_PF_FOLD) | OB_PF_SKIP_PLC;
   } else {
     const int last_type = (fl >> OB_PF_TYPE_SHIFT) & 3;
-    side->plc = OB_PLC_PITCH | (last_type != OB_FRAME_PLC_PERIODIC ? OB_PLC_FIRST : 0);
+    side->plc = OB_PLC_PITCH | (last_type != OB_FRAME_PLC_PERIODIC ? OB_PLC_FIRST : 0) | (packet_lost ? OB_PLC_PACKET : 0);
     fl |= OB_PF_FOLD;
   }
   fl = (fl & ~(3u << OB_PF_TYPE_SHIFT)) | ((uint32_t)(noise ? OB_FRAME_PLC_NOISE : OB_FRAME_PLC_PERIODIC) << OB_PF_TYPE_SHIFT);
@@ -384,7 +385,7 @@ OB_DEVNI void ent_lost_packet(const DecEntropyParams &p, int stream, ObFrameSide
   }
   const int N48 = a * ds;
   const int LM = N48 == 120 ? 0 : N48 == 240 ? 1 : N48 == 480 ? 2 : 3;
-  ent_lost_frame(p, stream, side, st, LM, fsz - rem, fl);
+  ent_lost_frame(p, stream, side, st, LM, fsz - rem, fl, 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -412,7 +413,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   if (status <= 0) { ent_finish(p, stream, side, st, status); return; }
   const uint32_t fl0 = st->plc_flags, dur0 = st->plc_dur;   // two loads; a loss-free stream stores neither back
   uint32_t fl = (fl0 & ~(3u << OB_PF_LM_SHIFT)) | ((uint32_t)LM << OB_PF_LM_SHIFT);  // Opus layer st->frame_size, per accepted packet (src/opus_decoder.c:842)
-  if (flen <= 1) { ent_lost_frame(p, stream, side, st, LM, p.frame_index * (N / p.downsample), fl); return; }  // DTX / lost frame inside the packet
+  if (flen <= 1) { ent_lost_frame(p, stream, side, st, LM, p.frame_index * (N / p.downsample), fl, 0); return; }  // DTX / lost frame inside the packet
   side->pcm_off = p.frame_index * (N / p.downsample);
   const int loss_dur = dur0 & 0xffff;
   if (loss_dur == 0) fl &= ~OB_PF_SKIP_PLC;  // celt_decoder.c:1299-1301

@@ -94,6 +94,73 @@ OB_DEV void comb_filter_inplace(float *cur, const float *hist, uint32_t pos, int
   }
 }
 
+// opus_pcm_soft_clip for one channel of one frame (src/opus.c:39-166), which opus_decode() applies before the int16 conversion
+// (src/opus_decoder.c:875-878): x[i*stride], i < n, in place.  The whole warp clamps to +-2 and looks for a sample beyond +-1; if there
+// is none and no curve is pending from the previous frame, the function is the identity (the common case: one pass over the frame).
+// Otherwise lane 0 runs the reference's serial scan.  The reference works on a whole packet: for packets of several frames this
+// per-frame form can differ from it where a clipped region crosses a frame boundary.
+OB_DEVNI void soft_clip_channel(float *x, int n, int stride, float *declip_mem, int lane) {
+  float mx = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float v0 = x[i * stride];
+    const float v = v0 > 2.f ? 2.f : v0 < -2.f ? -2.f : v0;
+    if (v != v0) x[i * stride] = v;
+    const float av = v < 0.f ? -v : v;
+    mx = av > mx ? av : mx;
+  }
+  mx = warp_max(mx);
+  float a = *declip_mem;
+  if (a == 0.f && mx <= 1.f) return;
+  wsync();
+  if (lane == 0) {
+    int i, curr = 0;
+#pragma unroll 1
+    for (i = 0; i < n; i++) {  // continue the previous frame's curve up to the first zero crossing
+      const float v = x[i * stride];
+      if (v * a >= 0) break;
+      x[i * stride] = v + a * v * v;
+    }
+    const float x0 = x[0];
+#pragma unroll 1
+    while (1) {
+#pragma unroll 1
+      for (i = curr; i < n; i++)
+        if (x[i * stride] > 1 || x[i * stride] < -1) break;
+      if (i == n) { a = 0.f; break; }
+      int peak_pos = i, start = i, end = i;
+      const float xi = x[i * stride];
+      float maxval = xi < 0.f ? -xi : xi;
+      while (start > 0 && xi * x[(start - 1) * stride] >= 0) start--;
+      while (end < n && xi * x[end * stride] >= 0) {
+        const float e = x[end * stride], ae = e < 0.f ? -e : e;
+        if (ae > maxval) { maxval = ae; peak_pos = end; }
+        end++;
+      }
+      const int special = (start == 0 && xi * x[0] >= 0);
+      a = f_div(maxval - 1, maxval * maxval);
+      a += a * 2.4e-7f;
+      if (xi > 0) a = -a;
+#pragma unroll 1
+      for (i = start; i < end; i++) { const float v = x[i * stride]; x[i * stride] = v + a * v * v; }
+      if (special && peak_pos >= 2) {
+        float offset = x0 - x[0];
+        const float delta = f_div(offset, (float)peak_pos);
+#pragma unroll 1
+        for (i = curr; i < peak_pos; i++) {
+          offset -= delta;
+          float v = x[i * stride] + offset;
+          v = v > 1.f ? 1.f : v < -1.f ? -1.f : v;
+          x[i * stride] = v;
+        }
+      }
+      curr = end;
+      if (curr == n) break;
+    }
+    *declip_mem = a;
+  }
+  wsync();
+}
+
 OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *smem) {
   const int lane = lane_id();
   const int ch = warp_in_block();  // output channel
@@ -260,6 +327,11 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
     float mlast = shfl(m, (N - 1) / seg);  // lane holding the last sample
     if (lane == 0) st->deemph_mem[ch] = mlast;
     wsync();
+  }
+  // ---- opus_decode()'s soft clipping of the int16 output; opus_decode_float() clears the memory (src/opus_decoder.c:875-878) ----
+  if (!(plc & OB_PLC_PACKET)) {   // a lost packet's frames are returned before this step (src/opus_decoder.c:764-778)
+    if (p.pcm_is_int16) soft_clip_channel(out, Nd, ds, &st->declip[ch], lane);
+    else if (lane == 0 && st->declip[ch] != 0.f) st->declip[ch] = 0.f;
   }
   // ---- interleave through shared memory, then fully coalesced stores ----
   bsync();

@@ -358,6 +358,11 @@ OB_DEVNI void dec_plc_block(const DecPlcParams &p, int stream, unsigned char *sm
       }
       const float mlast = shfl(m, (N - 1) / seg);
       if (lane == 0) st->deemph_mem[c] = mlast;
+      wsync();
+    }
+    if (!(side->plc & OB_PLC_PACKET)) {   // a DTX frame inside a packet is soft-clipped with the packet; a lost packet is not
+      if (p.pcm_is_int16) soft_clip_channel(y, Nd, ds, &st->declip[c], lane);
+      else if (lane == 0 && st->declip[c] != 0.f) st->declip[c] = 0.f;
     }
   }
   bsync();

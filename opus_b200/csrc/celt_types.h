@@ -38,13 +38,14 @@ typedef struct {
 #define OB_FRAME_PLC_NOISE 2
 #define OB_FRAME_PLC_PERIODIC 3
 /* ObFrameSide.plc: bits0-1 what the frame is (0 decoded, 1 noise PLC, 2 pitch PLC, 3 zeros: nothing decoded yet),
-   bit2 prefilter_and_fold before the synthesis, bit3 pitch PLC analyses (first lost frame of a burst) */
+   bit2 prefilter_and_fold before the synthesis, bit3 pitch PLC analyses (first lost frame of a burst), bit4 the whole packet is lost */
 #define OB_PLC_TYPE(x) ((x) & 3)
 #define OB_PLC_NOISE 1
 #define OB_PLC_PITCH 2
 #define OB_PLC_ZEROS 3
 #define OB_PLC_FOLD 4
 #define OB_PLC_FIRST 8
+#define OB_PLC_PACKET 16 /* the whole packet is lost (len == 0): opus_decode() returns such frames without soft clipping */
 #define OB_PLC_LPC_ORDER 24
 
 /* Per-stream synthesis state (one record per stream). */
@@ -53,6 +54,7 @@ typedef struct {
   float tail[2][OB_OVERLAP];        /* [0,60): last overlap/2 raw IMDCT outputs of the previous frame; after a pitch-based PLC frame
                                        all 120 samples that it extrapolated past the frame (celt_decoder.c:948-952) */
   float deemph_mem[2];
+  float declip[2];                  /* opus_pcm_soft_clip's declip_mem (int16 output only; Opus layer st->softclip_mem) */
   uint32_t pos;                     /* absolute position of the next output sample (mod 2^32) */
   int32_t last_pitch_index;         /* pitch-based PLC: period found at the first lost frame of the burst */
   float lpc[2][OB_PLC_LPC_ORDER];   /* pitch-based PLC: LPC of the last good signal */

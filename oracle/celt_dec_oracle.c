@@ -1986,7 +1986,7 @@ int orc_decode_stream_int16(int Fs, int channels, int frame_size, int nframes, c
   for (f = 0; f < nframes; f++) {
     int n = orc_opus_decode_float(st, sizes[f] ? pkts + (size_t)f * stride : NULL, sizes[f], tmp, frame_size);
     if (n < 0) { free(st); free(tmp); return n; }
-    orc_pcm_soft_clip(tmp, n, channels, declip);
+    if (sizes[f]) orc_pcm_soft_clip(tmp, n, channels, declip); /* a lost packet returns before the soft clipping (src/opus_decoder.c:764-778) */
     orc_float_to_int16(tmp, pcm + (size_t)f * frame_size * channels, n * channels);
     ranges[f] = st->final_range;
   }

@@ -127,3 +127,42 @@ def test_negative_length_skips_the_stream():
             gb, _ = b.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fs, dtype=np.float32)
         assert np.array_equal(ga, gb)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize('ch,fs', [(2, 960), (1, 480), (2, 120)])
+def test_int16_soft_clipping_vs_reference(ch, fs):
+    """opus_decode()'s int16 output on streams that overshoot full scale (opus_pcm_soft_clip, src/opus.c:39-166) against the reference's
+    int16 API.  Bound: 3 LSB (the float signal ahead
+    of the non-linearity is within 2e-5 of the reference; the emulated device code, 10x closer, stays within 1 LSB: test_emu_softclip.py)."""
+    import opus_b200
+    from test_oracle_softclip_vs_ref import loud_signal
+    L = util.load_ref('c')
+    n, nfr = 6, 10
+    pk = np.zeros((n, nfr, 1500), np.uint8)
+    sz = np.zeros((n, nfr), np.int32)
+    for s in range(n):
+        x = loud_signal(s * 7 + ch, nfr * fs, ch, s % 3)
+        p, z, _ = util.ref_encode(x, ch, fs, [64000, 24000, 96000][s % 3])
+        pk[s], sz[s] = p, z
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    out = np.zeros((n, nfr * fs, ch), np.int16)
+    rngs = np.zeros((n, nfr), np.uint32)
+    for t in range(nfr):
+        got, ns = dec.decode(np.ascontiguousarray(pk[:, t]), np.ascontiguousarray(sz[:, t]), frame_size=fs, dtype=np.int16)
+        assert (ns == fs).all()
+        out[:, t * fs:(t + 1) * fs] = got.reshape(n, fs, ch)
+        rngs[:, t] = dec.final_range()
+    dec.close()
+    clipped = 0
+    for s in range(n):
+        p, z = np.ascontiguousarray(pk[s]), np.ascontiguousarray(sz[s])
+        ref, rr = np.zeros((nfr * fs, ch), np.int16), np.zeros(nfr, np.uint32)
+        assert L.refh_decode_stream(48000, ch, fs, nfr, util._ptr(p), p.shape[1], util._ptr(z), util._ptr(ref), util._ptr(rr)) == 0
+        assert (rngs[s] == rr).all()
+        d = np.abs(out[s].astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= 3, (s, int(d.max()))
+        assert (d <= 1).mean() > 0.999
+        flt, fr = np.zeros((nfr * fs, ch), np.float32), np.zeros(nfr, np.uint32)
+        assert L.refh_decode_stream_float(48000, ch, fs, nfr, util._ptr(p), p.shape[1], util._ptr(z), util._ptr(flt), util._ptr(fr)) == 0
+        clipped += int((np.abs(util.to_int16(flt).astype(np.int32) - ref.astype(np.int32)) > 1).any())
+    assert clipped >= 2   # the test does exercise the non-linearity

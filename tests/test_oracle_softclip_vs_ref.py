@@ -55,6 +55,8 @@ def test_int16_decode_of_loud_streams(kind, ch, fs, br):
     x = loud_signal(kind * 10 + ch, nfr * fs, ch, kind)
     pk, sz, _ = util.ref_encode(x, ch, fs, br)
     sz = np.ascontiguousarray(sz, np.int32)
+    if kind == 1:
+        sz[5] = sz[6] = 0   # lost packets: concealed, and returned WITHOUT soft clipping (src/opus_decoder.c:764-778)
     T = len(sz)
     ref, rr = np.zeros((T * fs, ch), np.int16), np.zeros(T, np.uint32)
     assert L.refh_decode_stream(48000, ch, fs, T, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(ref), util._ptr(rr)) == 0
