@@ -315,6 +315,7 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
   }
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(SynthWS)));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_plc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlcWS)));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_plc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 8 CTAs of 26 KB per SM
 
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_synth, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the band decoder recurses over partitions (depth <= 5)

@@ -111,3 +111,18 @@ def test_emu_plc_long_and_odd_frame_sizes(fs_arg):
         assert ns[0] == want and fr[0] == rr[t]
         assert np.abs(pcm[0, :want * ch].reshape(want, ch) - ref[t * fs_arg:t * fs_arg + want]).max() < 1e-3
     d.close()
+
+
+@pytest.mark.parametrize('ch,fs48', [(2, 480), (1, 240)])
+def test_emu_dtx_frames_inside_a_packet(ch, fs48):
+    """code-2 packets whose second frame is 0 or 1 byte long: decoded frame + concealed frame in one packet (two launches of the call)"""
+    from test_oracle_plc_vs_ref import _dtx_packets
+    O = util.load_oracle()
+    nfr = 10
+    pk, sz = _dtx_packets(ch, fs48, nfr, 3 + ch)
+    fs = 2 * fs48
+    ref, rr = np.zeros((nfr * fs, ch), np.float32), np.zeros(nfr, np.uint32)
+    assert O.orc_decode_stream_float(ch, fs, nfr, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(ref), util._ptr(rr)) == 0
+    got, gr = emu_util.emu_decode_stream(pk, sz, ch, fs)
+    assert (gr == rr).all()
+    assert np.abs(got - ref).max() < 1e-3

@@ -166,3 +166,26 @@ def test_int16_soft_clipping_vs_reference(ch, fs):
         assert L.refh_decode_stream_float(48000, ch, fs, nfr, util._ptr(p), p.shape[1], util._ptr(z), util._ptr(flt), util._ptr(fr)) == 0
         clipped += int((np.abs(util.to_int16(flt).astype(np.int32) - ref.astype(np.int32)) > 1).any())
     assert clipped >= 2   # the test does exercise the non-linearity
+
+
+@pytest.mark.parametrize('ch,fs48', [(2, 480), (1, 240)])
+def test_dtx_frames_inside_a_packet(ch, fs48):
+    """code-2 packets whose second frame is 0 or 1 byte long: a decoded frame and a concealed frame in one packet"""
+    import opus_b200
+    from test_oracle_plc_vs_ref import _dtx_packets
+    n, nfr, fs = 5, 10, 2 * fs48
+    pks, szs = zip(*[_dtx_packets(ch, fs48, nfr, 3 + ch + s) for s in range(n)])
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    outs = np.zeros((n, nfr * fs, ch), np.float32)
+    rngs = np.zeros((n, nfr), np.uint32)
+    for t in range(nfr):
+        got, ns = dec.decode(np.ascontiguousarray(np.stack([p[t] for p in pks])), np.array([z[t] for z in szs], np.int32), frame_size=fs,
+                             dtype=np.float32)
+        assert (ns == fs).all(), ns
+        outs[:, t * fs:(t + 1) * fs] = got.reshape(n, fs, ch)
+        rngs[:, t] = dec.final_range()
+    dec.close()
+    for s in range(n):
+        ref, rr = _ref_decode(48000, ch, fs, pks[s], szs[s])
+        assert (rngs[s] == rr).all()
+        assert np.abs(outs[s] - ref).max() < PLC_TOL

@@ -95,3 +95,33 @@ def test_plc_long_and_odd_frame_sizes(fs_arg):
     got, gr = np.zeros((T * fs_arg, ch), np.float32), np.zeros(T, np.uint32)
     assert O.orc_decode_stream_float(ch, fs_arg, T, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(got), util._ptr(gr)) == 0
     assert (gr == rr).all() and np.array_equal(got, ref)
+
+
+def _dtx_packets(ch, fs48, nfr, seed):
+    """code-2 packets of two frames: a real frame followed by a 1-byte frame, which the decoder conceals (len <= 1: celt_decoder.c:1281)"""
+    x = util.sig_music(seed, 2 * nfr * fs48, ch).reshape(-1, ch)[:2 * nfr * fs48]
+    pk, sz, _ = util.ref_encode(x, ch, fs48, 64000)
+    out = np.zeros((nfr, 1500), np.uint8)
+    osz = np.zeros(nfr, np.int32)
+    for t in range(nfr):
+        a = bytes(pk[2 * t, 1:sz[2 * t]])
+        assert len(a) < 252
+        dtx = b'' if t % 3 == 2 else b'\x00'     # a 0-byte and a 1-byte second frame are both "lost"
+        p = bytes([int(pk[2 * t, 0]) | 2, len(a)]) + a + dtx
+        out[t, :len(p)] = np.frombuffer(p, np.uint8)
+        osz[t] = len(p)
+    return out, osz
+
+
+@pytest.mark.parametrize('ch,fs48', [(2, 480), (1, 240), (2, 120)])
+def test_dtx_frames_inside_a_packet(ch, fs48):
+    O, L = util.load_oracle(), util.load_ref('c')
+    nfr = 10
+    pk, sz = _dtx_packets(ch, fs48, nfr, 3 + ch)
+    fs = 2 * fs48
+    ref, rr = np.zeros((nfr * fs, ch), np.float32), np.zeros(nfr, np.uint32)
+    assert L.refh_decode_stream_float(48000, ch, fs, nfr, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(ref), util._ptr(rr)) == 0
+    got, gr = np.zeros((nfr * fs, ch), np.float32), np.zeros(nfr, np.uint32)
+    assert O.orc_decode_stream_float(ch, fs, nfr, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(got), util._ptr(gr)) == 0
+    assert (gr == rr).all() and np.array_equal(got, ref)
+    assert (rr == 0).all()   # the last frame of every packet is concealed: OPUS_GET_FINAL_RANGE reports 0
