@@ -11,6 +11,7 @@
  *   opus_decode_float(...)                         :566      opusb200_decode_float(...)
  *   opus_decoder_ctl(st, OPUS_RESET_STATE)         :586      opusb200_decoder_reset(dec)
  *   opus_decoder_ctl(st, OPUS_GET_FINAL_RANGE(&r)) :586      opusb200_decoder_get_final_range(dec, r[])
+ *   opus_decoder_ctl(st, OPUS_SET_GAIN(g)) etc.    :586      opusb200_decoder_ctl(dec, request, value) / _get_ctl(dec, request, v[])
  *   opus_decoder_destroy(st)                       :591      opusb200_decoder_destroy(dec)
  *
  * Below the API the frame path is the reference's celt_decode_with_ec() (celt/celt.h:172,
@@ -101,6 +102,13 @@ int opusb200_decoder_join(OpusB200Decoder *dec);
 
 /* OPUS_GET_FINAL_RANGE for every stream (host array of n_streams). */
 int opusb200_decoder_get_final_range(OpusB200Decoder *dec, uint32_t *final_range);
+/* opus_decoder_ctl() (include/opus.h:586, src/opus_decoder.c:1057-1215) for the integer requests that touch the decode path; the
+ * request numbers are include/opus_defines.h's.  Setters apply to every stream: 4034 OPUS_SET_GAIN (Q8 dB, -32768..32767),
+ * 4046 OPUS_SET_PHASE_INVERSION_DISABLED (0/1).  Getters fill one value per stream: 4033 OPUS_GET_PITCH, 4039
+ * OPUS_GET_LAST_PACKET_DURATION, 4045 OPUS_GET_GAIN, 4047 OPUS_GET_PHASE_INVERSION_DISABLED, 4029 OPUS_GET_SAMPLE_RATE.
+ * Anything else: OPUSB200_UNIMPLEMENTED. */
+int opusb200_decoder_ctl(OpusB200Decoder *dec, int request, int32_t value);
+int opusb200_decoder_get_ctl(OpusB200Decoder *dec, int request, int32_t *values);
 
 /* The CUDA stream the decoder enqueues on, as an opaque pointer (cudaStream_t). */
 void *opusb200_decoder_cuda_stream(OpusB200Decoder *dec);

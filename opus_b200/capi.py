@@ -21,7 +21,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 # every symbol include/opus_b200.h declares
 SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create', 'opusb200_decoder_destroy',
            'opusb200_decoder_reset', 'opusb200_decoder_n_streams', 'opusb200_decode', 'opusb200_decode_float',
-           'opusb200_decode_device', 'opusb200_decoder_sync', 'opusb200_decoder_set_pipelined', 'opusb200_decoder_join', 'opusb200_decoder_get_final_range',
+           'opusb200_decode_device', 'opusb200_decoder_sync', 'opusb200_decoder_set_pipelined', 'opusb200_decoder_join', 'opusb200_decoder_get_final_range', 'opusb200_decoder_ctl', 'opusb200_decoder_get_ctl',
            'opusb200_decoder_cuda_stream', 'opusb200_decoder_launch_count', 'opusb200_decoder_set_timing',
            'opusb200_decoder_get_timing', 'opusb200_decode_submit', 'opusb200_decode_wait', 'opusb200_celt_analysis_create', 'opusb200_encoder_create', 'opusb200_encoder_destroy',
            'opusb200_encoder_reset', 'opusb200_encoder_ctl_set', 'opusb200_encode_float', 'opusb200_encode_device',
@@ -87,6 +87,8 @@ def lib():
                                              ctypes.c_int, vp]
         L.opusb200_decoder_sync.argtypes = [vp]
         L.opusb200_decoder_get_final_range.argtypes = [vp, vp]
+        L.opusb200_decoder_ctl.argtypes = [vp, ctypes.c_int, ctypes.c_int32]
+        L.opusb200_decoder_get_ctl.argtypes = [vp, ctypes.c_int, vp]
         L.opusb200_decoder_cuda_stream.argtypes = [vp]
         L.opusb200_decoder_cuda_stream.restype = vp
         L.opusb200_decoder_launch_count.argtypes = [vp]

@@ -38,6 +38,7 @@ struct DecEntropyParams {
   int32_t *out_samples;   // [n_streams] or null: running per-stream result (samples/channel or error)
   int max_samples;        // per-channel capacity of each stream's pcm area, in OUTPUT-rate samples
   int downsample;         // 48000 / output rate (1, 2, 3, 4 or 6): celt_decoder.c:219-231
+  int disable_inv;        // OPUS_SET_PHASE_INVERSION_DISABLED (celt_decoder.c:1763-1771); mono output disables it by itself
 };
 
 // ---- exact integer helpers (celt/bands.c:68-91, celt/mathops.c:45-68, celt/rate.h:48-87) ----
@@ -287,8 +288,9 @@ OB_DEV void ent_finish(const DecEntropyParams &p, int stream, ObFrameSide *side,
   if (status < 0 || p.frame_index == 0) {
     st->last_status = rep;
     if (p.out_samples) p.out_samples[stream] = rep;
-  } else if (status > 0 && p.out_samples && p.out_samples[stream] >= 0) {
-    p.out_samples[stream] += rep;
+  } else if (status > 0) {
+    if (st->last_status >= 0) st->last_status += rep;   // OPUS_GET_LAST_PACKET_DURATION
+    if (p.out_samples && p.out_samples[stream] >= 0) p.out_samples[stream] += rep;
   }
 }
 
@@ -425,7 +427,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
 
   Emit e;
   e.leaves = sc->leaves; e.n_leaves = 0;
-  e.disable_inv = CC == 1;
+  e.disable_inv = CC == 1 || p.disable_inv;
   e.remaining_bits = 0;
   RangeDec &dec = e.ec;
   dec.init(pkt + foff, len);

@@ -30,6 +30,8 @@ struct DecSynthParams {
   int n_streams;
   int channels;
   int downsample;           // 48000 / output rate: every downsample-th de-emphasised sample is written (celt_decoder.c:300-405)
+  int apply_gain;           // OPUS_SET_GAIN != 0 (src/opus_decoder.c:686-700)
+  float gain;
 };
 
 struct SynthWS {  // per warp (= per output channel)
@@ -322,7 +324,9 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
     for (int j = j0; j < j1; j++) {
       float tmp = out[j] + 1e-30f + m;
       m = coef * tmp;
-      out[j] = tmp * (1 / 32768.f);
+      float v = tmp * (1 / 32768.f);
+      if (p.apply_gain) v = v * p.gain;
+      out[j] = v;
     }
     float mlast = shfl(m, (N - 1) / seg);  // lane holding the last sample
     if (lane == 0) st->deemph_mem[ch] = mlast;

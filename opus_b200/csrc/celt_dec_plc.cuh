@@ -27,6 +27,8 @@ struct DecPlcParams {
   int n_streams;
   int channels;
   int downsample;
+  int apply_gain;   // OPUS_SET_GAIN != 0: concealed audio is scaled like decoded audio
+  float gain;
 };
 
 constexpr int kPlcMaxPeriod = 1024, kPlcLagMax = 720, kPlcLagMin = 100, kPlcOrd = OB_PLC_LPC_ORDER;
@@ -354,7 +356,9 @@ OB_DEVNI void dec_plc_block(const DecPlcParams &p, int stream, unsigned char *sm
       for (int j = j0; j < j1; j++) {
         const float tmp = y[j] + 1e-30f + m;
         m = coef * tmp;
-        y[j] = tmp * (1 / 32768.f);
+        float v = tmp * (1 / 32768.f);
+        if (p.apply_gain) v = v * p.gain;
+        y[j] = v;
       }
       const float mlast = shfl(m, (N - 1) / seg);
       if (lane == 0) st->deemph_mem[c] = mlast;

@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
+#include <math.h>
 
 #include "../../include/opus_b200.h"
 #include "celt_dec_kernels.cuh"
@@ -172,6 +174,8 @@ extern "C" __global__ void ob_celt_dec_reset(ObDecBandState *bs, ObDecSynthState
 struct OpusB200Decoder {
   int device, channels, n;
   int downsample;   // 48000 / Fs of opusb200_decoder_create
+  int disable_inv, decode_gain;   // OPUS_SET_PHASE_INVERSION_DISABLED, OPUS_SET_GAIN (Q8 dB)
+  float gain;                     // 2^(decode_gain / (256 * 6.0206))
   int16_t *h_last_N; // host mirror of ObDecBandState.last_N (host-buffer API: sizes the frame-launch loop of a lost packet)
   cudaStream_t stream;
   ObDecBandState *bstate;
@@ -403,7 +407,7 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     DecEntropyParams ep;
     ep.packets = d_packets + (size_t)s0 * pkt_stride; ep.pkt_len = d_len + s0; ep.pkt_stride = pkt_stride; ep.n_streams = cn;
     ep.channels = d->channels; ep.frame_index = k; ep.state = d->bstate + s0; ep.side = d->side[par] + s0; ep.script = d->script[par] + s0;
-    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size; ep.downsample = d->downsample;
+    ep.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; ep.max_samples = frame_size; ep.downsample = d->downsample; ep.disable_inv = d->disable_inv;
     DecPvqParams pp;
     pp.side = d->side[par] + s0; pp.script = d->script[par] + s0; pp.state = d->bstate + s0; pp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; pp.n_streams = cn;
     if (timing) cudaEventRecord(d->ev[0], st);
@@ -427,11 +431,12 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     sp.side = d->side[par] + s0; sp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels; sp.downsample = d->downsample;
+    sp.apply_gain = d->decode_gain != 0; sp.gain = d->gain;
     ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), sb>>>(sp);
     {  // lost frames (len == 0, or a DTX frame inside a packet): concealed from the history ring; a no-op scan otherwise
       DecPlcParams lp;
       lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = pcm_stride; lp.pcm_is_int16 = pcm_is_int16;
-      lp.n_streams = cn; lp.channels = d->channels; lp.downsample = d->downsample;
+      lp.n_streams = cn; lp.channels = d->channels; lp.downsample = d->downsample; lp.apply_gain = sp.apply_gain; lp.gain = sp.gain;
       ob_celt_dec_plc<<<(cn + OB_PLC_CHUNK - 1) / OB_PLC_CHUNK, 64, sizeof(PlcWS), sb>>>(lp);
     }
     d->launches += 4;
@@ -597,6 +602,48 @@ int opusb200_decoder_get_final_range(OpusB200Decoder *d, uint32_t *final_range) 
   OB_CUDA(cudaMemcpy2DAsync(final_range, sizeof(uint32_t), &d->bstate[0].final_range, sizeof(ObDecBandState),
                             sizeof(uint32_t), d->n, cudaMemcpyDeviceToHost, d->stream));
   OB_CUDA(cudaStreamSynchronize(d->stream));
+  return OPUSB200_OK;
+}
+
+// opus_decoder_ctl() for the integer requests that touch the decode path (src/opus_decoder.c:1057-1215), applied to every stream.
+int opusb200_decoder_ctl(OpusB200Decoder *d, int request, int32_t value) {
+  if (!d) return OPUSB200_BAD_ARG;
+  switch (request) {
+    case 4034:  // OPUS_SET_GAIN: Q8 dB, pcm *= 2^(gain / (256 * 6.0206))  (celt_exp2 of the float build)
+      if (value < -32768 || value > 32767) return OPUSB200_BAD_ARG;
+      d->decode_gain = value;
+      d->gain = (float)exp(0.6931471805599453094 * (6.48814081e-4f * (float)value));
+      return OPUSB200_OK;
+    case 4046:  // OPUS_SET_PHASE_INVERSION_DISABLED
+      if (value < 0 || value > 1) return OPUSB200_BAD_ARG;
+      d->disable_inv = value;
+      return OPUSB200_OK;
+    default:
+      return OPUSB200_UNIMPLEMENTED;
+  }
+}
+
+// The getters, one value per stream: 4033 OPUS_GET_PITCH (the post-filter period of a CELT-only stream, 0 before its first packet),
+// 4039 OPUS_GET_LAST_PACKET_DURATION, 4045 OPUS_GET_GAIN, 4047 OPUS_GET_PHASE_INVERSION_DISABLED, 4029 OPUS_GET_SAMPLE_RATE.
+int opusb200_decoder_get_ctl(OpusB200Decoder *d, int request, int32_t *values) {
+  if (!d || !values) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->device));
+  if (request == 4045 || request == 4047 || request == 4029) {
+    const int32_t v = request == 4045 ? d->decode_gain : request == 4047 ? d->disable_inv : 48000 / d->downsample;
+    for (int s = 0; s < d->n; s++) values[s] = v;
+    return OPUSB200_OK;
+  }
+  if (request != 4033 && request != 4039) return OPUSB200_UNIMPLEMENTED;
+  OB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_in, 0));
+  if (d->last_b >= 0) OB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_a1[d->last_b], 0));   // the entropy kernel owns this state
+  const int32_t *src = request == 4033 ? &d->bstate[0].pf_period : &d->bstate[0].last_status;
+  OB_CUDA(cudaMemcpy2DAsync(values, sizeof(int32_t), src, sizeof(ObDecBandState), sizeof(int32_t), d->n, cudaMemcpyDeviceToHost, d->stream));
+  OB_CUDA(cudaStreamSynchronize(d->stream));
+  if (request == 4033) {   // a stream that has not decoded a packet reports 0 (src/opus_decoder.c:1143-1146)
+    std::vector<uint32_t> fl((size_t)d->n);
+    OB_CUDA(cudaMemcpy2D(fl.data(), sizeof(uint32_t), &d->bstate[0].plc_flags, sizeof(ObDecBandState), sizeof(uint32_t), d->n, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < d->n; s++) if (!(fl[s] & OB_PF_HAS_PACKET)) values[s] = 0;
+  }
   return OPUSB200_OK;
 }
 

@@ -94,6 +94,24 @@ class DecoderBatch:
             raise capi.OpusB200Error(r, 'opusb200_decoder_get_final_range')
         return fr
 
+    # -- opus_decoder_ctl(): integer requests of the decode path (include/opus_defines.h numbers) ----------------------------
+    OPUS_GET_SAMPLE_RATE, OPUS_GET_PITCH, OPUS_SET_GAIN, OPUS_GET_LAST_PACKET_DURATION, OPUS_GET_GAIN = 4029, 4033, 4034, 4039, 4045
+    OPUS_SET_PHASE_INVERSION_DISABLED, OPUS_GET_PHASE_INVERSION_DISABLED = 4046, 4047
+
+    def ctl(self, request, value):
+        """a setter, applied to every stream (OPUS_SET_GAIN, OPUS_SET_PHASE_INVERSION_DISABLED)"""
+        r = self._L.opusb200_decoder_ctl(self._h, int(request), int(value))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_ctl(%d)' % request)
+
+    def get_ctl(self, request):
+        """a getter: int32 [n_streams] (OPUS_GET_PITCH, OPUS_GET_LAST_PACKET_DURATION, OPUS_GET_GAIN, ...)"""
+        v = np.empty(self.n_streams, np.int32)
+        r = self._L.opusb200_decoder_get_ctl(self._h, int(request), _ptr(v))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_decoder_get_ctl(%d)' % request)
+        return v
+
     def set_timing(self, enable):
         self._L.opusb200_decoder_set_timing(self._h, 1 if enable else 0)
 

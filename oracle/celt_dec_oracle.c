@@ -1485,6 +1485,9 @@ typedef struct {
   int loss_duration, plc_duration, skip_plc, last_frame_type, prefilter_and_fold, last_pitch_index;
   float lpc[2][24];
   int last_frame_size48; /* Opus layer st->frame_size (48 kHz samples) of the last packet, for len <= 1 frames */
+  int disable_inv;       /* OPUS_SET_PHASE_INVERSION_DISABLED (celt_decoder.c:1763-1771) */
+  int decode_gain;       /* OPUS_SET_GAIN, Q8 dB (src/opus_decoder.c:686-700) */
+  int last_packet_duration;
 } OrcDecoder;
 static void decode_lost(OrcDecoder *st, int N, int LM);        /* celt_plc.inc */
 static void prefilter_and_fold(OrcDecoder *st, int N);
@@ -1673,7 +1676,7 @@ int orc_celt_decode_frame(OrcDecoder *st, const uint8_t *data, int len, float *p
   do memmove(decode_mem[c], decode_mem[c] + N, (DEC_BUF - N + OVERLAP) * sizeof(float)); while (++c < CC);
   decode_all_bands(start, end, X, C == 2 ? X + N : NULL, collapse_masks, pulses, shortBlocks, spread, dual_stereo,
                    intensity, tf_res, len * (8 << BITRES) - anti_collapse_rsv, balance, &dec, LM, codedBands, &st->rng,
-                   CC == 1 /* disable_inv = (channels==1), celt_decoder.c:253 */);
+                   CC == 1 || st->disable_inv /* disable_inv = (channels==1) at init, celt_decoder.c:253; OPUS_SET_PHASE_INVERSION_DISABLED */);
   if (anti_collapse_rsv > 0) anti_collapse_on = rd_bits(&dec, 1);
   decode_energy_finalise(start, end, oldBandE, fine_quant, fine_priority, len * 8 - rd_tell(&dec), &dec, C);
   if (anti_collapse_on)
@@ -1839,6 +1842,24 @@ int orc_packet_parse(const uint8_t *data, int len, int *toc_out, int offsets[48]
   return count;
 }
 
+/* OPUS_SET_GAIN: pcm *= 2^(gain/(256*6.0206)) (src/opus_decoder.c:686-700, float build) */
+static void apply_decode_gain(const OrcDecoder *st, float *pcm, int n) {
+  if (st->decode_gain) {
+    const float gain = (float)exp(0.6931471805599453094 * (6.48814081e-4f * st->decode_gain));
+    int i;
+    for (i = 0; i < n * st->channels; i++) pcm[i] = pcm[i] * gain;
+  }
+}
+/* the integer ctls of the decode path: 4034 OPUS_SET_GAIN, 4046 OPUS_SET_PHASE_INVERSION_DISABLED */
+int orc_decoder_ctl(OrcDecoder *st, int request, int value) {
+  if (request == 4034) { if (value < -32768 || value > 32767) return -1; st->decode_gain = value; return 0; }
+  if (request == 4046) { if (value < 0 || value > 1) return -1; st->disable_inv = value; return 0; }
+  return -5;
+}
+/* OPUS_GET_PITCH for a CELT-only stream (src/opus_decoder.c:1117-1133): the post-filter period, 0 before the first packet */
+int orc_decoder_get_pitch(const OrcDecoder *st) { return st->prev_mode_celt ? st->postfilter_period : 0; }
+int orc_decoder_get_last_packet_duration(const OrcDecoder *st) { return st->last_packet_duration; }
+
 /* opus_decode_frame() with data == NULL (src/opus_decoder.c:316-365, 598-613, 701-712): conceal `frame_size` output-rate samples */
 static int decode_frame_lost(OrcDecoder *st, float *pcm, int frame_size) {
   const int ds = st->downsample > 1 ? st->downsample : 1, F20 = 960 / ds, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
@@ -1865,6 +1886,7 @@ static int decode_frame_lost(OrcDecoder *st, float *pcm, int frame_size) {
   }
   ret = orc_celt_decode_frame(st, NULL, 0, pcm, audiosize * ds);
   st->final_range = 0;
+  if (ret > 0) apply_decode_gain(st, pcm, ret);
   return ret < 0 ? ret : audiosize;
 }
 
@@ -1883,6 +1905,7 @@ int orc_opus_decode_float(OrcDecoder *st, const uint8_t *data, int len, float *p
       if (ret < 0) return ret;
       pcm_count += ret;
     } while (pcm_count < max_frame_size);
+    st->last_packet_duration = pcm_count;
     return pcm_count;
   }
   count = orc_packet_parse(data, len, &toc, offsets, sizes);
@@ -1904,10 +1927,12 @@ int orc_opus_decode_float(OrcDecoder *st, const uint8_t *data, int len, float *p
       ret = orc_celt_decode_frame(st, data + offsets[i], sizes[i], pcm + nb * st->channels, framesize);
       st->final_range = st->rng;
       st->prev_mode_celt = 1;
+      if (ret > 0) apply_decode_gain(st, pcm + nb * st->channels, ret);
     }
     if (ret < 0) return ret;
     nb += ret;
   }
+  st->last_packet_duration = nb;
   return nb;
 }
 
@@ -1991,6 +2016,25 @@ int orc_decode_stream_int16(int Fs, int channels, int frame_size, int nframes, c
     ranges[f] = st->final_range;
   }
   free(st); free(tmp);
+  return 0;
+}
+
+/* as orc_decode_stream_float_fs, with set-ctls (request, value pairs) applied first and the pitch / last-packet-duration getters read back */
+int orc_decode_stream_float_ctl(int Fs, int channels, int frame_size, int nframes, const uint8_t *pkts, int stride, const int *sizes, float *pcm,
+                                uint32_t *ranges, int nctl, const int *ctls, int *pitch, int *duration) {
+  OrcDecoder *st = (OrcDecoder *)malloc(sizeof(OrcDecoder));
+  int f, i;
+  orc_decoder_init(st, channels);
+  if (orc_decoder_set_fs(st, Fs)) { free(st); return -1; }
+  for (i = 0; i < nctl; i++) if (orc_decoder_ctl(st, ctls[2 * i], ctls[2 * i + 1])) { free(st); return -1; }
+  for (f = 0; f < nframes; f++) {
+    int n = orc_opus_decode_float(st, sizes[f] ? pkts + (size_t)f * stride : NULL, sizes[f], pcm + (size_t)f * frame_size * channels, frame_size);
+    if (n < 0) { free(st); return n; }
+    ranges[f] = st->final_range;
+    pitch[f] = orc_decoder_get_pitch(st);
+    duration[f] = orc_decoder_get_last_packet_duration(st);
+  }
+  free(st);
   return 0;
 }
 

@@ -99,6 +99,26 @@ int refh_decode_stream_float(int Fs, int channels, int frame_size, int nframes, 
   return 0;
 }
 
+/* Float decode with integer "set" ctls applied after create (request, value pairs), reporting OPUS_GET_PITCH and
+ * OPUS_GET_LAST_PACKET_DURATION after every packet. */
+int refh_decode_stream_float_ctl(int Fs, int channels, int frame_size, int nframes, const unsigned char *pkts, int stride, const int *sizes,
+                                 float *pcm, unsigned int *ranges, int nctl, const int *ctls, int *pitch, int *duration) {
+  int err = 0, f, i;
+  OpusDecoder *dec = opus_decoder_create(Fs, channels, &err);
+  if (!dec) return err;
+  for (i = 0; i < nctl; i++)
+    if (opus_decoder_ctl(dec, ctls[2 * i], ctls[2 * i + 1]) != OPUS_OK) { opus_decoder_destroy(dec); return OPUS_BAD_ARG; }
+  for (f = 0; f < nframes; f++) {
+    int n = opus_decode_float(dec, sizes[f] ? pkts + (size_t)f * stride : NULL, sizes[f], pcm + (size_t)f * frame_size * channels, frame_size, 0);
+    if (n < 0) { opus_decoder_destroy(dec); return n; }
+    opus_decoder_ctl(dec, OPUS_GET_FINAL_RANGE(&ranges[f]));
+    opus_decoder_ctl(dec, OPUS_GET_PITCH(&pitch[f]));
+    opus_decoder_ctl(dec, OPUS_GET_LAST_PACKET_DURATION(&duration[f]));
+  }
+  opus_decoder_destroy(dec);
+  return 0;
+}
+
 /* Throughput harness for the CPU baseline (bench.py): `n` decoders are created once, then every
  * stream decodes its T packets `reps` times (state simply continues, as in the GPU bench).
  * pkts: [n][T][stride].  Returns the number of frames decoded, or a negative opus error. */

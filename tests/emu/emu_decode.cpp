@@ -6,11 +6,13 @@
 #include "../../opus_b200/csrc/celt_dec_plc.cuh"
 
 #include <stdio.h>
+#include <math.h>
 
 using namespace ob;
 
 struct EmuDecoder {
-  int n, channels, downsample, frame_size;
+  int n, channels, downsample, frame_size, disable_inv, decode_gain;
+  float gain;
   std::vector<ObDecBandState> bstate;
   std::vector<ObDecSynthState> sstate;
   std::vector<ObFrameSide> side;
@@ -49,6 +51,7 @@ void *emu_decoder_create(int n_streams, int channels) {
   d->channels = channels;
   d->downsample = 1;
   d->frame_size = 5760;
+  d->disable_inv = 0; d->decode_gain = 0; d->gain = 1.f;
   d->bstate.resize(n_streams);
   d->sstate.resize(n_streams);
   d->side.resize(n_streams);
@@ -61,6 +64,18 @@ void *emu_decoder_create(int n_streams, int channels) {
   return d;
 }
 void emu_decoder_set_fs(void *h, int Fs) { ((EmuDecoder *)h)->downsample = 48000 / Fs; }
+// OPUS_SET_GAIN (4034) / OPUS_SET_PHASE_INVERSION_DISABLED (4046), as opusb200_decoder_ctl
+void emu_decoder_ctl(void *h, int request, int value) {
+  EmuDecoder *d = (EmuDecoder *)h;
+  if (request == 4034) { d->decode_gain = value; d->gain = (float)exp(0.6931471805599453094 * (6.48814081e-4f * (float)value)); }
+  if (request == 4046) d->disable_inv = value;
+}
+int emu_decoder_get_ctl(void *h, int stream, int request) {
+  const ObDecBandState &b = ((EmuDecoder *)h)->bstate[stream];
+  if (request == 4033) return (b.plc_flags & OB_PF_HAS_PACKET) ? b.pf_period : 0;
+  if (request == 4039) return b.last_status;
+  return -1;
+}
 void emu_decoder_set_frame_size(void *h, int fs) { ((EmuDecoder *)h)->frame_size = fs; }  // opus_decode's frame_size (output-rate samples)
 // test hook: overwrite a stream's synthesis history with the oracle's (decode_mem[0 .. 2048+120), de-emphasis memory), so that a
 // concealed frame can be compared without the last-bit differences of the frames before it
@@ -80,7 +95,7 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
     DecEntropyParams ep;
     ep.packets = packets; ep.pkt_len = lens; ep.pkt_stride = stride; ep.n_streams = d->n; ep.channels = d->channels;
     ep.frame_index = k; ep.state = d->bstate.data(); ep.side = d->side.data(); ep.script = d->script.data();
-    ep.out_samples = out_samples; ep.max_samples = d->frame_size; ep.downsample = d->downsample;
+    ep.out_samples = out_samples; ep.max_samples = d->frame_size; ep.disable_inv = d->disable_inv; ep.downsample = d->downsample;
     emu_launch(entropy_entry, &ep, (d->n + 31) / 32, 32, 0);
     DecPvqParams pp;
     pp.side = d->side.data(); pp.script = d->script.data(); pp.state = d->bstate.data(); pp.X = d->X.data(); pp.n_streams = d->n;
@@ -98,12 +113,12 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
       DecSynthParams sp;
       sp.side = d->side.data() + s; sp.X = d->X.data() + (size_t)s * 2 * OB_MAXN; sp.state = d->sstate.data() + s;
       sp.pcm = pcm_is_int16 ? (void *)((int16_t *)pcm + (size_t)s * pcm_stride) : (void *)((float *)pcm + (size_t)s * pcm_stride);
-      sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels; sp.downsample = d->downsample;
+      sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels; sp.downsample = d->downsample; sp.apply_gain = d->decode_gain != 0; sp.gain = d->gain;
       const int lost_here = OB_PLC_TYPE(d->side[s].plc) >= OB_PLC_PITCH;   // (emulator only: skip the launch that would return at once)
       if (!lost_here) emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
       DecPlcParams lp;
       lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = 0; lp.pcm_is_int16 = pcm_is_int16; lp.n_streams = 1;
-      lp.channels = d->channels; lp.downsample = d->downsample;
+      lp.channels = d->channels; lp.downsample = d->downsample; lp.apply_gain = sp.apply_gain; lp.gain = sp.gain;
       if (lost_here) emu_launch(plc_entry, &lp, 1, 64, sizeof(PlcWS));
     }
   }

@@ -325,3 +325,40 @@ def test_output_rates_below_48k(Fs, ch, fs48):
         assert (rngs[s] == rr).all(), s
         _check(outs[s], ref)
         assert np.abs(out16[s].astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
+
+
+@pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+@pytest.mark.parametrize('ctls', [[(4034, 1536)], [(4046, 1)], [(4034, -2000), (4046, 1)]])
+def test_decoder_ctls_vs_reference(ctls):
+    """opusb200_decoder_ctl / _get_ctl: OPUS_SET_GAIN, OPUS_SET_PHASE_INVERSION_DISABLED, OPUS_GET_PITCH, OPUS_GET_LAST_PACKET_DURATION
+    (src/opus_decoder.c:1057-1215) against the reference decoder given the same ctls; no packet is lost here, so the +-1 LSB bar holds
+    (scaled by the gain)."""
+    import opus_b200
+    from test_oracle_decoder_ctl_vs_ref import run_ctl
+    ch, fs, n, nfr = 2, 960, 6, 8
+    rates = [24000, 16000, 32000, 64000, 20000, 48000]
+    pks, szs = [], []
+    for s in range(n):
+        x = (util.sig_harmonic if s % 2 else util.sig_music)(40 + s, nfr * fs, ch).reshape(-1, ch)[:nfr * fs]
+        p, z, _ = util.ref_encode(x, ch, fs, rates[s])
+        pks.append(p); szs.append(np.ascontiguousarray(z, np.int32))
+    refs = [run_ctl('ref', ch, fs, pks[s], szs[s], ctls) for s in range(n)]
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    for req, val in ctls:
+        dec.ctl(req, val)
+    g = 2.0 ** (dict(ctls).get(4034, 0) / (256 * 6.0206))
+    assert (dec.get_ctl(dec.OPUS_GET_GAIN) == dict(ctls).get(4034, 0)).all()
+    assert (dec.get_ctl(dec.OPUS_GET_PHASE_INVERSION_DISABLED) == dict(ctls).get(4046, 0)).all()
+    assert (dec.get_ctl(dec.OPUS_GET_SAMPLE_RATE) == 48000).all()
+    assert (dec.get_ctl(dec.OPUS_GET_PITCH) == 0).all()
+    for t in range(nfr):
+        got, ns = dec.decode(np.stack([p[t] for p in pks]), np.array([z[t] for z in szs], np.int32), frame_size=fs, dtype=np.float32)
+        assert (ns == fs).all()
+        assert (dec.final_range() == np.array([r[1][t] for r in refs], np.uint32)).all()
+        assert (dec.get_ctl(dec.OPUS_GET_PITCH) == np.array([r[2][t] for r in refs])).all()
+        assert (dec.get_ctl(dec.OPUS_GET_LAST_PACKET_DURATION) == np.array([r[3][t] for r in refs])).all()
+        for s in range(n):
+            assert np.abs(got[s].reshape(fs, ch) - refs[s][0][t * fs:(t + 1) * fs]).max() < FLOAT_TOL * max(1.0, g)
+    dec.close()
+    with pytest.raises(opus_b200.OpusB200Error):
+        opus_b200.DecoderBatch(1, channels=1).ctl(4034, 40000)
