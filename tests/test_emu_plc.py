@@ -126,3 +126,32 @@ def test_emu_dtx_frames_inside_a_packet(ch, fs48):
     got, gr = emu_util.emu_decode_stream(pk, sz, ch, fs)
     assert (gr == rr).all()
     assert np.abs(got - ref).max() < 1e-3
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_emu_plc_randomised(seed):
+    """seeded draws over channels, frame size, bit rate, output rate, int16/float output and the loss pattern"""
+    rng = np.random.default_rng(500 + seed)
+    ch = int(rng.integers(1, 3)); fs48 = int(rng.choice([120, 240, 480, 960])); br = int(rng.choice([16000, 32000, 64000, 128000]))
+    Fs = int(rng.choice([48000, 48000, 24000, 16000, 12000, 8000])); nfr = 14
+    lost = sorted(set(int(v) for v in rng.integers(1, nfr, size=int(rng.integers(2, 7)))))
+    sig = list(util.SIGNALS)[seed % 3]
+    if seed % 2 == 0:
+        _run(Fs, ch, fs48, br, lost, sig, nfr=nfr, cx=int(rng.integers(0, 11)))
+        return
+    # int16 output against the reference's int16 API (soft clipping is the identity at these levels; 1e-3 of full scale = 33 LSB)
+    L = util.load_ref('c')
+    x = util.SIGNALS[sig](seed, nfr * fs48, ch).reshape(-1, ch)[:nfr * fs48]
+    pk, sz, _ = util.ref_encode(x, ch, fs48, br)
+    sz = np.ascontiguousarray(sz, np.int32)
+    for t in lost:
+        sz[t] = 0
+    fsd = fs48 * Fs // 48000
+    ref, rr = np.zeros((nfr * fsd, ch), np.int16), np.zeros(nfr, np.uint32)
+    assert L.refh_decode_stream(Fs, ch, fsd, nfr, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(ref), util._ptr(rr)) == 0
+    d = emu_util.EmuDecoder(1, ch, Fs)
+    for t in range(nfr):
+        pcm, ns, fr = d.decode(pk[t:t + 1], sz[t:t + 1], int16=True, frame_size=fsd)
+        assert ns[0] == fsd and fr[0] == rr[t]
+        assert np.abs(pcm[0, :fsd * ch].reshape(fsd, ch).astype(np.int32) - ref[t * fsd:(t + 1) * fsd].astype(np.int32)).max() <= 33
+    d.close()
