@@ -113,7 +113,7 @@ typedef struct {
   /* oldLogE / oldLogE2 as they were BEFORE this frame's state update (written only when anti_collapse_on): the entropy kernel
      owns the energy state, so that the next frame's parsing does not wait for this frame's vector stage */
   float prevLogE[2][2 * OB_NBANDS];
-} ObFrameSide; /* 680 bytes */
+} ObFrameSide; /* 664 bytes */
 
 /* Per-stream script buffer written by the entropy kernel, read by the PVQ kernel. */
 typedef struct {
