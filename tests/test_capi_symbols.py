@@ -48,3 +48,21 @@ def test_product_does_not_touch_oracle():
                 if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
                     txt = open(os.path.join(root, f), errors='ignore').read()
                     assert 'liboracle' not in txt and 'oracle/' not in txt.replace('the reference oracle', ''), os.path.join(root, f)
+
+
+def test_header_is_plain_c_and_links(libpath, tmp_path):
+    """include/opus_b200.h must be usable from C (the reference is C): compile a C89-pedantic translation unit that takes the address of
+    every declared entry point, and link it against the library (no CUDA headers, no C++)."""
+    import subprocess
+    hdr = open(os.path.join(util.ROOT, 'include', 'opus_b200.h')).read()
+    names = sorted(set(re.findall(r'\b(opusb200_\w+)\s*\(', re.sub(r'/\*.*?\*/', '', hdr, flags=re.S))))
+    src = tmp_path / 'use_header.c'
+    src.write_text('#include "opus_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n  fn f[] = {\n' +
+                   ''.join('    (fn)%s,\n' % n for n in names) +
+                   '  };\n  printf("%d entry points, %s\\n", (int)(sizeof f / sizeof f[0]), opusb200_version());\n  return f[0] == 0;\n}\n')
+    exe = tmp_path / 'use_header'
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-Wno-pedantic', '-I', os.path.join(util.ROOT, 'include'),
+                        str(src), '-o', str(exe), libpath, '-Wl,-rpath,' + os.path.dirname(libpath)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and 'entry points' in r.stdout, (r.stdout, r.stderr)
