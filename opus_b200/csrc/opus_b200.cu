@@ -521,18 +521,23 @@ static int decode_submit(OpusB200Decoder *d, const unsigned char *packets, int p
   // How many frame launches does the call need?  The host walks the packet framing exactly as the entropy kernel will (the same
   // function), so it also knows each stream's frame size when a later packet is lost.
   int maxf = 1;
+  const int ds = d->downsample;
   for (int s = 0; s < d->n; s++) {
-    const unsigned char *pk = packets + (size_t)s * pkt_stride;
-    if (len[s] > 0) {
-      int off = 0, fl = 0;
-      const int c = ob::locate_frame(pk, len[s], 0, &off, &fl);
-      const int N = OB_SHORT_N << ((pk[0] >> 3) & 3);
-      if (c > 0 && (pk[0] & 0x80) && c * (N / d->downsample) <= frame_size) {   // what the entropy kernel accepts
+    const int l = len[s];
+    if (l > 0) {
+      const unsigned char *pk = packets + (size_t)s * pkt_stride;
+      const int toc = pk[0];
+      if (!(toc & 0x80)) continue;   // not CELT-only: the kernel rejects it
+      const int N = OB_SHORT_N << ((toc >> 3) & 3);
+      int c;
+      if ((toc & 3) == 0) c = l - 1 <= OB_MAX_PACKET ? 1 : -4;   // one frame: locate_frame's code-0 case, without the call
+      else { int off = 0, fl = 0; c = ob::locate_frame(pk, l, 0, &off, &fl); }
+      if (c > 0 && c * (N / ds) <= frame_size) {   // what the entropy kernel accepts
         d->h_last_N[s] = (int16_t)N;
         if (c > maxf) maxf = c;
       }
-    } else if (len[s] == 0) {  // lost: concealed over the whole frame_size, possibly in several frames
-      const int c = host_plc_frames(frame_size, d->downsample, d->h_last_N[s]);
+    } else if (l == 0) {  // lost: concealed over the whole frame_size, possibly in several frames
+      const int c = host_plc_frames(frame_size, ds, d->h_last_N[s]);
       if (c > maxf) maxf = c;
     }
   }
