@@ -26,6 +26,7 @@ struct EncFrameParams {
   unsigned char *packets;       // [n][pkt_stride]
   int32_t *nbytes;              // [n] bytes produced, or a negative error
   int first_stream = 0;   // this launch covers streams [first_stream, n_streams)
+  int end = OB_NBANDS;    // CELT_SET_END_BAND (celt/celt_encoder.c:3046-3053): 13 NB, 17 WB, 19 SWB, 21 FB
   int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf, vbr, constrained_vbr,
       loss_rate;
 };
@@ -218,8 +219,7 @@ OB_DEV float enc_median3(const float *x) {
 struct EncDyn { float maxDepth; int32_t tot_boost; };
 OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *bandLogE2, const float *oldBandE, int C, int *offsets, int lsb_depth, int isTransient, int LM,
                              int effectiveBytes, float tone_freq, float toneishness, int vbr, int constrained_vbr, int *importance,
-                             int *spread_weight) {
-  const int end = OB_NBANDS;
+                             int *spread_weight, int end) {
   float follower[2 * OB_NBANDS], noise_floor[OB_NBANDS], bandLogE3[OB_NBANDS];
   int32_t tot_boost = 0;
 #pragma unroll 1
@@ -353,8 +353,8 @@ OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *bandLogE2, cons
 
 // ---- quant_coarse_energy_impl (celt/quant_bands.c:156-254) ----
 OB_DEVNI int enc_coarse_impl(RangeEnc &enc, const float *eBands, float *oldEBands, int32_t budget, int32_t tell, const unsigned char *prob_model,
-                             float *error, int C, int LM, int intra, float max_decay) {
-  const int start = 0, end = OB_NBANDS;
+                             float *error, int C, int LM, int intra, float max_decay, int end) {
+  const int start = 0;
   int badness = 0;
   float prev[2] = {0.f, 0.f}, coef, beta;
   if (tell + 3 <= budget) re_bit_logp(enc, intra, 3);
@@ -411,8 +411,7 @@ OB_DEV float enc_l1(const float *tmp, int N, int LM, float bias) {
   return L1 + (LM * bias) * L1;
 }
 OB_DEVNI int enc_tf_analysis(int isTransient, int *tf_res, int lambda, const float *X, int N0, int LM, float tf_estimate, int tf_chan,
-                             const int *importance, float *tmp, float *tmp_1) {
-  const int len = OB_NBANDS;
+                             const int *importance, float *tmp, float *tmp_1, int len) {
   int metric[OB_NBANDS];
   unsigned path0 = 0, path1 = 0;   // one bit per band
   const float bias = .04f * enc_fmax(-.25f, .5f - tf_estimate);
@@ -477,8 +476,8 @@ OB_DEVNI int enc_tf_analysis(int isTransient, int *tf_res, int lambda, const flo
 }
 
 // ---- spreading_decision (celt/bands.c:470-562) ----
-OB_DEVNI int enc_spreading_decision(const float *X, ObEncState &st, int update_hf, int C, int M, const int *spread_weight) {
-  const int end = OB_NBANDS, N0 = M * OB_SHORT_N;
+OB_DEVNI int enc_spreading_decision(const float *X, ObEncState &st, int update_hf, int C, int M, const int *spread_weight, int end) {
+  const int N0 = M * OB_SHORT_N;
   int sum = 0, nbBands = 0, hf_sum = 0;
   if (M * (ob_ebands[end] - ob_ebands[end - 1]) <= 8) return 0;
 #pragma unroll 1
@@ -552,8 +551,8 @@ OB_DEVNI int32_t enc_compute_vbr(int32_t base_target, int LM, int32_t bitrate, i
 struct EncAlloc { int codedBands, intensity, dual_stereo; int32_t balance; };
 OB_DEVNI EncAlloc enc_compute_allocation(RangeEnc &enc, const int *offsets, const int *cap, int alloc_trim, int intensity, int dual_stereo,
                                           int32_t total, int *bits, int *ebits, int *fine_priority, int C, int LM, int prev,
-                                          int signalBandwidth) {
-  const int start = 0, end = OB_NBANDS, len = OB_NBANDS, nbAllocVectors = 11, alloc_floor = C << OB_BITRES, logM = LM << OB_BITRES,
+                                          int signalBandwidth, int end) {
+  const int start = 0, len = OB_NBANDS, nbAllocVectors = 11, alloc_floor = C << OB_BITRES, logM = LM << OB_BITRES,
             stereo = C > 1;
   int bits1[OB_NBANDS], bits2[OB_NBANDS], thresh[OB_NBANDS], trim_offset[OB_NBANDS];
   int skip_start = start, skip_rsv, intensity_rsv = 0, dual_stereo_rsv = 0, lo, hi, j, codedBands;
@@ -1133,7 +1132,7 @@ namespace ob {
 // folding / save buffers triple the thread's local memory)
 template <bool RDO>
 OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
-  const int C = p.C, LM = p.LM, M = 1 << LM, N = M * OB_SHORT_N, end = OB_NBANDS, start = 0;
+  const int C = p.C, LM = p.LM, M = 1 << LM, N = M * OB_SHORT_N, end = p.end, start = 0;
   ObEncState &st = p.state[stream];
   const ObEncFrameInfo fi = p.info[stream];
   float *Xg = p.X + (size_t)stream * C * N;
@@ -1228,11 +1227,11 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] += .5f * LM;
   if (LM > 0 && re_tell(enc) + 3 <= total_bits) re_bit_logp(enc, isTransient, 3);
   const EncDyn dyn = enc_dynalloc(bandLogE, have_bl2 ? bl2 : bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
-                                  p.constrained_vbr, importance, spread_weight);
+                                  p.constrained_vbr, importance, spread_weight, end);
   int tf_select = 0;
   if (effectiveBytes >= 15 * C && p.complexity >= 2 && toneishness < .98f) {   // enable_tf_analysis
     const int lambda = OB_IMAX(80, 20480 / effectiveBytes + 2);
-    tf_select = enc_tf_analysis(isTransient, tf_res, lambda, Xg, N, LM, tf_estimate, tf_chan, importance, bx, by);
+    tf_select = enc_tf_analysis(isTransient, tf_res, lambda, Xg, N, LM, tf_estimate, tf_chan, importance, bx, by, end);
   } else {
 #pragma unroll 1
     for (int i = 0; i < end; i++) tf_res[i] = isTransient;
@@ -1265,7 +1264,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
       const RangeEnc start_state = enc;
 #pragma unroll 1
       for (int i = 0; i < C * OB_NBANDS; i++) old_intra[i] = st.oldBandE[i];
-      const int badness1 = enc_coarse_impl(enc, bandLogE, old_intra, total_bits, t0, ob_e_prob + (LM * 2 + 1) * 42, err_intra, C, LM, 1, max_decay);
+      const int badness1 = enc_coarse_impl(enc, bandLogE, old_intra, total_bits, t0, ob_e_prob + (LM * 2 + 1) * 42, err_intra, C, LM, 1, max_decay, end);
       if (!intra) {
         unsigned char saved[160];
         const int32_t tell_intra = re_tell_frac(enc);
@@ -1275,7 +1274,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
 #pragma unroll 1
         for (uint32_t i = 0; i < nb1 - nb0 && i < 160; i++) saved[i] = enc.buf[nb0 + i];
         enc = start_state;
-        const int badness2 = enc_coarse_impl(enc, bandLogE, st.oldBandE, total_bits, t0, ob_e_prob + (LM * 2 + 0) * 42, error, C, LM, 0, max_decay);
+        const int badness2 = enc_coarse_impl(enc, bandLogE, st.oldBandE, total_bits, t0, ob_e_prob + (LM * 2 + 0) * 42, error, C, LM, 0, max_decay, end);
         if (two_pass && (badness1 < badness2 || (badness1 == badness2 && ((int32_t)re_tell_frac(enc)) + intra_bias > tell_intra))) {
           enc = intra_state;
 #pragma unroll 1
@@ -1289,7 +1288,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
         for (int i = 0; i < C * OB_NBANDS; i++) { st.oldBandE[i] = old_intra[i]; error[i] = err_intra[i]; }
       }
     } else {
-      enc_coarse_impl(enc, bandLogE, st.oldBandE, total_bits, t0, ob_e_prob + (LM * 2 + 0) * 42, error, C, LM, 0, max_decay);
+      enc_coarse_impl(enc, bandLogE, st.oldBandE, total_bits, t0, ob_e_prob + (LM * 2 + 0) * 42, error, C, LM, 0, max_decay, end);
     }
     if (intra) st.delayedIntra = new_distortion;
     else st.delayedIntra = (pc * pc) * st.delayedIntra + new_distortion;
@@ -1317,7 +1316,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   }
   if (re_tell(enc) + 4 <= total_bits) {
     if (shortBlocks || p.complexity < 3 || nbAvailableBytes < 10 * C) st.spread_decision = p.complexity == 0 ? 0 : 2;   // SPREAD_NONE : SPREAD_NORMAL
-    else st.spread_decision = enc_spreading_decision(Xg, st, pf_on && !shortBlocks, C, M, spread_weight);
+    else st.spread_decision = enc_spreading_decision(Xg, st, pf_on && !shortBlocks, C, M, spread_weight, end);
     re_icdf(enc, st.spread_decision, ob_spread_icdf, 5);
   } else st.spread_decision = 2;
 #pragma unroll 1
@@ -1443,7 +1442,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;
   bits -= anti_collapse_rsv;
   const EncAlloc al = enc_compute_allocation(enc, offsets, cap, alloc_trim, st.intensity, dual_stereo, bits, pulses, fine_quant, fine_priority, C, LM,
-                                             st.lastCodedBands, end - 1);
+                                             st.lastCodedBands, end - 1, end);
   st.intensity = al.intensity;
   dual_stereo = al.dual_stereo;
   const int codedBands = al.codedBands;
@@ -1472,7 +1471,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     if constexpr (RDO) {
       RdoScratch w;
       const int r = rdo_all_bands(enc, Xg, bandE, pulses, tf_res, shortBlocks, st.spread_decision, st.intensity,
-                                  nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, al.balance, LM, codedBands, st.rng, p.disable_inv, bx, by, tmp, w);
+                                  nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, al.balance, LM, codedBands, st.rng, p.disable_inv, bx, by, tmp, w, end);
       if (r) status = r;
     }
   } else {
@@ -1549,6 +1548,12 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   } else {
 #pragma unroll 1
     for (int i = 0; i < C * OB_NBANDS; i++) st.oldLogE[i] = enc_fmin(st.oldLogE[i], st.oldBandE[i]);
+  }
+  if (end < OB_NBANDS) {  // in case the end band were to change (celt/celt_encoder.c:2795-2807)
+#pragma unroll 1
+    for (int c = 0; c < C; c++)
+#pragma unroll 1
+      for (int i = end; i < OB_NBANDS; i++) { st.oldBandE[c * OB_NBANDS + i] = 0.f; st.oldLogE[c * OB_NBANDS + i] = st.oldLogE2[c * OB_NBANDS + i] = -28.f; }
   }
   if (isTransient || transient_got_disabled) st.consec_transient++;
   else st.consec_transient = 0;

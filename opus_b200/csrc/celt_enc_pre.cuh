@@ -466,8 +466,8 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
 }
 
 // patch_transient_decision (celt/celt_encoder.c:472-508), one thread; newE / oldE are [C][21]
-OB_DEVNI int enc_patch_transient(const float *newE, const float *oldE, int C) {
-  const int start = 0, end = OB_NBANDS;
+OB_DEVNI int enc_patch_transient(const float *newE, const float *oldE, int C, int end) {
+  const int start = 0;
   float spread_old[OB_NBANDS], mean_diff = 0.f;
   if (C == 1) {
     spread_old[start] = oldE[start];

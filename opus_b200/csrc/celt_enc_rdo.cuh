@@ -355,8 +355,8 @@ struct RdoScratch {
 };
 OB_DEVNI int rdo_all_bands(RangeEnc &enc, const float *Xg, const float *bandE, const int *pulses, const int *tf_res, int shortBlocks, int spread,
                            int intensity, int32_t total_bits, int32_t balance, int LM, int codedBands, uint32_t seed, int disable_inv, float *bx,
-                           float *by, float *tmp, RdoScratch &w) {
-  const int M = 1 << LM, N_ = M * OB_SHORT_N, B = shortBlocks ? M : 1, start = 0, end = OB_NBANDS, C = 2;
+                           float *by, float *tmp, RdoScratch &w, int end) {
+  const int M = 1 << LM, N_ = M * OB_SHORT_N, B = shortBlocks ? M : 1, start = 0, C = 2;
   int lowband_offset = 0, update_lowband = 1, status = 0;
   EncBand ctx;
   ctx.ec = &enc; ctx.bandE = bandE; ctx.intensity = intensity; ctx.spread = spread; ctx.disable_inv = disable_inv; ctx.seed = seed;

@@ -97,6 +97,7 @@ struct ObEncFrameInfo {
   int32_t pad[3];
 };
 struct EncAnalysisParams {
+  int end = OB_NBANDS;         // CELT_SET_END_BAND
   ObEncAnalysisState *state;   // [n_streams]
   const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
   const int32_t *short_blocks; // [n_streams] transient decision per stream, or null (= long blocks)
@@ -354,7 +355,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       const ObEncFrameInfo fi = p.info[stream];
       const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
       int patch = 0;
-      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->sc, p.enc_state[stream].oldBandE, C);
+      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->sc, p.enc_state[stream].oldBandE, C, p.end);
       ((int *)xch)[6] = patch;
     }
     bsync();

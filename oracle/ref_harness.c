@@ -298,3 +298,4 @@ int refh_celt_encode(CELTEncoder *st, const float *pcm, int frame_size, unsigned
   return n;
 }
 void refh_celt_encoder_set_cvbr(CELTEncoder *st, int v) { celt_encoder_ctl(st, OPUS_SET_VBR_CONSTRAINT(v)); }
+int refh_celt_encoder_set_end_band(CELTEncoder *st, int end) { return celt_encoder_ctl(st, CELT_SET_END_BAND(end)); }

@@ -214,6 +214,8 @@ extern "C" void emu_enc_state_init(ObEncState *st, int n) {
     st[s].delayedIntra = 1.f; st[s].spread_decision = 2; st[s].tonal_average = 256;
   }
 }
+static int g_enc_end = OB_NBANDS;   // CELT_SET_END_BAND for the next emu_celt_encode calls
+extern "C" void emu_celt_set_end_band(int end) { g_enc_end = end; }
 static int32_t g_enc_cov[3];   // frames that took the post-filter / patched-transient / transient paths (test coverage counters)
 // one frame for n streams: an_state/enc_state carried by the caller
 extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const float *pcm, int n, int C, int LM, int max_bytes, int bitrate, int lsb_depth,
@@ -225,12 +227,12 @@ extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const flo
   a.state = (ObEncAnalysisState *)an_state; a.pcm = pcm; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
   a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
   a.enc_state = enc_state; a.prefilter_mem = prefilter_mem; a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = bitrate; a.vbr = vbr;
-  a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0;
+  a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0; a.end = g_enc_end;
   emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32 + (complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams p;
   p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.bandLogE2 = Lg2.data(); p.packets = packets; p.nbytes = nbytes;
   p.n_streams = n; p.C = C; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = complexity; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
-  p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0; p.vbr = vbr; p.constrained_vbr = cvbr; p.loss_rate = 0;
+  p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0; p.vbr = vbr; p.constrained_vbr = cvbr; p.loss_rate = 0; p.end = g_enc_end;
   emu_launch(enc_frame_entry, &p, (n + 31) / 32, 32, 0);
   for (int s = 0; s < n; s++) rng[s] = enc_state[s].rng;
   for (int s = 0; s < n; s++) { g_enc_cov[0] += info[s].pf_on; g_enc_cov[1] += info[s].patched; g_enc_cov[2] += info[s].is_transient; }

@@ -14,12 +14,13 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1):
+def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1, end=21):
     R, O = util.load_ref(kind), util.load_oracle()
     x = (sig.astype(np.float32) / 32768.0).reshape(-1, fs * ch)[:nframes]
     rs = np.zeros(R.refh_celt_encoder_size(ch) + 64, np.uint8)
     assert R.refh_celt_encoder_init(_p(rs), ch, complexity, bitrate, vbr, lsb) == 0
     R.refh_celt_encoder_set_cvbr(_p(rs), cvbr)
+    assert R.refh_celt_encoder_set_end_band(_p(rs), end) == 0
     os_ = np.zeros(O.orc_encoder_size(), np.uint8)
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
@@ -28,6 +29,7 @@ def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, k
     O.orc_encoder_ctl(_p(os_), complexity, -1 if bitrate == -1000 else bitrate, vbr, lsb)
     O.orc_encoder_set_cvbr.restype = None
     O.orc_encoder_set_cvbr(_p(os_), cvbr)
+    assert O.orc_encoder_set_end_band(_p(os_), end) == 0
     out = []
     for f in range(len(x)):
         a, b = np.zeros(1275, np.uint8), np.zeros(1275, np.uint8)
@@ -176,3 +178,16 @@ def test_randomised_settings(seed):
         sig = sig * float(rng.choice([0.0005, 0.01, 0.2]))        # near-silent and quiet inputs
     for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nbytes, complexity, bitrate=bitrate, vbr=vbr, nframes=10, cvbr=cvbr):
         assert na == nbo and np.array_equal(a, b) and ra == rb, (seed, ch, fs, nbytes, complexity, vbr, kind, f, na, nbo)
+
+
+@pytest.mark.parametrize('end', [13, 17, 19])
+@pytest.mark.parametrize('ch,fs,complexity,bitrate,vbr', [(2, 960, 10, 64000, 1), (1, 480, 5, -1000, 0), (2, 240, 8, 32000, 0), (2, 120, 0, -1000, 0),
+                                                          (1, 960, 10, 24000, 1), (2, 480, 3, 96000, 1)])
+def test_end_band(end, ch, fs, complexity, bitrate, vbr):
+    """CELT_SET_END_BAND: NB / WB / SWB streams (end = 13 / 17 / 19), packets and final range bit-identical to the reference"""
+    sig = util.sig_music(end + ch + fs, fs * 12, ch)
+    nb = 1275 if bitrate != -1000 else max(8, 100 * fs // 960)
+    for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nb, complexity, bitrate=bitrate, vbr=vbr, end=end):
+        assert na == nbo, (f, na, nbo)
+        assert np.array_equal(a, b), (f, int(np.argmax(a != b)))
+        assert ra == rb

@@ -13,7 +13,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1):
+def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1, end=21):
     """x [nframes, fs*ch] float -> list of (packet bytes, range)"""
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
@@ -23,6 +23,7 @@ def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0,
     O.orc_encoder_ctl(_p(st), complexity, bitrate, vbr, lsb)
     O.orc_encoder_set_cvbr.restype = None
     O.orc_encoder_set_cvbr(_p(st), cvbr)
+    assert O.orc_encoder_set_end_band(_p(st), end) == 0
     out = []
     for f in range(len(x)):
         b = np.zeros(1275, np.uint8)
@@ -113,3 +114,35 @@ def test_emu_encoder_randomised(seed):
             assert nb[s] == wn, (seed, f, s, nb[s], wn, (ch, fs, nbytes, complexity, vbr, cvbr))
             assert np.array_equal(pk[s, :wn], wb), (seed, f, s, (ch, fs, nbytes, complexity, vbr, cvbr))
             assert rg[s] == wr
+
+
+@pytest.mark.parametrize('end', [13, 17, 19])
+@pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr', [(2, 960, 120, 10, 0), (1, 480, 60, 5, 0), (2, 240, 1275, 8, 1), (2, 120, 30, 2, 0), (1, 960, 1275, 4, 1)])
+def test_emu_encoder_end_band(end, ch, fs, nbytes, complexity, vbr):
+    """CELT_SET_END_BAND (celt/celt_encoder.c:3046-3053): narrowband / wideband / super-wideband CELT streams (end = 13 / 17 / 19)"""
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    n, nf = 4, 5
+    LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs]
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 48000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
+    x = np.stack([sigs[s % len(sigs)](end + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, end=end) for s in range(n)]
+    an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
+    es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
+    E.emu_enc_state_init(_p(es), n)
+    pmem = np.zeros((n, ch, 1024), np.float32)
+    E.emu_celt_set_end_band(end)
+    try:
+        for f in range(nf):
+            pcm = np.ascontiguousarray(x[:, f])
+            pk = np.zeros((n, nbytes), np.uint8)
+            nb = np.zeros(n, np.int32)
+            rng = np.zeros(n, np.uint32)
+            E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rng), complexity, vbr, 1, _p(pmem))
+            for s in range(n):
+                wn, wb, wr = want[s][f]
+                assert nb[s] == wn, (f, s, nb[s], wn)
+                assert np.array_equal(pk[s, :wn], wb), (f, s, int(np.argmax(pk[s, :wn] != wb)))
+                assert rng[s] == wr
+    finally:
+        E.emu_celt_set_end_band(21)

@@ -157,3 +157,29 @@ def test_encoder_randomised(seed):
                 assert np.array_equal(pk[s, :wn], wb), (seed, f, s)
                 assert rg[s] == wr
     enc.close()
+
+
+@pytest.mark.parametrize('end', [13, 17, 19])
+@pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr', [(2, 960, 120, 10, 0), (1, 480, 60, 5, 0), (2, 240, 1275, 8, 1)])
+def test_encoder_end_band(end, ch, fs, nbytes, complexity, vbr):
+    """CELT_SET_END_BAND (request 10012): narrowband / wideband / super-wideband CELT streams, bit-identical to the pinned oracle"""
+    import opus_b200
+    O = util.load_oracle()
+    n, nf = 8, 5
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 48000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
+    x = np.stack([sigs[s % len(sigs)](end + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, end=end) for s in range(n)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=complexity, bitrate=bitrate if vbr else None, vbr=bool(vbr))
+    enc.ctl(10012, end)
+    for f in range(nf):
+        pk, nb = enc.encode(np.ascontiguousarray(x[:, f]), nbytes)
+        rng = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            assert np.array_equal(pk[s, :wn], wb), (f, s)
+            assert rng[s] == wr
+    enc.close()
+    with pytest.raises(opus_b200.OpusB200Error):
+        opus_b200.EncoderBatch(1, channels=1).ctl(10012, 22)
