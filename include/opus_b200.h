@@ -181,6 +181,8 @@ int opusb200_silk_autocorrelation(OpusB200Ctx *ctx, float *results, const float 
  * run_analysis, silk_info, a shared range coder for hybrid frames) are absent, as in CELT-only custom-mode use.
  * nbytes[s] < 0 flags a per-stream failure (OPUS_INTERNAL_ERROR -3). ---- */
 typedef struct OpusB200Encoder OpusB200Encoder;
+/* Fs: 48000, 24000, 16000, 12000 or 8000, like celt_encoder_init (celt/celt_encoder.c:233-262): below 48 kHz the input is zero-stuffed to
+ * 48 kHz ahead of the pre-emphasis and the spectrum above Fs/2 is cleared; frame_size and the pcm of the encode calls are in Fs samples. */
 int opusb200_encoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Encoder **out);
 void opusb200_encoder_destroy(OpusB200Encoder *enc);
 int opusb200_encoder_reset(OpusB200Encoder *enc);                                   /* OPUS_RESET_STATE */

@@ -37,6 +37,7 @@ struct OpusB200Encoder {
   // settings (celt_encoder_ctl)
   int complexity, bitrate, vbr, constrained_vbr, lsb_depth, force_intra, disable_inv, disable_pf, loss_rate;
   int end;   // CELT_SET_END_BAND
+  int upsample;   // 48000 / Fs of opusb200_encoder_create: frame_size and the pcm are in Fs samples
   // staging for the host-buffer call
   float *d_pcm; size_t d_pcm_cap;
   unsigned char *d_pkt; size_t d_pkt_cap;
@@ -59,7 +60,8 @@ extern "C" int opusb200_encoder_reset(OpusB200Encoder *e) {
 extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int n_streams, OpusB200Encoder **out) {
   if (!out) return OPUSB200_BAD_ARG;
   *out = nullptr;
-  if (Fs != 48000 || (channels != 1 && channels != 2) || n_streams <= 0) return OPUSB200_BAD_ARG;
+  if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2) || n_streams <= 0)
+    return OPUSB200_BAD_ARG;   // celt_encoder_init: resampling_factor(Fs) must exist (celt/celt_encoder.c:255)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     fprintf(stderr, "opus_b200: no usable CUDA device (there is no CPU fallback)\n");
@@ -71,7 +73,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   memset(e, 0, sizeof(*e));
   e->device = device; e->channels = channels; e->n = n_streams;
   e->complexity = 5; e->bitrate = -1; e->vbr = 0; e->constrained_vbr = 1; e->lsb_depth = 24;   // celt_encoder_init defaults
-  e->end = OB_NBANDS;
+  e->end = OB_NBANDS; e->upsample = 48000 / Fs;
   OB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;
@@ -140,14 +142,14 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
                                       int max_data_bytes, int32_t *d_nbytes) {
   if (!e || !d_pcm || !d_packets || !d_nbytes || pkt_stride < max_data_bytes || max_data_bytes < 2) return OPUSB200_BAD_ARG;
   int LM = -1;
-  for (int l = 0; l <= 3; l++) if (frame_size == OB_SHORT_N << l) LM = l;
+  for (int l = 0; l <= 3; l++) if (frame_size * e->upsample == OB_SHORT_N << l) LM = l;   // frame_size counts input-rate samples (celt_encoder.c:1838)
   if (LM < 0) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(e->device));
   EncAnalysisParams a;
   a.state = e->an_state; a.pcm = d_pcm; a.short_blocks = nullptr; a.X = e->X; a.bandE = e->bandE; a.bandLogE = e->bandLogE; a.info = e->info;
   a.n_streams = e->n; a.C = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
   a.enc_state = e->state; a.prefilter_mem = e->prefilter_mem; a.bandLogE2 = e->bandLogE2; a.max_bytes = max_data_bytes; a.bitrate = e->bitrate;
-  a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate; a.end = e->end;
+  a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate; a.end = e->end; a.upsample = e->upsample;
   // the pitch-search buffers exist from complexity 5 only (PfWS: sc always, buf/xlp2 for the search)
   const size_t pf_smem = e->complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64;
   EncFrameParams p;

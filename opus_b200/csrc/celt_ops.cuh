@@ -98,6 +98,7 @@ struct ObEncFrameInfo {
 };
 struct EncAnalysisParams {
   int end = OB_NBANDS;         // CELT_SET_END_BAND
+  int upsample = 1;            // 48000 / input rate (celt_encoder_init, celt/celt_encoder.c:255): pcm holds N/upsample samples per channel
   ObEncAnalysisState *state;   // [n_streams]
   const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
   const int32_t *short_blocks; // [n_streams] transient decision per stream, or null (= long blocks)
@@ -208,6 +209,14 @@ OB_DEVNI int transient_unmask_warp(const float *__restrict__ in, float *__restri
   for (int o = 16; o; o >>= 1) unmask += shfl_xor(unmask, o);
   return 64 * unmask * 4 / (6 * (len2 - 17));
 }
+// compute_mdcts with upsample != 1 (celt/celt_encoder.c:544-556): scale the part of the spectrum that exists at the input rate, clear the rest
+OB_DEV void enc_mdct_upsample(float *freq, int N, int up, int lane) {
+  if (up == 1) return;
+  const int bound = N / up;
+  const float g = (float)up;
+  for (int j = lane; j < N; j += 32) freq[j] = j < bound ? f_mul(freq[j], g) : 0.f;
+  wsync();
+}
 // one CTA per stream, one warp per channel
 OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned char *smem) {
   const int lane = lane_id(), c = warp_in_block();
@@ -215,7 +224,8 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C;
   int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
   ObEncAnalysisState &st = p.state[stream];
-  const float *pcm = p.pcm + (size_t)stream * N * C + c;
+  const int up = p.upsample;
+  const float *pcm = p.pcm + (size_t)stream * (N / up) * C + c;
   // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
   const float coef0 = 0.85000610f;
   float mx_new = 0.f, mx_tail = 0.f;   // celt_maxabs over the fresh part and over the part overlapping the next frame
@@ -224,18 +234,33 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   // the analysis window starts with the UNFILTERED tail of the previous frame (celt/celt_encoder.c:2014); without a pre-filter
   // history that is the same as the MDCT overlap memory
   for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[(st.pf_head + kPfMaxPeriod - OB_OVERLAP + i) & (kPfMaxPeriod - 1)] : st.overlap_mem[c][i];
-  for (int i = lane; i < N; i += 32) {
-    const float s = pcm[(size_t)C * i];
-    const float x = f_mul(32768.f, s);
-    const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (i - 1)]));
-    ws->in[OB_OVERLAP + i] = f_add(x, -m);
-    if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
-    else mx_tail = fmaxf(mx_tail, fabsf(s));
+  if (up == 1) {
+    for (int i = lane; i < N; i += 32) {
+      const float s = pcm[(size_t)C * i];
+      const float x = f_mul(32768.f, s);
+      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (i - 1)]));
+      ws->in[OB_OVERLAP + i] = f_add(x, -m);
+      if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
+      else mx_tail = fmaxf(mx_tail, fabsf(s));
+    }
+  } else {
+    // input below 48 kHz: the samples are zero-stuffed to 48 kHz ahead of the pre-emphasis (celt/celt_encoder.c:583-589)
+    for (int i = lane; i < N; i += 32) {
+      const bool on = i % up == 0, prev_on = (i - 1) % up == 0;
+      const float s = on ? pcm[(size_t)C * (i / up)] : 0.f;
+      const float x = on ? f_mul(32768.f, s) : 0.f;
+      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, prev_on ? f_mul(32768.f, pcm[(size_t)C * ((i - 1) / up)]) : 0.f);
+      ws->in[OB_OVERLAP + i] = f_add(x, -m);
+      if (on) {
+        if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
+        else mx_tail = fmaxf(mx_tail, fabsf(s));
+      }
+    }
   }
   mx_new = warp_max(mx_new);
   mx_tail = warp_max(mx_tail);
   wsync();
-  if (lane == 0) st.preemph_mem[c] = f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)]));
+  if (lane == 0) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)])) : f_mul(coef0, 0.f);
   if (!pf_path) for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
   // cross-channel part: maxima and the tone detector need both channels' time signals
   float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
@@ -326,6 +351,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     // secondMdct (celt/celt_encoder.c:2077-2090): the long-block log energies of a transient frame, for dynalloc_analysis
     mdct_forward_from_ws(ws, LM, 0, freq, lane);
     wsync();
+    enc_mdct_upsample(freq, N, up, lane);
     if (lane < OB_NBANDS) {
       float sum = 0.f;
       const int j0 = M * ob_ebands[lane], j1 = M * ob_ebands[lane + 1];
@@ -339,6 +365,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   }
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
   wsync();
+  enc_mdct_upsample(freq, N, up, lane);
   if (pf_path && p.complexity >= 5 && LM > 0 && !transient) {
     // patch_transient_decision (celt/celt_encoder.c:2238-2257) needs both channels' log energies: first pass of the band sums
     float E0 = 0.f;
@@ -369,6 +396,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       transient = 1;
       mdct_forward_from_ws(ws, LM, 1, freq, lane);
       wsync();
+      enc_mdct_upsample(freq, N, up, lane);
     }
   }
   // band energies: one lane per band, summed in index order like celt_inner_prod_c

@@ -298,4 +298,15 @@ int refh_celt_encode(CELTEncoder *st, const float *pcm, int frame_size, unsigned
   return n;
 }
 void refh_celt_encoder_set_cvbr(CELTEncoder *st, int v) { celt_encoder_ctl(st, OPUS_SET_VBR_CONSTRAINT(v)); }
+/* as refh_celt_encoder_init for an input rate Fs in {48000, 24000, 16000, 12000, 8000} (st->upsample = 48000 / Fs) */
+int refh_celt_encoder_init_fs(CELTEncoder *st, int Fs, int channels, int complexity, int bitrate, int vbr, int lsb_depth) {
+  int ret = celt_encoder_init(st, Fs, channels, opus_select_arch());
+  if (ret != OPUS_OK) return ret;
+  celt_encoder_ctl(st, CELT_SET_SIGNALLING(0));
+  celt_encoder_ctl(st, OPUS_SET_COMPLEXITY(complexity));
+  celt_encoder_ctl(st, OPUS_SET_BITRATE(bitrate));
+  celt_encoder_ctl(st, OPUS_SET_VBR(vbr));
+  celt_encoder_ctl(st, OPUS_SET_LSB_DEPTH(lsb_depth));
+  return OPUS_OK;
+}
 int refh_celt_encoder_set_end_band(CELTEncoder *st, int end) { return celt_encoder_ctl(st, CELT_SET_END_BAND(end)); }

@@ -216,6 +216,8 @@ extern "C" void emu_enc_state_init(ObEncState *st, int n) {
 }
 static int g_enc_end = OB_NBANDS;   // CELT_SET_END_BAND for the next emu_celt_encode calls
 extern "C" void emu_celt_set_end_band(int end) { g_enc_end = end; }
+static int g_enc_up = 1;   // 48000 / input rate for the next emu_celt_encode calls (pcm then holds N/up samples per channel)
+extern "C" void emu_celt_set_upsample(int up) { g_enc_up = up; }
 static int32_t g_enc_cov[3];   // frames that took the post-filter / patched-transient / transient paths (test coverage counters)
 // one frame for n streams: an_state/enc_state carried by the caller
 extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const float *pcm, int n, int C, int LM, int max_bytes, int bitrate, int lsb_depth,
@@ -227,7 +229,7 @@ extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const flo
   a.state = (ObEncAnalysisState *)an_state; a.pcm = pcm; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
   a.info = info.data(); a.n_streams = n; a.C = C; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
   a.enc_state = enc_state; a.prefilter_mem = prefilter_mem; a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = bitrate; a.vbr = vbr;
-  a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0; a.end = g_enc_end;
+  a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0; a.end = g_enc_end; a.upsample = g_enc_up;
   emu_launch(enc_analysis_entry, &a, n, 32 * C, C * sizeof(MdctWS) + 32 + (complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams p;
   p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.bandLogE2 = Lg2.data(); p.packets = packets; p.nbytes = nbytes;

@@ -191,3 +191,33 @@ def test_end_band(end, ch, fs, complexity, bitrate, vbr):
         assert na == nbo, (f, na, nbo)
         assert np.array_equal(a, b), (f, int(np.argmax(a != b)))
         assert ra == rb
+
+
+@pytest.mark.parametrize('Fs,end', [(24000, 19), (16000, 17), (12000, 17), (8000, 13), (16000, 21)])
+@pytest.mark.parametrize('ch,fs48,complexity,bitrate,vbr', [(2, 960, 10, 48000, 1), (1, 480, 5, -1000, 0), (2, 240, 8, 32000, 0), (2, 120, 0, -1000, 0), (1, 960, 10, 24000, 1)])
+def test_input_rates(Fs, end, ch, fs48, complexity, bitrate, vbr):
+    """celt_encoder_init(Fs < 48000) (st->upsample): zero-stuffed pre-emphasis, cleared upper spectrum; packets and final range bit-identical"""
+    R, O = util.load_ref('c'), util.load_oracle()
+    up, nframes = 48000 // Fs, 10
+    fsd = fs48 // up
+    sig = util.sig_music(end + ch + fs48, fs48 * nframes, ch).reshape(-1, ch)[::up][:fsd * nframes]
+    x = (sig.astype(np.float32) / 32768.0).reshape(nframes, fsd * ch)
+    nbytes = 1275 if bitrate != -1000 else max(8, 100 * fs48 // 960)
+    rs = np.zeros(R.refh_celt_encoder_size(ch) + 64, np.uint8)
+    assert R.refh_celt_encoder_init_fs(_p(rs), Fs, ch, complexity, bitrate, vbr, 24) == 0
+    assert R.refh_celt_encoder_set_end_band(_p(rs), end) == 0
+    os_ = np.zeros(O.orc_encoder_size(), np.uint8)
+    O.orc_encoder_init.restype = None
+    O.orc_encoder_ctl.restype = None
+    O.orc_encoder_final_range.restype = ctypes.c_uint32
+    O.orc_encoder_init(_p(os_), ch)
+    O.orc_encoder_ctl(_p(os_), complexity, -1 if bitrate == -1000 else bitrate, vbr, 24)
+    assert O.orc_encoder_set_end_band(_p(os_), end) == 0 and O.orc_encoder_set_fs(_p(os_), Fs) == 0
+    for f in range(nframes):
+        a, b = np.zeros(1275, np.uint8), np.zeros(1275, np.uint8)
+        rng = ctypes.c_uint32(0)
+        xf = np.ascontiguousarray(x[f])
+        na = R.refh_celt_encode(_p(rs), _p(xf), fsd, _p(a), nbytes, ctypes.byref(rng))
+        nb = O.orc_celt_encode_frame(_p(os_), _p(xf), fsd, _p(b), nbytes)
+        assert na == nb, (f, na, nb)
+        assert np.array_equal(a[:na], b[:na]) and rng.value == O.orc_encoder_final_range(_p(os_))

@@ -13,7 +13,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1, end=21):
+def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1, end=21, Fs=48000):
     """x [nframes, fs*ch] float -> list of (packet bytes, range)"""
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
@@ -23,7 +23,7 @@ def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0,
     O.orc_encoder_ctl(_p(st), complexity, bitrate, vbr, lsb)
     O.orc_encoder_set_cvbr.restype = None
     O.orc_encoder_set_cvbr(_p(st), cvbr)
-    assert O.orc_encoder_set_end_band(_p(st), end) == 0
+    assert O.orc_encoder_set_end_band(_p(st), end) == 0 and O.orc_encoder_set_fs(_p(st), Fs) == 0
     out = []
     for f in range(len(x)):
         b = np.zeros(1275, np.uint8)
@@ -146,3 +146,40 @@ def test_emu_encoder_end_band(end, ch, fs, nbytes, complexity, vbr):
                 assert rng[s] == wr
     finally:
         E.emu_celt_set_end_band(21)
+
+
+@pytest.mark.parametrize('Fs,end', [(24000, 19), (16000, 17), (12000, 17), (8000, 13)])
+@pytest.mark.parametrize('ch,fs48,nbytes,complexity,vbr', [(2, 960, 100, 10, 0), (1, 480, 50, 5, 0), (2, 240, 1275, 8, 1), (2, 120, 25, 2, 0)])
+def test_emu_encoder_input_rates(Fs, end, ch, fs48, nbytes, complexity, vbr):
+    """celt_encoder_init(Fs < 48000): the input is zero-stuffed to 48 kHz in the pre-emphasis and the spectrum above Fs/2 is cleared
+    (celt/celt_encoder.c:255, 583-589, 544-556); with the end band the Opus layer would pick for that rate"""
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    n, nf, up = 4, 5, 48000 // Fs
+    fsd = fs48 // up
+    LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs48]
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 40000 * ch // 2 * (2 if fs48 < 480 else 1) if vbr else -1
+    x = np.stack([np.ascontiguousarray(sigs[s % len(sigs)](Fs // 1000 + s + fs48, fs48 * nf, ch).reshape(-1, ch)[::up][:fsd * nf]).astype(np.float32)
+                  .reshape(nf, fsd * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fsd, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, end=end, Fs=Fs) for s in range(n)]
+    an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
+    es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
+    E.emu_enc_state_init(_p(es), n)
+    pmem = np.zeros((n, ch, 1024), np.float32)
+    E.emu_celt_set_end_band(end)
+    E.emu_celt_set_upsample(up)
+    try:
+        for f in range(nf):
+            pcm = np.ascontiguousarray(x[:, f])
+            pk = np.zeros((n, nbytes), np.uint8)
+            nb = np.zeros(n, np.int32)
+            rng = np.zeros(n, np.uint32)
+            E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rng), complexity, vbr, 1, _p(pmem))
+            for s in range(n):
+                wn, wb, wr = want[s][f]
+                assert nb[s] == wn, (f, s, nb[s], wn)
+                assert np.array_equal(pk[s, :wn], wb), (f, s, int(np.argmax(pk[s, :wn] != wb)))
+                assert rng[s] == wr
+    finally:
+        E.emu_celt_set_end_band(21)
+        E.emu_celt_set_upsample(1)

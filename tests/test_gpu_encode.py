@@ -183,3 +183,30 @@ def test_encoder_end_band(end, ch, fs, nbytes, complexity, vbr):
     enc.close()
     with pytest.raises(opus_b200.OpusB200Error):
         opus_b200.EncoderBatch(1, channels=1).ctl(10012, 22)
+
+
+@pytest.mark.parametrize('Fs,end', [(24000, 19), (16000, 17), (8000, 13)])
+@pytest.mark.parametrize('ch,fs48,nbytes,complexity,vbr', [(2, 960, 100, 10, 0), (1, 480, 50, 5, 0), (2, 240, 1275, 8, 1)])
+def test_encoder_input_rates(Fs, end, ch, fs48, nbytes, complexity, vbr):
+    """opusb200_encoder_create(Fs < 48000) = celt_encoder_init(Fs): frame_size and the pcm are in Fs samples; with the end band the Opus
+    layer would pick for that rate.  Bit-identical to the pinned oracle."""
+    import opus_b200
+    O = util.load_oracle()
+    n, nf, up = 8, 5, 48000 // Fs
+    fsd = fs48 // up
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 40000 * ch // 2 * (2 if fs48 < 480 else 1) if vbr else -1
+    x = np.stack([np.ascontiguousarray(sigs[s % len(sigs)](Fs // 1000 + s + fs48, fs48 * nf, ch).reshape(-1, ch)[::up][:fsd * nf]).astype(np.float32)
+                  .reshape(nf, fsd * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fsd, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, end=end, Fs=Fs) for s in range(n)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, fs=Fs, complexity=complexity, bitrate=bitrate if vbr else None, vbr=bool(vbr))
+    enc.ctl(10012, end)
+    for f in range(nf):
+        pk, nb = enc.encode(np.ascontiguousarray(x[:, f]), nbytes)
+        rng = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            assert np.array_equal(pk[s, :wn], wb), (f, s)
+            assert rng[s] == wr
+    enc.close()
