@@ -27,6 +27,7 @@ struct EncFrameParams {
   int32_t *nbytes;              // [n] bytes produced, or a negative error
   int first_stream = 0;   // this launch covers streams [first_stream, n_streams)
   int end = OB_NBANDS;    // CELT_SET_END_BAND (celt/celt_encoder.c:3046-3053): 13 NB, 17 WB, 19 SWB, 21 FB
+  int CC = 0;             // input channels when they differ from the coded channels C (CELT_SET_CHANNELS); 0 = C
   int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf, vbr, constrained_vbr,
       loss_rate;
 };
@@ -1542,16 +1543,20 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   st.prefilter_period = pitch_index;
   st.prefilter_gain = fi.gain1;
   st.prefilter_tapset = fi.pf_tapset;
+  const int CC = p.CC ? p.CC : C;
+  if (CC == 2 && C == 1)   // celt/celt_encoder.c:2780-2782
+#pragma unroll 1
+    for (int i = 0; i < OB_NBANDS; i++) st.oldBandE[OB_NBANDS + i] = st.oldBandE[i];
   if (!isTransient) {
 #pragma unroll 1
-    for (int i = 0; i < C * OB_NBANDS; i++) { st.oldLogE2[i] = st.oldLogE[i]; st.oldLogE[i] = st.oldBandE[i]; }
+    for (int i = 0; i < CC * OB_NBANDS; i++) { st.oldLogE2[i] = st.oldLogE[i]; st.oldLogE[i] = st.oldBandE[i]; }
   } else {
 #pragma unroll 1
-    for (int i = 0; i < C * OB_NBANDS; i++) st.oldLogE[i] = enc_fmin(st.oldLogE[i], st.oldBandE[i]);
+    for (int i = 0; i < CC * OB_NBANDS; i++) st.oldLogE[i] = enc_fmin(st.oldLogE[i], st.oldBandE[i]);
   }
   if (end < OB_NBANDS) {  // in case the end band were to change (celt/celt_encoder.c:2795-2807)
 #pragma unroll 1
-    for (int c = 0; c < C; c++)
+    for (int c = 0; c < CC; c++)
 #pragma unroll 1
       for (int i = end; i < OB_NBANDS; i++) { st.oldBandE[c * OB_NBANDS + i] = 0.f; st.oldLogE[c * OB_NBANDS + i] = st.oldLogE2[c * OB_NBANDS + i] = -28.f; }
   }

@@ -37,6 +37,7 @@ struct OpusB200Encoder {
   // settings (celt_encoder_ctl)
   int complexity, bitrate, vbr, constrained_vbr, lsb_depth, force_intra, disable_inv, disable_pf, loss_rate;
   int end;   // CELT_SET_END_BAND
+  int stream_channels;   // CELT_SET_CHANNELS: coded channels (<= channels)
   int upsample;   // 48000 / Fs of opusb200_encoder_create: frame_size and the pcm are in Fs samples
   // staging for the host-buffer call
   float *d_pcm; size_t d_pcm_cap;
@@ -73,7 +74,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   memset(e, 0, sizeof(*e));
   e->device = device; e->channels = channels; e->n = n_streams;
   e->complexity = 5; e->bitrate = -1; e->vbr = 0; e->constrained_vbr = 1; e->lsb_depth = 24;   // celt_encoder_init defaults
-  e->end = OB_NBANDS; e->upsample = 48000 / Fs;
+  e->end = OB_NBANDS; e->upsample = 48000 / Fs; e->stream_channels = channels;
   OB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;
@@ -127,6 +128,7 @@ extern "C" int opusb200_encoder_ctl_set(OpusB200Encoder *e, int request, int32_t
     case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY
     case 4036: if (value < 8 || value > 24) return OPUSB200_BAD_ARG; e->lsb_depth = value; return OPUSB200_OK;  // OPUS_SET_LSB_DEPTH
     case 4046: e->disable_inv = value != 0; return OPUSB200_OK;                                                // OPUS_SET_PHASE_INVERSION_DISABLED
+    case 10008: if (value < 1 || value > e->channels) return OPUSB200_BAD_ARG; e->stream_channels = value; return OPUSB200_OK;   // CELT_SET_CHANNELS (celt/celt.h:111): mono coding of a stereo input
     case 10012: if (value < 1 || value > OB_NBANDS) return OPUSB200_BAD_ARG; e->end = value; return OPUSB200_OK;   // CELT_SET_END_BAND (celt/celt.h:119): 13 NB, 17 WB, 19 SWB, 21 FB
     default: return OPUSB200_UNIMPLEMENTED;
   }
@@ -147,14 +149,14 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   OB_CUDA(cudaSetDevice(e->device));
   EncAnalysisParams a;
   a.state = e->an_state; a.pcm = d_pcm; a.short_blocks = nullptr; a.X = e->X; a.bandE = e->bandE; a.bandLogE = e->bandLogE; a.info = e->info;
-  a.n_streams = e->n; a.C = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
+  a.n_streams = e->n; a.C = e->stream_channels; a.CC = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
   a.enc_state = e->state; a.prefilter_mem = e->prefilter_mem; a.bandLogE2 = e->bandLogE2; a.max_bytes = max_data_bytes; a.bitrate = e->bitrate;
   a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate; a.end = e->end; a.upsample = e->upsample;
   // the pitch-search buffers exist from complexity 5 only (PfWS: sc always, buf/xlp2 for the search)
   const size_t pf_smem = e->complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64;
   EncFrameParams p;
   p.state = e->state; p.info = e->info; p.X = e->X; p.bandE = e->bandE; p.bandLogE = e->bandLogE; p.bandLogE2 = e->bandLogE2; p.packets = d_packets; p.nbytes = d_nbytes;
-  p.C = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
+  p.C = e->stream_channels; p.CC = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf; p.end = e->end;
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
   // Chunking the batch (analysis of chunk k+1 on the library stream under the frame coder of chunk k on its own higher-priority
@@ -175,7 +177,7 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
       OB_CUDA(cudaStreamWaitEvent(sf, e->ev_an[k], 0));
     }
     p.first_stream = s0; p.n_streams = s1;
-    if (e->complexity >= 8 && e->channels == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    if (e->complexity >= 8 && e->stream_channels == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     else ob_celt_enc_frame<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     e->launches += 2;
     if (chunks > 1) OB_CUDA(cudaEventRecord(e->ev_fr[k], sf));

@@ -98,6 +98,7 @@ struct ObEncFrameInfo {
 };
 struct EncAnalysisParams {
   int end = OB_NBANDS;         // CELT_SET_END_BAND
+  int CC = 0;                  // input channels when they differ from the coded channels C (CELT_SET_CHANNELS: mono coding of a stereo input); 0 = C
   int upsample = 1;            // 48000 / input rate (celt_encoder_init, celt/celt_encoder.c:255): pcm holds N/upsample samples per channel
   ObEncAnalysisState *state;   // [n_streams]
   const float *pcm;            // [n_streams][N*C] interleaved, +-1.0 full scale
@@ -217,28 +218,40 @@ OB_DEV void enc_mdct_upsample(float *freq, int N, int up, int lane) {
   for (int j = lane; j < N; j += 32) freq[j] = j < bound ? f_mul(freq[j], g) : 0.f;
   wsync();
 }
+// compute_mdcts' tail (celt/celt_encoder.c:539-556) for the whole CTA: mono coding of a stereo input averages the two spectra into
+// channel 0's, then the upsample fix.  f0 / f1: the two warps' spectra (f1 unused unless CC == 2 && C == 1).
+OB_DEV void enc_mdct_tail(float *freq, float *f0, const float *f1, int N, int up, int C, int CC, int c, int lane) {
+  if (CC == 2 && C == 1) {
+    bsync();   // both spectra complete
+    if (c == 0) {
+      for (int j = lane; j < N; j += 32) f0[j] = f_add(f_mul(.5f, f0[j]), f_mul(.5f, f1[j]));
+      wsync();
+    }
+  }
+  if (c < C) enc_mdct_upsample(freq, N, up, lane);
+}
 // one CTA per stream, one warp per channel
 OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned char *smem) {
   const int lane = lane_id(), c = warp_in_block();
   MdctWS *ws = (MdctWS *)smem + c;
-  const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C;
+  const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C, CC = p.CC ? p.CC : p.C;   // C coded channels (CELT_SET_CHANNELS), CC input channels: one warp per INPUT channel
   int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
   ObEncAnalysisState &st = p.state[stream];
   const int up = p.upsample;
-  const float *pcm = p.pcm + (size_t)stream * (N / up) * C + c;
+  const float *pcm = p.pcm + (size_t)stream * (N / up) * CC + c;
   // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
   const float coef0 = 0.85000610f;
   float mx_new = 0.f, mx_tail = 0.f;   // celt_maxabs over the fresh part and over the part overlapping the next frame
   const bool pf_path = p.enc_state != nullptr && p.info != nullptr;   // the frame-encoder configuration (celt_enc_host.cuh)
-  float *pmem = pf_path ? p.prefilter_mem + ((size_t)stream * C + c) * kPfMaxPeriod : nullptr;
+  float *pmem = pf_path ? p.prefilter_mem + ((size_t)stream * CC + c) * kPfMaxPeriod : nullptr;
   // the analysis window starts with the UNFILTERED tail of the previous frame (celt/celt_encoder.c:2014); without a pre-filter
   // history that is the same as the MDCT overlap memory
   for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[(st.pf_head + kPfMaxPeriod - OB_OVERLAP + i) & (kPfMaxPeriod - 1)] : st.overlap_mem[c][i];
   if (up == 1) {
     for (int i = lane; i < N; i += 32) {
-      const float s = pcm[(size_t)C * i];
+      const float s = pcm[(size_t)CC * i];
       const float x = f_mul(32768.f, s);
-      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (i - 1)]));
+      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)CC * (i - 1)]));
       ws->in[OB_OVERLAP + i] = f_add(x, -m);
       if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
       else mx_tail = fmaxf(mx_tail, fabsf(s));
@@ -247,9 +260,9 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     // input below 48 kHz: the samples are zero-stuffed to 48 kHz ahead of the pre-emphasis (celt/celt_encoder.c:583-589)
     for (int i = lane; i < N; i += 32) {
       const bool on = i % up == 0, prev_on = (i - 1) % up == 0;
-      const float s = on ? pcm[(size_t)C * (i / up)] : 0.f;
+      const float s = on ? pcm[(size_t)CC * (i / up)] : 0.f;
       const float x = on ? f_mul(32768.f, s) : 0.f;
-      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, prev_on ? f_mul(32768.f, pcm[(size_t)C * ((i - 1) / up)]) : 0.f);
+      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, prev_on ? f_mul(32768.f, pcm[(size_t)CC * ((i - 1) / up)]) : 0.f);
       ws->in[OB_OVERLAP + i] = f_add(x, -m);
       if (on) {
         if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
@@ -260,10 +273,10 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   mx_new = warp_max(mx_new);
   mx_tail = warp_max(mx_tail);
   wsync();
-  if (lane == 0) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, pcm[(size_t)C * (N - 1)])) : f_mul(coef0, 0.f);
+  if (lane == 0) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, pcm[(size_t)CC * (N - 1)])) : f_mul(coef0, 0.f);
   if (!pf_path) for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
   // cross-channel part: maxima and the tone detector need both channels' time signals
-  float *xch = (float *)((MdctWS *)smem + C);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
+  float *xch = (float *)((MdctWS *)smem + CC);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
   if (lane == 0) { xch[c * 2] = mx_new; xch[c * 2 + 1] = mx_tail; }
   if (p.complexity >= 1 && p.info) {   // transient_analysis: lane 0 of each channel's warp walks its channel (f2 is free until the MDCT)
     const int um = transient_unmask_warp(ws->in, ws->f2, N + OB_OVERLAP, lane);
@@ -272,9 +285,9 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   bsync();
   if (c == 0 && p.info) {
     float a = xch[0], t = xch[1];
-    if (C == 2) { a = fmaxf(a, xch[2]); t = fmaxf(t, xch[3]); }
+    if (CC == 2) { a = fmaxf(a, xch[2]); t = fmaxf(t, xch[3]); }
     const float sample_max = fmaxf(fmaxf(st.overlap_max, a), t);
-    const float *in0 = ((MdctWS *)smem)->in, *in1 = C == 2 ? ((MdctWS *)smem + 1)->in : nullptr;
+    const float *in0 = ((MdctWS *)smem)->in, *in1 = CC == 2 ? ((MdctWS *)smem + 1)->in : nullptr;
     // tone_detect (celt/celt_encoder.c:1362-1402)
     float lpc[2] = {0.f, 0.f};
     int delay = 1;
@@ -297,7 +310,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       fi.pad[0] = fi.pad[1] = fi.pad[2] = 0;
       if (p.complexity >= 1) {   // the cross-channel tail of transient_analysis (celt/celt_encoder.c:437-461)
         int mask_metric = ((int *)xch)[4];
-        if (C == 2 && ((int *)xch)[5] > mask_metric) { mask_metric = ((int *)xch)[5]; fi.tf_chan = 1; }
+        if (CC == 2 && ((int *)xch)[5] > mask_metric) { mask_metric = ((int *)xch)[5]; fi.tf_chan = 1; }
         int is_tr = mask_metric > 200;
         if (fi.toneishness > .98f && fi.tone_freq < 0.026f) { is_tr = 0; mask_metric = 0; }
         const float tf_max = fmaxf(0.f, (float)sqrt((double)(27 * mask_metric)) - 42.f);
@@ -305,6 +318,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
         fi.tf_estimate = (float)sqrt(a > 0 ? a : 0.0);
         fi.is_transient = is_tr;
       }
+      if (CC == 2 && C == 1) fi.tf_chan = 0;   // celt/celt_encoder.c:2095-2096
       fi.toneishness = fminf(fi.toneishness, 1.f - fi.tf_estimate);   // celt/celt_encoder.c:2026, before a patched frame resets tf_estimate
       // short blocks need LM > 0 and 3 bits of room after the two header flags: always there unless the frame is silent
       // (celt/celt_encoder.c:2060-2067; the frame coder re-checks with the real range-coder position)
@@ -318,21 +332,21 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   bsync();   // the tone detector reads ws->in of both channels; the MDCT below overwrites it
   if (p.info) transient = ((int *)xch)[6];
   float *freq = ws->in;
-  PfWS *pw = (PfWS *)((unsigned char *)smem + (size_t)C * sizeof(MdctWS) + 32);
+  PfWS *pw = (PfWS *)((unsigned char *)smem + (size_t)CC * sizeof(MdctWS) + 32);
   if (pf_path) {   // run_prefilter (celt/celt_encoder.c:2029-2057): every thread of the CTA takes part
     const ObEncState &es = p.enc_state[stream];
     ObEncFrameInfo fi = p.info[stream];
     const EncBudget bud = enc_budget(p.max_bytes, p.bitrate, p.vbr, p.constrained_vbr, N, es.vbr_reservoir);
     const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
     PfArgs a;
-    for (int cc = 0; cc < C; cc++) {
+    for (int cc = 0; cc < CC; cc++) {
       a.in[cc] = ((MdctWS *)smem + cc)->in;
       a.fr[cc] = ((MdctWS *)smem + cc)->f2;
-      a.ring[cc] = p.prefilter_mem + ((size_t)stream * C + cc) * kPfMaxPeriod;
+      a.ring[cc] = p.prefilter_mem + ((size_t)stream * CC + cc) * kPfMaxPeriod;
       a.in_mem[cc] = st.overlap_mem[cc];
     }
     a.head = st.pf_head;
-    a.C = C; a.N = N; a.complexity = p.complexity; a.nbAvailableBytes = bud.nbAvailableBytes; a.prefilter_tapset = es.tapset_decision;
+    a.C = CC; a.N = N; a.complexity = p.complexity; a.nbAvailableBytes = bud.nbAvailableBytes; a.prefilter_tapset = es.tapset_decision;
     a.prev_period = es.prefilter_period; a.prev_tapset = es.prefilter_tapset; a.prev_gain = es.prefilter_gain; a.loss_rate = p.loss_rate;
     a.tf_estimate = fi.tf_estimate; a.tone_freq = fi.tone_freq; a.toneishness = fminf(fi.toneishness, 1.f - fi.tf_estimate);
     a.enabled = bud.nbAvailableBytes > 12 * C && !silence && bud.nbCompressedBytes * 8 >= 17 && !p.disable_pf;
@@ -347,12 +361,15 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     if (p.complexity >= 5) freq = pw->buf + c * OB_MAXN;
     bsync();
   }
+  // both warps' spectrum buffers (for the mono downmix)
+  float *freq0 = (pf_path && p.complexity >= 5) ? pw->buf : ((MdctWS *)smem)->in;
+  const float *freq1 = (pf_path && p.complexity >= 5) ? pw->buf + OB_MAXN : ((MdctWS *)smem + (CC - 1))->in;
   if (pf_path && p.complexity >= 8 && transient) {
     // secondMdct (celt/celt_encoder.c:2077-2090): the long-block log energies of a transient frame, for dynalloc_analysis
     mdct_forward_from_ws(ws, LM, 0, freq, lane);
     wsync();
-    enc_mdct_upsample(freq, N, up, lane);
-    if (lane < OB_NBANDS) {
+    enc_mdct_tail(freq, freq0, freq1, N, up, C, CC, c, lane);
+    if (c < C && lane < OB_NBANDS) {
       float sum = 0.f;
       const int j0 = M * ob_ebands[lane], j1 = M * ob_ebands[lane + 1];
 #pragma unroll 4
@@ -363,13 +380,14 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     }
     wsync();
   }
+  if (CC == 2 && C == 1) bsync();   // (the second-MDCT energies above read channel 0's spectrum buffer)
   mdct_forward_from_ws(ws, LM, transient, freq, lane);
   wsync();
-  enc_mdct_upsample(freq, N, up, lane);
+  enc_mdct_tail(freq, freq0, freq1, N, up, C, CC, c, lane);
   if (pf_path && p.complexity >= 5 && LM > 0 && !transient) {
     // patch_transient_decision (celt/celt_encoder.c:2238-2257) needs both channels' log energies: first pass of the band sums
     float E0 = 0.f;
-    if (lane < OB_NBANDS) {
+    if (c < C && lane < OB_NBANDS) {
       float sum = 0.f;
       const int j0 = M * ob_ebands[lane], j1 = M * ob_ebands[lane + 1];
 #pragma unroll 4
@@ -387,7 +405,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     }
     bsync();
     if (((int *)xch)[6]) {
-      if (lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = pw->sc[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
+      if (c < C && lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = pw->sc[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
       if (c == 0 && lane == 0) {
         ObEncFrameInfo fi = p.info[stream];
         fi.is_transient = 1; fi.short_blocks = 1; fi.patched = 1; fi.tf_estimate = .2f;
@@ -396,9 +414,10 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       transient = 1;
       mdct_forward_from_ws(ws, LM, 1, freq, lane);
       wsync();
-      enc_mdct_upsample(freq, N, up, lane);
+      enc_mdct_tail(freq, freq0, freq1, N, up, C, CC, c, lane);
     }
   }
+  if (c >= C) return;   // the second input channel of a mono-coded stream has nothing left to do (no barrier below)
   // band energies: one lane per band, summed in index order like celt_inner_prod_c
   float E = 0.f, g = 0.f;
   if (lane < OB_NBANDS) {

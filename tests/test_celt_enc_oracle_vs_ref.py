@@ -14,13 +14,13 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1, end=21):
+def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1, end=21, coded=None):
     R, O = util.load_ref(kind), util.load_oracle()
     x = (sig.astype(np.float32) / 32768.0).reshape(-1, fs * ch)[:nframes]
     rs = np.zeros(R.refh_celt_encoder_size(ch) + 64, np.uint8)
     assert R.refh_celt_encoder_init(_p(rs), ch, complexity, bitrate, vbr, lsb) == 0
     R.refh_celt_encoder_set_cvbr(_p(rs), cvbr)
-    assert R.refh_celt_encoder_set_end_band(_p(rs), end) == 0
+    assert R.refh_celt_encoder_set_end_band(_p(rs), end) == 0 and R.refh_celt_encoder_set_channels(_p(rs), coded or ch) == 0
     os_ = np.zeros(O.orc_encoder_size(), np.uint8)
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
@@ -29,7 +29,7 @@ def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, k
     O.orc_encoder_ctl(_p(os_), complexity, -1 if bitrate == -1000 else bitrate, vbr, lsb)
     O.orc_encoder_set_cvbr.restype = None
     O.orc_encoder_set_cvbr(_p(os_), cvbr)
-    assert O.orc_encoder_set_end_band(_p(os_), end) == 0
+    assert O.orc_encoder_set_end_band(_p(os_), end) == 0 and O.orc_encoder_set_channels(_p(os_), coded or ch) == 0
     out = []
     for f in range(len(x)):
         a, b = np.zeros(1275, np.uint8), np.zeros(1275, np.uint8)
@@ -221,3 +221,15 @@ def test_input_rates(Fs, end, ch, fs48, complexity, bitrate, vbr):
         nb = O.orc_celt_encode_frame(_p(os_), _p(xf), fsd, _p(b), nbytes)
         assert na == nb, (f, na, nb)
         assert np.array_equal(a[:na], b[:na]) and rng.value == O.orc_encoder_final_range(_p(os_))
+
+
+@pytest.mark.parametrize('fs', [960, 480, 240, 120])
+@pytest.mark.parametrize('complexity,bitrate,vbr', [(0, -1000, 0), (5, -1000, 0), (10, 32000, 1), (8, 16000, 0), (3, 24000, 1)])
+def test_mono_coding_of_stereo_input(fs, complexity, bitrate, vbr):
+    """CELT_SET_CHANNELS(1) on a stereo encoder (celt/celt_encoder.c:539-543, 2095-2096, 2780-2782): bit-identical to the reference"""
+    sig = util.sig_music(fs + complexity, fs * 12, 2)
+    nb = 1275 if bitrate != -1000 else max(8, 60 * fs // 960)
+    for (f, na, nbo, a, b, ra, rb) in encode_both(sig, 2, fs, nb, complexity, bitrate=bitrate, vbr=vbr, coded=1):
+        assert na == nbo, (f, na, nbo)
+        assert np.array_equal(a, b), (f, int(np.argmax(a != b)))
+        assert ra == rb

@@ -210,3 +210,27 @@ def test_encoder_input_rates(Fs, end, ch, fs48, nbytes, complexity, vbr):
             assert np.array_equal(pk[s, :wn], wb), (f, s)
             assert rng[s] == wr
     enc.close()
+
+
+@pytest.mark.parametrize('fs,nbytes,complexity,vbr,end', [(960, 60, 10, 0, 21), (480, 40, 5, 0, 17), (240, 1275, 8, 1, 21), (960, 80, 0, 0, 21)])
+def test_encoder_mono_coding_of_stereo_input(fs, nbytes, complexity, vbr, end):
+    """CELT_SET_CHANNELS(1) (request 10008) on a stereo encoder: both input channels analysed, their spectra averaged, one channel coded"""
+    import opus_b200
+    O = util.load_oracle()
+    n, nf, ch = 8, 5, 2
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 32000 * (2 if fs < 480 else 1) if vbr else -1
+    x = np.stack([sigs[s % len(sigs)](end + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, end=end, coded=1) for s in range(n)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=complexity, bitrate=bitrate if vbr else None, vbr=bool(vbr))
+    enc.ctl(10012, end)
+    enc.ctl(10008, 1)
+    for f in range(nf):
+        pk, nb = enc.encode(np.ascontiguousarray(x[:, f]), nbytes)
+        rng = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            assert np.array_equal(pk[s, :wn], wb), (f, s)
+            assert rng[s] == wr
+    enc.close()
