@@ -187,7 +187,7 @@ int opusb200_encoder_create(int device, int32_t Fs, int channels, int n_streams,
 void opusb200_encoder_destroy(OpusB200Encoder *enc);
 int opusb200_encoder_reset(OpusB200Encoder *enc);                                   /* OPUS_RESET_STATE */
 /* request = the OPUS_SET_*_REQUEST number of include/opus_defines.h: 4002 bitrate, 4006 vbr, 4020 vbr constraint, 4010 complexity
- * (0..10, default 5 like celt_encoder_init), 4014 packet loss %, 4036 lsb depth, 4046 phase inversion disabled, 10008 CELT_SET_CHANNELS (celt/celt.h:111; 1 on a stereo encoder = mono coding of the stereo
+ * (0..10, default 5 like celt_encoder_init), 4014 packet loss %, 4036 lsb depth, 4046 phase inversion disabled, 10002 CELT_SET_PREDICTION (0 intra only, 1 no pitch pre-filter, 2 default), 10008 CELT_SET_CHANNELS (celt/celt.h:111; 1 on a stereo encoder = mono coding of the stereo
  * input, as the Opus layer does at low rates), 10012 CELT_SET_END_BAND (celt/celt.h:119; 13 NB, 17 WB,
  * 19 SWB, 21 FB: what the Opus layer sets from the bandwidth); other requests
  * return OPUSB200_UNIMPLEMENTED */

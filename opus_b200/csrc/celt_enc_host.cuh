@@ -128,6 +128,7 @@ extern "C" int opusb200_encoder_ctl_set(OpusB200Encoder *e, int request, int32_t
     case 4010: if (value < 0 || value > 10) return OPUSB200_BAD_ARG; e->complexity = value; return OPUSB200_OK;  // OPUS_SET_COMPLEXITY
     case 4036: if (value < 8 || value > 24) return OPUSB200_BAD_ARG; e->lsb_depth = value; return OPUSB200_OK;  // OPUS_SET_LSB_DEPTH
     case 4046: e->disable_inv = value != 0; return OPUSB200_OK;                                                // OPUS_SET_PHASE_INVERSION_DISABLED
+    case 10002: if (value < 0 || value > 2) return OPUSB200_BAD_ARG; e->disable_pf = value <= 1; e->force_intra = value == 0; return OPUSB200_OK;   // CELT_SET_PREDICTION (celt/celt.h:97)
     case 10008: if (value < 1 || value > e->channels) return OPUSB200_BAD_ARG; e->stream_channels = value; return OPUSB200_OK;   // CELT_SET_CHANNELS (celt/celt.h:111): mono coding of a stereo input
     case 10012: if (value < 1 || value > OB_NBANDS) return OPUSB200_BAD_ARG; e->end = value; return OPUSB200_OK;   // CELT_SET_END_BAND (celt/celt.h:119): 13 NB, 17 WB, 19 SWB, 21 FB
     default: return OPUSB200_UNIMPLEMENTED;

@@ -309,5 +309,6 @@ int refh_celt_encoder_init_fs(CELTEncoder *st, int Fs, int channels, int complex
   celt_encoder_ctl(st, OPUS_SET_LSB_DEPTH(lsb_depth));
   return OPUS_OK;
 }
+int refh_celt_encoder_set_prediction(CELTEncoder *st, int v) { return celt_encoder_ctl(st, CELT_SET_PREDICTION(v)); }
 int refh_celt_encoder_set_channels(CELTEncoder *st, int c) { return celt_encoder_ctl(st, CELT_SET_CHANNELS(c)); }
 int refh_celt_encoder_set_end_band(CELTEncoder *st, int end) { return celt_encoder_ctl(st, CELT_SET_END_BAND(end)); }

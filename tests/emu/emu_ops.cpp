@@ -218,6 +218,8 @@ static int g_enc_end = OB_NBANDS;   // CELT_SET_END_BAND for the next emu_celt_e
 extern "C" void emu_celt_set_end_band(int end) { g_enc_end = end; }
 static int g_enc_up = 1;   // 48000 / input rate for the next emu_celt_encode calls (pcm then holds N/up samples per channel)
 extern "C" void emu_celt_set_upsample(int up) { g_enc_up = up; }
+static int g_enc_pred = 2;   // CELT_SET_PREDICTION for the next emu_celt_encode calls
+extern "C" void emu_celt_set_prediction(int v) { g_enc_pred = v; }
 static int g_enc_coded = 0;   // CELT_SET_CHANNELS for the next emu_celt_encode calls (0 = as many as the input has)
 extern "C" void emu_celt_set_channels(int c) { g_enc_coded = c; }
 static int32_t g_enc_cov[3];   // frames that took the post-filter / patched-transient / transient paths (test coverage counters)
@@ -232,12 +234,12 @@ extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const flo
   a.state = (ObEncAnalysisState *)an_state; a.pcm = pcm; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
   a.info = info.data(); a.n_streams = n; a.C = C; a.CC = CC; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
   a.enc_state = enc_state; a.prefilter_mem = prefilter_mem; a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = bitrate; a.vbr = vbr;
-  a.constrained_vbr = cvbr; a.disable_pf = 0; a.loss_rate = 0; a.end = g_enc_end; a.upsample = g_enc_up;
+  a.constrained_vbr = cvbr; a.disable_pf = g_enc_pred <= 1; a.loss_rate = 0; a.end = g_enc_end; a.upsample = g_enc_up;
   emu_launch(enc_analysis_entry, &a, n, 32 * CC, CC * sizeof(MdctWS) + 32 + (complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams p;
   p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.bandLogE2 = Lg2.data(); p.packets = packets; p.nbytes = nbytes;
   p.n_streams = n; p.C = C; p.CC = CC; p.LM = LM; p.pkt_stride = max_bytes; p.max_bytes = max_bytes; p.complexity = complexity; p.bitrate = bitrate; p.lsb_depth = lsb_depth;
-  p.force_intra = 0; p.disable_inv = 0; p.disable_pf = 0; p.vbr = vbr; p.constrained_vbr = cvbr; p.loss_rate = 0; p.end = g_enc_end;
+  p.force_intra = g_enc_pred == 0; p.disable_inv = 0; p.disable_pf = g_enc_pred <= 1; p.vbr = vbr; p.constrained_vbr = cvbr; p.loss_rate = 0; p.end = g_enc_end;
   emu_launch(enc_frame_entry, &p, (n + 31) / 32, 32, 0);
   for (int s = 0; s < n; s++) rng[s] = enc_state[s].rng;
   for (int s = 0; s < n; s++) { g_enc_cov[0] += info[s].pf_on; g_enc_cov[1] += info[s].patched; g_enc_cov[2] += info[s].is_transient; }

@@ -14,13 +14,14 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1, end=21, coded=None):
+def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, kind='c', nframes=12, cvbr=1, end=21, coded=None, prediction=2):
     R, O = util.load_ref(kind), util.load_oracle()
     x = (sig.astype(np.float32) / 32768.0).reshape(-1, fs * ch)[:nframes]
     rs = np.zeros(R.refh_celt_encoder_size(ch) + 64, np.uint8)
     assert R.refh_celt_encoder_init(_p(rs), ch, complexity, bitrate, vbr, lsb) == 0
     R.refh_celt_encoder_set_cvbr(_p(rs), cvbr)
     assert R.refh_celt_encoder_set_end_band(_p(rs), end) == 0 and R.refh_celt_encoder_set_channels(_p(rs), coded or ch) == 0
+    assert R.refh_celt_encoder_set_prediction(_p(rs), prediction) == 0
     os_ = np.zeros(O.orc_encoder_size(), np.uint8)
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
@@ -30,6 +31,7 @@ def encode_both(sig, ch, fs, nbytes, complexity, bitrate=-1000, vbr=0, lsb=24, k
     O.orc_encoder_set_cvbr.restype = None
     O.orc_encoder_set_cvbr(_p(os_), cvbr)
     assert O.orc_encoder_set_end_band(_p(os_), end) == 0 and O.orc_encoder_set_channels(_p(os_), coded or ch) == 0
+    assert O.orc_encoder_set_prediction(_p(os_), prediction) == 0
     out = []
     for f in range(len(x)):
         a, b = np.zeros(1275, np.uint8), np.zeros(1275, np.uint8)
@@ -230,6 +232,18 @@ def test_mono_coding_of_stereo_input(fs, complexity, bitrate, vbr):
     sig = util.sig_music(fs + complexity, fs * 12, 2)
     nb = 1275 if bitrate != -1000 else max(8, 60 * fs // 960)
     for (f, na, nbo, a, b, ra, rb) in encode_both(sig, 2, fs, nb, complexity, bitrate=bitrate, vbr=vbr, coded=1):
+        assert na == nbo, (f, na, nbo)
+        assert np.array_equal(a, b), (f, int(np.argmax(a != b)))
+        assert ra == rb
+
+
+@pytest.mark.parametrize('prediction', [0, 1])
+@pytest.mark.parametrize('ch,fs,complexity,bitrate,vbr', [(2, 960, 10, 64000, 1), (1, 480, 5, -1000, 0), (2, 240, 8, 32000, 0), (2, 120, 4, -1000, 0), (1, 960, 10, 24000, 1)])
+def test_prediction_ctl(prediction, ch, fs, complexity, bitrate, vbr):
+    """CELT_SET_PREDICTION 0 / 1 (force_intra, disable_pf): bit-identical to the reference"""
+    sig = util.sig_harmonic(prediction + ch + fs, fs * 12, ch)
+    nb = 1275 if bitrate != -1000 else max(8, 100 * fs // 960)
+    for (f, na, nbo, a, b, ra, rb) in encode_both(sig, ch, fs, nb, complexity, bitrate=bitrate, vbr=vbr, prediction=prediction):
         assert na == nbo, (f, na, nbo)
         assert np.array_equal(a, b), (f, int(np.argmax(a != b)))
         assert ra == rb

@@ -13,7 +13,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1, end=21, Fs=48000, coded=None):
+def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0, cvbr=1, end=21, Fs=48000, coded=None, prediction=2):
     """x [nframes, fs*ch] float -> list of (packet bytes, range)"""
     O.orc_encoder_init.restype = None
     O.orc_encoder_ctl.restype = None
@@ -24,7 +24,7 @@ def oracle_encode(O, x, ch, fs, nbytes, bitrate=-1, lsb=24, complexity=0, vbr=0,
     O.orc_encoder_set_cvbr.restype = None
     O.orc_encoder_set_cvbr(_p(st), cvbr)
     assert O.orc_encoder_set_end_band(_p(st), end) == 0 and O.orc_encoder_set_fs(_p(st), Fs) == 0
-    assert O.orc_encoder_set_channels(_p(st), coded or ch) == 0
+    assert O.orc_encoder_set_channels(_p(st), coded or ch) == 0 and O.orc_encoder_set_prediction(_p(st), prediction) == 0
     out = []
     for f in range(len(x)):
         b = np.zeros(1275, np.uint8)
@@ -219,3 +219,35 @@ def test_emu_encoder_mono_coding_of_stereo_input(fs, nbytes, complexity, vbr, en
     finally:
         E.emu_celt_set_end_band(21)
         E.emu_celt_set_channels(0)
+
+
+@pytest.mark.parametrize('prediction', [0, 1])
+@pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr', [(2, 960, 100, 10, 0), (1, 480, 50, 5, 0), (2, 240, 1275, 8, 1), (2, 960, 120, 4, 0)])
+def test_emu_encoder_prediction_ctl(prediction, ch, fs, nbytes, complexity, vbr):
+    """CELT_SET_PREDICTION (celt/celt_encoder.c:2974-2982): 0 = intra-coded energies only and no pitch pre-filter, 1 = no pre-filter"""
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    n, nf = 4, 5
+    LM = {120: 0, 240: 1, 480: 2, 960: 3}[fs]
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 48000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
+    x = np.stack([sigs[s % len(sigs)](prediction + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, prediction=prediction) for s in range(n)]
+    an = np.zeros(n * E.emu_enc_analysis_state_size(), np.uint8)
+    es = np.zeros(n * E.emu_enc_state_size(), np.uint8)
+    E.emu_enc_state_init(_p(es), n)
+    pmem = np.zeros((n, ch, 1024), np.float32)
+    E.emu_celt_set_prediction(prediction)
+    try:
+        for f in range(nf):
+            pcm = np.ascontiguousarray(x[:, f])
+            pk = np.zeros((n, nbytes), np.uint8)
+            nb = np.zeros(n, np.int32)
+            rng = np.zeros(n, np.uint32)
+            E.emu_celt_encode(_p(an), _p(es), _p(pcm), n, ch, LM, nbytes, bitrate, 24, _p(pk), _p(nb), _p(rng), complexity, vbr, 1, _p(pmem))
+            for s in range(n):
+                wn, wb, wr = want[s][f]
+                assert nb[s] == wn, (f, s, nb[s], wn)
+                assert np.array_equal(pk[s, :wn], wb), (f, s, int(np.argmax(pk[s, :wn] != wb)))
+                assert rng[s] == wr
+    finally:
+        E.emu_celt_set_prediction(2)

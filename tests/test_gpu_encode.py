@@ -234,3 +234,27 @@ def test_encoder_mono_coding_of_stereo_input(fs, nbytes, complexity, vbr, end):
             assert np.array_equal(pk[s, :wn], wb), (f, s)
             assert rng[s] == wr
     enc.close()
+
+
+@pytest.mark.parametrize('prediction', [0, 1])
+@pytest.mark.parametrize('ch,fs,nbytes,complexity,vbr', [(2, 960, 100, 10, 0), (1, 480, 50, 5, 0), (2, 240, 1275, 8, 1)])
+def test_encoder_prediction_ctl(prediction, ch, fs, nbytes, complexity, vbr):
+    """CELT_SET_PREDICTION (request 10002): 0 = intra-coded energies only and no pitch pre-filter, 1 = no pre-filter"""
+    import opus_b200
+    O = util.load_oracle()
+    n, nf = 8, 5
+    sigs = [util.sig_harmonic, util.sig_swell, util.sig_music, clicks]
+    bitrate = 48000 * ch // 2 * (2 if fs < 480 else 1) if vbr else -1
+    x = np.stack([sigs[s % len(sigs)](prediction + s + fs, fs * nf, ch).astype(np.float32).reshape(nf, fs * ch) / 32768.0 for s in range(n)])
+    want = [oracle_encode(O, x[s], ch, fs, nbytes, bitrate=bitrate, complexity=complexity, vbr=vbr, prediction=prediction) for s in range(n)]
+    enc = opus_b200.EncoderBatch(n, channels=ch, complexity=complexity, bitrate=bitrate if vbr else None, vbr=bool(vbr))
+    enc.ctl(10002, prediction)
+    for f in range(nf):
+        pk, nb = enc.encode(np.ascontiguousarray(x[:, f]), nbytes)
+        rng = enc.final_range()
+        for s in range(n):
+            wn, wb, wr = want[s][f]
+            assert nb[s] == wn, (f, s, nb[s], wn)
+            assert np.array_equal(pk[s, :wn], wb), (f, s)
+            assert rng[s] == wr
+    enc.close()
