@@ -7,6 +7,8 @@ import numpy as np
 from . import capi
 
 OPUS_SET_BITRATE_REQUEST, OPUS_SET_VBR_REQUEST, OPUS_SET_COMPLEXITY_REQUEST, OPUS_SET_LSB_DEPTH_REQUEST = 4002, 4006, 4010, 4036
+# celt/celt.h:97-120: the CELT-level requests the Opus layer sets per frame
+CELT_SET_PREDICTION_REQUEST, CELT_SET_CHANNELS_REQUEST, CELT_SET_END_BAND_REQUEST = 10002, 10008, 10012
 OPUS_SET_PHASE_INVERSION_DISABLED_REQUEST = 4046
 OPUS_SET_VBR_CONSTRAINT_REQUEST, OPUS_SET_PACKET_LOSS_PERC_REQUEST = 4020, 4014
 
