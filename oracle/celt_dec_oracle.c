@@ -2069,4 +2069,5 @@ int orc_decode_stream_float_fs(int Fs, int channels, int frame_size, int nframes
 }
 
 #include "celt_enc.inc"
+#include "opus_enc.inc"
 #include "celt_plc.inc"

@@ -312,3 +312,55 @@ int refh_celt_encoder_init_fs(CELTEncoder *st, int Fs, int channels, int complex
 int refh_celt_encoder_set_prediction(CELTEncoder *st, int v) { return celt_encoder_ctl(st, CELT_SET_PREDICTION(v)); }
 int refh_celt_encoder_set_channels(CELTEncoder *st, int c) { return celt_encoder_ctl(st, CELT_SET_CHANNELS(c)); }
 int refh_celt_encoder_set_end_band(CELTEncoder *st, int end) { return celt_encoder_ctl(st, CELT_SET_END_BAND(end)); }
+
+/* ---- the Opus layer's tonality / music analysis alone (src/analysis.c run_analysis), one stream, consecutive frames.
+ * out: nframes records of 11 floats + 19 bytes = our OrcAnalysisInfo layout is NOT assumed: fields are written one by one:
+ * [valid, tonality, tonality_slope, noisiness, activity, music_prob, music_prob_min, music_prob_max, bandwidth,
+ *  activity_probability, max_pitch_ratio, leak_boost[0..18]] as 30 floats per frame. ---- */
+#include "src/analysis.h"
+#include "src/opus_private.h"
+int refh_run_analysis_stream(int Fs, int channels, int frame_size, int nframes, const void *pcm, int is_int16, int lsb_depth, float *out) {
+  TonalityAnalysisState *t = (TonalityAnalysisState *)calloc(1, sizeof(*t));
+  const OpusCustomMode *m = refh_mode();
+  int f, k;
+  if (!t) return -7;
+  tonality_analysis_init(t, Fs);
+  for (f = 0; f < nframes; f++) {
+    AnalysisInfo info;
+    const void *p = is_int16 ? (const void *)((const opus_int16 *)pcm + (size_t)f * frame_size * channels)
+                             : (const void *)((const float *)pcm + (size_t)f * frame_size * channels);
+    memset(&info, 0, sizeof(info));
+    run_analysis(t, m, p, frame_size, frame_size, 0, -2, channels, Fs, lsb_depth, is_int16 ? downmix_int : downmix_float, &info);
+    float *o = out + 30 * f;
+    o[0] = (float)info.valid; o[1] = info.tonality; o[2] = info.tonality_slope; o[3] = info.noisiness; o[4] = info.activity;
+    o[5] = info.music_prob; o[6] = info.music_prob_min; o[7] = info.music_prob_max; o[8] = (float)info.bandwidth;
+    o[9] = info.activity_probability; o[10] = info.max_pitch_ratio;
+    for (k = 0; k < 19; k++) o[11 + k] = (float)info.leak_boost[k];
+  }
+  free(t);
+  return 0;
+}
+
+/* As refh_encode_stream_ex through opus_encode_float (pcm: interleaved floats +-1.0) */
+int refh_encode_stream_float_ex(int Fs, int channels, int application, int bitrate, int vbr, int complexity,
+                                int frame_size, int nframes, const float *pcm, unsigned char *out,
+                                int max_bytes, int *sizes, unsigned int *ranges, const int *ctls, int nctl) {
+  int err = 0, f, k;
+  OpusEncoder *enc = opus_encoder_create(Fs, channels, application, &err);
+  if (!enc) return err;
+  opus_encoder_ctl(enc, OPUS_SET_BITRATE(bitrate));
+  opus_encoder_ctl(enc, OPUS_SET_VBR(vbr));
+  opus_encoder_ctl(enc, OPUS_SET_COMPLEXITY(complexity));
+  for (k = 0; k < nctl; k++) {
+    err = opus_encoder_ctl(enc, ctls[2 * k], (opus_int32)ctls[2 * k + 1]);
+    if (err != OPUS_OK) { opus_encoder_destroy(enc); return err; }
+  }
+  for (f = 0; f < nframes; f++) {
+    int n = opus_encode_float(enc, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * max_bytes, max_bytes);
+    if (n < 0) { opus_encoder_destroy(enc); return n; }
+    sizes[f] = n;
+    opus_encoder_ctl(enc, OPUS_GET_FINAL_RANGE(&ranges[f]));
+  }
+  opus_encoder_destroy(enc);
+  return 0;
+}
