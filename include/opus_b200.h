@@ -202,6 +202,45 @@ int opusb200_encoder_sync(OpusB200Encoder *enc);
 void *opusb200_encoder_cuda_stream(OpusB200Encoder *enc);
 int64_t opusb200_encoder_launch_count(OpusB200Encoder *enc);
 
+/* ---- Batched Opus encoder: the reference's public encoder API for n independent streams (include/opus.h:170-355, src/opus_encoder.c).
+ *   opus_encoder_create(Fs, channels, application, &err)   include/opus.h:208   opusb200_opus_encoder_create(..., n_streams, ...)
+ *   opus_encode(st, pcm, frame_size, data, max_data_bytes) include/opus.h:266   opusb200_opus_encode(enc, pcm, frame_size, packets, stride, max_data_bytes, nbytes[])
+ *   opus_encode_float(...)                                 include/opus.h:343   opusb200_opus_encode_float(...)
+ *   opus_encoder_ctl(st, request, value)                   include/opus.h:355   opusb200_opus_encoder_ctl(enc, request, value)
+ *   opus_encoder_ctl(st, OPUS_GET_FINAL_RANGE(&r))                              opusb200_opus_encoder_get_final_range(enc, r[])
+ *   opus_encoder_destroy(st)                               include/opus.h:350   opusb200_opus_encoder_destroy(enc)
+ * application: OPUS_APPLICATION_RESTRICTED_CELT (2053) or OPUS_APPLICATION_RESTRICTED_LOWDELAY (2051), the two applications whose frames are
+ * always CELT-only; VOIP / AUDIO / RESTRICTED_SILK can select SILK and return OPUSB200_UNIMPLEMENTED.  Everything opus_encode() does for such
+ * an encoder runs on the device, per stream: run_analysis (src/analysis.c: tonality / bandwidth / music detector, from complexity 7 and Fs >= 16 kHz),
+ * the mono/stereo and bandwidth decisions with their hysteresis, dc_reject, the stereo width fade, the float API's NaN / level guard, the CELT
+ * encoder with st->analysis valid, the TOC byte.  Packets (TOC included) and OPUS_GET_FINAL_RANGE are bit-identical to the reference's C build
+ * given the same calls.  Frame sizes 2.5 / 5 / 10 / 20 ms; 40..120 ms (repacketised multi-frame packets), DTX and budgets below 3 bytes per
+ * frame return OPUSB200_UNIMPLEMENTED for the call.  Setters (request numbers of include/opus_defines.h, value semantics of opus_encoder_ctl):
+ * 4002 bitrate (-1000 OPUS_AUTO, -1 OPUS_BITRATE_MAX), 4004 max bandwidth, 4006 vbr, 4008 bandwidth, 4010 complexity, 4014 packet loss %,
+ * 4020 vbr constraint, 4022 force channels, 4024 signal, 4028 OPUS_RESET_STATE, 4036 lsb depth, 4042 prediction disabled, 4046 phase inversion disabled.
+ * nbytes[s] = packet length of stream s (TOC included) or a negative error code. ---- */
+typedef struct OpusB200OpusEncoder OpusB200OpusEncoder;
+int opusb200_opus_encoder_create(int device, int32_t Fs, int channels, int application, int n_streams, OpusB200OpusEncoder **out);
+void opusb200_opus_encoder_destroy(OpusB200OpusEncoder *enc);
+int opusb200_opus_encoder_reset(OpusB200OpusEncoder *enc);
+int opusb200_opus_encoder_ctl(OpusB200OpusEncoder *enc, int request, int32_t value);
+/* host buffers: pcm [n][frame_size*channels] interleaved, packets [n][pkt_stride] (pkt_stride >= max_data_bytes), nbytes [n] */
+int opusb200_opus_encode(OpusB200OpusEncoder *enc, const int16_t *pcm, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                         int32_t *nbytes);
+int opusb200_opus_encode_float(OpusB200OpusEncoder *enc, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                               int32_t *nbytes);
+/* device buffers (d_pcm int16 or float as pcm_is_int16 says); work is enqueued on the encoder's stream */
+int opusb200_opus_encode_device(OpusB200OpusEncoder *enc, const void *d_pcm, int pcm_is_int16, int frame_size, unsigned char *d_packets,
+                                int pkt_stride, int max_data_bytes, int32_t *d_nbytes);
+int opusb200_opus_encoder_get_final_range(OpusB200OpusEncoder *enc, uint32_t *final_range);
+int opusb200_opus_encoder_sync(OpusB200OpusEncoder *enc);
+void *opusb200_opus_encoder_cuda_stream(OpusB200OpusEncoder *enc);
+int64_t opusb200_opus_encoder_launch_count(OpusB200OpusEncoder *enc);
+/* Profiling aid: when enabled every kernel of a call is bracketed by CUDA events on the encoder's stream and the call waits for them (so not
+ * for throughput runs).  get_timing: accumulated device ms of [Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder]. */
+int opusb200_opus_encoder_set_timing(OpusB200OpusEncoder *enc, int enable);
+int opusb200_opus_encoder_get_timing(OpusB200OpusEncoder *enc, double *ms_kernels, int64_t *calls);
+
 /* ---- CELT encoder front end, fused: celt_preemphasis (celt/celt_encoder.c:557) -> compute_mdcts (:511) -> compute_band_energies
  * (celt/bands.c:151) -> amp2Log2 (celt/quant_bands.c:553) -> normalise_bands (celt/bands.c:169), i.e. lines 2007-2265 of
  * celt_encode_with_ec with the pitch pre-filter off.  The object keeps, per stream and channel, the pre-emphasis memory and

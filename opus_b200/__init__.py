@@ -10,6 +10,6 @@ from .capi import (OpusB200Error, lib, library_path, build_library, OPUS_OK, OPU
                    OPUS_INTERNAL_ERROR, OPUS_INVALID_PACKET, OPUS_UNIMPLEMENTED, OPUS_INVALID_STATE, OPUS_ALLOC_FAIL)
 from .decoder import DecoderBatch
 from .ops import Ops
-from .encoder import EncoderBatch
+from .encoder import EncoderBatch, OpusEncoderBatch
 
-__all__ = ['DecoderBatch', 'EncoderBatch', 'Ops', 'OpusB200Error', 'lib', 'library_path', 'build_library']
+__all__ = ['DecoderBatch', 'EncoderBatch', 'OpusEncoderBatch', 'Ops', 'OpusB200Error', 'lib', 'library_path', 'build_library']

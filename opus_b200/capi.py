@@ -37,7 +37,11 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_nnet_compute_gru', 'opusb200_nnet_compute_glu', 'opusb200_nnet_compute_conv1d',
            'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d',
            'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize',
-           'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free']
+           'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free',
+           'opusb200_opus_encoder_create', 'opusb200_opus_encoder_destroy', 'opusb200_opus_encoder_reset', 'opusb200_opus_encoder_ctl',
+           'opusb200_opus_encode', 'opusb200_opus_encode_float', 'opusb200_opus_encode_device', 'opusb200_opus_encoder_get_final_range',
+           'opusb200_opus_encoder_sync', 'opusb200_opus_encoder_cuda_stream', 'opusb200_opus_encoder_launch_count',
+           'opusb200_opus_encoder_set_timing', 'opusb200_opus_encoder_get_timing']
 
 
 class OpusB200Error(RuntimeError):
@@ -164,6 +168,22 @@ def lib():
         L.opusb200_encoder_cuda_stream.restype = vp
         L.opusb200_encoder_launch_count.argtypes = [vp]
         L.opusb200_encoder_launch_count.restype = ctypes.c_int64
+        L.opusb200_opus_encoder_create.argtypes = [ci, i32, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_opus_encoder_destroy.argtypes = [vp]
+        L.opusb200_opus_encoder_destroy.restype = None
+        L.opusb200_opus_encoder_reset.argtypes = [vp]
+        L.opusb200_opus_encoder_ctl.argtypes = [vp, ci, i32]
+        L.opusb200_opus_encode.argtypes = [vp, vp, ci, vp, ci, ci, vp]
+        L.opusb200_opus_encode_float.argtypes = [vp, vp, ci, vp, ci, ci, vp]
+        L.opusb200_opus_encode_device.argtypes = [vp, vp, ci, ci, vp, ci, ci, vp]
+        L.opusb200_opus_encoder_get_final_range.argtypes = [vp, vp]
+        L.opusb200_opus_encoder_sync.argtypes = [vp]
+        L.opusb200_opus_encoder_cuda_stream.argtypes = [vp]
+        L.opusb200_opus_encoder_cuda_stream.restype = vp
+        L.opusb200_opus_encoder_launch_count.argtypes = [vp]
+        L.opusb200_opus_encoder_launch_count.restype = ctypes.c_int64
+        L.opusb200_opus_encoder_set_timing.argtypes = [vp, ci]
+        L.opusb200_opus_encoder_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
         L.opusb200_host_alloc.argtypes = [ctypes.c_size_t]
         L.opusb200_host_alloc.restype = vp
         L.opusb200_host_free.argtypes = [vp]

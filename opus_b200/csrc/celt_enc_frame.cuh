@@ -30,6 +30,10 @@ struct EncFrameParams {
   int CC = 0;             // input channels when they differ from the coded channels C (CELT_SET_CHANNELS); 0 = C
   int n_streams, C, LM, pkt_stride, max_bytes, complexity, bitrate, lsb_depth, force_intra, disable_inv, disable_pf, vbr, constrained_vbr,
       loss_rate;
+  // Opus layer: per-stream coded channels / end band / AnalysisInfo (see EncAnalysisParams::ctl); toc_bytes is added to nbytes (the
+  // packet pointer then already skips the TOC byte)
+  const ObOpusFrameCtl *ctl = nullptr;
+  int toc_bytes = 0;
 };
 
 // ---- range encoder (celt/entenc.c:60-305), state in registers, bytes straight to the packet in HBM ----
@@ -220,7 +224,7 @@ OB_DEV float enc_median3(const float *x) {
 struct EncDyn { float maxDepth; int32_t tot_boost; };
 OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *bandLogE2, const float *oldBandE, int C, int *offsets, int lsb_depth, int isTransient, int LM,
                              int effectiveBytes, float tone_freq, float toneishness, int vbr, int constrained_vbr, int *importance,
-                             int *spread_weight, int end) {
+                             int *spread_weight, int end, const ObAnalysisInfo *an) {
   float follower[2 * OB_NBANDS], noise_floor[OB_NBANDS], bandLogE3[OB_NBANDS];
   int32_t tot_boost = 0;
 #pragma unroll 1
@@ -322,6 +326,9 @@ OB_DEVNI EncDyn enc_dynalloc(const float *bandLogE, const float *bandLogE2, cons
       follower[end - 2] += 1.f;
     }
   }
+  if (an && an->valid)   // celt/celt_encoder.c:1226-1230
+#pragma unroll 1
+    for (int i = 0; i < OB_IMIN(19, end); i++) follower[i] = follower[i] + (1.f / 64.f) * an->leak_boost[i];
   if (effectiveBytes > 320) follower[0] += enc_fmin(1.5f, 1e-3f * (effectiveBytes - 320));
 #pragma unroll 1
   for (int i = 0; i < end; i++) {
@@ -520,11 +527,13 @@ OB_DEVNI int enc_spreading_decision(const float *X, ObEncState &st, int update_h
 
 // ---- compute_vbr (celt/celt_encoder.c:1604-1717; analysis invalid, no lfe / surround mask) ----
 OB_DEVNI int32_t enc_compute_vbr(int32_t base_target, int LM, int32_t bitrate, int lastCodedBands, int C, int intensity, int constrained_vbr,
-                                 float stereo_saving, int tot_boost, float tf_estimate, float maxDepth, float temporal_vbr) {
+                                 float stereo_saving, int tot_boost, float tf_estimate, float maxDepth, float temporal_vbr,
+                                 const ObAnalysisInfo *an, int pitch_change) {
   const int coded_bands = lastCodedBands ? lastCodedBands : OB_NBANDS;
   int coded_bins = ob_ebands[coded_bands] << LM;
   if (C == 2) coded_bins += ob_ebands[OB_IMIN(intensity, coded_bands)] << LM;
   int32_t target = base_target;
+  if (an && an->valid && (double)an->activity < .4) target -= (int32_t)((coded_bins << OB_BITRES) * (.4f - an->activity));   // :1632-1633
   if (C == 2) {
     const int coded_stereo_bands = OB_IMIN(intensity, coded_bands);
     const int coded_stereo_dof = (ob_ebands[coded_stereo_bands] << LM) - coded_stereo_bands;
@@ -535,6 +544,12 @@ OB_DEVNI int32_t enc_compute_vbr(int32_t base_target, int LM, int32_t bitrate, i
   }
   target += tot_boost - (19 << LM);
   target += (int32_t)((tf_estimate - 0.044f) * target);
+  if (an && an->valid) {   // tonality boost (:1658-1670)
+    const float tonal = enc_fmax(0.f, an->tonality - .15f) - 0.12f;
+    int32_t tonal_target = target + (int32_t)((coded_bins << OB_BITRES) * 1.2f * tonal);
+    if (pitch_change) tonal_target += (int32_t)((coded_bins << OB_BITRES) * .8f);
+    target = tonal_target;
+  }
   const int bins = ob_ebands[OB_NBANDS - 2] << LM;
   int32_t floor_depth = (int32_t)((C * bins << OB_BITRES) * maxDepth);
   floor_depth = OB_IMAX(floor_depth, target >> 2);
@@ -1133,22 +1148,24 @@ namespace ob {
 // folding / save buffers triple the thread's local memory)
 template <bool RDO>
 OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
-  const int C = p.C, LM = p.LM, M = 1 << LM, N = M * OB_SHORT_N, end = p.end, start = 0;
+  const int LM = p.LM, M = 1 << LM, N = M * OB_SHORT_N, start = 0;
+  const int C = p.ctl ? p.ctl[stream].C : p.C, end = p.ctl ? p.ctl[stream].end : p.end, SC = p.ctl ? (p.CC ? p.CC : p.C) : p.C;
+  const ObAnalysisInfo *an = p.ctl ? &p.ctl[stream].analysis : nullptr;
   ObEncState &st = p.state[stream];
   const ObEncFrameInfo fi = p.info[stream];
-  float *Xg = p.X + (size_t)stream * C * N;
-  const float *bandE = p.bandE + (size_t)stream * C * OB_NBANDS;
+  float *Xg = p.X + (size_t)stream * SC * N;
+  const float *bandE = p.bandE + (size_t)stream * SC * OB_NBANDS;
   float bandLogE[2 * OB_NBANDS], error[2 * OB_NBANDS];
   int fine_quant[OB_NBANDS], pulses[OB_NBANDS], cap[OB_NBANDS], offsets[OB_NBANDS], fine_priority[OB_NBANDS], tf_res[OB_NBANDS];
   float bx[176], by[176], tmp[176];
 #pragma unroll 1
-  for (int i = 0; i < C * OB_NBANDS; i++) bandLogE[i] = p.bandLogE[(size_t)stream * C * OB_NBANDS + i];
+  for (int i = 0; i < C * OB_NBANDS; i++) bandLogE[i] = p.bandLogE[(size_t)stream * SC * OB_NBANDS + i];
   float bl2[2 * OB_NBANDS];
   // bandLogE2 differs from bandLogE for a patched frame and, from complexity 8, for every transient frame (second MDCT)
   const bool have_bl2 = p.bandLogE2 && (fi.patched || (p.complexity >= 8 && fi.short_blocks));
   if (have_bl2)
 #pragma unroll 1
-    for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] = p.bandLogE2[(size_t)stream * C * OB_NBANDS + i];
+    for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] = p.bandLogE2[(size_t)stream * SC * OB_NBANDS + i];
 
   int importance[OB_NBANDS], spread_weight[OB_NBANDS];
   const EncBudget bud = enc_budget(p.max_bytes, p.bitrate, p.vbr, p.constrained_vbr, N, st.vbr_reservoir);
@@ -1182,6 +1199,9 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   int status = 0;
   const int pf_on = fi.pf_on;
   int pitch_index = fi.pitch_index;
+  // celt/celt_encoder.c:2043-2045 (read by compute_vbr's tonality boost only)
+  const int pitch_change = (fi.gain1 > .4f || st.prefilter_gain > .4f) && (!(an && an->valid) || (double)an->tonality > .3) &&
+                           ((double)pitch_index > 1.26 * st.prefilter_period || (double)pitch_index < .79 * st.prefilter_period);
   if (pf_on == 0) {
     if (tell + 16 <= total_bits) re_bit_logp(enc, 0, 1);
   } else {
@@ -1228,7 +1248,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     for (int i = 0; i < C * OB_NBANDS; i++) bl2[i] += .5f * LM;
   if (LM > 0 && re_tell(enc) + 3 <= total_bits) re_bit_logp(enc, isTransient, 3);
   const EncDyn dyn = enc_dynalloc(bandLogE, have_bl2 ? bl2 : bandLogE, st.oldBandE, C, offsets, p.lsb_depth, isTransient, LM, effectiveBytes, fi.tone_freq, toneishness, p.vbr,
-                                  p.constrained_vbr, importance, spread_weight, end);
+                                  p.constrained_vbr, importance, spread_weight, end, an);
   int tf_select = 0;
   if (effectiveBytes >= 15 * C && p.complexity >= 2 && toneishness < .98f) {   // enable_tf_analysis
     const int lambda = OB_IMAX(80, 20480 / effectiveBytes + 2);
@@ -1398,6 +1418,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     diff /= C * (end - 1);
     trim -= enc_fmax(-2.f, enc_fmin(2.f, (diff + 1.f) / 6));
     trim -= 2 * tf_estimate;
+    if (an && an->valid) trim -= enc_fmax(-2.f, enc_fmin(2.f, (float)(2.f * (an->tonality_slope + .05f))));   // celt/celt_encoder.c:935-939
     alloc_trim = OB_IMAX(0, OB_IMIN(10, (int)floor((double)(.5f + trim))));
     re_icdf(enc, alloc_trim, ob_trim_icdf, 7);
     tell = re_tell_frac(enc);
@@ -1409,7 +1430,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     int32_t base_target = vbr_rate - ((40 * C + 20) << OB_BITRES);
     if (p.constrained_vbr) base_target += (st.vbr_offset >> lm_diff);
     int32_t target = enc_compute_vbr(base_target, LM, equiv_rate, st.lastCodedBands, C, st.intensity, p.constrained_vbr, st.stereo_saving, dyn.tot_boost,
-                                     tf_estimate, dyn.maxDepth, temporal_vbr);
+                                     tf_estimate, dyn.maxDepth, temporal_vbr, an, pitch_change);
     target = target + tell;
     nbAvailableBytes = (target + (1 << (OB_BITRES + 2))) >> (OB_BITRES + 3);
     nbAvailableBytes = OB_IMAX(min_allowed, nbAvailableBytes);
@@ -1442,8 +1463,14 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   int32_t bits = (((int32_t)nbCompressedBytes * 8) << OB_BITRES) - (int32_t)re_tell_frac(enc) - 1;
   const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;
   bits -= anti_collapse_rsv;
+  int signalBandwidth = end - 1;
+  if (an && an->valid) {   // celt/celt_encoder.c:2610-2624
+    const int min_bandwidth = equiv_rate < (int32_t)32000 * C ? 13 : equiv_rate < (int32_t)48000 * C ? 16 : equiv_rate < (int32_t)60000 * C ? 18
+                              : equiv_rate < (int32_t)80000 * C ? 19 : 20;
+    signalBandwidth = OB_IMAX(an->bandwidth, min_bandwidth);
+  }
   const EncAlloc al = enc_compute_allocation(enc, offsets, cap, alloc_trim, st.intensity, dual_stereo, bits, pulses, fine_quant, fine_priority, C, LM,
-                                             st.lastCodedBands, end - 1, end);
+                                             st.lastCodedBands, signalBandwidth, end);
   st.intensity = al.intensity;
   dual_stereo = al.dual_stereo;
   const int codedBands = al.codedBands;
@@ -1564,7 +1591,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   else st.consec_transient = 0;
   st.rng = enc.rng;
   re_done(enc);
-  p.nbytes[stream] = status ? status : (enc.error ? -3 : nbCompressedBytes);
+  p.nbytes[stream] = status ? status : (enc.error ? -3 : nbCompressedBytes + p.toc_bytes);
 }
 
 }  // namespace ob

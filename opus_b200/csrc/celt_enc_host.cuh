@@ -46,6 +46,11 @@ struct OpusB200Encoder {
   // the frame coder runs on a second stream, chunk by chunk behind the analysis kernel (see opusb200_encode_device)
   cudaStream_t stream_f[4];   // one per chunk: the frame coder is latency-bound per warp, so the chunks' coders must overlap each other too
   cudaEvent_t ev_an[4], ev_fr[4];
+  // profiling aid (opusb200_opus_encoder_set_timing): CUDA events around each kernel of a call, on the launching stream
+  int timing;
+  cudaEvent_t tev[5];
+  double t_ms[4];   // Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder
+  int64_t t_calls;
 };
 
 extern "C" int opusb200_encoder_reset(OpusB200Encoder *e) {
@@ -108,6 +113,7 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
   cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt);
+  if (e->tev[0]) for (int i = 0; i < 5; i++) cudaEventDestroy(e->tev[i]);
   for (int i = 0; i < 4; i++) {
     cudaStreamSynchronize(e->stream_f[i]);
     cudaStreamDestroy(e->stream_f[i]);
@@ -141,8 +147,9 @@ extern "C" int opusb200_encoder_sync(OpusB200Encoder *e) {
   return OPUSB200_OK;
 }
 // device pointers: pcm [n][frame_size*channels] float (+-1.0), packets [n][pkt_stride], nbytes [n]
-extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, int frame_size, unsigned char *d_packets, int pkt_stride,
-                                      int max_data_bytes, int32_t *d_nbytes) {
+// ctl != nullptr: the Opus layer in front (opus_enc_host.cuh): coded channels / end band / AnalysisInfo per stream, one TOC byte ahead of the payload
+static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_size, unsigned char *d_packets, int pkt_stride, int max_data_bytes,
+                              int32_t *d_nbytes, const ob::ObOpusFrameCtl *ctl) {
   if (!e || !d_pcm || !d_packets || !d_nbytes || pkt_stride < max_data_bytes || max_data_bytes < 2) return OPUSB200_BAD_ARG;
   int LM = -1;
   for (int l = 0; l <= 3; l++) if (frame_size * e->upsample == OB_SHORT_N << l) LM = l;   // frame_size counts input-rate samples (celt_encoder.c:1838)
@@ -153,6 +160,7 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   a.n_streams = e->n; a.C = e->stream_channels; a.CC = e->channels; a.LM = LM; a.complexity = e->complexity; a.lsb_depth = e->lsb_depth;
   a.enc_state = e->state; a.prefilter_mem = e->prefilter_mem; a.bandLogE2 = e->bandLogE2; a.max_bytes = max_data_bytes; a.bitrate = e->bitrate;
   a.vbr = e->vbr; a.constrained_vbr = e->constrained_vbr; a.disable_pf = e->disable_pf; a.loss_rate = e->loss_rate; a.end = e->end; a.upsample = e->upsample;
+  a.ctl = ctl;
   // the pitch-search buffers exist from complexity 5 only (PfWS: sc always, buf/xlp2 for the search)
   const size_t pf_smem = e->complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64;
   EncFrameParams p;
@@ -160,6 +168,7 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
   p.C = e->stream_channels; p.CC = e->channels; p.LM = LM; p.pkt_stride = pkt_stride; p.max_bytes = max_data_bytes; p.complexity = e->complexity;
   p.bitrate = e->bitrate; p.lsb_depth = e->lsb_depth; p.force_intra = e->force_intra; p.disable_inv = e->disable_inv; p.disable_pf = e->disable_pf; p.end = e->end;
   p.vbr = e->vbr; p.constrained_vbr = e->constrained_vbr; p.loss_rate = e->loss_rate;
+  p.ctl = ctl; p.toc_bytes = ctl ? 1 : 0;
   // Chunking the batch (analysis of chunk k+1 on the library stream under the frame coder of chunk k on its own higher-priority
   // stream) was measured and is OFF: 9.6 vs 5.9 ms at complexity 0, 56 vs 29 ms at complexity 10 for 65 536 streams.  Both
   // kernels are limited by how many of their warps are resident at once, and splitting the batch only lowers that.  The plumbing
@@ -171,22 +180,37 @@ extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, in
     const int s0 = k * per, s1 = OB_IMIN(e->n, s0 + per);
     if (s0 >= s1) break;
     a.first_stream = s0; a.n_streams = s1;
+    if (e->timing) cudaEventRecord(e->tev[2], e->stream);
     ob_celt_enc_analysis<<<s1 - s0, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
+    if (e->timing) cudaEventRecord(e->tev[3], e->stream);
     cudaStream_t sf = chunks > 1 ? e->stream_f[k] : e->stream;
     if (chunks > 1) {
       OB_CUDA(cudaEventRecord(e->ev_an[k], e->stream));
       OB_CUDA(cudaStreamWaitEvent(sf, e->ev_an[k], 0));
     }
     p.first_stream = s0; p.n_streams = s1;
-    if (e->complexity >= 8 && e->stream_channels == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    if (e->complexity >= 8 && (ctl ? e->channels : e->stream_channels) == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     else ob_celt_enc_frame<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     e->launches += 2;
+    if (e->timing) cudaEventRecord(e->tev[4], sf);
     if (chunks > 1) OB_CUDA(cudaEventRecord(e->ev_fr[k], sf));
   }
   if (chunks > 1)
     for (int k = 0; k < chunks; k++) OB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_fr[k], 0));
   OB_CUDA(cudaGetLastError());
+  if (e->timing) {   // (profiling runs only: the call then waits for its kernels)
+    OB_CUDA(cudaEventSynchronize(e->tev[4]));
+    float ms = 0.f;
+    if (ctl) { cudaEventElapsedTime(&ms, e->tev[0], e->tev[1]); e->t_ms[0] += ms; cudaEventElapsedTime(&ms, e->tev[1], e->tev[2]); e->t_ms[1] += ms; }
+    cudaEventElapsedTime(&ms, e->tev[2], e->tev[3]); e->t_ms[2] += ms;
+    cudaEventElapsedTime(&ms, e->tev[3], e->tev[4]); e->t_ms[3] += ms;
+    e->t_calls++;
+  }
   return OPUSB200_OK;
+}
+extern "C" int opusb200_encode_device(OpusB200Encoder *e, const float *d_pcm, int frame_size, unsigned char *d_packets, int pkt_stride,
+                                      int max_data_bytes, int32_t *d_nbytes) {
+  return celt_encode_launch(e, d_pcm, frame_size, d_packets, pkt_stride, max_data_bytes, d_nbytes, nullptr);
 }
 // host buffers; returns when the packets are on the host.  nbytes[s] = payload size (CBR: the same for all) or a negative code.
 extern "C" int opusb200_encode_float(OpusB200Encoder *e, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,

@@ -146,6 +146,8 @@ struct PfArgs {
   int head;                  // ring position of the oldest history sample
   int C, N, enabled, complexity, nbAvailableBytes, prefilter_tapset, prev_period, prev_tapset, loss_rate;
   float prev_gain, tf_estimate, tone_freq, toneishness;
+  int an_valid = 0;             // st->analysis.valid (CELT_SET_ANALYSIS): gain1 is scaled by max_pitch_ratio (celt/celt_encoder.c:1494-1495)
+  float an_max_pitch_ratio = 1.f;
 };
 OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
   const int tid = warp_in_block() * 32 + lane_id(), nth = warps_per_block() * 32;
@@ -389,6 +391,7 @@ OB_DEVNI PfDecision enc_prefilter_stage(PfWS *w, const PfArgs &a) {
       gain1 = w->sc[22];
     }
   }
+  if (a.an_valid) gain1 = (float)(gain1 * a.an_max_pitch_ratio);   // celt/celt_encoder.c:1494-1495
   // gain threshold and quantisation (celt/celt_encoder.c:1499-1536); every thread computes the same scalars
   float pf_threshold = .2f;
   {

@@ -14,6 +14,7 @@
 #include "celt_fft.cuh"
 #include "celt_vec.cuh"
 #include "celt_enc_pre.cuh"
+#include "opus_enc_layer.cuh"
 
 namespace ob {
 
@@ -114,7 +115,32 @@ struct EncAnalysisParams {
   float *bandLogE2 = nullptr;            // [n_streams][C*21]: the long-block log energies when the frame was patched to short blocks
   int max_bytes = 0, bitrate = -1, vbr = 0, constrained_vbr = 0, disable_pf = 0, loss_rate = 0;
   int first_stream = 0;                  // this launch covers streams [first_stream, first_stream + gridDim.x)
+  // Opus layer (opus_encode): per-stream coded channels / end band / AnalysisInfo, and the stereo width fade + guard applied to the
+  // dc-rejected input as it is read (src/opus_encoder.c:2011-2022, 2329-2349).  Arrays are then strided by the INPUT channel count.
+  const ObOpusFrameCtl *ctl = nullptr;
 };
+// the encoder's input sample (i, c) of one stream: the caller's PCM, or with the Opus layer in front the dc-rejected signal after
+// stereo_fade (src/opus_encoder.c:553-580) and the float guard
+struct EncPcmView {
+  const float *pcm;   // this stream's interleaved frame
+  int CC, fade, clear, inc;
+  float g1, g2;
+};
+OB_DEV float enc_pcm_at(const EncPcmView &v, int i, int c) {
+  if (v.clear) return 0.f;
+  const float x = v.pcm[(size_t)v.CC * i + c];
+  if (!v.fade) return x;
+  const float L = v.pcm[(size_t)2 * i], R = v.pcm[(size_t)2 * i + 1];
+  float g = v.g2;
+  if (i < OB_OVERLAP / v.inc) {
+    float w = ob_window[i * v.inc];
+    w = w * w;
+    g = w * v.g2 + (1.f - w) * v.g1;
+  }
+  float diff = .5f * (L - R);
+  diff = g * diff;
+  return c == 0 ? L - diff : R + diff;
+}
 // tone_lpc (celt/celt_encoder.c:1305-1360) on x = in0 (+ in1): the six running sums are independent sequential chains,
 // one lane each (lanes 0-2: r00 r01 r02, lanes 3-5: the three edge corrections); lane 0 solves the 2x2 system.
 OB_DEV int tone_lpc_warp(const float *in0, const float *in1, int len, int delay, float *lpc, int lane) {
@@ -234,11 +260,14 @@ OB_DEV void enc_mdct_tail(float *freq, float *f0, const float *f1, int N, int up
 OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned char *smem) {
   const int lane = lane_id(), c = warp_in_block();
   MdctWS *ws = (MdctWS *)smem + c;
-  const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, C = p.C, CC = p.CC ? p.CC : p.C;   // C coded channels (CELT_SET_CHANNELS), CC input channels: one warp per INPUT channel
+  const int LM = p.LM, N = OB_SHORT_N << LM, M = 1 << LM, CC = p.CC ? p.CC : p.C;   // C coded channels (CELT_SET_CHANNELS), CC input channels: one warp per INPUT channel
+  const int C = p.ctl ? p.ctl[stream].C : p.C, SC = p.ctl ? CC : p.C, end_band = p.ctl ? p.ctl[stream].end : p.end;   // SC: channel stride of the per-stream arrays
   int transient = p.short_blocks ? (p.short_blocks[stream] != 0) : 0;
   ObEncAnalysisState &st = p.state[stream];
   const int up = p.upsample;
-  const float *pcm = p.pcm + (size_t)stream * (N / up) * CC + c;
+  EncPcmView pv;
+  pv.pcm = p.pcm + (size_t)stream * (N / up) * CC; pv.CC = CC; pv.fade = 0; pv.clear = 0; pv.inc = up; pv.g1 = pv.g2 = 0.f;
+  if (p.ctl) { const ObOpusFrameCtl &k = p.ctl[stream]; pv.fade = k.fade; pv.clear = k.clear; pv.g1 = k.fade_g1; pv.g2 = k.fade_g2; }
   // pre-emphasis is a 2-tap FIR on the input: in[i] = x[i] - 0.85*x[i-1]  (m = coef0*x is carried, not the output)
   const float coef0 = 0.85000610f;
   float mx_new = 0.f, mx_tail = 0.f;   // celt_maxabs over the fresh part and over the part overlapping the next frame
@@ -249,9 +278,9 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[(st.pf_head + kPfMaxPeriod - OB_OVERLAP + i) & (kPfMaxPeriod - 1)] : st.overlap_mem[c][i];
   if (up == 1) {
     for (int i = lane; i < N; i += 32) {
-      const float s = pcm[(size_t)CC * i];
+      const float s = enc_pcm_at(pv, i, c);
       const float x = f_mul(32768.f, s);
-      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, pcm[(size_t)CC * (i - 1)]));
+      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, f_mul(32768.f, enc_pcm_at(pv, i - 1, c)));
       ws->in[OB_OVERLAP + i] = f_add(x, -m);
       if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
       else mx_tail = fmaxf(mx_tail, fabsf(s));
@@ -260,9 +289,9 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     // input below 48 kHz: the samples are zero-stuffed to 48 kHz ahead of the pre-emphasis (celt/celt_encoder.c:583-589)
     for (int i = lane; i < N; i += 32) {
       const bool on = i % up == 0, prev_on = (i - 1) % up == 0;
-      const float s = on ? pcm[(size_t)CC * (i / up)] : 0.f;
+      const float s = on ? enc_pcm_at(pv, i / up, c) : 0.f;
       const float x = on ? f_mul(32768.f, s) : 0.f;
-      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, prev_on ? f_mul(32768.f, pcm[(size_t)CC * ((i - 1) / up)]) : 0.f);
+      const float m = i == 0 ? st.preemph_mem[c] : f_mul(coef0, prev_on ? f_mul(32768.f, enc_pcm_at(pv, (i - 1) / up, c)) : 0.f);
       ws->in[OB_OVERLAP + i] = f_add(x, -m);
       if (on) {
         if (i < N - OB_OVERLAP) mx_new = fmaxf(mx_new, fabsf(s));
@@ -273,7 +302,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   mx_new = warp_max(mx_new);
   mx_tail = warp_max(mx_tail);
   wsync();
-  if (lane == 0) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, pcm[(size_t)CC * (N - 1)])) : f_mul(coef0, 0.f);
+  if (lane == 0) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, enc_pcm_at(pv, N - 1, c))) : f_mul(coef0, 0.f);
   if (!pf_path) for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
   // cross-channel part: maxima and the tone detector need both channels' time signals
   float *xch = (float *)((MdctWS *)smem + CC);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
@@ -350,6 +379,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     a.prev_period = es.prefilter_period; a.prev_tapset = es.prefilter_tapset; a.prev_gain = es.prefilter_gain; a.loss_rate = p.loss_rate;
     a.tf_estimate = fi.tf_estimate; a.tone_freq = fi.tone_freq; a.toneishness = fminf(fi.toneishness, 1.f - fi.tf_estimate);
     a.enabled = bud.nbAvailableBytes > 12 * C && !silence && bud.nbCompressedBytes * 8 >= 17 && !p.disable_pf;
+    if (p.ctl) { a.an_valid = p.ctl[stream].analysis.valid; a.an_max_pitch_ratio = p.ctl[stream].analysis.max_pitch_ratio; }
     const PfDecision d = enc_prefilter_stage(pw, a);
     if (c == 0 && lane == 0) {
       fi.pf_on = d.pf_on; fi.pitch_index = d.pitch_index; fi.qg = d.qg; fi.pf_tapset = d.tapset; fi.gain1 = d.gain1; fi.patched = 0;
@@ -376,7 +406,7 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       for (int j = j0; j < j1; j++) sum = f_add(sum, f_mul(freq[j], freq[j]));
       const float E0 = f_sqrt(f_add(1e-27f, sum));
       // (the frame kernel adds the LM/2 compensation, as for a patched frame)
-      p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = f_add((float)(1.442695040888963387 * log((double)E0)), -ob_emeans[lane]);
+      p.bandLogE2[(size_t)stream * SC * OB_NBANDS + c * OB_NBANDS + lane] = f_add((float)(1.442695040888963387 * log((double)E0)), -ob_emeans[lane]);
     }
     wsync();
   }
@@ -400,12 +430,12 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       const ObEncFrameInfo fi = p.info[stream];
       const int silence = fi.sample_max <= 1.f / (float)(1 << p.lsb_depth);
       int patch = 0;
-      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->sc, p.enc_state[stream].oldBandE, C, p.end);
+      if (!silence && !fi.is_transient) patch = enc_patch_transient(pw->sc, p.enc_state[stream].oldBandE, C, end_band);
       ((int *)xch)[6] = patch;
     }
     bsync();
     if (((int *)xch)[6]) {
-      if (c < C && lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane] = pw->sc[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
+      if (c < C && lane < OB_NBANDS && p.bandLogE2) p.bandLogE2[(size_t)stream * SC * OB_NBANDS + c * OB_NBANDS + lane] = pw->sc[c * OB_NBANDS + lane];   // the frame kernel adds the LM/2 compensation
       if (c == 0 && lane == 0) {
         ObEncFrameInfo fi = p.info[stream];
         fi.is_transient = 1; fi.short_blocks = 1; fi.patched = 1; fi.tf_estimate = .2f;
@@ -427,11 +457,11 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
     for (int j = j0; j < j1; j++) sum = f_add(sum, f_mul(freq[j], freq[j]));
     E = f_sqrt(f_add(1e-27f, sum));
     g = f_div(1.f, f_add(1e-27f, E));
-    const size_t o = (size_t)stream * C * OB_NBANDS + c * OB_NBANDS + lane;
+    const size_t o = (size_t)stream * SC * OB_NBANDS + c * OB_NBANDS + lane;
     p.bandE[o] = E;
     p.bandLogE[o] = f_add((float)(1.442695040888963387 * log((double)E)), -ob_emeans[lane]);
   }
-  float *X = p.X + (size_t)stream * C * N + (size_t)c * N;
+  float *X = p.X + (size_t)stream * SC * N + (size_t)c * N;
 #pragma unroll 1
   for (int b = 0; b < OB_NBANDS; b++) {
     const float gb = shfl(g, b);

@@ -1143,3 +1143,4 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 #include "fargan_host.cuh"
 #include "dred_host.cuh"
 #include "celt_enc_host.cuh"
+#include "opus_enc_host.cuh"

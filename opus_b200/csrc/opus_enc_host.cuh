@@ -1,0 +1,170 @@
+// opus_enc_host.cuh — kernel entry points and C ABI of the batched Opus encoder (the public opus_encode() surface of a CELT-only
+// encoder, n independent streams per call; included at the end of opus_b200.cu, after celt_enc_host.cuh).
+#pragma once
+#include "opus_enc_layer.cuh"
+
+extern "C" __global__ void __launch_bounds__(32) ob_opus_enc_pre(ob::OpusLayerParams p) {
+  extern __shared__ float ob_pre_tile[];
+  ob::opus_enc_pre_warp(p, blockIdx.x * 32, ob_pre_tile);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_opus_enc_analysis(ob::OpusLayerParams p) {
+  extern __shared__ __align__(16) unsigned char ob_an_smem[];
+  const int s = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (s < p.n_streams) ob::opus_enc_analysis_warp(p, s, (ob::AnWS *)ob_an_smem + (threadIdx.x >> 5));
+}
+extern "C" __global__ void ob_opus_enc_reset(ob::ObOpusEncState *st, int n, int channels) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) ob::opus_enc_state_init(st + s, channels);
+}
+
+struct OpusB200OpusEncoder {
+  OpusB200Encoder *celt;
+  int device, channels, n;
+  ob::OpusEncSettings cfg;   // opus_encoder_ctl settings
+  ob::ObOpusEncState *st;
+  ob::ObTonality *tonal;
+  ob::ObOpusPre *pre;
+  ob::ObOpusFrameCtl *ctl;
+  float *pcm_buf;
+  int analysis_was_on;
+  // staging of the host-buffer calls
+  void *d_pcm; size_t d_pcm_cap;
+  unsigned char *d_pkt; size_t d_pkt_cap;
+  int32_t *d_nbytes;
+  int64_t launches;
+};
+
+extern "C" int opusb200_opus_encoder_reset(OpusB200OpusEncoder *e) {   // OPUS_RESET_STATE
+  if (!e) return OPUSB200_BAD_ARG;
+  const int r = opusb200_encoder_reset(e->celt);
+  if (r != OPUSB200_OK) return r;
+  cudaStream_t s = e->celt->stream;
+  OB_CUDA(cudaMemsetAsync(e->st, 0, sizeof(ob::ObOpusEncState) * (size_t)e->n, s));
+  OB_CUDA(cudaMemsetAsync(e->tonal, 0, sizeof(ob::ObTonality) * (size_t)e->n, s));
+  ob_opus_enc_reset<<<(e->n + 127) / 128, 128, 0, s>>>(e->st, e->n, e->channels);
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_opus_encoder_create(int device, int32_t Fs, int channels, int application, int n_streams, OpusB200OpusEncoder **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  // the applications that can pick SILK (VOIP 2048, AUDIO 2049, RESTRICTED_SILK 2052) need the SILK encoder: not built
+  if (application == 2048 || application == 2049 || application == 2052) return OPUSB200_UNIMPLEMENTED;
+  if (application != 2051 && application != 2053) return OPUSB200_BAD_ARG;   // RESTRICTED_LOWDELAY, RESTRICTED_CELT
+  OpusB200Encoder *celt = nullptr;
+  int r = opusb200_encoder_create(device, Fs, channels, n_streams, &celt);
+  if (r != OPUSB200_OK) return r;
+  OpusB200OpusEncoder *e = new (std::nothrow) OpusB200OpusEncoder;
+  if (!e) { opusb200_encoder_destroy(celt); return OPUSB200_ALLOC_FAIL; }
+  memset(e, 0, sizeof(*e));
+  e->celt = celt; e->device = device; e->channels = channels; e->n = n_streams;
+  ob::opus_enc_settings_init(&e->cfg, Fs, channels, application);
+  const size_t n = (size_t)n_streams;
+  OB_CUDA(cudaMalloc(&e->st, sizeof(ob::ObOpusEncState) * n));
+  OB_CUDA(cudaMalloc(&e->tonal, sizeof(ob::ObTonality) * n));
+  OB_CUDA(cudaMalloc(&e->pre, sizeof(ob::ObOpusPre) * n));
+  OB_CUDA(cudaMalloc(&e->ctl, sizeof(ob::ObOpusFrameCtl) * n));
+  OB_CUDA(cudaMalloc(&e->pcm_buf, sizeof(float) * n * channels * OB_MAXN));
+  OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
+  OB_CUDA(cudaFuncSetAttribute(ob_opus_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(ob::AnWS)));
+  r = opusb200_opus_encoder_reset(e);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaStreamSynchronize(celt->stream));
+  *out = e;
+  return OPUSB200_OK;
+}
+extern "C" void opusb200_opus_encoder_destroy(OpusB200OpusEncoder *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->celt->stream);
+  cudaFree(e->st); cudaFree(e->tonal); cudaFree(e->pre); cudaFree(e->ctl); cudaFree(e->pcm_buf); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->d_nbytes);
+  opusb200_encoder_destroy(e->celt);
+  delete e;
+}
+// opus_encoder_ctl: the integer setters of the CELT-only path (src/opus_encoder.c:2783-3290; request numbers of include/opus_defines.h)
+extern "C" int opusb200_opus_encoder_ctl(OpusB200OpusEncoder *e, int request, int32_t value) {
+  if (!e) return OPUSB200_BAD_ARG;
+  if (request == 4046) return (value < 0 || value > 1) ? OPUSB200_BAD_ARG : opusb200_encoder_ctl_set(e->celt, 4046, value);   // OPUS_SET_PHASE_INVERSION_DISABLED
+  if (request == 4028) return opusb200_opus_encoder_reset(e);                                                                   // OPUS_RESET_STATE
+  return ob::opus_enc_settings_ctl(&e->cfg, request, value);
+}
+// opus_encode_native for n streams (device buffers).  d_pcm: [n][frame_size*channels] int16 or float; d_packets [n][pkt_stride]; d_nbytes [n]
+extern "C" int opusb200_opus_encode_device(OpusB200OpusEncoder *e, const void *d_pcm, int pcm_is_int16, int frame_size, unsigned char *d_packets,
+                                           int pkt_stride, int max_data_bytes_in, int32_t *d_nbytes) {
+  if (!e || !d_pcm || !d_packets || !d_nbytes) return OPUSB200_BAD_ARG;
+  ob::OpusCallPlan pl;
+  const int pr = ob::opus_enc_plan(e->cfg, frame_size, max_data_bytes_in, pcm_is_int16, &pl);
+  if (pr) return pr;
+  if (pkt_stride < pl.max_data_bytes) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = e->celt->stream;
+  if (!pl.run_analysis && e->analysis_was_on) OB_CUDA(cudaMemsetAsync(e->tonal, 0, sizeof(ob::ObTonality) * (size_t)e->n, s));   // tonality_analysis_reset (:1261-1263)
+  e->analysis_was_on = pl.run_analysis;
+  ob::OpusLayerParams p;
+  ob::opus_layer_params_init(&p, e->cfg, pl, frame_size, pcm_is_int16, e->n);
+  p.st = e->st; p.tonal = e->tonal; p.pre = e->pre; p.ctl = e->ctl; p.pcm = d_pcm; p.pcm_buf = e->pcm_buf; p.packets = d_packets; p.pkt_stride = pkt_stride;
+  if (e->celt->timing) cudaEventRecord(e->celt->tev[0], s);
+  ob_opus_enc_pre<<<(e->n + 31) / 32, 32, 32 * OB_PRE_TS * sizeof(float), s>>>(p);
+  if (e->celt->timing) cudaEventRecord(e->celt->tev[1], s);
+  ob_opus_enc_analysis<<<(e->n + 3) / 4, 128, 4 * sizeof(ob::AnWS), s>>>(p);
+  e->launches += 2;
+  OB_CUDA(cudaGetLastError());
+  // the CELT encoder as opus_encode_frame_native configures it (:2266-2294, 2445-2463); channels and end band go per stream through ctl
+  OpusB200Encoder *c = e->celt;
+  c->complexity = e->cfg.complexity; c->lsb_depth = pl.lsb; c->loss_rate = e->cfg.packet_loss;
+  c->disable_pf = pl.celt_disable_pf; c->force_intra = pl.celt_force_intra;
+  c->vbr = pl.celt_vbr; c->bitrate = pl.celt_bitrate; c->constrained_vbr = pl.celt_cvbr;
+  c->stream_channels = e->channels; c->end = OB_NBANDS;
+  const int64_t l0 = c->launches;
+  const int r = celt_encode_launch(c, e->pcm_buf, frame_size, d_packets + 1, pkt_stride, pl.max_data_bytes - 1, d_nbytes, e->ctl);
+  e->launches += c->launches - l0;
+  return r;
+}
+static int opus_encode_host(OpusB200OpusEncoder *e, const void *pcm, int is16, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                            int32_t *nbytes) {
+  if (!e || !pcm || !packets || !nbytes || frame_size <= 0 || frame_size > OB_MAXN) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = e->celt->stream;
+  const size_t pb = (is16 ? sizeof(int16_t) : sizeof(float)) * (size_t)e->n * frame_size * e->channels, kb = (size_t)e->n * pkt_stride;
+  if (e->d_pcm_cap < pb) { cudaFree(e->d_pcm); e->d_pcm = nullptr; e->d_pcm_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm, pb)); e->d_pcm_cap = pb; }
+  if (e->d_pkt_cap < kb) { cudaFree(e->d_pkt); e->d_pkt = nullptr; e->d_pkt_cap = 0; OB_CUDA(cudaMalloc(&e->d_pkt, kb)); e->d_pkt_cap = kb; }
+  OB_CUDA(cudaMemcpyAsync(e->d_pcm, pcm, pb, cudaMemcpyHostToDevice, s));
+  const int r = opusb200_opus_encode_device(e, e->d_pcm, is16, frame_size, e->d_pkt, pkt_stride, max_data_bytes, e->d_nbytes);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaMemcpyAsync(packets, e->d_pkt, kb, cudaMemcpyDeviceToHost, s));
+  OB_CUDA(cudaMemcpyAsync(nbytes, e->d_nbytes, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, s));
+  OB_CUDA(cudaStreamSynchronize(s));
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_opus_encode(OpusB200OpusEncoder *e, const int16_t *pcm, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                                    int32_t *nbytes) {
+  return opus_encode_host(e, pcm, 1, frame_size, packets, pkt_stride, max_data_bytes, nbytes);
+}
+extern "C" int opusb200_opus_encode_float(OpusB200OpusEncoder *e, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride,
+                                          int max_data_bytes, int32_t *nbytes) {
+  return opus_encode_host(e, pcm, 0, frame_size, packets, pkt_stride, max_data_bytes, nbytes);
+}
+extern "C" int opusb200_opus_encoder_get_final_range(OpusB200OpusEncoder *e, uint32_t *final_range) {
+  return e ? opusb200_encoder_get_final_range(e->celt, final_range) : OPUSB200_BAD_ARG;
+}
+// Profiling aid: CUDA events around each of the four kernels of a call (the call then waits for them: not for throughput runs).
+// get_timing: accumulated device milliseconds [Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder] and the calls they cover
+extern "C" int opusb200_opus_encoder_set_timing(OpusB200OpusEncoder *e, int enable) {
+  if (!e) return OPUSB200_BAD_ARG;
+  OpusB200Encoder *c = e->celt;
+  OB_CUDA(cudaSetDevice(e->device));
+  if (enable && !c->tev[0]) for (int i = 0; i < 5; i++) OB_CUDA(cudaEventCreate(&c->tev[i]));
+  c->timing = enable != 0;
+  for (int i = 0; i < 4; i++) c->t_ms[i] = 0.0;
+  c->t_calls = 0;
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_opus_encoder_get_timing(OpusB200OpusEncoder *e, double *ms_kernels, int64_t *calls) {
+  if (!e || !ms_kernels || !calls) return OPUSB200_BAD_ARG;
+  for (int i = 0; i < 4; i++) ms_kernels[i] = e->celt->t_ms[i];
+  *calls = e->celt->t_calls;
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_opus_encoder_sync(OpusB200OpusEncoder *e) { return e ? opusb200_encoder_sync(e->celt) : OPUSB200_BAD_ARG; }
+extern "C" void *opusb200_opus_encoder_cuda_stream(OpusB200OpusEncoder *e) { return e ? (void *)e->celt->stream : nullptr; }
+extern "C" int64_t opusb200_opus_encoder_launch_count(OpusB200OpusEncoder *e) { return e ? e->launches : 0; }

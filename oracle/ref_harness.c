@@ -364,3 +364,35 @@ int refh_encode_stream_float_ex(int Fs, int channels, int application, int bitra
   opus_encoder_destroy(enc);
   return 0;
 }
+
+/* Encode throughput sample for bench.py: n independent streams (one encoder each, created outside the timing by the caller's
+ * warm-up call pattern: creation is cheap next to T frames), T consecutive frames per stream, `reps` passes over the same PCM with the
+ * encoder state carried.  pcm: [n][T][frame_size*channels] int16.  Returns the number of frames encoded, or a negative error. */
+long refh_encode_bench(int Fs, int channels, int application, int bitrate, int vbr, int complexity, int frame_size, int n, int T,
+                       const opus_int16 *pcm, int reps, int max_bytes, long *bytes_out) {
+  long frames = 0, bytes = 0;
+  int s, f, r, err = 0;
+  unsigned char *buf = (unsigned char *)malloc(max_bytes);
+  OpusEncoder **enc = (OpusEncoder **)calloc(n, sizeof(*enc));
+  if (!buf || !enc) return -7;
+  for (s = 0; s < n; s++) {
+    enc[s] = opus_encoder_create(Fs, channels, application, &err);
+    if (!enc[s]) return err;
+    opus_encoder_ctl(enc[s], OPUS_SET_BITRATE(bitrate));
+    opus_encoder_ctl(enc[s], OPUS_SET_VBR(vbr));
+    opus_encoder_ctl(enc[s], OPUS_SET_COMPLEXITY(complexity));
+  }
+  for (r = 0; r < reps; r++)
+    for (f = 0; f < T; f++)   /* frame-major, like a batch server that advances every stream by one frame per step */
+      for (s = 0; s < n; s++) {
+        int nb = opus_encode(enc[s], pcm + ((size_t)s * T + f) * frame_size * channels, frame_size, buf, max_bytes);
+        if (nb < 0) return nb;
+        bytes += nb;
+        frames++;
+      }
+  for (s = 0; s < n; s++) opus_encoder_destroy(enc[s]);
+  free(enc);
+  free(buf);
+  if (bytes_out) *bytes_out = bytes;
+  return frames;
+}

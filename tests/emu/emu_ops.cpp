@@ -206,6 +206,14 @@ static void enc_frame_entry(void *a) {
   if (p.complexity >= 8 && p.C == 2) enc_frame_thread<true>(p, s);
   else enc_frame_thread<false>(p, s);
 }
+// with the Opus layer in front a stereo encoder at complexity >= 8 runs the RDO instantiation for every stream (mono-coded ones take its plain branch)
+static void enc_frame_entry_ctl(void *a) {
+  const EncFrameParams &p = *(const EncFrameParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s >= p.n_streams) return;
+  if (p.complexity >= 8 && p.CC == 2) enc_frame_thread<true>(p, s);
+  else enc_frame_thread<false>(p, s);
+}
 extern "C" int emu_enc_state_size(void) { return (int)sizeof(ObEncState); }
 extern "C" void emu_enc_state_init(ObEncState *st, int n) {
   memset(st, 0, sizeof(ObEncState) * (size_t)n);
@@ -245,3 +253,97 @@ extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const flo
   for (int s = 0; s < n; s++) { g_enc_cov[0] += info[s].pf_on; g_enc_cov[1] += info[s].patched; g_enc_cov[2] += info[s].is_transient; }
 }
 extern "C" void emu_enc_coverage(int32_t *out, int reset) { for (int i = 0; i < 3; i++) { out[i] = g_enc_cov[i]; if (reset) g_enc_cov[i] = 0; } }
+
+// ---- the Opus layer in front of the CELT encoder (opus_b200/csrc/opus_enc_layer.cuh): opus_encode() for n streams ----
+static void opus_pre_entry(void *a) {
+  const OpusLayerParams &p = *(const OpusLayerParams *)a;
+  opus_enc_pre_warp(p, block_id() * 32, (float *)dyn_smem());
+}
+static void opus_an_entry(void *a) {
+  const OpusLayerParams &p = *(const OpusLayerParams *)a;
+  if (block_id() < p.n_streams) opus_enc_analysis_warp(p, block_id(), (AnWS *)dyn_smem());
+}
+struct EmuOpusEncoder {
+  int n, channels;
+  OpusEncSettings cfg;
+  int disable_inv, analysis_was_on;
+  std::vector<ObOpusEncState> st;
+  std::vector<ObTonality> tonal;
+  std::vector<ObOpusPre> pre;
+  std::vector<ObOpusFrameCtl> ctl;
+  std::vector<float> pcm_buf, prefilter_mem;
+  std::vector<ObEncAnalysisState> an_state;
+  std::vector<ObEncState> enc_state;
+};
+extern "C" void *emu_opus_encoder_create(int n, int Fs, int channels, int application) {
+  EmuOpusEncoder *e = new EmuOpusEncoder;
+  e->n = n; e->channels = channels; e->disable_inv = 0; e->analysis_was_on = 0;
+  opus_enc_settings_init(&e->cfg, Fs, channels, application);
+  e->st.resize(n); e->tonal.resize(n); e->pre.resize(n); e->ctl.resize(n);
+  e->pcm_buf.assign((size_t)n * channels * OB_MAXN, 0.f);
+  e->prefilter_mem.assign((size_t)n * channels * kPfMaxPeriod, 0.f);
+  e->an_state.resize(n); e->enc_state.resize(n);
+  memset(e->tonal.data(), 0, sizeof(ObTonality) * n);
+  memset(e->an_state.data(), 0, sizeof(ObEncAnalysisState) * n);
+  memset(e->pre.data(), 0, sizeof(ObOpusPre) * n);
+  memset(e->ctl.data(), 0, sizeof(ObOpusFrameCtl) * n);
+  emu_enc_state_init(e->enc_state.data(), n);
+  for (int s = 0; s < n; s++) opus_enc_state_init(&e->st[s], channels);
+  return e;
+}
+extern "C" void emu_opus_encoder_destroy(void *h) { delete (EmuOpusEncoder *)h; }
+extern "C" int emu_opus_encoder_ctl(void *h, int request, int value) {
+  EmuOpusEncoder *e = (EmuOpusEncoder *)h;
+  if (request == 4046) { e->disable_inv = value; return 0; }
+  return opus_enc_settings_ctl(&e->cfg, request, value);
+}
+extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                               int32_t *nbytes, uint32_t *rng) {
+  EmuOpusEncoder *e = (EmuOpusEncoder *)h;
+  OpusCallPlan pl;
+  const int pr = opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
+  if (pr) return pr;
+  if (pkt_stride < pl.max_data_bytes) return -1;
+  const int n = e->n, CC = e->channels, up = 48000 / e->cfg.Fs;
+  if (!pl.run_analysis && e->analysis_was_on) memset(e->tonal.data(), 0, sizeof(ObTonality) * n);
+  e->analysis_was_on = pl.run_analysis;
+  OpusLayerParams p;
+  opus_layer_params_init(&p, e->cfg, pl, frame_size, is16, n);
+  p.st = e->st.data(); p.tonal = e->tonal.data(); p.pre = e->pre.data(); p.ctl = e->ctl.data(); p.pcm = pcm; p.pcm_buf = e->pcm_buf.data();
+  p.packets = packets; p.pkt_stride = pkt_stride;
+  emu_launch(opus_pre_entry, &p, (n + 31) / 32, 32, 32 * OB_PRE_TS * sizeof(float));
+  emu_launch(opus_an_entry, &p, n, 32, sizeof(AnWS));
+  int LM = -1;
+  for (int l = 0; l <= 3; l++) if (frame_size * up == OB_SHORT_N << l) LM = l;
+  if (LM < 0) return -1;
+  const int N = OB_SHORT_N << LM, cx = e->cfg.complexity, max_bytes = pl.max_data_bytes - 1;
+  std::vector<float> X((size_t)n * CC * N), E((size_t)n * CC * OB_NBANDS), Lg((size_t)n * CC * OB_NBANDS), Lg2((size_t)n * CC * OB_NBANDS);
+  std::vector<ObEncFrameInfo> info(n);
+  EncAnalysisParams a;
+  a.state = e->an_state.data(); a.pcm = e->pcm_buf.data(); a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
+  a.info = info.data(); a.n_streams = n; a.C = CC; a.CC = CC; a.LM = LM; a.complexity = cx; a.lsb_depth = pl.lsb;
+  a.enc_state = e->enc_state.data(); a.prefilter_mem = e->prefilter_mem.data(); a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = pl.celt_bitrate;
+  a.vbr = pl.celt_vbr; a.constrained_vbr = pl.celt_cvbr; a.disable_pf = pl.celt_disable_pf; a.loss_rate = e->cfg.packet_loss; a.end = OB_NBANDS; a.upsample = up;
+  a.ctl = e->ctl.data();
+  emu_launch(enc_analysis_entry, &a, n, 32 * CC, CC * sizeof(MdctWS) + 32 + (cx >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
+  EncFrameParams f;
+  f.state = e->enc_state.data(); f.info = info.data(); f.X = X.data(); f.bandE = E.data(); f.bandLogE = Lg.data(); f.bandLogE2 = Lg2.data();
+  f.packets = packets + 1; f.nbytes = nbytes; f.n_streams = n; f.C = CC; f.CC = CC; f.LM = LM; f.pkt_stride = pkt_stride; f.max_bytes = max_bytes;
+  f.complexity = cx; f.bitrate = pl.celt_bitrate; f.lsb_depth = pl.lsb; f.force_intra = pl.celt_force_intra; f.disable_inv = e->disable_inv;
+  f.disable_pf = pl.celt_disable_pf; f.vbr = pl.celt_vbr; f.constrained_vbr = pl.celt_cvbr; f.loss_rate = e->cfg.packet_loss; f.end = OB_NBANDS;
+  f.ctl = e->ctl.data(); f.toc_bytes = 1;
+  emu_launch(enc_frame_entry_ctl, &f, (n + 31) / 32, 32, 0);
+  for (int s = 0; s < n; s++) rng[s] = e->enc_state[s].rng;
+  return 0;
+}
+// the analysis alone (kernels P1 + P2), as 30 floats per stream like ref_harness.c's refh_run_analysis_stream
+extern "C" void emu_opus_last_analysis(void *h, float *out) {
+  EmuOpusEncoder *e = (EmuOpusEncoder *)h;
+  for (int s = 0; s < e->n; s++) {
+    const ObAnalysisInfo &i = e->ctl[s].analysis;
+    float *o = out + 30 * s;
+    o[0] = (float)i.valid; o[1] = i.tonality; o[2] = i.tonality_slope; o[3] = i.noisiness; o[4] = i.activity; o[5] = i.music_prob; o[6] = i.music_prob_min;
+    o[7] = i.music_prob_max; o[8] = (float)i.bandwidth; o[9] = i.activity_probability; o[10] = i.max_pitch_ratio;
+    for (int k = 0; k < 19; k++) o[11 + k] = (float)i.leak_boost[k];
+  }
+}
