@@ -286,7 +286,9 @@ OB_DEV void ent_finish(const DecEntropyParams &p, int stream, ObFrameSide *side,
   side->status = status;  // the later kernels see the 48 kHz frame length
   const int rep = status > 0 ? status / p.downsample : status;  // the caller sees output-rate samples (opus_decoder.c:735)
   if (status < 0 || p.frame_index == 0) {
-    st->last_status = rep;
+    // OPUS_GET_LAST_PACKET_DURATION is set by successful calls only (src/opus_decoder.c:880-883): an error or a stream that sits the
+    // call out (len < 0) leaves it alone; the caller sees the code in out_samples
+    if (status > 0) st->last_status = rep;
     if (p.out_samples) p.out_samples[stream] = rep;
   } else if (status > 0) {
     if (st->last_status >= 0) st->last_status += rep;   // OPUS_GET_LAST_PACKET_DURATION
@@ -401,6 +403,7 @@ OB_DEV void dec_entropy_thread(const DecEntropyParams &p, int stream) {
   const int plen = p.pkt_len[stream];
   if (plen < 0) { ent_finish(p, stream, side, st, 0); return; }   // this library's extension: the stream sits this call out
   if (plen == 0) { ent_lost_packet(p, stream, side, st); return; }  // opus_decode(data = NULL / len = 0): conceal frame_size samples
+  if (plen > p.pkt_stride) { ent_finish(p, stream, side, st, -1); return; }   // the packet would run into the next stream's row: OPUS_BAD_ARG
   const unsigned char *pkt = p.packets + (size_t)stream * p.pkt_stride;
   const int toc = pkt[0];
   int foff, flen;

@@ -102,7 +102,7 @@ extern "C" int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, con
     dst = d->d_state; dl = d->d_lat; df = d->d_feat;
   }
   // the time loop is launch-bound (tiny layers): replayed as a CUDA graph from the third call with the same pointers and nb_latents
-  DR_TRY(ob_graph_run(c, d->graph, dl, df, (long)nb_latents * 1000003L + (long)(size_t)dst % 1000003L, [&]() -> int {
+  DR_TRY(ob_graph_run(c, d->graph, dl, df, (long)nb_latents, [&]() -> int {
     // dred_rdovae_dec_init_states (:63-87)
     DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_HIDDEN_INIT], d->tmp, dst, n, NN_TANH, 1));
     DR_TRY(opusb200_nnet_compute_dense(c, d->l[DR_GRU_INIT], d->tmp2, d->tmp, n, NN_TANH, 1));
@@ -141,7 +141,7 @@ extern "C" int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, con
       DR_TRY(dr_copy2d(c, df + (size_t)q * kDrOut, nb_latents * kDrOut, d->tmp, kDrOut, kDrOut, n));
     }
     return OPUSB200_OK;
-  }));
+  }, dst));   // the full state pointer is part of the key (not a residue of it)
   OB_CUDA(cudaGetLastError());
   if (!on_device) {
     OB_CUDA(cudaMemcpyAsync(features, df, fb, cudaMemcpyDeviceToHost, c->stream));

@@ -60,6 +60,7 @@ static int nnet_scratch(OpusB200Ctx *c, int slot, size_t bytes, void **out) {
   if (c->scratch_bytes[slot] < bytes) {
     if (c->scratch[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch[slot]); }
     c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0;
+    c->scratch_gen++;   // graphs captured with the old pointer are stale (ob_graph_run re-captures)
     const size_t want = bytes + bytes / 4;
     if (cudaMalloc(&c->scratch[slot], want) != cudaSuccess) return -1;
     c->scratch_bytes[slot] = want;
@@ -157,16 +158,23 @@ extern "C" void opusb200_nnet_linear_destroy(OpusB200Linear *l) {
 // The first call with a given key (pointers + shape) runs eagerly (it sizes the scratch buffers and sets kernel attributes), the
 // second one is captured from the very same enqueue code and every later one replays the instantiated graph.  A failed capture
 // (e.g. a scratch buffer that had to grow) falls back to eager enqueueing.  OPUSB200_NO_GRAPHS=1 disables it.
-struct ObGraphCache { cudaGraphExec_t exec; const void *a, *b; long k; int state; };   // state: 0 new, 1 warmed, 2 captured, -1 disabled
-template <class F> static int ob_graph_run(OpusB200Ctx *c, ObGraphCache &g, const void *a, const void *b, long k, F &&enqueue) {
+// The key is the caller's pointers + shape AND the context's scratch generation: the captured kernels hold the shared scratch pointers,
+// and another object on the same context may have grown (= reallocated) them since.
+struct ObGraphCache { cudaGraphExec_t exec; const void *a, *b, *c3; long k; uint64_t gen; int state; };   // state: 0 new, 1 warmed, 2 captured, -1 disabled
+template <class F> static int ob_graph_run(OpusB200Ctx *c, ObGraphCache &g, const void *a, const void *b, long k, F &&enqueue, const void *c3 = nullptr) {
   static const bool off = getenv("OPUSB200_NO_GRAPHS") != nullptr;
   if (off || g.state < 0) return enqueue();
-  if (g.a != a || g.b != b || g.k != k) {
+  if (g.a != a || g.b != b || g.c3 != c3 || g.k != k || g.gen != c->scratch_gen) {
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    g.a = a; g.b = b; g.k = k; g.state = 0;
+    g.a = a; g.b = b; g.c3 = c3; g.k = k; g.gen = c->scratch_gen; g.state = 0;
   }
   if (g.state == 2) { OB_CUDA(cudaGraphLaunch(g.exec, c->stream)); return OPUSB200_OK; }
-  if (g.state == 0) { g.state = 1; return enqueue(); }
+  if (g.state == 0) {   // the eager warm-up may grow the scratch: key the next (captured) run on the generation it leaves behind
+    g.state = 1;
+    const int r0 = enqueue();
+    g.gen = c->scratch_gen;
+    return r0;
+  }
   if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.state = -1; return enqueue(); }
   const int r = enqueue();
   cudaGraph_t graph = nullptr;
@@ -198,13 +206,12 @@ static int nnet_umma_gemm(OpusB200Ctx *c, const OpusB200Linear *l, float *out, c
   static const bool fuse = getenv("OPUSB200_NNET_FUSE") != nullptr;
   u.act = (fuse && act != NN_SOFTMAX) ? act : NN_LINEAR; u.glu_in = fuse ? glu_in : nullptr;
   if (fused) *fused = fuse && act != NN_SOFTMAX;
-  static size_t smem_set = 0;
-  if (l->umma_smem > smem_set) {
+  if (l->umma_smem > c->umma_smem_set) {   // per device (= per context), not per process
     OB_CUDA(cudaFuncSetAttribute(ob_nnet_linear_i8_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l->umma_smem));
-    smem_set = l->umma_smem;
+    c->umma_smem_set = l->umma_smem;
   }
-  static int sms = 0;
-  if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  if (!c->sms) cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device);
+  const int sms = c->sms;
   ob_nnet_linear_i8_umma<<<mt < sms ? mt : sms, 320, l->umma_smem, c->stream>>>(u);
   c->launches++;
   OB_CUDA(cudaGetLastError());

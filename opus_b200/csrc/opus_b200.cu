@@ -418,6 +418,10 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     if (timing) cudaEventRecord(d->ev[1], st);
     else {
       OB_CUDA(cudaEventRecord(d->ev_a1[par], se));
+      // the parse reads the caller's packets / lengths and writes out_samples: whatever the caller enqueues next on the library stream
+      // (an upload of the next batch into the same buffers, a read of out_samples) is ordered after it.  This costs no overlap:
+      // consecutive parses serialise on the parsing stream anyway.
+      if (se != st) OB_CUDA(cudaStreamWaitEvent(st, d->ev_a1[par], 0));
       OB_CUDA(cudaStreamWaitEvent(sv, d->ev_a1[par], 0));
       OB_CUDA(cudaStreamWaitEvent(sv, d->ev_b[par], 0));   // X[par] is free once the synthesis of two frames ago has read it
     }
@@ -525,6 +529,7 @@ static int decode_submit(OpusB200Decoder *d, const unsigned char *packets, int p
   for (int s = 0; s < d->n; s++) {
     const int l = len[s];
     __builtin_prefetch(packets + (size_t)(s + 24) * pkt_stride);   // the TOC bytes are one cache miss per stream (measured: 0.48 -> 0.38 ms per 65 536 streams)
+    if (l > pkt_stride) continue;   // would run into the next stream's row: the kernel answers OPUS_BAD_ARG for this stream
     if (l > 0) {
       const unsigned char *pk = packets + (size_t)s * pkt_stride;
       const int toc = pk[0];
@@ -675,6 +680,8 @@ int opusb200_decoder_get_timing(OpusB200Decoder *d, double *ms_kernels, int64_t 
 struct OpusB200Ctx {
   int device; cudaStream_t stream; int max_smem_optin; int64_t launches;
   void *scratch[2]; size_t scratch_bytes[2];   // dnn temporaries (nnet_host.cuh)
+  uint64_t scratch_gen;                        // bumped whenever a scratch buffer is reallocated: captured CUDA graphs hold the old pointers
+  size_t umma_smem_set; int sms;               // per-device kernel attribute / SM count of the tcgen05 layer kernel (one context = one device)
 };
 
 int opusb200_ctx_create(int device, OpusB200Ctx **out) {
@@ -689,7 +696,7 @@ int opusb200_ctx_create(int device, OpusB200Ctx **out) {
   OpusB200Ctx *c = new (std::nothrow) OpusB200Ctx;
   if (!c) return OPUSB200_ALLOC_FAIL;
   c->device = device; c->launches = 0;
-  c->scratch[0] = c->scratch[1] = nullptr; c->scratch_bytes[0] = c->scratch_bytes[1] = 0;
+  c->scratch[0] = c->scratch[1] = nullptr; c->scratch_bytes[0] = c->scratch_bytes[1] = 0; c->scratch_gen = 0; c->umma_smem_set = 0; c->sms = 0;
   OB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
