@@ -63,6 +63,31 @@ def build_library(force=False):
         return out
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     subprocess.check_call([nvcc] + NVCC_FLAGS + ['-o', out, os.path.join(src_dir, 'opus_b200.cu')])
+    build_compat_library(force=True)
+    return out
+
+
+# the libopus-named entry points (include/opus_b200_compat.h) over the C ABI: plain C++ (no CUDA), linked against libopus_b200.so next to it
+COMPAT_SYMBOLS = ['opus_strerror', 'opus_get_version_string', 'opus_decoder_get_size', 'opus_decoder_create', 'opus_decoder_init', 'opus_decode',
+                  'opus_decode_float', 'opus_decoder_ctl', 'opus_decoder_destroy', 'opus_encoder_get_size', 'opus_encoder_create', 'opus_encoder_init',
+                  'opus_encode', 'opus_encode_float', 'opus_encoder_ctl', 'opus_encoder_destroy', 'opus_packet_parse', 'opus_packet_get_bandwidth',
+                  'opus_packet_get_samples_per_frame', 'opus_packet_get_nb_channels', 'opus_packet_get_nb_frames', 'opus_packet_get_nb_samples',
+                  'opus_decoder_get_nb_samples', 'opus_multistream_decoder_get_size', 'opus_multistream_decoder_create', 'opus_multistream_decoder_init',
+                  'opus_multistream_decode', 'opus_multistream_decode_float', 'opus_multistream_decoder_ctl', 'opus_multistream_decoder_destroy']
+
+
+def compat_library_path():
+    return os.path.join(_HERE, 'libopus_b200_compat.so')
+
+
+def build_compat_library(force=False):
+    out = compat_library_path()
+    src = os.path.join(_HERE, 'csrc', 'opus_compat.cpp')
+    deps = [src, os.path.join(ROOT, 'include', 'opus_b200_compat.h'), os.path.join(ROOT, 'include', 'opus_b200.h')]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-fvisibility=default', '-Wall', '-o', out, src, '-L' + _HERE, '-lopus_b200',
+                           '-Wl,-rpath,$ORIGIN'])
     return out
 
 

@@ -1113,30 +1113,36 @@ OB_DEVNI void enc_band_stereo(EncBand &ctx, float *X, float *Y, float *tmp, int 
     else { for (int j = 0; j < N; j++) X[j] = Y[j]; }
   }
   const EncTheta t = enc_theta(ctx, X, Y, N, b, B, B, LM, 1);
+  // one pair of enc_band_mono calls for the three shapes of the band (see rdo_band_stereo): threads that enter a function from
+  // different call sites do not reconverge inside it
+  int mbits, sbits, first_is_mid = 1;
+  float *xf = X;
   if (N == 2) {
-    int mbits = b, sbits = 0;
+    mbits = b; sbits = 0;
     if (t.itheta != 0 && t.itheta != 16384) sbits = 1 << OB_BITRES;
     mbits -= sbits;
     const int c = t.itheta > 8192;
     ctx.remaining_bits -= t.qalloc + sbits;
     float *x2 = c ? Y : X, *y2 = c ? X : Y;
     if (sbits) re_bits(*ctx.ec, x2[0] * y2[1] - x2[1] * y2[0] < 0, 1);
-    enc_band_mono(ctx, x2, tmp, N, mbits, B, LM);
+    xf = x2;
   } else {
-    int mbits = OB_IMAX(0, OB_IMIN(b, (b - t.delta) / 2)), sbits = b - mbits;
+    mbits = OB_IMAX(0, OB_IMIN(b, (b - t.delta) / 2)); sbits = b - mbits;
     ctx.remaining_bits -= t.qalloc;
-    int32_t rebalance = ctx.remaining_bits;
-    if (mbits >= sbits) {
-      enc_band_mono(ctx, X, tmp, N, mbits, B, LM);
+    first_is_mid = mbits >= sbits;
+    xf = first_is_mid ? X : Y;
+  }
+  int32_t rebalance = ctx.remaining_bits;
+  enc_band_mono(ctx, xf, tmp, N, (N == 2 || first_is_mid) ? mbits : sbits, B, LM);
+  if (N != 2) {
+    if (first_is_mid) {
       rebalance = mbits - (rebalance - ctx.remaining_bits);
       if (rebalance > 3 << OB_BITRES && t.itheta != 0) sbits += rebalance - (3 << OB_BITRES);
-      enc_band_mono(ctx, Y, tmp, N, sbits, B, LM);
     } else {
-      enc_band_mono(ctx, Y, tmp, N, sbits, B, LM);
       rebalance = sbits - (rebalance - ctx.remaining_bits);
       if (rebalance > 3 << OB_BITRES && t.itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
-      enc_band_mono(ctx, X, tmp, N, mbits, B, LM);
     }
+    enc_band_mono(ctx, first_is_mid ? Y : X, tmp, N, first_is_mid ? sbits : mbits, B, LM);
   }
 }
 
@@ -1530,11 +1536,11 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
       if (C == 2)
 #pragma unroll 1
         for (int j = 0; j < Nb; j++) by[j] = Xg[N + off + j];
-      if (dual_stereo) {
-        enc_band_mono(ctx, bx, tmp, Nb, b / 2, B, LM);
-        enc_band_mono(ctx, by, tmp, Nb, b / 2, B, LM);
-      } else if (C == 2) enc_band_stereo(ctx, bx, by, tmp, Nb, b, B, LM);
-      else enc_band_mono(ctx, bx, tmp, Nb, b, B, LM);
+      if (C == 2 && !dual_stereo) enc_band_stereo(ctx, bx, by, tmp, Nb, b, B, LM);
+      else {   // mono, or the two halves of a dual-stereo band: one call site
+#pragma unroll 1
+        for (int h = 0; h < (dual_stereo ? 2 : 1); h++) enc_band_mono(ctx, h ? by : bx, tmp, Nb, dual_stereo ? b / 2 : b, B, LM);
+      }
       balance += pulses[i] + t;
       ctx.avoid_split_noise = 0;
     }

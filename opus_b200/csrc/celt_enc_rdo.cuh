@@ -294,20 +294,48 @@ OB_DEVNI unsigned rdo_band_stereo(EncBand &ctx, float *X, float *Y, float *tmp, 
   else if (t.itheta == 16384) fill &= ((1 << B) - 1) << B;
   const float mid = (1.f / 32768) * t.imid, side = (1.f / 32768) * t.iside;
   unsigned cm;
+  // The three shapes of the band (N == 2; mid first; side first) go through the SAME two calls of rdo_band_mono: the lanes of a warp
+  // code different streams, and threads that reach a function from different call sites do not reconverge inside it.
+  int mbits, sbits, sign = 0, first_is_mid = 1, do_second = N != 2;
+  float *x2 = X, *y2 = Y;
   if (N == 2) {
-    int mbits = b, sbits = 0;
+    mbits = b; sbits = 0;
     if (t.itheta != 0 && t.itheta != 16384) sbits = 1 << OB_BITRES;
     mbits -= sbits;
     const int c = t.itheta > 8192;
     ctx.remaining_bits -= t.qalloc + sbits;
-    float *x2 = c ? Y : X, *y2 = c ? X : Y;
-    int sign = 0;
+    x2 = c ? Y : X; y2 = c ? X : Y;
     if (sbits) {
       sign = x2[0] * y2[1] - x2[1] * y2[0] < 0;
       re_bits(*ctx.ec, sign, 1);
     }
     sign = 1 - 2 * sign;
-    cm = rdo_band_mono(ctx, x2, tmp, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, orig_fill);
+  } else {
+    mbits = OB_IMAX(0, OB_IMIN(b, (b - t.delta) / 2)); sbits = b - mbits;
+    ctx.remaining_bits -= t.qalloc;
+    first_is_mid = mbits >= sbits;
+  }
+  int32_t rebalance = ctx.remaining_bits;
+  {   // first part: the mid (with the folding source and the lowband output) or the side
+    float *xf = N == 2 ? x2 : first_is_mid ? X : Y;
+    const int bf = (N == 2 || first_is_mid) ? mbits : sbits, midlike = N == 2 || first_is_mid;
+    cm = rdo_band_mono(ctx, xf, tmp, N, bf, B, midlike ? lowband : nullptr, LM, midlike ? lowband_out : nullptr, midlike ? 1.0f : side,
+                       midlike ? lowband_scratch : nullptr, N == 2 ? orig_fill : midlike ? fill : fill >> B);
+  }
+  if (do_second) {
+    if (first_is_mid) {
+      rebalance = mbits - (rebalance - ctx.remaining_bits);
+      if (rebalance > 3 << OB_BITRES && t.itheta != 0) sbits += rebalance - (3 << OB_BITRES);
+    } else {
+      rebalance = sbits - (rebalance - ctx.remaining_bits);
+      if (rebalance > 3 << OB_BITRES && t.itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
+    }
+    float *xs = first_is_mid ? Y : X;
+    const int midlike = !first_is_mid;
+    cm |= rdo_band_mono(ctx, xs, tmp, N, midlike ? mbits : sbits, B, midlike ? lowband : nullptr, LM, midlike ? lowband_out : nullptr, midlike ? 1.0f : side,
+                        midlike ? lowband_scratch : nullptr, midlike ? fill : fill >> B);
+  }
+  if (N == 2) {
     y2[0] = -sign * x2[1];
     y2[1] = sign * x2[0];
     X[0] = mid * X[0];
@@ -320,21 +348,6 @@ OB_DEVNI unsigned rdo_band_stereo(EncBand &ctx, float *X, float *Y, float *tmp, 
     t0 = X[1];
     X[1] = t0 - Y[1];
     Y[1] = t0 + Y[1];
-  } else {
-    int mbits = OB_IMAX(0, OB_IMIN(b, (b - t.delta) / 2)), sbits = b - mbits;
-    ctx.remaining_bits -= t.qalloc;
-    int32_t rebalance = ctx.remaining_bits;
-    if (mbits >= sbits) {
-      cm = rdo_band_mono(ctx, X, tmp, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, fill);
-      rebalance = mbits - (rebalance - ctx.remaining_bits);
-      if (rebalance > 3 << OB_BITRES && t.itheta != 0) sbits += rebalance - (3 << OB_BITRES);
-      cm |= rdo_band_mono(ctx, Y, tmp, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
-    } else {
-      cm = rdo_band_mono(ctx, Y, tmp, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
-      rebalance = sbits - (rebalance - ctx.remaining_bits);
-      if (rebalance > 3 << OB_BITRES && t.itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
-      cm |= rdo_band_mono(ctx, X, tmp, N, mbits, B, lowband, LM, lowband_out, 1.0f, lowband_scratch, fill);
-    }
   }
   if (N != 2) rdo_stereo_merge(X, Y, mid, N);
   if (t.inv)
@@ -399,50 +412,60 @@ OB_DEVNI int rdo_all_bands(RangeEnc &enc, const float *Xg, const float *bandE, c
     float *lowband_out = last ? nullptr : w.norm + off;
 #pragma unroll 1
     for (int j = 0; j < N; j++) { bx[j] = Xg[off + j]; by[j] = Xg[N_ + off + j]; }
-    if (i < intensity) {
+    {
+      // Below the intensity band the band is coded twice (theta rounded down, then up) and the better trial kept; above it once.  One
+      // call site in a trial loop, so that the streams of a warp stay together whichever case each of them is in.
+      const int rdo = i < intensity;
       const unsigned cm = x_cm | y_cm;
       const float minE = enc_fmin(bandE[i], bandE[i + OB_NBANDS]);   // compute_channel_weights (celt/bands.c:362-377)
       const float w0 = bandE[i] + minE / 3, w1 = bandE[i + OB_NBANDS] + minE / 3;
       const RangeEnc ec_save = enc;
       const EncBand ctx_save = ctx;
-      ctx.theta_round = -1;
-      x_cm = rdo_band_stereo(ctx, bx, by, tmp, N, b, B, lowband, LM, lowband_out, w.lowband_scratch, (int)cm);
-      const float dist0 = w0 * enc_dot(Xg + off, bx, N) + w1 * enc_dot(Xg + N_ + off, by, N);
-      const unsigned cm2 = x_cm;
-      const RangeEnc ec_save2 = enc;
-      const EncBand ctx_save2 = ctx;
-      if (!last)
+      RangeEnc ec_save2 = enc;
+      EncBand ctx_save2 = ctx;
+      float dist0 = 0.f;
+      unsigned cm2 = 0;
+      uint32_t nfront = 0, nend = 0;
 #pragma unroll 1
-        for (int j = 0; j < N; j++) w.norm_save2[j] = lowband_out[j];
-      // only the bytes the first trial wrote can differ between the trials: save those instead of the whole tail of the packet
-      const uint32_t nfront = ec_save2.offs - ec_save.offs, nend = ec_save2.end_offs - ec_save.end_offs;
-      if (nfront + nend > sizeof(w.bytes_save)) status = -3;
+      for (int trial = 0; trial < (rdo ? 2 : 1); trial++) {
+        if (trial) {
+          cm2 = x_cm;
+          ec_save2 = enc;
+          ctx_save2 = ctx;
+          if (!last)
 #pragma unroll 1
-      for (uint32_t k = 0; k < nfront && k < sizeof(w.bytes_save); k++) w.bytes_save[k] = enc.buf[ec_save.offs + k];
+            for (int j = 0; j < N; j++) w.norm_save2[j] = lowband_out[j];
+          // only the bytes the first trial wrote can differ between the trials: save those instead of the whole tail of the packet
+          nfront = ec_save2.offs - ec_save.offs; nend = ec_save2.end_offs - ec_save.end_offs;
+          if (nfront + nend > sizeof(w.bytes_save)) status = -3;
 #pragma unroll 1
-      for (uint32_t k = 0; k < nend && nfront + k < sizeof(w.bytes_save); k++) w.bytes_save[nfront + k] = enc.buf[enc.storage - ec_save2.end_offs + k];
-      enc = ec_save;
-      ctx = ctx_save;
+          for (uint32_t k = 0; k < nfront && k < sizeof(w.bytes_save); k++) w.bytes_save[k] = enc.buf[ec_save.offs + k];
 #pragma unroll 1
-      for (int j = 0; j < N; j++) { bx[j] = Xg[off + j]; by[j] = Xg[N_ + off + j]; }
-      ctx.theta_round = 1;
-      x_cm = rdo_band_stereo(ctx, bx, by, tmp, N, b, B, lowband, LM, lowband_out, w.lowband_scratch, (int)cm);
-      const float dist1 = w0 * enc_dot(Xg + off, bx, N) + w1 * enc_dot(Xg + N_ + off, by, N);
-      if (dist0 >= dist1) {
-        x_cm = cm2;
-        enc = ec_save2;
-        ctx = ctx_save2;
-        if (!last)
+          for (uint32_t k = 0; k < nend && nfront + k < sizeof(w.bytes_save); k++) w.bytes_save[nfront + k] = enc.buf[enc.storage - ec_save2.end_offs + k];
+          enc = ec_save;
+          ctx = ctx_save;
 #pragma unroll 1
-          for (int j = 0; j < N; j++) lowband_out[j] = w.norm_save2[j];
+          for (int j = 0; j < N; j++) { bx[j] = Xg[off + j]; by[j] = Xg[N_ + off + j]; }
+        }
+        ctx.theta_round = rdo ? (trial ? 1 : -1) : 0;
+        x_cm = rdo_band_stereo(ctx, bx, by, tmp, N, b, B, lowband, LM, lowband_out, w.lowband_scratch, (int)cm);
+        if (rdo) {
+          const float dist = w0 * enc_dot(Xg + off, bx, N) + w1 * enc_dot(Xg + N_ + off, by, N);
+          if (!trial) dist0 = dist;
+          else if (dist0 >= dist) {
+            x_cm = cm2;
+            enc = ec_save2;
+            ctx = ctx_save2;
+            if (!last)
 #pragma unroll 1
-        for (uint32_t k = 0; k < nfront && k < sizeof(w.bytes_save); k++) enc.buf[ec_save.offs + k] = w.bytes_save[k];
+              for (int j = 0; j < N; j++) lowband_out[j] = w.norm_save2[j];
 #pragma unroll 1
-        for (uint32_t k = 0; k < nend && nfront + k < sizeof(w.bytes_save); k++) enc.buf[enc.storage - ec_save2.end_offs + k] = w.bytes_save[nfront + k];
+            for (uint32_t k = 0; k < nfront && k < sizeof(w.bytes_save); k++) enc.buf[ec_save.offs + k] = w.bytes_save[k];
+#pragma unroll 1
+            for (uint32_t k = 0; k < nend && nfront + k < sizeof(w.bytes_save); k++) enc.buf[enc.storage - ec_save2.end_offs + k] = w.bytes_save[nfront + k];
+          }
+        }
       }
-    } else {
-      ctx.theta_round = 0;
-      x_cm = rdo_band_stereo(ctx, bx, by, tmp, N, b, B, lowband, LM, lowband_out, w.lowband_scratch, (int)(x_cm | y_cm));
     }
     y_cm = x_cm;
     w.collapse_masks[i * C + 0] = (unsigned char)x_cm;
