@@ -32,6 +32,8 @@ struct DecSynthParams {
   int downsample;           // 48000 / output rate: every downsample-th de-emphasised sample is written (celt_decoder.c:300-405)
   int apply_gain;           // OPUS_SET_GAIN != 0 (src/opus_decoder.c:686-700)
   float gain;
+  int defer_clip = 0;       // int16 output of a packet that may hold several frames: pcm is a FLOAT staging area and opus_decode()'s soft
+                            // clipping runs once over the whole packet afterwards (dec_softclip_packet_block), as in the reference
 };
 
 struct SynthWS {  // per warp (= per output channel)
@@ -334,7 +336,8 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   }
   // ---- opus_decode()'s soft clipping of the int16 output; opus_decode_float() clears the memory (src/opus_decoder.c:875-878) ----
   if (!(plc & OB_PLC_PACKET)) {   // a lost packet's frames are returned before this step (src/opus_decoder.c:764-778)
-    if (p.pcm_is_int16) soft_clip_channel(out, Nd, ds, &st->declip[ch], lane);
+    if (p.defer_clip) {}   // clipped per packet by dec_softclip_packet_block
+    else if (p.pcm_is_int16) soft_clip_channel(out, Nd, ds, &st->declip[ch], lane);
     else if (lane == 0 && st->declip[ch] != 0.f) st->declip[ch] = 0.f;
   }
   // ---- interleave through shared memory, then fully coalesced stores ----
@@ -361,6 +364,35 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
         o[e] = w0[c].out[OB_SYN_O + j * ds];
       }
     }
+  }
+}
+
+// opus_decode()'s soft clipping + int16 conversion over a whole packet (src/opus_decoder.c:875-878, src/opus.c:39-166), for packets that
+// may hold several frames: the synthesis / concealment kernels left the packet's float PCM in `stage`.  One CTA per stream, one warp per
+// channel for the (mostly skipped) clipping scan, then every thread converts and stores.
+struct DecClipParams {
+  float *stage;                 // [n_streams][stage_stride] interleaved float PCM of the packet
+  int stage_stride;
+  int16_t *pcm;                 // [n_streams][pcm_stride]
+  int pcm_stride;
+  const int32_t *out_samples;   // [n_streams] samples per channel the packet produced (<= 0: nothing)
+  const int32_t *pkt_len;       // [n_streams]; 0 = lost packet: returned without soft clipping (src/opus_decoder.c:764-778)
+  ObDecSynthState *state;
+  int n_streams, channels;
+};
+OB_DEV void dec_softclip_packet_block(const DecClipParams &p, int stream) {
+  const int lane = lane_id(), ch = warp_in_block(), CC = p.channels;
+  const int n = p.out_samples[stream];
+  if (n <= 0) return;
+  float *x = p.stage + (size_t)stream * p.stage_stride;
+  if (p.pkt_len[stream] != 0) soft_clip_channel(x + ch, n, CC, &p.state[stream].declip[ch], lane);
+  bsync();
+  int16_t *o = p.pcm + (size_t)stream * p.pcm_stride;
+  for (int e = ch * 32 + lane; e < n * CC; e += CC * 32) {
+    float v = x[e] * 32768.f;
+    v = v > -32768.f ? v : -32768.f;
+    v = v < 32767.f ? v : 32767.f;
+    o[e] = (int16_t)lrintf(v);
   }
 }
 

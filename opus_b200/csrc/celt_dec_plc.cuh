@@ -29,6 +29,7 @@ struct DecPlcParams {
   int downsample;
   int apply_gain;   // OPUS_SET_GAIN != 0: concealed audio is scaled like decoded audio
   float gain;
+  int defer_clip = 0;   // see DecSynthParams::defer_clip
 };
 
 constexpr int kPlcMaxPeriod = 1024, kPlcLagMax = 720, kPlcLagMin = 100, kPlcOrd = OB_PLC_LPC_ORDER;
@@ -365,7 +366,8 @@ OB_DEVNI void dec_plc_block(const DecPlcParams &p, int stream, unsigned char *sm
       wsync();
     }
     if (!(side->plc & OB_PLC_PACKET)) {   // a DTX frame inside a packet is soft-clipped with the packet; a lost packet is not
-      if (p.pcm_is_int16) soft_clip_channel(y, Nd, ds, &st->declip[c], lane);
+      if (p.defer_clip) {}
+      else if (p.pcm_is_int16) soft_clip_channel(y, Nd, ds, &st->declip[c], lane);
       else if (lane == 0 && st->declip[c] != 0.f) st->declip[c] = 0.f;
     }
   }

@@ -53,6 +53,9 @@ extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParam
 // 65 536 streams).  Small chunks on purpose: a concealed frame takes ~0.2 ms of mostly serial work (the 24-tap synthesis recursion),
 // so the lost streams of a batch should spread over as many CTAs as are resident (8 per SM) instead of queueing inside a few.
 #define OB_PLC_CHUNK 8
+extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_softclip_packet(DecClipParams p) {
+  if ((int)blockIdx.x < p.n_streams) dec_softclip_packet_block(p, blockIdx.x);
+}
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_plc(DecPlcParams p) {
   __shared__ unsigned lost_mask;
   if (threadIdx.x < 32) {
@@ -177,6 +180,7 @@ struct OpusB200Decoder {
   int disable_inv, decode_gain;   // OPUS_SET_PHASE_INVERSION_DISABLED, OPUS_SET_GAIN (Q8 dB)
   float gain;                     // 2^(decode_gain / (256 * 6.0206))
   int16_t *h_last_N; // host mirror of ObDecBandState.last_N (host-buffer API: sizes the frame-launch loop of a lost packet)
+  float *d_clip_stage; size_t d_clip_stage_cap;   // float PCM of multi-frame packets with int16 output (soft-clipped per packet)
   cudaStream_t stream;
   ObDecBandState *bstate;
   ObDecSynthState *sstate;
@@ -343,7 +347,7 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   cudaStreamSynchronize(d->stream2);
   cudaStreamDestroy(d->stream_e);
   cudaEventDestroy(d->ev_in);
-  cudaFree(d->bstate); cudaFree(d->sstate);
+  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->d_clip_stage);
   free(d->h_last_N);
   for (int b = 0; b < 2; b++) { cudaFree(d->script[b]); cudaFree(d->side[b]); cudaFree(d->X[b]); cudaEventDestroy(d->ev_a1[b]); cudaEventDestroy(d->ev_a2[b]); cudaEventDestroy(d->ev_b[b]); }
   cudaStreamDestroy(d->stream_v);
@@ -388,6 +392,20 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
   const size_t pvq_smem = ((sizeof(PvqShared) + 15) & ~(size_t)15) + (size_t)pw * sizeof(PvqWS);
   if ((int)pvq_smem > d->max_smem_optin) return OPUSB200_INTERNAL_ERROR;
   const size_t esz = pcm_is_int16 ? 2 : 4;
+  // int16 output of packets that may hold several frames: opus_decode() soft-clips the PACKET, so the frames go to a float staging
+  // area first and one more kernel clips and converts (one-frame packets keep the fused per-frame path, which is the same thing)
+  const bool defer_clip = pcm_is_int16 && max_frames_per_packet > 1;
+  const int stage_stride = frame_size * d->channels;
+  if (defer_clip) {
+    const size_t need = sizeof(float) * (size_t)d->n * stage_stride;
+    if (d->d_clip_stage_cap < need) {
+      OB_CUDA(cudaDeviceSynchronize());
+      cudaFree(d->d_clip_stage); d->d_clip_stage = nullptr; d->d_clip_stage_cap = 0;
+      OB_CUDA(cudaMalloc(&d->d_clip_stage, need));
+      d->d_clip_stage_cap = need;
+    }
+  }
+  cudaStream_t last_sb = st;
   for (int k = 0; k < max_frames_per_packet; k++) {
     const int par = d->par;
     d->par ^= 1;
@@ -436,10 +454,12 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels; sp.downsample = d->downsample;
     sp.apply_gain = d->decode_gain != 0; sp.gain = d->gain;
+    if (defer_clip) { sp.pcm = d->d_clip_stage + (size_t)s0 * stage_stride; sp.pcm_stride = stage_stride; sp.pcm_is_int16 = 0; sp.defer_clip = 1; }
+    last_sb = sb;
     ob_celt_dec_synth<<<cn, 32 * d->channels, d->channels * sizeof(SynthWS), sb>>>(sp);
     {  // lost frames (len == 0, or a DTX frame inside a packet): concealed from the history ring; a no-op scan otherwise
       DecPlcParams lp;
-      lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = pcm_stride; lp.pcm_is_int16 = pcm_is_int16;
+      lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = sp.pcm_stride; lp.pcm_is_int16 = sp.pcm_is_int16; lp.defer_clip = sp.defer_clip;
       lp.n_streams = cn; lp.channels = d->channels; lp.downsample = d->downsample; lp.apply_gain = sp.apply_gain; lp.gain = sp.gain;
       ob_celt_dec_plc<<<(cn + OB_PLC_CHUNK - 1) / OB_PLC_CHUNK, 64, sizeof(PlcWS), sb>>>(lp);
     }
@@ -457,6 +477,17 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
       cudaEventElapsedTime(&c, d->ev[2], d->ev[3]);
       d->kernel_ms[0] += a; d->kernel_ms[1] += b; d->kernel_ms[2] += c; d->timed_launches++;
     }
+  }
+  if (defer_clip) {   // after the last frame's synthesis / concealment, on their stream
+    DecClipParams cp;
+    cp.stage = d->d_clip_stage + (size_t)s0 * stage_stride; cp.stage_stride = stage_stride; cp.pcm = (int16_t *)d_pcm + (size_t)s0 * pcm_stride;
+    cp.pcm_stride = pcm_stride; cp.out_samples = (d_out_samples ? d_out_samples : d->d_out[0]) + s0; cp.pkt_len = d_len + s0; cp.state = d->sstate + s0;
+    cp.n_streams = cn; cp.channels = d->channels;
+    const bool timing = d->timing && st == d->stream;
+    // (out_samples is final: the last frame's synthesis on this stream already waited, through the vector stage, for the last parse)
+    ob_celt_dec_softclip_packet<<<cn, 32 * d->channels, 0, last_sb>>>(cp);
+    d->launches++;
+    if (!timing && d->last_b >= 0) OB_CUDA(cudaEventRecord(d->ev_b[d->last_b], last_sb));   // the join waits for the clip too
   }
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;

@@ -38,6 +38,10 @@ static void synth_entry(void *arg) {
   dec_synth_block(p, block_id(), dyn_smem());
 }
 
+static void clip_entry(void *arg) {
+  const DecClipParams &p = *(const DecClipParams *)arg;
+  dec_softclip_packet_block(p, block_id());
+}
 static void plc_entry(void *arg) {
   const DecPlcParams &p = *(const DecPlcParams *)arg;
   dec_plc_block(p, block_id(), dyn_smem());
@@ -91,6 +95,11 @@ void emu_decoder_destroy(void *h) { delete (EmuDecoder *)h; }
 int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const int *lens, void *pcm, int pcm_stride,
                        int pcm_is_int16, int *out_samples, unsigned *final_range) {
   EmuDecoder *d = (EmuDecoder *)h;
+  // like the CUDA host side: int16 output goes through a float staging area and one packet-wide soft clip (dec_softclip_packet_block)
+  // whenever a packet may hold several frames; the emulator always allows that
+  const int defer_clip = pcm_is_int16;
+  const int stage_stride = d->frame_size * d->channels;
+  std::vector<float> stage(defer_clip ? (size_t)d->n * stage_stride : 0, 0.f);
   for (int k = 0; k < 48; k++) {
     DecEntropyParams ep;
     ep.packets = packets; ep.pkt_len = lens; ep.pkt_stride = stride; ep.n_streams = d->n; ep.channels = d->channels;
@@ -114,13 +123,20 @@ int emu_decoder_decode(void *h, const unsigned char *packets, int stride, const 
       sp.side = d->side.data() + s; sp.X = d->X.data() + (size_t)s * 2 * OB_MAXN; sp.state = d->sstate.data() + s;
       sp.pcm = pcm_is_int16 ? (void *)((int16_t *)pcm + (size_t)s * pcm_stride) : (void *)((float *)pcm + (size_t)s * pcm_stride);
       sp.pcm_stride = 0; sp.frame_index = k; sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = 1; sp.channels = d->channels; sp.downsample = d->downsample; sp.apply_gain = d->decode_gain != 0; sp.gain = d->gain;
+      if (defer_clip) { sp.pcm = stage.data() + (size_t)s * stage_stride; sp.pcm_is_int16 = 0; sp.defer_clip = 1; }
       const int lost_here = OB_PLC_TYPE(d->side[s].plc) >= OB_PLC_PITCH;   // (emulator only: skip the launch that would return at once)
       if (!lost_here) emu_launch(synth_entry, &sp, 1, 32 * d->channels, sizeof(SynthWS) * d->channels);
       DecPlcParams lp;
-      lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = 0; lp.pcm_is_int16 = pcm_is_int16; lp.n_streams = 1;
+      lp.side = sp.side; lp.state = sp.state; lp.pcm = sp.pcm; lp.pcm_stride = 0; lp.pcm_is_int16 = sp.pcm_is_int16; lp.defer_clip = sp.defer_clip; lp.n_streams = 1;
       lp.channels = d->channels; lp.downsample = d->downsample; lp.apply_gain = sp.apply_gain; lp.gain = sp.gain;
       if (lost_here) emu_launch(plc_entry, &lp, 1, 64, sizeof(PlcWS));
     }
+  }
+  if (defer_clip) {
+    DecClipParams cp;
+    cp.stage = stage.data(); cp.stage_stride = stage_stride; cp.pcm = (int16_t *)pcm; cp.pcm_stride = pcm_stride; cp.out_samples = out_samples;
+    cp.pkt_len = lens; cp.state = d->sstate.data(); cp.n_streams = d->n; cp.channels = d->channels;
+    emu_launch(clip_entry, &cp, d->n, 32 * d->channels, 0);
   }
   for (int s = 0; s < d->n; s++) final_range[s] = d->bstate[s].final_range;
   return 0;

@@ -362,3 +362,33 @@ def test_decoder_ctls_vs_reference(ctls):
     dec.close()
     with pytest.raises(opus_b200.OpusB200Error):
         opus_b200.DecoderBatch(1, channels=1).ctl(4034, 40000)
+
+
+@pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+@pytest.mark.parametrize('ch,fs,br', [(2, 1920, 64000), (1, 2880, 48000)])
+def test_int16_soft_clipping_of_multiframe_packets_vs_reference(ch, fs, br):
+    """opus_decode() soft-clips the whole packet (src/opus_decoder.c:875-878): 40 / 60 ms packets of loud signals, int16 output, against the
+    reference's int16 API (+-1 LSB); the clipped regions run across the frames of a packet"""
+    import opus_b200
+    from test_oracle_softclip_vs_ref import loud_signal
+    L = util.load_ref('c')
+    nfr, n = 6, 5
+    pks, szs, refs = [], [], []
+    for s in range(n):
+        x = loud_signal(s * 10 + ch + fs, nfr * fs, ch, (0, 2, 0, 2, 0)[s])
+        pk, sz, _ = util.ref_encode(x, ch, fs, br)
+        sz = np.ascontiguousarray(sz, np.int32)
+        ref, rr = np.zeros((nfr * fs, ch), np.int16), np.zeros(nfr, np.uint32)
+        assert L.refh_decode_stream(48000, ch, fs, nfr, util._ptr(pk), pk.shape[1], util._ptr(sz), util._ptr(ref), util._ptr(rr)) == 0
+        pks.append(pk); szs.append(sz); refs.append(ref)
+    pk, sz = np.stack(pks), np.stack(szs)
+    dec = opus_b200.DecoderBatch(n, channels=ch)
+    worst = 0
+    for t in range(nfr):
+        got, ns = dec.decode(pk[:, t], sz[:, t], frame_size=fs, dtype=np.int16)
+        assert (ns == fs).all()
+        for s in range(n):
+            d = np.abs(got[s, :fs * ch].astype(np.int32) - refs[s][t * fs:(t + 1) * fs].reshape(-1).astype(np.int32))
+            worst = max(worst, int(d.max()))
+    dec.close()
+    assert worst <= 1, worst
