@@ -1,6 +1,12 @@
 // celt_enc_host.cuh — kernel entry points and C ABI of the batched CELT encoder (included at the end of opus_b200.cu).
 #pragma once
 #include "celt_enc_frame.cuh"
+#include "celt_enc_chains.cuh"
+
+extern "C" __global__ void __launch_bounds__(32) ob_celt_enc_chains(EncAnalysisParams p, float *scratch) {
+  extern __shared__ float ob_chain_tile[];
+  enc_chains_warp(p, p.first_stream + blockIdx.x * 32, ob_chain_tile, scratch + (size_t)blockIdx.x * OB_CH_SCRATCH_FLOATS);
+}
 
 extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame(EncFrameParams p) {
   const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,6 +53,7 @@ struct OpusB200Encoder {
   cudaStream_t stream_f[4];   // one per chunk: the frame coder is latency-bound per warp, so the chunks' coders must overlap each other too
   cudaEvent_t ev_an[4], ev_fr[4];
   // profiling aid (opusb200_opus_encoder_set_timing): CUDA events around each kernel of a call, on the launching stream
+  float *chain_scratch;   // [ceil(n/32)][OB_CH_SCRATCH_FLOATS]: the recurrence kernel's transposed tracks (celt_enc_chains.cuh)
   int timing;
   cudaEvent_t tev[5];
   double t_ms[4];   // Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder
@@ -100,6 +107,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->bandLogE2, sizeof(float) * n * channels * OB_NBANDS));
   OB_CUDA(cudaMalloc(&e->prefilter_mem, sizeof(float) * n * channels * kPfMaxPeriod));
   OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
+  OB_CUDA(cudaMalloc(&e->chain_scratch, sizeof(float) * ((n + 31) / 32) * OB_CH_SCRATCH_FLOATS));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32 + (int)sizeof(PfWS)));
   const int r = opusb200_encoder_reset(e);
   if (r != OPUSB200_OK) return r;
@@ -112,7 +120,7 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
-  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt);
+  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->chain_scratch);
   if (e->tev[0]) for (int i = 0; i < 5; i++) cudaEventDestroy(e->tev[i]);
   for (int i = 0; i < 4; i++) {
     cudaStreamSynchronize(e->stream_f[i]);
@@ -181,6 +189,13 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
     if (s0 >= s1) break;
     a.first_stream = s0; a.n_streams = s1;
     if (e->timing) cudaEventRecord(e->tev[2], e->stream);
+    // the transient / tone recurrences: one thread per stream ahead of the CTA-per-stream kernel (OPUSB200_ENC_NO_CHAINS=1: the old fused form)
+    static const bool no_chains = getenv("OPUSB200_ENC_NO_CHAINS") != nullptr;
+    a.chains_done = !no_chains && chunks == 1;
+    if (a.chains_done) {
+      ob_celt_enc_chains<<<(s1 - s0 + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float), e->stream>>>(a, e->chain_scratch);
+      e->launches++;
+    }
     ob_celt_enc_analysis<<<s1 - s0, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
     if (e->timing) cudaEventRecord(e->tev[3], e->stream);
     cudaStream_t sf = chunks > 1 ? e->stream_f[k] : e->stream;

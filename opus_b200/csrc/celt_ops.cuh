@@ -118,6 +118,8 @@ struct EncAnalysisParams {
   // Opus layer (opus_encode): per-stream coded channels / end band / AnalysisInfo, and the stereo width fade + guard applied to the
   // dc-rejected input as it is read (src/opus_encoder.c:2011-2022, 2329-2349).  Arrays are then strided by the INPUT channel count.
   const ObOpusFrameCtl *ctl = nullptr;
+  // the transient / tone recurrences already ran in ob_celt_enc_chains (celt_enc_chains.cuh): p.info[stream] holds their results
+  int chains_done = 0;
 };
 // the encoder's input sample (i, c) of one stream: the caller's PCM, or with the Opus layer in front the dc-rejected signal after
 // stereo_fade (src/opus_encoder.c:553-580) and the float guard
@@ -307,12 +309,14 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   // cross-channel part: maxima and the tone detector need both channels' time signals
   float *xch = (float *)((MdctWS *)smem + CC);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
   if (lane == 0) { xch[c * 2] = mx_new; xch[c * 2 + 1] = mx_tail; }
-  if (p.complexity >= 1 && p.info) {   // transient_analysis: lane 0 of each channel's warp walks its channel (f2 is free until the MDCT)
+  if (p.chains_done) {
+    if (c == 0 && lane == 0) ((int *)xch)[6] = p.info[stream].short_blocks;
+  } else if (p.complexity >= 1 && p.info) {   // transient_analysis: lane 0 of each channel's warp walks its channel (f2 is free until the MDCT)
     const int um = transient_unmask_warp(ws->in, ws->f2, N + OB_OVERLAP, lane);
     if (lane == 0) ((int *)xch)[4 + c] = um;
   }
   bsync();
-  if (c == 0 && p.info) {
+  if (c == 0 && p.info && !p.chains_done) {
     float a = xch[0], t = xch[1];
     if (CC == 2) { a = fmaxf(a, xch[2]); t = fmaxf(t, xch[3]); }
     const float sample_max = fmaxf(fmaxf(st.overlap_max, a), t);

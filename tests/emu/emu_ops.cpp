@@ -199,6 +199,20 @@ extern "C" void emu_celt_enc_analysis(void *state, const float *pcm, const int32
 
 // ---- frame encoder (analysis block + thread-per-stream coder) ----
 #include "../../opus_b200/csrc/celt_enc_frame.cuh"
+#include "../../opus_b200/csrc/celt_enc_chains.cuh"
+static std::vector<float> g_chain_scratch;
+static int g_enc_chains = 1;   // run the recurrence kernel ahead of the analysis block (the product's default); 0 = the fused single-kernel form
+extern "C" void emu_celt_set_chains(int on) { g_enc_chains = on; }
+static void enc_chains_entry(void *a) {
+  const EncAnalysisParams &p = *(const EncAnalysisParams *)a;
+  enc_chains_warp(p, block_id() * 32, (float *)dyn_smem(), g_chain_scratch.data() + (size_t)block_id() * OB_CH_SCRATCH_FLOATS);
+}
+static void emu_run_chains(EncAnalysisParams &a, int n) {
+  a.chains_done = g_enc_chains;
+  if (!g_enc_chains) return;
+  g_chain_scratch.assign((size_t)((n + 31) / 32) * OB_CH_SCRATCH_FLOATS, 0.f);
+  emu_launch(enc_chains_entry, &a, (n + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float));
+}
 static void enc_frame_entry(void *a) {
   const EncFrameParams &p = *(const EncFrameParams *)a;
   const int s = block_id() * 32 + lane_id();
@@ -243,6 +257,7 @@ extern "C" void emu_celt_encode(void *an_state, ObEncState *enc_state, const flo
   a.info = info.data(); a.n_streams = n; a.C = C; a.CC = CC; a.LM = LM; a.complexity = complexity; a.lsb_depth = lsb_depth;
   a.enc_state = enc_state; a.prefilter_mem = prefilter_mem; a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = bitrate; a.vbr = vbr;
   a.constrained_vbr = cvbr; a.disable_pf = g_enc_pred <= 1; a.loss_rate = 0; a.end = g_enc_end; a.upsample = g_enc_up;
+  emu_run_chains(a, n);
   emu_launch(enc_analysis_entry, &a, n, 32 * CC, CC * sizeof(MdctWS) + 32 + (complexity >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams p;
   p.state = enc_state; p.info = info.data(); p.X = X.data(); p.bandE = E.data(); p.bandLogE = Lg.data(); p.bandLogE2 = Lg2.data(); p.packets = packets; p.nbytes = nbytes;
@@ -325,6 +340,7 @@ extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_siz
   a.enc_state = e->enc_state.data(); a.prefilter_mem = e->prefilter_mem.data(); a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = pl.celt_bitrate;
   a.vbr = pl.celt_vbr; a.constrained_vbr = pl.celt_cvbr; a.disable_pf = pl.celt_disable_pf; a.loss_rate = e->cfg.packet_loss; a.end = OB_NBANDS; a.upsample = up;
   a.ctl = e->ctl.data();
+  emu_run_chains(a, n);
   emu_launch(enc_analysis_entry, &a, n, 32 * CC, CC * sizeof(MdctWS) + 32 + (cx >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams f;
   f.state = e->enc_state.data(); f.info = info.data(); f.X = X.data(); f.bandE = E.data(); f.bandLogE = Lg.data(); f.bandLogE2 = Lg2.data();

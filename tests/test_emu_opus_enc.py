@@ -133,3 +133,14 @@ def test_float_api_silence_and_guard():
 @pytest.mark.parametrize('ctl', [[(4008, 1103)], [(4022, 1)], [(4024, 3001)], [(4042, 1)], [(4036, 12)], [(4020, 0)]])
 def test_ctls(ctl):
     run_case(three_signals(31, 960 * 6, 2), 48000, 2, 960, 40000, 1, 10, ctls=ctl, nframes=6)
+
+
+def test_fused_front_end_without_the_chains_kernel():
+    """OPUSB200_ENC_NO_CHAINS=1 keeps the transient / tone recurrences inside the CTA-per-stream kernel: same packets"""
+    L = emu_util.load_emu_ops()
+    L.emu_celt_set_chains(0)
+    try:
+        run_case(three_signals(41, 960 * 5, 2), 48000, 2, 960, 64000, 1, 10, nframes=5)
+        run_case(three_signals(43, 480 * 6, 1), 48000, 1, 480, 32000, 0, 5, nframes=6)
+    finally:
+        L.emu_celt_set_chains(1)
