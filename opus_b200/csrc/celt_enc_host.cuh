@@ -54,6 +54,7 @@ struct OpusB200Encoder {
   cudaEvent_t ev_an[4], ev_fr[4];
   // profiling aid (opusb200_opus_encoder_set_timing): CUDA events around each kernel of a call, on the launching stream
   float *chain_scratch;   // [ceil(n/32)][OB_CH_SCRATCH_FLOATS]: the recurrence kernel's transposed tracks (celt_enc_chains.cuh)
+  float *in_buf;          // [n][channels][1080]: the pre-emphasised, pre-filtered analysis window it hands to the transform kernel
   int timing;
   cudaEvent_t tev[5];
   double t_ms[4];   // Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder
@@ -108,6 +109,7 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->prefilter_mem, sizeof(float) * n * channels * kPfMaxPeriod));
   OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
   OB_CUDA(cudaMalloc(&e->chain_scratch, sizeof(float) * ((n + 31) / 32) * OB_CH_SCRATCH_FLOATS));
+  OB_CUDA(cudaMalloc(&e->in_buf, sizeof(float) * n * channels * OB_CH_IN_STRIDE));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32 + (int)sizeof(PfWS)));
   const int r = opusb200_encoder_reset(e);
   if (r != OPUSB200_OK) return r;
@@ -120,7 +122,7 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
-  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->chain_scratch);
+  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->chain_scratch); cudaFree(e->in_buf);
   if (e->tev[0]) for (int i = 0; i < 5; i++) cudaEventDestroy(e->tev[i]);
   for (int i = 0; i < 4; i++) {
     cudaStreamSynchronize(e->stream_f[i]);
@@ -192,6 +194,7 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
     // the transient / tone recurrences: one thread per stream ahead of the CTA-per-stream kernel (OPUSB200_ENC_NO_CHAINS=1: the old fused form)
     static const bool no_chains = getenv("OPUSB200_ENC_NO_CHAINS") != nullptr;
     a.chains_done = !no_chains && chunks == 1;
+    a.in_buf = a.chains_done ? e->in_buf : nullptr;
     if (a.chains_done) {
       ob_celt_enc_chains<<<(s1 - s0 + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float), e->stream>>>(a, e->chain_scratch);
       e->launches++;

@@ -120,6 +120,9 @@ struct EncAnalysisParams {
   const ObOpusFrameCtl *ctl = nullptr;
   // the transient / tone recurrences already ran in ob_celt_enc_chains (celt_enc_chains.cuh): p.info[stream] holds their results
   int chains_done = 0;
+  // ... and so did run_prefilter: in_buf [n][CC][N + overlap (stride 1080)] holds the filtered window the transforms start from, every
+  // time-domain memory is up to date (null: the analysis kernel pre-emphasises and filters itself)
+  float *in_buf = nullptr;
 };
 // the encoder's input sample (i, c) of one stream: the caller's PCM, or with the Opus layer in front the dc-rejected signal after
 // stereo_fade (src/opus_encoder.c:553-580) and the float guard
@@ -277,6 +280,10 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   float *pmem = pf_path ? p.prefilter_mem + ((size_t)stream * CC + c) * kPfMaxPeriod : nullptr;
   // the analysis window starts with the UNFILTERED tail of the previous frame (celt/celt_encoder.c:2014); without a pre-filter
   // history that is the same as the MDCT overlap memory
+  if (p.in_buf) {   // ob_celt_enc_chains left the pre-emphasised, pre-filtered window
+    const float *src = p.in_buf + ((size_t)stream * CC + c) * (OB_MAXN + OB_OVERLAP);
+    for (int i = lane; i < N + OB_OVERLAP; i += 32) ws->in[i] = src[i];
+  } else {
   for (int i = lane; i < OB_OVERLAP; i += 32) ws->in[i] = pf_path ? pmem[(st.pf_head + kPfMaxPeriod - OB_OVERLAP + i) & (kPfMaxPeriod - 1)] : st.overlap_mem[c][i];
   if (up == 1) {
     for (int i = lane; i < N; i += 32) {
@@ -301,10 +308,11 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
       }
     }
   }
+  }
   mx_new = warp_max(mx_new);
   mx_tail = warp_max(mx_tail);
   wsync();
-  if (lane == 0) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, enc_pcm_at(pv, N - 1, c))) : f_mul(coef0, 0.f);
+  if (lane == 0 && !p.in_buf) st.preemph_mem[c] = up == 1 ? f_mul(coef0, f_mul(32768.f, enc_pcm_at(pv, N - 1, c))) : f_mul(coef0, 0.f);
   if (!pf_path) for (int i = lane; i < OB_OVERLAP; i += 32) st.overlap_mem[c][i] = ws->in[N + i];
   // cross-channel part: maxima and the tone detector need both channels' time signals
   float *xch = (float *)((MdctWS *)smem + CC);  // [2][2] maxima exchange, [4..5] transient metric per channel, [6] decision
@@ -366,7 +374,10 @@ OB_DEV void enc_analysis_block(const EncAnalysisParams &p, int stream, unsigned 
   if (p.info) transient = ((int *)xch)[6];
   float *freq = ws->in;
   PfWS *pw = (PfWS *)((unsigned char *)smem + (size_t)CC * sizeof(MdctWS) + 32);
-  if (pf_path) {   // run_prefilter (celt/celt_encoder.c:2029-2057): every thread of the CTA takes part
+  if (pf_path && p.in_buf) {
+    if (p.complexity >= 5) freq = pw->buf + c * OB_MAXN;   // the window stays for patch_transient_decision's second transform
+    bsync();
+  } else if (pf_path) {   // run_prefilter (celt/celt_encoder.c:2029-2057): every thread of the CTA takes part
     const ObEncState &es = p.enc_state[stream];
     ObEncFrameInfo fi = p.info[stream];
     const EncBudget bud = enc_budget(p.max_bytes, p.bitrate, p.vbr, p.constrained_vbr, N, es.vbr_reservoir);

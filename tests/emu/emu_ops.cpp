@@ -207,9 +207,13 @@ static void enc_chains_entry(void *a) {
   const EncAnalysisParams &p = *(const EncAnalysisParams *)a;
   enc_chains_warp(p, block_id() * 32, (float *)dyn_smem(), g_chain_scratch.data() + (size_t)block_id() * OB_CH_SCRATCH_FLOATS);
 }
+static std::vector<float> g_chain_in;
 static void emu_run_chains(EncAnalysisParams &a, int n) {
   a.chains_done = g_enc_chains;
+  a.in_buf = nullptr;
   if (!g_enc_chains) return;
+  g_chain_in.assign((size_t)n * 2 * OB_CH_IN_STRIDE, 0.f);
+  a.in_buf = g_chain_in.data();
   g_chain_scratch.assign((size_t)((n + 31) / 32) * OB_CH_SCRATCH_FLOATS, 0.f);
   emu_launch(enc_chains_entry, &a, (n + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float));
 }
