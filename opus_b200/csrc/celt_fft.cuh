@@ -12,36 +12,22 @@ OB_DEV const short *bitrev_table(int shift) {
   return shift == 0 ? ob_fft_bitrev480 : shift == 1 ? ob_fft_bitrev240 : shift == 2 ? ob_fft_bitrev120 : ob_fft_bitrev60;
 }
 
-struct cpx { float r, i; };
+struct alignas(8) cpx { float r, i; };   // 8-byte aligned: one LDS.64 / STS.64 per complex value
 OB_DEV cpx cmul(cpx a, cpx b) { cpx m; m.r = a.r * b.r - a.i * b.i; m.i = a.r * b.i + a.i * b.r; return m; }
 OB_DEV cpx ldtw(int k) { cpx t; t.r = ob_fft_tw[2 * k]; t.i = ob_fft_tw[2 * k + 1]; return t; }
 
-// All B blocks' FFTs of size nfft = 480>>shift, in place on digit-reversed data, stage order and
-// per-butterfly arithmetic of celt/kiss_fft.c:52-313,562-613.  F: B consecutive arrays of nfft cpx.
-OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
-  const short *fac = ob_fft_factors + 10 * shift;
-  const int nfft = 480 >> shift;
-  int fstride[6], L = 0, m;
-  fstride[0] = 1;
-  do {
-    int p = fac[2 * L];
-    m = fac[2 * L + 1];
-    fstride[L + 1] = fstride[L] * p;
-    L++;
-  } while (m != 1);
-  m = fac[2 * L - 1];
-  for (int st = L - 1; st >= 0; st--) {
-    const int m2 = st != 0 ? fac[2 * st - 1] : 1;
-    const int p = fac[2 * st];
-    const int Nn = fstride[st], fs = fstride[st] << shift;
-    const int per_blk = nfft / p;  // butterflies per block in this stage = Nn * m
-    wsync();
-    for (int q = lane; q < per_blk * nblk; q += 32) {
+// One stage of the transform for all blocks: radix P butterflies of span M (M2 = P * M), twiddle stride FS = fstride << shift.  Every constant
+// is a template parameter, so the butterfly index split (q -> block, i, j) costs no integer division.  Per-butterfly arithmetic as in
+// celt/kiss_fft.c:52-313.
+template <int P, int M, int M2, int FS, int NFFT> OB_DEV void fft_stage(cpx *F, int nblk, int lane) {
+  constexpr int p = P, m = M, m2 = M2, fs = FS, nfft = NFFT, per_blk = NFFT / P;
+  wsync();
+  for (int q = lane; q < per_blk * nblk; q += 32) {
       const int blk = q / per_blk, w = q - blk * per_blk;
       const int i = w / m, j = w - i * m;
       cpx *Fo = F + blk * nfft + i * m2 + j;
-      if (p == 4) {
-        if (m == 1) {
+      if constexpr (p == 4) {
+        if constexpr (m == 1) {
           cpx a0 = Fo[0], a1 = Fo[1], a2 = Fo[2], a3 = Fo[3], s0, s1;
           s0.r = a0.r - a2.r; s0.i = a0.i - a2.i;
           a0.r += a2.r; a0.i += a2.i;
@@ -67,7 +53,7 @@ OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
           o3.r = s5.r - s4.i; o3.i = s5.i + s4.r;
           Fo[0] = f0; Fo[m] = o1; Fo[2 * m] = o2; Fo[3 * m] = o3;
         }
-      } else if (p == 2) {  // m == 4 : Fo[0] pairs with Fo[4], fixed twiddles per j
+      } else if constexpr (p == 2) {  // m == 4 : Fo[0] pairs with Fo[4], fixed twiddles per j
         const float tw = 0.7071067812f;
         cpx *F2 = Fo + 4;
         cpx t, a = Fo[0], b = F2[0];
@@ -77,7 +63,7 @@ OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
         else { t.r = (b.i - b.r) * tw; t.i = (-(b.i + b.r)) * tw; }
         F2[0].r = a.r - t.r; F2[0].i = a.i - t.i;
         Fo[0].r = a.r + t.r; Fo[0].i = a.i + t.i;
-      } else if (p == 3) {
+      } else if constexpr (p == 3) {
         cpx epi3 = ldtw(fs * m);
         cpx f0 = Fo[0];
         cpx s1 = cmul(Fo[m], ldtw(j * fs)), s2 = cmul(Fo[2 * m], ldtw(2 * j * fs)), s3, s0;
@@ -118,7 +104,32 @@ OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
         o.r = s11.r - s12.r; o.i = s11.i - s12.i; Fo[3 * m] = o;
       }
     }
-    m = m2;
+}
+
+// All B blocks' FFTs of size nfft = 480>>shift, in place on digit-reversed data, stage order and per-butterfly arithmetic of
+// celt/kiss_fft.c:52-313,562-613 (factors of celt/static_modes_float.h: 480 = 4.2.4.3.5, 240 = 4.4.3.5, 120 = 4.2.3.5, 60 = 4.3.5, executed
+// from the innermost factor out).  F: B consecutive arrays of nfft cpx.
+OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
+  if (shift == 0) {
+    fft_stage<4, 1, 4, 120, 480>(F, nblk, lane);
+    fft_stage<2, 4, 8, 60, 480>(F, nblk, lane);
+    fft_stage<4, 8, 32, 15, 480>(F, nblk, lane);
+    fft_stage<3, 32, 96, 5, 480>(F, nblk, lane);
+    fft_stage<5, 96, 1, 1, 480>(F, nblk, lane);
+  } else if (shift == 1) {
+    fft_stage<4, 1, 4, 120, 240>(F, nblk, lane);
+    fft_stage<4, 4, 16, 30, 240>(F, nblk, lane);
+    fft_stage<3, 16, 48, 10, 240>(F, nblk, lane);
+    fft_stage<5, 48, 1, 2, 240>(F, nblk, lane);
+  } else if (shift == 2) {
+    fft_stage<4, 1, 4, 120, 120>(F, nblk, lane);
+    fft_stage<2, 4, 8, 60, 120>(F, nblk, lane);
+    fft_stage<3, 8, 24, 20, 120>(F, nblk, lane);
+    fft_stage<5, 24, 1, 4, 120>(F, nblk, lane);
+  } else {
+    fft_stage<4, 1, 4, 120, 60>(F, nblk, lane);
+    fft_stage<3, 4, 12, 40, 60>(F, nblk, lane);
+    fft_stage<5, 12, 1, 8, 60>(F, nblk, lane);
   }
   wsync();
 }
