@@ -33,15 +33,23 @@ extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_entropy(DecEntropy
   dec_entropy_thread(p, stream);
 }
 
-extern "C" __global__ void __launch_bounds__(512) ob_celt_dec_pvq(DecPvqParams p) {
+// Persistent: one CTA per SM, the PVQ table staged once per CTA; every warp keeps fetching the next stream from a global counter until the
+// batch is exhausted, so a warp that drew a cheap frame does not idle until the CTA's slowest stream is done (the shared-memory slice
+// per warp allows only one 13-14 warp CTA per SM).
+extern "C" __global__ void __launch_bounds__(512) ob_celt_dec_pvq(DecPvqParams p, int *next_stream) {
   PvqShared *tab = (PvqShared *)dyn_smem();
   for (int i = threadIdx.x; i < 1272; i += blockDim.x) tab->u[i] = ob_pvq_u[i];
   if (threadIdx.x < 15) tab->rowoff[threadIdx.x] = ob_pvq_rowoff[threadIdx.x];
   __syncthreads();
-  const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (stream >= p.n_streams) return;
   unsigned char *ws = dyn_smem() + ((sizeof(PvqShared) + 15) & ~(size_t)15) + (size_t)(threadIdx.x >> 5) * sizeof(PvqWS);
-  dec_pvq_warp(p, stream, tab, ws);
+  for (;;) {
+    int stream = 0;
+    if ((threadIdx.x & 31) == 0) stream = atomicAdd(next_stream, 1);
+    stream = __shfl_sync(0xffffffffu, stream, 0);
+    if (stream >= p.n_streams) break;
+    dec_pvq_warp(p, stream, tab, ws);
+    __syncwarp();
+  }
 }
 
 extern "C" __global__ void __launch_bounds__(64) ob_celt_dec_synth(DecSynthParams p) {
@@ -181,6 +189,8 @@ struct OpusB200Decoder {
   float gain;                     // 2^(decode_gain / (256 * 6.0206))
   int16_t *h_last_N; // host mirror of ObDecBandState.last_N (host-buffer API: sizes the frame-launch loop of a lost packet)
   float *d_clip_stage; size_t d_clip_stage_cap;   // float PCM of multi-frame packets with int16 output (soft-clipped per packet)
+  int *d_pvq_next;   // work counter of the persistent PVQ kernel
+  int sm_count;
   cudaStream_t stream;
   ObDecBandState *bstate;
   ObDecSynthState *sstate;
@@ -305,6 +315,8 @@ int opusb200_decoder_create(int device, int32_t Fs, int channels, int n_streams,
     OB_CUDA(cudaMallocHost(&d->h_out[b], sizeof(int32_t) * (size_t)n_streams));
   }
   OB_CUDA(cudaDeviceGetAttribute(&d->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  OB_CUDA(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device));
+  OB_CUDA(cudaMalloc(&d->d_pvq_next, sizeof(int)));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_pvq, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_dec_entropy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
@@ -347,7 +359,7 @@ void opusb200_decoder_destroy(OpusB200Decoder *d) {
   cudaStreamSynchronize(d->stream2);
   cudaStreamDestroy(d->stream_e);
   cudaEventDestroy(d->ev_in);
-  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->d_clip_stage);
+  cudaFree(d->bstate); cudaFree(d->sstate); cudaFree(d->d_clip_stage); cudaFree(d->d_pvq_next);
   free(d->h_last_N);
   for (int b = 0; b < 2; b++) { cudaFree(d->script[b]); cudaFree(d->side[b]); cudaFree(d->X[b]); cudaEventDestroy(d->ev_a1[b]); cudaEventDestroy(d->ev_a2[b]); cudaEventDestroy(d->ev_b[b]); }
   cudaStreamDestroy(d->stream_v);
@@ -443,7 +455,11 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
       OB_CUDA(cudaStreamWaitEvent(sv, d->ev_a1[par], 0));
       OB_CUDA(cudaStreamWaitEvent(sv, d->ev_b[par], 0));   // X[par] is free once the synthesis of two frames ago has read it
     }
-    ob_celt_dec_pvq<<<(cn + pw - 1) / pw, pw * 32, pvq_smem, sv>>>(pp);
+    {
+      const int ctas = OB_IMIN((cn + pw - 1) / pw, d->sm_count);
+      OB_CUDA(cudaMemsetAsync(d->d_pvq_next, 0, sizeof(int), sv));
+      ob_celt_dec_pvq<<<ctas, pw * 32, pvq_smem, sv>>>(pp, d->d_pvq_next);
+    }
     if (timing) cudaEventRecord(d->ev[2], st);
     else {
       OB_CUDA(cudaEventRecord(d->ev_a2[par], sv));
