@@ -1018,7 +1018,11 @@ OB_DEVNI void enc_partition(EncBand &ctx, float *X, float *y2, int N0, int b0, i
   EncPart st[6];
   int sp = 0;
   st[0].off = 0; st[0].N = (short)N0; st[0].b = b0; st[0].B = (signed char)B0_; st[0].LM = (signed char)LM0; st[0].phase = 0;
-  while (sp >= 0) {
+  // two alternating steps for all lanes together, see rdo_partition: (A) walk the tree to the next leaf with pulses, (B) quantise it
+  const unsigned lanes = converged_lanes();
+  int pend_K = 0;
+  for (;;) {
+  while (sp >= 0 && !pend_K) {
     EncPart &f = st[sp];
     const int i = ctx.band;
     if (f.phase == 0) {
@@ -1052,12 +1056,7 @@ OB_DEVNI void enc_partition(EncBand &ctx, float *X, float *y2, int N0, int b0, i
           curr_bits = q == 0 ? 0 : cache[q] + 1;
           ctx.remaining_bits -= curr_bits;
         }
-        if (q != 0) {   // alg_quant (celt/vq.c:552-617) without resynthesis
-          const int K = pseudo_to_pulses(q);
-          enc_exp_rotation(X + f.off, f.N, f.B, K, ctx.spread);
-          const uint32_t idx = enc_pvq_index(X + f.off, y2, f.N, K);
-          re_uint(*ctx.ec, idx, pvq_u(f.N, K) + pvq_u(f.N, K + 1));
-        }
+        if (q != 0) { pend_K = pseudo_to_pulses(q); continue; }   // step (B) below
         sp--;
       }
     } else if (f.phase == 1) {   // first half done: rebalance, then the other half
@@ -1072,6 +1071,17 @@ OB_DEVNI void enc_partition(EncBand &ctx, float *X, float *y2, int N0, int b0, i
       ch.b = second;
       sp++;
     } else sp--;
+  }
+    if (!ballot_among(lanes, pend_K != 0)) break;
+    if (pend_K) {   // alg_quant (celt/vq.c:552-617) without resynthesis
+      EncPart &f = st[sp];
+      const int K = pend_K;
+      enc_exp_rotation(X + f.off, f.N, f.B, K, ctx.spread);
+      const uint32_t idx = enc_pvq_index(X + f.off, y2, f.N, K);
+      re_uint(*ctx.ec, idx, pvq_u(f.N, K) + pvq_u(f.N, K + 1));
+      pend_K = 0;
+      sp--;
+    }
   }
 }
 OB_DEV void enc_band_n1(EncBand &ctx, const float *X, const float *Y) {  // celt/bands.c:934-968

@@ -106,7 +106,14 @@ OB_DEVNI unsigned rdo_partition(EncBand &ctx, float *X, float *y2, const float *
   unsigned ret = 0;
   st[0].off = 0; st[0].N = (short)N0; st[0].lb = lowband ? 0 : -1; st[0].b = b0; st[0].B = (signed char)B0_; st[0].LM = (signed char)LM0; st[0].phase = 0;
   st[0].gain = gain0; st[0].fill = fill0;
-  while (sp >= 0) {
+  // The walk alternates two steps for all lanes together: (A) advance the tree — splits, theta, pulse-less leaves — until a leaf with pulses is
+  // reached or the tree is done; (B) every lane that has such a leaf quantises it (rotation, pulse search, index, resynthesis: most of the
+  // band coder's instructions).  The vote between the steps keeps the lanes of a warp (= different streams) in the same pass of (B) instead
+  // of each running it alone whenever its own walk happens to get there.
+  const unsigned lanes = converged_lanes();
+  int pend_K = 0;   // > 0: the leaf at st[sp] waits for step (B)
+  for (;;) {
+  while (sp >= 0 && !pend_K) {
     RdoPart &f = st[sp];
     const int i = ctx.band;
     if (f.phase == 0) {
@@ -154,7 +161,7 @@ OB_DEVNI unsigned rdo_partition(EncBand &ctx, float *X, float *y2, const float *
         }
         float *Xp = X + f.off;
         unsigned cm = 0;
-        if (q != 0) cm = rdo_pvq(Xp, y2, f.N, pseudo_to_pulses(q), ctx.spread, f.B, *ctx.ec, f.gain);
+        if (q != 0) { pend_K = pseudo_to_pulses(q); continue; }   // step (B) below
         else {   // no pulse: fill the band anyway (celt/bands.c:1113-1160)
           const unsigned cm_mask = (1u << f.B) - 1;
           const int fill = f.fill & (int)cm_mask;
@@ -199,6 +206,14 @@ OB_DEVNI unsigned rdo_partition(EncBand &ctx, float *X, float *y2, const float *
     } else {
       f.cm |= f.second_x ? ret : ret << (f.B >> 1);
       ret = f.cm;
+      sp--;
+    }
+  }
+    if (!ballot_among(lanes, pend_K != 0)) break;   // every lane's tree is done
+    if (pend_K) {
+      RdoPart &f = st[sp];
+      ret = rdo_pvq(X + f.off, y2, f.N, pend_K, ctx.spread, f.B, *ctx.ec, f.gain);
+      pend_K = 0;
       sp--;
     }
   }

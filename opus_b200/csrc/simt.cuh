@@ -30,6 +30,10 @@ template <class T> OB_DEV T shfl_up(T v, int d) { return __shfl_up_sync(0xffffff
 template <class T> OB_DEV T shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 template <class T> OB_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 OB_DEV unsigned ballot(int p) { return __ballot_sync(0xffffffffu, p); }
+// For thread-per-item code whose lanes run independent items: the lanes that are together right now, and a vote among exactly those.
+// Used to line up an expensive step of a data-dependent loop (all lanes that need it execute it in the same pass).
+OB_DEV unsigned converged_lanes() { return __activemask(); }
+OB_DEV unsigned ballot_among(unsigned lanes, int p) { return __ballot_sync(lanes, p); }
 OB_DEV int clz32(uint32_t v) { return __clz((int)v); }
 OB_DEV int ffs32(uint32_t v) { return __ffs((int)v); }
 OB_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }

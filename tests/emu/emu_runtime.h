@@ -107,6 +107,9 @@ OB_DEV unsigned ballot(int p) {
   emu_yield();
   return r;
 }
+// thread-per-item code: on the emulator every lane runs its item alone, so "the lanes that are together" is the lane itself
+OB_DEV unsigned converged_lanes() { return 1u; }
+OB_DEV unsigned ballot_among(unsigned, int p) { return p ? 1u : 0u; }
 OB_DEV int clz32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 OB_DEV int ffs32(uint32_t v) { return __builtin_ffs((int)v); }
 OB_DEV float f_mul(float a, float b) { return a * b; }
