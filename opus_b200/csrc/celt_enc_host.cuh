@@ -194,7 +194,11 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
     // the transient / tone recurrences: one thread per stream ahead of the CTA-per-stream kernel (OPUSB200_ENC_NO_CHAINS=1: the old fused form)
     static const bool no_chains = getenv("OPUSB200_ENC_NO_CHAINS") != nullptr;
     a.chains_done = !no_chains && chunks == 1;
-    a.in_buf = a.chains_done ? e->in_buf : nullptr;
+    // OPUSB200_ENC_SERIAL_PF=1: run_prefilter too on the thread-per-stream kernel.  Measured (32 768 streams, complexity 10): the CTA-per-stream
+    // kernel drops from 8.4 to 0.95 ms but the serial kernel needs 21.6 ms — 2 M instructions per warp on 7 warps per SM is latency-bound, and
+    // the pitch correlations and the comb filter are lane-parallel work that belongs in the CTA-per-stream kernel.  Off by default.
+    static const bool serial_pf = getenv("OPUSB200_ENC_SERIAL_PF") != nullptr;
+    a.in_buf = (a.chains_done && serial_pf) ? e->in_buf : nullptr;
     if (a.chains_done) {
       ob_celt_enc_chains<<<(s1 - s0 + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float), e->stream>>>(a, e->chain_scratch);
       e->launches++;

@@ -122,7 +122,13 @@ extern "C" int opusb200_opus_encode_device(OpusB200OpusEncoder *e, const void *d
 }
 static int opus_encode_host(OpusB200OpusEncoder *e, const void *pcm, int is16, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
                             int32_t *nbytes) {
-  if (!e || !pcm || !packets || !nbytes || frame_size <= 0 || frame_size > OB_MAXN) return OPUSB200_BAD_ARG;
+  if (!e || !pcm || !packets || !nbytes || frame_size <= 0) return OPUSB200_BAD_ARG;
+  {   // the call's own verdict first (BAD_ARG for a frame size Opus does not have, UNIMPLEMENTED for the 40..120 ms multi-frame packets)
+    ob::OpusCallPlan pl;
+    const int pr = ob::opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
+    if (pr) return pr;
+    if (frame_size > OB_MAXN) return OPUSB200_BAD_ARG;
+  }
   OB_CUDA(cudaSetDevice(e->device));
   cudaStream_t s = e->celt->stream;
   const size_t pb = (is16 ? sizeof(int16_t) : sizeof(float)) * (size_t)e->n * frame_size * e->channels, kb = (size_t)e->n * pkt_stride;

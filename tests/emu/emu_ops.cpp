@@ -212,8 +212,10 @@ static void emu_run_chains(EncAnalysisParams &a, int n) {
   a.chains_done = g_enc_chains;
   a.in_buf = nullptr;
   if (!g_enc_chains) return;
-  g_chain_in.assign((size_t)n * 2 * OB_CH_IN_STRIDE, 0.f);
-  a.in_buf = g_chain_in.data();
+  if (g_enc_chains >= 2) {   // 2: run_prefilter too on the thread-per-stream kernel (OPUSB200_ENC_SERIAL_PF)
+    g_chain_in.assign((size_t)n * 2 * OB_CH_IN_STRIDE, 0.f);
+    a.in_buf = g_chain_in.data();
+  }
   g_chain_scratch.assign((size_t)((n + 31) / 32) * OB_CH_SCRATCH_FLOATS, 0.f);
   emu_launch(enc_chains_entry, &a, (n + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float));
 }

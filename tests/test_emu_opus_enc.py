@@ -135,12 +135,15 @@ def test_ctls(ctl):
     run_case(three_signals(31, 960 * 6, 2), 48000, 2, 960, 40000, 1, 10, ctls=ctl, nframes=6)
 
 
-def test_fused_front_end_without_the_chains_kernel():
-    """OPUSB200_ENC_NO_CHAINS=1 keeps the transient / tone recurrences inside the CTA-per-stream kernel: same packets"""
+@pytest.mark.parametrize('mode', [0, 2])
+def test_other_front_end_forms(mode):
+    """0 = OPUSB200_ENC_NO_CHAINS (every recurrence inside the CTA-per-stream kernel), 2 = OPUSB200_ENC_SERIAL_PF (run_prefilter too on the
+    thread-per-stream kernel): same packets as the default form"""
     L = emu_util.load_emu_ops()
-    L.emu_celt_set_chains(0)
+    L.emu_celt_set_chains(mode)
     try:
         run_case(three_signals(41, 960 * 5, 2), 48000, 2, 960, 64000, 1, 10, nframes=5)
         run_case(three_signals(43, 480 * 6, 1), 48000, 1, 480, 32000, 0, 5, nframes=6)
+        run_case([np.ascontiguousarray(x[::2]) for x in three_signals(45, 960 * 6, 2)], 24000, 2, 480, 32000, 1, 8, nframes=6)
     finally:
         L.emu_celt_set_chains(1)
