@@ -180,6 +180,7 @@ APP_RESTRICTED_CELT = 2053
 ENC_BYTES_KERNEL = {
     'ob_opus_enc_pre': 2 * 960 * 2 + 2 * 960 * 4 + 480 * 4 + 64,                    # int16 PCM in, dc-rejected float PCM out, 24 kHz analysis samples out, state
     'ob_opus_enc_analysis': 480 * 4 + 2 * (3 * 240 * 4 + 720 * 4) + 2 * 64 + 96,      # new samples in, phase + buffer state in/out, info ring slot in/out, ctl out
+    'ob_celt_enc_chains': 2 * 960 * 4 + 64 + 64,                                      # PCM in, recurrence state in/out, frame info out
     'ob_celt_enc_analysis': 2 * 960 * 4 + 2 * 2 * 1024 * 4 // 8 * 8 + 2 * 960 * 4 + 3 * 168 + 96,   # PCM in, pre-filter history in + frame out, X out, energies, ctl
     'ob_celt_enc_frame_rdo': 2 * 960 * 4 + 3 * 168 + 2 * 1100 + 96 + 170,            # X in, energies in, ObEncState in/out, ctl in, packet out
 }
@@ -543,6 +544,12 @@ def run_gpu_encode(args, rank, world, local_rank):
     if world > 1:
         dist.broadcast(t_pcm, 0)
     rows = parallel.fixture_rows(rank, world, n, ENC_BASE).to(dev)
+    # experiments on SIMT divergence (never the reported configuration): 'family' puts streams of the same signal family in a warp,
+    # 'same' gives all 32 lanes of a warp the same stream (the convergence ceiling)
+    if args.enc_group == 'family':
+        rows = rows[torch.argsort(rows % 4, stable=True)]
+    elif args.enc_group == 'same':
+        rows = (torch.arange(n, device=dev) // 32) % ENC_BASE
     d_pcm = t_pcm.permute(1, 0, 2)[:, rows].contiguous()          # [T][n][1920] int16, 8 GB at n = 65536
     d_pkt = torch.zeros((n, ENC_MAXB), dtype=torch.uint8, device=dev)
     d_nb = torch.zeros((n,), dtype=torch.int32, device=dev)
@@ -627,7 +634,7 @@ def run_gpu_encode(args, rank, world, local_rank):
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    names = {'opus_pre': 'ob_opus_enc_pre', 'opus_analysis': 'ob_opus_enc_analysis', 'celt_analysis': 'ob_celt_enc_analysis', 'celt_frame': 'ob_celt_enc_frame_rdo'}
+    names = {'opus_pre': 'ob_opus_enc_pre', 'opus_analysis': 'ob_opus_enc_analysis', 'celt_chains': 'ob_celt_enc_chains', 'celt_analysis': 'ob_celt_enc_analysis', 'celt_frame': 'ob_celt_enc_frame_rdo'}
     per = {}
     for short, name in names.items():
         t = kms[short] / max(1, calls) / 1000.0
@@ -686,6 +693,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--loss', type=float, default=0.0, help='fraction of packets lost and concealed (diagnostic runs only)')
     ap.add_argument('--workload', default='both', choices=['both', 'decode', 'encode'])
+    ap.add_argument('--enc-group', default='none', choices=['none', 'family', 'same'], help='experiment: how fixture streams are laid out over warps')
     ap.add_argument('--enc-warm-frames', type=int, default=50, help='frames every stream encodes before the timed region of the encode workload')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -237,7 +237,8 @@ int opusb200_opus_encoder_sync(OpusB200OpusEncoder *enc);
 void *opusb200_opus_encoder_cuda_stream(OpusB200OpusEncoder *enc);
 int64_t opusb200_opus_encoder_launch_count(OpusB200OpusEncoder *enc);
 /* Profiling aid: when enabled every kernel of a call is bracketed by CUDA events on the encoder's stream and the call waits for them (so not
- * for throughput runs).  get_timing: accumulated device ms of [Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder]. */
+ * for throughput runs).  get_timing: accumulated device ms, ms_kernels[5] = [Opus-layer pre-pass, Opus-layer analysis,
+ * CELT transient / tone recurrences, CELT analysis, CELT frame coder]. */
 int opusb200_opus_encoder_set_timing(OpusB200OpusEncoder *enc, int enable);
 int opusb200_opus_encoder_get_timing(OpusB200OpusEncoder *enc, double *ms_kernels, int64_t *calls);
 

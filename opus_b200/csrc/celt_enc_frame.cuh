@@ -199,7 +199,7 @@ OB_DEV float enc_fmax(float a, float b) { return a > b ? a : b; }
 OB_DEV float enc_fmin(float a, float b) { return a < b ? a : b; }
 OB_DEV float enc_dot(const float *x, const float *y, int n) {  // celt_inner_prod_c
   float s = 0.f;
-#pragma unroll 1
+#pragma unroll 4
   for (int i = 0; i < n; i++) s = s + x[i] * y[i];
   return s;
 }
@@ -745,39 +745,96 @@ OB_DEVNI EncAlloc enc_compute_allocation(RangeEnc &enc, const int *offsets, cons
 }
 
 // ---- band-level vector helpers on thread-private arrays ----
+// (the band vectors live in thread-private local memory: every loop below issues its loads ahead of the arithmetic and the stores that
+// depend on them, four elements at a time where the elements are independent, so one memory latency is paid per group, not per element)
 OB_DEV void enc_haar(float *X, int N0, int stride) {  // celt/bands.c:623-636
   N0 >>= 1;
 #pragma unroll 1
-  for (int i = 0; i < stride; i++)
+  for (int i = 0; i < stride; i++) {
+    float *P = X + i;
+    const int s2 = 2 * stride;
+    int j = 0;
 #pragma unroll 1
-    for (int j = 0; j < N0; j++) {
-      const float t1 = .70710678f * X[stride * 2 * j + i], t2 = .70710678f * X[stride * (2 * j + 1) + i];
-      X[stride * 2 * j + i] = t1 + t2;
-      X[stride * (2 * j + 1) + i] = t1 - t2;
+    for (; j + 4 <= N0; j += 4) {   // the butterflies are independent
+      float *Q = P + s2 * j;
+      const float a0 = Q[0], b0 = Q[stride], a1 = Q[s2], b1 = Q[s2 + stride], a2 = Q[2 * s2], b2 = Q[2 * s2 + stride], a3 = Q[3 * s2], b3 = Q[3 * s2 + stride];
+      const float t10 = .70710678f * a0, t20 = .70710678f * b0, t11 = .70710678f * a1, t21 = .70710678f * b1;
+      const float t12 = .70710678f * a2, t22 = .70710678f * b2, t13 = .70710678f * a3, t23 = .70710678f * b3;
+      Q[0] = t10 + t20; Q[stride] = t10 - t20;
+      Q[s2] = t11 + t21; Q[s2 + stride] = t11 - t21;
+      Q[2 * s2] = t12 + t22; Q[2 * s2 + stride] = t12 - t22;
+      Q[3 * s2] = t13 + t23; Q[3 * s2 + stride] = t13 - t23;
     }
+#pragma unroll 1
+    for (; j < N0; j++) {
+      const float t1 = .70710678f * P[s2 * j], t2 = .70710678f * P[s2 * j + stride];
+      P[s2 * j] = t1 + t2;
+      P[s2 * j + stride] = t1 - t2;
+    }
+  }
 }
 OB_TABLE unsigned char ob_enc_hadamard_order[30] = {1, 0, 3, 0, 2, 1, 7, 0, 4, 3, 6, 1, 5, 2, 15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5};
-OB_DEV void enc_deinterleave(float *X, float *tmp, int N0, int stride, int hadamard) {  // celt/bands.c:574-597
+OB_DEV void enc_deinterleave(float *__restrict__ X, float *__restrict__ tmp, int N0, int stride, int hadamard) {  // celt/bands.c:574-597
   const int N = N0 * stride;
 #pragma unroll 1
   for (int i = 0; i < stride; i++) {
     const int row = hadamard ? ob_enc_hadamard_order[stride - 2 + i] : i;
-#pragma unroll 1
-    for (int j = 0; j < N0; j++) tmp[row * N0 + j] = X[j * stride + i];
+    float *__restrict__ d = tmp + row * N0;
+    const float *__restrict__ q = X + i;
+#pragma unroll 4
+    for (int j = 0; j < N0; j++) d[j] = q[j * stride];
   }
-#pragma unroll 1
+#pragma unroll 4
   for (int j = 0; j < N; j++) X[j] = tmp[j];
 }
 OB_DEV void enc_rotate_pass(float *X, int len, int stride, float c, float s) {  // celt/vq.c:75-102
   const float ms = -s;
+  if (stride == 1) {   // the element a step has just written is the next step's x1 (forward) / x2 (backward): carried in a register
+    if (len < 2) return;
+    float cur = X[0];
+#pragma unroll 4
+    for (int i = 0; i < len - 1; i++) {
+      const float x2 = X[i + 1];
+      X[i] = c * cur + ms * x2;
+      cur = c * x2 + s * cur;
+    }
+    X[len - 1] = cur;
+    if (len < 3) return;
+    cur = X[len - 2];
+#pragma unroll 4
+    for (int i = len - 3; i >= 0; i--) {
+      const float x1 = X[i];
+      X[i + 1] = c * cur + s * x1;
+      cur = c * x1 + ms * cur;
+    }
+    X[0] = cur;
+    return;
+  }
+  // stride >= 2: steps i and i + 1 touch four different elements
+  int i = 0;
 #pragma unroll 1
-  for (int i = 0; i < len - stride; i++) {
+  for (; i + 2 <= len - stride; i += 2) {
+    const float x1 = X[i], x2 = X[i + stride], z1 = X[i + 1], z2 = X[i + 1 + stride];
+    X[i + stride] = c * x2 + s * x1;
+    X[i] = c * x1 + ms * x2;
+    X[i + 1 + stride] = c * z2 + s * z1;
+    X[i + 1] = c * z1 + ms * z2;
+  }
+  for (; i < len - stride; i++) {
     const float x1 = X[i], x2 = X[i + stride];
     X[i + stride] = c * x2 + s * x1;
     X[i] = c * x1 + ms * x2;
   }
+  i = len - 2 * stride - 1;
 #pragma unroll 1
-  for (int i = len - 2 * stride - 1; i >= 0; i--) {
+  for (; i >= 1; i -= 2) {
+    const float x1 = X[i], x2 = X[i + stride], z1 = X[i - 1], z2 = X[i - 1 + stride];
+    X[i + stride] = c * x2 + s * x1;
+    X[i] = c * x1 + ms * x2;
+    X[i - 1 + stride] = c * z2 + s * z1;
+    X[i - 1] = c * z1 + ms * z2;
+  }
+  for (; i >= 0; i--) {
     const float x1 = X[i], x2 = X[i + stride];
     X[i + stride] = c * x2 + s * x1;
     X[i] = c * x1 + ms * x2;
@@ -804,11 +861,11 @@ OB_DEVNI void enc_exp_rotation(float *X, int len, int stride, int K, int spread)
 // op_pvq_search_c (celt/vq.c:205-374) followed by icwrs (celt/cwrs.c:444-460): returns the codeword index.
 // X: the (rotated) partition, overwritten with |X|; y2: scratch holding 2*pulses
 // (the search returns yy for the resynthesis-enabled encoder; signs: bit set of the negative inputs)
-OB_DEVNI float enc_pvq_search(float *X, float *y2, int N, int K, uint32_t *signs) {
+OB_DEVNI float enc_pvq_search(float *__restrict__ X, float *__restrict__ y2, int N, int K, uint32_t *signs) {
   float sum = 0.f, xy = 0.f, yy = 0.f;   // sign bits live in a small bit set (N <= 176)
 #pragma unroll
   for (int j = 0; j < 6; j++) signs[j] = 0;
-#pragma unroll 1
+#pragma unroll 2
   for (int j = 0; j < N; j++) {
     const float x = X[j];
     if (x < 0) signs[j >> 5] |= 1u << (j & 31);
@@ -817,7 +874,7 @@ OB_DEVNI float enc_pvq_search(float *X, float *y2, int N, int K, uint32_t *signs
   }
   int pulsesLeft = K;
   if (K > (N >> 1)) {
-#pragma unroll 1
+#pragma unroll 4
     for (int j = 0; j < N; j++) sum += X[j];
     if (!(sum > 1e-15f && sum < 64.f)) {
       X[0] = 1.f;
@@ -826,7 +883,7 @@ OB_DEVNI float enc_pvq_search(float *X, float *y2, int N, int K, uint32_t *signs
       sum = 1.f;
     }
     const float rcp = (K + 0.8f) * (1.f / sum);
-#pragma unroll 1
+#pragma unroll 4
     for (int j = 0; j < N; j++) {
       const float x = X[j];
       const int iyj = (int)floorf(rcp * x);

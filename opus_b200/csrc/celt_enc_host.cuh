@@ -56,8 +56,8 @@ struct OpusB200Encoder {
   float *chain_scratch;   // [ceil(n/32)][OB_CH_SCRATCH_FLOATS]: the recurrence kernel's transposed tracks (celt_enc_chains.cuh)
   float *in_buf;          // [n][channels][1080]: the pre-emphasised, pre-filtered analysis window it hands to the transform kernel
   int timing;
-  cudaEvent_t tev[5];
-  double t_ms[4];   // Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder
+  cudaEvent_t tev[6];
+  double t_ms[5];   // Opus-layer pre-pass, Opus-layer analysis, CELT recurrences (thread per stream), CELT analysis, CELT frame coder
   int64_t t_calls;
 };
 
@@ -123,7 +123,7 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
   cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->chain_scratch); cudaFree(e->in_buf);
-  if (e->tev[0]) for (int i = 0; i < 5; i++) cudaEventDestroy(e->tev[i]);
+  if (e->tev[0]) for (int i = 0; i < 6; i++) cudaEventDestroy(e->tev[i]);
   for (int i = 0; i < 4; i++) {
     cudaStreamSynchronize(e->stream_f[i]);
     cudaStreamDestroy(e->stream_f[i]);
@@ -203,6 +203,7 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
       ob_celt_enc_chains<<<(s1 - s0 + 31) / 32, 32, 32 * OB_CH_TS * sizeof(float), e->stream>>>(a, e->chain_scratch);
       e->launches++;
     }
+    if (e->timing) cudaEventRecord(e->tev[5], e->stream);
     ob_celt_enc_analysis<<<s1 - s0, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
     if (e->timing) cudaEventRecord(e->tev[3], e->stream);
     cudaStream_t sf = chunks > 1 ? e->stream_f[k] : e->stream;
@@ -224,8 +225,9 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
     OB_CUDA(cudaEventSynchronize(e->tev[4]));
     float ms = 0.f;
     if (ctl) { cudaEventElapsedTime(&ms, e->tev[0], e->tev[1]); e->t_ms[0] += ms; cudaEventElapsedTime(&ms, e->tev[1], e->tev[2]); e->t_ms[1] += ms; }
-    cudaEventElapsedTime(&ms, e->tev[2], e->tev[3]); e->t_ms[2] += ms;
-    cudaEventElapsedTime(&ms, e->tev[3], e->tev[4]); e->t_ms[3] += ms;
+    cudaEventElapsedTime(&ms, e->tev[2], e->tev[5]); e->t_ms[2] += ms;
+    cudaEventElapsedTime(&ms, e->tev[5], e->tev[3]); e->t_ms[3] += ms;
+    cudaEventElapsedTime(&ms, e->tev[3], e->tev[4]); e->t_ms[4] += ms;
     e->t_calls++;
   }
   return OPUSB200_OK;

@@ -29,21 +29,23 @@ OB_DEVNI void rdo_exp_rotation_inv(float *X, int len, int stride, int K, int spr
     enc_rotate_pass(X + i * len, len, 1, c, s);
   }
 }
-OB_DEV void rdo_interleave(float *X, float *tmp, int N0, int stride, int hadamard) {  // celt/bands.c:599-621
+OB_DEV void rdo_interleave(float *__restrict__ X, float *__restrict__ tmp, int N0, int stride, int hadamard) {  // celt/bands.c:599-621
   const int N = N0 * stride;
 #pragma unroll 1
   for (int i = 0; i < stride; i++) {
     const int row = hadamard ? ob_enc_hadamard_order[stride - 2 + i] : i;
-#pragma unroll 1
-    for (int j = 0; j < N0; j++) tmp[j * stride + i] = X[row * N0 + j];
+    const float *__restrict__ q = X + row * N0;
+    float *__restrict__ d = tmp + i;
+#pragma unroll 4
+    for (int j = 0; j < N0; j++) d[j * stride] = q[j];
   }
-#pragma unroll 1
+#pragma unroll 4
   for (int j = 0; j < N; j++) X[j] = tmp[j];
 }
 OB_DEV void rdo_renormalise(float *X, int N, float gain) {  // celt/vq.c:695-722
   const float E = 1e-15f + enc_dot(X, X, N);
   const float g = rsqrt_ref(E) * gain;
-#pragma unroll 1
+#pragma unroll 4
   for (int i = 0; i < N; i++) X[i] = g * X[i];
 }
 OB_DEVNI void rdo_stereo_merge(float *X, float *Y, float mid, int N) {  // celt/bands.c:407-466
@@ -57,7 +59,7 @@ OB_DEVNI void rdo_stereo_merge(float *X, float *Y, float mid, int N) {  // celt/
     return;
   }
   const float lgain = rsqrt_ref(El), rgain = rsqrt_ref(Er);
-#pragma unroll 1
+#pragma unroll 2
   for (int j = 0; j < N; j++) {
     const float l = mid * X[j], r = Y[j];
     X[j] = lgain * (l - r);
@@ -76,14 +78,14 @@ OB_DEVNI unsigned rdo_pvq(float *X, float *y2, int N, int K, int spread, int B, 
 #pragma unroll 1
     for (int i = 0; i < B; i++) {
       int any = 0;
-#pragma unroll 1
+#pragma unroll 4
       for (int j = 0; j < N0; j++) any |= y2[i * N0 + j] != 0.f;
       cm |= (unsigned)any << i;
     }
   }
   re_uint(ec, enc_icwrs(y2, signs, N), pvq_u(N, K) + pvq_u(N, K + 1));
   const float g = rsqrt_ref(yy) * gain;   // normalise_residual (celt/vq.c:150-181)
-#pragma unroll 1
+#pragma unroll 4
   for (int j = 0; j < N; j++) {
     const int k = (int)(y2[j] * .5f);
     const int iy = ((signs[j >> 5] >> (j & 31)) & 1u) ? -k : k;

@@ -153,21 +153,22 @@ extern "C" int opusb200_opus_encode_float(OpusB200OpusEncoder *e, const float *p
 extern "C" int opusb200_opus_encoder_get_final_range(OpusB200OpusEncoder *e, uint32_t *final_range) {
   return e ? opusb200_encoder_get_final_range(e->celt, final_range) : OPUSB200_BAD_ARG;
 }
-// Profiling aid: CUDA events around each of the four kernels of a call (the call then waits for them: not for throughput runs).
-// get_timing: accumulated device milliseconds [Opus-layer pre-pass, Opus-layer analysis, CELT analysis, CELT frame coder] and the calls they cover
+// Profiling aid: CUDA events around each of the five kernels of a call (the call then waits for them: not for throughput runs).
+// get_timing: accumulated device milliseconds ms_kernels[5] = [Opus-layer pre-pass, Opus-layer analysis, CELT recurrences, CELT analysis, CELT frame coder]
+// and the calls they cover
 extern "C" int opusb200_opus_encoder_set_timing(OpusB200OpusEncoder *e, int enable) {
   if (!e) return OPUSB200_BAD_ARG;
   OpusB200Encoder *c = e->celt;
   OB_CUDA(cudaSetDevice(e->device));
-  if (enable && !c->tev[0]) for (int i = 0; i < 5; i++) OB_CUDA(cudaEventCreate(&c->tev[i]));
+  if (enable && !c->tev[0]) for (int i = 0; i < 6; i++) OB_CUDA(cudaEventCreate(&c->tev[i]));
   c->timing = enable != 0;
-  for (int i = 0; i < 4; i++) c->t_ms[i] = 0.0;
+  for (int i = 0; i < 5; i++) c->t_ms[i] = 0.0;
   c->t_calls = 0;
   return OPUSB200_OK;
 }
 extern "C" int opusb200_opus_encoder_get_timing(OpusB200OpusEncoder *e, double *ms_kernels, int64_t *calls) {
   if (!e || !ms_kernels || !calls) return OPUSB200_BAD_ARG;
-  for (int i = 0; i < 4; i++) ms_kernels[i] = e->celt->t_ms[i];
+  for (int i = 0; i < 5; i++) ms_kernels[i] = e->celt->t_ms[i];
   *calls = e->celt->t_calls;
   return OPUSB200_OK;
 }

@@ -143,10 +143,10 @@ class OpusEncoderBatch:
         self._L.opusb200_opus_encoder_set_timing(self._h, 1 if on else 0)
 
     def get_timing(self):
-        ms = (ctypes.c_double * 4)()
+        ms = (ctypes.c_double * 5)()
         calls = ctypes.c_int64(0)
         self._L.opusb200_opus_encoder_get_timing(self._h, ms, ctypes.byref(calls))
-        return dict(zip(('opus_pre', 'opus_analysis', 'celt_analysis', 'celt_frame'), list(ms))), calls.value
+        return dict(zip(('opus_pre', 'opus_analysis', 'celt_chains', 'celt_analysis', 'celt_frame'), list(ms))), calls.value
 
     def sync(self):
         self._L.opusb200_opus_encoder_sync(self._h)

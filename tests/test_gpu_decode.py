@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import util
+from conftest import note_err
 from test_oracle_golden import golden_cases
 
 pytestmark = pytest.mark.gpu
@@ -17,6 +18,7 @@ FLOAT_TOL = 2e-5
 def _check(got, ref):
     d = np.abs(util.to_int16(got).astype(np.int32) - util.to_int16(ref).astype(np.int32))
     assert d.max() <= 1, int(d.max())
+    note_err('decode_float', np.abs(got - ref).max())
     assert np.abs(got - ref).max() < FLOAT_TOL, float(np.abs(got - ref).max())
     return float((d != 0).mean())
 
@@ -358,6 +360,7 @@ def test_decoder_ctls_vs_reference(ctls):
         assert (dec.get_ctl(dec.OPUS_GET_PITCH) == np.array([r[2][t] for r in refs])).all()
         assert (dec.get_ctl(dec.OPUS_GET_LAST_PACKET_DURATION) == np.array([r[3][t] for r in refs])).all()
         for s in range(n):
+            note_err('decode_float_gain', np.abs(got[s].reshape(fs, ch) - refs[s][0][t * fs:(t + 1) * fs]).max() / max(1.0, g))
             assert np.abs(got[s].reshape(fs, ch) - refs[s][0][t * fs:(t + 1) * fs]).max() < FLOAT_TOL * max(1.0, g)
     dec.close()
     with pytest.raises(opus_b200.OpusB200Error):
