@@ -12,10 +12,19 @@ extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame(EncFrameParam
   const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
   if (s < p.n_streams) enc_frame_thread<false>(p, s);
 }
-extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame_rdo(EncFrameParams p) {   // complexity >= 8, stereo
+extern "C" __global__ void __launch_bounds__(64, 8) ob_celt_enc_frame_rdo(EncFrameParams p) {   // complexity >= 8, stereo; 128 registers
   const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
   if (s < p.n_streams) enc_frame_thread<true>(p, s);
 }
+// experiment (OPUSB200_ENC_REGS=96|80|64): the same kernel at a lower register cap, for more resident warps per scheduler
+#define OB_FRAME_RDO_VARIANT(name, blocks) \
+  extern "C" __global__ void __launch_bounds__(64, blocks) name(EncFrameParams p) { \
+    const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x; \
+    if (s < p.n_streams) enc_frame_thread<true>(p, s); \
+  }
+OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r96, 10)
+OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r80, 12)
+OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r64, 16)
 extern "C" __global__ void ob_celt_enc_reset(ObEncState *st, ObEncAnalysisState *an, int n) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -212,7 +221,13 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
       OB_CUDA(cudaStreamWaitEvent(sf, e->ev_an[k], 0));
     }
     p.first_stream = s0; p.n_streams = s1;
-    if (e->complexity >= 8 && (ctl ? e->channels : e->stream_channels) == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    static const int regs = getenv("OPUSB200_ENC_REGS") ? atoi(getenv("OPUSB200_ENC_REGS")) : 128;
+    if (e->complexity >= 8 && (ctl ? e->channels : e->stream_channels) == 2) {
+      if (regs == 96) ob_celt_enc_frame_rdo_r96<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+      else if (regs == 80) ob_celt_enc_frame_rdo_r80<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+      else if (regs == 64) ob_celt_enc_frame_rdo_r64<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+      else ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    }
     else ob_celt_enc_frame<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     e->launches += 2;
     if (e->timing) cudaEventRecord(e->tev[4], sf);
