@@ -1219,7 +1219,7 @@ namespace ob {
 
 // ---- frame driver ----  RDO: compiled with the theta-RDO band coder (complexity >= 8; a second kernel, because its
 // folding / save buffers triple the thread's local memory)
-template <bool RDO>
+template <bool RDO, bool SYNC = false>
 OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   const int LM = p.LM, M = 1 << LM, N = M * OB_SHORT_N, start = 0;
   const int C = p.ctl ? p.ctl[stream].C : p.C, end = p.ctl ? p.ctl[stream].end : p.end, SC = p.ctl ? (p.CC ? p.CC : p.C) : p.C;
@@ -1571,7 +1571,7 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
   if (RDO && C == 2 && !dual_stereo && p.complexity >= 8) {   // theta_rdo (celt/bands.c:1618)
     if constexpr (RDO) {
       RdoScratch w;
-      const int r = rdo_all_bands(enc, Xg, bandE, pulses, tf_res, shortBlocks, st.spread_decision, st.intensity,
+      const int r = rdo_all_bands<SYNC>(enc, Xg, bandE, pulses, tf_res, shortBlocks, st.spread_decision, st.intensity,
                                   nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, al.balance, LM, codedBands, st.rng, p.disable_inv, bx, by, tmp, w, end);
       if (r) status = r;
     }
@@ -1584,7 +1584,11 @@ OB_DEV void enc_frame_thread(const EncFrameParams &p, int stream) {
     int32_t balance = al.balance;
     const int32_t tb = nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv;
 #pragma unroll 1
-    for (int i = start; i < end; i++) {
+    for (int i = start; i < (SYNC ? OB_NBANDS : end); i++) {
+      if (SYNC) {   // (see rdo_all_bands)
+        bsync();
+        if (i >= end) continue;
+      }
       const int off = M * ob_ebands[i], Nb = M * ob_ebands[i + 1] - off;
       ctx.band = i;
       const int32_t t = re_tell_frac(enc);

@@ -22,6 +22,10 @@ extern "C" __global__ void __launch_bounds__(64, 8) ob_celt_enc_frame_rdo(EncFra
     const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x; \
     if (s < p.n_streams) enc_frame_thread<true>(p, s); \
   }
+extern "C" __global__ void __launch_bounds__(256, 2) ob_celt_enc_frame_rdo_sync(EncFrameParams p) {   // OPUSB200_ENC_SYNC=1: barrier per band
+  const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) enc_frame_thread<true, true>(p, s);
+}
 OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r96, 10)
 OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r80, 12)
 OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r64, 16)
@@ -223,7 +227,9 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
     p.first_stream = s0; p.n_streams = s1;
     static const int regs = getenv("OPUSB200_ENC_REGS") ? atoi(getenv("OPUSB200_ENC_REGS")) : 128;
     if (e->complexity >= 8 && (ctl ? e->channels : e->stream_channels) == 2) {
-      if (regs == 96) ob_celt_enc_frame_rdo_r96<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+      static const bool band_sync = getenv("OPUSB200_ENC_SYNC") != nullptr;
+      if (band_sync) ob_celt_enc_frame_rdo_sync<<<(s1 - s0 + 255) / 256, 256, 0, sf>>>(p);
+      else if (regs == 96) ob_celt_enc_frame_rdo_r96<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
       else if (regs == 80) ob_celt_enc_frame_rdo_r80<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
       else if (regs == 64) ob_celt_enc_frame_rdo_r64<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
       else ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);

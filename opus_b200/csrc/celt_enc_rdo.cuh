@@ -383,6 +383,9 @@ struct RdoScratch {
   unsigned char bytes_save[320];
   unsigned char collapse_masks[2 * OB_NBANDS];
 };
+// SYNC: the CTA's warps meet at a barrier before every band, so that the warps of an SM walk the (large) band-coder code together and share
+// its instruction-cache lines; every thread then runs all OB_NBANDS iterations (the barrier count must match), idle past its end band
+template <bool SYNC>
 OB_DEVNI int rdo_all_bands(RangeEnc &enc, const float *Xg, const float *bandE, const int *pulses, const int *tf_res, int shortBlocks, int spread,
                            int intensity, int32_t total_bits, int32_t balance, int LM, int codedBands, uint32_t seed, int disable_inv, float *bx,
                            float *by, float *tmp, RdoScratch &w, int end) {
@@ -395,7 +398,11 @@ OB_DEVNI int rdo_all_bands(RangeEnc &enc, const float *Xg, const float *bandE, c
 #pragma unroll 1
   for (int j = 0; j < 8 * 78; j++) w.norm[j] = 0.f;
 #pragma unroll 1
-  for (int i = start; i < end; i++) {
+  for (int i = start; i < (SYNC ? OB_NBANDS : end); i++) {
+    if (SYNC) {
+      bsync();
+      if (i >= end) continue;
+    }
     const int off = M * ob_ebands[i], N = M * ob_ebands[i + 1] - off, last = i == end - 1;
     ctx.band = i;
     const int32_t tell = re_tell_frac(enc);

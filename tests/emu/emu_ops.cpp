@@ -234,6 +234,19 @@ static void enc_frame_entry_ctl(void *a) {
   if (p.complexity >= 8 && p.CC == 2) enc_frame_thread<true>(p, s);
   else enc_frame_thread<false>(p, s);
 }
+// the barrier-per-band form of the frame coder (OPUSB200_ENC_SYNC): blocks of two warps; the emulator's barrier counts every thread of the
+// block, so a thread without a stream keeps the barrier count instead of exiting
+static int g_frame_sync = 0;
+extern "C" void emu_celt_set_frame_sync(int on) { g_frame_sync = on; }
+static void enc_frame_entry_sync(void *a) {
+  const EncFrameParams &p = *(const EncFrameParams *)a;
+  const int s = block_id() * 64 + warp_in_block() * 32 + lane_id();
+  if (s >= p.n_streams) {
+    for (int i = 0; i < OB_NBANDS; i++) bsync();
+    return;
+  }
+  enc_frame_thread<true, true>(p, s);
+}
 extern "C" int emu_enc_state_size(void) { return (int)sizeof(ObEncState); }
 extern "C" void emu_enc_state_init(ObEncState *st, int n) {
   memset(st, 0, sizeof(ObEncState) * (size_t)n);
@@ -354,7 +367,8 @@ extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_siz
   f.complexity = cx; f.bitrate = pl.celt_bitrate; f.lsb_depth = pl.lsb; f.force_intra = pl.celt_force_intra; f.disable_inv = e->disable_inv;
   f.disable_pf = pl.celt_disable_pf; f.vbr = pl.celt_vbr; f.constrained_vbr = pl.celt_cvbr; f.loss_rate = e->cfg.packet_loss; f.end = OB_NBANDS;
   f.ctl = e->ctl.data(); f.toc_bytes = 1;
-  emu_launch(enc_frame_entry_ctl, &f, (n + 31) / 32, 32, 0);
+  if (g_frame_sync && f.complexity >= 8 && f.CC == 2) emu_launch(enc_frame_entry_sync, &f, (n + 63) / 64, 64, 0);
+  else emu_launch(enc_frame_entry_ctl, &f, (n + 31) / 32, 32, 0);
   for (int s = 0; s < n; s++) rng[s] = e->enc_state[s].rng;
   return 0;
 }

@@ -135,6 +135,19 @@ def test_ctls(ctl):
     run_case(three_signals(31, 960 * 6, 2), 48000, 2, 960, 40000, 1, 10, ctls=ctl, nframes=6)
 
 
+def test_frame_coder_with_a_barrier_per_band():
+    """OPUSB200_ENC_SYNC: blocks of several warps that meet before every band (shared instruction-cache lines); 40 streams = 2 warps in one
+    block, streams of different end bands (a narrower bandwidth on some) and a mono-coded low rate in the same run"""
+    L = emu_util.load_emu_ops()
+    L.emu_celt_set_frame_sync(1)
+    try:
+        sigs = [s for k in range(14) for s in three_signals(50 + 3 * k, 960 * 3, 2)][:40]
+        run_case(sigs, 48000, 2, 960, 64000, 1, 10, nframes=3)
+        run_case(three_signals(47, 960 * 4, 2), 48000, 2, 960, 20000, 1, 10, ctls=[(4004, 1103)], nframes=4)
+    finally:
+        L.emu_celt_set_frame_sync(0)
+
+
 @pytest.mark.parametrize('mode', [0, 2])
 def test_other_front_end_forms(mode):
     """0 = OPUSB200_ENC_NO_CHAINS (every recurrence inside the CTA-per-stream kernel), 2 = OPUSB200_ENC_SERIAL_PF (run_prefilter too on the
