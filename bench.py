@@ -63,8 +63,47 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.p = None
+        self.th = None
+        self.rows = []
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self._phys_index())
+        bits = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown') else 0x8),
+                ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, mx, [n for n, b in bits if r & b]))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def _phys_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                return int(vis.split(',')[self.idx])
+            except Exception:
+                pass
+        return self.idx
 
     def start(self):
+        # NVML in a thread (10 ms period: even a 0.2 s timed region gets ~20 samples); nvidia-smi -lms as the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self._stop = threading.Event()
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.th = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
                                        '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -72,6 +111,13 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.th is not None:
+            self._stop.set()
+            self.th.join(timeout=2)
+            sm = sorted(r[0] for r in self.rows)
+            reasons = sorted({x for r in self.rows for x in r[2]})
+            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max((r[1] for r in self.rows), default=None), 'reasons': reasons,
+                    'samples': len(sm), 'source': 'nvml'}
         if not self.p:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.p.terminate()
@@ -92,10 +138,9 @@ class ClockSampler:
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        # samples under load = upper half
         sm_sorted = sorted(sm)
         med = sm_sorted[len(sm_sorted) // 2] if sm_sorted else None
-        return {'sm_mhz': med, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': med, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 # ---------------------------------------------------------------------------------------------
