@@ -638,32 +638,47 @@ def run_gpu_encode(args, rank, world, local_rank):
     value = parallel.aggregate_throughput(n, world, args.steps, ms_max)
     mean_bytes = float(d_nb.float().mean().item())
 
-    # ---- end to end: opusb200_opus_encode with pinned HOST int16 PCM in and HOST packets out, every step ----
+    # ---- end to end: pinned HOST int16 PCM in and HOST packets out, every step (opusb200_opus_encode_submit / _wait: the upload of step
+    # k+1 and the read-back of step k-1 run under the kernels of step k; every step's H2D and D2H are inside the timed region) ----
     L = opus_b200.lib()
     e2e_steps = max(3, min(args.steps, 8))
     hp = L.opusb200_host_alloc(n * FRAME * CH * 2 * e2e_steps)
-    hk = L.opusb200_host_alloc(n * ENC_MAXB)
+    hk = [L.opusb200_host_alloc(n * ENC_MAXB) for _ in range(2)]
     h_pcm = np.ctypeslib.as_array((ctypes.c_int16 * (n * FRAME * CH * e2e_steps)).from_address(hp)).reshape(e2e_steps, n, FRAME * CH)
-    h_pkt = np.ctypeslib.as_array((ctypes.c_uint8 * (n * ENC_MAXB)).from_address(hk)).reshape(n, ENC_MAXB)
-    h_nb = np.zeros(n, np.int32)
+    h_pkt = [np.ctypeslib.as_array((ctypes.c_uint8 * (n * ENC_MAXB)).from_address(a)).reshape(n, ENC_MAXB) for a in hk]
+    h_nb = [np.zeros(n, np.int32) for _ in range(2)]
     for i in range(e2e_steps):
         h_pcm[i] = d_pcm[(warm + args.steps + i) % T].cpu().numpy()
     vp = ctypes.c_void_p
+    for i in range(2):
+        enc.submit(h_pcm[i], h_pkt[i & 1], h_nb[i & 1], ENC_MAXB, FRAME)
+    enc.wait()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(ext)
     for i in range(e2e_steps):
-        r = L.opusb200_opus_encode(enc._h, vp(h_pcm[i].ctypes.data), FRAME, vp(hk), ENC_MAXB, ENC_MAXB, vp(h_nb.ctypes.data))
-        assert r == 0, r
+        enc.submit(h_pcm[i], h_pkt[i & 1], h_nb[i & 1], ENC_MAXB, FRAME)
+    enc.wait()   # returns when the last read-back is on the host; the closing event is recorded after it
     f1.record(ext)
     enc.sync()
+    e2e_ms = f0.elapsed_time(f1)
     barrier()
-    assert h_nb.min() > 2
-    e2e_val = parallel.aggregate_throughput(n, world, e2e_steps, parallel.max_over_ranks(f0.elapsed_time(f1), dev, world))
+    assert h_nb[0].min() > 2 and h_nb[1].min() > 2
+    # the synchronous call (opusb200_opus_encode: upload, kernels, read-back one after the other), for comparison
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(ext)
+    for i in range(min(3, e2e_steps)):
+        r = L.opusb200_opus_encode(enc._h, vp(h_pcm[i].ctypes.data), FRAME, vp(hk[0]), ENC_MAXB, ENC_MAXB, vp(h_nb[0].ctypes.data))
+        assert r == 0, r
+    g1.record(ext)
+    enc.sync()
+    e2e_sync_val = n * min(3, e2e_steps) / (g0.elapsed_time(g1) / 1000.0)
+    e2e_val = parallel.aggregate_throughput(n, world, e2e_steps, parallel.max_over_ranks(e2e_ms, dev, world))
     h2d = n * FRAME * CH * 2
     d2h = n * ENC_MAXB + n * 4
     L.opusb200_host_free(hp)
-    L.opusb200_host_free(hk)
+    for a in hk:
+        L.opusb200_host_free(a)
 
     # ---- per-kernel device time (CUDA events around each launch, on the launching stream) ----
     enc.set_timing(True)
@@ -708,7 +723,8 @@ def run_gpu_encode(args, rank, world, local_rank):
                    'l2': 'per-step working set (PCM 252 MB + spectra 503 MB + analysis state 0.9 GB at 65536 streams) exceeds the 126 MB L2',
                    'parallelism': 'streams sharded across GPUs, no steady-state collective'},
         'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                'call': 'opusb200_opus_encode (host int16 PCM in, host packets out)'},
+                'call': 'opusb200_opus_encode_submit/_wait (host int16 PCM in, host packets out, double-buffered)',
+                'sync_call_value_rank0': e2e_sync_val},
         'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'cpu_baseline': cb,
     }
 

@@ -155,11 +155,15 @@ int opusb200_pvq_search(OpusB200Ctx *ctx, float *X, int *iy, float *yy, const in
 int opusb200_silk_lpc_analysis_filter(OpusB200Ctx *ctx, int16_t *out, const int16_t *in, const int16_t *B, int n_items, int len,
                                       int d, int on_device);
 
-/* silk_resampler (silk/resampler.c:77 init, :183 process), encoder-side down-sampling with persistent
- * per-stream state; integer ratios 1:2, 1:3, 1:4, 1:6 (48->16 kHz is config 4's).  in [n][in_len],
- * out [n][in_len*Fs_out/Fs_in]; in_len a multiple of 1 ms, at most 40 ms. */
+/* silk_resampler (silk/resampler.c:77 silk_resampler_init, :183 silk_resampler) with persistent per-stream state, for every rate pair
+ * silk_resampler_init accepts: for_enc = 1 (the encoder's input resampler): 8/12/16/24/48 kHz -> 8/12/16 kHz (48->16 kHz is config 4's);
+ * for_enc = 0 (the decoder's output resampler): 8/12/16 kHz -> 8/12/16/24/48 kHz.  The four resampler functions of the reference: copy,
+ * silk_resampler_private_up2_HQ (2x), silk_resampler_private_IIR_FIR (2x + FIR interpolation: the other up-sampling ratios),
+ * silk_resampler_private_down_FIR (AR2 + FIR: 1:2, 1:3, 1:4, 1:6, and 2:3 / 3:4 with interpolated phases).  Other pairs: OPUSB200_BAD_ARG.
+ * in [n][in_len], out [n][in_len*Fs_out/Fs_in]; in_len a multiple of 1 ms, at most 40 ms.  _create = _create_ex(for_enc = 1). */
 typedef struct OpusB200SilkResampler OpusB200SilkResampler;
 int opusb200_silk_resampler_create(OpusB200Ctx *ctx, int n_streams, int32_t Fs_in, int32_t Fs_out, OpusB200SilkResampler **out);
+int opusb200_silk_resampler_create_ex(OpusB200Ctx *ctx, int n_streams, int32_t Fs_in, int32_t Fs_out, int for_enc, OpusB200SilkResampler **out);
 void opusb200_silk_resampler_destroy(OpusB200SilkResampler *rs);
 int opusb200_silk_resampler_reset(OpusB200SilkResampler *rs);
 int opusb200_silk_resampler_process(OpusB200SilkResampler *rs, const int16_t *in, int16_t *out, int in_len, int on_device);
@@ -229,6 +233,13 @@ int opusb200_opus_encode(OpusB200OpusEncoder *enc, const int16_t *pcm, int frame
                          int32_t *nbytes);
 int opusb200_opus_encode_float(OpusB200OpusEncoder *enc, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
                                int32_t *nbytes);
+/* The same call in two halves, for a batch server: submit enqueues the PCM upload, the kernels and the packet read-back of one call and returns;
+ * wait returns when every submitted call's packets and nbytes[] are on the host.  Two calls may be in flight (double-buffered staging: the upload
+ * of call k+1 and the read-back of call k-1 run under the kernels of call k); host buffers stay valid until the wait and should be pinned
+ * (opusb200_host_alloc) for the transfers to overlap.  Per-stream results are those of opus_encode() called in submit order. */
+int opusb200_opus_encode_submit(OpusB200OpusEncoder *enc, const void *pcm, int pcm_is_int16, int frame_size, unsigned char *packets, int pkt_stride,
+                                int max_data_bytes, int32_t *nbytes);
+int opusb200_opus_encode_wait(OpusB200OpusEncoder *enc);
 /* device buffers (d_pcm int16 or float as pcm_is_int16 says); work is enqueued on the encoder's stream */
 int opusb200_opus_encode_device(OpusB200OpusEncoder *enc, const void *d_pcm, int pcm_is_int16, int frame_size, unsigned char *d_packets,
                                 int pkt_stride, int max_data_bytes, int32_t *d_nbytes);

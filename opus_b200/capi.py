@@ -28,7 +28,7 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_encoder_get_final_range', 'opusb200_encoder_sync', 'opusb200_encoder_cuda_stream', 'opusb200_encoder_launch_count',
            'opusb200_celt_analysis_destroy', 'opusb200_celt_analysis_reset', 'opusb200_celt_analysis_process', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
            'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
-           'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create',
+           'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create', 'opusb200_silk_resampler_create_ex',
            'opusb200_silk_resampler_destroy', 'opusb200_silk_resampler_reset', 'opusb200_silk_resampler_process',
            'opusb200_silk_burg_modified', 'opusb200_silk_autocorrelation',
            'opusb200_silk_nsq_create', 'opusb200_silk_nsq_destroy', 'opusb200_silk_nsq_reset', 'opusb200_silk_nsq_process',
@@ -39,7 +39,7 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize',
            'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free',
            'opusb200_opus_encoder_create', 'opusb200_opus_encoder_destroy', 'opusb200_opus_encoder_reset', 'opusb200_opus_encoder_ctl',
-           'opusb200_opus_encode', 'opusb200_opus_encode_float', 'opusb200_opus_encode_device', 'opusb200_opus_encoder_get_final_range',
+           'opusb200_opus_encode', 'opusb200_opus_encode_float', 'opusb200_opus_encode_device', 'opusb200_opus_encode_submit', 'opusb200_opus_encode_wait', 'opusb200_opus_encoder_get_final_range',
            'opusb200_opus_encoder_sync', 'opusb200_opus_encoder_cuda_stream', 'opusb200_opus_encoder_launch_count',
            'opusb200_opus_encoder_set_timing', 'opusb200_opus_encoder_get_timing']
 
@@ -137,6 +137,7 @@ def lib():
         L.opusb200_pvq_search.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci]
         L.opusb200_silk_lpc_analysis_filter.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci]
         L.opusb200_silk_resampler_create.argtypes = [vp, ci, i32, i32, ctypes.POINTER(vp)]
+        L.opusb200_silk_resampler_create_ex.argtypes = [vp, ci, i32, i32, ci, ctypes.POINTER(vp)]
         L.opusb200_silk_resampler_destroy.argtypes = [vp]
         L.opusb200_silk_resampler_destroy.restype = None
         L.opusb200_silk_resampler_reset.argtypes = [vp]
@@ -201,6 +202,8 @@ def lib():
         L.opusb200_opus_encode.argtypes = [vp, vp, ci, vp, ci, ci, vp]
         L.opusb200_opus_encode_float.argtypes = [vp, vp, ci, vp, ci, ci, vp]
         L.opusb200_opus_encode_device.argtypes = [vp, vp, ci, ci, vp, ci, ci, vp]
+        L.opusb200_opus_encode_submit.argtypes = [vp, vp, ci, ci, vp, ci, ci, vp]
+        L.opusb200_opus_encode_wait.argtypes = [vp]
         L.opusb200_opus_encoder_get_final_range.argtypes = [vp, vp]
         L.opusb200_opus_encoder_sync.argtypes = [vp]
         L.opusb200_opus_encoder_cuda_stream.argtypes = [vp]

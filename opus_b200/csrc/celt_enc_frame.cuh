@@ -63,7 +63,7 @@ OB_DEVNI void re_carry_out(RangeEnc &e, int c) {
     e.rem = c & 0xFF;
   } else e.ext++;
 }
-OB_DEV void re_normalize(RangeEnc &e) {
+OB_DEVNI void re_normalize(RangeEnc &e) {
   while (e.rng <= (1u << 23)) {
     re_carry_out(e, (int)(e.val >> 23));
     e.val = (e.val << 8) & ((1u << 31) - 1);
@@ -197,7 +197,7 @@ OB_DEV float enc_exp2(float x) { return (float)exp(0.6931471805599453094 * (doub
 OB_DEV float enc_log2(float x) { return (float)(1.442695040888963387 * log((double)x)); }
 OB_DEV float enc_fmax(float a, float b) { return a > b ? a : b; }
 OB_DEV float enc_fmin(float a, float b) { return a < b ? a : b; }
-OB_DEV float enc_dot(const float *x, const float *y, int n) {  // celt_inner_prod_c
+OB_DEVNI float enc_dot(const float *x, const float *y, int n) {  // celt_inner_prod_c
   float s = 0.f;
 #pragma unroll 4
   for (int i = 0; i < n; i++) s = s + x[i] * y[i];
@@ -410,9 +410,9 @@ OB_DEVNI int enc_coarse_impl(RangeEnc &enc, const float *eBands, float *oldEBand
   return badness;
 }
 
-OB_DEV void enc_haar(float *X, int N0, int stride);
+OB_DEVNI void enc_haar(float *X, int N0, int stride);
 // ---- tf_analysis (celt/celt_encoder.c:648-822) ----
-OB_DEV float enc_l1(const float *tmp, int N, int LM, float bias) {
+OB_DEVNI float enc_l1(const float *tmp, int N, int LM, float bias) {
   float L1 = 0.f;
 #pragma unroll 1
   for (int i = 0; i < N; i++) L1 += fabsf(tmp[i]);
@@ -747,7 +747,7 @@ OB_DEVNI EncAlloc enc_compute_allocation(RangeEnc &enc, const int *offsets, cons
 // ---- band-level vector helpers on thread-private arrays ----
 // (the band vectors live in thread-private local memory: every loop below issues its loads ahead of the arithmetic and the stores that
 // depend on them, four elements at a time where the elements are independent, so one memory latency is paid per group, not per element)
-OB_DEV void enc_haar(float *X, int N0, int stride) {  // celt/bands.c:623-636
+OB_DEVNI void enc_haar(float *X, int N0, int stride) {  // celt/bands.c:623-636
   N0 >>= 1;
 #pragma unroll 1
   for (int i = 0; i < stride; i++) {
@@ -774,7 +774,7 @@ OB_DEV void enc_haar(float *X, int N0, int stride) {  // celt/bands.c:623-636
   }
 }
 OB_TABLE unsigned char ob_enc_hadamard_order[30] = {1, 0, 3, 0, 2, 1, 7, 0, 4, 3, 6, 1, 5, 2, 15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5};
-OB_DEV void enc_deinterleave(float *__restrict__ X, float *__restrict__ tmp, int N0, int stride, int hadamard) {  // celt/bands.c:574-597
+OB_DEVNI void enc_deinterleave(float *__restrict__ X, float *__restrict__ tmp, int N0, int stride, int hadamard) {  // celt/bands.c:574-597
   const int N = N0 * stride;
 #pragma unroll 1
   for (int i = 0; i < stride; i++) {
@@ -787,7 +787,7 @@ OB_DEV void enc_deinterleave(float *__restrict__ X, float *__restrict__ tmp, int
 #pragma unroll 4
   for (int j = 0; j < N; j++) X[j] = tmp[j];
 }
-OB_DEV void enc_rotate_pass(float *X, int len, int stride, float c, float s) {  // celt/vq.c:75-102
+OB_DEVNI void enc_rotate_pass(float *X, int len, int stride, float c, float s) {  // celt/vq.c:75-102
   const float ms = -s;
   if (stride == 1) {   // the element a step has just written is the next step's x1 (forward) / x2 (backward): carried in a register
     if (len < 2) return;

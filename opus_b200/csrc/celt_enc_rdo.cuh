@@ -29,7 +29,7 @@ OB_DEVNI void rdo_exp_rotation_inv(float *X, int len, int stride, int K, int spr
     enc_rotate_pass(X + i * len, len, 1, c, s);
   }
 }
-OB_DEV void rdo_interleave(float *__restrict__ X, float *__restrict__ tmp, int N0, int stride, int hadamard) {  // celt/bands.c:599-621
+OB_DEVNI void rdo_interleave(float *__restrict__ X, float *__restrict__ tmp, int N0, int stride, int hadamard) {  // celt/bands.c:599-621
   const int N = N0 * stride;
 #pragma unroll 1
   for (int i = 0; i < stride; i++) {
@@ -42,7 +42,7 @@ OB_DEV void rdo_interleave(float *__restrict__ X, float *__restrict__ tmp, int N
 #pragma unroll 4
   for (int j = 0; j < N; j++) X[j] = tmp[j];
 }
-OB_DEV void rdo_renormalise(float *X, int N, float gain) {  // celt/vq.c:695-722
+OB_DEVNI void rdo_renormalise(float *X, int N, float gain) {  // celt/vq.c:695-722
   const float E = 1e-15f + enc_dot(X, X, N);
   const float g = rsqrt_ref(E) * gain;
 #pragma unroll 4

@@ -15,6 +15,7 @@
 #include "celt_dec_kernels.cuh"
 #include "celt_dec_plc.cuh"
 #include "celt_ops.cuh"
+#include "celt_mdct_fast.cuh"
 #include "silk_ops.cuh"
 #include "silk_nsq.cuh"
 
@@ -92,8 +93,15 @@ extern "C" __global__ void __launch_bounds__(128) ob_mdct_forward(MdctFwdParams 
   if (item >= p.n_items) return;
   mdct_forward_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
 }
-extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_analysis(EncAnalysisParams p) {
-  enc_analysis_block(p, p.first_stream + blockIdx.x, dyn_smem());
+// blockDim = (32 * channels, teams): every team of a CTA is one stream with its own slice of the dynamic shared memory and its own named
+// barrier (simt.cuh bsync).  Streams that start together run through the same phases at about the same time, so an instruction line fetched
+// for one team serves the others too: the kernel's 250 KB of code otherwise streams through the 32 KB instruction cache once per stream.
+// long-block forward MDCT, FFT in registers, inputs and tables staged by cp.async.bulk (celt_mdct_fast.cuh); persistent, 2 CTAs per SM
+extern "C" __global__ void __launch_bounds__(kMdctFastWarps * 32, 2) ob_mdct_forward_tma(MdctFwdParams p) { mdct_forward_tma_block(p, dyn_smem()); }
+extern "C" __global__ void __launch_bounds__(512) ob_celt_enc_analysis(EncAnalysisParams p, int smem_per_team) {
+  const int stream = p.first_stream + blockIdx.x * blockDim.y + threadIdx.y;
+  if (stream >= p.n_streams) return;   // the whole team leaves: its barrier is its own
+  enc_analysis_block(p, stream, dyn_smem() + (size_t)threadIdx.y * smem_per_team);
 }
 extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, int smem_per_warp) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -747,6 +755,8 @@ int opusb200_ctx_create(int device, OpusB200Ctx **out) {
   OB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OB_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
+  OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MdctFastSmem)));
+  OB_CUDA(cudaFuncSetAttribute(ob_mdct_forward_tma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_pitch_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
   OB_CUDA(cudaFuncSetAttribute(ob_exp_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
@@ -790,8 +800,17 @@ int opusb200_mdct_forward(OpusB200Ctx *c, const float *in, float *out, int n_ite
   }
   MdctFwdParams p;
   p.in = pin; p.out = pout; p.n_items = n_items; p.in_stride = in_stride; p.out_stride = out_stride; p.LM = LM; p.transient = transient;
-  const int warps = 4;
-  ob_mdct_forward<<<(n_items + warps - 1) / warps, warps * 32, warps * sizeof(MdctWS), c->stream>>>(p);
+  // the long block (LM = 3, not transient) has the register-FFT kernel with bulk-copy staging; 16-byte aligned inputs (cp.async.bulk) and
+  // 8-byte aligned outputs hold for every cudaMalloc'ed buffer (strides 1080 / 960 floats).  OPUSB200_MDCT_SMEM_FFT=1 forces the general kernel.
+  static const bool force_general = getenv("OPUSB200_MDCT_SMEM_FFT") != nullptr;
+  if (LM == 3 && !transient && !force_general && ((uintptr_t)pin & 15) == 0 && ((uintptr_t)pout & 7) == 0) {
+    if (!c->sms) cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int npairs = (n_items + 1) / 2, want = (npairs + kMdctFastWarps - 1) / kMdctFastWarps;
+    ob_mdct_forward_tma<<<OB_IMIN(want, 2 * c->sms), kMdctFastWarps * 32, sizeof(MdctFastSmem), c->stream>>>(p);
+  } else {
+    const int warps = 4;
+    ob_mdct_forward<<<(n_items + warps - 1) / warps, warps * 32, warps * sizeof(MdctWS), c->stream>>>(p);
+  }
   c->launches++;
   OB_CUDA(cudaGetLastError());
   if (!on_device) {
@@ -854,7 +873,7 @@ int opusb200_celt_analysis_process(OpusB200CeltAnalysis *a, const float *pcm, co
     p.X = (float *)dX.p; p.bandE = (float *)dE.p; p.bandLogE = (float *)dL.p;
   }
   p.info = nullptr; p.complexity = 0; p.lsb_depth = 24;
-  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 32, c->stream>>>(p);
+  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 32, c->stream>>>(p, 0);
   c->launches++;
   OB_CUDA(cudaGetLastError());
   if (!on_device) {
@@ -1109,39 +1128,25 @@ struct OpusB200SilkResampler {
   SilkResamplerParams proto;
 };
 
-int opusb200_silk_resampler_create(OpusB200Ctx *c, int n_streams, int32_t Fs_in, int32_t Fs_out, OpusB200SilkResampler **out) {
+// silk_resampler_init (silk/resampler.c:77-180): for_enc = 1: 8/12/16/24/48 kHz -> 8/12/16 kHz; for_enc = 0: 8/12/16 kHz -> 8/12/16/24/48 kHz
+int opusb200_silk_resampler_create_ex(OpusB200Ctx *c, int n_streams, int32_t Fs_in, int32_t Fs_out, int for_enc, OpusB200SilkResampler **out) {
   if (!c || !out || n_streams <= 0) return OPUSB200_BAD_ARG;
   *out = nullptr;
-  static const int8_t delay_enc[5][3] = {{6, 0, 3}, {0, 7, 3}, {0, 1, 10}, {0, 2, 6}, {18, 10, 12}};  // silk/resampler.c:53-61
-  static const int16_t c12[14] = {616, -14323, -10, 39, 58, -46, -84, 120, 184, -315, -541, 1284, 5380, 9024};
-  static const int16_t c13[20] = {16102, -15162, -13, 0, 20, 26, 5, -31, -43, -4, 65, 90, 7, -157, -248, -44, 593, 1583, 2612, 3271};
-  static const int16_t c14[20] = {22500, -15099, 3, -14, -20, -15, 2, 25, 37, 25, -16, -71, -107, -79, 50, 292, 623, 982, 1288, 1464};
-  static const int16_t c16[20] = {27540, -15257, 17, 12, 8, 1, -10, -22, -30, -32, -22, 3, 44, 100, 168, 243, 317, 381, 429, 455};
-  const int ri = Fs_in == 8000 ? 0 : Fs_in == 12000 ? 1 : Fs_in == 16000 ? 2 : Fs_in == 24000 ? 3 : Fs_in == 48000 ? 4 : -1;
-  const int ro = Fs_out == 8000 ? 0 : Fs_out == 12000 ? 1 : Fs_out == 16000 ? 2 : -1;
-  if (ri < 0 || ro < 0) return OPUSB200_BAD_ARG;
-  const int16_t *cf;
-  int order;
-  if (Fs_out * 2 == Fs_in) { cf = c12; order = 24; }
-  else if (Fs_out * 3 == Fs_in) { cf = c13; order = 36; }
-  else if (Fs_out * 4 == Fs_in) { cf = c14; order = 36; }
-  else if (Fs_out * 6 == Fs_in) { cf = c16; order = 36; }
-  else return OPUSB200_UNIMPLEMENTED;  // fractional ratios (3:4, 2:3) and up-sampling: not on the hot path
+  SilkResamplerParams proto;
+  if (silk_resampler_setup(proto, Fs_in, Fs_out, for_enc)) return OPUSB200_BAD_ARG;
   OB_CUDA(cudaSetDevice(c->device));
   OpusB200SilkResampler *r = new (std::nothrow) OpusB200SilkResampler;
   if (!r) return OPUSB200_ALLOC_FAIL;
   r->ctx = c; r->n = n_streams; r->fs_in = Fs_in; r->fs_out = Fs_out;
   OB_CUDA(cudaMalloc(&r->state, sizeof(ObSilkResamplerState) * (size_t)n_streams));
   OB_CUDA(cudaMemsetAsync(r->state, 0, sizeof(ObSilkResamplerState) * (size_t)n_streams, c->stream));
-  SilkResamplerParams &p = r->proto;
-  memset(&p, 0, sizeof(p));
-  p.state = r->state; p.n_streams = n_streams; p.fir_order = order; p.fs_in_khz = Fs_in / 1000; p.fs_out_khz = Fs_out / 1000;
-  p.input_delay = delay_enc[ri][ro]; p.batch = p.fs_in_khz * 10;
-  p.inv_ratio_q16 = (int32_t)((((int64_t)Fs_in << 14) / Fs_out) << 2);
-  while ((int32_t)(((int64_t)p.inv_ratio_q16 * Fs_out) >> 16) < Fs_in) p.inv_ratio_q16++;
-  for (int i = 0; i < 2 + order / 2; i++) p.coefs[i] = cf[i];
+  r->proto = proto;
+  r->proto.state = r->state; r->proto.n_streams = n_streams;
   *out = r;
   return OPUSB200_OK;
+}
+int opusb200_silk_resampler_create(OpusB200Ctx *c, int n_streams, int32_t Fs_in, int32_t Fs_out, OpusB200SilkResampler **out) {
+  return opusb200_silk_resampler_create_ex(c, n_streams, Fs_in, Fs_out, 1, out);
 }
 void opusb200_silk_resampler_destroy(OpusB200SilkResampler *r) {
   if (!r) return;

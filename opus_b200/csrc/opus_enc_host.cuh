@@ -32,6 +32,14 @@ struct OpusB200OpusEncoder {
   unsigned char *d_pkt; size_t d_pkt_cap;
   int32_t *d_nbytes;
   int64_t launches;
+  // the pipelined host-buffer call (opusb200_opus_encode_submit / _wait): two staging slots, PCM upload and packet read-back on their own
+  // streams, so the upload of call k+1 and the read-back of call k-1 run under the kernels of call k
+  cudaStream_t st_in, st_out;
+  cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+  void *s_pcm[2]; size_t s_pcm_cap[2];
+  unsigned char *s_pkt[2]; size_t s_pkt_cap[2];
+  int32_t *s_nb[2], *h_nb[2], *user_nb[2];
+  int slot, pending[2];
 };
 
 extern "C" int opusb200_opus_encoder_reset(OpusB200OpusEncoder *e) {   // OPUS_RESET_STATE
@@ -78,6 +86,14 @@ extern "C" void opusb200_opus_encoder_destroy(OpusB200OpusEncoder *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->celt->stream);
   cudaFree(e->st); cudaFree(e->tonal); cudaFree(e->pre); cudaFree(e->ctl); cudaFree(e->pcm_buf); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->d_nbytes);
+  if (e->st_in) {
+    cudaStreamSynchronize(e->st_in); cudaStreamSynchronize(e->st_out);
+    for (int b = 0; b < 2; b++) {
+      cudaFree(e->s_pcm[b]); cudaFree(e->s_pkt[b]); cudaFree(e->s_nb[b]); cudaFreeHost(e->h_nb[b]);
+      cudaEventDestroy(e->ev_in[b]); cudaEventDestroy(e->ev_cmp[b]); cudaEventDestroy(e->ev_out[b]);
+    }
+    cudaStreamDestroy(e->st_in); cudaStreamDestroy(e->st_out);
+  }
   opusb200_encoder_destroy(e->celt);
   delete e;
 }
@@ -149,6 +165,75 @@ extern "C" int opusb200_opus_encode(OpusB200OpusEncoder *e, const int16_t *pcm, 
 extern "C" int opusb200_opus_encode_float(OpusB200OpusEncoder *e, const float *pcm, int frame_size, unsigned char *packets, int pkt_stride,
                                           int max_data_bytes, int32_t *nbytes) {
   return opus_encode_host(e, pcm, 0, frame_size, packets, pkt_stride, max_data_bytes, nbytes);
+}
+// The batch-server form of the host-buffer call.  submit: upload the PCM (own stream), encode, read the packets back (own stream), all
+// asynchronous; staging is double-buffered, so a caller that submits call k+1 before waiting for call k gets k+1's upload and k's read-back
+// under the kernels.  The host buffers must stay valid (and, for overlap, be pinned: opusb200_host_alloc) until opusb200_opus_encode_wait
+// returns; nbytes[] of every submitted call is filled in by the wait.  At most two calls in flight: a third submit first completes the oldest.
+extern "C" int opusb200_opus_encode_wait(OpusB200OpusEncoder *e) {
+  if (!e) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(e->device));
+  if (!e->st_in) return OPUSB200_OK;
+  OB_CUDA(cudaStreamSynchronize(e->st_out));
+  OB_CUDA(cudaStreamSynchronize(e->celt->stream));
+  for (int b = 0; b < 2; b++)
+    if (e->pending[b]) {
+      memcpy(e->user_nb[b], e->h_nb[b], sizeof(int32_t) * (size_t)e->n);
+      e->pending[b] = 0;
+    }
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_opus_encode_submit(OpusB200OpusEncoder *e, const void *pcm, int pcm_is_int16, int frame_size, unsigned char *packets,
+                                           int pkt_stride, int max_data_bytes, int32_t *nbytes) {
+  if (!e || !pcm || !packets || !nbytes || frame_size <= 0) return OPUSB200_BAD_ARG;
+  const int is16 = pcm_is_int16 ? 1 : 0;
+  {
+    ob::OpusCallPlan pl;
+    const int pr = ob::opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
+    if (pr) return pr;
+    if (frame_size > OB_MAXN || pkt_stride < pl.max_data_bytes) return OPUSB200_BAD_ARG;
+  }
+  OB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = e->celt->stream;
+  if (!e->st_in) {
+    OB_CUDA(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
+    OB_CUDA(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      OB_CUDA(cudaEventCreateWithFlags(&e->ev_in[b], cudaEventDisableTiming));
+      OB_CUDA(cudaEventCreateWithFlags(&e->ev_cmp[b], cudaEventDisableTiming));
+      OB_CUDA(cudaEventCreateWithFlags(&e->ev_out[b], cudaEventDisableTiming));
+      OB_CUDA(cudaMalloc(&e->s_nb[b], sizeof(int32_t) * (size_t)e->n));
+      OB_CUDA(cudaMallocHost(&e->h_nb[b], sizeof(int32_t) * (size_t)e->n));
+    }
+  }
+  const int b = e->slot;
+  if (e->pending[b]) {   // a third call in flight: finish the one that owns this slot
+    OB_CUDA(cudaEventSynchronize(e->ev_out[b]));
+    memcpy(e->user_nb[b], e->h_nb[b], sizeof(int32_t) * (size_t)e->n);
+    e->pending[b] = 0;
+  }
+  const size_t pb = (is16 ? sizeof(int16_t) : sizeof(float)) * (size_t)e->n * frame_size * e->channels, kb = (size_t)e->n * pkt_stride;
+  if (e->s_pcm_cap[b] < pb || e->s_pkt_cap[b] < kb) {
+    OB_CUDA(cudaStreamSynchronize(s)); OB_CUDA(cudaStreamSynchronize(e->st_in)); OB_CUDA(cudaStreamSynchronize(e->st_out));
+    if (e->s_pcm_cap[b] < pb) { cudaFree(e->s_pcm[b]); e->s_pcm[b] = nullptr; e->s_pcm_cap[b] = 0; OB_CUDA(cudaMalloc(&e->s_pcm[b], pb)); e->s_pcm_cap[b] = pb; }
+    if (e->s_pkt_cap[b] < kb) { cudaFree(e->s_pkt[b]); e->s_pkt[b] = nullptr; e->s_pkt_cap[b] = 0; OB_CUDA(cudaMalloc(&e->s_pkt[b], kb)); e->s_pkt_cap[b] = kb; }
+  }
+  OB_CUDA(cudaStreamWaitEvent(e->st_in, e->ev_cmp[b], 0));   // the kernels that last read this slot's PCM (no-op if none)
+  OB_CUDA(cudaMemcpyAsync(e->s_pcm[b], pcm, pb, cudaMemcpyHostToDevice, e->st_in));
+  OB_CUDA(cudaEventRecord(e->ev_in[b], e->st_in));
+  OB_CUDA(cudaStreamWaitEvent(s, e->ev_in[b], 0));
+  OB_CUDA(cudaStreamWaitEvent(s, e->ev_out[b], 0));          // the read-back that last used this slot's packet buffer
+  const int r = opusb200_opus_encode_device(e, e->s_pcm[b], is16, frame_size, e->s_pkt[b], pkt_stride, max_data_bytes, e->s_nb[b]);
+  if (r != OPUSB200_OK) return r;
+  OB_CUDA(cudaEventRecord(e->ev_cmp[b], s));
+  OB_CUDA(cudaStreamWaitEvent(e->st_out, e->ev_cmp[b], 0));
+  OB_CUDA(cudaMemcpyAsync(packets, e->s_pkt[b], kb, cudaMemcpyDeviceToHost, e->st_out));
+  OB_CUDA(cudaMemcpyAsync(e->h_nb[b], e->s_nb[b], sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, e->st_out));
+  OB_CUDA(cudaEventRecord(e->ev_out[b], e->st_out));
+  e->user_nb[b] = nbytes;
+  e->pending[b] = 1;
+  e->slot ^= 1;
+  return OPUSB200_OK;
 }
 extern "C" int opusb200_opus_encoder_get_final_range(OpusB200OpusEncoder *e, uint32_t *final_range) {
   return e ? opusb200_encoder_get_final_range(e->celt, final_range) : OPUSB200_BAD_ARG;

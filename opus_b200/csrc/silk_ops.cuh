@@ -3,8 +3,8 @@
 // parallel axis is the batch.  Thread-private arrays live in local memory, which the hardware
 // interleaves per lane — a warp's accesses to element k of 32 streams coalesce.
 //   ob_silk_lpc_analysis_filter : silk/LPC_analysis_filter.c:49-111
-//   ob_silk_resampler_down      : silk/resampler.c:183-219 + resampler_private_AR2.c + resampler_private_down_FIR.c
-//                                 (encoder-side integer-ratio down-sampling 1:2, 1:3, 1:4, 1:6)
+//   ob_silk_resampler_down      : silk_resampler (silk/resampler.c:77-219) for every rate pair silk_resampler_init accepts, both directions:
+//                                 copy, resampler_private_up2_HQ.c, resampler_private_IIR_FIR.c, resampler_private_AR2.c + _down_FIR.c
 #pragma once
 #include "simt.cuh"
 
@@ -44,19 +44,68 @@ OB_DEV void silk_lpc_analysis_filter_thread(const SilkLpcParams &p, int item) {
 
 // Per-stream resampler state (HBM).  Mirrors silk_resampler_state_struct (silk/resampler_structs.h:34-50).
 struct ObSilkResamplerState {
-  int32_t sIIR[2];
-  int32_t sFIR[36];
+  int32_t sIIR[6];
+  int32_t sFIR[36];    // down-FIR: int32 history; IIR_FIR: the first 8 int16 of this storage (the reference's union)
   int16_t delayBuf[48];
 };
+enum { OB_RS_COPY = 0, OB_RS_UP2 = 1, OB_RS_IIR_FIR = 2, OB_RS_DOWN = 3 };   // S->resampler_function (silk/resampler.c:74-77)
 struct SilkResamplerParams {
   ObSilkResamplerState *state;  // [n_streams]
   const int16_t *in;            // [n_streams][in_len]
   int16_t *out;                 // [n_streams][out_len]
   int n_streams, in_len, out_len;
-  int fir_order, fs_in_khz, fs_out_khz, input_delay, inv_ratio_q16, batch;
-  int16_t coefs[20];            // 2 AR + up to 18 FIR coefficients
+  int function, fir_order, fir_fracs, fs_in_khz, fs_out_khz, input_delay, inv_ratio_q16, batch;
+  int16_t coefs[30];            // 2 AR + up to 27 FIR coefficients (3 phases x 9)
+  SilkResamplerParams() : state(nullptr), in(nullptr), out(nullptr), n_streams(0), in_len(0), out_len(0), function(0), fir_order(0), fir_fracs(1),
+                          fs_in_khz(0), fs_out_khz(0), input_delay(0), inv_ratio_q16(0), batch(0), coefs{} {}
 };
+// silk_resampler_init (silk/resampler.c:77-180) as host code: fills the launch parameters for a rate pair; for_enc = 1: 8/12/16/24/48 kHz ->
+// 8/12/16 kHz, for_enc = 0: 8/12/16 kHz -> 8/12/16/24/48 kHz.  Returns -1 for a pair the reference rejects.
+static inline int silk_resampler_setup(SilkResamplerParams &p, int32_t Fs_in, int32_t Fs_out, int for_enc) {
+  static const int8_t delay_enc[5][3] = {{6, 0, 3}, {0, 7, 3}, {0, 1, 10}, {0, 2, 6}, {18, 10, 12}};  // silk/resampler.c:53-61
+  static const int8_t delay_dec[3][5] = {{4, 0, 2, 0, 0}, {0, 9, 4, 7, 4}, {0, 3, 12, 7, 7}};          // silk/resampler.c:63-68
+  // silk/resampler_rom.c:42-76
+  static const int16_t c34[29] = {-20694, -13867, -49, 64, 17, -157, 353, -496, 163, 11047, 22205, -39, 6, 91, -170, 186, 23, -896, 6336, 19928,
+                                  -19, -36, 102, -89, -24, 328, -951, 2568, 15909};
+  static const int16_t c23[20] = {-14457, -14019, 64, 128, -122, 36, 310, -768, 584, 9267, 17733, 12, 128, 18, -142, 288, -117, -865, 4123, 14459};
+  static const int16_t c12[14] = {616, -14323, -10, 39, 58, -46, -84, 120, 184, -315, -541, 1284, 5380, 9024};
+  static const int16_t c13[20] = {16102, -15162, -13, 0, 20, 26, 5, -31, -43, -4, 65, 90, 7, -157, -248, -44, 593, 1583, 2612, 3271};
+  static const int16_t c14[20] = {22500, -15099, 3, -14, -20, -15, 2, 25, 37, 25, -16, -71, -107, -79, 50, 292, 623, 982, 1288, 1464};
+  static const int16_t c16[20] = {27540, -15257, 17, 12, 8, 1, -10, -22, -30, -32, -22, 3, 44, 100, 168, 243, 317, 381, 429, 455};
+  const int ri = Fs_in == 8000 ? 0 : Fs_in == 12000 ? 1 : Fs_in == 16000 ? 2 : Fs_in == 24000 ? 3 : Fs_in == 48000 ? 4 : -1;
+  const int ro = Fs_out == 8000 ? 0 : Fs_out == 12000 ? 1 : Fs_out == 16000 ? 2 : Fs_out == 24000 ? 3 : Fs_out == 48000 ? 4 : -1;
+  if (ri < 0 || ro < 0 || (for_enc ? ro > 2 : ri > 2)) return -1;
+  const int16_t *cf = nullptr;
+  int order = 0, fracs = 1, ncoef = 0, function, up2x = 0;
+  if (Fs_out > Fs_in) {
+    if (Fs_out == 2 * Fs_in) function = OB_RS_UP2;
+    else { function = OB_RS_IIR_FIR; up2x = 1; }
+  } else if (Fs_out < Fs_in) {
+    function = OB_RS_DOWN;
+    if (Fs_out * 4 == Fs_in * 3) { cf = c34; order = 18; fracs = 3; ncoef = 29; }
+    else if (Fs_out * 3 == Fs_in * 2) { cf = c23; order = 18; fracs = 2; ncoef = 20; }
+    else if (Fs_out * 2 == Fs_in) { cf = c12; order = 24; ncoef = 14; }
+    else if (Fs_out * 3 == Fs_in) { cf = c13; order = 36; ncoef = 20; }
+    else if (Fs_out * 4 == Fs_in) { cf = c14; order = 36; ncoef = 20; }
+    else if (Fs_out * 6 == Fs_in) { cf = c16; order = 36; ncoef = 20; }
+    else return -1;
+  } else function = OB_RS_COPY;
+  p = SilkResamplerParams();
+  p.function = function; p.fir_order = order; p.fir_fracs = fracs;
+  p.fs_in_khz = Fs_in / 1000; p.fs_out_khz = Fs_out / 1000;
+  p.input_delay = for_enc ? delay_enc[ri][ro] : delay_dec[ri][ro]; p.batch = p.fs_in_khz * 10;
+  p.inv_ratio_q16 = (int32_t)((((int64_t)Fs_in << (14 + up2x)) / Fs_out) << 2);
+  while ((int32_t)(((int64_t)p.inv_ratio_q16 * Fs_out) >> 16) < (Fs_in << up2x)) p.inv_ratio_q16++;
+  for (int i = 0; i < ncoef; i++) p.coefs[i] = cf[i];
+  return 0;
+}
+// silk/resampler_rom.c:84-96 (1/24, 3/24, ... 23/24 sample interpolation), resampler_rom.h:45-46 (all-pass coefficients)
+OB_TABLE int16_t ob_silk_frac_fir_12[12][4] = {{189, -600, 617, 30567}, {117, -159, -1070, 29704}, {52, 221, -2392, 28276}, {-4, 529, -3350, 26341},
+                                               {-48, 758, -3956, 23973}, {-80, 905, -4235, 21254}, {-99, 972, -4222, 18278}, {-107, 967, -3957, 15143},
+                                               {-103, 896, -3487, 11950}, {-91, 773, -2865, 8798}, {-71, 611, -2143, 5784}, {-46, 425, -1375, 2996}};
 
+// AR2 + FIR down-sampling (silk/resampler_private_down_FIR.c:36-193, resampler_private_AR2.c:36-55): symmetric FIR of order 24 / 36 for the
+// integer ratios, 18 taps in 2 or 3 interpolation phases for 2:3 and 3:4
 OB_DEV int16_t *silk_down_fir(const SilkResamplerParams &p, int32_t *sIIR, int32_t *sFIR, int16_t *out, const int16_t *in, int inLen) {
   int32_t buf[480 + 36];
   const int order = p.fir_order, half = order >> 1;
@@ -80,9 +129,20 @@ OB_DEV int16_t *silk_down_fir(const SilkResamplerParams &p, int32_t *sIIR, int32
 #pragma unroll 1
     for (int32_t idx = 0; idx < maxi; idx += p.inv_ratio_q16) {
       const int32_t *b = buf + (idx >> 16);
-      int32_t r = silk_smulwb(b[0] + b[order - 1], p.coefs[2]);
+      int32_t r;
+      if (order == 18) {
+        const int ind = silk_smulwb(idx & 0xFFFF, p.fir_fracs);
+        const int16_t *c0 = &p.coefs[2 + 9 * ind], *c1 = &p.coefs[2 + 9 * (p.fir_fracs - 1 - ind)];
+        r = silk_smulwb(b[0], c0[0]);
 #pragma unroll 1
-      for (int k = 1; k < half; k++) r = silk_smlawb(r, b[k] + b[order - 1 - k], p.coefs[2 + k]);
+        for (int k = 1; k < 9; k++) r = silk_smlawb(r, b[k], c0[k]);
+#pragma unroll 1
+        for (int k = 0; k < 9; k++) r = silk_smlawb(r, b[17 - k], c1[k]);
+      } else {
+        r = silk_smulwb(b[0] + b[order - 1], p.coefs[2]);
+#pragma unroll 1
+        for (int k = 1; k < half; k++) r = silk_smlawb(r, b[k] + b[order - 1 - k], p.coefs[2 + k]);
+      }
       *out++ = silk_sat16(silk_rshift_round(r, 6));
     }
     in += nIn;
@@ -97,28 +157,108 @@ OB_DEV int16_t *silk_down_fir(const SilkResamplerParams &p, int32_t *sIIR, int32
   sIIR[0] = s0; sIIR[1] = s1;
   return out;
 }
+// 2x up-sampling by two chains of three all-pass sections (silk/resampler_private_up2_HQ.c:36-103); ostride = 1
+OB_DEV void silk_up2_hq(int32_t *S, int16_t *out, const int16_t *in, int len) {
+  int32_t s0 = S[0], s1 = S[1], s2 = S[2], s3 = S[3], s4 = S[4], s5 = S[5];
+#pragma unroll 1
+  for (int k = 0; k < len; k++) {
+    const int32_t in32 = (int32_t)((uint32_t)(int32_t)in[k] << 10);
+    int32_t Y, X, o1, o2;
+    Y = in32 - s0; X = silk_smulwb(Y, 1746); o1 = s0 + X; s0 = in32 + X;
+    Y = o1 - s1; X = silk_smulwb(Y, 14986); o2 = s1 + X; s1 = o1 + X;
+    Y = o2 - s2; X = silk_smlawb(Y, Y, 39083 - 65536); o1 = s2 + X; s2 = o2 + X;
+    out[2 * k] = silk_sat16(silk_rshift_round(o1, 10));
+    Y = in32 - s3; X = silk_smulwb(Y, 6854); o1 = s3 + X; s3 = in32 + X;
+    Y = o1 - s4; X = silk_smulwb(Y, 25769); o2 = s4 + X; s4 = o1 + X;
+    Y = o2 - s5; X = silk_smlawb(Y, Y, 55542 - 65536); o1 = s5 + X; s5 = o2 + X;
+    out[2 * k + 1] = silk_sat16(silk_rshift_round(o1, 10));
+  }
+  S[0] = s0; S[1] = s1; S[2] = s2; S[3] = s3; S[4] = s4; S[5] = s5;
+}
+// 2x up-sampling followed by FIR interpolation at 1/12-sample resolution (silk/resampler_private_IIR_FIR.c:35-107); sfir: 8 int16 of history
+OB_DEV int16_t *silk_iir_fir(const SilkResamplerParams &p, int32_t *sIIR, int16_t *sfir, int16_t *out, const int16_t *in, int inLen) {
+  int16_t buf[2 * 480 + 8];
+  int nIn = 0;
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) buf[k] = sfir[k];
+#pragma unroll 1
+  for (;;) {
+    nIn = inLen < p.batch ? inLen : p.batch;
+    silk_up2_hq(sIIR, &buf[8], in, nIn);
+    const int32_t maxi = nIn << 17;
+#pragma unroll 1
+    for (int32_t idx = 0; idx < maxi; idx += p.inv_ratio_q16) {
+      const int t = silk_smulwb(idx & 0xFFFF, 12);
+      const int16_t *b = &buf[idx >> 16];
+      int32_t r = (int32_t)b[0] * ob_silk_frac_fir_12[t][0];
+#pragma unroll
+      for (int k = 1; k < 4; k++) r += (int32_t)b[k] * ob_silk_frac_fir_12[t][k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) r += (int32_t)b[4 + k] * ob_silk_frac_fir_12[11 - t][3 - k];
+      *out++ = silk_sat16(silk_rshift_round(r, 15));
+    }
+    in += nIn;
+    inLen -= nIn;
+    if (inLen > 0) {
+#pragma unroll 1
+      for (int k = 0; k < 8; k++) buf[k] = buf[(nIn << 1) + k];
+    } else break;
+  }
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) sfir[k] = buf[(nIn << 1) + k];
+  return out;
+}
 
+// silk_resampler() (silk/resampler.c:183-219): the first millisecond comes from the delay buffer, the rest from the input
 OB_DEV void silk_resampler_thread(const SilkResamplerParams &p, int stream) {
   ObSilkResamplerState *S = p.state + stream;
   const int16_t *in = p.in + (size_t)stream * p.in_len;
   int16_t *out = p.out + (size_t)stream * p.out_len;
-  int32_t sIIR[2] = {S->sIIR[0], S->sIIR[1]};
-  int32_t sFIR[36];
   int16_t delay[48];
-#pragma unroll 1
-  for (int k = 0; k < 36; k++) sFIR[k] = S->sFIR[k];
   const int nSamples = p.fs_in_khz - p.input_delay;
 #pragma unroll 1
   for (int k = 0; k < p.input_delay; k++) delay[k] = S->delayBuf[k];
 #pragma unroll 1
   for (int k = 0; k < nSamples; k++) delay[p.input_delay + k] = in[k];
-  silk_down_fir(p, sIIR, sFIR, out, delay, p.fs_in_khz);
-  silk_down_fir(p, sIIR, sFIR, out + p.fs_out_khz, in + nSamples, p.in_len - p.fs_in_khz);
+  if (p.function == OB_RS_COPY) {
+#pragma unroll 1
+    for (int k = 0; k < p.fs_in_khz; k++) out[k] = delay[k];
+#pragma unroll 1
+    for (int k = 0; k < p.in_len - p.fs_in_khz; k++) out[p.fs_out_khz + k] = in[nSamples + k];
+  } else if (p.function == OB_RS_UP2) {
+    int32_t sIIR[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) sIIR[k] = S->sIIR[k];
+    silk_up2_hq(sIIR, out, delay, p.fs_in_khz);
+    silk_up2_hq(sIIR, out + p.fs_out_khz, in + nSamples, p.in_len - p.fs_in_khz);
+#pragma unroll
+    for (int k = 0; k < 6; k++) S->sIIR[k] = sIIR[k];
+  } else if (p.function == OB_RS_IIR_FIR) {
+    int32_t sIIR[6];
+    int16_t sfir[8];
+#pragma unroll
+    for (int k = 0; k < 6; k++) sIIR[k] = S->sIIR[k];
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) sfir[k] = ((const int16_t *)S->sFIR)[k];
+    silk_iir_fir(p, sIIR, sfir, out, delay, p.fs_in_khz);
+    silk_iir_fir(p, sIIR, sfir, out + p.fs_out_khz, in + nSamples, p.in_len - p.fs_in_khz);
+#pragma unroll
+    for (int k = 0; k < 6; k++) S->sIIR[k] = sIIR[k];
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) ((int16_t *)S->sFIR)[k] = sfir[k];
+  } else {
+    int32_t sIIR[2] = {S->sIIR[0], S->sIIR[1]};
+    int32_t sFIR[36];
+#pragma unroll 1
+    for (int k = 0; k < 36; k++) sFIR[k] = S->sFIR[k];
+    silk_down_fir(p, sIIR, sFIR, out, delay, p.fs_in_khz);
+    silk_down_fir(p, sIIR, sFIR, out + p.fs_out_khz, in + nSamples, p.in_len - p.fs_in_khz);
+#pragma unroll 1
+    for (int k = 0; k < 36; k++) S->sFIR[k] = sFIR[k];
+    S->sIIR[0] = sIIR[0]; S->sIIR[1] = sIIR[1];
+  }
 #pragma unroll 1
   for (int k = 0; k < p.input_delay; k++) S->delayBuf[k] = in[p.in_len - p.input_delay + k];
-#pragma unroll 1
-  for (int k = 0; k < 36; k++) S->sFIR[k] = sFIR[k];
-  S->sIIR[0] = sIIR[0]; S->sIIR[1] = sIIR[1];
 }
 
 // ---- float analysis kernels (row a17): double accumulators, one thread per item -----------------

@@ -14,7 +14,7 @@
 #define OB_HDNI __host__ __device__ __noinline__
 #define OB_MDEV __device__ __forceinline__
 #define OB_HD __host__ __device__ __forceinline__
-#define OB_TABLE static __device__ const
+#define OB_TABLE static __device__ const __align__(16)   // 16-byte aligned: the tables are cp.async.bulk sources (celt_mdct_fast.cuh)
 #define OB_RESTRICT __restrict__
 
 namespace ob {
@@ -24,7 +24,13 @@ OB_DEV int warps_per_block() { return blockDim.x >> 5; }
 OB_DEV int block_id() { return blockIdx.x; }
 OB_DEV int num_blocks() { return gridDim.x; }
 OB_DEV void wsync() { __syncwarp(); }
-OB_DEV void bsync() { __syncthreads(); }
+// Block barrier.  A kernel launched with blockDim.y > 1 holds blockDim.y independent TEAMS of blockDim.x threads (one stream each, e.g.
+// ob_celt_enc_analysis): every team then meets at its own named barrier, so teams may take different paths; warp_in_block / warps_per_block /
+// lane_id keep their meaning inside the team because blockDim.x is a multiple of 32.
+OB_DEV void bsync() {
+  if (blockDim.y == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(threadIdx.y + 1), "r"(blockDim.x) : "memory");
+}
 template <class T> OB_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <class T> OB_DEV T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 template <class T> OB_DEV T shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }

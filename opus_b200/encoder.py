@@ -132,6 +132,22 @@ class OpusEncoderBatch:
             raise capi.OpusB200Error(r, 'opusb200_opus_encoder_get_final_range')
         return fr
 
+    def submit(self, pcm, packets, nbytes, max_data_bytes=None, frame_size=None):
+        """opusb200_opus_encode_submit: enqueue one call on caller-owned host arrays (pcm int16 / float32 [n, frame_size*channels], packets uint8
+        [n, stride], nbytes int32 [n]); they must stay alive until wait()"""
+        assert pcm.flags.c_contiguous and packets.flags.c_contiguous and pcm.dtype in (np.int16, np.float32)
+        fs = frame_size or pcm.shape[1] // self.channels
+        stride = packets.shape[1]
+        r = self._L.opusb200_opus_encode_submit(self._h, _p(pcm), 1 if pcm.dtype == np.int16 else 0, fs, _p(packets), stride,
+                                                max_data_bytes or stride, _p(nbytes))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_opus_encode_submit')
+
+    def wait(self):
+        r = self._L.opusb200_opus_encode_wait(self._h)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_opus_encode_wait')
+
     def encode_device(self, d_pcm, pcm_is_int16, frame_size, d_packets, pkt_stride, max_data_bytes, d_nbytes):
         """device pointers (ints); enqueued on the encoder's stream"""
         r = self._L.opusb200_opus_encode_device(self._h, ctypes.c_void_p(d_pcm), int(pcm_is_int16), frame_size, ctypes.c_void_p(d_packets), pkt_stride,

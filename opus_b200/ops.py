@@ -84,8 +84,8 @@ class Ops:
         self._chk(self._L.opusb200_silk_autocorrelation(self._h, _p(out), _p(x), x.shape[0], x.shape[1], count, 0), 'silk_autocorrelation')
         return out
 
-    def silk_resampler(self, n_streams, fs_in, fs_out):
-        return SilkResampler(self, n_streams, fs_in, fs_out)
+    def silk_resampler(self, n_streams, fs_in, fs_out, for_enc=True):
+        return SilkResampler(self, n_streams, fs_in, fs_out, for_enc)
 
     def celt_analysis(self, n_streams, channels):
         return CeltAnalysis(self, n_streams, channels)
@@ -106,12 +106,12 @@ class Ops:
 
 
 class SilkResampler:
-    """n_streams encoder-side SILK resamplers (silk_resampler_init(S, fs_in, fs_out, 1) / silk_resampler)."""
+    """n_streams SILK resamplers (silk_resampler_init(S, fs_in, fs_out, for_enc) / silk_resampler)."""
 
-    def __init__(self, ops, n_streams, fs_in, fs_out):
+    def __init__(self, ops, n_streams, fs_in, fs_out, for_enc=True):
         self._ops, self._L, self.n, self.fs_in, self.fs_out = ops, ops._L, n_streams, fs_in, fs_out
         h = ctypes.c_void_p()
-        r = self._L.opusb200_silk_resampler_create(ops._h, n_streams, fs_in, fs_out, ctypes.byref(h))
+        r = self._L.opusb200_silk_resampler_create_ex(ops._h, n_streams, fs_in, fs_out, 1 if for_enc else 0, ctypes.byref(h))
         if r != 0:
             raise capi.OpusB200Error(r, 'opusb200_silk_resampler_create')
         self._h = h

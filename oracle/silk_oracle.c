@@ -24,43 +24,70 @@ void orc_silk_lpc_analysis_filter(int16_t *out, const int16_t *in, const int16_t
   memset(out, 0, d * sizeof(int16_t));
 }
 
-/* ---- down-sampling resampler, encoder side (silk/resampler.c:77-219, resampler_private_AR2.c,
- * resampler_private_down_FIR.c) for the integer-ratio cases 1:2, 1:3, 1:4, 1:6 ---- */
+/* ---- silk_resampler: every rate pair silk_resampler_init accepts (silk/resampler.c:77-219): encoder side 8/12/16/24/48 kHz -> 8/12/16 kHz,
+ * decoder side 8/12/16 kHz -> 8/12/16/24/48 kHz.  Four functions: copy, the 2x all-pass up-sampler (resampler_private_up2_HQ.c), 2x up-sampling
+ * followed by 1/12-sample FIR interpolation (resampler_private_IIR_FIR.c), AR2 + FIR down-sampling with 1, 2 or 3 interpolation phases
+ * (resampler_private_AR2.c, resampler_private_down_FIR.c). ---- */
+enum { ORC_RS_COPY = 0, ORC_RS_UP2 = 1, ORC_RS_IIR_FIR = 2, ORC_RS_DOWN = 3 };
 typedef struct {
-  int32_t sIIR[2];
-  int32_t sFIR[36];
+  int32_t sIIR[6];
+  int32_t sFIR[36];    /* down-FIR: int32 history; IIR_FIR: the first 8 int16 of this storage (silk_resampler_state_struct's union) */
   int16_t delayBuf[96];
-  int32_t fir_order, fs_in_khz, fs_out_khz, input_delay, inv_ratio_q16, batch;
+  int32_t function, fir_order, fir_fracs, fs_in_khz, fs_out_khz, input_delay, inv_ratio_q16, batch;
   const int16_t *coefs;
 } OrcResampler;
 
+/* filter constants: silk/resampler_rom.c:42-96, resampler_rom.h:45-46 */
+static const int16_t coefs_3_4[2 + 27] = {-20694, -13867, -49, 64, 17, -157, 353, -496, 163, 11047, 22205, -39, 6, 91, -170, 186, 23, -896, 6336, 19928,
+                                          -19, -36, 102, -89, -24, 328, -951, 2568, 15909};
+static const int16_t coefs_2_3[2 + 18] = {-14457, -14019, 64, 128, -122, 36, 310, -768, 584, 9267, 17733, 12, 128, 18, -142, 288, -117, -865, 4123, 14459};
 static const int16_t coefs_1_2[2 + 12] = {616, -14323, -10, 39, 58, -46, -84, 120, 184, -315, -541, 1284, 5380, 9024};
 static const int16_t coefs_1_3[2 + 18] = {16102, -15162, -13, 0, 20, 26, 5, -31, -43, -4, 65, 90, 7, -157, -248, -44, 593, 1583, 2612, 3271};
 static const int16_t coefs_1_4[2 + 18] = {22500, -15099, 3, -14, -20, -15, 2, 25, 37, 25, -16, -71, -107, -79, 50, 292, 623, 982, 1288, 1464};
 static const int16_t coefs_1_6[2 + 18] = {27540, -15257, 17, 12, 8, 1, -10, -22, -30, -32, -22, 3, 44, 100, 168, 243, 317, 381, 429, 455};
+static const int16_t frac_fir_12[12][4] = {{189, -600, 617, 30567}, {117, -159, -1070, 29704}, {52, 221, -2392, 28276}, {-4, 529, -3350, 26341},
+                                           {-48, 758, -3956, 23973}, {-80, 905, -4235, 21254}, {-99, 972, -4222, 18278}, {-107, 967, -3957, 15143},
+                                           {-103, 896, -3487, 11950}, {-91, 773, -2865, 8798}, {-71, 611, -2143, 5784}, {-46, 425, -1375, 2996}};
+static const int16_t up2_hq_0[3] = {1746, 14986, 39083 - 65536}, up2_hq_1[3] = {6854, 25769, 55542 - 65536};
 
 int orc_resampler_size(void) { return (int)sizeof(OrcResampler); }
 
-int orc_resampler_init(OrcResampler *S, int fs_in, int fs_out) {
+static int rate_id(int fs) { return fs == 8000 ? 0 : fs == 12000 ? 1 : fs == 16000 ? 2 : fs == 24000 ? 3 : fs == 48000 ? 4 : -1; }
+
+/* silk_resampler_init (resampler.c:77-180) */
+int orc_resampler_init2(OrcResampler *S, int fs_in, int fs_out, int for_enc) {
   static const int8_t delay_enc[5][3] = {{6, 0, 3}, {0, 7, 3}, {0, 1, 10}, {0, 2, 6}, {18, 10, 12}};
-  int ri = fs_in == 8000 ? 0 : fs_in == 12000 ? 1 : fs_in == 16000 ? 2 : fs_in == 24000 ? 3 : fs_in == 48000 ? 4 : -1;
-  int ro = fs_out == 8000 ? 0 : fs_out == 12000 ? 1 : fs_out == 16000 ? 2 : -1;
+  static const int8_t delay_dec[3][5] = {{4, 0, 2, 0, 0}, {0, 9, 4, 7, 4}, {0, 3, 12, 7, 7}};
+  const int ri = rate_id(fs_in), ro = rate_id(fs_out);
+  int up2x = 0;
   memset(S, 0, sizeof(*S));
   if (ri < 0 || ro < 0) return -1;
-  S->input_delay = delay_enc[ri][ro];
+  if (for_enc) { if (ro > 2) return -1; S->input_delay = delay_enc[ri][ro]; }
+  else { if (ri > 2) return -1; S->input_delay = delay_dec[ri][ro]; }
   S->fs_in_khz = fs_in / 1000;
   S->fs_out_khz = fs_out / 1000;
   S->batch = S->fs_in_khz * 10;
-  if (fs_out * 2 == fs_in) { S->fir_order = 24; S->coefs = coefs_1_2; }
-  else if (fs_out * 3 == fs_in) { S->fir_order = 36; S->coefs = coefs_1_3; }
-  else if (fs_out * 4 == fs_in) { S->fir_order = 36; S->coefs = coefs_1_4; }
-  else if (fs_out * 6 == fs_in) { S->fir_order = 36; S->coefs = coefs_1_6; }
-  else return -1;
-  S->inv_ratio_q16 = (int32_t)((((int64_t)fs_in << 14) / fs_out) << 2);
-  while ((int32_t)(((int64_t)S->inv_ratio_q16 * fs_out) >> 16) < fs_in) S->inv_ratio_q16++;
+  if (fs_out > fs_in) {
+    if (fs_out == 2 * fs_in) S->function = ORC_RS_UP2;
+    else { S->function = ORC_RS_IIR_FIR; up2x = 1; }
+  } else if (fs_out < fs_in) {
+    S->function = ORC_RS_DOWN;
+    S->fir_fracs = 1;
+    if (fs_out * 4 == fs_in * 3) { S->fir_fracs = 3; S->fir_order = 18; S->coefs = coefs_3_4; }
+    else if (fs_out * 3 == fs_in * 2) { S->fir_fracs = 2; S->fir_order = 18; S->coefs = coefs_2_3; }
+    else if (fs_out * 2 == fs_in) { S->fir_order = 24; S->coefs = coefs_1_2; }
+    else if (fs_out * 3 == fs_in) { S->fir_order = 36; S->coefs = coefs_1_3; }
+    else if (fs_out * 4 == fs_in) { S->fir_order = 36; S->coefs = coefs_1_4; }
+    else if (fs_out * 6 == fs_in) { S->fir_order = 36; S->coefs = coefs_1_6; }
+    else return -1;
+  } else S->function = ORC_RS_COPY;
+  S->inv_ratio_q16 = (int32_t)((((int64_t)fs_in << (14 + up2x)) / fs_out) << 2);
+  while ((int32_t)(((int64_t)S->inv_ratio_q16 * fs_out) >> 16) < (fs_in << up2x)) S->inv_ratio_q16++;
   return 0;
 }
+int orc_resampler_init(OrcResampler *S, int fs_in, int fs_out) { return orc_resampler_init2(S, fs_in, fs_out, 1); }
 
+/* resampler_private_down_FIR.c:36-193 with resampler_private_AR2.c:36-55 */
 static void down_fir(OrcResampler *S, int16_t *out, const int16_t *in, int inLen) {
   int32_t buf[480 + 36];
   const int16_t *fir = &S->coefs[2];
@@ -69,7 +96,7 @@ static void down_fir(OrcResampler *S, int16_t *out, const int16_t *in, int inLen
   memcpy(buf, S->sFIR, order * sizeof(int32_t));
   for (;;) {
     nIn = inLen < S->batch ? inLen : S->batch;
-    for (k = 0; k < nIn; k++) { /* AR2, resampler_private_AR2.c:36-55 */
+    for (k = 0; k < nIn; k++) {
       int32_t o = S->sIIR[0] + (int32_t)((uint32_t)(int32_t)in[k] << 8);
       buf[order + k] = o;
       o = (int32_t)((uint32_t)o << 2);
@@ -80,8 +107,17 @@ static void down_fir(OrcResampler *S, int16_t *out, const int16_t *in, int inLen
       int32_t idx, maxi = nIn << 16;
       for (idx = 0; idx < maxi; idx += S->inv_ratio_q16) {
         const int32_t *b = buf + (idx >> 16);
-        int32_t r = smulwb(b[0] + b[order - 1], fir[0]);
-        for (k = 1; k < half; k++) r = smlawb(r, b[k] + b[order - 1 - k], fir[k]);
+        int32_t r;
+        if (order == 18) {   /* interpolating phases: the fractional position picks one of fir_fracs coefficient sets, mirrored for the second half */
+          const int ind = smulwb(idx & 0xFFFF, S->fir_fracs);
+          const int16_t *c0 = &fir[9 * ind], *c1 = &fir[9 * (S->fir_fracs - 1 - ind)];
+          r = smulwb(b[0], c0[0]);
+          for (k = 1; k < 9; k++) r = smlawb(r, b[k], c0[k]);
+          for (k = 0; k < 9; k++) r = smlawb(r, b[17 - k], c1[k]);
+        } else {
+          r = smulwb(b[0] + b[order - 1], fir[0]);
+          for (k = 1; k < half; k++) r = smlawb(r, b[k] + b[order - 1 - k], fir[k]);
+        }
         *out++ = sat16(rshift_round(r, 6));
       }
     }
@@ -93,12 +129,66 @@ static void down_fir(OrcResampler *S, int16_t *out, const int16_t *in, int inLen
   memcpy(S->sFIR, &buf[nIn], order * sizeof(int32_t));
 }
 
+/* resampler_private_up2_HQ.c:36-103: three all-pass sections per output phase, state in Q10 */
+static void up2_hq(int32_t *S, int16_t *out, const int16_t *in, int len) {
+  int k;
+  for (k = 0; k < len; k++) {
+    const int32_t in32 = (int32_t)((uint32_t)(int32_t)in[k] << 10);
+    int32_t Y, X, o1, o2;
+    Y = in32 - S[0]; X = smulwb(Y, up2_hq_0[0]); o1 = S[0] + X; S[0] = in32 + X;
+    Y = o1 - S[1]; X = smulwb(Y, up2_hq_0[1]); o2 = S[1] + X; S[1] = o1 + X;
+    Y = o2 - S[2]; X = smlawb(Y, Y, up2_hq_0[2]); o1 = S[2] + X; S[2] = o2 + X;
+    out[2 * k] = sat16(rshift_round(o1, 10));
+    Y = in32 - S[3]; X = smulwb(Y, up2_hq_1[0]); o1 = S[3] + X; S[3] = in32 + X;
+    Y = o1 - S[4]; X = smulwb(Y, up2_hq_1[1]); o2 = S[4] + X; S[4] = o1 + X;
+    Y = o2 - S[5]; X = smlawb(Y, Y, up2_hq_1[2]); o1 = S[5] + X; S[5] = o2 + X;
+    out[2 * k + 1] = sat16(rshift_round(o1, 10));
+  }
+}
+
+/* resampler_private_IIR_FIR.c:35-107 */
+static void iir_fir(OrcResampler *S, int16_t *out, const int16_t *in, int inLen) {
+  int16_t buf[2 * 480 + 8];
+  int16_t *sfir16 = (int16_t *)S->sFIR;
+  int nIn, k;
+  memcpy(buf, sfir16, 8 * sizeof(int16_t));
+  for (;;) {
+    int32_t idx, maxi;
+    nIn = inLen < S->batch ? inLen : S->batch;
+    up2_hq(S->sIIR, &buf[8], in, nIn);
+    maxi = nIn << 17;
+    for (idx = 0; idx < maxi; idx += S->inv_ratio_q16) {
+      const int t = smulwb(idx & 0xFFFF, 12);
+      const int16_t *b = &buf[idx >> 16];
+      int32_t r = (int32_t)b[0] * frac_fir_12[t][0];
+      for (k = 1; k < 4; k++) r += (int32_t)b[k] * frac_fir_12[t][k];
+      for (k = 0; k < 4; k++) r += (int32_t)b[4 + k] * frac_fir_12[11 - t][3 - k];
+      *out++ = sat16(rshift_round(r, 15));
+    }
+    in += nIn;
+    inLen -= nIn;
+    if (inLen > 0) memcpy(buf, &buf[nIn << 1], 8 * sizeof(int16_t));
+    else break;
+  }
+  memcpy(sfir16, &buf[nIn << 1], 8 * sizeof(int16_t));
+}
+
+static void rs_run(OrcResampler *S, int16_t *out, const int16_t *in, int inLen) {
+  if (S->function == ORC_RS_UP2) up2_hq(S->sIIR, out, in, inLen);
+  else if (S->function == ORC_RS_IIR_FIR) iir_fir(S, out, in, inLen);
+  else down_fir(S, out, in, inLen);
+}
 /* silk_resampler(), resampler.c:183-219 */
 void orc_resampler_process(OrcResampler *S, int16_t *out, const int16_t *in, int inLen) {
   int nSamples = S->fs_in_khz - S->input_delay;
   memcpy(&S->delayBuf[S->input_delay], in, nSamples * sizeof(int16_t));
-  down_fir(S, out, S->delayBuf, S->fs_in_khz);
-  down_fir(S, &out[S->fs_out_khz], &in[nSamples], inLen - S->fs_in_khz);
+  if (S->function == ORC_RS_COPY) {
+    memcpy(out, S->delayBuf, S->fs_in_khz * sizeof(int16_t));
+    memcpy(&out[S->fs_out_khz], &in[nSamples], (inLen - S->fs_in_khz) * sizeof(int16_t));
+  } else {
+    rs_run(S, out, S->delayBuf, S->fs_in_khz);
+    rs_run(S, &out[S->fs_out_khz], &in[nSamples], inLen - S->fs_in_khz);
+  }
   memcpy(S->delayBuf, &in[inLen - S->input_delay], S->input_delay * sizeof(int16_t));
 }
 

@@ -7,6 +7,7 @@
 #include <string.h>
 #include "../../opus_b200/csrc/celt_types.h"
 #include "../../opus_b200/csrc/celt_ops.cuh"
+#include "../../opus_b200/csrc/celt_mdct_fast.cuh"
 
 using namespace ob;
 
@@ -15,7 +16,28 @@ static void xcorr_entry(void *a) { const XcorrParams &p = *(const XcorrParams *)
 static void rot_entry(void *a) { const VqParams &p = *(const VqParams *)a; exp_rotation_warp(p, block_id(), dyn_smem()); }
 static void search_entry(void *a) { const VqParams &p = *(const VqParams *)a; pvq_search_warp(p, block_id(), dyn_smem()); }
 
+// the register-FFT long-block MDCT (celt_mdct_fast.cuh): one warp, two transforms; shared memory = tables + 2 inputs + 2 point buffers
+struct FastMdctArgs { const float *in; float *out; int n; };
+static void mdct_fast_entry(void *a) {
+  const FastMdctArgs &p = *(const FastMdctArgs *)a;
+  unsigned char *sm = dyn_smem();
+  Mdct480Tabs *t = (Mdct480Tabs *)sm;
+  float *in0 = (float *)(sm + sizeof(Mdct480Tabs)), *in1 = in0 + 1080;
+  cpx *F0 = (cpx *)(in1 + 1080), *F1 = F0 + kF480Cpx;
+  const int lane = lane_id(), pair = block_id();
+  for (int i = lane; i < 960; i += 32) { t->trig[i] = ob_mdct_trig[i]; t->tw[i] = ob_fft_tw[i]; }
+  for (int i = lane; i < 120; i += 32) t->window[i] = ob_window[i];
+  for (int i = lane; i < 480; i += 32) t->bitrev[i] = ob_fft_bitrev480[i];
+  const bool two = 2 * pair + 1 < p.n;
+  for (int i = lane; i < 1080; i += 32) { in0[i] = p.in[(size_t)(2 * pair) * 1080 + i]; if (two) in1[i] = p.in[(size_t)(2 * pair + 1) * 1080 + i]; }
+  wsync();
+  mdct480_forward_pair(in0, two ? in1 : nullptr, F0, F1, t, p.out + (size_t)(2 * pair) * 960, p.out + (size_t)(2 * pair + 1) * 960, lane);
+}
 extern "C" {
+void emu_mdct_forward_fast(const float *in, float *out, int n) {
+  FastMdctArgs p = {in, out, n};
+  emu_launch(mdct_fast_entry, &p, (n + 1) / 2, 32, sizeof(Mdct480Tabs) + 2 * 1080 * sizeof(float) + 2 * kF480Cpx * sizeof(cpx) + 64);
+}
 void emu_mdct_forward(const float *in, float *out, int n, int LM, int transient) {
   MdctFwdParams p;
   p.in = in; p.out = out; p.n_items = n; p.in_stride = (120 << LM) + 120; p.out_stride = 120 << LM; p.LM = LM; p.transient = transient;
@@ -57,17 +79,16 @@ void emu_silk_lpc(int16_t *out, const int16_t *in, const int16_t *B, int n, int 
   emu_launch(lpc_entry, &p, (n + 31) / 32, 32, 0);
 }
 int emu_silk_resampler_state_size(void) { return (int)sizeof(ObSilkResamplerState); }
-// 48 kHz -> 16 kHz only (the emulator test's configuration)
-void emu_silk_resampler_48_16(void *state, const int16_t *in, int16_t *out, int n, int in_len) {
-  static const int16_t c13[20] = {16102, -15162, -13, 0, 20, 26, 5, -31, -43, -4, 65, 90, 7, -157, -248, -44, 593, 1583, 2612, 3271};
+// any rate pair silk_resampler_init accepts (silk_resampler_setup is the product's own host-side setup)
+int emu_silk_resampler(void *state, const int16_t *in, int16_t *out, int n, int in_len, int fs_in, int fs_out, int for_enc) {
   SilkResamplerParams p;
-  memset(&p, 0, sizeof(p));
-  p.state = (ObSilkResamplerState *)state; p.in = in; p.out = out; p.n_streams = n; p.in_len = in_len; p.out_len = in_len / 3;
-  p.fir_order = 36; p.fs_in_khz = 48; p.fs_out_khz = 16; p.input_delay = 12; p.batch = 480;
-  p.inv_ratio_q16 = (int32_t)((((int64_t)48000 << 14) / 16000) << 2);
-  while ((int32_t)(((int64_t)p.inv_ratio_q16 * 16000) >> 16) < 48000) p.inv_ratio_q16++;
-  for (int i = 0; i < 20; i++) p.coefs[i] = c13[i];
+  if (silk_resampler_setup(p, fs_in, fs_out, for_enc)) return -1;
+  p.state = (ObSilkResamplerState *)state; p.in = in; p.out = out; p.n_streams = n; p.in_len = in_len; p.out_len = in_len / (fs_in / 1000) * (fs_out / 1000);
   emu_launch(rs_entry, &p, (n + 31) / 32, 32, 0);
+  return 0;
+}
+void emu_silk_resampler_48_16(void *state, const int16_t *in, int16_t *out, int n, int in_len) {
+  emu_silk_resampler(state, in, out, n, in_len, 48000, 16000, 1);
 }
 }
 

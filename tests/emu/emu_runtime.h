@@ -28,6 +28,10 @@
 #define OB_RESTRICT __restrict__
 #define OB_KERNEL(name, ...) void name(__VA_ARGS__)
 
+// the CUDA vector types the kernel sources use for 8- and 16-byte accesses
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+
 namespace ob {
 struct EmuState {
   ucontext_t sched;

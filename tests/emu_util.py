@@ -17,10 +17,18 @@ def build_emu(name='emu_decode'):
     out = os.path.join(EMU_DIR, 'lib%s.so' % name)
     deps = [src, os.path.join(EMU_DIR, 'emu_runtime.h')] + [
         os.path.join(util.ROOT, 'opus_b200', 'csrc', f) for f in os.listdir(os.path.join(util.ROOT, 'opus_b200', 'csrc'))]
-    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+    def fresh():
+        return os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps)
+    if fresh():
         return out
-    subprocess.check_call(['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-unknown-pragmas',
-                           '-I' + os.path.join(util.ROOT, 'opus_b200', 'csrc'), '-I' + EMU_DIR, '-o', out, src])
+    import fcntl
+    with open(out + '.lock', 'w') as lk:   # pytest-xdist workers: one builds, the others wait and then find it fresh
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if not fresh():
+            tmp = out + '.tmp.%d' % os.getpid()
+            subprocess.check_call(['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-unknown-pragmas',
+                                   '-I' + os.path.join(util.ROOT, 'opus_b200', 'csrc'), '-I' + EMU_DIR, '-o', tmp, src])
+            os.replace(tmp, out)
     return out
 
 

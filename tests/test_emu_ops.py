@@ -26,6 +26,20 @@ def test_emu_mdct_forward(LM, transient):
         assert np.array_equal(got[i], want)
 
 
+@pytest.mark.parametrize('n', [1, 2, 5])
+def test_emu_mdct_forward_register_fft(n):
+    """celt_mdct_fast.cuh (long block, FFT in registers, two transforms per warp) is bit-identical to the oracle's clt_mdct_forward"""
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(50 + n)
+    x = (rng.standard_normal((n, 1080)) * 1000).astype(np.float32)
+    got = np.zeros((n, 960), np.float32)
+    E.emu_mdct_forward_fast(_f(x), _f(got), n)
+    for i in range(n):
+        want = np.zeros(960, np.float32)
+        O.orc_mdct_forward(_f(x[i]), _f(want), 3, 0)
+        assert np.array_equal(got[i], want), (i, int((got[i] != want).sum()))
+
+
 def test_emu_pitch_xcorr():
     E, O = emu_util.load_emu_ops(), util.load_oracle()
     rng = np.random.default_rng(6)
@@ -91,6 +105,28 @@ def test_emu_silk_lpc_and_resampler():
         w = np.zeros(320, np.int16)
         for i in range(n):
             O.orc_resampler_process(os_[i], _f(w), _f(xin[i]), 960)
+            assert np.array_equal(got[i], w), (fr, i)
+
+
+@pytest.mark.parametrize('fs_in,fs_out,for_enc', [(48000, 12000, 1), (16000, 12000, 1), (24000, 16000, 1), (12000, 8000, 1), (16000, 16000, 1), (8000, 16000, 0),
+                                                  (8000, 48000, 0), (12000, 48000, 0), (16000, 24000, 0), (12000, 16000, 0), (16000, 48000, 0), (8000, 12000, 0)])
+def test_emu_silk_resampler_rate_pairs(fs_in, fs_out, for_enc):
+    """the device resampler on the emulator for the four resampler functions (copy, 2x all-pass, up-sampling + FIR interpolation, down-FIR with
+    1 / 2 / 3 phases), three 20 ms frames with carried state, bit-exact against the oracle"""
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(fs_in // 1000 + fs_out // 100)
+    n, n_in, n_out = 33, fs_in // 50, fs_out // 50
+    st = np.zeros(n * E.emu_silk_resampler_state_size(), np.uint8)
+    os_ = [ctypes.create_string_buffer(O.orc_resampler_size()) for _ in range(n)]
+    for s in os_:
+        assert O.orc_resampler_init2(s, fs_in, fs_out, for_enc) == 0
+    for fr in range(3):
+        xin = rng.integers(-32768, 32768, size=(n, n_in)).astype(np.int16)
+        got = np.zeros((n, n_out), np.int16)
+        assert E.emu_silk_resampler(_f(st), _f(xin), _f(got), n, n_in, fs_in, fs_out, for_enc) == 0
+        w = np.zeros(n_out, np.int16)
+        for i in range(n):
+            O.orc_resampler_process(os_[i], _f(w), _f(xin[i]), n_in)
             assert np.array_equal(got[i], w), (fr, i)
 
 

@@ -22,6 +22,27 @@ def ops():
     o.close()
 
 
+@pytest.mark.parametrize('n', [1, 2, 77, 4001, 40000])
+def test_mdct_forward_long_block_kernel(ops, n):
+    """the long-block kernel (ob_mdct_forward_tma: FFT in registers, inputs and tables staged by cp.async.bulk, persistent CTAs, two transforms
+    per warp) against the oracle, and bit for bit against the general shared-memory kernel on every item"""
+    O = util.load_oracle()
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((n, 1080)) * rng.choice([1.0, 300.0, 32768.0], size=(n, 1))).astype(np.float32)
+    got = ops.mdct_forward(x, 3, 0)
+    want = np.zeros(960, np.float32)
+    for i in sorted(set(list(range(0, n, max(1, n // 40))) + [n - 1])):
+        O.orc_mdct_forward(_f(x[i]), _f(want), 3, 0)
+        assert np.array_equal(got[i], want), i
+    import subprocess, sys, os, tempfile
+    with tempfile.TemporaryDirectory() as d:   # the general kernel in a fresh process
+        np.save(os.path.join(d, 'x.npy'), x)
+        code = ("import sys, numpy as np; sys.path.insert(0, %r); import opus_b200; o = opus_b200.Ops(); "
+                "np.save(%r, o.mdct_forward(np.load(%r), 3, 0))" % (util.ROOT, os.path.join(d, 'y.npy'), os.path.join(d, 'x.npy')))
+        subprocess.check_call([sys.executable, '-c', code], env=dict(os.environ, OPUSB200_MDCT_SMEM_FFT='1'))
+        assert np.array_equal(got, np.load(os.path.join(d, 'y.npy')))
+
+
 @pytest.mark.parametrize('LM,transient', [(3, 0), (3, 1), (2, 0), (2, 1), (1, 0), (1, 1), (0, 0)])
 def test_mdct_forward(ops, LM, transient):
     O = util.load_oracle()
@@ -138,6 +159,37 @@ def test_silk_resampler(ops, fs_in, fs_out):
             O.orc_resampler_process(orc[i], _f(w), _f(x[i]), n_in)
             assert np.array_equal(got[i], w), (fr, i)
     rs.close()
+
+
+@pytest.mark.parametrize('fs_in,fs_out,for_enc', [(i, o, 1) for i in (8000, 12000, 16000, 24000, 48000) for o in (8000, 12000, 16000)] +
+                         [(i, o, 0) for i in (8000, 12000, 16000) for o in (8000, 12000, 16000, 24000, 48000)])
+def test_silk_resampler_every_rate_pair(ops, fs_in, fs_out, for_enc):
+    """all 30 (rate pair, direction) combinations silk_resampler_init accepts, 4 frames of 20 ms with carried state, bit-exact vs the oracle"""
+    O = util.load_oracle()
+    rng = np.random.default_rng(fs_in + fs_out + for_enc)
+    n = 333
+    rs = ops.silk_resampler(n, fs_in, fs_out, bool(for_enc))
+    check = list(range(0, n, 37))
+    orc = {i: ctypes.create_string_buffer(O.orc_resampler_size()) for i in check}
+    for s in orc.values():
+        assert O.orc_resampler_init2(s, fs_in, fs_out, for_enc) == 0
+    n_in, n_out = fs_in // 50, fs_out // 50
+    for fr in range(4):
+        x = rng.integers(-32768, 32768, size=(n, n_in)).astype(np.int16)
+        got = rs.process(x)
+        assert got.shape == (n, n_out)
+        w = np.zeros(n_out, np.int16)
+        for i in check:
+            O.orc_resampler_process(orc[i], _f(w), _f(x[i]), n_in)
+            assert np.array_equal(got[i], w), (fr, i)
+    rs.close()
+
+
+def test_silk_resampler_rejects_other_pairs(ops):
+    import opus_b200
+    for a, b, e in [(48000, 24000, 1), (24000, 48000, 0), (44100, 16000, 1), (16000, 44100, 0)]:
+        with pytest.raises(opus_b200.capi.OpusB200Error):
+            ops.silk_resampler(4, a, b, bool(e))
 
 
 def test_silk_burg_and_autocorr(ops):

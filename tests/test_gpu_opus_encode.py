@@ -117,3 +117,30 @@ def test_unsupported_calls_fail_loudly():
     r = L.opusb200_opus_encode(enc._h, _p(pcm), 1920, _p(pk), 1276, 1276, _p(nb))   # 40 ms: multi-frame packets are not built
     assert r == capi.OPUS_UNIMPLEMENTED, r
     enc.close()
+
+
+def test_submit_wait_matches_the_synchronous_call():
+    """opusb200_opus_encode_submit / _wait (double-buffered staging, transfers on their own streams) gives the packets of opusb200_opus_encode,
+    call for call, with two calls in flight"""
+    import opus_b200
+    n, fs, nf = 96, 960, 6
+    rng = np.random.default_rng(5)
+    t = np.arange(nf * fs)[None, :, None] / 48000.0
+    x = (8000 * np.sin(2 * np.pi * (200 + 30 * np.arange(n)[:, None, None]) * t * (1 + np.arange(2)[None, None, :])) + rng.normal(0, 900, (n, nf * fs, 2))).astype(np.int16)
+    a = opus_b200.OpusEncoderBatch(n, channels=2, bitrate=64000, vbr=True, complexity=10)
+    b = opus_b200.OpusEncoderBatch(n, channels=2, bitrate=64000, vbr=True, complexity=10)
+    want = [a.encode(np.ascontiguousarray(x[:, k * fs:(k + 1) * fs].reshape(n, -1)), 1276) for k in range(nf)]
+    pcm = [np.ascontiguousarray(x[:, k * fs:(k + 1) * fs].reshape(n, -1)) for k in range(nf)]
+    pk = [np.zeros((n, 1276), np.uint8) for _ in range(nf)]
+    nb = [np.zeros(n, np.int32) for _ in range(nf)]
+    for k in range(nf):
+        b.submit(pcm[k], pk[k], nb[k], 1276, fs)
+        if k % 2 == 1:
+            b.wait()
+    b.wait()
+    for k in range(nf):
+        assert (nb[k] == want[k][1]).all()
+        for s in range(n):
+            assert (pk[k][s, :nb[k][s]] == want[k][0][s, :nb[k][s]]).all()
+    assert (a.final_range() == b.final_range()).all()
+    a.close(); b.close()

@@ -48,6 +48,34 @@ def test_resampler_down(fs_in, fs_out):
         assert np.array_equal(a, b), frame
 
 
+ENC_PAIRS = [(i, o, 1) for i in (8000, 12000, 16000, 24000, 48000) for o in (8000, 12000, 16000)]
+DEC_PAIRS = [(i, o, 0) for i in (8000, 12000, 16000) for o in (8000, 12000, 16000, 24000, 48000)]
+
+
+@pytest.mark.parametrize('fs_in,fs_out,for_enc', ENC_PAIRS + DEC_PAIRS)
+@pytest.mark.parametrize('ms', [20, 10])
+def test_resampler_every_rate_pair(fs_in, fs_out, for_enc, ms):
+    """every pair silk_resampler_init accepts, both directions: copy, 2x all-pass up-sampling, up-sampling with FIR interpolation, down-sampling with
+    1 / 2 / 3 interpolation phases; 12 consecutive frames with the carried state"""
+    R, O = util.load_ref('c'), util.load_oracle()
+    rs = ctypes.create_string_buffer(R.refh_resampler_size())
+    os_ = ctypes.create_string_buffer(O.orc_resampler_size())
+    assert R.silk_resampler_init(rs, fs_in, fs_out, for_enc) == 0
+    assert O.orc_resampler_init2(os_, fs_in, fs_out, for_enc) == 0
+    rng = np.random.default_rng(fs_in // 1000 + fs_out + for_enc)
+    n_in, n_out = fs_in * ms // 1000, fs_out * ms // 1000
+    t = 0
+    for frame in range(12):
+        amp = [3000, 32767, 10][frame % 3]
+        x = (amp * np.sin(2 * np.pi * 440 * (np.arange(n_in) + t) / fs_in) + rng.integers(-amp // 4 - 1, amp // 4 + 1, size=n_in)).clip(-32768, 32767).astype(np.int16)
+        t += n_in
+        a = np.zeros(n_out, np.int16)
+        b = np.zeros(n_out, np.int16)
+        R.silk_resampler(rs, _p(a), _p(x), n_in)
+        O.orc_resampler_process(os_, _p(b), _p(x), n_in)
+        assert np.array_equal(a, b), frame
+
+
 @pytest.mark.parametrize('subfr,nb,D', [(96, 4, 16), (96, 2, 16), (50, 4, 10), (56, 4, 16)])
 def test_burg_and_autocorr(subfr, nb, D):
     R, O = util.load_ref('c'), util.load_oracle()
