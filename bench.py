@@ -729,6 +729,38 @@ def run_gpu_encode(args, rank, world, local_rank):
     }
 
 
+def run_mdct_kernel(local_rank, n_transforms=131072, reps=20):
+    """The one kernel of the path that IS bound by HBM (the standalone transform): the long-block forward MDCT
+    (ob_mdct_forward_tma), timed with CUDA events on the library stream; algorithmic bytes = 4320 in + 3840 out per transform, working set 1.07 GB."""
+    import torch
+    import opus_b200
+    dev = torch.device('cuda', local_rank)
+    ops = opus_b200.Ops(local_rank)
+    L = ops._L
+    stream = torch.cuda.ExternalStream(L.opusb200_ctx_cuda_stream(ops._h), device=dev)
+    x = torch.randn((n_transforms, 1080), dtype=torch.float32, device=dev)
+    o = torch.empty((n_transforms, 960), dtype=torch.float32, device=dev)
+    fn = lambda: L.opusb200_mdct_forward(ops._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(o.data_ptr()), n_transforms, 3, 0, 1)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            assert fn() == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ops.close()
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    peak = float(json.load(open(peaks_path))['hbm_gbs']) if os.path.exists(peaks_path) else 6650.0
+    gbs = n_transforms * 8160 / (ms * 1e-3) / 1e9
+    return {'kernel': 'ob_mdct_forward_tma', 'bound': 'hbm', 'what': 'clt_mdct_forward, 960-point long block, %d transforms per launch (65 536 stereo frames)' % n_transforms,
+            'ms_per_launch': ms, 'algorithmic_bytes_per_launch': n_transforms * 8160, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+            'launches_timed': reps, 'l2': 'working set 1.07 GB per launch exceeds the 126 MB L2'}
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     line = None
     if args.workload in ('both', 'decode'):
@@ -736,6 +768,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     enc = run_gpu_encode(args, rank, world, local_rank) if args.workload in ('both', 'encode') else None
     if rank != 0:
         return
+    if line is not None:
+        try:
+            line['mdct_kernel_roofline'] = run_mdct_kernel(local_rank)
+        except Exception as ex:   # diagnostic block: never take the bench line down
+            line['mdct_kernel_roofline'] = {'error': repr(ex)}
     if line is None:   # --workload encode: the encode block is the line
         line = enc
     elif enc is not None:

@@ -366,6 +366,34 @@ void opusb200_fargan_destroy(OpusB200Fargan *f);
 int opusb200_fargan_cont(OpusB200Fargan *f, const float *pcm0, const float *features0, int on_device);
 int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const float *features, int on_device);
 
+/* ---- Neural packet-loss concealment (dnn/lpcnet_plc.c, struct LPCNetPLCState of dnn/lpcnet_private.h:48-71): n streams that take their update /
+ * conceal calls in lockstep (the recovery decode of a batch: every stream conceals frame k in the same call), each with its own FEC / DRED feature
+ * queue, predictor state and PCM history.
+ *   lpcnet_plc_init + load (dnn/lpcnet_plc.c:58-86)   opusb200_lpcnet_plc_create   plc_layers = the 6 LinearLayers of the generated PLCModel struct
+ *                                                       (plc_data.h order: dense_in, dense_out, gru1 input / recurrent, gru2 input / recurrent),
+ *                                                       fargan_layers = the 20 of FARGAN (as opusb200_fargan_create); sizes checked like init_plcmodel
+ *   lpcnet_plc_reset (:44)                             opusb200_lpcnet_plc_reset
+ *   lpcnet_plc_fec_add (:88) / _fec_clear (:98)        opusb200_lpcnet_plc_fec_add (features [n][20]; have [n]: 1 = vector, 0 = the NULL call = a gap,
+ *                                                       < 0 = no call for this stream; have == NULL: vectors for all) / _fec_clear
+ *   lpcnet_plc_update (:143)                           opusb200_lpcnet_plc_update   (pcm [n][160] int16: a good frame of every stream)
+ *   lpcnet_plc_conceal (:156)                          opusb200_lpcnet_plc_conceal  (pcm [n][160] int16 out): compute_plc_pred / get_fec_or_pred /
+ *                                                       the attenuation table / queue_features / fargan_cont / fargan_synthesize_int
+ * PCM and state are bit-identical to the reference's lpcnet_plc.c (generic C branch of dnn/vec.h) given the same model and calls.
+ * Not built: the analysis of the decoded history that the first concealed frame after GOOD audio runs (burg_cepstral_analysis,
+ * lpcnet_compute_single_frame_features_float: dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c); such a conceal call returns OPUSB200_UNIMPLEMENTED and
+ * changes nothing.  Concealment from a reset state (with or without queued features) is complete. ---- */
+typedef struct OpusB200LpcnetPlc OpusB200LpcnetPlc;
+int opusb200_lpcnet_plc_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *plc_layers, int n_plc_layers, const OpusB200LinearLayer *fargan_layers,
+                               int n_fargan_layers, int su_bias, int n_streams, OpusB200LpcnetPlc **out);
+void opusb200_lpcnet_plc_destroy(OpusB200LpcnetPlc *plc);
+int opusb200_lpcnet_plc_reset(OpusB200LpcnetPlc *plc);
+int opusb200_lpcnet_plc_fec_add(OpusB200LpcnetPlc *plc, const float *features, const int32_t *have, int on_device);
+int opusb200_lpcnet_plc_fec_clear(OpusB200LpcnetPlc *plc);
+int opusb200_lpcnet_plc_update(OpusB200LpcnetPlc *plc, const int16_t *pcm, int on_device);
+int opusb200_lpcnet_plc_conceal(OpusB200LpcnetPlc *plc, int16_t *pcm, int on_device);
+/* parity aid: features [n][20], cont_features [n][100], gru1 / gru2 [n][128], counters [n][4] = fec_read_pos, fec_fill_pos, fec_skip, loss_count */
+int opusb200_lpcnet_plc_get_state(OpusB200LpcnetPlc *plc, float *features, float *cont_features, float *gru1, float *gru2, int32_t *counters);
+
 /* ---- DRED decoder network (dnn/dred_rdovae_dec.h:50-52, dnn/dred_rdovae_dec.c:44-145) -------------------------------------------
  * layers: the 29 LinearLayers of the generated `RDOVAEDec` struct (dred_rdovae_dec_data.h) in declaration order (init_rdovaedec).
  * opusb200_dred_decode_all = DRED_rdovae_decode_all(model, features, state, latents, nb_latents, arch) for n streams at once:

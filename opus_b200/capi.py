@@ -37,6 +37,8 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_nnet_compute_gru', 'opusb200_nnet_compute_glu', 'opusb200_nnet_compute_conv1d',
            'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d',
            'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize',
+           'opusb200_lpcnet_plc_create', 'opusb200_lpcnet_plc_destroy', 'opusb200_lpcnet_plc_reset', 'opusb200_lpcnet_plc_fec_add', 'opusb200_lpcnet_plc_fec_clear',
+           'opusb200_lpcnet_plc_update', 'opusb200_lpcnet_plc_conceal', 'opusb200_lpcnet_plc_get_state',
            'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free',
            'opusb200_opus_encoder_create', 'opusb200_opus_encoder_destroy', 'opusb200_opus_encoder_reset', 'opusb200_opus_encoder_ctl',
            'opusb200_opus_encode', 'opusb200_opus_encode_float', 'opusb200_opus_encode_device', 'opusb200_opus_encode_submit', 'opusb200_opus_encode_wait', 'opusb200_opus_encoder_get_final_range',
@@ -172,6 +174,15 @@ def lib():
         L.opusb200_fargan_destroy.restype = None
         L.opusb200_fargan_cont.argtypes = [vp, vp, vp, ci]
         L.opusb200_fargan_synthesize.argtypes = [vp, vp, vp, ci]
+        L.opusb200_lpcnet_plc_create.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_lpcnet_plc_destroy.argtypes = [vp]
+        L.opusb200_lpcnet_plc_destroy.restype = None
+        L.opusb200_lpcnet_plc_reset.argtypes = [vp]
+        L.opusb200_lpcnet_plc_fec_add.argtypes = [vp, vp, vp, ci]
+        L.opusb200_lpcnet_plc_fec_clear.argtypes = [vp]
+        L.opusb200_lpcnet_plc_update.argtypes = [vp, vp, ci]
+        L.opusb200_lpcnet_plc_conceal.argtypes = [vp, vp, ci]
+        L.opusb200_lpcnet_plc_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
         L.opusb200_decoder_set_pipelined.argtypes = [vp, ci]
         L.opusb200_decoder_join.argtypes = [vp]
         L.opusb200_decode_submit.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, vp]

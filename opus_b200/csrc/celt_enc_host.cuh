@@ -126,6 +126,8 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->in_buf, sizeof(float) * n * channels * OB_CH_IN_STRIDE));
   OB_CUDA(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   e->an_smem_set = 0;
+  // the analysis kernel lives on shared memory (25 KB per stream): ask for the largest carveout whatever the launch's own size is
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int r = opusb200_encoder_reset(e);
   if (r != OPUSB200_OK) return r;
   OB_CUDA(cudaStreamSynchronize(e->stream));

@@ -59,7 +59,7 @@ struct PfSig { const float *ring; const float *frame; int head; };
 OB_DEV float pf_at(const PfSig &p, int j) { return j < kPfMaxPeriod ? p.ring[(p.head + j) & (kPfMaxPeriod - 1)] : p.frame[j - kPfMaxPeriod]; }
 struct PfDecision { int pf_on, pitch_index, qg, tapset; float gain1; };
 
-OB_DEVNI float pf_dot(const float *x, const float *y, int n) {   // index order; unrolled so the loads run ahead of the serial sum
+OB_DEV float pf_dot(const float *x, const float *y, int n) {   // index order; unrolled so the loads run ahead of the serial sum
   float s = 0.f;
 #pragma unroll 8
   for (int i = 0; i < n; i++) s = s + x[i] * y[i];
@@ -108,7 +108,7 @@ OB_DEVNI void pf_find_best_pitch(const float *__restrict__ xcorr, const float *_
 OB_DEV float pf_pitch_gain(float xy, float xx, float yy) { return xy / (float)sqrt((double)(1 + xx * yy)); }
 
 // comb_filter with distinct input/output (celt/celt.c:238-313), elementwise over `tid`; x[k] = pre[base + k]
-OB_DEVNI void pf_comb(float *y, const PfSig &x, int base, int T0, int T1, int N, float g0, float g1, int tapset0, int tapset1, int overlap, int tid,
+OB_DEV void pf_comb(float *y, const PfSig &x, int base, int T0, int T1, int N, float g0, float g1, int tapset0, int tapset1, int overlap, int tid,
                     int nth) {
   if (g0 == 0 && g1 == 0) {
     for (int i = tid; i < N; i += nth) y[i] = pf_at(x, base + i);

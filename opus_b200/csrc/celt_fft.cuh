@@ -109,7 +109,7 @@ template <int P, int M, int M2, int FS, int NFFT> OB_DEV void fft_stage(cpx *F, 
 // All B blocks' FFTs of size nfft = 480>>shift, in place on digit-reversed data, stage order and per-butterfly arithmetic of
 // celt/kiss_fft.c:52-313,562-613 (factors of celt/static_modes_float.h: 480 = 4.2.4.3.5, 240 = 4.4.3.5, 120 = 4.2.3.5, 60 = 4.3.5, executed
 // from the innermost factor out).  F: B consecutive arrays of nfft cpx.
-OB_DEVNI void fft_stages(cpx *F, int shift, int nblk, int lane) {
+OB_DEV void fft_stages(cpx *F, int shift, int nblk, int lane) {
   if (shift == 0) {
     fft_stage<4, 1, 4, 120, 480>(F, nblk, lane);
     fft_stage<2, 4, 8, 60, 480>(F, nblk, lane);

@@ -27,7 +27,7 @@ struct MdctWS { float in[OB_MAXN + OB_OVERLAP + 8]; float f2[OB_MAXN]; };
 
 // forward MDCT of the B*N+overlap samples already in ws->in; coefficients go to `o` (HBM, or ws->in itself: the time
 // samples are dead once the pre-rotation has run)
-OB_DEVNI void mdct_forward_from_ws(MdctWS *ws, int LM, int transient, float *o, int lane) {
+OB_DEV void mdct_forward_from_ws(MdctWS *ws, int LM, int transient, float *o, int lane) {
   const int nblk = transient ? 1 << LM : 1, NB = transient ? OB_SHORT_N : OB_SHORT_N << LM;
   const int shift = transient ? 3 : 3 - LM;
   const int N2 = NB, N4 = NB >> 1, nfft = N4, overlap = OB_OVERLAP;

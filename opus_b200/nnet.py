@@ -186,6 +186,61 @@ class Fargan:
             pass
 
 
+class LpcnetPlc:
+    """Batched neural packet-loss concealment (dnn/lpcnet_plc.c): `plc_layers` = ctypes array of the 6 LinearLayers of PLCModel, `fargan_layers` = the
+    20 of FARGAN.  The streams take update / conceal calls in lockstep; each has its own FEC / DRED feature queue."""
+    NB_FEATURES, FRAME_SIZE = 20, 160
+
+    def __init__(self, ops, plc_layers, fargan_layers, n_streams, su_bias=False):
+        self._L, self.n = ops._L, n_streams
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_lpcnet_plc_create(ops._h, plc_layers, 6, fargan_layers, 20, 1 if su_bias else 0, n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_lpcnet_plc_create')
+        self._h = h
+
+    def _chk(self, r, what):
+        if r != 0:
+            raise capi.OpusB200Error(r, what)
+
+    def reset(self):
+        self._chk(self._L.opusb200_lpcnet_plc_reset(self._h), 'opusb200_lpcnet_plc_reset')
+
+    def fec_add(self, features, have=None):
+        """features [n][20]; have [n] int: 1 = this stream's vector, 0 = lpcnet_plc_fec_add(NULL), < 0 = no call (None: vectors for all)"""
+        features = np.ascontiguousarray(features, np.float32).reshape(self.n, self.NB_FEATURES)
+        hv = None if have is None else np.ascontiguousarray(have, np.int32)
+        self._chk(self._L.opusb200_lpcnet_plc_fec_add(self._h, _p(features), _p(hv) if hv is not None else None, 0), 'opusb200_lpcnet_plc_fec_add')
+
+    def fec_clear(self):
+        self._chk(self._L.opusb200_lpcnet_plc_fec_clear(self._h), 'opusb200_lpcnet_plc_fec_clear')
+
+    def update(self, pcm):
+        pcm = np.ascontiguousarray(pcm, np.int16).reshape(self.n, self.FRAME_SIZE)
+        self._chk(self._L.opusb200_lpcnet_plc_update(self._h, _p(pcm), 0), 'opusb200_lpcnet_plc_update')
+
+    def conceal(self):
+        out = np.empty((self.n, self.FRAME_SIZE), np.int16)
+        self._chk(self._L.opusb200_lpcnet_plc_conceal(self._h, _p(out), 0), 'opusb200_lpcnet_plc_conceal')
+        return out
+
+    def state(self):
+        bufs = [np.zeros((self.n, k), np.float32) for k in (20, 100, 128, 128)] + [np.zeros((self.n, 4), np.int32)]
+        self._chk(self._L.opusb200_lpcnet_plc_get_state(self._h, *[_p(b) for b in bufs]), 'opusb200_lpcnet_plc_get_state')
+        return bufs
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_lpcnet_plc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DredDecoder:
     """Batched DRED decoder network (dnn/dred_rdovae_dec.h): `layers` = ctypes array of the 29 LinearLayers of RDOVAEDec."""
 

@@ -65,3 +65,50 @@ void refh_dred_decode_all(float *features, const float *state, const float *late
   dred_ready();
   DRED_rdovae_decode_all(&g_dred_model, features, state, latents, nb_latents, 0);
 }
+
+/* ---- neural packet-loss concealment (dnn/lpcnet_plc.c, compiled unmodified with the generated random-weight plc_data.c) ----
+ * The history analysis of the first concealed frame after good audio (burg_cepstral_analysis, lpcnet_compute_single_frame_features_float:
+ * dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c) is NOT part of this build: the stand-ins below abort, and the tests drive the sequences that
+ * never reach them (concealment from a reset state, with or without FEC/DRED features: lpcnet_plc.c:160 loops zero times there). */
+#include <stdio.h>
+#include <stdlib.h>
+#include "lpcnet_private.h"
+int lpcnet_encoder_init(LPCNetEncState *st) { memset(st, 0, sizeof(*st)); return 0; }
+int lpcnet_encoder_load_model(LPCNetEncState *st, const void *data, int len) { (void)st; (void)data; (void)len; return 0; }
+void burg_cepstral_analysis(float *ceps, const float *x) { (void)ceps; (void)x; fprintf(stderr, "fargan_harness: burg_cepstral_analysis is not built\n"); abort(); }
+int lpcnet_compute_single_frame_features_float(LPCNetEncState *st, const float *pcm, float features[NB_TOTAL_FEATURES], int arch) {
+  (void)st; (void)pcm; (void)features; (void)arch;
+  fprintf(stderr, "fargan_harness: lpcnet_compute_single_frame_features_float is not built\n"); abort();
+}
+int refh_plc_state_size(void) { return (int)sizeof(LPCNetPLCState); }
+int refh_plc_init(LPCNetPLCState *st) { return lpcnet_plc_init(st); }
+void refh_plc_reset(LPCNetPLCState *st) { lpcnet_plc_reset(st); }
+void refh_plc_fec_add(LPCNetPLCState *st, const float *features) { lpcnet_plc_fec_add(st, features); }
+void refh_plc_fec_clear(LPCNetPLCState *st) { lpcnet_plc_fec_clear(st); }
+int refh_plc_conceal(LPCNetPLCState *st, opus_int16 *pcm) { return lpcnet_plc_conceal(st, pcm); }
+int refh_plc_nlayers(void) { return (int)(sizeof(PLCModel) / sizeof(LinearLayer)); }
+void refh_plc_layer(LPCNetPLCState *st, int i, const void **ptrs, int *dims) {
+  const LinearLayer *l = (const LinearLayer *)&st->model + i;
+  ptrs[0] = l->bias; ptrs[1] = l->subias; ptrs[2] = l->weights; ptrs[3] = l->float_weights; ptrs[4] = l->weights_idx; ptrs[5] = l->diag;
+  ptrs[6] = l->scale;
+  dims[0] = l->nb_inputs; dims[1] = l->nb_outputs;
+}
+/* the FARGAN model inside the PLC state (the same generated weights as refh_fargan_*) */
+void refh_plc_fargan_layer(LPCNetPLCState *st, int i, const void **ptrs, int *dims) { refh_fargan_layer(&st->fargan, i, ptrs, dims); }
+void refh_plc_get_state(const LPCNetPLCState *st, float *features, float *cont_features, float *gru1, float *gru2, float *pcm, int *ints) {
+  memcpy(features, st->features, sizeof(float) * NB_FEATURES);
+  memcpy(cont_features, st->cont_features, sizeof(st->cont_features));
+  memcpy(gru1, st->plc_net.gru1_state, sizeof(st->plc_net.gru1_state));
+  memcpy(gru2, st->plc_net.gru2_state, sizeof(st->plc_net.gru2_state));
+  memcpy(pcm, st->pcm, sizeof(st->pcm));
+  ints[0] = st->blend; ints[1] = st->loss_count; ints[2] = st->fec_read_pos; ints[3] = st->fec_fill_pos; ints[4] = st->fec_skip;
+  ints[5] = st->analysis_pos; ints[6] = st->predict_pos; ints[7] = st->analysis_gap;
+}
+/* compute_plc_pred alone (static in lpcnet_plc.c): the same four calls on the model, for the layer-level pin */
+void refh_plc_pred(LPCNetPLCState *st, float *out, const float *in) {
+  float tmp[PLC_DENSE_IN_OUT_SIZE];
+  compute_generic_dense(&st->model.plc_dense_in, tmp, in, ACTIVATION_TANH, 0);
+  compute_generic_gru(&st->model.plc_gru1_input, &st->model.plc_gru1_recurrent, st->plc_net.gru1_state, tmp, 0);
+  compute_generic_gru(&st->model.plc_gru2_input, &st->model.plc_gru2_recurrent, st->plc_net.gru2_state, st->plc_net.gru1_state, 0);
+  compute_generic_dense(&st->model.plc_dense_out, out, st->plc_net.gru2_state, ACTIVATION_LINEAR, 0);
+}

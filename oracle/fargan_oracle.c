@@ -159,3 +159,141 @@ void orc_fargan_get_state(const OrcFargan *st, float *pitch_buf, float *cond_con
   memcpy(g3, st->gru3_state, sizeof(st->gru3_state));
   misc[0] = st->deemph_mem; misc[1] = (float)st->last_period;
 }
+
+/* ---- neural packet-loss concealment: dnn/lpcnet_plc.c:44-207 (lpcnet_plc_reset, lpcnet_plc_fec_add / _clear, compute_plc_pred, get_fec_or_pred,
+ * queue_features, lpcnet_plc_update, lpcnet_plc_conceal) on top of the FARGAN restatement above.  The predictor is the 6 LinearLayers of the
+ * generated PLCModel struct (plc_data.h): dense_in, dense_out, gru1 input / recurrent, gru2 input / recurrent.
+ * NOT restated: the history analysis a first concealed frame runs when good audio came before it (burg_cepstral_analysis,
+ * lpcnet_compute_single_frame_features_float: dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c — SURVEY 8(f).4); orc_plc_conceal returns -1 and
+ * leaves the state alone when a call would need it.  Pinned against the reference's own lpcnet_plc.c compiled with seeded random weights
+ * (oracle/_ref/libfargan_ref.so, gen_plc_weights.py) by tests/test_plc_oracle_vs_ref.py. ---- */
+#define PLC_MAX_FEC 104            /* dnn/lpcnet_private.h:15 */
+#define CONT_VECTORS 5
+#define NB_TOTAL_FEATURES 36       /* dnn/lpcnet.h:36 */
+#define PLC_BUF_SIZE ((CONT_VECTORS + 10) * FRAME)
+#define PLC_IN (2 * NB_BANDS + NB_FEATURES + 1)
+enum { P_DENSE_IN, P_DENSE_OUT, P_GRU1_IN, P_GRU1_REC, P_GRU2_IN, P_GRU2_REC, P_COUNT };
+typedef struct { float gru1[128], gru2[128]; } OrcPlcNet;
+typedef struct {
+  OrcLinear l[P_COUNT];
+  OrcFargan fargan;
+  float fec[PLC_MAX_FEC][NB_FEATURES];
+  int analysis_gap, fec_read_pos, fec_fill_pos, fec_skip, analysis_pos, predict_pos;
+  float pcm[PLC_BUF_SIZE];
+  int blend;
+  float features[NB_TOTAL_FEATURES];
+  float cont_features[CONT_VECTORS * NB_FEATURES];
+  int loss_count;
+  OrcPlcNet net, bak[2];
+} OrcPlc;
+int orc_plc_size(void) { return (int)sizeof(OrcPlc); }
+void orc_plc_reset(OrcPlc *st) { /* lpcnet_plc.c:44-56: everything from `fec` on, the model and the vocoder stay */
+  memset(st->fec, 0, sizeof(*st) - ((char *)st->fec - (char *)st));
+  st->blend = 0;
+  st->loss_count = 0;
+  st->analysis_gap = 1;
+  st->analysis_pos = PLC_BUF_SIZE;
+  st->predict_pos = PLC_BUF_SIZE;
+}
+void orc_plc_init(OrcPlc *st, const OrcLinear *plc_layers, const OrcLinear *fargan_layers) {
+  memset(st, 0, sizeof(*st));
+  memcpy(st->l, plc_layers, sizeof(st->l));
+  orc_fargan_init(&st->fargan, fargan_layers);
+  orc_plc_reset(st);
+}
+void orc_plc_fec_add(OrcPlc *st, const float *features) { /* :88-96 */
+  if (!features) { st->fec_skip++; return; }
+  memcpy(st->fec[st->fec_fill_pos], features, NB_FEATURES * sizeof(float));
+  st->fec_fill_pos++;
+}
+void orc_plc_fec_clear(OrcPlc *st) { st->fec_read_pos = st->fec_fill_pos = st->fec_skip = 0; }
+/* compute_plc_pred, :103-113 */
+void orc_plc_pred(OrcPlc *st, float *out, const float *in) {
+  float tmp[128];
+  orc_nnet_dense(&st->l[P_DENSE_IN], tmp, in, ACT_TANH);
+  orc_nnet_gru(&st->l[P_GRU1_IN], &st->l[P_GRU1_REC], st->net.gru1, tmp);
+  orc_nnet_gru(&st->l[P_GRU2_IN], &st->l[P_GRU2_REC], st->net.gru2, st->net.gru1);
+  orc_nnet_dense(&st->l[P_DENSE_OUT], out, st->net.gru2, ACT_LINEAR);
+}
+static int plc_fec_or_pred(OrcPlc *st, float *out) { /* :115-133 */
+  float in[PLC_IN];
+  memset(in, 0, sizeof(in));
+  if (st->fec_read_pos != st->fec_fill_pos && st->fec_skip == 0) {
+    float discard[NB_FEATURES];
+    memcpy(out, st->fec[st->fec_read_pos], NB_FEATURES * sizeof(float));
+    st->fec_read_pos++;
+    memcpy(&in[2 * NB_BANDS], out, NB_FEATURES * sizeof(float));
+    in[2 * NB_BANDS + NB_FEATURES] = -1;
+    orc_plc_pred(st, discard, in);
+    return 1;
+  }
+  orc_plc_pred(st, out, in);
+  if (st->fec_skip > 0) st->fec_skip--;
+  return 0;
+}
+static void plc_queue(OrcPlc *st, const float *features) { /* :135-138 */
+  memmove(&st->cont_features[0], &st->cont_features[NB_FEATURES], (CONT_VECTORS - 1) * NB_FEATURES * sizeof(float));
+  memcpy(&st->cont_features[(CONT_VECTORS - 1) * NB_FEATURES], features, NB_FEATURES * sizeof(float));
+}
+int orc_plc_update(OrcPlc *st, const int16_t *pcm) { /* :143-153 */
+  int i;
+  if (st->analysis_pos - FRAME >= 0) st->analysis_pos -= FRAME;
+  else st->analysis_gap = 1;
+  if (st->predict_pos - FRAME >= 0) st->predict_pos -= FRAME;
+  memmove(st->pcm, &st->pcm[FRAME], (PLC_BUF_SIZE - FRAME) * sizeof(float));
+  for (i = 0; i < FRAME; i++) st->pcm[PLC_BUF_SIZE - FRAME + i] = (1.f / 32768.f) * pcm[i];
+  st->loss_count = 0;
+  st->blend = 0;
+  return 0;
+}
+int orc_plc_conceal(OrcPlc *st, int16_t *pcm) { /* :156-207 */
+  static const float att_table[10] = {0, 0, -.2, -.2, -.4, -.4, -.8, -.8, -1.6, -1.6};
+  float fpcm[FRAME];
+  int i;
+  if (st->blend == 0) {
+    if (st->analysis_pos + FRAME <= PLC_BUF_SIZE) return -1; /* the history analysis (:160-177) is not restated */
+    st->net = st->bak[0];
+    st->bak[0] = st->bak[1];
+    st->bak[1] = st->net;
+    plc_fec_or_pred(st, st->features);
+    plc_queue(st, st->features);
+    st->bak[0] = st->bak[1];
+    st->bak[1] = st->net;
+    plc_fec_or_pred(st, st->features);
+    plc_queue(st, st->features);
+    orc_fargan_cont(&st->fargan, &st->pcm[PLC_BUF_SIZE - CONT_SAMPLES], st->cont_features);
+    st->analysis_gap = 0;
+  }
+  st->bak[0] = st->bak[1];
+  st->bak[1] = st->net;
+  if (plc_fec_or_pred(st, st->features)) st->loss_count = 0;
+  else st->loss_count++;
+  {
+    const float a = st->loss_count >= 10 ? st->features[0] + att_table[9] - 2 * (st->loss_count - 9) : st->features[0] + att_table[st->loss_count];
+    st->features[0] = a > -15 ? a : -15;
+  }
+  orc_fargan_synthesize(&st->fargan, fpcm, st->features);
+  for (i = 0; i < FRAME; i++) { /* fargan_synthesize_int, dnn/fargan.c:219-225 */
+    float v = 32768.f * fpcm[i];
+    v = v > -32767 ? v : -32767;
+    v = v < 32767 ? v : 32767;
+    pcm[i] = (int16_t)(int)floor(.5 + v);
+  }
+  plc_queue(st, st->features);
+  if (st->analysis_pos - FRAME >= 0) st->analysis_pos -= FRAME;
+  else st->analysis_gap = 1;
+  st->predict_pos = PLC_BUF_SIZE;
+  memmove(st->pcm, &st->pcm[FRAME], (PLC_BUF_SIZE - FRAME) * sizeof(float));
+  for (i = 0; i < FRAME; i++) st->pcm[PLC_BUF_SIZE - FRAME + i] = (1.f / 32768.f) * pcm[i];
+  st->blend = 1;
+  return 0;
+}
+void orc_plc_get_state(const OrcPlc *st, float *features, float *cont_features, float *gru1, float *gru2, float *pcm, int *ints) {
+  memcpy(features, st->features, sizeof(float) * NB_FEATURES);
+  memcpy(cont_features, st->cont_features, sizeof(st->cont_features));
+  memcpy(gru1, st->net.gru1, sizeof(st->net.gru1));
+  memcpy(gru2, st->net.gru2, sizeof(st->net.gru2));
+  memcpy(pcm, st->pcm, sizeof(st->pcm));
+  ints[0] = st->blend; ints[1] = st->loss_count; ints[2] = st->fec_read_pos; ints[3] = st->fec_fill_pos; ints[4] = st->fec_skip;
+  ints[5] = st->analysis_pos; ints[6] = st->predict_pos; ints[7] = st->analysis_gap;
+}

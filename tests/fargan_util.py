@@ -101,3 +101,69 @@ def make_dred_inputs(seed, nb_latents, latent_dim, state_dim):
     latents = (0.5 * rng.standard_normal((nb_latents, latent_dim + 1))).astype(np.float32)
     latents[:, -1] = rng.uniform(0, 1, nb_latents)     # the quantiser-level input the encoder appends
     return state, latents
+
+
+class RefPlc:
+    """the reference's neural packet-loss concealment (dnn/lpcnet_plc.c) with the seeded random predictor of oracle/gen_plc_weights.py and the
+    FARGAN model above; the history analysis is not part of the build (oracle/fargan_harness.c): only sequences without good audio before a loss"""
+    NL = 6
+
+    def __init__(self, L):
+        self.L = L
+        self.st = np.zeros(L.refh_plc_state_size() + 64, np.uint8)
+        assert L.refh_plc_init(vp(self.st)) == 0
+
+    def _layers(self, fn, count):
+        arr = (util.CLinear * count)()
+        ptrs, dims = (ctypes.c_void_p * 7)(), (ctypes.c_int * 2)()
+        shapes = []
+        for i in range(count):
+            fn(vp(self.st), i, ptrs, dims)
+            for k, name in enumerate(('bias', 'subias', 'weights', 'float_weights', 'weights_idx', 'diag', 'scale')):
+                setattr(arr[i], name, ptrs[k])
+            arr[i].nb_inputs, arr[i].nb_outputs = dims[0], dims[1]
+            shapes.append((dims[0], dims[1]))
+        return arr, shapes
+
+    def layers(self):
+        return self._layers(self.L.refh_plc_layer, self.NL)
+
+    def fargan_layers(self):
+        return self._layers(self.L.refh_plc_fargan_layer, NL)
+
+    def fec_add(self, features):
+        self.L.refh_plc_fec_add(vp(self.st), vp(np.ascontiguousarray(features, np.float32)) if features is not None else None)
+
+    def fec_clear(self):
+        self.L.refh_plc_fec_clear(vp(self.st))
+
+    def reset(self):
+        self.L.refh_plc_reset(vp(self.st))
+
+    def conceal(self):
+        pcm = np.zeros(160, np.int16)
+        assert self.L.refh_plc_conceal(vp(self.st), vp(pcm)) == 0
+        return pcm
+
+    def state(self):
+        bufs = [np.zeros(k, np.float32) for k in (20, 100, 128, 128, 2400)] + [np.zeros(8, np.int32)]
+        self.L.refh_plc_get_state(vp(self.st), *[vp(b) for b in bufs])
+        return bufs
+
+
+def plc_schedule(seed, nframes):
+    """a DRED-style recovery: which of the concealed frames get a feature vector (lpcnet_plc_fec_add) and which a gap (fec_add(NULL));
+    returns a list of per-frame actions ('feat', vector) / ('skip',) / ('none',) applied BEFORE the conceal call of that frame"""
+    rng = np.random.default_rng(seed)
+    acts = []
+    for t in range(nframes):
+        u = rng.random()
+        if u < 0.55:
+            f = (0.5 * rng.standard_normal(20)).astype(np.float32)
+            f[18] = rng.uniform(-1.4, 1.4)
+            acts.append(('feat', f))
+        elif u < 0.7:
+            acts.append(('skip',))
+        else:
+            acts.append(('none',))
+    return acts

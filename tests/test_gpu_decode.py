@@ -2,7 +2,8 @@
 libopus_b200.so), against the oracle / the compiled reference / the golden fixtures.
 Bar: range decoder final state bit-exact on every packet; PCM within +-1 LSB at 16 bits
 (BASELINE.json north_star) — the only float differences are re-association in warp scans
-and tree reductions (measured: < 2e-5 of full scale)."""
+and tree reductions (measured on a B200, round 2: 3.0e-7 of full scale over every decode test of this file, profiles/r02_gpu_test_worst_errors.json;
+the float bound below is 2e-6)."""
 import numpy as np
 import pytest
 
@@ -12,7 +13,7 @@ from test_oracle_golden import golden_cases
 
 pytestmark = pytest.mark.gpu
 
-FLOAT_TOL = 2e-5
+FLOAT_TOL = 2e-6
 
 
 def _check(got, ref):

@@ -1,12 +1,15 @@
 """Packet-loss concealment of the CUDA decode path through the C ABI (len == 0 = lost packet, as opus_decode(data = NULL)), against the
 reference decoder fed the same loss pattern.  Final range bit-exact (0 on a lost frame), sample counts equal.
 
-PCM bound on streams with losses: 5e-3 of full scale.  The concealment re-estimates a 24th-order LPC from the decoded history, which
-amplifies the differences of the frames before the loss by a factor of 100-200 (measured): the reference's own C and SSE/AVX2 builds
-agree to 1e-7 without loss and differ by up to 4.7e-4 on the same concealed streams; the emulated device code (2e-6 from the reference
-on decoded frames) by 4e-4; the GPU (up to 2e-5 on decoded frames: libdevice exp2/cos) by 2.4e-3 on the worst stream here (a tonal
-signal losing every other packet).  tests/test_emu_plc.py checks the concealment arithmetic itself exactly, by giving the emulated
-device code the oracle's history before each lost frame.  Streams without loss in the same batch keep the +-1 LSB bar."""
+PCM bound on streams with losses.  The concealment re-estimates a 24th-order LPC from the decoded history and extrapolates with it, which amplifies
+last-bit differences of the frames before the loss by orders of magnitude: the reference's own C and SSE/AVX2 builds agree to 1e-7 without loss and
+differ by up to 2.9e-2 of full scale (median 1.6e-4) on the concealed streams of this file.  Measured on a B200 (tools/plc_gap_probe.py,
+profiles/r02_plc_gap_probe.txt, 214 lossy streams): the GPU is within 3.0e-7 of the reference's C build on every decoded frame, departs only at
+lost frames, and on every stream stays CLOSER to the C build than 2.6x the C-vs-SIMD difference of that same stream (max 3.5e-3 where the
+reference's two builds are 1.3e-2 apart; median 4.7e-5).  The bar is therefore per stream: max(5e-4, 4 x the reference's own C-vs-SIMD spread on
+that stream); without the SIMD build at hand (it travels with oracle/_ref) the old absolute 5e-3 applies.  tests/test_emu_plc.py checks the
+concealment arithmetic itself exactly, by giving the emulated device code the oracle's history before each lost frame.  Streams without loss in
+the same batch keep the +-1 LSB bar (2e-6 in float)."""
 import numpy as np
 import pytest
 
@@ -15,7 +18,8 @@ from conftest import note_err
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')]
 
-PLC_TOL = 5e-3
+PLC_TOL = 5e-3      # absolute fallback (no SIMD build of the reference at hand) and the bound of the int16 / DTX tests
+PLC_ABS, PLC_REL = 5e-4, 4.0   # per stream: max(PLC_ABS, PLC_REL x |ref_simd - ref_c|max of that stream)
 
 
 def _streams(n, ch, fs, nfr, seed):
@@ -30,8 +34,8 @@ def _streams(n, ch, fs, nfr, seed):
     return pk, sz
 
 
-def _ref_decode(Fs, ch, fsd, pk, sz):
-    L = util.load_ref('c')
+def _ref_decode(Fs, ch, fsd, pk, sz, kind='c'):
+    L = util.load_ref(kind)
     T = len(sz)
     p, z = np.ascontiguousarray(pk), np.ascontiguousarray(sz, np.int32)
     ref, rr = np.zeros((T * fsd, ch), np.float32), np.zeros(T, np.uint32)
@@ -68,17 +72,22 @@ def test_random_loss_patterns_vs_reference(ch, fs48, Fs):
         err = float(np.abs(outs[s] - ref).max())
         if not lost[s].any():
             note_err('plc_clean_stream', err)
-            assert err < 2e-5, (s, err)
+            assert err < 2e-6, (s, err)
             assert np.abs(util.to_int16(outs[s]).astype(np.int32) - util.to_int16(ref).astype(np.int32)).max() <= 1
         else:
-            assert err < PLC_TOL, (s, err)
+            if util.ref_available('simd'):
+                spread = float(np.abs(_ref_decode(Fs, ch, fsd, pk[s], sz[s], 'simd')[0] - ref).max())
+                note_err('plc_concealed_over_reference_spread', err / max(spread, PLC_ABS / PLC_REL))
+                assert err < max(PLC_ABS, PLC_REL * spread), (s, err, spread)
+            else:
+                assert err < PLC_TOL, (s, err)
             note_err('plc_concealed_stream', err)
             worst = max(worst, err)
             # frames before the first loss are ordinary decoded frames
             t0 = int(np.argmax(lost[s]))
             if t0:
                 note_err('plc_before_first_loss', np.abs(outs[s][:t0 * fsd] - ref[:t0 * fsd]).max())
-                assert np.abs(outs[s][:t0 * fsd] - ref[:t0 * fsd]).max() < 2e-5
+                assert np.abs(outs[s][:t0 * fsd] - ref[:t0 * fsd]).max() < 2e-6
     print('worst concealed-stream error', worst)
 
 
