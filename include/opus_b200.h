@@ -168,6 +168,25 @@ void opusb200_silk_resampler_destroy(OpusB200SilkResampler *rs);
 int opusb200_silk_resampler_reset(OpusB200SilkResampler *rs);
 int opusb200_silk_resampler_process(OpusB200SilkResampler *rs, const int16_t *in, int16_t *out, int in_len, int on_device);
 
+/* ---- A batch of range encoders (ec_enc, celt/entcode.h:62-88, celt/entenc.c) whose state stays on the device between calls, and the SILK
+ * excitation coder on it: silk_encode_pulses (silk/encode_pulses.c:59) with silk_shell_encoder (silk/shell_coder.c:78) and silk_encode_signs
+ * (silk/code_signs.c:40) — the first slice of the SILK frame pipeline.  Other symbols can be coded in front of and behind the
+ * pulses in the same coder (opusb200_range_encoder_icdf = ec_enc_icdf), as silk_encode_indices does ahead of them in
+ * silk_encode_frame_FLP (silk/float/encode_frame_FLP.c:290-300).  Bit-exact: buffer bytes, ec_tell_frac and final range.
+ *   ec_enc_init   celt/entenc.c:108   opusb200_range_encoder_init(re, storage)
+ *   ec_enc_icdf   celt/entenc.c:195   opusb200_range_encoder_icdf(re, symbols[n] (< 0: skip the stream), icdf, icdf_len <= 64, ftb, on_device)
+ *   silk_encode_pulses                opusb200_silk_encode_pulses(re, signal_type[n], quant_offset_type[n], pulses [n][pulses_stride] int8,
+ *                                     pulses_stride, frame_length (80..320: a multiple of 16, or 120), on_device)
+ *   ec_tell_frac + ec_enc_done :256   opusb200_range_encoder_done(re, bytes [n][storage], tell_frac[n], final_range[n], error[n]) ---- */
+typedef struct OpusB200RangeEncoder OpusB200RangeEncoder;
+int opusb200_range_encoder_create(OpusB200Ctx *ctx, int n_streams, int buf_bytes, OpusB200RangeEncoder **out);
+void opusb200_range_encoder_destroy(OpusB200RangeEncoder *re);
+int opusb200_range_encoder_init(OpusB200RangeEncoder *re, int storage);
+int opusb200_range_encoder_icdf(OpusB200RangeEncoder *re, const int32_t *symbols, const unsigned char *icdf, int icdf_len, int ftb, int on_device);
+int opusb200_silk_encode_pulses(OpusB200RangeEncoder *re, const int32_t *signal_type, const int32_t *quant_offset_type, const int8_t *pulses,
+                                int pulses_stride, int frame_length, int on_device);
+int opusb200_range_encoder_done(OpusB200RangeEncoder *re, unsigned char *bytes, uint32_t *tell_frac, uint32_t *final_range, int32_t *error);
+
 /* silk_burg_modified_FLP (silk/float/burg_modified_FLP.c:39; called from find_LPC_FLP.c:60,65):
  * x [n_items][nb_subfr*subfr_length] -> A [n_items][D] prediction coefficients, nrg [n_items] residual energy. */
 int opusb200_silk_burg_modified(OpusB200Ctx *ctx, float *A, float *nrg, const float *x, float minInvGain, int n_items,

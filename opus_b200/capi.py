@@ -28,7 +28,8 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_encoder_get_final_range', 'opusb200_encoder_sync', 'opusb200_encoder_cuda_stream', 'opusb200_encoder_launch_count',
            'opusb200_celt_analysis_destroy', 'opusb200_celt_analysis_reset', 'opusb200_celt_analysis_process', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
            'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
-           'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create', 'opusb200_silk_resampler_create_ex',
+           'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create', 'opusb200_silk_resampler_create_ex', 'opusb200_range_encoder_create', 'opusb200_range_encoder_destroy',
+           'opusb200_range_encoder_init', 'opusb200_range_encoder_icdf', 'opusb200_silk_encode_pulses', 'opusb200_range_encoder_done',
            'opusb200_silk_resampler_destroy', 'opusb200_silk_resampler_reset', 'opusb200_silk_resampler_process',
            'opusb200_silk_burg_modified', 'opusb200_silk_autocorrelation',
            'opusb200_silk_nsq_create', 'opusb200_silk_nsq_destroy', 'opusb200_silk_nsq_reset', 'opusb200_silk_nsq_process',
@@ -140,6 +141,13 @@ def lib():
         L.opusb200_silk_lpc_analysis_filter.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci]
         L.opusb200_silk_resampler_create.argtypes = [vp, ci, i32, i32, ctypes.POINTER(vp)]
         L.opusb200_silk_resampler_create_ex.argtypes = [vp, ci, i32, i32, ci, ctypes.POINTER(vp)]
+        L.opusb200_range_encoder_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_range_encoder_destroy.argtypes = [vp]
+        L.opusb200_range_encoder_destroy.restype = None
+        L.opusb200_range_encoder_init.argtypes = [vp, ci]
+        L.opusb200_range_encoder_icdf.argtypes = [vp, vp, vp, ci, ci, ci]
+        L.opusb200_silk_encode_pulses.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+        L.opusb200_range_encoder_done.argtypes = [vp, vp, vp, vp, vp]
         L.opusb200_silk_resampler_destroy.argtypes = [vp]
         L.opusb200_silk_resampler_destroy.restype = None
         L.opusb200_silk_resampler_reset.argtypes = [vp]

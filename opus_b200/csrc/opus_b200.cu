@@ -1202,5 +1202,6 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 #include "fargan_host.cuh"
 #include "dred_host.cuh"
 #include "plc_host.cuh"
+#include "silk_coder_host.cuh"
 #include "celt_enc_host.cuh"
 #include "opus_enc_host.cuh"

@@ -1,0 +1,136 @@
+// silk_coder_host.cuh — kernel entry points and C ABI of the batched range-encoder object and the SILK excitation coder on it
+// (silk_coder.cuh).  Included at the end of opus_b200.cu.
+#pragma once
+#include "silk_coder.cuh"
+
+extern "C" __global__ void __launch_bounds__(128) ob_silk_coder_init(ob::SilkCoderParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_coder_init_thread(p, s);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_silk_coder_icdf(ob::SilkCoderParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_coder_icdf_thread(p, s);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_silk_encode_pulses(ob::SilkCoderParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_encode_pulses_thread(p, s);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_silk_coder_done(ob::SilkCoderParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_coder_done_thread(p, s);
+}
+
+struct OpusB200RangeEncoder {
+  OpusB200Ctx *ctx;
+  int n, stride, storage;
+  ob::ObRangeEncState *state;
+  unsigned char *buf;
+  int32_t *d_i32[2];
+  int8_t *d_pulses; size_t d_pulses_cap;
+  uint32_t *d_u32[2];
+};
+static ob::SilkCoderParams rc_params(OpusB200RangeEncoder *r) {
+  ob::SilkCoderParams p;
+  memset(&p, 0, sizeof(p));
+  p.state = r->state; p.buf = r->buf; p.n = r->n; p.buf_stride = r->stride; p.storage = r->storage;
+  return p;
+}
+// n independent range encoders (ec_enc, celt/entcode.h:62-88) with buffers of buf_bytes (<= 1275 + slack) each
+extern "C" int opusb200_range_encoder_create(OpusB200Ctx *c, int n_streams, int buf_bytes, OpusB200RangeEncoder **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  if (!c || n_streams <= 0 || buf_bytes < 2 || buf_bytes > 4096) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200RangeEncoder *r = new (std::nothrow) OpusB200RangeEncoder;
+  if (!r) return OPUSB200_ALLOC_FAIL;
+  memset(r, 0, sizeof(*r));
+  r->ctx = c; r->n = n_streams; r->stride = (buf_bytes + 15) & ~15; r->storage = buf_bytes;
+  const size_t n = (size_t)n_streams;
+  if (cudaMalloc(&r->state, sizeof(ob::ObRangeEncState) * n) != cudaSuccess || cudaMalloc(&r->buf, n * r->stride) != cudaSuccess ||
+      cudaMalloc(&r->d_i32[0], sizeof(int32_t) * n) != cudaSuccess || cudaMalloc(&r->d_i32[1], sizeof(int32_t) * n) != cudaSuccess ||
+      cudaMalloc(&r->d_u32[0], sizeof(uint32_t) * n) != cudaSuccess || cudaMalloc(&r->d_u32[1], sizeof(uint32_t) * n) != cudaSuccess) {
+    cudaFree(r->state); cudaFree(r->buf); cudaFree(r->d_i32[0]); cudaFree(r->d_i32[1]); cudaFree(r->d_u32[0]); cudaFree(r->d_u32[1]);
+    delete r;
+    return OPUSB200_ALLOC_FAIL;
+  }
+  *out = r;
+  return OPUSB200_OK;
+}
+extern "C" void opusb200_range_encoder_destroy(OpusB200RangeEncoder *r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->state); cudaFree(r->buf); cudaFree(r->d_i32[0]); cudaFree(r->d_i32[1]); cudaFree(r->d_u32[0]); cudaFree(r->d_u32[1]); cudaFree(r->d_pulses);
+  delete r;
+}
+// ec_enc_init(&enc, buf, storage) for every stream (celt/entenc.c:108)
+extern "C" int opusb200_range_encoder_init(OpusB200RangeEncoder *r, int storage) {
+  if (!r || storage < 2 || storage > r->stride) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(r->ctx->device));
+  r->storage = storage;
+  ob::SilkCoderParams p = rc_params(r);
+  ob_silk_coder_init<<<(r->n + 127) / 128, 128, 0, r->ctx->stream>>>(p);
+  r->ctx->launches++;
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+// ec_enc_icdf(&enc, symbols[s], icdf, ftb) (celt/entenc.c:195): one symbol per stream from a table of icdf_len bytes; symbols[s] < 0 skips the stream
+extern "C" int opusb200_range_encoder_icdf(OpusB200RangeEncoder *r, const int32_t *symbols, const unsigned char *icdf, int icdf_len, int ftb, int on_device) {
+  if (!r || !symbols || !icdf || icdf_len <= 0 || icdf_len > 64 || ftb < 1 || ftb > 15) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = r->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkCoderParams p = rc_params(r);
+  memcpy(p.icdf, icdf, icdf_len);
+  p.ftb = ftb; p.symbols = symbols;
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(r->d_i32[0], symbols, sizeof(int32_t) * (size_t)r->n, cudaMemcpyHostToDevice, c->stream));
+    p.symbols = r->d_i32[0];
+  }
+  ob_silk_coder_icdf<<<(r->n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+// silk_encode_pulses(&enc, signalType, quantOffsetType, pulses, frame_length) (silk/encode_pulses.c:59): signal_type / quant_offset_type [n],
+// pulses [n][pulses_stride] int8 (pulses_stride >= frame_length), frame_length 80..320 (a multiple of 16, or 120 = 10 ms at 12 kHz)
+extern "C" int opusb200_silk_encode_pulses(OpusB200RangeEncoder *r, const int32_t *signal_type, const int32_t *quant_offset_type, const int8_t *pulses,
+                                           int pulses_stride, int frame_length, int on_device) {
+  if (!r || !signal_type || !quant_offset_type || !pulses || frame_length < 16 || frame_length > 320 || pulses_stride < frame_length) return OPUSB200_BAD_ARG;
+  if ((frame_length & 15) && frame_length != 120) return OPUSB200_BAD_ARG;   // celt_assert(frame_length == 12 * 10)
+  OpusB200Ctx *c = r->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkCoderParams p = rc_params(r);
+  p.signal_type = signal_type; p.quant_offset_type = quant_offset_type; p.pulses = pulses; p.pulses_stride = pulses_stride; p.frame_length = frame_length;
+  if (!on_device) {
+    const size_t pb = (size_t)r->n * pulses_stride;
+    if (r->d_pulses_cap < pb) { cudaFree(r->d_pulses); r->d_pulses = nullptr; r->d_pulses_cap = 0; OB_CUDA(cudaMalloc(&r->d_pulses, pb)); r->d_pulses_cap = pb; }
+    OB_CUDA(cudaMemcpyAsync(r->d_i32[0], signal_type, sizeof(int32_t) * (size_t)r->n, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(r->d_i32[1], quant_offset_type, sizeof(int32_t) * (size_t)r->n, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(r->d_pulses, pulses, pb, cudaMemcpyHostToDevice, c->stream));
+    p.signal_type = r->d_i32[0]; p.quant_offset_type = r->d_i32[1]; p.pulses = r->d_pulses;
+  }
+  ob_silk_encode_pulses<<<(r->n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+// ec_tell_frac, then ec_enc_done (celt/entenc.c:256): bytes [n][storage] (host), tell_frac [n] (bits in 1/8 units before the flush), final_range [n]
+// (OPUS_GET_FINAL_RANGE), error [n] (the encoder's error flag: buffer too small)
+extern "C" int opusb200_range_encoder_done(OpusB200RangeEncoder *r, unsigned char *bytes, uint32_t *tell_frac, uint32_t *final_range, int32_t *error) {
+  if (!r || !bytes) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = r->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkCoderParams p = rc_params(r);
+  p.tell_frac = r->d_u32[0]; p.final_range = r->d_u32[1];
+  ob_silk_coder_done<<<(r->n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  OB_CUDA(cudaMemcpy2DAsync(bytes, r->storage, r->buf, r->stride, r->storage, r->n, cudaMemcpyDeviceToHost, c->stream));
+  if (tell_frac) OB_CUDA(cudaMemcpyAsync(tell_frac, r->d_u32[0], sizeof(uint32_t) * (size_t)r->n, cudaMemcpyDeviceToHost, c->stream));
+  if (final_range) OB_CUDA(cudaMemcpyAsync(final_range, r->d_u32[1], sizeof(uint32_t) * (size_t)r->n, cudaMemcpyDeviceToHost, c->stream));
+  if (error) OB_CUDA(cudaMemcpy2DAsync(error, sizeof(int32_t), &r->state->error, sizeof(ob::ObRangeEncState), sizeof(int32_t), r->n, cudaMemcpyDeviceToHost, c->stream));
+  OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}

@@ -87,6 +87,9 @@ class Ops:
     def silk_resampler(self, n_streams, fs_in, fs_out, for_enc=True):
         return SilkResampler(self, n_streams, fs_in, fs_out, for_enc)
 
+    def range_encoder(self, n_streams, buf_bytes=1275):
+        return RangeEncoder(self, n_streams, buf_bytes)
+
     def celt_analysis(self, n_streams, channels):
         return CeltAnalysis(self, n_streams, channels)
 
@@ -96,6 +99,57 @@ class Ops:
     def close(self):
         if getattr(self, '_h', None):
             self._L.opusb200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RangeEncoder:
+    """n_streams range encoders with device-resident state (ec_enc) and the SILK excitation coder on them (silk_encode_pulses)."""
+
+    def __init__(self, ops, n_streams, buf_bytes=1275):
+        self._L, self.n = ops._L, n_streams
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_range_encoder_create(ops._h, n_streams, buf_bytes, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_range_encoder_create')
+        self._h = h
+        self.storage = buf_bytes
+
+    def _chk(self, r, what):
+        if r != 0:
+            raise capi.OpusB200Error(r, what)
+
+    def init(self, storage=None):
+        self.storage = storage or self.storage
+        self._chk(self._L.opusb200_range_encoder_init(self._h, self.storage), 'opusb200_range_encoder_init')
+
+    def icdf(self, symbols, icdf, ftb=8):
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        icdf = np.ascontiguousarray(icdf, np.uint8)
+        self._chk(self._L.opusb200_range_encoder_icdf(self._h, _p(symbols), _p(icdf), len(icdf), ftb, 0), 'opusb200_range_encoder_icdf')
+
+    def encode_pulses(self, signal_type, quant_offset_type, pulses, frame_length):
+        st = np.ascontiguousarray(signal_type, np.int32)
+        qo = np.ascontiguousarray(quant_offset_type, np.int32)
+        pulses = np.ascontiguousarray(pulses, np.int8)
+        assert pulses.shape[0] == self.n
+        self._chk(self._L.opusb200_silk_encode_pulses(self._h, _p(st), _p(qo), _p(pulses), pulses.shape[1], frame_length, 0), 'opusb200_silk_encode_pulses')
+
+    def done(self):
+        """-> (bytes [n][storage], tell_frac [n], final_range [n], error [n])"""
+        b = np.zeros((self.n, self.storage), np.uint8)
+        tf, fr, er = np.zeros(self.n, np.uint32), np.zeros(self.n, np.uint32), np.zeros(self.n, np.int32)
+        self._chk(self._L.opusb200_range_encoder_done(self._h, _p(b), _p(tf), _p(fr), _p(er)), 'opusb200_range_encoder_done')
+        return b, tf, fr, er
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_range_encoder_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -396,3 +396,19 @@ long refh_encode_bench(int Fs, int channels, int application, int bitrate, int v
   if (bytes_out) *bytes_out = bytes;
   return frames;
 }
+
+/* ---- SILK excitation coder (silk/encode_pulses.c, shell_coder.c, code_signs.c) on a reference range encoder ---- */
+#include "celt/entenc.h"
+typedef struct { ec_enc enc; unsigned char buf[1280]; } RefhSilkCoder;
+int refh_silk_coder_size(void) { return (int)sizeof(RefhSilkCoder); }
+void refh_silk_coder_init(RefhSilkCoder *c, int storage) { ec_enc_init(&c->enc, c->buf, (opus_uint32)storage); }
+void refh_silk_coder_icdf(RefhSilkCoder *c, int s, const unsigned char *icdf, int ftb) { ec_enc_icdf(&c->enc, s, icdf, (unsigned)ftb); }
+opus_uint32 refh_silk_coder_tell_frac(RefhSilkCoder *c) { return ec_tell_frac(&c->enc); }
+void refh_silk_encode_pulses(RefhSilkCoder *c, int signalType, int quantOffsetType, opus_int8 *pulses, int frame_length) {
+  silk_encode_pulses(&c->enc, signalType, quantOffsetType, pulses, frame_length);
+}
+opus_uint32 refh_silk_coder_done(RefhSilkCoder *c, unsigned char *out) {
+  ec_enc_done(&c->enc);
+  memcpy(out, c->buf, c->enc.storage);
+  return c->enc.rng;
+}

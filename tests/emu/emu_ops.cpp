@@ -404,3 +404,24 @@ extern "C" void emu_opus_last_analysis(void *h, float *out) {
     for (int k = 0; k < 19; k++) o[11 + k] = (float)i.leak_boost[k];
   }
 }
+
+// ---- SILK excitation coder (silk_coder.cuh): thread per stream on the emulator ----
+#include "../../opus_b200/csrc/silk_coder.cuh"
+static void sc_init_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_coder_init_thread(p, s); }
+static void sc_icdf_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_coder_icdf_thread(p, s); }
+static void sc_pulses_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_encode_pulses_thread(p, s); }
+static void sc_done_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_coder_done_thread(p, s); }
+extern "C" {
+int emu_silk_coder_state_size(void) { return (int)sizeof(ObRangeEncState); }
+// op: 0 init, 1 icdf (symbols, icdf table, ftb), 2 encode_pulses, 3 done
+void emu_silk_coder(int op, void *state, unsigned char *buf, int n, int stride, int storage, const int32_t *a0, const int32_t *a1, const int8_t *pulses,
+                    int pulses_stride, int frame_length, const unsigned char *icdf, int icdf_len, int ftb, uint32_t *tell_frac, uint32_t *final_range) {
+  SilkCoderParams p;
+  memset(&p, 0, sizeof(p));
+  p.state = (ObRangeEncState *)state; p.buf = buf; p.n = n; p.buf_stride = stride; p.storage = storage;
+  p.signal_type = a0; p.quant_offset_type = a1; p.symbols = a0; p.pulses = pulses; p.pulses_stride = pulses_stride; p.frame_length = frame_length;
+  if (icdf) memcpy(p.icdf, icdf, icdf_len);
+  p.ftb = ftb; p.tell_frac = tell_frac; p.final_range = final_range;
+  emu_launch(op == 0 ? sc_init_entry : op == 1 ? sc_icdf_entry : op == 2 ? sc_pulses_entry : sc_done_entry, &p, (n + 31) / 32, 32, 0);
+}
+}

@@ -168,3 +168,39 @@ def test_emu_enc_analysis(cc, lm):
             assert np.array_equal(En[s].view(np.uint32), Eo.view(np.uint32)), (f, s)
             assert np.array_equal(Lg[s].view(np.uint32), Lo.view(np.uint32))
             assert np.array_equal(X[s].view(np.uint32), Xo.view(np.uint32))
+
+
+@pytest.mark.parametrize('frame_length,kind', [(320, 1), (320, 2), (160, 0), (120, 1), (240, 3), (80, 2)])
+def test_emu_silk_encode_pulses(frame_length, kind):
+    """the device excitation coder (silk_coder.cuh) on the emulator against the oracle: buffer bytes, ec_tell_frac, final range; symbols in front"""
+    from test_silk_coder_oracle_vs_ref import make_pulses
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    O.orc_silk_coder_done.restype = ctypes.c_uint32
+    O.orc_silk_coder_tell_frac.restype = ctypes.c_uint32
+    rng = np.random.default_rng(7 * frame_length + kind)
+    n, storage, stride = 40, (1275 if kind == 2 else 300), 1280
+    P = make_pulses(rng, n, frame_length, kind)
+    st = rng.integers(0, 3, n).astype(np.int32)
+    qo = rng.integers(0, 2, n).astype(np.int32)
+    icdf = np.array([200, 120, 30, 0], np.uint8)
+    syms = [rng.integers(-1, 4, n).astype(np.int32) for _ in range(3)]   # -1: nothing for that stream
+    state = np.zeros(n * E.emu_silk_coder_state_size(), np.uint8)
+    buf = np.zeros((n, stride), np.uint8)
+    tf, fr = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    E.emu_silk_coder(0, _f(state), _f(buf), n, stride, storage, None, None, None, 0, 0, None, 0, 0, None, None)
+    for sy in syms:
+        E.emu_silk_coder(1, _f(state), _f(buf), n, stride, storage, _f(sy), None, None, 0, 0, _f(icdf), 4, 8, None, None)
+    E.emu_silk_coder(2, _f(state), _f(buf), n, stride, storage, _f(st), _f(qo), _f(P), P.shape[1], frame_length, None, 0, 0, None, None)
+    E.emu_silk_coder(3, _f(state), _f(buf), n, stride, storage, None, None, None, 0, 0, None, 0, 0, _f(tf), _f(fr))
+    for s in range(n):
+        oc = ctypes.create_string_buffer(O.orc_silk_coder_size())
+        O.orc_silk_coder_init(oc, storage)
+        for sy in syms:
+            if sy[s] >= 0:
+                O.orc_silk_coder_icdf(oc, int(sy[s]), _f(icdf), 8)
+        q = P[s].copy()
+        O.orc_silk_encode_pulses(oc, int(st[s]), int(qo[s]), _f(q), frame_length)
+        assert O.orc_silk_coder_tell_frac(oc) == tf[s], s
+        want = np.zeros(storage, np.uint8)
+        assert O.orc_silk_coder_done(oc, _f(want)) == fr[s], s
+        assert np.array_equal(buf[s, :storage], want), s

@@ -258,3 +258,40 @@ def test_celt_enc_analysis(ops, cc, lm):
             assert np.array_equal(X[s].view(np.uint32), Xo.view(np.uint32))
             assert np.abs(Lg[s].view(np.int32).astype(np.int64) - Lo.view(np.int32).astype(np.int64)).max() <= 1
     an.close()
+
+
+@pytest.mark.parametrize('frame_length,kind', [(320, 1), (320, 2), (160, 0), (120, 1), (240, 3), (80, 2)])
+def test_silk_encode_pulses(ops, frame_length, kind):
+    """silk_encode_pulses on the batched range-encoder object (state resident on the device between calls), symbols coded in front of the pulses:
+    buffer bytes, ec_tell_frac and final range against the oracle (pinned on the reference's silk_encode_pulses + ec_enc)"""
+    from test_silk_coder_oracle_vs_ref import make_pulses
+    O = util.load_oracle()
+    O.orc_silk_coder_done.restype = ctypes.c_uint32
+    O.orc_silk_coder_tell_frac.restype = ctypes.c_uint32
+    rng = np.random.default_rng(11 * frame_length + kind)
+    n, storage = 600, (1275 if kind == 2 else 300)
+    P = make_pulses(rng, n, frame_length, kind)
+    st = rng.integers(0, 3, n).astype(np.int32)
+    qo = rng.integers(0, 2, n).astype(np.int32)
+    icdf = np.array([200, 120, 30, 0], np.uint8)
+    syms = [rng.integers(-1, 4, n).astype(np.int32) for _ in range(3)]
+    re = ops.range_encoder(n, 1275)
+    re.init(storage)
+    for sy in syms:
+        re.icdf(sy, icdf, 8)
+    re.encode_pulses(st, qo, P, frame_length)
+    buf, tf, fr, er = re.done()
+    assert (er == 0).all()
+    for s in range(0, n, 7):
+        oc = ctypes.create_string_buffer(O.orc_silk_coder_size())
+        O.orc_silk_coder_init(oc, storage)
+        for sy in syms:
+            if sy[s] >= 0:
+                O.orc_silk_coder_icdf(oc, int(sy[s]), _f(icdf), 8)
+        q = P[s].copy()
+        O.orc_silk_encode_pulses(oc, int(st[s]), int(qo[s]), _f(q), frame_length)
+        assert O.orc_silk_coder_tell_frac(oc) == tf[s], s
+        want = np.zeros(storage, np.uint8)
+        assert O.orc_silk_coder_done(oc, _f(want)) == fr[s], s
+        assert np.array_equal(buf[s], want), s
+    re.close()

@@ -1,0 +1,65 @@
+"""Pins oracle/silk_coder_oracle.c (silk_encode_pulses + shell coder + sign coder on the range-encoder restatement) against the reference's
+silk_encode_pulses (silk/encode_pulses.c:59) driving the reference's own ec_enc: the whole output buffer after ec_enc_done, ec_tell_frac before it,
+and the final range, over signal types, quantisation offset types, frame lengths (incl. the zero-padded 10 ms @ 12 kHz frame) and pulse statistics
+from sparse to the down-scaling (LSB) regime."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.skipif(not util.ref_available('c'), reason='oracle/_ref not built')
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_pulses(rng, n, frame_length, kind):
+    """kind 0: sparse +-1; 1: laplacian with a few larger values; 2: dense and large (forces the right shifts / LSB coding); 3: all zero blocks mixed in"""
+    pad = ((frame_length + 15) // 16) * 16 + 16
+    p = np.zeros((n, pad), np.int8)
+    for s in range(n):
+        if kind == 0:
+            v = (rng.random(frame_length) < 0.15) * rng.choice([-1, 1], frame_length)
+        elif kind == 1:
+            v = np.round(rng.laplace(0, 0.9, frame_length))
+        elif kind == 2:
+            v = np.round(rng.laplace(0, 6.0, frame_length))
+        else:
+            v = np.round(rng.laplace(0, 1.5, frame_length)) * (np.repeat(rng.random((frame_length + 15) // 16) < 0.5, 16)[:frame_length])
+        p[s, :frame_length] = np.clip(v, -80, 80).astype(np.int8)
+        p[s, frame_length:] = 77   # garbage the coder must not read beyond its own zero padding
+    return p
+
+
+@pytest.mark.parametrize('frame_length', [320, 160, 240, 120, 80])
+@pytest.mark.parametrize('kind', [0, 1, 2, 3])
+def test_encode_pulses(frame_length, kind):
+    R, O = util.load_ref('c'), util.load_oracle()
+    R.refh_silk_coder_done.restype = ctypes.c_uint32
+    O.orc_silk_coder_done.restype = ctypes.c_uint32
+    R.refh_silk_coder_tell_frac.restype = ctypes.c_uint32
+    O.orc_silk_coder_tell_frac.restype = ctypes.c_uint32
+    rng = np.random.default_rng(frame_length + kind)
+    n = 24
+    P = make_pulses(rng, n, frame_length, kind)
+    storage = 1275 if kind == 2 else 400
+    for s in range(n):
+        st, qo = int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        rc = ctypes.create_string_buffer(R.refh_silk_coder_size())
+        oc = ctypes.create_string_buffer(O.orc_silk_coder_size())
+        R.refh_silk_coder_init(rc, storage)
+        O.orc_silk_coder_init(oc, storage)
+        icdf = np.array([200, 120, 30, 0], np.uint8)   # symbols in front of the pulses, as the indices are in the real frame
+        for sym in rng.integers(0, 4, 5):
+            R.refh_silk_coder_icdf(rc, int(sym), _p(icdf), 8)
+            O.orc_silk_coder_icdf(oc, int(sym), _p(icdf), 8)
+        a, b = P[s].copy(), P[s].copy()
+        R.refh_silk_encode_pulses(rc, st, qo, _p(a), frame_length)
+        O.orc_silk_encode_pulses(oc, st, qo, _p(b), frame_length)
+        assert R.refh_silk_coder_tell_frac(rc) == O.orc_silk_coder_tell_frac(oc), s
+        ba, bb = np.zeros(storage, np.uint8), np.zeros(storage, np.uint8)
+        ra, rb = R.refh_silk_coder_done(rc, _p(ba)), O.orc_silk_coder_done(oc, _p(bb))
+        assert ra == rb and np.array_equal(ba, bb), s
