@@ -38,9 +38,21 @@ extern "C" __global__ void __launch_bounds__(128) ob_celt_dec_entropy(DecEntropy
 // batch is exhausted, so a warp that drew a cheap frame does not idle until the CTA's slowest stream is done (the shared-memory slice
 // per warp allows only one 13-14 warp CTA per SM).
 extern "C" __global__ void __launch_bounds__(512) ob_celt_dec_pvq(DecPvqParams p, int *next_stream) {
+  // the PVQ U(n,k) table (5 KB) comes into shared memory once per persistent CTA by cp.async.bulk (the TMA unit's bulk copy) on an mbarrier
   PvqShared *tab = (PvqShared *)dyn_smem();
-  for (int i = threadIdx.x; i < 1272; i += blockDim.x) tab->u[i] = ob_pvq_u[i];
+  __shared__ __align__(8) unsigned long long tab_bar;
+  const uint32_t bar = tma::saddr(&tab_bar);
+  if (threadIdx.x == 0) {
+    tma::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma::mbar_expect_tx(bar, (uint32_t)sizeof(tab->u));
+    tma::bulk_g2s(tma::saddr(tab->u), ob_pvq_u, (uint32_t)sizeof(tab->u), bar);
+  }
   if (threadIdx.x < 15) tab->rowoff[threadIdx.x] = ob_pvq_rowoff[threadIdx.x];
+  tma::mbar_wait(bar, 0);
   __syncthreads();
   unsigned char *ws = dyn_smem() + ((sizeof(PvqShared) + 15) & ~(size_t)15) + (size_t)(threadIdx.x >> 5) * sizeof(PvqWS);
   for (;;) {
