@@ -186,6 +186,20 @@ int opusb200_range_encoder_icdf(OpusB200RangeEncoder *re, const int32_t *symbols
 int opusb200_silk_encode_pulses(OpusB200RangeEncoder *re, const int32_t *signal_type, const int32_t *quant_offset_type, const int8_t *pulses,
                                 int pulses_stride, int frame_length, int on_device);
 int opusb200_range_encoder_done(OpusB200RangeEncoder *re, unsigned char *bytes, uint32_t *tell_frac, uint32_t *final_range, int32_t *error);
+/* silk_encode_indices(psEncC, &enc, FrameIndex, 0, condCoding) (silk/encode_indices.c:35, with silk_NLSF_unpack): the side information of one SILK frame
+ * per stream.  OpusB200SilkIndices has SideInfoIndices' fields in SideInfoIndices' order (silk/structs.h:129-141), so the reference's struct casts to
+ * it; cond_coding [n]: CODE_INDEPENDENTLY 0, CODE_INDEPENDENTLY_NO_LTP_SCALING 1, CODE_CONDITIONALLY 2; fs_kHz (8 / 12 / 16) and nb_subfr (2 / 4)
+ * select the tables as silk_control_encoder does (silk/control_codec.c:212-296).  ec_prevSignalType / ec_prevLagIndex are kept per stream inside the
+ * object (opusb200_silk_coder_reset_state zeroes them).  Indices followed by opusb200_silk_encode_pulses = the bitstream of a SILK frame
+ * (silk/float/encode_frame_FLP.c:290-300). */
+typedef struct {
+  int8_t GainsIndices[4], LTPIndex[4], NLSFIndices[17];
+  int16_t lagIndex;
+  int8_t contourIndex, signalType, quantOffsetType, NLSFInterpCoef_Q2, PERIndex, LTP_scaleIndex, Seed;
+} OpusB200SilkIndices;
+int opusb200_silk_encode_indices(OpusB200RangeEncoder *re, int fs_kHz, int nb_subfr, const OpusB200SilkIndices *indices, const int32_t *cond_coding,
+                                 int on_device);
+int opusb200_silk_coder_reset_state(OpusB200RangeEncoder *re);
 
 /* silk_burg_modified_FLP (silk/float/burg_modified_FLP.c:39; called from find_LPC_FLP.c:60,65):
  * x [n_items][nb_subfr*subfr_length] -> A [n_items][D] prediction coefficients, nrg [n_items] residual energy. */

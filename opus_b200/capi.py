@@ -29,7 +29,7 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_celt_analysis_destroy', 'opusb200_celt_analysis_reset', 'opusb200_celt_analysis_process', 'opusb200_ctx_create', 'opusb200_ctx_destroy', 'opusb200_ctx_sync',
            'opusb200_ctx_cuda_stream', 'opusb200_mdct_forward', 'opusb200_pitch_xcorr', 'opusb200_exp_rotation',
            'opusb200_pvq_search', 'opusb200_silk_lpc_analysis_filter', 'opusb200_silk_resampler_create', 'opusb200_silk_resampler_create_ex', 'opusb200_range_encoder_create', 'opusb200_range_encoder_destroy',
-           'opusb200_range_encoder_init', 'opusb200_range_encoder_icdf', 'opusb200_silk_encode_pulses', 'opusb200_range_encoder_done',
+           'opusb200_range_encoder_init', 'opusb200_range_encoder_icdf', 'opusb200_silk_encode_pulses', 'opusb200_range_encoder_done', 'opusb200_silk_encode_indices', 'opusb200_silk_coder_reset_state',
            'opusb200_silk_resampler_destroy', 'opusb200_silk_resampler_reset', 'opusb200_silk_resampler_process',
            'opusb200_silk_burg_modified', 'opusb200_silk_autocorrelation',
            'opusb200_silk_nsq_create', 'opusb200_silk_nsq_destroy', 'opusb200_silk_nsq_reset', 'opusb200_silk_nsq_process',
@@ -148,6 +148,8 @@ def lib():
         L.opusb200_range_encoder_icdf.argtypes = [vp, vp, vp, ci, ci, ci]
         L.opusb200_silk_encode_pulses.argtypes = [vp, vp, vp, vp, ci, ci, ci]
         L.opusb200_range_encoder_done.argtypes = [vp, vp, vp, vp, vp]
+        L.opusb200_silk_encode_indices.argtypes = [vp, ci, ci, vp, vp, ci]
+        L.opusb200_silk_coder_reset_state.argtypes = [vp]
         L.opusb200_silk_resampler_destroy.argtypes = [vp]
         L.opusb200_silk_resampler_destroy.restype = None
         L.opusb200_silk_resampler_reset.argtypes = [vp]

@@ -39,6 +39,8 @@ struct DecPvqParams {
 struct PvqShared {
   uint32_t u[1272];
   short rowoff[16];
+  unsigned long long bar;   // the mbarrier the bulk copy of `u` completes on (it lives in the dynamic allocation: the kernel opts in to ALL of the
+                            // SM's shared memory, a static variable would not fit beside it)
 };
 // Per warp
 struct PvqWS {

@@ -15,6 +15,10 @@ extern "C" __global__ void __launch_bounds__(128) ob_silk_encode_pulses(ob::Silk
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < p.n) ob::silk_encode_pulses_thread(p, s);
 }
+extern "C" __global__ void __launch_bounds__(128) ob_silk_encode_indices(ob::SilkCoderParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_encode_indices_thread(p, s);
+}
 extern "C" __global__ void __launch_bounds__(128) ob_silk_coder_done(ob::SilkCoderParams p) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < p.n) ob::silk_coder_done_thread(p, s);
@@ -28,6 +32,8 @@ struct OpusB200RangeEncoder {
   int32_t *d_i32[2];
   int8_t *d_pulses; size_t d_pulses_cap;
   uint32_t *d_u32[2];
+  int32_t *silk_prev;          // [n][2]: ec_prevSignalType, ec_prevLagIndex
+  ob::ObSilkIndices *d_idx;
 };
 static ob::SilkCoderParams rc_params(OpusB200RangeEncoder *r) {
   ob::SilkCoderParams p;
@@ -48,11 +54,14 @@ extern "C" int opusb200_range_encoder_create(OpusB200Ctx *c, int n_streams, int 
   const size_t n = (size_t)n_streams;
   if (cudaMalloc(&r->state, sizeof(ob::ObRangeEncState) * n) != cudaSuccess || cudaMalloc(&r->buf, n * r->stride) != cudaSuccess ||
       cudaMalloc(&r->d_i32[0], sizeof(int32_t) * n) != cudaSuccess || cudaMalloc(&r->d_i32[1], sizeof(int32_t) * n) != cudaSuccess ||
-      cudaMalloc(&r->d_u32[0], sizeof(uint32_t) * n) != cudaSuccess || cudaMalloc(&r->d_u32[1], sizeof(uint32_t) * n) != cudaSuccess) {
+      cudaMalloc(&r->d_u32[0], sizeof(uint32_t) * n) != cudaSuccess || cudaMalloc(&r->d_u32[1], sizeof(uint32_t) * n) != cudaSuccess ||
+      cudaMalloc(&r->silk_prev, sizeof(int32_t) * 2 * n) != cudaSuccess || cudaMalloc(&r->d_idx, sizeof(ob::ObSilkIndices) * n) != cudaSuccess) {
+    cudaFree(r->silk_prev); cudaFree(r->d_idx);
     cudaFree(r->state); cudaFree(r->buf); cudaFree(r->d_i32[0]); cudaFree(r->d_i32[1]); cudaFree(r->d_u32[0]); cudaFree(r->d_u32[1]);
     delete r;
     return OPUSB200_ALLOC_FAIL;
   }
+  cudaMemsetAsync(r->silk_prev, 0, sizeof(int32_t) * 2 * n, c->stream);
   *out = r;
   return OPUSB200_OK;
 }
@@ -60,6 +69,7 @@ extern "C" void opusb200_range_encoder_destroy(OpusB200RangeEncoder *r) {
   if (!r) return;
   cudaSetDevice(r->ctx->device);
   cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->silk_prev); cudaFree(r->d_idx);
   cudaFree(r->state); cudaFree(r->buf); cudaFree(r->d_i32[0]); cudaFree(r->d_i32[1]); cudaFree(r->d_u32[0]); cudaFree(r->d_u32[1]); cudaFree(r->d_pulses);
   delete r;
 }
@@ -114,6 +124,34 @@ extern "C" int opusb200_silk_encode_pulses(OpusB200RangeEncoder *r, const int32_
   c->launches++;
   OB_CUDA(cudaGetLastError());
   if (!on_device) OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+// silk_encode_indices(psEncC, &enc, 0, 0, condCoding) (silk/encode_indices.c:35): indices [n] = SideInfoIndices of every stream, cond_coding [n];
+// fs_kHz 8 / 12 / 16 and nb_subfr 2 / 4 select the tables as silk_control_encoder does.  The encoder-state fields the function carries from frame
+// to frame (ec_prevSignalType, ec_prevLagIndex) live in the object; opusb200_silk_coder_reset_state clears them (silk_init_encoder).
+extern "C" int opusb200_silk_encode_indices(OpusB200RangeEncoder *r, int fs_kHz, int nb_subfr, const OpusB200SilkIndices *indices, const int32_t *cond_coding,
+                                            int on_device) {
+  if (!r || !indices || !cond_coding || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16) || (nb_subfr != 2 && nb_subfr != 4)) return OPUSB200_BAD_ARG;
+  static_assert(sizeof(OpusB200SilkIndices) == sizeof(ob::ObSilkIndices), "OpusB200SilkIndices mirrors SideInfoIndices");
+  OpusB200Ctx *c = r->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkCoderParams p = rc_params(r);
+  p.indices = (const ob::ObSilkIndices *)indices; p.cond_coding = cond_coding; p.silk_prev = r->silk_prev; p.fs_kHz = fs_kHz; p.nb_subfr = nb_subfr;
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(r->d_idx, indices, sizeof(ob::ObSilkIndices) * (size_t)r->n, cudaMemcpyHostToDevice, c->stream));
+    OB_CUDA(cudaMemcpyAsync(r->d_i32[0], cond_coding, sizeof(int32_t) * (size_t)r->n, cudaMemcpyHostToDevice, c->stream));
+    p.indices = r->d_idx; p.cond_coding = r->d_i32[0];
+  }
+  ob_silk_encode_indices<<<(r->n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_silk_coder_reset_state(OpusB200RangeEncoder *r) {
+  if (!r) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(r->ctx->device));
+  OB_CUDA(cudaMemsetAsync(r->silk_prev, 0, sizeof(int32_t) * 2 * (size_t)r->n, r->ctx->stream));
   return OPUSB200_OK;
 }
 // ec_tell_frac, then ec_enc_done (celt/entenc.c:256): bytes [n][storage] (host), tell_frac [n] (bits in 1/8 units before the flush), final_range [n]

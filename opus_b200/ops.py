@@ -140,6 +140,15 @@ class RangeEncoder:
         assert pulses.shape[0] == self.n
         self._chk(self._L.opusb200_silk_encode_pulses(self._h, _p(st), _p(qo), _p(pulses), pulses.shape[1], frame_length, 0), 'opusb200_silk_encode_pulses')
 
+    def encode_indices(self, fs_kHz, nb_subfr, indices, cond_coding):
+        """indices: a ctypes array of n SideInfoIndices-layout structs (or a uint8 array [n][36]); cond_coding [n]"""
+        cc = np.ascontiguousarray(cond_coding, np.int32)
+        ptr = _p(indices) if isinstance(indices, np.ndarray) else ctypes.cast(indices, ctypes.c_void_p)
+        self._chk(self._L.opusb200_silk_encode_indices(self._h, fs_kHz, nb_subfr, ptr, _p(cc), 0), 'opusb200_silk_encode_indices')
+
+    def reset_silk_state(self):
+        self._chk(self._L.opusb200_silk_coder_reset_state(self._h), 'opusb200_silk_coder_reset_state')
+
     def done(self):
         """-> (bytes [n][storage], tell_frac [n], final_range [n], error [n])"""
         b = np.zeros((self.n, self.storage), np.uint8)

@@ -412,3 +412,20 @@ opus_uint32 refh_silk_coder_done(RefhSilkCoder *c, unsigned char *out) {
   memcpy(out, c->buf, c->enc.storage);
   return c->enc.rng;
 }
+/* silk_encode_indices on a scratch encoder state that holds only what the function reads (silk/encode_indices.c:35-185) */
+#include "silk/tables.h"
+void refh_silk_encode_indices(RefhSilkCoder *c, int fs_kHz, int nb_subfr, const SideInfoIndices *ix, int condCoding, int *prev) {
+  static silk_encoder_state st;
+  memset(&st, 0, sizeof(st));
+  st.fs_kHz = fs_kHz; st.nb_subfr = nb_subfr;
+  st.psNLSF_CB = fs_kHz == 16 ? &silk_NLSF_CB_WB : &silk_NLSF_CB_NB_MB;
+  st.predictLPCOrder = fs_kHz == 16 ? 16 : 10;
+  st.pitch_lag_low_bits_iCDF = fs_kHz == 16 ? silk_uniform8_iCDF : fs_kHz == 12 ? silk_uniform6_iCDF : silk_uniform4_iCDF;
+  st.pitch_contour_iCDF = fs_kHz == 8 ? (nb_subfr == 4 ? silk_pitch_contour_NB_iCDF : silk_pitch_contour_10_ms_NB_iCDF)
+                                      : (nb_subfr == 4 ? silk_pitch_contour_iCDF : silk_pitch_contour_10_ms_iCDF);
+  st.indices = *ix;
+  st.ec_prevSignalType = prev[0]; st.ec_prevLagIndex = (opus_int16)prev[1];
+  silk_encode_indices(&st, &c->enc, 0, 0, condCoding);
+  prev[0] = st.ec_prevSignalType; prev[1] = st.ec_prevLagIndex;
+}
+int refh_silk_indices_size(void) { return (int)sizeof(SideInfoIndices); }

@@ -128,3 +128,64 @@ void orc_silk_encode_pulses(OrcSilkCoder *c, int signalType, int quantOffsetType
     }
   }
 }
+
+/* ---- silk_encode_indices (silk/encode_indices.c:35-185) with silk_NLSF_unpack (silk/NLSF_unpack.c:35-55): the side information of one SILK frame.
+ * OrcSilkIndices has SideInfoIndices' fields in SideInfoIndices' order (silk/structs.h:129-141); prev = {ec_prevSignalType, ec_prevLagIndex} of the
+ * encoder state, read and updated.  Table selection by fs_kHz / nb_subfr as silk_control_encoder does (silk/control_codec.c:212-296). ---- */
+typedef struct {
+  int8_t GainsIndices[4], LTPIndex[4], NLSFIndices[17];
+  int16_t lagIndex;
+  int8_t contourIndex, signalType, quantOffsetType, NLSFInterpCoef_Q2, PERIndex, LTP_scaleIndex, Seed;
+} OrcSilkIndices;
+int orc_silk_indices_size(void) { return (int)sizeof(OrcSilkIndices); }
+void orc_silk_encode_indices(OrcSilkCoder *c, int fs_kHz, int nb_subfr, const OrcSilkIndices *ix, int condCoding, int *prev) {
+  RangeEnc *e = &c->e;
+  const int wb = fs_kHz == 16, order = wb ? 16 : 10, typeOffset = 2 * ix->signalType + ix->quantOffsetType;
+  const unsigned char *cb1 = &ob_silk_NLSF_CB1_iCDF[wb ? 64 : 0], *sel = &ob_silk_NLSF_CB2_SELECT[wb ? 160 : 0], *cb2 = &ob_silk_NLSF_CB2_iCDF[wb ? 72 : 0];
+  int i, k;
+  if (typeOffset >= 2) re_icdf(e, typeOffset - 2, ob_silk_type_offset_VAD_iCDF, 8);
+  else re_icdf(e, typeOffset, ob_silk_type_offset_no_VAD_iCDF, 8);
+  if (condCoding == 2) re_icdf(e, ix->GainsIndices[0], ob_silk_delta_gain_iCDF, 8);
+  else {
+    re_icdf(e, ix->GainsIndices[0] >> 3, &ob_silk_gain_iCDF[8 * ix->signalType], 8);
+    re_icdf(e, ix->GainsIndices[0] & 7, ob_silk_uniform8_iCDF, 8);
+  }
+  for (i = 1; i < nb_subfr; i++) re_icdf(e, ix->GainsIndices[i], ob_silk_delta_gain_iCDF, 8);
+  re_icdf(e, ix->NLSFIndices[0], &cb1[(ix->signalType >> 1) * 32], 8);
+  for (i = 0; i < order; i++) { /* ec_ix of silk_NLSF_unpack: the entropy table of coefficient i, three bits per coefficient in the select table */
+    const int entry = sel[ix->NLSFIndices[0] * order / 2 + (i >> 1)];
+    const int ec_ix = (((i & 1) ? entry >> 5 : entry >> 1) & 7) * 9;
+    const int v = ix->NLSFIndices[i + 1];
+    if (v >= 4) {
+      re_icdf(e, 8, &cb2[ec_ix], 8);
+      re_icdf(e, v - 4, ob_silk_NLSF_EXT_iCDF, 8);
+    } else if (v <= -4) {
+      re_icdf(e, 0, &cb2[ec_ix], 8);
+      re_icdf(e, -v - 4, ob_silk_NLSF_EXT_iCDF, 8);
+    } else re_icdf(e, v + 4, &cb2[ec_ix], 8);
+  }
+  if (nb_subfr == 4) re_icdf(e, ix->NLSFInterpCoef_Q2, ob_silk_NLSF_interpolation_factor_iCDF, 8);
+  if (ix->signalType == 2) {
+    int encode_absolute = 1;
+    if (condCoding == 2 && prev[0] == 2) {
+      int delta = ix->lagIndex - prev[1];
+      if (delta < -8 || delta > 11) delta = 0;
+      else { delta += 9; encode_absolute = 0; }
+      re_icdf(e, delta, ob_silk_pitch_delta_iCDF, 8);
+    }
+    if (encode_absolute) {
+      const int half = fs_kHz >> 1, hi = ix->lagIndex / half, lo = ix->lagIndex - hi * half;
+      re_icdf(e, hi, ob_silk_pitch_lag_iCDF, 8);
+      re_icdf(e, lo, fs_kHz == 16 ? ob_silk_uniform8_iCDF : fs_kHz == 12 ? ob_silk_uniform6_iCDF : ob_silk_uniform4_iCDF, 8);
+    }
+    prev[1] = ix->lagIndex;
+    re_icdf(e, ix->contourIndex,
+            fs_kHz == 8 ? (nb_subfr == 4 ? ob_silk_pitch_contour_NB_iCDF : ob_silk_pitch_contour_10_ms_NB_iCDF)
+                        : (nb_subfr == 4 ? ob_silk_pitch_contour_iCDF : ob_silk_pitch_contour_10_ms_iCDF), 8);
+    re_icdf(e, ix->PERIndex, ob_silk_LTP_per_index_iCDF, 8);
+    for (k = 0; k < nb_subfr; k++) re_icdf(e, ix->LTPIndex[k], &ob_silk_LTP_gain_iCDF[ix->PERIndex == 0 ? 0 : ix->PERIndex == 1 ? 8 : 24], 8);
+    if (condCoding == 0) re_icdf(e, ix->LTP_scaleIndex, ob_silk_LTPscale_iCDF, 8);
+  }
+  prev[0] = ix->signalType;
+  re_icdf(e, ix->Seed, ob_silk_uniform4_iCDF, 8);
+}

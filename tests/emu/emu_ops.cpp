@@ -411,7 +411,16 @@ static void sc_init_entry(void *a) { const SilkCoderParams &p = *(const SilkCode
 static void sc_icdf_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_coder_icdf_thread(p, s); }
 static void sc_pulses_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_encode_pulses_thread(p, s); }
 static void sc_done_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_coder_done_thread(p, s); }
+static void sc_indices_entry(void *a) { const SilkCoderParams &p = *(const SilkCoderParams *)a; int s = block_id() * 32 + lane_id(); if (s < p.n) silk_encode_indices_thread(p, s); }
 extern "C" {
+void emu_silk_encode_indices(void *state, unsigned char *buf, int n, int stride, int storage, int fs_kHz, int nb_subfr, const void *indices, const int32_t *cond,
+                             int32_t *prev) {
+  SilkCoderParams p;
+  memset(&p, 0, sizeof(p));
+  p.state = (ObRangeEncState *)state; p.buf = buf; p.n = n; p.buf_stride = stride; p.storage = storage;
+  p.indices = (const ObSilkIndices *)indices; p.cond_coding = cond; p.silk_prev = prev; p.fs_kHz = fs_kHz; p.nb_subfr = nb_subfr;
+  emu_launch(sc_indices_entry, &p, (n + 31) / 32, 32, 0);
+}
 int emu_silk_coder_state_size(void) { return (int)sizeof(ObRangeEncState); }
 // op: 0 init, 1 icdf (symbols, icdf table, ftb), 2 encode_pulses, 3 done
 void emu_silk_coder(int op, void *state, unsigned char *buf, int n, int stride, int storage, const int32_t *a0, const int32_t *a1, const int8_t *pulses,

@@ -204,3 +204,44 @@ def test_emu_silk_encode_pulses(frame_length, kind):
         want = np.zeros(storage, np.uint8)
         assert O.orc_silk_coder_done(oc, _f(want)) == fr[s], s
         assert np.array_equal(buf[s, :storage], want), s
+
+
+@pytest.mark.parametrize('fs_kHz,nb_subfr', [(16, 4), (12, 2), (8, 4)])
+def test_emu_silk_frame_bitstream(fs_kHz, nb_subfr):
+    """three consecutive SILK frames per stream on the emulator: silk_encode_indices (with the carried pitch-lag state) + silk_encode_pulses in one
+    range coder per frame, against the oracle"""
+    from test_silk_coder_oracle_vs_ref import SilkIndices, random_indices, make_pulses
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    O.orc_silk_coder_done.restype = ctypes.c_uint32
+    O.orc_silk_coder_tell_frac.restype = ctypes.c_uint32
+    rng = np.random.default_rng(fs_kHz + nb_subfr)
+    n, storage, stride, fl = 36, 600, 608, 5 * nb_subfr * fs_kHz
+    state = np.zeros(n * E.emu_silk_coder_state_size(), np.uint8)
+    prev = np.zeros((n, 2), np.int32)
+    oprev = [(ctypes.c_int * 2)(0, 0) for _ in range(n)]
+    for frame in range(3):
+        cond = np.array([[0, 2, 2][frame] if s % 3 else [1, 0, 2][frame] for s in range(n)], np.int32)
+        idx = (SilkIndices * n)()
+        for s in range(n):
+            idx[s] = random_indices(rng, fs_kHz, nb_subfr, int(cond[s]))
+            if frame and s % 2:
+                idx[s].signalType = 2
+        P = make_pulses(rng, n, fl, frame)
+        st = np.array([idx[s].signalType for s in range(n)], np.int32)
+        qo = np.array([idx[s].quantOffsetType for s in range(n)], np.int32)
+        buf = np.zeros((n, stride), np.uint8)
+        tf, fr = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        E.emu_silk_coder(0, _f(state), _f(buf), n, stride, storage, None, None, None, 0, 0, None, 0, 0, None, None)
+        E.emu_silk_encode_indices(_f(state), _f(buf), n, stride, storage, fs_kHz, nb_subfr, ctypes.cast(idx, ctypes.c_void_p), _f(cond), _f(prev))
+        E.emu_silk_coder(2, _f(state), _f(buf), n, stride, storage, _f(st), _f(qo), _f(P), P.shape[1], fl, None, 0, 0, None, None)
+        E.emu_silk_coder(3, _f(state), _f(buf), n, stride, storage, None, None, None, 0, 0, None, 0, 0, _f(tf), _f(fr))
+        for s in range(n):
+            oc = ctypes.create_string_buffer(O.orc_silk_coder_size())
+            O.orc_silk_coder_init(oc, storage)
+            O.orc_silk_encode_indices(oc, fs_kHz, nb_subfr, ctypes.byref(idx[s]), int(cond[s]), oprev[s])
+            q = P[s].copy()
+            O.orc_silk_encode_pulses(oc, int(st[s]), int(qo[s]), _f(q), fl)
+            assert O.orc_silk_coder_tell_frac(oc) == tf[s], (frame, s)
+            want = np.zeros(storage, np.uint8)
+            assert O.orc_silk_coder_done(oc, _f(want)) == fr[s] and np.array_equal(buf[s, :storage], want), (frame, s)
+            assert list(oprev[s]) == list(prev[s]), (frame, s)

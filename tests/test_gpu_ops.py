@@ -295,3 +295,45 @@ def test_silk_encode_pulses(ops, frame_length, kind):
         assert O.orc_silk_coder_done(oc, _f(want)) == fr[s], s
         assert np.array_equal(buf[s], want), s
     re.close()
+
+
+@pytest.mark.parametrize('fs_kHz,nb_subfr', [(16, 4), (16, 2), (12, 4), (8, 4), (8, 2)])
+def test_silk_frame_bitstream(ops, fs_kHz, nb_subfr):
+    """the bitstream of a SILK frame on the device, three consecutive frames per stream: silk_encode_indices (independent / no-LTP-scaling /
+    conditional coding, the pitch-lag delta state carried inside the object) + silk_encode_pulses in one range coder; bytes, ec_tell_frac and final
+    range against the oracle (pinned on the reference's own functions)"""
+    from test_silk_coder_oracle_vs_ref import SilkIndices, random_indices, make_pulses
+    O = util.load_oracle()
+    O.orc_silk_coder_done.restype = ctypes.c_uint32
+    O.orc_silk_coder_tell_frac.restype = ctypes.c_uint32
+    rng = np.random.default_rng(100 + fs_kHz + nb_subfr)
+    n, storage, fl = 500, 600, 5 * nb_subfr * fs_kHz
+    check = list(range(0, n, 9))
+    oprev = {s: (ctypes.c_int * 2)(0, 0) for s in check}
+    re = ops.range_encoder(n, 608)
+    re.reset_silk_state()
+    for frame in range(3):
+        cond = np.array([[0, 2, 2][frame] if s % 3 else [1, 0, 2][frame] for s in range(n)], np.int32)
+        idx = (SilkIndices * n)()
+        for s in range(n):
+            idx[s] = random_indices(rng, fs_kHz, nb_subfr, int(cond[s]))
+            if frame and s % 2:
+                idx[s].signalType = 2
+        P = make_pulses(rng, n, fl, frame)
+        st = np.array([idx[s].signalType for s in range(n)], np.int32)
+        qo = np.array([idx[s].quantOffsetType for s in range(n)], np.int32)
+        re.init(storage)
+        re.encode_indices(fs_kHz, nb_subfr, idx, cond)
+        re.encode_pulses(st, qo, P, fl)
+        buf, tf, fr, er = re.done()
+        assert (er == 0).all()
+        for s in check:
+            oc = ctypes.create_string_buffer(O.orc_silk_coder_size())
+            O.orc_silk_coder_init(oc, storage)
+            O.orc_silk_encode_indices(oc, fs_kHz, nb_subfr, ctypes.byref(idx[s]), int(cond[s]), oprev[s])
+            q = P[s].copy()
+            O.orc_silk_encode_pulses(oc, int(st[s]), int(qo[s]), _f(q), fl)
+            assert O.orc_silk_coder_tell_frac(oc) == tf[s], (frame, s)
+            want = np.zeros(storage, np.uint8)
+            assert O.orc_silk_coder_done(oc, _f(want)) == fr[s] and np.array_equal(buf[s], want), (frame, s)
+    re.close()
