@@ -66,7 +66,6 @@ struct OpusB200Encoder {
   cudaStream_t stream_f[4];   // one per chunk: the frame coder is latency-bound per warp, so the chunks' coders must overlap each other too
   cudaEvent_t ev_an[4], ev_fr[4];
   // profiling aid (opusb200_opus_encoder_set_timing): CUDA events around each kernel of a call, on the launching stream
-  int max_smem_optin, an_smem_set;   // cudaDevAttrMaxSharedMemoryPerBlockOptin; the analysis kernel's current dynamic-smem opt-in
   float *chain_scratch;   // [ceil(n/32)][OB_CH_SCRATCH_FLOATS]: the recurrence kernel's transposed tracks (celt_enc_chains.cuh)
   float *in_buf;          // [n][channels][1080]: the pre-emphasised, pre-filtered analysis window it hands to the transform kernel
   int timing;
@@ -124,8 +123,10 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
   OB_CUDA(cudaMalloc(&e->chain_scratch, sizeof(float) * ((n + 31) / 32) * OB_CH_SCRATCH_FLOATS));
   OB_CUDA(cudaMalloc(&e->in_buf, sizeof(float) * n * channels * OB_CH_IN_STRIDE));
-  OB_CUDA(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  e->an_smem_set = 0;
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32 + (int)sizeof(PfWS)));
+  // the frame coder keeps its band vectors in thread-private local memory and uses no shared memory: give the L1 everything
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_frame_rdo, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+  OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_frame, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
   // the analysis kernel lives on shared memory (25 KB per stream): ask for the largest carveout whatever the launch's own size is
   OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int r = opusb200_encoder_reset(e);
@@ -221,18 +222,7 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
       e->launches++;
     }
     if (e->timing) cudaEventRecord(e->tev[5], e->stream);
-    {
-      // teams (streams) per CTA: as many as keep the SM as full as one-stream CTAs would (OPUSB200_ENC_AN_TEAMS overrides; 1 = the old launch)
-      static const int want_teams = getenv("OPUSB200_ENC_AN_TEAMS") ? atoi(getenv("OPUSB200_ENC_AN_TEAMS")) : 3;
-      const size_t per_team = (e->channels * sizeof(MdctWS) + 32 + pf_smem + 127) & ~(size_t)127;
-      int teams = OB_IMAX(1, OB_IMIN(want_teams, 15));
-      while (teams > 1 && (teams * per_team > (size_t)e->max_smem_optin || teams * 32 * e->channels > 512)) teams--;
-      if (teams * per_team > 48 * 1024 && e->an_smem_set < (int)(teams * per_team)) {
-        OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(teams * per_team)));
-        e->an_smem_set = (int)(teams * per_team);
-      }
-      ob_celt_enc_analysis<<<(s1 - s0 + teams - 1) / teams, dim3(32 * e->channels, teams), teams * per_team, e->stream>>>(a, (int)per_team);
-    }
+    ob_celt_enc_analysis<<<s1 - s0, 32 * e->channels, e->channels * sizeof(MdctWS) + 32 + pf_smem, e->stream>>>(a);
     if (e->timing) cudaEventRecord(e->tev[3], e->stream);
     cudaStream_t sf = chunks > 1 ? e->stream_f[k] : e->stream;
     if (chunks > 1) {

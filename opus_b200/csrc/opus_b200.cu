@@ -104,15 +104,10 @@ extern "C" __global__ void __launch_bounds__(128) ob_mdct_forward(MdctFwdParams 
   if (item >= p.n_items) return;
   mdct_forward_warp(p, item, dyn_smem() + (size_t)(threadIdx.x >> 5) * sizeof(MdctWS));
 }
-// blockDim = (32 * channels, teams): every team of a CTA is one stream with its own slice of the dynamic shared memory and its own named
-// barrier (simt.cuh bsync).  Streams that start together run through the same phases at about the same time, so an instruction line fetched
-// for one team serves the others too: the kernel's 250 KB of code otherwise streams through the 32 KB instruction cache once per stream.
 // long-block forward MDCT, FFT in registers, inputs and tables staged by cp.async.bulk (celt_mdct_fast.cuh); persistent, 2 CTAs per SM
 extern "C" __global__ void __launch_bounds__(kMdctFastWarps * 32, 2) ob_mdct_forward_tma(MdctFwdParams p) { mdct_forward_tma_block(p, dyn_smem()); }
-extern "C" __global__ void __launch_bounds__(512) ob_celt_enc_analysis(EncAnalysisParams p, int smem_per_team) {
-  const int stream = p.first_stream + blockIdx.x * blockDim.y + threadIdx.y;
-  if (stream >= p.n_streams) return;   // the whole team leaves: its barrier is its own
-  enc_analysis_block(p, stream, dyn_smem() + (size_t)threadIdx.y * smem_per_team);
+extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_analysis(EncAnalysisParams p) {
+  enc_analysis_block(p, p.first_stream + blockIdx.x, dyn_smem());
 }
 extern "C" __global__ void __launch_bounds__(128) ob_pitch_xcorr(XcorrParams p, int smem_per_warp) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -900,7 +895,7 @@ int opusb200_celt_analysis_process(OpusB200CeltAnalysis *a, const float *pcm, co
     p.X = (float *)dX.p; p.bandE = (float *)dE.p; p.bandLogE = (float *)dL.p;
   }
   p.info = nullptr; p.complexity = 0; p.lsb_depth = 24;
-  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 32, c->stream>>>(p, 0);
+  ob_celt_enc_analysis<<<a->n, 32 * C, C * sizeof(MdctWS) + 32, c->stream>>>(p);
   c->launches++;
   OB_CUDA(cudaGetLastError());
   if (!on_device) {

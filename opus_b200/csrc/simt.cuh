@@ -24,13 +24,11 @@ OB_DEV int warps_per_block() { return blockDim.x >> 5; }
 OB_DEV int block_id() { return blockIdx.x; }
 OB_DEV int num_blocks() { return gridDim.x; }
 OB_DEV void wsync() { __syncwarp(); }
-// Block barrier.  A kernel launched with blockDim.y > 1 holds blockDim.y independent TEAMS of blockDim.x threads (one stream each, e.g.
-// ob_celt_enc_analysis): every team then meets at its own named barrier, so teams may take different paths; warp_in_block / warps_per_block /
-// lane_id keep their meaning inside the team because blockDim.x is a multiple of 32.
-OB_DEV void bsync() {
-  if (blockDim.y == 1) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"r"(threadIdx.y + 1), "r"(blockDim.x) : "memory");
-}
+// Block barrier.  (Round 2 tried a per-team NAMED barrier here — bar.sync with a run-time id, several streams per CTA in the encoder's analysis
+// kernel — and measured what it costs: a run-time barrier id makes ptxas reserve all 16 hardware barriers for EVERY kernel that inlines this helper,
+// and CTAs per SM drop accordingly: ob_celt_dec_synth went from 2.0 to 4.2 ms, the one-stream analysis launch from 11.5 to 18-21 ms.  The 4 %
+// the grouping bought the analysis kernel was not worth a second barrier helper threaded through the shared pitch code.)
+OB_DEV void bsync() { __syncthreads(); }
 template <class T> OB_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <class T> OB_DEV T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 template <class T> OB_DEV T shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
