@@ -13,6 +13,7 @@
 #include "celt_dec_entropy.cuh"
 #include "celt_dec_pvq.cuh"
 #include "celt_fft.cuh"
+#include "celt_mdct_fast.cuh"
 
 namespace ob {
 
@@ -32,6 +33,7 @@ struct DecSynthParams {
   int downsample;           // 48000 / output rate: every downsample-th de-emphasised sample is written (celt_decoder.c:300-405)
   int apply_gain;           // OPUS_SET_GAIN != 0 (src/opus_decoder.c:686-700)
   float gain;
+  int force_smem_fft = 0;   // A/B aid: the general shared-memory FFT for long blocks too (OPUSB200_SYNTH_SMEM_FFT)
   int defer_clip = 0;       // int16 output of a packet that may hold several frames: pcm is a FLOAT staging area and opus_decode()'s soft
                             // clipping runs once over the whole packet afterwards (dec_softclip_packet_block), as in the reference
 };
@@ -39,8 +41,9 @@ struct DecSynthParams {
 struct SynthWS {  // per warp (= per output channel)
   float freq[OB_MAXN];            // denormalised MDCT coefficients, later the interleave staging area
   float out[64 + OB_MAXN + 64];   // [4..64): previous tail, [64..64+N): IMDCT output (16B aligned start)
-  float gain[2 * OB_NBANDS];
+  float gain[2 * OB_NBANDS + 2];   // (+2: the struct stays a multiple of 16 bytes, the second warp's arrays keep the 16-byte alignment of the first's)
 };
+static_assert(sizeof(SynthWS) % 16 == 0, "SynthWS: per-warp instances must keep 16-byte alignment (float4 accesses of the register FFT)");
 #define OB_SYN_O 4 /* out[OB_SYN_O + i] <-> reference out_syn[i] ; IMDCT data starts at OB_SYN_O+60 = 64 */
 
 // x[idx] with idx < 0 reaching into the stream's history ring (absolute position pos+idx)
@@ -244,8 +247,24 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
     for (int i = lane; i < OB_OVERLAP / 2; i += 32) out[i] = st->tail[ch][i];
   }
   wsync();
-  // ---- IMDCT pre-rotation into digit-reversed order (celt/mdct.c:304-331) ----
-  {
+  // ---- IMDCT ----
+  // long block (one 960-point transform): the register FFT of celt_mdct_fast.cuh, in place in the overlap-add area (two passes over shared memory
+  // instead of ten, no run-time butterfly indices); the arithmetic per butterfly is the reference's either way.  OPUSB200_SYNTH_SMEM_FFT keeps the
+  // general path for A/B runs.
+  if (nblk == 1 && shift == 0 && !p.force_smem_fft) {
+    const Mdct480Global tabs;
+    imdct480_warp(ws->freq, out + OB_OVERLAP / 2, &tabs, lane);
+    // TDAC mirror (celt/mdct.c:372-388)
+    for (int i = lane; i < OB_OVERLAP / 2; i += 32) {
+      float *xp1 = out + OB_OVERLAP - 1 - i, *yp1 = out + i;
+      float x1 = *xp1, x2 = *yp1;
+      float w1 = ob_window[i], w2 = ob_window[OB_OVERLAP - 1 - i];
+      *yp1 = x2 * w2 - x1 * w1;
+      *xp1 = x2 * w1 + x1 * w2;
+    }
+    wsync();
+  } else {
+    // pre-rotation into digit-reversed order (celt/mdct.c:304-331)
     const int N2 = NB, N4 = NB >> 1;  // mdct size is 2*NB
     const float *trig = ob_mdct_trig;
     for (int i = 0; i < shift; i++) trig += (1920 >> i) >> 1;

@@ -25,6 +25,7 @@ struct EncFrameParams {
   const float *bandLogE2;       // [n][C*21] valid where info.patched (else the same as bandLogE)
   unsigned char *packets;       // [n][pkt_stride]
   int32_t *nbytes;              // [n] bytes produced, or a negative error
+  const int32_t *perm = nullptr;   // frame-type binning: thread t codes stream perm[t] (null: stream t)
   int first_stream = 0;   // this launch covers streams [first_stream, n_streams)
   int end = OB_NBANDS;    // CELT_SET_END_BAND (celt/celt_encoder.c:3046-3053): 13 NB, 17 WB, 19 SWB, 21 FB
   int CC = 0;             // input channels when they differ from the coded channels C (CELT_SET_CHANNELS); 0 = C

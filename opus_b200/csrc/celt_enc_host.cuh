@@ -8,27 +8,38 @@ extern "C" __global__ void __launch_bounds__(32) ob_celt_enc_chains(EncAnalysisP
   enc_chains_warp(p, p.first_stream + blockIdx.x * 32, ob_chain_tile, scratch + (size_t)blockIdx.x * OB_CH_SCRATCH_FLOATS);
 }
 
+// Frame-type binning ahead of the thread-per-stream frame coder.  The coder's lanes are independent streams, and a frame coded with short blocks
+// (transient) walks a different path through quant_all_bands than a long-block frame (Hadamard / time-divide reordering, other band shapes): a warp
+// that holds both runs both.  Measured (profiles/r02_enc_stream_grouping.txt): warps of like streams 19.7 ms instead of 22.3, identical streams 8.3.
+// So each frame the streams are ranked by the analysis kernel's block-size decision and the coder takes stream perm[thread]: long-block frames
+// first, short-block frames packed at the end (order inside a bin = arrival order of the atomics: streams are independent, any order is correct).
+extern "C" __global__ void ob_celt_enc_bin_count(const ObEncFrameInfo *info, int32_t *slot, int32_t *counters, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int key = info[s].short_blocks != 0;
+  const unsigned peers = __match_any_sync(__activemask(), key);
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&counters[key], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  slot[s] = (base + __popc(peers & ((1u << lane) - 1))) * 2 + key;
+}
+extern "C" __global__ void ob_celt_enc_bin_place(const int32_t *slot, int32_t *perm, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int v = slot[s], key = v & 1, pos = v >> 1;
+  perm[key ? n - 1 - pos : pos] = s;
+}
 extern "C" __global__ void __launch_bounds__(64) ob_celt_enc_frame(EncFrameParams p) {
-  const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < p.n_streams) enc_frame_thread<false>(p, s);
+  const int t = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < p.n_streams) enc_frame_thread<false>(p, p.perm ? p.perm[t] : t);
 }
 extern "C" __global__ void __launch_bounds__(64, 8) ob_celt_enc_frame_rdo(EncFrameParams p) {   // complexity >= 8, stereo; 128 registers
-  const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < p.n_streams) enc_frame_thread<true>(p, s);
+  const int t = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < p.n_streams) enc_frame_thread<true>(p, p.perm ? p.perm[t] : t);
 }
-// experiment (OPUSB200_ENC_REGS=96|80|64): the same kernel at a lower register cap, for more resident warps per scheduler
-#define OB_FRAME_RDO_VARIANT(name, blocks) \
-  extern "C" __global__ void __launch_bounds__(64, blocks) name(EncFrameParams p) { \
-    const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x; \
-    if (s < p.n_streams) enc_frame_thread<true>(p, s); \
-  }
-extern "C" __global__ void __launch_bounds__(256, 2) ob_celt_enc_frame_rdo_sync(EncFrameParams p) {   // OPUSB200_ENC_SYNC=1: barrier per band
-  const int s = p.first_stream + blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < p.n_streams) enc_frame_thread<true, true>(p, s);
-}
-OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r96, 10)
-OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r80, 12)
-OB_FRAME_RDO_VARIANT(ob_celt_enc_frame_rdo_r64, 16)
+// (Round-2 experiments, measured and removed: the same kernel at register caps 96 / 80 / 64, twice the streams per GPU, and a variant with one
+// barrier per band for blocks of 8 warps — no gain; the barrier variant deadlocks under divergent control flow.  DESIGN.md section 2.2.)
 extern "C" __global__ void ob_celt_enc_reset(ObEncState *st, ObEncAnalysisState *an, int n) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -66,6 +77,7 @@ struct OpusB200Encoder {
   cudaStream_t stream_f[4];   // one per chunk: the frame coder is latency-bound per warp, so the chunks' coders must overlap each other too
   cudaEvent_t ev_an[4], ev_fr[4];
   // profiling aid (opusb200_opus_encoder_set_timing): CUDA events around each kernel of a call, on the launching stream
+  int32_t *bin_slot, *bin_perm, *bin_counters;   // frame-type binning (ob_celt_enc_bin_*): [n], [n], [2]
   float *chain_scratch;   // [ceil(n/32)][OB_CH_SCRATCH_FLOATS]: the recurrence kernel's transposed tracks (celt_enc_chains.cuh)
   float *in_buf;          // [n][channels][1080]: the pre-emphasised, pre-filtered analysis window it hands to the transform kernel
   int timing;
@@ -121,6 +133,9 @@ extern "C" int opusb200_encoder_create(int device, int32_t Fs, int channels, int
   OB_CUDA(cudaMalloc(&e->bandLogE2, sizeof(float) * n * channels * OB_NBANDS));
   OB_CUDA(cudaMalloc(&e->prefilter_mem, sizeof(float) * n * channels * kPfMaxPeriod));
   OB_CUDA(cudaMalloc(&e->d_nbytes, sizeof(int32_t) * n));
+  OB_CUDA(cudaMalloc(&e->bin_slot, sizeof(int32_t) * n));
+  OB_CUDA(cudaMalloc(&e->bin_perm, sizeof(int32_t) * n));
+  OB_CUDA(cudaMalloc(&e->bin_counters, sizeof(int32_t) * 2));
   OB_CUDA(cudaMalloc(&e->chain_scratch, sizeof(float) * ((n + 31) / 32) * OB_CH_SCRATCH_FLOATS));
   OB_CUDA(cudaMalloc(&e->in_buf, sizeof(float) * n * channels * OB_CH_IN_STRIDE));
   OB_CUDA(cudaFuncSetAttribute(ob_celt_enc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(MdctWS) + 32 + (int)sizeof(PfWS)));
@@ -140,7 +155,7 @@ extern "C" void opusb200_encoder_destroy(OpusB200Encoder *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   cudaFree(e->state); cudaFree(e->an_state); cudaFree(e->info); cudaFree(e->X); cudaFree(e->bandE); cudaFree(e->bandLogE); cudaFree(e->bandLogE2); cudaFree(e->prefilter_mem);
-  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->chain_scratch); cudaFree(e->in_buf);
+  cudaFree(e->d_nbytes); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->chain_scratch); cudaFree(e->in_buf); cudaFree(e->bin_slot); cudaFree(e->bin_perm); cudaFree(e->bin_counters);
   if (e->tev[0]) for (int i = 0; i < 6; i++) cudaEventDestroy(e->tev[i]);
   for (int i = 0; i < 4; i++) {
     cudaStreamSynchronize(e->stream_f[i]);
@@ -230,15 +245,16 @@ static int celt_encode_launch(OpusB200Encoder *e, const float *d_pcm, int frame_
       OB_CUDA(cudaStreamWaitEvent(sf, e->ev_an[k], 0));
     }
     p.first_stream = s0; p.n_streams = s1;
-    static const int regs = getenv("OPUSB200_ENC_REGS") ? atoi(getenv("OPUSB200_ENC_REGS")) : 128;
-    if (e->complexity >= 8 && (ctl ? e->channels : e->stream_channels) == 2) {
-      static const bool band_sync = getenv("OPUSB200_ENC_SYNC") != nullptr;
-      if (band_sync) ob_celt_enc_frame_rdo_sync<<<(s1 - s0 + 255) / 256, 256, 0, sf>>>(p);
-      else if (regs == 96) ob_celt_enc_frame_rdo_r96<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
-      else if (regs == 80) ob_celt_enc_frame_rdo_r80<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
-      else if (regs == 64) ob_celt_enc_frame_rdo_r64<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
-      else ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
+    static const bool no_bin = getenv("OPUSB200_ENC_NO_BIN") != nullptr;
+    p.perm = nullptr;
+    if (!no_bin && chunks == 1 && e->n >= 64) {
+      OB_CUDA(cudaMemsetAsync(e->bin_counters, 0, sizeof(int32_t) * 2, e->stream));
+      ob_celt_enc_bin_count<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->info, e->bin_slot, e->bin_counters, e->n);
+      ob_celt_enc_bin_place<<<(e->n + 255) / 256, 256, 0, e->stream>>>(e->bin_slot, e->bin_perm, e->n);
+      e->launches += 2;
+      p.perm = e->bin_perm;
     }
+    if (e->complexity >= 8 && (ctl ? e->channels : e->stream_channels) == 2) ob_celt_enc_frame_rdo<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     else ob_celt_enc_frame<<<(s1 - s0 + 63) / 64, 64, 0, sf>>>(p);
     e->launches += 2;
     if (e->timing) cudaEventRecord(e->tev[4], sf);

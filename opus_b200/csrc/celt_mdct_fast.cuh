@@ -32,9 +32,20 @@ struct alignas(16) Mdct480Tabs {
   float tw[960];       // ob_fft_tw: 480 complex twiddles
   float window[120];
   short bitrev[480];
+  OB_MDEV cpx get_tw(int k) const { return ((const cpx *)tw)[k]; }
+  OB_MDEV float get_trig(int i) const { return trig[i]; }
+  OB_MDEV float get_window(int i) const { return window[i]; }
+  OB_MDEV int get_bitrev(int i) const { return bitrev[i]; }
 };
-
-OB_DEV cpx f480_tw(const Mdct480Tabs *t, int k) { return ((const cpx *)t->tw)[k]; }
+// the same tables where the library keeps them (global memory, served by L1 / L2): for the kernels that run one transform per warp inside a
+// larger job and have no table stage of their own (the decoder's synthesis kernel)
+struct Mdct480Global {
+  OB_MDEV cpx get_tw(int k) const { return ldtw(k); }
+  OB_MDEV float get_trig(int i) const { return ob_mdct_trig[i]; }
+  OB_MDEV float get_window(int i) const { return ob_window[i]; }
+  OB_MDEV int get_bitrev(int i) const { return ob_fft_bitrev480[i]; }
+};
+template <class T> OB_DEV cpx f480_tw(const T *t, int k) { return t->get_tw(k); }
 
 // radix-4 butterfly of the first stage (m = 1, no twiddles), celt/kiss_fft.c:98-128
 OB_DEV void f480_bfly4_m1(cpx &a0, cpx &a1, cpx &a2, cpx &a3) {
@@ -111,7 +122,7 @@ OB_DEV void f480_bfly5(cpx &f0, cpx &f1, cpx &f2, cpx &f3, cpx &f4, cpx t1, cpx 
 
 // window + fold + pre-rotation of one transform (celt/mdct.c:157-226, N2 = 960, N4 = 480, overlap 120): lane j produces points
 // j + 32k and scatters them to their digit-reversed place in the padded layout.  in: 1080 samples.
-OB_DEV void mdct480_prerotate(const float *__restrict__ in, cpx *__restrict__ F, const Mdct480Tabs *__restrict__ t, int lane) {
+template <class T> OB_DEV void mdct480_prerotate(const float *__restrict__ in, cpx *__restrict__ F, const T *__restrict__ t, int lane) {
   constexpr int N2 = 960, N4 = 480, overlap = 120, q1 = (overlap + 3) >> 2;
   const float scale = f_div(1.f, (float)N4);
 #pragma unroll 3
@@ -120,7 +131,7 @@ OB_DEV void mdct480_prerotate(const float *__restrict__ in, cpx *__restrict__ F,
     const float *xp1 = in + (overlap >> 1) + 2 * i, *xp2 = in + N2 - 1 + (overlap >> 1) - 2 * i;
     float re, im;
     if (i < q1) {
-      const float w1 = t->window[(overlap >> 1) + 2 * i], w2 = t->window[(overlap >> 1) - 1 - 2 * i];
+      const float w1 = t->get_window((overlap >> 1) + 2 * i), w2 = t->get_window((overlap >> 1) - 1 - 2 * i);
       re = xp1[N2] * w2 + (*xp2) * w1;
       im = (*xp1) * w1 - xp2[-N2] * w2;
     } else if (i < N4 - q1) {
@@ -128,22 +139,22 @@ OB_DEV void mdct480_prerotate(const float *__restrict__ in, cpx *__restrict__ F,
       im = *xp1;
     } else {
       const int kk = i - (N4 - q1);
-      const float w1 = t->window[2 * kk], w2 = t->window[overlap - 1 - 2 * kk];
+      const float w1 = t->get_window(2 * kk), w2 = t->get_window(overlap - 1 - 2 * kk);
       re = -(xp1[-N2] * w1) + (*xp2) * w2;
       im = (*xp1) * w2 + xp2[N2] * w1;
     }
-    const float t0 = t->trig[i], t1 = t->trig[N4 + i];
+    const float t0 = t->get_trig(i), t1 = t->get_trig(N4 + i);
     const float yr = re * t0 - im * t1;
     const float yi = im * t0 + re * t1;
     cpx v;
     v.r = yr * scale;
     v.i = yi * scale;
-    F[f480_pos(t->bitrev[i])] = v;
+    F[f480_pos(t->get_bitrev(i))] = v;
   }
 }
 
 // stages 4(m=1), 2(m=4), 4(m=8) of one aligned group of 32 points, in registers.  G: the group's 32 complex values (16-byte aligned).
-OB_DEV void f480_group_stages(cpx *__restrict__ G, const Mdct480Tabs *__restrict__ t) {
+template <class T> OB_DEV void f480_group_stages(cpx *__restrict__ G, const T *__restrict__ t) {
   cpx v[32];
 #pragma unroll
   for (int e = 0; e < 32; e += 2) {
@@ -172,10 +183,7 @@ OB_DEV void f480_group_stages(cpx *__restrict__ G, const Mdct480Tabs *__restrict
 
 // stages 3(m=32), 5(m=96) and the post-rotation (celt/mdct.c:236-262) of one transform: lane j owns points j + 32k.  out: 960 coefficients
 // (8-byte aligned).
-OB_DEV void f480_column_stages_postrotate(const cpx *__restrict__ F, const Mdct480Tabs *__restrict__ t, float *__restrict__ out, int lane) {
-  cpx u[15];
-#pragma unroll
-  for (int k = 0; k < 15; k++) u[k] = F[k * kF480Pad + lane];
+template <class T> OB_DEV void f480_column_stages(cpx (&u)[15], const T *__restrict__ t, int lane) {
   {
     const cpx t1 = f480_tw(t, 5 * lane), t2 = f480_tw(t, 10 * lane);
     const float epi3_i = f480_tw(t, 160).i;
@@ -190,13 +198,19 @@ OB_DEV void f480_column_stages_postrotate(const cpx *__restrict__ F, const Mdct4
       f480_bfly5(u[a], u[3 + a], u[6 + a], u[9 + a], u[12 + a], f480_tw(t, jp), f480_tw(t, 2 * jp), f480_tw(t, 3 * jp), f480_tw(t, 4 * jp), ya, yb);
     }
   }
+}
+template <class T> OB_DEV void f480_column_stages_postrotate(const cpx *__restrict__ F, const T *__restrict__ t, float *__restrict__ out, int lane) {
+  cpx u[15];
+#pragma unroll
+  for (int k = 0; k < 15; k++) u[k] = F[k * kF480Pad + lane];
+  f480_column_stages(u, t, lane);
   // out[2i] = fp.i * t1 - fp.r * t0 from point i;  out[2i + 1] = out[N2 - 1 - 2i'] = fp.r * t1 + fp.i * t0 from point i' = 479 - i,
   // which is register 14 - k of lane 31 - j
   float A[15], B[15];
 #pragma unroll
   for (int k = 0; k < 15; k++) {
     const int i = lane + 32 * k;
-    const float t0 = t->trig[i], t1 = t->trig[480 + i];
+    const float t0 = t->get_trig(i), t1 = t->get_trig(480 + i);
     A[k] = u[k].i * t1 - u[k].r * t0;
     B[k] = u[k].r * t1 + u[k].i * t0;
   }
@@ -211,7 +225,7 @@ OB_DEV void f480_column_stages_postrotate(const cpx *__restrict__ F, const Mdct4
 
 // Two transforms by one warp.  in0 / in1: 1080 samples each (shared memory); F0 / F1: kF480Cpx complex each; out0 / out1: 960 coefficients
 // (in1 == nullptr: one transform only).
-OB_DEV void mdct480_forward_pair(const float *in0, const float *in1, cpx *F0, cpx *F1, const Mdct480Tabs *t, float *out0, float *out1, int lane) {
+template <class T> OB_DEV void mdct480_forward_pair(const float *in0, const float *in1, cpx *F0, cpx *F1, const T *t, float *out0, float *out1, int lane) {
   mdct480_prerotate(in0, F0, t, lane);
   if (in1) mdct480_prerotate(in1, F1, t, lane);
   wsync();
@@ -224,85 +238,52 @@ OB_DEV void mdct480_forward_pair(const float *in0, const float *in1, cpx *F0, cp
   if (in1) f480_column_stages_postrotate(F1, t, out1, lane);
 }
 
+// ---- the long-block INVERSE transform (clt_mdct_backward_c with shift 0, celt/mdct.c:268-369: pre-rotation into digit-reversed order, the same
+// 480-point FFT, post-rotation from both ends) for one warp.  freq: the 960 coefficients; buf: 1020 floats (16-byte aligned), used first as the
+// padded point array and overwritten in place with the 960 time-domain values in natural order (the caller's overlap-add area: the TDAC window
+// mirror of mdct.c:372-388 stays with the caller).  Per point p the post-rotation writes out[2p] = re*t0 + im*t1 of point p and
+// out[2p + 1] = re*t1 - im*t0 of point 479 - p (re / im = the FFT output's imaginary / real part), the pairing of the forward transform. ----
+template <class T> OB_DEV void imdct480_warp(const float *__restrict__ freq, float *__restrict__ buf, const T *__restrict__ t, int lane) {
+  constexpr int N2 = 960, N4 = 480;
+  cpx *F = (cpx *)buf;
+#pragma unroll 3
+  for (int k = 0; k < 15; k++) {
+    const int i = lane + 32 * k;
+    const float x1 = freq[2 * i], x2 = freq[N2 - 1 - 2 * i];
+    const float t0 = t->get_trig(i), t1 = t->get_trig(N4 + i);
+    const float yr = x2 * t0 + x1 * t1;
+    const float yi = x1 * t0 - x2 * t1;
+    cpx v;
+    v.r = yi;
+    v.i = yr;
+    F[f480_pos(t->get_bitrev(i))] = v;
+  }
+  wsync();
+  if (lane < 15) f480_group_stages(F + lane * kF480Pad, t);
+  wsync();
+  cpx u[15];
+#pragma unroll
+  for (int k = 0; k < 15; k++) u[k] = F[k * kF480Pad + lane];
+  wsync();   // every point is in a register: the buffer can take the natural-order output
+  f480_column_stages(u, t, lane);
+  float A[15], B[15];
+#pragma unroll
+  for (int k = 0; k < 15; k++) {
+    const int i = lane + 32 * k;
+    const float re = u[k].i, im = u[k].r;
+    const float t0 = t->get_trig(i), t1 = t->get_trig(N4 + i);
+    A[k] = re * t0 + im * t1;
+    B[k] = re * t1 - im * t0;
+  }
+#pragma unroll
+  for (int k = 0; k < 15; k++) {
+    const float b = shfl(B[14 - k], 31 - lane);
+    float2 o;
+    o.x = A[k]; o.y = b;
+    *(float2 *)(buf + 2 * (lane + 32 * k)) = o;
+  }
+  wsync();
+}
+
 }  // namespace ob
 
-#if defined(__CUDACC__)
-namespace ob {
-// ---- ob_mdct_forward_tma: persistent kernel, tables and inputs staged with cp.async.bulk (the bulk-copy engine of the TMA unit) ----
-// One CTA of kMdctFastWarps warps per SM slot; the four constant tables (9 KB) are copied into shared memory once per CTA, every warp
-// then loops over PAIRS of transforms: its two 4320-byte inputs arrive by bulk copy on the warp's own mbarrier, and the copy of the next
-// pair is issued as soon as the pre-rotation has consumed the current one, so it lands under the FFT.  Outputs go straight from
-// registers to HBM as coalesced 8-byte stores.  HBM traffic = the algorithmic 8160 B per transform (4320 in + 3840 out).
-namespace tma {
-__device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: a protocol error traps instead of hanging the GPU
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; spin++) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-}  // namespace tma
-
-constexpr int kMdctFastWarps = 6;
-struct alignas(16) MdctFastWarpWS { float in[2][1080]; cpx F[2][kF480Cpx]; };
-struct alignas(16) MdctFastSmem { Mdct480Tabs tabs; MdctFastWarpWS w[kMdctFastWarps]; unsigned long long bar[kMdctFastWarps + 1]; };
-
-OB_DEV void mdct_forward_tma_block(const MdctFwdParams &p, unsigned char *smem) {
-  MdctFastSmem *S = (MdctFastSmem *)smem;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t tab_bar = tma::saddr(&S->bar[kMdctFastWarps]), my_bar = tma::saddr(&S->bar[warp]);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i <= kMdctFastWarps; i++) tma::mbar_init(tma::saddr(&S->bar[i]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    tma::mbar_expect_tx(tab_bar, sizeof(Mdct480Tabs));
-    tma::bulk_g2s(tma::saddr(S->tabs.trig), ob_mdct_trig, sizeof(S->tabs.trig), tab_bar);
-    tma::bulk_g2s(tma::saddr(S->tabs.tw), ob_fft_tw, sizeof(S->tabs.tw), tab_bar);
-    tma::bulk_g2s(tma::saddr(S->tabs.window), ob_window, sizeof(S->tabs.window), tab_bar);
-    tma::bulk_g2s(tma::saddr(S->tabs.bitrev), ob_fft_bitrev480, sizeof(S->tabs.bitrev), tab_bar);
-  }
-  MdctFastWarpWS *w = &S->w[warp];
-  const int npairs = (p.n_items + 1) >> 1, stride = gridDim.x * kMdctFastWarps;
-  int pair = blockIdx.x * kMdctFastWarps + warp;
-  auto issue = [&](int pr) {   // lane 0: the two inputs of pair pr
-    const int two = 2 * pr + 1 < p.n_items;
-    tma::mbar_expect_tx(my_bar, (two ? 2u : 1u) * 4320u);
-    tma::bulk_g2s(tma::saddr(w->in[0]), p.in + (size_t)(2 * pr) * p.in_stride, 4320u, my_bar);
-    if (two) tma::bulk_g2s(tma::saddr(w->in[1]), p.in + (size_t)(2 * pr + 1) * p.in_stride, 4320u, my_bar);
-  };
-  if (lane == 0 && pair < npairs) issue(pair);
-  tma::mbar_wait(tab_bar, 0);
-  uint32_t phase = 0;
-  for (; pair < npairs; pair += stride) {
-    const bool two = 2 * pair + 1 < p.n_items;
-    tma::mbar_wait(my_bar, phase);
-    phase ^= 1;
-    mdct480_prerotate(w->in[0], w->F[0], &S->tabs, lane);
-    if (two) mdct480_prerotate(w->in[1], w->F[1], &S->tabs, lane);
-    __syncwarp();
-    if (lane == 0 && pair + stride < npairs) {   // the inputs are consumed: the next pair's copy runs under the FFT
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(pair + stride);
-    }
-    {
-      const int g = lane & 15, which = lane >> 4;
-      if (g < 15 && (which == 0 || two)) f480_group_stages(w->F[which] + g * kF480Pad, &S->tabs);
-    }
-    __syncwarp();
-    f480_column_stages_postrotate(w->F[0], &S->tabs, p.out + (size_t)(2 * pair) * p.out_stride, lane);
-    if (two) f480_column_stages_postrotate(w->F[1], &S->tabs, p.out + (size_t)(2 * pair + 1) * p.out_stride, lane);
-    __syncwarp();
-  }
-}
-}  // namespace ob
-#endif

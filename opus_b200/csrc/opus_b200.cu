@@ -15,7 +15,7 @@
 #include "celt_dec_kernels.cuh"
 #include "celt_dec_plc.cuh"
 #include "celt_ops.cuh"
-#include "celt_mdct_fast.cuh"
+#include "celt_mdct_tma.cuh"
 #include "silk_ops.cuh"
 #include "silk_nsq.cuh"
 
@@ -486,6 +486,8 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
       OB_CUDA(cudaStreamWaitEvent(sb, d->ev_a2[par], 0));
     }
     DecSynthParams sp;
+    static const int force_smem_fft = getenv("OPUSB200_SYNTH_SMEM_FFT") ? 1 : 0;
+    sp.force_smem_fft = force_smem_fft;
     sp.side = d->side[par] + s0; sp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels; sp.downsample = d->downsample;
