@@ -24,7 +24,10 @@
 namespace ob {
 
 constexpr int kF480Pad = 34, kF480Cpx = 15 * kF480Pad;
-OB_DEV int f480_pos(int i) { return (i >> 5) * kF480Pad + (i & 31); }
+template <int PAD = kF480Pad> OB_DEV int f480_pos(int i) { return (i >> 5) * PAD + (i & 31); }
+// PAD = 34 (16-byte group loads) everywhere except the encoder's analysis kernel, which has 3960 bytes to spare per warp, not 4080: PAD = 33 there
+// (8-byte group loads; the lane-per-group and lane-per-column access patterns stay conflict-free for any odd or even stride that is not a multiple of 16 words)
+constexpr int kF480PadSmall = 33;
 
 // the constant tables of the transform, staged in shared memory once per CTA (ob_mdct_fast_kernel: by cp.async.bulk)
 struct alignas(16) Mdct480Tabs {
@@ -122,7 +125,7 @@ OB_DEV void f480_bfly5(cpx &f0, cpx &f1, cpx &f2, cpx &f3, cpx &f4, cpx t1, cpx 
 
 // window + fold + pre-rotation of one transform (celt/mdct.c:157-226, N2 = 960, N4 = 480, overlap 120): lane j produces points
 // j + 32k and scatters them to their digit-reversed place in the padded layout.  in: 1080 samples.
-template <class T> OB_DEV void mdct480_prerotate(const float *__restrict__ in, cpx *__restrict__ F, const T *__restrict__ t, int lane) {
+template <int PAD = kF480Pad, class T> OB_DEV void mdct480_prerotate(const float *__restrict__ in, cpx *__restrict__ F, const T *__restrict__ t, int lane) {
   constexpr int N2 = 960, N4 = 480, overlap = 120, q1 = (overlap + 3) >> 2;
   const float scale = f_div(1.f, (float)N4);
 #pragma unroll 3
@@ -149,17 +152,22 @@ template <class T> OB_DEV void mdct480_prerotate(const float *__restrict__ in, c
     cpx v;
     v.r = yr * scale;
     v.i = yi * scale;
-    F[f480_pos(t->get_bitrev(i))] = v;
+    F[f480_pos<PAD>(t->get_bitrev(i))] = v;
   }
 }
 
 // stages 4(m=1), 2(m=4), 4(m=8) of one aligned group of 32 points, in registers.  G: the group's 32 complex values (16-byte aligned).
-template <class T> OB_DEV void f480_group_stages(cpx *__restrict__ G, const T *__restrict__ t) {
+template <bool WIDE = true, class T> OB_DEV void f480_group_stages(cpx *__restrict__ G, const T *__restrict__ t) {
   cpx v[32];
+  if (WIDE) {
 #pragma unroll
-  for (int e = 0; e < 32; e += 2) {
-    const float4 q = *(const float4 *)(G + e);
-    v[e].r = q.x; v[e].i = q.y; v[e + 1].r = q.z; v[e + 1].i = q.w;
+    for (int e = 0; e < 32; e += 2) {
+      const float4 q = *(const float4 *)(G + e);
+      v[e].r = q.x; v[e].i = q.y; v[e + 1].r = q.z; v[e + 1].i = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; e++) v[e] = G[e];
   }
 #pragma unroll
   for (int q = 0; q < 8; q++) f480_bfly4_m1(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -173,11 +181,16 @@ template <class T> OB_DEV void f480_group_stages(cpx *__restrict__ G, const T *_
 #pragma unroll
   for (int j = 0; j < 8; j++)   // twiddle stride 15 (fstride of this stage): indices are compile-time constants, the loads broadcast
     f480_bfly4(v[j], v[j + 8], v[j + 16], v[j + 24], f480_tw(t, 15 * j), f480_tw(t, 30 * j), f480_tw(t, 45 * j));
+  if (WIDE) {
 #pragma unroll
-  for (int e = 0; e < 32; e += 2) {
-    float4 q;
-    q.x = v[e].r; q.y = v[e].i; q.z = v[e + 1].r; q.w = v[e + 1].i;
-    *(float4 *)(G + e) = q;
+    for (int e = 0; e < 32; e += 2) {
+      float4 q;
+      q.x = v[e].r; q.y = v[e].i; q.z = v[e + 1].r; q.w = v[e + 1].i;
+      *(float4 *)(G + e) = q;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; e++) G[e] = v[e];
   }
 }
 
@@ -199,10 +212,10 @@ template <class T> OB_DEV void f480_column_stages(cpx (&u)[15], const T *__restr
     }
   }
 }
-template <class T> OB_DEV void f480_column_stages_postrotate(const cpx *__restrict__ F, const T *__restrict__ t, float *__restrict__ out, int lane) {
+template <int PAD = kF480Pad, class T> OB_DEV void f480_column_stages_postrotate(const cpx *__restrict__ F, const T *__restrict__ t, float *__restrict__ out, int lane) {
   cpx u[15];
 #pragma unroll
-  for (int k = 0; k < 15; k++) u[k] = F[k * kF480Pad + lane];
+  for (int k = 0; k < 15; k++) u[k] = F[k * PAD + lane];
   f480_column_stages(u, t, lane);
   // out[2i] = fp.i * t1 - fp.r * t0 from point i;  out[2i + 1] = out[N2 - 1 - 2i'] = fp.r * t1 + fp.i * t0 from point i' = 479 - i,
   // which is register 14 - k of lane 31 - j

@@ -12,6 +12,7 @@
 // These are the building blocks of the fused encoder (next round) and the B3-level parity surface.
 #pragma once
 #include "celt_fft.cuh"
+#include "celt_mdct_fast.cuh"
 #include "celt_vec.cuh"
 #include "celt_enc_pre.cuh"
 #include "opus_enc_layer.cuh"
@@ -23,11 +24,24 @@ struct MdctFwdParams {
   float *out;        // [n_items][out_stride]: B*N coefficients per item
   int n_items, in_stride, out_stride, LM, transient;
 };
-struct MdctWS { float in[OB_MAXN + OB_OVERLAP + 8]; float f2[OB_MAXN]; };
+struct MdctWS { float in[OB_MAXN + OB_OVERLAP + 4]; float f2[2 * 15 * kF480PadSmall + 2]; };   // f2: 480 complex points: 960 floats for the shared-memory FFT, 990 in the
+                                                                                              // padded layout (33 per group of 32) of the register FFT
 
 // forward MDCT of the B*N+overlap samples already in ws->in; coefficients go to `o` (HBM, or ws->in itself: the time
 // samples are dead once the pre-rotation has run)
-OB_DEV void mdct_forward_from_ws(MdctWS *ws, int LM, int transient, float *o, int lane) {
+// fast: the long block (LM = 3, one 960-point transform) takes the register FFT of celt_mdct_fast.cuh (tables from global memory); the arithmetic per
+// butterfly is the same, the results are bit-identical (the general kernel ob_mdct_forward passes false and stays the A/B reference)
+OB_DEV void mdct_forward_from_ws(MdctWS *ws, int LM, int transient, float *o, int lane, bool fast = true) {
+  if (fast && LM == 3 && !transient) {
+    const Mdct480Global tabs;
+    cpx *F = (cpx *)ws->f2;
+    mdct480_prerotate<kF480PadSmall>(ws->in, F, &tabs, lane);
+    wsync();
+    if (lane < 15) f480_group_stages<false>(F + lane * kF480PadSmall, &tabs);
+    wsync();
+    f480_column_stages_postrotate<kF480PadSmall>(F, &tabs, o, lane);
+    return;
+  }
   const int nblk = transient ? 1 << LM : 1, NB = transient ? OB_SHORT_N : OB_SHORT_N << LM;
   const int shift = transient ? 3 : 3 - LM;
   const int N2 = NB, N4 = NB >> 1, nfft = N4, overlap = OB_OVERLAP;
@@ -81,7 +95,7 @@ OB_DEV void mdct_forward_warp(const MdctFwdParams &p, int item, unsigned char *s
   const float *g = p.in + (size_t)item * p.in_stride;
   for (int i = lane; i < n_in; i += 32) ws->in[i] = g[i];
   wsync();
-  mdct_forward_from_ws(ws, p.LM, p.transient, p.out + (size_t)item * p.out_stride, lane);
+  mdct_forward_from_ws(ws, p.LM, p.transient, p.out + (size_t)item * p.out_stride, lane, false);
 }
 
 // ---- encoder front end, one warp per (stream, channel): pre-emphasis -> MDCT -> band energies -> log2 -> normalised bands
