@@ -33,6 +33,7 @@ struct DecSynthParams {
   int downsample;           // 48000 / output rate: every downsample-th de-emphasised sample is written (celt_decoder.c:300-405)
   int apply_gain;           // OPUS_SET_GAIN != 0 (src/opus_decoder.c:686-700)
   float gain;
+  int no_prefetch = 0;      // A/B aid: load the spectrum where it is used (OPUSB200_SYNTH_NO_PREFETCH)
   int force_smem_fft = 0;   // A/B aid: the general shared-memory FFT for long blocks too (OPUSB200_SYNTH_SMEM_FFT)
   int defer_clip = 0;       // int16 output of a packet that may hold several frames: pcm is a FLOAT staging area and opus_decode()'s soft
                             // clipping runs once over the whole packet afterwards (dec_softclip_packet_block), as in the reference
@@ -186,6 +187,22 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
   int bound = silence ? 0 : M * ob_ebands[end];
   const int ds = p.downsample, Nd = N / ds;
   if (ds != 1) bound = OB_IMIN(bound, Nd);  // celt_decoder.c:451-452
+  // ---- the spectrum: this lane's loads (30 values at N = 960) are issued before the band gains are computed, so that the HBM latency runs under
+  //      the 42 double-precision exp() of the gains (OPUSB200_SYNTH_NO_PREFETCH: load where the value is used, for A/B runs) ----
+  const float *X0 = p.X + (size_t)stream * 2 * OB_MAXN;
+  const float *X1 = X0 + N;
+  const int srcc = (C == 2 && CC == 2) ? ch : 0;
+  const float *Xs = srcc ? X1 : X0;
+  const bool downmix = CC == 1 && C == 2;
+  constexpr int kPer = OB_MAXN / 32;
+  float xv[kPer];
+  if (!p.no_prefetch) {
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int j = lane + 32 * k;
+      xv[k] = j < bound ? Xs[j] : 0.f;
+    }
+  }
   // ---- band gains (denormalise_bands, celt/bands.c:188-257) ----
   for (int i = lane; i < 2 * OB_NBANDS; i += 32) {
     int band = i >= OB_NBANDS ? i - OB_NBANDS : i;
@@ -193,26 +210,26 @@ OB_DEV void dec_synth_block(const DecSynthParams &p, int stream, unsigned char *
     ws->gain[i] = exp2_ref(32.f < lg ? 32.f : lg);
   }
   wsync();
-  // ---- load X, apply gains -> freq (coalesced) ----
+  // ---- apply gains -> freq ----
   {
-    const float *X0 = p.X + (size_t)stream * 2 * OB_MAXN;
-    const float *X1 = X0 + N;
-    const int srcc = (C == 2 && CC == 2) ? ch : 0;
-    const float *Xs = srcc ? X1 : X0;
     const float *gs = ws->gain + srcc * OB_NBANDS;
     int band = 0;
-    for (int j = lane; j < N; j += 32) {
-      float v = 0.f;
-      if (j < bound) {
-        int u = j >> LM;
-        while (ob_ebands[band + 1] <= u) band++;
-        v = Xs[j] * gs[band];
-        if (CC == 1 && C == 2) {  // downmix, celt_decoder.c:478-481
-          float v2 = X1[j] * ws->gain[OB_NBANDS + band];
-          v = (.5f * v) + (.5f * v2);
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int j = lane + 32 * k;
+      if (j < N) {
+        float v = 0.f;
+        if (j < bound) {
+          int u = j >> LM;
+          while (ob_ebands[band + 1] <= u) band++;
+          v = (p.no_prefetch ? Xs[j] : xv[k]) * gs[band];
+          if (downmix) {  // celt_decoder.c:478-481
+            float v2 = X1[j] * ws->gain[OB_NBANDS + band];
+            v = (.5f * v) + (.5f * v2);
+          }
         }
+        ws->freq[j] = v;
       }
-      ws->freq[j] = v;
     }
   }
   // previous tail -> out[0..60)

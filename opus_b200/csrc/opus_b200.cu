@@ -488,6 +488,8 @@ static int decode_launch(OpusB200Decoder *d, cudaStream_t st, int s0, int cn, co
     DecSynthParams sp;
     static const int force_smem_fft = getenv("OPUSB200_SYNTH_SMEM_FFT") ? 1 : 0;
     sp.force_smem_fft = force_smem_fft;
+    static const int no_prefetch = getenv("OPUSB200_SYNTH_NO_PREFETCH") ? 1 : 0;
+    sp.no_prefetch = no_prefetch;
     sp.side = d->side[par] + s0; sp.X = d->X[par] + (size_t)s0 * 2 * OB_MAXN; sp.state = d->sstate + s0;
     sp.pcm = (char *)d_pcm + (size_t)s0 * pcm_stride * esz; sp.pcm_stride = pcm_stride; sp.frame_index = k;
     sp.pcm_is_int16 = pcm_is_int16; sp.n_streams = cn; sp.channels = d->channels; sp.downsample = d->downsample;
