@@ -607,7 +607,7 @@ def run_gpu_encode(args, rank, world, local_rank):
     else:
         t_pcm = torch.empty((ENC_BASE, T, FRAME * CH), dtype=torch.int16, device=dev)
     if world > 1:
-        dist.broadcast(t_pcm, 0)
+        dist.broadcast(t_pcm.view(torch.uint8), 0)   # (NCCL has no int16: the bytes travel)
     rows = parallel.fixture_rows(rank, world, n, ENC_BASE).to(dev)
     # experiments on SIMT divergence (never the reported configuration): 'family' puts streams of the same signal family in a warp,
     # 'same' gives all 32 lanes of a warp the same stream (the convergence ceiling)

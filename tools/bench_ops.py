@@ -332,6 +332,59 @@ def main():
         cpu = time_cpu(one, 0.5)
     emit('celt_pvq_search_N16_K8', 'vectors', n * 8, ms, N * 8 + 8, cpu)
 
+    # ---- round 2: the decoder-side resampler (16 -> 48 kHz: 2x all-pass + FIR interpolation), 20 ms ----
+    rs = ops.silk_resampler(n, 16000, 48000, False)
+    xi = torch.from_numpy(rng.integers(-30000, 30000, size=(n, 320)).astype(np.int16)).to(dev)
+    yo = torch.empty((n, 960), dtype=torch.int16, device=dev)
+    fn = lambda: L.opusb200_silk_resampler_process(rs._h, dptr(xi), dptr(yo), 320, 1)
+    ms = time_gpu(stream, fn, a.reps)
+    cpu = None
+    if RC is not None:
+        st_ = ctypes.create_string_buffer(RC.refh_resampler_size())
+        RC.silk_resampler_init(st_, 16000, 48000, 0)
+        x1 = xi[0].cpu().numpy().copy()
+        y1 = np.zeros(960, np.int16)
+        cpu = time_cpu(lambda: RC.silk_resampler(st_, y1.ctypes.data_as(ctypes.c_void_p), x1.ctypes.data_as(ctypes.c_void_p), 320), 0.5)
+    emit('silk_resampler_16k_to_48k_20ms', 'frames', n, ms, 320 * 2 + 960 * 2 + 2 * 184, cpu)
+    rs.close()
+
+    # ---- round 2: the bitstream of a SILK frame (silk_encode_indices + silk_encode_pulses, WB 20 ms) on the device range-encoder object ----
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_silk_coder_oracle_vs_ref import SilkIndices, random_indices, make_pulses
+    base = 512
+    idx = (SilkIndices * base)()
+    r2 = np.random.default_rng(5)
+    for s_ in range(base):
+        idx[s_] = random_indices(r2, 16, 4, 0)
+    P = make_pulses(r2, base, 320, 1)
+    reps_n = (n + base - 1) // base
+    idx_np = np.frombuffer(idx, dtype=np.uint8).reshape(base, ctypes.sizeof(SilkIndices))
+    d_idx = torch.from_numpy(np.tile(idx_np, (reps_n, 1))[:n].copy()).to(dev)
+    d_P = torch.from_numpy(np.tile(P, (reps_n, 1))[:n].copy()).to(dev)
+    d_st = torch.from_numpy(np.tile(np.array([idx[s_].signalType for s_ in range(base)], np.int32), reps_n)[:n].copy()).to(dev)
+    d_qo = torch.from_numpy(np.tile(np.array([idx[s_].quantOffsetType for s_ in range(base)], np.int32), reps_n)[:n].copy()).to(dev)
+    d_cc = torch.zeros(n, dtype=torch.int32, device=dev)
+    re = ops.range_encoder(n, 608)
+
+    def silk_frame():
+        L.opusb200_range_encoder_init(re._h, 600)
+        L.opusb200_silk_encode_indices(re._h, 16, 4, dptr(d_idx), dptr(d_cc), 1)
+        L.opusb200_silk_encode_pulses(re._h, dptr(d_st), dptr(d_qo), dptr(d_P), P.shape[1], 320, 1)
+    ms = time_gpu(stream, silk_frame, a.reps)
+    cpu = None
+    if RC is not None:
+        rc = ctypes.create_string_buffer(RC.refh_silk_coder_size())
+        prev = (ctypes.c_int * 2)(0, 0)
+        q1 = P[0].copy()
+
+        def one_frame():
+            RC.refh_silk_coder_init(rc, 600)
+            RC.refh_silk_encode_indices(rc, 16, 4, ctypes.byref(idx[0]), 0, prev)
+            RC.refh_silk_encode_pulses(rc, int(idx[0].signalType), int(idx[0].quantOffsetType), q1.ctypes.data_as(ctypes.c_void_p), 320)
+        cpu = time_cpu(one_frame, 0.5)
+    emit('silk_frame_bitstream_wb_20ms', 'frames', n, ms, 36 + 320 + 100, cpu, 'indices + pulses through ec_enc; algorithmic bytes: indices + pulses in, ~100 B out')
+    re.close()
+
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'bench_ops.json'), 'w') as f:
         json.dump(out, f, indent=1)
