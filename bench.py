@@ -373,6 +373,20 @@ def cpu_encode_baseline(steps, warmup, streams_per_core=64, reps=4):
             'min': float(min(vals)), 'max': float(max(vals))}, tot_t / max(1, steps)
 
 
+_REAL_STDOUT_FD = None
+
+
+def print_result(obj):
+    """the one JSON line of the run, on the real stdout"""
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    sys.stdout.write(json.dumps(obj) + '\n')
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(2, 1)
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -400,7 +414,7 @@ def run_reference_arm(args, rank, world):
                      'config': {'workload': 'batched CELT encode via opus_encode, RESTRICTED_CELT, complexity 10, 48 kHz stereo 20 ms @64 kb/s VBR (BASELINE.json configs[2])',
                                 'sample': cb['sample'], 'cpu': cb['kind']},
                      'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps({
+    print_result({
         'impl': 'reference', 'metric': 'celt_decode_frames_per_s', 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * t / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -411,7 +425,7 @@ def run_reference_arm(args, rank, world):
                          'min': float(min(vals)), 'max': float(max(vals))},
         'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         **({'encode': enc_block} if enc_block else {}),
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------------------------
@@ -809,7 +823,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         line['encode'] = enc
         line['gpu_launches_decode'] = line['gpu_launches']
         line['gpu_launches'] = line['gpu_launches'] + enc['gpu_launches']
-    print(json.dumps(line))
+    print_result(line)
 
 
 def main():
@@ -827,6 +841,12 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly ONE line, the JSON result: whatever libraries print while the job runs (NCCL's version banner comes from C code, past
+    # sys.stdout) is sent to stderr by pointing file descriptor 1 there; print_result() points it back for the one line
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference_arm(args, rank, world)
         return

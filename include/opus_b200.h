@@ -399,6 +399,19 @@ void opusb200_fargan_destroy(OpusB200Fargan *f);
 int opusb200_fargan_cont(OpusB200Fargan *f, const float *pcm0, const float *features0, int on_device);
 int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const float *features, int on_device);
 
+/* ---- DRED encoder network (dnn/dred_rdovae_enc.h:48, dnn/dred_rdovae_enc.c:47-116; called per double frame from dred_process_frame,
+ * dnn/dred_encoder.c): layers = the 24 LinearLayers of the generated RDOVAEEnc struct in declaration order (enc_dense1, enc_zdense, gdense1, gdense2,
+ * enc_conv_dense1..5, enc_gru1..5 input / recurrent, enc_conv1..5), n streams in lockstep, one RDOVAEEncState per stream on the device.
+ *   opusb200_dred_encode_dframe(enc, latents [n][latent_dim], initial_state [n][state_dim], input [n][2 * 20 features], on_device)
+ * = dred_rdovae_encode_dframe for every stream; latents and state bit-identical to the reference given the same model.  The feature extraction in
+ * front of it (lpcnet_enc.c) and the entropy coding of the latents behind it (dred_encoder.c / dred_coding.c) are not built. ---- */
+typedef struct OpusB200DredEnc OpusB200DredEnc;
+int opusb200_dred_encoder_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int latent_dim, int state_dim,
+                                 int n_streams, OpusB200DredEnc **out);
+void opusb200_dred_encoder_destroy(OpusB200DredEnc *enc);
+int opusb200_dred_encoder_reset(OpusB200DredEnc *enc);
+int opusb200_dred_encode_dframe(OpusB200DredEnc *enc, float *latents, float *initial_state, const float *input, int on_device);
+
 /* ---- Neural packet-loss concealment (dnn/lpcnet_plc.c, struct LPCNetPLCState of dnn/lpcnet_private.h:48-71): n streams that take their update /
  * conceal calls in lockstep (the recovery decode of a batch: every stream conceals frame k in the same call), each with its own FEC / DRED feature
  * queue, predictor state and PCM history.

@@ -38,6 +38,7 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_nnet_compute_gru', 'opusb200_nnet_compute_glu', 'opusb200_nnet_compute_conv1d',
            'opusb200_nnet_conv2d_create', 'opusb200_nnet_conv2d_destroy', 'opusb200_nnet_compute_conv2d',
            'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize',
+           'opusb200_dred_encoder_create', 'opusb200_dred_encoder_destroy', 'opusb200_dred_encoder_reset', 'opusb200_dred_encode_dframe',
            'opusb200_lpcnet_plc_create', 'opusb200_lpcnet_plc_destroy', 'opusb200_lpcnet_plc_reset', 'opusb200_lpcnet_plc_fec_add', 'opusb200_lpcnet_plc_fec_clear',
            'opusb200_lpcnet_plc_update', 'opusb200_lpcnet_plc_conceal', 'opusb200_lpcnet_plc_get_state',
            'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free',
@@ -184,6 +185,11 @@ def lib():
         L.opusb200_fargan_destroy.restype = None
         L.opusb200_fargan_cont.argtypes = [vp, vp, vp, ci]
         L.opusb200_fargan_synthesize.argtypes = [vp, vp, vp, ci]
+        L.opusb200_dred_encoder_create.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_dred_encoder_destroy.argtypes = [vp]
+        L.opusb200_dred_encoder_destroy.restype = None
+        L.opusb200_dred_encoder_reset.argtypes = [vp]
+        L.opusb200_dred_encode_dframe.argtypes = [vp, vp, vp, vp, ci]
         L.opusb200_lpcnet_plc_create.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.POINTER(vp)]
         L.opusb200_lpcnet_plc_destroy.argtypes = [vp]
         L.opusb200_lpcnet_plc_destroy.restype = None

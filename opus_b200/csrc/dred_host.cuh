@@ -149,3 +149,125 @@ extern "C" int opusb200_dred_decode_all(OpusB200DredDec *d, float *features, con
   }
   return OPUSB200_OK;
 }
+
+// ---- the DRED ENCODER network (dnn/dred_rdovae_enc.c:47-116): dred_rdovae_encode_dframe for a batch of streams in lockstep.  Same DenseNet shape as
+// the decoder: one [n][544] activation matrix (dense1 64 + 5 x (GRU 32 + conv 64)), every layer reads its leading columns; conv1 has dilation 1,
+// conv2..5 dilation 2.  One call = one double feature frame (2 x 20 features) per stream -> 25 latents + the 50-value initial state. ----
+namespace ob {
+constexpr int kDeGru = 32, kDeConv = 64, kDeDense1 = 64, kDeBuf = kDeDense1 + 5 * (kDeGru + kDeConv), kDeLatPad = 32, kDeStatePad = 56;
+enum { DE_DENSE1 = 0, DE_ZDENSE = 1, DE_GDENSE1 = 2, DE_GDENSE2 = 3, DE_CONV_DENSE1 = 4, DE_GRU1_IN = 9, DE_CONV1 = 19, DE_COUNT = 24 };
+}
+struct OpusB200DredEnc {
+  OpusB200Ctx *ctx;
+  int n, latent_dim, state_dim, initialized;
+  OpusB200Linear *l[DE_COUNT];
+  float *buf;                 // [n][544] activation rows
+  float *gru[5], *conv[5];    // [n][32], [n][64 * dilation] layer memories
+  float *tmp, *tmp2;          // [n][128] scratch
+  float *d_in, *d_lat, *d_state;   // staging for host callers
+};
+static void de_free(OpusB200DredEnc *d) {
+  if (!d) return;
+  for (int i = 0; i < DE_COUNT; i++) opusb200_nnet_linear_destroy(d->l[i]);
+  cudaFree(d->buf); cudaFree(d->tmp); cudaFree(d->tmp2); cudaFree(d->d_in); cudaFree(d->d_lat); cudaFree(d->d_state);
+  for (int k = 0; k < 5; k++) { cudaFree(d->gru[k]); cudaFree(d->conv[k]); }
+  delete d;
+}
+// init_rdovaeenc: the 24 LinearLayers of the generated RDOVAEEnc struct (dred_rdovae_enc_data.h) in declaration order: enc_dense1, enc_zdense,
+// gdense1, gdense2, enc_conv_dense1..5, enc_gru1..5 (input, recurrent), enc_conv1..5; latent_dim / state_dim: DRED_LATENT_DIM / DRED_STATE_DIM
+// (the z / state layers are padded to a multiple of 8 outputs, the call returns the leading latent_dim / state_dim values like the reference)
+extern "C" int opusb200_dred_encoder_create(OpusB200Ctx *c, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int latent_dim, int state_dim,
+                                            int n_streams, OpusB200DredEnc **out) {
+  if (!out) return OPUSB200_BAD_ARG;
+  *out = nullptr;
+  if (!c || !layers || n_layers != DE_COUNT || n_streams <= 0 || latent_dim <= 0 || latent_dim > kDeLatPad || state_dim <= 0 || state_dim > kDeStatePad)
+    return OPUSB200_BAD_ARG;
+  static const int ins[DE_COUNT] = {40, 544, 544, 128, 96, 192, 288, 384, 480, 64, 32, 160, 32, 256, 32, 352, 32, 448, 32, 128, 128, 128, 128, 128};
+  static const int outs[DE_COUNT] = {64, kDeLatPad, 128, kDeStatePad, 64, 64, 64, 64, 64, 96, 96, 96, 96, 96, 96, 96, 96, 96, 96, 64, 64, 64, 64, 64};
+  for (int i = 0; i < DE_COUNT; i++)
+    if (layers[i].nb_inputs != ins[i] || layers[i].nb_outputs != outs[i]) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200DredEnc *d = new (std::nothrow) OpusB200DredEnc;
+  if (!d) return OPUSB200_ALLOC_FAIL;
+  memset(d, 0, sizeof(*d));
+  d->ctx = c; d->n = n_streams; d->latent_dim = latent_dim; d->state_dim = state_dim;
+  for (int i = 0; i < DE_COUNT; i++) {
+    const int r = opusb200_nnet_linear_create(c, &layers[i], su_bias, &d->l[i]);
+    if (r != OPUSB200_OK) { de_free(d); return r; }
+  }
+  const size_t n = (size_t)n_streams;
+  bool ok = cudaMalloc(&d->buf, sizeof(float) * n * kDeBuf) == cudaSuccess && cudaMalloc(&d->tmp, sizeof(float) * n * 128) == cudaSuccess &&
+            cudaMalloc(&d->tmp2, sizeof(float) * n * 128) == cudaSuccess && cudaMalloc(&d->d_in, sizeof(float) * n * 40) == cudaSuccess &&
+            cudaMalloc(&d->d_lat, sizeof(float) * n * kDeLatPad) == cudaSuccess && cudaMalloc(&d->d_state, sizeof(float) * n * kDeStatePad) == cudaSuccess;
+  for (int k = 0; k < 5 && ok; k++)
+    ok = cudaMalloc(&d->gru[k], sizeof(float) * n * kDeGru) == cudaSuccess && cudaMalloc(&d->conv[k], sizeof(float) * n * kDeConv * 2) == cudaSuccess;
+  if (!ok) { de_free(d); return OPUSB200_ALLOC_FAIL; }
+  for (int k = 0; k < 5; k++) cudaMemsetAsync(d->gru[k], 0, sizeof(float) * n * kDeGru, c->stream);
+  OB_CUDA(cudaStreamSynchronize(c->stream));
+  *out = d;
+  return OPUSB200_OK;
+}
+extern "C" void opusb200_dred_encoder_destroy(OpusB200DredEnc *d) {
+  if (!d) return;
+  cudaSetDevice(d->ctx->device);
+  cudaStreamSynchronize(d->ctx->stream);
+  de_free(d);
+}
+extern "C" int opusb200_dred_encoder_reset(OpusB200DredEnc *d) {   // a zeroed RDOVAEEncState
+  if (!d) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(d->ctx->device));
+  for (int k = 0; k < 5; k++) OB_CUDA(cudaMemsetAsync(d->gru[k], 0, sizeof(float) * (size_t)d->n * kDeGru, d->ctx->stream));
+  d->initialized = 0;
+  return OPUSB200_OK;
+}
+// dred_rdovae_encode_dframe for every stream: input [n][40] -> latents [n][latent_dim], initial_state [n][state_dim]
+extern "C" int opusb200_dred_encode_dframe(OpusB200DredEnc *d, float *latents, float *initial_state, const float *input, int on_device) {
+  if (!d || !latents || !initial_state || !input) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = d->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  const int n = d->n;
+  const float *din = input;
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(d->d_in, input, sizeof(float) * (size_t)n * 40, cudaMemcpyHostToDevice, c->stream));
+    din = d->d_in;
+  }
+  DR_TRY(opusb200_nnet_compute_dense(c, d->l[DE_DENSE1], d->tmp, din, n, NN_TANH, 1));
+  DR_TRY(dr_copy2d(c, d->buf, kDeBuf, d->tmp, kDeDense1, kDeDense1, n));
+  int col = kDeDense1;
+  for (int k = 0; k < 5; k++) {
+    const int dilation = k == 0 ? 1 : 2;
+    const OpusB200Linear *wi = d->l[DE_GRU1_IN + 2 * k], *wr = d->l[DE_GRU1_IN + 2 * k + 1];
+    float *zrh;
+    if (nnet_scratch(c, 1, sizeof(float) * (size_t)n * 6 * kDeGru, (void **)&zrh)) return (int)OPUSB200_ALLOC_FAIL;
+    float *recur = zrh + (size_t)n * 3 * kDeGru;
+    DR_TRY(nnet_linear_dev(c, wi, zrh, d->buf, n, NN_LINEAR, nullptr, nullptr, kDeBuf));
+    DR_TRY(nnet_linear_dev(c, wr, recur, d->gru[k], n));
+    NnetGruParams g;
+    g.state = d->gru[k]; g.zrh = zrh; g.recur = recur; g.n = n; g.N = kDeGru;
+    ob_nnet_gru<<<nblk((long)n * kDeGru, 256), 256, 0, c->stream>>>(g);
+    c->launches++;
+    DR_TRY(dr_copy2d(c, d->buf + col, kDeBuf, d->gru[k], kDeGru, kDeGru, n));
+    col += kDeGru;
+    if (!d->initialized) OB_CUDA(cudaMemsetAsync(d->conv[k], 0, sizeof(float) * (size_t)n * kDeConv * dilation, c->stream));   // conv1_cond_init (:39-45)
+    DR_TRY(nnet_linear_dev(c, d->l[DE_CONV_DENSE1 + k], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDeBuf));
+    DR_TRY(nnet_act_dev(c, d->tmp, d->tmp, n, kDeConv, NN_TANH));
+    DR_TRY(opusb200_nnet_compute_conv1d(c, d->l[DE_CONV1 + k], d->tmp2, d->conv[k], d->tmp, n, kDeConv, dilation, NN_TANH, 1));
+    DR_TRY(dr_copy2d(c, d->buf + col, kDeBuf, d->tmp2, kDeConv, kDeConv, n));
+    col += kDeConv;
+  }
+  float *dl = on_device ? nullptr : d->d_lat, *dsv = on_device ? nullptr : d->d_state;
+  DR_TRY(nnet_linear_dev(c, d->l[DE_ZDENSE], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDeBuf));
+  DR_TRY(dr_copy2d(c, on_device ? latents : dl, d->latent_dim, d->tmp, kDeLatPad, d->latent_dim, n));
+  DR_TRY(nnet_linear_dev(c, d->l[DE_GDENSE1], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDeBuf));
+  DR_TRY(nnet_act_dev(c, d->tmp, d->tmp, n, 128, NN_TANH));
+  DR_TRY(opusb200_nnet_compute_dense(c, d->l[DE_GDENSE2], d->tmp2, d->tmp, n, NN_LINEAR, 1));
+  DR_TRY(dr_copy2d(c, on_device ? initial_state : dsv, d->state_dim, d->tmp2, kDeStatePad, d->state_dim, n));
+  d->initialized = 1;
+  OB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    OB_CUDA(cudaMemcpyAsync(latents, dl, sizeof(float) * (size_t)n * d->latent_dim, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaMemcpyAsync(initial_state, dsv, sizeof(float) * (size_t)n * d->state_dim, cudaMemcpyDeviceToHost, c->stream));
+    OB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return OPUSB200_OK;
+}

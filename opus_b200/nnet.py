@@ -186,6 +186,41 @@ class Fargan:
             pass
 
 
+class DredEncoder:
+    """Batched DRED encoder network (dnn/dred_rdovae_enc.h): `layers` = ctypes array of the 24 LinearLayers of RDOVAEEnc."""
+
+    def __init__(self, ops, layers, n_streams, latent_dim=25, state_dim=50, su_bias=False):
+        self._L, self.n, self.latent_dim, self.state_dim = ops._L, n_streams, latent_dim, state_dim
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_dred_encoder_create(ops._h, layers, 24, 1 if su_bias else 0, latent_dim, state_dim, n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_encoder_create')
+        self._h = h
+
+    def encode_dframe(self, x):
+        """x [n][40] (two feature frames) -> (latents [n][latent_dim], initial_state [n][state_dim])"""
+        x = np.ascontiguousarray(x, np.float32).reshape(self.n, 40)
+        lat, st = np.empty((self.n, self.latent_dim), np.float32), np.empty((self.n, self.state_dim), np.float32)
+        r = self._L.opusb200_dred_encode_dframe(self._h, _p(lat), _p(st), _p(x), 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_encode_dframe')
+        return lat, st
+
+    def reset(self):
+        self._L.opusb200_dred_encoder_reset(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_dred_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LpcnetPlc:
     """Batched neural packet-loss concealment (dnn/lpcnet_plc.c): `plc_layers` = ctypes array of the 6 LinearLayers of PLCModel, `fargan_layers` = the
     20 of FARGAN.  The streams take update / conceal calls in lockstep; each has its own FEC / DRED feature queue."""

@@ -112,3 +112,27 @@ void refh_plc_pred(LPCNetPLCState *st, float *out, const float *in) {
   compute_generic_gru(&st->model.plc_gru2_input, &st->model.plc_gru2_recurrent, st->plc_net.gru2_state, st->plc_net.gru1_state, 0);
   compute_generic_dense(&st->model.plc_dense_out, out, st->plc_net.gru2_state, ACTIVATION_LINEAR, 0);
 }
+
+/* ---- DRED encoder network (dnn/dred_rdovae_enc.c, compiled unmodified with the generated random-weight dred_rdovae_enc_data.c) ---- */
+#include "dred_rdovae_enc.h"
+extern const WeightArray rdovaeenc_arrays[];
+static RDOVAEEnc g_dred_enc_model;
+static int g_dred_enc_ready = 0;
+static void dred_enc_ready(void) {
+  if (!g_dred_enc_ready) { init_rdovaeenc(&g_dred_enc_model, rdovaeenc_arrays); g_dred_enc_ready = 1; }
+}
+int refh_dred_enc_nlayers(void) { return (int)(sizeof(RDOVAEEnc) / sizeof(LinearLayer)); }
+void refh_dred_enc_layer(int i, const void **ptrs, int *dims) {
+  const LinearLayer *l;
+  dred_enc_ready();
+  l = (const LinearLayer *)&g_dred_enc_model + i;
+  ptrs[0] = l->bias; ptrs[1] = l->subias; ptrs[2] = l->weights; ptrs[3] = l->float_weights; ptrs[4] = l->weights_idx; ptrs[5] = l->diag;
+  ptrs[6] = l->scale;
+  dims[0] = l->nb_inputs; dims[1] = l->nb_outputs;
+}
+int refh_dred_enc_state_size(void) { return (int)sizeof(RDOVAEEncState); }
+/* input: 2 * DRED_NUM_FEATURES floats (a double feature frame); latents: DRED_LATENT_DIM, initial_state: DRED_STATE_DIM */
+void refh_dred_encode_dframe(RDOVAEEncState *st, float *latents, float *initial_state, const float *input) {
+  dred_enc_ready();
+  dred_rdovae_encode_dframe(st, &g_dred_enc_model, latents, initial_state, input, 0);
+}

@@ -1,8 +1,8 @@
 """oracle/gen_dred_weights.py — TEST INFRASTRUCTURE ONLY.
 Like gen_fargan_weights.py, for the DRED decoder (dnn/dred_rdovae_dec.c): the reference's own torch model (dnn/torch/rdovae/rdovae)
 with seeded RANDOM weights, block-sparsified the way its training does it, exported with the reference's own exporter using the
-layer list and flags of dnn/torch/rdovae/export_rdovae_weights.py (decoder half) into oracle/_ref/gen/dred_rdovae_dec_data.[ch]
-plus the constants header that script writes.  Pins the arithmetic of the decoder graph, not its quality."""
+layer list and flags of dnn/torch/rdovae/export_rdovae_weights.py into oracle/_ref/gen/dred_rdovae_dec_data.[ch] and (the encoder network,
+dnn/dred_rdovae_enc.c) dred_rdovae_enc_data.[ch], plus the constants header that script writes.  Pins the arithmetic of the graphs, not their quality."""
 import contextlib
 import io
 import os
@@ -65,6 +65,40 @@ with contextlib.redirect_stdout(io.StringIO()):
                for n, e in [('conv1.conv', 'dec_conv1'), ('conv2.conv', 'dec_conv2'), ('conv3.conv', 'dec_conv3'), ('conv4.conv', 'dec_conv4'),
                             ('conv5.conv', 'dec_conv5')])
 del w
+
+# ---- the encoder half (dnn/dred_rdovae_enc.c), same treatment; layer list and flags of export_rdovae_weights.py:190-237 ----
+enc = model.get_submodule('core_encoder.module')
+with torch.no_grad():
+    for name, p in enc.named_parameters():
+        if p.dim() >= 2:
+            p.mul_(1.5)
+for g in (enc.gru1, enc.gru2, enc.gru3, enc.gru4, enc.gru5):
+    block_sparsify(g.weight_ih_l0, 0.5)
+for c in (enc.conv1, enc.conv2, enc.conv3, enc.conv4, enc.conv5):
+    block_sparsify(c.conv_dense.weight, 0.5)
+def pad_rows(layer, rows):   # export_rdovae_weights.py:161-181: the latent / state outputs are padded to a multiple of 8 rows (quantised layers)
+    with torch.no_grad():
+        w_, b_ = layer.weight, layer.bias
+        pad = rows - w_.shape[0]
+        layer.weight = torch.nn.Parameter(torch.cat([w_, torch.zeros(pad, w_.shape[1])], dim=0))
+        layer.bias = torch.nn.Parameter(torch.cat([b_, torch.zeros(pad)], dim=0))
+
+
+pad_rows(enc.z_dense, (LATENT_DIM + 7) // 8 * 8)
+pad_rows(enc.state_dense_2, (STATE_DIM + 7) // 8 * 8)
+we = CWriter(os.path.join(OUT, 'dred_rdovae_enc_data'), message='seeded random model (oracle/gen_dred_weights.py)', model_struct_name='RDOVAEEnc')
+we.header.write('\n#include "dred_rdovae.h"\n#include "dred_rdovae_constants.h"\n\n')
+with contextlib.redirect_stdout(io.StringIO()):
+    for name, export_name, quantize in [('dense_1', 'enc_dense1', False), ('z_dense', 'enc_zdense', True), ('state_dense_1', 'gdense1', True),
+                                        ('state_dense_2', 'gdense2', True)]:
+        dump_torch_weights(we, enc.get_submodule(name), name=export_name, verbose=True, quantize=quantize, scale=None)
+    for k in range(1, 6):
+        dump_torch_weights(we, enc.get_submodule('conv%d.conv_dense' % k), name='enc_conv_dense%d' % k, verbose=True, sparse=True, quantize=True, scale=None)
+    enc_rnn = max(dump_torch_weights(we, enc.get_submodule('gru%d' % k), 'enc_gru%d' % k, verbose=True, input_sparse=True, quantize=True, scale=None,
+                                     recurrent_scale=None) for k in range(1, 6))
+    enc_conv = max(dump_torch_weights(we, enc.get_submodule('conv%d.conv' % k), 'enc_conv%d' % k, verbose=True, quantize=True, scale=None) for k in range(1, 6))
+del we
+rnn, conv = max(rnn, enc_rnn), max(conv, enc_conv)
 with open(os.path.join(OUT, 'dred_rdovae_constants.h'), 'w') as f:
     f.write('#ifndef DRED_RDOVAE_CONSTANTS_H\n#define DRED_RDOVAE_CONSTANTS_H\n')
     for k, v in [('DRED_NUM_FEATURES', FEATURE_DIM), ('DRED_LATENT_DIM', LATENT_DIM), ('DRED_STATE_DIM', STATE_DIM), ('DRED_PADDED_LATENT_DIM', (LATENT_DIM + 7) // 8 * 8),

@@ -167,3 +167,29 @@ def plc_schedule(seed, nframes):
         else:
             acts.append(('none',))
     return acts
+
+
+class RefDredEnc:
+    """the reference's DRED encoder network (dnn/dred_rdovae_enc.c) with the seeded random model of oracle/gen_dred_weights.py"""
+    NL = 24
+
+    def __init__(self, L):
+        self.L = L
+        self.st = np.zeros(L.refh_dred_enc_state_size() + 64, np.uint8)
+
+    def layers(self):
+        arr = (util.CLinear * self.NL)()
+        ptrs, dims = (ctypes.c_void_p * 7)(), (ctypes.c_int * 2)()
+        shapes = []
+        for i in range(self.NL):
+            self.L.refh_dred_enc_layer(i, ptrs, dims)
+            for k, name in enumerate(('bias', 'subias', 'weights', 'float_weights', 'weights_idx', 'diag', 'scale')):
+                setattr(arr[i], name, ptrs[k])
+            arr[i].nb_inputs, arr[i].nb_outputs = dims[0], dims[1]
+            shapes.append((dims[0], dims[1], bool(ptrs[4])))
+        return arr, shapes
+
+    def encode_dframe(self, x40):
+        lat, st = np.zeros(25, np.float32), np.zeros(50, np.float32)
+        self.L.refh_dred_encode_dframe(vp(self.st), vp(lat), vp(st), vp(np.ascontiguousarray(x40, np.float32)))
+        return lat, st

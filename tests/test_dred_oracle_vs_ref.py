@@ -25,3 +25,26 @@ def test_dred_decode_all_matches_reference(seed, nb):
     O.orc_dred_decode_all(layers, F.vp(got), F.vp(state), F.vp(latents), nb, ref.latent)
     assert np.array_equal(got, want), float(np.abs(got - want).max())
     assert float(np.abs(want).max()) > 1e-3
+
+
+@pytest.mark.skipif(R is None or not hasattr(R, 'refh_dred_encode_dframe'), reason='oracle/_ref/libfargan_ref.so without the DRED encoder')
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_dred_encode_dframe_matches_reference(seed):
+    """dred_rdovae_encode_dframe (dnn/dred_rdovae_enc.c:47): 30 consecutive double feature frames with the carried GRU / conv state: latents and
+    initial state bit-identical"""
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    ref = F.RefDredEnc(R)
+    layers, shapes = ref.layers()
+    assert shapes[0][:2] == (40, 64) and shapes[1][:2] == (544, 32) and shapes[3][:2] == (128, 56) and shapes[9][:2] == (64, 96) and shapes[17][:2] == (448, 96)
+    assert shapes[9][2] and shapes[4][2]          # input-sparse GRU matrices, sparse conv_dense layers
+    st = np.zeros(O.orc_dred_enc_size() + 64, np.uint8)
+    O.orc_dred_enc_init(F.vp(st), layers)
+    rng = np.random.default_rng(seed)
+    for t in range(30):
+        x = (0.6 * rng.standard_normal(40)).astype(np.float32)
+        wl, ws = ref.encode_dframe(x)
+        gl, gs = np.zeros(25, np.float32), np.zeros(50, np.float32)
+        O.orc_dred_encode_dframe(F.vp(st), F.vp(gl), F.vp(gs), F.vp(x))
+        assert np.array_equal(gl, wl) and np.array_equal(gs, ws), (t, float(np.abs(gl - wl).max()), float(np.abs(gs - ws).max()))
+    assert float(np.abs(wl).max()) > 1e-3
