@@ -68,24 +68,48 @@ void refh_dred_decode_all(float *features, const float *state, const float *late
 
 /* ---- neural packet-loss concealment (dnn/lpcnet_plc.c, compiled unmodified with the generated random-weight plc_data.c) ----
  * The history analysis of the first concealed frame after good audio (burg_cepstral_analysis, lpcnet_compute_single_frame_features_float:
- * dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c) is NOT part of this build: the stand-ins below abort, and the tests drive the sequences that
- * never reach them (concealment from a reset state, with or without FEC/DRED features: lpcnet_plc.c:160 loops zero times there). */
+ * dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c) is compiled unmodified too, with the generated random-weight pitchdnn_data.c. */
 #include <stdio.h>
 #include <stdlib.h>
 #include "lpcnet_private.h"
-int lpcnet_encoder_init(LPCNetEncState *st) { memset(st, 0, sizeof(*st)); return 0; }
-int lpcnet_encoder_load_model(LPCNetEncState *st, const void *data, int len) { (void)st; (void)data; (void)len; return 0; }
-void burg_cepstral_analysis(float *ceps, const float *x) { (void)ceps; (void)x; fprintf(stderr, "fargan_harness: burg_cepstral_analysis is not built\n"); abort(); }
-int lpcnet_compute_single_frame_features_float(LPCNetEncState *st, const float *pcm, float features[NB_TOTAL_FEATURES], int arch) {
-  (void)st; (void)pcm; (void)features; (void)arch;
-  fprintf(stderr, "fargan_harness: lpcnet_compute_single_frame_features_float is not built\n"); abort();
+
+/* ---- feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c) ---- */
+int refh_lpcnet_enc_state_size(void) { return (int)sizeof(LPCNetEncState); }
+void refh_lpcnet_enc_init(LPCNetEncState *st) { lpcnet_encoder_init(st); }
+void refh_lpcnet_enc_features(LPCNetEncState *st, const float *pcm, float *features) { lpcnet_compute_single_frame_features_float(st, pcm, features, 0); }
+void refh_lpcnet_enc_get(const LPCNetEncState *st, float *if_features, float *xcorr_features, float *lpc, float *misc /* dnn_pitch, pitch_filt, mem_preemph */) {
+  memcpy(if_features, st->if_features, sizeof(st->if_features));
+  memcpy(xcorr_features, st->xcorr_features, sizeof(st->xcorr_features));
+  memcpy(lpc, st->lpc, sizeof(st->lpc));
+  misc[0] = st->dnn_pitch; misc[1] = st->pitch_filt; misc[2] = st->mem_preemph;
 }
+/* the six linear layers of the pitch model: 0..3 dense (if_upsampler_1/2, downsampler, final_upsampler), 4 / 5 the GRU's input / recurrent half */
+void refh_pitchdnn_linear(LPCNetEncState *st, int i, const void **ptrs, int *dims) {
+  const PitchDNN *m = &st->pitchdnn.model;
+  const LinearLayer *l = i == 0 ? &m->dense_if_upsampler_1 : i == 1 ? &m->dense_if_upsampler_2 : i == 2 ? &m->dense_downsampler :
+                         i == 3 ? &m->dense_final_upsampler : i == 4 ? &m->gru_1_input : &m->gru_1_recurrent;
+  ptrs[0] = l->bias; ptrs[1] = l->subias; ptrs[2] = l->weights; ptrs[3] = l->float_weights; ptrs[4] = l->weights_idx; ptrs[5] = l->diag;
+  ptrs[6] = l->scale;
+  dims[0] = l->nb_inputs; dims[1] = l->nb_outputs;
+}
+void refh_pitchdnn_conv2d(LPCNetEncState *st, int i, const void **ptrs /* bias float_weights */, int *dims /* in_ch out_ch ktime kheight */) {
+  const Conv2dLayer *c = i == 0 ? &st->pitchdnn.model.conv2d_1 : &st->pitchdnn.model.conv2d_2;
+  ptrs[0] = c->bias; ptrs[1] = c->float_weights;
+  dims[0] = c->in_channels; dims[1] = c->out_channels; dims[2] = c->ktime; dims[3] = c->kheight;
+}
+float refh_pitchdnn_compute(LPCNetEncState *st, const float *if_features, const float *xcorr_features) {
+  return compute_pitchdnn(&st->pitchdnn, if_features, xcorr_features, 0);
+}
+void refh_burg_cepstral_analysis(float *ceps, const float *x) { burg_cepstral_analysis(ceps, x); }
+float refh_lpc_from_cepstrum(float *lpc, const float *cepstrum) { return lpc_from_cepstrum(lpc, cepstrum); }
+
 int refh_plc_state_size(void) { return (int)sizeof(LPCNetPLCState); }
 int refh_plc_init(LPCNetPLCState *st) { return lpcnet_plc_init(st); }
 void refh_plc_reset(LPCNetPLCState *st) { lpcnet_plc_reset(st); }
 void refh_plc_fec_add(LPCNetPLCState *st, const float *features) { lpcnet_plc_fec_add(st, features); }
 void refh_plc_fec_clear(LPCNetPLCState *st) { lpcnet_plc_fec_clear(st); }
 int refh_plc_conceal(LPCNetPLCState *st, opus_int16 *pcm) { return lpcnet_plc_conceal(st, pcm); }
+int refh_plc_update_pcm(LPCNetPLCState *st, opus_int16 *pcm) { return lpcnet_plc_update(st, pcm); }
 int refh_plc_nlayers(void) { return (int)(sizeof(PLCModel) / sizeof(LinearLayer)); }
 void refh_plc_layer(LPCNetPLCState *st, int i, const void **ptrs, int *dims) {
   const LinearLayer *l = (const LinearLayer *)&st->model + i;

@@ -193,3 +193,88 @@ class RefDredEnc:
         lat, st = np.zeros(25, np.float32), np.zeros(50, np.float32)
         self.L.refh_dred_encode_dframe(vp(self.st), vp(lat), vp(st), vp(np.ascontiguousarray(x40, np.float32)))
         return lat, st
+
+
+class RefLpcnetEnc:
+    """the reference's feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c) with the seeded random pitch model of
+    oracle/gen_pitchdnn_weights.py; also the weight source of the oracle and the device side"""
+
+    def __init__(self, L):
+        self.L = L
+        L.refh_pitchdnn_compute.restype = ctypes.c_float
+        self.st = np.zeros(L.refh_lpcnet_enc_state_size() + 64, np.uint8)
+        L.refh_lpcnet_enc_init(vp(self.st))
+
+    def linear(self):
+        arr = (util.CLinear * 6)()
+        ptrs, dims = (ctypes.c_void_p * 7)(), (ctypes.c_int * 2)()
+        shapes = []
+        for i in range(6):
+            self.L.refh_pitchdnn_linear(vp(self.st), i, ptrs, dims)
+            for k, name in enumerate(('bias', 'subias', 'weights', 'float_weights', 'weights_idx', 'diag', 'scale')):
+                setattr(arr[i], name, ptrs[k])
+            arr[i].nb_inputs, arr[i].nb_outputs = dims[0], dims[1]
+            shapes.append((dims[0], dims[1]))
+        return arr, shapes
+
+    def conv(self):
+        arr = (util.CConv2d * 2)()
+        ptrs, dims = (ctypes.c_void_p * 2)(), (ctypes.c_int * 4)()
+        for i in range(2):
+            self.L.refh_pitchdnn_conv2d(vp(self.st), i, ptrs, dims)
+            arr[i].bias, arr[i].float_weights = ptrs[0], ptrs[1]
+            arr[i].in_channels, arr[i].out_channels, arr[i].ktime, arr[i].kheight = dims[0], dims[1], dims[2], dims[3]
+        return arr
+
+    def features(self, pcm):
+        out = np.zeros(36, np.float32)
+        self.L.refh_lpcnet_enc_features(vp(self.st), vp(np.ascontiguousarray(pcm, np.float32)), vp(out))
+        return out
+
+    def get(self):
+        bufs = [np.zeros(k, np.float32) for k in (88, 224, 16, 3)]
+        self.L.refh_lpcnet_enc_get(vp(self.st), *[vp(b) for b in bufs])
+        return bufs
+
+
+class OrcLpcnetEnc:
+    """oracle/lpcnet_enc_oracle.c with the layers of a RefLpcnetEnc"""
+
+    def __init__(self, O, ref):
+        self.O, self.ref = O, ref
+        O.orc_pitchdnn_compute.restype = ctypes.c_float
+        self.lin, self.shapes = ref.linear()
+        self.cv = ref.conv()
+        self.st = np.zeros(O.orc_lpcnet_enc_size() + 64, np.uint8)
+        O.orc_lpcnet_enc_init(vp(self.st), self.lin, self.cv)
+
+    def reset(self):
+        self.O.orc_lpcnet_enc_reset(vp(self.st))
+
+    def features(self, pcm):
+        out = np.zeros(36, np.float32)
+        self.O.orc_lpcnet_enc_features(vp(self.st), vp(np.ascontiguousarray(pcm, np.float32)), vp(out))
+        return out
+
+    def get(self):
+        bufs = [np.zeros(k, np.float32) for k in (88, 224, 16, 3)]
+        self.O.orc_lpcnet_enc_get(vp(self.st), *[vp(b) for b in bufs])
+        return bufs
+
+
+def speech_like(seed, nframes, scale=8000.0):
+    """16 kHz test signal in int16 range: a pitched pulse train through a resonance, noise bursts, level changes and silence"""
+    rng = np.random.default_rng(seed)
+    n = nframes * 160
+    t = np.arange(n)
+    f0 = rng.uniform(80, 300) * (1 + 0.2 * np.sin(2 * np.pi * t / rng.uniform(4000, 9000)))
+    ph = np.cumsum(f0 / 16000.0)
+    x = np.zeros(n)
+    for h in range(1, 12):
+        x += np.sin(2 * np.pi * h * ph + rng.uniform(0, 6.28)) / h
+    x += 0.3 * rng.standard_normal(n)
+    env = np.clip(np.sin(2 * np.pi * t / rng.uniform(3000, 8000) + rng.uniform(0, 6.28)) + 0.6, 0, 1)
+    if rng.random() < 0.5:
+        a = rng.integers(0, max(1, n - 400))
+        env[a:a + 400] = 0
+    return (scale * rng.uniform(0.05, 1.0) * env * x).astype(np.float32)
