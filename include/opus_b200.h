@@ -412,6 +412,28 @@ void opusb200_dred_encoder_destroy(OpusB200DredEnc *enc);
 int opusb200_dred_encoder_reset(OpusB200DredEnc *enc);
 int opusb200_dred_encode_dframe(OpusB200DredEnc *enc, float *latents, float *initial_state, const float *input, int on_device);
 
+/* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
+ * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
+ * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).
+ *   lpcnet_encoder_init + load_model (lpcnet_enc.c:53-62)          opusb200_lpcnet_encoder_create   linear = the 6 LinearLayers of the generated PitchDNN
+ *                                                                   struct (pitchdnn_data.h: dense_if_upsampler_1, dense_if_upsampler_2, dense_downsampler,
+ *                                                                   dense_final_upsampler, gru_1_input, gru_1_recurrent), conv = conv2d_1, conv2d_2
+ *   lpcnet_encoder_init on a live object                            opusb200_lpcnet_encoder_reset
+ *   lpcnet_compute_single_frame_features / _float (:217-230)        opusb200_lpcnet_compute_single_frame_features (pcm [n][160] int16 or float in
+ *                                                                   int16 range, features [n][36] = 18 cepstral, pitch, correlation, 16 LPC)
+ *   burg_cepstral_analysis (freq.c:179-190)                         opusb200_burg_cepstral_analysis (x [n][160], ceps [n][36])
+ * Float arithmetic in the reference's order (generic C build); the double-precision libm calls on the path (log, pow, exp, sqrt) are the device's,
+ * so results can differ from the reference in the last bit of a float (tests/test_gpu_lpcnet_enc.py states the bound). ---- */
+typedef struct OpusB200LpcnetEnc OpusB200LpcnetEnc;
+int opusb200_lpcnet_encoder_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *linear, int n_linear, const OpusB200Conv2dLayer *conv, int n_conv,
+                                   int su_bias, int n_streams, OpusB200LpcnetEnc **out);
+void opusb200_lpcnet_encoder_destroy(OpusB200LpcnetEnc *enc);
+int opusb200_lpcnet_encoder_reset(OpusB200LpcnetEnc *enc);
+int opusb200_lpcnet_compute_single_frame_features(OpusB200LpcnetEnc *enc, const void *pcm, int pcm_is_int16, float *features, int on_device);
+/* parity aid (host buffers): if_features [n][88], xcorr_features [n][224], lpc [n][16], misc [n][3] = dnn_pitch, pitch_filt, mem_preemph */
+int opusb200_lpcnet_encoder_get_state(OpusB200LpcnetEnc *enc, float *if_features, float *xcorr_features, float *lpc, float *misc);
+int opusb200_burg_cepstral_analysis(OpusB200Ctx *ctx, float *ceps, const float *x, int n, int on_device);
+
 /* ---- Neural packet-loss concealment (dnn/lpcnet_plc.c, struct LPCNetPLCState of dnn/lpcnet_private.h:48-71): n streams that take their update /
  * conceal calls in lockstep (the recovery decode of a batch: every stream conceals frame k in the same call), each with its own FEC / DRED feature
  * queue, predictor state and PCM history.

@@ -41,6 +41,8 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_dred_encoder_create', 'opusb200_dred_encoder_destroy', 'opusb200_dred_encoder_reset', 'opusb200_dred_encode_dframe',
            'opusb200_lpcnet_plc_create', 'opusb200_lpcnet_plc_destroy', 'opusb200_lpcnet_plc_reset', 'opusb200_lpcnet_plc_fec_add', 'opusb200_lpcnet_plc_fec_clear',
            'opusb200_lpcnet_plc_update', 'opusb200_lpcnet_plc_conceal', 'opusb200_lpcnet_plc_get_state',
+           'opusb200_lpcnet_encoder_create', 'opusb200_lpcnet_encoder_destroy', 'opusb200_lpcnet_encoder_reset',
+           'opusb200_lpcnet_compute_single_frame_features', 'opusb200_lpcnet_encoder_get_state', 'opusb200_burg_cepstral_analysis',
            'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free',
            'opusb200_opus_encoder_create', 'opusb200_opus_encoder_destroy', 'opusb200_opus_encoder_reset', 'opusb200_opus_encoder_ctl',
            'opusb200_opus_encode', 'opusb200_opus_encode_float', 'opusb200_opus_encode_device', 'opusb200_opus_encode_submit', 'opusb200_opus_encode_wait', 'opusb200_opus_encoder_get_final_range',
@@ -199,6 +201,13 @@ def lib():
         L.opusb200_lpcnet_plc_update.argtypes = [vp, vp, ci]
         L.opusb200_lpcnet_plc_conceal.argtypes = [vp, vp, ci]
         L.opusb200_lpcnet_plc_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.opusb200_lpcnet_encoder_create.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.POINTER(vp)]
+        L.opusb200_lpcnet_encoder_destroy.argtypes = [vp]
+        L.opusb200_lpcnet_encoder_destroy.restype = None
+        L.opusb200_lpcnet_encoder_reset.argtypes = [vp]
+        L.opusb200_lpcnet_compute_single_frame_features.argtypes = [vp, vp, ci, vp, ci]
+        L.opusb200_lpcnet_encoder_get_state.argtypes = [vp, vp, vp, vp, vp]
+        L.opusb200_burg_cepstral_analysis.argtypes = [vp, vp, vp, ci, ci]
         L.opusb200_decoder_set_pipelined.argtypes = [vp, ci]
         L.opusb200_decoder_join.argtypes = [vp]
         L.opusb200_decode_submit.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, vp]

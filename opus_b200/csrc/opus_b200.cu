@@ -1211,6 +1211,7 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 #include "nnet_host.cuh"
 #include "fargan_host.cuh"
+#include "lpcnet_enc_host.cuh"
 #include "dred_host.cuh"
 #include "plc_host.cuh"
 #include "silk_coder_host.cuh"

@@ -221,6 +221,63 @@ class DredEncoder:
             pass
 
 
+class LpcnetEncoder:
+    """Batched LPCNet feature extraction (dnn/lpcnet_enc.c): `linear` = ctypes array of the 6 LinearLayers of the PitchDNN struct
+    (dense_if_upsampler_1, dense_if_upsampler_2, dense_downsampler, dense_final_upsampler, gru_1_input, gru_1_recurrent), `conv` = its two Conv2dLayers."""
+    FRAME_SIZE, NB_TOTAL_FEATURES = 160, 36
+
+    def __init__(self, ops, linear, conv, n_streams, su_bias=False):
+        self._L, self.n = ops._L, n_streams
+        h = ctypes.c_void_p()
+        r = self._L.opusb200_lpcnet_encoder_create(ops._h, linear, 6, conv, 2, 1 if su_bias else 0, n_streams, ctypes.byref(h))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_lpcnet_encoder_create')
+        self._h = h
+
+    def compute_single_frame_features(self, pcm):
+        """pcm [n][160] int16 or float (int16 range) -> features [n][36]"""
+        is16 = np.asarray(pcm).dtype == np.int16
+        pcm = np.ascontiguousarray(pcm, np.int16 if is16 else np.float32).reshape(self.n, 160)
+        out = np.empty((self.n, 36), np.float32)
+        r = self._L.opusb200_lpcnet_compute_single_frame_features(self._h, _p(pcm), 1 if is16 else 0, _p(out), 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_lpcnet_compute_single_frame_features')
+        return out
+
+    def get_state(self):
+        """(if_features [n][88], xcorr_features [n][224], lpc [n][16], misc [n][3] = dnn_pitch, pitch_filt, mem_preemph) of the last frame"""
+        bufs = [np.empty((self.n, k), np.float32) for k in (88, 224, 16, 3)]
+        r = self._L.opusb200_lpcnet_encoder_get_state(self._h, *[_p(b) for b in bufs])
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_lpcnet_encoder_get_state')
+        return bufs
+
+    def reset(self):
+        self._L.opusb200_lpcnet_encoder_reset(self._h)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.opusb200_lpcnet_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def burg_cepstral_analysis(ops, x):
+    """burg_cepstral_analysis (dnn/freq.c:179) of n frames: x [n][160] float (int16 range) -> ceps [n][36]"""
+    x = np.ascontiguousarray(x, np.float32)
+    n = x.shape[0]
+    out = np.empty((n, 36), np.float32)
+    r = ops._L.opusb200_burg_cepstral_analysis(ops._h, _p(out), _p(x.reshape(n, 160)), n, 0)
+    if r != 0:
+        raise capi.OpusB200Error(r, 'opusb200_burg_cepstral_analysis')
+    return out
+
+
 class LpcnetPlc:
     """Batched neural packet-loss concealment (dnn/lpcnet_plc.c): `plc_layers` = ctypes array of the 6 LinearLayers of PLCModel, `fargan_layers` = the
     20 of FARGAN.  The streams take update / conceal calls in lockstep; each has its own FEC / DRED feature queue."""

@@ -273,11 +273,10 @@ typedef struct {
   float xcorr_mem1[(NB_XCORR + 2) * 2];
   float xcorr_mem2[(NB_XCORR + 2) * 2 * 8];
 } OrcPitchDnn;
-float orc_pitchdnn_compute(OrcPitchDnn *st, const float *if_features, const float *xcorr_features) {
-  float if1_out[64], downsampler_in[NB_XCORR + 64], downsampler_out[64], output[192];
+/* the layers (pitchdnn.c:12-44): output [192] */
+void orc_pitchdnn_net(OrcPitchDnn *st, float *output, const float *if_features, const float *xcorr_features) {
+  float if1_out[64], downsampler_in[NB_XCORR + 64], downsampler_out[64];
   float conv1_tmp1[(NB_XCORR + 2) * 8] = {0}, conv1_tmp2[(NB_XCORR + 2) * 8] = {0};
-  float maxval = -1, sum = 0, count = 0;
-  int i, pos = 0;
   orc_nnet_dense(&st->l[PD_IF1], if1_out, if_features, ACT_TANH);
   orc_nnet_dense(&st->l[PD_IF2], &downsampler_in[NB_XCORR], if1_out, ACT_TANH);
   memcpy(&conv1_tmp1[1], xcorr_features, NB_XCORR * sizeof(float));
@@ -286,9 +285,14 @@ float orc_pitchdnn_compute(OrcPitchDnn *st, const float *if_features, const floa
   orc_nnet_dense(&st->l[PD_DOWN], downsampler_out, downsampler_in, ACT_TANH);
   orc_nnet_gru(&st->l[PD_GRU_IN], &st->l[PD_GRU_REC], st->gru_state, downsampler_out);
   orc_nnet_dense(&st->l[PD_FINAL], output, st->gru_state, ACT_LINEAR);
+}
+float orc_pitchdnn_compute(OrcPitchDnn *st, const float *if_features, const float *xcorr_features) {
+  float output[192], maxval = -1, sum = 0, count = 0;
+  int i, pos = 0;
+  orc_pitchdnn_net(st, output, if_features, xcorr_features);
   for (i = 0; i < 180; i++)
     if (output[i] > maxval) { pos = i; maxval = output[i]; }
-  for (i = pos - 2 > 0 ? pos - 2 : 0; i <= (pos + 2 < 179 ? pos + 2 : 179); i++) {
+  for (i = pos - 2 > 0 ? pos - 2 : 0; i <= (pos + 2 < 179 ? pos + 2 : 179); i++) { /* :45-58 */
     const float p = exp(output[i]);
     sum += p * i;
     count += p;

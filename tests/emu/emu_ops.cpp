@@ -434,3 +434,25 @@ void emu_silk_coder(int op, void *state, unsigned char *buf, int n, int stride, 
   emu_launch(op == 0 ? sc_init_entry : op == 1 ? sc_icdf_entry : op == 2 ? sc_pulses_entry : sc_done_entry, &p, (n + 31) / 32, 32, 0);
 }
 }
+
+// ---- LPCNet feature extraction (lpcnet_enc.cuh): the two warp kernels around the pitch network, and the Burg cepstrum ----
+#include "../../opus_b200/csrc/lpcnet_enc.cuh"
+static void le_analysis_entry(void *a) { lpcnet_enc_analysis_warp(*(const LpcnetEncParams *)a, block_id(), (LeWS *)dyn_smem()); }
+static void le_finish_entry(void *a) { lpcnet_enc_finish_warp(*(const LpcnetEncParams *)a, block_id(), (float *)dyn_smem()); }
+static void le_burg_entry(void *a) { lpcnet_burg_cepstrum_warp(*(const LpcnetBurgParams *)a, block_id(), (LeBurgWS *)dyn_smem()); }
+extern "C" int emu_lpcnet_enc_state_size(void) { return (int)sizeof(ObLpcnetEncState); }
+extern "C" void emu_lpcnet_enc_analysis(void *state, const void *pcm, int is16, float *if_features, float *conv_in, int n) {
+  LpcnetEncParams p = {};
+  p.state = (ObLpcnetEncState *)state; p.pcm = pcm; p.pcm_is_int16 = is16; p.if_features = if_features; p.conv_in = conv_in; p.n = n;
+  emu_launch(le_analysis_entry, &p, n, 32, sizeof(LeWS));
+}
+extern "C" void emu_lpcnet_enc_finish(void *state, const float *pitch_out, float *features, int n) {
+  LpcnetEncParams p = {};
+  p.state = (ObLpcnetEncState *)state; p.pitch_out = pitch_out; p.features = features; p.n = n;
+  emu_launch(le_finish_entry, &p, n, 32, kLeBuf * sizeof(float));
+}
+extern "C" void emu_lpcnet_burg(float *ceps, const float *x, int n) {
+  LpcnetBurgParams p;
+  p.ceps = ceps; p.x = x; p.n = n;
+  emu_launch(le_burg_entry, &p, n, 32, sizeof(LeBurgWS));
+}

@@ -1,0 +1,63 @@
+"""The device source of the LPCNet feature extraction (opus_b200/csrc/lpcnet_enc.cuh) compiled for the host-side warp emulator and compared with the
+oracle (which is pinned bit for bit on the reference's own lpcnet_enc.c / freq.c / pitchdnn.c / burg.c).  Same compiler, same libm: bit for bit.
+The pitch network between the two warp kernels is run with the oracle's layer functions here; on the GPU it runs on the nnet kernels
+(tests/test_gpu_lpcnet_enc.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu_util
+import fargan_util as fu
+import util
+
+L = fu.load_ref()
+pytestmark = pytest.mark.skipif(L is None, reason='oracle/_ref/libfargan_ref.so not built (needs /root/reference): it is the weight source')
+
+
+def _f(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize('is16', [0, 1])
+def test_frame_features_emulated(is16):
+    E = emu_util.load_emu_ops()
+    O = util.load_oracle()
+    E.emu_lpcnet_enc_state_size.restype = ctypes.c_int
+    n, nfr = 6, 14
+    ref = fu.RefLpcnetEnc(L)
+    orcs = [fu.OrcLpcnetEnc(O, ref) for _ in range(n)]
+    nets = [fu.OrcLpcnetEnc(O, ref) for _ in range(n)]   # only their pitch-network half is used: the layers between the two emulated kernels
+    sig = np.stack([fu.speech_like(40 + s, nfr, [8000.0, 30000.0, 50.0][s % 3]) for s in range(n)])
+    if is16:
+        sig = np.round(sig).astype(np.int16)
+    state = np.zeros(n * E.emu_lpcnet_enc_state_size(), np.uint8)
+    for t in range(nfr):
+        pcm = np.ascontiguousarray(sig[:, t * 160:(t + 1) * 160])
+        iff, cin, out, feat = np.zeros((n, 88), np.float32), np.zeros((n, 226), np.float32), np.zeros((n, 192), np.float32), np.zeros((n, 36), np.float32)
+        E.emu_lpcnet_enc_analysis(_f(state), _f(pcm), is16, _f(iff), _f(cin), n)
+        assert np.all(cin[:, 0] == 0) and np.all(cin[:, 225] == 0)
+        for s in range(n):
+            xc = np.ascontiguousarray(cin[s, 1:225])
+            O.orc_pitchdnn_net(fu.vp(nets[s].st), _f(out[s]), _f(iff[s]), _f(xc))
+        E.emu_lpcnet_enc_finish(_f(state), _f(out), _f(feat), n)
+        for s in range(n):
+            want = orcs[s].features(pcm[s].astype(np.float32))
+            w_if, w_xc, w_lpc, w_misc = orcs[s].get()
+            assert np.array_equal(iff[s], w_if), (t, s)
+            assert np.array_equal(cin[s, 1:225], w_xc), (t, s)
+            assert np.array_equal(feat[s], want), (t, s, np.abs(feat[s] - want).max())
+
+
+def test_burg_cepstrum_emulated():
+    E = emu_util.load_emu_ops()
+    O = util.load_oracle()
+    n = 9
+    x = np.stack([fu.speech_like(70 + s, 1, [8000.0, 30000.0, 3.0][s % 3]) for s in range(n)])
+    x[8] = 0
+    got = np.zeros((n, 36), np.float32)
+    E.emu_lpcnet_burg(_f(got), _f(x), n)
+    for s in range(n):
+        want = np.zeros(36, np.float32)
+        O.orc_burg_cepstral_analysis(_f(want), _f(x[s]))
+        assert np.array_equal(got[s], want), (s, np.abs(got[s] - want).max())
