@@ -446,15 +446,18 @@ int opusb200_burg_cepstral_analysis(OpusB200Ctx *ctx, float *ceps, const float *
  *   lpcnet_plc_update (:143)                           opusb200_lpcnet_plc_update   (pcm [n][160] int16: a good frame of every stream)
  *   lpcnet_plc_conceal (:156)                          opusb200_lpcnet_plc_conceal  (pcm [n][160] int16 out): compute_plc_pred / get_fec_or_pred /
  *                                                       the attenuation table / queue_features / fargan_cont / fargan_synthesize_int
- * PCM and state are bit-identical to the reference's lpcnet_plc.c (generic C branch of dnn/vec.h) given the same model and calls.
- * Not built: the analysis of the decoded history that the first concealed frame after GOOD audio runs (burg_cepstral_analysis,
- * lpcnet_compute_single_frame_features_float: dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c); such a conceal call returns OPUSB200_UNIMPLEMENTED and
- * changes nothing.  Concealment from a reset state (with or without queued features) is complete. ---- */
+ *   lpcnet_plc_load_model's pitch part (:75-86)        opusb200_lpcnet_plc_load_pitch_model (the PitchDNN layers, as opusb200_lpcnet_encoder_create)
+ * PCM and state are bit-identical to the reference's lpcnet_plc.c (generic C branch of dnn/vec.h) given the same model and calls, up to the libm
+ * note of the feature extraction above.  The first concealed frame after GOOD audio analyses the decoded history (:160-177: burg_cepstral_analysis,
+ * lpcnet_compute_single_frame_features_float, the predictor over the frames not analysed yet); that needs the pitch model: without it such a call
+ * returns OPUSB200_INVALID_STATE and changes nothing.  Concealment from a reset state (with or without queued features) never needs it. ---- */
 typedef struct OpusB200LpcnetPlc OpusB200LpcnetPlc;
 int opusb200_lpcnet_plc_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *plc_layers, int n_plc_layers, const OpusB200LinearLayer *fargan_layers,
                                int n_fargan_layers, int su_bias, int n_streams, OpusB200LpcnetPlc **out);
 void opusb200_lpcnet_plc_destroy(OpusB200LpcnetPlc *plc);
 int opusb200_lpcnet_plc_reset(OpusB200LpcnetPlc *plc);
+int opusb200_lpcnet_plc_load_pitch_model(OpusB200LpcnetPlc *plc, const OpusB200LinearLayer *linear, int n_linear, const OpusB200Conv2dLayer *conv,
+                                         int n_conv, int su_bias);
 int opusb200_lpcnet_plc_fec_add(OpusB200LpcnetPlc *plc, const float *features, const int32_t *have, int on_device);
 int opusb200_lpcnet_plc_fec_clear(OpusB200LpcnetPlc *plc);
 int opusb200_lpcnet_plc_update(OpusB200LpcnetPlc *plc, const int16_t *pcm, int on_device);

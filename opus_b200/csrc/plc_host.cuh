@@ -4,8 +4,9 @@
 // a stream has in its FEC / DRED feature queue is its own.  The predictor (dense 57 -> 128 tanh, two 128-unit int8 GRUs, dense 128 -> 20) runs on
 // the dnn/ layer kernels of nnet_host.cuh (int8 GRU matrices on the tensor cores, exact integers), the vocoder is the FARGAN object of
 // fargan_host.cuh; the glue kernels below are the per-stream bookkeeping.  Included at the end of opus_b200.cu after fargan_host.cuh.
-// NOT built: the history analysis a first concealed frame runs when good audio came before it (burg_cepstral_analysis,
-// lpcnet_compute_single_frame_features_float); opusb200_lpcnet_plc_conceal answers OPUSB200_UNIMPLEMENTED for such a call and changes nothing.
+// The history analysis a first concealed frame runs when good audio came before it (:160-177: burg_cepstral_analysis,
+// lpcnet_compute_single_frame_features_float and the predictor over the decoded frames not yet analysed) uses the feature extractor of
+// lpcnet_enc_host.cuh; it needs the pitch model (opusb200_lpcnet_plc_load_pitch_model), without it such a call answers OPUSB200_INVALID_STATE.
 #pragma once
 
 namespace ob {
@@ -21,7 +22,9 @@ struct PlcParams {
   const float *fpcm;           // finish: the vocoder's frame [n][160]
   int16_t *pcm;                // finish: [n][160]
   const int16_t *upd_pcm;      // update: [n][160]
-  int n, final_step, restore;
+  float *xf;                   // history analysis: the frame at analysis_pos, int16 range [n][160]
+  const float *feat36, *ceps36;   // history analysis: this frame's features [n][36] and Burg cepstra [n][36]
+  int n, final_step, restore, analysis_pos, predict;
 };
 }  // namespace ob
 
@@ -48,8 +51,35 @@ extern "C" __global__ void ob_plc_bak(ob::PlcParams p) {
   float *b0 = p.bak + s * 4 * ob::kPlcGru + k, *b1 = b0 + 2 * ob::kPlcGru;
   float v = *net;
   if (p.restore) { v = *b0; *net = v; }
+  if (p.restore == 2) return;   // plc_net = plc_bak[0] alone (:159), the rotations follow inside the history loop
   *b0 = *b1;
   *b1 = v;
+}
+// history analysis (:163-166): the decoded frame at analysis_pos back in int16 range
+extern "C" __global__ void ob_plc_hist_x(ob::PlcParams p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)p.n * ob::kPlcFrame) return;
+  const size_t s = i / ob::kPlcFrame, k = i % ob::kPlcFrame;
+  p.xf[i] = 32768.f * p.hist[s * ob::kPlcBuf + p.analysis_pos + k];
+}
+// history analysis (:169-176): features <- this frame's; when the frame also feeds the predictor: queue_features and plc_features = cepstra, features, 1
+extern "C" __global__ void ob_plc_hist_glue(ob::PlcParams p) {
+  const int s = blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6), k = threadIdx.x & 63;
+  if (s >= p.n) return;
+  const float *f36 = p.feat36 + (size_t)s * 36;
+  if (k < ob::kPlcFeat) p.features[(size_t)s * ob::kPlcFeat + k] = f36[k];
+  if (!p.predict) return;
+  float *cf = p.cont_features + (size_t)s * ob::kPlcContVec * ob::kPlcFeat;
+  float keep[ob::kPlcContVec - 1];
+#pragma unroll
+  for (int v = 0; v < ob::kPlcContVec - 1; v++) keep[v] = k < ob::kPlcFeat ? cf[(v + 1) * ob::kPlcFeat + k] : 0.f;
+  __syncwarp();
+  if (k < ob::kPlcFeat) {
+#pragma unroll
+    for (int v = 0; v < ob::kPlcContVec - 1; v++) cf[v * ob::kPlcFeat + k] = keep[v];
+    cf[(ob::kPlcContVec - 1) * ob::kPlcFeat + k] = f36[k];
+  }
+  if (k < ob::kPlcIn) p.in57[(size_t)s * ob::kPlcIn + k] = k < 2 * ob::kPlcBands ? p.ceps36[(size_t)s * 36 + k] : k < ob::kPlcIn - 1 ? f36[k - 2 * ob::kPlcBands] : 1.f;
 }
 // get_fec_or_pred, first half (:115-133): the predictor's input — all zeros, or the queued features with the "from FEC" flag
 extern "C" __global__ void ob_plc_pred_in(ob::PlcParams p) {
@@ -127,7 +157,8 @@ struct OpusB200LpcnetPlc {
   int n;
   OpusB200Fargan *fargan;
   OpusB200Linear *l[6];   // PLCModel order (plc_data.h): dense_in, dense_out, gru1 input / recurrent, gru2 input / recurrent
-  float *fec, *in57, *tmp128, *out20, *features, *cont_features, *gru1, *gru2, *bak, *hist, *fpcm, *pcm0, *d_feat;
+  float *fec, *in57, *tmp128, *out20, *features, *cont_features, *gru1, *gru2, *bak, *hist, *fpcm, *pcm0, *d_feat, *xf, *feat36, *ceps36;
+  OpusB200LpcnetEnc *enc;   // LPCNetPLCState.enc: the feature extractor of the history analysis (null until the pitch model is loaded)
   int32_t *cnt, *used_fec, *d_have;
   int16_t *d_pcm;
   int blend, analysis_pos, predict_pos, analysis_gap;   // lockstep state
@@ -135,8 +166,10 @@ struct OpusB200LpcnetPlc {
 static void plc_free(OpusB200LpcnetPlc *q) {
   if (!q) return;
   opusb200_fargan_destroy(q->fargan);
+  opusb200_lpcnet_encoder_destroy(q->enc);
   for (int i = 0; i < 6; i++) opusb200_nnet_linear_destroy(q->l[i]);
-  float **fb[] = {&q->fec, &q->in57, &q->tmp128, &q->out20, &q->features, &q->cont_features, &q->gru1, &q->gru2, &q->bak, &q->hist, &q->fpcm, &q->pcm0, &q->d_feat};
+  float **fb[] = {&q->fec, &q->in57, &q->tmp128, &q->out20, &q->features, &q->cont_features, &q->gru1, &q->gru2, &q->bak, &q->hist, &q->fpcm, &q->pcm0, &q->d_feat,
+                  &q->xf, &q->feat36, &q->ceps36};
   for (auto b : fb) cudaFree(*b);
   cudaFree(q->cnt); cudaFree(q->used_fec); cudaFree(q->d_have); cudaFree(q->d_pcm);
   delete q;
@@ -157,6 +190,7 @@ extern "C" int opusb200_lpcnet_plc_reset(OpusB200LpcnetPlc *q) {
                                        {q->features, sizeof(float) * n * ob::kPlcFeat}, {q->cont_features, sizeof(float) * n * ob::kPlcContVec * ob::kPlcFeat},
                                        {q->gru1, sizeof(float) * n * ob::kPlcGru}, {q->gru2, sizeof(float) * n * ob::kPlcGru}, {q->bak, sizeof(float) * n * 4 * ob::kPlcGru}};
   for (auto &a : z) OB_CUDA(cudaMemsetAsync(a.p, 0, a.b, c->stream));
+  if (q->enc) FG_TRY(opusb200_lpcnet_encoder_reset(q->enc));   // lpcnet_encoder_init(&st->enc), :48
   q->blend = 0; q->analysis_gap = 1; q->analysis_pos = ob::kPlcBuf; q->predict_pos = ob::kPlcBuf;
   return OPUSB200_OK;
 }
@@ -181,7 +215,8 @@ extern "C" int opusb200_lpcnet_plc_create(OpusB200Ctx *c, const OpusB200LinearLa
   const size_t n = (size_t)n_streams;
   struct { float **p; size_t w; } al[] = {{&q->fec, (size_t)ob::kPlcMaxFec * ob::kPlcFeat}, {&q->in57, ob::kPlcIn}, {&q->tmp128, 128}, {&q->out20, ob::kPlcFeat}, {&q->features, ob::kPlcFeat},
                                           {&q->cont_features, (size_t)ob::kPlcContVec * ob::kPlcFeat}, {&q->gru1, ob::kPlcGru}, {&q->gru2, ob::kPlcGru}, {&q->bak, 4 * ob::kPlcGru},
-                                          {&q->hist, ob::kPlcBuf}, {&q->fpcm, ob::kPlcFrame}, {&q->pcm0, 320}, {&q->d_feat, ob::kPlcFeat}};
+                                          {&q->hist, ob::kPlcBuf}, {&q->fpcm, ob::kPlcFrame}, {&q->pcm0, 320}, {&q->d_feat, ob::kPlcFeat},
+                                          {&q->xf, ob::kPlcFrame}, {&q->feat36, 36}, {&q->ceps36, 36}};
   for (auto &a : al)
     if (cudaMalloc(a.p, sizeof(float) * n * a.w) != cudaSuccess) { plc_free(q); return OPUSB200_ALLOC_FAIL; }
   if (cudaMalloc(&q->cnt, sizeof(int32_t) * n * 4) != cudaSuccess || cudaMalloc(&q->used_fec, sizeof(int32_t) * n) != cudaSuccess ||
@@ -264,6 +299,16 @@ static int plc_step(OpusB200LpcnetPlc *q, int restore, int final_step) {
   OB_CUDA(cudaGetLastError());
   return OPUSB200_OK;
 }
+// the pitch-model part of lpcnet_plc_load_model (:75-86: lpcnet_encoder_load_model): linear = the 6 LinearLayers, conv = the 2 Conv2dLayers of PitchDNN
+extern "C" int opusb200_lpcnet_plc_load_pitch_model(OpusB200LpcnetPlc *q, const OpusB200LinearLayer *linear, int n_linear, const OpusB200Conv2dLayer *conv, int n_conv,
+                                                    int su_bias) {
+  if (!q) return OPUSB200_BAD_ARG;
+  OpusB200LpcnetEnc *e = nullptr;
+  FG_TRY(opusb200_lpcnet_encoder_create(q->ctx, linear, n_linear, conv, n_conv, su_bias, q->n, &e));
+  opusb200_lpcnet_encoder_destroy(q->enc);
+  q->enc = e;
+  return OPUSB200_OK;
+}
 // lpcnet_plc_conceal (:156-207) for every stream: pcm [n][160] int16 out
 extern "C" int opusb200_lpcnet_plc_conceal(OpusB200LpcnetPlc *q, int16_t *pcm, int on_device) {
   if (!q || !pcm) return OPUSB200_BAD_ARG;
@@ -271,8 +316,41 @@ extern "C" int opusb200_lpcnet_plc_conceal(OpusB200LpcnetPlc *q, int16_t *pcm, i
   OB_CUDA(cudaSetDevice(c->device));
   const size_t n = (size_t)q->n;
   if (q->blend == 0) {
-    if (q->analysis_pos + ob::kPlcFrame <= ob::kPlcBuf) return OPUSB200_UNIMPLEMENTED;   // good audio came before: the history analysis is not built
-    FG_TRY(plc_step(q, 1, 0));
+    if (q->analysis_pos + ob::kPlcFrame <= ob::kPlcBuf) {   // good audio came before: analyse what has not been analysed yet (:160-177)
+      if (!q->enc) return OPUSB200_INVALID_STATE;             // the pitch model was not loaded
+      ob::PlcParams p = plc_params(q);
+      p.restore = 2;
+      ob_plc_bak<<<(unsigned)((n * 2 * ob::kPlcGru + 255) / 256), 256, 0, c->stream>>>(p);
+      c->launches++;
+      int count = 0;
+      while (q->analysis_pos + ob::kPlcFrame <= ob::kPlcBuf) {
+        p = plc_params(q);
+        p.xf = q->xf; p.feat36 = q->feat36; p.ceps36 = q->ceps36; p.analysis_pos = q->analysis_pos;
+        p.predict = (!q->analysis_gap || count > 0) && q->analysis_pos >= q->predict_pos;
+        ob_plc_hist_x<<<(unsigned)((n * ob::kPlcFrame + 255) / 256), 256, 0, c->stream>>>(p);
+        c->launches++;
+        OB_CUDA(cudaGetLastError());
+        if (p.predict) FG_TRY(lpcnet_burg_launch(c, q->ceps36, q->xf, q->n));   // burg_cepstral_analysis: only the predictor reads it
+        FG_TRY(lpcnet_enc_frame(q->enc, q->xf, 0, q->feat36));
+        ob_plc_hist_glue<<<(q->n + 3) / 4, 256, 0, c->stream>>>(p);
+        c->launches++;
+        OB_CUDA(cudaGetLastError());
+        if (p.predict) {
+          p.restore = 0;
+          ob_plc_bak<<<(unsigned)((n * 2 * ob::kPlcGru + 255) / 256), 256, 0, c->stream>>>(p);
+          c->launches++;
+          FG_TRY(opusb200_nnet_compute_dense(c, q->l[0], q->tmp128, q->in57, q->n, NN_TANH, 1));       // compute_plc_pred(st, st->features, plc_features)
+          FG_TRY(opusb200_nnet_compute_gru(c, q->l[2], q->l[3], q->gru1, q->tmp128, q->n, 1));
+          FG_TRY(opusb200_nnet_compute_gru(c, q->l[4], q->l[5], q->gru2, q->gru1, q->n, 1));
+          FG_TRY(opusb200_nnet_compute_dense(c, q->l[1], q->features, q->gru2, q->n, NN_LINEAR, 1));
+        }
+        q->analysis_pos += ob::kPlcFrame;
+        count++;
+      }
+      FG_TRY(plc_step(q, 0, 0));
+    } else {
+      FG_TRY(plc_step(q, 1, 0));
+    }
     FG_TRY(plc_step(q, 0, 0));
     OB_CUDA(cudaMemcpy2DAsync(q->pcm0, sizeof(float) * 320, q->hist + (ob::kPlcBuf - 320), sizeof(float) * ob::kPlcBuf, sizeof(float) * 320, n, cudaMemcpyDeviceToDevice,
                               c->stream));

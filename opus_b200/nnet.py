@@ -295,6 +295,10 @@ class LpcnetPlc:
         if r != 0:
             raise capi.OpusB200Error(r, what)
 
+    def load_pitch_model(self, linear, conv, su_bias=False):
+        """the PitchDNN layers (as LpcnetEncoder): needed by the history analysis of the first concealed frame after good audio"""
+        self._chk(self._L.opusb200_lpcnet_plc_load_pitch_model(self._h, linear, 6, conv, 2, 1 if su_bias else 0), 'opusb200_lpcnet_plc_load_pitch_model')
+
     def reset(self):
         self._chk(self._L.opusb200_lpcnet_plc_reset(self._h), 'opusb200_lpcnet_plc_reset')
 

@@ -163,9 +163,9 @@ void orc_fargan_get_state(const OrcFargan *st, float *pitch_buf, float *cond_con
 /* ---- neural packet-loss concealment: dnn/lpcnet_plc.c:44-207 (lpcnet_plc_reset, lpcnet_plc_fec_add / _clear, compute_plc_pred, get_fec_or_pred,
  * queue_features, lpcnet_plc_update, lpcnet_plc_conceal) on top of the FARGAN restatement above.  The predictor is the 6 LinearLayers of the
  * generated PLCModel struct (plc_data.h): dense_in, dense_out, gru1 input / recurrent, gru2 input / recurrent.
- * NOT restated: the history analysis a first concealed frame runs when good audio came before it (burg_cepstral_analysis,
- * lpcnet_compute_single_frame_features_float: dnn/burg.c, lpcnet_enc.c, freq.c, pitchdnn.c — SURVEY 8(f).4); orc_plc_conceal returns -1 and
- * leaves the state alone when a call would need it.  Pinned against the reference's own lpcnet_plc.c compiled with seeded random weights
+ * The history analysis a first concealed frame runs when good audio came before it (:160-177: burg_cepstral_analysis,
+ * lpcnet_compute_single_frame_features_float) uses lpcnet_enc_oracle.c through orc_plc_set_encoder(); without an encoder orc_plc_conceal returns -1
+ * and leaves the state alone when a call would need it.  Pinned against the reference's own lpcnet_plc.c compiled with seeded random weights
  * (oracle/_ref/libfargan_ref.so, gen_plc_weights.py) by tests/test_plc_oracle_vs_ref.py. ---- */
 #define PLC_MAX_FEC 104            /* dnn/lpcnet_private.h:15 */
 #define CONT_VECTORS 5
@@ -174,9 +174,13 @@ void orc_fargan_get_state(const OrcFargan *st, float *pitch_buf, float *cond_con
 #define PLC_IN (2 * NB_BANDS + NB_FEATURES + 1)
 enum { P_DENSE_IN, P_DENSE_OUT, P_GRU1_IN, P_GRU1_REC, P_GRU2_IN, P_GRU2_REC, P_COUNT };
 typedef struct { float gru1[128], gru2[128]; } OrcPlcNet;
+void orc_lpcnet_enc_reset(void *st);                                          /* lpcnet_enc_oracle.c */
+void orc_lpcnet_enc_features(void *st, const float *pcm, float *features);
+void orc_burg_cepstral_analysis(float *ceps, const float *x);
 typedef struct {
   OrcLinear l[P_COUNT];
   OrcFargan fargan;
+  void *enc;                        /* LPCNetPLCState.enc: an OrcLpcnetEnc of lpcnet_enc_oracle.c, or NULL */
   float fec[PLC_MAX_FEC][NB_FEATURES];
   int analysis_gap, fec_read_pos, fec_fill_pos, fec_skip, analysis_pos, predict_pos;
   float pcm[PLC_BUF_SIZE];
@@ -189,6 +193,7 @@ typedef struct {
 int orc_plc_size(void) { return (int)sizeof(OrcPlc); }
 void orc_plc_reset(OrcPlc *st) { /* lpcnet_plc.c:44-56: everything from `fec` on, the model and the vocoder stay */
   memset(st->fec, 0, sizeof(*st) - ((char *)st->fec - (char *)st));
+  if (st->enc) orc_lpcnet_enc_reset(st->enc); /* :48 */
   st->blend = 0;
   st->loss_count = 0;
   st->analysis_gap = 1;
@@ -201,6 +206,7 @@ void orc_plc_init(OrcPlc *st, const OrcLinear *plc_layers, const OrcLinear *farg
   orc_fargan_init(&st->fargan, fargan_layers);
   orc_plc_reset(st);
 }
+void orc_plc_set_encoder(OrcPlc *st, void *enc) { st->enc = enc; }
 void orc_plc_fec_add(OrcPlc *st, const float *features) { /* :88-96 */
   if (!features) { st->fec_skip++; return; }
   memcpy(st->fec[st->fec_fill_pos], features, NB_FEATURES * sizeof(float));
@@ -251,8 +257,25 @@ int orc_plc_conceal(OrcPlc *st, int16_t *pcm) { /* :156-207 */
   float fpcm[FRAME];
   int i;
   if (st->blend == 0) {
-    if (st->analysis_pos + FRAME <= PLC_BUF_SIZE) return -1; /* the history analysis (:160-177) is not restated */
+    int count = 0;
+    if (st->analysis_pos + FRAME <= PLC_BUF_SIZE && !st->enc) return -1; /* the history analysis needs the feature extractor */
     st->net = st->bak[0];
+    while (st->analysis_pos + FRAME <= PLC_BUF_SIZE) { /* :160-177 */
+      float x[FRAME], plc_features[PLC_IN];
+      for (i = 0; i < FRAME; i++) x[i] = 32768.f * st->pcm[st->analysis_pos + i];
+      orc_burg_cepstral_analysis(plc_features, x);
+      orc_lpcnet_enc_features(st->enc, x, st->features);
+      if ((!st->analysis_gap || count > 0) && st->analysis_pos >= st->predict_pos) {
+        plc_queue(st, st->features);
+        memcpy(&plc_features[2 * NB_BANDS], st->features, NB_FEATURES * sizeof(float));
+        plc_features[2 * NB_BANDS + NB_FEATURES] = 1;
+        st->bak[0] = st->bak[1];
+        st->bak[1] = st->net;
+        orc_plc_pred(st, st->features, plc_features);
+      }
+      st->analysis_pos += FRAME;
+      count++;
+    }
     st->bak[0] = st->bak[1];
     st->bak[1] = st->net;
     plc_fec_or_pred(st, st->features);

@@ -1,8 +1,9 @@
 """Pins the neural packet-loss concealment restatement (oracle/fargan_oracle.c: orc_plc_*, after dnn/lpcnet_plc.c) against the reference's own
 lpcnet_plc.c compiled with seeded random weights (oracle/gen_plc_weights.py + gen_fargan_weights.py, generic C branch of dnn/vec.h like the FARGAN
 pin).  Covered: compute_plc_pred, get_fec_or_pred (FEC / DRED features, gaps, pure prediction), the attenuation table, queue_features, the PCM
-history, fargan_cont + fargan_synthesize_int, lpcnet_plc_reset, fec_add / fec_clear.  NOT covered (not restated): the history analysis
-of a first concealed frame that follows good audio.  Bar: bit-identical int16 PCM and state."""
+history, fargan_cont + fargan_synthesize_int, lpcnet_plc_reset, fec_add / fec_clear, lpcnet_plc_update and the history analysis of a first concealed
+frame that follows good audio (burg_cepstral_analysis + lpcnet_compute_single_frame_features_float + the predictor over the frames not analysed
+yet, with lpcnet_enc_oracle.c as the feature extractor).  Bar: bit-identical int16 PCM and state."""
 import ctypes
 
 import numpy as np
@@ -70,10 +71,59 @@ def test_conceal_sequences(seed):
         assert np.array_equal(a, b)
 
 
-def test_history_analysis_is_reported_not_faked():
-    """after lpcnet_plc_update (good audio) the first conceal needs the feature analysis that is not restated: the oracle says so"""
+def test_history_analysis_needs_the_feature_extractor():
+    """after lpcnet_plc_update (good audio) the first conceal runs the feature analysis: without an encoder object the oracle says so"""
     ref = F.RefPlc(R)
     O, st, keep = _oracle(ref)
     pcm = np.zeros(160, np.int16)
     O.orc_plc_update(F.vp(st), F.vp(pcm))
     assert O.orc_plc_conceal(F.vp(st), F.vp(pcm)) == -1
+
+
+def loss_pattern(seed, nframes):
+    """good / lost per frame: bursts of 1..6 losses between runs of good audio, the first frames good"""
+    rng = np.random.default_rng(seed)
+    lost = np.zeros(nframes, bool)
+    t = int(rng.integers(3, 9))
+    while t < nframes:
+        k = int(rng.integers(1, 7))
+        lost[t:t + k] = True
+        t += k + int(rng.integers(1, 12))
+    return lost
+
+
+@pytest.mark.parametrize('seed', [1, 2, 3, 4])
+def test_update_conceal_sequences(seed):
+    """a decoder's life: good frames (lpcnet_plc_update), then a burst of losses, the first of which analyses the history"""
+    ref = F.RefPlc(R)
+    O, st, keep = _oracle(ref)
+    enc = F.OrcLpcnetEnc(O, F.RefLpcnetEnc(R))
+    O.orc_plc_set_encoder(F.vp(st), F.vp(enc.st))
+    O.orc_plc_reset(F.vp(st))
+    nfr = 70
+    audio = np.round(F.speech_like(900 + seed, nfr, 9000.0)).astype(np.int16)
+    lost = loss_pattern(seed, nfr)
+    rng = np.random.default_rng(seed)
+    analysed = 0
+    for t in range(nfr):
+        if not lost[t]:
+            frame = np.ascontiguousarray(audio[t * 160:(t + 1) * 160])
+            R.refh_plc_update_pcm(F.vp(ref.st), F.vp(frame))
+            O.orc_plc_update(F.vp(st), F.vp(frame))
+            continue
+        if seed % 2 and rng.random() < 0.4:   # a DRED vector for this frame
+            f = (0.5 * rng.standard_normal(20)).astype(np.float32)
+            ref.fec_add(f)
+            O.orc_plc_fec_add(F.vp(st), F.vp(f))
+        before = _state(O, st)[5][5]
+        want = ref.conceal()
+        got = np.zeros(160, np.int16)
+        assert O.orc_plc_conceal(F.vp(st), F.vp(got)) == 0
+        analysed += int(before + 160 <= 2400 and not lost[t - 1])
+        assert np.array_equal(got, want), (t, int(np.abs(got.astype(int) - want).max()))
+        if not lost[min(t + 1, nfr - 1)] and seed % 2:
+            ref.fec_clear()
+            O.orc_plc_fec_clear(F.vp(st))
+    assert analysed >= 3
+    for a, b in zip(_state(O, st), ref.state()):
+        assert np.array_equal(a, b)
