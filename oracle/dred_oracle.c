@@ -117,3 +117,118 @@ void orc_dred_encode_dframe(OrcDredEnc *st, float *latents, float *initial_state
   memcpy(initial_state, padded_state, 50 * sizeof(float));
   st->initialized = 1;
 }
+
+/* ---- DRED encoder front end: dnn/dred_encoder.c:70-260 (dred_encoder_reset, dred_process_frame, filter_df2t, dred_convert_to_16k,
+ * dred_compute_latents): the input is converted to 16 kHz mono in int16 range (zero-stuffing by `up`, a 7th-order elliptic low-pass in transposed
+ * direct form II, decimation by 3), buffered to double frames of 320 samples, each of which gives two feature vectors (lpcnet_enc_oracle.c) and one
+ * latent / state pair (orc_dred_encode_dframe) pushed at the front of the 104-deep ring buffers.  Pinned against the reference's own dred_encoder.c
+ * (oracle/_ref/libfargan_ref.so) by tests/test_dred_oracle_vs_ref.py. ---- */
+#include <math.h>
+#define DE_MAX_FRAMES 104     /* DRED_MAX_FRAMES, dnn/dred_config.h:52 */
+#define DE_REDUNDANCY 52      /* DRED_NUM_REDUNDANCY_FRAMES */
+#define DE_FRAME 160
+#define DE_DELAY (79 + 12 - 80) /* DRED_SILK_ENCODER_DELAY */
+#define DE_ORDER 8            /* RESAMPLING_ORDER, dnn/dred_encoder.h */
+void orc_lpcnet_enc_reset(void *st);
+void orc_lpcnet_enc_features(void *st, const float *pcm, float *features);
+typedef struct {
+  OrcDredEnc *net;
+  void *lpcnet;               /* an OrcLpcnetEnc */
+  int Fs, channels;
+  float input_buffer[4 * DE_FRAME];
+  int input_buffer_fill, dred_offset, latent_offset, last_extra_dred_offset;
+  float latents_buffer[DE_MAX_FRAMES * 25];
+  int latents_buffer_fill;
+  float state_buffer[DE_MAX_FRAMES * 50];
+  float resample_mem[DE_ORDER + 1];
+} OrcDredFront;
+int orc_dredenc_size(void) { return (int)sizeof(OrcDredFront); }
+void orc_dredenc_reset(OrcDredFront *e) { /* dred_encoder_reset, :70-78 */
+  memset(e->input_buffer, 0, sizeof(*e) - ((char *)e->input_buffer - (char *)e));
+  e->input_buffer_fill = DE_DELAY;
+  orc_lpcnet_enc_reset(e->lpcnet);
+  e->net->initialized = 0;
+  memset(e->net->gru, 0, sizeof(e->net->gru));
+  memset(e->net->conv, 0, sizeof(e->net->conv));
+}
+void orc_dredenc_init(OrcDredFront *e, OrcDredEnc *net, void *lpcnet, int Fs, int channels) {
+  memset(e, 0, sizeof(*e));
+  e->net = net; e->lpcnet = lpcnet; e->Fs = Fs; e->channels = channels;
+  orc_dredenc_reset(e);
+}
+static float de_to_int16(float x) { /* FLOAT2INT16, celt/float_cast.h:150-156 */
+  x = x * 32768.f;
+  x = x > -32768 ? x : -32768;
+  x = x < 32767 ? x : 32767;
+  return (float)(short)lrintf(x);
+}
+static void de_filter(const float *in, float *out, int len, float b0, const float *b, const float *a, float *mem) { /* filter_df2t, :109-126 */
+  int i, j;
+  for (i = 0; i < len; i++) {
+    const float xi = in[i], yi = xi * b0 + mem[0], nyi = -yi;
+    for (j = 0; j < DE_ORDER; j++) mem[j] = mem[j + 1] + b[j] * xi + a[j] * nyi;
+    out[i] = yi;
+  }
+}
+static void de_convert_to_16k(OrcDredFront *e, const float *in, int in_len, float *out, int out_len) { /* :133-213 */
+  static const float b48[8] = {0.005873358047f, 0.012980854831f, 0.014531340042f, 0.014531340042f, 0.012980854831f, 0.005873358047f, 0.004523418224f, 0.f};
+  static const float a48[8] = {-3.878718597768f, 7.748834257468f, -9.653651699533f, 8.007342726666f, -4.379450178552f, 1.463182111810f, -0.231720677804f, 0.f};
+  static const float b12[8] = {-0.001017101081f, 0.003673127243f, 0.001009165267f, 0.001009165267f, 0.003673127243f, -0.001017101081f, 0.002033596776f, 0.f};
+  static const float a12[8] = {-4.930414411612f, 11.291643096504f, -15.322037343815f, 13.216403930898f, -7.220409219553f, 2.310550142771f, -0.334338618782f, 0.f};
+  static const float b8[8] = {0.081670120929f, 0.180401598565f, 0.259391051971f, 0.259391051971f, 0.180401598565f, 0.081670120929f, 0.020109185709f, 0.f};
+  static const float a8[8] = {-1.393651933659f, 2.609789872676f, -2.403541968806f, 2.056814957331f, -1.148908574570f, 0.473001413788f, -0.110359852412f, 0.f};
+  float downmix[960 * 2];
+  const int up = e->Fs == 8000 ? 2 : e->Fs == 12000 ? 4 : e->Fs == 24000 ? 2 : 1;
+  int i;
+  memset(downmix, 0, up * in_len * sizeof(float));
+  if (e->channels == 1) for (i = 0; i < in_len; i++) downmix[up * i] = up * de_to_int16(in[i]) + 1e-30f;
+  else for (i = 0; i < in_len; i++) downmix[up * i] = up * de_to_int16(.5 * (in[2 * i] + in[2 * i + 1])) + 1e-30f;
+  if (e->Fs == 16000) memcpy(out, downmix, out_len * sizeof(float));
+  else if (e->Fs == 48000 || e->Fs == 24000) {
+    de_filter(downmix, downmix, up * in_len, 0.004523418224f, b48, a48, e->resample_mem);
+    for (i = 0; i < out_len; i++) out[i] = downmix[3 * i];
+  } else if (e->Fs == 12000) {
+    de_filter(downmix, downmix, up * in_len, 0.002033596776f, b12, a12, e->resample_mem);
+    for (i = 0; i < out_len; i++) out[i] = downmix[3 * i];
+  } else de_filter(downmix, out, out_len, 0.020109185709f, b8, a8, e->resample_mem);
+}
+static void de_process_frame(OrcDredFront *e) { /* dred_process_frame, :84-107 */
+  float feature_buffer[2 * 36], input[2 * 20];
+  memmove(e->latents_buffer + 25, e->latents_buffer, (DE_MAX_FRAMES - 1) * 25 * sizeof(float));
+  memmove(e->state_buffer + 50, e->state_buffer, (DE_MAX_FRAMES - 1) * 50 * sizeof(float));
+  orc_lpcnet_enc_features(e->lpcnet, e->input_buffer, feature_buffer);
+  orc_lpcnet_enc_features(e->lpcnet, e->input_buffer + DE_FRAME, feature_buffer + 36);
+  memcpy(input, feature_buffer, 20 * sizeof(float));
+  memcpy(input + 20, feature_buffer + 36, 20 * sizeof(float));
+  orc_dred_encode_dframe(e->net, e->latents_buffer, e->state_buffer, input);
+  e->latents_buffer_fill = e->latents_buffer_fill + 1 < DE_REDUNDANCY ? e->latents_buffer_fill + 1 : DE_REDUNDANCY;
+}
+void orc_dredenc_compute_latents(OrcDredFront *e, const float *pcm, int frame_size, int extra_delay) { /* dred_compute_latents, :215-250 */
+  int frame_size16k = frame_size * 16000 / e->Fs;
+  int curr_offset16k = 40 + extra_delay * 16000 / e->Fs - e->input_buffer_fill;
+  e->dred_offset = (int)floor((curr_offset16k + 20.f) / 40.f);
+  e->latent_offset = 0;
+  while (frame_size16k > 0) {
+    const int process_size16k = 2 * DE_FRAME < frame_size16k ? 2 * DE_FRAME : frame_size16k;
+    const int process_size = process_size16k * e->Fs / 16000;
+    de_convert_to_16k(e, pcm, process_size, &e->input_buffer[e->input_buffer_fill], process_size16k);
+    e->input_buffer_fill += process_size16k;
+    if (e->input_buffer_fill >= 2 * DE_FRAME) {
+      curr_offset16k += 320;
+      de_process_frame(e);
+      e->input_buffer_fill -= 2 * DE_FRAME;
+      memmove(&e->input_buffer[0], &e->input_buffer[2 * DE_FRAME], e->input_buffer_fill * sizeof(float));
+      if (e->dred_offset < 6) e->dred_offset += 8;
+      else e->latent_offset++;
+    }
+    pcm += process_size * e->channels;
+    frame_size16k -= process_size16k;
+  }
+}
+void orc_dredenc_get(const OrcDredFront *e, float *latents, float *state, float *input_buffer, float *resample_mem, int *ints) {
+  memcpy(latents, e->latents_buffer, sizeof(e->latents_buffer));
+  memcpy(state, e->state_buffer, sizeof(e->state_buffer));
+  memcpy(input_buffer, e->input_buffer, sizeof(e->input_buffer));
+  memcpy(resample_mem, e->resample_mem, sizeof(e->resample_mem));
+  ints[0] = e->input_buffer_fill; ints[1] = e->dred_offset; ints[2] = e->latent_offset; ints[3] = e->latents_buffer_fill; ints[4] = e->last_extra_dred_offset;
+}

@@ -160,3 +160,22 @@ void refh_dred_encode_dframe(RDOVAEEncState *st, float *latents, float *initial_
   dred_enc_ready();
   dred_rdovae_encode_dframe(st, &g_dred_enc_model, latents, initial_state, input, 0);
 }
+
+/* ---- DRED encoder front end (dnn/dred_encoder.c, compiled unmodified): 16 kHz conversion, feature extraction, latents and state ring buffers ---- */
+#include "dred_encoder.h"
+int refh_dredenc_size(void) { return (int)sizeof(DREDEnc); }
+void refh_dredenc_init(DREDEnc *e, int Fs, int channels) { dred_encoder_init(e, Fs, channels); }
+void refh_dredenc_reset(DREDEnc *e) { dred_encoder_reset(e); }
+int refh_dredenc_loaded(const DREDEnc *e) { return e->loaded; }
+void refh_dredenc_compute_latents(DREDEnc *e, const float *pcm, int frame_size, int extra_delay) { dred_compute_latents(e, pcm, frame_size, extra_delay, 0); }
+void refh_dredenc_get(const DREDEnc *e, float *latents, float *state, float *input_buffer, float *resample_mem, int *ints) {
+  memcpy(latents, e->latents_buffer, sizeof(e->latents_buffer));
+  memcpy(state, e->state_buffer, sizeof(e->state_buffer));
+  memcpy(input_buffer, e->input_buffer, sizeof(e->input_buffer));
+  memcpy(resample_mem, e->resample_mem, sizeof(e->resample_mem));
+  ints[0] = e->input_buffer_fill; ints[1] = e->dred_offset; ints[2] = e->latent_offset; ints[3] = e->latents_buffer_fill; ints[4] = e->last_extra_dred_offset;
+}
+int refh_dredenc_encode_silk_frame(DREDEnc *e, unsigned char *buf, int max_chunks, int max_bytes, int q0, int dQ, int qmax, unsigned char *activity_mem) {
+  return dred_encode_silk_frame(e, buf, max_chunks, max_bytes, q0, dQ, qmax, activity_mem, 0);
+}
+int refh_dredenc_const(int which) { return which == 0 ? DRED_MAX_FRAMES : which == 1 ? RESAMPLING_ORDER : which == 2 ? DRED_SILK_ENCODER_DELAY : -1; }

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(REF, 'dnn', 'torch', 'rdovae'))
 sys.path.insert(0, os.path.join(REF, 'dnn', 'torch', 'weight-exchange'))
 from rdovae import RDOVAE                               # noqa: E402
 from wexchange.torch import dump_torch_weights          # noqa: E402
-from wexchange.c_export import CWriter                  # noqa: E402
+from wexchange.c_export import CWriter, print_vector    # noqa: E402
 
 torch.manual_seed(0xD2ED)
 rng = np.random.default_rng(11)
@@ -106,4 +106,33 @@ with open(os.path.join(OUT, 'dred_rdovae_constants.h'), 'w') as f:
                  ('DRED_MAX_CONV_INPUTS', conv), ('DRED_DEC_MAX_RNN_NEURONS', rnn)]:
         f.write('#define %s %d\n' % (k, v))
     f.write('#endif\n')
+
+# ---- the statistical model of the latents (dred_rdovae_stats_data.[ch]): what dnn/dred_encoder.c's entropy coder reads.  Formulas of
+# dump_statistical_model (export_rdovae_weights.py:71-112) on the model's own (seeded random, widened) quantisation embedding; every dimension is kept.
+qemb = model.statistical_model.quant_embedding.weight.detach().clone()
+levels = qemb.shape[0]
+qemb = torch.reshape(qemb, (levels, 6, -1)) * 3.0 + torch.linspace(-1.0, 1.0, levels).reshape(levels, 1, 1) + 0.7 * torch.randn(levels, 6, qemb.numel() // (6 * levels))
+sw = CWriter(os.path.join(OUT, 'dred_rdovae_stats_data'), message='seeded random model (oracle/gen_dred_weights.py)', enable_binary_blob=False)
+sw.header.write('\n#include "opus_types.h"\n\n#include "dred_rdovae_constants.h"\n\n')
+for name, wq in (('latent', qemb[:, :, :LATENT_DIM]), ('state', qemb[:, :, LATENT_DIM:LATENT_DIM + STATE_DIM])):
+    quant_scales = torch.nn.functional.softplus(wq[:, 0, :]).numpy()
+    dead_zone = 0.05 * torch.nn.functional.softplus(wq[:, 1, :]).numpy()
+    r = torch.sigmoid(wq[:, 5, :]).numpy()
+    p0 = torch.sigmoid(wq[:, 4, :]).numpy()
+    p0 = 1 - r ** (0.5 + 0.5 * p0)
+    quant_scales = quant_scales * (255. / 256. / (1e-15 + np.max(quant_scales, axis=0)))
+    arrays = (('quant_scales', np.round(quant_scales * 2 ** 8).astype(np.uint16)), ('dead_zone', np.clip(np.round(dead_zone * 2 ** 8), 0, 255).astype(np.uint16)),
+              ('r', np.clip(np.round(r * 2 ** 8), 0, 255).astype(np.uint8)), ('p0', np.clip(np.round(p0 * 2 ** 8), 0, 255).astype(np.uint16)))
+    assert np.all(np.max(arrays[2][1], axis=0) > 0) and np.all(np.min(arrays[3][1], axis=0) < 255)   # the exporter would drop such a dimension
+    with contextlib.redirect_stdout(io.StringIO()):
+        for an, av in arrays:
+            print_vector(sw.source, av, 'dred_%s_%s_q8' % (name, an), dtype='opus_uint8', static=False)
+    n_dim = arrays[0][1].shape[1]
+    sw.header.write(''.join('extern const opus_uint8 dred_%s_%s_q8[%d];\n' % (name, an, levels * n_dim) for an, _ in arrays) + '\n')
+del sw
+for ext in ('.h', '.c'):   # the writer appends an (empty) model struct and its init function that do not compile as C: the arrays are all there is
+    path = os.path.join(OUT, 'dred_rdovae_stats_data' + ext)
+    txt = open(path).read()
+    cut = txt.index('struct Model') if ext == '.h' else txt.index('const WeightArray model_arrays')
+    open(path, 'w').write(txt[:cut] + ('\n#endif\n' if ext == '.h' else ''))
 print('wrote', os.path.join(OUT, 'dred_rdovae_dec_data.c'), 'max rnn', rnn, 'max conv inputs', conv)

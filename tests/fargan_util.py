@@ -278,3 +278,56 @@ def speech_like(seed, nframes, scale=8000.0):
         a = rng.integers(0, max(1, n - 400))
         env[a:a + 400] = 0
     return (scale * rng.uniform(0.05, 1.0) * env * x).astype(np.float32)
+
+
+class RefDredFront:
+    """the reference's DREDEnc object (dnn/dred_encoder.c) with the compiled-in seeded random models"""
+
+    def __init__(self, L, Fs, channels):
+        self.L = L
+        self.st = np.zeros(L.refh_dredenc_size() + 64, np.uint8)
+        L.refh_dredenc_init(vp(self.st), Fs, channels)
+        assert L.refh_dredenc_loaded(vp(self.st)) == 1
+
+    def compute_latents(self, pcm, frame_size, extra_delay=0):
+        self.L.refh_dredenc_compute_latents(vp(self.st), vp(np.ascontiguousarray(pcm, np.float32)), frame_size, extra_delay)
+
+    def get(self):
+        bufs = [np.zeros(k, np.float32) for k in (104 * 25, 104 * 50, 640, 9)] + [np.zeros(5, np.int32)]
+        self.L.refh_dredenc_get(vp(self.st), *[vp(b) for b in bufs])
+        return bufs
+
+
+class OrcDredFront:
+    """oracle/dred_oracle.c's front end on the layers of the reference library"""
+
+    def __init__(self, O, L, Fs, channels):
+        self.O = O
+        self.lp = OrcLpcnetEnc(O, RefLpcnetEnc(L))
+        self.layers, _ = RefDredEnc(L).layers()
+        self.net = np.zeros(O.orc_dred_enc_size() + 64, np.uint8)
+        O.orc_dred_enc_init(vp(self.net), self.layers)
+        self.st = np.zeros(O.orc_dredenc_size() + 64, np.uint8)
+        O.orc_dredenc_init(vp(self.st), vp(self.net), vp(self.lp.st), Fs, channels)
+
+    def compute_latents(self, pcm, frame_size, extra_delay=0):
+        self.O.orc_dredenc_compute_latents(vp(self.st), vp(np.ascontiguousarray(pcm, np.float32)), frame_size, extra_delay)
+
+    def reset(self):
+        self.O.orc_dredenc_reset(vp(self.st))
+
+    def get(self):
+        bufs = [np.zeros(k, np.float32) for k in (104 * 25, 104 * 50, 640, 9)] + [np.zeros(5, np.int32)]
+        self.O.orc_dredenc_get(vp(self.st), *[vp(b) for b in bufs])
+        return bufs
+
+
+def dred_input(seed, Fs, channels, nsamples):
+    """float PCM in [-1, 1) at Fs: a 16 kHz speech-like signal held / interpolated to Fs, the second channel a delayed copy"""
+    base = speech_like(seed, (nsamples * 16000 // Fs) // 160 + 2, 12000.0) / 32768.0
+    t = np.arange(nsamples) * (16000.0 / Fs)
+    x = np.interp(t, np.arange(base.size), base).astype(np.float32)
+    if channels == 1:
+        return x
+    y = np.roll(x, 7) * np.float32(0.8)
+    return np.stack([x, y], 1).reshape(-1).astype(np.float32)

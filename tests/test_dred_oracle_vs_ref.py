@@ -48,3 +48,34 @@ def test_dred_encode_dframe_matches_reference(seed):
         O.orc_dred_encode_dframe(F.vp(st), F.vp(gl), F.vp(gs), F.vp(x))
         assert np.array_equal(gl, wl) and np.array_equal(gs, ws), (t, float(np.abs(gl - wl).max()), float(np.abs(gs - ws).max()))
     assert float(np.abs(wl).max()) > 1e-3
+
+
+@pytest.mark.skipif(R is None or not hasattr(R, 'refh_dredenc_size'), reason='oracle/_ref/libfargan_ref.so without dnn/dred_encoder.c')
+@pytest.mark.parametrize('Fs,channels,frame_ms,extra', [(48000, 2, 20, 0), (48000, 1, 10, 0), (16000, 1, 20, 0), (24000, 2, 20, 120), (12000, 1, 40, 0), (8000, 1, 20, 0),
+                                                       (48000, 1, 2.5, 0)])
+def test_dred_compute_latents_matches_reference(Fs, channels, frame_ms, extra):
+    """dred_compute_latents over a run of frames (16 kHz conversion + feature extraction + RDOVAE encoder + ring buffers): everything bit for bit"""
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    ref = F.RefDredFront(R, Fs, channels)
+    orc = F.OrcDredFront(O, R, Fs, channels)
+    fs = int(Fs * frame_ms / 1000)
+    nfr = 14 if frame_ms >= 10 else 60
+    x = F.dred_input(3 + channels + Fs // 1000, Fs, channels, fs * nfr)
+    x[:4] = [1.5, -1.5, 0.99999, -1.0][:4]   # the int16 conversion saturates
+    seen = 0
+    for t in range(nfr):
+        frame = x[t * fs * channels:(t + 1) * fs * channels]
+        ref.compute_latents(frame, fs, extra)
+        orc.compute_latents(frame, fs, extra)
+        a, b = ref.get(), orc.get()
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v), t
+        seen = max(seen, int(a[4][3]))
+    assert seen >= 2 and np.abs(a[0][:25]).max() > 1e-3
+    orc.reset()
+    R.refh_dredenc_reset(F.vp(ref.st))
+    ref.compute_latents(x[:fs * channels], fs, extra)
+    orc.compute_latents(x[:fs * channels], fs, extra)
+    for u, v in zip(ref.get(), orc.get()):
+        assert np.array_equal(u, v)
