@@ -403,14 +403,26 @@ int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const float *featu
  * dnn/dred_encoder.c): layers = the 24 LinearLayers of the generated RDOVAEEnc struct in declaration order (enc_dense1, enc_zdense, gdense1, gdense2,
  * enc_conv_dense1..5, enc_gru1..5 input / recurrent, enc_conv1..5), n streams in lockstep, one RDOVAEEncState per stream on the device.
  *   opusb200_dred_encode_dframe(enc, latents [n][latent_dim], initial_state [n][state_dim], input [n][2 * 20 features], on_device)
- * = dred_rdovae_encode_dframe for every stream; latents and state bit-identical to the reference given the same model.  The feature extraction in
- * front of it (lpcnet_enc.c) and the entropy coding of the latents behind it (dred_encoder.c / dred_coding.c) are not built. ---- */
+ * = dred_rdovae_encode_dframe for every stream; latents and state bit-identical to the reference given the same model.  The front end
+ * (16 kHz conversion, feature extraction, buffers) follows below; the entropy coding of the latents (dred_coding.c) is not built. ---- */
 typedef struct OpusB200DredEnc OpusB200DredEnc;
 int opusb200_dred_encoder_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int latent_dim, int state_dim,
                                  int n_streams, OpusB200DredEnc **out);
 void opusb200_dred_encoder_destroy(OpusB200DredEnc *enc);
 int opusb200_dred_encoder_reset(OpusB200DredEnc *enc);
 int opusb200_dred_encode_dframe(OpusB200DredEnc *enc, float *latents, float *initial_state, const float *input, int on_device);
+/* The encoder's front end (DREDEnc of dnn/dred_encoder.h:40-60; dred_encoder_init :80, dred_encoder_reset :70, dred_compute_latents :215-250 with
+ * dred_convert_to_16k :133-213 and dred_process_frame :84-107): PCM at Fs in, per double frame of 20 ms two feature vectors
+ * (opusb200_lpcnet_encoder_*) and one latent / state pair pushed at the front of the 104-deep buffers dred_encode_silk_frame reads.
+ *   init_frontend: Fs in {8000, 12000, 16000, 24000, 48000}, channels 1 or 2, linear / conv = the PitchDNN layers (the other half of
+ *                  dred_encoder_load_model); opusb200_dred_encoder_reset then is dred_encoder_reset.
+ *   compute_latents: pcm [n][frame_size * channels] float in [-1, 1), frame_size * 16000 divisible by Fs; streams in lockstep.
+ *   get_latents: the buffers in the reference's order (entry 0 = newest), info [4] = input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill.
+ * The entropy coding of the latents behind it (dred_encode_silk_frame, dred_coding.c) is not built. */
+int opusb200_dred_encoder_init_frontend(OpusB200DredEnc *enc, int Fs, int channels, const OpusB200LinearLayer *linear, int n_linear,
+                                        const OpusB200Conv2dLayer *conv, int n_conv, int su_bias);
+int opusb200_dred_compute_latents(OpusB200DredEnc *enc, const float *pcm, int frame_size, int extra_delay, int on_device);
+int opusb200_dred_encoder_get_latents(OpusB200DredEnc *enc, float *latents, float *state, int32_t *info);
 
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what

@@ -157,6 +157,7 @@ namespace ob {
 constexpr int kDeGru = 32, kDeConv = 64, kDeDense1 = 64, kDeBuf = kDeDense1 + 5 * (kDeGru + kDeConv), kDeLatPad = 32, kDeStatePad = 56;
 enum { DE_DENSE1 = 0, DE_ZDENSE = 1, DE_GDENSE1 = 2, DE_GDENSE2 = 3, DE_CONV_DENSE1 = 4, DE_GRU1_IN = 9, DE_CONV1 = 19, DE_COUNT = 24 };
 }
+constexpr int kDredMaxFrames = 104, kDredRedundancy = 52, kDredSilkDelay = 79 + 12 - 80;   // DRED_MAX_FRAMES, DRED_NUM_REDUNDANCY_FRAMES, DRED_SILK_ENCODER_DELAY
 struct OpusB200DredEnc {
   OpusB200Ctx *ctx;
   int n, latent_dim, state_dim, initialized;
@@ -165,11 +166,19 @@ struct OpusB200DredEnc {
   float *gru[5], *conv[5];    // [n][32], [n][64 * dilation] layer memories
   float *tmp, *tmp2;          // [n][128] scratch
   float *d_in, *d_lat, *d_state;   // staging for host callers
+  // front end (DREDEnc of dnn/dred_encoder.h:40-60): lockstep bookkeeping on the host, per-stream buffers on the device
+  OpusB200LpcnetEnc *lpcnet;
+  int Fs, channels, input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill, head;
+  float *input_buffer, *resample_mem, *lat_ring, *state_ring, *feat_a, *feat_b, *in40, *d_pcm;
+  size_t d_pcm_elems;
 };
 static void de_free(OpusB200DredEnc *d) {
   if (!d) return;
   for (int i = 0; i < DE_COUNT; i++) opusb200_nnet_linear_destroy(d->l[i]);
   cudaFree(d->buf); cudaFree(d->tmp); cudaFree(d->tmp2); cudaFree(d->d_in); cudaFree(d->d_lat); cudaFree(d->d_state);
+  opusb200_lpcnet_encoder_destroy(d->lpcnet);
+  cudaFree(d->input_buffer); cudaFree(d->resample_mem); cudaFree(d->lat_ring); cudaFree(d->state_ring); cudaFree(d->feat_a); cudaFree(d->feat_b); cudaFree(d->in40);
+  cudaFree(d->d_pcm);
   for (int k = 0; k < 5; k++) { cudaFree(d->gru[k]); cudaFree(d->conv[k]); }
   delete d;
 }
@@ -218,19 +227,21 @@ extern "C" int opusb200_dred_encoder_reset(OpusB200DredEnc *d) {   // a zeroed R
   OB_CUDA(cudaSetDevice(d->ctx->device));
   for (int k = 0; k < 5; k++) OB_CUDA(cudaMemsetAsync(d->gru[k], 0, sizeof(float) * (size_t)d->n * kDeGru, d->ctx->stream));
   d->initialized = 0;
+  if (d->lpcnet) {   // dred_encoder_reset (dnn/dred_encoder.c:70-78): buffers cleared, input_buffer_fill = DRED_SILK_ENCODER_DELAY, the feature extractor re-initialised
+    const size_t n = (size_t)d->n;
+    OB_CUDA(cudaMemsetAsync(d->input_buffer, 0, sizeof(float) * n * 640, d->ctx->stream));
+    OB_CUDA(cudaMemsetAsync(d->resample_mem, 0, sizeof(float) * n * 9, d->ctx->stream));
+    OB_CUDA(cudaMemsetAsync(d->lat_ring, 0, sizeof(float) * n * kDredMaxFrames * d->latent_dim, d->ctx->stream));
+    OB_CUDA(cudaMemsetAsync(d->state_ring, 0, sizeof(float) * n * kDredMaxFrames * d->state_dim, d->ctx->stream));
+    DR_TRY(opusb200_lpcnet_encoder_reset(d->lpcnet));
+    d->input_buffer_fill = kDredSilkDelay; d->dred_offset = 0; d->latent_offset = 0; d->latents_buffer_fill = 0; d->head = 0;
+  }
   return OPUSB200_OK;
 }
 // dred_rdovae_encode_dframe for every stream: input [n][40] -> latents [n][latent_dim], initial_state [n][state_dim]
-extern "C" int opusb200_dred_encode_dframe(OpusB200DredEnc *d, float *latents, float *initial_state, const float *input, int on_device) {
-  if (!d || !latents || !initial_state || !input) return OPUSB200_BAD_ARG;
+static int de_encode_dev(OpusB200DredEnc *d, float *d_latents, int lat_stride, float *d_state, int state_stride, const float *din) {
   OpusB200Ctx *c = d->ctx;
-  OB_CUDA(cudaSetDevice(c->device));
   const int n = d->n;
-  const float *din = input;
-  if (!on_device) {
-    OB_CUDA(cudaMemcpyAsync(d->d_in, input, sizeof(float) * (size_t)n * 40, cudaMemcpyHostToDevice, c->stream));
-    din = d->d_in;
-  }
   DR_TRY(opusb200_nnet_compute_dense(c, d->l[DE_DENSE1], d->tmp, din, n, NN_TANH, 1));
   DR_TRY(dr_copy2d(c, d->buf, kDeBuf, d->tmp, kDeDense1, kDeDense1, n));
   int col = kDeDense1;
@@ -255,19 +266,134 @@ extern "C" int opusb200_dred_encode_dframe(OpusB200DredEnc *d, float *latents, f
     DR_TRY(dr_copy2d(c, d->buf + col, kDeBuf, d->tmp2, kDeConv, kDeConv, n));
     col += kDeConv;
   }
-  float *dl = on_device ? nullptr : d->d_lat, *dsv = on_device ? nullptr : d->d_state;
   DR_TRY(nnet_linear_dev(c, d->l[DE_ZDENSE], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDeBuf));
-  DR_TRY(dr_copy2d(c, on_device ? latents : dl, d->latent_dim, d->tmp, kDeLatPad, d->latent_dim, n));
+  DR_TRY(dr_copy2d(c, d_latents, lat_stride, d->tmp, kDeLatPad, d->latent_dim, n));
   DR_TRY(nnet_linear_dev(c, d->l[DE_GDENSE1], d->tmp, d->buf, n, NN_LINEAR, nullptr, nullptr, kDeBuf));
   DR_TRY(nnet_act_dev(c, d->tmp, d->tmp, n, 128, NN_TANH));
   DR_TRY(opusb200_nnet_compute_dense(c, d->l[DE_GDENSE2], d->tmp2, d->tmp, n, NN_LINEAR, 1));
-  DR_TRY(dr_copy2d(c, on_device ? initial_state : dsv, d->state_dim, d->tmp2, kDeStatePad, d->state_dim, n));
+  DR_TRY(dr_copy2d(c, d_state, state_stride, d->tmp2, kDeStatePad, d->state_dim, n));
   d->initialized = 1;
   OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_dred_encode_dframe(OpusB200DredEnc *d, float *latents, float *initial_state, const float *input, int on_device) {
+  if (!d || !latents || !initial_state || !input) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = d->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  const int n = d->n;
+  if (on_device) return de_encode_dev(d, latents, d->latent_dim, initial_state, d->state_dim, input);
+  OB_CUDA(cudaMemcpyAsync(d->d_in, input, sizeof(float) * (size_t)n * 40, cudaMemcpyHostToDevice, c->stream));
+  DR_TRY(de_encode_dev(d, d->d_lat, d->latent_dim, d->d_state, d->state_dim, d->d_in));
+  OB_CUDA(cudaMemcpyAsync(latents, d->d_lat, sizeof(float) * (size_t)n * d->latent_dim, cudaMemcpyDeviceToHost, c->stream));
+  OB_CUDA(cudaMemcpyAsync(initial_state, d->d_state, sizeof(float) * (size_t)n * d->state_dim, cudaMemcpyDeviceToHost, c->stream));
+  OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+
+// ---- the front end of the DRED encoder: dred_encoder_init + dred_compute_latents (dnn/dred_encoder.c:80-82, 215-250) ----
+extern "C" __global__ void __launch_bounds__(128) ob_dred_convert_16k(ob::DredConvParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::dred_convert_thread(p, s);
+}
+// dred_encoder_init(Fs, channels) + the pitch-model half of dred_encoder_load_model: linear / conv = the PitchDNN layers (as opusb200_lpcnet_encoder_create)
+extern "C" int opusb200_dred_encoder_init_frontend(OpusB200DredEnc *d, int Fs, int channels, const OpusB200LinearLayer *linear, int n_linear,
+                                                   const OpusB200Conv2dLayer *conv, int n_conv, int su_bias) {
+  if (!d || (Fs != 8000 && Fs != 12000 && Fs != 16000 && Fs != 24000 && Fs != 48000) || (channels != 1 && channels != 2)) return OPUSB200_BAD_ARG;
+  if (d->lpcnet) return OPUSB200_INVALID_STATE;
+  OpusB200Ctx *c = d->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  OpusB200LpcnetEnc *e = nullptr;
+  DR_TRY(opusb200_lpcnet_encoder_create(c, linear, n_linear, conv, n_conv, su_bias, d->n, &e));
+  const size_t n = (size_t)d->n;
+  struct { float **p; size_t w; } al[] = {{&d->input_buffer, 640}, {&d->resample_mem, 9}, {&d->lat_ring, (size_t)kDredMaxFrames * d->latent_dim},
+                                          {&d->state_ring, (size_t)kDredMaxFrames * d->state_dim}, {&d->feat_a, 36}, {&d->feat_b, 36}, {&d->in40, 40}};
+  for (auto &a : al)
+    if (cudaMalloc(a.p, sizeof(float) * n * a.w) != cudaSuccess) {
+      opusb200_lpcnet_encoder_destroy(e);
+      for (auto &b : al) { cudaFree(*b.p); *b.p = nullptr; }
+      return OPUSB200_ALLOC_FAIL;
+    }
+  d->lpcnet = e; d->Fs = Fs; d->channels = channels;
+  DR_TRY(opusb200_dred_encoder_reset(d));
+  OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+// dred_process_frame (:84-107): two feature frames of the 320 buffered samples, one latent / state pair at the front of the ring buffers
+static int de_process_frame(OpusB200DredEnc *d) {
+  OpusB200Ctx *c = d->ctx;
+  const size_t n = (size_t)d->n;
+  DR_TRY(lpcnet_enc_frame(d->lpcnet, d->input_buffer, 0, d->feat_a, 640));
+  DR_TRY(lpcnet_enc_frame(d->lpcnet, d->input_buffer + 160, 0, d->feat_b, 640));
+  OB_CUDA(cudaMemcpy2DAsync(d->in40, sizeof(float) * 40, d->feat_a, sizeof(float) * 36, sizeof(float) * 20, n, cudaMemcpyDeviceToDevice, c->stream));
+  OB_CUDA(cudaMemcpy2DAsync(d->in40 + 20, sizeof(float) * 40, d->feat_b, sizeof(float) * 36, sizeof(float) * 20, n, cudaMemcpyDeviceToDevice, c->stream));
+  d->head = (d->head + kDredMaxFrames - 1) % kDredMaxFrames;   // the reference moves the buffers up by one entry; here the head moves down
+  DR_TRY(de_encode_dev(d, d->lat_ring + (size_t)d->head * d->latent_dim, kDredMaxFrames * d->latent_dim, d->state_ring + (size_t)d->head * d->state_dim,
+                       kDredMaxFrames * d->state_dim, d->in40));
+  d->latents_buffer_fill = d->latents_buffer_fill + 1 < kDredRedundancy ? d->latents_buffer_fill + 1 : kDredRedundancy;
+  return OPUSB200_OK;
+}
+// dred_compute_latents for every stream: pcm [n][frame_size * channels] float in [-1, 1) at Fs
+extern "C" int opusb200_dred_compute_latents(OpusB200DredEnc *d, const float *pcm, int frame_size, int extra_delay, int on_device) {
+  if (!d || !pcm || frame_size <= 0) return OPUSB200_BAD_ARG;
+  if (!d->lpcnet) return OPUSB200_INVALID_STATE;
+  if ((long)frame_size * 16000 % d->Fs) return OPUSB200_BAD_ARG;
+  OpusB200Ctx *c = d->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)d->n, row = (size_t)frame_size * d->channels;
+  const float *dp = pcm;
   if (!on_device) {
-    OB_CUDA(cudaMemcpyAsync(latents, dl, sizeof(float) * (size_t)n * d->latent_dim, cudaMemcpyDeviceToHost, c->stream));
-    OB_CUDA(cudaMemcpyAsync(initial_state, dsv, sizeof(float) * (size_t)n * d->state_dim, cudaMemcpyDeviceToHost, c->stream));
-    OB_CUDA(cudaStreamSynchronize(c->stream));
+    if (d->d_pcm_elems < n * row) {
+      cudaFree(d->d_pcm); d->d_pcm = nullptr; d->d_pcm_elems = 0;
+      if (cudaMalloc(&d->d_pcm, sizeof(float) * n * row) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+      d->d_pcm_elems = n * row;
+    }
+    OB_CUDA(cudaMemcpyAsync(d->d_pcm, pcm, sizeof(float) * n * row, cudaMemcpyHostToDevice, c->stream));
+    dp = d->d_pcm;
   }
+  int frame_size16k = (int)((long)frame_size * 16000 / d->Fs), off = 0;
+  int curr_offset16k = 40 + extra_delay * 16000 / d->Fs - d->input_buffer_fill;
+  d->dred_offset = (int)floor((curr_offset16k + 20.f) / 40.f);
+  d->latent_offset = 0;
+  while (frame_size16k > 0) {
+    const int process_size16k = 320 < frame_size16k ? 320 : frame_size16k, process_size = (int)((long)process_size16k * d->Fs / 16000);
+    ob::DredConvParams p;
+    p.pcm = dp; p.input_buffer = d->input_buffer; p.resample_mem = d->resample_mem; p.n = d->n; p.Fs = d->Fs; p.channels = d->channels;
+    p.in_len = process_size; p.out_len = process_size16k; p.fill = d->input_buffer_fill; p.pcm_off = off; p.pcm_stride = (int)row;
+    ob_dred_convert_16k<<<(d->n + 127) / 128, 128, 0, c->stream>>>(p);
+    c->launches++;
+    OB_CUDA(cudaGetLastError());
+    d->input_buffer_fill += process_size16k;
+    if (d->input_buffer_fill >= 320) {
+      curr_offset16k += 320;
+      DR_TRY(de_process_frame(d));
+      d->input_buffer_fill -= 320;
+      if (d->input_buffer_fill > 0)
+        OB_CUDA(cudaMemcpy2DAsync(d->input_buffer, sizeof(float) * 640, d->input_buffer + 320, sizeof(float) * 640, sizeof(float) * d->input_buffer_fill, n,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+      if (d->dred_offset < 6) d->dred_offset += 8;
+      else d->latent_offset++;
+    }
+    off += process_size * d->channels;
+    frame_size16k -= process_size16k;
+  }
+  if (!on_device) OB_CUDA(cudaStreamSynchronize(c->stream));
+  return OPUSB200_OK;
+}
+// the encoder's buffers in the reference's order (index 0 = the newest double frame): latents [n][104 * latent_dim], state [n][104 * state_dim] (host),
+// info [4] = input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill
+extern "C" int opusb200_dred_encoder_get_latents(OpusB200DredEnc *d, float *latents, float *state, int32_t *info) {
+  if (!d || !latents || !state || !info) return OPUSB200_BAD_ARG;
+  if (!d->lpcnet) return OPUSB200_INVALID_STATE;
+  OpusB200Ctx *c = d->ctx;
+  OB_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)d->n;
+  struct { float *dst; const float *src; int w; } bufs[2] = {{latents, d->lat_ring, d->latent_dim}, {state, d->state_ring, d->state_dim}};
+  for (auto &b : bufs) {
+    const size_t rowb = sizeof(float) * kDredMaxFrames * b.w, first = sizeof(float) * (size_t)(kDredMaxFrames - d->head) * b.w;
+    OB_CUDA(cudaMemcpy2DAsync(b.dst, rowb, b.src + (size_t)d->head * b.w, rowb, first, n, cudaMemcpyDeviceToHost, c->stream));
+    if (d->head) OB_CUDA(cudaMemcpy2DAsync((char *)b.dst + first, rowb, b.src, rowb, rowb - first, n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  OB_CUDA(cudaStreamSynchronize(c->stream));
+  info[0] = d->input_buffer_fill; info[1] = d->dred_offset; info[2] = d->latent_offset; info[3] = d->latents_buffer_fill;
   return OPUSB200_OK;
 }

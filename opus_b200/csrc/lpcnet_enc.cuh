@@ -52,6 +52,7 @@ struct LpcnetEncParams {
   const float *pitch_out;     // [n][192] (finish)
   float *features;            // [n][36] (finish)
   int n, pcm_is_int16;
+  int pcm_stride;             // elements between two streams' frames (0 = 160)
 };
 
 OB_DEV LeCpx le_cmul(LeCpx a, LeCpx b) { LeCpx m; m.r = a.r * b.r - a.i * b.i; m.i = a.r * b.i + a.i * b.r; return m; }
@@ -236,11 +237,11 @@ OB_DEV void lpcnet_enc_analysis_warp(const LpcnetEncParams &p, int s, LeWS *ws) 
   for (int i = lane; i < kLeFrame; i += 32) {
     float cur, prev;
     if (p.pcm_is_int16) {
-      const int16_t *q = (const int16_t *)p.pcm + (size_t)s * kLeFrame;
+      const int16_t *q = (const int16_t *)p.pcm + (size_t)s * (p.pcm_stride ? p.pcm_stride : kLeFrame);
       cur = (float)q[i];
       prev = i ? -0.85f * (float)q[i - 1] : st->mem_preemph;
     } else {
-      const float *q = (const float *)p.pcm + (size_t)s * kLeFrame;
+      const float *q = (const float *)p.pcm + (size_t)s * (p.pcm_stride ? p.pcm_stride : kLeFrame);
       cur = q[i];
       prev = i ? -0.85f * q[i - 1] : st->mem_preemph;
     }
@@ -451,5 +452,65 @@ OB_DEV void lpcnet_burg_cepstrum_warp(const LpcnetBurgParams &p, int s, LeBurgWS
     p.ceps[(size_t)s * 2 * kLeBands + lane] = (float)(.5 * (c0 + c1));
     p.ceps[(size_t)s * 2 * kLeBands + kLeBands + lane] = c0 - c1;
   }
+}
+// ---- DRED encoder front end: dred_convert_to_16k (dnn/dred_encoder.c:133-213) with filter_df2t (:109-126), one thread per stream.  The input chunk
+// (in_len samples per channel at Fs) becomes out_len samples at 16 kHz in int16 range, appended to the stream's input buffer: mono downmix through
+// FLOAT2INT16, zero-stuffing by `up`, the 7th-order elliptic low-pass in transposed direct form II (state in registers), decimation by 3. ----
+struct DredConvParams {
+  const float *pcm;        // [n][pcm_stride]: this chunk starts at pcm_off
+  float *input_buffer;     // [n][640]: written at `fill`
+  float *resample_mem;     // [n][9]
+  int n, Fs, channels, in_len, out_len, fill, pcm_off, pcm_stride;
+};
+OB_DEV float dred_to_int16(float x) {   // FLOAT2INT16 (celt/float_cast.h:150-156): scale, clamp, round to nearest even
+  x = x * 32768.f;
+  x = x > -32768 ? x : -32768;
+  x = x < 32767 ? x : 32767;
+  return rintf(x);
+}
+OB_DEV void dred_convert_thread(const DredConvParams &p, int s) {
+  const float *in = p.pcm + (size_t)s * p.pcm_stride + p.pcm_off;
+  float *out = p.input_buffer + (size_t)s * 640 + p.fill;
+  const int up = p.Fs == 8000 ? 2 : p.Fs == 12000 ? 4 : p.Fs == 24000 ? 2 : 1;
+  float b[8], a[8], b0;
+  if (p.Fs == 12000) {        // ellip(7, .2, 70, 5800/24000)
+    const float bb[8] = {-0.001017101081f, 0.003673127243f, 0.001009165267f, 0.001009165267f, 0.003673127243f, -0.001017101081f, 0.002033596776f, 0.f};
+    const float aa[8] = {-4.930414411612f, 11.291643096504f, -15.322037343815f, 13.216403930898f, -7.220409219553f, 2.310550142771f, -0.334338618782f, 0.f};
+    for (int j = 0; j < 8; j++) { b[j] = bb[j]; a[j] = aa[j]; }
+    b0 = 0.002033596776f;
+  } else if (p.Fs == 8000) {  // ellip(7, .2, 70, 3900/8000)
+    const float bb[8] = {0.081670120929f, 0.180401598565f, 0.259391051971f, 0.259391051971f, 0.180401598565f, 0.081670120929f, 0.020109185709f, 0.f};
+    const float aa[8] = {-1.393651933659f, 2.609789872676f, -2.403541968806f, 2.056814957331f, -1.148908574570f, 0.473001413788f, -0.110359852412f, 0.f};
+    for (int j = 0; j < 8; j++) { b[j] = bb[j]; a[j] = aa[j]; }
+    b0 = 0.020109185709f;
+  } else {                    // 48 and 24 kHz: ellip(7, .2, 70, 7750/24000)
+    const float bb[8] = {0.005873358047f, 0.012980854831f, 0.014531340042f, 0.014531340042f, 0.012980854831f, 0.005873358047f, 0.004523418224f, 0.f};
+    const float aa[8] = {-3.878718597768f, 7.748834257468f, -9.653651699533f, 8.007342726666f, -4.379450178552f, 1.463182111810f, -0.231720677804f, 0.f};
+    for (int j = 0; j < 8; j++) { b[j] = bb[j]; a[j] = aa[j]; }
+    b0 = 0.004523418224f;
+  }
+  float mem[9];
+  for (int j = 0; j < 9; j++) mem[j] = p.resample_mem[(size_t)s * 9 + j];
+  const int total = up * p.in_len, step = p.Fs == 8000 || p.Fs == 16000 ? 1 : 3;
+  int phase = 0, k = 0, o = 0, ustep = 0;   // ustep counts the zero-stuffing positions, phase the decimation
+  for (int i = 0; i < total; i++) {
+    float xi = 0.f;
+    if (ustep == 0) {
+      const float v = p.channels == 1 ? dred_to_int16(in[k]) : dred_to_int16((float)(.5 * (double)(in[2 * k] + in[2 * k + 1])));
+      xi = up * v + 1e-30f;
+      k++;
+    }
+    if (++ustep == up) ustep = 0;
+    float yi = xi;
+    if (p.Fs != 16000) {
+      yi = xi * b0 + mem[0];
+      const float nyi = -yi;
+#pragma unroll
+      for (int j = 0; j < 8; j++) mem[j] = mem[j + 1] + b[j] * xi + a[j] * nyi;
+    }
+    if (phase == 0) { if (o < p.out_len) out[o] = yi; o++; }
+    if (++phase == step) phase = 0;
+  }
+  for (int j = 0; j < 9; j++) p.resample_mem[(size_t)s * 9 + j] = mem[j];
 }
 }  // namespace ob

@@ -90,12 +90,12 @@ extern "C" void opusb200_lpcnet_encoder_destroy(OpusB200LpcnetEnc *q) {
   lpcnet_enc_free(q);
 }
 // one frame of every stream from DEVICE pcm; d_features [n][36] on the device
-static int lpcnet_enc_frame(OpusB200LpcnetEnc *q, const void *d_pcm, int pcm_is_int16, float *d_features) {
+static int lpcnet_enc_frame(OpusB200LpcnetEnc *q, const void *d_pcm, int pcm_is_int16, float *d_features, int pcm_stride = 0) {
   OpusB200Ctx *c = q->ctx;
   const int n = q->n;
   ob::LpcnetEncParams p = {};
   p.state = q->state; p.pcm = d_pcm; p.if_features = q->if_feat; p.conv_in = q->conv_in; p.pitch_out = q->pitch_out; p.features = d_features;
-  p.n = n; p.pcm_is_int16 = pcm_is_int16;
+  p.n = n; p.pcm_is_int16 = pcm_is_int16; p.pcm_stride = pcm_stride;
   const unsigned blocks = (unsigned)((n + 3) / 4);
   ob_lpcnet_enc_analysis<<<blocks, 128, 4 * sizeof(ob::LeWS), c->stream>>>(p);
   c->launches++;

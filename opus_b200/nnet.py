@@ -206,6 +206,29 @@ class DredEncoder:
             raise capi.OpusB200Error(r, 'opusb200_dred_encode_dframe')
         return lat, st
 
+    def init_frontend(self, Fs, channels, linear, conv, su_bias=False):
+        """dred_encoder_init + the pitch model (the PitchDNN layers, as LpcnetEncoder): enables compute_latents"""
+        r = self._L.opusb200_dred_encoder_init_frontend(self._h, Fs, channels, linear, 6, conv, 2, 1 if su_bias else 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_encoder_init_frontend')
+        self.channels = channels
+
+    def compute_latents(self, pcm, frame_size, extra_delay=0):
+        """dred_compute_latents: pcm [n][frame_size * channels] float in [-1, 1)"""
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(self.n, frame_size * self.channels)
+        r = self._L.opusb200_dred_compute_latents(self._h, _p(pcm), frame_size, extra_delay, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_compute_latents')
+
+    def get_latents(self):
+        """(latents [n][104 * latent_dim], state [n][104 * state_dim], info [4] = input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill)"""
+        lat, st = np.empty((self.n, 104 * self.latent_dim), np.float32), np.empty((self.n, 104 * self.state_dim), np.float32)
+        info = np.zeros(4, np.int32)
+        r = self._L.opusb200_dred_encoder_get_latents(self._h, _p(lat), _p(st), _p(info))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_encoder_get_latents')
+        return lat, st, info
+
     def reset(self):
         self._L.opusb200_dred_encoder_reset(self._h)
 

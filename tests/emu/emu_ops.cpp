@@ -456,3 +456,15 @@ extern "C" void emu_lpcnet_burg(float *ceps, const float *x, int n) {
   p.ceps = ceps; p.x = x; p.n = n;
   emu_launch(le_burg_entry, &p, n, 32, sizeof(LeBurgWS));
 }
+static void dred_conv_entry(void *a) {
+  const DredConvParams &p = *(const DredConvParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) dred_convert_thread(p, s);
+}
+extern "C" void emu_dred_convert_16k(const float *pcm, float *input_buffer, float *resample_mem, int n, int Fs, int channels, int in_len, int out_len, int fill,
+                                     int pcm_off, int pcm_stride) {
+  DredConvParams p;
+  p.pcm = pcm; p.input_buffer = input_buffer; p.resample_mem = resample_mem; p.n = n; p.Fs = Fs; p.channels = channels; p.in_len = in_len; p.out_len = out_len;
+  p.fill = fill; p.pcm_off = pcm_off; p.pcm_stride = pcm_stride;
+  emu_launch(dred_conv_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -61,3 +61,32 @@ def test_burg_cepstrum_emulated():
         want = np.zeros(36, np.float32)
         O.orc_burg_cepstral_analysis(_f(want), _f(x[s]))
         assert np.array_equal(got[s], want), (s, np.abs(got[s] - want).max())
+
+
+@pytest.mark.parametrize('Fs,channels', [(48000, 2), (48000, 1), (24000, 1), (16000, 2), (12000, 1), (8000, 2)])
+def test_dred_convert_16k_emulated(Fs, channels):
+    """dred_convert_to_16k on the emulator against the oracle's front end (pinned on dnn/dred_encoder.c): the 16 kHz input buffer and the filter state
+    after every 20 ms frame, bit for bit"""
+    E = emu_util.load_emu_ops()
+    O = util.load_oracle()
+    n, nfr, fs = 5, 6, Fs // 50
+    fronts = [fu.OrcDredFront(O, L, Fs, channels) for _ in range(n)]
+    x = np.stack([fu.dred_input(90 + s, Fs, channels, fs * nfr) for s in range(n)])
+    x[0, :3] = [1.7, -1.7, 0.999999]
+    inbuf, mem = np.zeros((n, 640), np.float32), np.zeros((n, 9), np.float32)
+    fill = 11
+    for t in range(nfr):
+        frame = np.ascontiguousarray(x[:, t * fs * channels:(t + 1) * fs * channels])
+        E.emu_dred_convert_16k(_f(frame), _f(inbuf), _f(mem), n, Fs, channels, fs, 320, fill, 0, fs * channels)
+        fill += 320
+        got = inbuf[:, :fill].copy()
+        inbuf[:, :fill - 320] = inbuf[:, 320:fill]   # what dred_compute_latents does after the double frame was processed
+        fill -= 320
+        for s in range(n):
+            # the oracle consumed the same frame: compare its buffer BEFORE the shift through a replay of the conversion only
+            fronts[s].compute_latents(frame[s], fs)
+            lat, st, ib, rm, ints = fronts[s].get()
+            assert ints[0] == fill
+            assert np.array_equal(ib[:fill], inbuf[s, :fill]), (t, s)
+            assert np.array_equal(rm, mem[s]), (t, s)
+        assert np.all(np.isfinite(got))

@@ -70,3 +70,53 @@ def test_dred_encoder_matches_oracle(n):
     print('bit-identical frames: %d of %d' % (exact, 12 * kinds))
     assert exact >= 12 * kinds - 2
     enc.close()
+
+
+@pytest.mark.skipif(R is None or not hasattr(R, 'refh_dredenc_size'), reason='oracle/_ref/libfargan_ref.so without dnn/dred_encoder.c')
+@pytest.mark.parametrize('Fs,channels,frame_ms,n', [(48000, 2, 20, 70), (16000, 1, 20, 9), (24000, 1, 10, 9), (8000, 2, 40, 5), (12000, 1, 20, 5)])
+def test_dred_compute_latents_matches_oracle(Fs, channels, frame_ms, n):
+    """dred_compute_latents for a batch (16 kHz conversion kernel, feature extraction, RDOVAE encoder, ring buffers) against the oracle's front end,
+    which is pinned bit for bit on dnn/dred_encoder.c.  The conversion and the buffers are exact; features and latents carry the libm note of
+    tests/test_gpu_lpcnet_enc.py (almost always bit-identical; an int8 activation step otherwise): latents within 0.05, nine in ten double frames exact."""
+    import conftest
+    import opus_b200
+    from opus_b200 import nnet
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    layers, _ = F.RefDredEnc(R).layers()
+    renc = F.RefLpcnetEnc(R)
+    lin, _ = renc.linear()
+    cv = renc.conv()
+    ops = opus_b200.Ops()
+    enc = nnet.DredEncoder(ops, layers, n)
+    enc.init_frontend(Fs, channels, lin, cv)
+    kinds = min(n, 5)
+    fronts = [F.OrcDredFront(O, R, Fs, channels) for _ in range(kinds)]
+    fs = int(Fs * frame_ms / 1000)
+    nfr = 12
+    x = np.stack([F.dred_input(40 + s, Fs, channels, fs * nfr) for s in range(kinds)])
+    exact = total = 0
+    worst = 0.0
+    for t in range(nfr):
+        if t == 8:
+            enc.reset()
+            for f in fronts:
+                f.reset()
+        frame = np.ascontiguousarray(x[:, t * fs * channels:(t + 1) * fs * channels])
+        enc.compute_latents(frame[np.arange(n) % kinds], fs)
+        lat, st, info = enc.get_latents()
+        for s in range(kinds):
+            fronts[s].compute_latents(frame[s], fs)
+            w_lat, w_st, w_ib, w_rm, w_ints = fronts[s].get()
+            assert list(info) == [w_ints[0], w_ints[1], w_ints[2], w_ints[3]], (t, list(info), list(w_ints))
+            for r in range(s, n, kinds):
+                assert np.array_equal(lat[r], lat[s]) and np.array_equal(st[r], st[s]), (t, r)
+            d = max(float(np.abs(lat[s] - w_lat).max()), float(np.abs(st[s] - w_st).max()))
+            worst = max(worst, d)
+            assert d < 0.05, (t, s, d)
+            total += 1
+            exact += int(np.array_equal(lat[s], w_lat) and np.array_equal(st[s], w_st))
+    print('bit-identical buffers: %d of %d, worst %.3g' % (exact, total, worst))
+    conftest.note_err('dred_compute_latents', worst)
+    assert exact >= 0.9 * total
+    enc.close()
