@@ -124,6 +124,7 @@ void orc_dred_encode_dframe(OrcDredEnc *st, float *latents, float *initial_state
  * latent / state pair (orc_dred_encode_dframe) pushed at the front of the 104-deep ring buffers.  Pinned against the reference's own dred_encoder.c
  * (oracle/_ref/libfargan_ref.so) by tests/test_dred_oracle_vs_ref.py. ---- */
 #include <math.h>
+#include <stdlib.h>
 #define DE_MAX_FRAMES 104     /* DRED_MAX_FRAMES, dnn/dred_config.h:52 */
 #define DE_REDUNDANCY 52      /* DRED_NUM_REDUNDANCY_FRAMES */
 #define DE_FRAME 160
@@ -231,4 +232,133 @@ void orc_dredenc_get(const OrcDredFront *e, float *latents, float *state, float 
   memcpy(input_buffer, e->input_buffer, sizeof(e->input_buffer));
   memcpy(resample_mem, e->resample_mem, sizeof(e->resample_mem));
   ints[0] = e->input_buffer_fill; ints[1] = e->dred_offset; ints[2] = e->latent_offset; ints[3] = e->latents_buffer_fill; ints[4] = e->last_extra_dred_offset;
+}
+
+/* ---- entropy coding of the buffered latents: dred_encode_silk_frame (dnn/dred_encoder.c:281-383) with dred_encode_latents (:252-270),
+ * dred_voice_active (:272-279), compute_quantizer (dnn/dred_coding.c:39-44), ec_laplace_encode_p0 (celt/laplace.c:136-162), ec_enc_icdf16
+ * (celt/entenc.c:175-184) on the range-encoder restatement of celt_rangeenc.inc.  The statistical model (dred_rdovae_stats_data.c: eight uint8
+ * tables) is passed in: stats[0..3] latent quant_scales / dead_zone / r / p0, stats[4..7] the same for the state. ---- */
+static int ilog32(uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; }
+#define BITRES 3
+#define IMIN(a, b) ((a) < (b) ? (a) : (b))
+#include "celt_rangeenc.inc"
+void orc_nnet_activation(float *out, const float *in, int N, int act);
+static void re_icdf16(RangeEnc *e, int s, const uint16_t *icdf, unsigned ftb) {
+  const uint32_t r = e->rng >> ftb;
+  if (s > 0) {
+    e->val += e->rng - r * icdf[s - 1];
+    e->rng = r * (icdf[s - 1] - icdf[s]);
+  } else e->rng -= r * icdf[s];
+  re_normalize(e);
+}
+static void laplace_p0(RangeEnc *e, int value, uint16_t p0, uint16_t decay) {
+  uint16_t sign_icdf[3], icdf[8];
+  int i;
+  sign_icdf[0] = 32768 - p0;
+  sign_icdf[1] = sign_icdf[0] / 2;
+  sign_icdf[2] = 0;
+  re_icdf16(e, value == 0 ? 0 : (value > 0 ? 1 : 2), sign_icdf, 15);
+  value = abs(value);
+  if (value) {
+    icdf[0] = 7 > decay ? 7 : decay;
+    for (i = 1; i < 7; i++) {
+      const int v = (icdf[i - 1] * (int32_t)decay) >> 15;
+      icdf[i] = 7 - i > v ? 7 - i : v;
+    }
+    icdf[7] = 0;
+    value--;
+    do {
+      re_icdf16(e, value < 7 ? value : 7, icdf, 15);
+      value -= 7;
+    } while (value >= 0);
+  }
+}
+static void encode_latents(RangeEnc *e, const float *x, const uint8_t *scale, const uint8_t *dzone, const uint8_t *r, const uint8_t *p0, int dim) {
+  float xq[64], delta[64], deadzone[64];
+  int q[64], i;
+  const float eps = .1f;
+  for (i = 0; i < dim; i++) {
+    delta[i] = dzone[i] * (1.f / 256.f);
+    xq[i] = x[i] * scale[i] * (1.f / 256.f);
+    deadzone[i] = xq[i] / (delta[i] + eps);
+  }
+  orc_nnet_activation(deadzone, deadzone, dim, ACT_TANH);
+  for (i = 0; i < dim; i++) {
+    xq[i] = xq[i] - delta[i] * deadzone[i];
+    q[i] = (int)floor(.5f + xq[i]);
+  }
+  for (i = 0; i < dim; i++) {
+    if (r[i] == 0 || p0[i] == 255) q[i] = 0;
+    else laplace_p0(e, q[i], p0[i] << 7, r[i] << 7);
+  }
+}
+static int voice_active(const uint8_t *activity_mem, int offset) {
+  int i;
+  for (i = 0; i < 16; i++) {
+    if (8 * offset + i >= DE_MAX_FRAMES * 4) break;
+    if (activity_mem[8 * offset + i] == 1) return 1;
+  }
+  return 0;
+}
+static int dred_quantizer(int q0, int dQ, int qmax, int i) {
+  static const int dQ_table[8] = {0, 2, 3, 4, 6, 8, 12, 16};
+  const int quant = q0 + (dQ_table[dQ] * i + 8) / 16;
+  return quant > qmax ? qmax : quant;
+}
+void orc_dredenc_set_last_extra(OrcDredFront *e, int v) { e->last_extra_dred_offset = v; }
+int orc_dredenc_encode_silk_frame(OrcDredFront *e, const uint8_t *const *stats, uint8_t *buf, int max_chunks, int max_bytes, int q0, int dQ, int qmax,
+                                  const uint8_t *activity_mem) {
+  RangeEnc ec, bak;
+  int i, latent_offset = e->latent_offset, extra_dred_offset = 0, dred_encoded = 0, delayed_dred = 0, prev_active = 0, total_offset, fill, lim;
+  if (activity_mem[0] && e->last_extra_dred_offset > 0) {
+    latent_offset = e->last_extra_dred_offset;
+    delayed_dred = 1;
+    e->last_extra_dred_offset = 0;
+  }
+  while (latent_offset < e->latents_buffer_fill - 1 && !voice_active(activity_mem, latent_offset)) {
+    latent_offset++;
+    extra_dred_offset++;
+  }
+  if (!delayed_dred) e->last_extra_dred_offset = extra_dred_offset;
+  re_init(&ec, buf, (uint32_t)max_bytes);
+  re_uint(&ec, q0, 16);
+  re_uint(&ec, dQ, 8);
+  total_offset = 16 - (e->dred_offset - extra_dred_offset * 8);
+  if (total_offset > 31) {
+    re_uint(&ec, 1, 2);
+    re_uint(&ec, total_offset >> 5, 256);
+    re_uint(&ec, total_offset & 31, 32);
+  } else {
+    re_uint(&ec, 0, 2);
+    re_uint(&ec, total_offset, 32);
+  }
+  if (q0 < 14 && dQ > 0) {
+    const int nvals = 15 - (q0 + 1);
+    re_encode(&ec, qmax >= 15 ? 0 : nvals + qmax - (q0 + 1), qmax >= 15 ? nvals : nvals + qmax - q0, 2 * nvals);
+  }
+  encode_latents(&ec, &e->state_buffer[latent_offset * 50], stats[4] + q0 * 50, stats[5] + q0 * 50, stats[6] + q0 * 50, stats[7] + q0 * 50, 50);
+  if (re_tell(&ec) > 8 * max_bytes) return 0;
+  bak = ec;
+  lim = 2 * max_chunks < e->latents_buffer_fill - latent_offset ? 2 * max_chunks : e->latents_buffer_fill - latent_offset;
+  for (i = 0; i < lim; i += 2) {
+    const int off = dred_quantizer(q0, dQ, qmax, i / 2) * 25;
+    int active;
+    encode_latents(&ec, e->latents_buffer + (i + latent_offset) * 25, stats[0] + off, stats[1] + off, stats[2] + off, stats[3] + off, 25);
+    if (re_tell(&ec) > 8 * max_bytes) {
+      if (i == 0) return 0;
+      break;
+    }
+    active = voice_active(activity_mem, i + latent_offset);
+    if (active || prev_active) {
+      bak = ec;
+      dred_encoded = i + 2;
+    }
+    prev_active = active;
+  }
+  if (dred_encoded == 0 || (dred_encoded <= 2 && extra_dred_offset)) return 0;
+  ec = bak;
+  fill = (re_tell(&ec) + 7) / 8;
+  re_shrink(&ec, fill);
+  re_done(&ec);
+  return fill;
 }

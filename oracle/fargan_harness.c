@@ -179,3 +179,20 @@ int refh_dredenc_encode_silk_frame(DREDEnc *e, unsigned char *buf, int max_chunk
   return dred_encode_silk_frame(e, buf, max_chunks, max_bytes, q0, dQ, qmax, activity_mem, 0);
 }
 int refh_dredenc_const(int which) { return which == 0 ? DRED_MAX_FRAMES : which == 1 ? RESAMPLING_ORDER : which == 2 ? DRED_SILK_ENCODER_DELAY : -1; }
+/* the statistical model of the latents (dred_rdovae_stats_data.c): which = 0..3 latent quant_scales / dead_zone / r / p0, 4..7 the same for the state */
+#include "dred_rdovae_stats_data.h"
+const unsigned char *refh_dred_stats(int which, int *len) {
+  switch (which) {
+    case 0: *len = sizeof(dred_latent_quant_scales_q8); return dred_latent_quant_scales_q8;
+    case 1: *len = sizeof(dred_latent_dead_zone_q8); return dred_latent_dead_zone_q8;
+    case 2: *len = sizeof(dred_latent_r_q8); return dred_latent_r_q8;
+    case 3: *len = sizeof(dred_latent_p0_q8); return dred_latent_p0_q8;
+    case 4: *len = sizeof(dred_state_quant_scales_q8); return dred_state_quant_scales_q8;
+    case 5: *len = sizeof(dred_state_dead_zone_q8); return dred_state_dead_zone_q8;
+    case 6: *len = sizeof(dred_state_r_q8); return dred_state_r_q8;
+    case 7: *len = sizeof(dred_state_p0_q8); return dred_state_p0_q8;
+  }
+  *len = 0;
+  return NULL;
+}
+void refh_dredenc_set_last_extra(DREDEnc *e, int v) { e->last_extra_dred_offset = v; }

@@ -331,3 +331,32 @@ def dred_input(seed, Fs, channels, nsamples):
         return x
     y = np.roll(x, 7) * np.float32(0.8)
     return np.stack([x, y], 1).reshape(-1).astype(np.float32)
+
+
+def dred_stats(L):
+    """the eight uint8 tables of the reference library's statistical model: (ctypes array of 8 pointers, list of numpy copies)"""
+    L.refh_dred_stats.restype = ctypes.c_void_p
+    ptrs = (ctypes.c_void_p * 8)()
+    arrays = []
+    for k in range(8):
+        ln = ctypes.c_int()
+        ptrs[k] = L.refh_dred_stats(k, ctypes.byref(ln))
+        arrays.append(np.ctypeslib.as_array(ctypes.cast(ptrs[k], ctypes.POINTER(ctypes.c_uint8)), (ln.value,)).copy())
+    return ptrs, arrays
+
+
+def dred_activity(seed, kind):
+    """activity_mem of dred_encode_silk_frame (DRED_MAX_FRAMES * 4 bytes, one per 2.5 ms, newest first)"""
+    rng = np.random.default_rng(seed)
+    a = np.zeros(416, np.uint8)
+    if kind == 'all':
+        a[:] = 1
+    elif kind == 'bursts':
+        t = 0
+        while t < 416:
+            k = int(rng.integers(4, 60))
+            a[t:t + k] = rng.random() < 0.6
+            t += k
+    elif kind == 'late':      # silence now, speech further back
+        a[int(rng.integers(20, 120)):] = 1
+    return a

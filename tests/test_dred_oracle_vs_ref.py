@@ -79,3 +79,39 @@ def test_dred_compute_latents_matches_reference(Fs, channels, frame_ms, extra):
     orc.compute_latents(x[:fs * channels], fs, extra)
     for u, v in zip(ref.get(), orc.get()):
         assert np.array_equal(u, v)
+
+
+@pytest.mark.skipif(R is None or not hasattr(R, 'refh_dred_stats'), reason='oracle/_ref/libfargan_ref.so without dnn/dred_encoder.c')
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_dred_encode_silk_frame_matches_reference(seed):
+    """dred_encode_silk_frame after every 20 ms frame of a run: returned size, payload bytes and the carried last_extra_dred_offset, bit for bit,
+    over activity patterns (all active / bursts / silence now / none), quantiser settings and byte budgets (incl. too small ones -> 0)"""
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    Fs, ch, fs = 16000, 1, 320
+    ref = F.RefDredFront(R, Fs, ch)
+    orc = F.OrcDredFront(O, R, Fs, ch)
+    stats, _ = F.dred_stats(R)
+    rng = np.random.default_rng(seed)
+    nfr = 30
+    x = F.dred_input(60 + seed, Fs, ch, fs * nfr)
+    sizes = []
+    for t in range(nfr):
+        frame = x[t * fs:(t + 1) * fs]
+        ref.compute_latents(frame, fs)
+        orc.compute_latents(frame, fs)
+        kind = ['all', 'bursts', 'late', 'none'][int(rng.integers(0, 4))] if t > 2 else 'all'
+        act = F.dred_activity(seed * 100 + t, kind)
+        q0 = int(rng.integers(0, 14))
+        dQ = int(rng.integers(0, 8))
+        qmax = int(rng.integers(q0 + 1, 16)) if dQ else q0
+        max_chunks = int(rng.integers(1, 27))
+        max_bytes = int(rng.choice([6, 20, 60, 200, 1000]))
+        a, b = np.zeros(1000, np.uint8), np.zeros(1000, np.uint8)
+        ra = R.refh_dredenc_encode_silk_frame(F.vp(ref.st), F.vp(a), max_chunks, max_bytes, q0, dQ, qmax, F.vp(act.copy()))
+        rb = O.orc_dredenc_encode_silk_frame(F.vp(orc.st), stats, F.vp(b), max_chunks, max_bytes, q0, dQ, qmax, F.vp(act))
+        assert ra == rb, (t, ra, rb)
+        assert np.array_equal(a[:ra], b[:rb]), t
+        assert ref.get()[4][4] == orc.get()[4][4], t
+        sizes.append(ra)
+    assert max(sizes) > 30 and min(sizes) == 0
