@@ -404,7 +404,7 @@ int opusb200_fargan_synthesize(OpusB200Fargan *f, float *pcm, const float *featu
  * enc_conv_dense1..5, enc_gru1..5 input / recurrent, enc_conv1..5), n streams in lockstep, one RDOVAEEncState per stream on the device.
  *   opusb200_dred_encode_dframe(enc, latents [n][latent_dim], initial_state [n][state_dim], input [n][2 * 20 features], on_device)
  * = dred_rdovae_encode_dframe for every stream; latents and state bit-identical to the reference given the same model.  The front end
- * (16 kHz conversion, feature extraction, buffers) follows below; the entropy coding of the latents (dred_coding.c) is not built. ---- */
+ * (16 kHz conversion, feature extraction, buffers) and the entropy coding of the latents follow below. ---- */
 typedef struct OpusB200DredEnc OpusB200DredEnc;
 int opusb200_dred_encoder_create(OpusB200Ctx *ctx, const OpusB200LinearLayer *layers, int n_layers, int su_bias, int latent_dim, int state_dim,
                                  int n_streams, OpusB200DredEnc **out);
@@ -418,11 +418,18 @@ int opusb200_dred_encode_dframe(OpusB200DredEnc *enc, float *latents, float *ini
  *                  dred_encoder_load_model); opusb200_dred_encoder_reset then is dred_encoder_reset.
  *   compute_latents: pcm [n][frame_size * channels] float in [-1, 1), frame_size * 16000 divisible by Fs; streams in lockstep.
  *   get_latents: the buffers in the reference's order (entry 0 = newest), info [4] = input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill.
- * The entropy coding of the latents behind it (dred_encode_silk_frame, dred_coding.c) is not built. */
+ *   load_stats: the statistical model of the latents (dred_rdovae_stats_data.h): 8 uint8 tables of 16 levels x dim in the order latent
+ *               quant_scales / dead_zone / r / p0, then the state's four.
+ *   encode_silk_frame: dred_encode_silk_frame (dnn/dred_encoder.c:281-383) for every stream — the DRED payload of this packet from the buffered
+ *               latents: buf [n][buf_stride], activity_mem [n][416] (one byte per 2.5 ms, newest first), nbytes [n] = the reference's return
+ *               value per stream (0 = no DRED this time); q0 / dQ / qmax / max_chunks / max_bytes are the batch's.  Bit-exact. */
 int opusb200_dred_encoder_init_frontend(OpusB200DredEnc *enc, int Fs, int channels, const OpusB200LinearLayer *linear, int n_linear,
                                         const OpusB200Conv2dLayer *conv, int n_conv, int su_bias);
 int opusb200_dred_compute_latents(OpusB200DredEnc *enc, const float *pcm, int frame_size, int extra_delay, int on_device);
 int opusb200_dred_encoder_get_latents(OpusB200DredEnc *enc, float *latents, float *state, int32_t *info);
+int opusb200_dred_encoder_load_stats(OpusB200DredEnc *enc, const unsigned char *const *tables, int n_tables);
+int opusb200_dred_encode_silk_frame(OpusB200DredEnc *enc, unsigned char *buf, int buf_stride, int max_chunks, int max_bytes, int q0, int dQ, int qmax,
+                                    const unsigned char *activity_mem, int32_t *nbytes, int on_device);
 
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what

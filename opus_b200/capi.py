@@ -40,6 +40,7 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_fargan_create', 'opusb200_fargan_destroy', 'opusb200_fargan_cont', 'opusb200_fargan_synthesize',
            'opusb200_dred_encoder_create', 'opusb200_dred_encoder_destroy', 'opusb200_dred_encoder_reset', 'opusb200_dred_encode_dframe',
            'opusb200_dred_encoder_init_frontend', 'opusb200_dred_compute_latents', 'opusb200_dred_encoder_get_latents',
+           'opusb200_dred_encoder_load_stats', 'opusb200_dred_encode_silk_frame',
            'opusb200_lpcnet_plc_create', 'opusb200_lpcnet_plc_destroy', 'opusb200_lpcnet_plc_reset', 'opusb200_lpcnet_plc_fec_add', 'opusb200_lpcnet_plc_fec_clear',
            'opusb200_lpcnet_plc_update', 'opusb200_lpcnet_plc_conceal', 'opusb200_lpcnet_plc_get_state', 'opusb200_lpcnet_plc_load_pitch_model',
            'opusb200_lpcnet_encoder_create', 'opusb200_lpcnet_encoder_destroy', 'opusb200_lpcnet_encoder_reset',
@@ -196,6 +197,8 @@ def lib():
         L.opusb200_dred_encoder_init_frontend.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci]
         L.opusb200_dred_compute_latents.argtypes = [vp, vp, ci, ci, ci]
         L.opusb200_dred_encoder_get_latents.argtypes = [vp, vp, vp, vp]
+        L.opusb200_dred_encoder_load_stats.argtypes = [vp, vp, ci]
+        L.opusb200_dred_encode_silk_frame.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci]
         L.opusb200_lpcnet_plc_create.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.POINTER(vp)]
         L.opusb200_lpcnet_plc_destroy.argtypes = [vp]
         L.opusb200_lpcnet_plc_destroy.restype = None

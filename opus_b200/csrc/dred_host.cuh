@@ -171,6 +171,10 @@ struct OpusB200DredEnc {
   int Fs, channels, input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill, head;
   float *input_buffer, *resample_mem, *lat_ring, *state_ring, *feat_a, *feat_b, *in40, *d_pcm;
   size_t d_pcm_elems;
+  // entropy coding (dred_coding_host.cuh)
+  uint8_t *stats, *activity, *d_buf;
+  int32_t *last_extra, *d_nbytes;
+  size_t d_buf_bytes;
 };
 static void de_free(OpusB200DredEnc *d) {
   if (!d) return;
@@ -178,7 +182,7 @@ static void de_free(OpusB200DredEnc *d) {
   cudaFree(d->buf); cudaFree(d->tmp); cudaFree(d->tmp2); cudaFree(d->d_in); cudaFree(d->d_lat); cudaFree(d->d_state);
   opusb200_lpcnet_encoder_destroy(d->lpcnet);
   cudaFree(d->input_buffer); cudaFree(d->resample_mem); cudaFree(d->lat_ring); cudaFree(d->state_ring); cudaFree(d->feat_a); cudaFree(d->feat_b); cudaFree(d->in40);
-  cudaFree(d->d_pcm);
+  cudaFree(d->d_pcm); cudaFree(d->stats); cudaFree(d->activity); cudaFree(d->d_buf); cudaFree(d->last_extra); cudaFree(d->d_nbytes);
   for (int k = 0; k < 5; k++) { cudaFree(d->gru[k]); cudaFree(d->conv[k]); }
   delete d;
 }
@@ -235,6 +239,7 @@ extern "C" int opusb200_dred_encoder_reset(OpusB200DredEnc *d) {   // a zeroed R
     OB_CUDA(cudaMemsetAsync(d->state_ring, 0, sizeof(float) * n * kDredMaxFrames * d->state_dim, d->ctx->stream));
     DR_TRY(opusb200_lpcnet_encoder_reset(d->lpcnet));
     d->input_buffer_fill = kDredSilkDelay; d->dred_offset = 0; d->latent_offset = 0; d->latents_buffer_fill = 0; d->head = 0;
+    if (d->last_extra) OB_CUDA(cudaMemsetAsync(d->last_extra, 0, sizeof(int32_t) * n, d->ctx->stream));
   }
   return OPUSB200_OK;
 }

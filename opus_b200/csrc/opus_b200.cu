@@ -1216,4 +1216,5 @@ void opusb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 #include "plc_host.cuh"
 #include "silk_coder_host.cuh"
 #include "celt_enc_host.cuh"
+#include "dred_coding_host.cuh"
 #include "opus_enc_host.cuh"

@@ -220,6 +220,21 @@ class DredEncoder:
         if r != 0:
             raise capi.OpusB200Error(r, 'opusb200_dred_compute_latents')
 
+    def load_stats(self, tables):
+        """the statistical model: ctypes array of 8 uint8 pointers (latent quant_scales / dead_zone / r / p0, then the state's)"""
+        r = self._L.opusb200_dred_encoder_load_stats(self._h, tables, 8)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_encoder_load_stats')
+
+    def encode_silk_frame(self, activity_mem, max_chunks, max_bytes, q0, dQ, qmax):
+        """dred_encode_silk_frame: activity_mem [n][416] uint8 -> (payload [n][max_bytes] uint8, nbytes [n])"""
+        act = np.ascontiguousarray(activity_mem, np.uint8).reshape(self.n, 416)
+        buf, nb = np.zeros((self.n, max_bytes), np.uint8), np.zeros(self.n, np.int32)
+        r = self._L.opusb200_dred_encode_silk_frame(self._h, _p(buf), max_bytes, max_chunks, max_bytes, q0, dQ, qmax, _p(act), _p(nb), 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_dred_encode_silk_frame')
+        return buf, nb
+
     def get_latents(self):
         """(latents [n][104 * latent_dim], state [n][104 * state_dim], info [4] = input_buffer_fill, dred_offset, latent_offset, latents_buffer_fill)"""
         lat, st = np.empty((self.n, 104 * self.latent_dim), np.float32), np.empty((self.n, 104 * self.state_dim), np.float32)

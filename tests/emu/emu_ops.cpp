@@ -468,3 +468,22 @@ extern "C" void emu_dred_convert_16k(const float *pcm, float *input_buffer, floa
   p.fill = fill; p.pcm_off = pcm_off; p.pcm_stride = pcm_stride;
   emu_launch(dred_conv_entry, &p, (n + 31) / 32, 32, 0);
 }
+
+// ---- DRED entropy coding (dred_coding.cuh), one thread per stream ----
+#include "../../opus_b200/csrc/dred_coding.cuh"
+static void dred_code_entry(void *a) {
+  const DredCodeParams &p = *(const DredCodeParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) p.nbytes[s] = dred_encode_silk_frame_thread(p, s);
+}
+extern "C" void emu_dred_encode_silk_frame(const float *lat_ring, const float *state_ring, const uint8_t *const *stats, const uint8_t *activity, int32_t *last_extra,
+                                           unsigned char *buf, int32_t *nbytes, const int32_t *ints /* n buf_stride head latent_dim state_dim fill latent_offset
+                                           dred_offset max_chunks max_bytes q0 dQ qmax */) {
+  DredCodeParams p;
+  p.lat_ring = lat_ring; p.state_ring = state_ring;
+  for (int k = 0; k < 8; k++) p.stats[k] = stats[k];
+  p.activity = activity; p.last_extra = last_extra; p.buf = buf; p.nbytes = nbytes;
+  p.n = ints[0]; p.buf_stride = ints[1]; p.head = ints[2]; p.latent_dim = ints[3]; p.state_dim = ints[4]; p.latents_buffer_fill = ints[5]; p.latent_offset = ints[6];
+  p.dred_offset = ints[7]; p.max_chunks = ints[8]; p.max_bytes = ints[9]; p.q0 = ints[10]; p.dQ = ints[11]; p.qmax = ints[12];
+  emu_launch(dred_code_entry, &p, (p.n + 31) / 32, 32, 0);
+}

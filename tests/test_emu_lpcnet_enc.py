@@ -90,3 +90,45 @@ def test_dred_convert_16k_emulated(Fs, channels):
             assert np.array_equal(ib[:fill], inbuf[s, :fill]), (t, s)
             assert np.array_equal(rm, mem[s]), (t, s)
         assert np.all(np.isfinite(got))
+
+
+@pytest.mark.parametrize('seed', [1, 2])
+def test_dred_encode_silk_frame_emulated(seed):
+    """dred_encode_silk_frame on the emulator (thread per stream, head-indexed rings) against the oracle (pinned on dnn/dred_encoder.c): sizes, payload
+    bytes and the carried last_extra_dred_offset, for streams with different activity histories"""
+    E = emu_util.load_emu_ops()
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    n, nfr, fs = 6, 16, 320
+    fronts = [fu.OrcDredFront(O, L, 16000, 1) for _ in range(n)]
+    stats, keep = fu.dred_stats(L)
+    rng = np.random.default_rng(seed)
+    x = np.stack([fu.dred_input(120 + seed * 10 + s, 16000, 1, fs * nfr) for s in range(n)])
+    last_extra = np.zeros(n, np.int32)
+    head = 0
+    lat_ring, st_ring = np.zeros((n, 104, 25), np.float32), np.zeros((n, 104, 50), np.float32)
+    nonzero = 0
+    for t in range(nfr):
+        for s in range(n):
+            fronts[s].compute_latents(x[s, t * fs:(t + 1) * fs], fs)
+        lat, st, ib, rm, ints = fronts[0].get()
+        head = (head + 103) % 104     # one double frame per 20 ms at 16 kHz: the device's ring moves its head, the reference moves the data
+        for s in range(n):
+            l_s, s_s = fronts[s].get()[:2]
+            lat_ring[s] = np.roll(l_s.reshape(104, 25), head, 0)
+            st_ring[s] = np.roll(s_s.reshape(104, 50), head, 0)
+        act = np.stack([fu.dred_activity(seed * 1000 + t * 10 + s, ['all', 'bursts', 'late', 'none', 'bursts', 'all'][(s + t) % 6]) for s in range(n)])
+        q0, dQ = int(rng.integers(0, 14)), int(rng.integers(0, 8))
+        qmax = int(rng.integers(q0 + 1, 16)) if dQ else q0
+        max_chunks, max_bytes = int(rng.integers(1, 27)), int(rng.choice([8, 40, 200, 600]))
+        buf, nb = np.zeros((n, 600), np.uint8), np.zeros(n, np.int32)
+        iv = np.array([n, 600, head, 25, 50, ints[3], ints[2], ints[1], max_chunks, max_bytes, q0, dQ, qmax], np.int32)
+        E.emu_dred_encode_silk_frame(_f(lat_ring), _f(st_ring), stats, _f(act), _f(last_extra), _f(buf), _f(nb), _f(iv))
+        for s in range(n):
+            want = np.zeros(600, np.uint8)
+            r = O.orc_dredenc_encode_silk_frame(fu.vp(fronts[s].st), stats, fu.vp(want), max_chunks, max_bytes, q0, dQ, qmax, fu.vp(act[s]))
+            assert r == nb[s], (t, s, r, nb[s])
+            assert np.array_equal(buf[s, :r], want[:r]), (t, s)
+            assert fronts[s].get()[4][4] == last_extra[s], (t, s)
+            nonzero += int(r > 0)
+    assert nonzero > n * nfr // 4

@@ -120,3 +120,46 @@ def test_dred_compute_latents_matches_oracle(Fs, channels, frame_ms, n):
     conftest.note_err('dred_compute_latents', worst)
     assert exact >= 0.9 * total
     enc.close()
+
+
+@pytest.mark.skipif(R is None or not hasattr(R, 'refh_dred_stats'), reason='oracle/_ref/libfargan_ref.so without dnn/dred_encoder.c')
+@pytest.mark.parametrize('n', [6, 200])
+def test_dred_encode_silk_frame_matches_oracle(n):
+    """the whole DRED encoder: dred_compute_latents + dred_encode_silk_frame per 20 ms packet, every stream with its own audio and voice-activity
+    history, against the oracle (pinned bit for bit on dnn/dred_encoder.c).  Bar: payload sizes and bytes identical."""
+    import opus_b200
+    from opus_b200 import nnet
+    O = util.load_oracle()
+    O.orc_nnet_set_su_bias(0)
+    layers, _ = F.RefDredEnc(R).layers()
+    renc = F.RefLpcnetEnc(R)
+    lin, _ = renc.linear()
+    cv = renc.conv()
+    stats, keep = F.dred_stats(R)
+    ops = opus_b200.Ops()
+    enc = nnet.DredEncoder(ops, layers, n)
+    enc.init_frontend(16000, 1, lin, cv)
+    enc.load_stats(stats)
+    kinds, nfr, fs = min(n, 6), 18, 320
+    fronts = [F.OrcDredFront(O, R, 16000, 1) for _ in range(kinds)]
+    x = np.stack([F.dred_input(150 + s, 16000, 1, fs * nfr) for s in range(kinds)])
+    rng = np.random.default_rng(4)
+    nonzero = 0
+    for t in range(nfr):
+        frame = np.ascontiguousarray(x[:, t * fs:(t + 1) * fs])
+        enc.compute_latents(frame[np.arange(n) % kinds], fs)
+        act = np.stack([F.dred_activity(t * 10 + s, ['all', 'bursts', 'late', 'none', 'bursts', 'all'][(s + t) % 6]) for s in range(kinds)])
+        q0, dQ = int(rng.integers(0, 14)), int(rng.integers(0, 8))
+        qmax = int(rng.integers(q0 + 1, 16)) if dQ else q0
+        max_chunks, max_bytes = int(rng.integers(1, 27)), int(rng.choice([8, 40, 200, 600]))
+        buf, nb = enc.encode_silk_frame(act[np.arange(n) % kinds], max_chunks, max_bytes, q0, dQ, qmax)
+        for s in range(kinds):
+            fronts[s].compute_latents(frame[s], fs)
+            want = np.zeros(600, np.uint8)
+            r = O.orc_dredenc_encode_silk_frame(F.vp(fronts[s].st), stats, F.vp(want), max_chunks, max_bytes, q0, dQ, qmax, F.vp(act[s]))
+            for q in range(s, n, kinds):
+                assert nb[q] == r, (t, q, int(nb[q]), r)
+                assert np.array_equal(buf[q, :r], want[:r]), (t, q)
+            nonzero += int(r > 0)
+    assert nonzero > kinds * nfr // 4
+    enc.close()
