@@ -24,7 +24,7 @@
  * sizes 2.5/5/10/20 ms, all frame-packing codes, packet-loss concealment (a lost packet is len[s] == 0, like
  * opus_decode(data = NULL); DTX frames inside a packet are concealed too: celt_decode_lost, celt/celt_decoder.c:679-1090,
  * pitch-based and noise PLC; no DEEP_PLC).  int16 output is soft-clipped like opus_decode() does (opus_pcm_soft_clip, src/opus.c:39-166,
- * applied per frame: identical to the reference for one-frame packets), float output is not, like opus_decode_float().
+ * once over all frames of a packet, src/opus_decoder.c:875-878), float output is not, like opus_decode_float().
  * SILK/hybrid packets and FEC return OPUS_UNIMPLEMENTED per stream.
  * There is NO CPU fallback: every entry point fails with OPUS_INTERNAL_ERROR if no CUDA device
  * is usable. */
