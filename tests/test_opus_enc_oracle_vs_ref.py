@@ -143,3 +143,29 @@ def test_small_output_buffers():
     for mb in (30, 61, 100, 200):
         check_same(encode_both(x, 48000, 2, 960, 64000, 1, 10, max_bytes=mb), mb)
         check_same(encode_both(x, 48000, 2, 960, 64000, 0, 10, max_bytes=mb), mb)
+
+
+# 40 .. 120 ms: the 20 ms frames are coded one by one and repacketised (src/opus_encoder.c:1698-1838, src/repacketizer.c): code 1 / 2 / 3 packets,
+# VBR and CBR (padded to the CBR size), run_analysis over the whole packet with tonality_get_info per 20 ms frame
+@pytest.mark.parametrize('fs_ms', [40, 60, 80, 100, 120])
+@pytest.mark.parametrize('ch,bitrate,vbr,cx', [(2, 64000, 1, 10), (2, 96000, 0, 10), (1, 32000, 1, 5), (2, 24000, 1, 8), (1, 20000, 0, 9)])
+def test_multiframe_packets(fs_ms, ch, bitrate, vbr, cx):
+    Fs = 48000
+    fs = Fs * fs_ms // 1000
+    x = util.SIGNALS['music'](20 + ch + fs_ms, fs * 8, ch)
+    x[3 * fs:3 * fs + fs // 3] = 0
+    res = encode_both(x, Fs, ch, fs, bitrate, vbr, cx, max_bytes=1276 * 6 if fs_ms <= 120 else 1276)
+    check_same(res, (fs_ms, ch, bitrate, vbr, cx))
+    sizes = res[0][1]
+    assert sizes.min() > 10
+    codes = {int(res[0][0][f, 0]) & 3 for f in range(len(sizes))}
+    assert codes <= ({1, 2, 3} if fs_ms == 40 else {3}), codes
+
+
+@pytest.mark.parametrize('Fs,fs_ms', [(24000, 60), (16000, 40)])
+def test_multiframe_other_rates_float_api(Fs, fs_ms):
+    fs = Fs * fs_ms // 1000
+    x = resample_sig(util.SIGNALS['tonal'](31, 48000 * 2, 2), Fs)
+    x = np.ascontiguousarray(x[:(x.shape[0] // fs) * fs].astype(np.float32) / 32768.0)
+    res = encode_both(x, Fs, 2, fs, 40000, 1, 10, app=APP_LD, is_int16=False, max_bytes=1276 * 3)
+    check_same(res, (Fs, fs_ms))
