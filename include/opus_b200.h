@@ -251,8 +251,9 @@ int64_t opusb200_encoder_launch_count(OpusB200Encoder *enc);
  * an encoder runs on the device, per stream: run_analysis (src/analysis.c: tonality / bandwidth / music detector, from complexity 7 and Fs >= 16 kHz),
  * the mono/stereo and bandwidth decisions with their hysteresis, dc_reject, the stereo width fade, the float API's NaN / level guard, the CELT
  * encoder with st->analysis valid, the TOC byte.  Packets (TOC included) and OPUS_GET_FINAL_RANGE are bit-identical to the reference's C build
- * given the same calls.  Frame sizes 2.5 / 5 / 10 / 20 ms; 40..120 ms (repacketised multi-frame packets), DTX and budgets below 3 bytes per
- * frame return OPUSB200_UNIMPLEMENTED for the call.  Setters (request numbers of include/opus_defines.h, value semantics of opus_encoder_ctl):
+ * given the same calls.  Frame sizes 2.5 / 5 / 10 / 20 ms and 40 .. 120 ms (20 ms frames coded one by one and repacketised, code 1 / 2 / 3 packets with
+ * the CBR padding: src/opus_encoder.c:1698-1838, src/repacketizer.c; pkt_stride must hold the packet: up to max_data_bytes); DTX and budgets below
+ * 3 bytes per frame return OPUSB200_UNIMPLEMENTED for the call.  Setters (request numbers of include/opus_defines.h, value semantics of opus_encoder_ctl):
  * 4002 bitrate (-1000 OPUS_AUTO, -1 OPUS_BITRATE_MAX), 4004 max bandwidth, 4006 vbr, 4008 bandwidth, 4010 complexity, 4014 packet loss %,
  * 4020 vbr constraint, 4022 force channels, 4024 signal, 4028 OPUS_RESET_STATE, 4036 lsb depth, 4042 prediction disabled, 4046 phase inversion disabled.
  * nbytes[s] = packet length of stream s (TOC included) or a negative error code. ---- */

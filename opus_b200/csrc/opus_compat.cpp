@@ -326,7 +326,7 @@ void opus_encoder_destroy(OpusEncoder *st) {
 }
 static opus_int32 encode_common(OpusEncoder *st, const void *pcm, int is16, int frame_size, unsigned char *data, opus_int32 max_data_bytes) {
   if (!st || st->magic != kEncMagic || !pcm || !data || max_data_bytes <= 0) return OPUS_BAD_ARG;
-  const int stride = max_data_bytes > 1276 * 6 ? 1276 * 6 : max_data_bytes;
+  const int stride = max_data_bytes > 1280 * 6 ? 1280 * 6 : max_data_bytes;   // room for six 1276-byte frames and their code-3 sizes
   int32_t nb = 0;
   const int r = is16 ? opusb200_opus_encode(st->e, (const int16_t *)pcm, frame_size, data, stride, max_data_bytes, &nb)
                      : opusb200_opus_encode_float(st->e, (const float *)pcm, frame_size, data, stride, max_data_bytes, &nb);

@@ -12,6 +12,14 @@ extern "C" __global__ void __launch_bounds__(128) ob_opus_enc_analysis(ob::OpusL
   const int s = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (s < p.n_streams) ob::opus_enc_analysis_warp(p, s, (ob::AnWS *)ob_an_smem + (threadIdx.x >> 5));
 }
+extern "C" __global__ void __launch_bounds__(64) ob_opus_enc_multiframe_decide(ob::OpusLayerParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) ob::opus_multiframe_decide_thread(p, s);
+}
+extern "C" __global__ void __launch_bounds__(64) ob_opus_repacketize(ob::OpusLayerParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n_streams) ob::opus_repacketize_thread(p, s);
+}
 extern "C" __global__ void ob_opus_enc_reset(ob::ObOpusEncState *st, int n, int channels) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n) ob::opus_enc_state_init(st + s, channels);
@@ -32,6 +40,9 @@ struct OpusB200OpusEncoder {
   unsigned char *d_pkt; size_t d_pkt_cap;
   int32_t *d_nbytes;
   int64_t launches;
+  // 40..120 ms packets: per-frame hand-off records, dc-rejected PCM, one-frame packets and their sizes (allocated at the first such call)
+  ob::ObOpusPre *mf_pre; ob::ObOpusFrameCtl *mf_ctl; float *mf_pcm_buf; unsigned char *mf_pkt; int32_t *mf_nbytes;
+  int mf_frames, mf_stride;
   // the pipelined host-buffer call (opusb200_opus_encode_submit / _wait): two staging slots, PCM upload and packet read-back on their own
   // streams, so the upload of call k+1 and the read-back of call k-1 run under the kernels of call k
   cudaStream_t st_in, st_out;
@@ -86,6 +97,7 @@ extern "C" void opusb200_opus_encoder_destroy(OpusB200OpusEncoder *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->celt->stream);
   cudaFree(e->st); cudaFree(e->tonal); cudaFree(e->pre); cudaFree(e->ctl); cudaFree(e->pcm_buf); cudaFree(e->d_pcm); cudaFree(e->d_pkt); cudaFree(e->d_nbytes);
+  cudaFree(e->mf_pre); cudaFree(e->mf_ctl); cudaFree(e->mf_pcm_buf); cudaFree(e->mf_pkt); cudaFree(e->mf_nbytes);
   if (e->st_in) {
     cudaStreamSynchronize(e->st_in); cudaStreamSynchronize(e->st_out);
     for (int b = 0; b < 2; b++) {
@@ -104,6 +116,57 @@ extern "C" int opusb200_opus_encoder_ctl(OpusB200OpusEncoder *e, int request, in
   if (request == 4028) return opusb200_opus_encoder_reset(e);                                                                   // OPUS_RESET_STATE
   return ob::opus_enc_settings_ctl(&e->cfg, request, value);
 }
+// 40..120 ms (src/opus_encoder.c:1698-1838): P1 + the analysis chunk of P2 for every 20 ms frame, the packet's decisions and the per-frame controls,
+// the CELT kernels frame by frame into one-frame packets, then the repacketizer
+static int opus_encode_multiframe(OpusB200OpusEncoder *e, const ob::OpusCallPlan &pl, const void *d_pcm, int pcm_is_int16, int frame_size,
+                                  unsigned char *d_packets, int pkt_stride, int32_t *d_nbytes) {
+  cudaStream_t s = e->celt->stream;
+  const size_t n = (size_t)e->n;
+  const int nb = pl.nb_frames, fs = pl.enc_frame_size, CC = e->channels, stride = (pl.max_data_bytes + 15) & ~15;
+  if (e->mf_frames < nb || e->mf_stride < stride) {
+    cudaFree(e->mf_pre); cudaFree(e->mf_ctl); cudaFree(e->mf_pcm_buf); cudaFree(e->mf_pkt); cudaFree(e->mf_nbytes);
+    e->mf_pre = nullptr; e->mf_ctl = nullptr; e->mf_pcm_buf = nullptr; e->mf_pkt = nullptr; e->mf_nbytes = nullptr; e->mf_frames = 0;
+    const int st2 = stride > e->mf_stride ? stride : e->mf_stride;
+    if (cudaMalloc(&e->mf_pre, sizeof(ob::ObOpusPre) * n * 6) != cudaSuccess || cudaMalloc(&e->mf_ctl, sizeof(ob::ObOpusFrameCtl) * n * 6) != cudaSuccess ||
+        cudaMalloc(&e->mf_pcm_buf, sizeof(float) * n * 6 * CC * OB_MAXN) != cudaSuccess || cudaMalloc(&e->mf_pkt, n * 6 * st2) != cudaSuccess ||
+        cudaMalloc(&e->mf_nbytes, sizeof(int32_t) * n * 6) != cudaSuccess)
+      return OPUSB200_ALLOC_FAIL;
+    e->mf_frames = 6; e->mf_stride = st2;
+  }
+  if (!pl.run_analysis && e->analysis_was_on) OB_CUDA(cudaMemsetAsync(e->tonal, 0, sizeof(ob::ObTonality) * n, s));
+  e->analysis_was_on = pl.run_analysis;
+  ob::OpusLayerParams p;
+  ob::opus_layer_params_init(&p, e->cfg, pl, fs, pcm_is_int16, e->n);
+  p.st = e->st; p.tonal = e->tonal; p.pcm = d_pcm; p.packets = d_packets; p.pkt_stride = pkt_stride;
+  p.multi = 1; p.pcm_row = frame_size * CC; p.nb_frames = nb; p.packet_frame_size = frame_size; p.pre_all = e->mf_pre; p.ctl_all = e->mf_ctl;
+  p.tmp_packets = e->mf_pkt; p.tmp_stride = e->mf_stride; p.tmp_nbytes = e->mf_nbytes; p.out_nbytes = d_nbytes; p.repacketize_len = pl.repacketize_len;
+  p.pad = !e->cfg.use_vbr;
+  for (int i = 0; i < nb; i++) {
+    p.pre = e->mf_pre + (size_t)i * n; p.ctl = e->mf_ctl + (size_t)i * n; p.pcm_buf = e->mf_pcm_buf + (size_t)i * n * CC * OB_MAXN; p.pcm_off = i * fs * CC;
+    ob_opus_enc_pre<<<(e->n + 31) / 32, 32, 32 * OB_PRE_TS * sizeof(float), s>>>(p);
+    e->launches++;
+    if (pl.run_analysis) { ob_opus_enc_analysis<<<(e->n + 3) / 4, 128, 4 * sizeof(ob::AnWS), s>>>(p); e->launches++; }
+  }
+  ob_opus_enc_multiframe_decide<<<(e->n + 63) / 64, 64, 0, s>>>(p);
+  e->launches++;
+  OB_CUDA(cudaGetLastError());
+  OpusB200Encoder *c = e->celt;
+  c->complexity = e->cfg.complexity; c->lsb_depth = pl.lsb; c->loss_rate = e->cfg.packet_loss;
+  c->disable_pf = pl.celt_disable_pf; c->force_intra = pl.celt_force_intra;
+  c->vbr = pl.celt_vbr; c->bitrate = pl.celt_bitrate; c->constrained_vbr = pl.celt_cvbr;
+  c->stream_channels = e->channels; c->end = OB_NBANDS;
+  for (int i = 0; i < nb; i++) {
+    const int64_t l0 = c->launches;
+    const int r = celt_encode_launch(c, e->mf_pcm_buf + (size_t)i * n * CC * OB_MAXN, fs, e->mf_pkt + (size_t)i * n * e->mf_stride + 1, e->mf_stride,
+                                     pl.max_data_bytes - 1, e->mf_nbytes + (size_t)i * n, e->mf_ctl + (size_t)i * n);
+    e->launches += c->launches - l0;
+    if (r != OPUSB200_OK) return r;
+  }
+  ob_opus_repacketize<<<(e->n + 63) / 64, 64, 0, s>>>(p);
+  e->launches++;
+  OB_CUDA(cudaGetLastError());
+  return OPUSB200_OK;
+}
 // opus_encode_native for n streams (device buffers).  d_pcm: [n][frame_size*channels] int16 or float; d_packets [n][pkt_stride]; d_nbytes [n]
 extern "C" int opusb200_opus_encode_device(OpusB200OpusEncoder *e, const void *d_pcm, int pcm_is_int16, int frame_size, unsigned char *d_packets,
                                            int pkt_stride, int max_data_bytes_in, int32_t *d_nbytes) {
@@ -111,9 +174,14 @@ extern "C" int opusb200_opus_encode_device(OpusB200OpusEncoder *e, const void *d
   ob::OpusCallPlan pl;
   const int pr = ob::opus_enc_plan(e->cfg, frame_size, max_data_bytes_in, pcm_is_int16, &pl);
   if (pr) return pr;
-  if (pkt_stride < pl.max_data_bytes) return OPUSB200_BAD_ARG;
+  if (pl.nb_frames == 1 && pkt_stride < pl.max_data_bytes) return OPUSB200_BAD_ARG;
+  if (pl.nb_frames > 1) {   // CBR pads the packet to repacketize_len; VBR needs room for what the frames can produce
+    const int need = e->cfg.use_vbr ? pl.nb_frames * (pl.max_data_bytes + 2) : pl.repacketize_len;
+    if (pkt_stride < (need < pl.repacketize_len ? need : pl.repacketize_len)) return OPUSB200_BAD_ARG;
+  }
   OB_CUDA(cudaSetDevice(e->device));
   cudaStream_t s = e->celt->stream;
+  if (pl.nb_frames > 1) return opus_encode_multiframe(e, pl, d_pcm, pcm_is_int16, frame_size, d_packets, pkt_stride, d_nbytes);
   if (!pl.run_analysis && e->analysis_was_on) OB_CUDA(cudaMemsetAsync(e->tonal, 0, sizeof(ob::ObTonality) * (size_t)e->n, s));   // tonality_analysis_reset (:1261-1263)
   e->analysis_was_on = pl.run_analysis;
   ob::OpusLayerParams p;
@@ -143,7 +211,7 @@ static int opus_encode_host(OpusB200OpusEncoder *e, const void *pcm, int is16, i
     ob::OpusCallPlan pl;
     const int pr = ob::opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
     if (pr) return pr;
-    if (frame_size > OB_MAXN) return OPUSB200_BAD_ARG;
+    if (frame_size > 6 * OB_MAXN) return OPUSB200_BAD_ARG;
   }
   OB_CUDA(cudaSetDevice(e->device));
   cudaStream_t s = e->celt->stream;
@@ -191,7 +259,7 @@ extern "C" int opusb200_opus_encode_submit(OpusB200OpusEncoder *e, const void *p
     ob::OpusCallPlan pl;
     const int pr = ob::opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
     if (pr) return pr;
-    if (frame_size > OB_MAXN || pkt_stride < pl.max_data_bytes) return OPUSB200_BAD_ARG;
+    if (frame_size > 6 * OB_MAXN || (pl.nb_frames == 1 && pkt_stride < pl.max_data_bytes)) return OPUSB200_BAD_ARG;
   }
   OB_CUDA(cudaSetDevice(e->device));
   cudaStream_t s = e->celt->stream;

@@ -89,6 +89,17 @@ struct OpusLayerParams {
   float *pcm_buf;          // [n][frame_size*channels] out: dc-rejected input of the CELT encoder
   unsigned char *packets;  // [n][pkt_stride]: byte 0 receives the TOC
   int pkt_stride;
+  // 40..120 ms packets (src/opus_encoder.c:1698-1838): the 20 ms frames go through P1 / P2 one by one with `multi` set — P1 reads its frame at
+  // pcm_off inside rows of pcm_row samples, P2 runs the tonality analysis of the chunk and leaves get_info / the decisions to opus_multiframe_decide_thread
+  int multi = 0, pcm_row = 0, pcm_off = 0;
+  int nb_frames = 1, packet_frame_size = 0;   // decide kernel: the packet's frame count and whole size (p.frame_size is the 20 ms frame then)
+  ObOpusPre *pre_all = nullptr;               // [nb_frames][n]
+  ObOpusFrameCtl *ctl_all = nullptr;          // [nb_frames][n]
+  unsigned char *tmp_packets = nullptr;       // [nb_frames][n][tmp_stride]: the one-frame packets (TOC + payload)
+  int tmp_stride = 0;
+  const int32_t *tmp_nbytes = nullptr;        // [nb_frames][n]: bytes of every one-frame packet (TOC included), negative = error
+  int32_t *out_nbytes = nullptr;              // [n]: the repacketised size
+  int repacketize_len = 0, pad = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -99,6 +110,8 @@ struct OpusEncSettings {   // opus_encoder_ctl state (OpusEncoder, src/opus_enco
       complexity, packet_loss, prediction_disabled;
 };
 struct OpusCallPlan {
+  int nb_frames, enc_frame_size;         // 40..120 ms: nb_frames 20 ms frames, repacketised (:1698-1838); else 1 / frame_size
+  int32_t repacketize_len, curr_max;     // multi-frame: the packet's size bound, and every frame's (TOC included; the third bound of :1795 never binds)
   int32_t bitrate_bps, max_data_bytes;   // st->bitrate_bps and the packet size bound after the CBR rounding (:1325-1334), TOC included
   int run_analysis, lsb;
   int celt_vbr, celt_bitrate, celt_cvbr, celt_disable_pf, celt_force_intra;   // what opus_encode_frame_native sets on the CELT encoder (:2284-2294, :2445-2463)
@@ -144,16 +157,15 @@ inline int opus_enc_plan(const OpusEncSettings &e, int frame_size, int max_data_
   if (400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs && 25 * frame_size != Fs &&
       50 * frame_size != 3 * Fs && 50 * frame_size != 4 * Fs && 50 * frame_size != 5 * Fs && 50 * frame_size != 6 * Fs)
     return -1;
-  if (frame_size > Fs / 50) return -5;   // 40..120 ms: repacketised multi-frame packets (:1698-1838) are not built
   const int frame_rate = Fs / frame_size;
-  int32_t bitrate_bps;
+  int32_t bitrate_bps, cbr_bytes = -1;
   {   // user_bitrate_to_bitrate (:733-745)
     const int32_t max_bitrate = opus_bits_to_bitrate(max_data_bytes * 8, Fs, frame_size);
     const int32_t user = e.user_bitrate_bps == -1000 ? 60 * Fs / frame_size + Fs * e.channels : e.user_bitrate_bps == -1 ? 1500000 : e.user_bitrate_bps;
     bitrate_bps = user < max_bitrate ? user : max_bitrate;
   }
   if (!e.use_vbr) {
-    int32_t cbr_bytes = (opus_bitrate_to_bits(bitrate_bps, Fs, frame_size) + 4) / 8;
+    cbr_bytes = (opus_bitrate_to_bits(bitrate_bps, Fs, frame_size) + 4) / 8;
     if (cbr_bytes > max_data_bytes) cbr_bytes = max_data_bytes;
     bitrate_bps = opus_bits_to_bitrate(cbr_bytes * 8, Fs, frame_size);
     max_data_bytes = cbr_bytes > 1 ? cbr_bytes : 1;
@@ -161,6 +173,18 @@ inline int opus_enc_plan(const OpusEncSettings &e, int frame_size, int max_data_
   if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * (int32_t)frame_rate < 300 || bitrate_bps < 2400)))
     return -5;   // the 'PLC frame' packets of a budget too small to code anything (:1340-1406) are not built
   o->max_data_bytes = max_data_bytes < 1276 ? max_data_bytes : 1276;
+  o->nb_frames = 1; o->enc_frame_size = frame_size; o->repacketize_len = o->curr_max = 0;
+  if (frame_size > Fs / 50) {   // :1698-1795
+    o->enc_frame_size = Fs / 50;
+    o->nb_frames = frame_size / o->enc_frame_size;
+    const int max_header_bytes = o->nb_frames == 2 ? 3 : (2 + (o->nb_frames - 1) * 2);
+    o->repacketize_len = (e.use_vbr || e.user_bitrate_bps == -1) ? max_data_bytes_in : (cbr_bytes < max_data_bytes_in ? cbr_bytes : max_data_bytes_in);
+    const int32_t max_len_sum = o->nb_frames + o->repacketize_len - max_header_bytes, a = opus_bitrate_to_bits(bitrate_bps, Fs, o->enc_frame_size) / 8,
+                  b = max_len_sum / o->nb_frames;
+    o->curr_max = a < b ? a : b;
+    if (o->curr_max < 2) return -5;
+    o->max_data_bytes = o->curr_max < 1276 ? o->curr_max : 1276;   // what opus_encode_frame_native gets for every 20 ms frame
+  }
   o->bitrate_bps = bitrate_bps;
   o->run_analysis = e.complexity >= 7 && Fs >= 16000;   // :1252
   o->lsb = (pcm_is_int16 ? 16 : 24) < e.lsb_depth ? (pcm_is_int16 ? 16 : 24) : e.lsb_depth;
@@ -221,7 +245,7 @@ OB_DEV void opus_enc_pre_warp(const OpusLayerParams &p, int first_stream, float 
     for (int r = 0; r < 32; r++) {
       const int sr = first_stream + r;
       if (sr >= p.n_streams) break;
-      for (int j = lane; j < cnt; j += 32) tile[r * OB_PRE_TS + j] = pre_load_sample(p.pcm, is16, (size_t)sr * total + base + j);
+      for (int j = lane; j < cnt; j += 32) tile[r * OB_PRE_TS + j] = pre_load_sample(p.pcm, is16, (size_t)sr * (p.pcm_row ? p.pcm_row : total) + p.pcm_off + base + j);
     }
     wsync();
     if (live) {
@@ -590,10 +614,12 @@ OB_DEV int opus_toc_celt(int framerate, int bandwidth, int channels) {   // gen_
   if (tmp < 0) tmp = 0;
   return 0x80 | (tmp << 5) | (period << 3) | ((channels == 2) << 2);
 }
-OB_DEVNI void opus_layer_decide(const OpusLayerParams &p, ObOpusEncState *st, const ObOpusPre *pre, const ObAnalysisInfo &ai, ObOpusFrameCtl *ctl) {
+// frame_size: the packet's (the rate decisions see the packet's frame rate); toc_frame_size: the coded frame's (20 ms inside a multi-frame packet)
+OB_DEVNI void opus_layer_decide(const OpusLayerParams &p, ObOpusEncState *st, int silence, int clear, const ObAnalysisInfo &ai, ObOpusFrameCtl *ctl,
+                                int frame_size, int toc_frame_size) {
   const int BW_NB = 1101, BW_MB = 1102, BW_WB = 1103, BW_SWB = 1104, BW_FB = 1105, AUTO = -1000;
-  const int frame_rate = p.Fs / p.frame_size;
-  if (!pre->silence) st->voice_ratio = -1;
+  const int frame_rate = p.Fs / frame_size;
+  if (!silence) st->voice_ratio = -1;
   int detected_bandwidth = 0;
   if (ai.valid) {
     if (p.signal_type == AUTO) {
@@ -656,8 +682,8 @@ OB_DEVNI void opus_layer_decide(const OpusLayerParams &p, ObOpusEncState *st, co
   const int bw = st->bandwidth;
   ctl->end = bw == BW_NB ? 13 : (bw == BW_MB || bw == BW_WB) ? 17 : bw == BW_SWB ? 19 : 21;
   ctl->C = st->stream_channels;
-  ctl->toc = opus_toc_celt(frame_rate, bw, st->stream_channels);
-  ctl->clear = pre->clear;
+  ctl->toc = opus_toc_celt(p.Fs / toc_frame_size, bw, st->stream_channels);
+  ctl->clear = clear;
   ctl->fade = 0;
   ctl->fade_g1 = ctl->fade_g2 = 0.f;
   {
@@ -694,8 +720,10 @@ OB_DEV void opus_enc_analysis_warp(const OpusLayerParams &p, int s, AnWS *w) {
       ai.tonality = ai.tonality_slope = ai.noisiness = ai.activity = ai.music_prob = ai.music_prob_min = ai.music_prob_max = 0.f;
       ai.bandwidth = 0; ai.activity_probability = ai.max_pitch_ratio = 0.f;
       for (int i = 0; i < 20; i++) ai.leak_boost[i] = 0;
-      opus_layer_decide(p, st, pre, ai, ctl);
-      p.packets[(size_t)s * p.pkt_stride] = (unsigned char)ctl->toc;
+      if (!p.multi) {
+        opus_layer_decide(p, st, pre->silence, pre->clear, ai, ctl, p.frame_size, p.frame_size);
+        p.packets[(size_t)s * p.pkt_stride] = (unsigned char)ctl->toc;
+      }
     }
     return;
   }
@@ -935,11 +963,106 @@ OB_DEV void opus_enc_analysis_warp(const OpusLayerParams &p, int s, AnWS *w) {
     }
   }
   wsync();
-  if (lane == 0) {
+  if (lane == 0 && !p.multi) {
     an_get_info(tonal, &ai, p.frame_size, Fs);
-    opus_layer_decide(p, st, pre, ai, ctl);
+    opus_layer_decide(p, st, pre->silence, pre->clear, ai, ctl, p.frame_size, p.frame_size);
     p.packets[(size_t)s * p.pkt_stride] = (unsigned char)ctl->toc;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// 40..120 ms packets: one thread per stream after the P1 / P2 passes of all the packet's 20 ms frames.  The packet's decisions from
+// tonality_get_info over the whole packet (run_analysis, src/analysis.c:968-971), then — read position reset as in :1727-1733 — the analysis info of
+// every 20 ms frame for its own CELT call (:1799-1802), and the frame controls: TOC of a 20 ms frame, float guard of that frame, stereo fade from the
+// previous width in the first frame and at the new width in the others (hybrid_stereo_width_Q14 is updated by the first).
+// ---------------------------------------------------------------------------------------------------------------------------
+OB_DEV void opus_multiframe_decide_thread(const OpusLayerParams &p, int s) {
+  ObOpusEncState *st = p.st + s;
+  ObAnalysisInfo ai;
+  ai.valid = 0;
+  ai.tonality = ai.tonality_slope = ai.noisiness = ai.activity = ai.music_prob = ai.music_prob_min = ai.music_prob_max = 0.f;
+  ai.bandwidth = 0; ai.activity_probability = ai.max_pitch_ratio = 0.f;
+  for (int i = 0; i < 20; i++) ai.leak_boost[i] = 0;
+  ObTonality *tonal = p.run_analysis ? p.tonal + s : nullptr;
+  int pos_bak = 0, sub_bak = 0, silence = 1;
+  if (tonal) {
+    pos_bak = tonal->read_pos; sub_bak = tonal->read_subframe;
+    an_get_info(tonal, &ai, p.packet_frame_size, p.Fs);
+  }
+  for (int i = 0; i < p.nb_frames; i++) silence &= p.pre_all[(size_t)i * p.n_streams + s].silence;
+  ObOpusFrameCtl c0;
+  opus_layer_decide(p, st, silence, 0, ai, &c0, p.packet_frame_size, p.frame_size);
+  if (tonal) { tonal->read_pos = pos_bak; tonal->read_subframe = sub_bak; }
+  for (int i = 0; i < p.nb_frames; i++) {
+    ObOpusFrameCtl *c = p.ctl_all + (size_t)i * p.n_streams + s;
+    *c = c0;
+    if (tonal) an_get_info(tonal, &c->analysis, p.frame_size, p.Fs);
+    c->clear = p.pre_all[(size_t)i * p.n_streams + s].clear;
+    if (i > 0) {
+      c->fade = c0.fade && c0.fade_g2 > 0.f;
+      c->fade_g1 = c->fade_g2 = c->fade ? c0.fade_g2 : 0.f;
+    }
+    p.tmp_packets[((size_t)i * p.n_streams + s) * p.tmp_stride] = (unsigned char)c0.toc;
+  }
+}
+// opus_repacketizer_cat of the packet's one-frame packets + opus_repacketizer_out_range_impl(rp, 0, nb_frames, data, repacketize_len, 0, pad, NULL, 0)
+// (src/repacketizer.c:88-152, 160-365; no extensions): code 1 / 2 for two frames, code 3 otherwise or when the CBR padding is needed
+OB_DEV int opus_repack_size(int size, unsigned char *data) {   // encode_size
+  if (size < 252) { data[0] = (unsigned char)size; return 1; }
+  data[0] = (unsigned char)(252 + (size & 0x3));
+  data[1] = (unsigned char)((size - (int)data[0]) >> 2);
+  return 2;
+}
+OB_DEV void opus_repacketize_thread(const OpusLayerParams &p, int s) {
+  const int nb = p.nb_frames, maxlen = p.repacketize_len, pad = p.pad;
+  unsigned char *data = p.packets + (size_t)s * p.pkt_stride, *ptr = data;
+  int len[6], tot_size = 0, bad = 0;
+  for (int i = 0; i < nb; i++) { len[i] = p.tmp_nbytes[(size_t)i * p.n_streams + s] - 1; bad |= len[i] < 0; }   // the frame kernel counts the TOC
+  if (bad) { p.out_nbytes[s] = -3; return; }
+  const unsigned char toc = p.tmp_packets[(size_t)s * p.tmp_stride] & 0xFC;
+  if (nb == 2) {
+    if (len[1] == len[0]) {
+      tot_size = 2 * len[0] + 1;
+      if (tot_size > maxlen) { p.out_nbytes[s] = -3; return; }
+      *ptr++ = toc | 0x1;
+    } else {
+      tot_size = len[0] + len[1] + 2 + (len[0] >= 252);
+      if (tot_size > maxlen) { p.out_nbytes[s] = -3; return; }
+      *ptr++ = toc | 0x2;
+      ptr += opus_repack_size(len[0], ptr);
+    }
+  }
+  if (nb > 2 || (pad && tot_size < maxlen)) {
+    int vbr = 0;
+    ptr = data;
+    tot_size = 0;
+    for (int i = 1; i < nb; i++) if (len[i] != len[0]) { vbr = 1; break; }
+    if (vbr) {
+      tot_size += 2;
+      for (int i = 0; i < nb - 1; i++) tot_size += 1 + (len[i] >= 252) + len[i];
+      tot_size += len[nb - 1];
+    } else tot_size += nb * len[0] + 2;
+    if (tot_size > maxlen) { p.out_nbytes[s] = -3; return; }
+    *ptr++ = toc | 0x3;
+    *ptr++ = (unsigned char)(vbr ? (nb | 0x80) : nb);
+    const int pad_amount = pad ? (maxlen - tot_size) : 0;
+    if (pad_amount != 0) {
+      const int nb_255s = (pad_amount - 1) / 255;
+      data[1] |= 0x40;
+      if (tot_size + nb_255s + 1 > maxlen) { p.out_nbytes[s] = -3; return; }
+      for (int i = 0; i < nb_255s; i++) *ptr++ = 255;
+      *ptr++ = (unsigned char)(pad_amount - 255 * nb_255s - 1);
+      tot_size += pad_amount;
+    }
+    if (vbr) for (int i = 0; i < nb - 1; i++) ptr += opus_repack_size(len[i], ptr);
+  }
+  for (int i = 0; i < nb; i++) {
+    const unsigned char *f = p.tmp_packets + ((size_t)i * p.n_streams + s) * p.tmp_stride + 1;
+    for (int k = 0; k < len[i]; k++) ptr[k] = f[k];
+    ptr += len[i];
+  }
+  if (pad) while (ptr < data + maxlen) *ptr++ = 0;
+  p.out_nbytes[s] = tot_size;
 }
 
 }  // namespace ob

@@ -352,22 +352,10 @@ extern "C" int emu_opus_encoder_ctl(void *h, int request, int value) {
   if (request == 4046) { e->disable_inv = value; return 0; }
   return opus_enc_settings_ctl(&e->cfg, request, value);
 }
-extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
-                               int32_t *nbytes, uint32_t *rng) {
-  EmuOpusEncoder *e = (EmuOpusEncoder *)h;
-  OpusCallPlan pl;
-  const int pr = opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
-  if (pr) return pr;
-  if (pkt_stride < pl.max_data_bytes) return -1;
+// the CELT kernels of one frame for every stream (celt_encode_launch of celt_enc_host.cuh): packets receive the payload behind the TOC byte
+static int emu_opus_celt_frame(EmuOpusEncoder *e, const OpusCallPlan &pl, const float *pcm_buf, const ObOpusFrameCtl *ctl, int frame_size, unsigned char *packets,
+                               int pkt_stride, int32_t *nbytes) {
   const int n = e->n, CC = e->channels, up = 48000 / e->cfg.Fs;
-  if (!pl.run_analysis && e->analysis_was_on) memset(e->tonal.data(), 0, sizeof(ObTonality) * n);
-  e->analysis_was_on = pl.run_analysis;
-  OpusLayerParams p;
-  opus_layer_params_init(&p, e->cfg, pl, frame_size, is16, n);
-  p.st = e->st.data(); p.tonal = e->tonal.data(); p.pre = e->pre.data(); p.ctl = e->ctl.data(); p.pcm = pcm; p.pcm_buf = e->pcm_buf.data();
-  p.packets = packets; p.pkt_stride = pkt_stride;
-  emu_launch(opus_pre_entry, &p, (n + 31) / 32, 32, 32 * OB_PRE_TS * sizeof(float));
-  emu_launch(opus_an_entry, &p, n, 32, sizeof(AnWS));
   int LM = -1;
   for (int l = 0; l <= 3; l++) if (frame_size * up == OB_SHORT_N << l) LM = l;
   if (LM < 0) return -1;
@@ -375,11 +363,11 @@ extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_siz
   std::vector<float> X((size_t)n * CC * N), E((size_t)n * CC * OB_NBANDS), Lg((size_t)n * CC * OB_NBANDS), Lg2((size_t)n * CC * OB_NBANDS);
   std::vector<ObEncFrameInfo> info(n);
   EncAnalysisParams a;
-  a.state = e->an_state.data(); a.pcm = e->pcm_buf.data(); a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
+  a.state = e->an_state.data(); a.pcm = pcm_buf; a.short_blocks = nullptr; a.X = X.data(); a.bandE = E.data(); a.bandLogE = Lg.data();
   a.info = info.data(); a.n_streams = n; a.C = CC; a.CC = CC; a.LM = LM; a.complexity = cx; a.lsb_depth = pl.lsb;
   a.enc_state = e->enc_state.data(); a.prefilter_mem = e->prefilter_mem.data(); a.bandLogE2 = Lg2.data(); a.max_bytes = max_bytes; a.bitrate = pl.celt_bitrate;
   a.vbr = pl.celt_vbr; a.constrained_vbr = pl.celt_cvbr; a.disable_pf = pl.celt_disable_pf; a.loss_rate = e->cfg.packet_loss; a.end = OB_NBANDS; a.upsample = up;
-  a.ctl = e->ctl.data();
+  a.ctl = ctl;
   emu_run_chains(a, n);
   emu_launch(enc_analysis_entry, &a, n, 32 * CC, CC * sizeof(MdctWS) + 32 + (cx >= 5 ? sizeof(PfWS) : sizeof(float) * 64));
   EncFrameParams f;
@@ -387,9 +375,68 @@ extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_siz
   f.packets = packets + 1; f.nbytes = nbytes; f.n_streams = n; f.C = CC; f.CC = CC; f.LM = LM; f.pkt_stride = pkt_stride; f.max_bytes = max_bytes;
   f.complexity = cx; f.bitrate = pl.celt_bitrate; f.lsb_depth = pl.lsb; f.force_intra = pl.celt_force_intra; f.disable_inv = e->disable_inv;
   f.disable_pf = pl.celt_disable_pf; f.vbr = pl.celt_vbr; f.constrained_vbr = pl.celt_cvbr; f.loss_rate = e->cfg.packet_loss; f.end = OB_NBANDS;
-  f.ctl = e->ctl.data(); f.toc_bytes = 1;
+  f.ctl = ctl; f.toc_bytes = 1;
   if (g_frame_sync && f.complexity >= 8 && f.CC == 2) emu_launch(enc_frame_entry_sync, &f, (n + 63) / 64, 64, 0);
   else emu_launch(enc_frame_entry_ctl, &f, (n + 31) / 32, 32, 0);
+  return 0;
+}
+static void opus_mf_decide_entry(void *a) {
+  const OpusLayerParams &p = *(const OpusLayerParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n_streams) opus_multiframe_decide_thread(p, s);
+}
+static void opus_repack_entry(void *a) {
+  const OpusLayerParams &p = *(const OpusLayerParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n_streams) opus_repacketize_thread(p, s);
+}
+extern "C" int emu_opus_encode(void *h, const void *pcm, int is16, int frame_size, unsigned char *packets, int pkt_stride, int max_data_bytes,
+                               int32_t *nbytes, uint32_t *rng) {
+  EmuOpusEncoder *e = (EmuOpusEncoder *)h;
+  OpusCallPlan pl;
+  const int pr = opus_enc_plan(e->cfg, frame_size, max_data_bytes, is16, &pl);
+  if (pr) return pr;
+  const int n = e->n, CC = e->channels;
+  if (!pl.run_analysis && e->analysis_was_on) memset(e->tonal.data(), 0, sizeof(ObTonality) * n);
+  e->analysis_was_on = pl.run_analysis;
+  OpusLayerParams p;
+  if (pl.nb_frames == 1) {
+    if (pkt_stride < pl.max_data_bytes) return -1;
+    opus_layer_params_init(&p, e->cfg, pl, frame_size, is16, n);
+    p.st = e->st.data(); p.tonal = e->tonal.data(); p.pre = e->pre.data(); p.ctl = e->ctl.data(); p.pcm = pcm; p.pcm_buf = e->pcm_buf.data();
+    p.packets = packets; p.pkt_stride = pkt_stride;
+    emu_launch(opus_pre_entry, &p, (n + 31) / 32, 32, 32 * OB_PRE_TS * sizeof(float));
+    emu_launch(opus_an_entry, &p, n, 32, sizeof(AnWS));
+    const int r = emu_opus_celt_frame(e, pl, e->pcm_buf.data(), e->ctl.data(), frame_size, packets, pkt_stride, nbytes);
+    if (r) return r;
+  } else {   // opus_encode_multiframe of opus_enc_host.cuh
+    const int nb = pl.nb_frames, fs = pl.enc_frame_size, stride = (pl.max_data_bytes + 15) & ~15;
+    std::vector<ObOpusPre> pre((size_t)nb * n);
+    std::vector<ObOpusFrameCtl> ctl((size_t)nb * n);
+    std::vector<float> pcm_buf((size_t)nb * n * CC * OB_MAXN);
+    std::vector<unsigned char> tmp((size_t)nb * n * stride);
+    std::vector<int32_t> tnb((size_t)nb * n);
+    memset(pre.data(), 0, sizeof(ObOpusPre) * pre.size());
+    memset(ctl.data(), 0, sizeof(ObOpusFrameCtl) * ctl.size());
+    opus_layer_params_init(&p, e->cfg, pl, fs, is16, n);
+    p.st = e->st.data(); p.tonal = e->tonal.data(); p.pcm = pcm; p.packets = packets; p.pkt_stride = pkt_stride;
+    p.multi = 1; p.pcm_row = frame_size * CC; p.nb_frames = nb; p.packet_frame_size = frame_size; p.pre_all = pre.data(); p.ctl_all = ctl.data();
+    p.tmp_packets = tmp.data(); p.tmp_stride = stride; p.tmp_nbytes = tnb.data(); p.out_nbytes = nbytes; p.repacketize_len = pl.repacketize_len;
+    p.pad = !e->cfg.use_vbr;
+    for (int i = 0; i < nb; i++) {
+      p.pre = pre.data() + (size_t)i * n; p.ctl = ctl.data() + (size_t)i * n; p.pcm_buf = pcm_buf.data() + (size_t)i * n * CC * OB_MAXN; p.pcm_off = i * fs * CC;
+      emu_launch(opus_pre_entry, &p, (n + 31) / 32, 32, 32 * OB_PRE_TS * sizeof(float));
+      if (pl.run_analysis) emu_launch(opus_an_entry, &p, n, 32, sizeof(AnWS));
+    }
+    emu_launch(opus_mf_decide_entry, &p, (n + 31) / 32, 32, 0);
+    for (int i = 0; i < nb; i++) {
+      const int r = emu_opus_celt_frame(e, pl, pcm_buf.data() + (size_t)i * n * CC * OB_MAXN, ctl.data() + (size_t)i * n, fs, tmp.data() + (size_t)i * n * stride, stride,
+                                        tnb.data() + (size_t)i * n);
+      if (r) return r;
+    }
+    emu_launch(opus_repack_entry, &p, (n + 31) / 32, 32, 0);
+    for (int s = 0; s < n; s++) e->ctl[s] = ctl[(size_t)(nb - 1) * n + s];
+  }
   for (int s = 0; s < n; s++) rng[s] = e->enc_state[s].rng;
   return 0;
 }

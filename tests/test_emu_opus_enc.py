@@ -160,3 +160,20 @@ def test_other_front_end_forms(mode):
         run_case([np.ascontiguousarray(x[::2]) for x in three_signals(45, 960 * 6, 2)], 24000, 2, 480, 32000, 1, 8, nframes=6)
     finally:
         L.emu_celt_set_chains(1)
+
+
+@pytest.mark.parametrize('fs_ms,ch,bitrate,vbr,cx', [(40, 2, 64000, 1, 10), (60, 2, 24000, 1, 10), (120, 1, 32000, 0, 9), (80, 2, 96000, 0, 5), (100, 2, 20000, 1, 8)])
+def test_multiframe_packets(fs_ms, ch, bitrate, vbr, cx):
+    """40 .. 120 ms: P1 / P2 per 20 ms frame, the packet's decisions, the CELT kernels frame by frame, the repacketizer (code 1 / 2 / 3, CBR padding;
+    low stereo rates bring the stereo fade and mono-coded streams into it) against the oracle, which is pinned on opus_encode()"""
+    fs = 48 * fs_ms
+    nfr = 5
+    run_case(three_signals(60 + fs_ms, fs * nfr, ch), 48000, ch, fs, bitrate, vbr, cx, nframes=nfr, max_bytes=1276 * 6)
+
+
+def test_multiframe_float_api_with_guard_and_other_rate():
+    Fs, fs = 24000, 24 * 60
+    x = [np.ascontiguousarray(s[::2]).astype(np.float32) / 32768.0 for s in three_signals(77, 2 * fs * 4, 2)]
+    x[1][fs + 700:fs + 720] = 3e4     # the float guard fires in one 20 ms frame of the second packet
+    x[2][2 * fs:3 * fs] = 0           # a silent packet
+    run_case(x, Fs, 2, fs, 40000, 1, 10, nframes=4, max_bytes=1276 * 3)

@@ -112,10 +112,12 @@ def test_unsupported_calls_fail_loudly():
         opus_b200.OpusEncoderBatch(4, application=util.OPUS_APPLICATION_AUDIO)   # may select SILK: not built
     enc = opus_b200.OpusEncoderBatch(4)
     L = capi.lib()
-    pcm = np.zeros((4, 2 * 1920), np.int16)
+    pcm = np.zeros((4, 2 * 960), np.int16)
     pk, nb = np.zeros((4, 1276), np.uint8), np.zeros(4, np.int32)
-    r = L.opusb200_opus_encode(enc._h, _p(pcm), 1920, _p(pk), 1276, 1276, _p(nb))   # 40 ms: multi-frame packets are not built
+    r = L.opusb200_opus_encode(enc._h, _p(pcm), 960, _p(pk), 1276, 2, _p(nb))   # a 2-byte budget: the reference emits a 'PLC frame' packet, not built
     assert r == capi.OPUS_UNIMPLEMENTED, r
+    r = L.opusb200_opus_encode(enc._h, _p(pcm), 1000, _p(pk), 1276, 1276, _p(nb))   # not an Opus frame size
+    assert r == capi.OPUS_BAD_ARG, r
     enc.close()
 
 
@@ -143,4 +145,35 @@ def test_submit_wait_matches_the_synchronous_call():
         for s in range(n):
             assert (pk[k][s, :nb[k][s]] == want[k][0][s, :nb[k][s]]).all()
     assert (a.final_range() == b.final_range()).all()
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize('fs_ms,ch,bitrate,vbr,cx,n', [(40, 2, 64000, 1, 10, 70), (60, 2, 24000, 1, 10, 40), (120, 1, 32000, 0, 9, 40), (80, 2, 96000, 0, 5, 40),
+                                                         (100, 2, 20000, 1, 8, 40)])
+def test_multiframe_packets(fs_ms, ch, bitrate, vbr, cx, n):
+    """opus_encode() with 40 .. 120 ms frames: 20 ms frames coded one by one and repacketised (src/opus_encoder.c:1698-1838): packets (code 1 / 2 / 3,
+    CBR padding) and final range identical to the reference's"""
+    fs = 48 * fs_ms
+    run_case(many_signals(70 + fs_ms, fs * 4, ch, k=2), 48000, ch, fs, bitrate, vbr, cx, nframes=4, n=n, max_bytes=1276 * 6)
+
+
+def test_multiframe_float_api_other_rate_and_pipelined_call():
+    import opus_b200
+    Fs, fs, n = 24000, 24 * 60, 24
+    base = [np.ascontiguousarray(s[::2]).astype(np.float32) / 32768.0 for s in three_signals(88, 2 * fs * 4, 2)]
+    base[1][fs + 700:fs + 720] = 3e4
+    run_case(base, Fs, 2, fs, 40000, 1, 10, nframes=4, n=n, max_bytes=1276 * 3, app=util.OPUS_APPLICATION_RESTRICTED_LOWDELAY)
+    # the pipelined host-buffer call takes the same path
+    x = np.stack([base[s % 3][:4 * fs].reshape(-1) for s in range(n)])
+    a = opus_b200.OpusEncoderBatch(n, channels=2, fs=Fs, bitrate=40000, vbr=True, complexity=10)
+    b = opus_b200.OpusEncoderBatch(n, channels=2, fs=Fs, bitrate=40000, vbr=True, complexity=10)
+    for k in range(4):
+        fr = np.ascontiguousarray(x[:, k * fs * 2:(k + 1) * fs * 2])
+        want, wn = a.encode(fr, 1276 * 3, frame_size=fs)
+        pk, nb = np.zeros((n, 1276 * 3), np.uint8), np.zeros(n, np.int32)
+        b.submit(fr, pk, nb, 1276 * 3, fs)
+        b.wait()
+        assert (nb == wn).all()
+        for s in range(n):
+            assert (pk[s, :nb[s]] == want[s, :wn[s]]).all()
     a.close(); b.close()
