@@ -432,6 +432,22 @@ int opusb200_dred_encoder_load_stats(OpusB200DredEnc *enc, const unsigned char *
 int opusb200_dred_encode_silk_frame(OpusB200DredEnc *enc, unsigned char *buf, int buf_stride, int max_chunks, int max_bytes, int q0, int dQ, int qmax,
                                     const unsigned char *activity_mem, int32_t *nbytes, int on_device);
 
+/* silk_process_gains_FLP (silk/float/process_gains_FLP.c:35-103; call site silk/float/encode_frame_FLP.c:172) with silk_gains_quant
+ * (silk/gain_quant.c:40-95): the gain quantiser of a SILK frame — another slice of SURVEY 8(f).3.  One record per stream holds what the function
+ * reads and writes in silk_encoder_state_FLP / silk_encoder_control_FLP: in: Gains, ResNrg, LTPredCodGain, input_quality, coding_quality, signalType,
+ * quantOffsetType, SNR_dB_Q7, input_tilt_Q15, speech_activity_Q8, condCoding (0 / 1 / 2 as silk/define.h:97-99), LastGainIndex; out: Gains
+ * (quantised), GainsUnq_Q16, GainsIndices, LastGainIndex, lastGainIndexPrev, quantOffsetType, Lambda.  nb_subfr 2 or 4.  Bit-exact. */
+typedef struct {
+  float Gains[4], ResNrg[4];
+  float LTPredCodGain, input_quality, coding_quality, Lambda;
+  int32_t GainsUnq_Q16[4];
+  int32_t signalType, quantOffsetType, SNR_dB_Q7, input_tilt_Q15, speech_activity_Q8, condCoding;
+  int8_t GainsIndices[4];
+  int8_t LastGainIndex, lastGainIndexPrev, pad[2];
+} OpusB200SilkGains;
+int opusb200_silk_process_gains(OpusB200Ctx *ctx, OpusB200SilkGains *frames, int n, int nb_subfr, int subfr_length, int nStatesDelayedDecision,
+                                int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

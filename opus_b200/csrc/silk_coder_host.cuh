@@ -172,3 +172,34 @@ extern "C" int opusb200_range_encoder_done(OpusB200RangeEncoder *r, unsigned cha
   OB_CUDA(cudaStreamSynchronize(c->stream));
   return OPUSB200_OK;
 }
+
+// ---- silk_process_gains_FLP for n streams (silk_ops.cuh: silk_process_gains_thread): frames [n] records, in place ----
+extern "C" __global__ void __launch_bounds__(128) ob_silk_process_gains(ob::SilkGainsParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_process_gains_thread(p, s);
+}
+extern "C" int opusb200_silk_process_gains(OpusB200Ctx *c, OpusB200SilkGains *frames, int n, int nb_subfr, int subfr_length, int nStatesDelayedDecision,
+                                           int on_device) {
+  static_assert(sizeof(OpusB200SilkGains) == sizeof(ob::ObSilkGains), "OpusB200SilkGains mirrors ObSilkGains");
+  if (!c || !frames || n <= 0 || (nb_subfr != 2 && nb_subfr != 4) || subfr_length <= 0 || nStatesDelayedDecision < 1 || nStatesDelayedDecision > 4)
+    return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkGainsParams p;
+  p.n = n; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length; p.nStatesDelayedDecision = nStatesDelayedDecision;
+  const size_t bytes = sizeof(ob::ObSilkGains) * (size_t)n;
+  ob::ObSilkGains *d = (ob::ObSilkGains *)frames;
+  if (!on_device) {
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMemcpyAsync(d, frames, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { cudaFree(d); return OPUSB200_INTERNAL_ERROR; }
+  }
+  p.frames = d;
+  ob_silk_process_gains<<<(n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  int r = cudaGetLastError() == cudaSuccess ? OPUSB200_OK : OPUSB200_INTERNAL_ERROR;
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d);
+  }
+  return r;
+}

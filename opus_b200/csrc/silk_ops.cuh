@@ -397,4 +397,87 @@ OB_DEV void silk_autocorr_thread(const SilkAutocorrParams &p, int idx) {
   p.results[idx] = lag < p.size ? (float)silk_inner_product_flp(x, x + lag, p.size - lag) : 0.f;
 }
 
+// ---- gain processing and quantisation of a SILK frame: silk_process_gains_FLP (silk/float/process_gains_FLP.c:35-103), silk_gains_quant
+// (silk/gain_quant.c:40-95), silk_lin2log / silk_log2lin (silk/lin2log.c, log2lin.c).  One thread per stream; the record is the stream's view of
+// silk_encoder_state_FLP / silk_encoder_control_FLP (what the function reads and writes). ----
+struct ObSilkGains {   // == OpusB200SilkGains (include/opus_b200.h)
+  float Gains[4], ResNrg[4];
+  float LTPredCodGain, input_quality, coding_quality, Lambda;
+  int32_t GainsUnq_Q16[4];
+  int32_t signalType, quantOffsetType, SNR_dB_Q7, input_tilt_Q15, speech_activity_Q8, condCoding;
+  int8_t GainsIndices[4];
+  int8_t LastGainIndex, lastGainIndexPrev, pad[2];
+};
+struct SilkGainsParams { ObSilkGains *frames; int n, nb_subfr, subfr_length, nStatesDelayedDecision; };
+OB_DEV int32_t silk_smlawb_(int32_t a, int32_t b, int32_t c) { return a + silk_smulwb(b, c); }
+OB_DEV int32_t silk_lin2log(int32_t inLin) {
+  const int lz = clz32((uint32_t)inLin), rot = 24 - lz;
+  const uint32_t x = (uint32_t)inLin;
+  const uint32_t r = rot == 0 ? x : rot < 0 ? ((x << (uint32_t)(-rot)) | (x >> (uint32_t)(32 + rot))) : ((x << (uint32_t)(32 - rot)) | (x >> (uint32_t)rot));   // silk_ROR32
+  const int32_t frac_Q7 = (int32_t)(r & 0x7f);
+  return silk_smlawb_(frac_Q7, frac_Q7 * (128 - frac_Q7), 179) + ((31 - lz) << 7);
+}
+OB_DEV int32_t silk_log2lin(int32_t inLog_Q7) {
+  if (inLog_Q7 < 0) return 0;
+  if (inLog_Q7 >= 3967) return 0x7FFFFFFF;
+  int32_t out = 1 << (inLog_Q7 >> 7);
+  const int32_t frac_Q7 = inLog_Q7 & 0x7F, poly = silk_smlawb_(frac_Q7, (int32_t)(int16_t)frac_Q7 * (int32_t)(int16_t)(128 - frac_Q7), -174);
+  if (inLog_Q7 < 2048) out = out + ((out * poly) >> 7);
+  else out = out + (out >> 7) * poly;
+  return out;
+}
+OB_DEV int silk_limit_int(int a, int lo, int hi) { return a < lo ? lo : a > hi ? hi : a; }
+OB_DEV void silk_gains_quant(int8_t *ind, int32_t *gain_Q16, int8_t *prev_ind, int conditional, int nb_subfr) {
+  const int kOffset = (2 * 128) / 6 + 16 * 128, kScale = (65536 * (64 - 1)) / (((88 - 2) * 128) / 6), kInvScale = (65536 * (((88 - 2) * 128) / 6)) / (64 - 1);
+  int8_t prev = *prev_ind;
+  for (int k = 0; k < nb_subfr; k++) {
+    int8_t v = (int8_t)silk_smulwb(kScale, silk_lin2log(gain_Q16[k]) - kOffset);
+    if (v < prev) v++;
+    v = (int8_t)silk_limit_int(v, 0, 63);
+    if (k == 0 && conditional == 0) {
+      v = (int8_t)silk_limit_int(v, prev - 4, 63);
+      prev = v;
+    } else {
+      v = (int8_t)(v - prev);
+      const int thr = 2 * 36 - 64 + prev;
+      if (v > thr) v = (int8_t)(thr + ((v - thr + 1) >> 1));
+      v = (int8_t)silk_limit_int(v, -4, 36);
+      if (v > thr) {
+        prev = (int8_t)(prev + ((v << 1) - thr));
+        prev = prev < 63 ? prev : 63;
+      } else prev = (int8_t)(prev + v);
+      v = (int8_t)(v + 4);
+    }
+    ind[k] = v;
+    const int32_t lg = silk_smulwb(kInvScale, prev) + kOffset;
+    gain_Q16[k] = silk_log2lin(lg < 3967 ? lg : 3967);
+  }
+  *prev_ind = prev;
+}
+OB_DEV void silk_process_gains_thread(const SilkGainsParams &p, int s) {
+  ObSilkGains g = p.frames[s];
+  const int nb = p.nb_subfr;
+  int32_t q16[4];
+  if (g.signalType == 2) {
+    const float sg = 1.0f - 0.5f * (float)(1.0 / (1.0 + exp(-(double)(0.25f * (g.LTPredCodGain - 12.0f)))));
+    for (int k = 0; k < nb; k++) g.Gains[k] *= sg;
+  }
+  const float InvMaxSqrVal = (float)(pow((double)2.0f, (double)(0.33f * (21.0f - g.SNR_dB_Q7 * (1 / 128.0f)))) / p.subfr_length);
+  for (int k = 0; k < nb; k++) {
+    float gain = g.Gains[k];
+    gain = (float)sqrt((double)(gain * gain + g.ResNrg[k] * InvMaxSqrVal));
+    g.Gains[k] = gain < 32767.0f ? gain : 32767.0f;
+  }
+  for (int k = 0; k < nb; k++) { q16[k] = (int32_t)(g.Gains[k] * 65536.0f); g.GainsUnq_Q16[k] = q16[k]; }
+  g.lastGainIndexPrev = g.LastGainIndex;
+  silk_gains_quant(g.GainsIndices, q16, &g.LastGainIndex, g.condCoding == 2, nb);
+  for (int k = 0; k < nb; k++) g.Gains[k] = q16[k] / 65536.0f;
+  if (g.signalType == 2) g.quantOffsetType = (g.LTPredCodGain + g.input_tilt_Q15 * (1.0f / 32768.0f) > 1.0f) ? 0 : 1;
+  const int qo = (g.signalType >> 1) ? (g.quantOffsetType ? 100 : 32) : (g.quantOffsetType ? 240 : 100);   // silk_Quantization_Offsets_Q10
+  const float quant_offset = qo / 1024.0f;
+  g.Lambda = 1.2f + -0.05f * p.nStatesDelayedDecision + -0.2f * g.speech_activity_Q8 * (1.0f / 256.0f) + -0.1f * g.input_quality + -0.2f * g.coding_quality +
+             0.8f * quant_offset;
+  p.frames[s] = g;
+}
+
 }  // namespace ob

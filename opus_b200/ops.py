@@ -87,6 +87,14 @@ class Ops:
     def silk_resampler(self, n_streams, fs_in, fs_out, for_enc=True):
         return SilkResampler(self, n_streams, fs_in, fs_out, for_enc)
 
+    def silk_process_gains(self, frames, nb_subfr, subfr_length, n_states_delayed_decision):
+        """silk_process_gains_FLP for n streams: frames = ctypes array of OpusB200SilkGains-shaped records (processed in place)"""
+        n = len(frames)
+        r = self._L.opusb200_silk_process_gains(self._h, ctypes.cast(frames, ctypes.c_void_p), n, nb_subfr, subfr_length, n_states_delayed_decision, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_process_gains')
+        return frames
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

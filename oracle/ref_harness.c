@@ -429,3 +429,33 @@ void refh_silk_encode_indices(RefhSilkCoder *c, int fs_kHz, int nb_subfr, const 
   prev[0] = st.ec_prevSignalType; prev[1] = st.ec_prevLagIndex;
 }
 int refh_silk_indices_size(void) { return (int)sizeof(SideInfoIndices); }
+
+/* ---- silk_process_gains_FLP on scratch encoder structs that hold what the function reads (silk/float/process_gains_FLP.c:35-103) ---- */
+#include "silk/float/main_FLP.h"
+typedef struct {
+  float Gains[4], ResNrg[4];
+  float LTPredCodGain, input_quality, coding_quality, Lambda;
+  opus_int32 GainsUnq_Q16[4];
+  opus_int32 signalType, quantOffsetType, SNR_dB_Q7, input_tilt_Q15, speech_activity_Q8, condCoding;
+  opus_int8 GainsIndices[4];
+  opus_int8 LastGainIndex, lastGainIndexPrev, pad[2];
+} RefhSilkGains;   /* == OrcSilkGains */
+void refh_silk_process_gains(RefhSilkGains *g, int nb_subfr, int subfr_length, int nStatesDelayedDecision) {
+  static silk_encoder_state_FLP st;
+  static silk_encoder_control_FLP ctl;
+  int k;
+  memset(&st, 0, sizeof(st));
+  memset(&ctl, 0, sizeof(ctl));
+  st.sCmn.nb_subfr = nb_subfr; st.sCmn.subfr_length = subfr_length; st.sCmn.nStatesDelayedDecision = nStatesDelayedDecision;
+  st.sCmn.indices.signalType = (opus_int8)g->signalType; st.sCmn.indices.quantOffsetType = (opus_int8)g->quantOffsetType;
+  st.sCmn.SNR_dB_Q7 = g->SNR_dB_Q7; st.sCmn.input_tilt_Q15 = g->input_tilt_Q15; st.sCmn.speech_activity_Q8 = g->speech_activity_Q8;
+  st.sShape.LastGainIndex = g->LastGainIndex;
+  for (k = 0; k < 4; k++) { ctl.Gains[k] = g->Gains[k]; ctl.ResNrg[k] = g->ResNrg[k]; }
+  ctl.LTPredCodGain = g->LTPredCodGain; ctl.input_quality = g->input_quality; ctl.coding_quality = g->coding_quality;
+  silk_process_gains_FLP(&st, &ctl, g->condCoding);
+  for (k = 0; k < 4; k++) { g->Gains[k] = ctl.Gains[k]; g->GainsUnq_Q16[k] = ctl.GainsUnq_Q16[k]; g->GainsIndices[k] = st.sCmn.indices.GainsIndices[k]; }
+  g->Lambda = ctl.Lambda; g->quantOffsetType = st.sCmn.indices.quantOffsetType; g->LastGainIndex = st.sShape.LastGainIndex;
+  g->lastGainIndexPrev = ctl.lastGainIndexPrev;
+}
+opus_int32 refh_silk_lin2log(opus_int32 x) { return silk_lin2log(x); }
+opus_int32 refh_silk_log2lin(opus_int32 x) { return silk_log2lin(x); }

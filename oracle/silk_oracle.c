@@ -301,3 +301,92 @@ float orc_silk_burg_modified(float *A, const float *x, float minInvGain, int sub
   }
   return (float)nrg_f;
 }
+
+/* ---- gain processing and quantisation of a SILK frame: silk_process_gains_FLP (silk/float/process_gains_FLP.c:35-103),
+ * silk_gains_quant (silk/gain_quant.c:40-95), silk_lin2log / silk_log2lin (silk/lin2log.c, log2lin.c), silk_CLZ_FRAC (silk/Inlines.h:52-62). ---- */
+static int32_t orc_ror32(int32_t a32, int rot) { /* silk_ROR32, silk/macros.h */
+  const uint32_t x = (uint32_t)a32, r = (uint32_t)rot, m = (uint32_t)-rot;
+  if (rot == 0) return a32;
+  if (rot < 0) return (int32_t)((x << m) | (x >> (32 - m)));
+  return (int32_t)((x << (32 - r)) | (x >> r));
+}
+int32_t orc_silk_lin2log(int32_t inLin) {
+  const int lz = inLin ? __builtin_clz((uint32_t)inLin) : 32;
+  const int32_t frac_Q7 = orc_ror32(inLin, 24 - lz) & 0x7f;
+  return smlawb(frac_Q7, frac_Q7 * (128 - frac_Q7), 179) + ((31 - lz) << 7);
+}
+int32_t orc_silk_log2lin(int32_t inLog_Q7) {
+  int32_t out, frac_Q7;
+  if (inLog_Q7 < 0) return 0;
+  if (inLog_Q7 >= 3967) return 0x7FFFFFFF;
+  out = 1 << (inLog_Q7 >> 7);
+  frac_Q7 = inLog_Q7 & 0x7F;
+  if (inLog_Q7 < 2048) out = out + ((out * smlawb(frac_Q7, (int16_t)frac_Q7 * (int32_t)(int16_t)(128 - frac_Q7), -174)) >> 7);
+  else out = out + (out >> 7) * smlawb(frac_Q7, (int16_t)frac_Q7 * (int32_t)(int16_t)(128 - frac_Q7), -174);
+  return out;
+}
+#define G_OFFSET ((2 * 128) / 6 + 16 * 128)
+#define G_SCALE_Q16 ((65536 * (64 - 1)) / (((88 - 2) * 128) / 6))
+#define G_INV_SCALE_Q16 ((65536 * (((88 - 2) * 128) / 6)) / (64 - 1))
+static int limit_int(int a, int lo, int hi) { return a < lo ? lo : a > hi ? hi : a; } /* silk_LIMIT with lo <= hi */
+void orc_silk_gains_quant(int8_t *ind, int32_t *gain_Q16, int8_t *prev_ind, int conditional, int nb_subfr) {
+  int k;
+  for (k = 0; k < nb_subfr; k++) {
+    ind[k] = (int8_t)smulwb(G_SCALE_Q16, orc_silk_lin2log(gain_Q16[k]) - G_OFFSET);
+    if (ind[k] < *prev_ind) ind[k]++;
+    ind[k] = (int8_t)limit_int(ind[k], 0, 63);
+    if (k == 0 && conditional == 0) {
+      ind[k] = (int8_t)limit_int(ind[k], *prev_ind - 4, 63);
+      *prev_ind = ind[k];
+    } else {
+      int thr;
+      ind[k] = ind[k] - *prev_ind;
+      thr = 2 * 36 - 64 + *prev_ind;
+      if (ind[k] > thr) ind[k] = (int8_t)(thr + ((ind[k] - thr + 1) >> 1));
+      ind[k] = (int8_t)limit_int(ind[k], -4, 36);
+      if (ind[k] > thr) {
+        *prev_ind += (ind[k] << 1) - thr;
+        *prev_ind = *prev_ind < 63 ? *prev_ind : 63;
+      } else *prev_ind += ind[k];
+      ind[k] -= -4;
+    }
+    {
+      const int32_t v = smulwb(G_INV_SCALE_Q16, *prev_ind) + G_OFFSET;
+      gain_Q16[k] = orc_silk_log2lin(v < 3967 ? v : 3967);
+    }
+  }
+}
+typedef struct { /* one stream's view of silk_encoder_state_FLP / silk_encoder_control_FLP: what silk_process_gains_FLP reads and writes */
+  float Gains[4], ResNrg[4];
+  float LTPredCodGain, input_quality, coding_quality, Lambda;
+  int32_t GainsUnq_Q16[4];
+  int32_t signalType, quantOffsetType, SNR_dB_Q7, input_tilt_Q15, speech_activity_Q8, condCoding;
+  int8_t GainsIndices[4];
+  int8_t LastGainIndex, lastGainIndexPrev, pad[2];
+} OrcSilkGains;
+void orc_silk_process_gains(OrcSilkGains *g, int nb_subfr, int subfr_length, int nStatesDelayedDecision) {
+  static const int16_t quant_offsets_Q10[2][2] = {{100, 240}, {32, 100}}; /* silk_Quantization_Offsets_Q10, silk/tables_other.c */
+  int32_t pGains_Q16[4];
+  float s, InvMaxSqrVal, gain, quant_offset;
+  int k;
+  if (g->signalType == 2) {
+    s = 1.0f - 0.5f * (float)(1.0 / (1.0 + exp(-(0.25f * (g->LTPredCodGain - 12.0f)))));
+    for (k = 0; k < nb_subfr; k++) g->Gains[k] *= s;
+  }
+  InvMaxSqrVal = (float)(pow(2.0f, 0.33f * (21.0f - g->SNR_dB_Q7 * (1 / 128.0f))) / subfr_length);
+  for (k = 0; k < nb_subfr; k++) {
+    gain = g->Gains[k];
+    gain = (float)sqrt(gain * gain + g->ResNrg[k] * InvMaxSqrVal);
+    g->Gains[k] = gain < 32767.0f ? gain : 32767.0f;
+  }
+  for (k = 0; k < nb_subfr; k++) pGains_Q16[k] = (int32_t)(g->Gains[k] * 65536.0f);
+  memcpy(g->GainsUnq_Q16, pGains_Q16, nb_subfr * sizeof(int32_t));
+  g->lastGainIndexPrev = g->LastGainIndex;
+  orc_silk_gains_quant(g->GainsIndices, pGains_Q16, &g->LastGainIndex, g->condCoding == 2, nb_subfr); /* CODE_CONDITIONALLY == 2 */
+  for (k = 0; k < nb_subfr; k++) g->Gains[k] = pGains_Q16[k] / 65536.0f;
+  if (g->signalType == 2) g->quantOffsetType = (g->LTPredCodGain + g->input_tilt_Q15 * (1.0f / 32768.0f) > 1.0f) ? 0 : 1;
+  quant_offset = quant_offsets_Q10[g->signalType >> 1][g->quantOffsetType] / 1024.0f;
+  g->Lambda = 1.2f + -0.05f * nStatesDelayedDecision + -0.2f * g->speech_activity_Q8 * (1.0f / 256.0f) + -0.1f * g->input_quality + -0.2f * g->coding_quality +
+              0.8f * quant_offset;
+}
+int orc_silk_gains_size(void) { return (int)sizeof(OrcSilkGains); }

@@ -534,3 +534,15 @@ extern "C" void emu_dred_encode_silk_frame(const float *lat_ring, const float *s
   p.dred_offset = ints[7]; p.max_chunks = ints[8]; p.max_bytes = ints[9]; p.q0 = ints[10]; p.dQ = ints[11]; p.qmax = ints[12];
   emu_launch(dred_code_entry, &p, (p.n + 31) / 32, 32, 0);
 }
+
+// ---- silk_process_gains_FLP (silk_ops.cuh), thread per stream ----
+static void silk_gains_entry(void *a) {
+  const SilkGainsParams &p = *(const SilkGainsParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_process_gains_thread(p, s);
+}
+extern "C" void emu_silk_process_gains(void *frames, int n, int nb_subfr, int subfr_length, int nstates) {
+  SilkGainsParams p;
+  p.frames = (ObSilkGains *)frames; p.n = n; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length; p.nStatesDelayedDecision = nstates;
+  emu_launch(silk_gains_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -245,3 +245,28 @@ def test_emu_silk_frame_bitstream(fs_kHz, nb_subfr):
             want = np.zeros(storage, np.uint8)
             assert O.orc_silk_coder_done(oc, _f(want)) == fr[s] and np.array_equal(buf[s, :storage], want), (frame, s)
             assert list(oprev[s]) == list(prev[s]), (frame, s)
+
+
+def test_silk_process_gains_emulated():
+    """silk_process_gains_FLP + silk_gains_quant: the device source on the emulator against the oracle (pinned on the reference's functions), streams with
+    carried LastGainIndex over several frames"""
+    from test_silk_gains_oracle_vs_ref import Gains, random_frame, fields
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(12)
+    n = 70
+    for nb_subfr, subfr_length, nstates in [(4, 80, 4), (2, 60, 1)]:
+        last = [10] * n
+        for frame in range(8):
+            recs = (Gains * n)()
+            want = []
+            for s in range(n):
+                recs[s] = random_frame(rng, last[s], frame)
+                w = Gains.from_buffer_copy(bytes(recs[s]))
+                O.orc_silk_process_gains(ctypes.byref(w), nb_subfr, subfr_length, nstates)
+                want.append(w)
+            E.emu_silk_process_gains(ctypes.cast(recs, ctypes.c_void_p), n, nb_subfr, subfr_length, nstates)
+            for s in range(n):
+                fa, fb = fields(recs[s]), fields(want[s])
+                assert np.array_equal(np.array(fa[0], np.float32).view(np.uint32), np.array(fb[0], np.float32).view(np.uint32)), (frame, s)
+                assert fa[1:] == fb[1:], (frame, s, fa, fb)
+                last[s] = recs[s].LastGainIndex

