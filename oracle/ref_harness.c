@@ -459,3 +459,33 @@ void refh_silk_process_gains(RefhSilkGains *g, int nb_subfr, int subfr_length, i
 }
 opus_int32 refh_silk_lin2log(opus_int32 x) { return silk_lin2log(x); }
 opus_int32 refh_silk_log2lin(opus_int32 x) { return silk_log2lin(x); }
+
+/* ---- silk_process_NLSFs on a scratch encoder state that holds what the function reads (silk/process_NLSFs.c:35-107) ---- */
+typedef struct {
+  opus_int16 NLSF_Q15[16];
+  opus_int16 prev_NLSFq_Q15[16];
+  opus_int16 PredCoef_Q12[2][16];
+  opus_int8 NLSFIndices[17];
+  opus_int8 NLSFInterpCoef_Q2, signalType, useInterpolatedNLSFs;
+  opus_int32 speech_activity_Q8, NLSF_MSVQ_Survivors;
+} RefhSilkNlsf;   /* == OrcSilkNlsf */
+void refh_silk_process_NLSFs(RefhSilkNlsf *f, int wb, int nb_subfr) {
+  static silk_encoder_state st;
+  memset(&st, 0, sizeof(st));
+  st.psNLSF_CB = wb ? &silk_NLSF_CB_WB : &silk_NLSF_CB_NB_MB;
+  st.predictLPCOrder = wb ? 16 : 10;
+  st.nb_subfr = nb_subfr;
+  st.speech_activity_Q8 = f->speech_activity_Q8;
+  st.useInterpolatedNLSFs = f->useInterpolatedNLSFs;
+  st.NLSF_MSVQ_Survivors = f->NLSF_MSVQ_Survivors;
+  st.indices.NLSFInterpCoef_Q2 = f->NLSFInterpCoef_Q2;
+  st.indices.signalType = f->signalType;
+  silk_process_NLSFs(&st, f->PredCoef_Q12, f->NLSF_Q15, f->prev_NLSFq_Q15);
+  memcpy(f->NLSFIndices, st.indices.NLSFIndices, 17);
+}
+void refh_silk_NLSF2A(opus_int16 *a_Q12, const opus_int16 *NLSF, int d) { silk_NLSF2A(a_Q12, NLSF, d, 0); }
+void refh_silk_NLSF_stabilize(opus_int16 *NLSF_Q15, int wb) {
+  const silk_NLSF_CB_struct *cb = wb ? &silk_NLSF_CB_WB : &silk_NLSF_CB_NB_MB;
+  silk_NLSF_stabilize(NLSF_Q15, cb->deltaMin_Q15, cb->order);
+}
+opus_int32 refh_silk_LPC_inverse_pred_gain(const opus_int16 *A_Q12, int order) { return silk_LPC_inverse_pred_gain_c(A_Q12, order); }

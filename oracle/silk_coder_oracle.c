@@ -13,6 +13,7 @@
 
 static int ilog32(uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; }
 #define BITRES 3
+#define IMIN(a, b) ((a) < (b) ? (a) : (b))
 #include "celt_rangeenc.inc"
 
 typedef struct { RangeEnc e; uint8_t buf[1280]; } OrcSilkCoder;
