@@ -448,6 +448,21 @@ typedef struct {
 int opusb200_silk_process_gains(OpusB200Ctx *ctx, OpusB200SilkGains *frames, int n, int nb_subfr, int subfr_length, int nStatesDelayedDecision,
                                 int on_device);
 
+/* silk_process_NLSFs (silk/process_NLSFs.c:35-107; call site silk/float/wrappers_FLP.c:103 from find_pred_coefs_FLP.c:103): the NLSF quantiser of a
+ * SILK frame — laroia weights, interpolation, silk_NLSF_encode (first-stage VQ, survivors, delayed-decision trellis), silk_NLSF_decode, the stabiliser
+ * and silk_NLSF2A for both half-frames.  One record per stream: in: NLSF_Q15 (unquantised), prev_NLSFq_Q15, NLSFInterpCoef_Q2, signalType,
+ * useInterpolatedNLSFs, speech_activity_Q8, NLSF_MSVQ_Survivors (2..32); out: NLSF_Q15 (quantised), NLSFIndices [order + 1], PredCoef_Q12 [2][order].
+ * fs_kHz 8 / 12 (order 10) or 16 (order 16).  Bit-exact. */
+typedef struct {
+  int16_t NLSF_Q15[16];
+  int16_t prev_NLSFq_Q15[16];
+  int16_t PredCoef_Q12[2][16];
+  int8_t NLSFIndices[17];
+  int8_t NLSFInterpCoef_Q2, signalType, useInterpolatedNLSFs;
+  int32_t speech_activity_Q8, NLSF_MSVQ_Survivors;
+} OpusB200SilkNlsf;
+int opusb200_silk_process_nlsfs(OpusB200Ctx *ctx, OpusB200SilkNlsf *frames, int n, int fs_kHz, int nb_subfr, int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

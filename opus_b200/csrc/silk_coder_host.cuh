@@ -203,3 +203,33 @@ extern "C" int opusb200_silk_process_gains(OpusB200Ctx *c, OpusB200SilkGains *fr
   }
   return r;
 }
+
+// ---- silk_process_NLSFs for n streams (silk_nlsf.cuh: silk_process_nlsfs_thread): frames [n] records, in place ----
+#include "silk_nlsf.cuh"
+extern "C" __global__ void __launch_bounds__(64) ob_silk_process_nlsfs(ob::SilkNlsfParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_process_nlsfs_thread(p, s);
+}
+extern "C" int opusb200_silk_process_nlsfs(OpusB200Ctx *c, OpusB200SilkNlsf *frames, int n, int fs_kHz, int nb_subfr, int on_device) {
+  static_assert(sizeof(OpusB200SilkNlsf) == sizeof(ob::ObSilkNlsf), "OpusB200SilkNlsf mirrors ObSilkNlsf");
+  if (!c || !frames || n <= 0 || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16) || (nb_subfr != 2 && nb_subfr != 4)) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkNlsfParams p;
+  p.n = n; p.wb = fs_kHz == 16; p.nb_subfr = nb_subfr;
+  const size_t bytes = sizeof(ob::ObSilkNlsf) * (size_t)n;
+  ob::ObSilkNlsf *d = (ob::ObSilkNlsf *)frames;
+  if (!on_device) {
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMemcpyAsync(d, frames, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { cudaFree(d); return OPUSB200_INTERNAL_ERROR; }
+  }
+  p.frames = d;
+  ob_silk_process_nlsfs<<<(n + 63) / 64, 64, 0, c->stream>>>(p);
+  c->launches++;
+  int r = cudaGetLastError() == cudaSuccess ? OPUSB200_OK : OPUSB200_INTERNAL_ERROR;
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d);
+  }
+  return r;
+}

@@ -1,0 +1,447 @@
+// silk_nlsf.cuh — the NLSF processing of a SILK frame, one THREAD per stream: silk_process_NLSFs (silk/process_NLSFs.c:35-107) with
+// silk_NLSF_VQ_weights_laroia (NLSF_VQ_weights_laroia.c:41-80), silk_interpolate (interpolate.c:35-51), silk_NLSF_encode (NLSF_encode.c:38-124: first-stage
+// VQ over the 32 codebook vectors, NLSF_VQ.c:35-76; survivors sorted by silk_insertion_sort_increasing, sort.c:40-82; per survivor the delayed-decision
+// trellis quantiser of the residual, NLSF_del_dec_quant.c:35-215), silk_NLSF_decode (NLSF_decode.c:35-93), silk_NLSF_unpack (NLSF_unpack.c:35-54),
+// silk_NLSF_stabilize (NLSF_stabilize.c:46-142) and silk_NLSF2A (NLSF2A.c:45-140) with silk_LPC_fit (LPC_fit.c:36-82), silk_LPC_inverse_pred_gain
+// (LPC_inv_pred_gain.c:43-141) and silk_bwexpander_32 (bwexpander_32.c:36-50).  Everything is serial integer arithmetic on one 10 / 16 coefficient vector
+// (a survivor search with data-dependent trellis decisions), so the parallel axis is the batch, as in the other index-producing kernels; the tables are
+// the generated silk_tables_data.h.  Integer work: bit-exact.
+#pragma once
+#include "simt.cuh"
+#include "silk_ops.cuh"   // silk_smulwb, silk_lin2log
+#include "silk_tables_data.h"
+
+namespace ob {
+constexpr int kNlsfMaxOrder = 16, kNlsfStates = 4, kNlsfAmp = 4, kNlsfAmpExt = 10;
+struct ObSilkNlsf {   // == OpusB200SilkNlsf (include/opus_b200.h): one stream's view of silk_encoder_state for silk_process_NLSFs
+  int16_t NLSF_Q15[16];          // in: unquantised, out: quantised
+  int16_t prev_NLSFq_Q15[16];
+  int16_t PredCoef_Q12[2][16];   // out
+  int8_t NLSFIndices[17];        // out
+  int8_t NLSFInterpCoef_Q2, signalType, useInterpolatedNLSFs;
+  int32_t speech_activity_Q8, NLSF_MSVQ_Survivors;
+};
+struct SilkNlsfParams { ObSilkNlsf *frames; int n, wb, nb_subfr; };
+
+OB_DEV int32_t nl_smulbb(int32_t a, int32_t b) { return (int32_t)(int16_t)a * (int32_t)(int16_t)b; }
+OB_DEV int32_t nl_smmul(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * b) >> 32); }
+OB_DEV int32_t nl_smulww(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * b) >> 16); }
+OB_DEV int32_t nl_rr(int32_t a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
+OB_DEV int64_t nl_rr64(int64_t a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
+OB_DEV int32_t nl_abs(int32_t a) { return a < 0 ? -a : a; }
+OB_DEV int32_t nl_lshift_sat32(int32_t a, int s) {
+  const int32_t lo = INT32_MIN >> s, hi = INT32_MAX >> s;
+  a = a < lo ? lo : a > hi ? hi : a;
+  return (int32_t)((uint32_t)a << s);
+}
+OB_DEV int32_t nl_sub_sat32(int32_t a, int32_t b) {
+  const int64_t d = (int64_t)a - b;
+  return d > INT32_MAX ? INT32_MAX : d < INT32_MIN ? INT32_MIN : (int32_t)d;
+}
+// silk_DIV32_varQ / silk_INVERSE32_varQ (silk/Inlines.h:93-178)
+OB_DEV int32_t nl_div32_varQ(int32_t a32, int32_t b32, int Qres) {
+  const int a_headrm = clz32((uint32_t)nl_abs(a32)) - 1, b_headrm = clz32((uint32_t)nl_abs(b32)) - 1;
+  int32_t a_nrm = (int32_t)((uint32_t)a32 << a_headrm);
+  const int32_t b_nrm = (int32_t)((uint32_t)b32 << b_headrm), b_inv = (INT32_MAX >> 2) / (b_nrm >> 16);
+  int32_t result = silk_smulwb(a_nrm, b_inv);
+  a_nrm = (int32_t)((uint32_t)a_nrm - ((uint32_t)nl_smmul(b_nrm, result) << 3));
+  result = result + silk_smulwb(a_nrm, b_inv);
+  const int lshift = 29 + a_headrm - b_headrm - Qres;
+  if (lshift < 0) return nl_lshift_sat32(result, -lshift);
+  return lshift < 32 ? result >> lshift : 0;
+}
+OB_DEV int32_t nl_inverse32_varQ(int32_t b32, int Qres) {
+  const int b_headrm = clz32((uint32_t)nl_abs(b32)) - 1;
+  const int32_t b_nrm = (int32_t)((uint32_t)b32 << b_headrm), b_inv = (INT32_MAX >> 2) / (b_nrm >> 16);
+  int32_t result = (int32_t)((uint32_t)b_inv << 16);
+  const int32_t err_Q32 = (int32_t)((uint32_t)(((int32_t)1 << 29) - silk_smulwb(b_nrm, b_inv)) << 3);
+  result = (int32_t)(result + (((int64_t)err_Q32 * b_inv) >> 16));
+  const int lshift = 61 - b_headrm - Qres;
+  if (lshift <= 0) return nl_lshift_sat32(result, -lshift);
+  return lshift < 32 ? result >> lshift : 0;
+}
+struct NlsfCB {   // silk_NLSF_CB_struct (silk/structs.h:84-97) of silk_NLSF_CB_NB_MB / silk_NLSF_CB_WB
+  int order, quantStepSize_Q16, invQuantStepSize_Q6;
+  const unsigned char *CB1_NLSF_Q8;
+  const short *CB1_Wght_Q9;
+  const unsigned char *CB1_iCDF, *pred_Q8, *ec_sel, *ec_Rates_Q5;
+  const short *deltaMin_Q15;
+};
+OB_DEV NlsfCB nlsf_cb(int wb) {
+  NlsfCB cb;
+  cb.order = wb ? 16 : 10;
+  cb.quantStepSize_Q16 = wb ? 9830 : 11796;    // SILK_FIX_CONST(0.15 / 0.18, 16)
+  cb.invQuantStepSize_Q6 = wb ? 427 : 356;     // SILK_FIX_CONST(1 / 0.15, 6), (1 / 0.18, 6)
+  cb.CB1_NLSF_Q8 = ob_silk_NLSF_CB1_Q8 + (wb ? 320 : 0);
+  cb.CB1_Wght_Q9 = ob_silk_NLSF_CB1_Wght_Q9 + (wb ? 320 : 0);
+  cb.CB1_iCDF = ob_silk_NLSF_CB1_iCDF + (wb ? 64 : 0);
+  cb.pred_Q8 = ob_silk_NLSF_PRED_Q8 + (wb ? 18 : 0);
+  cb.ec_sel = ob_silk_NLSF_CB2_SELECT + (wb ? 160 : 0);
+  cb.ec_Rates_Q5 = ob_silk_NLSF_CB2_BITS_Q5 + (wb ? 72 : 0);
+  cb.deltaMin_Q15 = ob_silk_NLSF_DELTA_MIN_Q15 + (wb ? 11 : 0);
+  return cb;
+}
+// silk_insertion_sort_increasing: the K smallest of a[0..L) in order, with their indices
+OB_DEV void nlsf_sort_increasing(int32_t *a, int *idx, int L, int K) {
+  for (int i = 0; i < K; i++) idx[i] = i;
+  for (int i = 1; i < K; i++) {
+    const int32_t value = a[i];
+    int j;
+    for (j = i - 1; j >= 0 && value < a[j]; j--) { a[j + 1] = a[j]; idx[j + 1] = idx[j]; }
+    a[j + 1] = value;
+    idx[j + 1] = i;
+  }
+  for (int i = K; i < L; i++) {
+    const int32_t value = a[i];
+    if (value < a[K - 1]) {
+      int j;
+      for (j = K - 2; j >= 0 && value < a[j]; j--) { a[j + 1] = a[j]; idx[j + 1] = idx[j]; }
+      a[j + 1] = value;
+      idx[j + 1] = i;
+    }
+  }
+}
+OB_DEVNI void nlsf_stabilize(int16_t *NLSF_Q15, const short *NDeltaMin_Q15, int L) {
+  for (int loops = 0; loops < 20; loops++) {
+    int32_t min_diff = NLSF_Q15[0] - NDeltaMin_Q15[0], diff;
+    int I = 0;
+    for (int i = 1; i <= L - 1; i++) {
+      diff = NLSF_Q15[i] - (NLSF_Q15[i - 1] + NDeltaMin_Q15[i]);
+      if (diff < min_diff) { min_diff = diff; I = i; }
+    }
+    diff = (1 << 15) - (NLSF_Q15[L - 1] + NDeltaMin_Q15[L]);
+    if (diff < min_diff) { min_diff = diff; I = L; }
+    if (min_diff >= 0) return;
+    if (I == 0) NLSF_Q15[0] = NDeltaMin_Q15[0];
+    else if (I == L) NLSF_Q15[L - 1] = (int16_t)((1 << 15) - NDeltaMin_Q15[L]);
+    else {
+      int32_t min_center = 0, max_center = 1 << 15;
+      for (int k = 0; k < I; k++) min_center += NDeltaMin_Q15[k];
+      min_center += NDeltaMin_Q15[I] >> 1;
+      for (int k = L; k > I; k--) max_center -= NDeltaMin_Q15[k];
+      max_center -= NDeltaMin_Q15[I] >> 1;
+      int32_t c = nl_rr((int32_t)NLSF_Q15[I - 1] + (int32_t)NLSF_Q15[I], 1);
+      if (min_center > max_center) c = c > min_center ? min_center : c < max_center ? max_center : c;   // silk_LIMIT_32 orders its bounds itself
+      else c = c > max_center ? max_center : c < min_center ? min_center : c;
+      NLSF_Q15[I - 1] = (int16_t)((int16_t)c - (NDeltaMin_Q15[I] >> 1));
+      NLSF_Q15[I] = (int16_t)(NLSF_Q15[I - 1] + NDeltaMin_Q15[I]);
+    }
+  }
+  // fall back: sort, then force the spacings (:112-141)
+  for (int i = 1; i < L; i++) {
+    const int value = NLSF_Q15[i];
+    int j;
+    for (j = i - 1; j >= 0 && value < NLSF_Q15[j]; j--) NLSF_Q15[j + 1] = NLSF_Q15[j];
+    NLSF_Q15[j + 1] = (int16_t)value;
+  }
+  NLSF_Q15[0] = NLSF_Q15[0] > NDeltaMin_Q15[0] ? NLSF_Q15[0] : NDeltaMin_Q15[0];
+  for (int i = 1; i < L; i++) {
+    int32_t s = (int32_t)NLSF_Q15[i - 1] + NDeltaMin_Q15[i];
+    s = s > 32767 ? 32767 : s < -32768 ? -32768 : s;
+    NLSF_Q15[i] = (int16_t)(NLSF_Q15[i] > s ? NLSF_Q15[i] : s);
+  }
+  { const int v = (1 << 15) - NDeltaMin_Q15[L]; NLSF_Q15[L - 1] = (int16_t)(NLSF_Q15[L - 1] < v ? NLSF_Q15[L - 1] : v); }
+  for (int i = L - 2; i >= 0; i--) { const int v = NLSF_Q15[i + 1] - NDeltaMin_Q15[i + 1]; NLSF_Q15[i] = (int16_t)(NLSF_Q15[i] < v ? NLSF_Q15[i] : v); }
+}
+OB_DEV int32_t nlsf_w(int32_t d) { return ((int32_t)1 << 17) / (d > 1 ? d : 1); }   // 1 << (15 + NLSF_W_Q) over the clamped spacing
+OB_DEVNI void nlsf_weights_laroia(int16_t *pW, const int16_t *x, int D) {
+  int32_t t1 = nlsf_w(x[0]), t2 = nlsf_w(x[1] - x[0]);
+  pW[0] = (int16_t)(t1 + t2 < 32767 ? t1 + t2 : 32767);
+  for (int k = 1; k < D - 1; k += 2) {
+    t1 = nlsf_w(x[k + 1] - x[k]);
+    pW[k] = (int16_t)(t1 + t2 < 32767 ? t1 + t2 : 32767);
+    t2 = nlsf_w(x[k + 2] - x[k + 1]);
+    pW[k + 1] = (int16_t)(t1 + t2 < 32767 ? t1 + t2 : 32767);
+  }
+  t1 = nlsf_w((1 << 15) - x[D - 1]);
+  pW[D - 1] = (int16_t)(t1 + t2 < 32767 ? t1 + t2 : 32767);
+}
+OB_DEV void nlsf_unpack(int16_t *ec_ix, unsigned char *pred_Q8, const NlsfCB &cb, int CB1_index) {
+  const unsigned char *sel = &cb.ec_sel[CB1_index * cb.order / 2];
+  for (int i = 0; i < cb.order; i += 2) {
+    const unsigned char entry = *sel++;
+    ec_ix[i] = (int16_t)(((entry >> 1) & 7) * 9);
+    pred_Q8[i] = cb.pred_Q8[i + (entry & 1) * (cb.order - 1)];
+    ec_ix[i + 1] = (int16_t)(((entry >> 5) & 7) * 9);
+    pred_Q8[i + 1] = cb.pred_Q8[i + ((entry >> 4) & 1) * (cb.order - 1) + 1];
+  }
+}
+OB_DEVNI void nlsf_decode(int16_t *pNLSF_Q15, const int8_t *NLSFIndices, const NlsfCB &cb) {
+  unsigned char pred_Q8[kNlsfMaxOrder];
+  int16_t ec_ix[kNlsfMaxOrder], res_Q10[kNlsfMaxOrder];
+  const unsigned char *el = &cb.CB1_NLSF_Q8[NLSFIndices[0] * cb.order];
+  const short *wq = &cb.CB1_Wght_Q9[NLSFIndices[0] * cb.order];
+  nlsf_unpack(ec_ix, pred_Q8, cb, NLSFIndices[0]);
+  int out_Q10 = 0;
+  for (int i = cb.order - 1; i >= 0; i--) {   // silk_NLSF_residual_dequant
+    const int pred_Q10 = nl_smulbb(out_Q10, (int16_t)pred_Q8[i]) >> 8;
+    out_Q10 = (int)((uint32_t)(int32_t)NLSFIndices[1 + i] << 10);
+    if (out_Q10 > 0) out_Q10 -= 102;        // SILK_FIX_CONST(NLSF_QUANT_LEVEL_ADJ, 10)
+    else if (out_Q10 < 0) out_Q10 += 102;
+    out_Q10 = pred_Q10 + silk_smulwb(out_Q10, cb.quantStepSize_Q16);
+    res_Q10[i] = (int16_t)out_Q10;
+  }
+  for (int i = 0; i < cb.order; i++) {
+    const int32_t t = ((int32_t)((uint32_t)(int32_t)res_Q10[i] << 14)) / wq[i] + ((int32_t)(int16_t)el[i] << 7);
+    pNLSF_Q15[i] = (int16_t)(t < 0 ? 0 : t > 32767 ? 32767 : t);
+  }
+  nlsf_stabilize(pNLSF_Q15, cb.deltaMin_Q15, cb.order);
+}
+OB_DEVNI int32_t nlsf_del_dec_quant(int8_t *indices, const int16_t *x_Q10, const int16_t *w_Q5, const unsigned char *pred_coef_Q8, const int16_t *ec_ix,
+                                    const unsigned char *ec_rates_Q5, int quant_step_size_Q16, int16_t inv_quant_step_size_Q6, int32_t mu_Q20, int order) {
+  int ind_sort[kNlsfStates];
+  int8_t ind[kNlsfStates][kNlsfMaxOrder];
+  int16_t prev_out_Q10[2 * kNlsfStates];
+  int32_t RD_Q25[2 * kNlsfStates], RD_min_Q25[kNlsfStates], RD_max_Q25[kNlsfStates];
+  int16_t out0_table[2 * kNlsfAmpExt], out1_table[2 * kNlsfAmpExt];
+  for (int i = -kNlsfAmpExt; i <= kNlsfAmpExt - 1; i++) {
+    int16_t o0 = (int16_t)(i * 1024), o1 = (int16_t)(o0 + 1024);
+    if (i > 0) { o0 = (int16_t)(o0 - 102); o1 = (int16_t)(o1 - 102); }
+    else if (i == 0) o1 = (int16_t)(o1 - 102);
+    else if (i == -1) o0 = (int16_t)(o0 + 102);
+    else { o0 = (int16_t)(o0 + 102); o1 = (int16_t)(o1 + 102); }
+    out0_table[i + kNlsfAmpExt] = (int16_t)(nl_smulbb(o0, quant_step_size_Q16) >> 16);
+    out1_table[i + kNlsfAmpExt] = (int16_t)(nl_smulbb(o1, quant_step_size_Q16) >> 16);
+  }
+  int nStates = 1;
+  RD_Q25[0] = 0;
+  prev_out_Q10[0] = 0;
+  for (int i = order - 1; i >= 0; i--) {
+    const unsigned char *rates_Q5 = &ec_rates_Q5[ec_ix[i]];
+    const int in_Q10 = x_Q10[i];
+    for (int j = 0; j < nStates; j++) {
+      const int pred_Q10 = nl_smulbb((int16_t)pred_coef_Q8[i], prev_out_Q10[j]) >> 8;
+      const int res_Q10 = in_Q10 - pred_Q10;
+      int ind_tmp = nl_smulbb(inv_quant_step_size_Q6, res_Q10) >> 16;
+      ind_tmp = ind_tmp < -kNlsfAmpExt ? -kNlsfAmpExt : ind_tmp > kNlsfAmpExt - 1 ? kNlsfAmpExt - 1 : ind_tmp;
+      ind[j][i] = (int8_t)ind_tmp;
+      const int16_t out0_Q10 = (int16_t)(out0_table[ind_tmp + kNlsfAmpExt] + pred_Q10), out1_Q10 = (int16_t)(out1_table[ind_tmp + kNlsfAmpExt] + pred_Q10);
+      prev_out_Q10[j] = out0_Q10;
+      prev_out_Q10[j + nStates] = out1_Q10;
+      int rate0_Q5, rate1_Q5;
+      if (ind_tmp + 1 >= kNlsfAmp) {
+        if (ind_tmp + 1 == kNlsfAmp) { rate0_Q5 = rates_Q5[ind_tmp + kNlsfAmp]; rate1_Q5 = 280; }
+        else { rate0_Q5 = (280 - 43 * kNlsfAmp) + nl_smulbb(43, ind_tmp); rate1_Q5 = rate0_Q5 + 43; }
+      } else if (ind_tmp <= -kNlsfAmp) {
+        if (ind_tmp == -kNlsfAmp) { rate0_Q5 = 280; rate1_Q5 = rates_Q5[ind_tmp + 1 + kNlsfAmp]; }
+        else { rate0_Q5 = (280 - 43 * kNlsfAmp) + nl_smulbb(-43, ind_tmp); rate1_Q5 = rate0_Q5 - 43; }
+      } else { rate0_Q5 = rates_Q5[ind_tmp + kNlsfAmp]; rate1_Q5 = rates_Q5[ind_tmp + 1 + kNlsfAmp]; }
+      const int32_t RD_tmp = RD_Q25[j];
+      int diff_Q10 = in_Q10 - out0_Q10;
+      RD_Q25[j] = (RD_tmp + nl_smulbb(diff_Q10, diff_Q10) * w_Q5[i]) + nl_smulbb(mu_Q20, rate0_Q5);
+      diff_Q10 = in_Q10 - out1_Q10;
+      RD_Q25[j + nStates] = (RD_tmp + nl_smulbb(diff_Q10, diff_Q10) * w_Q5[i]) + nl_smulbb(mu_Q20, rate1_Q5);
+    }
+    if (nStates <= kNlsfStates / 2) {
+      for (int j = 0; j < nStates; j++) ind[j + nStates][i] = (int8_t)(ind[j][i] + 1);
+      nStates <<= 1;
+      for (int j = nStates; j < kNlsfStates; j++) ind[j][i] = ind[j - nStates][i];
+    } else {
+      for (int j = 0; j < kNlsfStates; j++) {   // sort lower and upper half of RD_Q25, pairwise
+        if (RD_Q25[j] > RD_Q25[j + kNlsfStates]) {
+          RD_max_Q25[j] = RD_Q25[j];
+          RD_min_Q25[j] = RD_Q25[j + kNlsfStates];
+          RD_Q25[j] = RD_min_Q25[j];
+          RD_Q25[j + kNlsfStates] = RD_max_Q25[j];
+          const int16_t t = prev_out_Q10[j];
+          prev_out_Q10[j] = prev_out_Q10[j + kNlsfStates];
+          prev_out_Q10[j + kNlsfStates] = t;
+          ind_sort[j] = j + kNlsfStates;
+        } else {
+          RD_min_Q25[j] = RD_Q25[j];
+          RD_max_Q25[j] = RD_Q25[j + kNlsfStates];
+          ind_sort[j] = j;
+        }
+      }
+      while (true) {   // the best of the losing half replaces the worst of the winning half while that improves things
+        int32_t min_max_Q25 = INT32_MAX, max_min_Q25 = 0;
+        int ind_min_max = 0, ind_max_min = 0;
+        for (int j = 0; j < kNlsfStates; j++) {
+          if (min_max_Q25 > RD_max_Q25[j]) { min_max_Q25 = RD_max_Q25[j]; ind_min_max = j; }
+          if (max_min_Q25 < RD_min_Q25[j]) { max_min_Q25 = RD_min_Q25[j]; ind_max_min = j; }
+        }
+        if (min_max_Q25 >= max_min_Q25) break;
+        ind_sort[ind_max_min] = ind_sort[ind_min_max] ^ kNlsfStates;
+        RD_Q25[ind_max_min] = RD_Q25[ind_min_max + kNlsfStates];
+        prev_out_Q10[ind_max_min] = prev_out_Q10[ind_min_max + kNlsfStates];
+        RD_min_Q25[ind_max_min] = 0;
+        RD_max_Q25[ind_min_max] = INT32_MAX;
+        for (int k = 0; k < kNlsfMaxOrder; k++) ind[ind_max_min][k] = ind[ind_min_max][k];
+      }
+      for (int j = 0; j < kNlsfStates; j++) ind[j][i] = (int8_t)(ind[j][i] + (ind_sort[j] >> 2));
+    }
+  }
+  int ind_tmp = 0;
+  int32_t min_Q25 = INT32_MAX;
+  for (int j = 0; j < 2 * kNlsfStates; j++) if (min_Q25 > RD_Q25[j]) { min_Q25 = RD_Q25[j]; ind_tmp = j; }
+  for (int j = 0; j < order; j++) indices[j] = ind[ind_tmp & (kNlsfStates - 1)][j];
+  indices[0] = (int8_t)(indices[0] + (ind_tmp >> 2));
+  return min_Q25;
+}
+OB_DEVNI void nlsf_encode(int8_t *NLSFIndices, int16_t *pNLSF_Q15, const NlsfCB &cb, const int16_t *pW_Q2, int NLSF_mu_Q20, int nSurvivors, int signalType) {
+  int32_t err_Q24[32], RD_Q25[32];
+  int tempIndices1[32];
+  int8_t tempIndices2[32 * kNlsfMaxOrder];
+  int16_t res_Q10[kNlsfMaxOrder], W_adj_Q5[kNlsfMaxOrder], ec_ix[kNlsfMaxOrder];
+  unsigned char pred_Q8[kNlsfMaxOrder];
+  nlsf_stabilize(pNLSF_Q15, cb.deltaMin_Q15, cb.order);
+  for (int i = 0; i < 32; i++) {   // silk_NLSF_VQ
+    const unsigned char *c = &cb.CB1_NLSF_Q8[i * cb.order];
+    const short *w = &cb.CB1_Wght_Q9[i * cb.order];
+    int32_t sum = 0, pred = 0;
+    for (int m = cb.order - 2; m >= 0; m -= 2) {
+      int32_t dw = nl_smulbb(pNLSF_Q15[m + 1] - ((int32_t)c[m + 1] << 7), w[m + 1]);
+      sum = sum + nl_abs(dw - (pred >> 1));
+      pred = dw;
+      dw = nl_smulbb(pNLSF_Q15[m] - ((int32_t)c[m] << 7), w[m]);
+      sum = sum + nl_abs(dw - (pred >> 1));
+      pred = dw;
+    }
+    err_Q24[i] = sum;
+  }
+  nlsf_sort_increasing(err_Q24, tempIndices1, 32, nSurvivors);
+  for (int s = 0; s < nSurvivors; s++) {
+    const int ind1 = tempIndices1[s];
+    const unsigned char *el = &cb.CB1_NLSF_Q8[ind1 * cb.order];
+    const short *wq = &cb.CB1_Wght_Q9[ind1 * cb.order];
+    for (int i = 0; i < cb.order; i++) {
+      const int32_t W_tmp_Q9 = wq[i];
+      const int16_t tmp_Q15 = (int16_t)((int16_t)el[i] << 7);
+      res_Q10[i] = (int16_t)(nl_smulbb(pNLSF_Q15[i] - tmp_Q15, W_tmp_Q9) >> 14);
+      W_adj_Q5[i] = (int16_t)nl_div32_varQ((int32_t)pW_Q2[i], nl_smulbb(W_tmp_Q9, W_tmp_Q9), 21);
+    }
+    nlsf_unpack(ec_ix, pred_Q8, cb, ind1);
+    RD_Q25[s] = nlsf_del_dec_quant(&tempIndices2[s * kNlsfMaxOrder], res_Q10, W_adj_Q5, pred_Q8, ec_ix, cb.ec_Rates_Q5, cb.quantStepSize_Q16,
+                                   (int16_t)cb.invQuantStepSize_Q6, NLSF_mu_Q20, cb.order);
+    const unsigned char *iCDF_ptr = &cb.CB1_iCDF[(signalType >> 1) * 32];
+    const int prob_Q8 = ind1 == 0 ? 256 - iCDF_ptr[ind1] : iCDF_ptr[ind1 - 1] - iCDF_ptr[ind1];
+    const int bits_q7 = (8 << 7) - silk_lin2log(prob_Q8);
+    RD_Q25[s] = RD_Q25[s] + nl_smulbb(bits_q7, NLSF_mu_Q20 >> 2);
+  }
+  int bestIndex;
+  nlsf_sort_increasing(RD_Q25, &bestIndex, nSurvivors, 1);
+  NLSFIndices[0] = (int8_t)tempIndices1[bestIndex];
+  for (int i = 0; i < cb.order; i++) NLSFIndices[1 + i] = tempIndices2[bestIndex * kNlsfMaxOrder + i];
+  nlsf_decode(pNLSF_Q15, NLSFIndices, cb);
+}
+OB_DEV void nlsf_bwexpander_32(int32_t *ar, int d, int32_t chirp_Q16) {
+  const int32_t chirp_minus_one_Q16 = chirp_Q16 - 65536;
+  for (int i = 0; i < d - 1; i++) {
+    ar[i] = nl_smulww(chirp_Q16, ar[i]);
+    chirp_Q16 += nl_rr(chirp_Q16 * chirp_minus_one_Q16, 16);
+  }
+  ar[d - 1] = nl_smulww(chirp_Q16, ar[d - 1]);
+}
+OB_DEVNI int32_t nlsf_lpc_inverse_pred_gain(const int16_t *A_Q12, int order) {
+  const int QA = 24;
+  const int32_t A_LIMIT = 16773022;   // SILK_FIX_CONST(0.99975, 24)
+  int32_t A_QA[kNlsfMaxOrder], DC_resp = 0, invGain_Q30 = 1 << 30;
+  for (int k = 0; k < order; k++) { DC_resp += A_Q12[k]; A_QA[k] = (int32_t)((uint32_t)(int32_t)A_Q12[k] << (QA - 12)); }
+  if (DC_resp >= 4096) return 0;
+  int k;
+  for (k = order - 1; k > 0; k--) {
+    if (A_QA[k] > A_LIMIT || A_QA[k] < -A_LIMIT) return 0;
+    const int32_t rc_Q31 = -(int32_t)((uint32_t)A_QA[k] << (31 - QA)), rc_mult1_Q30 = (1 << 30) - nl_smmul(rc_Q31, rc_Q31);
+    invGain_Q30 = (int32_t)((uint32_t)nl_smmul(invGain_Q30, rc_mult1_Q30) << 2);
+    if (invGain_Q30 < 107374) return 0;   // SILK_FIX_CONST(1.0f / MAX_PREDICTION_POWER_GAIN, 30)
+    const int mult2Q = 32 - clz32((uint32_t)nl_abs(rc_mult1_Q30));
+    const int32_t rc_mult2 = nl_inverse32_varQ(rc_mult1_Q30, mult2Q + 30);
+    for (int n = 0; n < (k + 1) >> 1; n++) {
+      const int32_t tmp1 = A_QA[n], tmp2 = A_QA[k - n - 1];
+      int64_t tmp64 = nl_rr64((int64_t)nl_sub_sat32(tmp1, (int32_t)nl_rr64((int64_t)tmp2 * rc_Q31, 31)) * rc_mult2, mult2Q);
+      if (tmp64 > INT32_MAX || tmp64 < INT32_MIN) return 0;
+      A_QA[n] = (int32_t)tmp64;
+      tmp64 = nl_rr64((int64_t)nl_sub_sat32(tmp2, (int32_t)nl_rr64((int64_t)tmp1 * rc_Q31, 31)) * rc_mult2, mult2Q);
+      if (tmp64 > INT32_MAX || tmp64 < INT32_MIN) return 0;
+      A_QA[k - n - 1] = (int32_t)tmp64;
+    }
+  }
+  if (A_QA[k] > A_LIMIT || A_QA[k] < -A_LIMIT) return 0;
+  const int32_t rc_Q31 = -(int32_t)((uint32_t)A_QA[0] << (31 - QA)), rc_mult1_Q30 = (1 << 30) - nl_smmul(rc_Q31, rc_Q31);
+  invGain_Q30 = (int32_t)((uint32_t)nl_smmul(invGain_Q30, rc_mult1_Q30) << 2);
+  if (invGain_Q30 < 107374) return 0;
+  return invGain_Q30;
+}
+OB_DEV void nlsf_find_poly(int32_t *out, const int32_t *cLSF, int dd) {
+  const int QA = 16;
+  out[0] = 1 << QA;
+  out[1] = -cLSF[0];
+  for (int k = 1; k < dd; k++) {
+    const int32_t ftmp = cLSF[2 * k];
+    out[k + 1] = (int32_t)((uint32_t)out[k - 1] << 1) - (int32_t)nl_rr64((int64_t)ftmp * out[k], QA);
+    for (int n = k; n > 1; n--) out[n] += out[n - 2] - (int32_t)nl_rr64((int64_t)ftmp * out[n - 1], QA);
+    out[1] -= ftmp;
+  }
+}
+OB_DEVNI void nlsf_NLSF2A(int16_t *a_Q12, const int16_t *NLSF, int d) {
+  const unsigned char ordering16[16] = {0, 15, 8, 7, 4, 11, 12, 3, 2, 13, 10, 5, 6, 9, 14, 1}, ordering10[10] = {0, 9, 6, 3, 4, 5, 8, 1, 2, 7};
+  const int QA = 16, dd = d >> 1;
+  int32_t cos_LSF_QA[kNlsfMaxOrder], P[kNlsfMaxOrder / 2 + 1], Q[kNlsfMaxOrder / 2 + 1], a32_QA1[kNlsfMaxOrder];
+  for (int k = 0; k < d; k++) {
+    const int32_t f_int = NLSF[k] >> (15 - 7), f_frac = NLSF[k] - (f_int << (15 - 7));
+    const int32_t cos_val = ob_silk_LSFCosTab_Q12[f_int], delta = ob_silk_LSFCosTab_Q12[f_int + 1] - cos_val;
+    cos_LSF_QA[d == 16 ? ordering16[k] : ordering10[k]] = nl_rr((int32_t)((uint32_t)cos_val << 8) + delta * f_frac, 20 - QA);
+  }
+  nlsf_find_poly(P, &cos_LSF_QA[0], dd);
+  nlsf_find_poly(Q, &cos_LSF_QA[1], dd);
+  for (int k = 0; k < dd; k++) {
+    const int32_t Ptmp = P[k + 1] + P[k], Qtmp = Q[k + 1] - Q[k];
+    a32_QA1[k] = -Qtmp - Ptmp;
+    a32_QA1[d - k - 1] = Qtmp - Ptmp;
+  }
+  {   // silk_LPC_fit(a_Q12, a32_QA1, 12, QA + 1, d)
+    const int sh = QA + 1 - 12;
+    int i, idx = 0;
+    for (i = 0; i < 10; i++) {
+      int32_t maxabs = 0;
+      for (int k = 0; k < d; k++) {
+        const int32_t absval = nl_abs(a32_QA1[k]);
+        if (absval > maxabs) { maxabs = absval; idx = k; }
+      }
+      maxabs = nl_rr(maxabs, sh);
+      if (maxabs > 32767) {
+        maxabs = maxabs < 163838 ? maxabs : 163838;
+        const int32_t chirp_Q16 = 65470 - ((int32_t)((uint32_t)(maxabs - 32767) << 14)) / ((maxabs * (idx + 1)) >> 2);   // SILK_FIX_CONST(0.999, 16)
+        nlsf_bwexpander_32(a32_QA1, d, chirp_Q16);
+      } else break;
+    }
+    if (i == 10) {
+      for (int k = 0; k < d; k++) {
+        const int32_t v = nl_rr(a32_QA1[k], sh);
+        a_Q12[k] = (int16_t)(v > 32767 ? 32767 : v < -32768 ? -32768 : v);
+        a32_QA1[k] = (int32_t)((uint32_t)(int32_t)a_Q12[k] << sh);
+      }
+    } else for (int k = 0; k < d; k++) a_Q12[k] = (int16_t)nl_rr(a32_QA1[k], sh);
+  }
+  for (int i = 0; nlsf_lpc_inverse_pred_gain(a_Q12, d) == 0 && i < 16; i++) {
+    nlsf_bwexpander_32(a32_QA1, d, 65536 - (int32_t)((uint32_t)2 << i));
+    for (int k = 0; k < d; k++) a_Q12[k] = (int16_t)nl_rr(a32_QA1[k], QA + 1 - 12);
+  }
+}
+OB_DEV void nlsf_interpolate(int16_t *xi, const int16_t *x0, const int16_t *x1, int ifact_Q2, int d) {
+  for (int i = 0; i < d; i++) xi[i] = (int16_t)(x0[i] + (nl_smulbb(x1[i] - x0[i], ifact_Q2) >> 2));
+}
+OB_DEV void silk_process_nlsfs_thread(const SilkNlsfParams &p, int s) {
+  ObSilkNlsf f = p.frames[s];
+  const NlsfCB cb = nlsf_cb(p.wb);
+  const int order = cb.order;
+  int16_t tmp0[kNlsfMaxOrder], W[kNlsfMaxOrder], W0[kNlsfMaxOrder];
+  int NLSF_mu_Q20 = 3146 + silk_smulwb(-268434, f.speech_activity_Q8);   // SILK_FIX_CONST(0.003, 20), SILK_FIX_CONST(-0.001, 28)
+  if (p.nb_subfr == 2) NLSF_mu_Q20 = NLSF_mu_Q20 + (NLSF_mu_Q20 >> 1);
+  nlsf_weights_laroia(W, f.NLSF_Q15, order);
+  const int doInterpolate = f.useInterpolatedNLSFs == 1 && f.NLSFInterpCoef_Q2 < 4;
+  if (doInterpolate) {
+    nlsf_interpolate(tmp0, f.prev_NLSFq_Q15, f.NLSF_Q15, f.NLSFInterpCoef_Q2, order);
+    nlsf_weights_laroia(W0, tmp0, order);
+    const int16_t i_sqr_Q15 = (int16_t)(nl_smulbb(f.NLSFInterpCoef_Q2, f.NLSFInterpCoef_Q2) << 11);
+    for (int i = 0; i < order; i++) W[i] = (int16_t)((W[i] >> 1) + (nl_smulbb(W0[i], i_sqr_Q15) >> 16));
+  }
+  nlsf_encode(f.NLSFIndices, f.NLSF_Q15, cb, W, NLSF_mu_Q20, f.NLSF_MSVQ_Survivors, f.signalType);
+  nlsf_NLSF2A(f.PredCoef_Q12[1], f.NLSF_Q15, order);
+  if (doInterpolate) {
+    nlsf_interpolate(tmp0, f.prev_NLSFq_Q15, f.NLSF_Q15, f.NLSFInterpCoef_Q2, order);
+    nlsf_NLSF2A(f.PredCoef_Q12[0], tmp0, order);
+  } else for (int i = 0; i < order; i++) f.PredCoef_Q12[0][i] = f.PredCoef_Q12[1][i];
+  p.frames[s] = f;
+}
+}  // namespace ob

@@ -95,6 +95,13 @@ class Ops:
             raise capi.OpusB200Error(r, 'opusb200_silk_process_gains')
         return frames
 
+    def silk_process_nlsfs(self, frames, fs_kHz, nb_subfr):
+        """silk_process_NLSFs for n streams: frames = ctypes array of OpusB200SilkNlsf-shaped records (processed in place)"""
+        r = self._L.opusb200_silk_process_nlsfs(self._h, ctypes.cast(frames, ctypes.c_void_p), len(frames), fs_kHz, nb_subfr, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_process_nlsfs')
+        return frames
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

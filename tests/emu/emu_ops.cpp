@@ -546,3 +546,16 @@ extern "C" void emu_silk_process_gains(void *frames, int n, int nb_subfr, int su
   p.frames = (ObSilkGains *)frames; p.n = n; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length; p.nStatesDelayedDecision = nstates;
   emu_launch(silk_gains_entry, &p, (n + 31) / 32, 32, 0);
 }
+
+// ---- silk_process_NLSFs (silk_nlsf.cuh), thread per stream ----
+#include "../../opus_b200/csrc/silk_nlsf.cuh"
+static void silk_nlsf_entry(void *a) {
+  const SilkNlsfParams &p = *(const SilkNlsfParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_process_nlsfs_thread(p, s);
+}
+extern "C" void emu_silk_process_nlsfs(void *frames, int n, int wb, int nb_subfr) {
+  SilkNlsfParams p;
+  p.frames = (ObSilkNlsf *)frames; p.n = n; p.wb = wb; p.nb_subfr = nb_subfr;
+  emu_launch(silk_nlsf_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -270,3 +270,25 @@ def test_silk_process_gains_emulated():
                 assert np.array_equal(np.array(fa[0], np.float32).view(np.uint32), np.array(fb[0], np.float32).view(np.uint32)), (frame, s)
                 assert fa[1:] == fb[1:], (frame, s, fa, fb)
                 last[s] = recs[s].LastGainIndex
+
+
+@pytest.mark.parametrize('wb,nb_subfr', [(1, 4), (0, 2)])
+def test_silk_process_nlsfs_emulated(wb, nb_subfr):
+    """silk_process_NLSFs: the device source on the emulator against the oracle (pinned on the reference): indices, quantised NLSFs, both coefficient sets"""
+    from test_silk_nlsf_oracle_vs_ref import Nlsf, random_frame, same
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(30 + wb)
+    n, order = 40, 16 if wb else 10
+    prev = [None] * n
+    for frame in range(6):
+        recs = (Nlsf * n)()
+        want = []
+        for s in range(n):
+            recs[s] = random_frame(rng, wb, prev[s])
+            w = Nlsf.from_buffer_copy(bytes(recs[s]))
+            O.orc_silk_process_NLSFs(ctypes.byref(w), wb, nb_subfr)
+            want.append(w)
+        E.emu_silk_process_nlsfs(ctypes.cast(recs, ctypes.c_void_p), n, wb, nb_subfr)
+        for s in range(n):
+            assert same(recs[s], want[s], order), (frame, s, list(recs[s].NLSFIndices), list(want[s].NLSFIndices))
+            prev[s] = list(want[s].NLSF_Q15)

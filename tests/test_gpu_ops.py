@@ -373,3 +373,30 @@ def test_silk_process_gains():
                 recs[s].LastGainIndex = want[s].LastGainIndex
     print('bit-identical records: %d of %d' % (exact, total))
     assert exact >= 0.995 * total
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fs_kHz,nb_subfr', [(16, 4), (8, 4), (12, 2)])
+def test_silk_process_nlsfs(fs_kHz, nb_subfr):
+    """opusb200_silk_process_nlsfs against the oracle (pinned bit for bit on silk_process_NLSFs): NLSF indices, quantised NLSFs and the prediction
+    coefficients of both half-frames identical, for streams that carry their previous quantised NLSFs from frame to frame"""
+    import opus_b200
+    from test_silk_nlsf_oracle_vs_ref import Nlsf, random_frame, same
+    O = util.load_oracle()
+    ops = opus_b200.Ops()
+    wb = int(fs_kHz == 16)
+    rng = np.random.default_rng(40 + fs_kHz)
+    n, order = 300, 16 if wb else 10
+    prev = [None] * n
+    for frame in range(5):
+        recs = (Nlsf * n)()
+        want = []
+        for s in range(n):
+            recs[s] = random_frame(rng, wb, prev[s])
+            w = Nlsf.from_buffer_copy(bytes(recs[s]))
+            O.orc_silk_process_NLSFs(ctypes.byref(w), wb, nb_subfr)
+            want.append(w)
+        ops.silk_process_nlsfs(recs, fs_kHz, nb_subfr)
+        for s in range(n):
+            assert same(recs[s], want[s], order), (frame, s)
+            prev[s] = list(want[s].NLSF_Q15)
