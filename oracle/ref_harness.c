@@ -489,3 +489,22 @@ void refh_silk_NLSF_stabilize(opus_int16 *NLSF_Q15, int wb) {
   silk_NLSF_stabilize(NLSF_Q15, cb->deltaMin_Q15, cb->order);
 }
 opus_int32 refh_silk_LPC_inverse_pred_gain(const opus_int16 *A_Q12, int order) { return silk_LPC_inverse_pred_gain_c(A_Q12, order); }
+
+/* ---- silk_find_LPC_FLP on a scratch encoder state (silk/float/find_LPC_FLP.c:36-105) ---- */
+typedef struct {
+  opus_int16 NLSF_Q15[16];
+  opus_int16 prev_NLSFq_Q15[16];
+  float minInvGain;
+  opus_int32 useInterpolatedNLSFs, first_frame_after_reset;
+  opus_int32 NLSFInterpCoef_Q2;
+} RefhSilkFindLpc;   /* == OrcSilkFindLpc */
+void refh_silk_find_LPC(RefhSilkFindLpc *f, const float *x, int order, int nb_subfr, int subfr_length) {
+  static silk_encoder_state st;
+  memset(&st, 0, sizeof(st));
+  st.predictLPCOrder = order; st.nb_subfr = nb_subfr; st.subfr_length = subfr_length;
+  st.useInterpolatedNLSFs = f->useInterpolatedNLSFs; st.first_frame_after_reset = f->first_frame_after_reset;
+  memcpy(st.prev_NLSFq_Q15, f->prev_NLSFq_Q15, sizeof(st.prev_NLSFq_Q15));
+  silk_find_LPC_FLP(&st, f->NLSF_Q15, x, f->minInvGain, 0);
+  f->NLSFInterpCoef_Q2 = st.indices.NLSFInterpCoef_Q2;
+}
+void refh_silk_A2NLSF(opus_int16 *NLSF, opus_int32 *a_Q16, int d) { silk_A2NLSF(NLSF, a_Q16, d); }

@@ -500,3 +500,161 @@ void orc_silk_process_NLSFs(OrcSilkNlsf *f, int wb, int nb_subfr) {
     orc_silk_NLSF2A(f->PredCoef_Q12[0], pNLSF0_temp_Q15, order);
   } else memcpy(f->PredCoef_Q12[0], f->PredCoef_Q12[1], order * sizeof(int16_t));
 }
+
+/* ---- LPC estimation of a SILK frame: silk_find_LPC_FLP (silk/float/find_LPC_FLP.c:36-105) with silk_A2NLSF (silk/A2NLSF.c:45-267), the float wrappers
+ * silk_A2NLSF_FLP / silk_NLSF2A_FLP (silk/float/wrappers_FLP.c:36-72), silk_LPC_analysis_filter_FLP (orders 10 and 16,
+ * silk/float/LPC_analysis_filter_FLP.c:43-139, 214-248) and silk_energy_FLP (silk/float/energy_FLP.c:35-59) on the Burg restatement of silk_oracle.c. ---- */
+#include <math.h>
+float orc_silk_burg_modified(float *A, const float *x, float minInvGain, int subfr_length, int nb_subfr, int D); /* silk_oracle.c */
+static void a2nlsf_trans_poly(int32_t *p, int dd) {
+  int k, n;
+  for (k = 2; k <= dd; k++) {
+    for (n = dd; n > k; n--) p[n - 2] -= p[n];
+    p[k - 2] -= (int32_t)((uint32_t)p[k] << 1);
+  }
+}
+static int32_t a2nlsf_eval_poly(const int32_t *p, int32_t x, int dd) {
+  const int32_t x_Q16 = (int32_t)((uint32_t)x << 4);
+  int32_t y32 = p[dd];
+  int n;
+  for (n = dd - 1; n >= 0; n--) y32 = (int32_t)(p[n] + (((int64_t)y32 * x_Q16) >> 16)); /* silk_SMLAWW */
+  return y32;
+}
+static void a2nlsf_init(const int32_t *a_Q16, int32_t *P, int32_t *Q, int dd) {
+  int k;
+  P[dd] = 1 << 16;
+  Q[dd] = 1 << 16;
+  for (k = 0; k < dd; k++) {
+    P[k] = -a_Q16[dd - k - 1] - a_Q16[dd + k];
+    Q[k] = -a_Q16[dd - k - 1] + a_Q16[dd + k];
+  }
+  for (k = dd; k > 0; k--) {
+    P[k - 1] -= P[k];
+    Q[k - 1] += Q[k];
+  }
+  a2nlsf_trans_poly(P, dd);
+  a2nlsf_trans_poly(Q, dd);
+}
+void orc_silk_A2NLSF(int16_t *NLSF, int32_t *a_Q16, int d) {
+  const int dd = d >> 1;
+  int i = 0, k = 1, m, root_ix, ffrac;
+  int32_t xlo, xhi, xmid, ylo, yhi, ymid, thr = 0, nom, den, P[MAX_ORDER / 2 + 1], Q[MAX_ORDER / 2 + 1], *p = P;
+  a2nlsf_init(a_Q16, P, Q, dd);
+  xlo = ob_silk_LSFCosTab_Q12[0];
+  ylo = a2nlsf_eval_poly(p, xlo, dd);
+  if (ylo < 0) {
+    NLSF[0] = 0;
+    p = Q;
+    ylo = a2nlsf_eval_poly(p, xlo, dd);
+    root_ix = 1;
+  } else root_ix = 0;
+  while (1) {
+    xhi = ob_silk_LSFCosTab_Q12[k];
+    yhi = a2nlsf_eval_poly(p, xhi, dd);
+    if ((ylo <= 0 && yhi >= thr) || (ylo >= 0 && yhi <= -thr)) {
+      thr = yhi == 0 ? 1 : 0;
+      ffrac = -256;
+      for (m = 0; m < 3; m++) {
+        xmid = rshift_round(xlo + xhi, 1);
+        ymid = a2nlsf_eval_poly(p, xmid, dd);
+        if ((ylo <= 0 && ymid >= 0) || (ylo >= 0 && ymid <= 0)) { xhi = xmid; yhi = ymid; }
+        else { xlo = xmid; ylo = ymid; ffrac = ffrac + (128 >> m); }
+      }
+      if (abs(ylo) < 65536) {
+        den = ylo - yhi;
+        nom = (int32_t)((uint32_t)ylo << (8 - 3)) + (den >> 1);
+        if (den != 0) ffrac += nom / den;
+      } else ffrac += ylo / ((ylo - yhi) >> (8 - 3));
+      { const int32_t v = (int32_t)((uint32_t)k << 8) + ffrac; NLSF[root_ix] = (int16_t)(v < 32767 ? v : 32767); }
+      root_ix++;
+      if (root_ix >= d) break;
+      p = (root_ix & 1) ? Q : P;
+      xlo = ob_silk_LSFCosTab_Q12[k - 1];
+      ylo = (int32_t)((uint32_t)(int32_t)(1 - (root_ix & 2)) << 12);
+    } else {
+      k++;
+      xlo = xhi;
+      ylo = yhi;
+      thr = 0;
+      if (k > 128) {
+        i++;
+        if (i > 16) { /* white spectrum */
+          NLSF[0] = (int16_t)((1 << 15) / (d + 1));
+          for (k = 1; k < d; k++) NLSF[k] = (int16_t)(NLSF[k - 1] + NLSF[0]);
+          return;
+        }
+        bwexpander_32(a_Q16, d, 65536 - (int32_t)((uint32_t)1 << i));
+        a2nlsf_init(a_Q16, P, Q, dd);
+        p = P;
+        xlo = ob_silk_LSFCosTab_Q12[0];
+        ylo = a2nlsf_eval_poly(p, xlo, dd);
+        if (ylo < 0) {
+          NLSF[0] = 0;
+          p = Q;
+          ylo = a2nlsf_eval_poly(p, xlo, dd);
+          root_ix = 1;
+        } else root_ix = 0;
+        k = 1;
+      }
+    }
+  }
+}
+static void a2nlsf_flp(int16_t *NLSF_Q15, const float *pAR, int order) {
+  int32_t a_fix_Q16[MAX_ORDER];
+  int i;
+  for (i = 0; i < order; i++) a_fix_Q16[i] = (int32_t)lrintf(pAR[i] * 65536.0f);
+  orc_silk_A2NLSF(NLSF_Q15, a_fix_Q16, order);
+}
+static double energy_flp(const float *data, int n) {
+  double r = 0.0;
+  int i;
+  for (i = 0; i < n - 3; i += 4)
+    r += data[i + 0] * (double)data[i + 0] + data[i + 1] * (double)data[i + 1] + data[i + 2] * (double)data[i + 2] + data[i + 3] * (double)data[i + 3];
+  for (; i < n; i++) r += data[i] * (double)data[i];
+  return r;
+}
+static void lpc_analysis_filter_flp(float *r_LPC, const float *PredCoef, const float *s, int length, int Order) {
+  int ix, j;
+  for (ix = Order; ix < length; ix++) {
+    const float *s_ptr = &s[ix - 1];
+    float LPC_pred = s_ptr[0] * PredCoef[0];
+    for (j = 1; j < Order; j++) LPC_pred = LPC_pred + s_ptr[-j] * PredCoef[j];
+    r_LPC[ix] = s_ptr[1] - LPC_pred;
+  }
+  memset(r_LPC, 0, Order * sizeof(float));
+}
+typedef struct { /* what silk_find_LPC_FLP reads and writes in silk_encoder_state; == OpusB200SilkFindLpc */
+  int16_t NLSF_Q15[16];         /* out */
+  int16_t prev_NLSFq_Q15[16];
+  float minInvGain;
+  int32_t useInterpolatedNLSFs, first_frame_after_reset;
+  int32_t NLSFInterpCoef_Q2;    /* out */
+} OrcSilkFindLpc;
+int orc_silk_find_lpc_size(void) { return (int)sizeof(OrcSilkFindLpc); }
+/* x: nb_subfr * (subfr_length + order) samples */
+void orc_silk_find_LPC(OrcSilkFindLpc *f, const float *x, int order, int nb_subfr, int subfr_length_in) {
+  const int subfr_length = subfr_length_in + order;
+  float a[MAX_ORDER], a_tmp[MAX_ORDER], res_nrg, res_nrg_2nd, res_nrg_interp, LPC_res[2 * (80 + 16) + 16];
+  int16_t NLSF0_Q15[MAX_ORDER], a_fix_Q12[MAX_ORDER];
+  int k, i;
+  f->NLSFInterpCoef_Q2 = 4;
+  res_nrg = orc_silk_burg_modified(a, x, f->minInvGain, subfr_length, nb_subfr, order);
+  if (f->useInterpolatedNLSFs && !f->first_frame_after_reset && nb_subfr == 4) {
+    res_nrg -= orc_silk_burg_modified(a_tmp, x + 2 * subfr_length, f->minInvGain, subfr_length, 2, order);
+    a2nlsf_flp(f->NLSF_Q15, a_tmp, order);
+    res_nrg_2nd = 3.402823466e+38f; /* silk_float_MAX = FLT_MAX */
+    for (k = 3; k >= 0; k--) {
+      interpolate(NLSF0_Q15, f->prev_NLSFq_Q15, f->NLSF_Q15, k, order);
+      orc_silk_NLSF2A(a_fix_Q12, NLSF0_Q15, order);
+      for (i = 0; i < order; i++) a_tmp[i] = (float)a_fix_Q12[i] * (1.0f / 4096.0f);
+      lpc_analysis_filter_flp(LPC_res, a_tmp, x, 2 * subfr_length, order);
+      res_nrg_interp = (float)(energy_flp(LPC_res + order, subfr_length - order) + energy_flp(LPC_res + order + subfr_length, subfr_length - order));
+      if (res_nrg_interp < res_nrg) {
+        res_nrg = res_nrg_interp;
+        f->NLSFInterpCoef_Q2 = k;
+      } else if (res_nrg_interp > res_nrg_2nd) break;
+      res_nrg_2nd = res_nrg_interp;
+    }
+  }
+  if (f->NLSFInterpCoef_Q2 == 4) a2nlsf_flp(f->NLSF_Q15, a, order);
+}
