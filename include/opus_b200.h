@@ -463,6 +463,20 @@ typedef struct {
 } OpusB200SilkNlsf;
 int opusb200_silk_process_nlsfs(OpusB200Ctx *ctx, OpusB200SilkNlsf *frames, int n, int fs_kHz, int nb_subfr, int on_device);
 
+/* silk_find_LPC_FLP (silk/float/find_LPC_FLP.c:36-105; call site silk/float/find_pred_coefs_FLP.c:100): the LPC estimation of a SILK frame — Burg over
+ * the frame and, with NLSF interpolation on, over its second half; silk_A2NLSF; the search over the interpolation factor (silk_interpolate, silk_NLSF2A,
+ * the float LPC analysis filter, residual energies).  x [n][nb_subfr * (subfr_length + order)]: the pre-whitened frame with `order` samples of history
+ * in front of every subframe; order 10 or 16.  in: prev_NLSFq_Q15, minInvGain, useInterpolatedNLSFs, first_frame_after_reset; out: NLSF_Q15 (the input
+ * of opusb200_silk_process_nlsfs), NLSFInterpCoef_Q2.  Integer parts exact; the Burg recursion is double precision (a17). */
+typedef struct {
+  int16_t NLSF_Q15[16];
+  int16_t prev_NLSFq_Q15[16];
+  float minInvGain;
+  int32_t useInterpolatedNLSFs, first_frame_after_reset;
+  int32_t NLSFInterpCoef_Q2;
+} OpusB200SilkFindLpc;
+int opusb200_silk_find_lpc(OpusB200Ctx *ctx, OpusB200SilkFindLpc *frames, const float *x, int n, int order, int nb_subfr, int subfr_length, int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

@@ -233,3 +233,39 @@ extern "C" int opusb200_silk_process_nlsfs(OpusB200Ctx *c, OpusB200SilkNlsf *fra
   }
   return r;
 }
+
+// ---- silk_find_LPC_FLP for n streams (silk_nlsf.cuh: silk_find_lpc_thread): frames [n] records in place, x [n][nb_subfr * (subfr_length + order)] ----
+extern "C" __global__ void __launch_bounds__(64) ob_silk_find_lpc(ob::SilkFindLpcParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_find_lpc_thread(p, s);
+}
+extern "C" int opusb200_silk_find_lpc(OpusB200Ctx *c, OpusB200SilkFindLpc *frames, const float *x, int n, int order, int nb_subfr, int subfr_length,
+                                      int on_device) {
+  static_assert(sizeof(OpusB200SilkFindLpc) == sizeof(ob::ObSilkFindLpc), "OpusB200SilkFindLpc mirrors ObSilkFindLpc");
+  if (!c || !frames || !x || n <= 0 || (order != 10 && order != 16) || (nb_subfr != 2 && nb_subfr != 4) || subfr_length <= order || subfr_length > 80)
+    return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkFindLpcParams p;
+  p.n = n; p.order = order; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length;
+  const size_t fb = sizeof(ob::ObSilkFindLpc) * (size_t)n, xb = sizeof(float) * (size_t)n * nb_subfr * (subfr_length + order);
+  ob::ObSilkFindLpc *d = (ob::ObSilkFindLpc *)frames;
+  float *dx = nullptr;
+  if (!on_device) {
+    if (cudaMalloc(&d, fb) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMalloc(&dx, xb) != cudaSuccess) { cudaFree(d); return OPUSB200_ALLOC_FAIL; }
+    if (cudaMemcpyAsync(d, frames, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+      cudaFree(d); cudaFree(dx);
+      return OPUSB200_INTERNAL_ERROR;
+    }
+  }
+  p.frames = d; p.x = on_device ? x : dx;
+  ob_silk_find_lpc<<<(n + 63) / 64, 64, 0, c->stream>>>(p);
+  c->launches++;
+  int r = cudaGetLastError() == cudaSuccess ? OPUSB200_OK : OPUSB200_INTERNAL_ERROR;
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, fb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d); cudaFree(dx);
+  }
+  return r;
+}

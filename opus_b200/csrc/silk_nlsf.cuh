@@ -444,4 +444,150 @@ OB_DEV void silk_process_nlsfs_thread(const SilkNlsfParams &p, int s) {
   } else for (int i = 0; i < order; i++) f.PredCoef_Q12[0][i] = f.PredCoef_Q12[1][i];
   p.frames[s] = f;
 }
+// ---- LPC estimation of a SILK frame: silk_find_LPC_FLP (silk/float/find_LPC_FLP.c:36-105) — Burg over the frame, and with NLSF interpolation on, Burg over
+// the second half, silk_A2NLSF (silk/A2NLSF.c:45-267), then the search over the interpolation factor: interpolated NLSFs -> silk_NLSF2A -> float LPC analysis
+// filter over the first half (silk/float/LPC_analysis_filter_FLP.c) -> residual energy (silk/float/energy_FLP.c).  One thread per stream. ----
+struct ObSilkFindLpc {   // == OpusB200SilkFindLpc
+  int16_t NLSF_Q15[16];         // out
+  int16_t prev_NLSFq_Q15[16];
+  float minInvGain;
+  int32_t useInterpolatedNLSFs, first_frame_after_reset;
+  int32_t NLSFInterpCoef_Q2;    // out
+};
+struct SilkFindLpcParams { ObSilkFindLpc *frames; const float *x; int n, order, nb_subfr, subfr_length; };   // x [n][nb_subfr * (subfr_length + order)]
+OB_DEV void a2nlsf_trans_poly(int32_t *p, int dd) {
+  for (int k = 2; k <= dd; k++) {
+    for (int n = dd; n > k; n--) p[n - 2] -= p[n];
+    p[k - 2] -= (int32_t)((uint32_t)p[k] << 1);
+  }
+}
+OB_DEV int32_t a2nlsf_eval_poly(const int32_t *p, int32_t x, int dd) {
+  const int32_t x_Q16 = (int32_t)((uint32_t)x << 4);
+  int32_t y32 = p[dd];
+  for (int n = dd - 1; n >= 0; n--) y32 = (int32_t)(p[n] + (((int64_t)y32 * x_Q16) >> 16));   // silk_SMLAWW
+  return y32;
+}
+OB_DEV void a2nlsf_init(const int32_t *a_Q16, int32_t *P, int32_t *Q, int dd) {
+  P[dd] = 1 << 16;
+  Q[dd] = 1 << 16;
+  for (int k = 0; k < dd; k++) {
+    P[k] = -a_Q16[dd - k - 1] - a_Q16[dd + k];
+    Q[k] = -a_Q16[dd - k - 1] + a_Q16[dd + k];
+  }
+  for (int k = dd; k > 0; k--) {
+    P[k - 1] -= P[k];
+    Q[k - 1] += Q[k];
+  }
+  a2nlsf_trans_poly(P, dd);
+  a2nlsf_trans_poly(Q, dd);
+}
+OB_DEVNI void nlsf_A2NLSF(int16_t *NLSF, int32_t *a_Q16, int d) {
+  const int dd = d >> 1;
+  int i = 0, k = 1, root_ix;
+  int32_t xlo, xhi, ylo, yhi, thr = 0, P[kNlsfMaxOrder / 2 + 1], Q[kNlsfMaxOrder / 2 + 1];
+  const int32_t *p = P;
+  a2nlsf_init(a_Q16, P, Q, dd);
+  xlo = ob_silk_LSFCosTab_Q12[0];
+  ylo = a2nlsf_eval_poly(p, xlo, dd);
+  if (ylo < 0) {
+    NLSF[0] = 0;
+    p = Q;
+    ylo = a2nlsf_eval_poly(p, xlo, dd);
+    root_ix = 1;
+  } else root_ix = 0;
+  while (true) {
+    xhi = ob_silk_LSFCosTab_Q12[k];
+    yhi = a2nlsf_eval_poly(p, xhi, dd);
+    if ((ylo <= 0 && yhi >= thr) || (ylo >= 0 && yhi <= -thr)) {
+      thr = yhi == 0 ? 1 : 0;
+      int ffrac = -256;
+      for (int m = 0; m < 3; m++) {   // BIN_DIV_STEPS_A2NLSF_FIX
+        const int32_t xmid = nl_rr(xlo + xhi, 1), ymid = a2nlsf_eval_poly(p, xmid, dd);
+        if ((ylo <= 0 && ymid >= 0) || (ylo >= 0 && ymid <= 0)) { xhi = xmid; yhi = ymid; }
+        else { xlo = xmid; ylo = ymid; ffrac = ffrac + (128 >> m); }
+      }
+      if (nl_abs(ylo) < 65536) {
+        const int32_t den = ylo - yhi, nom = (int32_t)((uint32_t)ylo << (8 - 3)) + (den >> 1);
+        if (den != 0) ffrac += nom / den;
+      } else ffrac += ylo / ((ylo - yhi) >> (8 - 3));
+      const int32_t v = (int32_t)((uint32_t)k << 8) + ffrac;
+      NLSF[root_ix] = (int16_t)(v < 32767 ? v : 32767);
+      root_ix++;
+      if (root_ix >= d) break;
+      p = (root_ix & 1) ? Q : P;
+      xlo = ob_silk_LSFCosTab_Q12[k - 1];
+      ylo = (int32_t)((uint32_t)(int32_t)(1 - (root_ix & 2)) << 12);
+    } else {
+      k++;
+      xlo = xhi;
+      ylo = yhi;
+      thr = 0;
+      if (k > 128) {   // LSF_COS_TAB_SZ_FIX: not all roots found — expand the bandwidth and start again
+        i++;
+        if (i > 16) {   // MAX_ITERATIONS_A2NLSF_FIX: white spectrum
+          NLSF[0] = (int16_t)((1 << 15) / (d + 1));
+          for (k = 1; k < d; k++) NLSF[k] = (int16_t)(NLSF[k - 1] + NLSF[0]);
+          return;
+        }
+        nlsf_bwexpander_32(a_Q16, d, 65536 - (int32_t)((uint32_t)1 << i));
+        a2nlsf_init(a_Q16, P, Q, dd);
+        p = P;
+        xlo = ob_silk_LSFCosTab_Q12[0];
+        ylo = a2nlsf_eval_poly(p, xlo, dd);
+        if (ylo < 0) {
+          NLSF[0] = 0;
+          p = Q;
+          ylo = a2nlsf_eval_poly(p, xlo, dd);
+          root_ix = 1;
+        } else root_ix = 0;
+        k = 1;
+      }
+    }
+  }
+}
+OB_DEV void nlsf_a2nlsf_flp(int16_t *NLSF_Q15, const float *pAR, int order) {   // silk_A2NLSF_FLP: silk_float2int rounds to nearest even
+  int32_t a_fix_Q16[kNlsfMaxOrder];
+  for (int i = 0; i < order; i++) a_fix_Q16[i] = (int32_t)rintf(pAR[i] * 65536.0f);
+  nlsf_A2NLSF(NLSF_Q15, a_fix_Q16, order);
+}
+OB_DEV void silk_find_lpc_thread(const SilkFindLpcParams &p, int s) {
+  ObSilkFindLpc f = p.frames[s];
+  const int order = p.order, nb_subfr = p.nb_subfr, subfr_length = p.subfr_length + order;
+  const float *x = p.x + (size_t)s * nb_subfr * subfr_length;
+  float a[kNlsfMaxOrder], a_tmp[kNlsfMaxOrder], nrg[1], LPC_res[2 * (80 + 16)];
+  int16_t NLSF0_Q15[kNlsfMaxOrder], a_fix_Q12[kNlsfMaxOrder];
+  f.NLSFInterpCoef_Q2 = 4;
+  SilkBurgParams b;
+  b.A = a; b.nrg = nrg; b.x = x; b.minInvGain = f.minInvGain; b.n_items = 1; b.subfr_length = subfr_length; b.nb_subfr = nb_subfr; b.D = order;
+  silk_burg_thread(b, 0);
+  float res_nrg = nrg[0];
+  if (f.useInterpolatedNLSFs && !f.first_frame_after_reset && nb_subfr == 4) {
+    b.A = a_tmp; b.x = x + 2 * subfr_length; b.nb_subfr = 2;
+    silk_burg_thread(b, 0);
+    res_nrg -= nrg[0];
+    nlsf_a2nlsf_flp(f.NLSF_Q15, a_tmp, order);
+    float res_nrg_2nd = 3.402823466e+38f;   // silk_float_MAX
+    for (int k = 3; k >= 0; k--) {
+      nlsf_interpolate(NLSF0_Q15, f.prev_NLSFq_Q15, f.NLSF_Q15, k, order);
+      nlsf_NLSF2A(a_fix_Q12, NLSF0_Q15, order);
+      for (int i = 0; i < order; i++) a_tmp[i] = (float)a_fix_Q12[i] * (1.0f / 4096.0f);
+      for (int ix = order; ix < 2 * subfr_length; ix++) {   // silk_LPC_analysis_filter_FLP: the products summed left to right
+        const float *sp = &x[ix - 1];
+        float pred = sp[0] * a_tmp[0];
+        for (int j = 1; j < order; j++) pred = pred + sp[-j] * a_tmp[j];
+        LPC_res[ix] = sp[1] - pred;
+      }
+      for (int ix = 0; ix < order; ix++) LPC_res[ix] = 0.f;
+      const float res_nrg_interp = (float)(silk_inner_product_flp(LPC_res + order, LPC_res + order, subfr_length - order) +
+                                           silk_inner_product_flp(LPC_res + order + subfr_length, LPC_res + order + subfr_length, subfr_length - order));
+      if (res_nrg_interp < res_nrg) {
+        res_nrg = res_nrg_interp;
+        f.NLSFInterpCoef_Q2 = k;
+      } else if (res_nrg_interp > res_nrg_2nd) break;
+      res_nrg_2nd = res_nrg_interp;
+    }
+  }
+  if (f.NLSFInterpCoef_Q2 == 4) nlsf_a2nlsf_flp(f.NLSF_Q15, a, order);
+  p.frames[s] = f;
+}
 }  // namespace ob

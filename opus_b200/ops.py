@@ -102,6 +102,15 @@ class Ops:
             raise capi.OpusB200Error(r, 'opusb200_silk_process_nlsfs')
         return frames
 
+    def silk_find_lpc(self, frames, x, order, nb_subfr, subfr_length):
+        """silk_find_LPC_FLP for n streams: frames = ctypes array of OpusB200SilkFindLpc-shaped records (in place), x float32 [n, nb_subfr * (subfr_length + order)]"""
+        x = np.ascontiguousarray(x, np.float32)
+        r = self._L.opusb200_silk_find_lpc(self._h, ctypes.cast(frames, ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), len(frames), order, nb_subfr,
+                                           subfr_length, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_find_lpc')
+        return frames
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

@@ -559,3 +559,13 @@ extern "C" void emu_silk_process_nlsfs(void *frames, int n, int wb, int nb_subfr
   p.frames = (ObSilkNlsf *)frames; p.n = n; p.wb = wb; p.nb_subfr = nb_subfr;
   emu_launch(silk_nlsf_entry, &p, (n + 31) / 32, 32, 0);
 }
+static void silk_find_lpc_entry(void *a) {
+  const SilkFindLpcParams &p = *(const SilkFindLpcParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_find_lpc_thread(p, s);
+}
+extern "C" void emu_silk_find_lpc(void *frames, const float *x, int n, int order, int nb_subfr, int subfr_length) {
+  SilkFindLpcParams p;
+  p.frames = (ObSilkFindLpc *)frames; p.x = x; p.n = n; p.order = order; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length;
+  emu_launch(silk_find_lpc_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -292,3 +292,23 @@ def test_silk_process_nlsfs_emulated(wb, nb_subfr):
         for s in range(n):
             assert same(recs[s], want[s], order), (frame, s, list(recs[s].NLSFIndices), list(want[s].NLSFIndices))
             prev[s] = list(want[s].NLSF_Q15)
+
+
+@pytest.mark.parametrize('order,nb_subfr,subfr_length', [(16, 4, 80), (10, 4, 60), (16, 2, 80)])
+def test_silk_find_lpc_emulated(order, nb_subfr, subfr_length):
+    """silk_find_LPC_FLP (Burg, A2NLSF, the interpolation search): the device source on the emulator against the oracle (pinned on the reference)"""
+    from test_silk_find_lpc_oracle_vs_ref import FindLpc, lpc_input, random_case
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(50 + order + nb_subfr)
+    n = 36
+    x = np.stack([lpc_input(rng, order, nb_subfr, subfr_length, s % 4) for s in range(n)])
+    recs = (FindLpc * n)()
+    want = []
+    for s in range(n):
+        recs[s] = random_case(rng, order, s % 7)
+        w = FindLpc.from_buffer_copy(bytes(recs[s]))
+        O.orc_silk_find_LPC(ctypes.byref(w), x[s].ctypes.data_as(ctypes.c_void_p), order, nb_subfr, subfr_length)
+        want.append(w)
+    E.emu_silk_find_lpc(ctypes.cast(recs, ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), n, order, nb_subfr, subfr_length)
+    for s in range(n):
+        assert list(recs[s].NLSF_Q15)[:order] == list(want[s].NLSF_Q15)[:order] and recs[s].NLSFInterpCoef_Q2 == want[s].NLSFInterpCoef_Q2, s

@@ -400,3 +400,34 @@ def test_silk_process_nlsfs(fs_kHz, nb_subfr):
         for s in range(n):
             assert same(recs[s], want[s], order), (frame, s)
             prev[s] = list(want[s].NLSF_Q15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('order,nb_subfr,subfr_length', [(16, 4, 80), (10, 4, 60), (16, 2, 80)])
+def test_silk_find_lpc(order, nb_subfr, subfr_length):
+    """opusb200_silk_find_lpc against the oracle (pinned bit for bit on silk_find_LPC_FLP): NLSFs and the interpolation factor.  The Burg recursion and the
+    residual energies are double precision with one sqrt on a clamped path: bit-identical on all but a rare stream, which may move an NLSF by an LSB"""
+    import opus_b200
+    from test_silk_find_lpc_oracle_vs_ref import FindLpc, lpc_input, random_case
+    O = util.load_oracle()
+    ops = opus_b200.Ops()
+    rng = np.random.default_rng(60 + order + nb_subfr)
+    n = 200
+    x = np.stack([lpc_input(rng, order, nb_subfr, subfr_length, s % 4) for s in range(n)])
+    recs = (FindLpc * n)()
+    want = []
+    for s in range(n):
+        recs[s] = random_case(rng, order, s % 7)
+        w = FindLpc.from_buffer_copy(bytes(recs[s]))
+        O.orc_silk_find_LPC(ctypes.byref(w), x[s].ctypes.data_as(ctypes.c_void_p), order, nb_subfr, subfr_length)
+        want.append(w)
+    ops.silk_find_lpc(recs, x, order, nb_subfr, subfr_length)
+    exact = 0
+    for s in range(n):
+        a, b = np.array(list(recs[s].NLSF_Q15)[:order]), np.array(list(want[s].NLSF_Q15)[:order])
+        same_k = recs[s].NLSFInterpCoef_Q2 == want[s].NLSFInterpCoef_Q2
+        exact += int(same_k and np.array_equal(a, b))
+        if same_k:
+            assert np.abs(a - b).max() <= 2, (s, a, b)
+    print('bit-identical streams: %d of %d' % (exact, n))
+    assert exact >= 0.97 * n
