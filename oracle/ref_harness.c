@@ -508,3 +508,44 @@ void refh_silk_find_LPC(RefhSilkFindLpc *f, const float *x, int order, int nb_su
   f->NLSFInterpCoef_Q2 = st.indices.NLSFInterpCoef_Q2;
 }
 void refh_silk_A2NLSF(opus_int16 *NLSF, opus_int32 *a_Q16, int d) { silk_A2NLSF(NLSF, a_Q16, d); }
+
+/* ---- silk_find_pred_coefs_FLP on scratch encoder structs (silk/float/find_pred_coefs_FLP.c:35-120) ---- */
+typedef struct {
+  float Gains[4];
+  opus_int32 pitchL[4];
+  float coding_quality;
+  opus_int32 signalType, condCoding, first_frame_after_reset, useInterpolatedNLSFs, PacketLoss_perc, nFramesPerPacket, LBRR_flag, SNR_dB_Q7, speech_activity_Q8,
+      NLSF_MSVQ_Survivors;
+  opus_int16 prev_NLSFq_Q15[16];
+  opus_int32 sum_log_gain_Q7;
+  float LTPCoef[20], LTPredCodGain, LTP_scale, PredCoef[2][16], ResNrg[4];
+  opus_int8 LTPIndex[4], PERIndex, LTP_scaleIndex, NLSFInterpCoef_Q2, pad;
+  opus_int8 NLSFIndices[17], pad2[3];
+} RefhSilkPredCoefs;   /* == OrcSilkPredCoefs */
+void refh_silk_find_pred_coefs(RefhSilkPredCoefs *c, const float *res_pitch, const float *x, int order, int nb_subfr, int subfr_length) {
+  static silk_encoder_state_FLP st;
+  static silk_encoder_control_FLP ctl;
+  int k;
+  memset(&st, 0, sizeof(st));
+  memset(&ctl, 0, sizeof(ctl));
+  st.sCmn.nb_subfr = nb_subfr; st.sCmn.subfr_length = subfr_length; st.sCmn.predictLPCOrder = order; st.sCmn.ltp_mem_length = 4 * subfr_length;
+  st.sCmn.psNLSF_CB = order == 16 ? &silk_NLSF_CB_WB : &silk_NLSF_CB_NB_MB;
+  st.sCmn.indices.signalType = (opus_int8)c->signalType;
+  st.sCmn.first_frame_after_reset = c->first_frame_after_reset; st.sCmn.useInterpolatedNLSFs = c->useInterpolatedNLSFs;
+  st.sCmn.PacketLoss_perc = c->PacketLoss_perc; st.sCmn.nFramesPerPacket = c->nFramesPerPacket; st.sCmn.LBRR_flag = c->LBRR_flag;
+  st.sCmn.SNR_dB_Q7 = c->SNR_dB_Q7; st.sCmn.speech_activity_Q8 = c->speech_activity_Q8; st.sCmn.NLSF_MSVQ_Survivors = c->NLSF_MSVQ_Survivors;
+  st.sCmn.sum_log_gain_Q7 = c->sum_log_gain_Q7;
+  memcpy(st.sCmn.prev_NLSFq_Q15, c->prev_NLSFq_Q15, sizeof(st.sCmn.prev_NLSFq_Q15));
+  for (k = 0; k < 4; k++) { ctl.Gains[k] = c->Gains[k]; ctl.pitchL[k] = c->pitchL[k]; }
+  ctl.coding_quality = c->coding_quality;
+  silk_find_pred_coefs_FLP(&st, &ctl, res_pitch, x, c->condCoding);
+  memcpy(c->prev_NLSFq_Q15, st.sCmn.prev_NLSFq_Q15, sizeof(c->prev_NLSFq_Q15));
+  c->sum_log_gain_Q7 = st.sCmn.sum_log_gain_Q7;
+  memcpy(c->LTPCoef, ctl.LTPCoef, sizeof(c->LTPCoef));
+  c->LTPredCodGain = ctl.LTPredCodGain; c->LTP_scale = ctl.LTP_scale;
+  memcpy(c->PredCoef, ctl.PredCoef, sizeof(c->PredCoef));
+  memcpy(c->ResNrg, ctl.ResNrg, sizeof(c->ResNrg));
+  memcpy(c->LTPIndex, st.sCmn.indices.LTPIndex, 4);
+  c->PERIndex = st.sCmn.indices.PERIndex; c->LTP_scaleIndex = st.sCmn.indices.LTP_scaleIndex; c->NLSFInterpCoef_Q2 = st.sCmn.indices.NLSFInterpCoef_Q2;
+  memcpy(c->NLSFIndices, st.sCmn.indices.NLSFIndices, 17);
+}

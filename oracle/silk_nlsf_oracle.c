@@ -658,3 +658,240 @@ void orc_silk_find_LPC(OrcSilkFindLpc *f, const float *x, int order, int nb_subf
   }
   if (f->NLSFInterpCoef_Q2 == 4) a2nlsf_flp(f->NLSF_Q15, a, order);
 }
+
+/* ---- the prediction analysis of a SILK frame: silk_find_pred_coefs_FLP (silk/float/find_pred_coefs_FLP.c:35-120) = silk_find_LTP_FLP
+ * (float/find_LTP_FLP.c:34-65 with corrMatrix_FLP.c:38-95), silk_quant_LTP_gains[_FLP] (quant_LTP_gains.c:34-132, float/wrappers_FLP.c:175-209) with
+ * silk_VQ_WMat_EC_c (VQ_WMat_EC.c:35-131), silk_LTP_scale_ctrl_FLP (float/LTP_scale_ctrl_FLP.c:34-58), silk_LTP_analysis_filter_FLP
+ * (float/LTP_analysis_filter_FLP.c:34-75), silk_find_LPC_FLP and silk_process_NLSFs[_FLP] (above), silk_residual_energy_FLP
+ * (float/residual_energy_FLP.c:91-117). ---- */
+int32_t orc_silk_log2lin(int32_t inLog_Q7); /* silk_oracle.c */
+typedef struct { /* what silk_find_pred_coefs_FLP reads and writes in silk_encoder_state_FLP / silk_encoder_control_FLP; == OpusB200SilkPredCoefs */
+  float Gains[4];
+  int32_t pitchL[4];
+  float coding_quality;
+  int32_t signalType, condCoding, first_frame_after_reset, useInterpolatedNLSFs, PacketLoss_perc, nFramesPerPacket, LBRR_flag, SNR_dB_Q7, speech_activity_Q8,
+      NLSF_MSVQ_Survivors;
+  int16_t prev_NLSFq_Q15[16];   /* in / out */
+  int32_t sum_log_gain_Q7;      /* in / out */
+  float LTPCoef[20], LTPredCodGain, LTP_scale, PredCoef[2][16], ResNrg[4];   /* out */
+  int8_t LTPIndex[4], PERIndex, LTP_scaleIndex, NLSFInterpCoef_Q2, pad;
+  int8_t NLSFIndices[17], pad2[3];
+} OrcSilkPredCoefs;
+int orc_silk_pred_coefs_size(void) { return (int)sizeof(OrcSilkPredCoefs); }
+static int32_t add_pos_sat32(int32_t a, int32_t b) { return (((uint32_t)a + (uint32_t)b) & 0x80000000u) ? INT32_MAX : a + b; }
+static void vq_wmat_ec(int8_t *ind, int32_t *res_nrg_Q15, int32_t *rate_dist_Q8, int *gain_Q7, const int32_t *XX, const int32_t *xX, const int8_t *cb_Q7,
+                       const uint8_t *cb_gain_Q7, const uint8_t *cl_Q5, int subfr_len, int32_t max_gain_Q7, int L) {
+  int32_t neg[5], sum1, sum2;
+  int k, j;
+  for (j = 0; j < 5; j++) neg[j] = -(int32_t)((uint32_t)xX[j] << 7);
+  *rate_dist_Q8 = INT32_MAX;
+  *res_nrg_Q15 = INT32_MAX;
+  *ind = 0;
+  for (k = 0; k < L; k++, cb_Q7 += 5) {
+    const int gain_tmp_Q7 = cb_gain_Q7[k];
+    const int32_t d = gain_tmp_Q7 - max_gain_Q7, penalty = (int32_t)((uint32_t)(d > 0 ? d : 0) << 11);
+    sum1 = 32801; /* SILK_FIX_CONST(1.001, 15) */
+    sum2 = neg[0] + XX[1] * cb_Q7[1];
+    sum2 = sum2 + XX[2] * cb_Q7[2];
+    sum2 = sum2 + XX[3] * cb_Q7[3];
+    sum2 = sum2 + XX[4] * cb_Q7[4];
+    sum2 = (int32_t)((uint32_t)sum2 << 1);
+    sum2 = sum2 + XX[0] * cb_Q7[0];
+    sum1 = smlawb(sum1, sum2, cb_Q7[0]);
+    sum2 = neg[1] + XX[7] * cb_Q7[2];
+    sum2 = sum2 + XX[8] * cb_Q7[3];
+    sum2 = sum2 + XX[9] * cb_Q7[4];
+    sum2 = (int32_t)((uint32_t)sum2 << 1);
+    sum2 = sum2 + XX[6] * cb_Q7[1];
+    sum1 = smlawb(sum1, sum2, cb_Q7[1]);
+    sum2 = neg[2] + XX[13] * cb_Q7[3];
+    sum2 = sum2 + XX[14] * cb_Q7[4];
+    sum2 = (int32_t)((uint32_t)sum2 << 1);
+    sum2 = sum2 + XX[12] * cb_Q7[2];
+    sum1 = smlawb(sum1, sum2, cb_Q7[2]);
+    sum2 = neg[3] + XX[19] * cb_Q7[4];
+    sum2 = (int32_t)((uint32_t)sum2 << 1);
+    sum2 = sum2 + XX[18] * cb_Q7[3];
+    sum1 = smlawb(sum1, sum2, cb_Q7[3]);
+    sum2 = (int32_t)((uint32_t)neg[4] << 1);
+    sum2 = sum2 + XX[24] * cb_Q7[4];
+    sum1 = smlawb(sum1, sum2, cb_Q7[4]);
+    if (sum1 >= 0) {
+      const int32_t bits_res_Q8 = smulbb(subfr_len, orc_silk_lin2log(sum1 + penalty) - (15 << 7)), bits_tot_Q8 = bits_res_Q8 + ((int32_t)cl_Q5[k] << 2);
+      if (bits_tot_Q8 <= *rate_dist_Q8) {
+        *rate_dist_Q8 = bits_tot_Q8;
+        *res_nrg_Q15 = sum1 + penalty;
+        *ind = (int8_t)k;
+        *gain_Q7 = gain_tmp_Q7;
+      }
+    }
+  }
+}
+static void quant_LTP_gains(int16_t *B_Q14, int8_t *cbk_index, int8_t *periodicity_index, int32_t *sum_log_gain_Q7, int *pred_gain_dB_Q7, const int32_t *XX_Q17,
+                            const int32_t *xX_Q17, int subfr_len, int nb_subfr) {
+  static const int cb_off[3] = {0, 8, 24}, cb_size[3] = {8, 16, 32};
+  int32_t min_rate_dist_Q7 = INT32_MAX, best_sum_log_gain_Q7 = 0, res_nrg_Q15 = 0;
+  int8_t temp_idx[4];
+  int j, k;
+  for (k = 0; k < 3; k++) {
+    const int32_t gain_safety = 51; /* SILK_FIX_CONST(0.4, 7) */
+    const uint8_t *cl = (const uint8_t *)ob_silk_LTP_gain_BITS_Q5 + cb_off[k], *cg = (const uint8_t *)ob_silk_LTP_vq_gain + cb_off[k];
+    const int8_t *cb = (const int8_t *)ob_silk_LTP_gain_vq + 5 * cb_off[k];
+    int32_t rate_dist_Q7 = 0, sum_log_gain_tmp_Q7 = *sum_log_gain_Q7, nrg = 0;
+    for (j = 0; j < nb_subfr; j++) {
+      const int32_t max_gain_Q7 = orc_silk_log2lin((5333 - sum_log_gain_tmp_Q7) + 896) - gain_safety; /* MAX_SUM_LOG_GAIN_DB / 6 and 7 in Q7 */
+      int32_t res_nrg_subfr, rate_dist_subfr, t;
+      int gain_Q7 = 0;
+      vq_wmat_ec(&temp_idx[j], &res_nrg_subfr, &rate_dist_subfr, &gain_Q7, XX_Q17 + 25 * j, xX_Q17 + 5 * j, cb, cg, cl, subfr_len, max_gain_Q7, cb_size[k]);
+      nrg = add_pos_sat32(nrg, res_nrg_subfr);
+      rate_dist_Q7 = add_pos_sat32(rate_dist_Q7, rate_dist_subfr);
+      t = sum_log_gain_tmp_Q7 + orc_silk_lin2log(gain_safety + gain_Q7) - 896;
+      sum_log_gain_tmp_Q7 = t > 0 ? t : 0;
+    }
+    res_nrg_Q15 = nrg;
+    if (rate_dist_Q7 <= min_rate_dist_Q7) {
+      min_rate_dist_Q7 = rate_dist_Q7;
+      *periodicity_index = (int8_t)k;
+      memcpy(cbk_index, temp_idx, nb_subfr);
+      best_sum_log_gain_Q7 = sum_log_gain_tmp_Q7;
+    }
+  }
+  {
+    const int8_t *cb = (const int8_t *)ob_silk_LTP_gain_vq + 5 * cb_off[*periodicity_index];
+    for (j = 0; j < nb_subfr; j++)
+      for (k = 0; k < 5; k++) B_Q14[j * 5 + k] = (int16_t)(cb[cbk_index[j] * 5 + k] * 128);
+  }
+  res_nrg_Q15 = nb_subfr == 2 ? res_nrg_Q15 >> 1 : res_nrg_Q15 >> 2;
+  *sum_log_gain_Q7 = best_sum_log_gain_Q7;
+  *pred_gain_dB_Q7 = smulbb(-3, orc_silk_lin2log(res_nrg_Q15) - (15 << 7));
+}
+static double inner_flp(const float *a, const float *b, int n) {
+  double r = 0.0;
+  int i;
+  for (i = 0; i < n - 3; i += 4)
+    r += a[i + 0] * (double)b[i + 0] + a[i + 1] * (double)b[i + 1] + a[i + 2] * (double)b[i + 2] + a[i + 3] * (double)b[i + 3];
+  for (; i < n; i++) r += a[i] * (double)b[i];
+  return r;
+}
+static void corr_matrix_flp(const float *x, int L, int Order, float *XX) {
+  const float *ptr1 = &x[Order - 1], *ptr2 = &x[Order - 2];
+  double energy = energy_flp(ptr1, L);
+  int j, lag;
+  XX[0] = (float)energy;
+  for (j = 1; j < Order; j++) {
+    energy += ptr1[-j] * ptr1[-j] - ptr1[L - j] * ptr1[L - j];
+    XX[j * Order + j] = (float)energy;
+  }
+  for (lag = 1; lag < Order; lag++) {
+    energy = inner_flp(ptr1, ptr2, L);
+    XX[lag * Order + 0] = (float)energy;
+    XX[0 * Order + lag] = (float)energy;
+    for (j = 1; j < Order - lag; j++) {
+      energy += ptr1[-j] * ptr2[-j] - ptr1[L - j] * ptr2[L - j];
+      XX[(lag + j) * Order + j] = (float)energy;
+      XX[j * Order + lag + j] = (float)energy;
+    }
+    ptr2--;
+  }
+}
+/* res_pitch points at the current frame of the pitch residual (history in front of it), x at the current frame of the input (history in front of it) */
+void orc_silk_find_pred_coefs(OrcSilkPredCoefs *c, const float *res_pitch, const float *x, int order, int nb_subfr, int subfr_length) {
+  float XXLTP[4 * 25], xXLTP[4 * 5], invGains[4], LPC_in_pre[4 * 16 + 320], minInvGain;
+  int16_t NLSF_Q15[16] = {0};
+  int i, j, k;
+  for (i = 0; i < nb_subfr; i++) invGains[i] = 1.0f / c->Gains[i];
+  if (c->signalType == 2) {
+    const float *r_ptr = res_pitch;
+    int32_t XX_Q17[100], xX_Q17[20];
+    int16_t B_Q14[20];
+    int pred_gain_dB_Q7, round_loss;
+    for (k = 0; k < nb_subfr; k++) { /* silk_find_LTP_FLP */
+      const float *lag_ptr = r_ptr - (c->pitchL[k] + 5 / 2);
+      float *XX = XXLTP + 25 * k, *xX = xXLTP + 5 * k, xx, temp;
+      corr_matrix_flp(lag_ptr, subfr_length, 5, XX);
+      for (j = 0; j < 5; j++) xX[j] = (float)inner_flp(&lag_ptr[4 - j], r_ptr, subfr_length);
+      xx = (float)energy_flp(r_ptr, subfr_length + 5);
+      temp = 0.03f * 0.5f * (XX[0] + XX[24]) + 1.0f;
+      temp = 1.0f / (xx > temp ? xx : temp);
+      for (j = 0; j < 25; j++) XX[j] *= temp;
+      for (j = 0; j < 5; j++) xX[j] *= temp;
+      r_ptr += subfr_length;
+    }
+    for (i = 0; i < nb_subfr * 25; i++) XX_Q17[i] = (int32_t)lrintf(XXLTP[i] * 131072.0f);
+    for (i = 0; i < nb_subfr * 5; i++) xX_Q17[i] = (int32_t)lrintf(xXLTP[i] * 131072.0f);
+    quant_LTP_gains(B_Q14, c->LTPIndex, &c->PERIndex, &c->sum_log_gain_Q7, &pred_gain_dB_Q7, XX_Q17, xX_Q17, subfr_length, nb_subfr);
+    for (i = 0; i < nb_subfr * 5; i++) c->LTPCoef[i] = (float)B_Q14[i] * (1.0f / 16384.0f);
+    c->LTPredCodGain = (float)pred_gain_dB_Q7 * (1.0f / 128.0f);
+    if (c->condCoding == 0) { /* silk_LTP_scale_ctrl_FLP */
+      round_loss = c->PacketLoss_perc * c->nFramesPerPacket;
+      if (c->LBRR_flag) round_loss = 2 + smulbb(round_loss, round_loss) / 100;
+      c->LTP_scaleIndex = (int8_t)(smulbb((int32_t)c->LTPredCodGain, round_loss) > orc_silk_log2lin(2900 - c->SNR_dB_Q7));
+      c->LTP_scaleIndex = (int8_t)(c->LTP_scaleIndex + (smulbb((int32_t)c->LTPredCodGain, round_loss) > orc_silk_log2lin(3900 - c->SNR_dB_Q7)));
+    } else c->LTP_scaleIndex = 0;
+    { static const int16_t scales[3] = {15565, 12288, 8192}; c->LTP_scale = (float)scales[c->LTP_scaleIndex] / 16384.0f; }
+    { /* silk_LTP_analysis_filter_FLP */
+      const float *x_ptr = x - order;
+      float *res = LPC_in_pre;
+      for (k = 0; k < nb_subfr; k++) {
+        const float *x_lag_ptr = x_ptr - c->pitchL[k], inv_gain = invGains[k], *B = &c->LTPCoef[k * 5];
+        for (i = 0; i < subfr_length + order; i++) {
+          res[i] = x_ptr[i];
+          for (j = 0; j < 5; j++) res[i] -= B[j] * x_lag_ptr[5 / 2 - j];
+          res[i] *= inv_gain;
+          x_lag_ptr++;
+        }
+        res += subfr_length + order;
+        x_ptr += subfr_length;
+      }
+    }
+  } else {
+    const float *x_ptr = x - order;
+    float *pre = LPC_in_pre;
+    for (i = 0; i < nb_subfr; i++) {
+      for (j = 0; j < subfr_length + order; j++) pre[j] = invGains[i] * x_ptr[j];
+      pre += subfr_length + order;
+      x_ptr += subfr_length;
+    }
+    memset(c->LTPCoef, 0, nb_subfr * 5 * sizeof(float));
+    c->LTPredCodGain = 0.0f;
+    c->sum_log_gain_Q7 = 0;
+  }
+  if (c->first_frame_after_reset) minInvGain = 1.0f / 1e2f;
+  else {
+    minInvGain = (float)pow(2, c->LTPredCodGain / 3) / 1e4f;
+    minInvGain /= 0.25f + 0.75f * c->coding_quality;
+  }
+  {
+    OrcSilkFindLpc f;
+    OrcSilkNlsf q;
+    memset(&f, 0, sizeof(f));
+    memset(&q, 0, sizeof(q));
+    memcpy(f.prev_NLSFq_Q15, c->prev_NLSFq_Q15, sizeof(f.prev_NLSFq_Q15));
+    f.minInvGain = minInvGain; f.useInterpolatedNLSFs = c->useInterpolatedNLSFs; f.first_frame_after_reset = c->first_frame_after_reset;
+    orc_silk_find_LPC(&f, LPC_in_pre, order, nb_subfr, subfr_length);
+    memcpy(NLSF_Q15, f.NLSF_Q15, order * sizeof(int16_t));
+    c->NLSFInterpCoef_Q2 = (int8_t)f.NLSFInterpCoef_Q2;
+    memcpy(q.NLSF_Q15, NLSF_Q15, sizeof(q.NLSF_Q15));
+    memcpy(q.prev_NLSFq_Q15, c->prev_NLSFq_Q15, sizeof(q.prev_NLSFq_Q15));
+    q.NLSFInterpCoef_Q2 = c->NLSFInterpCoef_Q2; q.signalType = (int8_t)c->signalType; q.useInterpolatedNLSFs = (int8_t)c->useInterpolatedNLSFs;
+    q.speech_activity_Q8 = c->speech_activity_Q8; q.NLSF_MSVQ_Survivors = c->NLSF_MSVQ_Survivors;
+    orc_silk_process_NLSFs(&q, order == 16, nb_subfr);
+    memcpy(NLSF_Q15, q.NLSF_Q15, order * sizeof(int16_t));
+    memcpy(c->NLSFIndices, q.NLSFIndices, 17);
+    for (j = 0; j < 2; j++)
+      for (i = 0; i < order; i++) c->PredCoef[j][i] = (float)q.PredCoef_Q12[j][i] * (1.0f / 4096.0f);
+  }
+  { /* silk_residual_energy_FLP */
+    const int shift = order + subfr_length;
+    float LPC_res[(320 + 4 * 16) / 2];
+    lpc_analysis_filter_flp(LPC_res, c->PredCoef[0], LPC_in_pre, 2 * shift, order);
+    c->ResNrg[0] = (float)(c->Gains[0] * c->Gains[0] * energy_flp(LPC_res + order, subfr_length));
+    c->ResNrg[1] = (float)(c->Gains[1] * c->Gains[1] * energy_flp(LPC_res + order + shift, subfr_length));
+    if (nb_subfr == 4) {
+      lpc_analysis_filter_flp(LPC_res, c->PredCoef[1], LPC_in_pre + 2 * shift, 2 * shift, order);
+      c->ResNrg[2] = (float)(c->Gains[2] * c->Gains[2] * energy_flp(LPC_res + order, subfr_length));
+      c->ResNrg[3] = (float)(c->Gains[3] * c->Gains[3] * energy_flp(LPC_res + order + shift, subfr_length));
+    }
+  }
+  memcpy(c->prev_NLSFq_Q15, NLSF_Q15, sizeof(c->prev_NLSFq_Q15));
+}
