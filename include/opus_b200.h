@@ -477,6 +477,29 @@ typedef struct {
 } OpusB200SilkFindLpc;
 int opusb200_silk_find_lpc(OpusB200Ctx *ctx, OpusB200SilkFindLpc *frames, const float *x, int n, int order, int nb_subfr, int subfr_length, int on_device);
 
+/* silk_find_pred_coefs_FLP (silk/float/find_pred_coefs_FLP.c:35-120; call site silk/float/encode_frame_FLP.c:163): the whole prediction analysis of a
+ * SILK frame in one call per batch.  Voiced frames: silk_find_LTP_FLP, silk_quant_LTP_gains (silk_VQ_WMat_EC), silk_LTP_scale_ctrl_FLP,
+ * silk_LTP_analysis_filter_FLP; all frames: silk_find_LPC_FLP, silk_process_NLSFs, silk_residual_energy_FLP.
+ * res_pitch / x [n][sig_stride] float: the pitch-analysis residual and the input signal of every stream with the current frame at frame_off (history in
+ * front: >= 18 ms + 2 + order samples; 5 samples behind the frame are read).  One record per stream — in: Gains, pitchL, coding_quality, signalType,
+ * condCoding, first_frame_after_reset, useInterpolatedNLSFs, PacketLoss_perc, nFramesPerPacket, LBRR_flag, SNR_dB_Q7, speech_activity_Q8,
+ * NLSF_MSVQ_Survivors; in / out: prev_NLSFq_Q15, sum_log_gain_Q7; out: LTPCoef, LTPIndex, PERIndex, LTP_scaleIndex, LTP_scale, LTPredCodGain,
+ * NLSFInterpCoef_Q2, NLSFIndices, PredCoef [2][order], ResNrg.  The integer parts are exact; see tests/test_gpu_ops.py for the float bound. */
+typedef struct {
+  float Gains[4];
+  int32_t pitchL[4];
+  float coding_quality;
+  int32_t signalType, condCoding, first_frame_after_reset, useInterpolatedNLSFs, PacketLoss_perc, nFramesPerPacket, LBRR_flag, SNR_dB_Q7, speech_activity_Q8,
+      NLSF_MSVQ_Survivors;
+  int16_t prev_NLSFq_Q15[16];
+  int32_t sum_log_gain_Q7;
+  float LTPCoef[20], LTPredCodGain, LTP_scale, PredCoef[2][16], ResNrg[4];
+  int8_t LTPIndex[4], PERIndex, LTP_scaleIndex, NLSFInterpCoef_Q2, pad;
+  int8_t NLSFIndices[17], pad2[3];
+} OpusB200SilkPredCoefs;
+int opusb200_silk_find_pred_coefs(OpusB200Ctx *ctx, OpusB200SilkPredCoefs *frames, const float *res_pitch, const float *x, int n, int sig_stride, int frame_off,
+                                  int fs_kHz, int nb_subfr, int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

@@ -269,3 +269,43 @@ extern "C" int opusb200_silk_find_lpc(OpusB200Ctx *c, OpusB200SilkFindLpc *frame
   }
   return r;
 }
+
+// ---- silk_find_pred_coefs_FLP for n streams (silk_nlsf.cuh: silk_find_pred_coefs_thread) ----
+extern "C" __global__ void __launch_bounds__(64) ob_silk_find_pred_coefs(ob::SilkPredCoefsParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_find_pred_coefs_thread(p, s);
+}
+extern "C" int opusb200_silk_find_pred_coefs(OpusB200Ctx *c, OpusB200SilkPredCoefs *frames, const float *res_pitch, const float *x, int n, int sig_stride,
+                                             int frame_off, int fs_kHz, int nb_subfr, int on_device) {
+  static_assert(sizeof(OpusB200SilkPredCoefs) == sizeof(ob::ObSilkPredCoefs), "OpusB200SilkPredCoefs mirrors ObSilkPredCoefs");
+  if (!c || !frames || !res_pitch || !x || n <= 0 || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16) || (nb_subfr != 2 && nb_subfr != 4)) return OPUSB200_BAD_ARG;
+  const int order = fs_kHz == 16 ? 16 : 10, subfr_length = 5 * fs_kHz;
+  // history: the longest pitch lag (18 ms) + LTP_ORDER / 2 + order in front of the frame; behind it LTP_ORDER samples of the residual are read
+  if (frame_off < 18 * fs_kHz + 2 + order || sig_stride < frame_off + nb_subfr * subfr_length + 5) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkPredCoefsParams p;
+  p.n = n; p.sig_stride = sig_stride; p.frame_off = frame_off; p.order = order; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length;
+  const size_t fb = sizeof(ob::ObSilkPredCoefs) * (size_t)n, sb = sizeof(float) * (size_t)n * sig_stride;
+  ob::ObSilkPredCoefs *d = (ob::ObSilkPredCoefs *)frames;
+  float *dr = nullptr, *dx = nullptr;
+  int r = OPUSB200_OK;
+  if (!on_device) {
+    if (cudaMalloc(&d, fb) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMalloc(&dr, sb) != cudaSuccess || cudaMalloc(&dx, sb) != cudaSuccess) { cudaFree(d); cudaFree(dr); return OPUSB200_ALLOC_FAIL; }
+    if (cudaMemcpyAsync(d, frames, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaMemcpyAsync(dr, res_pitch, sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(dx, x, sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (r == OPUSB200_OK) {
+    p.frames = d; p.res_pitch = on_device ? res_pitch : dr; p.x = on_device ? x : dx;
+    ob_silk_find_pred_coefs<<<(n + 63) / 64, 64, 0, c->stream>>>(p);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, fb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d); cudaFree(dr); cudaFree(dx);
+  }
+  return r;
+}

@@ -421,13 +421,12 @@ OB_DEVNI void nlsf_NLSF2A(int16_t *a_Q12, const int16_t *NLSF, int d) {
 OB_DEV void nlsf_interpolate(int16_t *xi, const int16_t *x0, const int16_t *x1, int ifact_Q2, int d) {
   for (int i = 0; i < d; i++) xi[i] = (int16_t)(x0[i] + (nl_smulbb(x1[i] - x0[i], ifact_Q2) >> 2));
 }
-OB_DEV void silk_process_nlsfs_thread(const SilkNlsfParams &p, int s) {
-  ObSilkNlsf f = p.frames[s];
-  const NlsfCB cb = nlsf_cb(p.wb);
+OB_DEVNI void silk_process_nlsfs_core(ObSilkNlsf &f, int wb, int nb_subfr_) {
+  const NlsfCB cb = nlsf_cb(wb);
   const int order = cb.order;
   int16_t tmp0[kNlsfMaxOrder], W[kNlsfMaxOrder], W0[kNlsfMaxOrder];
   int NLSF_mu_Q20 = 3146 + silk_smulwb(-268434, f.speech_activity_Q8);   // SILK_FIX_CONST(0.003, 20), SILK_FIX_CONST(-0.001, 28)
-  if (p.nb_subfr == 2) NLSF_mu_Q20 = NLSF_mu_Q20 + (NLSF_mu_Q20 >> 1);
+  if (nb_subfr_ == 2) NLSF_mu_Q20 = NLSF_mu_Q20 + (NLSF_mu_Q20 >> 1);
   nlsf_weights_laroia(W, f.NLSF_Q15, order);
   const int doInterpolate = f.useInterpolatedNLSFs == 1 && f.NLSFInterpCoef_Q2 < 4;
   if (doInterpolate) {
@@ -442,6 +441,10 @@ OB_DEV void silk_process_nlsfs_thread(const SilkNlsfParams &p, int s) {
     nlsf_interpolate(tmp0, f.prev_NLSFq_Q15, f.NLSF_Q15, f.NLSFInterpCoef_Q2, order);
     nlsf_NLSF2A(f.PredCoef_Q12[0], tmp0, order);
   } else for (int i = 0; i < order; i++) f.PredCoef_Q12[0][i] = f.PredCoef_Q12[1][i];
+}
+OB_DEV void silk_process_nlsfs_thread(const SilkNlsfParams &p, int s) {
+  ObSilkNlsf f = p.frames[s];
+  silk_process_nlsfs_core(f, p.wb, p.nb_subfr);
   p.frames[s] = f;
 }
 // ---- LPC estimation of a SILK frame: silk_find_LPC_FLP (silk/float/find_LPC_FLP.c:36-105) — Burg over the frame, and with NLSF interpolation on, Burg over
@@ -550,10 +553,8 @@ OB_DEV void nlsf_a2nlsf_flp(int16_t *NLSF_Q15, const float *pAR, int order) {   
   for (int i = 0; i < order; i++) a_fix_Q16[i] = (int32_t)rintf(pAR[i] * 65536.0f);
   nlsf_A2NLSF(NLSF_Q15, a_fix_Q16, order);
 }
-OB_DEV void silk_find_lpc_thread(const SilkFindLpcParams &p, int s) {
-  ObSilkFindLpc f = p.frames[s];
-  const int order = p.order, nb_subfr = p.nb_subfr, subfr_length = p.subfr_length + order;
-  const float *x = p.x + (size_t)s * nb_subfr * subfr_length;
+OB_DEVNI void silk_find_lpc_core(ObSilkFindLpc &f, const float *x, int order, int nb_subfr, int subfr_length_in) {
+  const int subfr_length = subfr_length_in + order;
   float a[kNlsfMaxOrder], a_tmp[kNlsfMaxOrder], nrg[1], LPC_res[2 * (80 + 16)];
   int16_t NLSF0_Q15[kNlsfMaxOrder], a_fix_Q12[kNlsfMaxOrder];
   f.NLSFInterpCoef_Q2 = 4;
@@ -588,6 +589,224 @@ OB_DEV void silk_find_lpc_thread(const SilkFindLpcParams &p, int s) {
     }
   }
   if (f.NLSFInterpCoef_Q2 == 4) nlsf_a2nlsf_flp(f.NLSF_Q15, a, order);
+}
+OB_DEV void silk_find_lpc_thread(const SilkFindLpcParams &p, int s) {
+  ObSilkFindLpc f = p.frames[s];
+  silk_find_lpc_core(f, p.x + (size_t)s * p.nb_subfr * (p.subfr_length + p.order), p.order, p.nb_subfr, p.subfr_length);
   p.frames[s] = f;
+}
+// ---- the prediction analysis of a SILK frame: silk_find_pred_coefs_FLP (silk/float/find_pred_coefs_FLP.c:35-120) — for voiced frames silk_find_LTP_FLP
+// (find_LTP_FLP.c:34-65, corrMatrix_FLP.c:38-95), silk_quant_LTP_gains (quant_LTP_gains.c:34-132 with silk_VQ_WMat_EC_c, VQ_WMat_EC.c:35-131, through the
+// float wrapper wrappers_FLP.c:175-209), silk_LTP_scale_ctrl_FLP (LTP_scale_ctrl_FLP.c:34-58) and silk_LTP_analysis_filter_FLP (LTP_analysis_filter_FLP.c:34-75);
+// then silk_find_LPC_FLP, silk_process_NLSFs and silk_residual_energy_FLP (residual_energy_FLP.c:91-117).  One thread per stream. ----
+struct ObSilkPredCoefs {   // == OpusB200SilkPredCoefs
+  float Gains[4];
+  int32_t pitchL[4];
+  float coding_quality;
+  int32_t signalType, condCoding, first_frame_after_reset, useInterpolatedNLSFs, PacketLoss_perc, nFramesPerPacket, LBRR_flag, SNR_dB_Q7, speech_activity_Q8,
+      NLSF_MSVQ_Survivors;
+  int16_t prev_NLSFq_Q15[16];   // in / out
+  int32_t sum_log_gain_Q7;      // in / out
+  float LTPCoef[20], LTPredCodGain, LTP_scale, PredCoef[2][16], ResNrg[4];   // out
+  int8_t LTPIndex[4], PERIndex, LTP_scaleIndex, NLSFInterpCoef_Q2, pad;
+  int8_t NLSFIndices[17], pad2[3];
+};
+// res_pitch / x: [n][sig_stride] with the current frame at frame_off (history in front: at least the longest pitch lag + LTP_ORDER / 2 + order samples)
+struct SilkPredCoefsParams { ObSilkPredCoefs *frames; const float *res_pitch, *x; int n, sig_stride, frame_off, order, nb_subfr, subfr_length; };
+OB_DEV int32_t nl_add_pos_sat32(int32_t a, int32_t b) { return (((uint32_t)a + (uint32_t)b) & 0x80000000u) ? INT32_MAX : a + b; }
+OB_DEVNI void silk_vq_wmat_ec(int8_t *ind, int32_t *res_nrg_Q15, int32_t *rate_dist_Q8, int *gain_Q7, const int32_t *XX, const int32_t *xX, const signed char *cb_Q7,
+                              const unsigned char *cb_gain_Q7, const unsigned char *cl_Q5, int subfr_len, int32_t max_gain_Q7, int L) {
+  int32_t neg[5];
+  for (int j = 0; j < 5; j++) neg[j] = -(int32_t)((uint32_t)xX[j] << 7);
+  *rate_dist_Q8 = INT32_MAX;
+  *res_nrg_Q15 = INT32_MAX;
+  *ind = 0;
+  for (int k = 0; k < L; k++, cb_Q7 += 5) {
+    const int gain_tmp_Q7 = cb_gain_Q7[k];
+    const int32_t d = gain_tmp_Q7 - max_gain_Q7, penalty = (int32_t)((uint32_t)(d > 0 ? d : 0) << 11);
+    const int32_t c0 = cb_Q7[0], c1 = cb_Q7[1], c2 = cb_Q7[2], c3 = cb_Q7[3], c4 = cb_Q7[4];
+    int32_t sum1 = 32801, sum2;   // SILK_FIX_CONST(1.001, 15)
+    sum2 = neg[0] + XX[1] * c1; sum2 = sum2 + XX[2] * c2; sum2 = sum2 + XX[3] * c3; sum2 = sum2 + XX[4] * c4;
+    sum2 = (int32_t)((uint32_t)sum2 << 1); sum2 = sum2 + XX[0] * c0;
+    sum1 = sum1 + silk_smulwb(sum2, c0);
+    sum2 = neg[1] + XX[7] * c2; sum2 = sum2 + XX[8] * c3; sum2 = sum2 + XX[9] * c4;
+    sum2 = (int32_t)((uint32_t)sum2 << 1); sum2 = sum2 + XX[6] * c1;
+    sum1 = sum1 + silk_smulwb(sum2, c1);
+    sum2 = neg[2] + XX[13] * c3; sum2 = sum2 + XX[14] * c4;
+    sum2 = (int32_t)((uint32_t)sum2 << 1); sum2 = sum2 + XX[12] * c2;
+    sum1 = sum1 + silk_smulwb(sum2, c2);
+    sum2 = neg[3] + XX[19] * c4;
+    sum2 = (int32_t)((uint32_t)sum2 << 1); sum2 = sum2 + XX[18] * c3;
+    sum1 = sum1 + silk_smulwb(sum2, c3);
+    sum2 = (int32_t)((uint32_t)neg[4] << 1); sum2 = sum2 + XX[24] * c4;
+    sum1 = sum1 + silk_smulwb(sum2, c4);
+    if (sum1 >= 0) {
+      const int32_t bits_tot_Q8 = nl_smulbb(subfr_len, silk_lin2log(sum1 + penalty) - (15 << 7)) + ((int32_t)cl_Q5[k] << 2);
+      if (bits_tot_Q8 <= *rate_dist_Q8) {
+        *rate_dist_Q8 = bits_tot_Q8;
+        *res_nrg_Q15 = sum1 + penalty;
+        *ind = (int8_t)k;
+        *gain_Q7 = gain_tmp_Q7;
+      }
+    }
+  }
+}
+OB_DEVNI void silk_quant_ltp_gains(int16_t *B_Q14, int8_t *cbk_index, int8_t *periodicity_index, int32_t *sum_log_gain_Q7, int *pred_gain_dB_Q7,
+                                   const int32_t *XX_Q17, const int32_t *xX_Q17, int subfr_len, int nb_subfr) {
+  int32_t min_rate_dist_Q7 = INT32_MAX, best_sum_log_gain_Q7 = 0, res_nrg_Q15 = 0;
+  int8_t temp_idx[4];
+  for (int k = 0; k < 3; k++) {
+    const int off = k == 0 ? 0 : k == 1 ? 8 : 24, size = 8 << k;
+    const int32_t gain_safety = 51;   // SILK_FIX_CONST(0.4, 7)
+    int32_t rate_dist_Q7 = 0, sum_log_gain_tmp_Q7 = *sum_log_gain_Q7, nrg = 0;
+    for (int j = 0; j < nb_subfr; j++) {
+      const int32_t max_gain_Q7 = silk_log2lin((5333 - sum_log_gain_tmp_Q7) + 896) - gain_safety;   // MAX_SUM_LOG_GAIN_DB / 6 and 7 in Q7
+      int32_t res_nrg_subfr, rate_dist_subfr;
+      int gain_Q7 = 0;
+      silk_vq_wmat_ec(&temp_idx[j], &res_nrg_subfr, &rate_dist_subfr, &gain_Q7, XX_Q17 + 25 * j, xX_Q17 + 5 * j, ob_silk_LTP_gain_vq + 5 * off, ob_silk_LTP_vq_gain + off,
+                      ob_silk_LTP_gain_BITS_Q5 + off, subfr_len, max_gain_Q7, size);
+      nrg = nl_add_pos_sat32(nrg, res_nrg_subfr);
+      rate_dist_Q7 = nl_add_pos_sat32(rate_dist_Q7, rate_dist_subfr);
+      const int32_t t = sum_log_gain_tmp_Q7 + silk_lin2log(gain_safety + gain_Q7) - 896;
+      sum_log_gain_tmp_Q7 = t > 0 ? t : 0;
+    }
+    res_nrg_Q15 = nrg;   // the value the last codebook leaves behind is the one the reference reports (quant_LTP_gains.c:122-131)
+    if (rate_dist_Q7 <= min_rate_dist_Q7) {
+      min_rate_dist_Q7 = rate_dist_Q7;
+      *periodicity_index = (int8_t)k;
+      for (int j = 0; j < nb_subfr; j++) cbk_index[j] = temp_idx[j];
+      best_sum_log_gain_Q7 = sum_log_gain_tmp_Q7;
+    }
+  }
+  const int off = *periodicity_index == 0 ? 0 : *periodicity_index == 1 ? 8 : 24;
+  for (int j = 0; j < nb_subfr; j++)
+    for (int k = 0; k < 5; k++) B_Q14[j * 5 + k] = (int16_t)(ob_silk_LTP_gain_vq[5 * (off + cbk_index[j]) + k] * 128);
+  res_nrg_Q15 = nb_subfr == 2 ? res_nrg_Q15 >> 1 : res_nrg_Q15 >> 2;
+  *sum_log_gain_Q7 = best_sum_log_gain_Q7;
+  *pred_gain_dB_Q7 = nl_smulbb(-3, silk_lin2log(res_nrg_Q15) - (15 << 7));
+}
+OB_DEVNI void silk_corr_matrix_flp(const float *x, int L, float *XX) {   // silk_corrMatrix_FLP, Order = LTP_ORDER
+  const float *ptr1 = &x[4], *ptr2 = &x[3];
+  double energy = silk_inner_product_flp(ptr1, ptr1, L);
+  XX[0] = (float)energy;
+  for (int j = 1; j < 5; j++) {
+    energy += (double)(ptr1[-j] * ptr1[-j] - ptr1[L - j] * ptr1[L - j]);
+    XX[j * 5 + j] = (float)energy;
+  }
+  for (int lag = 1; lag < 5; lag++) {
+    energy = silk_inner_product_flp(ptr1, ptr2, L);
+    XX[lag * 5] = (float)energy;
+    XX[lag] = (float)energy;
+    for (int j = 1; j < 5 - lag; j++) {
+      energy += (double)(ptr1[-j] * ptr2[-j] - ptr1[L - j] * ptr2[L - j]);
+      XX[(lag + j) * 5 + j] = (float)energy;
+      XX[j * 5 + lag + j] = (float)energy;
+    }
+    ptr2--;
+  }
+}
+OB_DEV void silk_lpc_res_flp(float *r, const float *a, const float *s, int length, int order) {   // silk_LPC_analysis_filter_FLP
+  for (int ix = order; ix < length; ix++) {
+    const float *sp = &s[ix - 1];
+    float pred = sp[0] * a[0];
+    for (int j = 1; j < order; j++) pred = pred + sp[-j] * a[j];
+    r[ix] = sp[1] - pred;
+  }
+  for (int ix = 0; ix < order; ix++) r[ix] = 0.f;
+}
+OB_DEV void silk_find_pred_coefs_thread(const SilkPredCoefsParams &p, int s) {
+  ObSilkPredCoefs c = p.frames[s];
+  const int order = p.order, nb_subfr = p.nb_subfr, subfr_length = p.subfr_length;
+  const float *res_pitch = p.res_pitch + (size_t)s * p.sig_stride + p.frame_off, *x = p.x + (size_t)s * p.sig_stride + p.frame_off;
+  float invGains[4], LPC_in_pre[4 * 16 + 320], minInvGain;
+  for (int i = 0; i < nb_subfr; i++) invGains[i] = 1.0f / c.Gains[i];
+  if (c.signalType == 2) {
+    float XXLTP[4 * 25], xXLTP[4 * 5];
+    int32_t XX_Q17[100], xX_Q17[20];
+    int16_t B_Q14[20];
+    const float *r_ptr = res_pitch;
+    for (int k = 0; k < nb_subfr; k++) {   // silk_find_LTP_FLP
+      const float *lag_ptr = r_ptr - (c.pitchL[k] + 2);
+      float *XX = XXLTP + 25 * k, *xX = xXLTP + 5 * k;
+      silk_corr_matrix_flp(lag_ptr, subfr_length, XX);
+      for (int j = 0; j < 5; j++) xX[j] = (float)silk_inner_product_flp(&lag_ptr[4 - j], r_ptr, subfr_length);
+      const float xx = (float)silk_inner_product_flp(r_ptr, r_ptr, subfr_length + 5);
+      float temp = 0.03f * 0.5f * (XX[0] + XX[24]) + 1.0f;   // LTP_CORR_INV_MAX
+      temp = 1.0f / (xx > temp ? xx : temp);
+      for (int j = 0; j < 25; j++) XX[j] *= temp;
+      for (int j = 0; j < 5; j++) xX[j] *= temp;
+      r_ptr += subfr_length;
+    }
+    for (int i = 0; i < nb_subfr * 25; i++) XX_Q17[i] = (int32_t)rintf(XXLTP[i] * 131072.0f);
+    for (int i = 0; i < nb_subfr * 5; i++) xX_Q17[i] = (int32_t)rintf(xXLTP[i] * 131072.0f);
+    int pred_gain_dB_Q7;
+    silk_quant_ltp_gains(B_Q14, c.LTPIndex, &c.PERIndex, &c.sum_log_gain_Q7, &pred_gain_dB_Q7, XX_Q17, xX_Q17, subfr_length, nb_subfr);
+    for (int i = 0; i < nb_subfr * 5; i++) c.LTPCoef[i] = (float)B_Q14[i] * (1.0f / 16384.0f);
+    c.LTPredCodGain = (float)pred_gain_dB_Q7 * (1.0f / 128.0f);
+    if (c.condCoding == 0) {   // silk_LTP_scale_ctrl_FLP
+      int round_loss = c.PacketLoss_perc * c.nFramesPerPacket;
+      if (c.LBRR_flag) round_loss = 2 + nl_smulbb(round_loss, round_loss) / 100;
+      const int32_t g = nl_smulbb((int32_t)c.LTPredCodGain, round_loss);
+      c.LTP_scaleIndex = (int8_t)((g > silk_log2lin(2900 - c.SNR_dB_Q7)) + (g > silk_log2lin(3900 - c.SNR_dB_Q7)));
+    } else c.LTP_scaleIndex = 0;
+    c.LTP_scale = (float)(c.LTP_scaleIndex == 0 ? 15565 : c.LTP_scaleIndex == 1 ? 12288 : 8192) / 16384.0f;   // silk_LTPScales_table_Q14
+    const float *x_ptr = x - order;
+    float *res = LPC_in_pre;
+    for (int k = 0; k < nb_subfr; k++) {   // silk_LTP_analysis_filter_FLP
+      const float *x_lag_ptr = x_ptr - c.pitchL[k], inv_gain = invGains[k], *B = &c.LTPCoef[k * 5];
+      for (int i = 0; i < subfr_length + order; i++) {
+        float v = x_ptr[i];
+        for (int j = 0; j < 5; j++) v -= B[j] * x_lag_ptr[2 - j];
+        res[i] = v * inv_gain;
+        x_lag_ptr++;
+      }
+      res += subfr_length + order;
+      x_ptr += subfr_length;
+    }
+  } else {
+    const float *x_ptr = x - order;
+    float *pre = LPC_in_pre;
+    for (int i = 0; i < nb_subfr; i++) {
+      for (int j = 0; j < subfr_length + order; j++) pre[j] = invGains[i] * x_ptr[j];
+      pre += subfr_length + order;
+      x_ptr += subfr_length;
+    }
+    for (int i = 0; i < nb_subfr * 5; i++) c.LTPCoef[i] = 0.f;
+    c.LTPredCodGain = 0.0f;
+    c.sum_log_gain_Q7 = 0;
+  }
+  if (c.first_frame_after_reset) minInvGain = 1.0f / 1e2f;
+  else {
+    minInvGain = (float)pow(2.0, (double)(c.LTPredCodGain / 3)) / 1e4f;
+    minInvGain /= 0.25f + 0.75f * c.coding_quality;
+  }
+  ObSilkFindLpc f;
+  for (int i = 0; i < 16; i++) { f.NLSF_Q15[i] = 0; f.prev_NLSFq_Q15[i] = c.prev_NLSFq_Q15[i]; }
+  f.minInvGain = minInvGain; f.useInterpolatedNLSFs = c.useInterpolatedNLSFs; f.first_frame_after_reset = c.first_frame_after_reset; f.NLSFInterpCoef_Q2 = 4;
+  silk_find_lpc_core(f, LPC_in_pre, order, nb_subfr, subfr_length);
+  c.NLSFInterpCoef_Q2 = (int8_t)f.NLSFInterpCoef_Q2;
+  ObSilkNlsf q;
+  for (int i = 0; i < 16; i++) { q.NLSF_Q15[i] = i < order ? f.NLSF_Q15[i] : 0; q.prev_NLSFq_Q15[i] = c.prev_NLSFq_Q15[i]; }
+  q.NLSFInterpCoef_Q2 = c.NLSFInterpCoef_Q2; q.signalType = (int8_t)c.signalType; q.useInterpolatedNLSFs = (int8_t)c.useInterpolatedNLSFs;
+  q.speech_activity_Q8 = c.speech_activity_Q8; q.NLSF_MSVQ_Survivors = c.NLSF_MSVQ_Survivors;
+  for (int i = 0; i < 17; i++) q.NLSFIndices[i] = 0;
+  silk_process_nlsfs_core(q, order == 16, nb_subfr);
+  for (int i = 0; i < 17; i++) c.NLSFIndices[i] = q.NLSFIndices[i];
+  for (int j = 0; j < 2; j++)
+    for (int i = 0; i < 16; i++) c.PredCoef[j][i] = i < order ? (float)q.PredCoef_Q12[j][i] * (1.0f / 4096.0f) : 0.f;
+  {   // silk_residual_energy_FLP
+    const int shift = order + subfr_length;
+    float LPC_res[192];
+    silk_lpc_res_flp(LPC_res, c.PredCoef[0], LPC_in_pre, 2 * shift, order);
+    c.ResNrg[0] = (float)((double)(c.Gains[0] * c.Gains[0]) * silk_inner_product_flp(LPC_res + order, LPC_res + order, subfr_length));
+    c.ResNrg[1] = (float)((double)(c.Gains[1] * c.Gains[1]) * silk_inner_product_flp(LPC_res + order + shift, LPC_res + order + shift, subfr_length));
+    if (nb_subfr == 4) {
+      silk_lpc_res_flp(LPC_res, c.PredCoef[1], LPC_in_pre + 2 * shift, 2 * shift, order);
+      c.ResNrg[2] = (float)((double)(c.Gains[2] * c.Gains[2]) * silk_inner_product_flp(LPC_res + order, LPC_res + order, subfr_length));
+      c.ResNrg[3] = (float)((double)(c.Gains[3] * c.Gains[3]) * silk_inner_product_flp(LPC_res + order + shift, LPC_res + order + shift, subfr_length));
+    }
+  }
+  for (int i = 0; i < 16; i++) c.prev_NLSFq_Q15[i] = i < order ? q.NLSF_Q15[i] : 0;
+  p.frames[s] = c;
 }
 }  // namespace ob

@@ -111,6 +111,16 @@ class Ops:
             raise capi.OpusB200Error(r, 'opusb200_silk_find_lpc')
         return frames
 
+    def silk_find_pred_coefs(self, frames, res_pitch, x, frame_off, fs_kHz, nb_subfr):
+        """silk_find_pred_coefs_FLP for n streams: frames = ctypes array of OpusB200SilkPredCoefs-shaped records (in place); res_pitch / x float32
+        [n, stride] with the current frame at frame_off"""
+        res_pitch, x = np.ascontiguousarray(res_pitch, np.float32), np.ascontiguousarray(x, np.float32)
+        r = self._L.opusb200_silk_find_pred_coefs(self._h, ctypes.cast(frames, ctypes.c_void_p), res_pitch.ctypes.data_as(ctypes.c_void_p),
+                                                  x.ctypes.data_as(ctypes.c_void_p), len(frames), x.shape[1], frame_off, fs_kHz, nb_subfr, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_find_pred_coefs')
+        return frames
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

@@ -569,3 +569,15 @@ extern "C" void emu_silk_find_lpc(void *frames, const float *x, int n, int order
   p.frames = (ObSilkFindLpc *)frames; p.x = x; p.n = n; p.order = order; p.nb_subfr = nb_subfr; p.subfr_length = subfr_length;
   emu_launch(silk_find_lpc_entry, &p, (n + 31) / 32, 32, 0);
 }
+static void silk_pred_coefs_entry(void *a) {
+  const SilkPredCoefsParams &p = *(const SilkPredCoefsParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_find_pred_coefs_thread(p, s);
+}
+extern "C" void emu_silk_find_pred_coefs(void *frames, const float *res_pitch, const float *x, int n, int sig_stride, int frame_off, int order, int nb_subfr,
+                                         int subfr_length) {
+  SilkPredCoefsParams p;
+  p.frames = (ObSilkPredCoefs *)frames; p.res_pitch = res_pitch; p.x = x; p.n = n; p.sig_stride = sig_stride; p.frame_off = frame_off; p.order = order;
+  p.nb_subfr = nb_subfr; p.subfr_length = subfr_length;
+  emu_launch(silk_pred_coefs_entry, &p, (n + 31) / 32, 32, 0);
+}

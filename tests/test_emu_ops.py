@@ -312,3 +312,30 @@ def test_silk_find_lpc_emulated(order, nb_subfr, subfr_length):
     E.emu_silk_find_lpc(ctypes.cast(recs, ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), n, order, nb_subfr, subfr_length)
     for s in range(n):
         assert list(recs[s].NLSF_Q15)[:order] == list(want[s].NLSF_Q15)[:order] and recs[s].NLSFInterpCoef_Q2 == want[s].NLSFInterpCoef_Q2, s
+
+
+@pytest.mark.parametrize('fs_kHz,nb_subfr', [(16, 4), (8, 4), (12, 2)])
+def test_silk_find_pred_coefs_emulated(fs_kHz, nb_subfr):
+    """silk_find_pred_coefs_FLP (the whole prediction analysis of a SILK frame): the device source on the emulator against the oracle (pinned on the
+    reference), streams that carry sum_log_gain and the previous NLSFs over several frames"""
+    from test_silk_pred_coefs_oracle_vs_ref import PredCoefs, random_case, outputs, HIST
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    order, subfr_length = (16 if fs_kHz == 16 else 10), 5 * fs_kHz
+    rng = np.random.default_rng(70 + fs_kHz)
+    n = 20
+    prev, slg = [[0] * 16 for _ in range(n)], [0] * n
+    for frame in range(4):
+        recs = (PredCoefs * n)()
+        want, R_, X_ = [], [], []
+        for s in range(n):
+            recs[s], res, x = random_case(rng, order, nb_subfr, subfr_length, fs_kHz, frame, prev[s], slg[s])
+            w = PredCoefs.from_buffer_copy(bytes(recs[s]))
+            O.orc_silk_find_pred_coefs(ctypes.byref(w), res[HIST:].ctypes.data_as(ctypes.c_void_p), x[HIST:].ctypes.data_as(ctypes.c_void_p), order, nb_subfr, subfr_length)
+            want.append(w); R_.append(res); X_.append(x)
+        R_, X_ = np.stack(R_), np.stack(X_)
+        E.emu_silk_find_pred_coefs(ctypes.cast(recs, ctypes.c_void_p), R_.ctypes.data_as(ctypes.c_void_p), X_.ctypes.data_as(ctypes.c_void_p), n, R_.shape[1], HIST, order,
+                                   nb_subfr, subfr_length)
+        for s in range(n):
+            oa, ob = outputs(recs[s], order, nb_subfr), outputs(want[s], order, nb_subfr)
+            assert oa == ob, (frame, s, [i for i in range(len(oa)) if oa[i] != ob[i]])
+            prev[s], slg[s] = list(want[s].prev_NLSFq_Q15), want[s].sum_log_gain_Q7
