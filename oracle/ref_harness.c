@@ -549,3 +549,33 @@ void refh_silk_find_pred_coefs(RefhSilkPredCoefs *c, const float *res_pitch, con
   c->PERIndex = st.sCmn.indices.PERIndex; c->LTP_scaleIndex = st.sCmn.indices.LTP_scaleIndex; c->NLSFInterpCoef_Q2 = st.sCmn.indices.NLSFInterpCoef_Q2;
   memcpy(c->NLSFIndices, st.sCmn.indices.NLSFIndices, 17);
 }
+
+/* ---- silk_noise_shape_analysis_FLP on scratch encoder structs (silk/float/noise_shape_analysis_FLP.c:138-350) ---- */
+typedef struct {
+  opus_int32 SNR_dB_Q7, input_quality_bands_Q15[2], useCBR, speech_activity_Q8, signalType, warping_Q16;
+  float LTPCorr, predGain;
+  opus_int32 pitchL[4];
+  float HarmShapeGain_smth, Tilt_smth;
+  float input_quality, coding_quality;
+  opus_int32 quantOffsetType;
+  float AR[4 * 24], Gains[4], LF_MA_shp[4], LF_AR_shp[4], HarmShapeGain[4], Tilt[4];
+} RefhSilkNoiseShape;   /* == OrcSilkNoiseShape */
+void refh_silk_noise_shape_analysis(RefhSilkNoiseShape *c, const float *pitch_res, const float *x, int fs_kHz, int nb_subfr, int shapingLPCOrder) {
+  static silk_encoder_state_FLP st;
+  static silk_encoder_control_FLP ctl;
+  int k;
+  memset(&st, 0, sizeof(st));
+  memset(&ctl, 0, sizeof(ctl));
+  st.sCmn.fs_kHz = fs_kHz; st.sCmn.nb_subfr = nb_subfr; st.sCmn.subfr_length = 5 * fs_kHz; st.sCmn.la_shape = 5 * fs_kHz;
+  st.sCmn.shapeWinLength = 5 * fs_kHz + 2 * st.sCmn.la_shape; st.sCmn.shapingLPCOrder = shapingLPCOrder;
+  st.sCmn.SNR_dB_Q7 = c->SNR_dB_Q7; st.sCmn.input_quality_bands_Q15[0] = c->input_quality_bands_Q15[0]; st.sCmn.input_quality_bands_Q15[1] = c->input_quality_bands_Q15[1];
+  st.sCmn.useCBR = c->useCBR; st.sCmn.speech_activity_Q8 = c->speech_activity_Q8; st.sCmn.indices.signalType = (opus_int8)c->signalType;
+  st.sCmn.warping_Q16 = c->warping_Q16; st.LTPCorr = c->LTPCorr; ctl.predGain = c->predGain;
+  st.sShape.HarmShapeGain_smth = c->HarmShapeGain_smth; st.sShape.Tilt_smth = c->Tilt_smth;
+  for (k = 0; k < 4; k++) ctl.pitchL[k] = c->pitchL[k];
+  silk_noise_shape_analysis_FLP(&st, &ctl, pitch_res, x);
+  c->HarmShapeGain_smth = st.sShape.HarmShapeGain_smth; c->Tilt_smth = st.sShape.Tilt_smth;
+  c->input_quality = ctl.input_quality; c->coding_quality = ctl.coding_quality; c->quantOffsetType = st.sCmn.indices.quantOffsetType;
+  memcpy(c->AR, ctl.AR, sizeof(c->AR)); memcpy(c->Gains, ctl.Gains, sizeof(c->Gains)); memcpy(c->LF_MA_shp, ctl.LF_MA_shp, sizeof(c->LF_MA_shp));
+  memcpy(c->LF_AR_shp, ctl.LF_AR_shp, sizeof(c->LF_AR_shp)); memcpy(c->HarmShapeGain, ctl.HarmShapeGain, sizeof(c->HarmShapeGain)); memcpy(c->Tilt, ctl.Tilt, sizeof(c->Tilt));
+}

@@ -390,3 +390,192 @@ void orc_silk_process_gains(OrcSilkGains *g, int nb_subfr, int subfr_length, int
               0.8f * quant_offset;
 }
 int orc_silk_gains_size(void) { return (int)sizeof(OrcSilkGains); }
+
+/* ---- noise shaping analysis of a SILK frame: silk_noise_shape_analysis_FLP (silk/float/noise_shape_analysis_FLP.c:36-350) with silk_apply_sine_window_FLP
+ * (float/apply_sine_window_FLP.c:38-80), silk_warped_autocorrelation_FLP (float/warped_autocorrelation_FLP.c:35-75), silk_autocorrelation_FLP,
+ * silk_schur_FLP (float/schur_FLP.c:34-70), silk_k2a_FLP (float/k2a_FLP.c:35-55), silk_bwexpander_FLP (float/bwexpander_FLP.c:35-50). ---- */
+#define NS_MAX_ORDER 24
+typedef struct { /* what the function reads and writes in silk_encoder_state_FLP / silk_encoder_control_FLP; == OpusB200SilkNoiseShape */
+  int32_t SNR_dB_Q7, input_quality_bands_Q15[2], useCBR, speech_activity_Q8, signalType, warping_Q16;
+  float LTPCorr, predGain;
+  int32_t pitchL[4];
+  float HarmShapeGain_smth, Tilt_smth;                     /* in / out (silk_shape_state_FLP) */
+  float input_quality, coding_quality;                     /* out */
+  int32_t quantOffsetType;                                 /* out */
+  float AR[4 * NS_MAX_ORDER], Gains[4], LF_MA_shp[4], LF_AR_shp[4], HarmShapeGain[4], Tilt[4];   /* out */
+} OrcSilkNoiseShape;
+int orc_silk_noise_shape_size(void) { return (int)sizeof(OrcSilkNoiseShape); }
+static void ns_sine_window(float *w, const float *px, int win_type, int length) {
+  const float freq = 3.1415926536f / (length + 1), c = 2.0f - freq * freq;
+  float S0 = win_type < 2 ? 0.0f : 1.0f, S1 = win_type < 2 ? freq : 0.5f * c;
+  int k;
+  for (k = 0; k < length; k += 4) {
+    w[k + 0] = px[k + 0] * 0.5f * (S0 + S1);
+    w[k + 1] = px[k + 1] * S1;
+    S0 = c * S1 - S0;
+    w[k + 2] = px[k + 2] * 0.5f * (S1 + S0);
+    w[k + 3] = px[k + 3] * S0;
+    S1 = c * S0 - S1;
+  }
+}
+static void ns_bwexpander(float *ar, int d, float chirp) {
+  float cfac = chirp;
+  int i;
+  for (i = 0; i < d - 1; i++) { ar[i] *= cfac; cfac *= chirp; }
+  ar[d - 1] *= cfac;
+}
+static void ns_limit(float *coefs, float lambda, float limit, int order, int warped) { /* warped_true2monic_coefs / limit_coefs */
+  float tmp, maxabs, chirp, gain = 0;
+  int i, iter, ind = 0;
+  if (warped) {
+    for (i = order - 1; i > 0; i--) coefs[i - 1] -= lambda * coefs[i];
+    gain = (1.0f - lambda * lambda) / (1.0f + lambda * coefs[0]);
+    for (i = 0; i < order; i++) coefs[i] *= gain;
+  }
+  for (iter = 0; iter < 10; iter++) {
+    maxabs = -1.0f;
+    for (i = 0; i < order; i++) {
+      tmp = coefs[i] < 0 ? -coefs[i] : coefs[i];
+      if (tmp > maxabs) { maxabs = tmp; ind = i; }
+    }
+    if (maxabs <= limit) return;
+    if (warped) {
+      for (i = 1; i < order; i++) coefs[i - 1] += lambda * coefs[i];
+      gain = 1.0f / gain;
+      for (i = 0; i < order; i++) coefs[i] *= gain;
+    }
+    chirp = 0.99f - (0.8f + 0.1f * iter) * (maxabs - limit) / (maxabs * (ind + 1));
+    ns_bwexpander(coefs, order, chirp);
+    if (warped) {
+      for (i = order - 1; i > 0; i--) coefs[i - 1] -= lambda * coefs[i];
+      gain = (1.0f - lambda * lambda) / (1.0f + lambda * coefs[0]);
+      for (i = 0; i < order; i++) coefs[i] *= gain;
+    }
+  }
+}
+/* pitch_res: the frame's residual from the pitch analysis; x: the frame of the input with la_shape samples in front and shapeWinLength - la_shape -
+ * subfr_length behind the last subframe's start */
+void orc_silk_noise_shape_analysis(OrcSilkNoiseShape *c, const float *pitch_res, const float *x, int fs_kHz, int nb_subfr, int shapingLPCOrder) {
+  const int subfr_length = 5 * fs_kHz, la_shape = 5 * fs_kHz, shapeWinLength = 5 * fs_kHz + 2 * la_shape, order = shapingLPCOrder;
+  float SNR_adj_dB, HarmShapeGain, Tilt, nrg, strength, BWExp, gain_mult, gain_add, b, warping, x_windowed[240], auto_corr[NS_MAX_ORDER + 1], rc[NS_MAX_ORDER + 1];
+  const float *x_ptr = x - la_shape;
+  int k, i, n;
+  SNR_adj_dB = c->SNR_dB_Q7 * (1 / 128.0f);
+  c->input_quality = 0.5f * (c->input_quality_bands_Q15[0] + c->input_quality_bands_Q15[1]) * (1.0f / 32768.0f);
+  c->coding_quality = (float)(1.0 / (1.0 + exp(-(0.25f * (SNR_adj_dB - 20.0f)))));
+  if (c->useCBR == 0) {
+    b = 1.0f - c->speech_activity_Q8 * (1.0f / 256.0f);
+    SNR_adj_dB -= 2.0f * c->coding_quality * (0.5f + 0.5f * c->input_quality) * b * b;
+  }
+  if (c->signalType == 2) SNR_adj_dB += 2.0f * c->LTPCorr;
+  else SNR_adj_dB += (-0.4f * c->SNR_dB_Q7 * (1 / 128.0f) + 6.0f) * (1.0f - c->input_quality);
+  if (c->signalType == 2) c->quantOffsetType = 0;
+  else {
+    const int nSamples = 2 * fs_kHz, nSegs = (5 * nb_subfr) / 2;
+    float energy_variation = 0.0f, log_energy_prev = 0.0f, log_energy;
+    const float *p = pitch_res;
+    for (k = 0; k < nSegs; k++) {
+      nrg = (float)nSamples + (float)inner_product_flp(p, p, nSamples);
+      log_energy = (float)(3.32192809488736 * log10((double)nrg));
+      if (k > 0) energy_variation += log_energy - log_energy_prev < 0 ? -(log_energy - log_energy_prev) : log_energy - log_energy_prev;
+      log_energy_prev = log_energy;
+      p += nSamples;
+    }
+    c->quantOffsetType = energy_variation > 0.6f * (nSegs - 1) ? 0 : 1;
+  }
+  strength = 1e-3f * c->predGain;
+  BWExp = 0.94f / (1.0f + strength * strength);
+  warping = (float)c->warping_Q16 / 65536.0f + 0.01f * c->coding_quality;
+  for (k = 0; k < nb_subfr; k++) {
+    const int flat_part = fs_kHz * 3, slope_part = (shapeWinLength - flat_part) / 2;
+    float *AR = &c->AR[k * NS_MAX_ORDER];
+    ns_sine_window(x_windowed, x_ptr, 1, slope_part);
+    memcpy(x_windowed + slope_part, x_ptr + slope_part, flat_part * sizeof(float));
+    ns_sine_window(x_windowed + slope_part + flat_part, x_ptr + slope_part + flat_part, 2, slope_part);
+    x_ptr += subfr_length;
+    if (c->warping_Q16 > 0) {
+      double state[NS_MAX_ORDER + 1] = {0}, C[NS_MAX_ORDER + 1] = {0}, tmp1, tmp2;
+      for (n = 0; n < shapeWinLength; n++) {
+        tmp1 = x_windowed[n];
+        for (i = 0; i < order; i += 2) {
+          tmp2 = state[i] + warping * state[i + 1] - warping * tmp1;
+          state[i] = tmp1;
+          C[i] += state[0] * tmp1;
+          tmp1 = state[i + 1] + warping * state[i + 2] - warping * tmp2;
+          state[i + 1] = tmp2;
+          C[i + 1] += state[0] * tmp2;
+        }
+        state[order] = tmp1;
+        C[order] += state[0] * tmp1;
+      }
+      for (i = 0; i < order + 1; i++) auto_corr[i] = (float)C[i];
+    } else {
+      for (i = 0; i < order + 1; i++) auto_corr[i] = (float)inner_product_flp(x_windowed, x_windowed + i, shapeWinLength - i);
+    }
+    auto_corr[0] += auto_corr[0] * 3e-5f + 1.0f;
+    { /* silk_schur_FLP */
+      double Cs[NS_MAX_ORDER + 1][2] = {{0}}, Ctmp1, Ctmp2, rc_tmp;
+      for (i = 0; i <= order; i++) Cs[i][0] = Cs[i][1] = auto_corr[i];
+      for (i = 0; i < order; i++) {
+        const double den = Cs[0][1] > 1e-9f ? Cs[0][1] : 1e-9f; /* silk_max_float is a macro: the comparison and the result stay double */
+        rc_tmp = -Cs[i + 1][0] / den;
+        rc[i] = (float)rc_tmp;
+        for (n = 0; n < order - i; n++) {
+          Ctmp1 = Cs[n + i + 1][0];
+          Ctmp2 = Cs[n][1];
+          Cs[n + i + 1][0] = Ctmp1 + Ctmp2 * rc_tmp;
+          Cs[n][1] = Ctmp2 + Ctmp1 * rc_tmp;
+        }
+      }
+      nrg = (float)Cs[0][1];
+    }
+    for (i = 0; i < order; i++) { /* silk_k2a_FLP */
+      const float rck = rc[i];
+      for (n = 0; n < (i + 1) >> 1; n++) {
+        const float tmp1 = AR[n], tmp2 = AR[i - n - 1];
+        AR[n] = tmp1 + tmp2 * rck;
+        AR[i - n - 1] = tmp2 + tmp1 * rck;
+      }
+      AR[i] = -rck;
+    }
+    c->Gains[k] = (float)sqrt(nrg);
+    if (c->warping_Q16 > 0) { /* warped_gain */
+      const float lambda = -warping;
+      float gain = AR[order - 1];
+      for (i = order - 2; i >= 0; i--) gain = lambda * gain + AR[i];
+      c->Gains[k] *= (float)(1.0f / (1.0f - lambda * gain));
+    }
+    ns_bwexpander(AR, order, BWExp);
+    ns_limit(AR, warping, 3.999f, order, c->warping_Q16 > 0);
+  }
+  gain_mult = (float)pow(2.0f, -0.16f * SNR_adj_dB);
+  gain_add = (float)pow(2.0f, 0.16f * 2);
+  for (k = 0; k < nb_subfr; k++) { c->Gains[k] *= gain_mult; c->Gains[k] += gain_add; }
+  strength = 4.0f * (1.0f + 0.5f * (c->input_quality_bands_Q15[0] * (1.0f / 32768.0f) - 1.0f));
+  strength *= c->speech_activity_Q8 * (1.0f / 256.0f);
+  if (c->signalType == 2) {
+    for (k = 0; k < nb_subfr; k++) {
+      b = 0.2f / fs_kHz + 3.0f / c->pitchL[k];
+      c->LF_MA_shp[k] = -1.0f + b;
+      c->LF_AR_shp[k] = 1.0f - b - b * strength;
+    }
+    Tilt = -0.25f - (1 - 0.25f) * 0.35f * c->speech_activity_Q8 * (1.0f / 256.0f);
+  } else {
+    b = 1.3f / fs_kHz;
+    c->LF_MA_shp[0] = -1.0f + b;
+    c->LF_AR_shp[0] = 1.0f - b - b * strength * 0.6f;
+    for (k = 1; k < nb_subfr; k++) { c->LF_MA_shp[k] = c->LF_MA_shp[0]; c->LF_AR_shp[k] = c->LF_AR_shp[0]; }
+    Tilt = -0.25f;
+  }
+  if (c->signalType == 2) {
+    HarmShapeGain = 0.3f;
+    HarmShapeGain += 0.2f * (1.0f - (1.0f - c->coding_quality) * c->input_quality);
+    HarmShapeGain *= (float)sqrt(c->LTPCorr);
+  } else HarmShapeGain = 0.0f;
+  for (k = 0; k < nb_subfr; k++) {
+    c->HarmShapeGain_smth += 0.4f * (HarmShapeGain - c->HarmShapeGain_smth);
+    c->HarmShapeGain[k] = c->HarmShapeGain_smth;
+    c->Tilt_smth += 0.4f * (Tilt - c->Tilt_smth);
+    c->Tilt[k] = c->Tilt_smth;
+  }
+}
