@@ -500,6 +500,24 @@ typedef struct {
 int opusb200_silk_find_pred_coefs(OpusB200Ctx *ctx, OpusB200SilkPredCoefs *frames, const float *res_pitch, const float *x, int n, int sig_stride, int frame_off,
                                   int fs_kHz, int nb_subfr, int on_device);
 
+/* silk_noise_shape_analysis_FLP (silk/float/noise_shape_analysis_FLP.c:138-350; call site silk/float/encode_frame_FLP.c:158): the noise shaping
+ * analysis of a SILK frame — coding / input quality and the SNR adjustment, the sparseness measure (quantOffsetType of unvoiced frames), per subframe
+ * the windowed (warped) autocorrelation, Schur recursion, step-up, bandwidth expansion and coefficient limiting (AR, 24 slots per subframe) and the
+ * initial gains; gain tweaking; low-frequency, tilt and harmonic shaping with their smoothers (HarmShapeGain_smth / Tilt_smth carried in the record).
+ * pitch_res [n][res_stride]: the frame's residual; x [n][x_stride] with the frame at x_off (5 ms in front, 5 ms look-ahead behind).  shapingLPCOrder
+ * even, <= 24 (12 / 14 / 16 / 24 by complexity, silk/control_codec.c).  Float arithmetic in the reference's order; doubles where it uses them. */
+typedef struct {
+  int32_t SNR_dB_Q7, input_quality_bands_Q15[2], useCBR, speech_activity_Q8, signalType, warping_Q16;
+  float LTPCorr, predGain;
+  int32_t pitchL[4];
+  float HarmShapeGain_smth, Tilt_smth;
+  float input_quality, coding_quality;
+  int32_t quantOffsetType;
+  float AR[4 * 24], Gains[4], LF_MA_shp[4], LF_AR_shp[4], HarmShapeGain[4], Tilt[4];
+} OpusB200SilkNoiseShape;
+int opusb200_silk_noise_shape_analysis(OpusB200Ctx *ctx, OpusB200SilkNoiseShape *frames, const float *pitch_res, int res_stride, const float *x, int x_stride,
+                                       int x_off, int n, int fs_kHz, int nb_subfr, int shapingLPCOrder, int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

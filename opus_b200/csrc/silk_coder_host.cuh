@@ -309,3 +309,44 @@ extern "C" int opusb200_silk_find_pred_coefs(OpusB200Ctx *c, OpusB200SilkPredCoe
   }
   return r;
 }
+
+// ---- silk_noise_shape_analysis_FLP for n streams (silk_nlsf.cuh: silk_noise_shape_thread) ----
+extern "C" __global__ void __launch_bounds__(64) ob_silk_noise_shape_analysis(ob::SilkNoiseShapeParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_noise_shape_thread(p, s);
+}
+extern "C" int opusb200_silk_noise_shape_analysis(OpusB200Ctx *c, OpusB200SilkNoiseShape *frames, const float *pitch_res, int res_stride, const float *x, int x_stride,
+                                                  int x_off, int n, int fs_kHz, int nb_subfr, int shapingLPCOrder, int on_device) {
+  static_assert(sizeof(OpusB200SilkNoiseShape) == sizeof(ob::ObSilkNoiseShape), "OpusB200SilkNoiseShape mirrors ObSilkNoiseShape");
+  if (!c || !frames || !pitch_res || !x || n <= 0 || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16) || (nb_subfr != 2 && nb_subfr != 4) || shapingLPCOrder < 2 ||
+      shapingLPCOrder > 24 || (shapingLPCOrder & 1))
+    return OPUSB200_BAD_ARG;
+  const int frame = 5 * fs_kHz * nb_subfr, la = 5 * fs_kHz;
+  if (res_stride < frame || x_off < la || x_stride < x_off + frame + la) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkNoiseShapeParams p;
+  p.n = n; p.res_stride = res_stride; p.x_stride = x_stride; p.x_off = x_off; p.fs_kHz = fs_kHz; p.nb_subfr = nb_subfr; p.shapingLPCOrder = shapingLPCOrder;
+  const size_t fb = sizeof(ob::ObSilkNoiseShape) * (size_t)n, rb = sizeof(float) * (size_t)n * res_stride, xb = sizeof(float) * (size_t)n * x_stride;
+  ob::ObSilkNoiseShape *d = (ob::ObSilkNoiseShape *)frames;
+  float *dr = nullptr, *dx = nullptr;
+  int r = OPUSB200_OK;
+  if (!on_device) {
+    if (cudaMalloc(&d, fb) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMalloc(&dr, rb) != cudaSuccess || cudaMalloc(&dx, xb) != cudaSuccess) { cudaFree(d); cudaFree(dr); return OPUSB200_ALLOC_FAIL; }
+    if (cudaMemcpyAsync(d, frames, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaMemcpyAsync(dr, pitch_res, rb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (r == OPUSB200_OK) {
+    p.frames = d; p.pitch_res = on_device ? pitch_res : dr; p.x = on_device ? x : dx;
+    ob_silk_noise_shape_analysis<<<(n + 63) / 64, 64, 0, c->stream>>>(p);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, fb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d); cudaFree(dr); cudaFree(dx);
+  }
+  return r;
+}

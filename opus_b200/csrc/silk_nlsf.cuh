@@ -809,4 +809,188 @@ OB_DEV void silk_find_pred_coefs_thread(const SilkPredCoefsParams &p, int s) {
   for (int i = 0; i < 16; i++) c.prev_NLSFq_Q15[i] = i < order ? q.NLSF_Q15[i] : 0;
   p.frames[s] = c;
 }
+// ---- noise shaping analysis of a SILK frame: silk_noise_shape_analysis_FLP (silk/float/noise_shape_analysis_FLP.c:36-350) with silk_apply_sine_window_FLP,
+// silk_warped_autocorrelation_FLP / silk_autocorrelation_FLP, silk_schur_FLP, silk_k2a_FLP, silk_bwexpander_FLP.  One thread per stream: the warped
+// autocorrelation is a serial all-pass recursion over the window (double precision, as in the reference). ----
+constexpr int kNsMaxOrder = 24;
+struct ObSilkNoiseShape {   // == OpusB200SilkNoiseShape
+  int32_t SNR_dB_Q7, input_quality_bands_Q15[2], useCBR, speech_activity_Q8, signalType, warping_Q16;
+  float LTPCorr, predGain;
+  int32_t pitchL[4];
+  float HarmShapeGain_smth, Tilt_smth;                     // in / out
+  float input_quality, coding_quality;                     // out
+  int32_t quantOffsetType;                                 // out
+  float AR[4 * kNsMaxOrder], Gains[4], LF_MA_shp[4], LF_AR_shp[4], HarmShapeGain[4], Tilt[4];   // out
+};
+// pitch_res [n][res_stride]: the frame's residual from the pitch analysis; x [n][x_stride] with the frame at x_off (la_shape samples in front, look-ahead behind)
+struct SilkNoiseShapeParams { ObSilkNoiseShape *frames; const float *pitch_res, *x; int n, res_stride, x_stride, x_off, fs_kHz, nb_subfr, shapingLPCOrder; };
+OB_DEV void ns_sine_window(float *w, const float *px, int win_type, int length) {
+  const float freq = 3.1415926536f / (length + 1), c = 2.0f - freq * freq;
+  float S0 = win_type < 2 ? 0.0f : 1.0f, S1 = win_type < 2 ? freq : 0.5f * c;
+  for (int k = 0; k < length; k += 4) {
+    w[k + 0] = px[k + 0] * 0.5f * (S0 + S1);
+    w[k + 1] = px[k + 1] * S1;
+    S0 = c * S1 - S0;
+    w[k + 2] = px[k + 2] * 0.5f * (S1 + S0);
+    w[k + 3] = px[k + 3] * S0;
+    S1 = c * S0 - S1;
+  }
+}
+OB_DEV void ns_bwexpander(float *ar, int d, float chirp) {
+  float cfac = chirp;
+  for (int i = 0; i < d - 1; i++) { ar[i] *= cfac; cfac *= chirp; }
+  ar[d - 1] *= cfac;
+}
+OB_DEVNI void ns_limit(float *coefs, float lambda, float limit, int order, int warped) {   // warped_true2monic_coefs / limit_coefs
+  float gain = 0.f;
+  int ind = 0;
+  if (warped) {
+    for (int i = order - 1; i > 0; i--) coefs[i - 1] -= lambda * coefs[i];
+    gain = (1.0f - lambda * lambda) / (1.0f + lambda * coefs[0]);
+    for (int i = 0; i < order; i++) coefs[i] *= gain;
+  }
+  for (int iter = 0; iter < 10; iter++) {
+    float maxabs = -1.0f;
+    for (int i = 0; i < order; i++) {
+      const float tmp = fabsf(coefs[i]);
+      if (tmp > maxabs) { maxabs = tmp; ind = i; }
+    }
+    if (maxabs <= limit) return;
+    if (warped) {
+      for (int i = 1; i < order; i++) coefs[i - 1] += lambda * coefs[i];
+      gain = 1.0f / gain;
+      for (int i = 0; i < order; i++) coefs[i] *= gain;
+    }
+    const float chirp = 0.99f - (0.8f + 0.1f * iter) * (maxabs - limit) / (maxabs * (ind + 1));
+    ns_bwexpander(coefs, order, chirp);
+    if (warped) {
+      for (int i = order - 1; i > 0; i--) coefs[i - 1] -= lambda * coefs[i];
+      gain = (1.0f - lambda * lambda) / (1.0f + lambda * coefs[0]);
+      for (int i = 0; i < order; i++) coefs[i] *= gain;
+    }
+  }
+}
+OB_DEV void silk_noise_shape_thread(const SilkNoiseShapeParams &p, int s) {
+  ObSilkNoiseShape c = p.frames[s];
+  const int fs_kHz = p.fs_kHz, nb_subfr = p.nb_subfr, order = p.shapingLPCOrder, subfr_length = 5 * fs_kHz, la_shape = 5 * fs_kHz, shapeWinLength = 15 * fs_kHz;
+  const float *pitch_res = p.pitch_res + (size_t)s * p.res_stride, *x_ptr = p.x + (size_t)s * p.x_stride + p.x_off - la_shape;
+  float x_windowed[240], auto_corr[kNsMaxOrder + 1], rc[kNsMaxOrder + 1];
+  float SNR_adj_dB = c.SNR_dB_Q7 * (1 / 128.0f);
+  c.input_quality = 0.5f * (c.input_quality_bands_Q15[0] + c.input_quality_bands_Q15[1]) * (1.0f / 32768.0f);
+  c.coding_quality = (float)(1.0 / (1.0 + exp(-(double)(0.25f * (SNR_adj_dB - 20.0f)))));
+  if (c.useCBR == 0) {
+    const float b = 1.0f - c.speech_activity_Q8 * (1.0f / 256.0f);
+    SNR_adj_dB -= 2.0f * c.coding_quality * (0.5f + 0.5f * c.input_quality) * b * b;   // BG_SNR_DECR_dB
+  }
+  if (c.signalType == 2) SNR_adj_dB += 2.0f * c.LTPCorr;                               // HARM_SNR_INCR_dB
+  else SNR_adj_dB += (-0.4f * c.SNR_dB_Q7 * (1 / 128.0f) + 6.0f) * (1.0f - c.input_quality);
+  if (c.signalType == 2) c.quantOffsetType = 0;
+  else {   // sparseness: fluctuation of the log energy per 2 ms
+    const int nSamples = 2 * fs_kHz, nSegs = (5 * nb_subfr) / 2;
+    float energy_variation = 0.0f, log_energy_prev = 0.0f;
+    for (int k = 0; k < nSegs; k++) {
+      const float *q = pitch_res + k * nSamples;
+      const float nrg = (float)nSamples + (float)silk_inner_product_flp(q, q, nSamples);
+      const float log_energy = (float)(3.32192809488736 * log10((double)nrg));
+      if (k > 0) energy_variation += fabsf(log_energy - log_energy_prev);
+      log_energy_prev = log_energy;
+    }
+    c.quantOffsetType = energy_variation > 0.6f * (nSegs - 1) ? 0 : 1;
+  }
+  float strength = 1e-3f * c.predGain;
+  const float BWExp = 0.94f / (1.0f + strength * strength);
+  const float warping = (float)c.warping_Q16 / 65536.0f + 0.01f * c.coding_quality;
+  for (int k = 0; k < nb_subfr; k++) {
+    const int flat_part = fs_kHz * 3, slope_part = (shapeWinLength - flat_part) / 2;
+    float *AR = &c.AR[k * kNsMaxOrder];
+    ns_sine_window(x_windowed, x_ptr, 1, slope_part);
+    for (int i = 0; i < flat_part; i++) x_windowed[slope_part + i] = x_ptr[slope_part + i];
+    ns_sine_window(x_windowed + slope_part + flat_part, x_ptr + slope_part + flat_part, 2, slope_part);
+    x_ptr += subfr_length;
+    if (c.warping_Q16 > 0) {
+      double state[kNsMaxOrder + 1], C[kNsMaxOrder + 1];
+      for (int i = 0; i <= kNsMaxOrder; i++) { state[i] = 0.0; C[i] = 0.0; }
+      for (int n = 0; n < shapeWinLength; n++) {
+        double tmp1 = x_windowed[n];
+        for (int i = 0; i < order; i += 2) {
+          const double tmp2 = state[i] + warping * state[i + 1] - warping * tmp1;
+          state[i] = tmp1;
+          C[i] += state[0] * tmp1;
+          tmp1 = state[i + 1] + warping * state[i + 2] - warping * tmp2;
+          state[i + 1] = tmp2;
+          C[i + 1] += state[0] * tmp2;
+        }
+        state[order] = tmp1;
+        C[order] += state[0] * tmp1;
+      }
+      for (int i = 0; i < order + 1; i++) auto_corr[i] = (float)C[i];
+    } else {
+      for (int i = 0; i < order + 1; i++) auto_corr[i] = (float)silk_inner_product_flp(x_windowed, x_windowed + i, shapeWinLength - i);
+    }
+    auto_corr[0] += auto_corr[0] * 3e-5f + 1.0f;   // SHAPE_WHITE_NOISE_FRACTION
+    float nrg;
+    {   // silk_schur_FLP
+      double Cs[kNsMaxOrder + 1][2];
+      for (int i = 0; i <= order; i++) Cs[i][0] = Cs[i][1] = auto_corr[i];
+      for (int i = 0; i < order; i++) {
+        const double den = Cs[0][1] > (double)1e-9f ? Cs[0][1] : (double)1e-9f, rc_tmp = -Cs[i + 1][0] / den;
+        rc[i] = (float)rc_tmp;
+        for (int n = 0; n < order - i; n++) {
+          const double Ctmp1 = Cs[n + i + 1][0], Ctmp2 = Cs[n][1];
+          Cs[n + i + 1][0] = Ctmp1 + Ctmp2 * rc_tmp;
+          Cs[n][1] = Ctmp2 + Ctmp1 * rc_tmp;
+        }
+      }
+      nrg = (float)Cs[0][1];
+    }
+    for (int i = 0; i < order; i++) {   // silk_k2a_FLP
+      const float rck = rc[i];
+      for (int n = 0; n < (i + 1) >> 1; n++) {
+        const float tmp1 = AR[n], tmp2 = AR[i - n - 1];
+        AR[n] = tmp1 + tmp2 * rck;
+        AR[i - n - 1] = tmp2 + tmp1 * rck;
+      }
+      AR[i] = -rck;
+    }
+    c.Gains[k] = (float)sqrt((double)nrg);
+    if (c.warping_Q16 > 0) {   // warped_gain
+      const float lambda = -warping;
+      float gain = AR[order - 1];
+      for (int i = order - 2; i >= 0; i--) gain = lambda * gain + AR[i];
+      c.Gains[k] *= 1.0f / (1.0f - lambda * gain);
+    }
+    ns_bwexpander(AR, order, BWExp);
+    ns_limit(AR, warping, 3.999f, order, c.warping_Q16 > 0);
+  }
+  const float gain_mult = (float)pow((double)2.0f, (double)(-0.16f * SNR_adj_dB)), gain_add = (float)pow((double)2.0f, (double)(0.16f * 2));
+  for (int k = 0; k < nb_subfr; k++) { c.Gains[k] *= gain_mult; c.Gains[k] += gain_add; }
+  strength = 4.0f * (1.0f + 0.5f * (c.input_quality_bands_Q15[0] * (1.0f / 32768.0f) - 1.0f));
+  strength *= c.speech_activity_Q8 * (1.0f / 256.0f);
+  float Tilt, HarmShapeGain;
+  if (c.signalType == 2) {
+    for (int k = 0; k < nb_subfr; k++) {
+      const float b = 0.2f / fs_kHz + 3.0f / c.pitchL[k];
+      c.LF_MA_shp[k] = -1.0f + b;
+      c.LF_AR_shp[k] = 1.0f - b - b * strength;
+    }
+    Tilt = -0.25f - (1 - 0.25f) * 0.35f * c.speech_activity_Q8 * (1.0f / 256.0f);
+    HarmShapeGain = 0.3f;
+    HarmShapeGain += 0.2f * (1.0f - (1.0f - c.coding_quality) * c.input_quality);
+    HarmShapeGain *= (float)sqrt((double)c.LTPCorr);
+  } else {
+    const float b = 1.3f / fs_kHz;
+    c.LF_MA_shp[0] = -1.0f + b;
+    c.LF_AR_shp[0] = 1.0f - b - b * strength * 0.6f;
+    for (int k = 1; k < nb_subfr; k++) { c.LF_MA_shp[k] = c.LF_MA_shp[0]; c.LF_AR_shp[k] = c.LF_AR_shp[0]; }
+    Tilt = -0.25f;
+    HarmShapeGain = 0.0f;
+  }
+  for (int k = 0; k < nb_subfr; k++) {
+    c.HarmShapeGain_smth += 0.4f * (HarmShapeGain - c.HarmShapeGain_smth);
+    c.HarmShapeGain[k] = c.HarmShapeGain_smth;
+    c.Tilt_smth += 0.4f * (Tilt - c.Tilt_smth);
+    c.Tilt[k] = c.Tilt_smth;
+  }
+  p.frames[s] = c;
+}
 }  // namespace ob

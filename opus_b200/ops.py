@@ -121,6 +121,16 @@ class Ops:
             raise capi.OpusB200Error(r, 'opusb200_silk_find_pred_coefs')
         return frames
 
+    def silk_noise_shape_analysis(self, frames, pitch_res, x, x_off, fs_kHz, nb_subfr, shaping_order):
+        """silk_noise_shape_analysis_FLP for n streams: frames = ctypes array of OpusB200SilkNoiseShape-shaped records (in place); pitch_res float32
+        [n, >= frame], x float32 [n, stride] with the frame at x_off"""
+        pitch_res, x = np.ascontiguousarray(pitch_res, np.float32), np.ascontiguousarray(x, np.float32)
+        r = self._L.opusb200_silk_noise_shape_analysis(self._h, ctypes.cast(frames, ctypes.c_void_p), pitch_res.ctypes.data_as(ctypes.c_void_p), pitch_res.shape[1],
+                                                       x.ctypes.data_as(ctypes.c_void_p), x.shape[1], x_off, len(frames), fs_kHz, nb_subfr, shaping_order, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_noise_shape_analysis')
+        return frames
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

@@ -581,3 +581,15 @@ extern "C" void emu_silk_find_pred_coefs(void *frames, const float *res_pitch, c
   p.nb_subfr = nb_subfr; p.subfr_length = subfr_length;
   emu_launch(silk_pred_coefs_entry, &p, (n + 31) / 32, 32, 0);
 }
+static void silk_noise_shape_entry(void *a) {
+  const SilkNoiseShapeParams &p = *(const SilkNoiseShapeParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_noise_shape_thread(p, s);
+}
+extern "C" void emu_silk_noise_shape(void *frames, const float *pitch_res, int res_stride, const float *x, int x_stride, int x_off, int n, int fs_kHz, int nb_subfr,
+                                     int order) {
+  SilkNoiseShapeParams p;
+  p.frames = (ObSilkNoiseShape *)frames; p.pitch_res = pitch_res; p.x = x; p.n = n; p.res_stride = res_stride; p.x_stride = x_stride; p.x_off = x_off;
+  p.fs_kHz = fs_kHz; p.nb_subfr = nb_subfr; p.shapingLPCOrder = order;
+  emu_launch(silk_noise_shape_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -339,3 +339,29 @@ def test_silk_find_pred_coefs_emulated(fs_kHz, nb_subfr):
             oa, ob = outputs(recs[s], order, nb_subfr), outputs(want[s], order, nb_subfr)
             assert oa == ob, (frame, s, [i for i in range(len(oa)) if oa[i] != ob[i]])
             prev[s], slg[s] = list(want[s].prev_NLSFq_Q15), want[s].sum_log_gain_Q7
+
+
+@pytest.mark.parametrize('fs_kHz,nb_subfr,order', [(16, 4, 24), (8, 4, 12), (12, 2, 14)])
+def test_silk_noise_shape_emulated(fs_kHz, nb_subfr, order):
+    """silk_noise_shape_analysis_FLP: the device source on the emulator against the oracle (pinned on the reference), smoother states carried over frames"""
+    from test_silk_noise_shape_oracle_vs_ref import NoiseShape, frame_input, random_case, outputs
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(90 + fs_kHz)
+    n = 24
+    state = [(np.float32(0), np.float32(0))] * n
+    for frame in range(4):
+        recs = (NoiseShape * n)()
+        want, R_, X_ = [], [], []
+        for s in range(n):
+            res, x, la = frame_input(rng, fs_kHz, nb_subfr, (s + frame) % 3)
+            recs[s] = random_case(rng, fs_kHz, state[s])
+            w = NoiseShape.from_buffer_copy(bytes(recs[s]))
+            O.orc_silk_noise_shape_analysis(ctypes.byref(w), res.ctypes.data_as(ctypes.c_void_p), x[la:].ctypes.data_as(ctypes.c_void_p), fs_kHz, nb_subfr, order)
+            want.append(w); R_.append(res); X_.append(x)
+        R_, X_ = np.stack(R_), np.stack(X_)
+        E.emu_silk_noise_shape(ctypes.cast(recs, ctypes.c_void_p), R_.ctypes.data_as(ctypes.c_void_p), R_.shape[1], X_.ctypes.data_as(ctypes.c_void_p), X_.shape[1],
+                               5 * fs_kHz, n, fs_kHz, nb_subfr, order)
+        for s in range(n):
+            oa, ob = outputs(recs[s], nb_subfr, order), outputs(want[s], nb_subfr, order)
+            assert oa == ob, (frame, s, [i for i in range(len(oa)) if oa[i] != ob[i]])
+            state[s] = (want[s].HarmShapeGain_smth, want[s].Tilt_smth)

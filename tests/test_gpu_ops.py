@@ -465,3 +465,41 @@ def test_silk_find_pred_coefs(fs_kHz, nb_subfr):
             prev[s], slg[s] = list(want[s].prev_NLSFq_Q15), want[s].sum_log_gain_Q7
     print('bit-identical records: %d of %d' % (exact, total))
     assert exact >= 0.97 * total
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fs_kHz,nb_subfr,order', [(16, 4, 24), (8, 4, 12), (12, 2, 14)])
+def test_silk_noise_shape_analysis(fs_kHz, nb_subfr, order):
+    """opusb200_silk_noise_shape_analysis against the oracle (pinned bit for bit on silk_noise_shape_analysis_FLP).  The libm calls on the path are exp,
+    log10, sqrt and pow of doubles: the device's can differ from glibc in the last bit of a float now and then.  Bar: shaping coefficients and gains within
+    1e-5 relative on every stream, the integer decision identical, and most records bit-identical."""
+    import opus_b200
+    from test_silk_noise_shape_oracle_vs_ref import NoiseShape, frame_input, random_case, outputs
+    O = util.load_oracle()
+    ops = opus_b200.Ops()
+    rng = np.random.default_rng(95 + fs_kHz)
+    n = 120
+    state = [(np.float32(0), np.float32(0))] * n
+    exact = total = 0
+    for frame in range(3):
+        recs = (NoiseShape * n)()
+        want, R_, X_ = [], [], []
+        for s in range(n):
+            res, x, la = frame_input(rng, fs_kHz, nb_subfr, (s + frame) % 3)
+            recs[s] = random_case(rng, fs_kHz, state[s])
+            w = NoiseShape.from_buffer_copy(bytes(recs[s]))
+            O.orc_silk_noise_shape_analysis(ctypes.byref(w), res.ctypes.data_as(ctypes.c_void_p), x[la:].ctypes.data_as(ctypes.c_void_p), fs_kHz, nb_subfr, order)
+            want.append(w); R_.append(res); X_.append(x)
+        ops.silk_noise_shape_analysis(recs, np.stack(R_), np.stack(X_), 5 * fs_kHz, fs_kHz, nb_subfr, order)
+        for s in range(n):
+            oa, ob = outputs(recs[s], nb_subfr, order), outputs(want[s], nb_subfr, order)
+            total += 1
+            exact += int(oa == ob)
+            assert recs[s].quantOffsetType == want[s].quantOffsetType or want[s].signalType != 2, (frame, s)
+            for k in range(nb_subfr):
+                a, b = np.array(recs[s].AR[k * 24:k * 24 + order]), np.array(want[s].AR[k * 24:k * 24 + order])
+                assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(b).max()), (frame, s, k)
+                assert abs(recs[s].Gains[k] - want[s].Gains[k]) <= 1e-5 * abs(want[s].Gains[k]), (frame, s, k)
+            state[s] = (want[s].HarmShapeGain_smth, want[s].Tilt_smth)
+    print('bit-identical records: %d of %d' % (exact, total))
+    assert exact >= 0.9 * total
