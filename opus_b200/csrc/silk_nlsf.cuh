@@ -101,7 +101,7 @@ OB_DEV void nlsf_sort_increasing(int32_t *a, int *idx, int L, int K) {
     }
   }
 }
-OB_DEVNI void nlsf_stabilize(int16_t *NLSF_Q15, const short *NDeltaMin_Q15, int L) {
+OB_DEV void nlsf_stabilize(int16_t *NLSF_Q15, const short *NDeltaMin_Q15, int L) {
   for (int loops = 0; loops < 20; loops++) {
     int32_t min_diff = NLSF_Q15[0] - NDeltaMin_Q15[0], diff;
     int I = 0;
@@ -144,7 +144,7 @@ OB_DEVNI void nlsf_stabilize(int16_t *NLSF_Q15, const short *NDeltaMin_Q15, int 
   for (int i = L - 2; i >= 0; i--) { const int v = NLSF_Q15[i + 1] - NDeltaMin_Q15[i + 1]; NLSF_Q15[i] = (int16_t)(NLSF_Q15[i] < v ? NLSF_Q15[i] : v); }
 }
 OB_DEV int32_t nlsf_w(int32_t d) { return ((int32_t)1 << 17) / (d > 1 ? d : 1); }   // 1 << (15 + NLSF_W_Q) over the clamped spacing
-OB_DEVNI void nlsf_weights_laroia(int16_t *pW, const int16_t *x, int D) {
+OB_DEV void nlsf_weights_laroia(int16_t *pW, const int16_t *x, int D) {
   int32_t t1 = nlsf_w(x[0]), t2 = nlsf_w(x[1] - x[0]);
   pW[0] = (int16_t)(t1 + t2 < 32767 ? t1 + t2 : 32767);
   for (int k = 1; k < D - 1; k += 2) {
@@ -166,7 +166,7 @@ OB_DEV void nlsf_unpack(int16_t *ec_ix, unsigned char *pred_Q8, const NlsfCB &cb
     pred_Q8[i + 1] = cb.pred_Q8[i + ((entry >> 4) & 1) * (cb.order - 1) + 1];
   }
 }
-OB_DEVNI void nlsf_decode(int16_t *pNLSF_Q15, const int8_t *NLSFIndices, const NlsfCB &cb) {
+OB_DEV void nlsf_decode(int16_t *pNLSF_Q15, const int8_t *NLSFIndices, const NlsfCB &cb) {
   unsigned char pred_Q8[kNlsfMaxOrder];
   int16_t ec_ix[kNlsfMaxOrder], res_Q10[kNlsfMaxOrder];
   const unsigned char *el = &cb.CB1_NLSF_Q8[NLSFIndices[0] * cb.order];
@@ -187,7 +187,7 @@ OB_DEVNI void nlsf_decode(int16_t *pNLSF_Q15, const int8_t *NLSFIndices, const N
   }
   nlsf_stabilize(pNLSF_Q15, cb.deltaMin_Q15, cb.order);
 }
-OB_DEVNI int32_t nlsf_del_dec_quant(int8_t *indices, const int16_t *x_Q10, const int16_t *w_Q5, const unsigned char *pred_coef_Q8, const int16_t *ec_ix,
+OB_DEV int32_t nlsf_del_dec_quant(int8_t *indices, const int16_t *x_Q10, const int16_t *w_Q5, const unsigned char *pred_coef_Q8, const int16_t *ec_ix,
                                     const unsigned char *ec_rates_Q5, int quant_step_size_Q16, int16_t inv_quant_step_size_Q6, int32_t mu_Q20, int order) {
   int ind_sort[kNlsfStates];
   int8_t ind[kNlsfStates][kNlsfMaxOrder];
@@ -278,7 +278,7 @@ OB_DEVNI int32_t nlsf_del_dec_quant(int8_t *indices, const int16_t *x_Q10, const
   indices[0] = (int8_t)(indices[0] + (ind_tmp >> 2));
   return min_Q25;
 }
-OB_DEVNI void nlsf_encode(int8_t *NLSFIndices, int16_t *pNLSF_Q15, const NlsfCB &cb, const int16_t *pW_Q2, int NLSF_mu_Q20, int nSurvivors, int signalType) {
+OB_DEV void nlsf_encode(int8_t *NLSFIndices, int16_t *pNLSF_Q15, const NlsfCB &cb, const int16_t *pW_Q2, int NLSF_mu_Q20, int nSurvivors, int signalType) {
   int32_t err_Q24[32], RD_Q25[32];
   int tempIndices1[32];
   int8_t tempIndices2[32 * kNlsfMaxOrder];
@@ -332,7 +332,7 @@ OB_DEV void nlsf_bwexpander_32(int32_t *ar, int d, int32_t chirp_Q16) {
   }
   ar[d - 1] = nl_smulww(chirp_Q16, ar[d - 1]);
 }
-OB_DEVNI int32_t nlsf_lpc_inverse_pred_gain(const int16_t *A_Q12, int order) {
+OB_DEV int32_t nlsf_lpc_inverse_pred_gain(const int16_t *A_Q12, int order) {
   const int QA = 24;
   const int32_t A_LIMIT = 16773022;   // SILK_FIX_CONST(0.99975, 24)
   int32_t A_QA[kNlsfMaxOrder], DC_resp = 0, invGain_Q30 = 1 << 30;
@@ -373,7 +373,7 @@ OB_DEV void nlsf_find_poly(int32_t *out, const int32_t *cLSF, int dd) {
     out[1] -= ftmp;
   }
 }
-OB_DEVNI void nlsf_NLSF2A(int16_t *a_Q12, const int16_t *NLSF, int d) {
+OB_DEV void nlsf_NLSF2A(int16_t *a_Q12, const int16_t *NLSF, int d) {
   const unsigned char ordering16[16] = {0, 15, 8, 7, 4, 11, 12, 3, 2, 13, 10, 5, 6, 9, 14, 1}, ordering10[10] = {0, 9, 6, 3, 4, 5, 8, 1, 2, 7};
   const int QA = 16, dd = d >> 1;
   int32_t cos_LSF_QA[kNlsfMaxOrder], P[kNlsfMaxOrder / 2 + 1], Q[kNlsfMaxOrder / 2 + 1], a32_QA1[kNlsfMaxOrder];
@@ -421,7 +421,7 @@ OB_DEVNI void nlsf_NLSF2A(int16_t *a_Q12, const int16_t *NLSF, int d) {
 OB_DEV void nlsf_interpolate(int16_t *xi, const int16_t *x0, const int16_t *x1, int ifact_Q2, int d) {
   for (int i = 0; i < d; i++) xi[i] = (int16_t)(x0[i] + (nl_smulbb(x1[i] - x0[i], ifact_Q2) >> 2));
 }
-OB_DEVNI void silk_process_nlsfs_core(ObSilkNlsf &f, int wb, int nb_subfr_) {
+OB_DEV void silk_process_nlsfs_core(ObSilkNlsf &f, int wb, int nb_subfr_) {
   const NlsfCB cb = nlsf_cb(wb);
   const int order = cb.order;
   int16_t tmp0[kNlsfMaxOrder], W[kNlsfMaxOrder], W0[kNlsfMaxOrder];
@@ -484,7 +484,7 @@ OB_DEV void a2nlsf_init(const int32_t *a_Q16, int32_t *P, int32_t *Q, int dd) {
   a2nlsf_trans_poly(P, dd);
   a2nlsf_trans_poly(Q, dd);
 }
-OB_DEVNI void nlsf_A2NLSF(int16_t *NLSF, int32_t *a_Q16, int d) {
+OB_DEV void nlsf_A2NLSF(int16_t *NLSF, int32_t *a_Q16, int d) {
   const int dd = d >> 1;
   int i = 0, k = 1, root_ix;
   int32_t xlo, xhi, ylo, yhi, thr = 0, P[kNlsfMaxOrder / 2 + 1], Q[kNlsfMaxOrder / 2 + 1];
@@ -553,7 +553,7 @@ OB_DEV void nlsf_a2nlsf_flp(int16_t *NLSF_Q15, const float *pAR, int order) {   
   for (int i = 0; i < order; i++) a_fix_Q16[i] = (int32_t)rintf(pAR[i] * 65536.0f);
   nlsf_A2NLSF(NLSF_Q15, a_fix_Q16, order);
 }
-OB_DEVNI void silk_find_lpc_core(ObSilkFindLpc &f, const float *x, int order, int nb_subfr, int subfr_length_in) {
+OB_DEV void silk_find_lpc_core(ObSilkFindLpc &f, const float *x, int order, int nb_subfr, int subfr_length_in) {
   const int subfr_length = subfr_length_in + order;
   float a[kNlsfMaxOrder], a_tmp[kNlsfMaxOrder], nrg[1], LPC_res[2 * (80 + 16)];
   int16_t NLSF0_Q15[kNlsfMaxOrder], a_fix_Q12[kNlsfMaxOrder];
@@ -614,7 +614,7 @@ struct ObSilkPredCoefs {   // == OpusB200SilkPredCoefs
 // res_pitch / x: [n][sig_stride] with the current frame at frame_off (history in front: at least the longest pitch lag + LTP_ORDER / 2 + order samples)
 struct SilkPredCoefsParams { ObSilkPredCoefs *frames; const float *res_pitch, *x; int n, sig_stride, frame_off, order, nb_subfr, subfr_length; };
 OB_DEV int32_t nl_add_pos_sat32(int32_t a, int32_t b) { return (((uint32_t)a + (uint32_t)b) & 0x80000000u) ? INT32_MAX : a + b; }
-OB_DEVNI void silk_vq_wmat_ec(int8_t *ind, int32_t *res_nrg_Q15, int32_t *rate_dist_Q8, int *gain_Q7, const int32_t *XX, const int32_t *xX, const signed char *cb_Q7,
+OB_DEV void silk_vq_wmat_ec(int8_t *ind, int32_t *res_nrg_Q15, int32_t *rate_dist_Q8, int *gain_Q7, const int32_t *XX, const int32_t *xX, const signed char *cb_Q7,
                               const unsigned char *cb_gain_Q7, const unsigned char *cl_Q5, int subfr_len, int32_t max_gain_Q7, int L) {
   int32_t neg[5];
   for (int j = 0; j < 5; j++) neg[j] = -(int32_t)((uint32_t)xX[j] << 7);
@@ -651,7 +651,7 @@ OB_DEVNI void silk_vq_wmat_ec(int8_t *ind, int32_t *res_nrg_Q15, int32_t *rate_d
     }
   }
 }
-OB_DEVNI void silk_quant_ltp_gains(int16_t *B_Q14, int8_t *cbk_index, int8_t *periodicity_index, int32_t *sum_log_gain_Q7, int *pred_gain_dB_Q7,
+OB_DEV void silk_quant_ltp_gains(int16_t *B_Q14, int8_t *cbk_index, int8_t *periodicity_index, int32_t *sum_log_gain_Q7, int *pred_gain_dB_Q7,
                                    const int32_t *XX_Q17, const int32_t *xX_Q17, int subfr_len, int nb_subfr) {
   int32_t min_rate_dist_Q7 = INT32_MAX, best_sum_log_gain_Q7 = 0, res_nrg_Q15 = 0;
   int8_t temp_idx[4];
@@ -685,7 +685,7 @@ OB_DEVNI void silk_quant_ltp_gains(int16_t *B_Q14, int8_t *cbk_index, int8_t *pe
   *sum_log_gain_Q7 = best_sum_log_gain_Q7;
   *pred_gain_dB_Q7 = nl_smulbb(-3, silk_lin2log(res_nrg_Q15) - (15 << 7));
 }
-OB_DEVNI void silk_corr_matrix_flp(const float *x, int L, float *XX) {   // silk_corrMatrix_FLP, Order = LTP_ORDER
+OB_DEV void silk_corr_matrix_flp(const float *x, int L, float *XX) {   // silk_corrMatrix_FLP, Order = LTP_ORDER
   const float *ptr1 = &x[4], *ptr2 = &x[3];
   double energy = silk_inner_product_flp(ptr1, ptr1, L);
   XX[0] = (float)energy;
@@ -841,7 +841,7 @@ OB_DEV void ns_bwexpander(float *ar, int d, float chirp) {
   for (int i = 0; i < d - 1; i++) { ar[i] *= cfac; cfac *= chirp; }
   ar[d - 1] *= cfac;
 }
-OB_DEVNI void ns_limit(float *coefs, float lambda, float limit, int order, int warped) {   // warped_true2monic_coefs / limit_coefs
+OB_DEV void ns_limit(float *coefs, float lambda, float limit, int order, int warped) {   // warped_true2monic_coefs / limit_coefs
   float gain = 0.f;
   int ind = 0;
   if (warped) {
