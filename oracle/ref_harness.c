@@ -579,3 +579,27 @@ void refh_silk_noise_shape_analysis(RefhSilkNoiseShape *c, const float *pitch_re
   memcpy(c->AR, ctl.AR, sizeof(c->AR)); memcpy(c->Gains, ctl.Gains, sizeof(c->Gains)); memcpy(c->LF_MA_shp, ctl.LF_MA_shp, sizeof(c->LF_MA_shp));
   memcpy(c->LF_AR_shp, ctl.LF_AR_shp, sizeof(c->LF_AR_shp)); memcpy(c->HarmShapeGain, ctl.HarmShapeGain, sizeof(c->HarmShapeGain)); memcpy(c->Tilt, ctl.Tilt, sizeof(c->Tilt));
 }
+
+/* ---- silk_find_pitch_lags_FLP on scratch encoder structs (silk/float/find_pitch_lags_FLP.c:36-132) ---- */
+typedef struct {
+  opus_int32 signalType, first_frame_after_reset, speech_activity_Q8, prevSignalType, input_tilt_Q15, prevLag, pitchEstimationThreshold_Q16;
+  float LTPCorr, predGain;
+  opus_int32 pitchL[4];
+  opus_int32 lagIndex, contourIndex;
+} RefhSilkPitch;   /* == OrcSilkPitch */
+void refh_silk_find_pitch_lags(RefhSilkPitch *c, float *res, const float *x, int fs_kHz, int nb_subfr, int lpc_order, int complexity) {
+  static silk_encoder_state_FLP st;
+  static silk_encoder_control_FLP ctl;
+  int k;
+  memset(&st, 0, sizeof(st));
+  memset(&ctl, 0, sizeof(ctl));
+  st.sCmn.fs_kHz = fs_kHz; st.sCmn.nb_subfr = nb_subfr; st.sCmn.la_pitch = 2 * fs_kHz; st.sCmn.frame_length = 5 * nb_subfr * fs_kHz; st.sCmn.ltp_mem_length = 20 * fs_kHz;
+  st.sCmn.pitch_LPC_win_length = (5 * nb_subfr + 4) * fs_kHz; st.sCmn.pitchEstimationLPCOrder = lpc_order; st.sCmn.pitchEstimationComplexity = complexity;
+  st.sCmn.indices.signalType = (opus_int8)c->signalType; st.sCmn.first_frame_after_reset = c->first_frame_after_reset; st.sCmn.speech_activity_Q8 = c->speech_activity_Q8;
+  st.sCmn.prevSignalType = c->prevSignalType; st.sCmn.input_tilt_Q15 = c->input_tilt_Q15; st.sCmn.prevLag = c->prevLag;
+  st.sCmn.pitchEstimationThreshold_Q16 = c->pitchEstimationThreshold_Q16; st.LTPCorr = c->LTPCorr;
+  silk_find_pitch_lags_FLP(&st, &ctl, res, x, 0);
+  c->signalType = st.sCmn.indices.signalType; c->LTPCorr = st.LTPCorr; c->predGain = ctl.predGain;
+  for (k = 0; k < 4; k++) c->pitchL[k] = ctl.pitchL[k];
+  c->lagIndex = st.sCmn.indices.lagIndex; c->contourIndex = st.sCmn.indices.contourIndex;
+}

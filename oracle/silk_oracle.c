@@ -579,3 +579,346 @@ void orc_silk_noise_shape_analysis(OrcSilkNoiseShape *c, const float *pitch_res,
     c->Tilt[k] = c->Tilt_smth;
   }
 }
+
+/* ---- pitch analysis of a SILK frame: silk_find_pitch_lags_FLP (silk/float/find_pitch_lags_FLP.c:36-132) and silk_pitch_analysis_core_FLP
+ * (silk/float/pitch_analysis_core_FLP.c:66-630: decimation to 8 and 4 kHz through silk_resampler_down2 / _down2_3 (silk/resampler_down2.c:37-74,
+ * resampler_down2_3.c:41-103, resampler_private_AR2.c:36-54), the three search stages, the lag codebooks of silk/pitch_est_tables.c), with
+ * silk_insertion_sort_decreasing_FLP (silk/float/sort_FLP.c:39-83) and the C build of celt_pitch_xcorr (every lag summed in index order). ---- */
+static const int8_t pe_cb2[4][11] = {{0, 2, -1, -1, -1, 0, 0, 1, 1, 0, 1}, {0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0}, {0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0},
+                                     {0, -1, 2, 1, 0, 1, 1, 0, 0, -1, -1}};                                  /* silk_CB_lags_stage2 */
+static const int8_t pe_cb3[4][34] = {
+    {0, 0, 1, -1, 0, 1, -1, 0, -1, 1, -2, 2, -2, -2, 2, -3, 2, 3, -3, -4, 3, -4, 4, 4, -5, 5, -6, -5, 6, -7, 6, 5, 8, -9},
+    {0, 0, 1, 0, 0, 0, 0, 0, 0, 0, -1, 1, 0, 0, 1, -1, 0, 1, -1, -1, 1, -1, 2, 1, -1, 2, -2, -2, 2, -2, 2, 2, 3, -3},
+    {0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 1, -1, 1, 0, 0, 2, 1, -1, 2, -1, -1, 2, -1, 2, 2, -1, 3, -2, -2, -2, 3},
+    {0, 1, 0, 0, 1, 0, 1, -1, 2, -1, 2, -1, 2, 3, -2, 3, -2, -2, 4, 4, -3, 5, -3, -4, 6, -4, 6, 5, -5, 8, -6, -5, -7, 9}}; /* silk_CB_lags_stage3 */
+static const int8_t pe_range3[3][4][2] = {{{-5, 8}, {-1, 6}, {-1, 6}, {-4, 10}}, {{-6, 10}, {-2, 6}, {-1, 6}, {-5, 10}}, {{-9, 12}, {-3, 7}, {-2, 7}, {-7, 13}}};
+static const int8_t pe_nb3[3] = {16, 24, 34};
+static const int8_t pe_cb2_10[2][3] = {{0, 1, 0}, {0, 0, 1}};
+static const int8_t pe_cb3_10[2][12] = {{0, 0, 1, -1, 1, -1, 2, -2, 2, -2, 3, -3}, {0, 1, 0, 1, -1, 2, -1, 2, -2, 3, -2, 3}};
+static const int8_t pe_range3_10[2][2] = {{-3, 7}, {-2, 7}};
+static int16_t pe_sat16(int32_t a) { return (int16_t)(a > 32767 ? 32767 : a < -32768 ? -32768 : a); }
+static void pe_down2(int32_t *S, int16_t *out, const int16_t *in, int inLen) {
+  int k;
+  for (k = 0; k < inLen >> 1; k++) {
+    int32_t in32 = (int32_t)in[2 * k] * 1024, Y = in32 - S[0], X = smlawb(Y, Y, 39809 - 65536), out32 = S[0] + X;
+    S[0] = in32 + X;
+    in32 = (int32_t)in[2 * k + 1] * 1024;
+    Y = in32 - S[1];
+    X = smulwb(Y, 9872);
+    out32 = out32 + S[1];
+    out32 = out32 + X;
+    S[1] = in32 + X;
+    out[k] = pe_sat16(rshift_round(out32, 11));
+  }
+}
+static void pe_down2_3(int32_t *S, int16_t *out, const int16_t *in, int inLen) { /* inLen <= RESAMPLER_MAX_BATCH_SIZE_IN (480): one batch */
+  static const int16_t C[6] = {-2797, -6507, 4697, 10739, 1567, 8276}; /* silk_Resampler_2_3_COEFS_LQ */
+  int32_t buf[480 + 4], *bp = buf;
+  int k, counter = inLen;
+  memcpy(buf, S, 4 * sizeof(int32_t));
+  for (k = 0; k < inLen; k++) { /* silk_resampler_private_AR2 */
+    int32_t out32 = S[4] + (int32_t)in[k] * 256;
+    buf[4 + k] = out32;
+    out32 = (int32_t)((uint32_t)out32 << 2);
+    S[4] = smlawb(S[5], out32, C[0]);
+    S[5] = smulwb(out32, C[1]);
+  }
+  while (counter > 2) {
+    int32_t r = smulwb(bp[0], C[2]);
+    r = smlawb(r, bp[1], C[3]);
+    r = smlawb(r, bp[2], C[5]);
+    r = smlawb(r, bp[3], C[4]);
+    *out++ = pe_sat16(rshift_round(r, 6));
+    r = smulwb(bp[1], C[4]);
+    r = smlawb(r, bp[2], C[5]);
+    r = smlawb(r, bp[3], C[3]);
+    r = smlawb(r, bp[4], C[2]);
+    *out++ = pe_sat16(rshift_round(r, 6));
+    bp += 3;
+    counter -= 3;
+  }
+  memcpy(S, &buf[inLen], 4 * sizeof(int32_t));
+}
+static void pe_sort_decreasing(float *a, int *idx, int L, int K) {
+  int i, j;
+  for (i = 0; i < K; i++) idx[i] = i;
+  for (i = 1; i < K; i++) {
+    const float value = a[i];
+    for (j = i - 1; j >= 0 && value > a[j]; j--) { a[j + 1] = a[j]; idx[j + 1] = idx[j]; }
+    a[j + 1] = value;
+    idx[j + 1] = i;
+  }
+  for (i = K; i < L; i++) {
+    const float value = a[i];
+    if (value > a[K - 1]) {
+      for (j = K - 2; j >= 0 && value > a[j]; j--) { a[j + 1] = a[j]; idx[j + 1] = idx[j]; }
+      a[j + 1] = value;
+      idx[j + 1] = i;
+    }
+  }
+}
+static float pe_log2(double x) { return (float)(3.32192809488736 * log10(x)); }
+static float pe_dot(const float *a, const float *b, int n) { float s = 0; int i; for (i = 0; i < n; i++) s = s + a[i] * b[i]; return s; } /* celt_pitch_xcorr_c */
+/* returns 0 voiced / 1 unvoiced */
+int orc_silk_pitch_analysis_core(const float *frame, int *pitch_out, int16_t *lagIndex, int8_t *contourIndex, float *LTPCorr, int prevLag, float search_thres1,
+                                 float search_thres2, int Fs_kHz, int complexity, int nb_subfr) {
+  float frame_8kHz[40 * 8], frame_4kHz[40 * 4], C[4][(288 >> 1) + 5], xcorr[18 * 4 - 2 * 4 + 1], CC[11], threshold, contour_bias, Cmax, CCmax, CCmax_b, CCmax_new_b,
+      CCmax_new, lag_log2, prevLag_log2, delta_lag_log2_sqr, energies_st3[4][34][5], cross_corr_st3[4][34][5];
+  int16_t frame_8_FIX[40 * 8], frame_4_FIX[40 * 4], frame_in_FIX[16 * 40], d_comp[(288 >> 1) + 5];
+  int32_t filt_state[6];
+  const float *target_ptr, *basis_ptr;
+  double cross_corr, normalizer, energy, energy_tmp;
+  int d_srch[24], length_d_srch, length_d_comp, i, k, d, j, CBimax, CBimax_new, lag, start_lag, end_lag, lag_new, cbk_size, lag_counter, nb_cbk_search;
+  const int frame_length = (20 + nb_subfr * 5) * Fs_kHz, frame_length_4kHz = (20 + nb_subfr * 5) * 4, frame_length_8kHz = (20 + nb_subfr * 5) * 8,
+            sf_length = 5 * Fs_kHz, sf_length_4kHz = 20, sf_length_8kHz = 40, min_lag = 2 * Fs_kHz, min_lag_4kHz = 8, min_lag_8kHz = 16,
+            max_lag = 18 * Fs_kHz - 1, max_lag_4kHz = 72, max_lag_8kHz = 18 * 8 - 1;
+  const int8_t *Lag_CB_ptr;
+  if (Fs_kHz == 16) {
+    for (k = frame_length - 1; k >= 0; k--) frame_in_FIX[k] = pe_sat16((int32_t)lrintf(frame[k]));
+    memset(filt_state, 0, 2 * sizeof(int32_t));
+    pe_down2(filt_state, frame_8_FIX, frame_in_FIX, frame_length);
+    for (k = 0; k < frame_length_8kHz; k++) frame_8kHz[k] = (float)frame_8_FIX[k];
+  } else if (Fs_kHz == 12) {
+    for (k = frame_length - 1; k >= 0; k--) frame_in_FIX[k] = pe_sat16((int32_t)lrintf(frame[k]));
+    memset(filt_state, 0, 6 * sizeof(int32_t));
+    pe_down2_3(filt_state, frame_8_FIX, frame_in_FIX, frame_length);
+    for (k = 0; k < frame_length_8kHz; k++) frame_8kHz[k] = (float)frame_8_FIX[k];
+  } else {
+    for (k = frame_length_8kHz - 1; k >= 0; k--) frame_8_FIX[k] = pe_sat16((int32_t)lrintf(frame[k]));
+  }
+  memset(filt_state, 0, 2 * sizeof(int32_t));
+  pe_down2(filt_state, frame_4_FIX, frame_8_FIX, frame_length_8kHz);
+  for (k = 0; k < frame_length_4kHz; k++) frame_4kHz[k] = (float)frame_4_FIX[k];
+  for (i = frame_length_4kHz - 1; i > 0; i--) { /* silk_ADD_SAT16 on floats: (int32)a + b, saturated, truncated to int16 */
+    const float t = (int32_t)frame_4kHz[i] + frame_4kHz[i - 1];
+    frame_4kHz[i] = (float)(int16_t)(t > 32767 ? 32767 : t < -32768 ? -32768 : t);
+  }
+  /* first stage, 4 kHz */
+  memset(C, 0, sizeof(float) * nb_subfr * ((288 >> 1) + 5));
+  target_ptr = &frame_4kHz[sf_length_4kHz << 2];
+  for (k = 0; k < nb_subfr >> 1; k++) {
+    basis_ptr = target_ptr - min_lag_4kHz;
+    for (i = 0; i < max_lag_4kHz - min_lag_4kHz + 1; i++) xcorr[i] = pe_dot(target_ptr, target_ptr - max_lag_4kHz + i, sf_length_8kHz);
+    cross_corr = xcorr[max_lag_4kHz - min_lag_4kHz];
+    normalizer = inner_product_flp(target_ptr, target_ptr, sf_length_8kHz) + inner_product_flp(basis_ptr, basis_ptr, sf_length_8kHz) + sf_length_8kHz * 4000.0f;
+    C[0][min_lag_4kHz] += (float)(2 * cross_corr / normalizer);
+    for (d = min_lag_4kHz + 1; d <= max_lag_4kHz; d++) {
+      basis_ptr--;
+      cross_corr = xcorr[max_lag_4kHz - d];
+      normalizer += basis_ptr[0] * (double)basis_ptr[0] - basis_ptr[sf_length_8kHz] * (double)basis_ptr[sf_length_8kHz];
+      C[0][d] += (float)(2 * cross_corr / normalizer);
+    }
+    target_ptr += sf_length_8kHz;
+  }
+  for (i = max_lag_4kHz; i >= min_lag_4kHz; i--) C[0][i] -= C[0][i] * i / 4096.0f;
+  length_d_srch = 4 + 2 * complexity;
+  pe_sort_decreasing(&C[0][min_lag_4kHz], d_srch, max_lag_4kHz - min_lag_4kHz + 1, length_d_srch);
+  Cmax = C[0][min_lag_4kHz];
+  if (Cmax < 0.2f) {
+    memset(pitch_out, 0, nb_subfr * sizeof(int));
+    *LTPCorr = 0.0f; *lagIndex = 0; *contourIndex = 0;
+    return 1;
+  }
+  threshold = search_thres1 * Cmax;
+  for (i = 0; i < length_d_srch; i++) {
+    if (C[0][min_lag_4kHz + i] > threshold) d_srch[i] = (d_srch[i] + min_lag_4kHz) << 1;
+    else { length_d_srch = i; break; }
+  }
+  for (i = min_lag_8kHz - 5; i < max_lag_8kHz + 5; i++) d_comp[i] = 0;
+  for (i = 0; i < length_d_srch; i++) d_comp[d_srch[i]] = 1;
+  for (i = max_lag_8kHz + 3; i >= min_lag_8kHz; i--) d_comp[i] += d_comp[i - 1] + d_comp[i - 2];
+  length_d_srch = 0;
+  for (i = min_lag_8kHz; i < max_lag_8kHz + 1; i++) if (d_comp[i + 1] > 0) d_srch[length_d_srch++] = i;
+  for (i = max_lag_8kHz + 3; i >= min_lag_8kHz; i--) d_comp[i] += d_comp[i - 1] + d_comp[i - 2] + d_comp[i - 3];
+  length_d_comp = 0;
+  for (i = min_lag_8kHz; i < max_lag_8kHz + 4; i++) if (d_comp[i] > 0) d_comp[length_d_comp++] = (int16_t)(i - 2);
+  /* second stage, 8 kHz */
+  memset(C, 0, sizeof(C));
+  target_ptr = Fs_kHz == 8 ? &frame[20 * 8] : &frame_8kHz[20 * 8];
+  for (k = 0; k < nb_subfr; k++) {
+    energy_tmp = inner_product_flp(target_ptr, target_ptr, sf_length_8kHz) + 1.0;
+    for (j = 0; j < length_d_comp; j++) {
+      d = d_comp[j];
+      basis_ptr = target_ptr - d;
+      cross_corr = inner_product_flp(basis_ptr, target_ptr, sf_length_8kHz);
+      if (cross_corr > 0.0f) {
+        energy = inner_product_flp(basis_ptr, basis_ptr, sf_length_8kHz);
+        C[k][d] = (float)(2 * cross_corr / (energy + energy_tmp));
+      } else C[k][d] = 0.0f;
+    }
+    target_ptr += sf_length_8kHz;
+  }
+  CCmax = 0.0f; CCmax_b = -1000.0f; CBimax = 0; lag = -1;
+  if (prevLag > 0) {
+    if (Fs_kHz == 12) prevLag = (prevLag << 1) / 3;
+    else if (Fs_kHz == 16) prevLag = prevLag >> 1;
+    prevLag_log2 = pe_log2((float)prevLag);
+  } else prevLag_log2 = 0;
+  if (nb_subfr == 4) {
+    cbk_size = 11; Lag_CB_ptr = &pe_cb2[0][0];
+    nb_cbk_search = (Fs_kHz == 8 && complexity > 0) ? 11 : 3;
+  } else { cbk_size = 3; Lag_CB_ptr = &pe_cb2_10[0][0]; nb_cbk_search = 3; }
+  for (k = 0; k < length_d_srch; k++) {
+    d = d_srch[k];
+    for (j = 0; j < nb_cbk_search; j++) {
+      CC[j] = 0.0f;
+      for (i = 0; i < nb_subfr; i++) CC[j] += C[i][d + Lag_CB_ptr[i * cbk_size + j]];
+    }
+    CCmax_new = -1000.0f; CBimax_new = 0;
+    for (i = 0; i < nb_cbk_search; i++) if (CC[i] > CCmax_new) { CCmax_new = CC[i]; CBimax_new = i; }
+    lag_log2 = pe_log2((float)d);
+    CCmax_new_b = CCmax_new - 0.2f * nb_subfr * lag_log2;
+    if (prevLag > 0) {
+      delta_lag_log2_sqr = lag_log2 - prevLag_log2;
+      delta_lag_log2_sqr *= delta_lag_log2_sqr;
+      CCmax_new_b -= 0.2f * nb_subfr * (*LTPCorr) * delta_lag_log2_sqr / (delta_lag_log2_sqr + 0.5f);
+    }
+    if (CCmax_new_b > CCmax_b && CCmax_new > nb_subfr * search_thres2) { CCmax_b = CCmax_new_b; CCmax = CCmax_new; lag = d; CBimax = CBimax_new; }
+  }
+  if (lag == -1) {
+    memset(pitch_out, 0, 4 * sizeof(int));
+    *LTPCorr = 0.0f; *lagIndex = 0; *contourIndex = 0;
+    return 1;
+  }
+  *LTPCorr = (float)(CCmax / nb_subfr);
+  if (Fs_kHz > 8) {
+    const int8_t *range, *cb3;
+    int nb3, cb3_size;
+    float scratch[22];
+    if (Fs_kHz == 12) lag = rshift_round((int32_t)(int16_t)lag * 3, 1);
+    else lag = lag << 1;
+    lag = lag < min_lag ? min_lag : lag > max_lag ? max_lag : lag;
+    start_lag = lag - 2 > min_lag ? lag - 2 : min_lag;
+    end_lag = lag + 2 < max_lag ? lag + 2 : max_lag;
+    lag_new = lag; CBimax = 0; CCmax = -1000.0f;
+    if (nb_subfr == 4) { range = &pe_range3[complexity][0][0]; cb3 = &pe_cb3[0][0]; nb3 = pe_nb3[complexity]; cb3_size = 34; }
+    else { range = &pe_range3_10[0][0]; cb3 = &pe_cb3_10[0][0]; nb3 = 12; cb3_size = 12; }
+    target_ptr = &frame[sf_length << 2];
+    for (k = 0; k < nb_subfr; k++) { /* silk_P_Ana_calc_corr_st3 / _energy_st3 */
+      const int lag_low = range[k * 2], lag_high = range[k * 2 + 1], lag_diff = lag_high - lag_low + 1;
+      float xc[22], en[22];
+      for (i = 0; i < lag_diff; i++) xc[i] = pe_dot(target_ptr, target_ptr - start_lag - lag_high + i, sf_length);
+      lag_counter = 0;
+      for (j = lag_low; j <= lag_high; j++) scratch[lag_counter++] = xc[lag_high - j];
+      for (i = 0; i < nb3; i++) {
+        const int idx = cb3[k * cb3_size + i] - lag_low;
+        for (j = 0; j < 5; j++) cross_corr_st3[k][i][j] = scratch[idx + j];
+      }
+      basis_ptr = target_ptr - (start_lag + lag_low);
+      energy = inner_product_flp(basis_ptr, basis_ptr, sf_length) + 1e-3;
+      en[0] = (float)energy;
+      for (i = 1; i < lag_diff; i++) {
+        energy -= basis_ptr[sf_length - i] * (double)basis_ptr[sf_length - i];
+        energy += basis_ptr[-i] * (double)basis_ptr[-i];
+        en[i] = (float)energy;
+      }
+      for (i = 0; i < nb3; i++) {
+        const int idx = cb3[k * cb3_size + i] - lag_low;
+        for (j = 0; j < 5; j++) energies_st3[k][i][j] = en[idx + j];
+      }
+      target_ptr += sf_length;
+    }
+    lag_counter = 0;
+    contour_bias = 0.05f / lag;
+    nb_cbk_search = nb3; cbk_size = cb3_size; Lag_CB_ptr = cb3;
+    target_ptr = &frame[20 * Fs_kHz];
+    energy_tmp = inner_product_flp(target_ptr, target_ptr, nb_subfr * sf_length) + 1.0;
+    for (d = start_lag; d <= end_lag; d++) {
+      for (j = 0; j < nb_cbk_search; j++) {
+        cross_corr = 0.0;
+        energy = energy_tmp;
+        for (k = 0; k < nb_subfr; k++) { cross_corr += cross_corr_st3[k][j][lag_counter]; energy += energies_st3[k][j][lag_counter]; }
+        if (cross_corr > 0.0) { CCmax_new = (float)(2 * cross_corr / energy); CCmax_new *= 1.0f - contour_bias * j; }
+        else CCmax_new = 0.0f;
+        if (CCmax_new > CCmax && (d + (int)pe_cb3[0][j]) <= max_lag) { CCmax = CCmax_new; lag_new = d; CBimax = j; }
+      }
+      lag_counter++;
+    }
+    for (k = 0; k < nb_subfr; k++) {
+      const int v = lag_new + Lag_CB_ptr[k * cbk_size + CBimax], hi = 18 * Fs_kHz;
+      pitch_out[k] = v < min_lag ? min_lag : v > hi ? hi : v; /* silk_LIMIT( v, min_lag, PE_MAX_LAG_MS * Fs_kHz ) */
+    }
+    *lagIndex = (int16_t)(lag_new - min_lag);
+    *contourIndex = (int8_t)CBimax;
+  } else {
+    for (k = 0; k < nb_subfr; k++) {
+      const int v = lag + Lag_CB_ptr[k * cbk_size + CBimax];
+      pitch_out[k] = v < min_lag_8kHz ? min_lag_8kHz : v > 18 * 8 ? 18 * 8 : v;
+    }
+    *lagIndex = (int16_t)(lag - min_lag_8kHz);
+    *contourIndex = (int8_t)CBimax;
+  }
+  return 0;
+}
+typedef struct { /* what silk_find_pitch_lags_FLP reads and writes in the encoder structs; == OpusB200SilkPitch */
+  int32_t signalType;                                  /* in: 0 = no voice activity; out: 1 unvoiced / 2 voiced (0 stays) */
+  int32_t first_frame_after_reset, speech_activity_Q8, prevSignalType, input_tilt_Q15, prevLag, pitchEstimationThreshold_Q16;
+  float LTPCorr;                                       /* in / out */
+  float predGain;                                      /* out */
+  int32_t pitchL[4];                                   /* out */
+  int32_t lagIndex, contourIndex;                      /* out */
+} OrcSilkPitch;
+int orc_silk_pitch_size(void) { return (int)sizeof(OrcSilkPitch); }
+/* x: the frame of the input with ltp_mem_length (20 ms) samples in front and la_pitch (2 ms) behind; res [la_pitch + frame_length + ltp_mem_length] out */
+void orc_silk_find_pitch_lags(OrcSilkPitch *c, float *res, const float *x, int fs_kHz, int nb_subfr, int lpc_order, int complexity) {
+  const int la_pitch = 2 * fs_kHz, frame_length = 5 * nb_subfr * fs_kHz, ltp_mem_length = 20 * fs_kHz, buf_len = la_pitch + frame_length + ltp_mem_length,
+            win_length = (5 * nb_subfr + 4) * fs_kHz;
+  const float *x_buf = x - ltp_mem_length, *x_buf_ptr = x_buf + buf_len - win_length;
+  float auto_corr[17], A[16], refl_coef[16], Wsig[24 * 16], res_nrg, thrhld;
+  double Cs[17][2], rc_tmp;
+  int i, n;
+  ns_sine_window(Wsig, x_buf_ptr, 1, la_pitch);
+  memcpy(Wsig + la_pitch, x_buf_ptr + la_pitch, (win_length - (la_pitch << 1)) * sizeof(float));
+  ns_sine_window(Wsig + win_length - la_pitch, x_buf_ptr + win_length - la_pitch, 2, la_pitch);
+  for (i = 0; i < lpc_order + 1; i++) auto_corr[i] = (float)inner_product_flp(Wsig, Wsig + i, win_length - i);
+  auto_corr[0] += auto_corr[0] * 1e-3f + 1;
+  for (i = 0; i <= lpc_order; i++) Cs[i][0] = Cs[i][1] = auto_corr[i];
+  for (i = 0; i < lpc_order; i++) { /* silk_schur_FLP */
+    rc_tmp = -Cs[i + 1][0] / (Cs[0][1] > 1e-9f ? Cs[0][1] : 1e-9f);
+    refl_coef[i] = (float)rc_tmp;
+    for (n = 0; n < lpc_order - i; n++) {
+      const double Ctmp1 = Cs[n + i + 1][0], Ctmp2 = Cs[n][1];
+      Cs[n + i + 1][0] = Ctmp1 + Ctmp2 * rc_tmp;
+      Cs[n][1] = Ctmp2 + Ctmp1 * rc_tmp;
+    }
+  }
+  res_nrg = (float)Cs[0][1];
+  c->predGain = auto_corr[0] / (res_nrg > 1.0f ? res_nrg : 1.0f);
+  for (i = 0; i < lpc_order; i++) { /* silk_k2a_FLP */
+    const float rck = refl_coef[i];
+    for (n = 0; n < (i + 1) >> 1; n++) {
+      const float t1 = A[n], t2 = A[i - n - 1];
+      A[n] = t1 + t2 * rck;
+      A[i - n - 1] = t2 + t1 * rck;
+    }
+    A[i] = -rck;
+  }
+  ns_bwexpander(A, lpc_order, 0.99f);
+  for (i = lpc_order; i < buf_len; i++) { /* silk_LPC_analysis_filter_FLP (orders 6 .. 16: the products summed left to right) */
+    const float *sp = &x_buf[i - 1];
+    float pred = sp[0] * A[0];
+    for (n = 1; n < lpc_order; n++) pred = pred + sp[-n] * A[n];
+    res[i] = sp[1] - pred;
+  }
+  memset(res, 0, lpc_order * sizeof(float));
+  if (c->signalType != 0 && c->first_frame_after_reset == 0) {
+    int pitch[4] = {0, 0, 0, 0};
+    int16_t lagIndex = 0;
+    int8_t contourIndex = 0;
+    thrhld = 0.6f;
+    thrhld -= 0.004f * lpc_order;
+    thrhld -= 0.1f * c->speech_activity_Q8 * (1.0f / 256.0f);
+    thrhld -= 0.15f * (c->prevSignalType >> 1);
+    thrhld -= 0.1f * c->input_tilt_Q15 * (1.0f / 32768.0f);
+    if (orc_silk_pitch_analysis_core(res, pitch, &lagIndex, &contourIndex, &c->LTPCorr, c->prevLag, c->pitchEstimationThreshold_Q16 / 65536.0f, thrhld, fs_kHz,
+                                     complexity, nb_subfr) == 0)
+      c->signalType = 2;
+    else c->signalType = 1;
+    for (i = 0; i < 4; i++) c->pitchL[i] = pitch[i];
+    c->lagIndex = lagIndex;
+    c->contourIndex = contourIndex;
+  } else {
+    memset(c->pitchL, 0, sizeof(c->pitchL));
+    c->lagIndex = 0; c->contourIndex = 0; c->LTPCorr = 0;
+  }
+}
