@@ -518,6 +518,23 @@ typedef struct {
 int opusb200_silk_noise_shape_analysis(OpusB200Ctx *ctx, OpusB200SilkNoiseShape *frames, const float *pitch_res, int res_stride, const float *x, int x_stride,
                                        int x_off, int n, int fs_kHz, int nb_subfr, int shapingLPCOrder, int on_device);
 
+/* silk_find_pitch_lags_FLP (silk/float/find_pitch_lags_FLP.c:36-132; call site silk/float/encode_frame_FLP.c:153) with silk_pitch_analysis_core_FLP
+ * (silk/float/pitch_analysis_core_FLP.c:66-630): the pitch analysis of a SILK frame — the whitened residual of history + frame + look-ahead (res out,
+ * the input of opusb200_silk_noise_shape_analysis and opusb200_silk_find_pred_coefs), the voicing decision, the four pitch lags with their lag / contour
+ * indices, LTPCorr and predGain.  x [n][x_stride] with the frame at x_off (20 ms in front, 2 ms behind); res [n][res_stride >= (22 + 5 nb_subfr) fs_kHz].
+ * lpc_order in {6, 8, 10, 12, 16} (pitchEstimationLPCOrder), complexity 0..2 (pitchEstimationComplexity).  in: signalType (0 = no voice activity: no
+ * search), first_frame_after_reset, speech_activity_Q8, prevSignalType, input_tilt_Q15, prevLag, pitchEstimationThreshold_Q16, LTPCorr. */
+typedef struct {
+  int32_t signalType;
+  int32_t first_frame_after_reset, speech_activity_Q8, prevSignalType, input_tilt_Q15, prevLag, pitchEstimationThreshold_Q16;
+  float LTPCorr;
+  float predGain;
+  int32_t pitchL[4];
+  int32_t lagIndex, contourIndex;
+} OpusB200SilkPitch;
+int opusb200_silk_find_pitch_lags(OpusB200Ctx *ctx, OpusB200SilkPitch *frames, float *res, int res_stride, const float *x, int x_stride, int x_off, int n, int fs_kHz,
+                                  int nb_subfr, int lpc_order, int complexity, int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

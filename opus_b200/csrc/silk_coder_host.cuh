@@ -350,3 +350,47 @@ extern "C" int opusb200_silk_noise_shape_analysis(OpusB200Ctx *c, OpusB200SilkNo
   }
   return r;
 }
+
+// ---- silk_find_pitch_lags_FLP for n streams (silk_pitch.cuh: silk_find_pitch_lags_thread) ----
+#include "silk_pitch.cuh"
+extern "C" __global__ void __launch_bounds__(64) ob_silk_find_pitch_lags(ob::SilkPitchParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_find_pitch_lags_thread(p, s);
+}
+extern "C" int opusb200_silk_find_pitch_lags(OpusB200Ctx *c, OpusB200SilkPitch *frames, float *res, int res_stride, const float *x, int x_stride, int x_off, int n,
+                                             int fs_kHz, int nb_subfr, int lpc_order, int complexity, int on_device) {
+  static_assert(sizeof(OpusB200SilkPitch) == sizeof(ob::ObSilkPitch), "OpusB200SilkPitch mirrors ObSilkPitch");
+  if (!c || !frames || !res || !x || n <= 0 || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16) || (nb_subfr != 2 && nb_subfr != 4) || complexity < 0 || complexity > 2 ||
+      (lpc_order != 6 && lpc_order != 8 && lpc_order != 10 && lpc_order != 12 && lpc_order != 16))
+    return OPUSB200_BAD_ARG;
+  const int buf_len = (22 + 5 * nb_subfr) * fs_kHz;
+  if (res_stride < buf_len || x_off < 20 * fs_kHz || x_stride < x_off + (5 * nb_subfr + 2) * fs_kHz) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkPitchParams p;
+  p.n = n; p.x_stride = x_stride; p.x_off = x_off; p.res_stride = res_stride; p.fs_kHz = fs_kHz; p.nb_subfr = nb_subfr; p.lpc_order = lpc_order; p.complexity = complexity;
+  const size_t fb = sizeof(ob::ObSilkPitch) * (size_t)n, rb = sizeof(float) * (size_t)n * res_stride, xb = sizeof(float) * (size_t)n * x_stride;
+  ob::ObSilkPitch *d = (ob::ObSilkPitch *)frames;
+  float *dr = res, *dx = nullptr;
+  int r = OPUSB200_OK;
+  if (!on_device) {
+    if (cudaMalloc(&d, fb) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    dr = nullptr;
+    if (cudaMalloc(&dr, rb) != cudaSuccess || cudaMalloc(&dx, xb) != cudaSuccess) { cudaFree(d); cudaFree(dr); return OPUSB200_ALLOC_FAIL; }
+    if (cudaMemcpyAsync(d, frames, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaMemcpyAsync(dx, x, xb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (r == OPUSB200_OK) {
+    p.frames = d; p.res = dr; p.x = on_device ? x : dx;
+    ob_silk_find_pitch_lags<<<(n + 63) / 64, 64, 0, c->stream>>>(p);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (!on_device) {
+    if (r == OPUSB200_OK && (cudaMemcpyAsync(frames, d, fb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                             cudaMemcpyAsync(res, dr, rb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess))
+      r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d); cudaFree(dr); cudaFree(dx);
+  }
+  return r;
+}

@@ -131,6 +131,17 @@ class Ops:
             raise capi.OpusB200Error(r, 'opusb200_silk_noise_shape_analysis')
         return frames
 
+    def silk_find_pitch_lags(self, frames, x, x_off, fs_kHz, nb_subfr, lpc_order, complexity):
+        """silk_find_pitch_lags_FLP for n streams: frames = ctypes array of OpusB200SilkPitch-shaped records (in place), x float32 [n, stride] with the
+        frame at x_off; returns the residual float32 [n, (22 + 5 nb_subfr) fs_kHz]"""
+        x = np.ascontiguousarray(x, np.float32)
+        res = np.zeros((len(frames), (22 + 5 * nb_subfr) * fs_kHz), np.float32)
+        r = self._L.opusb200_silk_find_pitch_lags(self._h, ctypes.cast(frames, ctypes.c_void_p), res.ctypes.data_as(ctypes.c_void_p), res.shape[1],
+                                                  x.ctypes.data_as(ctypes.c_void_p), x.shape[1], x_off, len(frames), fs_kHz, nb_subfr, lpc_order, complexity, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_find_pitch_lags')
+        return res
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

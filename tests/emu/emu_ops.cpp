@@ -593,3 +593,18 @@ extern "C" void emu_silk_noise_shape(void *frames, const float *pitch_res, int r
   p.fs_kHz = fs_kHz; p.nb_subfr = nb_subfr; p.shapingLPCOrder = order;
   emu_launch(silk_noise_shape_entry, &p, (n + 31) / 32, 32, 0);
 }
+
+// ---- silk_find_pitch_lags_FLP (silk_pitch.cuh), thread per stream ----
+#include "../../opus_b200/csrc/silk_pitch.cuh"
+static void silk_pitch_entry(void *a) {
+  const SilkPitchParams &p = *(const SilkPitchParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_find_pitch_lags_thread(p, s);
+}
+extern "C" void emu_silk_find_pitch_lags(void *frames, float *res, int res_stride, const float *x, int x_stride, int x_off, int n, int fs_kHz, int nb_subfr, int order,
+                                         int complexity) {
+  SilkPitchParams p;
+  p.frames = (ObSilkPitch *)frames; p.res = res; p.x = x; p.n = n; p.x_stride = x_stride; p.x_off = x_off; p.res_stride = res_stride; p.fs_kHz = fs_kHz;
+  p.nb_subfr = nb_subfr; p.lpc_order = order; p.complexity = complexity;
+  emu_launch(silk_pitch_entry, &p, (n + 31) / 32, 32, 0);
+}

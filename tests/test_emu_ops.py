@@ -365,3 +365,34 @@ def test_silk_noise_shape_emulated(fs_kHz, nb_subfr, order):
             oa, ob = outputs(recs[s], nb_subfr, order), outputs(want[s], nb_subfr, order)
             assert oa == ob, (frame, s, [i for i in range(len(oa)) if oa[i] != ob[i]])
             state[s] = (want[s].HarmShapeGain_smth, want[s].Tilt_smth)
+
+
+@pytest.mark.parametrize('fs_kHz,nb_subfr,order,complexity', [(16, 4, 16, 2), (8, 4, 10, 1), (12, 4, 12, 1), (16, 2, 16, 0), (12, 2, 12, 2)])
+def test_silk_find_pitch_lags_emulated(fs_kHz, nb_subfr, order, complexity):
+    """silk_find_pitch_lags_FLP + silk_pitch_analysis_core_FLP: the device source on the emulator against the oracle (pinned on the reference): residual,
+    voicing decision, lags, indices, LTPCorr, predGain; streams carry the previous lag / type / correlation over frames"""
+    from test_silk_pitch_oracle_vs_ref import Pitch, pitch_input, random_case, outputs
+    E, O = emu_util.load_emu_ops(), util.load_oracle()
+    rng = np.random.default_rng(100 + fs_kHz + nb_subfr)
+    n, hist, buf_len = 20, 20 * fs_kHz, (22 + 5 * nb_subfr) * fs_kHz
+    prev = [(0, 0, np.float32(0))] * n
+    voiced = 0
+    for frame in range(4):
+        recs = (Pitch * n)()
+        X_ = np.stack([pitch_input(rng, fs_kHz, nb_subfr, (s + frame // 2) % 3) for s in range(n)])
+        want, wres = [], []
+        for s in range(n):
+            recs[s] = random_case(rng, fs_kHz, frame, prev[s])
+            w = Pitch.from_buffer_copy(bytes(recs[s]))
+            r = np.zeros(buf_len, np.float32)
+            O.orc_silk_find_pitch_lags(ctypes.byref(w), r.ctypes.data_as(ctypes.c_void_p), X_[s, hist:].ctypes.data_as(ctypes.c_void_p), fs_kHz, nb_subfr, order, complexity)
+            want.append(w); wres.append(r)
+        res = np.zeros((n, buf_len), np.float32)
+        E.emu_silk_find_pitch_lags(ctypes.cast(recs, ctypes.c_void_p), res.ctypes.data_as(ctypes.c_void_p), buf_len, X_.ctypes.data_as(ctypes.c_void_p), X_.shape[1], hist, n,
+                                   fs_kHz, nb_subfr, order, complexity)
+        for s in range(n):
+            assert np.array_equal(res[s].view(np.uint32), wres[s].view(np.uint32)), (frame, s)
+            assert outputs(recs[s]) == outputs(want[s]), (frame, s, outputs(recs[s]), outputs(want[s]))
+            voiced += int(want[s].signalType == 2)
+            prev[s] = (want[s].signalType, want[s].pitchL[nb_subfr - 1] if want[s].signalType == 2 else 0, want[s].LTPCorr)
+    assert voiced > 5

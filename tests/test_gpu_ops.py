@@ -503,3 +503,38 @@ def test_silk_noise_shape_analysis(fs_kHz, nb_subfr, order):
             state[s] = (want[s].HarmShapeGain_smth, want[s].Tilt_smth)
     print('bit-identical records: %d of %d' % (exact, total))
     assert exact >= 0.9 * total
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fs_kHz,nb_subfr,order,complexity', [(16, 4, 16, 2), (8, 4, 10, 1), (12, 4, 12, 1), (16, 2, 16, 0)])
+def test_silk_find_pitch_lags(fs_kHz, nb_subfr, order, complexity):
+    """opusb200_silk_find_pitch_lags against the oracle (pinned bit for bit on silk_find_pitch_lags_FLP / silk_pitch_analysis_core_FLP).  The float path has one
+    libm call family (log10 for the lag biases): a last-bit difference can flip a near-tie between two candidate lags on a rare frame.  Bar: the residual
+    within 1e-6 relative everywhere, voicing decision / lags / indices identical on at least 97 % of the stream-frames."""
+    import opus_b200
+    from test_silk_pitch_oracle_vs_ref import Pitch, pitch_input, random_case, outputs
+    O = util.load_oracle()
+    ops = opus_b200.Ops()
+    rng = np.random.default_rng(110 + fs_kHz + nb_subfr)
+    n, hist, buf_len = 120, 20 * fs_kHz, (22 + 5 * nb_subfr) * fs_kHz
+    prev = [(0, 0, np.float32(0))] * n
+    exact = total = voiced = 0
+    for frame in range(3):
+        recs = (Pitch * n)()
+        X_ = np.stack([pitch_input(rng, fs_kHz, nb_subfr, (s + frame) % 3) for s in range(n)])
+        want, wres = [], []
+        for s in range(n):
+            recs[s] = random_case(rng, fs_kHz, frame, prev[s])
+            w = Pitch.from_buffer_copy(bytes(recs[s]))
+            r = np.zeros(buf_len, np.float32)
+            O.orc_silk_find_pitch_lags(ctypes.byref(w), r.ctypes.data_as(ctypes.c_void_p), X_[s, hist:].ctypes.data_as(ctypes.c_void_p), fs_kHz, nb_subfr, order, complexity)
+            want.append(w); wres.append(r)
+        res = ops.silk_find_pitch_lags(recs, X_, hist, fs_kHz, nb_subfr, order, complexity)
+        for s in range(n):
+            assert np.abs(res[s] - wres[s]).max() <= 1e-6 * max(1.0, np.abs(wres[s]).max()), (frame, s)
+            total += 1
+            exact += int(outputs(recs[s]) == outputs(want[s]) and np.array_equal(res[s].view(np.uint32), wres[s].view(np.uint32)))
+            voiced += int(want[s].signalType == 2)
+            prev[s] = (want[s].signalType, want[s].pitchL[nb_subfr - 1] if want[s].signalType == 2 else 0, want[s].LTPCorr)
+    print('bit-identical stream-frames: %d of %d (%d voiced)' % (exact, total, voiced))
+    assert exact >= 0.97 * total and voiced > 20
