@@ -432,7 +432,7 @@ int opusb200_dred_encoder_load_stats(OpusB200DredEnc *enc, const unsigned char *
 int opusb200_dred_encode_silk_frame(OpusB200DredEnc *enc, unsigned char *buf, int buf_stride, int max_chunks, int max_bytes, int q0, int dQ, int qmax,
                                     const unsigned char *activity_mem, int32_t *nbytes, int on_device);
 
-/* silk_process_gains_FLP (silk/float/process_gains_FLP.c:35-103; call site silk/float/encode_frame_FLP.c:172) with silk_gains_quant
+/* silk_process_gains_FLP (silk/float/process_gains_FLP.c:36-103; call site silk/float/encode_frame_FLP.c:166) with silk_gains_quant
  * (silk/gain_quant.c:40-95): the gain quantiser of a SILK frame — another slice of SURVEY 8(f).3.  One record per stream holds what the function
  * reads and writes in silk_encoder_state_FLP / silk_encoder_control_FLP: in: Gains, ResNrg, LTPredCodGain, input_quality, coding_quality, signalType,
  * quantOffsetType, SNR_dB_Q7, input_tilt_Q15, speech_activity_Q8, condCoding (0 / 1 / 2 as silk/define.h:97-99), LastGainIndex; out: Gains
@@ -448,7 +448,7 @@ typedef struct {
 int opusb200_silk_process_gains(OpusB200Ctx *ctx, OpusB200SilkGains *frames, int n, int nb_subfr, int subfr_length, int nStatesDelayedDecision,
                                 int on_device);
 
-/* silk_process_NLSFs (silk/process_NLSFs.c:35-107; call site silk/float/wrappers_FLP.c:103 from find_pred_coefs_FLP.c:103): the NLSF quantiser of a
+/* silk_process_NLSFs (silk/process_NLSFs.c:35-107; call site silk/float/wrappers_FLP.c:84 from find_pred_coefs_FLP.c:108): the NLSF quantiser of a
  * SILK frame — laroia weights, interpolation, silk_NLSF_encode (first-stage VQ, survivors, delayed-decision trellis), silk_NLSF_decode, the stabiliser
  * and silk_NLSF2A for both half-frames.  One record per stream: in: NLSF_Q15 (unquantised), prev_NLSFq_Q15, NLSFInterpCoef_Q2, signalType,
  * useInterpolatedNLSFs, speech_activity_Q8, NLSF_MSVQ_Survivors (2..32); out: NLSF_Q15 (quantised), NLSFIndices [order + 1], PredCoef_Q12 [2][order].
@@ -463,7 +463,7 @@ typedef struct {
 } OpusB200SilkNlsf;
 int opusb200_silk_process_nlsfs(OpusB200Ctx *ctx, OpusB200SilkNlsf *frames, int n, int fs_kHz, int nb_subfr, int on_device);
 
-/* silk_find_LPC_FLP (silk/float/find_LPC_FLP.c:36-105; call site silk/float/find_pred_coefs_FLP.c:100): the LPC estimation of a SILK frame — Burg over
+/* silk_find_LPC_FLP (silk/float/find_LPC_FLP.c:37-105; call site silk/float/find_pred_coefs_FLP.c:105): the LPC estimation of a SILK frame — Burg over
  * the frame and, with NLSF interpolation on, over its second half; silk_A2NLSF; the search over the interpolation factor (silk_interpolate, silk_NLSF2A,
  * the float LPC analysis filter, residual energies).  x [n][nb_subfr * (subfr_length + order)]: the pre-whitened frame with `order` samples of history
  * in front of every subframe; order 10 or 16.  in: prev_NLSFq_Q15, minInvGain, useInterpolatedNLSFs, first_frame_after_reset; out: NLSF_Q15 (the input
@@ -477,7 +477,7 @@ typedef struct {
 } OpusB200SilkFindLpc;
 int opusb200_silk_find_lpc(OpusB200Ctx *ctx, OpusB200SilkFindLpc *frames, const float *x, int n, int order, int nb_subfr, int subfr_length, int on_device);
 
-/* silk_find_pred_coefs_FLP (silk/float/find_pred_coefs_FLP.c:35-120; call site silk/float/encode_frame_FLP.c:163): the whole prediction analysis of a
+/* silk_find_pred_coefs_FLP (silk/float/find_pred_coefs_FLP.c:35-116; call site silk/float/encode_frame_FLP.c:161): the whole prediction analysis of a
  * SILK frame in one call per batch.  Voiced frames: silk_find_LTP_FLP, silk_quant_LTP_gains (silk_VQ_WMat_EC), silk_LTP_scale_ctrl_FLP,
  * silk_LTP_analysis_filter_FLP; all frames: silk_find_LPC_FLP, silk_process_NLSFs, silk_residual_energy_FLP.
  * res_pitch / x [n][sig_stride] float: the pitch-analysis residual and the input signal of every stream with the current frame at frame_off (history in
@@ -500,7 +500,7 @@ typedef struct {
 int opusb200_silk_find_pred_coefs(OpusB200Ctx *ctx, OpusB200SilkPredCoefs *frames, const float *res_pitch, const float *x, int n, int sig_stride, int frame_off,
                                   int fs_kHz, int nb_subfr, int on_device);
 
-/* silk_noise_shape_analysis_FLP (silk/float/noise_shape_analysis_FLP.c:138-350; call site silk/float/encode_frame_FLP.c:158): the noise shaping
+/* silk_noise_shape_analysis_FLP (silk/float/noise_shape_analysis_FLP.c:147-350; call site silk/float/encode_frame_FLP.c:156): the noise shaping
  * analysis of a SILK frame — coding / input quality and the SNR adjustment, the sparseness measure (quantOffsetType of unvoiced frames), per subframe
  * the windowed (warped) autocorrelation, Schur recursion, step-up, bandwidth expansion and coefficient limiting (AR, 24 slots per subframe) and the
  * initial gains; gain tweaking; low-frequency, tilt and harmonic shaping with their smoothers (HarmShapeGain_smth / Tilt_smth carried in the record).
@@ -518,7 +518,7 @@ typedef struct {
 int opusb200_silk_noise_shape_analysis(OpusB200Ctx *ctx, OpusB200SilkNoiseShape *frames, const float *pitch_res, int res_stride, const float *x, int x_stride,
                                        int x_off, int n, int fs_kHz, int nb_subfr, int shapingLPCOrder, int on_device);
 
-/* silk_find_pitch_lags_FLP (silk/float/find_pitch_lags_FLP.c:36-132; call site silk/float/encode_frame_FLP.c:153) with silk_pitch_analysis_core_FLP
+/* silk_find_pitch_lags_FLP (silk/float/find_pitch_lags_FLP.c:36-132; call site silk/float/encode_frame_FLP.c:151) with silk_pitch_analysis_core_FLP
  * (silk/float/pitch_analysis_core_FLP.c:66-630): the pitch analysis of a SILK frame — the whitened residual of history + frame + look-ahead (res out,
  * the input of opusb200_silk_noise_shape_analysis and opusb200_silk_find_pred_coefs), the voicing decision, the four pitch lags with their lag / contour
  * indices, LTPCorr and predGain.  x [n][x_stride] with the frame at x_off (20 ms in front, 2 ms behind); res [n][res_stride >= (22 + 5 nb_subfr) fs_kHz].
