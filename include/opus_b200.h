@@ -535,6 +535,28 @@ typedef struct {
 int opusb200_silk_find_pitch_lags(OpusB200Ctx *ctx, OpusB200SilkPitch *frames, float *res, int res_stride, const float *x, int x_stride, int x_off, int n, int fs_kHz,
                                   int nb_subfr, int lpc_order, int complexity, int on_device);
 
+/* silk_VAD_Init (silk/VAD.c:46-76), silk_encode_do_VAD_FLP (silk/float/encode_frame_FLP.c:45-82; call sites silk/enc_API.c:465,480) with
+ * silk_VAD_GetSA_Q8_c (silk/VAD.c:82-297) inside, and silk_HP_variable_cutoff (silk/HP_variable_cutoff.c:39-77; call site silk/enc_API.c:409): the
+ * voice activity detector of a SILK frame — another slice of SURVEY 8(f).3.  One record per stream = silk_VAD_state (silk/structs.h:74-85; HPstate
+ * widened to 32 bits) followed by the silk_encoder_state fields the three functions read and write: speech_activity_Q8, input_tilt_Q15,
+ * input_quality_bands_Q15, indices.signalType, noSpeechCounter, inDTX, VAD_flags[nFramesEncoded] (VAD_flag), prevSignalType, prevLag,
+ * variable_HP_smth1_Q15.  The caller carries the record from frame to frame.
+ *   opusb200_silk_vad_init          fills n records on the host (constants; no device work)
+ *   opusb200_silk_encode_do_vad     pcm [n][pcm_stride] int16, the frame_length samples the reference reads at inputBuf + 1; frame_length = 10 or 20 ms
+ *                                   at fs_kHz 8 / 12 / 16; activity [n] = the Opus-level decision (0 = VAD_NO_ACTIVITY) or NULL = active everywhere
+ *   opusb200_silk_hp_variable_cutoff  updates variable_HP_smth1_Q15 where prevSignalType is voiced (prevLag in 1..32767 then)
+ * on_device != 0: frames / pcm / activity are device pointers and the call only enqueues.  All integer, bit-exact. */
+typedef struct {
+  int32_t AnaState[2], AnaState1[2], AnaState2[2], XnrgSubfr[4], NrgRatioSmth_Q8[4], HPstate, NL[4], inv_NL[4], NoiseLevelBias[4], counter;
+  int32_t speech_activity_Q8, input_tilt_Q15, input_quality_bands_Q15[4];
+  int32_t signalType, noSpeechCounter, inDTX, VAD_flag;
+  int32_t prevSignalType, prevLag, variable_HP_smth1_Q15;
+} OpusB200SilkVad;
+int opusb200_silk_vad_init(OpusB200SilkVad *frames, int n);
+int opusb200_silk_encode_do_vad(OpusB200Ctx *ctx, OpusB200SilkVad *frames, const int16_t *pcm, int pcm_stride, const int32_t *activity, int n, int frame_length,
+                                int fs_kHz, int on_device);
+int opusb200_silk_hp_variable_cutoff(OpusB200Ctx *ctx, OpusB200SilkVad *frames, int n, int fs_kHz, int on_device);
+
 /* ---- LPCNet feature extraction (dnn/lpcnet_enc.c, freq.c, pitchdnn.c, burg.c; struct LPCNetEncState of dnn/lpcnet_private.h:25-43): n streams
  * that take one 10 ms frame of 16 kHz audio per call.  It produces the 36 features the DRED encoder codes (dnn/dred_encoder.c:101-102) and is what
  * lpcnet_plc_conceal runs over the decoded history (dnn/lpcnet_plc.c:160-177).

@@ -43,7 +43,7 @@ SYMBOLS = ['opusb200_version', 'opusb200_device_count', 'opusb200_decoder_create
            'opusb200_dred_encoder_load_stats', 'opusb200_dred_encode_silk_frame',
            'opusb200_lpcnet_plc_create', 'opusb200_lpcnet_plc_destroy', 'opusb200_lpcnet_plc_reset', 'opusb200_lpcnet_plc_fec_add', 'opusb200_lpcnet_plc_fec_clear',
            'opusb200_lpcnet_plc_update', 'opusb200_lpcnet_plc_conceal', 'opusb200_lpcnet_plc_get_state', 'opusb200_lpcnet_plc_load_pitch_model',
-           'opusb200_silk_process_gains', 'opusb200_silk_process_nlsfs', 'opusb200_silk_find_lpc', 'opusb200_silk_find_pred_coefs', 'opusb200_silk_noise_shape_analysis', 'opusb200_silk_find_pitch_lags', 'opusb200_lpcnet_encoder_create', 'opusb200_lpcnet_encoder_destroy', 'opusb200_lpcnet_encoder_reset',
+           'opusb200_silk_process_gains', 'opusb200_silk_process_nlsfs', 'opusb200_silk_find_lpc', 'opusb200_silk_find_pred_coefs', 'opusb200_silk_noise_shape_analysis', 'opusb200_silk_vad_init', 'opusb200_silk_encode_do_vad', 'opusb200_silk_hp_variable_cutoff', 'opusb200_silk_find_pitch_lags', 'opusb200_lpcnet_encoder_create', 'opusb200_lpcnet_encoder_destroy', 'opusb200_lpcnet_encoder_reset',
            'opusb200_lpcnet_compute_single_frame_features', 'opusb200_lpcnet_encoder_get_state', 'opusb200_burg_cepstral_analysis',
            'opusb200_dred_decoder_create', 'opusb200_dred_decoder_destroy', 'opusb200_dred_decode_all', 'opusb200_host_alloc', 'opusb200_host_free',
            'opusb200_opus_encoder_create', 'opusb200_opus_encoder_destroy', 'opusb200_opus_encoder_reset', 'opusb200_opus_encoder_ctl',
@@ -214,6 +214,9 @@ def lib():
         L.opusb200_silk_find_lpc.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci]
         L.opusb200_silk_find_pred_coefs.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci]
         L.opusb200_silk_find_pitch_lags.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci]
+        L.opusb200_silk_vad_init.argtypes = [vp, ci]
+        L.opusb200_silk_encode_do_vad.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci]
+        L.opusb200_silk_hp_variable_cutoff.argtypes = [vp, vp, ci, ci, ci]
         L.opusb200_silk_noise_shape_analysis.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci]
         L.opusb200_lpcnet_encoder_create.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.POINTER(vp)]
         L.opusb200_lpcnet_encoder_destroy.argtypes = [vp]

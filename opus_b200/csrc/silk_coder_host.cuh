@@ -394,3 +394,86 @@ extern "C" int opusb200_silk_find_pitch_lags(OpusB200Ctx *c, OpusB200SilkPitch *
   }
   return r;
 }
+
+// ---- silk_VAD_Init / silk_encode_do_VAD_FLP / silk_HP_variable_cutoff for n streams (silk_vad.cuh) ----
+#include "silk_vad.cuh"
+extern "C" __global__ void __launch_bounds__(128) ob_silk_encode_do_vad(ob::SilkVadParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_encode_do_vad_thread(p, s);
+}
+extern "C" __global__ void __launch_bounds__(128) ob_silk_hp_variable_cutoff(ob::SilkHpCutoffParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < p.n) ob::silk_hp_variable_cutoff_thread(p, s);
+}
+extern "C" int opusb200_silk_vad_init(OpusB200SilkVad *frames, int n) {   // silk_VAD_Init: constants only, written on the host into the caller's records
+  static_assert(sizeof(OpusB200SilkVad) == sizeof(ob::ObSilkVad), "OpusB200SilkVad mirrors ObSilkVad");
+  if (!frames || n <= 0) return OPUSB200_BAD_ARG;
+  memset(frames, 0, sizeof(OpusB200SilkVad) * (size_t)n);
+  for (int s = 0; s < n; s++) {
+    for (int b = 0; b < 4; b++) {
+      const int bias = 50 / (b + 1);   // VAD_NOISE_LEVELS_BIAS: approximately pink noise
+      frames[s].NoiseLevelBias[b] = bias > 1 ? bias : 1;
+      frames[s].NL[b] = 100 * frames[s].NoiseLevelBias[b];
+      frames[s].inv_NL[b] = 0x7FFFFFFF / frames[s].NL[b];
+      frames[s].NrgRatioSmth_Q8[b] = 100 * 256;   // 20 dB
+    }
+    frames[s].counter = 15;
+  }
+  return OPUSB200_OK;
+}
+extern "C" int opusb200_silk_encode_do_vad(OpusB200Ctx *c, OpusB200SilkVad *frames, const int16_t *pcm, int pcm_stride, const int32_t *activity, int n,
+                                           int frame_length, int fs_kHz, int on_device) {
+  if (!c || !frames || !pcm || n <= 0 || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16) || (frame_length != 10 * fs_kHz && frame_length != 20 * fs_kHz) ||
+      pcm_stride < frame_length)
+    return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkVadParams p;
+  p.n = n; p.pcm_stride = pcm_stride; p.frame_length = frame_length; p.fs_kHz = fs_kHz;
+  const size_t fb = sizeof(ob::ObSilkVad) * (size_t)n, xb = sizeof(int16_t) * (size_t)n * pcm_stride, ab = sizeof(int32_t) * (size_t)n;
+  ob::ObSilkVad *d = (ob::ObSilkVad *)frames;
+  int16_t *dx = nullptr;
+  int32_t *da = nullptr;
+  int r = OPUSB200_OK;
+  if (!on_device) {
+    if (cudaMalloc(&d, fb) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMalloc(&dx, xb) != cudaSuccess || (activity && cudaMalloc(&da, ab) != cudaSuccess)) { cudaFree(d); cudaFree(dx); return OPUSB200_ALLOC_FAIL; }
+    if (cudaMemcpyAsync(d, frames, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaMemcpyAsync(dx, pcm, xb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        (activity && cudaMemcpyAsync(da, activity, ab, cudaMemcpyHostToDevice, c->stream) != cudaSuccess))
+      r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (r == OPUSB200_OK) {
+    p.frames = d; p.pcm = on_device ? pcm : dx; p.activity = on_device ? activity : da;
+    ob_silk_encode_do_vad<<<(n + 127) / 128, 128, 0, c->stream>>>(p);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+  }
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, fb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d); cudaFree(dx); cudaFree(da);
+  }
+  return r;
+}
+extern "C" int opusb200_silk_hp_variable_cutoff(OpusB200Ctx *c, OpusB200SilkVad *frames, int n, int fs_kHz, int on_device) {
+  if (!c || !frames || n <= 0 || (fs_kHz != 8 && fs_kHz != 12 && fs_kHz != 16)) return OPUSB200_BAD_ARG;
+  if (!on_device) for (int s = 0; s < n; s++) if (frames[s].prevSignalType == 2 && (frames[s].prevLag <= 0 || frames[s].prevLag > 32767)) return OPUSB200_BAD_ARG;
+  OB_CUDA(cudaSetDevice(c->device));
+  ob::SilkHpCutoffParams p;
+  p.n = n; p.fs_kHz = fs_kHz;
+  const size_t fb = sizeof(ob::ObSilkVad) * (size_t)n;
+  ob::ObSilkVad *d = (ob::ObSilkVad *)frames;
+  if (!on_device) {
+    if (cudaMalloc(&d, fb) != cudaSuccess) return OPUSB200_ALLOC_FAIL;
+    if (cudaMemcpyAsync(d, frames, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { cudaFree(d); return OPUSB200_INTERNAL_ERROR; }
+  }
+  p.frames = d;
+  ob_silk_hp_variable_cutoff<<<(n + 127) / 128, 128, 0, c->stream>>>(p);
+  c->launches++;
+  int r = cudaGetLastError() == cudaSuccess ? OPUSB200_OK : OPUSB200_INTERNAL_ERROR;
+  if (!on_device) {
+    if (r == OPUSB200_OK && cudaMemcpyAsync(frames, d, fb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) r = OPUSB200_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && r == OPUSB200_OK) r = OPUSB200_INTERNAL_ERROR;
+    cudaFree(d);
+  }
+  return r;
+}

@@ -142,6 +142,31 @@ class Ops:
             raise capi.OpusB200Error(r, 'opusb200_silk_find_pitch_lags')
         return res
 
+    def silk_vad_init(self, frames):
+        """silk_VAD_Init for n streams: frames = ctypes array of OpusB200SilkVad-shaped records (filled on the host)"""
+        r = self._L.opusb200_silk_vad_init(ctypes.cast(frames, ctypes.c_void_p), len(frames))
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_vad_init')
+        return frames
+
+    def silk_encode_do_vad(self, frames, pcm, fs_kHz, activity=None, frame_length=None):
+        """silk_encode_do_VAD_FLP for n streams: frames = ctypes array of OpusB200SilkVad-shaped records (in place), pcm int16 [n, frame_length]
+        (10 or 20 ms at fs_kHz; or [n, stride] with frame_length given), activity int32 [n] = the Opus-level decision per stream or None"""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        act = None if activity is None else np.ascontiguousarray(activity, np.int32)
+        r = self._L.opusb200_silk_encode_do_vad(self._h, ctypes.cast(frames, ctypes.c_void_p), pcm.ctypes.data_as(ctypes.c_void_p), pcm.shape[1],
+                                                None if act is None else act.ctypes.data_as(ctypes.c_void_p), len(frames), frame_length or pcm.shape[1], fs_kHz, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_encode_do_vad')
+        return frames
+
+    def silk_hp_variable_cutoff(self, frames, fs_kHz):
+        """silk_HP_variable_cutoff for n streams: updates variable_HP_smth1_Q15 of the voiced streams' records in place"""
+        r = self._L.opusb200_silk_hp_variable_cutoff(self._h, ctypes.cast(frames, ctypes.c_void_p), len(frames), fs_kHz, 0)
+        if r != 0:
+            raise capi.OpusB200Error(r, 'opusb200_silk_hp_variable_cutoff')
+        return frames
+
     def range_encoder(self, n_streams, buf_bytes=1275):
         return RangeEncoder(self, n_streams, buf_bytes)
 

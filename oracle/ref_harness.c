@@ -603,3 +603,59 @@ void refh_silk_find_pitch_lags(RefhSilkPitch *c, float *res, const float *x, int
   for (k = 0; k < 4; k++) c->pitchL[k] = ctl.pitchL[k];
   c->lagIndex = st.sCmn.indices.lagIndex; c->contourIndex = st.sCmn.indices.contourIndex;
 }
+
+/* ---- silk_VAD_Init / silk_encode_do_VAD_FLP (silk_VAD_GetSA_Q8 inside) / silk_HP_variable_cutoff on a scratch encoder struct
+ * (silk/VAD.c:46-360, silk/float/encode_frame_FLP.c:45-82, silk/HP_variable_cutoff.c:39-77) ---- */
+typedef struct {
+  opus_int32 AnaState[2], AnaState1[2], AnaState2[2], XnrgSubfr[4], NrgRatioSmth_Q8[4], HPstate, NL[4], inv_NL[4], NoiseLevelBias[4], counter;
+  opus_int32 speech_activity_Q8, input_tilt_Q15, input_quality_bands_Q15[4];
+  opus_int32 signalType, noSpeechCounter, inDTX, VAD_flag;
+  opus_int32 prevSignalType, prevLag, variable_HP_smth1_Q15;
+} RefhSilkVad;   /* == OrcSilkVad */
+static void refh_vad_load(silk_encoder_state *s, const RefhSilkVad *c) {
+  int b;
+  silk_VAD_state *v = &s->sVAD;
+  for (b = 0; b < 2; b++) { v->AnaState[b] = c->AnaState[b]; v->AnaState1[b] = c->AnaState1[b]; v->AnaState2[b] = c->AnaState2[b]; }
+  for (b = 0; b < 4; b++) { v->XnrgSubfr[b] = c->XnrgSubfr[b]; v->NrgRatioSmth_Q8[b] = c->NrgRatioSmth_Q8[b]; v->NL[b] = c->NL[b]; v->inv_NL[b] = c->inv_NL[b];
+    v->NoiseLevelBias[b] = c->NoiseLevelBias[b]; s->input_quality_bands_Q15[b] = c->input_quality_bands_Q15[b]; }
+  v->HPstate = (opus_int16)c->HPstate; v->counter = c->counter;
+  s->speech_activity_Q8 = c->speech_activity_Q8; s->input_tilt_Q15 = c->input_tilt_Q15; s->indices.signalType = (opus_int8)c->signalType;
+  s->noSpeechCounter = c->noSpeechCounter; s->inDTX = c->inDTX; s->prevSignalType = c->prevSignalType; s->prevLag = c->prevLag;
+  s->variable_HP_smth1_Q15 = c->variable_HP_smth1_Q15;
+}
+static void refh_vad_store(RefhSilkVad *c, const silk_encoder_state *s) {
+  int b;
+  const silk_VAD_state *v = &s->sVAD;
+  for (b = 0; b < 2; b++) { c->AnaState[b] = v->AnaState[b]; c->AnaState1[b] = v->AnaState1[b]; c->AnaState2[b] = v->AnaState2[b]; }
+  for (b = 0; b < 4; b++) { c->XnrgSubfr[b] = v->XnrgSubfr[b]; c->NrgRatioSmth_Q8[b] = v->NrgRatioSmth_Q8[b]; c->NL[b] = v->NL[b]; c->inv_NL[b] = v->inv_NL[b];
+    c->NoiseLevelBias[b] = v->NoiseLevelBias[b]; c->input_quality_bands_Q15[b] = s->input_quality_bands_Q15[b]; }
+  c->HPstate = v->HPstate; c->counter = v->counter;
+  c->speech_activity_Q8 = s->speech_activity_Q8; c->input_tilt_Q15 = s->input_tilt_Q15; c->signalType = s->indices.signalType;
+  c->noSpeechCounter = s->noSpeechCounter; c->inDTX = s->inDTX; c->prevSignalType = s->prevSignalType; c->prevLag = s->prevLag;
+  c->variable_HP_smth1_Q15 = s->variable_HP_smth1_Q15;
+}
+void refh_silk_vad_init(RefhSilkVad *c) {
+  static silk_encoder_state_FLP st;
+  memset(&st, 0, sizeof(st));
+  memset(c, 0, sizeof(*c));
+  silk_VAD_Init(&st.sCmn.sVAD);
+  refh_vad_store(c, &st.sCmn);
+}
+void refh_silk_encode_do_vad(RefhSilkVad *c, const opus_int16 *pIn, int frame_length, int fs_kHz, int activity) {
+  static silk_encoder_state_FLP st;
+  memset(&st, 0, sizeof(st));
+  refh_vad_load(&st.sCmn, c);
+  st.sCmn.frame_length = frame_length; st.sCmn.fs_kHz = fs_kHz; st.sCmn.nFramesEncoded = 0;
+  memcpy(st.sCmn.inputBuf + 1, pIn, (size_t)frame_length * sizeof(opus_int16));
+  silk_encode_do_VAD_FLP(&st, activity);
+  refh_vad_store(c, &st.sCmn);
+  c->VAD_flag = st.sCmn.VAD_flags[0];
+}
+void refh_silk_hp_variable_cutoff(RefhSilkVad *c, int fs_kHz) {
+  static silk_encoder_state_FLP st[2];
+  memset(st, 0, sizeof(st));
+  refh_vad_load(&st[0].sCmn, c);
+  st[0].sCmn.fs_kHz = fs_kHz;
+  silk_HP_variable_cutoff(st);
+  refh_vad_store(c, &st[0].sCmn);
+}

@@ -922,3 +922,170 @@ void orc_silk_find_pitch_lags(OrcSilkPitch *c, float *res, const float *x, int f
     c->lagIndex = 0; c->contourIndex = 0; c->LTPCorr = 0;
   }
 }
+
+/* ---- voice activity detection of a SILK frame: silk_VAD_Init / silk_VAD_GetSA_Q8_c / silk_VAD_GetNoiseLevels (silk/VAD.c:46-360),
+ * silk_ana_filt_bank_1 (silk/ana_filt_bank_1.c:39-74), silk_SQRT_APPROX (silk/Inlines.h:67-90), silk_sigm_Q15 (silk/sigm_Q15.c:49-76), the VAD / DTX
+ * flags of silk_encode_do_VAD_FLP (silk/float/encode_frame_FLP.c:45-82) and silk_HP_variable_cutoff (silk/HP_variable_cutoff.c:39-77).  The record is
+ * silk_VAD_state plus the silk_encoder_state fields those functions read and write. ---- */
+typedef struct {
+  int32_t AnaState[2], AnaState1[2], AnaState2[2], XnrgSubfr[4], NrgRatioSmth_Q8[4], HPstate, NL[4], inv_NL[4], NoiseLevelBias[4], counter;
+  int32_t speech_activity_Q8, input_tilt_Q15, input_quality_bands_Q15[4];
+  int32_t signalType, noSpeechCounter, inDTX, VAD_flag;
+  int32_t prevSignalType, prevLag, variable_HP_smth1_Q15;
+} OrcSilkVad;
+static int32_t vad_add_pos_sat32(int32_t a, int32_t b) { const uint32_t s = (uint32_t)a + (uint32_t)b; return (s & 0x80000000u) ? 0x7FFFFFFF : (int32_t)s; }
+static int32_t vad_sqrt_approx(int32_t x) {
+  int lz; int32_t y, frac_Q7;
+  if (x <= 0) return 0;
+  lz = __builtin_clz((uint32_t)x);
+  frac_Q7 = orc_ror32(x, 24 - lz) & 0x7f;
+  y = (lz & 1) ? 32768 : 46214;
+  y >>= (lz >> 1);
+  return smlawb(y, y, (int16_t)213 * (int32_t)(int16_t)frac_Q7);
+}
+static int vad_sigm_Q15(int in_Q5) {
+  static const int32_t slope_Q10[6] = {237, 153, 73, 30, 12, 7}, pos_Q15[6] = {16384, 23955, 28861, 31213, 32178, 32548}, neg_Q15[6] = {16384, 8812, 3906, 1554, 589, 219};
+  if (in_Q5 < 0) {
+    in_Q5 = -in_Q5;
+    if (in_Q5 >= 6 * 32) return 0;
+    return neg_Q15[in_Q5 >> 5] - (int16_t)slope_Q10[in_Q5 >> 5] * (int32_t)(int16_t)(in_Q5 & 0x1F);
+  }
+  if (in_Q5 >= 6 * 32) return 32767;
+  return pos_Q15[in_Q5 >> 5] + (int16_t)slope_Q10[in_Q5 >> 5] * (int32_t)(int16_t)(in_Q5 & 0x1F);
+}
+static int16_t vad_sat16(int32_t a) { return (int16_t)(a > 32767 ? 32767 : a < -32768 ? -32768 : a); }
+static int32_t vad_rshift_round(int32_t a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
+static void vad_ana_filt_bank_1(const int16_t *in, int32_t *S, int16_t *outL, int16_t *outH, int N) {
+  const int N2 = N >> 1; int k;
+  for (k = 0; k < N2; k++) {
+    int32_t in32 = (int32_t)in[2 * k] * 1024, Y, X, out_1, out_2;
+    Y = in32 - S[0]; X = smlawb(Y, Y, -24290); out_1 = S[0] + X; S[0] = in32 + X;
+    in32 = (int32_t)in[2 * k + 1] * 1024;
+    Y = in32 - S[1]; X = smulwb(Y, 5394 << 1); out_2 = S[1] + X; S[1] = in32 + X;
+    outL[k] = vad_sat16(vad_rshift_round(out_2 + out_1, 11));
+    outH[k] = vad_sat16(vad_rshift_round(out_2 - out_1, 11));
+  }
+}
+void orc_silk_vad_init(OrcSilkVad *c) {
+  int b;
+  memset(c, 0, sizeof(*c));
+  for (b = 0; b < 4; b++) {
+    const int32_t bias = 50 / (b + 1);
+    c->NoiseLevelBias[b] = bias > 1 ? bias : 1;
+    c->NL[b] = 100 * c->NoiseLevelBias[b];
+    c->inv_NL[b] = 0x7FFFFFFF / c->NL[b];
+    c->NrgRatioSmth_Q8[b] = 100 * 256;
+  }
+  c->counter = 15;
+}
+static void vad_noise_levels(const int32_t *pX, OrcSilkVad *c) {
+  int k, coef, min_coef;
+  if (c->counter < 1000) { min_coef = 32767 / ((c->counter >> 4) + 1); c->counter++; } else min_coef = 0;
+  for (k = 0; k < 4; k++) {
+    int32_t nl = c->NL[k];
+    const int32_t nrg = vad_add_pos_sat32(pX[k], c->NoiseLevelBias[k]), inv_nrg = 0x7FFFFFFF / nrg;
+    if (nrg > (int32_t)((uint32_t)nl << 3)) coef = 1024 >> 3;
+    else if (nrg < nl) coef = 1024;
+    else coef = smulwb((int32_t)(((int64_t)inv_nrg * nl) >> 16), 1024 << 1);
+    if (coef < min_coef) coef = min_coef;
+    c->inv_NL[k] = smlawb(c->inv_NL[k], inv_nrg - c->inv_NL[k], coef);
+    nl = 0x7FFFFFFF / c->inv_NL[k];
+    c->NL[k] = nl < 0x00FFFFFF ? nl : 0x00FFFFFF;
+  }
+}
+/* silk_VAD_GetSA_Q8_c: pIn = frame_length samples (inputBuf + 1); frame_length = 10 or 20 ms at fs_kHz. */
+void orc_silk_vad_get_sa(OrcSilkVad *c, const int16_t *pIn, int frame_length, int fs_kHz) {
+  int16_t X[512 / 2 + 512 / 4 + 512 / 8 + 512 / 8 + 512 / 4];
+  int32_t Xnrg[4], ratio_Q8[4], sumSquared = 0, speech_nrg, smooth_coef_Q16;
+  int X_offset[4], b, s, i, SA_Q15, pSNR_dB_Q7, input_tilt = 0, SNR_Q7;
+  static const int32_t tiltWeights[4] = {30000, 6000, -12000, -12000};
+  const int d1 = frame_length >> 1, d2 = frame_length >> 2, d3 = frame_length >> 3;
+  int16_t hp_tmp;
+  X_offset[0] = 0; X_offset[1] = d3 + d2; X_offset[2] = X_offset[1] + d3; X_offset[3] = X_offset[2] + d2;
+  vad_ana_filt_bank_1(pIn, c->AnaState, X, X + X_offset[3], frame_length);
+  vad_ana_filt_bank_1(X, c->AnaState1, X, X + X_offset[2], d1);
+  vad_ana_filt_bank_1(X, c->AnaState2, X, X + X_offset[1], d2);
+  X[d3 - 1] = (int16_t)(X[d3 - 1] >> 1);
+  hp_tmp = X[d3 - 1];
+  for (i = d3 - 1; i > 0; i--) { X[i - 1] = (int16_t)(X[i - 1] >> 1); X[i] = (int16_t)(X[i] - X[i - 1]); }
+  X[0] = (int16_t)(X[0] - (int16_t)c->HPstate);
+  c->HPstate = hp_tmp;
+  for (b = 0; b < 4; b++) {
+    const int sh = 4 - b < 3 ? 4 - b : 3, dl = frame_length >> sh, sl = dl >> 2;
+    int off = 0;
+    Xnrg[b] = c->XnrgSubfr[b];
+    for (s = 0; s < 4; s++) {
+      sumSquared = 0;
+      for (i = 0; i < sl; i++) { const int32_t x_tmp = X[X_offset[b] + i + off] >> 3; sumSquared += x_tmp * x_tmp; }
+      Xnrg[b] = vad_add_pos_sat32(Xnrg[b], s < 3 ? sumSquared : sumSquared >> 1);
+      off += sl;
+    }
+    c->XnrgSubfr[b] = sumSquared;
+  }
+  vad_noise_levels(Xnrg, c);
+  sumSquared = 0;
+  for (b = 0; b < 4; b++) {
+    speech_nrg = Xnrg[b] - c->NL[b];
+    if (speech_nrg > 0) {
+      if ((Xnrg[b] & 0xFF800000) == 0) ratio_Q8[b] = (int32_t)((uint32_t)Xnrg[b] << 8) / (c->NL[b] + 1);
+      else ratio_Q8[b] = Xnrg[b] / ((c->NL[b] >> 8) + 1);
+      SNR_Q7 = orc_silk_lin2log(ratio_Q8[b]) - 8 * 128;
+      sumSquared += (int16_t)SNR_Q7 * (int32_t)(int16_t)SNR_Q7;
+      if (speech_nrg < (1 << 20)) SNR_Q7 = smulwb((int32_t)((uint32_t)vad_sqrt_approx(speech_nrg) << 6), SNR_Q7);
+      input_tilt = smlawb(input_tilt, tiltWeights[b], SNR_Q7);
+    } else ratio_Q8[b] = 256;
+  }
+  sumSquared = sumSquared / 4;
+  pSNR_dB_Q7 = (int16_t)(3 * vad_sqrt_approx(sumSquared));
+  SA_Q15 = vad_sigm_Q15(smulwb(45000, pSNR_dB_Q7) - 128);
+  c->input_tilt_Q15 = (vad_sigm_Q15(input_tilt) - 16384) * 2;
+  speech_nrg = 0;
+  for (b = 0; b < 4; b++) speech_nrg += (b + 1) * ((Xnrg[b] - c->NL[b]) >> 4);
+  if (frame_length == 20 * fs_kHz) speech_nrg >>= 1;
+  if (speech_nrg <= 0) SA_Q15 >>= 1;
+  else if (speech_nrg < 16384) {
+    speech_nrg = (int32_t)((uint32_t)speech_nrg << 16);
+    speech_nrg = vad_sqrt_approx(speech_nrg);
+    SA_Q15 = smulwb(32768 + speech_nrg, SA_Q15);
+  }
+  c->speech_activity_Q8 = (SA_Q15 >> 7) < 255 ? (SA_Q15 >> 7) : 255;
+  smooth_coef_Q16 = smulwb(4096, smulwb(SA_Q15, SA_Q15));
+  if (frame_length == 10 * fs_kHz) smooth_coef_Q16 >>= 1;
+  for (b = 0; b < 4; b++) {
+    c->NrgRatioSmth_Q8[b] = smlawb(c->NrgRatioSmth_Q8[b], ratio_Q8[b] - c->NrgRatioSmth_Q8[b], smooth_coef_Q16);
+    SNR_Q7 = 3 * (orc_silk_lin2log(c->NrgRatioSmth_Q8[b]) - 8 * 128);
+    c->input_quality_bands_Q15[b] = vad_sigm_Q15((SNR_Q7 - 16 * 128) >> 4);
+  }
+}
+/* silk_encode_do_VAD_FLP: the VAD, the Opus-level activity override and the VAD / DTX bookkeeping (VAD_flag = VAD_flags[nFramesEncoded]). */
+void orc_silk_encode_do_vad(OrcSilkVad *c, const int16_t *pIn, int frame_length, int fs_kHz, int activity) {
+  const int thr = 13;   /* SILK_FIX_CONST(SPEECH_ACTIVITY_DTX_THRES = 0.05, 8) */
+  orc_silk_vad_get_sa(c, pIn, frame_length, fs_kHz);
+  if (activity == 0 && c->speech_activity_Q8 >= thr) c->speech_activity_Q8 = thr - 1;
+  if (c->speech_activity_Q8 < thr) {
+    c->signalType = 0;
+    c->noSpeechCounter++;
+    if (c->noSpeechCounter <= 10) c->inDTX = 0;
+    else if (c->noSpeechCounter > 20 + 10) { c->noSpeechCounter = 10; c->inDTX = 0; }
+    c->VAD_flag = 0;
+  } else {
+    c->noSpeechCounter = 0; c->inDTX = 0; c->signalType = 1; c->VAD_flag = 1;
+  }
+}
+/* silk_HP_variable_cutoff: the pitch-driven smoother of the high-pass cutoff (the second smoother is opus_encode_native's, src/opus_encoder.c:1974). */
+void orc_silk_hp_variable_cutoff(OrcSilkVad *c, int fs_kHz) {
+  if (c->prevSignalType == 2) {
+    const int32_t pitch_freq_Hz_Q16 = (int32_t)((uint32_t)(fs_kHz * 1000) << 16) / (int16_t)c->prevLag;
+    int32_t pitch_freq_log_Q7 = orc_silk_lin2log(pitch_freq_Hz_Q16) - (16 << 7), delta_freq_Q7;
+    const int quality_Q15 = c->input_quality_bands_Q15[0];
+    pitch_freq_log_Q7 = smlawb(pitch_freq_log_Q7, smulwb((int32_t)((uint32_t)(-quality_Q15) << 2), quality_Q15),
+                               pitch_freq_log_Q7 - (orc_silk_lin2log(60 << 16) - (16 << 7)));
+    delta_freq_Q7 = pitch_freq_log_Q7 - (c->variable_HP_smth1_Q15 >> 8);
+    if (delta_freq_Q7 < 0) delta_freq_Q7 *= 3;
+    if (delta_freq_Q7 > 51) delta_freq_Q7 = 51; else if (delta_freq_Q7 < -51) delta_freq_Q7 = -51;   /* SILK_FIX_CONST(0.4, 7) = 51 */
+    c->variable_HP_smth1_Q15 = smlawb(c->variable_HP_smth1_Q15, (int16_t)c->speech_activity_Q8 * (int32_t)(int16_t)delta_freq_Q7, 6554);   /* SILK_FIX_CONST(0.1, 16) */
+    { const int32_t lo = orc_silk_lin2log(60) << 8, hi = orc_silk_lin2log(100) << 8;
+      if (c->variable_HP_smth1_Q15 < lo) c->variable_HP_smth1_Q15 = lo; else if (c->variable_HP_smth1_Q15 > hi) c->variable_HP_smth1_Q15 = hi; }
+  }
+}
+int orc_silk_vad_size(void) { return (int)sizeof(OrcSilkVad); }

@@ -608,3 +608,26 @@ extern "C" void emu_silk_find_pitch_lags(void *frames, float *res, int res_strid
   p.nb_subfr = nb_subfr; p.lpc_order = order; p.complexity = complexity;
   emu_launch(silk_pitch_entry, &p, (n + 31) / 32, 32, 0);
 }
+
+// ---- silk_encode_do_VAD_FLP / silk_HP_variable_cutoff (silk_vad.cuh), thread per stream ----
+#include "../../opus_b200/csrc/silk_vad.cuh"
+static void silk_vad_entry(void *a) {
+  const SilkVadParams &p = *(const SilkVadParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_encode_do_vad_thread(p, s);
+}
+static void silk_hp_cutoff_entry(void *a) {
+  const SilkHpCutoffParams &p = *(const SilkHpCutoffParams *)a;
+  const int s = block_id() * 32 + lane_id();
+  if (s < p.n) silk_hp_variable_cutoff_thread(p, s);
+}
+extern "C" void emu_silk_encode_do_vad(void *frames, const int16_t *pcm, int pcm_stride, const int32_t *activity, int n, int frame_length, int fs_kHz) {
+  SilkVadParams p;
+  p.frames = (ObSilkVad *)frames; p.pcm = pcm; p.activity = activity; p.n = n; p.pcm_stride = pcm_stride; p.frame_length = frame_length; p.fs_kHz = fs_kHz;
+  emu_launch(silk_vad_entry, &p, (n + 31) / 32, 32, 0);
+}
+extern "C" void emu_silk_hp_variable_cutoff(void *frames, int n, int fs_kHz) {
+  SilkHpCutoffParams p;
+  p.frames = (ObSilkVad *)frames; p.n = n; p.fs_kHz = fs_kHz;
+  emu_launch(silk_hp_cutoff_entry, &p, (n + 31) / 32, 32, 0);
+}

@@ -396,3 +396,27 @@ def test_silk_find_pitch_lags_emulated(fs_kHz, nb_subfr, order, complexity):
             voiced += int(want[s].signalType == 2)
             prev[s] = (want[s].signalType, want[s].pitchL[nb_subfr - 1] if want[s].signalType == 2 else 0, want[s].LTPCorr)
     assert voiced > 5
+
+
+@pytest.mark.parametrize('fs_kHz,frame_ms,pad', [(16, 20, 0), (12, 20, 3), (8, 20, 8), (16, 10, 1), (12, 10, 0), (8, 10, 5)])
+def test_silk_encode_do_vad_emulated(fs_kHz, frame_ms, pad):
+    """silk_encode_do_VAD_FLP (silk_VAD_GetSA_Q8 streamed through the three filter banks in registers) + silk_HP_variable_cutoff: the device source on
+    the emulator against the oracle (pinned on the reference), 40 frames with the whole record carried; pad shifts the streams' rows off 16-byte alignment
+    so that both the vector and the scalar load paths run"""
+    from test_silk_vad_oracle_vs_ref import drive_vad
+    E = emu_util.load_emu_ops()
+
+    def init(recs):
+        O = util.load_oracle()
+        for s in range(len(recs)):
+            O.orc_silk_vad_init(ctypes.byref(recs[s]))
+
+    def do_vad(recs, pcm, activity, frame_length):
+        E.emu_silk_encode_do_vad(ctypes.cast(recs, ctypes.c_void_p), pcm.ctypes.data_as(ctypes.c_void_p), pcm.shape[1], activity.ctypes.data_as(ctypes.c_void_p), len(recs),
+                                 frame_length, fs_kHz)
+
+    def hp(recs):
+        E.emu_silk_hp_variable_cutoff(ctypes.cast(recs, ctypes.c_void_p), len(recs), fs_kHz)
+
+    same, total, active = drive_vad(init, do_vad, hp, 40, fs_kHz, frame_ms, 40, 500 + fs_kHz + frame_ms, pad)
+    assert same == total and 50 < active < total - 50

@@ -538,3 +538,20 @@ def test_silk_find_pitch_lags(fs_kHz, nb_subfr, order, complexity):
             prev[s] = (want[s].signalType, want[s].pitchL[nb_subfr - 1] if want[s].signalType == 2 else 0, want[s].LTPCorr)
     print('bit-identical stream-frames: %d of %d (%d voiced)' % (exact, total, voiced))
     assert exact >= 0.97 * total and voiced > 20
+
+
+@pytest.mark.parametrize('fs_kHz,frame_ms,pad', [(16, 20, 0), (12, 20, 3), (8, 10, 8), (16, 10, 1)])
+def test_silk_encode_do_vad(fs_kHz, frame_ms, pad):
+    """opusb200_silk_vad_init / _encode_do_vad / _hp_variable_cutoff against the oracle (pinned bit for bit on silk_VAD_Init, silk_encode_do_VAD_FLP with
+    silk_VAD_GetSA_Q8 inside, silk_HP_variable_cutoff): 300 streams x 30 frames with the whole record carried (filter-bank states, noise levels, smoothed
+    ratios, DTX counters, the cutoff smoother); pad moves the rows off 16-byte alignment so both load paths run"""
+    import opus_b200
+    from test_silk_vad_oracle_vs_ref import drive_vad
+    ops = opus_b200.Ops()
+    try:
+        same, total, active = drive_vad(ops.silk_vad_init, lambda recs, pcm, act, fl: ops.silk_encode_do_vad(recs, pcm, fs_kHz, act, fl),
+                                        lambda recs: ops.silk_hp_variable_cutoff(recs, fs_kHz), 300, fs_kHz, frame_ms, 30, 900 + fs_kHz + frame_ms, pad)
+    finally:
+        ops.close()
+    print('bit-identical stream-frames: %d of %d (%d active)' % (same, total, active))
+    assert same == total and 300 < active < total - 300

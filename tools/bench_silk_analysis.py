@@ -39,6 +39,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--n', type=int, default=65536)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--only', default='', help="'vad_pitch' = only the voice activity detector and the pitch analysis")
     a = ap.parse_args()
     n, base = a.n, 128
     ops = opus_b200.Ops(0)
@@ -53,6 +54,35 @@ def main():
         if cpu_s:
             rec['speedup_vs_1core'] = rec['units_per_s'] * cpu_s
         print(json.dumps(rec), flush=True)
+
+
+    # ---- voice activity detector and pitch analysis ----
+    from test_silk_vad_oracle_vs_ref import Vad, vad_signal
+    from test_silk_pitch_oracle_vs_ref import Pitch, pitch_input, random_case as pitch_case
+    v = (Vad * base)()
+    ops.silk_vad_init(v)
+    pcm = np.stack([vad_signal(rng, 16, 320, 2)[1] for _ in range(base)])
+    d, dx = tile_records(v, n), tile_rows(pcm, n)
+    ms = time_gpu(stream, lambda: L.opusb200_silk_encode_do_vad(ops._h, dptr(d), dptr(dx), 320, None, n, 320, 16, 1), a.reps)
+    one = Vad.from_buffer_copy(bytes(v[3]))
+    emit('silk_encode_do_VAD_FLP (silk_VAD_GetSA_Q8)', ms,
+         time_cpu(lambda: R.refh_silk_encode_do_vad(ctypes.byref(one), pcm[3].ctypes.data_as(ctypes.c_void_p), 320, 16, 1)) if R else None)
+    rec = {'op': 'silk_encode_do_VAD_FLP roofline', 'bytes_per_stream_frame': 2 * 320 + 2 * ctypes.sizeof(Vad), 'achieved_GBps': (2 * 320 + 2 * ctypes.sizeof(Vad)) * n / (ms * 1e-3) / 1e9}
+    print(json.dumps(rec), flush=True)
+    pt = (Pitch * base)()
+    X_ = np.stack([pitch_input(rng, 16, 4, s % 3) for s in range(base)])
+    for s in range(base):
+        pt[s] = pitch_case(rng, 16, 1, (0, 0, np.float32(0)))
+    buf_len = (22 + 5 * 4) * 16
+    d, dx = tile_records(pt, n), tile_rows(X_, n)
+    dres = torch.empty((n, buf_len), dtype=torch.float32, device='cuda')
+    ms = time_gpu(stream, lambda: L.opusb200_silk_find_pitch_lags(ops._h, dptr(d), dptr(dres), buf_len, dptr(dx), X_.shape[1], 320, n, 16, 4, 16, 2, 1), a.reps)
+    rr = np.zeros(buf_len, np.float32)
+    emit('silk_find_pitch_lags_FLP (complexity 2)', ms,
+         time_cpu(lambda: R.refh_silk_find_pitch_lags(ctypes.byref(Pitch.from_buffer_copy(bytes(pt[3]))), rr.ctypes.data_as(ctypes.c_void_p),
+                                                      X_[3, 320:].ctypes.data_as(ctypes.c_void_p), 16, 4, 16, 2)) if R else None)
+    if a.only == 'vad_pitch':
+        return
 
     g = (Gains * base)()
     for s in range(base):
